@@ -1,0 +1,359 @@
+/*
+ * b2_copr.h — C ABI of the B200-native coprocessor batch-execution engine.
+ *
+ * This is the drop-in boundary for TiKV's DAG-pushdown hot path.  Every entry
+ * point names the reference interface it replaces (paths relative to the
+ * tikv/tikv tree):
+ *
+ *   b2_exec_*           <- trait BatchExecutor
+ *                          components/tidb_query_executors/src/interface.rs:36-97
+ *   b2_batch            <- struct BatchExecuteResult             interface.rs:205-236
+ *   b2_dag_handle       <- RequestHandler::handle_request for BatchDagHandler
+ *                          src/coprocessor/mod.rs:67-94, src/coprocessor/dag/mod.rs:189-192
+ *   b2_check_supported  <- BatchExecutorsRunner::check_supported
+ *                          components/tidb_query_executors/src/runner.rs:111-206
+ *   b2_checksum_handle  <- ChecksumContext::handle_request       src/coprocessor/checksum.rs:59-98
+ *   b2_region_source    <- trait Storage (bulk instead of row-at-a-time pull)
+ *                          components/tidb_query_common/src/storage/mod.rs:32-71
+ *   b2_dag_plan         <- tipb::DagRequest as consumed by build_executors, runner.rs:252-603
+ *
+ * Plain C types only: pointers, sizes, PODs.  No C++/torch types cross this line.
+ * Handles are single-threaded (externally synchronised), like `BatchExecutor: Send`.
+ * Output memory is callee-owned and valid until the next call on the same handle.
+ */
+#ifndef B2_COPR_H_
+#define B2_COPR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_ABI_VERSION 1
+
+/* ---- status codes (tidb_query_common::error::Error classes, dag/mod.rs:231-244) ---- */
+enum {
+  B2_OK = 0,
+  B2_ERR_STORAGE = 1,        /* Error::Storage: bad write record, default CF miss, ... */
+  B2_ERR_KEY_IS_LOCKED = 2,  /* txn_types::ErrorInner::KeyIsLocked (lock.rs:457-476) */
+  B2_ERR_WRITE_CONFLICT = 3, /* RcCheckTs newer version (forward.rs:342-354) */
+  B2_ERR_EVALUATE = 4,       /* Error::Evaluate{code,msg}; code in b2_error_info.mysql_code */
+  B2_ERR_CORRUPTED = 5,      /* row / datum decode failure (other_err! in table_scan_executor.rs) */
+  B2_ERR_DEADLINE = 6,
+  B2_ERR_UNSUPPORTED = 7,    /* plan not supported on the device path: host falls back */
+  B2_ERR_CUDA = 8,
+  B2_ERR_INVALID_ARG = 9
+};
+
+/* MySQL error codes preserved across the boundary */
+#define B2_MYSQL_ERR_DATA_OUT_OF_RANGE 1690
+#define B2_MYSQL_ERR_TRUNCATED 1292
+#define B2_MYSQL_ERR_DIVISION_BY_ZERO 1365
+
+/* ---- field types (tidb_query_datatype/src/def/field_type.rs; MySQL protocol codes) ---- */
+enum {
+  B2_TP_TINY = 1, B2_TP_SHORT = 2, B2_TP_LONG = 3, B2_TP_FLOAT = 4, B2_TP_DOUBLE = 5,
+  B2_TP_NULL = 6, B2_TP_TIMESTAMP = 7, B2_TP_LONGLONG = 8, B2_TP_INT24 = 9, B2_TP_DATE = 10,
+  B2_TP_DURATION = 11, B2_TP_DATETIME = 12, B2_TP_YEAR = 13, B2_TP_VARCHAR = 15, B2_TP_BIT = 16,
+  B2_TP_JSON = 0xf5, B2_TP_NEWDECIMAL = 0xf6, B2_TP_ENUM = 0xf7, B2_TP_SET = 0xf8,
+  B2_TP_BLOB = 0xfc, B2_TP_VARSTRING = 0xfd, B2_TP_STRING = 0xfe
+};
+#define B2_FLAG_NOT_NULL 1u
+#define B2_FLAG_UNSIGNED 32u
+
+/* extra column ids (codec/table.rs:49-57) */
+#define B2_EXTRA_PHYSICAL_TABLE_ID_COL_ID (-3)
+#define B2_EXTRA_COMMIT_TS_COL_ID (-5)
+
+/* ---- data source: sorted column-family blocks ---------------------------------------
+ * One block = n KV entries in ascending key order (RocksDB iteration order, data prefix
+ * 'z' already stripped as RegionSnapshot does).  Entry i: key  = keys[key_offs[i]..key_offs[i+1])
+ *                                                        value= vals[val_offs[i]..val_offs[i+1])
+ * Heaps must be 16-byte aligned and readable up to the next multiple of 16 bytes past
+ * offs[n] (the loader moves whole 16-byte lines).  All versions of one user key live in the
+ * same block.  `location` says where the pointers live.                                    */
+enum { B2_LOC_HOST = 0, B2_LOC_DEVICE = 1 };
+
+typedef struct b2_cf_block {
+  const uint8_t* keys;
+  const uint32_t* key_offs; /* n+1 entries */
+  const uint8_t* vals;
+  const uint32_t* val_offs; /* n+1 entries */
+  uint32_t n;
+  uint32_t _pad;
+} b2_cf_block;
+
+/* kvrpcpb::IsolationLevel */
+enum { B2_ISO_SI = 0, B2_ISO_RC = 1, B2_ISO_RC_CHECK_TS = 2 };
+
+typedef struct b2_region_source {
+  int32_t location;              /* of write/default blocks; lock block is always host memory */
+  int32_t device;                /* CUDA ordinal for B2_LOC_DEVICE pointers / where to run */
+  const b2_cf_block* write;      /* CF_WRITE blocks, globally ordered */
+  uint32_t n_write;
+  const b2_cf_block* dflt;       /* CF_DEFAULT blocks (long values), may be NULL */
+  uint32_t n_dflt;
+  const b2_cf_block* lock;       /* CF_LOCK, host memory, may be NULL (or RC isolation) */
+  uint64_t read_ts;              /* ScannerConfig::ts */
+  int32_t isolation_level;
+  int32_t check_has_newer_ts_data;
+  const uint64_t* bypass_locks;  /* TsSet */
+  uint32_t n_bypass_locks;
+  const uint64_t* access_locks;  /* non-empty => B2_ERR_UNSUPPORTED when one is hit */
+  uint32_t n_access_locks;
+} b2_region_source;
+
+/* raw (not memcomparable-encoded) key range, like coppb::KeyRange */
+typedef struct b2_key_range {
+  const uint8_t* start; uint32_t start_len;
+  const uint8_t* end;   uint32_t end_len;
+} b2_key_range;
+
+/* ---- plan descriptor ------------------------------------------------------------------ */
+/* tipb::ColumnInfo as used by BatchTableScanExecutor::new (table_scan_executor.rs:56-150) */
+typedef struct b2_column_info {
+  int64_t col_id;
+  int32_t tp;                /* B2_TP_* */
+  uint32_t flag;             /* B2_FLAG_* */
+  int32_t pk_handle;         /* int handle stored in the key */
+  uint32_t default_len;
+  const uint8_t* default_val;/* datum-encoded default, NULL/0 = none */
+} b2_column_info;
+
+/* RPN node kinds (tidb_query_expr/src/types/expr.rs:11-30) */
+enum { B2_RPN_CONST_NULL = 0, B2_RPN_CONST_INT = 1, B2_RPN_CONST_UINT = 2, B2_RPN_CONST_REAL = 3,
+       B2_RPN_COLUMN_REF = 4, B2_RPN_FN = 5 };
+
+/* Scalar function signatures.  Names follow tipb::ScalarFuncSig; numeric values follow
+ * tipb expression.proto as pinned by Cargo.lock (pingcap/tipb @ 1374320b, not vendored in
+ * the reference tree) and are re-exported by name in INTEGRATION.md's binding.            */
+enum {
+  B2_SIG_LT_INT = 100, B2_SIG_LT_REAL = 101,
+  B2_SIG_LE_INT = 110, B2_SIG_LE_REAL = 111,
+  B2_SIG_GT_INT = 120, B2_SIG_GT_REAL = 121,
+  B2_SIG_GE_INT = 130, B2_SIG_GE_REAL = 131,
+  B2_SIG_EQ_INT = 140, B2_SIG_EQ_REAL = 141,
+  B2_SIG_NE_INT = 150, B2_SIG_NE_REAL = 151,
+  B2_SIG_NULLEQ_INT = 160, B2_SIG_NULLEQ_REAL = 161,
+  B2_SIG_PLUS_REAL = 200, B2_SIG_PLUS_INT = 203,
+  B2_SIG_MINUS_REAL = 204, B2_SIG_MINUS_INT = 207,
+  B2_SIG_MULTIPLY_REAL = 208, B2_SIG_MULTIPLY_INT = 210,
+  B2_SIG_MULTIPLY_INT_UNSIGNED = 218,
+  B2_SIG_LOGICAL_AND = 3101, B2_SIG_LOGICAL_OR = 3102, B2_SIG_LOGICAL_XOR = 3103,
+  B2_SIG_UNARY_NOT_INT = 3104, B2_SIG_UNARY_NOT_REAL = 3106,
+  B2_SIG_REAL_IS_NULL = 3114, B2_SIG_INT_IS_NULL = 3116,
+  B2_SIG_INT_IS_TRUE = 3118, B2_SIG_REAL_IS_TRUE = 3119,
+  B2_SIG_INT_IS_FALSE = 3121, B2_SIG_REAL_IS_FALSE = 3122
+};
+
+typedef struct b2_rpn_node {
+  int32_t kind;       /* B2_RPN_* */
+  int32_t sig;        /* B2_SIG_* when kind == FN */
+  int32_t n_args;     /* FN arity */
+  int32_t field_tp;   /* return field type B2_TP_* */
+  uint32_t field_flag;/* return field flags (UNSIGNED matters for compare dispatch, lib.rs:223-259) */
+  int32_t _pad;
+  int64_t i64;        /* CONST_INT/UINT payload, or COLUMN_REF offset into the child schema */
+  double f64;         /* CONST_REAL payload */
+} b2_rpn_node;
+
+typedef struct b2_rpn_expr {
+  const b2_rpn_node* nodes; /* post-order */
+  uint32_t n_nodes;
+  uint32_t _pad;
+} b2_rpn_expr;
+
+/* tipb::ExprType aggregate kinds (tidb_query_aggr/src/parser.rs:67-88) */
+enum { B2_AGG_COUNT = 3001, B2_AGG_SUM = 3002, B2_AGG_AVG = 3003, B2_AGG_MIN = 3004,
+       B2_AGG_MAX = 3005, B2_AGG_FIRST = 3006 };
+
+typedef struct b2_aggr_desc {
+  int32_t kind;      /* B2_AGG_* */
+  int32_t _pad;
+  b2_rpn_expr arg;   /* argument expression (COUNT(1) = one CONST_INT node) */
+} b2_aggr_desc;
+
+typedef struct b2_order_by {
+  b2_rpn_expr expr;
+  int32_t desc;
+  int32_t _pad;
+} b2_order_by;
+
+/* tipb::ExecType */
+enum { B2_EXEC_TABLE_SCAN = 0, B2_EXEC_INDEX_SCAN = 1, B2_EXEC_SELECTION = 2,
+       B2_EXEC_AGGREGATION = 3 /* hash */, B2_EXEC_TOPN = 4, B2_EXEC_LIMIT = 5,
+       B2_EXEC_STREAM_AGG = 6 };
+
+typedef struct b2_executor_desc {
+  int32_t tp; /* B2_EXEC_* */
+  int32_t desc;                       /* TableScan.desc */
+  int64_t table_id;                   /* TableScan */
+  const b2_column_info* columns;      /* TableScan */
+  uint32_t n_columns;
+  uint32_t n_conditions;
+  const b2_rpn_expr* conditions;      /* Selection: AND of conditions */
+  const b2_rpn_expr* group_by;        /* Aggregation */
+  uint32_t n_group_by;
+  uint32_t n_aggrs;
+  const b2_aggr_desc* aggrs;          /* Aggregation */
+  const b2_order_by* order_by;        /* TopN */
+  uint32_t n_order_by;
+  uint32_t _pad;
+  uint64_t limit;                     /* TopN / Limit */
+} b2_executor_desc;
+
+typedef struct b2_dag_plan {
+  const b2_executor_desc* executors;  /* executors[0] is the scan, like DagRequest.executors */
+  uint32_t n_executors;
+  uint32_t n_output_offsets;
+  const uint32_t* output_offsets;     /* NULL = all columns */
+  uint64_t flags;                     /* DagRequest.flags (expr/ctx.rs:24-52) */
+} b2_dag_plan;
+
+typedef struct b2_exec_config {
+  int32_t output_location;  /* B2_LOC_HOST: results copied to host memory; B2_LOC_DEVICE: device ptrs */
+  int32_t staging_tiles;    /* 0 = default */
+  uint64_t cuda_stream;     /* 0 = handle creates its own stream; else a cudaStream_t to run on */
+  uint64_t reserved[4];
+} b2_exec_config;
+
+/* ---- results ------------------------------------------------------------------------------ */
+enum { B2_COL_I64 = 0, B2_COL_F64 = 1, B2_COL_DECIMAL = 2 };
+
+/* #[repr(C)] Decimal, codec/mysql/decimal.rs:927-942 (raw 40 bytes as write_decimal_to_chunk dumps) */
+typedef struct b2_decimal {
+  uint8_t int_cnt, frac_cnt, result_frac_cnt, negative;
+  uint32_t word_buf[9];
+} b2_decimal;
+
+/* one decoded column: ChunkedVecSized<T>{data, bitmap} (chunked_vec_sized.rs:17-22) */
+typedef struct b2_column {
+  int32_t kind;               /* B2_COL_* */
+  int32_t field_tp;
+  uint32_t field_flag;
+  uint32_t _pad;
+  uint64_t len;
+  const void* data;           /* len elements of i64 / f64 / b2_decimal; NULL cells hold 0 */
+  const uint64_t* null_bitmap;/* bit i (word i>>6, bit i&63) = 1 => non-null (bit_vec.rs:25-38) */
+} b2_column;
+
+enum { B2_DRAIN_REMAIN = 0, B2_DRAIN_DRAINED = 1, B2_DRAIN_PAGING = 2 };
+
+/* BatchExecuteResult: logical_rows is the identity here (columns come back compacted) */
+typedef struct b2_batch {
+  const b2_column* columns;
+  uint32_t n_columns;
+  int32_t is_drained;         /* B2_DRAIN_* */
+  uint64_t n_rows;
+  uint32_t n_warnings;
+  uint32_t _pad;
+} b2_batch;
+
+/* ExecSummary (execute_stats.rs:8-16) + the scan counters callers read back (stats.rs:95-114) */
+typedef struct b2_exec_stats {
+  uint64_t num_iterations;
+  uint64_t num_produced_rows;
+  uint64_t time_processed_ns;   /* device time from CUDA events */
+  uint64_t write_entries_scanned; /* CF_WRITE entries visited (all versions) */
+  uint64_t write_processed_keys;  /* rows returned by the MVCC scan */
+  uint64_t processed_size;        /* sum(len(user_key)+len(value)) over returned rows, forward.rs:517-519 */
+  uint64_t default_lookups;       /* CF_DEFAULT fetches */
+  uint64_t lock_processed_keys;
+  int32_t met_newer_ts_data;      /* -1 unknown, 0 not met, 1 met (NewerTsCheckState) */
+  int32_t _pad;
+} b2_exec_stats;
+
+typedef struct b2_error_info {
+  int32_t status;
+  int32_t mysql_code;
+  uint64_t entry_index;  /* global CF_WRITE entry index of the failing row, or ~0 */
+  char message[232];
+} b2_error_info;
+
+typedef struct b2_exec b2_exec; /* opaque */
+
+/* version / build info, following the coprocessor_plugin_api precedent
+ * (components/coprocessor_plugin_api/src/util.rs:7-33) */
+uint32_t b2_abi_version(void);
+const char* b2_build_info(void);
+
+/* thread-local message of the last failing call on this thread */
+const char* b2_last_error_message(void);
+
+/* runner.rs:111-206 — B2_OK or B2_ERR_UNSUPPORTED (message says why) */
+int32_t b2_check_supported(const b2_dag_plan* plan);
+
+/* interface.rs:36-97 */
+int32_t b2_exec_open(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges,
+                     const b2_region_source* src, const b2_exec_config* cfg, b2_exec** out);
+/* schema(): field types of the outermost executor's output columns */
+int32_t b2_exec_schema(b2_exec* h, int32_t* field_tps, uint32_t* field_flags, uint32_t* n_inout);
+/* next_batch(scan_rows).  On error the batch still describes the rows produced before it
+ * (interface.rs:229-235) and b2_exec_last_error gives details. */
+int32_t b2_exec_next_batch(b2_exec* h, uint64_t scan_rows, b2_batch* out);
+int32_t b2_exec_collect_stats(b2_exec* h, b2_exec_stats* out);
+int32_t b2_exec_last_error(b2_exec* h, b2_error_info* out);
+/* storage_impl.rs:108-123: no newer-ts data and no lock seen */
+int32_t b2_exec_can_be_cached(b2_exec* h);
+void b2_exec_close(b2_exec* h);
+
+/* RequestHandler::handle_request for a DAG: run to drain.  Result columns are owned by *out_handle
+ * (close it with b2_exec_close). */
+int32_t b2_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges,
+                      const b2_region_source* src, const b2_exec_config* cfg,
+                      b2_batch* out, b2_exec** out_handle);
+
+/* tipb::ChecksumResponse */
+typedef struct b2_checksum_response {
+  uint64_t checksum;
+  uint64_t total_kvs;
+  uint64_t total_bytes;
+} b2_checksum_response;
+
+/* checksum.rs:59-98 with ChecksumRewriteRule{old_prefix,new_prefix} */
+int32_t b2_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges,
+                           const uint8_t* old_prefix, uint32_t old_prefix_len,
+                           const uint8_t* new_prefix, uint32_t new_prefix_len,
+                           const b2_region_source* src, const b2_exec_config* cfg,
+                           b2_checksum_response* out, b2_exec_stats* stats);
+
+/* ---- synthetic region generator (tooling for tests/bench) -----------------
+ * Builds HBM-resident CF_WRITE blocks for a table with an int handle PK and `n_cols` i64
+ * columns (ids 1..n_cols), row format v2 (or v1), one Put version per key plus optional
+ * older/newer/Lock/Delete versions.  Values follow xorshift64* of (seed, handle, col).     */
+typedef struct b2_gen_spec {
+  int64_t table_id;
+  uint64_t first_handle;
+  uint64_t n_rows;
+  uint32_t n_cols;
+  int32_t row_format;        /* 1 or 2 */
+  uint64_t seed;
+  /* column c (0-based) value = mix(seed,handle,c) mapped into [col_lo[c], col_lo[c]+col_range[c])
+   * (col_range 0 = full-range i64); null_per_million[c] rows are NULL */
+  const int64_t* col_lo;
+  const uint64_t* col_range;
+  const uint32_t* null_per_million;
+  uint32_t extra_versions_per_million; /* keys that get a newer-than-read_ts version + an older Put */
+  uint32_t delete_per_million;         /* keys whose visible version is a Delete */
+  uint32_t lock_rec_per_million;       /* keys with a Lock/Rollback record above the visible Put */
+  uint64_t commit_ts;                  /* visible version commit ts (start_ts = commit_ts-1) */
+  uint64_t newer_ts;                   /* commit ts for the newer-than-read versions */
+} b2_gen_spec;
+
+typedef struct b2_gen_block {
+  b2_cf_block block;     /* device pointers owned by the generator handle */
+  uint64_t key_bytes;
+  uint64_t val_bytes;
+  uint64_t n_user_keys;
+} b2_gen_block;
+
+typedef struct b2_gen b2_gen; /* opaque owner of generated device memory */
+int32_t b2_gen_create(int32_t device, const b2_gen_spec* spec, b2_gen** out, b2_gen_block* out_block);
+void b2_gen_destroy(b2_gen* g);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2_COPR_H_ */

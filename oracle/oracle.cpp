@@ -1,0 +1,309 @@
+// TEST INFRASTRUCTURE — CPU oracle, not product code.
+//
+// C entry points of the oracle: a CPU restatement of TiKV's coprocessor hot path used (a) as the
+// parity checker by tests/ and __graft_entry__.smoke(), (b) as the timed "port" CPU baseline by
+// bench.py.  Nothing under tikv_b200/ may link or call this file.
+//
+// Pinned against the reference's own golden vectors (tests/test_oracle_golden.py): memcomparable
+// bytes (tikv_util/src/codec/bytes.rs:352-), Key+ts (txn_types/src/types.rs:890-914), row v2 byte
+// arrays (row/v2/encoder_for_test.rs:543-609), write-record cases (txn_types/src/write.rs:504-549),
+// table-scan fixture (table_scan_executor.rs:496-512), CRC-64/XZ check value.
+#include <cstdio>
+#include <cstdlib>
+#include <atomic>
+#include <thread>
+
+#include "orc_exec.h"
+
+using namespace orc;
+
+struct orc_result {
+  Error err;
+  uint64_t n_rows = 0;
+  std::vector<LazyColumn> cols;       // decoded; ET_DECIMAL cols index into decimals
+  std::vector<Decimal> decimals;
+  std::vector<std::vector<Decimal>> dec_cols;  // per column decimal cells
+  std::vector<FieldType> schema;
+  Statistics stats;
+  int met_newer = NEWER_UNKNOWN;
+  uint64_t scanned_rows = 0;
+  std::string dec_str;
+};
+
+static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src,
+                            CfView* w, CfView* l, CfView* d, std::unique_ptr<Executor>* out, TableScanExecutor** scan_out, Error* err) {
+  if (plan->n_executors == 0 || plan->executors[0].tp != B2_EXEC_TABLE_SCAN) { *err = Error::make(B2_ERR_UNSUPPORTED, "first executor must be TableScan"); return false; }
+  auto scan = std::make_unique<TableScanExecutor>();
+  scan->init(plan->executors[0]);
+  w->init(src->write, src->n_write);
+  d->init(src->dflt, src->dflt ? src->n_dflt : 0);
+  l->init(src->lock, src->lock ? 1 : 0);
+  RangesScanner& rs = scan->rs;
+  rs.w = w; rs.l = l; rs.d = d;
+  rs.base_cfg.ts = src->read_ts;
+  rs.base_cfg.isolation_level = src->isolation_level;
+  rs.base_cfg.check_has_newer_ts_data = src->check_has_newer_ts_data;
+  rs.base_cfg.bypass_locks.assign(src->bypass_locks, src->bypass_locks + src->n_bypass_locks);
+  rs.base_cfg.access_locks.assign(src->access_locks, src->access_locks + src->n_access_locks);
+  for (uint32_t i = 0; i < n_ranges; ++i)
+    rs.ranges.emplace_back(Bytes(ranges[i].start, ranges[i].start + ranges[i].start_len), Bytes(ranges[i].end, ranges[i].end + ranges[i].end_len));
+  *scan_out = scan.get();
+  std::unique_ptr<Executor> cur = std::move(scan);
+  for (uint32_t i = 1; i < plan->n_executors; ++i) {
+    const b2_executor_desc& e = plan->executors[i];
+    if (e.tp == B2_EXEC_SELECTION) {
+      auto s = std::make_unique<SelectionExecutor>();
+      s->conditions.assign(e.conditions, e.conditions + e.n_conditions);
+      s->src = std::move(cur);
+      cur = std::move(s);
+    } else if (e.tp == B2_EXEC_AGGREGATION || e.tp == B2_EXEC_STREAM_AGG) {
+      if (e.n_group_by > 1) { *err = Error::make(B2_ERR_UNSUPPORTED, "multi-column GROUP BY (slow hash agg) not restated"); return false; }
+      auto a = std::make_unique<AggExecutor>();
+      const auto& sch = cur->schema();
+      auto ret_type = [&](const b2_rpn_expr& x, FieldType* ft) {
+        const b2_rpn_node& last = x.nodes[x.n_nodes - 1];
+        if (last.kind == B2_RPN_COLUMN_REF) *ft = sch[(size_t)last.i64]; else { ft->tp = last.field_tp; ft->flag = last.field_flag; }
+      };
+      for (uint32_t k = 0; k < e.n_aggrs; ++k) {
+        AggFn f; f.kind = e.aggrs[k].kind; f.arg = e.aggrs[k].arg;
+        FieldType ft; ret_type(f.arg, &ft);
+        const b2_rpn_node& last = f.arg.nodes[f.arg.n_nodes - 1];
+        f.arg_et = last.kind == B2_RPN_CONST_REAL ? ET_REAL : (last.kind == B2_RPN_CONST_INT || last.kind == B2_RPN_CONST_UINT ? ET_INT : eval_type_of(ft.tp));
+        f.arg_unsigned = ft.is_unsigned();
+        if (f.arg_et != ET_INT && f.arg_et != ET_REAL) { *err = Error::make(B2_ERR_UNSUPPORTED, "aggregate over non Int/Real"); return false; }
+        if (f.kind != B2_AGG_COUNT && f.kind != B2_AGG_SUM && f.kind != B2_AGG_AVG) { *err = Error::make(B2_ERR_UNSUPPORTED, "aggregate kind"); return false; }
+        a->fns.push_back(f);
+        FieldType cnt; cnt.tp = B2_TP_LONGLONG; cnt.flag = B2_FLAG_UNSIGNED;  // impl_count.rs:35-40
+        FieldType sum; if (f.arg_et == ET_REAL) { sum.tp = B2_TP_DOUBLE; } else { sum.tp = B2_TP_NEWDECIMAL; }
+        if (f.kind == B2_AGG_COUNT || f.kind == B2_AGG_AVG) a->schema_.push_back(cnt);
+        if (f.kind == B2_AGG_SUM || f.kind == B2_AGG_AVG) a->schema_.push_back(sum);
+      }
+      if (e.n_group_by == 1) {
+        a->has_group = true; a->group_by = e.group_by[0];
+        ret_type(a->group_by, &a->group_ft);
+        a->group_et = eval_type_of(a->group_ft.tp);
+        if (a->group_et != ET_INT && a->group_et != ET_REAL) { *err = Error::make(B2_ERR_UNSUPPORTED, "group by non Int/Real"); return false; }
+        a->schema_.push_back(a->group_ft);
+      }
+      a->src = std::move(cur);
+      cur = std::move(a);
+    } else if (e.tp == B2_EXEC_TOPN) {
+      auto t = std::make_unique<TopNExecutor>();
+      for (uint32_t k = 0; k < e.n_order_by; ++k) t->order.push_back({e.order_by[k].expr, e.order_by[k].desc != 0});
+      t->n = e.limit;
+      t->src = std::move(cur);
+      cur = std::move(t);
+    } else { *err = Error::make(B2_ERR_UNSUPPORTED, "executor type " + std::to_string(e.tp)); return false; }
+  }
+  *out = std::move(cur);
+  return true;
+}
+
+extern "C" {
+
+// BatchExecutorsRunner::handle_request (runner.rs:739-851): run to drain, collect decoded output rows.
+int orc_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src, orc_result** out) {
+  orc_result* res = new orc_result();
+  *out = res;
+  CfView w, l, d;
+  std::unique_ptr<Executor> root;
+  TableScanExecutor* scan = nullptr;
+  if (!build_executors(plan, ranges, n_ranges, src, &w, &l, &d, &root, &scan, &res->err)) return res->err.status;
+  const auto& sch = root->schema();
+  std::vector<uint32_t> offs;
+  if (plan->output_offsets) offs.assign(plan->output_offsets, plan->output_offsets + plan->n_output_offsets);
+  else for (uint32_t i = 0; i < sch.size(); ++i) offs.push_back(i);
+  res->cols.assign(offs.size(), LazyColumn());
+  res->dec_cols.assign(offs.size(), std::vector<Decimal>());
+  for (size_t k = 0; k < offs.size(); ++k) { res->schema.push_back(sch[offs[k]]); res->cols[k].decoded = true; res->cols[k].et = eval_type_of(sch[offs[k]].tp); }
+  size_t batch_size = BATCH_INITIAL_SIZE;
+  AggExecutor* agg = dynamic_cast<AggExecutor*>(root.get());
+  for (;;) {
+    Batch b;
+    root->next_batch(batch_size, &b);
+    for (size_t k = 0; k < offs.size(); ++k) {
+      LazyColumn& c = b.cols.empty() ? res->cols[k] : b.cols[offs[k]];
+      if (b.cols.empty()) break;
+      std::string perr;
+      if (!ensure_decoded(c, sch[offs[k]], b.logical_rows, &perr)) { if (b.err.ok()) b.err = Error::make(B2_ERR_CORRUPTED, perr); b.logical_rows.clear(); break; }
+    }
+    if (!b.cols.empty())
+      for (size_t r : b.logical_rows) {
+        for (size_t k = 0; k < offs.size(); ++k) {
+          const LazyColumn& c = b.cols[offs[k]];
+          LazyColumn& o = res->cols[k];
+          o.nn.push_back(c.nn[r]);
+          if (c.et == ET_REAL) o.f64.push_back(c.f64[r]);
+          else if (c.et == ET_DECIMAL) { res->dec_cols[k].push_back(agg->dec_col[(size_t)c.i64[r]]); o.i64.push_back(0); }
+          else o.i64.push_back(c.i64[r]);
+        }
+        res->n_rows++;
+      }
+    if (!b.err.ok()) { res->err = b.err; break; }
+    if (b.is_drained) break;
+    if (batch_size < BATCH_MAX_SIZE) { batch_size *= BATCH_GROW_FACTOR; if (batch_size > BATCH_MAX_SIZE) batch_size = BATCH_MAX_SIZE; }  // runner.rs:1098-1105
+  }
+  scan->rs.accumulate();
+  res->stats = scan->rs.total;
+  res->met_newer = scan->rs.met_newer;
+  res->scanned_rows = scan->rs.rows;
+  return res->err.status;
+}
+
+uint64_t orc_result_rows(orc_result* r) { return r->n_rows; }
+uint32_t orc_result_cols(orc_result* r) { return (uint32_t)r->cols.size(); }
+int orc_result_col_kind(orc_result* r, uint32_t c) { return r->cols[c].et == ET_REAL ? B2_COL_F64 : (r->cols[c].et == ET_DECIMAL ? B2_COL_DECIMAL : B2_COL_I64); }
+const int64_t* orc_result_col_i64(orc_result* r, uint32_t c) { return r->cols[c].i64.data(); }
+const double* orc_result_col_f64(orc_result* r, uint32_t c) { return r->cols[c].f64.data(); }
+const uint8_t* orc_result_col_nonnull(orc_result* r, uint32_t c) { return r->cols[c].nn.data(); }
+const b2_decimal* orc_result_col_decimal(orc_result* r, uint32_t c) { return (const b2_decimal*)r->dec_cols[c].data(); }
+const char* orc_result_decimal_str(orc_result* r, uint32_t c, uint64_t row) { r->dec_str = dec_to_string(r->dec_cols[c][row]); return r->dec_str.c_str(); }
+int orc_result_status(orc_result* r) { return r->err.status; }
+int orc_result_mysql_code(orc_result* r) { return r->err.mysql_code; }
+const char* orc_result_message(orc_result* r) { return r->err.msg.c_str(); }
+void orc_result_stats(orc_result* r, uint64_t* out8) {
+  out8[0] = r->stats.write.next; out8[1] = r->stats.write.seek; out8[2] = r->stats.write.over_seek_bound; out8[3] = r->stats.write.processed_keys;
+  out8[4] = r->stats.processed_size; out8[5] = r->stats.data.processed_keys; out8[6] = r->stats.lock.processed_keys; out8[7] = (uint64_t)(int64_t)r->met_newer;
+}
+void orc_result_free(orc_result* r) { delete r; }
+
+// ChecksumContext::handle_request (src/coprocessor/checksum.rs:59-98)
+int orc_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges, const uint8_t* old_prefix, uint32_t old_len, const uint8_t* new_prefix,
+                        uint32_t new_len, const b2_region_source* src, b2_checksum_response* out, char* errbuf, size_t errbuf_len) {
+  CfView w, l, d;
+  w.init(src->write, src->n_write);
+  d.init(src->dflt, src->dflt ? src->n_dflt : 0);
+  l.init(src->lock, src->lock ? 1 : 0);
+  RangesScanner rs;
+  rs.w = &w; rs.l = &l; rs.d = &d;
+  rs.base_cfg.ts = src->read_ts;
+  rs.base_cfg.isolation_level = src->isolation_level;
+  rs.base_cfg.bypass_locks.assign(src->bypass_locks, src->bypass_locks + src->n_bypass_locks);
+  for (uint32_t i = 0; i < n_ranges; ++i)
+    rs.ranges.emplace_back(Bytes(ranges[i].start, ranges[i].start + ranges[i].start_len), Bytes(ranges[i].end, ranges[i].end + ranges[i].end_len));
+  Crc64Digest prefix_digest;
+  prefix_digest.write(old_prefix, old_len);
+  uint64_t checksum = 0, total_kvs = 0, total_bytes = 0;
+  for (;;) {
+    Bytes k; ScanOutput so; Error e;
+    int r = rs.next(&k, &so, &e);
+    if (r < 0) { snprintf(errbuf, errbuf_len, "%s", e.msg.c_str()); return e.status; }
+    if (r == 0) break;
+    if (k.size() < new_len || memcmp(k.data(), new_prefix, new_len) != 0) { snprintf(errbuf, errbuf_len, "Wrong prefix expect"); return B2_ERR_STORAGE; }
+    Crc64Digest dg = prefix_digest;  // checksum_crc64_xor :105-114
+    dg.write(k.data() + new_len, k.size() - new_len);
+    dg.write(so.value.data(), so.value.size());
+    checksum ^= dg.sum64();
+    total_kvs += 1;
+    total_bytes += k.size() + so.value.size() + old_len - new_len;
+  }
+  out->checksum = checksum; out->total_kvs = total_kvs; out->total_bytes = total_bytes;
+  return B2_OK;
+}
+
+// One region task per thread (TiKV read pool shape): run `n_tasks` independent DAG requests, each over its
+// own region source, on `n_threads` threads.  Returns total rows produced; used by bench.py's CPU baseline.
+uint64_t orc_dag_handle_parallel(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* srcs, uint32_t n_tasks,
+                                 uint32_t n_threads, uint64_t* scanned_rows_out, int* status_out) {
+  std::vector<uint64_t> rows(n_tasks, 0), scanned(n_tasks, 0);
+  std::vector<int> status(n_tasks, 0);
+  std::vector<std::thread> th;
+  std::atomic<uint32_t> next{0};
+  for (uint32_t t = 0; t < n_threads; ++t)
+    th.emplace_back([&]() {
+      for (;;) {
+        uint32_t i = next.fetch_add(1);
+        if (i >= n_tasks) break;
+        orc_result* r = nullptr;
+        status[i] = orc_dag_handle(plan, ranges, n_ranges, &srcs[i], &r);
+        rows[i] = r->n_rows; scanned[i] = r->scanned_rows;
+        delete r;
+      }
+    });
+  for (auto& x : th) x.join();
+  uint64_t total = 0, sc = 0; int st = 0;
+  for (uint32_t i = 0; i < n_tasks; ++i) { total += rows[i]; sc += scanned[i]; if (status[i]) st = status[i]; }
+  *scanned_rows_out = sc; *status_out = st;
+  return total;
+}
+
+
+// Raw MVCC scan over [lower, upper) (encoded user keys; NULL = unbounded) — pins ForwardScanner against the
+// reference's scanner unit tests (forward.rs:1179-1727), including exact next/seek statistics.
+struct orc_scan { std::vector<Bytes> keys, vals; Statistics st; Error err; int met_newer; };
+orc_scan* orc_mvcc_scan(const b2_region_source* src, const uint8_t* lower, size_t lower_len, const uint8_t* upper, size_t upper_len) {
+  orc_scan* r = new orc_scan();
+  CfView w, l, d;
+  w.init(src->write, src->n_write);
+  d.init(src->dflt, src->dflt ? src->n_dflt : 0);
+  l.init(src->lock, src->lock ? 1 : 0);
+  ScannerConfig cfg;
+  cfg.ts = src->read_ts; cfg.isolation_level = src->isolation_level; cfg.check_has_newer_ts_data = src->check_has_newer_ts_data;
+  cfg.bypass_locks.assign(src->bypass_locks, src->bypass_locks + src->n_bypass_locks);
+  cfg.access_locks.assign(src->access_locks, src->access_locks + src->n_access_locks);
+  if (lower) { cfg.has_lower = true; cfg.lower_bound.assign(lower, lower + lower_len); }
+  if (upper) { cfg.has_upper = true; cfg.upper_bound.assign(upper, upper + upper_len); }
+  ForwardScanner fs;
+  fs.init(cfg, &w, &l, &d);
+  for (;;) {
+    ScanOutput so;
+    int rc = fs.read_next(&so, &r->err);
+    if (rc <= 0) break;
+    r->keys.push_back(so.user_key); r->vals.push_back(so.value);
+  }
+  r->st = fs.statistics; r->met_newer = fs.met_newer_ts_data;
+  return r;
+}
+uint64_t orc_scan_rows(orc_scan* r) { return r->keys.size(); }
+const uint8_t* orc_scan_key(orc_scan* r, uint64_t i, size_t* len) { *len = r->keys[i].size(); return r->keys[i].data(); }
+const uint8_t* orc_scan_val(orc_scan* r, uint64_t i, size_t* len) { *len = r->vals[i].size(); return r->vals[i].data(); }
+int orc_scan_status(orc_scan* r) { return r->err.status; }
+void orc_scan_stats(orc_scan* r, uint64_t* out8) {
+  out8[0] = r->st.write.next; out8[1] = r->st.write.seek; out8[2] = r->st.write.over_seek_bound; out8[3] = r->st.write.processed_keys;
+  out8[4] = r->st.processed_size; out8[5] = r->st.data.processed_keys; out8[6] = r->st.lock.processed_keys; out8[7] = (uint64_t)(int64_t)r->met_newer;
+}
+void orc_scan_free(orc_scan* r) { delete r; }
+
+// ---- codec hooks for the golden-vector tests ----
+size_t orc_encode_bytes(const uint8_t* p, size_t n, uint8_t* out) { Bytes b; encode_bytes(b, Slice(p, n)); memcpy(out, b.data(), b.size()); return b.size(); }
+int64_t orc_decode_bytes(const uint8_t* p, size_t n, uint8_t* out, size_t* out_len) {
+  Bytes k; size_t c = decode_bytes(Slice(p, n), &k);
+  if (c == (size_t)-1) return -1;
+  memcpy(out, k.data(), k.size()); *out_len = k.size();
+  return (int64_t)c;
+}
+size_t orc_key_append_ts(const uint8_t* p, size_t n, uint64_t ts, uint8_t* out) { Bytes b = key_append_ts(Bytes(p, p + n), ts); memcpy(out, b.data(), b.size()); return b.size(); }
+size_t orc_encode_var_u64(uint64_t v, uint8_t* out) { Bytes b; encode_var_u64(b, v); memcpy(out, b.data(), b.size()); return b.size(); }
+size_t orc_encode_var_i64(int64_t v, uint8_t* out) { Bytes b; encode_var_i64(b, v); memcpy(out, b.data(), b.size()); return b.size(); }
+size_t orc_decode_var_u64(const uint8_t* p, size_t n, uint64_t* v) { return decode_var_u64(Slice(p, n), v); }
+size_t orc_decode_var_i64(const uint8_t* p, size_t n, int64_t* v) { return decode_var_i64(Slice(p, n), v); }
+uint64_t orc_encode_i64_cmp(int64_t v) { return (uint64_t)v ^ SIGN_MARK; }
+uint64_t orc_encode_f64_cmp(double f) { return encode_f64_to_cmp_u64(f); }
+double orc_decode_f64_cmp(uint64_t u) { return decode_cmp_u64_to_f64(u); }
+size_t orc_encode_row_key(int64_t table_id, int64_t handle, uint8_t* out) { Bytes b = encode_row_key(table_id, handle); memcpy(out, b.data(), b.size()); return b.size(); }
+uint64_t orc_crc64(const uint8_t* p, size_t n) { Crc64Digest d; d.write(p, n); return d.sum64(); }
+size_t orc_split_datum(const uint8_t* p, size_t n) { std::string e; return split_datum(Slice(p, n), &e); }
+
+// write record: returns 0 ok. fields: [type, start_ts, has_short, short_off, short_len, overlapped, has_gc_fence, gc_fence, lc_kind, lc_ts, lc_versions, txn_source]
+int orc_write_parse(const uint8_t* p, size_t n, uint64_t* f12) {
+  WriteRef w; std::string e;
+  if (!write_parse(Slice(p, n), &w, &e)) return 1;
+  f12[0] = w.write_type; f12[1] = w.start_ts; f12[2] = w.has_short_value; f12[3] = w.has_short_value ? (uint64_t)(w.short_value.p - p) : 0;
+  f12[4] = w.has_short_value ? w.short_value.n : 0; f12[5] = w.has_overlapped_rollback; f12[6] = w.has_gc_fence; f12[7] = w.gc_fence;
+  f12[8] = w.last_change; f12[9] = w.last_change_ts; f12[10] = w.estimated_versions_to_last_change; f12[11] = w.txn_source;
+  return 0;
+}
+int orc_write_check_gc_fence(const uint8_t* p, size_t n, uint64_t read_ts) {
+  WriteRef w; std::string e;
+  if (!write_parse(Slice(p, n), &w, &e)) return -1;
+  return write_check_gc_fence_as_latest_version(w, read_ts);
+}
+
+// decimal hooks
+void orc_decimal_from_i64(int64_t v, b2_decimal* out) { Decimal d = dec_from_i64(v); memcpy(out, &d, 40); }
+void orc_decimal_from_u64(uint64_t v, b2_decimal* out) { Decimal d = dec_from_u64(v); memcpy(out, &d, 40); }
+int orc_decimal_add(const b2_decimal* a, const b2_decimal* b, b2_decimal* out) { Decimal r; int st = dec_add(*(const Decimal*)a, *(const Decimal*)b, &r); memcpy(out, &r, 40); return st; }
+size_t orc_decimal_to_string(const b2_decimal* a, char* out, size_t cap) { std::string s = dec_to_string(*(const Decimal*)a); snprintf(out, cap, "%s", s.c_str()); return s.size(); }
+int orc_decimal_cmp(const b2_decimal* a, const b2_decimal* b) { return dec_cmp(*(const Decimal*)a, *(const Decimal*)b); }
+
+}  // extern "C"

@@ -1,0 +1,409 @@
+"""Pins the CPU oracle (and the independent Python encoders in kvfmt.py) against golden vectors and
+known-answer tests held by the reference's own unit tests.  Each case cites its source in tikv/tikv."""
+import ctypes as C
+import struct
+
+import pytest
+
+import kvfmt
+import orc
+from tikv_b200 import ffi
+from tikv_b200.plan import ColumnDef, Plan, col, const_int, lt
+
+
+def _buf(n=256):
+    return C.create_string_buffer(n)
+
+
+# components/tikv_util/src/codec/bytes.rs:352- test_enc_dec_bytes (asc column)
+MEMCMP = [
+    (b"", [0, 0, 0, 0, 0, 0, 0, 0, 247]),
+    (bytes([0]), [0, 0, 0, 0, 0, 0, 0, 0, 248]),
+    (bytes([1, 2, 3]), [1, 2, 3, 0, 0, 0, 0, 0, 250]),
+    (bytes([1, 2, 3, 0]), [1, 2, 3, 0, 0, 0, 0, 0, 251]),
+    (bytes([1, 2, 3, 4, 5, 6, 7]), [1, 2, 3, 4, 5, 6, 7, 0, 254]),
+    (bytes(8), [0, 0, 0, 0, 0, 0, 0, 0, 255, 0, 0, 0, 0, 0, 0, 0, 0, 247]),
+    (bytes([1, 2, 3, 4, 5, 6, 7, 8]), [1, 2, 3, 4, 5, 6, 7, 8, 255, 0, 0, 0, 0, 0, 0, 0, 0, 247]),
+    (bytes([1, 2, 3, 4, 5, 6, 7, 8, 9]), [1, 2, 3, 4, 5, 6, 7, 8, 255, 9, 0, 0, 0, 0, 0, 0, 0, 248]),
+]
+
+
+@pytest.mark.parametrize("src,enc", MEMCMP)
+def test_memcomparable_bytes(src, enc):
+    L = orc.lib()
+    out = _buf()
+    n = L.orc_encode_bytes(src, len(src), out)
+    assert list(out.raw[:n]) == enc
+    assert list(kvfmt.enc_bytes_memcmp(src)) == enc
+    # appended timestamp must not affect the decode result (bytes.rs:405-425)
+    with_ts = bytes(enc) + kvfmt.enc_u64_desc(0)
+    dec, ln = _buf(), C.c_size_t()
+    consumed = L.orc_decode_bytes(with_ts, len(with_ts), dec, C.byref(ln))
+    assert consumed == len(enc) and dec.raw[:ln.value] == src
+
+
+def test_memcomparable_bad_padding():
+    L = orc.lib()
+    dec, ln = _buf(), C.c_size_t()
+    bad = bytes([1, 2, 3, 0, 0, 0, 0, 1, 250])  # non-zero padding byte
+    assert L.orc_decode_bytes(bad, len(bad), dec, C.byref(ln)) == -1
+    assert L.orc_decode_bytes(bytes(5), 5, dec, C.byref(ln)) == -1  # eof
+
+
+def test_key_append_ts():
+    # components/txn_types/src/types.rs:890-914 test_append_ts
+    L = orc.lib()
+    out = _buf()
+    n = L.orc_key_append_ts(b"abc", 3, 100, out)
+    assert out.raw[:n] == b"abc" + bytes([0xFF] * 7 + [0x9B])
+    k = kvfmt.enc_bytes_memcmp(b"z")
+    n = L.orc_key_append_ts(k, len(k), 1000, out)
+    assert list(out.raw[:n]) == [ord("z"), 0, 0, 0, 0, 0, 0, 0, 0xF8, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFC, 0x17]
+    assert kvfmt.write_key(b"z", 1000) == out.raw[:n]
+
+
+def _pb_varint(v):  # protobuf uint64 wire format (components/codec/src/number.rs:1794-1816 cross-check)
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+VARINT_SAMPLES = [0, 1, 127, 128, 255, 256, 16383, 16384, (1 << 32) - 1, 1 << 32, (1 << 63) - 1, 1 << 63, (1 << 64) - 1]
+
+
+def test_varint_matches_protobuf():
+    L = orc.lib()
+    out = _buf(16)
+    for v in VARINT_SAMPLES:
+        n = L.orc_encode_var_u64(v, out)
+        assert out.raw[:n] == _pb_varint(v) == kvfmt.enc_var_u64(v)
+        got = C.c_uint64()
+        assert L.orc_decode_var_u64(out.raw[:n], n, C.byref(got)) == n and got.value == v
+    for v in [0, -1, 1, -64, 63, 64, -65, (1 << 63) - 1, -(1 << 63), 1000, -1000]:
+        n = L.orc_encode_var_i64(v, out)
+        zz = ((v << 1) ^ (v >> 63)) & ((1 << 64) - 1)  # protobuf sint64 zig-zag
+        assert out.raw[:n] == _pb_varint(zz) == kvfmt.enc_var_i64(v)
+        got = C.c_int64()
+        assert L.orc_decode_var_i64(out.raw[:n], n, C.byref(got)) == n and got.value == v
+    # eof on truncated input
+    got = C.c_uint64()
+    assert L.orc_decode_var_u64(bytes([0x80, 0x80]), 2, C.byref(got)) == 0
+
+
+def test_order_preserving_numbers():
+    # components/tikv_util/src/codec/number.rs test_order: encoded order == numeric order
+    L = orc.lib()
+    ints = [-(1 << 63), -1000, -1, 0, 1, 1000, (1 << 63) - 1]
+    enc = [L.orc_encode_i64_cmp(v) for v in ints]
+    assert enc == sorted(enc)
+    assert [struct.unpack(">Q", kvfmt.enc_i64_cmp(v))[0] for v in ints] == enc
+    floats = [float("-inf"), -1e300, -1.5, -0.0, 0.0, 1e-300, 2.5, 1e300, float("inf")]
+    encf = [L.orc_encode_f64_cmp(f) for f in floats]
+    assert all(a <= b for a, b in zip(encf, encf[1:]))
+    for f, e in zip(floats, encf):
+        assert L.orc_decode_f64_cmp(e) == f
+        assert struct.unpack(">Q", kvfmt.enc_f64_cmp(f))[0] == e
+
+
+def test_row_key():
+    # components/tidb_query_datatype/src/codec/table.rs:187-193
+    L = orc.lib()
+    out = _buf()
+    n = L.orc_encode_row_key(7, -3, out)
+    assert out.raw[:n] == b"t" + struct.pack(">Q", 7 ^ (1 << 63)) + b"_r" + struct.pack(">Q", ((-3) & ((1 << 64) - 1)) ^ (1 << 63))
+    assert kvfmt.row_key(7, -3) == out.raw[:n] and n == 19
+
+
+def test_crc64_xz_check_value():
+    # crc64fast 0.1.0 = CRC-64/XZ; published check("123456789") = 0x995DC9BBDF1939FA
+    assert orc.lib().orc_crc64(b"123456789", 9) == 0x995DC9BBDF1939FA
+    assert orc.lib().orc_crc64(b"", 0) == 0
+
+
+# ---- row v2: components/tidb_query_datatype/src/codec/row/v2/encoder_for_test.rs:543-609 ----
+V2_UNSIGNED = [128, 0, 2, 0, 0, 0, 1, 2, 8, 0, 9, 0, 255, 255, 255, 255, 255, 255, 255, 255, 255]
+V2_MIXED = [
+    128, 0, 11, 0, 1, 0, 1, 3, 6, 7, 8, 9, 12, 13, 14, 15, 16, 33, 2, 0, 3, 0, 11, 0, 14, 0, 16, 0, 24, 0, 25, 0, 33, 0, 36, 0, 65, 0, 69,
+    0, 232, 3, 3, 64, 3, 51, 51, 51, 51, 51, 50, 97, 98, 99, 255, 127, 191, 252, 204, 204, 204, 204, 204, 205, 2, 0, 0, 0, 135, 51, 230,
+    158, 25, 1, 0, 129, 1, 1, 0, 0, 0, 28, 0, 0, 0, 19, 0, 0, 0, 3, 0, 12, 22, 0, 0, 0, 107, 101, 121, 5, 118, 97, 108, 117, 101, 0, 202,
+    154, 59,
+]
+V2_BIG = [128, 1, 4, 0, 1, 0, 1, 0, 0, 0, 3, 0, 0, 0, 8, 0, 0, 0, 12, 0, 0, 0, 79, 1, 0, 0, 2, 0, 0, 0, 3, 0, 0, 0, 5, 0, 0, 0, 6, 0, 0, 0,
+          232, 3, 3, 255, 127, 2]
+
+
+def test_row_v2_python_encoder_matches_golden():
+    assert list(kvfmt.row_v2([(1, (1 << 64) - 1, "uint"), (2, -1, "int")])) == V2_UNSIGNED
+    assert list(kvfmt.row_v2([(1, 1000, "int"), (12, 2, "int"), (335, None, "int"), (3, 3, "int"), (8, 32767, "int")])) == V2_BIG
+
+
+def _scan_one_row(value, columns, table_id=7, handle=1):
+    r = kvfmt.Region().put(kvfmt.row_key(table_id, handle), bytes(value), 5, 6).build(read_ts=100)
+    p = Plan().table_scan(table_id, columns).build()
+    return orc.dag_handle(p, [kvfmt.table_range(table_id)], r)
+
+
+def test_row_v2_golden_decode():
+    res = _scan_one_row(V2_UNSIGNED, [ColumnDef(1, unsigned=True), ColumnDef(2)])
+    assert res.status == 0 and res.rows() == [(-1, -1)]  # u64::MAX reinterpreted as i64 (datum_codec.rs:401-421)
+    cols = [ColumnDef(1), ColumnDef(12), ColumnDef(33), ColumnDef(3, unsigned=True), ColumnDef(8),
+            ColumnDef(9, tp=ffi.TP_DOUBLE), ColumnDef(6, tp=ffi.TP_DOUBLE)]
+    res = _scan_one_row(V2_MIXED, cols)
+    assert res.status == 0 and res.rows() == [(1000, 2, None, 3, 32767, 1.8, -1.8)]
+    res = _scan_one_row(V2_BIG, [ColumnDef(1), ColumnDef(12), ColumnDef(335), ColumnDef(3), ColumnDef(8), ColumnDef(99)])
+    assert res.status == 0 and res.rows() == [(1000, 2, None, 3, 32767, None)]
+
+
+def test_row_v2_search_offsets():
+    # row_slice.rs:416-448: big row {1:1000, 356:2, 33:NULL, 3:3, 64123:5}
+    v = kvfmt.row_v2([(1, 1000, "int"), (356, 2, "int"), (33, None, "int"), (3, 3, "int"), (64123, 5, "int")])
+    assert v[1] & 1  # BIG
+    res = _scan_one_row(v, [ColumnDef(1), ColumnDef(356), ColumnDef(33), ColumnDef(3), ColumnDef(64123), ColumnDef(333), ColumnDef(64124)])
+    assert res.rows() == [(1000, 2, None, 3, 5, None, None)]
+
+
+# ---- write records: components/txn_types/src/write.rs:504-549, 566-590 ----
+def _parse(b):
+    f = (C.c_uint64 * 12)()
+    rc = orc.lib().orc_write_parse(b, len(b), f)
+    return rc, list(f)
+
+
+def test_write_record_round_trip():
+    P, D, LK, R = 0, 1, 2, 3
+    cases = [
+        (kvfmt.write_record(b"P", 0, short_value=b"short_value"), dict(t=P, ts=0, sv=b"short_value")),
+        (kvfmt.write_record(b"D", 1 << 20), dict(t=D, ts=1 << 20)),
+        (kvfmt.write_record(b"R", 1 << 40, short_value=b"p"), dict(t=R, ts=1 << 40, sv=b"p")),
+        (kvfmt.write_record(b"R", 1 << 41), dict(t=R, ts=1 << 41)),
+        (kvfmt.write_record(b"P", 123, overlapped_rollback=True), dict(t=P, ts=123, ov=1)),
+        (kvfmt.write_record(b"P", 123, overlapped_rollback=True, gc_fence=1234567), dict(t=P, ts=123, ov=1, gf=1234567)),
+        (kvfmt.write_record(b"P", 456, short_value=b"short_value", overlapped_rollback=True, gc_fence=0), dict(t=P, ts=456, sv=b"short_value", ov=1, gf=0)),
+        (kvfmt.write_record(b"P", 456, short_value=b"short_value", overlapped_rollback=True, gc_fence=421397468076048385),
+         dict(t=P, ts=456, sv=b"short_value", ov=1, gf=421397468076048385)),
+        (kvfmt.write_record(b"L", 456, last_change=(345, 11)), dict(t=LK, ts=456, lc=(1, 345, 11))),
+        (kvfmt.write_record(b"L", 456, last_change=(0, 1)), dict(t=LK, ts=456, lc=(2, 0, 1))),
+        (kvfmt.write_record(b"L", 456, txn_source=1), dict(t=LK, ts=456, src=1)),
+    ]
+    for raw, exp in cases:
+        rc, f = _parse(raw)
+        assert rc == 0
+        assert f[0] == exp["t"] and f[1] == exp["ts"]
+        sv = exp.get("sv")
+        assert f[2] == (sv is not None)
+        if sv is not None:
+            assert raw[f[3]:f[3] + f[4]] == sv
+        assert f[5] == exp.get("ov", 0)
+        assert f[6] == ("gf" in exp) and f[7] == exp.get("gf", 0)
+        assert tuple(f[8:11]) == exp.get("lc", (0, 0, 0))
+        assert f[11] == exp.get("src", 0)
+    assert _parse(b"")[0] != 0
+    lock = kvfmt.write_record(b"L", 1, short_value=b"short_value")
+    assert _parse(lock[:1])[0] != 0
+    rc, f = _parse(lock + b"unknown")  # unknown tail bytes are ignored (:544-547)
+    assert rc == 0 and f[0] == LK and f[4] == len(b"short_value")
+
+
+@pytest.mark.parametrize("gc_fence,read_ts,expect", [
+    (None, 10, True), (None, 100, True), (None, (1 << 64) - 1, True), (0, 100, True), (0, (1 << 64) - 1, True),
+    (100, 50, True), (100, 100, False), (100, 150, False), (100, (1 << 64) - 1, False)])
+def test_check_gc_fence(gc_fence, read_ts, expect):
+    raw = kvfmt.write_record(b"P", 5, overlapped_rollback=True, gc_fence=gc_fence)
+    assert orc.lib().orc_write_check_gc_fence(raw, len(raw), read_ts) == int(expect)
+
+
+# ---- MVCC forward scanner: src/storage/mvcc/reader/scanner/forward.rs latest_kv_tests ----
+def _uk(raw):
+    return kvfmt.enc_bytes_memcmp(raw)
+
+
+def test_scanner_get_out_of_bound():
+    # forward.rs:1179-1245: a_7 put; b_4..b_0 rollbacks [b'R', ts]; read at 10
+    r = kvfmt.Region().put(b"a", b"value", 7, 7)
+    for ts in range(5):
+        r.raw_write(b"b", ts, bytes([ord("R"), ts]))
+    st, rows, stats = orc.mvcc_scan(r.build(read_ts=10))
+    assert st == 0 and rows == [(_uk(b"a"), b"value")]
+    assert stats["write_seek"] == 1 and stats["write_next"] == 1 + 5
+    assert stats["processed_size"] == len(_uk(b"a")) + len(b"value")
+
+
+def test_scanner_move_next_user_key_out_of_bound():
+    SB = 8
+    # case 1 forward.rs:1253-1318
+    r = kvfmt.Region().put(b"a", b"a_value", SB * 2, SB * 2)
+    for ts in range(SB // 2):
+        r.raw_write(b"b", ts, bytes([ord("R"), ts]))
+    r.put(b"b", b"b_value", SB // 2, SB // 2)
+    st, rows, stats = orc.mvcc_scan(r.build(read_ts=SB * 2))
+    assert rows == [(_uk(b"a"), b"a_value"), (_uk(b"b"), b"b_value")]
+    assert stats["write_seek"] == 1 and stats["write_next"] == 1 + (SB // 2 + 1)
+    # case 2 forward.rs:1320-1395: SEEK_BOUND-1 rollbacks below the put -> falls back to seek
+    r = kvfmt.Region().put(b"a", b"a_value", SB * 2, SB * 2)
+    for ts in range(1, SB):
+        r.raw_write(b"b", ts, bytes([ord("R"), ts]))
+    r.put(b"b", b"b_value", SB, SB)
+    st, rows, stats = orc.mvcc_scan(r.build(read_ts=SB * 2))
+    assert rows == [(_uk(b"a"), b"a_value"), (_uk(b"b"), b"b_value")]
+    assert stats["write_seek"] == 1 + 1 and stats["write_next"] == 1 + (SB - 1) and stats["over_seek_bound"] == 1
+
+
+def test_scanner_skip_versions_by_seek():
+    # forward.rs:1648-1727 (last_change values as the txn layer writes them)
+    r = kvfmt.Region()
+    r.put(b"k1", b"v11", 1, 5).put(b"k1", b"v12", 6, 8).put(b"k2", b"v21", 2, 6).put(b"k4", b"v41", 3, 7)
+    for i, start_ts in enumerate(range(10, 30, 2)):
+        r.lock_rec(b"k1", start_ts, start_ts + 1, last_change=(8, i + 1))
+        r.lock_rec(b"k3", start_ts, start_ts + 1, last_change=(0, 1))
+        r.lock_rec(b"k4", start_ts, start_ts + 1, last_change=(7, i + 1))
+    r.put(b"k1", b"v13", 40, 45).put(b"k2", b"v22", 41, 46).put(b"k3", b"v32", 42, 47)
+    st, rows, stats = orc.mvcc_scan(r.build(read_ts=35))
+    assert st == 0 and rows == [(_uk(b"k1"), b"v12"), (_uk(b"k2"), b"v21"), (_uk(b"k4"), b"v41")]
+    # per-call stats in the reference: (next 3, seek 2) + (next 2, seek 0) + (next 9, seek 2)
+    assert stats["write_next"] == 3 + 2 + 9 and stats["write_seek"] == 4
+    assert stats["met_newer"] == 1
+
+
+def test_scanner_range_and_locks():
+    r = kvfmt.Region()
+    for i in range(1, 7):
+        r.put(b"k%d" % i, b"v%d" % i, 2, 3)
+    st, rows, _ = orc.mvcc_scan(r.build(read_ts=10), lower=_uk(b"k2"), upper=_uk(b"k5"))
+    assert [v for _, v in rows] == [b"v2", b"v3", b"v4"]
+    # SI: a Put lock with ts <= read_ts blocks (lock.rs:343-416); ts > read_ts, Lock-type and bypassed locks do not
+    r.add_lock(b"k3", kvfmt.lock_record(b"P", b"k3", 5))
+    st, rows, _ = orc.mvcc_scan(r.build(read_ts=10))
+    assert st == ffi.B2_ERR_KEY_IS_LOCKED and [v for _, v in rows] == [b"v1", b"v2"]
+    st, rows, _ = orc.mvcc_scan(r.build(read_ts=10, bypass=[5]))
+    assert st == 0 and len(rows) == 6
+    st, rows, _ = orc.mvcc_scan(r.build(read_ts=4))
+    assert st == 0 and len(rows) == 6
+    st, rows, _ = orc.mvcc_scan(r.build(read_ts=10, isolation=ffi.ISO_RC))
+    assert st == 0 and len(rows) == 6
+    r2 = kvfmt.Region().put(b"a", b"x", 1, 2).add_lock(b"a", kvfmt.lock_record(b"L", b"a", 1))
+    assert orc.mvcc_scan(r2.build(read_ts=10))[0] == 0
+    r3 = kvfmt.Region().put(b"a", b"x", 1, 2).add_lock(b"a", kvfmt.lock_record(b"P", b"a", 1, min_commit_ts=11))
+    assert orc.mvcc_scan(r3.build(read_ts=10))[0] == 0
+
+
+def test_scanner_delete_gc_fence_long_value():
+    big = bytes(range(256)) * 2
+    r = (kvfmt.Region().put(b"a", b"old", 1, 2).delete(b"a", 3, 4)
+         .put(b"b", big, 5, 6)
+         .put(b"c", b"fenced", 1, 2, overlapped_rollback=True, gc_fence=5)
+         .put(b"d", b"ok", 1, 2, overlapped_rollback=True, gc_fence=50))
+    st, rows, stats = orc.mvcc_scan(r.build(read_ts=10))
+    assert st == 0 and rows == [(_uk(b"b"), big), (_uk(b"d"), b"ok")]
+    assert stats["data_processed_keys"] == 1
+    st, rows, _ = orc.mvcc_scan(r.build(read_ts=3))
+    assert [v for _, v in rows] == [b"old", b"fenced", b"ok"]
+
+
+# ---- table scan: components/tidb_query_executors/src/table_scan_executor.rs:496-512 fixed table ----
+def _fixture_region(fmt=1):
+    T = 7
+    rows = {
+        1: [(2, 10, "int"), (4, 5.2, "f64")],
+        3: [(4, None, "f64"), (2, -5, "int")],
+        4: [(2, None, "int")],
+        5: [(4, 0.1, "f64")],
+        6: [],
+    }
+    r = kvfmt.Region()
+    for h, cols in rows.items():
+        if fmt == 1:
+            d = [(cid, kvfmt.datum_null() if v is None else (kvfmt.datum_int(v) if k == "int" else kvfmt.datum_f64(v))) for cid, v, k in cols]
+            val = kvfmt.row_v1(d)
+        else:
+            val = kvfmt.row_v2(cols)
+        r.put(kvfmt.row_key(T, h), val, 10, 20)
+    return T, r
+
+
+FIXTURE_COLUMNS = [ColumnDef(1, pk_handle=True), ColumnDef(2), ColumnDef(4, tp=ffi.TP_DOUBLE, default=kvfmt.datum_f64(4.5))]
+FIXTURE_EXPECT = [(1, 10, 5.2), (3, -5, None), (4, None, 4.5), (5, None, 0.1), (6, None, 4.5)]
+
+
+@pytest.mark.parametrize("fmt", [1, 2])
+def test_table_scan_fixture(fmt):
+    T, r = _fixture_region(fmt)
+    p = Plan().table_scan(T, FIXTURE_COLUMNS).build()
+    res = orc.dag_handle(p, [kvfmt.table_range(T)], r.build(read_ts=100))
+    assert res.status == 0 and res.rows() == FIXTURE_EXPECT
+    # point / split ranges give the same rows (table_scan_executor.rs:644-700 whole-table range mixes)
+    ranges = [kvfmt.table_range(T, 1, 2), kvfmt.table_range(T, 2, 5), kvfmt.table_range(T, 5, 100)]
+    res = orc.dag_handle(p, ranges, r.build(read_ts=100))
+    assert res.rows() == FIXTURE_EXPECT
+    # columns in another order + only some columns (test_basic variants :780-823)
+    p2 = Plan().table_scan(T, [FIXTURE_COLUMNS[2], FIXTURE_COLUMNS[0]]).build()
+    res = orc.dag_handle(p2, [kvfmt.table_range(T)], r.build(read_ts=100))
+    assert res.rows() == [(c, a) for a, _, c in FIXTURE_EXPECT]
+
+
+def test_table_scan_corrupted_and_missing_not_null():
+    # table_scan_executor.rs:882-1010 test_corrupted_data: rows before the bad one are returned, then the error
+    T = 5
+    r = kvfmt.Region()
+    r.put(kvfmt.row_key(T, 0), kvfmt.row_v1([(2, kvfmt.datum_int(5)), (3, kvfmt.datum_int(7))]), 1, 2)
+    r.put(kvfmt.row_key(T, 1), kvfmt.row_v1([(2, kvfmt.datum_int(5))]) + bytes([kvfmt.VAR_INT]), 1, 2)  # truncated col id
+    r.put(kvfmt.row_key(T, 2), kvfmt.row_v1([(2, kvfmt.datum_int(1)), (3, kvfmt.datum_int(2))]), 1, 2)
+    cols = [ColumnDef(1, pk_handle=True), ColumnDef(2), ColumnDef(3)]
+    res = orc.dag_handle(Plan().table_scan(T, cols).build(), [kvfmt.table_range(T)], r.build(read_ts=10))
+    assert res.status == ffi.B2_ERR_CORRUPTED and res.rows() == [(0, 5, 7)]
+    r = kvfmt.Region().put(kvfmt.row_key(T, 0), kvfmt.row_v1([(2, kvfmt.datum_int(5))]), 1, 2)
+    cols = [ColumnDef(1, pk_handle=True), ColumnDef(2), ColumnDef(3, not_null=True)]
+    res = orc.dag_handle(Plan().table_scan(T, cols).build(), [kvfmt.table_range(T)], r.build(read_ts=10))
+    assert res.status == ffi.B2_ERR_CORRUPTED and "NOT NULL" in res.message and res.n_rows == 0
+
+
+def test_selection_and_lazy_decode():
+    # selection_executor.rs: NULL predicate result filters the row; decode errors only surface for live rows
+    T = 9
+    r = kvfmt.Region()
+    r.put(kvfmt.row_key(T, 1), kvfmt.row_v1([(2, kvfmt.datum_int(1)), (3, kvfmt.datum_int(10))]), 1, 2)
+    r.put(kvfmt.row_key(T, 2), kvfmt.row_v1([(2, kvfmt.datum_null()), (3, kvfmt.datum_int(20))]), 1, 2)
+    r.put(kvfmt.row_key(T, 3), kvfmt.row_v1([(2, kvfmt.datum_int(100)), (3, kvfmt.datum_bytes(b"zz"))]), 1, 2)  # col 3 undecodable as Int
+    r.put(kvfmt.row_key(T, 4), kvfmt.row_v1([(2, kvfmt.datum_int(-7)), (3, kvfmt.datum_int(40))]), 1, 2)
+    cols = [ColumnDef(1, pk_handle=True), ColumnDef(2), ColumnDef(3)]
+    p = Plan().table_scan(T, cols).selection(lt(col(1), const_int(50))).build()
+    res = orc.dag_handle(p, [kvfmt.table_range(T)], r.build(read_ts=10))
+    assert res.status == 0 and res.rows() == [(1, 1, 10), (4, -7, 40)]
+    p = Plan().table_scan(T, cols).selection(lt(col(1), const_int(500))).build()
+    res = orc.dag_handle(p, [kvfmt.table_range(T)], r.build(read_ts=10))
+    assert res.status == ffi.B2_ERR_CORRUPTED
+
+
+def test_decimal_value_semantics():
+    L = orc.lib()
+    a, b, c = ffi.Decimal(), ffi.Decimal(), ffi.Decimal()
+    out = _buf(128)
+    import random
+    rng = random.Random(7)
+    samples = [0, 1, -1, 999999999, 1000000000, -1000000000, (1 << 63) - 1, -(1 << 63), 10 ** 18, -(10 ** 18) + 1]
+    samples += [rng.randrange(-(1 << 63), 1 << 63) for _ in range(200)]
+    acc_py, first = 0, True
+    acc = ffi.Decimal()
+    L.orc_decimal_from_i64(0, C.byref(acc))
+    for v in samples:
+        L.orc_decimal_from_i64(v, C.byref(a))
+        n = L.orc_decimal_to_string(C.byref(a), out, 128)
+        assert out.value[:n].decode() == str(v)
+        assert L.orc_decimal_add(C.byref(acc), C.byref(a), C.byref(c)) == 0
+        acc_py += v
+        n = L.orc_decimal_to_string(C.byref(c), out, 128)
+        assert int(out.value[:n].decode()) == acc_py
+        acc = ffi.Decimal.from_buffer_copy(bytes(c))
+    L.orc_decimal_from_u64((1 << 64) - 1, C.byref(a))
+    n = L.orc_decimal_to_string(C.byref(a), out, 128)
+    assert out.value[:n].decode() == str((1 << 64) - 1)
+    # do_add grows a word when the top words sum >= 999,999,999 (decimal.rs:505-507): value stays exact
+    L.orc_decimal_from_i64(999999999, C.byref(a)); L.orc_decimal_from_i64(1, C.byref(b))
+    L.orc_decimal_add(C.byref(a), C.byref(b), C.byref(c))
+    n = L.orc_decimal_to_string(C.byref(c), out, 128)
+    assert out.value[:n].decode() == "1000000000" and c.int_cnt == 18

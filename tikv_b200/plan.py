@@ -1,0 +1,197 @@
+"""Host-side plan builder: the flat POD equivalent of tipb::DagRequest that crosses the C ABI.
+
+Mirrors the reference's test builder `DagSelect` (components/test_coprocessor/src/dag.rs) in spirit:
+    DagSelect.from(table).where(...).aggr_sum(col).group_by([col]).build()
+Expressions are written as trees and lowered to RPN post-order exactly like
+tidb_query_expr/src/types/expr_builder.rs:251-330 does for tipb::Expr trees.
+"""
+import ctypes as C
+
+from . import ffi
+
+_INT_TPS = {ffi.TP_TINY, ffi.TP_SHORT, ffi.TP_INT24, ffi.TP_LONG, ffi.TP_LONGLONG, ffi.TP_YEAR, ffi.TP_BIT}
+_REAL_TPS = {ffi.TP_FLOAT, ffi.TP_DOUBLE}
+
+
+def eval_kind(tp):
+    if tp in _INT_TPS:
+        return "int"
+    if tp in _REAL_TPS:
+        return "real"
+    if tp == ffi.TP_NEWDECIMAL:
+        return "decimal"
+    return "other"
+
+
+class Expr:
+    """Expression tree node; `.tp/.flag` is the node's return FieldType."""
+
+    def __init__(self, kind, tp, flag=0, sig=0, args=(), i64=0, f64=0.0):
+        self.kind, self.tp, self.flag, self.sig, self.args, self.i64, self.f64 = kind, tp, flag, sig, tuple(args), i64, f64
+
+    def rpn(self, out=None):
+        out = [] if out is None else out
+        for a in self.args:
+            a.rpn(out)
+        n = ffi.RpnNode()
+        n.kind, n.sig, n.n_args, n.field_tp, n.field_flag = self.kind, self.sig, len(self.args), self.tp, self.flag
+        n.i64, n.f64 = self.i64, self.f64
+        out.append(n)
+        return out
+
+    @property
+    def ekind(self):
+        return eval_kind(self.tp)
+
+
+def col(offset, tp=ffi.TP_LONGLONG, unsigned=False):
+    return Expr(ffi.RPN_COLUMN_REF, tp, ffi.FLAG_UNSIGNED if unsigned else 0, i64=offset)
+
+
+def const_int(v):
+    return Expr(ffi.RPN_CONST_INT, ffi.TP_LONGLONG, 0, i64=int(v))
+
+
+def const_uint(v):
+    v = int(v)
+    return Expr(ffi.RPN_CONST_UINT, ffi.TP_LONGLONG, ffi.FLAG_UNSIGNED, i64=v - (1 << 64) if v >= (1 << 63) else v)
+
+
+def const_real(v):
+    return Expr(ffi.RPN_CONST_REAL, ffi.TP_DOUBLE, 0, f64=float(v))
+
+
+def null(tp=ffi.TP_LONGLONG):
+    return Expr(ffi.RPN_CONST_NULL, tp, 0)
+
+
+def fn(sig_name, *args, ret_tp=ffi.TP_LONGLONG, unsigned=False):
+    return Expr(ffi.RPN_FN, ret_tp, ffi.FLAG_UNSIGNED if unsigned else 0, sig=ffi.SIG[sig_name], args=args)
+
+
+def _cmp(name, a, b):
+    k = "REAL" if a.ekind == "real" else "INT"
+    return fn(f"{name}_{k}", a, b)
+
+
+def lt(a, b): return _cmp("LT", a, b)
+def le(a, b): return _cmp("LE", a, b)
+def gt(a, b): return _cmp("GT", a, b)
+def ge(a, b): return _cmp("GE", a, b)
+def eq(a, b): return _cmp("EQ", a, b)
+def ne(a, b): return _cmp("NE", a, b)
+def nulleq(a, b): return _cmp("NULLEQ", a, b)
+def and_(a, b): return fn("LOGICAL_AND", a, b)
+def or_(a, b): return fn("LOGICAL_OR", a, b)
+def xor_(a, b): return fn("LOGICAL_XOR", a, b)
+def not_(a): return fn("UNARY_NOT_REAL" if a.ekind == "real" else "UNARY_NOT_INT", a)
+def is_null(a): return fn("REAL_IS_NULL" if a.ekind == "real" else "INT_IS_NULL", a)
+
+
+def _arith(name, a, b):
+    if a.ekind == "real":
+        return fn(f"{name}_REAL", a, b, ret_tp=ffi.TP_DOUBLE)
+    uns = bool((a.flag | b.flag) & ffi.FLAG_UNSIGNED)
+    return fn(f"{name}_INT", a, b, ret_tp=ffi.TP_LONGLONG, unsigned=uns)
+
+
+def plus(a, b): return _arith("PLUS", a, b)
+def minus(a, b): return _arith("MINUS", a, b)
+def multiply(a, b): return _arith("MULTIPLY", a, b)
+
+
+class ColumnDef:
+    def __init__(self, col_id, tp=ffi.TP_LONGLONG, unsigned=False, not_null=False, pk_handle=False, default=None):
+        self.col_id, self.tp, self.pk_handle, self.default = col_id, tp, pk_handle, default
+        self.flag = (ffi.FLAG_UNSIGNED if unsigned else 0) | (ffi.FLAG_NOT_NULL if not_null else 0)
+
+
+class Plan:
+    """Owns every ctypes object referenced by `self.c` (a b2_dag_plan)."""
+
+    def __init__(self):
+        self._keep = []
+        self._execs = []
+        self.c = None
+        self.columns = []
+
+    def _expr(self, e):
+        nodes = e.rpn()
+        arr = (ffi.RpnNode * len(nodes))(*nodes)
+        self._keep.append(arr)
+        x = ffi.RpnExpr()
+        x.nodes, x.n_nodes = arr, len(nodes)
+        return x
+
+    def table_scan(self, table_id, columns, desc=False):
+        self.columns = list(columns)
+        arr = (ffi.ColumnInfo * len(columns))()
+        for i, cd in enumerate(columns):
+            arr[i].col_id, arr[i].tp, arr[i].flag, arr[i].pk_handle = cd.col_id, cd.tp, cd.flag, int(cd.pk_handle)
+            if cd.default is not None:
+                buf = C.create_string_buffer(bytes(cd.default), len(cd.default))
+                self._keep.append(buf)
+                arr[i].default_val = C.cast(buf, C.c_char_p)
+                arr[i].default_len = len(cd.default)
+        self._keep.append(arr)
+        e = ffi.ExecutorDesc()
+        e.tp, e.desc, e.table_id, e.columns, e.n_columns = ffi.EXEC_TABLE_SCAN, int(desc), table_id, arr, len(columns)
+        self._execs.append(e)
+        return self
+
+    def selection(self, *conds):
+        arr = (ffi.RpnExpr * len(conds))(*[self._expr(c) for c in conds])
+        self._keep.append(arr)
+        e = ffi.ExecutorDesc()
+        e.tp, e.conditions, e.n_conditions = ffi.EXEC_SELECTION, arr, len(conds)
+        self._execs.append(e)
+        return self
+
+    def aggregation(self, aggs, group_by=()):
+        """aggs: list of (kind, Expr) with kind in {'count','sum','avg'}."""
+        kinds = {"count": ffi.AGG_COUNT, "sum": ffi.AGG_SUM, "avg": ffi.AGG_AVG, "min": ffi.AGG_MIN, "max": ffi.AGG_MAX}
+        a = (ffi.AggrDesc * len(aggs))()
+        for i, (k, ex) in enumerate(aggs):
+            a[i].kind = kinds[k]
+            a[i].arg = self._expr(ex)
+        g = (ffi.RpnExpr * max(1, len(group_by)))(*[self._expr(x) for x in group_by])
+        self._keep += [a, g]
+        e = ffi.ExecutorDesc()
+        e.tp, e.aggrs, e.n_aggrs, e.group_by, e.n_group_by = ffi.EXEC_AGGREGATION, a, len(aggs), g, len(group_by)
+        self._execs.append(e)
+        return self
+
+    def topn(self, order_by, limit):
+        """order_by: list of (Expr, desc)."""
+        o = (ffi.OrderBy * len(order_by))()
+        for i, (ex, desc) in enumerate(order_by):
+            o[i].expr = self._expr(ex)
+            o[i].desc = int(desc)
+        self._keep.append(o)
+        e = ffi.ExecutorDesc()
+        e.tp, e.order_by, e.n_order_by, e.limit = ffi.EXEC_TOPN, o, len(order_by), limit
+        self._execs.append(e)
+        return self
+
+    def build(self, output_offsets=None):
+        arr = (ffi.ExecutorDesc * len(self._execs))(*self._execs)
+        self._keep.append(arr)
+        p = ffi.DagPlan()
+        p.executors, p.n_executors = arr, len(self._execs)
+        if output_offsets is not None:
+            oo = (C.c_uint32 * len(output_offsets))(*output_offsets)
+            self._keep.append(oo)
+            p.output_offsets, p.n_output_offsets = oo, len(output_offsets)
+        self.c = p
+        return self
+
+
+def key_ranges(ranges):
+    """ranges: list of (start_bytes, end_bytes) raw keys -> (ctypes array, keepalive)."""
+    arr = (ffi.KeyRange * len(ranges))()
+    keep = []
+    for i, (s, e) in enumerate(ranges):
+        s, e = bytes(s), bytes(e)
+        keep += [s, e]
+        arr[i].start, arr[i].start_len, arr[i].end, arr[i].end_len = s, len(s), e, len(e)
+    return arr, keep
