@@ -353,6 +353,13 @@ typedef struct b2_gen b2_gen; /* opaque owner of generated device memory */
 int32_t b2_gen_create(int32_t device, const b2_gen_spec* spec, b2_gen** out, b2_gen_block* out_block);
 void b2_gen_destroy(b2_gen* g);
 
+/* tooling: plain device<->host copies and pinned host memory so harnesses need no second CUDA binding */
+int32_t b2_copy_to_host(int32_t device, void* dst, const void* src_device, uint64_t bytes);
+int32_t b2_copy_to_device(int32_t device, void* dst_device, const void* src, uint64_t bytes);
+int32_t b2_device_count(void);
+void* b2_host_alloc_pinned(uint64_t bytes);
+void b2_host_free_pinned(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,236 @@
+// TEST HARNESS (not product, not oracle): drives the *device* row logic of tikv_b200/csrc/b2_device.h and the plan
+// lowering of plan_compile.h on the CPU, entry by entry, the way scan_kernel does on the GPU.  There is no GPU in the
+// authoring container; this lets `pytest -m "not gpu"` check the MVCC / row-decode / RPN / accumulator code that the
+// kernels execute against the oracle before any GPU time is spent.  Kernel-only mechanics (tickets, look-back,
+// shared-memory tables, atomics) are covered by the `-m gpu` tests.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../tikv_b200/csrc/plan_compile.h"
+
+using namespace b2;
+
+struct emu_result {
+  int status = 0;
+  int dev_err = 0;
+  uint64_t err_entry = ~0ull;
+  std::string msg;
+  std::vector<int> kinds;
+  std::vector<std::vector<uint64_t>> data;      // per output column: bits (i64 / f64)
+  std::vector<std::vector<b2_decimal>> dec;     // per output column: decimals (when kind == DECIMAL)
+  std::vector<std::vector<uint8_t>> nonnull;
+  uint64_t n_rows = 0;
+  uint64_t processed_keys = 0, processed_size = 0, met_newer = 0, dflt = 0;
+  uint64_t checksum = 0, total_kvs = 0, total_bytes = 0;
+};
+
+static uint32_t lower_bound_block(const b2_cf_block& B, const std::vector<uint8_t>& key) {
+  uint32_t lo = 0, hi = B.n;
+  while (lo < hi) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    if (bytes_cmp(B.keys + B.key_offs[mid], B.key_offs[mid + 1] - B.key_offs[mid], key.data(), (uint32_t)key.size()) < 0) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+static BlockView view_of(const b2_cf_block& c) { BlockView v; v.keys = c.keys; v.koff = c.key_offs; v.vals = c.vals; v.voff = c.val_offs; v.n = c.n; return v; }
+
+struct GroupAcc { uint64_t w[MAX_ACC_WORDS]; };
+
+extern "C" {
+
+emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src) {
+  emu_result* R = new emu_result();
+  CompiledPlan cp;
+  R->status = compile_plan(plan, &cp, &R->msg);
+  if (R->status) return R;
+  DevPlan& P = cp.dev;
+  P.read_ts = src->read_ts; P.isolation = src->isolation_level;
+  std::vector<BlockView> dviews;
+  for (uint32_t i = 0; src->dflt && i < src->n_dflt; ++i) dviews.push_back(view_of(src->dflt[i]));
+  DefaultCf dflt; dflt.blocks = dviews.data(); dflt.n_blocks = (uint32_t)dviews.size();
+
+  size_t n_out = P.mode == PM_SCAN ? (size_t)P.n_out : cp.output_offsets.size();
+  R->data.resize(n_out); R->dec.resize(n_out); R->nonnull.resize(n_out); R->kinds.resize(n_out);
+  std::map<std::pair<int, uint64_t>, GroupAcc> groups;  // (is_null, key bits)
+  std::vector<std::pair<int, uint64_t>> group_order;
+  GroupAcc single; memset(&single, 0, sizeof(single));
+  uint64_t live_rows = 0;
+  uint64_t err = ~0ull;
+  auto report = [&](uint64_t entry, int code) { uint64_t v = (entry << 8) | (unsigned)code; if (v < err) err = v; };
+
+  uint64_t base = 0;
+  std::vector<uint64_t> bases;
+  for (uint32_t b = 0; b < src->n_write; ++b) { bases.push_back(base); base += src->write[b].n; }
+  for (uint32_t r = 0; r < n_ranges; ++r) {
+    std::vector<uint8_t> lo = encode_memcomparable(ranges[r].start, ranges[r].start_len), hi = encode_memcomparable(ranges[r].end, ranges[r].end_len);
+    for (uint32_t b = 0; b < src->n_write; ++b) {
+      BlockView blk = view_of(src->write[b]);
+      uint32_t e_lo = lower_bound_block(src->write[b], lo), e_hi = lower_bound_block(src->write[b], hi);
+      for (uint32_t e = e_lo; e < e_hi; ++e) {
+        bool start = (e == e_lo) || !same_user_key(blk, e - 1, e);
+        if (!start) continue;
+        RunOut ro;
+        resolve_run(blk, e, e_hi, P.read_ts, P.isolation, dflt, &ro);
+        R->met_newer |= ro.met_newer; R->dflt += ro.dflt_lookup;
+        if (ro.err) { report(bases[b] + e, ro.err); continue; }
+        if (!ro.found) continue;
+        uint32_t ko = blk.koff[e], kl = blk.koff[e + 1] - ko;
+        R->processed_keys++; R->processed_size += (kl - 8) + ro.val_len;
+        Row row; Cells cells;
+        row.enc_key = blk.keys + ko; row.enc_key_len = kl - 8; row.commit_ts = ro.commit_ts;
+        int er = row_open(ro.val, ro.val_len, &row.rv);
+        if (!er) er = row_split(P, row, cells);
+        bool keep = false;
+        if (!er) er = eval_conds(P, row, cells, &keep);
+        if (er) { report(bases[b] + e, er); continue; }
+        if (!keep) continue;
+        live_rows++;
+        if (err != ~0ull) continue;  // the host discards rows at/after the first failing entry
+        if (P.mode == PM_SCAN) {
+          for (int k = 0; k < P.n_out; ++k) {
+            Value v;
+            int e2 = cell_value(P, row, cells, P.out_cols[k], &v);
+            if (e2) { report(bases[b] + e, e2); v.null = true; v.bits = 0; }
+            R->data[k].push_back(v.null ? 0 : v.bits); R->nonnull[k].push_back(!v.null);
+          }
+          R->n_rows++;
+        } else if (P.mode == PM_AGG) {
+          GroupAcc* acc = &single;
+          if (P.has_group) {
+            Value gk;
+            int e2 = eval_expr(P, P.group, row, cells, &gk, nullptr);
+            if (e2) { report(bases[b] + e, e2); continue; }
+            if (P.group_et == 1 && !gk.null && bits_f64(gk.bits) == 0.0) gk.bits = 0;
+            auto key = std::make_pair((int)gk.null, gk.null ? 0ull : gk.bits);
+            auto it = groups.find(key);
+            if (it == groups.end()) { GroupAcc z; memset(&z, 0, sizeof(z)); it = groups.emplace(key, z).first; group_order.push_back(key); }
+            acc = &it->second;
+          }
+          for (int a = 0; a < P.n_aggs; ++a) {
+            const DevAgg g = P.aggs[a];
+            Value v;
+            int e2 = eval_expr(P, g.arg, row, cells, &v, nullptr);
+            if (e2) { report(bases[b] + e, e2); continue; }
+            if (v.null) continue;
+            acc->w[g.acc_off] += 1;
+            if (g.kind == 0) continue;
+            if (g.arg_et == 1) acc->w[g.acc_off + 1] = f64_bits(bits_f64(acc->w[g.acc_off + 1]) + bits_f64(v.bits));
+            else {
+              acc->w[g.acc_off + 1] += v.bits & 0xffffffffull;
+              acc->w[g.acc_off + 2] += g.arg_unsigned ? (v.bits >> 32) : (uint64_t)((int64_t)v.bits >> 32);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (err != ~0ull) {
+    R->dev_err = (int)(err & 0xff); R->err_entry = err >> 8;
+    R->status = (R->dev_err >= 20 && R->dev_err < 30) ? B2_ERR_EVALUATE : (R->dev_err <= 5 && R->dev_err != DE_WRITE_CONFLICT ? B2_ERR_STORAGE : (R->dev_err == DE_WRITE_CONFLICT ? B2_ERR_WRITE_CONFLICT : B2_ERR_CORRUPTED));
+    if (P.mode == PM_SCAN) {
+      // keep only rows before the failing entry: they were pushed in order, rows after it were skipped above
+    }
+  }
+  if (P.mode == PM_SCAN) {
+    for (int k = 0; k < P.n_out; ++k) R->kinds[k] = cp.schema[cp.output_offsets[k]].kind;
+  } else if (P.mode == PM_AGG && err == ~0ull) {
+    // agg_result_kernel restated: accumulators -> [aggregates..., group key]
+    std::vector<std::pair<std::pair<int, uint64_t>, GroupAcc>> gs;
+    if (P.has_group) for (auto& k : group_order) gs.push_back({k, groups[k]});
+    else if (live_rows > 0) gs.push_back({{0, 0ull}, single});
+    size_t ncol = cp.schema.size();
+    std::vector<std::vector<uint64_t>> data(ncol);
+    std::vector<std::vector<b2_decimal>> dec(ncol);
+    std::vector<std::vector<uint8_t>> nn(ncol);
+    for (auto& g : gs) {
+      int c = 0;
+      const uint64_t* acc = g.second.w;
+      for (int a = 0; a < P.n_aggs; ++a) {
+        const DevAgg ag = P.aggs[a];
+        uint64_t cnt = acc[ag.acc_off];
+        if (ag.kind == 0 || ag.kind == 2) { data[c].push_back(cnt); nn[c].push_back(1); dec[c].push_back(b2_decimal{}); ++c; }
+        if (ag.kind == 1 || ag.kind == 2) {
+          bool has = cnt != 0;
+          b2_decimal d{};
+          if (ag.arg_et == 1) data[c].push_back(has ? acc[ag.acc_off + 1] : 0);
+          else { if (has) limbs_to_decimal(acc[ag.acc_off + 1], acc[ag.acc_off + 2], ag.arg_unsigned, &d); data[c].push_back(0); }
+          dec[c].push_back(d); nn[c].push_back(has);
+          ++c;
+        }
+      }
+      if (P.has_group) { data[c].push_back(g.first.first ? 0 : g.first.second); nn[c].push_back(!g.first.first); dec[c].push_back(b2_decimal{}); }
+    }
+    for (size_t i = 0; i < cp.output_offsets.size(); ++i) {
+      uint32_t k = cp.output_offsets[i];
+      R->kinds[i] = cp.schema[k].kind; R->data[i] = data[k]; R->dec[i] = dec[k]; R->nonnull[i] = nn[k];
+    }
+    R->n_rows = gs.size();
+  }
+  return R;
+}
+
+// checksum_kernel restated on the host with the same helpers
+emu_result* emu_checksum(const b2_key_range* ranges, uint32_t n_ranges, const uint8_t* old_prefix, uint32_t old_len, const uint8_t* new_prefix, uint32_t new_len,
+                         const b2_region_source* src) {
+  emu_result* R = new emu_result();
+  std::vector<BlockView> dviews;
+  for (uint32_t i = 0; src->dflt && i < src->n_dflt; ++i) dviews.push_back(view_of(src->dflt[i]));
+  DefaultCf dflt; dflt.blocks = dviews.data(); dflt.n_blocks = (uint32_t)dviews.size();
+  uint64_t st = ~0ull;
+  for (uint32_t i = 0; i < old_len; ++i) st = crc64_table_entry((uint8_t)(st ^ old_prefix[i])) ^ (st >> 8);
+  for (uint32_t r = 0; r < n_ranges; ++r) {
+    std::vector<uint8_t> lo = encode_memcomparable(ranges[r].start, ranges[r].start_len), hi = encode_memcomparable(ranges[r].end, ranges[r].end_len);
+    for (uint32_t b = 0; b < src->n_write; ++b) {
+      BlockView blk = view_of(src->write[b]);
+      uint32_t e_lo = lower_bound_block(src->write[b], lo), e_hi = lower_bound_block(src->write[b], hi);
+      for (uint32_t e = e_lo; e < e_hi; ++e) {
+        if (!((e == e_lo) || !same_user_key(blk, e - 1, e))) continue;
+        RunOut ro;
+        resolve_run(blk, e, e_hi, src->read_ts, src->isolation_level, dflt, &ro);
+        if (ro.err) { R->status = B2_ERR_STORAGE; R->dev_err = ro.err; continue; }
+        if (!ro.found) continue;
+        const uint8_t* ek = blk.keys + blk.koff[e];
+        uint32_t ekl = blk.koff[e + 1] - blk.koff[e] - 8;
+        int rawlen = raw_key_len(ek, ekl);
+        if (rawlen < 0) { R->status = B2_ERR_STORAGE; continue; }
+        bool ok = (uint32_t)rawlen >= new_len;
+        for (uint32_t j = 0; ok && j < new_len; ++j) ok = raw_at(ek, j) == new_prefix[j];
+        if (!ok) { R->status = B2_ERR_STORAGE; R->msg = "Wrong prefix expect"; continue; }
+        uint64_t c = st;
+        for (uint32_t j = new_len; j < (uint32_t)rawlen; ++j) c = crc64_table_entry((uint8_t)(c ^ raw_at(ek, j))) ^ (c >> 8);
+        for (uint32_t j = 0; j < ro.val_len; ++j) c = crc64_table_entry((uint8_t)(c ^ ro.val[j])) ^ (c >> 8);
+        R->checksum ^= ~c; R->total_kvs++; R->total_bytes += (uint64_t)rawlen + ro.val_len + old_len - new_len;
+      }
+    }
+  }
+  return R;
+}
+
+int emu_status(emu_result* r) { return r->status; }
+int emu_dev_err(emu_result* r) { return r->dev_err; }
+uint64_t emu_err_entry(emu_result* r) { return r->err_entry; }
+const char* emu_message(emu_result* r) { return r->msg.c_str(); }
+uint64_t emu_rows(emu_result* r) { return r->n_rows; }
+uint32_t emu_cols(emu_result* r) { return (uint32_t)r->data.size(); }
+int emu_col_kind(emu_result* r, uint32_t c) { return r->kinds[c]; }
+const uint64_t* emu_col_data(emu_result* r, uint32_t c) { return r->data[c].data(); }
+const b2_decimal* emu_col_dec(emu_result* r, uint32_t c) { return r->dec[c].data(); }
+const uint8_t* emu_col_nonnull(emu_result* r, uint32_t c) { return r->nonnull[c].data(); }
+void emu_stats(emu_result* r, uint64_t* out7) {
+  out7[0] = r->processed_keys; out7[1] = r->processed_size; out7[2] = r->met_newer; out7[3] = r->dflt;
+  out7[4] = r->checksum; out7[5] = r->total_kvs; out7[6] = r->total_bytes;
+}
+void emu_free(emu_result* r) { delete r; }
+int emu_check_supported(const b2_dag_plan* plan, char* msg, size_t cap) {
+  CompiledPlan cp; std::string m;
+  int rc = compile_plan(plan, &cp, &m);
+  snprintf(msg, cap, "%s", m.c_str());
+  return rc;
+}
+
+}  // extern "C"

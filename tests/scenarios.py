@@ -1,0 +1,155 @@
+"""Seeded synthetic regions + DAG plans shared by the CPU (device-logic emulation) and GPU parity tests.
+
+Data shape follows SURVEY.md §8(d)'s "dirty" variant: several versions per key, Deletes, Lock/Rollback records
+(with and without last_change jumps), versions newer than read_ts, long values in CF_DEFAULT, NULLs, missing
+columns with defaults, both row formats in one region.
+"""
+import random
+
+import kvfmt
+from tikv_b200 import ffi
+from tikv_b200.plan import (ColumnDef, Plan, and_, col, const_int, const_real, const_uint, eq, ge, gt, is_null, le, lt, minus, multiply,
+                            ne, not_, null, nulleq, or_, plus, xor_)
+
+TABLE = 1000
+READ_TS = 1000
+
+# schema: handle PK, c1 i64, c2 i64 (small domain, nullable), c3 u64, c4 f64, c5 i64 with default 77, c6 i32-domain key
+COLUMNS = [
+    ColumnDef(100, pk_handle=True),
+    ColumnDef(1),
+    ColumnDef(2),
+    ColumnDef(3, unsigned=True),
+    ColumnDef(4, tp=ffi.TP_DOUBLE),
+    ColumnDef(5, default=kvfmt.datum_int(77)),
+    ColumnDef(6, tp=ffi.TP_LONG),
+]
+C_H, C1, C2, C3, C4, C5, C6 = range(7)
+
+
+def _row_value(rng, fmt, full_range=True):
+    c1 = rng.randrange(-(1 << 63), 1 << 63) if full_range else rng.randrange(-(1 << 40), 1 << 40)
+    c2 = None if rng.random() < 0.1 else rng.randrange(-50, 50)
+    c3 = rng.choice([0, 1, (1 << 64) - 1, 1 << 63, rng.randrange(0, 1 << 64)])
+    c4 = None if rng.random() < 0.05 else rng.choice([0.0, -0.0, 1.5, -2.25, rng.uniform(-1e6, 1e6)])
+    c5 = None if rng.random() < 0.5 else rng.randrange(-1000, 1000)  # None => column missing => default 77
+    c5_explicit_null = rng.random() < 0.1
+    c6 = rng.randrange(0, 16)
+    if fmt == 2:
+        cols = [(1, c1, "int"), (2, c2, "int"), (3, c3, "uint"), (4, c4, "f64"), (6, c6, "int")]
+        if c5 is not None:
+            cols.append((5, None if c5_explicit_null else c5, "int"))
+        rng.shuffle(cols)
+        return kvfmt.row_v2(cols)
+    d = [(1, kvfmt.datum_int(c1)), (2, kvfmt.datum_null() if c2 is None else kvfmt.datum_int(c2)),
+         (3, kvfmt.datum_uint(c3) if rng.random() < 0.5 else kvfmt.datum_uint(c3, comparable=True)),
+         (4, kvfmt.datum_null() if c4 is None else kvfmt.datum_f64(c4)), (6, kvfmt.datum_int(c6, comparable=rng.random() < 0.3))]
+    if c5 is not None:
+        d.append((5, kvfmt.datum_null() if c5_explicit_null else kvfmt.datum_int(c5)))
+    if rng.random() < 0.2:
+        d.append((99, kvfmt.datum_bytes(b"unknown column")))  # unknown column ids are skipped
+    rng.shuffle(d)
+    return kvfmt.row_v1(d)
+
+
+def dirty_region(seed, n_keys=600, full_range=True, long_values=True):
+    """Region with every MVCC shape the forward scanner handles."""
+    rng = random.Random(seed)
+    r = kvfmt.Region()
+    for h in range(n_keys):
+        key = kvfmt.row_key(TABLE, h * 3 - 100)
+        shape = rng.random()
+        fmt = 2 if rng.random() < 0.6 else 1
+        val = _row_value(rng, fmt, full_range)
+        if shape < 0.45:  # single visible put
+            r.put(key, val, 10, 20)
+        elif shape < 0.55:  # older + visible + newer-than-read_ts versions
+            r.put(key, _row_value(rng, fmt, full_range), 5, 8)
+            r.put(key, val, 10, 20)
+            r.put(key, _row_value(rng, fmt, full_range), READ_TS + 5, READ_TS + 9)
+        elif shape < 0.62:  # visible version is a Delete
+            r.put(key, val, 10, 20)
+            r.delete(key, 30, 40)
+        elif shape < 0.70:  # Lock / Rollback records above the visible put (step by next)
+            r.put(key, val, 10, 20)
+            r.lock_rec(key, 30, 31, last_change=(20, 1))
+            r.rollback(key, 50)
+            r.lock_rec(key, 60, 61)  # last_change unknown
+        elif shape < 0.76:  # many lock records: last_change jump (estimated versions >= SEEK_BOUND)
+            r.put(key, _row_value(rng, fmt, full_range), 2, 3)
+            r.put(key, val, 10, 20)
+            for i in range(10):
+                r.lock_rec(key, 100 + 2 * i, 101 + 2 * i, last_change=(20, i + 1))
+        elif shape < 0.80:  # only lock records, last change does not exist
+            for i in range(3):
+                r.lock_rec(key, 100 + 2 * i, 101 + 2 * i, last_change=(0, 1))
+        elif shape < 0.85 and long_values:  # long value -> CF_DEFAULT
+            big = kvfmt.row_v2([(1, rng.randrange(-100, 100), "int"), (2, 1, "int"), (3, 5, "uint"), (4, 2.5, "f64"), (6, 3, "int"),
+                                (7, bytes(rng.randrange(256) for _ in range(300)), "bytes")])
+            r.put(key, big, 10, 20)
+        elif shape < 0.90:  # gc fence: fenced (invisible) or not
+            r.put(key, val, 10, 20, overlapped_rollback=True, gc_fence=rng.choice([0, 500, READ_TS, READ_TS + 1, 30]))
+        elif shape < 0.95:  # only versions newer than read_ts
+            r.put(key, val, READ_TS + 1, READ_TS + 2)
+        else:  # 12 newer versions: move_write_cursor_to_ts goes over SEEK_BOUND
+            r.put(key, val, 10, 20)
+            for i in range(12):
+                r.put(key, _row_value(rng, fmt, full_range), READ_TS + 10 + 2 * i, READ_TS + 11 + 2 * i)
+    return r
+
+
+WHOLE = [kvfmt.table_range(TABLE)]
+
+
+def plans():
+    """(name, Plan) list.  Column offsets refer to COLUMNS."""
+    P = []
+
+    def scan():
+        return Plan().table_scan(TABLE, COLUMNS)
+
+    P.append(("scan_all", scan().build()))
+    P.append(("scan_subset_cols", scan().build(output_offsets=[C4, C_H, C2])))
+    P.append(("sel_lt_const", scan().selection(lt(col(C1), const_int(0))).build()))
+    P.append(("sel_handle_range", scan().selection(ge(col(C_H), const_int(50)), le(col(C_H), const_int(900))).build()))
+    P.append(("sel_null_semantics", scan().selection(gt(col(C2), const_int(-10))).build()))
+    P.append(("sel_nulleq", scan().selection(nulleq(col(C2), null())).build()))
+    P.append(("sel_is_null_or", scan().selection(or_(is_null(col(C2)), eq(col(C2), const_int(7)))).build()))
+    P.append(("sel_not_xor", scan().selection(xor_(not_(gt(col(C2), const_int(0))), lt(col(C6), const_int(8)))).build()))
+    P.append(("sel_unsigned_cmp", scan().selection(gt(col(C3, unsigned=True), const_uint(1 << 63))).build()))
+    P.append(("sel_mixed_sign_cmp", scan().selection(lt(col(C2), col(C3, unsigned=True))).build()))
+    P.append(("sel_uint_vs_int", scan().selection(ge(col(C3, unsigned=True), col(C2))).build()))
+    P.append(("sel_real", scan().selection(le(col(C4, tp=ffi.TP_DOUBLE), const_real(1.5))).build()))
+    P.append(("sel_real_ne", scan().selection(ne(col(C4, tp=ffi.TP_DOUBLE), const_real(0.0))).build()))
+    P.append(("sel_default_col", scan().selection(eq(col(C5), const_int(77))).build()))
+    P.append(("sel_arith", scan().selection(lt(plus(col(C2), multiply(col(C6), const_int(3))), const_int(20))).build()))
+    P.append(("sel_arith_minus", scan().selection(gt(minus(col(C6), col(C2)), const_int(10))).build()))
+    P.append(("sel_and_two_conds", scan().selection(and_(lt(col(C2), const_int(25)), gt(col(C6), const_int(2))), ne(col(C5), const_int(0))).build()))
+    P.append(("count_star", scan().aggregation([("count", const_int(1))]).build()))
+    P.append(("count_col_sum_avg", scan().aggregation([("count", col(C2)), ("sum", col(C2)), ("avg", col(C6))]).build()))
+    P.append(("sum_fullrange", scan().aggregation([("sum", col(C1)), ("count", const_int(1))]).build()))
+    P.append(("sum_unsigned", scan().aggregation([("sum", col(C3, unsigned=True))]).build()))
+    P.append(("agg_after_filter", scan().selection(lt(col(C1), const_int(0))).aggregation([("count", const_int(1)), ("sum", col(C1))]).build()))
+    P.append(("agg_no_input", scan().selection(lt(col(C6), const_int(-5))).aggregation([("count", const_int(1)), ("sum", col(C1))]).build()))
+    P.append(("group_by_small", scan().aggregation([("sum", col(C1)), ("count", const_int(1))], group_by=[col(C6, tp=ffi.TP_LONG)]).build()))
+    P.append(("group_by_nullable", scan().aggregation([("count", const_int(1)), ("avg", col(C1)), ("sum", col(C5))], group_by=[col(C2)]).build()))
+    P.append(("group_by_handle_many", scan().aggregation([("sum", col(C6)), ("count", col(C2))], group_by=[col(C_H)]).build()))
+    P.append(("group_by_expr", scan().aggregation([("count", const_int(1))], group_by=[plus(col(C6), const_int(100))]).build()))
+    P.append(("group_by_real", scan().aggregation([("count", const_int(1))], group_by=[col(C4, tp=ffi.TP_DOUBLE)]).build()))
+    P.append(("group_filter_offsets", scan().selection(ge(col(C6), const_int(4))).aggregation([("sum", col(C2)), ("count", const_int(1))], group_by=[col(C6, tp=ffi.TP_LONG)]).build(output_offsets=[2, 0])))
+    return P
+
+
+def real_sum_plans():
+    def scan():
+        return Plan().table_scan(TABLE, COLUMNS)
+    return [("sum_real", scan().aggregation([("sum", col(C4, tp=ffi.TP_DOUBLE)), ("avg", col(C4, tp=ffi.TP_DOUBLE))]).build()),
+            ("sum_real_group", scan().aggregation([("sum", col(C4, tp=ffi.TP_DOUBLE))], group_by=[col(C6, tp=ffi.TP_LONG)]).build())]
+
+
+def is_agg(name):
+    return name.startswith(("count", "sum", "agg", "group"))
+
+
+def split_ranges():
+    return [kvfmt.table_range(TABLE, -1000, 50), kvfmt.table_range(TABLE, 50, 51), kvfmt.table_range(TABLE, 400, 1000), kvfmt.table_range(TABLE, 1200, 5000)]

@@ -1,0 +1,76 @@
+"""`-m "not gpu"`: the C-ABI library builds for sm_100a, loads, and exports every symbol include/b2_copr.h declares.
+No compute call is made (there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from tikv_b200 import ffi
+    return ffi.lib()
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "b2_copr.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in b2_copr.h but not exported by libb2copr.so"
+    from tikv_b200 import ffi
+    assert set(ffi.EXPORTED_SYMBOLS) == set(names)
+
+
+def test_abi_version_and_structs(lib):
+    from tikv_b200 import ffi
+    assert lib.b2_abi_version() == 1
+    assert b"sm_100a" in lib.b2_build_info()
+    # struct sizes the Rust/cgo side would mirror
+    assert C.sizeof(ffi.Decimal) == 40 and C.sizeof(ffi.CfBlock) == 40 and C.sizeof(ffi.RpnNode) == 40
+    assert C.sizeof(ffi.Column) == 40 and C.sizeof(ffi.ChecksumResponse) == 24
+
+
+def test_sass_is_sm100a(lib):
+    """The shipped library must contain sm_100a SASS for the hot kernels (no PTX-only / other-arch fallback)."""
+    import subprocess
+    so = os.path.join(ROOT, "tikv_b200", "_build", "libb2copr.so")
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_check_supported_without_gpu(lib):
+    from tikv_b200 import ffi
+    from tikv_b200.plan import ColumnDef, Plan, col, const_int, lt
+    cols = [ColumnDef(1, pk_handle=True), ColumnDef(2), ColumnDef(3, tp=ffi.TP_VARCHAR)]
+    ok = Plan().table_scan(5, cols).selection(lt(col(1), const_int(3))).build(output_offsets=[0, 1])
+    assert lib.b2_check_supported(C.byref(ok.c)) == ffi.B2_OK
+    bad = Plan().table_scan(5, cols).build()
+    assert lib.b2_check_supported(C.byref(bad.c)) == ffi.B2_ERR_UNSUPPORTED
+    assert b"Int/Real" in lib.b2_last_error_message()
+
+
+def test_open_fails_loudly_without_cuda(lib):
+    """No CPU fallback: without a CUDA device b2_exec_open reports B2_ERR_CUDA."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import kvfmt
+    from tikv_b200 import ffi
+    from tikv_b200.executor import B2Error, BatchExecutor
+    from tikv_b200.plan import ColumnDef, Plan
+    r = kvfmt.Region().put(kvfmt.row_key(5, 1), kvfmt.row_v2([(2, 1, "int")]), 1, 2).build(read_ts=10)
+    p = Plan().table_scan(5, [ColumnDef(1, pk_handle=True), ColumnDef(2)]).build()
+    with pytest.raises(B2Error) as ei:
+        BatchExecutor(p, [kvfmt.table_range(5)], r)
+    assert ei.value.status == ffi.B2_ERR_CUDA and "no CPU fallback" in ei.value.message

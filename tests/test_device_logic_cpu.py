@@ -1,0 +1,137 @@
+"""`-m "not gpu"`: the device row logic (b2_device.h) + plan lowering, driven entry-by-entry on the CPU by
+tests/host_emul.cpp, must agree with the oracle on every scenario.  The `-m gpu` twin (test_gpu_parity.py) runs the
+same scenarios through the CUDA kernels and the C ABI."""
+import pytest
+
+import emu
+import kvfmt
+import orc
+import scenarios as sc
+from compare import assert_same_rows
+from tikv_b200 import ffi
+from tikv_b200.plan import ColumnDef, Plan, col, const_int, lt, multiply, plus
+
+PLANS = sc.plans()
+
+
+@pytest.fixture(scope="module")
+def regions():
+    return {seed: sc.dirty_region(seed) for seed in (1, 2)}
+
+
+@pytest.mark.parametrize("name,plan", PLANS, ids=[n for n, _ in PLANS])
+@pytest.mark.parametrize("seed", [1, 2])
+def test_emulated_device_logic_matches_oracle(name, plan, seed, regions):
+    for n_blocks, ranges in ((1, sc.WHOLE), (3, sc.split_ranges())):
+        region = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=n_blocks)
+        exp = orc.dag_handle(plan, ranges, region)
+        got = emu.dag_handle(plan, ranges, region)
+        assert exp.status == 0
+        assert_same_rows(got, exp, ordered=not sc.is_agg(name), ctx=f"{name}/seed{seed}/blocks{n_blocks}")
+        assert got.stats["processed_keys"] == exp.stats["processed_keys"]
+        assert got.stats["processed_size"] == exp.stats["processed_size"]
+        assert got.stats["default_lookups"] == exp.stats["data_processed_keys"]
+        assert bool(got.stats["met_newer"]) == (exp.stats["met_newer"] == 1)
+
+
+@pytest.mark.parametrize("name,plan", sc.real_sum_plans())
+def test_real_sum_close_to_oracle(name, plan, regions):
+    region = regions[1].build(read_ts=sc.READ_TS)
+    exp = orc.dag_handle(plan, sc.WHOLE, region)
+    got = emu.dag_handle(plan, sc.WHOLE, region)
+    assert_same_rows(got, exp, ordered=False, float_rel_tol=1e-12, ctx=name)
+
+
+def test_isolation_levels_and_read_ts(regions):
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).build()
+    for ts in (1, 9, 25, 45, 150, sc.READ_TS, sc.READ_TS + 100, (1 << 64) - 1):
+        region = regions[2].build(read_ts=ts, isolation=ffi.ISO_RC)
+        assert_same_rows(emu.dag_handle(plan, sc.WHOLE, region), orc.dag_handle(plan, sc.WHOLE, region), ctx=f"ts{ts}")
+    region = regions[2].build(read_ts=sc.READ_TS, isolation=ffi.ISO_RC_CHECK_TS)
+    exp, got = orc.dag_handle(plan, sc.WHOLE, region), emu.dag_handle(plan, sc.WHOLE, region)
+    assert exp.status == ffi.B2_ERR_WRITE_CONFLICT == got.status
+    assert got.rows() == exp.rows()
+
+
+def test_checksum_matches_oracle(regions):
+    for seed in (1, 2):
+        region = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=2)
+        for ranges in (sc.WHOLE, sc.split_ranges()):
+            st, exp, _ = orc.checksum(ranges, region)
+            st2, got = emu.checksum(ranges, region)
+            assert st == 0 == st2 and got == exp and exp[1] > 0
+    prefix_old, prefix_new = b"t" + kvfmt.enc_i64_cmp(42), b"t" + kvfmt.enc_i64_cmp(sc.TABLE)
+    region = regions[1].build(read_ts=sc.READ_TS)
+    st, exp, _ = orc.checksum(sc.WHOLE, region, prefix_old, prefix_new)
+    st2, got = emu.checksum(sc.WHOLE, region, prefix_old, prefix_new)
+    assert st == 0 == st2 and got == exp
+    st, _, msg = orc.checksum(sc.WHOLE, region, b"", b"x")
+    st2, _ = emu.checksum(sc.WHOLE, region, b"", b"x")
+    assert st != 0 and st2 != 0
+
+
+def _err_region():
+    T = sc.TABLE
+    r = kvfmt.Region()
+    for h in range(40):
+        r.put(kvfmt.row_key(T, h), kvfmt.row_v2([(1, h, "int"), (2, h % 5, "int"), (3, 7, "uint"), (4, 1.0, "f64"), (6, 1, "int")]), 10, 20)
+    return r
+
+
+def test_errors_match_oracle():
+    T = sc.TABLE
+    cols = sc.COLUMNS
+    # corrupted row in the middle: rows before it, then CORRUPTED
+    r = _err_region()
+    r.put(kvfmt.row_key(T, 20), kvfmt.row_v1([(1, kvfmt.datum_int(5))]) + bytes([kvfmt.VAR_INT, 0x80]), 30, 40)
+    plan = Plan().table_scan(T, cols).build()
+    region = r.build(read_ts=100)
+    exp, got = orc.dag_handle(plan, sc.WHOLE, region), emu.dag_handle(plan, sc.WHOLE, region)
+    assert exp.status == ffi.B2_ERR_CORRUPTED == got.status and got.rows() == exp.rows() and len(exp.rows()) == 20
+    # v2 int with a 3-byte width
+    r = _err_region()
+    bad = bytearray(kvfmt.row_v2([(1, 70000, "int"), (2, 1, "int")]))
+    bad[8] = 3  # first end-offset: value 1 becomes 3 bytes wide
+    r.put(kvfmt.row_key(T, 7), bytes(bad), 30, 40)
+    region = r.build(read_ts=100)
+    exp, got = orc.dag_handle(plan, sc.WHOLE, region), emu.dag_handle(plan, sc.WHOLE, region)
+    assert exp.status == ffi.B2_ERR_CORRUPTED == got.status and got.rows() == exp.rows()
+    # BIGINT overflow in an expression -> Evaluate error 1690
+    r = _err_region()
+    r.put(kvfmt.row_key(T, 1000), kvfmt.row_v2([(1, (1 << 62), "int"), (2, 4, "int"), (3, 7, "uint"), (6, 1, "int")]), 10, 20)
+    p2 = Plan().table_scan(T, cols).selection(lt(multiply(col(sc.C1), const_int(4)), const_int(100))).build()
+    region = r.build(read_ts=100)
+    exp, got = orc.dag_handle(p2, sc.WHOLE, region), emu.dag_handle(p2, sc.WHOLE, region)
+    assert exp.status == ffi.B2_ERR_EVALUATE == got.status and exp.mysql_code == 1690
+    # bad write record / missing default CF value -> Storage error
+    r = _err_region().raw_write(kvfmt.row_key(T, 5), 50, b"Xjunk")
+    region = r.build(read_ts=100)
+    exp, got = orc.dag_handle(plan, sc.WHOLE, region), emu.dag_handle(plan, sc.WHOLE, region)
+    assert exp.status == ffi.B2_ERR_STORAGE == got.status and got.rows() == exp.rows()
+    r = _err_region()
+    r.write.append((kvfmt.write_key(kvfmt.row_key(T, 3), 60), kvfmt.write_record(b"P", 55)))  # long value without CF_DEFAULT entry
+    region = r.build(read_ts=100)
+    exp, got = orc.dag_handle(plan, sc.WHOLE, region), emu.dag_handle(plan, sc.WHOLE, region)
+    assert exp.status == ffi.B2_ERR_STORAGE == got.status and got.rows() == exp.rows()
+    # decode error only matters for rows that are still selected (lazy decode)
+    r = _err_region()
+    r.put(kvfmt.row_key(T, 500), kvfmt.row_v1([(1, kvfmt.datum_int(1)), (2, kvfmt.datum_bytes(b"zz")), (6, kvfmt.datum_int(1))]), 10, 20)
+    p3 = Plan().table_scan(T, cols).selection(lt(col(sc.C_H), const_int(100))).build(output_offsets=[sc.C_H, sc.C2])
+    region = r.build(read_ts=100)
+    exp, got = orc.dag_handle(p3, sc.WHOLE, region), emu.dag_handle(p3, sc.WHOLE, region)
+    assert exp.status == 0 == got.status and got.rows() == exp.rows()
+    p4 = Plan().table_scan(T, cols).build(output_offsets=[sc.C_H, sc.C2])
+    exp, got = orc.dag_handle(p4, sc.WHOLE, region), emu.dag_handle(p4, sc.WHOLE, region)
+    assert exp.status == ffi.B2_ERR_CORRUPTED == got.status
+
+
+def test_check_supported_mirrors_runner():
+    cols = [ColumnDef(1, pk_handle=True), ColumnDef(2), ColumnDef(3, tp=ffi.TP_VARCHAR)]
+    ok = Plan().table_scan(5, cols).selection(lt(col(1), const_int(3))).build(output_offsets=[0, 1])
+    assert emu.check_supported(ok)[0] == 0
+    assert emu.check_supported(Plan().table_scan(5, cols).build())[0] == ffi.B2_ERR_UNSUPPORTED  # varchar output
+    assert emu.check_supported(Plan().table_scan(5, cols, desc=True).build(output_offsets=[0]))[0] == ffi.B2_ERR_UNSUPPORTED
+    two = Plan().table_scan(5, cols).aggregation([("count", const_int(1))], group_by=[col(0), col(1)]).build()
+    assert emu.check_supported(two)[0] == ffi.B2_ERR_UNSUPPORTED
+    rc, msg = emu.check_supported(Plan().table_scan(5, cols).selection(lt(col(2), const_int(3))).build(output_offsets=[0]))
+    assert rc == ffi.B2_ERR_UNSUPPORTED and "Int/Real" in msg

@@ -1,0 +1,287 @@
+"""`-m gpu`: parity of the CUDA path (through the C ABI) against the oracle on seeded inputs.
+Bit-exact for ints / counts / decimals / CRC; f64 SUM within 1e-12 relative (atomic summation order)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import kvfmt
+import orc
+import scenarios as sc
+from compare import assert_same_rows
+from tikv_b200 import ffi
+from tikv_b200.executor import BatchExecutor, DagHandler, DeviceRegion, checksum
+from tikv_b200.plan import ColumnDef, Plan, col, const_int, lt, multiply
+
+pytestmark = pytest.mark.gpu
+
+PLANS = sc.plans()
+
+
+@pytest.fixture(scope="module")
+def regions():
+    return {seed: sc.dirty_region(seed, n_keys=900) for seed in (1, 2)}
+
+
+@pytest.mark.parametrize("name,plan", PLANS, ids=[n for n, _ in PLANS])
+def test_host_source_matches_oracle(name, plan, regions):
+    """HOST-resident blocks: the engine stages them to HBM itself (H2D inside the call)."""
+    for seed, n_blocks, ranges in ((1, 1, sc.WHOLE), (2, 3, sc.split_ranges())):
+        region = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=n_blocks)
+        exp = orc.dag_handle(plan, ranges, region)
+        got = DagHandler(plan, ranges, region).handle_request()
+        assert_same_rows(got, exp, ordered=not sc.is_agg(name), ctx=f"{name}/seed{seed}")
+        assert got.stats.write_processed_keys == exp.stats["processed_keys"]
+        assert got.stats.processed_size == exp.stats["processed_size"]
+        assert got.stats.default_lookups == exp.stats["data_processed_keys"]
+        assert got.stats.met_newer_ts_data == exp.stats["met_newer"]
+
+
+@pytest.mark.parametrize("name,plan", PLANS[:6] + PLANS[-8:], ids=[n for n, _ in PLANS[:6] + PLANS[-8:]])
+def test_device_source_matches_oracle(name, plan, regions):
+    host = regions[1].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    dev = DeviceRegion(host)
+    exp = orc.dag_handle(plan, sc.split_ranges(), host)
+    got = DagHandler(plan, sc.split_ranges(), dev).handle_request()
+    assert_same_rows(got, exp, ordered=not sc.is_agg(name), ctx=name)
+
+
+@pytest.mark.parametrize("scan_rows", [1, 7, 100, 256, 257, 1000])
+def test_small_batches_keep_order(scan_rows, regions):
+    """next_batch(scan_rows) with tiny batches: many launches, look-back across tiles, rows stay in key order."""
+    host = regions[2].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(lt(col(sc.C1), const_int(1 << 62))).build()
+    exp = orc.dag_handle(plan, sc.WHOLE, host)
+    got = DagHandler(plan, sc.WHOLE, host, batch_rows=scan_rows).handle_request()
+    assert_same_rows(got, exp, ordered=True, ctx=f"scan_rows={scan_rows}")
+
+
+def test_batch_executor_interface(regions):
+    host = regions[1].build(read_ts=sc.READ_TS)
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).build(output_offsets=[sc.C_H, sc.C4])
+    with BatchExecutor(plan, sc.WHOLE, host) as ex:
+        assert ex.schema() == [(ffi.TP_LONGLONG, 0), (ffi.TP_DOUBLE, 0)]
+        r = ex.next_batch(500)
+        assert not r.is_drained and r.kinds == [ffi.COL_I64, ffi.COL_F64]
+        n = r.n_rows
+        while not r.is_drained:
+            r = ex.next_batch(500)
+            n += r.n_rows
+        st = ex.collect_exec_stats()
+        assert st.num_produced_rows == n == orc.dag_handle(plan, sc.WHOLE, host).n_rows
+        assert st.write_entries_scanned == host.n_entries and st.time_processed_ns > 0
+        assert not ex.can_be_cached()  # the region holds versions newer than read_ts
+    clean = kvfmt.Region()
+    for h in range(10):
+        clean.put(kvfmt.row_key(sc.TABLE, h), kvfmt.row_v2([(1, h, "int")]), 10, 20)
+    with BatchExecutor(plan, sc.WHOLE, clean.build(read_ts=100)) as ex:
+        assert ex.next_batch(1 << 20).n_rows == 10 and ex.can_be_cached()
+
+
+@pytest.mark.parametrize("name,plan", sc.real_sum_plans())
+def test_real_sum(name, plan, regions):
+    host = regions[1].build(read_ts=sc.READ_TS)
+    assert_same_rows(DagHandler(plan, sc.WHOLE, host).handle_request(), orc.dag_handle(plan, sc.WHOLE, host), ordered=False,
+                     float_rel_tol=1e-12, ctx=name)
+
+
+def test_isolation_levels_and_read_ts(regions):
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).build()
+    for ts in (1, 25, 150, sc.READ_TS + 100, (1 << 64) - 1):
+        region = regions[2].build(read_ts=ts, isolation=ffi.ISO_RC)
+        assert_same_rows(DagHandler(plan, sc.WHOLE, region).handle_request(), orc.dag_handle(plan, sc.WHOLE, region), ctx=f"ts{ts}")
+    region = regions[2].build(read_ts=sc.READ_TS, isolation=ffi.ISO_RC_CHECK_TS)
+    exp, got = orc.dag_handle(plan, sc.WHOLE, region), DagHandler(plan, sc.WHOLE, region).handle_request()
+    assert exp.status == ffi.B2_ERR_WRITE_CONFLICT == got.status and got.rows() == exp.rows()
+
+
+def test_locks(regions):
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).build(output_offsets=[sc.C_H])
+    r = kvfmt.Region()
+    for h in range(50):
+        r.put(kvfmt.row_key(sc.TABLE, h), kvfmt.row_v2([(1, h, "int")]), 10, 20)
+    r.add_lock(kvfmt.row_key(sc.TABLE, 30), kvfmt.lock_record(b"P", kvfmt.row_key(sc.TABLE, 30), 50))
+    r.add_lock(kvfmt.row_key(sc.TABLE, 10), kvfmt.lock_record(b"L", kvfmt.row_key(sc.TABLE, 10), 50))  # Lock-type locks never block
+    for kw in (dict(read_ts=100), dict(read_ts=100, bypass=[50]), dict(read_ts=40), dict(read_ts=100, isolation=ffi.ISO_RC)):
+        region = r.build(**kw)
+        exp, got = orc.dag_handle(plan, sc.WHOLE, region), DagHandler(plan, sc.WHOLE, region).handle_request()
+        assert exp.status == got.status and got.rows() == exp.rows(), kw
+    region = r.build(read_ts=100)
+    got = DagHandler(plan, sc.WHOLE, region).handle_request()
+    assert got.status == ffi.B2_ERR_KEY_IS_LOCKED and got.n_rows == 30 and not got.can_be_cached
+    agg = Plan().table_scan(sc.TABLE, sc.COLUMNS).aggregation([("count", const_int(1))]).build()
+    assert DagHandler(agg, sc.WHOLE, region).handle_request().status == ffi.B2_ERR_KEY_IS_LOCKED
+
+
+def test_errors_match_oracle():
+    T, cols = sc.TABLE, sc.COLUMNS
+    base = kvfmt.Region()
+    for h in range(600):
+        base.put(kvfmt.row_key(T, h), kvfmt.row_v2([(1, h, "int"), (2, h % 5, "int"), (3, 7, "uint"), (4, 1.0, "f64"), (6, 1, "int")]), 10, 20)
+
+    def with_extra(fn):
+        r = kvfmt.Region()
+        r.write, r.dflt = list(base.write), list(base.dflt)
+        fn(r)
+        return r.build(read_ts=100)
+
+    plan = Plan().table_scan(T, cols).build()
+    cases = [
+        (plan, with_extra(lambda r: r.put(kvfmt.row_key(T, 333), kvfmt.row_v1([(1, kvfmt.datum_int(5))]) + bytes([kvfmt.VAR_INT, 0x80]), 30, 40)), ffi.B2_ERR_CORRUPTED),
+        (plan, with_extra(lambda r: r.raw_write(kvfmt.row_key(T, 5), 50, b"Xjunk")), ffi.B2_ERR_STORAGE),
+        (plan, with_extra(lambda r: r.write.append((kvfmt.write_key(kvfmt.row_key(T, 3), 60), kvfmt.write_record(b"P", 55)))), ffi.B2_ERR_STORAGE),
+        (Plan().table_scan(T, cols).selection(lt(multiply(col(sc.C1), const_int(4)), const_int(100))).build(),
+         with_extra(lambda r: r.put(kvfmt.row_key(T, 1000), kvfmt.row_v2([(1, 1 << 62, "int"), (6, 1, "int")]), 10, 20)), ffi.B2_ERR_EVALUATE),
+    ]
+    for p, region, status in cases:
+        exp, got = orc.dag_handle(p, sc.WHOLE, region), DagHandler(p, sc.WHOLE, region).handle_request()
+        assert exp.status == status == got.status, (got.message, exp.message)
+        assert got.rows() == exp.rows()
+        if status == ffi.B2_ERR_EVALUATE:
+            assert got.mysql_code == exp.mysql_code == 1690
+
+
+def test_checksum_matches_oracle(regions):
+    for seed in (1, 2):
+        host = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=2)
+        for region in (host, DeviceRegion(host)):
+            for ranges in (sc.WHOLE, sc.split_ranges()):
+                st, exp, _ = orc.checksum(ranges, host)
+                rc, got, msg = checksum(ranges, region)
+                assert st == 0 == rc and got == exp and exp[1] > 0, msg
+    old, new = b"t" + kvfmt.enc_i64_cmp(42), b"t" + kvfmt.enc_i64_cmp(sc.TABLE)
+    host = regions[1].build(read_ts=sc.READ_TS)
+    st, exp, _ = orc.checksum(sc.WHOLE, host, old, new)
+    rc, got, _ = checksum(sc.WHOLE, host, old, new)
+    assert rc == 0 == st and got == exp
+    assert checksum(sc.WHOLE, host, b"", b"x")[0] != 0
+
+
+def _gen_block(n_rows, n_cols, fmt, seed, lo=None, rng=None, nulls=None, extra=0, delete=0, lockrec=0, first_handle=0):
+    L = ffi.lib()
+    spec = ffi.GenSpec()
+    spec.table_id, spec.first_handle, spec.n_rows, spec.n_cols, spec.row_format, spec.seed = sc.TABLE, first_handle, n_rows, n_cols, fmt, seed
+    keep = []
+    if lo is not None:
+        a = (C.c_int64 * n_cols)(*lo); b = (C.c_uint64 * n_cols)(*rng); keep += [a, b]
+        spec.col_lo, spec.col_range = a, b
+    if nulls is not None:
+        c = (C.c_uint32 * n_cols)(*nulls); keep.append(c)
+        spec.null_per_million = c
+    spec.extra_versions_per_million, spec.delete_per_million, spec.lock_rec_per_million = extra, delete, lockrec
+    spec.commit_ts, spec.newer_ts = 100, 5000
+    g, blk = C.c_void_p(), ffi.GenBlock()
+    rc = L.b2_gen_create(0, C.byref(spec), C.byref(g), C.byref(blk))
+    assert rc == 0, L.b2_last_error_message()
+    return g, blk
+
+
+def _block_to_host(blk):
+    L = ffi.lib()
+    n = blk.block.n
+    keys = np.zeros(((blk.key_bytes + 31) // 16) * 16, dtype=np.uint8); vals = np.zeros(((blk.val_bytes + 31) // 16) * 16, dtype=np.uint8)
+    koff = np.zeros(n + 1, dtype=np.uint32); voff = np.zeros(n + 1, dtype=np.uint32)
+    assert L.b2_copy_to_host(0, keys.ctypes.data, blk.block.keys, blk.key_bytes) == 0
+    assert L.b2_copy_to_host(0, vals.ctypes.data, blk.block.vals, blk.val_bytes) == 0
+    assert L.b2_copy_to_host(0, koff.ctypes.data, blk.block.key_offs, 4 * (n + 1)) == 0
+    assert L.b2_copy_to_host(0, voff.ctypes.data, blk.block.val_offs, 4 * (n + 1)) == 0
+    hb = ffi.CfBlock()
+    hb.keys, hb.key_offs, hb.vals, hb.val_offs, hb.n = keys.ctypes.data, koff.ctypes.data, vals.ctypes.data, voff.ctypes.data, n
+    return hb, (keys, vals, koff, voff)
+
+
+def _source(blocks, location, read_ts=1000):
+    arr = (ffi.CfBlock * len(blocks))(*blocks)
+    s = ffi.RegionSource()
+    s.location, s.device, s.write, s.n_write, s.read_ts, s.isolation_level, s.check_has_newer_ts_data = location, 0, arr, len(blocks), read_ts, ffi.ISO_SI, 1
+
+    class R:
+        pass
+    r = R()
+    r.c, r._arr = s, arr
+    return r
+
+
+MIX_MASK = (1 << 64) - 1
+
+
+def _mix64(x):
+    x ^= x >> 33; x = (x * 0xff51afd7ed558ccd) & MIX_MASK; x ^= x >> 33; x = (x * 0xc4ceb9fe1a85ec53) & MIX_MASK; x ^= x >> 33
+    return x
+
+
+def _gen_mix(seed, handle, salt):
+    return _mix64(seed ^ ((handle * 0x9E3779B97F4A7C15) & MIX_MASK) ^ (((salt + 1) * 0xBF58476D1CE4E5B9) & MIX_MASK))
+
+
+@pytest.mark.parametrize("fmt", [2, 1])
+def test_generated_region_parity(fmt):
+    """Device generator -> (a) closed-form check of decoded values, (b) oracle on the D2H copy == CUDA path on HBM."""
+    n_cols, n_rows, seed = 8, 20000, 0x525C682A2F7CE3DB
+    lo = [0, 0, -(1 << 40), 0, 0, 0, 0, 0]
+    rng = [0, 1024, 1 << 41, 0, 0, 0, 3, 0]
+    nulls = [0, 0, 0, 10000, 0, 0, 0, 0]
+    g, blk = _gen_block(n_rows, n_cols, fmt, seed, lo, rng, nulls, extra=20000, delete=20000, lockrec=20000)
+    try:
+        hb, keep = _block_to_host(blk)
+        host, dev = _source([hb], ffi.LOC_HOST), _source([blk.block], ffi.LOC_DEVICE)
+        columns = [ColumnDef(100, pk_handle=True)] + [ColumnDef(i + 1) for i in range(n_cols)]
+        scan = Plan().table_scan(sc.TABLE, columns).build()
+        exp = orc.dag_handle(scan, sc.WHOLE, host)
+        assert exp.status == 0 and 0.97 * n_rows < exp.n_rows < n_rows
+        for row in exp.rows()[:2000]:
+            h = row[0]
+            for c in range(n_cols):
+                want = None
+                if not (nulls[c] and _gen_mix(seed, h, 500 + c) % 1000000 < nulls[c]):
+                    x = _gen_mix(seed, h, c)
+                    want = (lo[c] + x % rng[c]) if rng[c] else (x - (1 << 64) if x >= (1 << 63) else x)
+                assert row[1 + c] == want, (h, c)
+        for name, plan in (("scan", scan),
+                           ("filter", Plan().table_scan(sc.TABLE, columns).selection(lt(col(1), const_int(0))).build()),
+                           ("group", Plan().table_scan(sc.TABLE, columns).aggregation([("sum", col(3)), ("count", const_int(1)), ("avg", col(4))], group_by=[col(2)]).build()),
+                           ("group3", Plan().table_scan(sc.TABLE, columns).aggregation([("sum", col(1))], group_by=[col(7)]).build()),
+                           ("count", Plan().table_scan(sc.TABLE, columns).aggregation([("count", const_int(1)), ("sum", col(1))]).build())):
+            e = orc.dag_handle(plan, sc.WHOLE, host)
+            gres = DagHandler(plan, sc.WHOLE, dev).handle_request()
+            assert_same_rows(gres, e, ordered=name in ("scan", "filter"), ctx=f"gen/{name}/v{fmt}")
+        st, echk, _ = orc.checksum(sc.WHOLE, host)
+        rc, gchk, _ = checksum(sc.WHOLE, dev)
+        assert st == 0 == rc and echk == gchk
+    finally:
+        ffi.lib().b2_gen_destroy(g)
+
+
+def test_large_scale_properties():
+    """At a size the oracle does not run: size-independent properties of the CUDA path on generated data."""
+    n_rows, n_cols, seed = 4_000_000, 8, 77
+    blocks, gens = [], []
+    for i in range(2):
+        g, blk = _gen_block(n_rows // 2, n_cols, 2, seed, [0] * 8, [0, 1000, 0, 0, 0, 0, 0, 0], None, first_handle=i * (n_rows // 2))
+        gens.append(g); blocks.append(blk.block)
+    try:
+        dev = _source(blocks, ffi.LOC_DEVICE)
+        columns = [ColumnDef(100, pk_handle=True)] + [ColumnDef(i + 1) for i in range(n_cols)]
+        cnt = DagHandler(Plan().table_scan(sc.TABLE, columns).aggregation([("count", const_int(1)), ("sum", col(0))]).build(), sc.WHOLE, dev).handle_request()
+        assert cnt.rows() == [(n_rows, n_rows * (n_rows - 1) // 2)]
+        # partition property: filter(x < 0) + filter(x >= 0) row counts add up; group counts add up to the total
+        from tikv_b200.plan import ge
+        neg = DagHandler(Plan().table_scan(sc.TABLE, columns).selection(lt(col(1), const_int(0))).aggregation([("count", const_int(1))]).build(), sc.WHOLE, dev).handle_request()
+        pos = DagHandler(Plan().table_scan(sc.TABLE, columns).selection(ge(col(1), const_int(0))).aggregation([("count", const_int(1))]).build(), sc.WHOLE, dev).handle_request()
+        assert neg.rows()[0][0] + pos.rows()[0][0] == n_rows and abs(neg.rows()[0][0] - n_rows // 2) < n_rows // 100
+        grp = DagHandler(Plan().table_scan(sc.TABLE, columns).aggregation([("count", const_int(1)), ("sum", col(0))], group_by=[col(2)]).build(), sc.WHOLE, dev).handle_request()
+        assert grp.n_rows == 1000 and sum(r[0] for r in grp.rows()) == n_rows and sum(r[1] for r in grp.rows()) == n_rows * (n_rows - 1) // 2
+        # scan + filter keeps key order (handles strictly increasing) and splits consistently across batch sizes
+        filt = Plan().table_scan(sc.TABLE, columns).selection(lt(col(2), const_int(10))).build(output_offsets=[0, 2])
+        a = DagHandler(filt, sc.WHOLE, dev, batch_rows=1 << 22).handle_request()
+        b = DagHandler(filt, sc.WHOLE, dev, batch_rows=300_000).handle_request()
+        ha = np.asarray(a.columns[0]); assert np.all(np.diff(ha) > 0) and a.columns == b.columns
+        assert all(0 <= v < 10 for v in a.columns[1][:1000])
+        # checksum of the union == XOR of the parts, kv counts add (checksum.rs: order/partition independent)
+        _, whole, _ = checksum(sc.WHOLE, dev)
+        _, p0, _ = checksum([kvfmt.table_range(sc.TABLE, 0, n_rows // 3)], dev)
+        _, p1, _ = checksum([kvfmt.table_range(sc.TABLE, n_rows // 3, n_rows)], dev)
+        assert whole[0] == p0[0] ^ p1[0] and whole[1] == p0[1] + p1[1] == n_rows and whole[2] == p0[2] + p1[2]
+    finally:
+        for g in gens:
+            ffi.lib().b2_gen_destroy(g)

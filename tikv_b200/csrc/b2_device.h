@@ -1,0 +1,903 @@
+// Per-entry / per-row device logic of the coprocessor hot path (MVCC visibility, row decode, RPN).
+// Every function is __host__ __device__ so tests/host_emul.cpp can drive exactly this code on the CPU
+// (a debug harness; the product only ever runs it inside the sm_100a kernels in kernels.cu).
+//
+// Reference semantics being reproduced (tikv/tikv paths):
+//   src/storage/mvcc/reader/scanner/forward.rs:172-515     latest-version forward scan
+//   components/txn_types/src/write.rs:296-361, 425-442     write record
+//   components/tidb_query_executors/src/table_scan_executor.rs:200-281, 365-475
+//   components/tidb_query_datatype/src/codec/row/v2/{row_slice.rs:74-166,330-357, compat_v1.rs:13-129}
+//   components/tidb_query_datatype/src/codec/{datum.rs:1117-1155, datum_codec.rs:401-446}
+//   components/tidb_query_expr/src/{impl_compare.rs:63-240, impl_op.rs:8-127, impl_arithmetic.rs:42-398}
+#pragma once
+#include <stdint.h>
+
+#include "../../include/b2_copr.h"
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#define B2_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define B2_HD inline
+#define B2_HD_NOINLINE inline
+#endif
+
+namespace b2 {
+
+// ---- limits of the device plan ----
+enum { MAX_COLS = 64, MAX_NODES = 96, MAX_CONDS = 8, MAX_AGGS = 8, MAX_ORDER = 4, MAX_STACK = 8, MAX_ACC_WORDS = 24 };
+
+// ---- device error codes (mapped to B2_ERR_* + message in engine.cu) ----
+enum DevErr {
+  DE_NONE = 0,
+  DE_BAD_WRITE = 1,          // WriteRef::parse failure                     -> STORAGE
+  DE_KEY_TOO_SHORT = 2,      // key shorter than the 8-byte ts suffix       -> STORAGE
+  DE_DEFAULT_NOT_FOUND = 3,  // near_load_data_by_write miss                -> STORAGE
+  DE_WRITE_CONFLICT = 4,     // RcCheckTs newer version                     -> WRITE_CONFLICT
+  DE_BAD_USER_KEY = 5,       // memcomparable decode of user key failed     -> STORAGE
+  DE_BAD_RECORD_KEY = 6,     // check_record_key / decode_int_handle        -> CORRUPTED
+  DE_ROW_COLID_NOT_VARINT = 7,   // "Unable to decode row: column id must be VAR_INT"
+  DE_ROW_EOF = 8,            // unexpected eof while splitting the row
+  DE_ROW_BAD_DATUM = 9,      // split_datum: unsupported flag / too short
+  DE_ROW_V2_BAD_INT = 10,    // "Failed to decode row v2 data as i64/u64"
+  DE_ROW_V2_RANGE = 11,      // value slice / checksum cut out of range (reference panics)
+  DE_MISSING_NOT_NULL = 12,  // "Data is corrupted, missing data for NOT NULL column"
+  DE_MISSING_COMMIT_TS = 13,
+  DE_DATUM_DECODE = 14,      // ensure_decoded: flag not decodable as the column's eval type
+  DE_OVERFLOW_BIGINT = 20,   // 1690 BIGINT value is out of range
+  DE_OVERFLOW_UBIGINT = 21,  // 1690 BIGINT UNSIGNED
+  DE_OVERFLOW_DOUBLE = 22,   // 1690 DOUBLE
+  DE_UNSUPPORTED_SIG = 30,
+  DE_UNSUPPORTED_TYPE = 31,  // row holds a type the device path does not materialise
+};
+
+// ---- plan as seen by the kernels ----
+enum ColKind { CK_INT = 0, CK_REAL = 1, CK_OTHER = 2 };
+enum ColRole { CR_NORMAL = 0, CR_HANDLE = 1, CR_TABLE_ID = 2, CR_COMMIT_TS = 3, CR_SHADOWED = 4 /* duplicate col id: never filled */ };
+enum V2Class { V2_INT = 0, V2_UINT = 1, V2_COPY = 2, V2_BYTES = 3, V2_NIL = 4, V2_UNSUPPORTED = 5 };  // write_v2_as_datum arms
+enum DefState { DS_NONE = 0, DS_VALUE = 1, DS_NULL = 2, DS_ERROR = 3 };
+
+struct DevCol {
+  int64_t col_id;
+  int64_t default_bits;
+  uint8_t kind, role, is_unsigned, not_null, tp, v2_class, def_state, _pad;
+};
+struct DevNode {
+  int32_t sig;
+  uint8_t kind, n_args, et /*0 int 1 real*/, is_unsigned;
+  int64_t imm;  // const bits (i64 or f64 bits) or column offset
+};
+struct DevExpr { uint16_t start, n; };
+struct DevAgg { DevExpr arg; uint8_t kind /*0 count 1 sum 2 avg*/, arg_et, arg_unsigned, acc_off; };
+struct DevOrder { DevExpr e; uint8_t desc, et, is_unsigned, _pad; };
+
+enum PlanMode { PM_SCAN = 0, PM_AGG = 1, PM_TOPN = 2, PM_CHECKSUM = 3 };
+
+struct DevPlan {
+  int32_t mode;
+  int32_t n_cols;
+  int32_t n_nodes, n_conds;
+  int32_t n_aggs, has_group, acc_words;
+  int32_t n_order;
+  int32_t n_out;
+  int32_t isolation;  // B2_ISO_*
+  int32_t need_value;  // 0 when no column is read from the row value (key-only)
+  int32_t has_handle_cols;
+  uint64_t read_ts;
+  uint64_t limit;
+  DevExpr conds[MAX_CONDS];
+  DevExpr group;
+  uint8_t group_et, group_unsigned, _p0, _p1;
+  DevAgg aggs[MAX_AGGS];
+  DevOrder order[MAX_ORDER];
+  uint8_t out_cols[MAX_COLS];
+  DevCol cols[MAX_COLS];
+  DevNode nodes[MAX_NODES];
+};
+
+// One CF block on the device.
+struct BlockView {
+  const uint8_t* keys;
+  const uint32_t* koff;
+  const uint8_t* vals;
+  const uint32_t* voff;
+  uint32_t n;
+};
+
+// ---- byte access -------------------------------------------------------------------------------
+B2_HD uint32_t ld8(const uint8_t* p) { return *p; }
+B2_HD uint64_t ld_be64(const uint8_t* p) {
+  uint64_t v = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v = (v << 8) | p[i];
+  return v;
+}
+B2_HD uint64_t ld_le(const uint8_t* p, int n) {  // n in {1,2,4,8}
+  uint64_t v = 0;
+  for (int i = n - 1; i >= 0; --i) v = (v << 8) | p[i];
+  return v;
+}
+B2_HD bool bytes_eq(const uint8_t* a, const uint8_t* b, uint32_t n) {
+  // compare from the tail: record keys share their table prefix and differ in the handle
+  for (uint32_t i = n; i > 0; --i)
+    if (a[i - 1] != b[i - 1]) return false;
+  return true;
+}
+B2_HD int bytes_cmp(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn) {
+  uint32_t m = an < bn ? an : bn;
+  for (uint32_t i = 0; i < m; ++i) {
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  }
+  return an < bn ? -1 : (an > bn ? 1 : 0);
+}
+
+// components/codec/src/number.rs:445-483 try_decode_var_u64. returns bytes consumed, 0 = eof
+B2_HD uint32_t dec_var_u64(const uint8_t* p, uint32_t n, uint64_t* out) {
+  uint64_t v = 0;
+  if (n >= 10) {
+    for (uint32_t i = 0; i < 9; ++i) {
+      uint64_t b = p[i];
+      v |= (b & 0x7f) << (7 * i);
+      if (b < 0x80) { *out = v; return i + 1; }
+    }
+    v |= ((uint64_t)p[9] & 1) << 63;
+    *out = v;
+    return 10;
+  }
+  uint32_t i = 0, shift = 0;
+  while (i < n && p[i] >= 0x80) { v |= (uint64_t)(p[i] & 0x7f) << shift; shift += 7; ++i; }
+  if (i == n) return 0;
+  v |= (uint64_t)p[i] << shift;
+  *out = v;
+  return i + 1;
+}
+// components/tikv_util/src/codec/number.rs:224-275 (overflow error on a 10th byte > 1)
+B2_HD uint32_t dec_var_u64_tu(const uint8_t* p, uint32_t n, uint64_t* out) {
+  uint64_t v = 0;
+  for (uint32_t i = 0; i < n && i < 10; ++i) {
+    uint64_t b = p[i];
+    if (i == 9) {
+      if (b > 1) return 0;
+      *out = v | (b << 63);
+      return 10;
+    }
+    v |= (b & 0x7f) << (7 * i);
+    if (b < 0x80) { *out = v; return i + 1; }
+  }
+  return 0;
+}
+B2_HD uint32_t dec_var_i64(const uint8_t* p, uint32_t n, int64_t* out) {
+  uint64_t uv;
+  uint32_t c = dec_var_u64(p, n, &uv);
+  if (!c) return 0;
+  int64_t v = (int64_t)(uv >> 1);
+  if (uv & 1) v = ~v;
+  *out = v;
+  return c;
+}
+B2_HD uint32_t first_var_int_len(const uint8_t* p, uint32_t n) {  // number.rs:530-567
+  uint32_t lim = n >= 10 ? 9 : n;
+  for (uint32_t i = 0; i < lim; ++i)
+    if (p[i] < 0x80) return i + 1;
+  return n >= 10 ? 10 : n;
+}
+
+B2_HD double cmp_u64_to_f64(uint64_t u) {  // tikv_util/src/codec/number.rs:36-42
+  const uint64_t S = 0x8000000000000000ull;
+  if (u & S) u &= ~S; else u = ~u;
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)u);
+#else
+  double f;
+  __builtin_memcpy(&f, &u, 8);
+  return f;
+#endif
+}
+B2_HD uint64_t f64_bits(double f) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(f);
+#else
+  uint64_t u;
+  __builtin_memcpy(&u, &f, 8);
+  return u;
+#endif
+}
+B2_HD double bits_f64(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)u);
+#else
+  double f;
+  __builtin_memcpy(&f, &u, 8);
+  return f;
+#endif
+}
+
+// ---- keys --------------------------------------------------------------------------------------
+B2_HD uint64_t key_commit_ts(const uint8_t* k, uint32_t klen) { return ~ld_be64(k + klen - 8); }
+
+// entries i and j of the same block share their user key? (types.rs:249-267 is_user_key_eq)
+B2_HD bool same_user_key(const BlockView& b, uint32_t i, uint32_t j) {
+  uint32_t ai = b.koff[i], al = b.koff[i + 1] - ai;
+  uint32_t bi = b.koff[j], bl = b.koff[j + 1] - bi;
+  if (al != bl) return false;
+  if (al < 8) return al == 0 ? true : bytes_eq(b.keys + ai, b.keys + bi, al);
+  return bytes_eq(b.keys + ai, b.keys + bi, al - 8);
+}
+
+// Memcomparable user key -> raw key view (bytes.rs:178-228).  We never materialise the raw key: raw byte j
+// lives at enc[j + j/8].  Returns raw length, or -1 if the encoding is invalid.
+B2_HD int raw_key_len(const uint8_t* enc, uint32_t enc_len) {
+  uint32_t off = 0;
+  int raw = 0;
+  for (;;) {
+    if (off + 9 > enc_len) return -1;
+    uint32_t marker = enc[off + 8];
+    uint32_t pad = 0xffu - marker;
+    if (pad == 0) { raw += 8; off += 9; continue; }
+    if (pad > 8) return -1;
+    for (uint32_t i = 8 - pad; i < 8; ++i)
+      if (enc[off + i] != 0) return -1;
+    raw += 8 - pad;
+    return raw;  // trailing bytes after the terminal group are ignored (decode_bytes leaves them to the caller)
+  }
+}
+B2_HD uint32_t raw_at(const uint8_t* enc, uint32_t j) { return enc[j + (j >> 3)]; }
+B2_HD uint64_t raw_be64(const uint8_t* enc, uint32_t j) {
+  uint64_t v = 0;
+  for (uint32_t i = 0; i < 8; ++i) v = (v << 8) | raw_at(enc, j + i);
+  return v;
+}
+
+// ---- write record --------------------------------------------------------------------------------
+struct WriteRec {
+  uint8_t type;  // 'P','D','L','R'
+  uint8_t has_short, has_gc_fence, lc_kind;  // lc_kind: 0 unknown 1 exist 2 not-exist
+  uint32_t short_off, short_len;
+  uint64_t start_ts, gc_fence, lc_ts, lc_versions;
+};
+
+B2_HD int parse_write(const uint8_t* p, uint32_t n, WriteRec* w) {
+  if (n == 0) return DE_BAD_WRITE;
+  uint8_t t = p[0];
+  if (t != 'P' && t != 'D' && t != 'L' && t != 'R') return DE_BAD_WRITE;
+  w->type = t;
+  w->has_short = 0; w->has_gc_fence = 0; w->lc_kind = 0; w->gc_fence = 0; w->short_off = 0; w->short_len = 0;
+  uint32_t pos = 1;
+  uint32_t c = dec_var_u64(p + pos, n - pos, &w->start_ts);
+  if (!c) return DE_BAD_WRITE;
+  pos += c;
+  uint64_t lc_ts = 0, lc_ver = 0;
+  while (pos < n) {
+    uint8_t tag = p[pos++];
+    if (tag == 'v') {
+      if (pos >= n) return DE_BAD_WRITE;
+      uint32_t len = p[pos++];
+      if (n - pos < len) return DE_BAD_WRITE;  // reference panics
+      w->has_short = 1; w->short_off = pos; w->short_len = len;
+      pos += len;
+    } else if (tag == 'R') {
+    } else if (tag == 'F') {
+      if (n - pos < 8) return DE_BAD_WRITE;
+      w->has_gc_fence = 1; w->gc_fence = ld_be64(p + pos);
+      pos += 8;
+    } else if (tag == 'l') {
+      if (n - pos < 8) return DE_BAD_WRITE;
+      lc_ts = ld_be64(p + pos);
+      pos += 8;
+      uint32_t m = dec_var_u64_tu(p + pos, n - pos, &lc_ver);
+      if (!m) return DE_BAD_WRITE;
+      pos += m;
+    } else if (tag == 'S') {
+      uint64_t src;
+      uint32_t m = dec_var_u64_tu(p + pos, n - pos, &src);
+      if (!m) return DE_BAD_WRITE;
+      pos += m;
+    } else {
+      break;
+    }
+  }
+  if (lc_ts == 0) w->lc_kind = lc_ver > 0 ? 2 : 0;
+  else {
+    if (lc_ver == 0) return DE_BAD_WRITE;  // LastChange::make_exist assert
+    w->lc_kind = 1;
+  }
+  w->lc_ts = lc_ts; w->lc_versions = lc_ver;
+  return DE_NONE;
+}
+
+// ---- MVCC: resolve the run of versions that starts at entry `e0` -------------------------------------
+struct DefaultCf {  // CF_DEFAULT blocks (global order) for long values
+  const BlockView* blocks;
+  uint32_t n_blocks;
+};
+
+struct RunOut {
+  int err;            // DevErr
+  int found;          // 1 = a visible Put
+  uint32_t entry;     // index of the chosen CF_WRITE entry
+  const uint8_t* val; // row value bytes (inside CF_WRITE value or CF_DEFAULT)
+  uint32_t val_len;
+  uint64_t commit_ts;
+  uint32_t met_newer; // saw a version newer than read_ts
+  uint32_t dflt_lookup;
+  uint32_t steps;     // entries visited
+};
+
+// near_load_data_by_write (scanner/mod.rs:371-402): exact-match lookup of user_key ‖ !start_ts in CF_DEFAULT
+B2_HD bool default_lookup(const DefaultCf& d, const uint8_t* ukey, uint32_t uklen, uint64_t start_ts, const uint8_t** val, uint32_t* vlen) {
+  uint8_t ts[8];
+  uint64_t nts = ~start_ts;
+  for (int i = 0; i < 8; ++i) ts[i] = (uint8_t)(nts >> (8 * (7 - i)));
+  for (uint32_t bi = 0; bi < d.n_blocks; ++bi) {
+    const BlockView& b = d.blocks[bi];
+    uint32_t lo = 0, hi = b.n;
+    while (lo < hi) {
+      uint32_t mid = lo + (hi - lo) / 2;
+      const uint8_t* k = b.keys + b.koff[mid];
+      uint32_t kl = b.koff[mid + 1] - b.koff[mid];
+      // compare k with ukey‖ts
+      uint32_t m = kl < uklen ? kl : uklen;
+      int c = bytes_cmp(k, m, ukey, m);
+      if (c == 0) {
+        if (kl < uklen) c = -1;
+        else c = bytes_cmp(k + uklen, kl - uklen, ts, 8);
+      }
+      if (c < 0) lo = mid + 1; else hi = mid;
+    }
+    if (lo < b.n) {
+      const uint8_t* k = b.keys + b.koff[lo];
+      uint32_t kl = b.koff[lo + 1] - b.koff[lo];
+      if (kl == uklen + 8 && bytes_eq(k, ukey, uklen) && bytes_eq(k + uklen, ts, 8)) {
+        *val = b.vals + b.voff[lo];
+        *vlen = b.voff[lo + 1] - b.voff[lo];
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+// forward.rs:310-375 (move_write_cursor_to_ts) + :433-515 (LatestKvPolicy::handle_write), restated as a walk over
+// the contiguous run of versions [e0, e_hi) of one user key.  `e_hi` is the range's upper bound entry.
+B2_HD void resolve_run(const BlockView& b, uint32_t e0, uint32_t e_hi, uint64_t read_ts, int isolation, const DefaultCf& dflt, RunOut* o) {
+  o->err = DE_NONE; o->found = 0; o->met_newer = 0; o->dflt_lookup = 0; o->steps = 1;
+  uint32_t i = e0;
+  uint32_t k0 = b.koff[e0], kl0 = b.koff[e0 + 1] - k0;
+  if (kl0 < 8) { o->err = DE_KEY_TOO_SHORT; o->entry = e0; return; }
+  // move to the first version with commit_ts <= read_ts
+  for (;;) {
+    uint32_t ko = b.koff[i], kl = b.koff[i + 1] - ko;
+    uint64_t cts = key_commit_ts(b.keys + ko, kl);
+    if (cts <= read_ts) break;
+    o->met_newer = 1;
+    if (isolation == B2_ISO_RC_CHECK_TS) { o->err = DE_WRITE_CONFLICT; o->entry = i; return; }
+    ++i; o->steps++;
+    if (i >= e_hi || !same_user_key(b, e0, i)) return;
+  }
+  for (;;) {
+    uint32_t vo = b.voff[i], vl = b.voff[i + 1] - vo;
+    WriteRec w;
+    int e = parse_write(b.vals + vo, vl, &w);
+    if (e) { o->err = e; o->entry = i; return; }
+    if (w.has_gc_fence && w.gc_fence != 0 && w.gc_fence <= read_ts) return;  // write.rs:425-442
+    if (w.type == 'P') {
+      uint32_t ko = b.koff[i], kl = b.koff[i + 1] - ko;
+      o->commit_ts = key_commit_ts(b.keys + ko, kl);
+      o->entry = i;
+      if (w.has_short) { o->val = b.vals + vo + w.short_off; o->val_len = w.short_len; o->found = 1; return; }
+      o->dflt_lookup = 1;
+      if (!default_lookup(dflt, b.keys + k0, kl0 - 8, w.start_ts, &o->val, &o->val_len)) { o->err = DE_DEFAULT_NOT_FOUND; return; }
+      o->found = 1;
+      return;
+    }
+    if (w.type == 'D') return;
+    // Lock / Rollback
+    if (w.lc_kind == 2) return;
+    if (w.lc_kind == 1 && w.lc_versions >= 8 /* SEEK_BOUND */) {
+      // seek to user_key ‖ last_change_ts: first later version with commit_ts <= last_change_ts
+      for (;;) {
+        ++i; o->steps++;
+        if (i >= e_hi || !same_user_key(b, e0, i)) return;
+        uint32_t ko = b.koff[i], kl = b.koff[i + 1] - ko;
+        if (key_commit_ts(b.keys + ko, kl) <= w.lc_ts) break;
+      }
+    } else {
+      ++i; o->steps++;
+      if (i >= e_hi || !same_user_key(b, e0, i)) return;
+    }
+  }
+}
+
+// ---- row access ----------------------------------------------------------------------------------
+enum CellKind { CELL_MISSING = 0, CELL_V1 = 1, CELL_V2 = 2, CELL_NULL = 3 };
+
+struct RowView {
+  const uint8_t* v;
+  uint32_t n;
+  uint8_t fmt;  // 0 = no columns, 1 = v1, 2 = v2
+  // v2 header
+  uint8_t big;
+  uint16_t nn_cnt, null_cnt;
+  uint32_t ids_off, null_ids_off, offs_off, vals_off, vals_len;
+};
+
+struct Cells {  // per-column cell location for v1 rows (filled by row_split)
+  uint32_t off[MAX_COLS];
+  uint32_t len_kind[MAX_COLS];  // len << 2 | kind
+};
+
+// split_datum (datum.rs:1117-1155, desc = false): length of the first datum or 0 + err
+B2_HD uint32_t split_datum(const uint8_t* p, uint32_t n, int* err) {
+  if (n == 0) { *err = DE_ROW_BAD_DATUM; return 0; }
+  uint32_t pos;
+  const uint8_t* r = p + 1;
+  uint32_t rn = n - 1;
+  switch (p[0]) {
+    case 3: case 4: case 5: case 7: pos = 8; break;  // INT, UINT, FLOAT, DURATION
+    case 1: {  // BYTES: memcomparable groups
+      uint32_t idx = 8;
+      for (;;) {
+        if (rn < idx + 1) { pos = rn; break; }
+        if (r[idx] != 0xff) { pos = idx + 1; break; }
+        idx += 9;
+      }
+      break;
+    }
+    case 2: {  // COMPACT_BYTES
+      int64_t len;
+      uint32_t c = dec_var_i64(r, rn, &len);
+      if (!c) pos = rn;
+      else {
+        uint64_t t = (uint64_t)len + c;
+        pos = t < rn ? (uint32_t)t : rn;
+      }
+      break;
+    }
+    case 0: pos = 0; break;  // NIL
+    case 6: {  // DECIMAL: prec, frac, bin
+      if (rn < 2) { *err = DE_ROW_BAD_DATUM; return 0; }
+      uint32_t prec = r[0], frac = r[1];
+      if (prec < frac) { *err = DE_ROW_BAD_DATUM; return 0; }
+      const uint8_t d2b[10] = {0, 1, 1, 2, 2, 3, 3, 4, 4, 4};
+      uint32_t ic = prec - frac;
+      pos = (ic / 9) * 4 + d2b[ic % 9] + (frac / 9) * 4 + d2b[frac % 9] + 2;
+      break;
+    }
+    case 8: case 9: pos = first_var_int_len(r, rn); break;  // VAR_INT / VAR_UINT
+    default: *err = DE_ROW_BAD_DATUM; return 0;  // JSON / vector / unknown: not handled on the device
+  }
+  if (n < pos + 1) { *err = DE_ROW_BAD_DATUM; return 0; }
+  return pos + 1;
+}
+
+B2_HD uint32_t v2_id(const RowView& r, uint32_t base, uint32_t i) {
+  return r.big ? (uint32_t)ld_le(r.v + base + 4 * i, 4) : r.v[base + i];
+}
+B2_HD uint32_t v2_off(const RowView& r, uint32_t i) {
+  return r.big ? (uint32_t)ld_le(r.v + r.offs_off + 4 * i, 4) : (uint32_t)ld_le(r.v + r.offs_off + 2 * i, 2);
+}
+// LeBytes::binary_search (row_slice.rs:330-357)
+B2_HD bool v2_search(const RowView& r, uint32_t base, uint32_t cnt, uint32_t id, uint32_t* idx) {
+  if (cnt == 0) return false;
+  uint32_t size = cnt, lo = 0, steps = 20;
+  while (steps > 0 && size > 1) {
+    uint32_t half = size / 2, mid = lo + half;
+    if (!(v2_id(r, base, mid) > id)) lo = mid;
+    size -= half;
+    --steps;
+  }
+  if (v2_id(r, base, lo) == id) { *idx = lo; return true; }
+  return false;
+}
+
+// RowSlice::from_bytes (row_slice.rs:74-115)
+B2_HD int row_open(const uint8_t* v, uint32_t n, RowView* r) {
+  r->v = v; r->n = n;
+  if (n == 0 || (n == 1 && v[0] == 0)) { r->fmt = 0; return DE_NONE; }  // table_scan_executor.rs:377-378
+  if (v[0] != 128) { r->fmt = 1; return DE_NONE; }
+  r->fmt = 2;
+  if (n < 6) return DE_ROW_EOF;
+  uint32_t flags = v[1];
+  r->big = flags & 1;
+  r->nn_cnt = (uint16_t)(v[2] | (v[3] << 8));
+  r->null_cnt = (uint16_t)(v[4] | (v[5] << 8));
+  uint32_t idw = r->big ? 4 : 1, ofw = r->big ? 4 : 2;
+  uint64_t pos = 6;
+  r->ids_off = (uint32_t)pos; pos += (uint64_t)r->nn_cnt * idw;
+  if (pos > n) return DE_ROW_EOF;
+  r->null_ids_off = (uint32_t)pos; pos += (uint64_t)r->null_cnt * idw;
+  if (pos > n) return DE_ROW_EOF;
+  r->offs_off = (uint32_t)pos; pos += (uint64_t)r->nn_cnt * ofw;
+  if (pos > n) return DE_ROW_EOF;
+  r->vals_off = (uint32_t)pos; r->vals_len = n - (uint32_t)pos;
+  if (flags & 2) {  // WITH_CHECKSUM: cut_checksum_bytes :231-259 + assert len 5 or 9
+    uint32_t last = r->nn_cnt == 0 ? 0 : v2_off(*r, r->nn_cnt - 1u);
+    if (last > r->vals_len) return DE_ROW_V2_RANGE;
+    uint32_t ck = r->vals_len - last;
+    if (ck != 5 && ck != 9) return DE_ROW_V2_RANGE;
+    r->vals_len = last;
+  }
+  return DE_NONE;
+}
+
+// Locate column `c` of the plan in a v2 row (process_v2 :261-279).
+B2_HD int v2_locate(const RowView& r, int64_t col_id, uint32_t* off, uint32_t* len, int* err) {
+  int64_t upper = r.big ? 0xffffffffll : 0xffll;
+  if (!(col_id > 0 && col_id <= upper)) return CELL_MISSING;
+  uint32_t idx;
+  if (v2_search(r, r.ids_off, r.nn_cnt, (uint32_t)col_id, &idx)) {
+    uint32_t end = v2_off(r, idx), start = idx > 0 ? v2_off(r, idx - 1) : 0;
+    if (start > end || end > r.vals_len) { *err = DE_ROW_V2_RANGE; return CELL_MISSING; }
+    *off = r.vals_off + start; *len = end - start;
+    return CELL_V2;
+  }
+  if (v2_search(r, r.null_ids_off, r.null_cnt, (uint32_t)col_id, &idx)) return CELL_NULL;
+  return CELL_MISSING;
+}
+
+struct Row {
+  RowView rv;
+  const uint8_t* enc_key;  // encoded user key (memcomparable), without ts
+  uint32_t enc_key_len;
+  uint64_t commit_ts;
+  uint64_t filled;  // bitmask of plan columns present in the row (bit c)
+};
+
+// process_kv_pair (table_scan_executor.rs:365-475): everything that can fail regardless of which rows are
+// later selected.  For v1 rows it records the cell of every plan column in `cells`.
+B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
+  const RowView& r = row.rv;
+  uint64_t filled = 0;
+  int err = DE_NONE;
+  if (r.fmt == 1) {
+    uint32_t pos = 0, n = r.n;
+    int decoded = 0;
+    while (pos < n && decoded < P.n_cols) {
+      if (r.v[pos] != 8) return DE_ROW_COLID_NOT_VARINT;
+      ++pos;
+      int64_t cid;
+      uint32_t c = dec_var_i64(r.v + pos, n - pos, &cid);
+      if (!c) return DE_ROW_EOF;
+      pos += c;
+      uint32_t dl = split_datum(r.v + pos, n - pos, &err);
+      if (!dl) return err;
+      // column_id_index lookup: last plan column with this id that is not a handle / shadowed
+      for (int k = 0; k < P.n_cols; ++k) {
+        if (P.cols[k].col_id == cid && P.cols[k].role != CR_HANDLE && P.cols[k].role != CR_SHADOWED) {
+          if (!((filled >> k) & 1)) {
+            cells.off[k] = pos; cells.len_kind[k] = (dl << 2) | CELL_V1;
+            filled |= 1ull << k;
+            ++decoded;
+          }
+          break;
+        }
+      }
+      pos += dl;
+    }
+  } else if (r.fmt == 2) {
+    for (int k = 0; k < P.n_cols; ++k) {
+      const DevCol& c = P.cols[k];
+      if (c.role == CR_HANDLE || c.role == CR_SHADOWED) continue;
+      uint32_t off = 0, len = 0;
+      int kind = v2_locate(r, c.col_id, &off, &len, &err);
+      if (err) return err;
+      if (kind == CELL_V2) {
+        if (c.v2_class == V2_INT || c.v2_class == V2_UINT) {
+          if (len != 1 && len != 2 && len != 4 && len != 8) return DE_ROW_V2_BAD_INT;
+        } else if (c.v2_class == V2_UNSUPPORTED) return DE_UNSUPPORTED_TYPE;
+        filled |= 1ull << k;
+      } else if (kind == CELL_NULL) filled |= 1ull << k;
+    }
+  }
+  // key side (:386-442)
+  int rawlen = raw_key_len(row.enc_key, row.enc_key_len);
+  if (rawlen < 0) return DE_BAD_USER_KEY;
+  const uint8_t* ek = row.enc_key;
+  bool rec_ok = rawlen >= 11 && raw_at(ek, 0) == 't' && raw_at(ek, 9) == '_' && raw_at(ek, 10) == 'r';
+  if (P.has_handle_cols) {
+    if (!rec_ok || rawlen < 19) return DE_BAD_RECORD_KEY;
+  } else if (!rec_ok) return DE_BAD_RECORD_KEY;
+  for (int k = 0; k < P.n_cols; ++k) {
+    const DevCol& c = P.cols[k];
+    if (c.role == CR_HANDLE || c.role == CR_TABLE_ID || c.role == CR_COMMIT_TS) { filled |= 1ull << k; continue; }
+    if (!((filled >> k) & 1)) {
+      if (c.def_state == DS_NONE && c.not_null) return DE_MISSING_NOT_NULL;
+    }
+  }
+  row.filled = filled;
+  return DE_NONE;
+}
+
+struct Value { uint64_t bits; bool null; };
+
+// Decode plan column `k` of the row (LazyBatchColumn::ensure_decoded for one cell, lazy_column.rs:165-221).
+B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k, Value* out) {
+  const DevCol& c = P.cols[k];
+  out->null = false; out->bits = 0;
+  const uint64_t S = 0x8000000000000000ull;
+  if (c.role == CR_HANDLE) { out->bits = raw_be64(row.enc_key, 11) ^ S; return DE_NONE; }       // table.rs:214-218
+  if (c.role == CR_TABLE_ID) { out->bits = raw_be64(row.enc_key, 1) ^ S; return DE_NONE; }
+  if (c.role == CR_COMMIT_TS) { out->bits = row.commit_ts; return DE_NONE; }
+  if (c.kind == CK_OTHER) return DE_UNSUPPORTED_TYPE;
+  const RowView& r = row.rv;
+  const uint8_t* p = nullptr;
+  uint32_t len = 0;
+  int kind = CELL_MISSING;
+  if ((row.filled >> k) & 1) {
+    if (r.fmt == 1) { p = r.v + cells.off[k]; len = cells.len_kind[k] >> 2; kind = cells.len_kind[k] & 3; }
+    else {
+      uint32_t off = 0;
+      int err = DE_NONE;
+      kind = v2_locate(r, c.col_id, &off, &len, &err);
+      p = r.v + off;
+    }
+  }
+  if (kind == CELL_NULL) { out->null = true; return DE_NONE; }
+  if (kind == CELL_MISSING) {
+    if (c.def_state == DS_VALUE) { out->bits = (uint64_t)c.default_bits; return DE_NONE; }
+    if (c.def_state == DS_ERROR) return DE_DATUM_DECODE;
+    out->null = true;  // DS_NULL, or nullable without default
+    return DE_NONE;
+  }
+  if (kind == CELL_V2) {
+    if (c.kind == CK_INT) {
+      // compat_v1.rs:13-38: sign- or zero-extend by width, then INT/UINT datum -> i64 bits
+      uint64_t u = ld_le(p, (int)len);
+      if (c.v2_class == V2_INT && len < 8) {
+        uint32_t sh = 64 - 8 * len;
+        u = (uint64_t)(((int64_t)(u << sh)) >> sh);
+      }
+      out->bits = u;
+      return DE_NONE;
+    }
+    // Real: payload copied as FLOAT datum; read_datum_payload_f64 needs 8 bytes
+    if (len < 8) return DE_DATUM_DECODE;
+    double f = cmp_u64_to_f64(ld_be64(p));
+    if (c.tp == B2_TP_FLOAT) f = (double)(float)f;
+    if (f != f) { out->null = true; return DE_NONE; }
+    out->bits = f64_bits(f);
+    return DE_NONE;
+  }
+  // v1 datum (datum_codec.rs:401-446)
+  uint8_t flag = p[0];
+  const uint8_t* q = p + 1;
+  uint32_t qn = len - 1;
+  if (flag == 0) { out->null = true; return DE_NONE; }
+  if (c.kind == CK_INT) {
+    if (flag == 3) { if (qn < 8) return DE_DATUM_DECODE; out->bits = ld_be64(q) ^ S; return DE_NONE; }
+    if (flag == 4) { if (qn < 8) return DE_DATUM_DECODE; out->bits = ld_be64(q); return DE_NONE; }
+    if (flag == 8) { int64_t v; if (!dec_var_i64(q, qn, &v)) return DE_DATUM_DECODE; out->bits = (uint64_t)v; return DE_NONE; }
+    if (flag == 9) { uint64_t v; if (!dec_var_u64(q, qn, &v)) return DE_DATUM_DECODE; out->bits = v; return DE_NONE; }
+    return DE_DATUM_DECODE;
+  }
+  if (flag == 5) {
+    if (qn < 8) return DE_DATUM_DECODE;
+    double f = cmp_u64_to_f64(ld_be64(q));
+    if (c.tp == B2_TP_FLOAT) f = (double)(float)f;
+    if (f != f) { out->null = true; return DE_NONE; }
+    out->bits = f64_bits(f);
+    return DE_NONE;
+  }
+  return DE_DATUM_DECODE;
+}
+
+// ---- RPN evaluation for one row -----------------------------------------------------------------------
+B2_HD int cmp_i64(int64_t a, bool au, int64_t b, bool bu) {  // impl_compare.rs:63-149
+  if (!au && !bu) return a < b ? -1 : (a > b ? 1 : 0);
+  if (au && bu) return (uint64_t)a < (uint64_t)b ? -1 : ((uint64_t)a > (uint64_t)b ? 1 : 0);
+  if (au) { if (b < 0 || a < 0) return 1; return a < b ? -1 : (a > b ? 1 : 0); }
+  if (a < 0 || b < 0) return -1;
+  return a < b ? -1 : (a > b ? 1 : 0);
+}
+
+B2_HD bool add_ovf_i64(int64_t a, int64_t b, int64_t* r) {
+  uint64_t s = (uint64_t)a + (uint64_t)b;
+  *r = (int64_t)s;
+  return ((a ^ (int64_t)s) & (b ^ (int64_t)s)) < 0;
+}
+B2_HD bool sub_ovf_i64(int64_t a, int64_t b, int64_t* r) {
+  uint64_t s = (uint64_t)a - (uint64_t)b;
+  *r = (int64_t)s;
+  return ((a ^ b) & (a ^ (int64_t)s)) < 0;
+}
+B2_HD bool add_ovf_u64(uint64_t a, uint64_t b, uint64_t* r) { *r = a + b; return *r < a; }
+B2_HD bool sub_ovf_u64(uint64_t a, uint64_t b, uint64_t* r) { *r = a - b; return a < b; }
+B2_HD uint64_t mulhi_u64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+B2_HD bool mul_ovf_u64(uint64_t a, uint64_t b, uint64_t* r) { *r = a * b; return mulhi_u64(a, b) != 0; }
+B2_HD bool mul_ovf_i64(int64_t a, int64_t b, int64_t* r) {
+  // magnitude product must fit: |a*b| <= 2^63-1, or == 2^63 when the result is negative
+  uint64_t ua = a < 0 ? (uint64_t)0 - (uint64_t)a : (uint64_t)a, ub = b < 0 ? (uint64_t)0 - (uint64_t)b : (uint64_t)b, m;
+  bool neg = (a < 0) != (b < 0);
+  if (mul_ovf_u64(ua, ub, &m)) return true;
+  if (neg) { if (m > 0x8000000000000000ull) return true; *r = (int64_t)((uint64_t)0 - m); return false; }
+  if (m > 0x7fffffffffffffffull) return true;
+  *r = (int64_t)m;
+  return false;
+}
+B2_HD bool f64_finite(double x) { return (f64_bits(x) & 0x7ff0000000000000ull) != 0x7ff0000000000000ull; }
+B2_HD bool f64_isinf(double x) { return (f64_bits(x) & 0x7fffffffffffffffull) == 0x7ff0000000000000ull; }
+
+B2_HD int eval_expr(const DevPlan& P, DevExpr ex, const Row& row, const Cells& cells, Value* result, bool* res_unsigned) {
+  int64_t sv[MAX_STACK];
+  uint8_t sn[MAX_STACK];  // bit0 null, bit1 unsigned
+  int sp = 0;
+  for (uint32_t k = ex.start; k < (uint32_t)ex.start + ex.n; ++k) {
+    const DevNode& nd = P.nodes[k];
+    if (nd.kind == B2_RPN_COLUMN_REF) {
+      Value v;
+      int e = cell_value(P, row, cells, (int)nd.imm, &v);
+      if (e) return e;
+      sv[sp] = (int64_t)v.bits; sn[sp] = (v.null ? 1 : 0) | (P.cols[nd.imm].is_unsigned ? 2 : 0);
+      ++sp;
+      continue;
+    }
+    if (nd.kind != B2_RPN_FN) {  // constants
+      sv[sp] = nd.imm; sn[sp] = (nd.kind == B2_RPN_CONST_NULL ? 1 : 0) | (nd.is_unsigned ? 2 : 0);
+      ++sp;
+      continue;
+    }
+    int64_t b = 0; uint8_t bf = 0;
+    if (nd.n_args == 2) { --sp; b = sv[sp]; bf = sn[sp]; }
+    --sp;
+    int64_t a = sv[sp]; uint8_t af = sn[sp];
+    bool an = af & 1, bn = bf & 1, au = af & 2, bu = bf & 2;
+    int64_t r = 0; bool rn = true;
+    int sig = nd.sig;
+    int base = sig / 10 * 10;
+    bool real = (sig % 10) == 1;
+    if (sig >= 100 && sig < 170) {  // comparisons
+      bool nulleq = base == B2_SIG_NULLEQ_INT;
+      if (an && bn) { if (nulleq) { rn = false; r = 1; } }
+      else if (an || bn) { if (nulleq) { rn = false; r = 0; } }
+      else {
+        int c;
+        if (real) { double x = bits_f64((uint64_t)a), y = bits_f64((uint64_t)b); c = x < y ? -1 : (x > y ? 1 : 0); }
+        else c = cmp_i64(a, au, b, bu);
+        bool t;
+        switch (base) {
+          case B2_SIG_LT_INT: t = c < 0; break;
+          case B2_SIG_LE_INT: t = c <= 0; break;
+          case B2_SIG_GT_INT: t = c > 0; break;
+          case B2_SIG_GE_INT: t = c >= 0; break;
+          case B2_SIG_NE_INT: t = c != 0; break;
+          default: t = c == 0; break;  // EQ, NULLEQ
+        }
+        rn = false; r = t;
+      }
+    } else {
+      switch (sig) {
+        case B2_SIG_LOGICAL_AND:
+          if ((!an && a == 0) || (!bn && b == 0)) { rn = false; r = 0; }
+          else if (!an && !bn) { rn = false; r = 1; }
+          break;
+        case B2_SIG_LOGICAL_OR:
+          if (!an && !bn && a == 0 && b == 0) { rn = false; r = 0; }
+          else if ((an && bn) || (an && b == 0) || (bn && a == 0)) {}
+          else { rn = false; r = 1; }
+          break;
+        case B2_SIG_LOGICAL_XOR: if (!an && !bn) { rn = false; r = (a == 0) != (b == 0); } break;
+        case B2_SIG_UNARY_NOT_INT: if (!an) { rn = false; r = a == 0; } break;
+        case B2_SIG_UNARY_NOT_REAL: if (!an) { rn = false; r = bits_f64((uint64_t)a) == 0.0; } break;
+        case B2_SIG_INT_IS_NULL: case B2_SIG_REAL_IS_NULL: rn = false; r = an; break;
+        case B2_SIG_INT_IS_TRUE: rn = false; r = !an && a != 0; break;
+        case B2_SIG_REAL_IS_TRUE: rn = false; r = !an && bits_f64((uint64_t)a) != 0.0; break;
+        case B2_SIG_INT_IS_FALSE: rn = false; r = !an && a == 0; break;
+        case B2_SIG_REAL_IS_FALSE: rn = false; r = !an && bits_f64((uint64_t)a) == 0.0; break;
+        case B2_SIG_PLUS_INT: case B2_SIG_MINUS_INT: case B2_SIG_MULTIPLY_INT: case B2_SIG_MULTIPLY_INT_UNSIGNED: {
+          if (an || bn) break;
+          bool xu = au, yu = bu, ovf;
+          if (sig == B2_SIG_MULTIPLY_INT_UNSIGNED) xu = yu = true;
+          uint64_t w = 0;
+          if (sig == B2_SIG_PLUS_INT) {
+            if (!xu && !yu) ovf = add_ovf_i64(a, b, &r);
+            else if (xu && yu) { ovf = add_ovf_u64((uint64_t)a, (uint64_t)b, &w); r = (int64_t)w; }
+            else {
+              int64_t s = xu ? b : a; uint64_t u = (uint64_t)(xu ? a : b);
+              if (s >= 0) ovf = add_ovf_u64((uint64_t)s, u, &w); else ovf = sub_ovf_u64(u, (uint64_t)0 - (uint64_t)s, &w);
+              r = (int64_t)w;
+            }
+          } else if (sig == B2_SIG_MINUS_INT) {
+            if (!xu && !yu) ovf = sub_ovf_i64(a, b, &r);
+            else if (xu && yu) { ovf = sub_ovf_u64((uint64_t)a, (uint64_t)b, &w); r = (int64_t)w; }
+            else if (!xu) { if (a >= 0) ovf = sub_ovf_u64((uint64_t)a, (uint64_t)b, &w); else ovf = true; r = (int64_t)w; }
+            else { if (b >= 0) ovf = sub_ovf_u64((uint64_t)a, (uint64_t)b, &w); else ovf = add_ovf_u64((uint64_t)a, (uint64_t)0 - (uint64_t)b, &w); r = (int64_t)w; }
+          } else {
+            if (!xu && !yu) ovf = mul_ovf_i64(a, b, &r);
+            else if (xu && yu) { ovf = mul_ovf_u64((uint64_t)a, (uint64_t)b, &w); r = (int64_t)w; }
+            else { int64_t s = xu ? b : a; uint64_t u = (uint64_t)(xu ? a : b); if (s >= 0) ovf = mul_ovf_u64((uint64_t)s, u, &w); else ovf = true; r = (int64_t)w; }
+          }
+          if (ovf) return (xu || yu) ? DE_OVERFLOW_UBIGINT : DE_OVERFLOW_BIGINT;
+          rn = false;
+          break;
+        }
+        case B2_SIG_PLUS_REAL: case B2_SIG_MINUS_REAL: case B2_SIG_MULTIPLY_REAL: {
+          if (an || bn) break;
+          double x = bits_f64((uint64_t)a), y = bits_f64((uint64_t)b);
+          double z = sig == B2_SIG_PLUS_REAL ? x + y : (sig == B2_SIG_MINUS_REAL ? x - y : x * y);
+          bool bad = sig == B2_SIG_MULTIPLY_REAL ? f64_isinf(z) : !f64_finite(z);
+          if (bad) return DE_OVERFLOW_DOUBLE;
+          rn = false; r = (int64_t)f64_bits(z);
+          break;
+        }
+        default: return DE_UNSUPPORTED_SIG;
+      }
+    }
+    sv[sp] = r; sn[sp] = (rn ? 1 : 0) | (nd.is_unsigned ? 2 : 0);
+    ++sp;
+  }
+  result->bits = (uint64_t)sv[0];
+  result->null = sn[0] & 1;
+  if (res_unsigned) *res_unsigned = sn[0] & 2;
+  return DE_NONE;
+}
+
+// AND of the selection conditions on one row (selection_executor.rs:81-195): sequential, stop at first false/NULL
+B2_HD int eval_conds(const DevPlan& P, const Row& row, const Cells& cells, bool* keep) {
+  *keep = true;
+  for (int i = 0; i < P.n_conds; ++i) {
+    Value v;
+    const DevExpr ex = P.conds[i];
+    int e = eval_expr(P, ex, row, cells, &v, nullptr);
+    if (e) return e;
+    bool t;
+    if (v.null) t = false;
+    else if (P.nodes[ex.start + ex.n - 1].et == 1) t = bits_f64(v.bits) != 0.0;
+    else t = v.bits != 0;
+    if (!t) { *keep = false; return DE_NONE; }
+  }
+  return DE_NONE;
+}
+
+// fx-like 64-bit mixer for the group hash table (any good mixer works: group order is unspecified)
+B2_HD uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
+// CRC-64/XZ bytewise step table entry (reflected poly 0xC96C5795D7870F42), computed — not stored — on the host
+B2_HD uint64_t crc64_table_entry(uint32_t i) {
+  uint64_t c = i;
+  for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0xC96C5795D7870F42ull : (c >> 1);
+  return c;
+}
+
+// exact i128/u128 value hi * 2^32 + lo -> MySQL Decimal words (base 1e9), canonical form of Decimal::from (decimal.rs:1787-1815)
+B2_HD void limbs_to_decimal(unsigned long long lo, unsigned long long hi, bool is_unsigned, b2_decimal* d) {
+  // value = hi * 2^32 + lo as 128-bit two's complement (hi sign-extended when signed)
+  unsigned long long w0 = lo + (hi << 32);                 // low 64 bits
+  unsigned long long carry = w0 < lo ? 1ull : 0ull;
+  unsigned long long hi_ext = is_unsigned ? (hi >> 32) : (unsigned long long)((long long)hi >> 32);
+  unsigned long long w1 = hi_ext + carry;                  // high 64 bits
+  bool neg = !is_unsigned && ((long long)w1 < 0);
+  if (neg) {  // magnitude
+    w0 = ~w0 + 1;
+    w1 = ~w1 + (w0 == 0 ? 1ull : 0ull);
+  }
+  // repeated division of the 128-bit magnitude by 1e9 using 32-bit limbs
+  unsigned int limb[4] = {(unsigned int)(w1 >> 32), (unsigned int)w1, (unsigned int)(w0 >> 32), (unsigned int)w0};
+  unsigned int words[9];
+  int nw = 0;
+  for (;;) {
+    unsigned long long rem = 0;
+    bool nonzero = false;
+    for (int i = 0; i < 4; ++i) {
+      unsigned long long cur = (rem << 32) | limb[i];
+      limb[i] = (unsigned int)(cur / 1000000000ull);
+      rem = cur % 1000000000ull;
+      nonzero |= limb[i] != 0;
+    }
+    words[nw++] = (unsigned int)rem;
+    if (!nonzero || nw == 9) break;
+  }
+  d->int_cnt = (uint8_t)(nw * 9); d->frac_cnt = 0; d->result_frac_cnt = 0; d->negative = neg;
+  for (int i = 0; i < 9; ++i) d->word_buf[i] = i < nw ? words[nw - 1 - i] : 0;
+}
+
+
+}  // namespace b2

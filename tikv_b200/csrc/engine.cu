@@ -1,0 +1,1010 @@
+// Host engine behind the C ABI (include/b2_copr.h): plan lowering, range/lock handling, block staging over two
+// CUDA streams, kernel launches, result materialisation and error mapping.
+//
+// Reference counterparts: BatchExecutor trait (tidb_query_executors/src/interface.rs:36-97), BatchExecutorsRunner
+// (runner.rs:606-851), TikvStorage/RangesScanner (src/coprocessor/dag/storage_impl.rs:39-123,
+// tidb_query_common/src/storage/scanner.rs:122-221), lock checks of LatestKvPolicy::handle_lock
+// (src/storage/mvcc/reader/scanner/forward.rs:384-431, txn_types/src/lock.rs:343-416, 520-611),
+// ChecksumContext (src/coprocessor/checksum.rs:26-98).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "kernels.cuh"
+#include "plan_compile.h"
+
+using namespace b2;
+
+static thread_local std::string g_last_error;
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) {                                                                             \
+      fail(B2_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                             \
+      return B2_ERR_CUDA;                                                                                \
+    }                                                                                                    \
+  } while (0)
+
+namespace {
+
+struct DevBuf {  // growable device allocation
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct HostBuf {  // growable pinned host allocation
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, n);
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct SrcBlock {  // caller's block descriptor + sizes
+  b2_cf_block c;
+  uint64_t key_bytes = 0, val_bytes = 0;
+  uint64_t entry_base = 0;
+};
+
+struct Unit { uint32_t range_idx, block_idx, e_lo, e_hi; };
+
+struct StageSlot {
+  DevBuf keys, koff, vals, voff;
+  int block = -1;
+  cudaEvent_t ready = nullptr, free_ev = nullptr;
+  bool free_recorded = false;
+};
+
+// ---- lock records (host): the subset of Lock::parse that check_ts_conflict_si needs ----
+struct HostLock { uint8_t type = 0; std::vector<uint8_t> primary; uint64_t ts = 0, min_commit_ts = 0; bool async_commit = false; };
+
+bool parse_compact_bytes(const uint8_t*& p, size_t& n, std::vector<uint8_t>* out) {
+  int64_t len;
+  uint32_t c = dec_var_i64(p, (uint32_t)n, &len);
+  if (!c || len < 0 || (uint64_t)len > n - c) return false;
+  if (out) out->assign(p + c, p + c + len);
+  p += c + len; n -= c + (size_t)len;
+  return true;
+}
+bool parse_lock(const uint8_t* p, size_t n, HostLock* l) {
+  if (n == 0) return false;
+  uint8_t t = p[0];
+  if (t != 'P' && t != 'D' && t != 'L' && t != 'S' && t != 'H') return false;
+  l->type = t;
+  if (t == 'H') return true;
+  ++p; --n;
+  if (!parse_compact_bytes(p, n, &l->primary)) return false;
+  uint32_t c = dec_var_u64_tu(p, (uint32_t)n, &l->ts);
+  if (!c) return false;
+  p += c; n -= c;
+  if (n == 0) return true;
+  uint64_t ttl;
+  c = dec_var_u64_tu(p, (uint32_t)n, &ttl);
+  if (!c) return false;
+  p += c; n -= c;
+  while (n > 0) {
+    uint8_t tag = *p++; --n;
+    if (tag == 'v') { if (n < 1 || n - 1 < p[0]) return false; size_t k = 1 + p[0]; p += k; n -= k; }
+    else if (tag == 'f' || tag == 't' || tag == 'c' || tag == 'g') { if (n < 8) return false; if (tag == 'c') l->min_commit_ts = ld_be64(p); p += 8; n -= 8; }
+    else if (tag == 'a') {
+      l->async_commit = true;
+      uint64_t cnt; c = dec_var_u64_tu(p, (uint32_t)n, &cnt);
+      if (!c) return false;
+      p += c; n -= c;
+      for (uint64_t i = 0; i < cnt; ++i) if (!parse_compact_bytes(p, n, nullptr)) return false;
+    } else if (tag == 'r') {
+      uint64_t cnt; c = dec_var_u64_tu(p, (uint32_t)n, &cnt);
+      if (!c || n - c < cnt * 8) return false;
+      p += c + cnt * 8; n -= c + cnt * 8;
+    } else if (tag == 'l') {
+      if (n < 8) return false;
+      p += 8; n -= 8;
+      uint64_t v; c = dec_var_u64_tu(p, (uint32_t)n, &v);
+      if (!c) return false;
+      p += c; n -= c;
+    } else if (tag == 's') { uint64_t v; c = dec_var_u64_tu(p, (uint32_t)n, &v); if (!c) return false; p += c; n -= c; }
+    else if (tag == 'F') {}
+    else break;
+  }
+  return true;
+}
+
+int cmp_bytes_host(const uint8_t* a, size_t an, const uint8_t* b, size_t bn) {
+  size_t m = std::min(an, bn);
+  int c = m ? memcmp(a, b, m) : 0;
+  if (c) return c;
+  return an < bn ? -1 : (an > bn ? 1 : 0);
+}
+
+const char* dev_err_message(int code, int* status, int* mysql) {
+  *mysql = 0;
+  switch (code) {
+    case DE_BAD_WRITE: *status = B2_ERR_STORAGE; return "bad format write";
+    case DE_KEY_TOO_SHORT: *status = B2_ERR_STORAGE; return "key is too short to carry a timestamp";
+    case DE_DEFAULT_NOT_FOUND: *status = B2_ERR_STORAGE; return "default not found";
+    case DE_WRITE_CONFLICT: *status = B2_ERR_WRITE_CONFLICT; return "write conflict (RcCheckTs): a newer version exists";
+    case DE_BAD_USER_KEY: *status = B2_ERR_STORAGE; return "invalid memcomparable user key";
+    case DE_BAD_RECORD_KEY: *status = B2_ERR_CORRUPTED; return "record key expected";
+    case DE_ROW_COLID_NOT_VARINT: *status = B2_ERR_CORRUPTED; return "Unable to decode row: column id must be VAR_INT";
+    case DE_ROW_EOF: *status = B2_ERR_CORRUPTED; return "unexpected eof while decoding row";
+    case DE_ROW_BAD_DATUM: *status = B2_ERR_CORRUPTED; return "unsupported or truncated datum in row";
+    case DE_ROW_V2_BAD_INT: *status = B2_ERR_CORRUPTED; return "Failed to decode row v2 data as i64/u64";
+    case DE_ROW_V2_RANGE: *status = B2_ERR_CORRUPTED; return "row v2 value slice out of range";
+    case DE_MISSING_NOT_NULL: *status = B2_ERR_CORRUPTED; return "Data is corrupted, missing data for NOT NULL column";
+    case DE_MISSING_COMMIT_TS: *status = B2_ERR_CORRUPTED; return "Query asks for _tidb_commit_ts, but the data is missing";
+    case DE_DATUM_DECODE: *status = B2_ERR_CORRUPTED; return "Unsupported datum flag for the column's vector type";
+    case DE_OVERFLOW_BIGINT: *status = B2_ERR_EVALUATE; *mysql = B2_MYSQL_ERR_DATA_OUT_OF_RANGE; return "BIGINT value is out of range";
+    case DE_OVERFLOW_UBIGINT: *status = B2_ERR_EVALUATE; *mysql = B2_MYSQL_ERR_DATA_OUT_OF_RANGE; return "BIGINT UNSIGNED value is out of range";
+    case DE_OVERFLOW_DOUBLE: *status = B2_ERR_EVALUATE; *mysql = B2_MYSQL_ERR_DATA_OUT_OF_RANGE; return "DOUBLE value is out of range";
+    case DE_UNSUPPORTED_SIG: *status = B2_ERR_UNSUPPORTED; return "scalar function not supported on the device";
+    case DE_UNSUPPORTED_TYPE: *status = B2_ERR_UNSUPPORTED; return "column type not supported on the device";
+    default: *status = B2_ERR_CUDA; return "unknown device error";
+  }
+}
+
+}  // namespace
+
+struct b2_exec {
+  CompiledPlan cp;
+  int device = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  bool own_stream = false;
+  int out_loc = B2_LOC_DEVICE;
+  int src_loc = B2_LOC_DEVICE;
+  uint64_t read_ts = 0;
+  int isolation = B2_ISO_SI;
+  bool check_newer = false;
+
+  std::vector<SrcBlock> wblocks, dblocks;
+  std::vector<std::vector<uint8_t>> range_lo, range_hi;  // encoded bounds per range (hi possibly cut by a lock)
+  std::vector<int> range_lock_err;                      // 1 = range ends with KeyIsLocked
+  std::vector<uint64_t> range_lock_ts;
+  std::vector<Unit> units;
+  size_t cur_unit = 0;
+  uint32_t cur_entry = 0;
+  bool started = false, drained = false, failed = false;
+  bool saw_lock = false;
+  uint64_t lock_keys_seen = 0;
+
+  // device state
+  DevBuf ctr_buf, status_buf, out_data, out_bitmap, dflt_views, dflt_store;
+  DevBuf tbl_keys, tbl_occ, tbl_acc, grp_keys, grp_null, grp_acc, res_ptrs;
+  std::vector<DevBuf> res_cols, res_bitmaps;
+  unsigned int tbl_cap = 0;
+  StageSlot slots[2];
+  HostBuf h_out, h_ctr;
+  uint64_t out_cap = 0;
+
+  // results exposed through b2_batch
+  std::vector<b2_column> cols;
+  b2_error_info last_err{};
+  b2_exec_stats stats{};
+  uint64_t entries_scanned = 0;
+
+  int fail(int status, const std::string& msg, int mysql = 0, uint64_t entry = ~0ull) {
+    last_err.status = status; last_err.mysql_code = mysql; last_err.entry_index = entry;
+    snprintf(last_err.message, sizeof(last_err.message), "%s", msg.c_str());
+    g_last_error = msg;
+    failed = true;
+    return status;
+  }
+
+  ~b2_exec() {
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+    for (auto& s : slots) {
+      s.keys.release(); s.koff.release(); s.vals.release(); s.voff.release();
+      if (s.ready) cudaEventDestroy(s.ready);
+      if (s.free_ev) cudaEventDestroy(s.free_ev);
+    }
+    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &grp_keys, &grp_null, &grp_acc, &res_ptrs}) b->release();
+    for (auto& b : res_cols) b.release();
+    for (auto& b : res_bitmaps) b.release();
+    h_out.release(); h_ctr.release();
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+
+  Counters* ctr() { return (Counters*)ctr_buf.p; }
+
+  // ---- source setup ----
+  int read_offs_end(const b2_cf_block& b, uint64_t* kb, uint64_t* vb) {
+    uint32_t k = 0, v = 0;
+    if (b.n == 0) { *kb = *vb = 0; return B2_OK; }
+    if (src_loc == B2_LOC_HOST) { k = b.key_offs[b.n]; v = b.val_offs[b.n]; }
+    else {
+      CUDA_TRY(cudaMemcpy(&k, b.key_offs + b.n, 4, cudaMemcpyDeviceToHost));
+      CUDA_TRY(cudaMemcpy(&v, b.val_offs + b.n, 4, cudaMemcpyDeviceToHost));
+    }
+    *kb = k; *vb = v;
+    return B2_OK;
+  }
+
+  int setup_source(const b2_region_source* src, const b2_key_range* ranges, uint32_t n_ranges) {
+    src_loc = src->location;
+    read_ts = src->read_ts; isolation = src->isolation_level; check_newer = src->check_has_newer_ts_data != 0;
+    uint64_t base = 0;
+    for (uint32_t i = 0; i < src->n_write; ++i) {
+      SrcBlock sb; sb.c = src->write[i]; sb.entry_base = base;
+      int rc = read_offs_end(sb.c, &sb.key_bytes, &sb.val_bytes);
+      if (rc) return rc;
+      base += sb.c.n;
+      wblocks.push_back(sb);
+    }
+    for (uint32_t i = 0; src->dflt && i < src->n_dflt; ++i) {
+      SrcBlock sb; sb.c = src->dflt[i];
+      int rc = read_offs_end(sb.c, &sb.key_bytes, &sb.val_bytes);
+      if (rc) return rc;
+      dblocks.push_back(sb);
+    }
+    // CF_DEFAULT views on the device (host sources are copied once; long values are rare)
+    if (!dblocks.empty()) {
+      std::vector<BlockView> views;
+      if (src_loc == B2_LOC_HOST) {
+        size_t total = 0;
+        for (auto& d : dblocks) total += ((d.key_bytes + 31) & ~15ull) + ((d.val_bytes + 31) & ~15ull) + 2 * (((size_t)d.c.n + 1) * 4 + 16);
+        CUDA_TRY(dflt_store.reserve(total));
+        uint8_t* p = (uint8_t*)dflt_store.p;
+        for (auto& d : dblocks) {
+          BlockView v; v.n = d.c.n;
+          auto put = [&](const void* srcp, size_t bytes) -> const void* {
+            uint8_t* dst = p;
+            if (bytes) cudaMemcpyAsync(dst, srcp, bytes, cudaMemcpyHostToDevice, stream);
+            p += (bytes + 31) & ~15ull;
+            return dst;
+          };
+          v.keys = (const uint8_t*)put(d.c.keys, d.key_bytes);
+          v.vals = (const uint8_t*)put(d.c.vals, d.val_bytes);
+          v.koff = (const uint32_t*)put(d.c.key_offs, ((size_t)d.c.n + 1) * 4);
+          v.voff = (const uint32_t*)put(d.c.val_offs, ((size_t)d.c.n + 1) * 4);
+          views.push_back(v);
+        }
+      } else {
+        for (auto& d : dblocks) { BlockView v; v.keys = d.c.keys; v.koff = d.c.key_offs; v.vals = d.c.vals; v.voff = d.c.val_offs; v.n = d.c.n; views.push_back(v); }
+      }
+      CUDA_TRY(dflt_views.reserve(views.size() * sizeof(BlockView)));
+      CUDA_TRY(cudaMemcpyAsync(dflt_views.p, views.data(), views.size() * sizeof(BlockView), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    // ranges -> encoded bounds (Range::from_pb_range + Key::from_raw)
+    for (uint32_t i = 0; i < n_ranges; ++i) {
+      range_lo.push_back(encode_memcomparable(ranges[i].start, ranges[i].start_len));
+      range_hi.push_back(encode_memcomparable(ranges[i].end, ranges[i].end_len));
+      range_lock_err.push_back(0);
+      range_lock_ts.push_back(0);
+    }
+    // CF_LOCK (host memory): LatestKvPolicy::handle_lock for every lock inside a range, in key order
+    if (src->lock && src->lock->n && isolation != B2_ISO_RC) {
+      const b2_cf_block& L = *src->lock;
+      for (uint32_t r = 0; r < n_ranges; ++r) {
+        for (uint32_t i = 0; i < L.n; ++i) {
+          const uint8_t* k = L.keys + L.key_offs[i];
+          size_t kn = L.key_offs[i + 1] - L.key_offs[i];
+          if (cmp_bytes_host(k, kn, range_lo[r].data(), range_lo[r].size()) < 0) continue;
+          if (cmp_bytes_host(k, kn, range_hi[r].data(), range_hi[r].size()) >= 0) break;
+          saw_lock = true;
+          HostLock lk;
+          if (!parse_lock(L.vals + L.val_offs[i], L.val_offs[i + 1] - L.val_offs[i], &lk)) return fail(B2_ERR_STORAGE, "bad format lock");
+          bool conflict;
+          if (isolation == B2_ISO_SI) {
+            conflict = !(lk.type == 'H' || lk.ts > read_ts || lk.type == 'L' || lk.type == 'S' || lk.min_commit_ts > read_ts);
+            for (uint32_t b = 0; conflict && b < src->n_bypass_locks; ++b) if (src->bypass_locks[b] == lk.ts) conflict = false;
+            if (conflict && read_ts == ~0ull && !lk.async_commit) {
+              // reading the latest committed version of the primary key ignores its own lock
+              int rl = raw_key_len(k, (uint32_t)kn);
+              if (rl >= 0 && (size_t)rl == lk.primary.size()) {
+                bool same = true;
+                for (int j = 0; j < rl && same; ++j) same = raw_at(k, j) == lk.primary[j];
+                if (same) conflict = false;
+              }
+            }
+          } else {  // RcCheckTs: lock.rs:418-455
+            conflict = !(lk.type == 'H' || lk.type == 'L' || lk.type == 'S');
+            for (uint32_t b = 0; conflict && b < src->n_bypass_locks; ++b) if (src->bypass_locks[b] == lk.ts) conflict = false;
+          }
+          if (!conflict) continue;
+          for (uint32_t a = 0; a < src->n_access_locks; ++a)
+            if (src->access_locks[a] == lk.ts) return fail(B2_ERR_UNSUPPORTED, "access_locks read-through is not supported on the device path");
+          // rows before this key are produced, then the request fails (forward.rs:401-428)
+          range_hi[r].assign(k, k + kn);
+          range_lock_err[r] = isolation == B2_ISO_SI ? B2_ERR_KEY_IS_LOCKED : B2_ERR_WRITE_CONFLICT;
+          range_lock_ts[r] = lk.ts;
+          lock_keys_seen++;
+          break;
+        }
+        if (range_lock_err[r]) { range_lo.resize(r + 1); range_hi.resize(r + 1); range_lock_err.resize(r + 1); range_lock_ts.resize(r + 1); break; }
+      }
+    }
+    return compute_units();
+  }
+
+  // lower_bound of every range bound in every CF_WRITE block
+  int compute_units() {
+    uint32_t nr = (uint32_t)range_lo.size(), nb = (uint32_t)wblocks.size();
+    if (!nr || !nb) return B2_OK;
+    std::vector<uint32_t> res((size_t)nb * nr * 2);
+    if (src_loc == B2_LOC_HOST) {
+      for (uint32_t b = 0; b < nb; ++b)
+        for (uint32_t q = 0; q < nr * 2; ++q) {
+          const std::vector<uint8_t>& key = (q & 1) ? range_hi[q / 2] : range_lo[q / 2];
+          const b2_cf_block& B = wblocks[b].c;
+          uint32_t lo = 0, hi = B.n;
+          while (lo < hi) {
+            uint32_t mid = lo + (hi - lo) / 2;
+            if (cmp_bytes_host(B.keys + B.key_offs[mid], B.key_offs[mid + 1] - B.key_offs[mid], key.data(), key.size()) < 0) lo = mid + 1; else hi = mid;
+          }
+          res[(size_t)b * nr * 2 + q] = lo;
+        }
+    } else {
+      std::vector<uint8_t> flat;
+      std::vector<uint32_t> offs(1, 0);
+      for (uint32_t r = 0; r < nr; ++r) {
+        flat.insert(flat.end(), range_lo[r].begin(), range_lo[r].end()); offs.push_back((uint32_t)flat.size());
+        flat.insert(flat.end(), range_hi[r].begin(), range_hi[r].end()); offs.push_back((uint32_t)flat.size());
+      }
+      std::vector<BlockView> views;
+      for (auto& w : wblocks) { BlockView v; v.keys = w.c.keys; v.koff = w.c.key_offs; v.vals = w.c.vals; v.voff = w.c.val_offs; v.n = w.c.n; views.push_back(v); }
+      DevBuf d_views, d_flat, d_offs, d_res;
+      cudaError_t e = d_views.reserve(views.size() * sizeof(BlockView));
+      if (e == cudaSuccess) e = d_flat.reserve(flat.size() + 16);
+      if (e == cudaSuccess) e = d_offs.reserve(offs.size() * 4);
+      if (e == cudaSuccess) e = d_res.reserve(res.size() * 4);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_views.p, views.data(), views.size() * sizeof(BlockView), cudaMemcpyHostToDevice, stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_flat.p, flat.data(), flat.size(), cudaMemcpyHostToDevice, stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_offs.p, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, stream);
+      if (e == cudaSuccess) e = launch_bounds_search((const BlockView*)d_views.p, nb, (const uint8_t*)d_flat.p, (const uint32_t*)d_offs.p, nr * 2, (uint32_t*)d_res.p, stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(res.data(), d_res.p, res.size() * 4, cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+      d_views.release(); d_flat.release(); d_offs.release(); d_res.release();
+      if (e != cudaSuccess) return fail(B2_ERR_CUDA, std::string("range bounds search: ") + cudaGetErrorString(e));
+    }
+    for (uint32_t r = 0; r < nr; ++r)
+      for (uint32_t b = 0; b < nb; ++b) {
+        uint32_t lo = res[(size_t)b * nr * 2 + 2 * r], hi = res[(size_t)b * nr * 2 + 2 * r + 1];
+        if (hi > lo) units.push_back(Unit{r, b, lo, hi});
+      }
+    return B2_OK;
+  }
+
+  // ---- block residency ----
+  int acquire_block(uint32_t bi, BlockView* v) {
+    const SrcBlock& sb = wblocks[bi];
+    if (src_loc == B2_LOC_DEVICE) { v->keys = sb.c.keys; v->koff = sb.c.key_offs; v->vals = sb.c.vals; v->voff = sb.c.val_offs; v->n = sb.c.n; return B2_OK; }
+    StageSlot* s = nullptr;
+    for (auto& x : slots) if (x.block == (int)bi) s = &x;
+    if (!s) {
+      int rc = stage_block(bi, &s);
+      if (rc) return rc;
+    }
+    CUDA_TRY(cudaStreamWaitEvent(stream, s->ready, 0));
+    v->keys = (const uint8_t*)s->keys.p; v->koff = (const uint32_t*)s->koff.p; v->vals = (const uint8_t*)s->vals.p; v->voff = (const uint32_t*)s->voff.p; v->n = sb.c.n;
+    return B2_OK;
+  }
+  int stage_block(uint32_t bi, StageSlot** out) {
+    const SrcBlock& sb = wblocks[bi];
+    // pick the slot not holding the previous block (two slots alternate)
+    StageSlot* s = &slots[bi & 1];
+    if (!s->ready) { CUDA_TRY(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&s->free_ev, cudaEventDisableTiming)); }
+    if (s->free_recorded) CUDA_TRY(cudaStreamWaitEvent(copy_stream, s->free_ev, 0));
+    size_t kb = (sb.key_bytes + 31) & ~15ull, vb = (sb.val_bytes + 31) & ~15ull, ob = ((size_t)sb.c.n + 1) * 4;
+    if (s->keys.cap < kb || s->vals.cap < vb || s->koff.cap < ob || s->voff.cap < ob) {
+      CUDA_TRY(cudaStreamSynchronize(stream));  // buffers may still be in use
+      CUDA_TRY(s->keys.reserve(kb)); CUDA_TRY(s->vals.reserve(vb)); CUDA_TRY(s->koff.reserve(ob)); CUDA_TRY(s->voff.reserve(ob));
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->keys.p, sb.c.keys, sb.key_bytes, cudaMemcpyHostToDevice, copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(s->vals.p, sb.c.vals, sb.val_bytes, cudaMemcpyHostToDevice, copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(s->koff.p, sb.c.key_offs, ob, cudaMemcpyHostToDevice, copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(s->voff.p, sb.c.val_offs, ob, cudaMemcpyHostToDevice, copy_stream));
+    CUDA_TRY(cudaEventRecord(s->ready, copy_stream));
+    s->block = (int)bi;
+    stats.default_lookups += 0;
+    h2d_bytes += sb.key_bytes + sb.val_bytes + 2 * ob;
+    *out = s;
+    return B2_OK;
+  }
+  void release_block(uint32_t bi) {
+    if (src_loc == B2_LOC_DEVICE) return;
+    for (auto& x : slots)
+      if (x.block == (int)bi) { cudaEventRecord(x.free_ev, stream); x.free_recorded = true; }
+  }
+  void prefetch_after(size_t unit_idx) {
+    if (src_loc == B2_LOC_DEVICE) return;
+    for (size_t u = unit_idx + 1; u < units.size(); ++u) {
+      if (units[u].block_idx == units[unit_idx].block_idx) continue;
+      bool have = false;
+      for (auto& x : slots) if (x.block == (int)units[u].block_idx) have = true;
+      if (!have) { StageSlot* s; stage_block(units[u].block_idx, &s); }
+      return;
+    }
+  }
+  uint64_t h2d_bytes = 0;
+
+  int init_device_state() {
+    CUDA_TRY(ctr_buf.reserve(sizeof(Counters)));
+    CUDA_TRY(h_ctr.reserve(sizeof(Counters)));
+    Counters z;
+    memset(&z, 0, sizeof(z));
+    z.err = ~0ull;
+    CUDA_TRY(cudaMemcpyAsync(ctr_buf.p, &z, sizeof(z), cudaMemcpyHostToDevice, stream));
+    return B2_OK;
+  }
+  int read_counters(Counters* c) {
+    CUDA_TRY(cudaMemcpyAsync(h_ctr.p, ctr_buf.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    memcpy(c, h_ctr.p, sizeof(Counters));
+    return B2_OK;
+  }
+  void fill_stats(const Counters& c) {
+    stats.write_entries_scanned = entries_scanned;
+    stats.write_processed_keys = c.processed_keys;
+    stats.processed_size = c.processed_size;
+    stats.default_lookups = c.default_lookups;
+    stats.lock_processed_keys = lock_keys_seen;
+    stats.met_newer_ts_data = check_newer ? ((c.met_newer || saw_lock) ? 1 : 0) : -1;
+    met_newer_any = c.met_newer || saw_lock;
+  }
+  bool met_newer_any = false;
+
+  int device_error(const Counters& c) {
+    if (c.err == ~0ull) return B2_OK;
+    int status, mysql;
+    const char* m = dev_err_message((int)(c.err & 0xff), &status, &mysql);
+    return fail(status, m, mysql, c.err >> 8);
+  }
+
+  ScanArgs base_args(const Unit& u, const BlockView& v) {
+    ScanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.blk = v;
+    a.dflt.blocks = (const BlockView*)dflt_views.p; a.dflt.n_blocks = (uint32_t)dblocks.size();
+    a.e_lo = u.e_lo; a.e_hi = u.e_hi;
+    a.entry_base = wblocks[u.block_idx].entry_base;
+    a.ctr = ctr();
+    return a;
+  }
+
+  // ---- PM_SCAN: up to `scan_rows` CF_WRITE entries per call, appended in key order into one set of columns ----
+  // One pass = one launch per (range, block) unit touched; launches chain on the stream through the device-side
+  // row counter (out_rows -> out_base), so there is a single host sync per batch.
+  int run_scan_pass(uint64_t budget, uint64_t stop_before, bool* hit_lock_range, uint32_t* lock_range, Counters* c) {
+    size_t n_out = cp.dev.n_out;
+    // capacity = entries this pass may cover
+    uint64_t need = 0, left = budget;
+    {
+      size_t u = cur_unit; uint32_t e = cur_entry;
+      while (left && u < units.size()) {
+        uint32_t lo = std::max(e, units[u].e_lo);
+        uint64_t take = std::min<uint64_t>(left, units[u].e_hi - lo);
+        need += take; left -= take;
+        ++u; e = 0;
+      }
+    }
+    uint64_t cap = std::max<uint64_t>(64, (need + 63) & ~63ull);
+    if (cap > out_cap) {
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      CUDA_TRY(out_data.reserve(cap * 8 * n_out)); CUDA_TRY(out_bitmap.reserve(cap / 8 * n_out));
+      out_cap = cap;
+    }
+    CUDA_TRY(cudaMemsetAsync(out_bitmap.p, 0xff, out_cap / 8 * n_out, stream));
+    Counters z;
+    memset(&z, 0, sizeof(z));
+    z.err = ~0ull;
+    // keep request-level statistics, reset the per-batch row counters
+    CUDA_TRY(cudaMemsetAsync(&ctr()->out_rows, 0, 8, stream));
+    CUDA_TRY(cudaMemsetAsync(&ctr()->out_base, 0, 8, stream));
+    if (!scan_grid) scan_grid = scan_max_grid(PM_SCAN, 0);
+    *hit_lock_range = false;
+    while (budget && cur_unit < units.size()) {
+      const Unit& u = units[cur_unit];
+      if (cur_entry < u.e_lo) cur_entry = u.e_lo;
+      uint64_t base = wblocks[u.block_idx].entry_base;
+      uint32_t c_lo = cur_entry, c_hi = (uint32_t)std::min<uint64_t>(u.e_hi, (uint64_t)c_lo + budget);
+      bool stop_here = false;
+      if (stop_before != ~0ull && base + c_hi > stop_before) {
+        c_hi = stop_before > base + c_lo ? (uint32_t)(stop_before - base) : c_lo;
+        stop_here = true;
+      }
+      if (c_hi > c_lo) {
+        uint32_t n_tiles = (c_hi - c_lo + TILE - 1) / TILE;
+        CUDA_TRY(status_buf.reserve(((size_t)n_tiles + 1) * 8));
+        CUDA_TRY(cudaMemsetAsync(status_buf.p, 0, ((size_t)n_tiles + 1) * 8, stream));
+        BlockView v;
+        int rc = acquire_block(u.block_idx, &v);
+        if (rc) return rc;
+        ScanArgs a = base_args(u, v);
+        a.c_lo = c_lo; a.c_hi = c_hi;
+        if (stop_here) a.e_hi = c_hi;  // the failing entry is a run start: nothing before it can reach past it
+        a.tile_status = (unsigned long long*)status_buf.p;
+        a.out_data = (unsigned long long*)out_data.p; a.out_bitmap = (unsigned long long*)out_bitmap.p;
+        a.out_cap = out_cap;
+        CUDA_TRY(launch_scan(cp.dev, a, scan_grid, 0, stream));
+        CUDA_TRY(cudaMemcpyAsync(&ctr()->out_base, &ctr()->out_rows, 8, cudaMemcpyDeviceToDevice, stream));
+        release_block(u.block_idx);
+        entries_scanned += c_hi - c_lo;
+        budget -= c_hi - c_lo;
+        stats.num_iterations++;
+      }
+      cur_entry = c_hi;
+      if (stop_here) break;
+      if (c_hi >= u.e_hi) {
+        prefetch_after(cur_unit);
+        bool range_end = cur_unit + 1 >= units.size() || units[cur_unit + 1].range_idx != u.range_idx;
+        cur_unit++;
+        cur_entry = cur_unit < units.size() ? units[cur_unit].e_lo : 0;
+        if (range_end && range_lock_err[u.range_idx]) { *hit_lock_range = true; *lock_range = u.range_idx; break; }
+      }
+    }
+    return read_counters(c);
+  }
+
+  int next_scan_batch(uint64_t scan_rows, b2_batch* out) {
+    cols.clear();
+    uint64_t budget = std::max<uint64_t>(1, std::min<uint64_t>(scan_rows, 1ull << 31));
+    uint64_t produced = 0;
+    while (!drained && !failed && produced == 0) {
+      if (cur_unit >= units.size()) { drained = true; break; }
+      size_t save_unit = cur_unit; uint32_t save_entry = cur_entry; uint64_t save_scanned = entries_scanned;
+      bool hit_lock = false; uint32_t lock_r = 0;
+      Counters c;
+      int rc = run_scan_pass(budget, ~0ull, &hit_lock, &lock_r, &c);
+      if (rc) return rc;
+      fill_stats(c);
+      produced = c.out_rows;
+      if (c.err != ~0ull) {
+        // rows before the failing row stay valid (interface.rs:229-235): redo this batch up to it, then report
+        cur_unit = save_unit; cur_entry = save_entry; entries_scanned = save_scanned;
+        Counters z; memset(&z, 0, sizeof(z)); z.err = ~0ull;
+        CUDA_TRY(cudaMemcpyAsync(ctr_buf.p, &z, sizeof(z), cudaMemcpyHostToDevice, stream));
+        Counters c2;
+        rc = run_scan_pass(budget, c.err >> 8, &hit_lock, &lock_r, &c2);
+        if (rc) return rc;
+        produced = c2.err == ~0ull ? c2.out_rows : 0;
+        device_error(c);
+        drained = true;
+        break;
+      }
+      if (hit_lock) { lock_failure(lock_r); drained = true; break; }
+    }
+    if (!failed && cur_unit >= units.size()) {
+      drained = true;
+      check_trailing_lock();
+    }
+    return publish_scan_columns(produced, out);
+  }
+  int scan_grid = 0;
+
+  void lock_failure(uint32_t r) {
+    fail(range_lock_err[r], "key is locked, lock_version=" + std::to_string(range_lock_ts[r]));
+  }
+  // a conflicting lock in a range that produced no unit still fails the request
+  void check_trailing_lock() {
+    if (failed) return;
+    for (size_t r = 0; r < range_lock_err.size(); ++r)
+      if (range_lock_err[r]) { lock_failure((uint32_t)r); return; }
+  }
+
+  int publish_scan_columns(uint64_t n_rows, b2_batch* out) {
+    size_t n_out = cp.dev.n_out;
+    cols.resize(n_out);
+    const uint8_t* data = (const uint8_t*)out_data.p;
+    const uint8_t* bm = (const uint8_t*)out_bitmap.p;
+    if (out_loc == B2_LOC_HOST && n_rows) {
+      size_t per_col = n_rows * 8, per_bm = ((n_rows + 63) / 64) * 8;
+      CUDA_TRY(h_out.reserve((per_col + per_bm) * n_out));
+      uint8_t* hp = (uint8_t*)h_out.p;
+      for (size_t k = 0; k < n_out; ++k) {
+        CUDA_TRY(cudaMemcpyAsync(hp + k * per_col, data + k * out_cap * 8, per_col, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(hp + n_out * per_col + k * per_bm, bm + k * (out_cap / 8), per_bm, cudaMemcpyDeviceToHost, stream));
+      }
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      d2h_bytes += (per_col + per_bm) * n_out;
+      for (size_t k = 0; k < n_out; ++k) {
+        cols[k].data = hp + k * per_col;
+        cols[k].null_bitmap = (const uint64_t*)(hp + n_out * per_col + k * per_bm);
+      }
+    } else {
+      for (size_t k = 0; k < n_out; ++k) {
+        cols[k].data = n_rows ? data + k * out_cap * 8 : nullptr;
+        cols[k].null_bitmap = n_rows ? (const uint64_t*)(bm + k * (out_cap / 8)) : nullptr;
+      }
+    }
+    for (size_t k = 0; k < n_out; ++k) {
+      const OutCol& oc = cp.schema[cp.dev.mode == PM_SCAN ? cp.output_offsets[k] : k];
+      cols[k].kind = oc.kind; cols[k].field_tp = oc.field_tp; cols[k].field_flag = oc.field_flag; cols[k].len = n_rows;
+    }
+    out->columns = cols.data(); out->n_columns = (uint32_t)n_out; out->n_rows = n_rows;
+    out->is_drained = drained ? B2_DRAIN_DRAINED : B2_DRAIN_REMAIN;
+    stats.num_produced_rows += n_rows;
+    return failed ? last_err.status : B2_OK;
+  }
+  uint64_t d2h_bytes = 0;
+
+  // ---- PM_AGG: everything in one go ----
+  int alloc_table(unsigned int cap) {
+    size_t W = cp.dev.acc_words;
+    CUDA_TRY(tbl_keys.reserve(((size_t)cap + 1) * 8));
+    CUDA_TRY(tbl_occ.reserve(((size_t)cap + 1) * 4));
+    CUDA_TRY(tbl_acc.reserve(((size_t)cap + 1) * 8 * W));
+    CUDA_TRY(cudaMemsetAsync(tbl_occ.p, 0, ((size_t)cap + 1) * 4, stream));
+    CUDA_TRY(cudaMemsetAsync(tbl_acc.p, 0, ((size_t)cap + 1) * 8 * W, stream));
+    tbl_cap = cap;
+    return B2_OK;
+  }
+
+  int run_agg(b2_batch* out) {
+    const DevPlan& P = cp.dev;
+    uint64_t total_entries = 0;
+    for (auto& u : units) total_entries += u.e_hi - u.e_lo;
+    unsigned int cap = 1;
+    if (P.has_group) {
+      cap = 1u << 16;
+      while (cap < (1u << 22) && (uint64_t)cap < total_entries * 2) cap <<= 1;
+    }
+    size_t smem = 0;
+    uint32_t smem_slots = 0;
+    if (P.has_group) {
+      smem_slots = 2048;
+      while (smem_slots > 64 && (size_t)smem_slots * (12 + 8 * P.acc_words) > 64 * 1024) smem_slots >>= 1;
+      smem = (size_t)smem_slots * (12 + 8 * P.acc_words);
+    }
+    Counters c;
+    for (;;) {
+      int rc = alloc_table(cap);
+      if (rc) return rc;
+      rc = init_device_state();
+      if (rc) return rc;
+      int grid = scan_max_grid(PM_AGG, smem);
+      entries_scanned = 0;
+      for (size_t ui = 0; ui < units.size(); ++ui) {
+        const Unit& u = units[ui];
+        BlockView v;
+        rc = acquire_block(u.block_idx, &v);
+        if (rc) return rc;
+        ScanArgs a = base_args(u, v);
+        a.c_lo = u.e_lo; a.c_hi = u.e_hi;
+        a.tbl.keys = (unsigned long long*)tbl_keys.p; a.tbl.occ = (unsigned int*)tbl_occ.p; a.tbl.acc = (unsigned long long*)tbl_acc.p; a.tbl.cap = tbl_cap;
+        a.smem_slots = smem_slots;
+        CUDA_TRY(launch_scan(P, a, grid, smem, stream));
+        release_block(u.block_idx);
+        prefetch_after(ui);
+        entries_scanned += u.e_hi - u.e_lo;
+        stats.num_iterations++;
+      }
+      rc = read_counters(&c);
+      if (rc) return rc;
+      if (c.agg_overflow && cap < (1u << 30)) {  // group table full: grow and redo (partial results are discarded)
+        cap <<= 2;
+        for (auto& s : slots) s.block = -1;
+        continue;
+      }
+      break;
+    }
+    fill_stats(c);
+    drained = true;
+    if (c.agg_overflow) return fail(B2_ERR_UNSUPPORTED, "group table exceeded the device capacity");
+    if (c.err != ~0ull) { device_error(c); return publish_agg(0, nullptr, nullptr, nullptr, out); }
+    check_trailing_lock();
+    if (failed) return publish_agg(0, nullptr, nullptr, nullptr, out);
+    unsigned int n_groups;
+    const unsigned long long *gk = nullptr, *ga = nullptr;
+    const unsigned char* gn = nullptr;
+    if (!P.has_group) {
+      n_groups = c.live_rows > 0 ? 1 : 0;  // simple_aggr_executor.rs:141-148, 233-248
+      ga = (const unsigned long long*)tbl_acc.p;
+    } else {
+      size_t W = P.acc_words;
+      CUDA_TRY(grp_keys.reserve(((size_t)tbl_cap + 1) * 8)); CUDA_TRY(grp_null.reserve((size_t)tbl_cap + 1)); CUDA_TRY(grp_acc.reserve(((size_t)tbl_cap + 1) * 8 * W));
+      AggTable t; t.keys = (unsigned long long*)tbl_keys.p; t.occ = (unsigned int*)tbl_occ.p; t.acc = (unsigned long long*)tbl_acc.p; t.cap = tbl_cap;
+      CUDA_TRY(launch_agg_finalize(P, t, ctr(), (unsigned long long*)grp_keys.p, (unsigned char*)grp_null.p, (unsigned long long*)grp_acc.p, stream));
+      int rc = read_counters(&c);
+      if (rc) return rc;
+      n_groups = c.n_groups;
+      gk = (const unsigned long long*)grp_keys.p; gn = (const unsigned char*)grp_null.p; ga = (const unsigned long long*)grp_acc.p;
+    }
+    return publish_agg(n_groups, gk, gn, ga, out);
+  }
+
+  int publish_agg(unsigned int n_groups, const unsigned long long* gk, const unsigned char* gn, const unsigned long long* ga, b2_batch* out) {
+    const DevPlan& P = cp.dev;
+    size_t ncol = cp.schema.size();
+    res_cols.resize(ncol); res_bitmaps.resize(ncol);
+    std::vector<void*> ptrs(2 * ncol, nullptr);
+    size_t bm_bytes = (((size_t)n_groups + 63) / 64) * 8;
+    for (size_t k = 0; k < ncol; ++k) {
+      size_t esz = cp.schema[k].kind == B2_COL_DECIMAL ? 40 : 8;
+      CUDA_TRY(res_cols[k].reserve(std::max<size_t>(8, (size_t)n_groups * esz)));
+      CUDA_TRY(res_bitmaps[k].reserve(std::max<size_t>(8, bm_bytes)));
+      CUDA_TRY(cudaMemsetAsync(res_bitmaps[k].p, 0xff, std::max<size_t>(8, bm_bytes), stream));
+      ptrs[k] = res_cols[k].p; ptrs[ncol + k] = res_bitmaps[k].p;
+    }
+    if (n_groups) {
+      CUDA_TRY(res_ptrs.reserve(ptrs.size() * sizeof(void*)));
+      CUDA_TRY(cudaMemcpyAsync(res_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(launch_agg_result(P, n_groups, gk, gn, ga, (unsigned long long**)res_ptrs.p, (unsigned long long**)res_ptrs.p + ncol, stream));
+    }
+    // deliver the requested output offsets
+    size_t n_out = cp.output_offsets.size();
+    cols.assign(n_out, b2_column{});
+    size_t host_off = 0;
+    if (out_loc == B2_LOC_HOST && n_groups) {
+      size_t total = 0;
+      for (size_t i = 0; i < n_out; ++i) total += (size_t)n_groups * (cp.schema[cp.output_offsets[i]].kind == B2_COL_DECIMAL ? 40 : 8) + bm_bytes;
+      CUDA_TRY(h_out.reserve(total));
+    }
+    for (size_t i = 0; i < n_out; ++i) {
+      uint32_t k = cp.output_offsets[i];
+      const OutCol& oc = cp.schema[k];
+      size_t esz = oc.kind == B2_COL_DECIMAL ? 40 : 8;
+      cols[i].kind = oc.kind; cols[i].field_tp = oc.field_tp; cols[i].field_flag = oc.field_flag; cols[i].len = n_groups;
+      if (out_loc == B2_LOC_HOST && n_groups) {
+        uint8_t* hp = (uint8_t*)h_out.p + host_off;
+        CUDA_TRY(cudaMemcpyAsync(hp, res_cols[k].p, (size_t)n_groups * esz, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(hp + (size_t)n_groups * esz, res_bitmaps[k].p, bm_bytes, cudaMemcpyDeviceToHost, stream));
+        cols[i].data = hp; cols[i].null_bitmap = (const uint64_t*)(hp + (size_t)n_groups * esz);
+        host_off += (size_t)n_groups * esz + bm_bytes;
+        d2h_bytes += (size_t)n_groups * esz + bm_bytes;
+      } else {
+        cols[i].data = n_groups ? res_cols[k].p : nullptr;
+        cols[i].null_bitmap = n_groups ? (const uint64_t*)res_bitmaps[k].p : nullptr;
+      }
+    }
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    out->columns = cols.data(); out->n_columns = (uint32_t)n_out; out->n_rows = n_groups; out->n_warnings = 0;
+    out->is_drained = B2_DRAIN_DRAINED;
+    stats.num_produced_rows += n_groups;
+    return failed ? last_err.status : B2_OK;
+  }
+
+  int next_batch(uint64_t scan_rows, b2_batch* out) {
+    memset(out, 0, sizeof(*out));
+    cudaSetDevice(device);
+    if (failed || drained) { out->is_drained = B2_DRAIN_DRAINED; return failed ? last_err.status : B2_OK; }
+    if (!started) {
+      started = true;
+      if (cp.dev.mode == PM_SCAN) { int rc = init_device_state(); if (rc) return rc; }
+    }
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    cudaEventRecord(t0, stream);
+    int rc;
+    if (cp.dev.mode == PM_SCAN) rc = next_scan_batch(scan_rows, out);
+    else if (cp.dev.mode == PM_AGG) rc = run_agg(out);
+    else rc = fail(B2_ERR_UNSUPPORTED, "TopN is not wired on the device path yet");
+    cudaEventRecord(t1, stream);
+    cudaEventSynchronize(t1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    stats.time_processed_ns += (uint64_t)(ms * 1e6);
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    return rc;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+uint32_t b2_abi_version(void) { return B2_ABI_VERSION; }
+const char* b2_build_info(void) { return "tikv_b200 libb2copr sm_100a (CUDA " __DATE__ ")"; }
+const char* b2_last_error_message(void) { return g_last_error.c_str(); }
+
+int32_t b2_check_supported(const b2_dag_plan* plan) {
+  CompiledPlan cp;
+  std::string msg;
+  int rc = compile_plan(plan, &cp, &msg);
+  if (rc == B2_OK && cp.dev.mode == PM_TOPN) { rc = B2_ERR_UNSUPPORTED; msg = "TopN is not wired on the device path yet"; }
+  if (rc) g_last_error = msg;
+  return rc;
+}
+
+int32_t b2_exec_open(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src,
+                     const b2_exec_config* cfg, b2_exec** out) {
+  if (!plan || !src || !out) { g_last_error = "null argument"; return B2_ERR_INVALID_ARG; }
+  std::unique_ptr<b2_exec> h(new b2_exec());
+  std::string msg;
+  int rc = compile_plan(plan, &h->cp, &msg);
+  if (rc) { g_last_error = msg; return rc; }
+  if (h->cp.dev.mode == PM_TOPN) { g_last_error = "TopN is not wired on the device path yet"; return B2_ERR_UNSUPPORTED; }
+  h->device = src->device;
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) { g_last_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e) + " (the CUDA device path is required; there is no CPU fallback)"; return B2_ERR_CUDA; }
+  if (cfg && cfg->cuda_stream) { h->stream = (cudaStream_t)cfg->cuda_stream; h->own_stream = false; }
+  else { e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking); if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return B2_ERR_CUDA; } h->own_stream = true; }
+  e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return B2_ERR_CUDA; }
+  h->out_loc = cfg ? cfg->output_location : B2_LOC_DEVICE;
+  h->cp.dev.read_ts = src->read_ts;
+  h->cp.dev.isolation = src->isolation_level;
+  rc = h->setup_source(src, ranges, n_ranges);
+  if (rc) { g_last_error = h->last_err.message; return rc; }
+  *out = h.release();
+  return B2_OK;
+}
+
+int32_t b2_exec_schema(b2_exec* h, int32_t* field_tps, uint32_t* field_flags, uint32_t* n_inout) {
+  uint32_t n = (uint32_t)h->cp.output_offsets.size();
+  if (field_tps && field_flags)
+    for (uint32_t i = 0; i < n && i < *n_inout; ++i) { field_tps[i] = h->cp.schema[h->cp.output_offsets[i]].field_tp; field_flags[i] = h->cp.schema[h->cp.output_offsets[i]].field_flag; }
+  *n_inout = n;
+  return B2_OK;
+}
+
+int32_t b2_exec_next_batch(b2_exec* h, uint64_t scan_rows, b2_batch* out) { return h->next_batch(scan_rows, out); }
+
+int32_t b2_exec_collect_stats(b2_exec* h, b2_exec_stats* out) { *out = h->stats; return B2_OK; }
+int32_t b2_exec_last_error(b2_exec* h, b2_error_info* out) { *out = h->last_err; return B2_OK; }
+int32_t b2_exec_can_be_cached(b2_exec* h) { return (h->check_newer && !h->met_newer_any && !h->saw_lock) ? 1 : 0; }
+void b2_exec_close(b2_exec* h) { delete h; }
+
+int32_t b2_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src,
+                      const b2_exec_config* cfg, b2_batch* out, b2_exec** out_handle) {
+  b2_exec* h = nullptr;
+  int rc = b2_exec_open(plan, ranges, n_ranges, src, cfg, &h);
+  if (rc) return rc;
+  *out_handle = h;
+  // run to drain in one batch: aggregations always do; scans process every unit in one go when the source is one chunk
+  return h->next_batch(~0ull, out);
+}
+
+int32_t b2_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges, const uint8_t* old_prefix, uint32_t old_prefix_len,
+                           const uint8_t* new_prefix, uint32_t new_prefix_len, const b2_region_source* src, const b2_exec_config* cfg,
+                           b2_checksum_response* out, b2_exec_stats* stats) {
+  std::unique_ptr<b2_exec> h(new b2_exec());
+  h->device = src->device;
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) { g_last_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return B2_ERR_CUDA; }
+  if (cfg && cfg->cuda_stream) h->stream = (cudaStream_t)cfg->cuda_stream;
+  else { if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return B2_ERR_CUDA; h->own_stream = true; }
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return B2_ERR_CUDA;
+  h->cp.dev.mode = PM_CHECKSUM;
+  int rc = h->setup_source(src, ranges, n_ranges);
+  if (rc) { g_last_error = h->last_err.message; return rc; }
+  rc = h->init_device_state();
+  if (rc) return rc;
+  // crc register after the old prefix (checksum.rs:75-76 prefix_digest)
+  uint64_t st = ~0ull;
+  for (uint32_t i = 0; i < old_prefix_len; ++i) st = crc64_table_entry((uint8_t)(st ^ old_prefix[i])) ^ (st >> 8);
+  DevBuf d_prefix;
+  if (d_prefix.reserve(new_prefix_len + 16) != cudaSuccess) return B2_ERR_CUDA;
+  if (new_prefix_len) cudaMemcpyAsync(d_prefix.p, new_prefix, new_prefix_len, cudaMemcpyHostToDevice, h->stream);
+  for (size_t ui = 0; ui < h->units.size(); ++ui) {
+    const Unit& u = h->units[ui];
+    BlockView v;
+    rc = h->acquire_block(u.block_idx, &v);
+    if (rc) { d_prefix.release(); return rc; }
+    ChecksumArgs a;
+    memset(&a, 0, sizeof(a));
+    a.blk = v; a.dflt.blocks = (const BlockView*)h->dflt_views.p; a.dflt.n_blocks = (uint32_t)h->dblocks.size();
+    a.e_lo = u.e_lo; a.e_hi = u.e_hi; a.entry_base = h->wblocks[u.block_idx].entry_base;
+    a.read_ts = h->read_ts; a.isolation = h->isolation; a.init_state = st;
+    a.new_prefix = (const uint8_t*)d_prefix.p; a.new_prefix_len = new_prefix_len; a.old_prefix_len = old_prefix_len;
+    a.ctr = h->ctr();
+    cudaError_t ce = launch_checksum(a, 0, h->stream);
+    if (ce != cudaSuccess) { g_last_error = cudaGetErrorString(ce); d_prefix.release(); return B2_ERR_CUDA; }
+    h->release_block(u.block_idx);
+    h->prefetch_after(ui);
+    h->entries_scanned += u.e_hi - u.e_lo;
+  }
+  Counters c;
+  rc = h->read_counters(&c);
+  d_prefix.release();
+  if (rc) return rc;
+  h->fill_stats(c);
+  if (stats) *stats = h->stats;
+  if (c.err != ~0ull) {
+    if (c.bad_prefix) { g_last_error = "Wrong prefix expect"; return B2_ERR_STORAGE; }
+    h->device_error(c);
+    return h->last_err.status;
+  }
+  h->check_trailing_lock();
+  if (h->failed) return h->last_err.status;
+  out->checksum = c.checksum; out->total_kvs = c.total_kvs; out->total_bytes = c.total_bytes;
+  return B2_OK;
+}
+
+// ---- generator -----------------------------------------------------------------------------------------------
+struct b2_gen {
+  int device = 0;
+  DevBuf keys, koff, vals, voff, row_entries, row_vals, scan_tmp, d_lo, d_range, d_null;
+};
+
+int32_t b2_gen_create(int32_t device, const b2_gen_spec* spec, b2_gen** out, b2_gen_block* out_block) {
+  if (!spec || !out || !out_block) return B2_ERR_INVALID_ARG;
+  if (spec->n_cols == 0 || spec->n_cols > 24 || (spec->row_format != 1 && spec->row_format != 2) || spec->commit_ts < 12 || spec->n_rows >= (1ull << 31)) {
+    g_last_error = "generator spec out of range (1..24 columns, row format 1|2, commit_ts >= 12, < 2^31 rows)";
+    return B2_ERR_INVALID_ARG;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return B2_ERR_CUDA; }
+  std::unique_ptr<b2_gen> g(new b2_gen());
+  g->device = device;
+  auto fail = [&](int st, const std::string& m) { g_last_error = m; return st; };
+  (void)fail;
+  b2_gen_spec s = *spec;
+  size_t n = spec->n_rows, nc = spec->n_cols;
+#define GEN_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { g_last_error = std::string(#x) + ": " + cudaGetErrorString(_e); return B2_ERR_CUDA; } } while (0)
+  GEN_TRY(g->d_lo.reserve(nc * 8)); GEN_TRY(g->d_range.reserve(nc * 8)); GEN_TRY(g->d_null.reserve(nc * 4));
+  std::vector<int64_t> lo(nc, 0); std::vector<uint64_t> range(nc, 0); std::vector<uint32_t> nul(nc, 0);
+  for (size_t c = 0; c < nc; ++c) { if (spec->col_lo) lo[c] = spec->col_lo[c]; if (spec->col_range) range[c] = spec->col_range[c]; if (spec->null_per_million) nul[c] = spec->null_per_million[c]; }
+  GEN_TRY(cudaMemcpy(g->d_lo.p, lo.data(), nc * 8, cudaMemcpyHostToDevice));
+  GEN_TRY(cudaMemcpy(g->d_range.p, range.data(), nc * 8, cudaMemcpyHostToDevice));
+  GEN_TRY(cudaMemcpy(g->d_null.p, nul.data(), nc * 4, cudaMemcpyHostToDevice));
+  s.col_lo = (const int64_t*)g->d_lo.p; s.col_range = (const uint64_t*)g->d_range.p; s.null_per_million = (const uint32_t*)g->d_null.p;
+  GEN_TRY(g->row_entries.reserve((n + 1) * 4)); GEN_TRY(g->row_vals.reserve((n + 1) * 4));
+  GEN_TRY(cudaMemset(g->row_entries.p, 0, (n + 1) * 4)); GEN_TRY(cudaMemset(g->row_vals.p, 0, (n + 1) * 4));
+  GEN_TRY(launch_gen_sizes(s, (uint32_t*)g->row_entries.p, (uint32_t*)g->row_vals.p, 0));
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (uint32_t*)g->row_entries.p, (uint32_t*)g->row_entries.p, (int)(n + 1));
+  GEN_TRY(g->scan_tmp.reserve(tmp_bytes + 16));
+  // 32-bit prefix sums: value heap must stay below 4 GiB (u32 offsets of the block format)
+  GEN_TRY(cub::DeviceScan::ExclusiveSum(g->scan_tmp.p, tmp_bytes, (uint32_t*)g->row_entries.p, (uint32_t*)g->row_entries.p, (int)(n + 1)));
+  GEN_TRY(cub::DeviceScan::ExclusiveSum(g->scan_tmp.p, tmp_bytes, (uint32_t*)g->row_vals.p, (uint32_t*)g->row_vals.p, (int)(n + 1)));
+  uint32_t n_entries = 0, val_bytes = 0;
+  GEN_TRY(cudaMemcpy(&n_entries, (uint32_t*)g->row_entries.p + n, 4, cudaMemcpyDeviceToHost));
+  GEN_TRY(cudaMemcpy(&val_bytes, (uint32_t*)g->row_vals.p + n, 4, cudaMemcpyDeviceToHost));
+  // guard against u32 wrap of the value heap (rows are < 300 bytes each)
+  if ((uint64_t)n * 16 > 0xffffffffull && val_bytes < n) { g_last_error = "generated value heap exceeds 4 GiB; use more, smaller blocks"; return B2_ERR_INVALID_ARG; }
+  uint64_t key_bytes = (uint64_t)n_entries * 35;
+  if (key_bytes > 0xfffffff0ull) { g_last_error = "generated key heap exceeds 4 GiB; use more, smaller blocks"; return B2_ERR_INVALID_ARG; }
+  GEN_TRY(g->keys.reserve(((size_t)key_bytes + 31) & ~15ull)); GEN_TRY(g->vals.reserve(((size_t)val_bytes + 31) & ~15ull));
+  GEN_TRY(g->koff.reserve(((size_t)n_entries + 1) * 4)); GEN_TRY(g->voff.reserve(((size_t)n_entries + 1) * 4));
+  GenArgs a;
+  a.spec = s; a.keys = (uint8_t*)g->keys.p; a.koff = (uint32_t*)g->koff.p; a.vals = (uint8_t*)g->vals.p; a.voff = (uint32_t*)g->voff.p;
+  a.row_entry_off = (const uint32_t*)g->row_entries.p; a.row_val_off = (const uint32_t*)g->row_vals.p;
+  GEN_TRY(launch_gen_write(a, 0));
+  GEN_TRY(cudaDeviceSynchronize());
+  g->row_entries.release(); g->row_vals.release(); g->scan_tmp.release();
+  memset(out_block, 0, sizeof(*out_block));
+  out_block->block.keys = (const uint8_t*)g->keys.p; out_block->block.key_offs = (const uint32_t*)g->koff.p;
+  out_block->block.vals = (const uint8_t*)g->vals.p; out_block->block.val_offs = (const uint32_t*)g->voff.p;
+  out_block->block.n = n_entries;
+  out_block->key_bytes = key_bytes; out_block->val_bytes = val_bytes; out_block->n_user_keys = n;
+  *out = g.release();
+  return B2_OK;
+#undef GEN_TRY
+}
+
+void b2_gen_destroy(b2_gen* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  for (DevBuf* b : {&g->keys, &g->koff, &g->vals, &g->voff, &g->row_entries, &g->row_vals, &g->scan_tmp, &g->d_lo, &g->d_range, &g->d_null}) b->release();
+  delete g;
+}
+
+int32_t b2_copy_to_host(int32_t device, void* dst, const void* src_device, uint64_t bytes) {
+  if (cudaSetDevice(device) != cudaSuccess) return B2_ERR_CUDA;
+  cudaError_t e = cudaMemcpy(dst, src_device, bytes, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return B2_ERR_CUDA; }
+  return B2_OK;
+}
+int32_t b2_copy_to_device(int32_t device, void* dst_device, const void* src, uint64_t bytes) {
+  if (cudaSetDevice(device) != cudaSuccess) return B2_ERR_CUDA;
+  cudaError_t e = cudaMemcpy(dst_device, src, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return B2_ERR_CUDA; }
+  return B2_OK;
+}
+int32_t b2_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+void* b2_host_alloc_pinned(uint64_t bytes) { void* p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr; return p; }
+void b2_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

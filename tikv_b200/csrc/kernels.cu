@@ -1,0 +1,690 @@
+// sm_100a kernels of the coprocessor hot path.
+//
+//   scan_kernel<PM_SCAN>  MVCC forward scan -> row decode -> RPN selection -> ordered compaction into columns
+//                         (BatchTableScan + BatchSelection; table_scan_executor.rs, selection_executor.rs)
+//   scan_kernel<PM_AGG>   same front end, then COUNT/SUM/AVG into a per-CTA shared-memory group table that is
+//                         flushed into the HBM group table (BatchSimpleAggregation / BatchFastHashAggregation)
+//   checksum_kernel       MVCC scan -> CRC-64/XZ per KV -> XOR fold (src/coprocessor/checksum.rs:59-114)
+//   gen_*                 synthetic region generator (tooling)
+//
+// One thread owns one CF_WRITE entry; only the thread sitting on the first version of a user key does work for
+// that key (walks its versions, decodes the row).  CTAs are persistent and pull 256-entry tiles.
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void report_err(Counters* c, uint64_t global_entry, int code) {
+  atomicMin(&c->err, (unsigned long long)((global_entry << 8) | (unsigned)code));
+}
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  return *(const volatile unsigned long long*)p;
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- HBM group table ----------------------------------------------------------------------------------
+// returns slot index, or 0xffffffff when the table is full
+__device__ unsigned int table_find_or_insert(const AggTable& t, uint64_t key, bool is_null) {
+  if (is_null) {
+    if (ld_acquire_u32(&t.occ[t.cap]) != 2) atomicExch(&t.occ[t.cap], 2u);
+    return t.cap;
+  }
+  unsigned int mask = t.cap - 1;
+  unsigned int s = (unsigned int)mix64(key) & mask;
+  for (unsigned int probes = 0; probes < t.cap; ++probes) {
+    unsigned int o = ld_acquire_u32(&t.occ[s]);
+    if (o == 0) {
+      o = atomicCAS(&t.occ[s], 0u, 1u);
+      if (o == 0) {
+        t.keys[s] = key;
+        st_release_u32(&t.occ[s], 2u);
+        return s;
+      }
+    }
+    while (o == 1) o = ld_acquire_u32(&t.occ[s]);
+    if (t.keys[s] == key) return s;
+    s = (s + 1) & mask;
+  }
+  return 0xffffffffu;
+}
+
+// accumulate one aggregate argument into `acc` words (global or shared)
+//   COUNT: [cnt]            SUM/AVG(int): [cnt, sum of low 32 bits, sum of high 32 bits]   SUM/AVG(real): [cnt, f64]
+// The two 32-bit limb sums cannot overflow below 2^32 rows and give the exact i128 sum = hi * 2^32 + lo.
+template <typename Acc>
+__device__ __forceinline__ void acc_update(Acc* acc, const DevAgg& g, const Value& v) {
+  if (v.null) return;
+  atomicAdd(&acc[g.acc_off], 1ull);
+  if (g.kind == 0) return;
+  if (g.arg_et == 1) {
+    atomicAdd(reinterpret_cast<double*>(&acc[g.acc_off + 1]), bits_f64(v.bits));
+  } else {
+    unsigned long long lo = v.bits & 0xffffffffull;
+    unsigned long long hi = g.arg_unsigned ? (v.bits >> 32) : (unsigned long long)((long long)v.bits >> 32);
+    atomicAdd(&acc[g.acc_off + 1], lo);
+    atomicAdd(&acc[g.acc_off + 2], hi);
+  }
+}
+
+// ---- the fused scan kernel -------------------------------------------------------------------------------
+struct SmemTable {  // per-CTA group table (dynamic shared memory): keys | acc | occ
+  unsigned long long* keys;
+  unsigned long long* acc;
+  unsigned int* occ;
+  unsigned int slots;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TILE) scan_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned int s_warp_cnt[TILE / 32];
+  __shared__ unsigned long long s_base;
+  __shared__ unsigned int s_tbl_used;
+
+  const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t n_tiles = (A.c_hi - A.c_lo + TILE - 1) / TILE;
+  const unsigned long long out_base = MODE == PM_SCAN ? A.ctr->out_base : 0ull;  // stable during this launch
+
+  SmemTable st;
+  st.slots = 0;
+  if (MODE == PM_AGG && P.has_group && A.smem_slots) {
+    st.slots = A.smem_slots;
+    st.keys = reinterpret_cast<unsigned long long*>(dyn_smem);
+    st.acc = st.keys + st.slots;
+    st.occ = reinterpret_cast<unsigned int*>(st.acc + (size_t)st.slots * P.acc_words);
+    for (unsigned int i = tid; i < st.slots; i += TILE) st.occ[i] = 0;
+    for (unsigned int i = tid; i < st.slots * P.acc_words; i += TILE) st.acc[i] = 0;
+    if (tid == 0) s_tbl_used = 0;
+    __syncthreads();
+  }
+
+  // per-thread statistics, reduced once at the end
+  unsigned long long t_keys = 0, t_size = 0, t_live = 0, t_dflt = 0;
+  unsigned int t_newer = 0;
+  // no-group aggregation: per-thread partial accumulators (registers), reduced at the end
+  unsigned long long t_acc[MODE == PM_AGG ? MAX_ACC_WORDS : 1];
+  if (MODE == PM_AGG) {
+#pragma unroll
+    for (int i = 0; i < MAX_ACC_WORDS; ++i) t_acc[i] = 0;
+  }
+
+  for (uint32_t iter = 0;; ++iter) {
+    uint32_t tile;
+    if (MODE == PM_SCAN) {
+      // tiles are claimed in order so that the decoupled look-back below only ever waits on running CTAs
+      if (tid == 0) s_tile = (unsigned int)atomicAdd(&A.tile_status[n_tiles], 1ull);
+      __syncthreads();
+      tile = s_tile;
+    } else {
+      tile = blockIdx.x + iter * gridDim.x;
+    }
+    if (tile >= n_tiles) break;
+    const uint32_t e = A.c_lo + tile * TILE + tid;
+
+    bool live = false;
+    Row row;
+    Cells cells;
+    if (e < A.c_hi) {
+      bool start = (e == A.e_lo) || !same_user_key(A.blk, e - 1, e);
+      if (start) {
+        RunOut ro;
+        resolve_run(A.blk, e, A.e_hi, P.read_ts, P.isolation, A.dflt, &ro);
+        t_newer |= ro.met_newer;
+        t_dflt += ro.dflt_lookup;
+        if (ro.err) {
+          report_err(A.ctr, A.entry_base + e, ro.err);
+        } else if (ro.found) {
+          uint32_t ko = A.blk.koff[e], kl = A.blk.koff[e + 1] - ko;
+          t_keys += 1;
+          t_size += (kl - 8) + ro.val_len;
+          row.enc_key = A.blk.keys + ko;
+          row.enc_key_len = kl - 8;
+          row.commit_ts = ro.commit_ts;
+          int err = row_open(ro.val, ro.val_len, &row.rv);
+          if (!err) err = row_split(P, row, cells);
+          bool keep = false;
+          if (!err) err = eval_conds(P, row, cells, &keep);
+          if (err) report_err(A.ctr, A.entry_base + e, err);
+          else live = keep;
+        }
+      }
+    }
+    t_live += live;
+
+    if (MODE == PM_SCAN) {
+      // ---- ordered compaction: ballot/popc inside the warp, smem across warps, look-back across tiles ----
+      unsigned int bal = __ballot_sync(0xffffffffu, live);
+      unsigned int lane_off = __popc(bal & ((1u << lane) - 1));
+      if (lane == 0) s_warp_cnt[wid] = __popc(bal);
+      __syncthreads();
+      unsigned int warp_off = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < TILE / 32; ++w) {
+        unsigned int c = s_warp_cnt[w];
+        if (w < (int)wid) warp_off += c;
+        total += c;
+      }
+      if (tid == 0) {
+        const unsigned long long F_AGG = 1ull << 62, F_INC = 2ull << 62, VMASK = (1ull << 62) - 1;
+        unsigned long long excl = 0;
+        if (tile == 0) {
+          atomicExch(&A.tile_status[0], F_INC | total);
+        } else {
+          atomicExch(&A.tile_status[tile], F_AGG | total);
+          uint32_t j = tile - 1;
+          for (;;) {
+            unsigned long long s = ld_volatile_u64(&A.tile_status[j]);
+            if ((s >> 62) == 0) continue;
+            excl += s & VMASK;
+            if ((s >> 62) == 2) break;
+            --j;
+          }
+          atomicExch(&A.tile_status[tile], F_INC | (excl + total));
+        }
+        s_base = excl;
+        if (total) atomicAdd(&A.ctr->out_rows, (unsigned long long)total);
+      }
+      __syncthreads();
+      if (live) {
+        unsigned long long idx = out_base + s_base + warp_off + lane_off;
+        if (idx < A.out_cap) {
+          for (int k = 0; k < P.n_out; ++k) {
+            Value v;
+            int err = cell_value(P, row, cells, P.out_cols[k], &v);
+            if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; v.bits = 0; }
+            A.out_data[(size_t)k * A.out_cap + idx] = v.null ? 0ull : v.bits;
+            if (v.null) atomicAnd(&A.out_bitmap[(size_t)k * (A.out_cap / 64) + (idx >> 6)], ~(1ull << (idx & 63)));
+          }
+        }
+      }
+      __syncthreads();  // s_warp_cnt / s_base reused by the next tile
+    } else if (MODE == PM_AGG) {
+      if (live) {
+        if (!P.has_group) {
+          // BatchSimpleAggregation: one state set; accumulate privately
+          for (int a = 0; a < P.n_aggs; ++a) {
+            const DevAgg g = P.aggs[a];
+            Value v;
+            int err = eval_expr(P, g.arg, row, cells, &v, nullptr);
+            if (err) { report_err(A.ctr, A.entry_base + e, err); continue; }
+            if (v.null) continue;
+            t_acc[g.acc_off] += 1;
+            if (g.kind == 0) continue;
+            if (g.arg_et == 1) {
+              t_acc[g.acc_off + 1] = f64_bits(bits_f64(t_acc[g.acc_off + 1]) + bits_f64(v.bits));
+            } else {
+              t_acc[g.acc_off + 1] += v.bits & 0xffffffffull;
+              t_acc[g.acc_off + 2] += g.arg_unsigned ? (v.bits >> 32) : (unsigned long long)((long long)v.bits >> 32);
+            }
+          }
+        } else {
+          // BatchFastHashAggregation: group key -> slot (calc_groups_each_row), then per-aggregate update
+          Value gk;
+          int err = eval_expr(P, P.group, row, cells, &gk, nullptr);
+          if (err) report_err(A.ctr, A.entry_base + e, err);
+          else {
+            if (P.group_et == 1 && !gk.null && bits_f64(gk.bits) == 0.0) gk.bits = 0;  // -0.0 and 0.0 are one group
+            unsigned long long* acc = nullptr;  // shared-memory accumulators when the key is resident in the CTA table
+            unsigned int gslot = 0xffffffffu;
+            if (st.slots && !gk.null) {
+              unsigned int mask = st.slots - 1, s = (unsigned int)(mix64(gk.bits) >> 20) & mask;
+              for (int probes = 0; probes < 8; ++probes) {
+                unsigned int o = *(volatile unsigned int*)&st.occ[s];
+                if (o == 0 && *(volatile unsigned int*)&s_tbl_used < (st.slots >> 1) + (st.slots >> 2)) {
+                  o = atomicCAS(&st.occ[s], 0u, 1u);
+                  if (o == 0) {
+                    st.keys[s] = gk.bits;
+                    __threadfence_block();
+                    atomicExch(&st.occ[s], 2u);
+                    atomicAdd(&s_tbl_used, 1u);
+                    acc = st.acc + (size_t)s * P.acc_words;
+                    break;
+                  }
+                }
+                if (o == 0) break;  // table is at its load limit: go to HBM
+                while (o == 1) o = *(volatile unsigned int*)&st.occ[s];
+                if (*(volatile unsigned long long*)&st.keys[s] == gk.bits) { acc = st.acc + (size_t)s * P.acc_words; break; }
+                s = (s + 1) & mask;
+              }
+            }
+            if (!acc) {
+              gslot = table_find_or_insert(A.tbl, gk.bits, gk.null);
+              if (gslot == 0xffffffffu) atomicExch(&A.ctr->agg_overflow, 1u);
+            }
+            if (acc || gslot != 0xffffffffu) {
+              for (int a = 0; a < P.n_aggs; ++a) {
+                const DevAgg g = P.aggs[a];
+                Value v;
+                int err2 = eval_expr(P, g.arg, row, cells, &v, nullptr);
+                if (err2) { report_err(A.ctr, A.entry_base + e, err2); continue; }
+                if (acc) acc_update(acc, g, v);
+                else acc_update(A.tbl.acc + (size_t)gslot * P.acc_words, g, v);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue: flush CTA-private state ----
+  if (MODE == PM_AGG) {
+    if (!P.has_group) {
+      // warp-shuffle tree, then one atomic per warp into slot 0 of the HBM table
+      for (int w = 0; w < P.acc_words; ++w) {
+        bool is_real = false;
+        for (int a = 0; a < P.n_aggs; ++a)
+          if (P.aggs[a].kind != 0 && P.aggs[a].arg_et == 1 && P.aggs[a].acc_off + 1 == w) is_real = true;
+        unsigned long long x = t_acc[w];
+        if (is_real) {
+          double d = bits_f64(x);
+          for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+          if (lane == 0 && d != 0.0) atomicAdd(reinterpret_cast<double*>(&A.tbl.acc[w]), d);
+        } else {
+          for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+          if (lane == 0 && x) atomicAdd(&A.tbl.acc[w], x);
+        }
+      }
+    } else if (st.slots) {
+      __syncthreads();
+      for (unsigned int s = tid; s < st.slots; s += TILE) {
+        if (st.occ[s] != 2) continue;
+        unsigned int gslot = table_find_or_insert(A.tbl, st.keys[s], false);
+        if (gslot == 0xffffffffu) { atomicExch(&A.ctr->agg_overflow, 1u); continue; }
+        for (int a = 0; a < P.n_aggs; ++a) {
+          const DevAgg g = P.aggs[a];
+          const unsigned long long* src = st.acc + (size_t)s * P.acc_words + g.acc_off;
+          unsigned long long* dst = A.tbl.acc + (size_t)gslot * P.acc_words + g.acc_off;
+          if (src[0] == 0) continue;
+          atomicAdd(&dst[0], src[0]);
+          if (g.kind == 0) continue;
+          if (g.arg_et == 1) atomicAdd(reinterpret_cast<double*>(&dst[1]), bits_f64(src[1]));
+          else { atomicAdd(&dst[1], src[1]); atomicAdd(&dst[2], src[2]); }
+        }
+      }
+    }
+  }
+  // statistics
+  for (int off = 16; off > 0; off >>= 1) {
+    t_keys += __shfl_xor_sync(0xffffffffu, t_keys, off);
+    t_size += __shfl_xor_sync(0xffffffffu, t_size, off);
+    t_live += __shfl_xor_sync(0xffffffffu, t_live, off);
+    t_dflt += __shfl_xor_sync(0xffffffffu, t_dflt, off);
+    t_newer |= __shfl_xor_sync(0xffffffffu, t_newer, off);
+  }
+  if (lane == 0) {
+    if (t_keys) atomicAdd(&A.ctr->processed_keys, t_keys);
+    if (t_size) atomicAdd(&A.ctr->processed_size, t_size);
+    if (t_live) atomicAdd(&A.ctr->live_rows, t_live);
+    if (t_dflt) atomicAdd(&A.ctr->default_lookups, t_dflt);
+    if (t_newer) atomicOr(&A.ctr->met_newer, 1u);
+  }
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+int scan_max_grid(int mode, size_t smem) {
+  int per_sm = 0;
+  cudaError_t e;
+  if (mode == PM_SCAN) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_SCAN>, TILE, smem);
+  else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_AGG>, TILE, smem);
+  if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * num_sms();
+}
+
+cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if (a.c_hi <= a.c_lo) return cudaSuccess;
+  uint32_t n_tiles = (a.c_hi - a.c_lo + TILE - 1) / TILE;
+  if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
+  if (plan.mode == PM_SCAN) {
+    scan_kernel<PM_SCAN><<<grid, TILE, smem, s>>>(plan, a);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_kernel<PM_AGG><<<grid, TILE, smem, s>>>(plan, a);
+  }
+  return cudaGetLastError();
+}
+
+// ---- aggregation result materialisation ---------------------------------------------------------------------
+__global__ void agg_finalize_kernel(const __grid_constant__ DevPlan P, AggTable t, Counters* ctr, unsigned long long* out_keys,
+                                    unsigned char* out_key_null, unsigned long long* out_acc) {
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > t.cap) return;
+  if (t.occ[i] != 2) return;
+  unsigned int g = atomicAdd(&ctr->n_groups, 1u);
+  out_keys[g] = i == t.cap ? 0ull : t.keys[i];
+  out_key_null[g] = i == t.cap;
+  for (int w = 0; w < P.acc_words; ++w) out_acc[(size_t)g * P.acc_words + w] = t.acc[(size_t)i * P.acc_words + w];
+}
+
+cudaError_t launch_agg_finalize(const DevPlan& plan, const AggTable& t, Counters* ctr, unsigned long long* out_keys, unsigned char* out_key_null,
+                                unsigned long long* out_acc, cudaStream_t s) {
+  unsigned int n = t.cap + 1;
+  agg_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(plan, t, ctr, out_keys, out_key_null, out_acc);
+  return cudaGetLastError();
+}
+
+// one thread per group: accumulators -> result columns [aggregates..., group key] (fast_hash_aggr_executor.rs:383-413)
+__global__ void agg_result_kernel(const __grid_constant__ DevPlan P, unsigned int n_groups, const unsigned long long* g_keys, const unsigned char* g_null,
+                                  const unsigned long long* g_acc, unsigned long long** col_data, unsigned long long** col_bitmap) {
+  unsigned int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  int c = 0;
+  const unsigned long long* acc = g_acc + (size_t)g * P.acc_words;
+  for (int a = 0; a < P.n_aggs; ++a) {
+    const DevAgg ag = P.aggs[a];
+    unsigned long long cnt = acc[ag.acc_off];
+    if (ag.kind == 0 || ag.kind == 2) { col_data[c][g] = cnt; ++c; }  // COUNT, or AVG's count column
+    if (ag.kind == 1 || ag.kind == 2) {
+      bool has = cnt != 0;
+      if (ag.arg_et == 1) col_data[c][g] = has ? acc[ag.acc_off + 1] : 0ull;
+      else {
+        b2_decimal d;
+        if (has) limbs_to_decimal(acc[ag.acc_off + 1], acc[ag.acc_off + 2], ag.arg_unsigned, &d);
+        else { d.int_cnt = 1; d.frac_cnt = 0; d.result_frac_cnt = 0; d.negative = 0; for (int i = 0; i < 9; ++i) d.word_buf[i] = 0; }
+        reinterpret_cast<b2_decimal*>(col_data[c])[g] = d;
+      }
+      if (!has) atomicAnd(&col_bitmap[c][g >> 6], ~(1ull << (g & 63)));
+      ++c;
+    }
+  }
+  if (P.has_group) {
+    col_data[c][g] = g_null[g] ? 0ull : g_keys[g];
+    if (g_null[g]) atomicAnd(&col_bitmap[c][g >> 6], ~(1ull << (g & 63)));
+  }
+}
+
+cudaError_t launch_agg_result(const DevPlan& plan, unsigned int n_groups, const unsigned long long* g_keys, const unsigned char* g_null,
+                              const unsigned long long* g_acc, unsigned long long** col_data, unsigned long long** col_bitmap, cudaStream_t s) {
+  if (!n_groups) return cudaSuccess;
+  agg_result_kernel<<<(n_groups + 127) / 128, 128, 0, s>>>(plan, n_groups, g_keys, g_null, g_acc, col_data, col_bitmap);
+  return cudaGetLastError();
+}
+
+// ---- checksum ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE) checksum_kernel(const __grid_constant__ ChecksumArgs A) {
+  __shared__ unsigned long long s_tab[256];
+  __shared__ unsigned long long s_red[3][TILE / 32];
+  const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  s_tab[tid] = crc64_table_entry(tid);
+  __syncthreads();
+  const uint32_t n = A.e_hi - A.e_lo;
+  const uint32_t n_tiles = (n + TILE - 1) / TILE;
+  unsigned long long x = 0, kvs = 0, bytes = 0;
+  unsigned int newer = 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t e = A.e_lo + tile * TILE + tid;
+    if (e >= A.e_hi) continue;
+    bool start = (e == A.e_lo) || !same_user_key(A.blk, e - 1, e);
+    if (!start) continue;
+    RunOut ro;
+    resolve_run(A.blk, e, A.e_hi, A.read_ts, A.isolation, A.dflt, &ro);
+    newer |= ro.met_newer;
+    if (ro.err) { report_err(A.ctr, A.entry_base + e, ro.err); continue; }
+    if (!ro.found) continue;
+    const uint8_t* ek = A.blk.keys + A.blk.koff[e];
+    uint32_t ekl = A.blk.koff[e + 1] - A.blk.koff[e] - 8;
+    int rawlen = raw_key_len(ek, ekl);
+    if (rawlen < 0) { report_err(A.ctr, A.entry_base + e, DE_BAD_USER_KEY); continue; }
+    bool ok = (uint32_t)rawlen >= A.new_prefix_len;
+    for (uint32_t j = 0; ok && j < A.new_prefix_len; ++j) ok = raw_at(ek, j) == A.new_prefix[j];
+    if (!ok) { atomicExch(&A.ctr->bad_prefix, 1u); report_err(A.ctr, A.entry_base + e, DE_BAD_RECORD_KEY); continue; }
+    unsigned long long c = A.init_state;
+    for (uint32_t j = A.new_prefix_len; j < (uint32_t)rawlen; ++j) c = s_tab[(uint8_t)(c ^ raw_at(ek, j))] ^ (c >> 8);
+    for (uint32_t j = 0; j < ro.val_len; ++j) c = s_tab[(uint8_t)(c ^ ro.val[j])] ^ (c >> 8);
+    x ^= ~c;
+    kvs += 1;
+    bytes += (unsigned long long)rawlen + ro.val_len + A.old_prefix_len - A.new_prefix_len;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    x ^= __shfl_xor_sync(0xffffffffu, x, off);
+    kvs += __shfl_xor_sync(0xffffffffu, kvs, off);
+    bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
+    newer |= __shfl_xor_sync(0xffffffffu, newer, off);
+  }
+  if (lane == 0) { s_red[0][wid] = x; s_red[1][wid] = kvs; s_red[2][wid] = bytes; if (newer) atomicOr(&A.ctr->met_newer, 1u); }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long X = 0, K = 0, B = 0;
+    for (int w = 0; w < TILE / 32; ++w) { X ^= s_red[0][w]; K += s_red[1][w]; B += s_red[2][w]; }
+    if (K) { atomicXor(&A.ctr->checksum, X); atomicAdd(&A.ctr->total_kvs, K); atomicAdd(&A.ctr->total_bytes, B); }
+  }
+}
+
+cudaError_t launch_checksum(const ChecksumArgs& a, int grid, cudaStream_t s) {
+  if (a.e_hi <= a.e_lo) return cudaSuccess;
+  uint32_t n_tiles = (a.e_hi - a.e_lo + TILE - 1) / TILE;
+  if (grid <= 0) grid = num_sms() * 4;
+  if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
+  checksum_kernel<<<grid, TILE, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ---- range bounds: lower_bound of each encoded key in each block -------------------------------------------
+__global__ void bounds_kernel(const BlockView* blocks, uint32_t n_blocks, const uint8_t* bounds, const uint32_t* bound_offs, uint32_t n_bounds, uint32_t* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_blocks * n_bounds) return;
+  uint32_t bi = i / n_bounds, qi = i % n_bounds;
+  const BlockView b = blocks[bi];
+  const uint8_t* q = bounds + bound_offs[qi];
+  uint32_t qn = bound_offs[qi + 1] - bound_offs[qi];
+  uint32_t lo = 0, hi = b.n;
+  while (lo < hi) {
+    uint32_t mid = lo + (hi - lo) / 2;
+    if (bytes_cmp(b.keys + b.koff[mid], b.koff[mid + 1] - b.koff[mid], q, qn) < 0) lo = mid + 1; else hi = mid;
+  }
+  out[i] = lo;
+}
+
+cudaError_t launch_bounds_search(const BlockView* blocks, uint32_t n_blocks, const uint8_t* bounds, const uint32_t* bound_offs, uint32_t n_bounds,
+                                 uint32_t* out, cudaStream_t s) {
+  uint32_t n = n_blocks * n_bounds;
+  if (!n) return cudaSuccess;
+  bounds_kernel<<<(n + 63) / 64, 64, 0, s>>>(blocks, n_blocks, bounds, bound_offs, n_bounds, out);
+  return cudaGetLastError();
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, unsigned long long v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+cudaError_t launch_fill_u64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  fill_u64_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, v, n);
+  return cudaGetLastError();
+}
+
+// ---- synthetic region generator ---------------------------------------------------------------------------------
+__host__ __device__ inline uint64_t gen_mix(uint64_t seed, uint64_t handle, uint64_t salt) {
+  return mix64(seed ^ (handle * 0x9E3779B97F4A7C15ull) ^ ((salt + 1) * 0xBF58476D1CE4E5B9ull));
+}
+struct GenRow { int kind; /*0 plain,1 extra versions,2 delete,3 lock record*/ uint32_t entries; };
+__device__ __forceinline__ GenRow gen_row_kind(const b2_gen_spec& s, uint64_t handle) {
+  uint64_t r = gen_mix(s.seed, handle, 1000) % 1000000ull;
+  GenRow g;
+  if (r < s.extra_versions_per_million) { g.kind = 1; g.entries = 3; }
+  else if (r < (uint64_t)s.extra_versions_per_million + s.delete_per_million) { g.kind = 2; g.entries = 2; }
+  else if (r < (uint64_t)s.extra_versions_per_million + s.delete_per_million + s.lock_rec_per_million) { g.kind = 3; g.entries = 2; }
+  else { g.kind = 0; g.entries = 1; }
+  return g;
+}
+__device__ __forceinline__ bool gen_value(const b2_gen_spec& s, uint64_t handle, uint32_t c, uint64_t version_salt, int64_t* v) {
+  if (s.null_per_million && s.null_per_million[c]) {
+    if (gen_mix(s.seed, handle, 500 + c) % 1000000ull < s.null_per_million[c]) return false;
+  }
+  uint64_t x = gen_mix(s.seed + version_salt, handle, c);
+  uint64_t range = s.col_range ? s.col_range[c] : 0;
+  int64_t lo = s.col_lo ? s.col_lo[c] : 0;
+  *v = range ? (int64_t)((uint64_t)lo + x % range) : (int64_t)x;
+  return true;
+}
+__device__ __forceinline__ uint32_t int_width(int64_t v) {
+  if (v >= -128 && v <= 127) return 1;
+  if (v >= -32768 && v <= 32767) return 2;
+  if (v >= -2147483648ll && v <= 2147483647ll) return 4;
+  return 8;
+}
+__device__ __forceinline__ uint32_t varint_len(uint64_t v) { uint32_t n = 1; while (v >= 0x80) { v >>= 7; ++n; } return n; }
+__device__ __forceinline__ uint32_t put_varint(uint8_t* p, uint64_t v) { uint32_t n = 0; while (v >= 0x80) { p[n++] = (uint8_t)(v | 0x80); v >>= 7; } p[n++] = (uint8_t)v; return n; }
+__device__ __forceinline__ uint64_t zigzag(int64_t v) { uint64_t u = (uint64_t)v << 1; return v < 0 ? ~u : u; }
+
+// size (write=false) or bytes (write=true) of the row value of `handle`
+__device__ uint32_t gen_row_bytes(const b2_gen_spec& s, uint64_t handle, uint64_t version_salt, uint8_t* out, bool write) {
+  uint32_t n = 0;
+  if (s.row_format == 2) {
+    uint32_t nn = 0, nul = 0, total = 0;
+    for (uint32_t c = 0; c < s.n_cols; ++c) { int64_t v; if (gen_value(s, handle, c, version_salt, &v)) { ++nn; total += int_width(v); } else ++nul; }
+    n = 6 + nn + nul + 2 * nn + total;
+    if (!write) return n;
+    out[0] = 128; out[1] = 0; out[2] = (uint8_t)nn; out[3] = (uint8_t)(nn >> 8); out[4] = (uint8_t)nul; out[5] = (uint8_t)(nul >> 8);
+    uint32_t p_ids = 6, p_null = 6 + nn, p_off = 6 + nn + nul, p_val = p_off + 2 * nn, end = 0;
+    for (uint32_t c = 0; c < s.n_cols; ++c) {
+      int64_t v;
+      if (gen_value(s, handle, c, version_salt, &v)) {
+        uint32_t w = int_width(v);
+        out[p_ids++] = (uint8_t)(c + 1);
+        for (uint32_t i = 0; i < w; ++i) out[p_val + end + i] = (uint8_t)((uint64_t)v >> (8 * i));
+        end += w;
+        out[p_off] = (uint8_t)end; out[p_off + 1] = (uint8_t)(end >> 8); p_off += 2;
+      } else out[p_null++] = (uint8_t)(c + 1);
+    }
+    return n;
+  }
+  // row format v1: [VAR_INT colid][VAR_INT zigzag | NIL]
+  for (uint32_t c = 0; c < s.n_cols; ++c) {
+    int64_t v;
+    bool nonnull = gen_value(s, handle, c, version_salt, &v);
+    if (write) { out[n] = 8; n += 1 + put_varint(out + n + 1, zigzag((int64_t)(c + 1))); }
+    else n += 1 + varint_len(zigzag((int64_t)(c + 1)));
+    if (nonnull) { if (write) { out[n] = 8; n += 1 + put_varint(out + n + 1, zigzag(v)); } else n += 1 + varint_len(zigzag(v)); }
+    else { if (write) out[n] = 0; n += 1; }
+  }
+  return n;
+}
+// write record sizes: type + varint(start_ts) + ['v' len row] (+ 'l' u64 varint for lock records)
+__device__ __forceinline__ uint32_t put_write_header(uint8_t* p, uint8_t type, uint64_t start_ts, bool write) {
+  if (write) { p[0] = type; return 1 + put_varint(p + 1, start_ts); }
+  return 1 + varint_len(start_ts);
+}
+
+__global__ void gen_sizes_kernel(const __grid_constant__ b2_gen_spec s, uint32_t* row_entries, uint32_t* row_val_bytes) {
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= s.n_rows) return;
+  uint64_t handle = s.first_handle + r;
+  GenRow g = gen_row_kind(s, handle);
+  uint32_t row = gen_row_bytes(s, handle, 0, nullptr, false);
+  uint32_t bytes = 0;
+  if (g.kind == 0) bytes = put_write_header(nullptr, 'P', s.commit_ts - 1, false) + 2 + row;
+  else if (g.kind == 1) {
+    bytes = put_write_header(nullptr, 'P', s.newer_ts - 1, false) + 2 + gen_row_bytes(s, handle, 77, nullptr, false);
+    bytes += put_write_header(nullptr, 'P', s.commit_ts - 1, false) + 2 + row;
+    bytes += put_write_header(nullptr, 'P', s.commit_ts - 11, false) + 2 + gen_row_bytes(s, handle, 99, nullptr, false);
+  } else if (g.kind == 2) {
+    bytes = put_write_header(nullptr, 'D', s.commit_ts - 1, false);
+    bytes += put_write_header(nullptr, 'P', s.commit_ts - 11, false) + 2 + gen_row_bytes(s, handle, 99, nullptr, false);
+  } else {
+    bytes = put_write_header(nullptr, 'L', s.commit_ts, false) + 1 + 8 + 1;
+    bytes += put_write_header(nullptr, 'P', s.commit_ts - 1, false) + 2 + row;
+  }
+  row_entries[r] = g.entries;
+  row_val_bytes[r] = bytes;
+}
+
+__device__ void gen_put_key(const b2_gen_spec& s, uint64_t handle, uint64_t commit_ts, uint8_t* k) {
+  // memcomparable('t' ‖ i64cmp(table_id) ‖ "_r" ‖ i64cmp(handle)) ‖ !commit_ts  (35 bytes)
+  uint8_t raw[19];
+  raw[0] = 't';
+  uint64_t t = (uint64_t)s.table_id ^ 0x8000000000000000ull, h = handle ^ 0x8000000000000000ull;
+  for (int i = 0; i < 8; ++i) { raw[1 + i] = (uint8_t)(t >> (8 * (7 - i))); raw[11 + i] = (uint8_t)(h >> (8 * (7 - i))); }
+  raw[9] = '_'; raw[10] = 'r';
+  for (int i = 0; i < 8; ++i) { k[i] = raw[i]; k[9 + i] = raw[8 + i]; }
+  k[8] = 0xff; k[17] = 0xff;
+  k[18] = raw[16]; k[19] = raw[17]; k[20] = raw[18];
+  for (int i = 21; i < 26; ++i) k[i] = 0;
+  k[26] = 0xff - 5;
+  uint64_t nts = ~commit_ts;
+  for (int i = 0; i < 8; ++i) k[27 + i] = (uint8_t)(nts >> (8 * (7 - i)));
+}
+
+__device__ uint32_t gen_put_record(const b2_gen_spec& s, uint64_t handle, uint8_t type, uint64_t start_ts, uint64_t version_salt, bool with_row, uint8_t* v) {
+  uint32_t n = put_write_header(v, type, start_ts, true);
+  if (with_row) {
+    uint32_t row = gen_row_bytes(s, handle, version_salt, v + n + 2, true);
+    v[n] = 'v'; v[n + 1] = (uint8_t)row;
+    n += 2 + row;
+  }
+  return n;
+}
+
+__global__ void gen_write_kernel(const __grid_constant__ GenArgs a) {
+  const b2_gen_spec& s = a.spec;
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > s.n_rows) return;
+  if (r == s.n_rows) {  // terminal offsets
+    uint32_t e = a.row_entry_off[r];
+    a.koff[e] = e * 35u;
+    a.voff[e] = a.row_val_off[r];
+    return;
+  }
+  uint64_t handle = s.first_handle + r;
+  GenRow g = gen_row_kind(s, handle);
+  uint32_t e = a.row_entry_off[r];
+  uint32_t vo = a.row_val_off[r];
+  // versions are emitted newest first (descending commit_ts)
+  uint64_t cts[3]; uint8_t typ[3]; uint64_t sts[3]; uint64_t salt[3]; bool with_row[3];
+  int n = 0;
+  if (g.kind == 1) { cts[n] = s.newer_ts; typ[n] = 'P'; sts[n] = s.newer_ts - 1; salt[n] = 77; with_row[n] = true; ++n; }
+  if (g.kind == 3) { cts[n] = s.commit_ts + 1; typ[n] = 'L'; sts[n] = s.commit_ts; salt[n] = 0; with_row[n] = false; ++n; }
+  if (g.kind == 2) { cts[n] = s.commit_ts; typ[n] = 'D'; sts[n] = s.commit_ts - 1; salt[n] = 0; with_row[n] = false; ++n; }
+  else { cts[n] = s.commit_ts; typ[n] = 'P'; sts[n] = s.commit_ts - 1; salt[n] = 0; with_row[n] = true; ++n; }
+  if (g.kind == 1 || g.kind == 2) { cts[n] = s.commit_ts - 10; typ[n] = 'P'; sts[n] = s.commit_ts - 11; salt[n] = 99; with_row[n] = true; ++n; }
+  for (int i = 0; i < n; ++i) {
+    a.koff[e + i] = (e + i) * 35u;
+    gen_put_key(s, handle, cts[i], a.keys + (size_t)(e + i) * 35u);
+    a.voff[e + i] = vo;
+    uint32_t len = gen_put_record(s, handle, typ[i], sts[i], salt[i], with_row[i], a.vals + vo);
+    if (typ[i] == 'L') {  // last_change -> the Put right below (commit_ts), 1 version away
+      uint8_t* p = a.vals + vo + len;
+      p[0] = 'l';
+      for (int b = 0; b < 8; ++b) p[1 + b] = (uint8_t)(s.commit_ts >> (8 * (7 - b)));
+      p[9] = 1;
+      len += 10;
+    }
+    vo += len;
+  }
+}
+
+cudaError_t launch_gen_sizes(const b2_gen_spec& spec, uint32_t* row_entries, uint32_t* row_val_bytes, cudaStream_t s) {
+  if (!spec.n_rows) return cudaSuccess;
+  gen_sizes_kernel<<<(unsigned)((spec.n_rows + 255) / 256), 256, 0, s>>>(spec, row_entries, row_val_bytes);
+  return cudaGetLastError();
+}
+cudaError_t launch_gen_write(const GenArgs& a, cudaStream_t s) {
+  gen_write_kernel<<<(unsigned)((a.spec.n_rows + 1 + 255) / 256), 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace b2

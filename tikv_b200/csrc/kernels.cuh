@@ -1,0 +1,91 @@
+// Kernel-side structures and launch wrappers shared by kernels.cu (device) and engine.cu (host).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "b2_device.h"
+
+namespace b2 {
+
+enum { TILE = 256 };  // entries per tile = threads per CTA
+
+// Counters accumulated across all launches of one request (device memory, zero-initialised except err).
+struct Counters {
+  unsigned long long err;              // min over failing rows of (global_entry << 8 | DevErr); ~0 = none
+  unsigned long long out_rows;         // rows written by PM_SCAN launches (reset per batch by the host)
+  unsigned long long out_base;         // rows written by earlier launches of the same batch (copied from out_rows between launches)
+  unsigned long long live_rows;        // rows that passed MVCC + selection
+  unsigned long long processed_keys;   // rows returned by the MVCC scan
+  unsigned long long processed_size;   // sum(len(user_key) + len(value))
+  unsigned long long entries_scanned;  // CF_WRITE entries covered
+  unsigned long long default_lookups;
+  unsigned long long checksum, total_kvs, total_bytes;  // checksum mode
+  unsigned int met_newer;
+  unsigned int agg_overflow;           // global group table full
+  unsigned int n_groups;               // finalize: number of groups emitted
+  unsigned int bad_prefix;             // checksum: key without new_prefix
+};
+
+// Open-addressing group table in HBM (fast_hash_aggr_executor.rs:216-229 `Groups`): slot = hash(key) & mask,
+// linear probing.  Slot `cap` is the NULL-key group; accumulators are u64 words per slot.
+struct AggTable {
+  unsigned long long* keys;  // cap + 1
+  unsigned int* occ;         // cap + 1: 0 empty, 1 being claimed, 2 ready
+  unsigned long long* acc;   // (cap + 1) * acc_words
+  unsigned int cap;          // power of two
+};
+
+struct ScanArgs {
+  BlockView blk;
+  DefaultCf dflt;
+  uint32_t e_lo, e_hi;  // entries of the block inside the key range
+  uint32_t c_lo, c_hi;  // chunk handled by this launch (runs *starting* in [c_lo, c_hi))
+  uint64_t entry_base;  // global index of blk entry 0
+  Counters* ctr;
+  // PM_SCAN
+  unsigned long long* tile_status;  // n_tiles + 1 words, zeroed per launch; last word = ticket
+  unsigned long long* out_data;     // n_out columns, each `out_cap` u64 cells
+  unsigned long long* out_bitmap;   // n_out columns, each out_cap/64 words pre-filled with 1s
+  uint64_t out_cap;
+  // PM_AGG
+  AggTable tbl;
+  uint32_t smem_slots;              // per-CTA table slots (power of two), 0 = disabled
+  // PM_TOPN
+  unsigned long long* topn_items;   // per-CTA candidate lists
+  unsigned int* topn_counts;
+};
+
+struct ChecksumArgs {
+  BlockView blk;
+  DefaultCf dflt;
+  uint32_t e_lo, e_hi;
+  uint64_t entry_base;
+  uint64_t read_ts;
+  int32_t isolation;
+  uint64_t init_state;    // crc register after old_prefix
+  const uint8_t* new_prefix;
+  uint32_t new_prefix_len, old_prefix_len;
+  Counters* ctr;
+};
+
+struct GenArgs {
+  b2_gen_spec spec;  // pointers inside are device pointers
+  uint8_t* keys; uint32_t* koff; uint8_t* vals; uint32_t* voff;
+  const uint32_t* row_entry_off;   // exclusive scan of entries per row (n_rows + 1)
+  const uint32_t* row_val_off;     // exclusive scan of value bytes per row (n_rows + 1)
+};
+
+// launchers (kernels.cu)
+cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t smem, cudaStream_t s);
+int scan_max_grid(int mode, size_t smem);  // occupancy-based persistent grid size
+cudaError_t launch_agg_finalize(const DevPlan& plan, const AggTable& t, Counters* ctr, unsigned long long* out_keys, unsigned char* out_key_null,
+                                unsigned long long* out_acc, cudaStream_t s);
+cudaError_t launch_agg_result(const DevPlan& plan, unsigned int n_groups, const unsigned long long* g_keys, const unsigned char* g_null,
+                              const unsigned long long* g_acc, unsigned long long** col_data, unsigned long long** col_bitmap, cudaStream_t s);
+cudaError_t launch_checksum(const ChecksumArgs& a, int grid, cudaStream_t s);
+cudaError_t launch_bounds_search(const BlockView* blocks, uint32_t n_blocks, const uint8_t* bounds, const uint32_t* bound_offs, uint32_t n_bounds,
+                                 uint32_t* out, cudaStream_t s);
+cudaError_t launch_gen_sizes(const b2_gen_spec& spec, uint32_t* row_entries, uint32_t* row_val_bytes, cudaStream_t s);
+cudaError_t launch_gen_write(const GenArgs& a, cudaStream_t s);
+cudaError_t launch_fill_u64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t s);
+
+}  // namespace b2

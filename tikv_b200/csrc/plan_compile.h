@@ -1,0 +1,269 @@
+// Host-side lowering of the ABI plan (b2_dag_plan) into the device plan (DevPlan).
+// Mirrors what BatchExecutorsRunner::check_supported / build_executors do on the CPU
+// (components/tidb_query_executors/src/runner.rs:111-206, 252-603) plus the aggregate SUM/AVG cast rewrite
+// (components/tidb_query_aggr/src/util.rs:31-66).  Pure C++ (no CUDA) so the host emulation test can use it.
+#pragma once
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b2_device.h"
+
+namespace b2 {
+
+struct OutCol { int kind; int field_tp; uint32_t field_flag; };
+
+struct CompiledPlan {
+  DevPlan dev;
+  std::vector<OutCol> schema;            // output schema of the outermost executor
+  std::vector<uint32_t> output_offsets;  // indices into `schema` delivered to the caller
+};
+
+inline int col_kind_of_tp(int tp) {  // def/eval_type.rs:53-95
+  switch (tp) {
+    case B2_TP_TINY: case B2_TP_SHORT: case B2_TP_INT24: case B2_TP_LONG: case B2_TP_LONGLONG: case B2_TP_YEAR: case B2_TP_BIT: return CK_INT;
+    case B2_TP_FLOAT: case B2_TP_DOUBLE: return CK_REAL;
+    default: return CK_OTHER;
+  }
+}
+inline int v2_class_of(int tp, bool is_unsigned) {  // compat_v1.rs:55-129 write_v2_as_datum
+  switch (tp) {
+    case B2_TP_TINY: case B2_TP_SHORT: case B2_TP_INT24: case B2_TP_LONG: case B2_TP_LONGLONG: return is_unsigned ? V2_UINT : V2_INT;
+    case B2_TP_YEAR: case B2_TP_DURATION: return V2_INT;
+    case B2_TP_DATE: case B2_TP_DATETIME: case B2_TP_TIMESTAMP: case B2_TP_ENUM: case B2_TP_BIT: case B2_TP_SET: return V2_UINT;
+    case B2_TP_FLOAT: case B2_TP_DOUBLE: case B2_TP_NEWDECIMAL: case B2_TP_JSON: return V2_COPY;
+    case B2_TP_VARCHAR: case B2_TP_VARSTRING: case B2_TP_STRING: case B2_TP_BLOB: case 0xf9: case 0xfa: case 0xfb: case 0xff: return V2_BYTES;
+    case B2_TP_NULL: return V2_NIL;
+    default: return V2_UNSUPPORTED;
+  }
+}
+
+// lower one RPN expression; returns false + msg when unsupported
+inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* ret_et, uint8_t* ret_unsigned, int* ret_tp, uint32_t* ret_flag, std::string* msg) {
+  if (x.n_nodes == 0 || !x.nodes) { *msg = "empty expression"; return false; }
+  if (P.n_nodes + (int)x.n_nodes > MAX_NODES) { *msg = "too many expression nodes"; return false; }
+  out->start = (uint16_t)P.n_nodes; out->n = (uint16_t)x.n_nodes;
+  uint8_t st_et[MAX_STACK];
+  int sp = 0;
+  for (uint32_t i = 0; i < x.n_nodes; ++i) {
+    const b2_rpn_node& s = x.nodes[i];
+    DevNode d;
+    d.sig = s.sig; d.kind = (uint8_t)s.kind; d.n_args = (uint8_t)s.n_args; d.et = 0; d.is_unsigned = (s.field_flag & B2_FLAG_UNSIGNED) ? 1 : 0; d.imm = s.i64;
+    switch (s.kind) {
+      case B2_RPN_CONST_INT: d.et = 0; break;
+      case B2_RPN_CONST_UINT: d.et = 0; d.is_unsigned = 1; break;
+      case B2_RPN_CONST_REAL: d.et = 1; d.imm = (int64_t)f64_bits(s.f64); break;
+      case B2_RPN_CONST_NULL: {
+        int k = col_kind_of_tp(s.field_tp);
+        if (k == CK_OTHER) { *msg = "NULL constant of a non Int/Real type"; return false; }
+        d.et = (uint8_t)k; d.imm = 0;
+        break;
+      }
+      case B2_RPN_COLUMN_REF: {
+        if (s.i64 < 0 || s.i64 >= P.n_cols) { *msg = "column offset out of range"; return false; }
+        const DevCol& c = P.cols[s.i64];
+        if (c.kind == CK_OTHER) { *msg = "expression over a column that is not Int/Real"; return false; }
+        d.et = c.kind; d.is_unsigned = c.is_unsigned;
+        break;
+      }
+      case B2_RPN_FN: {
+        int sig = s.sig, na = s.n_args;
+        bool cmp = sig >= 100 && sig < 170 && (sig % 10 == 0 || sig % 10 == 1);
+        bool real_args = false, real_ret = false;
+        int want = 2;
+        if (cmp) real_args = (sig % 10) == 1;
+        else switch (sig) {
+          case B2_SIG_PLUS_REAL: case B2_SIG_MINUS_REAL: case B2_SIG_MULTIPLY_REAL: real_args = real_ret = true; break;
+          case B2_SIG_PLUS_INT: case B2_SIG_MINUS_INT: case B2_SIG_MULTIPLY_INT: case B2_SIG_MULTIPLY_INT_UNSIGNED:
+          case B2_SIG_LOGICAL_AND: case B2_SIG_LOGICAL_OR: case B2_SIG_LOGICAL_XOR: break;
+          case B2_SIG_UNARY_NOT_INT: case B2_SIG_INT_IS_NULL: case B2_SIG_INT_IS_TRUE: case B2_SIG_INT_IS_FALSE: want = 1; break;
+          case B2_SIG_UNARY_NOT_REAL: case B2_SIG_REAL_IS_NULL: case B2_SIG_REAL_IS_TRUE: case B2_SIG_REAL_IS_FALSE: want = 1; real_args = true; break;
+          default: *msg = "ScalarFunction sig " + std::to_string(sig) + " is not supported on the device path"; return false;
+        }
+        if (na != want || sp < na) { *msg = "bad arity for sig " + std::to_string(sig); return false; }
+        for (int k = 0; k < na; ++k)
+          if (st_et[sp - 1 - k] != (real_args ? 1 : 0)) { *msg = "argument eval type does not match sig " + std::to_string(sig); return false; }
+        sp -= na;
+        d.et = real_ret ? 1 : 0;
+        break;
+      }
+      default: *msg = "bad rpn node kind"; return false;
+    }
+    if (sp >= MAX_STACK) { *msg = "expression too deep"; return false; }
+    st_et[sp++] = d.et;
+    P.nodes[P.n_nodes++] = d;
+  }
+  if (sp != 1) { *msg = "expression does not reduce to one value"; return false; }
+  const b2_rpn_node& last = x.nodes[x.n_nodes - 1];
+  const DevNode& dl = P.nodes[P.n_nodes - 1];
+  if (ret_et) *ret_et = dl.et;
+  if (ret_unsigned) *ret_unsigned = dl.is_unsigned;
+  if (last.kind == B2_RPN_COLUMN_REF) {
+    if (ret_tp) *ret_tp = P.cols[last.i64].tp;
+    if (ret_flag) *ret_flag = (P.cols[last.i64].is_unsigned ? B2_FLAG_UNSIGNED : 0) | (P.cols[last.i64].not_null ? B2_FLAG_NOT_NULL : 0);
+  } else {
+    if (ret_tp) *ret_tp = last.field_tp ? last.field_tp : (dl.et ? B2_TP_DOUBLE : B2_TP_LONGLONG);
+    if (ret_flag) *ret_flag = last.field_flag;
+  }
+  return true;
+}
+
+// decode a datum-encoded column default (datum_codec.rs:401-446) at plan time
+inline void lower_default(const b2_column_info& ci, DevCol& c) {
+  c.def_state = DS_NONE; c.default_bits = 0;
+  if (!ci.default_val || ci.default_len == 0) return;
+  const uint8_t* p = ci.default_val;
+  uint32_t n = ci.default_len;
+  const uint64_t S = 0x8000000000000000ull;
+  uint8_t flag = p[0];
+  if (flag == 0) { c.def_state = DS_NULL; return; }
+  c.def_state = DS_ERROR;
+  if (c.kind == CK_INT) {
+    if ((flag == 3 || flag == 4) && n >= 9) { c.default_bits = (int64_t)(ld_be64(p + 1) ^ (flag == 3 ? S : 0)); c.def_state = DS_VALUE; }
+    else if (flag == 8) { int64_t v; if (dec_var_i64(p + 1, n - 1, &v)) { c.default_bits = v; c.def_state = DS_VALUE; } }
+    else if (flag == 9) { uint64_t v; if (dec_var_u64(p + 1, n - 1, &v)) { c.default_bits = (int64_t)v; c.def_state = DS_VALUE; } }
+  } else if (c.kind == CK_REAL) {
+    if (flag == 5 && n >= 9) {
+      double f = cmp_u64_to_f64(ld_be64(p + 1));
+      if (c.tp == B2_TP_FLOAT) f = (double)(float)f;
+      if (f != f) c.def_state = DS_NULL; else { c.default_bits = (int64_t)f64_bits(f); c.def_state = DS_VALUE; }
+    }
+  } else {
+    c.def_state = DS_VALUE;  // never materialised on the device; only "has a default" matters
+  }
+}
+
+// returns B2_OK or B2_ERR_UNSUPPORTED / B2_ERR_INVALID_ARG with *msg set
+inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string* msg) {
+  DevPlan& P = out->dev;
+  memset(&P, 0, sizeof(P));
+  if (!plan || plan->n_executors == 0 || !plan->executors) { *msg = "empty plan"; return B2_ERR_INVALID_ARG; }
+  const b2_executor_desc& scan = plan->executors[0];
+  if (scan.tp != B2_EXEC_TABLE_SCAN) { *msg = "first executor must be TableScan (index scans are not on the device path yet)"; return B2_ERR_UNSUPPORTED; }
+  if (scan.desc) { *msg = "backward scan is not supported on the device path"; return B2_ERR_UNSUPPORTED; }
+  if (scan.n_columns == 0 || scan.n_columns > MAX_COLS) { *msg = "TableScan with 0 or more than 64 columns"; return B2_ERR_UNSUPPORTED; }
+  P.n_cols = (int)scan.n_columns;
+  for (int i = 0; i < P.n_cols; ++i) {
+    const b2_column_info& ci = scan.columns[i];
+    DevCol& c = P.cols[i];
+    c.col_id = ci.col_id; c.tp = (uint8_t)ci.tp;
+    c.is_unsigned = (ci.flag & B2_FLAG_UNSIGNED) ? 1 : 0;
+    c.not_null = (ci.flag & B2_FLAG_NOT_NULL) ? 1 : 0;
+    c.kind = (uint8_t)col_kind_of_tp(ci.tp);
+    c.v2_class = (uint8_t)v2_class_of(ci.tp, c.is_unsigned);
+    c.role = CR_NORMAL;
+    if (ci.pk_handle) { c.role = CR_HANDLE; c.kind = CK_INT; P.has_handle_cols = 1; }
+    else if (ci.col_id == B2_EXTRA_PHYSICAL_TABLE_ID_COL_ID) { c.role = CR_TABLE_ID; c.kind = CK_INT; }
+    else if (ci.col_id == B2_EXTRA_COMMIT_TS_COL_ID) { c.role = CR_COMMIT_TS; c.kind = CK_INT; }
+    lower_default(ci, c);
+  }
+  // duplicate column ids: only the last one is ever filled (table_scan_executor.rs:90-94)
+  for (int i = 0; i < P.n_cols; ++i) {
+    if (P.cols[i].role == CR_HANDLE) continue;
+    for (int j = i + 1; j < P.n_cols; ++j)
+      if (P.cols[j].role != CR_HANDLE && P.cols[j].col_id == P.cols[i].col_id) { P.cols[i].role = CR_SHADOWED; break; }
+  }
+  P.mode = PM_SCAN;
+  std::vector<OutCol> schema;
+  for (int i = 0; i < P.n_cols; ++i) {
+    OutCol oc;
+    oc.kind = P.cols[i].kind == CK_REAL ? B2_COL_F64 : B2_COL_I64;
+    oc.field_tp = P.cols[i].tp; oc.field_flag = scan.columns[i].flag;
+    schema.push_back(oc);
+  }
+  bool terminal = false;
+  for (uint32_t ei = 1; ei < plan->n_executors; ++ei) {
+    const b2_executor_desc& e = plan->executors[ei];
+    if (terminal) { *msg = "executors after Aggregation/TopN are not supported on the device path"; return B2_ERR_UNSUPPORTED; }
+    if (e.tp == B2_EXEC_SELECTION) {
+      for (uint32_t k = 0; k < e.n_conditions; ++k) {
+        if (P.n_conds >= MAX_CONDS) { *msg = "too many selection conditions"; return B2_ERR_UNSUPPORTED; }
+        if (!lower_expr(e.conditions[k], P, &P.conds[P.n_conds], nullptr, nullptr, nullptr, nullptr, msg)) return B2_ERR_UNSUPPORTED;
+        P.n_conds++;
+      }
+    } else if (e.tp == B2_EXEC_AGGREGATION || e.tp == B2_EXEC_STREAM_AGG) {
+      if (e.n_group_by > 1) { *msg = "multi-column GROUP BY (BatchSlowHashAggregation) is not on the device path yet"; return B2_ERR_UNSUPPORTED; }
+      if (e.n_aggrs == 0 || e.n_aggrs > MAX_AGGS) { *msg = "0 or too many aggregate functions"; return B2_ERR_UNSUPPORTED; }
+      P.mode = PM_AGG; terminal = true;
+      schema.clear();
+      int acc = 0;
+      for (uint32_t k = 0; k < e.n_aggrs; ++k) {
+        DevAgg& g = P.aggs[k];
+        int tp; uint32_t flag; uint8_t et, uns;
+        if (!lower_expr(e.aggrs[k].arg, P, &g.arg, &et, &uns, &tp, &flag, msg)) return B2_ERR_UNSUPPORTED;
+        g.arg_et = et; g.arg_unsigned = uns;
+        g.acc_off = (uint8_t)acc;
+        switch (e.aggrs[k].kind) {
+          case B2_AGG_COUNT: g.kind = 0; acc += 1; break;
+          case B2_AGG_SUM: g.kind = 1; acc += et ? 2 : 3; break;
+          case B2_AGG_AVG: g.kind = 2; acc += et ? 2 : 3; break;
+          default: *msg = "aggregate function " + std::to_string(e.aggrs[k].kind) + " is not on the device path yet"; return B2_ERR_UNSUPPORTED;
+        }
+        if (g.kind != 0 && !et && tp == B2_TP_BIT) { *msg = "SUM/AVG over BIT (cast to DOUBLE) is not supported"; return B2_ERR_UNSUPPORTED; }
+        if (acc > MAX_ACC_WORDS) { *msg = "aggregate state too large"; return B2_ERR_UNSUPPORTED; }
+        OutCol cnt = {B2_COL_I64, B2_TP_LONGLONG, B2_FLAG_UNSIGNED | B2_FLAG_NOT_NULL};  // impl_count.rs:35-40
+        OutCol sum = et ? OutCol{B2_COL_F64, B2_TP_DOUBLE, 0} : OutCol{B2_COL_DECIMAL, B2_TP_NEWDECIMAL, 0};
+        if (g.kind == 0 || g.kind == 2) schema.push_back(cnt);
+        if (g.kind == 1 || g.kind == 2) schema.push_back(sum);
+      }
+      P.n_aggs = (int)e.n_aggrs; P.acc_words = acc;
+      if (e.n_group_by == 1) {
+        int tp; uint32_t flag; uint8_t et, uns;
+        if (!lower_expr(e.group_by[0], P, &P.group, &et, &uns, &tp, &flag, msg)) return B2_ERR_UNSUPPORTED;
+        P.has_group = 1; P.group_et = et; P.group_unsigned = uns;
+        schema.push_back(OutCol{et ? B2_COL_F64 : B2_COL_I64, tp, flag});
+      }
+    } else if (e.tp == B2_EXEC_TOPN) {
+      if (e.n_order_by == 0 || e.n_order_by > MAX_ORDER) { *msg = "TopN with 0 or more than 4 order-by expressions"; return B2_ERR_UNSUPPORTED; }
+      P.mode = PM_TOPN; terminal = true;
+      for (uint32_t k = 0; k < e.n_order_by; ++k) {
+        DevOrder& o = P.order[k];
+        uint8_t et, uns;
+        if (!lower_expr(e.order_by[k].expr, P, &o.e, &et, &uns, nullptr, nullptr, msg)) return B2_ERR_UNSUPPORTED;
+        o.desc = e.order_by[k].desc ? 1 : 0; o.et = et; o.is_unsigned = uns;
+      }
+      P.n_order = (int)e.n_order_by; P.limit = e.limit;
+    } else {
+      *msg = "executor type " + std::to_string(e.tp) + " is not supported on the device path";
+      return B2_ERR_UNSUPPORTED;
+    }
+  }
+  out->schema = schema;
+  out->output_offsets.clear();
+  if (plan->output_offsets && plan->n_output_offsets) {
+    for (uint32_t i = 0; i < plan->n_output_offsets; ++i) {
+      if (plan->output_offsets[i] >= schema.size()) { *msg = "output offset out of range"; return B2_ERR_INVALID_ARG; }
+      out->output_offsets.push_back(plan->output_offsets[i]);
+    }
+  } else {
+    for (uint32_t i = 0; i < schema.size(); ++i) out->output_offsets.push_back(i);
+  }
+  if (P.mode == PM_SCAN || P.mode == PM_TOPN) {
+    // materialised scan columns must be Int/Real on the device path
+    std::vector<uint32_t> mat;
+    if (P.mode == PM_TOPN) for (int i = 0; i < P.n_cols; ++i) mat.push_back(i); else mat = out->output_offsets;
+    if (mat.size() > MAX_COLS) { *msg = "too many output columns"; return B2_ERR_UNSUPPORTED; }
+    for (size_t i = 0; i < mat.size(); ++i) {
+      if (P.cols[mat[i]].kind == CK_OTHER) { *msg = "output column " + std::to_string(mat[i]) + " is not Int/Real: device path cannot materialise it yet"; return B2_ERR_UNSUPPORTED; }
+      P.out_cols[i] = (uint8_t)mat[i];
+    }
+    P.n_out = (int)mat.size();
+  }
+  return B2_OK;
+}
+
+// memcomparable encoding of a raw key (tikv_util/src/codec/bytes.rs:25-55), for range bounds
+inline std::vector<uint8_t> encode_memcomparable(const uint8_t* p, size_t n) {
+  std::vector<uint8_t> out;
+  size_t idx = 0;
+  while (idx <= n) {
+    size_t remain = n - idx, pad = 0;
+    if (remain >= 8) out.insert(out.end(), p + idx, p + idx + 8);
+    else { pad = 8 - remain; out.insert(out.end(), p + idx, p + n); out.insert(out.end(), pad, 0); }
+    out.push_back((uint8_t)(0xff - pad));
+    idx += 8;
+  }
+  return out;
+}
+
+}  // namespace b2

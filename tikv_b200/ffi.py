@@ -141,7 +141,8 @@ class GenBlock(C.Structure):
 EXPORTED_SYMBOLS = [
     "b2_abi_version", "b2_build_info", "b2_last_error_message", "b2_check_supported", "b2_exec_open", "b2_exec_schema",
     "b2_exec_next_batch", "b2_exec_collect_stats", "b2_exec_last_error", "b2_exec_can_be_cached", "b2_exec_close",
-    "b2_dag_handle", "b2_checksum_handle", "b2_gen_create", "b2_gen_destroy",
+    "b2_dag_handle", "b2_checksum_handle", "b2_gen_create", "b2_gen_destroy", "b2_copy_to_host", "b2_copy_to_device",
+    "b2_device_count", "b2_host_alloc_pinned", "b2_host_free_pinned",
 ]
 
 _lib = None
@@ -185,6 +186,15 @@ def lib():
     L.b2_gen_create.restype = i32
     L.b2_gen_destroy.argtypes = [vp]
     L.b2_gen_destroy.restype = None
+    L.b2_copy_to_host.argtypes = [i32, vp, vp, u64]
+    L.b2_copy_to_host.restype = i32
+    L.b2_copy_to_device.argtypes = [i32, vp, vp, u64]
+    L.b2_copy_to_device.restype = i32
+    L.b2_device_count.restype = i32
+    L.b2_host_alloc_pinned.argtypes = [u64]
+    L.b2_host_alloc_pinned.restype = vp
+    L.b2_host_free_pinned.argtypes = [vp]
+    L.b2_host_free_pinned.restype = None
     if L.b2_abi_version() != 1:
         raise RuntimeError("libb2copr ABI version mismatch")
     _lib = L
