@@ -263,6 +263,10 @@ typedef struct b2_exec_stats {
   uint64_t lock_processed_keys;
   int32_t met_newer_ts_data;      /* -1 unknown, 0 not met, 1 met (NewerTsCheckState) */
   int32_t _pad;
+  uint64_t kernel_time_ns;        /* CUDA-event time spent inside the dominant (scan) kernel launches */
+  uint64_t kernel_launches;       /* launches of this library's kernels */
+  uint64_t h2d_bytes;             /* bytes staged host->device by the engine (host-resident sources) */
+  uint64_t d2h_bytes;             /* result bytes copied device->host */
 } b2_exec_stats;
 
 typedef struct b2_error_info {

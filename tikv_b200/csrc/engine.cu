@@ -220,6 +220,7 @@ struct b2_exec {
       if (s.ready) cudaEventDestroy(s.ready);
       if (s.free_ev) cudaEventDestroy(s.free_ev);
     }
+    for (auto& e : kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &grp_keys, &grp_null, &grp_acc, &res_ptrs}) b->release();
     for (auto& b : res_cols) b.release();
     for (auto& b : res_bitmaps) b.release();
@@ -454,7 +455,27 @@ struct b2_exec {
     CUDA_TRY(cudaMemcpyAsync(h_ctr.p, ctr_buf.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     memcpy(c, h_ctr.p, sizeof(Counters));
+    harvest_kernel_times();
     return B2_OK;
+  }
+  // CUDA events bracketing every launch of the dominant kernel (roofline numerator / denominator in bench.py)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kev;
+  size_t kev_used = 0;
+  void kernel_begin() {
+    if (kev_used == kev.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      kev.push_back({a, b});
+    }
+    cudaEventRecord(kev[kev_used].first, stream);
+  }
+  void kernel_end() { cudaEventRecord(kev[kev_used].second, stream); ++kev_used; stats.kernel_launches++; }
+  void harvest_kernel_times() {  // call after a stream synchronize
+    for (size_t i = 0; i < kev_used; ++i) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, kev[i].first, kev[i].second) == cudaSuccess) stats.kernel_time_ns += (uint64_t)(ms * 1e6);
+    }
+    kev_used = 0;
   }
   void fill_stats(const Counters& c) {
     stats.write_entries_scanned = entries_scanned;
@@ -463,6 +484,7 @@ struct b2_exec {
     stats.default_lookups = c.default_lookups;
     stats.lock_processed_keys = lock_keys_seen;
     stats.met_newer_ts_data = check_newer ? ((c.met_newer || saw_lock) ? 1 : 0) : -1;
+    stats.h2d_bytes = h2d_bytes; stats.d2h_bytes = d2h_bytes;
     met_newer_any = c.met_newer || saw_lock;
   }
   bool met_newer_any = false;
@@ -539,7 +561,9 @@ struct b2_exec {
         a.tile_status = (unsigned long long*)status_buf.p;
         a.out_data = (unsigned long long*)out_data.p; a.out_bitmap = (unsigned long long*)out_bitmap.p;
         a.out_cap = out_cap;
+        kernel_begin();
         CUDA_TRY(launch_scan(cp.dev, a, scan_grid, 0, stream));
+        kernel_end();
         CUDA_TRY(cudaMemcpyAsync(&ctr()->out_base, &ctr()->out_rows, 8, cudaMemcpyDeviceToDevice, stream));
         release_block(u.block_idx);
         entries_scanned += c_hi - c_lo;
@@ -686,7 +710,9 @@ struct b2_exec {
         a.c_lo = u.e_lo; a.c_hi = u.e_hi;
         a.tbl.keys = (unsigned long long*)tbl_keys.p; a.tbl.occ = (unsigned int*)tbl_occ.p; a.tbl.acc = (unsigned long long*)tbl_acc.p; a.tbl.cap = tbl_cap;
         a.smem_slots = smem_slots;
+        kernel_begin();
         CUDA_TRY(launch_scan(P, a, grid, smem, stream));
+        kernel_end();
         release_block(u.block_idx);
         prefetch_after(ui);
         entries_scanned += u.e_hi - u.e_lo;
@@ -900,7 +926,9 @@ int32_t b2_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges, const 
     a.read_ts = h->read_ts; a.isolation = h->isolation; a.init_state = st;
     a.new_prefix = (const uint8_t*)d_prefix.p; a.new_prefix_len = new_prefix_len; a.old_prefix_len = old_prefix_len;
     a.ctr = h->ctr();
+    h->kernel_begin();
     cudaError_t ce = launch_checksum(a, 0, h->stream);
+    h->kernel_end();
     if (ce != cudaSuccess) { g_last_error = cudaGetErrorString(ce); d_prefix.release(); return B2_ERR_CUDA; }
     h->release_block(u.block_idx);
     h->prefetch_after(ui);

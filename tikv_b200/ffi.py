@@ -115,7 +115,8 @@ class ExecStats(C.Structure):
     _fields_ = [("num_iterations", C.c_uint64), ("num_produced_rows", C.c_uint64), ("time_processed_ns", C.c_uint64),
                 ("write_entries_scanned", C.c_uint64), ("write_processed_keys", C.c_uint64), ("processed_size", C.c_uint64),
                 ("default_lookups", C.c_uint64), ("lock_processed_keys", C.c_uint64), ("met_newer_ts_data", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("_pad", C.c_int32), ("kernel_time_ns", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class ErrorInfo(C.Structure):
