@@ -102,7 +102,10 @@ static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges,
 extern "C" {
 
 // BatchExecutorsRunner::handle_request (runner.rs:739-851): run to drain, collect decoded output rows.
-int orc_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src, orc_result** out) {
+// keep_rows = 0: every batch is still decoded and appended to the response buffers, but the buffers are recycled per
+// batch (the reference streams / pages its response chunks, runner.rs:790-806) so a timed run does not hold the
+// whole result in memory.
+static int orc_dag_handle_impl(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src, orc_result** out, int keep_rows) {
   orc_result* res = new orc_result();
   *out = res;
   CfView w, l, d;
@@ -139,6 +142,8 @@ int orc_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t
         }
         res->n_rows++;
       }
+    if (!keep_rows)
+      for (size_t k = 0; k < offs.size(); ++k) { res->cols[k].nn.clear(); res->cols[k].i64.clear(); res->cols[k].f64.clear(); res->dec_cols[k].clear(); }
     if (!b.err.ok()) { res->err = b.err; break; }
     if (b.is_drained) break;
     if (batch_size < BATCH_MAX_SIZE) { batch_size *= BATCH_GROW_FACTOR; if (batch_size > BATCH_MAX_SIZE) batch_size = BATCH_MAX_SIZE; }  // runner.rs:1098-1105
@@ -148,6 +153,10 @@ int orc_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t
   res->met_newer = scan->rs.met_newer;
   res->scanned_rows = scan->rs.rows;
   return res->err.status;
+}
+
+int orc_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src, orc_result** out) {
+  return orc_dag_handle_impl(plan, ranges, n_ranges, src, out, 1);
 }
 
 uint64_t orc_result_rows(orc_result* r) { return r->n_rows; }
@@ -215,7 +224,7 @@ uint64_t orc_dag_handle_parallel(const b2_dag_plan* plan, const b2_key_range* ra
         uint32_t i = next.fetch_add(1);
         if (i >= n_tasks) break;
         orc_result* r = nullptr;
-        status[i] = orc_dag_handle(plan, ranges, n_ranges, &srcs[i], &r);
+        status[i] = orc_dag_handle_impl(plan, ranges, n_ranges, &srcs[i], &r, 0);
         rows[i] = r->n_rows; scanned[i] = r->scanned_rows;
         delete r;
       }

@@ -209,6 +209,7 @@ struct TableScanExecutor : Executor {
   std::unordered_map<int64_t, size_t> column_id_index;
   std::vector<size_t> handle_indices;
   std::vector<uint8_t> is_column_filled;
+  Bytes datum_buf_;
   RangesScanner rs;
   bool ended = false;
 
@@ -305,7 +306,8 @@ struct TableScanExecutor : Executor {
         size_t end = get_off(pos), start = pos > 0 ? get_off(pos - 1) : 0;
         if (start > end || end > values.n) { *err = "row v2 value slice out of range (panic)"; return false; }
         Slice src = values.sub(start, end - start);
-        Bytes datum;
+        Bytes& datum = datum_buf_;  // scratch reused across cells
+        datum.clear();
         const FieldType& ft = schema_[idx];
         switch (ft.tp) {
           case B2_TP_TINY: case B2_TP_SHORT: case B2_TP_INT24: case B2_TP_LONG: case B2_TP_LONGLONG: case B2_TP_YEAR:
@@ -392,8 +394,9 @@ struct TableScanExecutor : Executor {
     out->cols.assign(schema_.size(), LazyColumn());
     for (size_t i = 0; i < schema_.size(); ++i) if (is_decoded_col(i)) { out->cols[i].decoded = true; out->cols[i].et = ET_INT; }
     out->is_drained = false; out->err = Error();
+    Bytes raw_key; ScanOutput so;  // buffers reused across rows
     for (size_t i = 0; i < scan_rows; ++i) {
-      Bytes raw_key; ScanOutput so; Error e;
+      Error e;
       int r = rs.next(&raw_key, &so, &e);
       if (r < 0) { out->err = e; break; }
       if (r == 0) { out->is_drained = true; break; }

@@ -275,6 +275,7 @@ struct ForwardScanner {
   Cursor write, lock, dflt;
   bool has_lock_cursor = false, dflt_ready = false;
   bool is_started = false;
+  Bytes cur_key_buf_;
   Statistics statistics;
   int met_newer_ts_data = NEWER_UNKNOWN;
 
@@ -394,7 +395,8 @@ struct ForwardScanner {
     for (;;) {
       bool wv = write.valid();
       bool lv = has_lock_cursor && lock.valid();
-      Bytes current_user_key;
+      Bytes& current_user_key = cur_key_buf_;  // buffer reused across rows (Key::from_encoded_slice reserves once)
+      current_user_key.clear();
       bool has_write, has_lock;
       if (!wv && !lv) return 0;
       if (!wv) { Slice lk = lock.key(); current_user_key.assign(lk.p, lk.p + lk.n); has_write = false; has_lock = true; }

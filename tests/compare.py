@@ -27,3 +27,18 @@ def assert_same_rows(got, exp, ordered=True, float_rel_tol=None, ctx=""):
                  (math.isclose(x, y, rel_tol=float_rel_tol, abs_tol=float_rel_tol) if isinstance(x, float) else x == y))
                 for x, y in zip(a, b))
         assert ok, f"{ctx}: row {i}: {a} != oracle {b}"
+
+
+def assert_topn(got, exp, exact, key_cols, ctx=""):
+    """TopN parity: exact rows when ties are broken by the sort key itself; otherwise the multiset of sort keys
+    (ties at the cut keep heap-order-dependent rows in the reference)."""
+    assert got.status == exp.status, f"{ctx}: status {got.status} != oracle {exp.status} ({exp.message})"
+    g, e = got.rows(), exp.rows()
+    assert len(g) == len(e), f"{ctx}: {len(g)} rows != oracle {len(e)}"
+    if exact:
+        for i, (a, b) in enumerate(zip(g, e)):
+            assert _key(a) == _key(b), f"{ctx}: row {i}: {a} != oracle {b}"
+    else:
+        ka = [tuple(r[c] for c in key_cols) for r in g]
+        kb = [tuple(r[c] for c in key_cols) for r in e]
+        assert ka == kb, f"{ctx}: sort keys differ"

@@ -56,6 +56,8 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
 
   size_t n_out = P.mode == PM_SCAN ? (size_t)P.n_out : cp.output_offsets.size();
   R->data.resize(n_out); R->dec.resize(n_out); R->nonnull.resize(n_out); R->kinds.resize(n_out);
+  struct TopRow { TopItem it; std::vector<uint64_t> bits; std::vector<uint8_t> nn; };
+  std::vector<TopRow> top_rows;
   std::map<std::pair<int, uint64_t>, GroupAcc> groups;  // (is_null, key bits)
   std::vector<std::pair<int, uint64_t>> group_order;
   GroupAcc single; memset(&single, 0, sizeof(single));
@@ -99,6 +101,17 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
             R->data[k].push_back(v.null ? 0 : v.bits); R->nonnull[k].push_back(!v.null);
           }
           R->n_rows++;
+        } else if (P.mode == PM_TOPN) {
+          TopRow tr;
+          int e2 = make_item(P, row, cells, bases[b] + e, &tr.it);
+          if (e2) { report(bases[b] + e, e2); continue; }
+          for (int k = 0; k < P.n_out; ++k) {
+            Value v;
+            int e3 = cell_value(P, row, cells, P.out_cols[k], &v);
+            if (e3) { v.null = true; v.bits = 0; tr.it.slot = (unsigned)e3; }  // decode errors only matter for surviving rows
+            tr.bits.push_back(v.null ? 0 : v.bits); tr.nn.push_back(!v.null);
+          }
+          top_rows.push_back(std::move(tr));
         } else if (P.mode == PM_AGG) {
           GroupAcc* acc = &single;
           if (P.has_group) {
@@ -135,6 +148,19 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
     if (P.mode == PM_SCAN) {
       // keep only rows before the failing entry: they were pushed in order, rows after it were skipped above
     }
+  }
+  if (P.mode == PM_TOPN && err == ~0ull) {
+    std::sort(top_rows.begin(), top_rows.end(), [&](const TopRow& a, const TopRow& b) { return item_less(a.it, b.it, P); });
+    size_t n = std::min<size_t>(top_rows.size(), P.limit);
+    for (size_t i = 0; i < cp.output_offsets.size(); ++i) {
+      uint32_t k = cp.output_offsets[i];
+      R->kinds[i] = cp.schema[k].kind;
+      for (size_t r = 0; r < n; ++r) {
+        if (top_rows[r].it.slot && R->status == 0) { R->status = B2_ERR_CORRUPTED; R->dev_err = (int)top_rows[r].it.slot; }
+        R->data[i].push_back(top_rows[r].bits[k]); R->nonnull[i].push_back(top_rows[r].nn[k]);
+      }
+    }
+    R->n_rows = R->status ? 0 : n;
   }
   if (P.mode == PM_SCAN) {
     for (int k = 0; k < P.n_out; ++k) R->kinds[k] = cp.schema[cp.output_offsets[k]].kind;

@@ -147,6 +147,24 @@ def real_sum_plans():
             ("sum_real_group", scan().aggregation([("sum", col(C4, tp=ffi.TP_DOUBLE))], group_by=[col(C6, tp=ffi.TP_LONG)]).build())]
 
 
+def topn_plans():
+    """(name, Plan, exact) — exact=False when ties at the cut make the surviving rows ambiguous in the reference too
+    (TopNHeap keeps whichever tied rows its binary heap happens to hold): then only the sort keys are compared."""
+    def scan():
+        return Plan().table_scan(TABLE, COLUMNS)
+    return [
+        ("topn_two_keys", scan().topn([(col(C2), True), (col(C1), False)], 50).build(), True, None),
+        ("topn_real_desc_handle", scan().topn([(col(C4, tp=ffi.TP_DOUBLE), True), (col(C_H), False)], 30).build(), True, None),
+        ("topn_expr", scan().topn([(plus(col(C6), col(C2)), False), (col(C_H), True)], 40).build(), True, None),
+        ("topn_all_rows", scan().topn([(col(C1), False), (col(C_H), False)], 2000).build(), True, None),
+        ("topn_all_rows_ties", scan().topn([(col(C1), False)], 2000).build(), False, [C1]),
+        ("topn_zero", scan().topn([(col(C1), False)], 0).build(), True, None),
+        ("topn_after_filter", scan().selection(lt(col(C6), const_int(8))).topn([(col(C1), True)], 25).build(output_offsets=[C1, C6, C_H]), True, None),
+        ("topn_unsigned_ties", scan().topn([(col(C3, unsigned=True), False)], 20).build(), False, [C3]),
+        ("topn_small_domain_ties", scan().topn([(col(C6), True), (col(C2), False)], 60).build(), False, [C6, C2]),
+    ]
+
+
 def is_agg(name):
     return name.startswith(("count", "sum", "agg", "group"))
 

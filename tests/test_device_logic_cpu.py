@@ -135,3 +135,11 @@ def test_check_supported_mirrors_runner():
     assert emu.check_supported(two)[0] == ffi.B2_ERR_UNSUPPORTED
     rc, msg = emu.check_supported(Plan().table_scan(5, cols).selection(lt(col(2), const_int(3))).build(output_offsets=[0]))
     assert rc == ffi.B2_ERR_UNSUPPORTED and "Int/Real" in msg
+
+
+@pytest.mark.parametrize("name,plan,exact,keys", sc.topn_plans(), ids=[t[0] for t in sc.topn_plans()])
+def test_topn_device_logic_matches_oracle(name, plan, exact, keys, regions):
+    from compare import assert_topn
+    for seed, n_blocks, ranges in ((1, 1, sc.WHOLE), (2, 3, sc.split_ranges())):
+        region = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=n_blocks)
+        assert_topn(emu.dag_handle(plan, ranges, region), orc.dag_handle(plan, ranges, region), exact, keys, ctx=f"{name}/seed{seed}")

@@ -900,4 +900,50 @@ B2_HD void limbs_to_decimal(unsigned long long lo, unsigned long long hi, bool i
 }
 
 
+// One TopN candidate: order-by values as order-preserving words + global entry id as the final tie-break
+// (earlier rows win ties, like TopNHeap::add_row's strict `<`, top_n_heap.rs:46-50).
+struct TopItem {
+  unsigned long long w[MAX_ORDER];
+  unsigned long long id;  // global CF_WRITE entry index of the row's first version
+  unsigned int nulls;     // bit k: order-by value k is NULL; bit 31: empty slot (sorts last)
+  unsigned int slot;      // (source list << 16) | index, filled by the merge kernel
+};
+
+// HeapItemUnsafe::cmp_sort_key (top_n_heap.rs:188-222) + ScalarValueRef::cmp_sort_key (scalar.rs:374-411):
+// column by column, NULL < any value, unsigned compare for unsigned field types, reversed for DESC; the entry id
+// makes the order total so that the earliest rows win ties.
+B2_HD bool item_less(const TopItem& a, const TopItem& b, const DevPlan& P) {
+  bool ea = a.nulls >> 31, eb = b.nulls >> 31;
+  if (ea || eb) return !ea && eb;
+  for (int k = 0; k < P.n_order; ++k) {
+    unsigned int na = (a.nulls >> k) & 1, nb = (b.nulls >> k) & 1;
+    int c;
+    if (na || nb) c = (int)nb - (int)na;  // NULL (n=1) sorts first: a NULL, b not -> -1
+    else c = a.w[k] < b.w[k] ? -1 : (a.w[k] > b.w[k] ? 1 : 0);
+    if (c == 0) continue;
+    if (P.order[k].desc) c = -c;
+    return c < 0;
+  }
+  return a.id < b.id;
+}
+
+B2_HD int make_item(const DevPlan& P, const Row& row, const Cells& cells, uint64_t id, TopItem* it) {
+  it->nulls = 0; it->id = id; it->slot = 0;
+  for (int k = 0; k < MAX_ORDER; ++k) it->w[k] = 0;
+  for (int k = 0; k < P.n_order; ++k) {
+    Value v;
+    int e = eval_expr(P, P.order[k].e, row, cells, &v, nullptr);
+    if (e) return e;
+    if (v.null) { it->nulls |= 1u << k; continue; }
+    unsigned long long w = v.bits;
+    if (P.order[k].et == 1) {
+      if (bits_f64(w) == 0.0) w = 0;  // -0.0 == 0.0
+      w = (w >> 63) ? ~w : (w | 0x8000000000000000ull);
+    } else if (!P.order[k].is_unsigned) w ^= 0x8000000000000000ull;
+    it->w[k] = w;
+  }
+  return DE_NONE;
+}
+
+
 }  // namespace b2

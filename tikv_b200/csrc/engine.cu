@@ -221,6 +221,7 @@ struct b2_exec {
       if (s.free_ev) cudaEventDestroy(s.free_ev);
     }
     for (auto& e : kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (DevBuf* b : {&tn_lists, &tn_counts, &tn_pair, &tn_pair_cnt, &tn_tmp, &tn_tmp_cnt, &tn_blk_pay, &tn_blk_null, &tn_run_pay, &tn_run_null, &tn_tmp_pay, &tn_tmp_null, &tn_bitmap}) b->release();
     for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &grp_keys, &grp_null, &grp_acc, &res_ptrs}) b->release();
     for (auto& b : res_cols) b.release();
     for (auto& b : res_bitmaps) b.release();
@@ -803,6 +804,108 @@ struct b2_exec {
     return failed ? last_err.status : B2_OK;
   }
 
+  // ---- PM_TOPN: per unit: per-CTA candidate lists -> unit top-N -> payload gather -> merge into the running top-N ----
+  DevBuf tn_lists, tn_counts, tn_pair, tn_pair_cnt, tn_tmp, tn_tmp_cnt, tn_blk_pay, tn_blk_null, tn_run_pay, tn_run_null, tn_tmp_pay, tn_tmp_null, tn_bitmap;
+
+  int run_topn(b2_batch* out) {
+    const DevPlan& P = cp.dev;
+    drained = true;
+    uint32_t limit = (uint32_t)P.limit, n_out = (uint32_t)P.n_out;
+    int rc = init_device_state();
+    if (rc) return rc;
+    uint32_t n = 0;
+    if (limit > 0 && !units.empty()) {  // top_n_executor.rs:304-312: n == 0 drains immediately
+      uint32_t cap = 512;
+      while (cap < limit + TILE) cap <<= 1;
+      size_t smem = topn_smem_bytes(cap);
+      int grid = scan_max_grid(PM_TOPN, smem);
+      size_t isz = sizeof(TopItem);
+      CUDA_TRY(tn_lists.reserve((size_t)grid * limit * isz)); CUDA_TRY(tn_counts.reserve((size_t)grid * 4));
+      CUDA_TRY(tn_pair.reserve((size_t)2 * limit * isz)); CUDA_TRY(tn_pair_cnt.reserve(8));
+      CUDA_TRY(tn_tmp.reserve((size_t)limit * isz)); CUDA_TRY(tn_tmp_cnt.reserve(4));
+      size_t pay_bytes = (size_t)n_out * limit * 8, null_bytes = (size_t)n_out * limit;
+      for (DevBuf* b : {&tn_blk_pay, &tn_run_pay, &tn_tmp_pay}) CUDA_TRY(b->reserve(pay_bytes));
+      for (DevBuf* b : {&tn_blk_null, &tn_run_null, &tn_tmp_null}) CUDA_TRY(b->reserve(null_bytes));
+      CUDA_TRY(cudaMemsetAsync(tn_pair_cnt.p, 0, 8, stream));
+      TopItem* pair = (TopItem*)tn_pair.p;
+      unsigned int* pair_cnt = (unsigned int*)tn_pair_cnt.p;
+      for (size_t ui = 0; ui < units.size(); ++ui) {
+        const Unit& u = units[ui];
+        BlockView v;
+        rc = acquire_block(u.block_idx, &v);
+        if (rc) return rc;
+        ScanArgs a = base_args(u, v);
+        a.c_lo = u.e_lo; a.c_hi = u.e_hi;
+        uint32_t n_tiles = (u.e_hi - u.e_lo + TILE - 1) / TILE;
+        uint32_t g = (uint32_t)std::min<uint32_t>((uint32_t)grid, n_tiles);
+        a.topn.items = (TopItem*)tn_lists.p; a.topn.counts = (unsigned int*)tn_counts.p; a.topn.n_lists = g; a.topn.stride = limit;
+        a.topn_cap = cap;
+        CUDA_TRY(cudaMemsetAsync(tn_counts.p, 0, (size_t)grid * 4, stream));
+        kernel_begin();
+        CUDA_TRY(launch_scan(P, a, (int)g, smem, stream));
+        kernel_end();
+        // unit top-N (sorted) lands in the second half of `pair`
+        TopNLists unit_out; unit_out.items = pair + limit; unit_out.counts = pair_cnt + 1; unit_out.n_lists = 1; unit_out.stride = limit;
+        CUDA_TRY(launch_topn_merge(P, a.topn, unit_out, cap, stream));
+        CUDA_TRY(launch_topn_gather(P, a, pair + limit, pair_cnt + 1, (unsigned long long*)tn_blk_pay.p, (unsigned char*)tn_blk_null.p, limit, stream));
+        // running top-N (first half) + unit top-N -> tmp, then back into the first half
+        TopNLists both; both.items = pair; both.counts = pair_cnt; both.n_lists = 2; both.stride = limit;
+        TopNLists merged; merged.items = (TopItem*)tn_tmp.p; merged.counts = (unsigned int*)tn_tmp_cnt.p; merged.n_lists = 1; merged.stride = limit;
+        CUDA_TRY(launch_topn_merge(P, both, merged, cap, stream));
+        CUDA_TRY(launch_topn_copy((const TopItem*)tn_tmp.p, (const unsigned int*)tn_tmp_cnt.p, n_out, limit, (const unsigned long long*)tn_run_pay.p,
+                                  (const unsigned char*)tn_run_null.p, (const unsigned long long*)tn_blk_pay.p, (const unsigned char*)tn_blk_null.p,
+                                  (unsigned long long*)tn_tmp_pay.p, (unsigned char*)tn_tmp_null.p, stream));
+        CUDA_TRY(cudaMemcpyAsync(pair, tn_tmp.p, (size_t)limit * isz, cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(pair_cnt, tn_tmp_cnt.p, 4, cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(tn_run_pay.p, tn_tmp_pay.p, pay_bytes, cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(tn_run_null.p, tn_tmp_null.p, null_bytes, cudaMemcpyDeviceToDevice, stream));
+        release_block(u.block_idx);
+        prefetch_after(ui);
+        entries_scanned += u.e_hi - u.e_lo;
+        stats.num_iterations++;
+        stats.kernel_launches += 4;
+      }
+      CUDA_TRY(cudaMemcpyAsync(h_ctr.p, pair_cnt, 4, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      n = *(uint32_t*)h_ctr.p;
+    }
+    Counters c;
+    rc = read_counters(&c);
+    if (rc) return rc;
+    fill_stats(c);
+    if (c.err != ~0ull) { device_error(c); n = 0; }
+    else { check_trailing_lock(); if (failed) n = 0; }
+    // publish: payload columns of the running list, NULL flags packed into BitVec words
+    uint32_t words = (std::max<uint32_t>(limit, 1) + 63) / 64;
+    if (n) {
+      CUDA_TRY(tn_bitmap.reserve((size_t)n_out * words * 8));
+      CUDA_TRY(launch_pack_nulls((const unsigned char*)tn_run_null.p, n_out, limit, n, (unsigned long long*)tn_bitmap.p, words, stream));
+    }
+    size_t n_sel = cp.output_offsets.size();
+    cols.assign(n_sel, b2_column{});
+    if (out_loc == B2_LOC_HOST && n) CUDA_TRY(h_out.reserve(n_sel * ((size_t)n * 8 + (size_t)words * 8)));
+    for (size_t i = 0; i < n_sel; ++i) {
+      uint32_t k = cp.output_offsets[i];
+      const OutCol& oc = cp.schema[k];
+      cols[i].kind = oc.kind; cols[i].field_tp = oc.field_tp; cols[i].field_flag = oc.field_flag; cols[i].len = n;
+      if (!n) continue;
+      const uint8_t* d = (const uint8_t*)tn_run_pay.p + (size_t)k * limit * 8;
+      const uint8_t* bm = (const uint8_t*)tn_bitmap.p + (size_t)k * words * 8;
+      if (out_loc == B2_LOC_HOST) {
+        uint8_t* hp = (uint8_t*)h_out.p + i * ((size_t)n * 8 + (size_t)words * 8);
+        CUDA_TRY(cudaMemcpyAsync(hp, d, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(hp + (size_t)n * 8, bm, (size_t)words * 8, cudaMemcpyDeviceToHost, stream));
+        cols[i].data = hp; cols[i].null_bitmap = (const uint64_t*)(hp + (size_t)n * 8);
+        d2h_bytes += (size_t)n * 8 + (size_t)words * 8;
+      } else { cols[i].data = d; cols[i].null_bitmap = (const uint64_t*)bm; }
+    }
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    out->columns = cols.data(); out->n_columns = (uint32_t)n_sel; out->n_rows = n; out->n_warnings = 0;
+    out->is_drained = B2_DRAIN_DRAINED;
+    stats.num_produced_rows += n;
+    return failed ? last_err.status : B2_OK;
+  }
+
   int next_batch(uint64_t scan_rows, b2_batch* out) {
     memset(out, 0, sizeof(*out));
     cudaSetDevice(device);
@@ -817,7 +920,7 @@ struct b2_exec {
     int rc;
     if (cp.dev.mode == PM_SCAN) rc = next_scan_batch(scan_rows, out);
     else if (cp.dev.mode == PM_AGG) rc = run_agg(out);
-    else rc = fail(B2_ERR_UNSUPPORTED, "TopN is not wired on the device path yet");
+    else rc = run_topn(out);
     cudaEventRecord(t1, stream);
     cudaEventSynchronize(t1);
     float ms = 0;
@@ -839,7 +942,6 @@ int32_t b2_check_supported(const b2_dag_plan* plan) {
   CompiledPlan cp;
   std::string msg;
   int rc = compile_plan(plan, &cp, &msg);
-  if (rc == B2_OK && cp.dev.mode == PM_TOPN) { rc = B2_ERR_UNSUPPORTED; msg = "TopN is not wired on the device path yet"; }
   if (rc) g_last_error = msg;
   return rc;
 }
@@ -851,7 +953,6 @@ int32_t b2_exec_open(const b2_dag_plan* plan, const b2_key_range* ranges, uint32
   std::string msg;
   int rc = compile_plan(plan, &h->cp, &msg);
   if (rc) { g_last_error = msg; return rc; }
-  if (h->cp.dev.mode == PM_TOPN) { g_last_error = "TopN is not wired on the device path yet"; return B2_ERR_UNSUPPORTED; }
   h->device = src->device;
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) { g_last_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e) + " (the CUDA device path is required; there is no CPU fallback)"; return B2_ERR_CUDA; }

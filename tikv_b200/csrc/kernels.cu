@@ -76,6 +76,36 @@ __device__ __forceinline__ void acc_update(Acc* acc, const DevAgg& g, const Valu
   }
 }
 
+// ---- TopN helpers --------------------------------------------------------------------------------------------
+// Sort `cap` candidates in shared memory (bitonic, all threads), keep the best `limit`.
+__device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int limit, unsigned int* s_cnt, unsigned int* s_have_thr, TopItem* s_thr,
+                                 const DevPlan& P) {
+  const unsigned int tid = threadIdx.x, nt = blockDim.x;
+  unsigned int cnt = *s_cnt;
+  for (unsigned int i = cnt + tid; i < cap; i += nt) items[i].nulls = 0x80000000u;
+  __syncthreads();
+  for (unsigned int k = 2; k <= cap; k <<= 1) {
+    for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned int i = tid; i < cap; i += nt) {
+        unsigned int x = i ^ j;
+        if (x > i) {
+          bool up = (i & k) == 0;
+          TopItem a = items[i], b = items[x];
+          bool swap = up ? item_less(b, a, P) : item_less(a, b, P);
+          if (swap) { items[i] = b; items[x] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) {
+    unsigned int keep = cnt < limit ? cnt : limit;
+    *s_cnt = keep;
+    if (keep == limit && limit > 0) { *s_thr = items[limit - 1]; *s_have_thr = 1; }
+  }
+  __syncthreads();
+}
+
 // ---- the fused scan kernel -------------------------------------------------------------------------------
 struct SmemTable {  // per-CTA group table (dynamic shared memory): keys | acc | occ
   unsigned long long* keys;
@@ -106,6 +136,15 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const __grid_constant__ DevP
     for (unsigned int i = tid; i < st.slots; i += TILE) st.occ[i] = 0;
     for (unsigned int i = tid; i < st.slots * P.acc_words; i += TILE) st.acc[i] = 0;
     if (tid == 0) s_tbl_used = 0;
+    __syncthreads();
+  }
+
+  // PM_TOPN: per-CTA candidate buffer (dynamic shared memory) + current threshold
+  __shared__ unsigned int s_top_cnt, s_top_have_thr;
+  __shared__ TopItem s_top_thr;
+  TopItem* top_items = reinterpret_cast<TopItem*>(dyn_smem);
+  if (MODE == PM_TOPN) {
+    if (tid == 0) { s_top_cnt = 0; s_top_have_thr = 0; }
     __syncthreads();
   }
 
@@ -209,6 +248,20 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const __grid_constant__ DevP
         }
       }
       __syncthreads();  // s_warp_cnt / s_base reused by the next tile
+    } else if (MODE == PM_TOPN) {
+      // BatchTopN: keep the `limit` smallest rows under the order-by key.  A row is a candidate only if it beats
+      // the CTA's current threshold (the limit-th best seen so far); candidates are sorted when the buffer fills.
+      if (live) {
+        TopItem it;
+        int err = make_item(P, row, cells, A.entry_base + e, &it);
+        if (err) report_err(A.ctr, A.entry_base + e, err);
+        else if (!s_top_have_thr || item_less(it, s_top_thr, P)) {
+          unsigned int pos = atomicAdd(&s_top_cnt, 1u);
+          top_items[pos] = it;  // pos < topn_cap: the buffer is compacted whenever fewer than TILE slots remain
+        }
+      }
+      __syncthreads();
+      if (s_top_cnt + TILE > A.topn_cap) cta_topn_compact(top_items, A.topn_cap, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
     } else if (MODE == PM_AGG) {
       if (live) {
         if (!P.has_group) {
@@ -279,6 +332,13 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const __grid_constant__ DevP
   }
 
   // ---- epilogue: flush CTA-private state ----
+  if (MODE == PM_TOPN) {
+    __syncthreads();
+    cta_topn_compact(top_items, A.topn_cap, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
+    unsigned int keep = s_top_cnt;
+    for (unsigned int i = tid; i < keep; i += TILE) A.topn.items[(size_t)blockIdx.x * A.topn.stride + i] = top_items[i];
+    if (tid == 0) A.topn.counts[blockIdx.x] = keep;
+  }
   if (MODE == PM_AGG) {
     if (!P.has_group) {
       // warp-shuffle tree, then one atomic per warp into slot 0 of the HBM table
@@ -347,7 +407,13 @@ int scan_max_grid(int mode, size_t smem) {
   int per_sm = 0;
   cudaError_t e;
   if (mode == PM_SCAN) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_SCAN>, TILE, smem);
-  else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_AGG>, TILE, smem);
+  else if (mode == PM_TOPN) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_TOPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_TOPN>, TILE, smem);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_AGG>, TILE, smem);
+  }
   if (e != cudaSuccess || per_sm < 1) per_sm = 1;
   return per_sm * num_sms();
 }
@@ -358,10 +424,136 @@ cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
   if (plan.mode == PM_SCAN) {
     scan_kernel<PM_SCAN><<<grid, TILE, smem, s>>>(plan, a);
+  } else if (plan.mode == PM_TOPN) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_TOPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_kernel<PM_TOPN><<<grid, TILE, smem, s>>>(plan, a);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     scan_kernel<PM_AGG><<<grid, TILE, smem, s>>>(plan, a);
   }
+  return cudaGetLastError();
+}
+
+// ---- TopN: merge candidate lists, gather row payloads ------------------------------------------------------------
+size_t topn_smem_bytes(uint32_t cap) { return (size_t)cap * sizeof(TopItem); }
+
+// one CTA streams every item of `in` through the same threshold buffer and leaves the best `limit`, sorted, in out list 0
+__global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant__ DevPlan P, TopNLists in, TopNLists out, unsigned int cap) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ unsigned int s_cnt, s_have_thr;
+  __shared__ TopItem s_thr;
+  TopItem* items = reinterpret_cast<TopItem*>(dyn_smem);
+  const unsigned int tid = threadIdx.x;
+  if (tid == 0) { s_cnt = 0; s_have_thr = 0; }
+  __syncthreads();
+  const unsigned int total = in.n_lists * in.stride;
+  for (unsigned int base = 0; base < total; base += TILE) {
+    unsigned int f = base + tid;
+    if (f < total) {
+      unsigned int l = f / in.stride, i = f % in.stride;
+      if (i < in.counts[l]) {
+        TopItem it = in.items[(size_t)l * in.stride + i];
+        it.slot = (l << 16) | i;
+        if (!s_have_thr || item_less(it, s_thr, P)) {
+          unsigned int pos = atomicAdd(&s_cnt, 1u);
+          items[pos] = it;
+        }
+      }
+    }
+    __syncthreads();
+    if (s_cnt + TILE > cap) cta_topn_compact(items, cap, (unsigned int)P.limit, &s_cnt, &s_have_thr, &s_thr, P);
+  }
+  __syncthreads();
+  cta_topn_compact(items, cap, (unsigned int)P.limit, &s_cnt, &s_have_thr, &s_thr, P);
+  unsigned int keep = s_cnt;
+  for (unsigned int i = tid; i < keep; i += TILE) out.items[i] = items[i];
+  if (tid == 0) out.counts[0] = keep;
+}
+
+cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const TopNLists& out, uint32_t cap, cudaStream_t s) {
+  size_t smem = topn_smem_bytes(cap);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(topn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  topn_merge_kernel<<<1, TILE, smem, s>>>(plan, in, out, cap);
+  return cudaGetLastError();
+}
+
+// decode every scan column of the selected rows (take_all_append_to, top_n_heap.rs:56-133); one thread per row
+__global__ void topn_gather_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A, const TopItem* items, const unsigned int* count,
+                                   unsigned long long* pay, unsigned char* pay_null, unsigned int stride) {
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *count) return;
+  uint32_t e = (uint32_t)(items[i].id - A.entry_base);
+  RunOut ro;
+  resolve_run(A.blk, e, A.e_hi, P.read_ts, P.isolation, A.dflt, &ro);
+  Row row;
+  Cells cells;
+  int err = ro.err ? ro.err : (ro.found ? DE_NONE : DE_BAD_WRITE);
+  if (!err) {
+    uint32_t ko = A.blk.koff[e], kl = A.blk.koff[e + 1] - ko;
+    row.enc_key = A.blk.keys + ko; row.enc_key_len = kl - 8; row.commit_ts = ro.commit_ts;
+    err = row_open(ro.val, ro.val_len, &row.rv);
+    if (!err) err = row_split(P, row, cells);
+  }
+  for (int k = 0; k < P.n_out; ++k) {
+    Value v; v.null = true; v.bits = 0;
+    if (!err) {
+      int e2 = cell_value(P, row, cells, P.out_cols[k], &v);
+      if (e2) { report_err(A.ctr, items[i].id, e2); v.null = true; v.bits = 0; }
+    }
+    pay[(size_t)k * stride + i] = v.null ? 0ull : v.bits;
+    pay_null[(size_t)k * stride + i] = v.null ? 1 : 0;
+  }
+  if (err) report_err(A.ctr, items[i].id, err);
+}
+
+cudaError_t launch_topn_gather(const DevPlan& plan, const ScanArgs& a, const TopItem* items, const unsigned int* count, unsigned long long* pay,
+                               unsigned char* pay_null, uint32_t stride, cudaStream_t s) {
+  if (!stride) return cudaSuccess;
+  topn_gather_kernel<<<(stride + 127) / 128, 128, 0, s>>>(plan, a, items, count, pay, pay_null, stride);
+  return cudaGetLastError();
+}
+
+// payload of the merged list: row i comes from list (slot >> 16), index (slot & 0xffff)
+__global__ void topn_copy_kernel(const TopItem* items, const unsigned int* count, unsigned int n_out, unsigned int stride, const unsigned long long* pay0,
+                                 const unsigned char* null0, const unsigned long long* pay1, const unsigned char* null1, unsigned long long* pay_out,
+                                 unsigned char* null_out) {
+  unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *count) return;
+  unsigned int l = items[i].slot >> 16, j = items[i].slot & 0xffffu;
+  const unsigned long long* p = l ? pay1 : pay0;
+  const unsigned char* q = l ? null1 : null0;
+  for (unsigned int k = 0; k < n_out; ++k) {
+    pay_out[(size_t)k * stride + i] = p[(size_t)k * stride + j];
+    null_out[(size_t)k * stride + i] = q[(size_t)k * stride + j];
+  }
+}
+
+cudaError_t launch_topn_copy(const TopItem* items, const unsigned int* count, uint32_t n_out, uint32_t stride, const unsigned long long* pay0,
+                             const unsigned char* null0, const unsigned long long* pay1, const unsigned char* null1, unsigned long long* pay_out,
+                             unsigned char* null_out, cudaStream_t s) {
+  if (!stride) return cudaSuccess;
+  topn_copy_kernel<<<(stride + 127) / 128, 128, 0, s>>>(items, count, n_out, stride, pay0, null0, pay1, null1, pay_out, null_out);
+  return cudaGetLastError();
+}
+
+// byte-per-cell NULL flags -> BitVec words (bit = 1 means non-null)
+__global__ void pack_nulls_kernel(const unsigned char* nulls, unsigned int n_cols, unsigned int stride, unsigned int n, unsigned long long* bitmaps,
+                                  unsigned int words_per_col) {
+  unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_cols * words_per_col) return;
+  unsigned int k = t / words_per_col, w = t % words_per_col;
+  unsigned long long bits = 0;
+  for (unsigned int b = 0; b < 64; ++b) {
+    unsigned int i = w * 64 + b;
+    if (i >= n || !nulls[(size_t)k * stride + i]) bits |= 1ull << b;
+  }
+  bitmaps[(size_t)k * words_per_col + w] = bits;
+}
+
+cudaError_t launch_pack_nulls(const unsigned char* nulls, uint32_t n_cols, uint32_t stride, uint32_t n, unsigned long long* bitmaps, uint32_t words_per_col, cudaStream_t s) {
+  unsigned int t = n_cols * words_per_col;
+  if (!t) return cudaSuccess;
+  pack_nulls_kernel<<<(t + 127) / 128, 128, 0, s>>>(nulls, n_cols, stride, n, bitmaps, words_per_col);
   return cudaGetLastError();
 }
 

@@ -34,6 +34,12 @@ struct AggTable {
   unsigned int cap;          // power of two
 };
 
+struct TopNLists {
+  TopItem* items;        // n_lists * stride
+  unsigned int* counts;  // n_lists
+  unsigned int n_lists, stride;
+};
+
 struct ScanArgs {
   BlockView blk;
   DefaultCf dflt;
@@ -50,8 +56,8 @@ struct ScanArgs {
   AggTable tbl;
   uint32_t smem_slots;              // per-CTA table slots (power of two), 0 = disabled
   // PM_TOPN
-  unsigned long long* topn_items;   // per-CTA candidate lists
-  unsigned int* topn_counts;
+  TopNLists topn;                   // per-CTA result lists (stride = limit)
+  uint32_t topn_cap;                // shared-memory candidate capacity (power of two >= limit + TILE)
 };
 
 struct ChecksumArgs {
@@ -81,6 +87,15 @@ cudaError_t launch_agg_finalize(const DevPlan& plan, const AggTable& t, Counters
                                 unsigned long long* out_acc, cudaStream_t s);
 cudaError_t launch_agg_result(const DevPlan& plan, unsigned int n_groups, const unsigned long long* g_keys, const unsigned char* g_null,
                               const unsigned long long* g_acc, unsigned long long** col_data, unsigned long long** col_bitmap, cudaStream_t s);
+// TopN: merge `in` lists into the best `limit` items (sorted) -> out list 0; gather decodes the rows of a list
+cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const TopNLists& out, uint32_t cap, cudaStream_t s);
+cudaError_t launch_topn_gather(const DevPlan& plan, const ScanArgs& a, const TopItem* items, const unsigned int* count, unsigned long long* pay,
+                               unsigned char* pay_null, uint32_t stride, cudaStream_t s);
+cudaError_t launch_topn_copy(const TopItem* items, const unsigned int* count, uint32_t n_out, uint32_t stride, const unsigned long long* pay0,
+                             const unsigned char* null0, const unsigned long long* pay1, const unsigned char* null1, unsigned long long* pay_out,
+                             unsigned char* null_out, cudaStream_t s);
+cudaError_t launch_pack_nulls(const unsigned char* nulls, uint32_t n_cols, uint32_t stride, uint32_t n, unsigned long long* bitmaps, uint32_t words_per_col, cudaStream_t s);
+size_t topn_smem_bytes(uint32_t cap);
 cudaError_t launch_checksum(const ChecksumArgs& a, int grid, cudaStream_t s);
 cudaError_t launch_bounds_search(const BlockView* blocks, uint32_t n_blocks, const uint8_t* bounds, const uint32_t* bound_offs, uint32_t n_bounds,
                                  uint32_t* out, cudaStream_t s);

@@ -222,6 +222,7 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
         if (!lower_expr(e.order_by[k].expr, P, &o.e, &et, &uns, nullptr, nullptr, msg)) return B2_ERR_UNSUPPORTED;
         o.desc = e.order_by[k].desc ? 1 : 0; o.et = et; o.is_unsigned = uns;
       }
+      if (e.limit > 2048) { *msg = "TopN limit above 2048 is not on the device path yet"; return B2_ERR_UNSUPPORTED; }
       P.n_order = (int)e.n_order_by; P.limit = e.limit;
     } else {
       *msg = "executor type " + std::to_string(e.tp) + " is not supported on the device path";
