@@ -60,7 +60,7 @@ enum DefState { DS_NONE = 0, DS_VALUE = 1, DS_NULL = 2, DS_ERROR = 3 };
 struct DevCol {
   int64_t col_id;
   int64_t default_bits;
-  uint8_t kind, role, is_unsigned, not_null, tp, v2_class, def_state, _pad;
+  uint8_t kind, role, is_unsigned, not_null, tp, v2_class, def_state, v2_hint;
 };
 struct DevNode {
   int32_t sig;
@@ -105,23 +105,56 @@ struct BlockView {
 };
 
 // ---- byte access -------------------------------------------------------------------------------
-B2_HD uint32_t ld8(const uint8_t* p) { return *p; }
-B2_HD uint64_t ld_be64(const uint8_t* p) {
-  uint64_t v = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v = (v << 8) | p[i];
+// Unaligned 8-byte little-endian load built from aligned 32-bit words + funnel shifts (3 word loads instead of 8
+// byte loads).  It may touch up to 3 bytes before and 11 bytes after `p`, always inside the same 16-byte-padded
+// heap (ABI contract in b2_copr.h) or the padded shared-memory stage.
+B2_HD uint64_t ld64(const uint8_t* p) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long a = (unsigned long long)p;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~3ull);
+  uint32_t s = (uint32_t)(a & 3u) * 8u;
+  uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+  uint32_t lo = __funnelshift_r(w0, w1, s), hi = __funnelshift_r(w1, w2, s);
+  return ((uint64_t)hi << 32) | lo;
+#else
+  uint64_t v;
+  __builtin_memcpy(&v, p, 8);
   return v;
+#endif
 }
-B2_HD uint64_t ld_le(const uint8_t* p, int n) {  // n in {1,2,4,8}
-  uint64_t v = 0;
-  for (int i = n - 1; i >= 0; --i) v = (v << 8) | p[i];
+B2_HD uint32_t ld32(const uint8_t* p) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long a = (unsigned long long)p;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~3ull);
+  return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3u) * 8u);
+#else
+  uint32_t v;
+  __builtin_memcpy(&v, p, 4);
   return v;
+#endif
+}
+B2_HD uint64_t bswap64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  return ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+#else
+  return __builtin_bswap64(v);
+#endif
+}
+B2_HD uint32_t ld8(const uint8_t* p) { return *p; }
+B2_HD uint64_t ld_be64(const uint8_t* p) { return bswap64(ld64(p)); }
+B2_HD uint64_t ld_le(const uint8_t* p, int n) {  // n in {1,2,4,8}
+  uint64_t v = ld64(p);
+  return n >= 8 ? v : (v & ((1ull << (8 * n)) - 1));
 }
 B2_HD bool bytes_eq(const uint8_t* a, const uint8_t* b, uint32_t n) {
-  // compare from the tail: record keys share their table prefix and differ in the handle
-  for (uint32_t i = n; i > 0; --i)
-    if (a[i - 1] != b[i - 1]) return false;
-  return true;
+  // 8 bytes at a time from the tail: record keys share their table prefix and differ in the handle
+  while (n >= 8) {
+    n -= 8;
+    if (ld64(a + n) != ld64(b + n)) return false;
+  }
+  if (n == 0) return true;
+  return ((ld64(a) ^ ld64(b)) & ((1ull << (8 * n)) - 1)) == 0;
 }
 B2_HD int bytes_cmp(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn) {
   uint32_t m = an < bn ? an : bn;
@@ -134,6 +167,12 @@ B2_HD int bytes_cmp(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn
 // components/codec/src/number.rs:445-483 try_decode_var_u64. returns bytes consumed, 0 = eof
 B2_HD uint32_t dec_var_u64(const uint8_t* p, uint32_t n, uint64_t* out) {
   uint64_t v = 0;
+  if (n == 0) return 0;
+  {  // fast path: 1- and 2-byte varints (column ids, start_ts deltas, small ints) from one word load
+    uint32_t w = ld32(p);
+    if ((w & 0x80u) == 0) { *out = w & 0x7fu; return 1; }
+    if (n >= 2 && (w & 0x8000u) == 0) { *out = (w & 0x7fu) | (((w >> 8) & 0x7fu) << 7); return 2; }
+  }
   if (n >= 10) {
     for (uint32_t i = 0; i < 9; ++i) {
       uint64_t b = p[i];
@@ -229,6 +268,10 @@ B2_HD bool same_user_key(const BlockView& b, uint32_t i, uint32_t j) {
 B2_HD int raw_key_len(const uint8_t* enc, uint32_t enc_len) {
   uint32_t off = 0;
   int raw = 0;
+  if (enc_len == 27) {  // int-handle record key: two full groups + a 3-byte tail (markers FF FF FA, 5 zero pad bytes)
+    uint64_t tail = ld64(enc + 19);  // enc[19..26]
+    if (enc[8] == 0xff && enc[17] == 0xff && (tail >> 16) == 0xfa0000000000ull) return 19;
+  }
   for (;;) {
     if (off + 9 > enc_len) return -1;
     uint32_t marker = enc[off + 8];
@@ -243,6 +286,14 @@ B2_HD int raw_key_len(const uint8_t* enc, uint32_t enc_len) {
 }
 B2_HD uint32_t raw_at(const uint8_t* enc, uint32_t j) { return enc[j + (j >> 3)]; }
 B2_HD uint64_t raw_be64(const uint8_t* enc, uint32_t j) {
+  if (j == 11) {  // int handle: raw[11..15] = enc[12..16], raw[16..18] = enc[18..20]
+    uint64_t a = bswap64(ld64(enc + 12)), b = bswap64(ld64(enc + 18));
+    return (a & 0xffffffffff000000ull) | (b >> 40);
+  }
+  if (j == 1) {  // table id: raw[1..7] = enc[1..7], raw[8] = enc[9]
+    uint64_t a = bswap64(ld64(enc + 1));
+    return (a & 0xffffffffffffff00ull) | enc[9];
+  }
   uint64_t v = 0;
   for (uint32_t i = 0; i < 8; ++i) v = (v << 8) | raw_at(enc, j + i);
   return v;
@@ -347,7 +398,7 @@ B2_HD bool default_lookup(const DefaultCf& d, const uint8_t* ukey, uint32_t ukle
     if (lo < b.n) {
       const uint8_t* k = b.keys + b.koff[lo];
       uint32_t kl = b.koff[lo + 1] - b.koff[lo];
-      if (kl == uklen + 8 && bytes_eq(k, ukey, uklen) && bytes_eq(k + uklen, ts, 8)) {
+      if (kl == uklen + 8 && bytes_eq(k, ukey, uklen) && ld_be64(k + uklen) == nts) {
         *val = b.vals + b.voff[lo];
         *vlen = b.voff[lo + 1] - b.voff[lo];
         return true;
@@ -497,10 +548,11 @@ B2_HD int row_open(const uint8_t* v, uint32_t n, RowView* r) {
   if (v[0] != 128) { r->fmt = 1; return DE_NONE; }
   r->fmt = 2;
   if (n < 6) return DE_ROW_EOF;
-  uint32_t flags = v[1];
+  uint64_t hdr = ld64(v);  // 0x80, flags, u16 non-null count, u16 null count
+  uint32_t flags = (uint32_t)(hdr >> 8) & 0xffu;
   r->big = flags & 1;
-  r->nn_cnt = (uint16_t)(v[2] | (v[3] << 8));
-  r->null_cnt = (uint16_t)(v[4] | (v[5] << 8));
+  r->nn_cnt = (uint16_t)(hdr >> 16);
+  r->null_cnt = (uint16_t)(hdr >> 32);
   uint32_t idw = r->big ? 4 : 1, ofw = r->big ? 4 : 2;
   uint64_t pos = 6;
   r->ids_off = (uint32_t)pos; pos += (uint64_t)r->nn_cnt * idw;
@@ -521,12 +573,17 @@ B2_HD int row_open(const uint8_t* v, uint32_t n, RowView* r) {
 }
 
 // Locate column `c` of the plan in a v2 row (process_v2 :261-279).
-B2_HD int v2_locate(const RowView& r, int64_t col_id, uint32_t* off, uint32_t* len, int* err) {
+// `hint` = position the column would have if the row held exactly the plan's columns (the common case): one id
+// compare replaces the binary search.
+B2_HD int v2_locate(const RowView& r, int64_t col_id, uint32_t hint, uint32_t* off, uint32_t* len, int* err) {
   int64_t upper = r.big ? 0xffffffffll : 0xffll;
   if (!(col_id > 0 && col_id <= upper)) return CELL_MISSING;
-  uint32_t idx;
-  if (v2_search(r, r.ids_off, r.nn_cnt, (uint32_t)col_id, &idx)) {
-    uint32_t end = v2_off(r, idx), start = idx > 0 ? v2_off(r, idx - 1) : 0;
+  uint32_t idx = hint;
+  bool hit = hint < r.nn_cnt && v2_id(r, r.ids_off, hint) == (uint32_t)col_id;
+  if (hit || v2_search(r, r.ids_off, r.nn_cnt, (uint32_t)col_id, &idx)) {
+    uint32_t end, start;
+    if (!r.big && idx > 0) { uint32_t w = ld32(r.v + r.offs_off + 2 * idx - 2); start = w & 0xffffu; end = w >> 16; }
+    else { end = v2_off(r, idx); start = idx > 0 ? v2_off(r, idx - 1) : 0; }
     if (start > end || end > r.vals_len) { *err = DE_ROW_V2_RANGE; return CELL_MISSING; }
     *off = r.vals_off + start; *len = end - start;
     return CELL_V2;
@@ -579,7 +636,7 @@ B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
       const DevCol& c = P.cols[k];
       if (c.role == CR_HANDLE || c.role == CR_SHADOWED) continue;
       uint32_t off = 0, len = 0;
-      int kind = v2_locate(r, c.col_id, &off, &len, &err);
+      int kind = v2_locate(r, c.col_id, c.v2_hint, &off, &len, &err);
       if (err) return err;
       if (kind == CELL_V2) {
         if (c.v2_class == V2_INT || c.v2_class == V2_UINT) {
@@ -587,6 +644,7 @@ B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
         } else if (c.v2_class == V2_UNSUPPORTED) return DE_UNSUPPORTED_TYPE;
         filled |= 1ull << k;
       } else if (kind == CELL_NULL) filled |= 1ull << k;
+      if (kind != CELL_MISSING) { cells.off[k] = off; cells.len_kind[k] = (len << 2) | (uint32_t)kind; }
     }
   }
   // key side (:386-442)
@@ -624,13 +682,7 @@ B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k
   uint32_t len = 0;
   int kind = CELL_MISSING;
   if ((row.filled >> k) & 1) {
-    if (r.fmt == 1) { p = r.v + cells.off[k]; len = cells.len_kind[k] >> 2; kind = cells.len_kind[k] & 3; }
-    else {
-      uint32_t off = 0;
-      int err = DE_NONE;
-      kind = v2_locate(r, c.col_id, &off, &len, &err);
-      p = r.v + off;
-    }
+    p = r.v + cells.off[k]; len = cells.len_kind[k] >> 2; kind = cells.len_kind[k] & 3;  // located once by row_split
   }
   if (kind == CELL_NULL) { out->null = true; return DE_NONE; }
   if (kind == CELL_MISSING) {
@@ -723,7 +775,65 @@ B2_HD bool mul_ovf_i64(int64_t a, int64_t b, int64_t* r) {
 B2_HD bool f64_finite(double x) { return (f64_bits(x) & 0x7ff0000000000000ull) != 0x7ff0000000000000ull; }
 B2_HD bool f64_isinf(double x) { return (f64_bits(x) & 0x7fffffffffffffffull) == 0x7ff0000000000000ull; }
 
+B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const Cells& cells, Value* result, bool* res_unsigned);
+
+// leaf node (column reference or constant) -> value + flags (bit0 null, bit1 unsigned)
+B2_HD int eval_leaf(const DevPlan& P, const DevNode& nd, const Row& row, const Cells& cells, int64_t* v, uint32_t* f) {
+  if (nd.kind == B2_RPN_COLUMN_REF) {
+    Value x;
+    int e = cell_value(P, row, cells, (int)nd.imm, &x);
+    if (e) return e;
+    *v = (int64_t)x.bits; *f = (x.null ? 1u : 0u) | (P.cols[nd.imm].is_unsigned ? 2u : 0u);
+    return DE_NONE;
+  }
+  *v = nd.imm; *f = (nd.kind == B2_RPN_CONST_NULL ? 1u : 0u) | (nd.is_unsigned ? 2u : 0u);
+  return DE_NONE;
+}
+
+// RpnExpression::eval for one row.  Leaves and `leaf <cmp> leaf` (the shape of almost every pushed-down predicate,
+// group key and aggregate argument) are evaluated in registers; everything else goes through the stack machine.
 B2_HD int eval_expr(const DevPlan& P, DevExpr ex, const Row& row, const Cells& cells, Value* result, bool* res_unsigned) {
+  const DevNode& n0 = P.nodes[ex.start];
+  if (ex.n == 1 && n0.kind != B2_RPN_FN) {
+    int64_t v; uint32_t f;
+    int e = eval_leaf(P, n0, row, cells, &v, &f);
+    if (e) return e;
+    result->bits = (uint64_t)v; result->null = f & 1;
+    if (res_unsigned) *res_unsigned = f & 2;
+    return DE_NONE;
+  }
+  if (ex.n == 3) {
+    const DevNode& n1 = P.nodes[ex.start + 1];
+    const DevNode& n2 = P.nodes[ex.start + 2];
+    int sig = n2.sig;
+    if (n0.kind != B2_RPN_FN && n1.kind != B2_RPN_FN && n2.kind == B2_RPN_FN && sig >= 100 && sig < 160) {
+      int64_t a, b; uint32_t af, bf;
+      int e = eval_leaf(P, n0, row, cells, &a, &af);
+      if (e) return e;
+      e = eval_leaf(P, n1, row, cells, &b, &bf);
+      if (e) return e;
+      if (res_unsigned) *res_unsigned = n2.is_unsigned;
+      if ((af | bf) & 1) { result->null = true; result->bits = 0; return DE_NONE; }  // NULL-propagating compare
+      int c;
+      if (sig % 10 == 1) { double x = bits_f64((uint64_t)a), y = bits_f64((uint64_t)b); c = x < y ? -1 : (x > y ? 1 : 0); }
+      else c = cmp_i64(a, af & 2, b, bf & 2);
+      bool t;
+      switch (sig / 10 * 10) {
+        case B2_SIG_LT_INT: t = c < 0; break;
+        case B2_SIG_LE_INT: t = c <= 0; break;
+        case B2_SIG_GT_INT: t = c > 0; break;
+        case B2_SIG_GE_INT: t = c >= 0; break;
+        case B2_SIG_NE_INT: t = c != 0; break;
+        default: t = c == 0; break;
+      }
+      result->null = false; result->bits = t;
+      return DE_NONE;
+    }
+  }
+  return eval_expr_general(P, ex, row, cells, result, res_unsigned);
+}
+
+B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const Cells& cells, Value* result, bool* res_unsigned) {
   int64_t sv[MAX_STACK];
   uint8_t sn[MAX_STACK];  // bit0 null, bit1 unsigned
   int sp = 0;

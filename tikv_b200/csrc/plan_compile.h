@@ -163,6 +163,13 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
     for (int j = i + 1; j < P.n_cols; ++j)
       if (P.cols[j].role != CR_HANDLE && P.cols[j].col_id == P.cols[i].col_id) { P.cols[i].role = CR_SHADOWED; break; }
   }
+  // v2 position hint: rank of the column id among the ids a row is expected to hold (the plan's own columns)
+  for (int i = 0; i < P.n_cols; ++i) {
+    int rank = 0;
+    for (int j = 0; j < P.n_cols; ++j)
+      if (j != i && P.cols[j].role == CR_NORMAL && P.cols[j].col_id > 0 && P.cols[j].col_id < P.cols[i].col_id) ++rank;
+    P.cols[i].v2_hint = (uint8_t)rank;
+  }
   P.mode = PM_SCAN;
   std::vector<OutCol> schema;
   for (int i = 0; i < P.n_cols; ++i) {
