@@ -32,7 +32,7 @@ def assert_same_rows(got, exp, ordered=True, float_rel_tol=None, ctx=""):
 def assert_topn(got, exp, exact, key_cols, ctx=""):
     """TopN parity: exact rows when ties are broken by the sort key itself; otherwise the multiset of sort keys
     (ties at the cut keep heap-order-dependent rows in the reference)."""
-    assert got.status == exp.status, f"{ctx}: status {got.status} != oracle {exp.status} ({exp.message})"
+    assert got.status == exp.status, f"{ctx}: status {got.status} ({getattr(got, 'message', '')}) != oracle {exp.status} ({exp.message})"
     g, e = got.rows(), exp.rows()
     assert len(g) == len(e), f"{ctx}: {len(g)} rows != oracle {len(e)}"
     if exact:

@@ -102,6 +102,12 @@ struct BlockView {
   const uint8_t* vals;
   const uint32_t* voff;
   uint32_t n;
+  // entry accessors: the MVCC walk is written against these so that a shared-memory staged window of the block
+  // (kernels.cu StagedView) can stand in for the HBM arrays
+  B2_HD const uint8_t* kptr(uint32_t i) const { return keys + koff[i]; }
+  B2_HD uint32_t klen(uint32_t i) const { return koff[i + 1] - koff[i]; }
+  B2_HD const uint8_t* vptr(uint32_t i) const { return vals + voff[i]; }
+  B2_HD uint32_t vlen(uint32_t i) const { return voff[i + 1] - voff[i]; }
 };
 
 // ---- byte access -------------------------------------------------------------------------------
@@ -255,12 +261,14 @@ B2_HD double bits_f64(uint64_t u) {
 B2_HD uint64_t key_commit_ts(const uint8_t* k, uint32_t klen) { return ~ld_be64(k + klen - 8); }
 
 // entries i and j of the same block share their user key? (types.rs:249-267 is_user_key_eq)
-B2_HD bool same_user_key(const BlockView& b, uint32_t i, uint32_t j) {
-  uint32_t ai = b.koff[i], al = b.koff[i + 1] - ai;
-  uint32_t bi = b.koff[j], bl = b.koff[j + 1] - bi;
+template <class V>
+B2_HD bool same_user_key(const V& b, uint32_t i, uint32_t j) {
+  uint32_t al = b.klen(i), bl = b.klen(j);
   if (al != bl) return false;
-  if (al < 8) return al == 0 ? true : bytes_eq(b.keys + ai, b.keys + bi, al);
-  return bytes_eq(b.keys + ai, b.keys + bi, al - 8);
+  const uint8_t* a = b.kptr(i);
+  const uint8_t* c = b.kptr(j);
+  if (al < 8) return al == 0 ? true : bytes_eq(a, c, al);
+  return bytes_eq(a, c, al - 8);
 }
 
 // Memcomparable user key -> raw key view (bytes.rs:178-228).  We never materialise the raw key: raw byte j
@@ -410,15 +418,16 @@ B2_HD bool default_lookup(const DefaultCf& d, const uint8_t* ukey, uint32_t ukle
 
 // forward.rs:310-375 (move_write_cursor_to_ts) + :433-515 (LatestKvPolicy::handle_write), restated as a walk over
 // the contiguous run of versions [e0, e_hi) of one user key.  `e_hi` is the range's upper bound entry.
-B2_HD void resolve_run(const BlockView& b, uint32_t e0, uint32_t e_hi, uint64_t read_ts, int isolation, const DefaultCf& dflt, RunOut* o) {
+template <class V>
+B2_HD void resolve_run(const V& b, uint32_t e0, uint32_t e_hi, uint64_t read_ts, int isolation, const DefaultCf& dflt, RunOut* o) {
   o->err = DE_NONE; o->found = 0; o->met_newer = 0; o->dflt_lookup = 0; o->steps = 1;
   uint32_t i = e0;
-  uint32_t k0 = b.koff[e0], kl0 = b.koff[e0 + 1] - k0;
+  const uint8_t* k0 = b.kptr(e0);
+  uint32_t kl0 = b.klen(e0);
   if (kl0 < 8) { o->err = DE_KEY_TOO_SHORT; o->entry = e0; return; }
   // move to the first version with commit_ts <= read_ts
   for (;;) {
-    uint32_t ko = b.koff[i], kl = b.koff[i + 1] - ko;
-    uint64_t cts = key_commit_ts(b.keys + ko, kl);
+    uint64_t cts = key_commit_ts(b.kptr(i), b.klen(i));
     if (cts <= read_ts) break;
     o->met_newer = 1;
     if (isolation == B2_ISO_RC_CHECK_TS) { o->err = DE_WRITE_CONFLICT; o->entry = i; return; }
@@ -426,18 +435,18 @@ B2_HD void resolve_run(const BlockView& b, uint32_t e0, uint32_t e_hi, uint64_t 
     if (i >= e_hi || !same_user_key(b, e0, i)) return;
   }
   for (;;) {
-    uint32_t vo = b.voff[i], vl = b.voff[i + 1] - vo;
+    const uint8_t* vp = b.vptr(i);
+    uint32_t vl = b.vlen(i);
     WriteRec w;
-    int e = parse_write(b.vals + vo, vl, &w);
+    int e = parse_write(vp, vl, &w);
     if (e) { o->err = e; o->entry = i; return; }
     if (w.has_gc_fence && w.gc_fence != 0 && w.gc_fence <= read_ts) return;  // write.rs:425-442
     if (w.type == 'P') {
-      uint32_t ko = b.koff[i], kl = b.koff[i + 1] - ko;
-      o->commit_ts = key_commit_ts(b.keys + ko, kl);
+      o->commit_ts = key_commit_ts(b.kptr(i), b.klen(i));
       o->entry = i;
-      if (w.has_short) { o->val = b.vals + vo + w.short_off; o->val_len = w.short_len; o->found = 1; return; }
+      if (w.has_short) { o->val = vp + w.short_off; o->val_len = w.short_len; o->found = 1; return; }
       o->dflt_lookup = 1;
-      if (!default_lookup(dflt, b.keys + k0, kl0 - 8, w.start_ts, &o->val, &o->val_len)) { o->err = DE_DEFAULT_NOT_FOUND; return; }
+      if (!default_lookup(dflt, k0, kl0 - 8, w.start_ts, &o->val, &o->val_len)) { o->err = DE_DEFAULT_NOT_FOUND; return; }
       o->found = 1;
       return;
     }
@@ -449,8 +458,7 @@ B2_HD void resolve_run(const BlockView& b, uint32_t e0, uint32_t e_hi, uint64_t 
       for (;;) {
         ++i; o->steps++;
         if (i >= e_hi || !same_user_key(b, e0, i)) return;
-        uint32_t ko = b.koff[i], kl = b.koff[i + 1] - ko;
-        if (key_commit_ts(b.keys + ko, kl) <= w.lc_ts) break;
+        if (key_commit_ts(b.kptr(i), b.klen(i)) <= w.lc_ts) break;
       }
     } else {
       ++i; o->steps++;

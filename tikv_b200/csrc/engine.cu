@@ -497,6 +497,19 @@ struct b2_exec {
     return fail(status, m, mysql, c.err >> 8);
   }
 
+  // shared-memory staging: capacities from the block's average entry size (+30 %), stages placed after `mode_bytes`
+  size_t setup_staging(ScanArgs* a, const SrcBlock& sb, size_t mode_bytes) {
+    uint32_t n = std::max<uint32_t>(1, sb.c.n), ents = scan_stage_entries();
+    auto cap = [&](uint64_t total) { uint64_t c = (total * ents / n) * 13 / 10 + 256; c = (c + 15) & ~15ull; return (uint32_t)std::min<uint64_t>(c, 72 * 1024); };
+    a->stage_key_cap = cap(sb.key_bytes); a->stage_val_cap = cap(sb.val_bytes);
+    a->stage_off = (uint32_t)((mode_bytes + 15) & ~15ull);
+    size_t total = a->stage_off + scan_stage_bytes(a->stage_key_cap, a->stage_val_cap);
+    if (!use_staging || total > 200 * 1024) { a->staging = 0; a->stage_key_cap = a->stage_val_cap = 0; return mode_bytes; }
+    a->staging = 1;
+    return total;
+  }
+  bool use_staging = true;
+
   ScanArgs base_args(const Unit& u, const BlockView& v) {
     ScanArgs a;
     memset(&a, 0, sizeof(a));
@@ -537,7 +550,6 @@ struct b2_exec {
     // keep request-level statistics, reset the per-batch row counters
     CUDA_TRY(cudaMemsetAsync(&ctr()->out_rows, 0, 8, stream));
     CUDA_TRY(cudaMemsetAsync(&ctr()->out_base, 0, 8, stream));
-    if (!scan_grid) scan_grid = scan_max_grid(PM_SCAN, 0);
     *hit_lock_range = false;
     while (budget && cur_unit < units.size()) {
       const Unit& u = units[cur_unit];
@@ -562,10 +574,27 @@ struct b2_exec {
         a.tile_status = (unsigned long long*)status_buf.p;
         a.out_data = (unsigned long long*)out_data.p; a.out_bitmap = (unsigned long long*)out_bitmap.p;
         a.out_cap = out_cap;
+        size_t smem = setup_staging(&a, wblocks[u.block_idx], scan_out_stage_bytes());
+        a.out_stage_off = 0;
+        if (getenv("B2_TRACE") && !trace_done) { trace_buf.reserve(128 * 8 * 8); cudaMemsetAsync(trace_buf.p, 0, 128 * 8 * 8, stream); a.trace = (unsigned long long*)trace_buf.p; }
+        if (smem != scan_smem) { scan_smem = smem; scan_grid = scan_max_grid(PM_SCAN, smem); }
         kernel_begin();
-        CUDA_TRY(launch_scan(cp.dev, a, scan_grid, 0, stream));
+        CUDA_TRY(launch_scan(cp.dev, a, scan_grid, smem, stream));
         kernel_end();
         CUDA_TRY(cudaMemcpyAsync(&ctr()->out_base, &ctr()->out_rows, 8, cudaMemcpyDeviceToDevice, stream));
+        if (a.trace && !trace_done) {
+          trace_done = true;
+          std::vector<unsigned long long> t(128 * 8);
+          cudaStreamSynchronize(stream);
+          cudaMemcpy(t.data(), trace_buf.p, t.size() * 8, cudaMemcpyDeviceToHost);
+          fprintf(stderr, "B2_TRACE tile: wait_full decode+pred sync1 lookback sync2 outputs sync3 | cycle (SM clocks, CTA 0 thread 0)\n");
+          for (int i = 1; i < 40; ++i) {
+            unsigned long long* r = &t[i * 8];
+            if (!r[6]) break;
+            fprintf(stderr, "B2_TRACE %3d: %7lld %7lld %7lld %7lld %7lld %7lld %7lld | %7lld\n", i, (long long)(r[5] - r[4]), (long long)(r[0] - r[5]), (long long)(r[1] - r[0]),
+                    (long long)(r[2] - r[1]), (long long)(r[3] - r[2]), (long long)(r[7] - r[3]), (long long)(r[6] - r[7]), (long long)(r[6] - t[(i - 1) * 8 + 6]));
+          }
+        }
         release_block(u.block_idx);
         entries_scanned += c_hi - c_lo;
         budget -= c_hi - c_lo;
@@ -619,6 +648,9 @@ struct b2_exec {
     return publish_scan_columns(produced, out);
   }
   int scan_grid = 0;
+  DevBuf trace_buf;
+  bool trace_done = false;
+  size_t scan_smem = ~(size_t)0;
 
   void lock_failure(uint32_t r) {
     fail(range_lock_err[r], "key is locked, lock_version=" + std::to_string(range_lock_ts[r]));
@@ -690,8 +722,8 @@ struct b2_exec {
     size_t smem = 0;
     uint32_t smem_slots = 0;
     if (P.has_group) {
-      smem_slots = 2048;
-      while (smem_slots > 64 && (size_t)smem_slots * (12 + 8 * P.acc_words) > 64 * 1024) smem_slots >>= 1;
+      smem_slots = 1024;
+      while (smem_slots > 64 && (size_t)smem_slots * (12 + 8 * P.acc_words) > 36 * 1024) smem_slots >>= 1;
       smem = (size_t)smem_slots * (12 + 8 * P.acc_words);
     }
     Counters c;
@@ -700,7 +732,8 @@ struct b2_exec {
       if (rc) return rc;
       rc = init_device_state();
       if (rc) return rc;
-      int grid = scan_max_grid(PM_AGG, smem);
+      int grid = 0;
+      size_t grid_smem = ~(size_t)0;
       entries_scanned = 0;
       for (size_t ui = 0; ui < units.size(); ++ui) {
         const Unit& u = units[ui];
@@ -711,8 +744,10 @@ struct b2_exec {
         a.c_lo = u.e_lo; a.c_hi = u.e_hi;
         a.tbl.keys = (unsigned long long*)tbl_keys.p; a.tbl.occ = (unsigned int*)tbl_occ.p; a.tbl.acc = (unsigned long long*)tbl_acc.p; a.tbl.cap = tbl_cap;
         a.smem_slots = smem_slots;
+        size_t tot = setup_staging(&a, wblocks[u.block_idx], smem);
+        if (tot != grid_smem) { grid_smem = tot; grid = scan_max_grid(PM_AGG, tot); }
         kernel_begin();
-        CUDA_TRY(launch_scan(P, a, grid, smem, stream));
+        CUDA_TRY(launch_scan(P, a, grid, tot, stream));
         kernel_end();
         release_block(u.block_idx);
         prefetch_after(ui);
@@ -818,7 +853,9 @@ struct b2_exec {
       uint32_t cap = 512;
       while (cap < limit + TILE) cap <<= 1;
       size_t smem = topn_smem_bytes(cap);
-      int grid = scan_max_grid(PM_TOPN, smem);
+      ScanArgs probe; memset(&probe, 0, sizeof(probe));
+      size_t tot0 = setup_staging(&probe, wblocks[units[0].block_idx], smem);
+      int grid = scan_max_grid(PM_TOPN, std::max(tot0, smem));
       size_t isz = sizeof(TopItem);
       CUDA_TRY(tn_lists.reserve((size_t)grid * limit * isz)); CUDA_TRY(tn_counts.reserve((size_t)grid * 4));
       CUDA_TRY(tn_pair.reserve((size_t)2 * limit * isz)); CUDA_TRY(tn_pair_cnt.reserve(8));
@@ -840,9 +877,10 @@ struct b2_exec {
         uint32_t g = (uint32_t)std::min<uint32_t>((uint32_t)grid, n_tiles);
         a.topn.items = (TopItem*)tn_lists.p; a.topn.counts = (unsigned int*)tn_counts.p; a.topn.n_lists = g; a.topn.stride = limit;
         a.topn_cap = cap;
+        size_t tot = setup_staging(&a, wblocks[u.block_idx], smem);
         CUDA_TRY(cudaMemsetAsync(tn_counts.p, 0, (size_t)grid * 4, stream));
         kernel_begin();
-        CUDA_TRY(launch_scan(P, a, (int)g, smem, stream));
+        CUDA_TRY(launch_scan(P, a, (int)g, tot, stream));
         kernel_end();
         // unit top-N (sorted) lands in the second half of `pair`
         TopNLists unit_out; unit_out.items = pair + limit; unit_out.counts = pair_cnt + 1; unit_out.n_lists = 1; unit_out.stride = limit;

@@ -76,14 +76,17 @@ __device__ __forceinline__ void acc_update(Acc* acc, const DevAgg& g, const Valu
   }
 }
 
+// barrier over the 256 row-decoding threads only (the scan kernel runs a 9th, producer-only warp)
+__device__ __forceinline__ void cta256_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 // ---- TopN helpers --------------------------------------------------------------------------------------------
 // Sort `cap` candidates in shared memory (bitonic, all threads), keep the best `limit`.
 __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int limit, unsigned int* s_cnt, unsigned int* s_have_thr, TopItem* s_thr,
                                  const DevPlan& P) {
-  const unsigned int tid = threadIdx.x, nt = blockDim.x;
+  const unsigned int tid = threadIdx.x, nt = TILE;  // always called by exactly 256 threads
   unsigned int cnt = *s_cnt;
   for (unsigned int i = cnt + tid; i < cap; i += nt) items[i].nulls = 0x80000000u;
-  __syncthreads();
+  cta256_sync();
   for (unsigned int k = 2; k <= cap; k <<= 1) {
     for (unsigned int j = k >> 1; j > 0; j >>= 1) {
       for (unsigned int i = tid; i < cap; i += nt) {
@@ -95,7 +98,7 @@ __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int 
           if (swap) { items[i] = b; items[x] = a; }
         }
       }
-      __syncthreads();
+      cta256_sync();
     }
   }
   if (tid == 0) {
@@ -103,8 +106,60 @@ __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int 
     *s_cnt = keep;
     if (keep == limit && limit > 0) { *s_thr = items[limit - 1]; *s_have_thr = 1; }
   }
-  __syncthreads();
+  cta256_sync();
 }
+
+// ---- TMA bulk staging of a tile's bytes into shared memory --------------------------------------------------------
+// Each 256-entry tile's key bytes, value bytes and offset slices are contiguous in the block's heaps, so one elected
+// thread moves them with four 1-D bulk copies (cp.async.bulk, completion on an mbarrier) while the CTA is still
+// decoding the previous tile.  Threads then parse rows out of shared memory: HBM sees only full-line streaming
+// reads instead of 32 scattered byte addresses per warp instruction.
+// Stage capacities (key / value bytes) are chosen per launch from the block's average entry size (ScanArgs); a tile
+// that does not fit is simply read from HBM.
+enum { STAGE_LOOK = 8, STAGE_OFF_CAP = 1104, N_STAGES = 2, OUT_CHUNK = 4 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct TileMeta {
+  uint32_t tile;            // tile index, >= n_tiles means "no more work"
+  uint32_t staged;          // 1: entries [w_lo, w_hi) are resident in the stage
+  uint32_t w_lo, w_hi;
+  long long keys_adj, vals_adj;  // stage_ptr + adj + heap_offset = address of that heap byte in shared memory
+  int koff_adj, voff_adj;        // stage_off_ptr[adj + entry] = offset of `entry`
+};
+
+// A block whose window [w_lo, w_hi) lives in shared memory; everything else falls through to HBM.
+struct StagedView {
+  BlockView g;
+  const uint8_t* skeys; const uint32_t* skoff; const uint8_t* svals; const uint32_t* svoff;
+  uint32_t w_lo, w_n;
+  __device__ __forceinline__ bool in(uint32_t i) const { return i - w_lo < w_n; }
+  __device__ __forceinline__ const uint8_t* kptr(uint32_t i) const { return in(i) ? skeys + skoff[i] : g.keys + g.koff[i]; }
+  __device__ __forceinline__ uint32_t klen(uint32_t i) const { return in(i) ? skoff[i + 1] - skoff[i] : g.koff[i + 1] - g.koff[i]; }
+  __device__ __forceinline__ const uint8_t* vptr(uint32_t i) const { return in(i) ? svals + svoff[i] : g.vals + g.voff[i]; }
+  __device__ __forceinline__ uint32_t vlen(uint32_t i) const { return in(i) ? svoff[i + 1] - svoff[i] : g.voff[i + 1] - g.voff[i]; }
+};
 
 // ---- the fused scan kernel -------------------------------------------------------------------------------
 struct SmemTable {  // per-CTA group table (dynamic shared memory): keys | acc | occ
@@ -115,7 +170,7 @@ struct SmemTable {  // per-CTA group table (dynamic shared memory): keys | acc |
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TILE) scan_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A) {
+__global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned int s_tile;
   __shared__ unsigned int s_warp_cnt[TILE / 32];
@@ -158,36 +213,155 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const __grid_constant__ DevP
     for (int i = 0; i < MAX_ACC_WORDS; ++i) t_acc[i] = 0;
   }
 
-  for (uint32_t iter = 0;; ++iter) {
-    uint32_t tile;
-    if (MODE == PM_SCAN) {
-      // tiles are claimed in order so that the decoupled look-back below only ever waits on running CTAs
-      if (tid == 0) s_tile = (unsigned int)atomicAdd(&A.tile_status[n_tiles], 1ull);
-      __syncthreads();
-      tile = s_tile;
-    } else {
-      tile = blockIdx.x + iter * gridDim.x;
+  // ---- tile pipeline --------------------------------------------------------------------------------------------
+  // Warp 8 is the producer: it claims tiles, reads the four offsets that bound a tile's bytes and issues the bulk
+  // copies, running up to N_STAGES tiles ahead.  Warps 0-7 decode.  full[s]: producer -> consumers (bytes landed, meta
+  // published); empty[s]: consumers -> producer (stage may be refilled).
+  __shared__ __align__(8) unsigned long long s_full[N_STAGES];
+  __shared__ __align__(8) unsigned long long s_empty[N_STAGES];
+  __shared__ TileMeta s_meta[N_STAGES];
+  __shared__ __align__(8) unsigned long long s_cnt_ready, s_base_ready;  // consumers -> scan warp -> consumers (PM_SCAN)
+  __shared__ unsigned int s_total;
+  unsigned char* stage_base = dyn_smem + A.stage_off;
+  const uint32_t STAGE_KEY_CAP = A.stage_key_cap, STAGE_VAL_CAP = A.stage_val_cap;
+  const uint32_t STAGE_BYTES = STAGE_KEY_CAP + STAGE_VAL_CAP + 2 * STAGE_OFF_CAP;
+  if (tid == 0) {
+    for (int i = 0; i < N_STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], TILE / 32); }
+    mbar_init(&s_cnt_ready, 1); mbar_init(&s_base_ready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();  // last CTA-wide barrier: from here on the two roles only meet through the mbarriers
+
+  if (wid == TILE / 32) {
+    if (lane == 0) {
+      for (uint32_t k = 0;; ++k) {
+        const int slot = (int)(k % N_STAGES);
+        long long tp0 = clock64();
+        mbar_wait(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1);
+        long long tp1 = clock64();
+        TileMeta m;
+        m.staged = 0; m.w_lo = 0; m.w_hi = 0; m.keys_adj = 0; m.vals_adj = 0; m.koff_adj = 0; m.voff_adj = 0;
+        // PM_SCAN claims tiles in order so that the decoupled look-back below only ever waits on running CTAs
+        if (MODE == PM_SCAN) m.tile = (uint32_t)atomicAdd(&A.tile_status[n_tiles], 1ull);
+        else m.tile = blockIdx.x + k * gridDim.x;
+        uint32_t tx = 0;
+        if (m.tile < n_tiles && A.staging) {
+          uint32_t e0 = A.c_lo + m.tile * TILE;
+          uint32_t e1 = e0 + TILE < A.c_hi ? e0 + TILE : A.c_hi;
+          uint32_t w_lo = e0 > A.e_lo ? e0 - 1 : e0;
+          uint32_t w_hi = e1 + STAGE_LOOK < A.e_hi ? e1 + STAGE_LOOK : A.e_hi;
+          uint32_t k0 = A.blk.koff[w_lo], k1 = A.blk.koff[w_hi], v0 = A.blk.voff[w_lo], v1 = A.blk.voff[w_hi];
+          unsigned long long ka = (unsigned long long)(A.blk.keys + k0), va = (unsigned long long)(A.blk.vals + v0);
+          unsigned long long oa = (unsigned long long)(A.blk.koff + w_lo), ob = (unsigned long long)(A.blk.voff + w_lo);
+          uint32_t kpad = (uint32_t)(ka & 15), vpad = (uint32_t)(va & 15), opad = (uint32_t)(oa & 15), qpad = (uint32_t)(ob & 15);
+          uint32_t kbytes = (kpad + (k1 - k0) + 15) & ~15u, vbytes = (vpad + (v1 - v0) + 15) & ~15u;
+          uint32_t obytes = (opad + (w_hi - w_lo + 1) * 4 + 15) & ~15u, qbytes = (qpad + (w_hi - w_lo + 1) * 4 + 15) & ~15u;
+          if (kbytes + 16 <= STAGE_KEY_CAP && vbytes + 16 <= STAGE_VAL_CAP && obytes <= STAGE_OFF_CAP && qbytes <= STAGE_OFF_CAP) {
+            m.staged = 1; m.w_lo = w_lo; m.w_hi = w_hi;
+            m.keys_adj = (long long)kpad - (long long)k0; m.vals_adj = (long long)vpad - (long long)v0;
+            m.koff_adj = (int)(opad / 4) - (int)w_lo; m.voff_adj = (int)(qpad / 4) - (int)w_lo;
+            s_meta[slot] = m;
+            unsigned char* st = stage_base + (size_t)slot * STAGE_BYTES;
+            tx = kbytes + vbytes + obytes + qbytes;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // consumers' generic reads of this stage vs. the async writes
+            mbar_expect_tx(&s_full[slot], tx);
+            bulk_g2s(st, (const void*)(ka - kpad), kbytes, &s_full[slot]);
+            bulk_g2s(st + STAGE_KEY_CAP, (const void*)(va - vpad), vbytes, &s_full[slot]);
+            bulk_g2s(st + STAGE_KEY_CAP + STAGE_VAL_CAP, (const void*)(oa - opad), obytes, &s_full[slot]);
+            bulk_g2s(st + STAGE_KEY_CAP + STAGE_VAL_CAP + STAGE_OFF_CAP, (const void*)(ob - qpad), qbytes, &s_full[slot]);
+          }
+        }
+        if (!tx) {
+          s_meta[slot] = m;
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_full[slot])) : "memory");
+        }
+        if (m.tile >= n_tiles) break;
+      }
     }
+    return;
+  }
+
+  if (wid == TILE / 32 + 1) {
+    // ---- scan warp (PM_SCAN): decoupled look-back, one warp wide.  Lane l inspects tile (j - l); the nearest tile that
+    // already knows its inclusive prefix ends the walk, the aggregates in between are summed with shuffles.
+    if (MODE != PM_SCAN) return;
+    const unsigned long long F_AGG = 1ull << 62, F_INC = 2ull << 62, VMASK = (1ull << 62) - 1;
+    for (uint32_t k = 0;; ++k) {
+      const int cur = (int)(k % N_STAGES);
+      mbar_wait(&s_full[cur], (k / N_STAGES) & 1);
+      const uint32_t tile = s_meta[cur].tile;
+      if (tile >= n_tiles) break;
+      mbar_wait(&s_cnt_ready, k & 1);
+      const unsigned long long total = s_total;
+      unsigned long long excl = 0;
+      if (tile == 0) {
+        if (lane == 0) atomicExch(&A.tile_status[0], F_INC | total);
+      } else {
+        if (lane == 0) atomicExch(&A.tile_status[tile], F_AGG | total);
+        long long j = (long long)tile - 1;
+        for (;;) {
+          long long idx = j - (long long)lane;
+          unsigned long long sres = idx >= 0 ? ld_volatile_u64(&A.tile_status[idx]) : F_INC;  // before tile 0: prefix 0
+          unsigned int flag = (unsigned int)(sres >> 62);
+          unsigned int m_inc = __ballot_sync(0xffffffffu, flag == 2), m_zero = __ballot_sync(0xffffffffu, flag == 0);
+          unsigned int upto = m_inc ? (__ffs(m_inc) - 1) : 31;             // lanes 0..upto matter
+          unsigned int need = upto == 31 ? 0xffffffffu : ((2u << upto) - 1);
+          if (m_zero & need) continue;                                       // a needed predecessor has not published yet
+          unsigned long long v = (lane <= upto) ? (sres & VMASK) : 0ull;
+          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+          excl += v;
+          if (m_inc) break;
+          j -= 32;
+        }
+        if (lane == 0) atomicExch(&A.tile_status[tile], F_INC | (excl + total));
+      }
+      if (lane == 0) {
+        s_base = excl;
+        if (total) atomicAdd(&A.ctr->out_rows, total);
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_base_ready)) : "memory");
+      }
+    }
+    return;
+  }
+
+  for (uint32_t k = 0;; ++k) {
+    const int cur = (int)(k % N_STAGES);
+    long long tc0 = clock64();
+    mbar_wait(&s_full[cur], (k / N_STAGES) & 1);
+    if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) { A.trace[k * 8 + 4] = tc0; A.trace[k * 8 + 5] = clock64(); }
+    const TileMeta m = s_meta[cur];
+    const uint32_t tile = m.tile;
     if (tile >= n_tiles) break;
+    StagedView sv;
+    sv.g = A.blk; sv.w_lo = 0; sv.w_n = 0;
+    sv.skeys = nullptr; sv.skoff = nullptr; sv.svals = nullptr; sv.svoff = nullptr;
+    if (m.staged) {
+      unsigned char* st = stage_base + (size_t)cur * STAGE_BYTES;
+      sv.w_lo = m.w_lo; sv.w_n = m.w_hi - m.w_lo;
+      sv.skeys = st + m.keys_adj;
+      sv.svals = st + STAGE_KEY_CAP + m.vals_adj;
+      sv.skoff = reinterpret_cast<const uint32_t*>(st + STAGE_KEY_CAP + STAGE_VAL_CAP) + m.koff_adj;
+      sv.svoff = reinterpret_cast<const uint32_t*>(st + STAGE_KEY_CAP + STAGE_VAL_CAP + STAGE_OFF_CAP) + m.voff_adj;
+    }
     const uint32_t e = A.c_lo + tile * TILE + tid;
 
     bool live = false;
     Row row;
     Cells cells;
     if (e < A.c_hi) {
-      bool start = (e == A.e_lo) || !same_user_key(A.blk, e - 1, e);
+      bool start = (e == A.e_lo) || !same_user_key(sv, e - 1, e);
       if (start) {
         RunOut ro;
-        resolve_run(A.blk, e, A.e_hi, P.read_ts, P.isolation, A.dflt, &ro);
+        resolve_run(sv, e, A.e_hi, P.read_ts, P.isolation, A.dflt, &ro);
         t_newer |= ro.met_newer;
         t_dflt += ro.dflt_lookup;
         if (ro.err) {
           report_err(A.ctr, A.entry_base + e, ro.err);
         } else if (ro.found) {
-          uint32_t ko = A.blk.koff[e], kl = A.blk.koff[e + 1] - ko;
+          uint32_t kl = sv.klen(e);
           t_keys += 1;
           t_size += (kl - 8) + ro.val_len;
-          row.enc_key = A.blk.keys + ko;
+          row.enc_key = sv.kptr(e);
           row.enc_key_len = kl - 8;
           row.commit_ts = ro.commit_ts;
           int err = row_open(ro.val, ro.val_len, &row.rv);
@@ -203,10 +377,12 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const __grid_constant__ DevP
 
     if (MODE == PM_SCAN) {
       // ---- ordered compaction: ballot/popc inside the warp, smem across warps, look-back across tiles ----
+      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 0] = clock64();
       unsigned int bal = __ballot_sync(0xffffffffu, live);
       unsigned int lane_off = __popc(bal & ((1u << lane) - 1));
       if (lane == 0) s_warp_cnt[wid] = __popc(bal);
-      __syncthreads();
+      cta256_sync();
+      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 1] = clock64();
       unsigned int warp_off = 0, total = 0;
 #pragma unroll
       for (int w = 0; w < TILE / 32; ++w) {
@@ -214,40 +390,43 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const __grid_constant__ DevP
         if (w < (int)wid) warp_off += c;
         total += c;
       }
-      if (tid == 0) {
-        const unsigned long long F_AGG = 1ull << 62, F_INC = 2ull << 62, VMASK = (1ull << 62) - 1;
-        unsigned long long excl = 0;
-        if (tile == 0) {
-          atomicExch(&A.tile_status[0], F_INC | total);
-        } else {
-          atomicExch(&A.tile_status[tile], F_AGG | total);
-          uint32_t j = tile - 1;
-          for (;;) {
-            unsigned long long s = ld_volatile_u64(&A.tile_status[j]);
-            if ((s >> 62) == 0) continue;
-            excl += s & VMASK;
-            if ((s >> 62) == 2) break;
-            --j;
-          }
-          atomicExch(&A.tile_status[tile], F_INC | (excl + total));
-        }
-        s_base = excl;
-        if (total) atomicAdd(&A.ctr->out_rows, (unsigned long long)total);
-      }
-      __syncthreads();
-      if (live) {
-        unsigned long long idx = out_base + s_base + warp_off + lane_off;
-        if (idx < A.out_cap) {
-          for (int k = 0; k < P.n_out; ++k) {
+      // the scan warp (warp 9) turns the tile's row count into its global output base while we decode the columns
+      if (tid == 0) { s_total = total; asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready)) : "memory"); }
+      // Output columns go through a small shared-memory transpose buffer, OUT_CHUNK columns at a time: rows are placed
+      // at their tile-local compacted position (known without the look-back result), which hides the look-back latency
+      // behind the column decode and turns the HBM writes into contiguous 8-byte runs.
+      unsigned long long* obuf = reinterpret_cast<unsigned long long*>(dyn_smem + A.out_stage_off);
+      unsigned char* onull = reinterpret_cast<unsigned char*>(obuf + OUT_CHUNK * TILE);
+      const unsigned int pos = warp_off + lane_off;
+      for (int c0 = 0; c0 < P.n_out; c0 += OUT_CHUNK) {
+        const int nc = P.n_out - c0 < OUT_CHUNK ? P.n_out - c0 : OUT_CHUNK;
+        if (live) {
+          for (int kk = 0; kk < nc; ++kk) {
             Value v;
-            int err = cell_value(P, row, cells, P.out_cols[k], &v);
+            int err = cell_value(P, row, cells, P.out_cols[c0 + kk], &v);
             if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; v.bits = 0; }
-            A.out_data[(size_t)k * A.out_cap + idx] = v.null ? 0ull : v.bits;
-            if (v.null) atomicAnd(&A.out_bitmap[(size_t)k * (A.out_cap / 64) + (idx >> 6)], ~(1ull << (idx & 63)));
+            obuf[kk * TILE + pos] = v.null ? 0ull : v.bits;
+            onull[kk * TILE + pos] = v.null;
           }
         }
+        cta256_sync();  // chunk staged
+        if (c0 == 0) {
+          if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 2] = clock64();
+          mbar_wait(&s_base_ready, k & 1);  // look-back result published by the scan warp
+          if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 3] = clock64();
+        }
+        const unsigned long long base = out_base + s_base;
+        for (unsigned int i = tid; i < (unsigned int)nc * total; i += TILE) {
+          unsigned int kk = i / total, r = i - kk * total;
+          unsigned long long idx = base + r;
+          if (idx < A.out_cap) {
+            A.out_data[(size_t)(c0 + kk) * A.out_cap + idx] = obuf[kk * TILE + r];
+            if (onull[kk * TILE + r]) atomicAnd(&A.out_bitmap[(size_t)(c0 + kk) * (A.out_cap / 64) + (idx >> 6)], ~(1ull << (idx & 63)));
+          }
+        }
+        cta256_sync();  // buffer (and s_warp_cnt / s_base after the last chunk) free for reuse
       }
-      __syncthreads();  // s_warp_cnt / s_base reused by the next tile
+      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 7] = clock64();
     } else if (MODE == PM_TOPN) {
       // BatchTopN: keep the `limit` smallest rows under the order-by key.  A row is a candidate only if it beats
       // the CTA's current threshold (the limit-th best seen so far); candidates are sorted when the buffer fills.
@@ -260,7 +439,7 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const __grid_constant__ DevP
           top_items[pos] = it;  // pos < topn_cap: the buffer is compacted whenever fewer than TILE slots remain
         }
       }
-      __syncthreads();
+      cta256_sync();
       if (s_top_cnt + TILE > A.topn_cap) cta_topn_compact(top_items, A.topn_cap, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
     } else if (MODE == PM_AGG) {
       if (live) {
@@ -329,11 +508,14 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const __grid_constant__ DevP
         }
       }
     }
+    if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 6] = clock64();
+    __syncwarp();  // this warp is done with stage `cur`: let the producer refill it
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[cur])) : "memory");
   }
 
   // ---- epilogue: flush CTA-private state ----
   if (MODE == PM_TOPN) {
-    __syncthreads();
+    cta256_sync();
     cta_topn_compact(top_items, A.topn_cap, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
     unsigned int keep = s_top_cnt;
     for (unsigned int i = tid; i < keep; i += TILE) A.topn.items[(size_t)blockIdx.x * A.topn.stride + i] = top_items[i];
@@ -357,7 +539,7 @@ __global__ void __launch_bounds__(TILE) scan_kernel(const __grid_constant__ DevP
         }
       }
     } else if (st.slots) {
-      __syncthreads();
+      cta256_sync();
       for (unsigned int s = tid; s < st.slots; s += TILE) {
         if (st.occ[s] != 2) continue;
         unsigned int gslot = table_find_or_insert(A.tbl, st.keys[s], false);
@@ -403,16 +585,22 @@ static int num_sms() {
   return g_num_sms;
 }
 
+size_t scan_stage_bytes(uint32_t key_cap, uint32_t val_cap) { return (size_t)N_STAGES * (key_cap + val_cap + 2 * STAGE_OFF_CAP); }
+uint32_t scan_stage_entries() { return TILE + STAGE_LOOK + 1; }
+size_t scan_out_stage_bytes() { return (size_t)OUT_CHUNK * TILE * 9; }
+
 int scan_max_grid(int mode, size_t smem) {
   int per_sm = 0;
   cudaError_t e;
-  if (mode == PM_SCAN) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_SCAN>, TILE, smem);
-  else if (mode == PM_TOPN) {
+  if (mode == PM_SCAN) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_SCAN>, TILE + 64, smem);
+  } else if (mode == PM_TOPN) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_TOPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_TOPN>, TILE, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_TOPN>, TILE + 64, smem);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_AGG>, TILE, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_AGG>, TILE + 64, smem);
   }
   if (e != cudaSuccess || per_sm < 1) per_sm = 1;
   return per_sm * num_sms();
@@ -423,13 +611,14 @@ cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t
   uint32_t n_tiles = (a.c_hi - a.c_lo + TILE - 1) / TILE;
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
   if (plan.mode == PM_SCAN) {
-    scan_kernel<PM_SCAN><<<grid, TILE, smem, s>>>(plan, a);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_kernel<PM_SCAN><<<grid, TILE + 64, smem, s>>>(plan, a);
   } else if (plan.mode == PM_TOPN) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_TOPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_kernel<PM_TOPN><<<grid, TILE, smem, s>>>(plan, a);
+    scan_kernel<PM_TOPN><<<grid, TILE + 64, smem, s>>>(plan, a);
   } else {
     if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_kernel<PM_AGG><<<grid, TILE, smem, s>>>(plan, a);
+    scan_kernel<PM_AGG><<<grid, TILE + 64, smem, s>>>(plan, a);
   }
   return cudaGetLastError();
 }

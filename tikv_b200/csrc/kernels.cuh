@@ -55,6 +55,11 @@ struct ScanArgs {
   // PM_AGG
   AggTable tbl;
   uint32_t smem_slots;              // per-CTA table slots (power of two), 0 = disabled
+  unsigned long long* trace;        // debug (B2_TRACE=1): per-tile clock64 stamps of CTA 0, 8 words per tile
+  uint32_t staging;                 // 1: stage tiles through shared memory with bulk copies
+  uint32_t stage_off;               // byte offset of the stages inside dynamic shared memory (multiple of 16)
+  uint32_t out_stage_off;           // PM_SCAN: byte offset of the output transpose buffer (multiple of 16)
+  uint32_t stage_key_cap, stage_val_cap;  // bytes per stage for key / value heaps (multiples of 16)
   // PM_TOPN
   TopNLists topn;                   // per-CTA result lists (stride = limit)
   uint32_t topn_cap;                // shared-memory candidate capacity (power of two >= limit + TILE)
@@ -83,6 +88,9 @@ struct GenArgs {
 // launchers (kernels.cu)
 cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t smem, cudaStream_t s);
 int scan_max_grid(int mode, size_t smem);  // occupancy-based persistent grid size
+size_t scan_stage_bytes(uint32_t key_cap, uint32_t val_cap);  // dynamic shared memory needed by the tile stages
+size_t scan_out_stage_bytes();             // PM_SCAN output transpose buffer
+uint32_t scan_stage_entries();             // entries a stage must hold (tile + look-behind/ahead)
 cudaError_t launch_agg_finalize(const DevPlan& plan, const AggTable& t, Counters* ctr, unsigned long long* out_keys, unsigned char* out_key_null,
                                 unsigned long long* out_acc, cudaStream_t s);
 cudaError_t launch_agg_result(const DevPlan& plan, unsigned int n_groups, const unsigned long long* g_keys, const unsigned char* g_null,
