@@ -289,6 +289,11 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = (in_bytes + out_bytes) / kernel_s / 1e9 if kernel_s > 0 else 0.0
+    # DRAM traffic per launch from the committed ncu --set full capture (bytes per entry x entries per launch)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "scan_kernel_r1_traffic.json")
+    if os.path.exists(tpath) and launches:
+        traffic = json.load(open(tpath))["dram_bytes_per_entry"] * n_entries * args.steps / launches
 
     # ---- end to end with host buffers ----
     e2e = None
@@ -333,7 +338,7 @@ def main():
                    "rows_per_gpu": args.rows, "cf_write_entries_per_gpu": n_entries, "blocks_per_gpu": args.blocks, "entries_per_batch": args.chunk,
                    "selectivity": rows_out / max(1, args.rows), "parallelism": f"region-sharded x{world}, no data-path collective",
                    "l2": f"inputs {in_bytes / 1e9:.1f} GB per pass >> 126 MB L2 (no flush needed)", "setup_s": round(time.time() - t_setup, 1)},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": (in_bytes + out_bytes) * args.steps / max(1, launches),
                      "kernel": "scan_kernel<PM_SCAN>", "algorithmic_bytes_per_step": in_bytes + out_bytes, "kernel_ms_per_step": kernel_s * 1e3, "peak_source": peak_src},
         "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches), "clocks": clocks,
     }

@@ -303,6 +303,21 @@ int32_t b2_exec_last_error(b2_exec* h, b2_error_info* out);
 int32_t b2_exec_can_be_cached(b2_exec* h);
 void b2_exec_close(b2_exec* h);
 
+/* Partial aggregation state of an Aggregation pipeline, for the multi-GPU / multi-region final merge (what TiDB's
+ * final HashAgg does with the per-region partial results; fast_hash_aggr_executor.rs emits partial results only).
+ * Valid after the drained batch was produced.  Per group `acc_words` additive u64 words, per aggregate in plan order:
+ *   COUNT: [count]   SUM/AVG over Int: [count, sum of low 32 bits, sum of high 32 bits]   SUM/AVG over Real: [count, f64] */
+typedef struct b2_agg_partials {
+  uint32_t n_groups;
+  uint32_t acc_words;
+  int32_t location;           /* always B2_LOC_DEVICE */
+  int32_t has_group;
+  const uint64_t* keys;       /* n_groups group keys (bits); unused without GROUP BY */
+  const uint8_t* key_null;    /* n_groups flags */
+  const uint64_t* acc;        /* n_groups * acc_words */
+} b2_agg_partials;
+int32_t b2_exec_agg_partials(b2_exec* h, b2_agg_partials* out);
+
 /* RequestHandler::handle_request for a DAG: run to drain.  Result columns are owned by *out_handle
  * (close it with b2_exec_close). */
 int32_t b2_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges,

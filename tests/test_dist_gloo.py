@@ -1,0 +1,117 @@
+"""`-m "not gpu"`: the N>1 path on CPU — two gloo ranks, each owning half of the regions, partial results merged with
+tikv_b200.dist exactly as the NCCL ranks do on GPUs.  Partial results here come from the oracle (no GPU); the merged
+answer must equal the oracle's answer over the whole key space."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _i64(v):
+    v &= (1 << 64) - 1
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import kvfmt
+    import orc
+    import scenarios as sc
+    from tikv_b200 import dist as bd
+    from tikv_b200.plan import Plan, col, const_int
+
+    region = sc.dirty_region(5, n_keys=400).build(read_ts=sc.READ_TS)
+    # this rank's share of the key space (regions are disjoint handle ranges)
+    cuts = [-1000, 500, 5000]
+    mine = [kvfmt.table_range(sc.TABLE, cuts[rank], cuts[rank + 1])]
+
+    # hash aggregation: partial (count, sum limbs) per group -> all_gather + re-aggregate
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).aggregation([("count", const_int(1)), ("sum", col(sc.C1))], group_by=[col(sc.C2)]).build()
+    part = orc.dag_handle(plan, mine, region)
+    keys = torch.tensor([0 if r[2] is None else r[2] for r in part.rows()], dtype=torch.int64)
+    nul = torch.tensor([r[2] is None for r in part.rows()], dtype=torch.bool)
+    acc = torch.tensor([[r[0], 1, _i64(r[1] & 0xFFFFFFFF), _i64(r[1] >> 32)] for r in part.rows()], dtype=torch.int64).reshape(-1, 4)
+    k, n, a = bd.merge_agg_partials(keys, nul, acc)
+    def keyf(t):
+        return (t[0] is not None, t[0] or 0)
+    merged = sorted((((None if n[i] else int(k[i])), int(a[i, 0]), bd.limbs_to_int(int(a[i, 2]), int(a[i, 3]))) for i in range(k.shape[0])), key=keyf)
+    whole = orc.dag_handle(plan, sc.WHOLE, region)
+    expect = sorted(((r[2], r[0], r[1]) for r in whole.rows()), key=keyf)
+    ok_agg = merged == expect and len(expect) > 10
+
+    # TopN: ORDER BY c2 DESC, c1 ASC LIMIT 40
+    tplan = Plan().table_scan(sc.TABLE, sc.COLUMNS).topn([(col(sc.C2), True), (col(sc.C1), False)], 40).build(output_offsets=[sc.C_H, sc.C1, sc.C2])
+    tp = orc.dag_handle(tplan, mine, region)
+    cols = [torch.tensor([0 if v is None else v for v in c], dtype=torch.int64) for c in tp.columns]
+    nls = [torch.tensor([v is None for v in c], dtype=torch.bool) for c in tp.columns]
+    mc, mn = bd.merge_topn(cols, nls, [(2, True, "i64"), (1, False, "i64")], 40)
+    got_rows = [tuple(None if mn[j][i] else int(mc[j][i]) for j in range(3)) for i in range(mc[0].shape[0])]
+    ok_topn = got_rows == orc.dag_handle(tplan, sc.WHOLE, region).rows()
+
+    # checksum: XOR of partial folds
+    st, (c, kv, by), _ = orc.checksum(mine, region)
+    mcsum = bd.merge_checksum(c, kv, by)
+    ok_ck = mcsum == orc.checksum(sc.WHOLE, region)[1]
+
+    q.put((rank, bool(ok_agg), bool(ok_topn), bool(ok_ck), bd.shard_blocks(7, world, rank)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_merge_matches_oracle():
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1:4] for r in res] == [(True, True, True), (True, True, True)], res
+    assert res[0][4] + res[1][4] == list(range(7))  # every block assigned exactly once, in order
+
+
+def test_merge_single_process_semantics():
+    sys.path.insert(0, ROOT)
+    from tikv_b200 import dist as bd
+    keys = torch.tensor([5, 7, 5, 0, 0], dtype=torch.int64)
+    nul = torch.tensor([False, False, False, True, True])
+    acc = torch.tensor([[1, 10, 0], [2, 20, 0], [3, (1 << 32) - 1, -1], [4, 1, 0], [5, 2, 0]], dtype=torch.int64)
+    k, n, a = bd.merge_agg_partials(keys, nul, acc)
+    rows = sorted((bool(n[i]), int(k[i]), [int(x) for x in a[i]]) for i in range(3))
+    assert rows == [(False, 5, [4, 10 + (1 << 32) - 1, -1]), (False, 7, [2, 20, 0]), (True, 0, [9, 3, 0])]
+    assert bd.limbs_to_int(10 + (1 << 32) - 1, -1) == 9 and bd.limbs_to_int(5, 3, unsigned=True) == 3 * (1 << 32) + 5
+    # f64 word merge
+    f = torch.tensor([[1, 0], [1, 0]], dtype=torch.int64)
+    f[:, 1] = torch.tensor([1.5, 2.25], dtype=torch.float64).view(torch.int64)
+    k, n, a = bd.merge_agg_partials(torch.tensor([1, 1]), torch.tensor([False, False]), f, real_words=(1,))
+    assert a[0, 0] == 2 and a[0, 1:2].view(torch.float64).item() == 3.75
+    # TopN with NULLs: asc puts NULL first, desc puts NULL last
+    c, nl = bd.merge_topn([torch.tensor([3, 1, 0, 2])], [torch.tensor([False, False, True, False])], [(0, False, "i64")], 3)
+    assert [None if nl[0][i] else int(c[0][i]) for i in range(3)] == [None, 1, 2]
+    c, nl = bd.merge_topn([torch.tensor([3, 1, 0, 2])], [torch.tensor([False, False, True, False])], [(0, True, "i64")], 4)
+    assert [None if nl[0][i] else int(c[0][i]) for i in range(4)] == [3, 2, 1, None]
+    c, nl = bd.merge_topn([torch.tensor([-1, 1, 5])], [torch.tensor([False, False, False])], [(0, False, "u64")], 3)
+    assert [int(x) for x in c[0]] == [1, 5, -1]  # -1 is u64::MAX
+    assert bd.merge_checksum(7, 1, 2) == (7, 1, 2)

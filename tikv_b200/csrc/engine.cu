@@ -785,8 +785,12 @@ struct b2_exec {
       n_groups = c.n_groups;
       gk = (const unsigned long long*)grp_keys.p; gn = (const unsigned char*)grp_null.p; ga = (const unsigned long long*)grp_acc.p;
     }
+    part_n = n_groups; part_keys = gk; part_null = gn; part_acc = ga;
     return publish_agg(n_groups, gk, gn, ga, out);
   }
+  unsigned int part_n = 0;
+  const unsigned long long *part_keys = nullptr, *part_acc = nullptr;
+  const unsigned char* part_null = nullptr;
 
   int publish_agg(unsigned int n_groups, const unsigned long long* gk, const unsigned char* gn, const unsigned long long* ga, b2_batch* out) {
     const DevPlan& P = cp.dev;
@@ -1021,6 +1025,13 @@ int32_t b2_exec_collect_stats(b2_exec* h, b2_exec_stats* out) { *out = h->stats;
 int32_t b2_exec_last_error(b2_exec* h, b2_error_info* out) { *out = h->last_err; return B2_OK; }
 int32_t b2_exec_can_be_cached(b2_exec* h) { return (h->check_newer && !h->met_newer_any && !h->saw_lock) ? 1 : 0; }
 void b2_exec_close(b2_exec* h) { delete h; }
+
+int32_t b2_exec_agg_partials(b2_exec* h, b2_agg_partials* out) {
+  if (h->cp.dev.mode != PM_AGG || !h->drained) { g_last_error = "no aggregation state: not an Aggregation pipeline or not drained yet"; return B2_ERR_INVALID_ARG; }
+  out->n_groups = h->part_n; out->acc_words = (uint32_t)h->cp.dev.acc_words; out->location = B2_LOC_DEVICE; out->has_group = h->cp.dev.has_group;
+  out->keys = (const uint64_t*)h->part_keys; out->key_null = (const uint8_t*)h->part_null; out->acc = (const uint64_t*)h->part_acc;
+  return B2_OK;
+}
 
 int32_t b2_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src,
                       const b2_exec_config* cfg, b2_batch* out, b2_exec** out_handle) {

@@ -127,6 +127,11 @@ class ChecksumResponse(C.Structure):
     _fields_ = [("checksum", C.c_uint64), ("total_kvs", C.c_uint64), ("total_bytes", C.c_uint64)]
 
 
+class AggPartials(C.Structure):
+    _fields_ = [("n_groups", C.c_uint32), ("acc_words", C.c_uint32), ("location", C.c_int32), ("has_group", C.c_int32),
+                ("keys", C.c_void_p), ("key_null", C.c_void_p), ("acc", C.c_void_p)]
+
+
 class GenSpec(C.Structure):
     _fields_ = [("table_id", C.c_int64), ("first_handle", C.c_uint64), ("n_rows", C.c_uint64), ("n_cols", C.c_uint32),
                 ("row_format", C.c_int32), ("seed", C.c_uint64), ("col_lo", C.POINTER(C.c_int64)),
@@ -142,7 +147,7 @@ class GenBlock(C.Structure):
 EXPORTED_SYMBOLS = [
     "b2_abi_version", "b2_build_info", "b2_last_error_message", "b2_check_supported", "b2_exec_open", "b2_exec_schema",
     "b2_exec_next_batch", "b2_exec_collect_stats", "b2_exec_last_error", "b2_exec_can_be_cached", "b2_exec_close",
-    "b2_dag_handle", "b2_checksum_handle", "b2_gen_create", "b2_gen_destroy", "b2_copy_to_host", "b2_copy_to_device",
+    "b2_exec_agg_partials", "b2_dag_handle", "b2_checksum_handle", "b2_gen_create", "b2_gen_destroy", "b2_copy_to_host", "b2_copy_to_device",
     "b2_device_count", "b2_host_alloc_pinned", "b2_host_free_pinned",
 ]
 
@@ -177,6 +182,8 @@ def lib():
     L.b2_exec_last_error.restype = i32
     L.b2_exec_can_be_cached.argtypes = [vp]
     L.b2_exec_can_be_cached.restype = i32
+    L.b2_exec_agg_partials.argtypes = [vp, C.POINTER(AggPartials)]
+    L.b2_exec_agg_partials.restype = i32
     L.b2_exec_close.argtypes = [vp]
     L.b2_exec_close.restype = None
     L.b2_dag_handle.argtypes = [C.POINTER(DagPlan), C.POINTER(KeyRange), u32, C.POINTER(RegionSource), C.POINTER(ExecConfig), C.POINTER(Batch), C.POINTER(vp)]
