@@ -30,11 +30,11 @@ def test_agg_partials_merge_two_shards():
     keys = torch.cat([p[0] for p in parts]); nul = torch.cat([p[1] for p in parts]); acc = torch.cat([p[2] for p in parts])
     k, n, a = bd.merge_agg_partials(keys, nul, acc)
     assert a.shape[1] == 1 + 3 + 3  # COUNT | SUM(int) | AVG(int)
-    got = sorted(((None if n[i] else int(k[i])), int(a[i, 0]), bd.limbs_to_int(int(a[i, 2]), int(a[i, 3])), int(a[i, 4]),
-                  bd.limbs_to_int(int(a[i, 5]), int(a[i, 6]), unsigned=True)) for i in range(k.shape[0]))
+    got = [((None if n[i] else int(k[i])), int(a[i, 0]), bd.limbs_to_int(int(a[i, 2]), int(a[i, 3])), int(a[i, 4]),
+            bd.limbs_to_int(int(a[i, 5]), int(a[i, 6]), unsigned=True)) for i in range(k.shape[0])]
     exp = orc.dag_handle(plan, sc.WHOLE, region)
     # oracle columns: count, sum, avg_count, avg_sum, key
-    want = sorted((r[4], r[0], r[1] if r[1] is not None else 0, r[2], r[3] if r[3] is not None else 0) for r in exp.rows())
+    want = [(r[4], r[0], r[1] if r[1] is not None else 0, r[2], r[3] if r[3] is not None else 0) for r in exp.rows()]
     key = lambda t: (t[0] is not None, t[0] or 0)
     assert sorted(got, key=key) == sorted(want, key=key) and len(want) > 50
 

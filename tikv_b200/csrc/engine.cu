@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -35,31 +36,86 @@ static thread_local std::string g_last_error;
 
 namespace {
 
-struct DevBuf {  // growable device allocation
-  void* p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e == cudaSuccess) cap = n;
+// Request-scoped buffers come from a small caching pool (per process, per device): a coprocessor request is short and
+// cudaMalloc / cudaMallocHost / cudaFree cost more than the request itself (and cudaFree synchronises the device).
+struct BufPool {
+  struct Blk { void* p; size_t cap; int device; };
+  std::mutex mu;
+  std::vector<Blk> free_list;
+  size_t held = 0, limit;
+  bool pinned;
+  BufPool(bool pinned_, size_t limit_) : limit(limit_), pinned(pinned_) {}
+  cudaError_t get(size_t n, void** p, size_t* cap) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      size_t best = free_list.size();
+      for (size_t i = 0; i < free_list.size(); ++i)
+        if ((pinned || free_list[i].device == dev) && free_list[i].cap >= n && free_list[i].cap <= 2 * n + (1 << 20) && (best == free_list.size() || free_list[i].cap < free_list[best].cap)) best = i;
+      if (best != free_list.size()) {
+        *p = free_list[best].p; *cap = free_list[best].cap;
+        held -= free_list[best].cap;
+        free_list.erase(free_list.begin() + best);
+        return cudaSuccess;
+      }
+    }
+    size_t want = (n + 255) & ~(size_t)255;
+    cudaError_t e = pinned ? cudaMallocHost(p, want) : cudaMalloc(p, want);
+    if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
+      trim(0);
+      cudaGetLastError();
+      e = pinned ? cudaMallocHost(p, want) : cudaMalloc(p, want);
+    }
+    if (e == cudaSuccess) *cap = want;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void put(void* p, size_t cap) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    free_list.push_back(Blk{p, cap, dev});
+    held += cap;
+    while (held > limit && !free_list.empty()) {  // evict the largest
+      size_t big = 0;
+      for (size_t i = 1; i < free_list.size(); ++i) if (free_list[i].cap > free_list[big].cap) big = i;
+      if (pinned) cudaFreeHost(free_list[big].p); else cudaFree(free_list[big].p);
+      held -= free_list[big].cap;
+      free_list.erase(free_list.begin() + big);
+    }
+  }
+  void trim(size_t keep) {
+    std::lock_guard<std::mutex> g(mu);
+    while (held > keep && !free_list.empty()) {
+      if (pinned) cudaFreeHost(free_list.back().p); else cudaFree(free_list.back().p);
+      held -= free_list.back().cap;
+      free_list.pop_back();
+    }
+  }
 };
-struct HostBuf {  // growable pinned host allocation
+BufPool& dev_pool() { static BufPool p(false, 24ull << 30); return p; }
+BufPool& host_pool() { static BufPool p(true, 8ull << 30); return p; }
+
+struct DevBuf {  // growable device allocation (pooled)
   void* p = nullptr;
   size_t cap = 0;
   cudaError_t reserve(size_t n) {
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr; cap = 0;
-    cudaError_t e = cudaMallocHost(&p, n);
-    if (e == cudaSuccess) cap = n;
-    return e;
+    if (p) cudaDeviceSynchronize();  // growing: in-flight work may still touch the old block before it goes back to the pool
+    release();
+    return dev_pool().get(n, &p, &cap);
   }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  void release() { if (p) dev_pool().put(p, cap); p = nullptr; cap = 0; }
+};
+struct HostBuf {  // growable pinned host allocation (pooled)
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    release();
+    return host_pool().get(n, &p, &cap);
+  }
+  void release() { if (p) host_pool().put(p, cap); p = nullptr; cap = 0; }
 };
 
 struct SrcBlock {  // caller's block descriptor + sizes
