@@ -83,6 +83,9 @@ struct DevPlan {
   int32_t isolation;  // B2_ISO_*
   int32_t need_value;  // 0 when no column is read from the row value (key-only)
   int32_t has_handle_cols;
+  int32_t fast_n;      // > 0: rows holding exactly these `fast_n` non-null column ids (and no NULL ids) take the register fast path
+  int32_t _fpad;
+  uint64_t fast_ids;   // the expected sorted non-null id bytes of such a row, packed little-endian (fast_n <= 8)
   uint64_t read_ts;
   uint64_t limit;
   DevExpr conds[MAX_CONDS];
@@ -326,6 +329,12 @@ B2_HD int parse_write(const uint8_t* p, uint32_t n, WriteRec* w) {
   if (!c) return DE_BAD_WRITE;
   pos += c;
   uint64_t lc_ts = 0, lc_ver = 0;
+  // the overwhelmingly common record: Put/.. + start_ts + 'v' len row, nothing after it
+  if (pos + 2 <= n && p[pos] == 'v' && pos + 2 + p[pos + 1] == n) {
+    w->has_short = 1; w->short_off = pos + 2; w->short_len = p[pos + 1];
+    w->lc_ts = 0; w->lc_versions = 0;
+    return DE_NONE;
+  }
   while (pos < n) {
     uint8_t tag = p[pos++];
     if (tag == 'v') {
@@ -606,6 +615,8 @@ struct Row {
   uint32_t enc_key_len;
   uint64_t commit_ts;
   uint64_t filled;  // bitmask of plan columns present in the row (bit c)
+  uint32_t fast;    // 1: v2 row with exactly the plan's columns, all non-null: cells come from the two offset words below
+  uint64_t o_lo, o_hi;  // the row's u16 end-offsets 0..3 / 4..7
 };
 
 // process_kv_pair (table_scan_executor.rs:365-475): everything that can fail regardless of which rows are
@@ -613,6 +624,7 @@ struct Row {
 B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
   const RowView& r = row.rv;
   uint64_t filled = 0;
+  row.fast = 0;
   int err = DE_NONE;
   if (r.fmt == 1) {
     uint32_t pos = 0, n = r.n;
@@ -638,6 +650,26 @@ B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
         }
       }
       pos += dl;
+    }
+  } else if (r.fmt == 2 && P.fast_n > 0 && !r.big && r.nn_cnt == (uint32_t)P.fast_n && r.null_cnt == 0 &&
+             ((ld64(r.v + r.ids_off) ^ P.fast_ids) & (P.fast_n >= 8 ? ~0ull : ((1ull << (8 * P.fast_n)) - 1))) == 0) {
+    // exact-layout fast path: the row holds precisely the plan's columns, all non-null (process_v2 would find column
+    // k at position v2_hint).  Keep the end-offsets in two registers; no per-column search, no Cells traffic.
+    row.fast = 1;
+    row.o_lo = ld64(r.v + r.offs_off);
+    row.o_hi = P.fast_n > 4 ? ld64(r.v + r.offs_off + 8) : 0;
+    for (int k = 0; k < P.n_cols; ++k) {
+      const DevCol& c = P.cols[k];
+      if (c.role != CR_NORMAL) continue;
+      uint32_t h = c.v2_hint;
+      uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
+      uint32_t start = h == 0 ? 0u : ((uint32_t)((h - 1 < 4 ? row.o_lo : row.o_hi) >> (((h - 1) & 3) * 16)) & 0xffffu);
+      if (start > end || end > r.vals_len) return DE_ROW_V2_RANGE;
+      uint32_t len = end - start;
+      if (c.v2_class == V2_INT || c.v2_class == V2_UINT) {
+        if (len != 1 && len != 2 && len != 4 && len != 8) return DE_ROW_V2_BAD_INT;
+      } else if (c.v2_class == V2_UNSUPPORTED) return DE_UNSUPPORTED_TYPE;
+      filled |= 1ull << k;
     }
   } else if (r.fmt == 2) {
     for (int k = 0; k < P.n_cols; ++k) {
@@ -689,7 +721,12 @@ B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k
   const uint8_t* p = nullptr;
   uint32_t len = 0;
   int kind = CELL_MISSING;
-  if ((row.filled >> k) & 1) {
+  if (row.fast) {
+    uint32_t h = c.v2_hint;
+    uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
+    uint32_t start = h == 0 ? 0u : ((uint32_t)((h - 1 < 4 ? row.o_lo : row.o_hi) >> (((h - 1) & 3) * 16)) & 0xffffu);
+    p = r.v + r.vals_off + start; len = end - start; kind = CELL_V2;
+  } else if ((row.filled >> k) & 1) {
     p = r.v + cells.off[k]; len = cells.len_kind[k] >> 2; kind = cells.len_kind[k] & 3;  // located once by row_split
   }
   if (kind == CELL_NULL) { out->null = true; return DE_NONE; }

@@ -135,6 +135,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         : "memory");
   } while (!ok);
 }
+// same, for the service warps whose waits last a whole tile: back off instead of burning issue slots
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(200);
+  }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
                "r"(bytes), "r"(smem_u32(bar))
@@ -237,7 +250,7 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
       for (uint32_t k = 0;; ++k) {
         const int slot = (int)(k % N_STAGES);
         long long tp0 = clock64();
-        mbar_wait(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1);
+        mbar_wait_sleep(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1);
         long long tp1 = clock64();
         TileMeta m;
         m.staged = 0; m.w_lo = 0; m.w_hi = 0; m.keys_adj = 0; m.vals_adj = 0; m.koff_adj = 0; m.voff_adj = 0;
@@ -288,10 +301,10 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
     const unsigned long long F_AGG = 1ull << 62, F_INC = 2ull << 62, VMASK = (1ull << 62) - 1;
     for (uint32_t k = 0;; ++k) {
       const int cur = (int)(k % N_STAGES);
-      mbar_wait(&s_full[cur], (k / N_STAGES) & 1);
+      mbar_wait_sleep(&s_full[cur], (k / N_STAGES) & 1);
       const uint32_t tile = s_meta[cur].tile;
       if (tile >= n_tiles) break;
-      mbar_wait(&s_cnt_ready, k & 1);
+      mbar_wait_sleep(&s_cnt_ready, k & 1);
       const unsigned long long total = s_total;
       unsigned long long excl = 0;
       if (tile == 0) {
@@ -416,12 +429,13 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
           if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 3] = clock64();
         }
         const unsigned long long base = out_base + s_base;
-        for (unsigned int i = tid; i < (unsigned int)nc * total; i += TILE) {
-          unsigned int kk = i / total, r = i - kk * total;
-          unsigned long long idx = base + r;
-          if (idx < A.out_cap) {
-            A.out_data[(size_t)(c0 + kk) * A.out_cap + idx] = obuf[kk * TILE + r];
-            if (onull[kk * TILE + r]) atomicAnd(&A.out_bitmap[(size_t)(c0 + kk) * (A.out_cap / 64) + (idx >> 6)], ~(1ull << (idx & 63)));
+        for (int kk = 0; kk < nc; ++kk) {
+          unsigned long long* dst = A.out_data + (size_t)(c0 + kk) * A.out_cap + base;
+          for (unsigned int r = tid; r < total; r += TILE) {
+            if (base + r < A.out_cap) {
+              dst[r] = obuf[kk * TILE + r];
+              if (onull[kk * TILE + r]) atomicAnd(&A.out_bitmap[(size_t)(c0 + kk) * (A.out_cap / 64) + ((base + r) >> 6)], ~(1ull << ((base + r) & 63)));
+            }
           }
         }
         cta256_sync();  // buffer (and s_warp_cnt / s_base after the last chunk) free for reuse

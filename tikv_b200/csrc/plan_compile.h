@@ -3,6 +3,7 @@
 // (components/tidb_query_executors/src/runner.rs:111-206, 252-603) plus the aggregate SUM/AVG cast rewrite
 // (components/tidb_query_aggr/src/util.rs:31-66).  Pure C++ (no CUDA) so the host emulation test can use it.
 #pragma once
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -169,6 +170,23 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
     for (int j = 0; j < P.n_cols; ++j)
       if (j != i && P.cols[j].role == CR_NORMAL && P.cols[j].col_id > 0 && P.cols[j].col_id < P.cols[i].col_id) ++rank;
     P.cols[i].v2_hint = (uint8_t)rank;
+  }
+  // exact-layout fast path: the sorted ids of the plan's row-stored columns, when there are at most 8 of them (< 256)
+  {
+    std::vector<int64_t> ids;
+    bool ok = true;
+    for (int i = 0; i < P.n_cols; ++i) {
+      if (P.cols[i].role == CR_SHADOWED) ok = false;
+      if (P.cols[i].role != CR_NORMAL) continue;
+      if (P.cols[i].col_id <= 0 || P.cols[i].col_id > 255) ok = false;
+      ids.push_back(P.cols[i].col_id);
+    }
+    std::sort(ids.begin(), ids.end());
+    P.fast_n = 0; P.fast_ids = 0;
+    if (ok && !ids.empty() && ids.size() <= 8) {
+      P.fast_n = (int32_t)ids.size();
+      for (size_t i = 0; i < ids.size(); ++i) P.fast_ids |= (uint64_t)ids[i] << (8 * i);
+    }
   }
   P.mode = PM_SCAN;
   std::vector<OutCol> schema;
