@@ -85,6 +85,9 @@ struct DevPlan {
   int32_t has_handle_cols;
   int32_t fast_n;      // > 0: rows holding exactly these `fast_n` non-null column ids (and no NULL ids) take the register fast path
   int32_t _fpad;
+  uint64_t fast_filled;  // `filled` mask of such a row (every row-stored plan column)
+  uint32_t fast_cls;     // 2 bits per stored column in id order: 0 copy, 1 integer width check, 2 unsupported type
+  uint32_t _fpad2;
   uint64_t fast_ids;   // the expected sorted non-null id bytes of such a row, packed little-endian (fast_n <= 8)
   uint64_t read_ts;
   uint64_t limit;
@@ -658,19 +661,22 @@ B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
     row.fast = 1;
     row.o_lo = ld64(r.v + r.offs_off);
     row.o_hi = P.fast_n > 4 ? ld64(r.v + r.offs_off + 8) : 0;
-    for (int k = 0; k < P.n_cols; ++k) {
-      const DevCol& c = P.cols[k];
-      if (c.role != CR_NORMAL) continue;
-      uint32_t h = c.v2_hint;
-      uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
-      uint32_t start = h == 0 ? 0u : ((uint32_t)((h - 1 < 4 ? row.o_lo : row.o_hi) >> (((h - 1) & 3) * 16)) & 0xffffu);
-      if (start > end || end > r.vals_len) return DE_ROW_V2_RANGE;
-      uint32_t len = end - start;
-      if (c.v2_class == V2_INT || c.v2_class == V2_UINT) {
-        if (len != 1 && len != 2 && len != 4 && len != 8) return DE_ROW_V2_BAD_INT;
-      } else if (c.v2_class == V2_UNSUPPORTED) return DE_UNSUPPORTED_TYPE;
-      filled |= 1ull << k;
+    // one pass over the (at most 8) stored columns in id order: offsets must be monotone and inside the value area,
+    // integer-class columns must be 1/2/4/8 bytes wide (compat_v1.rs:13-38)
+    uint32_t prev = 0;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      if (h < P.fast_n) {
+        uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
+        if (end < prev || end > r.vals_len) return DE_ROW_V2_RANGE;
+        uint32_t len = end - prev;
+        uint32_t cls = (P.fast_cls >> (2 * h)) & 3u;  // 0 copy, 1 int-width check, 2 unsupported
+        if (cls == 1 && len != 1 && len != 2 && len != 4 && len != 8) return DE_ROW_V2_BAD_INT;
+        if (cls == 2) return DE_UNSUPPORTED_TYPE;
+        prev = end;
+      }
     }
+    filled = P.fast_filled;
   } else if (r.fmt == 2) {
     for (int k = 0; k < P.n_cols; ++k) {
       const DevCol& c = P.cols[k];
@@ -695,7 +701,7 @@ B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
   if (P.has_handle_cols) {
     if (!rec_ok || rawlen < 19) return DE_BAD_RECORD_KEY;
   } else if (!rec_ok) return DE_BAD_RECORD_KEY;
-  for (int k = 0; k < P.n_cols; ++k) {
+  for (int k = 0; !row.fast && k < P.n_cols; ++k) {
     const DevCol& c = P.cols[k];
     if (c.role == CR_HANDLE || c.role == CR_TABLE_ID || c.role == CR_COMMIT_TS) { filled |= 1ull << k; continue; }
     if (!((filled >> k) & 1)) {
@@ -713,6 +719,19 @@ B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k
   const DevCol& c = P.cols[k];
   out->null = false; out->bits = 0;
   const uint64_t S = 0x8000000000000000ull;
+  if (row.fast && c.role == CR_NORMAL && c.kind == CK_INT) {  // hot case: integer column of an exact-layout v2 row
+    uint32_t h = c.v2_hint;
+    uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
+    uint32_t start = h == 0 ? 0u : ((uint32_t)((h - 1 < 4 ? row.o_lo : row.o_hi) >> (((h - 1) & 3) * 16)) & 0xffffu);
+    uint32_t len = end - start;
+    uint64_t u = ld64(row.rv.v + row.rv.vals_off + start);
+    if (len < 8) {
+      uint32_t sh = 64 - 8 * len;
+      u = c.v2_class == V2_INT ? (uint64_t)(((int64_t)(u << sh)) >> sh) : ((u << sh) >> sh);
+    }
+    out->bits = u;
+    return DE_NONE;
+  }
   if (c.role == CR_HANDLE) { out->bits = raw_be64(row.enc_key, 11) ^ S; return DE_NONE; }       // table.rs:214-218
   if (c.role == CR_TABLE_ID) { out->bits = raw_be64(row.enc_key, 1) ^ S; return DE_NONE; }
   if (c.role == CR_COMMIT_TS) { out->bits = row.commit_ts; return DE_NONE; }

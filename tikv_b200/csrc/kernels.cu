@@ -135,18 +135,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         : "memory");
   } while (!ok);
 }
-// same, for the service warps whose waits last a whole tile: back off instead of burning issue slots
+// same, for the service warps whose waits last a whole tile: let the hardware suspend the thread (time hint in ns)
+// instead of burning issue slots on polls
 __device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, uint32_t parity) {
   uint32_t ok;
-  for (;;) {
+  do {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
-    if (ok) break;
-    __nanosleep(200);
-  }
+  } while (!ok);
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),

@@ -182,10 +182,19 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
       ids.push_back(P.cols[i].col_id);
     }
     std::sort(ids.begin(), ids.end());
-    P.fast_n = 0; P.fast_ids = 0;
+    P.fast_n = 0; P.fast_ids = 0; P.fast_cls = 0; P.fast_filled = 0;
     if (ok && !ids.empty() && ids.size() <= 8) {
       P.fast_n = (int32_t)ids.size();
       for (size_t i = 0; i < ids.size(); ++i) P.fast_ids |= (uint64_t)ids[i] << (8 * i);
+      for (int i = 0; i < P.n_cols; ++i) {
+        const DevCol& col = P.cols[i];
+        if (col.role == CR_HANDLE || col.role == CR_TABLE_ID || col.role == CR_COMMIT_TS) P.fast_filled |= 1ull << i;
+        if (col.role != CR_NORMAL) continue;
+        P.fast_filled |= 1ull << i;
+        size_t rank = std::lower_bound(ids.begin(), ids.end(), col.col_id) - ids.begin();
+        uint32_t cls = (col.v2_class == V2_INT || col.v2_class == V2_UINT) ? 1u : (col.v2_class == V2_UNSUPPORTED ? 2u : 0u);
+        P.fast_cls |= cls << (2 * rank);
+      }
     }
   }
   P.mode = PM_SCAN;
