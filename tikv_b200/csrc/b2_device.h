@@ -671,7 +671,7 @@ B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
         if (end < prev || end > r.vals_len) return DE_ROW_V2_RANGE;
         uint32_t len = end - prev;
         uint32_t cls = (P.fast_cls >> (2 * h)) & 3u;  // 0 copy, 1 int-width check, 2 unsupported
-        if (cls == 1 && len != 1 && len != 2 && len != 4 && len != 8) return DE_ROW_V2_BAD_INT;
+        if (cls == 1 && (len > 8 || !((0x116u >> len) & 1u))) return DE_ROW_V2_BAD_INT;  // widths 1, 2, 4, 8
         if (cls == 2) return DE_UNSUPPORTED_TYPE;
         prev = end;
       }

@@ -1120,20 +1120,23 @@ int32_t b2_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges, const 
   DevBuf d_prefix;
   if (d_prefix.reserve(new_prefix_len + 16) != cudaSuccess) return B2_ERR_CUDA;
   if (new_prefix_len) cudaMemcpyAsync(d_prefix.p, new_prefix, new_prefix_len, cudaMemcpyHostToDevice, h->stream);
+  if (new_prefix_len > 32) { g_last_error = "new_prefix longer than 32 bytes"; d_prefix.release(); return B2_ERR_UNSUPPORTED; }
+  size_t ck_smem = ~(size_t)0;
+  int ck_grid = 0;
+  h->cp.dev.read_ts = h->read_ts; h->cp.dev.isolation = h->isolation;
   for (size_t ui = 0; ui < h->units.size(); ++ui) {
     const Unit& u = h->units[ui];
     BlockView v;
     rc = h->acquire_block(u.block_idx, &v);
     if (rc) { d_prefix.release(); return rc; }
-    ChecksumArgs a;
-    memset(&a, 0, sizeof(a));
-    a.blk = v; a.dflt.blocks = (const BlockView*)h->dflt_views.p; a.dflt.n_blocks = (uint32_t)h->dblocks.size();
-    a.e_lo = u.e_lo; a.e_hi = u.e_hi; a.entry_base = h->wblocks[u.block_idx].entry_base;
-    a.read_ts = h->read_ts; a.isolation = h->isolation; a.init_state = st;
-    a.new_prefix = (const uint8_t*)d_prefix.p; a.new_prefix_len = new_prefix_len; a.old_prefix_len = old_prefix_len;
-    a.ctr = h->ctr();
+    ScanArgs a = h->base_args(u, v);
+    a.c_lo = u.e_lo; a.c_hi = u.e_hi;
+    a.ck_init_state = st; a.ck_new_prefix_len = new_prefix_len; a.ck_old_prefix_len = old_prefix_len;
+    memcpy(a.ck_new_prefix, new_prefix, new_prefix_len);
+    size_t smem = h->setup_staging(&a, h->wblocks[u.block_idx], scan_crc_table_bytes());
+    if (smem != ck_smem) { ck_smem = smem; ck_grid = scan_max_grid(PM_CHECKSUM, smem); }
     h->kernel_begin();
-    cudaError_t ce = launch_checksum(a, 0, h->stream);
+    cudaError_t ce = launch_scan(h->cp.dev, a, ck_grid, smem, h->stream);
     h->kernel_end();
     if (ce != cudaSuccess) { g_last_error = cudaGetErrorString(ce); d_prefix.release(); return B2_ERR_CUDA; }
     h->release_block(u.block_idx);

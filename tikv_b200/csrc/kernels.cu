@@ -215,6 +215,15 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
     __syncthreads();
   }
 
+  // PM_CHECKSUM: bytewise CRC-64/XZ table, replicated 16x (entry i of copy c at [i * 16 + c]) so that the 64-bit
+  // lookups of a half-warp never share a bank pair
+  unsigned long long ck_x = 0, ck_kvs = 0, ck_bytes = 0;
+  unsigned long long* crc_tab = reinterpret_cast<unsigned long long*>(dyn_smem);
+  if (MODE == PM_CHECKSUM) {
+    for (unsigned int i = tid; i < 256 * 16; i += blockDim.x) crc_tab[i] = crc64_table_entry(i >> 4);
+    __syncthreads();
+  }
+
   // per-thread statistics, reduced once at the end
   unsigned long long t_keys = 0, t_size = 0, t_live = 0, t_dflt = 0;
   unsigned int t_newer = 0;
@@ -234,35 +243,47 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
   __shared__ TileMeta s_meta[N_STAGES];
   __shared__ __align__(8) unsigned long long s_cnt_ready, s_base_ready;  // consumers -> scan warp -> consumers (PM_SCAN)
   __shared__ unsigned int s_total;
+  __shared__ unsigned int s_chunk_null[2];  // any NULL cell staged in the current / next output chunk
   unsigned char* stage_base = dyn_smem + A.stage_off;
   const uint32_t STAGE_KEY_CAP = A.stage_key_cap, STAGE_VAL_CAP = A.stage_val_cap;
   const uint32_t STAGE_BYTES = STAGE_KEY_CAP + STAGE_VAL_CAP + 2 * STAGE_OFF_CAP;
   if (tid == 0) {
     for (int i = 0; i < N_STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], TILE / 32); }
     mbar_init(&s_cnt_ready, 1); mbar_init(&s_base_ready, 1);
+    s_chunk_null[0] = 0; s_chunk_null[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();  // last CTA-wide barrier: from here on the two roles only meet through the mbarriers
 
   if (wid == TILE / 32) {
     if (lane == 0) {
+      // software-pipelined by one tile: the ticket and the four bounding offsets of tile k+1 are fetched while the
+      // producer would otherwise idle on empty[slot]; only the bulk copies themselves wait for the stage
+      uint32_t nx_tile, nx_wlo = 0, nx_whi = 0, nx_k0 = 0, nx_k1 = 0, nx_v0 = 0, nx_v1 = 0;
+      auto claim = [&](uint32_t k) {
+        // PM_SCAN claims tiles in order so that the decoupled look-back only ever waits on running CTAs
+        if (MODE == PM_SCAN) nx_tile = (uint32_t)atomicAdd(&A.tile_status[n_tiles], 1ull);
+        else nx_tile = blockIdx.x + k * gridDim.x;
+        if (nx_tile < n_tiles && A.staging) {
+          uint32_t e0 = A.c_lo + nx_tile * TILE;
+          uint32_t e1 = e0 + TILE < A.c_hi ? e0 + TILE : A.c_hi;
+          nx_wlo = e0 > A.e_lo ? e0 - 1 : e0;
+          nx_whi = e1 + STAGE_LOOK < A.e_hi ? e1 + STAGE_LOOK : A.e_hi;
+          nx_k0 = A.blk.koff[nx_wlo]; nx_k1 = A.blk.koff[nx_whi]; nx_v0 = A.blk.voff[nx_wlo]; nx_v1 = A.blk.voff[nx_whi];
+        }
+      };
+      // (ordered mode claims late instead: a ticket held early would stall every successor's look-back)
+      if (MODE != PM_SCAN) claim(0);
       for (uint32_t k = 0;; ++k) {
         const int slot = (int)(k % N_STAGES);
-        long long tp0 = clock64();
-        mbar_wait_sleep(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1);
-        long long tp1 = clock64();
         TileMeta m;
         m.staged = 0; m.w_lo = 0; m.w_hi = 0; m.keys_adj = 0; m.vals_adj = 0; m.koff_adj = 0; m.voff_adj = 0;
-        // PM_SCAN claims tiles in order so that the decoupled look-back below only ever waits on running CTAs
-        if (MODE == PM_SCAN) m.tile = (uint32_t)atomicAdd(&A.tile_status[n_tiles], 1ull);
-        else m.tile = blockIdx.x + k * gridDim.x;
+        if (MODE == PM_SCAN) { mbar_wait_sleep(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1); claim(k); }
+        m.tile = nx_tile;
+        const uint32_t w_lo = nx_wlo, w_hi = nx_whi, k0 = nx_k0, k1 = nx_k1, v0 = nx_v0, v1 = nx_v1;
+        if (MODE != PM_SCAN) mbar_wait_sleep(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1);
         uint32_t tx = 0;
         if (m.tile < n_tiles && A.staging) {
-          uint32_t e0 = A.c_lo + m.tile * TILE;
-          uint32_t e1 = e0 + TILE < A.c_hi ? e0 + TILE : A.c_hi;
-          uint32_t w_lo = e0 > A.e_lo ? e0 - 1 : e0;
-          uint32_t w_hi = e1 + STAGE_LOOK < A.e_hi ? e1 + STAGE_LOOK : A.e_hi;
-          uint32_t k0 = A.blk.koff[w_lo], k1 = A.blk.koff[w_hi], v0 = A.blk.voff[w_lo], v1 = A.blk.voff[w_hi];
           unsigned long long ka = (unsigned long long)(A.blk.keys + k0), va = (unsigned long long)(A.blk.vals + v0);
           unsigned long long oa = (unsigned long long)(A.blk.koff + w_lo), ob = (unsigned long long)(A.blk.voff + w_lo);
           uint32_t kpad = (uint32_t)(ka & 15), vpad = (uint32_t)(va & 15), opad = (uint32_t)(oa & 15), qpad = (uint32_t)(ob & 15);
@@ -288,6 +309,7 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_full[slot])) : "memory");
         }
         if (m.tile >= n_tiles) break;
+        if (MODE != PM_SCAN) claim(k + 1);
       }
     }
     return;
@@ -336,6 +358,7 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
     return;
   }
 
+  uint32_t chunk_ctr = 0;
   for (uint32_t k = 0;; ++k) {
     const int cur = (int)(k % N_STAGES);
     long long tc0 = clock64();
@@ -369,6 +392,36 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
         t_dflt += ro.dflt_lookup;
         if (ro.err) {
           report_err(A.ctr, A.entry_base + e, ro.err);
+        } else if (ro.found && MODE == PM_CHECKSUM) {
+          // checksum_crc64_xor (checksum.rs:105-114): CRC-64/XZ of old_prefix ‖ raw_key[len(new_prefix)..] ‖ value
+          uint32_t kl = sv.klen(e);
+          const uint8_t* ek = sv.kptr(e);
+          t_keys += 1;
+          t_size += (kl - 8) + ro.val_len;
+          int rawlen = raw_key_len(ek, kl - 8);
+          bool okp = rawlen >= 0 && (uint32_t)rawlen >= A.ck_new_prefix_len;
+          for (uint32_t j = 0; okp && j < A.ck_new_prefix_len; ++j) okp = raw_at(ek, j) == A.ck_new_prefix[j];
+          if (rawlen < 0) report_err(A.ctr, A.entry_base + e, DE_BAD_USER_KEY);
+          else if (!okp) { atomicExch(&A.ctr->bad_prefix, 1u); report_err(A.ctr, A.entry_base + e, DE_BAD_RECORD_KEY); }
+          else {
+            const unsigned long long* tab = crc_tab + (lane & 15);  // 16 interleaved copies: lane l only touches bank pair l % 16
+            unsigned long long c = A.ck_init_state;
+            for (uint32_t j = A.ck_new_prefix_len; j < (uint32_t)rawlen; ++j) c = tab[((uint32_t)(c ^ raw_at(ek, j)) & 0xffu) * 16] ^ (c >> 8);
+            const uint8_t* vp = ro.val;
+            uint32_t vn = ro.val_len, j = 0;
+            for (; j + 8 <= vn; j += 8) {  // 8 value bytes per unaligned word load
+              unsigned long long w = ld64(vp + j);
+#pragma unroll
+              for (int b = 0; b < 8; ++b) { c = tab[((uint32_t)(c ^ w) & 0xffu) * 16] ^ (c >> 8); w >>= 8; }
+            }
+            if (j < vn) {
+              unsigned long long w = ld64(vp + j);
+              for (; j < vn; ++j) { c = tab[((uint32_t)(c ^ w) & 0xffu) * 16] ^ (c >> 8); w >>= 8; }
+            }
+            ck_x ^= ~c;
+            ck_kvs += 1;
+            ck_bytes += (unsigned long long)rawlen + ro.val_len + A.ck_old_prefix_len - A.ck_new_prefix_len;
+          }
         } else if (ro.found) {
           uint32_t kl = sv.klen(e);
           t_keys += 1;
@@ -419,6 +472,7 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
             if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; v.bits = 0; }
             obuf[kk * TILE + pos] = v.null ? 0ull : v.bits;
             onull[kk * TILE + pos] = v.null;
+            if (v.null) s_chunk_null[chunk_ctr & 1] = 1;  // benign race: any writer stores 1
           }
         }
         cta256_sync();  // chunk staged
@@ -428,16 +482,18 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
           if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 3] = clock64();
         }
         const unsigned long long base = out_base + s_base;
+        const bool any_null = s_chunk_null[chunk_ctr & 1] != 0;
+        if (tid == 0) s_chunk_null[(chunk_ctr + 1) & 1] = 0;  // the other flag is idle until the next chunk's decode (after the sync below)
+        const unsigned int lim = base + total <= A.out_cap ? total : (base < A.out_cap ? (unsigned int)(A.out_cap - base) : 0u);
         for (int kk = 0; kk < nc; ++kk) {
           unsigned long long* dst = A.out_data + (size_t)(c0 + kk) * A.out_cap + base;
-          for (unsigned int r = tid; r < total; r += TILE) {
-            if (base + r < A.out_cap) {
-              dst[r] = obuf[kk * TILE + r];
+          for (unsigned int r = tid; r < lim; r += TILE) dst[r] = obuf[kk * TILE + r];
+          if (any_null)  // NULL cells are rare: the bitmap is pre-filled with ones and only cleared where needed
+            for (unsigned int r = tid; r < lim; r += TILE)
               if (onull[kk * TILE + r]) atomicAnd(&A.out_bitmap[(size_t)(c0 + kk) * (A.out_cap / 64) + ((base + r) >> 6)], ~(1ull << ((base + r) & 63)));
-            }
-          }
         }
         cta256_sync();  // buffer (and s_warp_cnt / s_base after the last chunk) free for reuse
+        ++chunk_ctr;
       }
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 7] = clock64();
     } else if (MODE == PM_TOPN) {
@@ -527,6 +583,14 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
   }
 
   // ---- epilogue: flush CTA-private state ----
+  if (MODE == PM_CHECKSUM) {
+    for (int off = 16; off > 0; off >>= 1) {
+      ck_x ^= __shfl_xor_sync(0xffffffffu, ck_x, off);
+      ck_kvs += __shfl_xor_sync(0xffffffffu, ck_kvs, off);
+      ck_bytes += __shfl_xor_sync(0xffffffffu, ck_bytes, off);
+    }
+    if (lane == 0 && ck_kvs) { atomicXor(&A.ctr->checksum, ck_x); atomicAdd(&A.ctr->total_kvs, ck_kvs); atomicAdd(&A.ctr->total_bytes, ck_bytes); }
+  }
   if (MODE == PM_TOPN) {
     cta256_sync();
     cta_topn_compact(top_items, A.topn_cap, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
@@ -601,6 +665,7 @@ static int num_sms() {
 size_t scan_stage_bytes(uint32_t key_cap, uint32_t val_cap) { return (size_t)N_STAGES * (key_cap + val_cap + 2 * STAGE_OFF_CAP); }
 uint32_t scan_stage_entries() { return TILE + STAGE_LOOK + 1; }
 size_t scan_out_stage_bytes() { return (size_t)OUT_CHUNK * TILE * 9; }
+size_t scan_crc_table_bytes() { return 256 * 16 * 8; }
 
 int scan_max_grid(int mode, size_t smem) {
   int per_sm = 0;
@@ -608,6 +673,9 @@ int scan_max_grid(int mode, size_t smem) {
   if (mode == PM_SCAN) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_SCAN>, TILE + 64, smem);
+  } else if (mode == PM_CHECKSUM) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_CHECKSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_CHECKSUM>, TILE + 64, smem);
   } else if (mode == PM_TOPN) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_TOPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_TOPN>, TILE + 64, smem);
@@ -626,6 +694,9 @@ cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t
   if (plan.mode == PM_SCAN) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     scan_kernel<PM_SCAN><<<grid, TILE + 64, smem, s>>>(plan, a);
+  } else if (plan.mode == PM_CHECKSUM) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_CHECKSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_kernel<PM_CHECKSUM><<<grid, TILE + 64, smem, s>>>(plan, a);
   } else if (plan.mode == PM_TOPN) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_TOPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     scan_kernel<PM_TOPN><<<grid, TILE + 64, smem, s>>>(plan, a);

@@ -60,6 +60,10 @@ struct ScanArgs {
   uint32_t stage_off;               // byte offset of the stages inside dynamic shared memory (multiple of 16)
   uint32_t out_stage_off;           // PM_SCAN: byte offset of the output transpose buffer (multiple of 16)
   uint32_t stage_key_cap, stage_val_cap;  // bytes per stage for key / value heaps (multiples of 16)
+  // PM_CHECKSUM
+  uint64_t ck_init_state;           // crc register after old_prefix
+  uint32_t ck_new_prefix_len, ck_old_prefix_len;
+  uint8_t ck_new_prefix[32];
   // PM_TOPN
   TopNLists topn;                   // per-CTA result lists (stride = limit)
   uint32_t topn_cap;                // shared-memory candidate capacity (power of two >= limit + TILE)
@@ -89,6 +93,7 @@ struct GenArgs {
 cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t smem, cudaStream_t s);
 int scan_max_grid(int mode, size_t smem);  // occupancy-based persistent grid size
 size_t scan_stage_bytes(uint32_t key_cap, uint32_t val_cap);  // dynamic shared memory needed by the tile stages
+size_t scan_crc_table_bytes();             // PM_CHECKSUM replicated CRC table
 size_t scan_out_stage_bytes();             // PM_SCAN output transpose buffer
 uint32_t scan_stage_entries();             // entries a stage must hold (tile + look-behind/ahead)
 cudaError_t launch_agg_finalize(const DevPlan& plan, const AggTable& t, Counters* ctr, unsigned long long* out_keys, unsigned char* out_key_null,
