@@ -116,7 +116,7 @@ __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int 
 // reads instead of 32 scattered byte addresses per warp instruction.
 // Stage capacities (key / value bytes) are chosen per launch from the block's average entry size (ScanArgs); a tile
 // that does not fit is simply read from HBM.
-enum { STAGE_LOOK = 8, STAGE_OFF_CAP = 1104, N_STAGES = 2, OUT_CHUNK = 4 };
+enum { STAGE_LOOK = 8, STAGE_OFF_CAP = 1104, N_STAGES = 2, OUT_CHUNK = 8 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -184,8 +184,7 @@ struct SmemTable {  // per-CTA group table (dynamic shared memory): keys | acc |
 template <int MODE>
 __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ unsigned int s_tile;
-  __shared__ unsigned int s_warp_cnt[TILE / 32];
+  __shared__ unsigned int s_warp_cnt[2][TILE / 32];  // by tile parity: a fast warp may start the next tile while others still read
   __shared__ unsigned long long s_base;
   __shared__ unsigned int s_tbl_used;
 
@@ -243,14 +242,12 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
   __shared__ TileMeta s_meta[N_STAGES];
   __shared__ __align__(8) unsigned long long s_cnt_ready, s_base_ready;  // consumers -> scan warp -> consumers (PM_SCAN)
   __shared__ unsigned int s_total;
-  __shared__ unsigned int s_chunk_null[2];  // any NULL cell staged in the current / next output chunk
   unsigned char* stage_base = dyn_smem + A.stage_off;
   const uint32_t STAGE_KEY_CAP = A.stage_key_cap, STAGE_VAL_CAP = A.stage_val_cap;
   const uint32_t STAGE_BYTES = STAGE_KEY_CAP + STAGE_VAL_CAP + 2 * STAGE_OFF_CAP;
   if (tid == 0) {
     for (int i = 0; i < N_STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], TILE / 32); }
     mbar_init(&s_cnt_ready, 1); mbar_init(&s_base_ready, 1);
-    s_chunk_null[0] = 0; s_chunk_null[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();  // last CTA-wide barrier: from here on the two roles only meet through the mbarriers
@@ -358,7 +355,6 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
     return;
   }
 
-  uint32_t chunk_ctr = 0;
   for (uint32_t k = 0;; ++k) {
     const int cur = (int)(k % N_STAGES);
     long long tc0 = clock64();
@@ -445,56 +441,58 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 0] = clock64();
       unsigned int bal = __ballot_sync(0xffffffffu, live);
       unsigned int lane_off = __popc(bal & ((1u << lane) - 1));
-      if (lane == 0) s_warp_cnt[wid] = __popc(bal);
+      if (lane == 0) s_warp_cnt[k & 1][wid] = __popc(bal);
       cta256_sync();
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 1] = clock64();
       unsigned int warp_off = 0, total = 0;
 #pragma unroll
       for (int w = 0; w < TILE / 32; ++w) {
-        unsigned int c = s_warp_cnt[w];
+        unsigned int c = s_warp_cnt[k & 1][w];
         if (w < (int)wid) warp_off += c;
         total += c;
       }
       // the scan warp (warp 9) turns the tile's row count into its global output base while we decode the columns
       if (tid == 0) { s_total = total; asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready)) : "memory"); }
-      // Output columns go through a small shared-memory transpose buffer, OUT_CHUNK columns at a time: rows are placed
-      // at their tile-local compacted position (known without the look-back result), which hides the look-back latency
-      // behind the column decode and turns the HBM writes into contiguous 8-byte runs.
-      unsigned long long* obuf = reinterpret_cast<unsigned long long*>(dyn_smem + A.out_stage_off);
-      unsigned char* onull = reinterpret_cast<unsigned char*>(obuf + OUT_CHUNK * TILE);
+      // Selected rows are written straight from registers: lanes with consecutive compacted positions store to
+      // consecutive 8-byte slots of each output column, so a warp's store is one contiguous run (L2 merges the partial
+      // sectors at run boundaries).  OUT_CHUNK columns are decoded before the first store so that the look-back latency
+      // (scan warp) hides behind the decode.
       const unsigned int pos = warp_off + lane_off;
+      unsigned long long base = 0;
       for (int c0 = 0; c0 < P.n_out; c0 += OUT_CHUNK) {
-        const int nc = P.n_out - c0 < OUT_CHUNK ? P.n_out - c0 : OUT_CHUNK;
+        unsigned long long vals[OUT_CHUNK];
+        unsigned int nullm = 0;
         if (live) {
-          for (int kk = 0; kk < nc; ++kk) {
-            Value v;
-            int err = cell_value(P, row, cells, P.out_cols[c0 + kk], &v);
-            if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; v.bits = 0; }
-            obuf[kk * TILE + pos] = v.null ? 0ull : v.bits;
-            onull[kk * TILE + pos] = v.null;
-            if (v.null) s_chunk_null[chunk_ctr & 1] = 1;  // benign race: any writer stores 1
+#pragma unroll
+          for (int kk = 0; kk < OUT_CHUNK; ++kk) {
+            vals[kk] = 0;
+            if (c0 + kk < P.n_out) {
+              Value v;
+              int err = cell_value(P, row, cells, P.out_cols[c0 + kk], &v);
+              if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; }
+              vals[kk] = v.null ? 0ull : v.bits;
+              nullm |= (unsigned int)v.null << kk;
+            }
           }
         }
-        cta256_sync();  // chunk staged
         if (c0 == 0) {
           if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 2] = clock64();
           mbar_wait(&s_base_ready, k & 1);  // look-back result published by the scan warp
           if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 3] = clock64();
+          base = out_base + s_base + pos;
         }
-        const unsigned long long base = out_base + s_base;
-        const bool any_null = s_chunk_null[chunk_ctr & 1] != 0;
-        if (tid == 0) s_chunk_null[(chunk_ctr + 1) & 1] = 0;  // the other flag is idle until the next chunk's decode (after the sync below)
-        const unsigned int lim = base + total <= A.out_cap ? total : (base < A.out_cap ? (unsigned int)(A.out_cap - base) : 0u);
-        for (int kk = 0; kk < nc; ++kk) {
-          unsigned long long* dst = A.out_data + (size_t)(c0 + kk) * A.out_cap + base;
-          for (unsigned int r = tid; r < lim; r += TILE) dst[r] = obuf[kk * TILE + r];
-          if (any_null)  // NULL cells are rare: the bitmap is pre-filled with ones and only cleared where needed
-            for (unsigned int r = tid; r < lim; r += TILE)
-              if (onull[kk * TILE + r]) atomicAnd(&A.out_bitmap[(size_t)(c0 + kk) * (A.out_cap / 64) + ((base + r) >> 6)], ~(1ull << ((base + r) & 63)));
+        if (live && base < A.out_cap) {
+#pragma unroll
+          for (int kk = 0; kk < OUT_CHUNK; ++kk) {
+            if (c0 + kk < P.n_out) {
+              A.out_data[(size_t)(c0 + kk) * A.out_cap + base] = vals[kk];
+              if ((nullm >> kk) & 1u)  // NULL cells are rare: the bitmap is pre-filled with ones and only cleared where needed
+                atomicAnd(&A.out_bitmap[(size_t)(c0 + kk) * (A.out_cap / 64) + (base >> 6)], ~(1ull << (base & 63)));
+            }
+          }
         }
-        cta256_sync();  // buffer (and s_warp_cnt / s_base after the last chunk) free for reuse
-        ++chunk_ctr;
       }
+      if (P.n_out == 0) mbar_wait(&s_base_ready, k & 1);  // keep the phase of the hand-shake in step
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 7] = clock64();
     } else if (MODE == PM_TOPN) {
       // BatchTopN: keep the `limit` smallest rows under the order-by key.  A row is a candidate only if it beats
@@ -664,7 +662,7 @@ static int num_sms() {
 
 size_t scan_stage_bytes(uint32_t key_cap, uint32_t val_cap) { return (size_t)N_STAGES * (key_cap + val_cap + 2 * STAGE_OFF_CAP); }
 uint32_t scan_stage_entries() { return TILE + STAGE_LOOK + 1; }
-size_t scan_out_stage_bytes() { return (size_t)OUT_CHUNK * TILE * 9; }
+size_t scan_out_stage_bytes() { return 0; }
 size_t scan_crc_table_bytes() { return 256 * 16 * 8; }
 
 int scan_max_grid(int mode, size_t smem) {
