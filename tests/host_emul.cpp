@@ -94,11 +94,23 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
         live_rows++;
         if (err != ~0ull) continue;  // the host discards rows at/after the first failing entry
         if (P.mode == PM_SCAN) {
-          for (int k = 0; k < P.n_out; ++k) {
+          // same split as scan_kernel<PM_SCAN>: fast rows feed integer outputs by stored position, the rest by cell_value
+          auto put = [&](int k) {
             Value v;
             int e2 = cell_value(P, row, cells, P.out_cols[k], &v);
             if (e2) { report(bases[b] + e, e2); v.null = true; v.bits = 0; }
             R->data[k].push_back(v.null ? 0 : v.bits); R->nonnull[k].push_back(!v.null);
+          };
+          if (row.fast) {
+            uint32_t prev = 0;
+            for (int h = 0; h < 8 && h < P.fast_n; ++h) {
+              uint32_t end = fast_end(row, h);
+              if (P.fast_out[h] >= 0) { R->data[P.fast_out[h]].push_back(fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u)); R->nonnull[P.fast_out[h]].push_back(true); }
+              prev = end;
+            }
+            for (int j = 0; j < P.n_out_slow; ++j) put(P.out_slow[j]);
+          } else {
+            for (int k = 0; k < P.n_out; ++k) put(k);
           }
           R->n_rows++;
         } else if (P.mode == PM_TOPN) {

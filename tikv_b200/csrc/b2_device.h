@@ -86,8 +86,11 @@ struct DevPlan {
   int32_t fast_n;      // > 0: rows holding exactly these `fast_n` non-null column ids (and no NULL ids) take the register fast path
   int32_t _fpad;
   uint64_t fast_filled;  // `filled` mask of such a row (every row-stored plan column)
-  uint32_t fast_cls;     // 2 bits per stored column in id order: 0 copy, 1 integer width check, 2 unsupported type
-  uint32_t _fpad2;
+  uint32_t fast_cls;     // bit h: stored column h (id order) is integer-class (width must be 1/2/4/8)
+  uint32_t fast_uns;     // bit h: stored column h is zero-extended (unsigned)
+  int8_t fast_out[8];    // PM_SCAN: output column fed by stored column h (first occurrence), or -1
+  int32_t n_out_slow;    // PM_SCAN: outputs of a fast row that still go through cell_value (handle, Real, repeats ...)
+  int32_t _fpad2;
   uint64_t fast_ids;   // the expected sorted non-null id bytes of such a row, packed little-endian (fast_n <= 8)
   uint64_t read_ts;
   uint64_t limit;
@@ -97,6 +100,7 @@ struct DevPlan {
   DevAgg aggs[MAX_AGGS];
   DevOrder order[MAX_ORDER];
   uint8_t out_cols[MAX_COLS];
+  uint8_t out_slow[MAX_COLS];  // indices into out_cols
   DevCol cols[MAX_COLS];
   DevNode nodes[MAX_NODES];
 };
@@ -622,6 +626,50 @@ struct Row {
   uint64_t o_lo, o_hi;  // the row's u16 end-offsets 0..3 / 4..7
 };
 
+B2_HD uint32_t shr_clamp(uint32_t v, uint32_t sh) {  // v >> sh, 0 for sh >= 32
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_rc(v, 0u, sh);
+#else
+  return sh >= 32 ? 0u : v >> sh;
+#endif
+}
+// end offset of stored column h of a fast row (h is a compile-time constant after unrolling)
+B2_HD uint32_t fast_end(const Row& row, int h) { return (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu; }
+// integer cell of a fast row: stored column h spans [start, end) of the value area (compat_v1.rs:13-38)
+B2_HD uint64_t fast_int_cell(const Row& row, uint32_t start, uint32_t end, bool zero_extend) {
+  uint64_t u = ld64(row.rv.v + row.rv.vals_off + start);
+  uint32_t len = end - start;
+  if (len < 8) {
+    uint32_t sh = 64 - 8 * len;
+    u = zero_extend ? ((u << sh) >> sh) : (uint64_t)(((int64_t)(u << sh)) >> sh);
+  }
+  return u;
+}
+// Does this v2 row hold exactly the plan's columns (process_v2 would find column k at position v2_hint), all
+// non-null, offsets monotone and inside the value area, integer-class columns 1/2/4/8 bytes wide?  On success the
+// end-offsets stay in two registers: no per-column search, no Cells traffic.
+B2_HD bool fast_row_probe(const DevPlan& P, Row& row) {
+  const RowView& r = row.rv;
+  row.fast = 0;
+  if (!(P.fast_n > 0 && !r.big && r.nn_cnt == (uint32_t)P.fast_n && r.null_cnt == 0)) return false;
+  if (((ld64(r.v + r.ids_off) ^ P.fast_ids) & (P.fast_n >= 8 ? ~0ull : ((1ull << (8 * P.fast_n)) - 1))) != 0) return false;
+  row.o_lo = ld64(r.v + r.offs_off);
+  row.o_hi = P.fast_n > 4 ? ld64(r.v + r.offs_off + 8) : 0;
+  uint32_t prev = 0, bad = 0;
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    if (h < P.fast_n) {
+      uint32_t end = fast_end(row, h);
+      if ((P.fast_cls >> h) & 1u) bad |= ~shr_clamp(0x116u, end - prev);  // widths 1, 2, 4, 8 (a decreasing offset wraps to a huge width)
+      else bad |= end < prev ? 1u : 0u;
+      prev = end;
+    }
+  }
+  if ((bad & 1u) || prev > r.vals_len) return false;
+  row.fast = 1;
+  return true;
+}
+
 // process_kv_pair (table_scan_executor.rs:365-475): everything that can fail regardless of which rows are
 // later selected.  For v1 rows it records the cell of every plan column in `cells`.
 B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
@@ -654,28 +702,9 @@ B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
       }
       pos += dl;
     }
-  } else if (r.fmt == 2 && P.fast_n > 0 && !r.big && r.nn_cnt == (uint32_t)P.fast_n && r.null_cnt == 0 &&
-             ((ld64(r.v + r.ids_off) ^ P.fast_ids) & (P.fast_n >= 8 ? ~0ull : ((1ull << (8 * P.fast_n)) - 1))) == 0) {
-    // exact-layout fast path: the row holds precisely the plan's columns, all non-null (process_v2 would find column
-    // k at position v2_hint).  Keep the end-offsets in two registers; no per-column search, no Cells traffic.
-    row.fast = 1;
-    row.o_lo = ld64(r.v + r.offs_off);
-    row.o_hi = P.fast_n > 4 ? ld64(r.v + r.offs_off + 8) : 0;
-    // one pass over the (at most 8) stored columns in id order: offsets must be monotone and inside the value area,
-    // integer-class columns must be 1/2/4/8 bytes wide (compat_v1.rs:13-38)
-    uint32_t prev = 0;
-#pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      if (h < P.fast_n) {
-        uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
-        if (end < prev || end > r.vals_len) return DE_ROW_V2_RANGE;
-        uint32_t len = end - prev;
-        uint32_t cls = (P.fast_cls >> (2 * h)) & 3u;  // 0 copy, 1 int-width check, 2 unsupported
-        if (cls == 1 && (len > 8 || !((0x116u >> len) & 1u))) return DE_ROW_V2_BAD_INT;  // widths 1, 2, 4, 8
-        if (cls == 2) return DE_UNSUPPORTED_TYPE;
-        prev = end;
-      }
-    }
+  } else if (r.fmt == 2 && fast_row_probe(P, row)) {
+    // exact-layout fast path: the row holds precisely the plan's columns, all non-null, with well-formed offsets and
+    // integer widths (anything else, including rows that would raise an error, takes the general branch below)
     filled = P.fast_filled;
   } else if (r.fmt == 2) {
     for (int k = 0; k < P.n_cols; ++k) {
@@ -723,13 +752,7 @@ B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k
     uint32_t h = c.v2_hint;
     uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
     uint32_t start = h == 0 ? 0u : ((uint32_t)((h - 1 < 4 ? row.o_lo : row.o_hi) >> (((h - 1) & 3) * 16)) & 0xffffu);
-    uint32_t len = end - start;
-    uint64_t u = ld64(row.rv.v + row.rv.vals_off + start);
-    if (len < 8) {
-      uint32_t sh = 64 - 8 * len;
-      u = c.v2_class == V2_INT ? (uint64_t)(((int64_t)(u << sh)) >> sh) : ((u << sh) >> sh);
-    }
-    out->bits = u;
+    out->bits = fast_int_cell(row, start, end, c.v2_class != V2_INT);
     return DE_NONE;
   }
   if (c.role == CR_HANDLE) { out->bits = raw_be64(row.enc_key, 11) ^ S; return DE_NONE; }       // table.rs:214-218

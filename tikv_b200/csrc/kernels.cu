@@ -116,7 +116,7 @@ __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int 
 // reads instead of 32 scattered byte addresses per warp instruction.
 // Stage capacities (key / value bytes) are chosen per launch from the block's average entry size (ScanArgs); a tile
 // that does not fit is simply read from HBM.
-enum { STAGE_LOOK = 8, STAGE_OFF_CAP = 1104, N_STAGES = 2, OUT_CHUNK = 8 };
+enum { STAGE_LOOK = 8, STAGE_OFF_CAP = 1104, N_STAGES = 2 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -455,44 +455,47 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
       if (tid == 0) { s_total = total; asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready)) : "memory"); }
       // Selected rows are written straight from registers: lanes with consecutive compacted positions store to
       // consecutive 8-byte slots of each output column, so a warp's store is one contiguous run (L2 merges the partial
-      // sectors at run boundaries).  OUT_CHUNK columns are decoded before the first store so that the look-back latency
+      // sectors at run boundaries).  The columns are decoded before the first store so that the look-back latency
       // (scan warp) hides behind the decode.
       const unsigned int pos = warp_off + lane_off;
-      unsigned long long base = 0;
-      for (int c0 = 0; c0 < P.n_out; c0 += OUT_CHUNK) {
-        unsigned long long vals[OUT_CHUNK];
-        unsigned int nullm = 0;
-        if (live) {
+      // fast rows: the (at most 8) stored integer columns are decoded by stored position, so every shift is a
+      // compile-time constant; they sit in registers while the scan warp finishes the look-back
+      unsigned long long vals[8];
+      const bool fast = live && row.fast;
+      if (fast) {
+        uint32_t prev = 0;
 #pragma unroll
-          for (int kk = 0; kk < OUT_CHUNK; ++kk) {
-            vals[kk] = 0;
-            if (c0 + kk < P.n_out) {
-              Value v;
-              int err = cell_value(P, row, cells, P.out_cols[c0 + kk], &v);
-              if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; }
-              vals[kk] = v.null ? 0ull : v.bits;
-              nullm |= (unsigned int)v.null << kk;
-            }
-          }
-        }
-        if (c0 == 0) {
-          if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 2] = clock64();
-          mbar_wait(&s_base_ready, k & 1);  // look-back result published by the scan warp
-          if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 3] = clock64();
-          base = out_base + s_base + pos;
-        }
-        if (live && base < A.out_cap) {
-#pragma unroll
-          for (int kk = 0; kk < OUT_CHUNK; ++kk) {
-            if (c0 + kk < P.n_out) {
-              A.out_data[(size_t)(c0 + kk) * A.out_cap + base] = vals[kk];
-              if ((nullm >> kk) & 1u)  // NULL cells are rare: the bitmap is pre-filled with ones and only cleared where needed
-                atomicAnd(&A.out_bitmap[(size_t)(c0 + kk) * (A.out_cap / 64) + (base >> 6)], ~(1ull << (base & 63)));
-            }
+        for (int h = 0; h < 8; ++h) {
+          vals[h] = 0;
+          if (h < P.fast_n) {
+            uint32_t end = fast_end(row, h);
+            if (P.fast_out[h] >= 0) vals[h] = fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u);
+            prev = end;
           }
         }
       }
-      if (P.n_out == 0) mbar_wait(&s_base_ready, k & 1);  // keep the phase of the hand-shake in step
+      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 2] = clock64();
+      mbar_wait(&s_base_ready, k & 1);  // look-back result published by the scan warp
+      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 3] = clock64();
+      const unsigned long long base = out_base + s_base + pos;
+      if (live && base < A.out_cap) {
+        auto put = [&](int oc) {  // general cell: any role / kind, may be NULL
+          Value v;
+          int err = cell_value(P, row, cells, P.out_cols[oc], &v);
+          if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; }
+          A.out_data[(size_t)oc * A.out_cap + base] = v.null ? 0ull : v.bits;
+          if (v.null)  // NULL cells are rare: the bitmap is pre-filled with ones and only cleared where needed
+            atomicAnd(&A.out_bitmap[(size_t)oc * (A.out_cap / 64) + (base >> 6)], ~(1ull << (base & 63)));
+        };
+        if (fast) {
+#pragma unroll
+          for (int h = 0; h < 8; ++h)
+            if (h < P.fast_n && P.fast_out[h] >= 0) A.out_data[(size_t)P.fast_out[h] * A.out_cap + base] = vals[h];
+          for (int j = 0; j < P.n_out_slow; ++j) put(P.out_slow[j]);
+        } else {
+          for (int oc = 0; oc < P.n_out; ++oc) put(oc);
+        }
+      }
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 7] = clock64();
     } else if (MODE == PM_TOPN) {
       // BatchTopN: keep the `limit` smallest rows under the order-by key.  A row is a candidate only if it beats

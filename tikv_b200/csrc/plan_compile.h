@@ -179,10 +179,12 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
       if (P.cols[i].role == CR_SHADOWED) ok = false;
       if (P.cols[i].role != CR_NORMAL) continue;
       if (P.cols[i].col_id <= 0 || P.cols[i].col_id > 255) ok = false;
+      if (P.cols[i].v2_class == V2_UNSUPPORTED) ok = false;  // such a row raises an error: general path
       ids.push_back(P.cols[i].col_id);
     }
     std::sort(ids.begin(), ids.end());
-    P.fast_n = 0; P.fast_ids = 0; P.fast_cls = 0; P.fast_filled = 0;
+    P.fast_n = 0; P.fast_ids = 0; P.fast_cls = 0; P.fast_uns = 0; P.fast_filled = 0; P.n_out_slow = 0;
+    for (int h = 0; h < 8; ++h) P.fast_out[h] = -1;
     if (ok && !ids.empty() && ids.size() <= 8) {
       P.fast_n = (int32_t)ids.size();
       for (size_t i = 0; i < ids.size(); ++i) P.fast_ids |= (uint64_t)ids[i] << (8 * i);
@@ -192,8 +194,8 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
         if (col.role != CR_NORMAL) continue;
         P.fast_filled |= 1ull << i;
         size_t rank = std::lower_bound(ids.begin(), ids.end(), col.col_id) - ids.begin();
-        uint32_t cls = (col.v2_class == V2_INT || col.v2_class == V2_UINT) ? 1u : (col.v2_class == V2_UNSUPPORTED ? 2u : 0u);
-        P.fast_cls |= cls << (2 * rank);
+        if (col.v2_class == V2_INT || col.v2_class == V2_UINT) P.fast_cls |= 1u << rank;
+        if (col.v2_class != V2_INT) P.fast_uns |= 1u << rank;
       }
     }
   }
@@ -283,6 +285,12 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
       P.out_cols[i] = (uint8_t)mat[i];
     }
     P.n_out = (int)mat.size();
+    // fast rows feed integer outputs straight from their stored position; everything else goes through cell_value
+    for (int i = 0; i < P.n_out; ++i) {
+      const DevCol& col = P.cols[P.out_cols[i]];
+      if (P.fast_n > 0 && col.role == CR_NORMAL && col.kind == CK_INT && P.fast_out[col.v2_hint] < 0) P.fast_out[col.v2_hint] = (int8_t)i;
+      else P.out_slow[P.n_out_slow++] = (uint8_t)i;
+    }
   }
   return B2_OK;
 }
