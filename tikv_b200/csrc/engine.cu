@@ -556,10 +556,21 @@ struct b2_exec {
   // shared-memory staging: capacities from the block's average entry size (+30 %), stages placed after `mode_bytes`
   size_t setup_staging(ScanArgs* a, const SrcBlock& sb, size_t mode_bytes) {
     uint32_t n = std::max<uint32_t>(1, sb.c.n), ents = scan_stage_entries();
-    auto cap = [&](uint64_t total) { uint64_t c = (total * ents / n) * 13 / 10 + 256; c = (c + 15) & ~15ull; return (uint32_t)std::min<uint64_t>(c, 72 * 1024); };
-    a->stage_key_cap = cap(sb.key_bytes); a->stage_val_cap = cap(sb.val_bytes);
+    // stage capacity = average bytes of a tile's entries + slack; the slack shrinks (30 % .. 6 %) while that lets two
+    // CTAs share an SM's shared memory.  A tile that does not fit is read from HBM directly.
+    auto cap = [&](uint64_t total, uint64_t pct) { uint64_t c = (total * ents / n) * pct / 100 + 256; c = (c + 15) & ~15ull; return (uint32_t)std::min<uint64_t>(c, 72 * 1024); };
     a->stage_off = (uint32_t)((mode_bytes + 15) & ~15ull);
-    size_t total = a->stage_off + scan_stage_bytes(a->stage_key_cap, a->stage_val_cap);
+    const size_t two_per_sm = (233472 / 2) - 1024 - 512;  // SM shared memory / 2 - per-CTA reserve - static
+    size_t total = 0;
+    for (uint64_t pct : {130, 120, 112, 106}) {
+      a->stage_key_cap = cap(sb.key_bytes, pct); a->stage_val_cap = cap(sb.val_bytes, pct);
+      total = a->stage_off + scan_stage_bytes(a->stage_key_cap, a->stage_val_cap);
+      if (total <= two_per_sm) break;
+    }
+    if (total > two_per_sm) {
+      a->stage_key_cap = cap(sb.key_bytes, 130); a->stage_val_cap = cap(sb.val_bytes, 130);
+      total = a->stage_off + scan_stage_bytes(a->stage_key_cap, a->stage_val_cap);
+    }
     if (!use_staging || total > 200 * 1024) { a->staging = 0; a->stage_key_cap = a->stage_val_cap = 0; return mode_bytes; }
     a->staging = 1;
     return total;
@@ -643,7 +654,7 @@ struct b2_exec {
           std::vector<unsigned long long> t(128 * 8);
           cudaStreamSynchronize(stream);
           cudaMemcpy(t.data(), trace_buf.p, t.size() * 8, cudaMemcpyDeviceToHost);
-          fprintf(stderr, "B2_TRACE tile: wait_full decode+pred sync1 lookback sync2 outputs sync3 | cycle (SM clocks, CTA 0 thread 0)\n");
+          fprintf(stderr, "B2_TRACE tile: wait_full decode+pred sync1 out_decode obuf_wait out_store tail | cycle (SM clocks, CTA 0 thread 0)\n");
           for (int i = 1; i < 40; ++i) {
             unsigned long long* r = &t[i * 8];
             if (!r[6]) break;

@@ -116,7 +116,8 @@ __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int 
 // reads instead of 32 scattered byte addresses per warp instruction.
 // Stage capacities (key / value bytes) are chosen per launch from the block's average entry size (ScanArgs); a tile
 // that does not fit is simply read from HBM.
-enum { STAGE_LOOK = 8, STAGE_OFF_CAP = 1104, N_STAGES = 2 };
+enum { STAGE_LOOK = 8, STAGE_OFF_CAP = 1104, N_STAGES = 2, OBUF_COLS = 4, N_OBUF = 3, N_CNT = 4 };
+enum { OBUF_BYTES = OBUF_COLS * TILE * 8, ONULL_WORDS = OBUF_COLS * (TILE / 32) };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -185,7 +186,6 @@ template <int MODE>
 __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned int s_warp_cnt[2][TILE / 32];  // by tile parity: a fast warp may start the next tile while others still read
-  __shared__ unsigned long long s_base;
   __shared__ unsigned int s_tbl_used;
 
   const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -240,14 +240,23 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
   __shared__ __align__(8) unsigned long long s_full[N_STAGES];
   __shared__ __align__(8) unsigned long long s_empty[N_STAGES];
   __shared__ TileMeta s_meta[N_STAGES];
-  __shared__ __align__(8) unsigned long long s_cnt_ready, s_base_ready;  // consumers -> scan warp -> consumers (PM_SCAN)
-  __shared__ unsigned int s_total;
+  // PM_SCAN: consumers -> scan warp.  cnt_ready[k % N_CNT]: tile k's row count (and tile index) posted;
+  // obuf_full / obuf_empty[q]: output chunk buffer q handed to the scan warp / drained to HBM
+  __shared__ __align__(8) unsigned long long s_cnt_ready[N_CNT], s_obuf_full[N_OBUF], s_obuf_empty[N_OBUF];
+  __shared__ unsigned int s_total[N_CNT], s_tile_of[N_CNT];
   unsigned char* stage_base = dyn_smem + A.stage_off;
   const uint32_t STAGE_KEY_CAP = A.stage_key_cap, STAGE_VAL_CAP = A.stage_val_cap;
   const uint32_t STAGE_BYTES = STAGE_KEY_CAP + STAGE_VAL_CAP + 2 * STAGE_OFF_CAP;
+  // PM_SCAN output chunk buffers (dynamic shared memory): N_OBUF x [OBUF_COLS][TILE] values, then the NULL masks
+  unsigned long long* obuf_base = reinterpret_cast<unsigned long long*>(dyn_smem + A.out_stage_off);
+  unsigned int* onull_base = reinterpret_cast<unsigned int*>(dyn_smem + A.out_stage_off + N_OBUF * OBUF_BYTES);
+  const uint32_t n_rounds = P.n_out > 0 ? (uint32_t)(P.n_out + OBUF_COLS - 1) / OBUF_COLS : 1u;
+  if (MODE == PM_SCAN)
+    for (unsigned int i = tid; i < N_OBUF * ONULL_WORDS; i += blockDim.x) onull_base[i] = 0;
   if (tid == 0) {
     for (int i = 0; i < N_STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], TILE / 32); }
-    mbar_init(&s_cnt_ready, 1); mbar_init(&s_base_ready, 1);
+    for (int i = 0; i < N_CNT; ++i) mbar_init(&s_cnt_ready[i], 1);
+    for (int i = 0; i < N_OBUF; ++i) { mbar_init(&s_obuf_full[i], TILE / 32); mbar_init(&s_obuf_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();  // last CTA-wide barrier: from here on the two roles only meet through the mbarriers
@@ -313,17 +322,17 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
   }
 
   if (wid == TILE / 32 + 1) {
-    // ---- scan warp (PM_SCAN): decoupled look-back, one warp wide.  Lane l inspects tile (j - l); the nearest tile that
-    // already knows its inclusive prefix ends the walk, the aggregates in between are summed with shuffles.
+    // ---- scan warp (PM_SCAN): turns each tile's row count into its global output base (decoupled look-back, one
+    // warp wide: lane l inspects tile (j - l); the nearest tile that already knows its inclusive prefix ends the walk,
+    // the aggregates in between are summed with shuffles), then drains the tile's output chunks from shared memory to
+    // HBM.  The decoding warps never wait for the look-back.
     if (MODE != PM_SCAN) return;
     const unsigned long long F_AGG = 1ull << 62, F_INC = 2ull << 62, VMASK = (1ull << 62) - 1;
     for (uint32_t k = 0;; ++k) {
-      const int cur = (int)(k % N_STAGES);
-      mbar_wait_sleep(&s_full[cur], (k / N_STAGES) & 1);
-      const uint32_t tile = s_meta[cur].tile;
+      mbar_wait_sleep(&s_cnt_ready[k % N_CNT], (k / N_CNT) & 1);
+      const uint32_t tile = s_tile_of[k % N_CNT];
       if (tile >= n_tiles) break;
-      mbar_wait_sleep(&s_cnt_ready, k & 1);
-      const unsigned long long total = s_total;
+      const unsigned long long total = s_total[k % N_CNT];
       unsigned long long excl = 0;
       if (tile == 0) {
         if (lane == 0) atomicExch(&A.tile_status[0], F_INC | total);
@@ -346,10 +355,36 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
         }
         if (lane == 0) atomicExch(&A.tile_status[tile], F_INC | (excl + total));
       }
-      if (lane == 0) {
-        s_base = excl;
-        if (total) atomicAdd(&A.ctr->out_rows, total);
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_base_ready)) : "memory");
+      if (lane == 0 && total) atomicAdd(&A.ctr->out_rows, total);
+      const unsigned long long base = out_base + excl;
+      const unsigned int lim = base + total <= A.out_cap ? (unsigned int)total : (base < A.out_cap ? (unsigned int)(A.out_cap - base) : 0u);
+      for (uint32_t r = 0; r < n_rounds; ++r) {
+        const uint32_t g = k * n_rounds + r, q = g % N_OBUF;
+        mbar_wait_sleep(&s_obuf_full[q], (g / N_OBUF) & 1);
+        const int c0 = (int)r * OBUF_COLS;
+        const int nc = P.n_out - c0 < OBUF_COLS ? P.n_out - c0 : OBUF_COLS;
+        const unsigned long long* ob = obuf_base + (size_t)q * (OBUF_COLS * TILE);
+        unsigned long long* dst = A.out_data + (size_t)c0 * A.out_cap + base;
+        for (unsigned int i = lane; i < lim; i += 32) {
+#pragma unroll
+          for (int c = 0; c < OBUF_COLS; ++c)
+            if (c < nc) dst[(size_t)c * A.out_cap + i] = ob[c * TILE + i];
+        }
+        // NULL cells are rare: the bitmap is pre-filled with ones and only cleared where needed
+        unsigned int* on = onull_base + q * ONULL_WORDS;
+        unsigned int w = on[lane];  // ONULL_WORDS == 32: word (column c, rows 32 j ..) at [c * 8 + j]
+        if (w) {
+          on[lane] = 0;
+          const int c = (int)(lane / (TILE / 32));
+          while (w) {
+            unsigned int bit = __ffs(w) - 1;
+            w &= w - 1;
+            unsigned long long row_at = base + (lane % (TILE / 32)) * 32 + bit;
+            if (row_at < A.out_cap) atomicAnd(&A.out_bitmap[(size_t)(c0 + c) * (A.out_cap / 64) + (row_at >> 6)], ~(1ull << (row_at & 63)));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_obuf_empty[q])) : "memory");
       }
     }
     return;
@@ -362,7 +397,13 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
     if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) { A.trace[k * 8 + 4] = tc0; A.trace[k * 8 + 5] = clock64(); }
     const TileMeta m = s_meta[cur];
     const uint32_t tile = m.tile;
-    if (tile >= n_tiles) break;
+    if (tile >= n_tiles) {
+      if (MODE == PM_SCAN && tid == 0) {  // tell the scan warp there is no tile k
+        s_tile_of[k % N_CNT] = tile;
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready[k % N_CNT])) : "memory");
+      }
+      break;
+    }
     StagedView sv;
     sv.g = A.blk; sv.w_lo = 0; sv.w_n = 0;
     sv.skeys = nullptr; sv.skoff = nullptr; sv.svals = nullptr; sv.svoff = nullptr;
@@ -451,15 +492,12 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
         if (w < (int)wid) warp_off += c;
         total += c;
       }
-      // the scan warp (warp 9) turns the tile's row count into its global output base while we decode the columns
-      if (tid == 0) { s_total = total; asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready)) : "memory"); }
-      // Selected rows are written straight from registers: lanes with consecutive compacted positions store to
-      // consecutive 8-byte slots of each output column, so a warp's store is one contiguous run (L2 merges the partial
-      // sectors at run boundaries).  The columns are decoded before the first store so that the look-back latency
-      // (scan warp) hides behind the decode.
+      // Selected rows go to shared memory at their tile-local compacted position, OBUF_COLS columns per chunk; the
+      // scan warp (warp 9) turns the tile's row count into its global output base and drains the chunks to HBM as
+      // contiguous 8-byte runs, so the look-back latency never stalls the decode.
       const unsigned int pos = warp_off + lane_off;
       // fast rows: the (at most 8) stored integer columns are decoded by stored position, so every shift is a
-      // compile-time constant; they sit in registers while the scan warp finishes the look-back
+      // compile-time constant
       unsigned long long vals[8];
       const bool fast = live && row.fast;
       if (fast) {
@@ -475,26 +513,40 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
         }
       }
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 2] = clock64();
-      mbar_wait(&s_base_ready, k & 1);  // look-back result published by the scan warp
-      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 3] = clock64();
-      const unsigned long long base = out_base + s_base + pos;
-      if (live && base < A.out_cap) {
-        auto put = [&](int oc) {  // general cell: any role / kind, may be NULL
-          Value v;
-          int err = cell_value(P, row, cells, P.out_cols[oc], &v);
-          if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; }
-          A.out_data[(size_t)oc * A.out_cap + base] = v.null ? 0ull : v.bits;
-          if (v.null)  // NULL cells are rare: the bitmap is pre-filled with ones and only cleared where needed
-            atomicAnd(&A.out_bitmap[(size_t)oc * (A.out_cap / 64) + (base >> 6)], ~(1ull << (base & 63)));
-        };
-        if (fast) {
-#pragma unroll
-          for (int h = 0; h < 8; ++h)
-            if (h < P.fast_n && P.fast_out[h] >= 0) A.out_data[(size_t)P.fast_out[h] * A.out_cap + base] = vals[h];
-          for (int j = 0; j < P.n_out_slow; ++j) put(P.out_slow[j]);
-        } else {
-          for (int oc = 0; oc < P.n_out; ++oc) put(oc);
+      for (uint32_t r = 0; r < n_rounds; ++r) {
+        const uint32_t g = k * n_rounds + r, q = g % N_OBUF;
+        mbar_wait(&s_obuf_empty[q], ((g / N_OBUF) & 1) ^ 1);  // chunk buffer drained (N_OBUF chunks ago)
+        if (r == 0) {
+          if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 3] = clock64();
+          // (posted after the wait: at most N_OBUF <= N_CNT - 1 tiles are ever pending at the scan warp)
+          if (tid == 0) { s_total[k % N_CNT] = total; s_tile_of[k % N_CNT] = tile; asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready[k % N_CNT])) : "memory"); }
         }
+        if (live) {
+          unsigned long long* ob = obuf_base + (size_t)q * (OBUF_COLS * TILE) + pos;
+          auto put = [&](int oc) {  // general cell: any role / kind, may be NULL
+            Value v;
+            int err = cell_value(P, row, cells, P.out_cols[oc], &v);
+            if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; }
+            ob[(oc % OBUF_COLS) * TILE] = v.null ? 0ull : v.bits;
+            if (v.null) atomicOr(&onull_base[q * ONULL_WORDS + (oc % OBUF_COLS) * (TILE / 32) + (pos >> 5)], 1u << (pos & 31));
+          };
+          if (fast) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+              if (h < P.fast_n) {
+                const int oc = P.fast_out[h];
+                if (oc >= 0 && (uint32_t)oc / OBUF_COLS == r) ob[(oc % OBUF_COLS) * TILE] = vals[h];
+              }
+            }
+            for (int j = 0; j < P.n_out_slow; ++j)
+              if ((uint32_t)P.out_slow[j] / OBUF_COLS == r) put(P.out_slow[j]);
+          } else {
+            const int c_end = (int)(r + 1) * OBUF_COLS < P.n_out ? (int)(r + 1) * OBUF_COLS : P.n_out;
+            for (int oc = (int)r * OBUF_COLS; oc < c_end; ++oc) put(oc);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_obuf_full[q])) : "memory");
       }
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 7] = clock64();
     } else if (MODE == PM_TOPN) {
@@ -665,7 +717,7 @@ static int num_sms() {
 
 size_t scan_stage_bytes(uint32_t key_cap, uint32_t val_cap) { return (size_t)N_STAGES * (key_cap + val_cap + 2 * STAGE_OFF_CAP); }
 uint32_t scan_stage_entries() { return TILE + STAGE_LOOK + 1; }
-size_t scan_out_stage_bytes() { return 0; }
+size_t scan_out_stage_bytes() { return (size_t)N_OBUF * OBUF_BYTES + (size_t)N_OBUF * ONULL_WORDS * 4; }
 size_t scan_crc_table_bytes() { return 256 * 16 * 8; }
 
 int scan_max_grid(int mode, size_t smem) {
