@@ -77,7 +77,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
         bool start = (e == e_lo) || !same_user_key(blk, e - 1, e);
         if (!start) continue;
         RunOut ro;
-        resolve_run(blk, e, e_hi, P.read_ts, P.isolation, dflt, &ro);
+        resolve_run(blk, e, e_hi, e_hi, P.read_ts, P.isolation, dflt, &ro);
         R->met_newer |= ro.met_newer; R->dflt += ro.dflt_lookup;
         if (ro.err) { report(bases[b] + e, ro.err); continue; }
         if (!ro.found) continue;
@@ -229,7 +229,7 @@ emu_result* emu_checksum(const b2_key_range* ranges, uint32_t n_ranges, const ui
       for (uint32_t e = e_lo; e < e_hi; ++e) {
         if (!((e == e_lo) || !same_user_key(blk, e - 1, e))) continue;
         RunOut ro;
-        resolve_run(blk, e, e_hi, src->read_ts, src->isolation_level, dflt, &ro);
+        resolve_run(blk, e, e_hi, e_hi, src->read_ts, src->isolation_level, dflt, &ro);
         if (ro.err) { R->status = B2_ERR_STORAGE; R->dev_err = ro.err; continue; }
         if (!ro.found) continue;
         const uint8_t* ek = blk.keys + blk.koff[e];

@@ -112,8 +112,9 @@ struct BlockView {
   const uint8_t* vals;
   const uint32_t* voff;
   uint32_t n;
+  static constexpr bool kWholeBlock = true;
   // entry accessors: the MVCC walk is written against these so that a shared-memory staged window of the block
-  // (kernels.cu StagedView) can stand in for the HBM arrays
+  // (kernels.cu SmemView) can stand in for the HBM arrays
   B2_HD const uint8_t* kptr(uint32_t i) const { return keys + koff[i]; }
   B2_HD uint32_t klen(uint32_t i) const { return koff[i + 1] - koff[i]; }
   B2_HD const uint8_t* vptr(uint32_t i) const { return vals + voff[i]; }
@@ -126,9 +127,10 @@ struct BlockView {
 // heap (ABI contract in b2_copr.h) or the padded shared-memory stage.
 B2_HD uint64_t ld64(const uint8_t* p) {
 #if defined(__CUDA_ARCH__)
-  unsigned long long a = (unsigned long long)p;
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~3ull);
-  uint32_t s = (uint32_t)(a & 3u) * 8u;
+  // (pointer arithmetic instead of integer masking keeps the address space visible to the compiler: LDS for staged bytes)
+  uint32_t mis = (uint32_t)(unsigned long long)p & 3u;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p - mis);
+  uint32_t s = mis * 8u;
   uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
   uint32_t lo = __funnelshift_r(w0, w1, s), hi = __funnelshift_r(w1, w2, s);
   return ((uint64_t)hi << 32) | lo;
@@ -140,9 +142,9 @@ B2_HD uint64_t ld64(const uint8_t* p) {
 }
 B2_HD uint32_t ld32(const uint8_t* p) {
 #if defined(__CUDA_ARCH__)
-  unsigned long long a = (unsigned long long)p;
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~3ull);
-  return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3u) * 8u);
+  uint32_t mis = (uint32_t)(unsigned long long)p & 3u;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p - mis);
+  return __funnelshift_r(w[0], w[1], mis * 8u);
 #else
   uint32_t v;
   __builtin_memcpy(&v, p, 4);
@@ -396,6 +398,7 @@ struct RunOut {
   uint32_t met_newer; // saw a version newer than read_ts
   uint32_t dflt_lookup;
   uint32_t steps;     // entries visited
+  uint32_t truncated; // the walk needed an entry at or beyond `walk_hi` (not resident in this view): redo on the whole block
 };
 
 // near_load_data_by_write (scanner/mod.rs:371-402): exact-match lookup of user_key ‖ !start_ts in CF_DEFAULT
@@ -433,10 +436,11 @@ B2_HD bool default_lookup(const DefaultCf& d, const uint8_t* ukey, uint32_t ukle
 }
 
 // forward.rs:310-375 (move_write_cursor_to_ts) + :433-515 (LatestKvPolicy::handle_write), restated as a walk over
-// the contiguous run of versions [e0, e_hi) of one user key.  `e_hi` is the range's upper bound entry.
+// the contiguous run of versions [e0, e_hi) of one user key.  `e_hi` is the range's upper bound entry; the view `b`
+// only holds entries below `walk_hi` (<= e_hi; the whole block: walk_hi == e_hi).
 template <class V>
-B2_HD void resolve_run(const V& b, uint32_t e0, uint32_t e_hi, uint64_t read_ts, int isolation, const DefaultCf& dflt, RunOut* o) {
-  o->err = DE_NONE; o->found = 0; o->met_newer = 0; o->dflt_lookup = 0; o->steps = 1;
+B2_HD void resolve_run(const V& b, uint32_t e0, uint32_t e_hi, uint32_t walk_hi, uint64_t read_ts, int isolation, const DefaultCf& dflt, RunOut* o) {
+  o->err = DE_NONE; o->found = 0; o->met_newer = 0; o->dflt_lookup = 0; o->steps = 1; o->truncated = 0;
   uint32_t i = e0;
   const uint8_t* k0 = b.kptr(e0);
   uint32_t kl0 = b.klen(e0);
@@ -448,7 +452,9 @@ B2_HD void resolve_run(const V& b, uint32_t e0, uint32_t e_hi, uint64_t read_ts,
     o->met_newer = 1;
     if (isolation == B2_ISO_RC_CHECK_TS) { o->err = DE_WRITE_CONFLICT; o->entry = i; return; }
     ++i; o->steps++;
-    if (i >= e_hi || !same_user_key(b, e0, i)) return;
+    if (i >= e_hi) return;
+    if (i >= walk_hi) { o->truncated = 1; return; }
+    if (!same_user_key(b, e0, i)) return;
   }
   for (;;) {
     const uint8_t* vp = b.vptr(i);
@@ -461,10 +467,15 @@ B2_HD void resolve_run(const V& b, uint32_t e0, uint32_t e_hi, uint64_t read_ts,
       o->commit_ts = key_commit_ts(b.kptr(i), b.klen(i));
       o->entry = i;
       if (w.has_short) { o->val = vp + w.short_off; o->val_len = w.short_len; o->found = 1; return; }
-      o->dflt_lookup = 1;
-      if (!default_lookup(dflt, k0, kl0 - 8, w.start_ts, &o->val, &o->val_len)) { o->err = DE_DEFAULT_NOT_FOUND; return; }
-      o->found = 1;
-      return;
+      if constexpr (!V::kWholeBlock) {
+        o->truncated = 1;  // the value lives in CF_DEFAULT (HBM): such rows are resolved through the block view
+        return;
+      } else {
+        o->dflt_lookup = 1;
+        if (!default_lookup(dflt, k0, kl0 - 8, w.start_ts, &o->val, &o->val_len)) { o->err = DE_DEFAULT_NOT_FOUND; return; }
+        o->found = 1;
+        return;
+      }
     }
     if (w.type == 'D') return;
     // Lock / Rollback
@@ -473,12 +484,16 @@ B2_HD void resolve_run(const V& b, uint32_t e0, uint32_t e_hi, uint64_t read_ts,
       // seek to user_key ‖ last_change_ts: first later version with commit_ts <= last_change_ts
       for (;;) {
         ++i; o->steps++;
-        if (i >= e_hi || !same_user_key(b, e0, i)) return;
+        if (i >= e_hi) return;
+        if (i >= walk_hi) { o->truncated = 1; return; }
+        if (!same_user_key(b, e0, i)) return;
         if (key_commit_ts(b.kptr(i), b.klen(i)) <= w.lc_ts) break;
       }
     } else {
       ++i; o->steps++;
-      if (i >= e_hi || !same_user_key(b, e0, i)) return;
+      if (i >= e_hi) return;
+      if (i >= walk_hi) { o->truncated = 1; return; }
+      if (!same_user_key(b, e0, i)) return;
     }
   }
 }

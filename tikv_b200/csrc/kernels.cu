@@ -4,12 +4,13 @@
 //                         (BatchTableScan + BatchSelection; table_scan_executor.rs, selection_executor.rs)
 //   scan_kernel<PM_AGG>   same front end, then COUNT/SUM/AVG into a per-CTA shared-memory group table that is
 //                         flushed into the HBM group table (BatchSimpleAggregation / BatchFastHashAggregation)
-//   checksum_kernel       MVCC scan -> CRC-64/XZ per KV -> XOR fold (src/coprocessor/checksum.rs:59-114)
 //   gen_*                 synthetic region generator (tooling)
 //
 // One thread owns one CF_WRITE entry; only the thread sitting on the first version of a user key does work for
 // that key (walks its versions, decodes the row).  CTAs are persistent and pull 256-entry tiles.
 #include <cuda_runtime.h>
+
+#include <type_traits>
 
 #include "kernels.cuh"
 
@@ -162,17 +163,81 @@ struct TileMeta {
   int koff_adj, voff_adj;        // stage_off_ptr[adj + entry] = offset of `entry`
 };
 
-// A block whose window [w_lo, w_hi) lives in shared memory; everything else falls through to HBM.
-struct StagedView {
-  BlockView g;
+// A tile's window of the block, resident in shared memory (all four pointers are shared-memory addresses, which the
+// compiler can see: every access below compiles to LDS with 32-bit addressing).  Only entries [w_lo, w_hi) exist here.
+struct SmemView {
   const uint8_t* skeys; const uint32_t* skoff; const uint8_t* svals; const uint32_t* svoff;
-  uint32_t w_lo, w_n;
-  __device__ __forceinline__ bool in(uint32_t i) const { return i - w_lo < w_n; }
-  __device__ __forceinline__ const uint8_t* kptr(uint32_t i) const { return in(i) ? skeys + skoff[i] : g.keys + g.koff[i]; }
-  __device__ __forceinline__ uint32_t klen(uint32_t i) const { return in(i) ? skoff[i + 1] - skoff[i] : g.koff[i + 1] - g.koff[i]; }
-  __device__ __forceinline__ const uint8_t* vptr(uint32_t i) const { return in(i) ? svals + svoff[i] : g.vals + g.voff[i]; }
-  __device__ __forceinline__ uint32_t vlen(uint32_t i) const { return in(i) ? svoff[i + 1] - svoff[i] : g.voff[i + 1] - g.voff[i]; }
+  static constexpr bool kWholeBlock = false;
+  __device__ __forceinline__ const uint8_t* kptr(uint32_t i) const { return skeys + skoff[i]; }
+  __device__ __forceinline__ uint32_t klen(uint32_t i) const { return skoff[i + 1] - skoff[i]; }
+  __device__ __forceinline__ const uint8_t* vptr(uint32_t i) const { return svals + svoff[i]; }
+  __device__ __forceinline__ uint32_t vlen(uint32_t i) const { return svoff[i + 1] - svoff[i]; }
 };
+
+// ---- per-entry front end: MVCC resolve -> row open/split -> predicate (or CRC in PM_CHECKSUM) ----------------------
+struct EntryStats {  // per-thread partial statistics / checksum state
+  unsigned long long keys, size, dflt, ck_x, ck_kvs, ck_bytes;
+  unsigned int newer;
+};
+enum { P1_NONE = 0, P1_LIVE = 1, P1_REDO = 2 };
+
+// The thread sitting on the first version of a user key resolves that key.  P1_REDO: the shared-memory window was not
+// enough (run longer than the look-ahead, or a long value in CF_DEFAULT) and nothing has been committed: the caller
+// repeats the entry on the whole block.
+template <int MODE, class V>
+__device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A, const V& view, uint32_t walk_hi, uint32_t e, Row& row, Cells& cells,
+                                            EntryStats& ts, const unsigned long long* crc_tab, unsigned int lane) {
+  bool start = (e == A.e_lo) || !same_user_key(view, e - 1, e);
+  if (!start) return P1_NONE;
+  RunOut ro;
+  resolve_run(view, e, A.e_hi, walk_hi, P.read_ts, P.isolation, A.dflt, &ro);
+  if (ro.truncated) return P1_REDO;
+  ts.newer |= ro.met_newer;
+  ts.dflt += ro.dflt_lookup;
+  if (ro.err) { report_err(A.ctr, A.entry_base + e, ro.err); return P1_NONE; }
+  if (!ro.found) return P1_NONE;
+  const uint32_t kl = view.klen(e);
+  const uint8_t* ek = view.kptr(e);
+  ts.keys += 1;
+  ts.size += (kl - 8) + ro.val_len;
+  if (MODE == PM_CHECKSUM) {
+    // checksum_crc64_xor (checksum.rs:105-114): CRC-64/XZ of old_prefix ‖ raw_key[len(new_prefix)..] ‖ value
+    int rawlen = raw_key_len(ek, kl - 8);
+    bool okp = rawlen >= 0 && (uint32_t)rawlen >= A.ck_new_prefix_len;
+    for (uint32_t j = 0; okp && j < A.ck_new_prefix_len; ++j) okp = raw_at(ek, j) == A.ck_new_prefix[j];
+    if (rawlen < 0) report_err(A.ctr, A.entry_base + e, DE_BAD_USER_KEY);
+    else if (!okp) { atomicExch(&A.ctr->bad_prefix, 1u); report_err(A.ctr, A.entry_base + e, DE_BAD_RECORD_KEY); }
+    else {
+      const unsigned long long* tab = crc_tab + (lane & 15);  // 16 interleaved copies: lane l only touches bank pair l % 16
+      unsigned long long c = A.ck_init_state;
+      for (uint32_t j = A.ck_new_prefix_len; j < (uint32_t)rawlen; ++j) c = tab[((uint32_t)(c ^ raw_at(ek, j)) & 0xffu) * 16] ^ (c >> 8);
+      const uint8_t* vp = ro.val;
+      uint32_t vn = ro.val_len, j = 0;
+      for (; j + 8 <= vn; j += 8) {  // 8 value bytes per unaligned word load
+        unsigned long long w = ld64(vp + j);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { c = tab[((uint32_t)(c ^ w) & 0xffu) * 16] ^ (c >> 8); w >>= 8; }
+      }
+      if (j < vn) {
+        unsigned long long w = ld64(vp + j);
+        for (; j < vn; ++j) { c = tab[((uint32_t)(c ^ w) & 0xffu) * 16] ^ (c >> 8); w >>= 8; }
+      }
+      ts.ck_x ^= ~c;
+      ts.ck_kvs += 1;
+      ts.ck_bytes += (unsigned long long)rawlen + ro.val_len + A.ck_old_prefix_len - A.ck_new_prefix_len;
+    }
+    return P1_NONE;
+  }
+  row.enc_key = ek;
+  row.enc_key_len = kl - 8;
+  row.commit_ts = ro.commit_ts;
+  int err = row_open(ro.val, ro.val_len, &row.rv);
+  if (!err) err = row_split(P, row, cells);
+  bool keep = false;
+  if (!err) err = eval_conds(P, row, cells, &keep);
+  if (err) { report_err(A.ctr, A.entry_base + e, err); return P1_NONE; }
+  return keep ? P1_LIVE : P1_NONE;
+}
 
 // ---- the fused scan kernel -------------------------------------------------------------------------------
 struct SmemTable {  // per-CTA group table (dynamic shared memory): keys | acc | occ
@@ -183,7 +248,7 @@ struct SmemTable {  // per-CTA group table (dynamic shared memory): keys | acc |
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A) {
+__global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned int s_warp_cnt[2][TILE / 32];  // by tile parity: a fast warp may start the next tile while others still read
   __shared__ unsigned int s_tbl_used;
@@ -216,7 +281,6 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
 
   // PM_CHECKSUM: bytewise CRC-64/XZ table, replicated 16x (entry i of copy c at [i * 16 + c]) so that the 64-bit
   // lookups of a half-warp never share a bank pair
-  unsigned long long ck_x = 0, ck_kvs = 0, ck_bytes = 0;
   unsigned long long* crc_tab = reinterpret_cast<unsigned long long*>(dyn_smem);
   if (MODE == PM_CHECKSUM) {
     for (unsigned int i = tid; i < 256 * 16; i += blockDim.x) crc_tab[i] = crc64_table_entry(i >> 4);
@@ -224,8 +288,9 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
   }
 
   // per-thread statistics, reduced once at the end
-  unsigned long long t_keys = 0, t_size = 0, t_live = 0, t_dflt = 0;
-  unsigned int t_newer = 0;
+  EntryStats ts;
+  ts.keys = ts.size = ts.dflt = ts.ck_x = ts.ck_kvs = ts.ck_bytes = 0; ts.newer = 0;
+  unsigned long long t_live = 0;
   // no-group aggregation: per-thread partial accumulators (registers), reduced at the end
   unsigned long long t_acc[MODE == PM_AGG ? MAX_ACC_WORDS : 1];
   if (MODE == PM_AGG) {
@@ -244,6 +309,7 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
   // obuf_full / obuf_empty[q]: output chunk buffer q handed to the scan warp / drained to HBM
   __shared__ __align__(8) unsigned long long s_cnt_ready[N_CNT], s_obuf_full[N_OBUF], s_obuf_empty[N_OBUF];
   __shared__ unsigned int s_total[N_CNT], s_tile_of[N_CNT];
+  __shared__ unsigned int s_redo[4];  // per tile (mod 4): some thread could not resolve its row inside the shared-memory window
   unsigned char* stage_base = dyn_smem + A.stage_off;
   const uint32_t STAGE_KEY_CAP = A.stage_key_cap, STAGE_VAL_CAP = A.stage_val_cap;
   const uint32_t STAGE_BYTES = STAGE_KEY_CAP + STAGE_VAL_CAP + 2 * STAGE_OFF_CAP;
@@ -256,6 +322,7 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
   if (tid == 0) {
     for (int i = 0; i < N_STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], TILE / 32); }
     for (int i = 0; i < N_CNT; ++i) mbar_init(&s_cnt_ready[i], 1);
+    for (int i = 0; i < 4; ++i) s_redo[i] = 0;
     for (int i = 0; i < N_OBUF; ++i) { mbar_init(&s_obuf_full[i], TILE / 32); mbar_init(&s_obuf_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -390,102 +457,45 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
     return;
   }
 
-  for (uint32_t k = 0;; ++k) {
-    const int cur = (int)(k % N_STAGES);
-    long long tc0 = clock64();
-    mbar_wait(&s_full[cur], (k / N_STAGES) & 1);
-    if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) { A.trace[k * 8 + 4] = tc0; A.trace[k * 8 + 5] = clock64(); }
-    const TileMeta m = s_meta[cur];
-    const uint32_t tile = m.tile;
-    if (tile >= n_tiles) {
-      if (MODE == PM_SCAN && tid == 0) {  // tell the scan warp there is no tile k
-        s_tile_of[k % N_CNT] = tile;
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready[k % N_CNT])) : "memory");
-      }
-      break;
-    }
-    StagedView sv;
-    sv.g = A.blk; sv.w_lo = 0; sv.w_n = 0;
-    sv.skeys = nullptr; sv.skoff = nullptr; sv.svals = nullptr; sv.svoff = nullptr;
-    if (m.staged) {
-      unsigned char* st = stage_base + (size_t)cur * STAGE_BYTES;
-      sv.w_lo = m.w_lo; sv.w_n = m.w_hi - m.w_lo;
-      sv.skeys = st + m.keys_adj;
-      sv.svals = st + STAGE_KEY_CAP + m.vals_adj;
-      sv.skoff = reinterpret_cast<const uint32_t*>(st + STAGE_KEY_CAP + STAGE_VAL_CAP) + m.koff_adj;
-      sv.svoff = reinterpret_cast<const uint32_t*>(st + STAGE_KEY_CAP + STAGE_VAL_CAP + STAGE_OFF_CAP) + m.voff_adj;
-    }
+  // One tile, front end to back end, over a view of the block.  Instantiated twice: on the shared-memory window (hot:
+  // every byte access is an LDS) and on the HBM arrays (tiles that did not fit the stage, or that hold a row the window
+  // cannot resolve: a version run longer than the look-ahead, a long value in CF_DEFAULT).  Returns true when the
+  // shared-memory attempt must be repeated on the whole block; nothing has been committed in that case.
+  auto tile_body = [&](const auto& view, const uint32_t walk_hi, const uint32_t k, const uint32_t tile) -> bool {
+    using V = typename std::remove_cv<typename std::remove_reference<decltype(view)>::type>::type;
     const uint32_t e = A.c_lo + tile * TILE + tid;
-
     bool live = false;
     Row row;
     Cells cells;
-    if (e < A.c_hi) {
-      bool start = (e == A.e_lo) || !same_user_key(sv, e - 1, e);
-      if (start) {
-        RunOut ro;
-        resolve_run(sv, e, A.e_hi, P.read_ts, P.isolation, A.dflt, &ro);
-        t_newer |= ro.met_newer;
-        t_dflt += ro.dflt_lookup;
-        if (ro.err) {
-          report_err(A.ctr, A.entry_base + e, ro.err);
-        } else if (ro.found && MODE == PM_CHECKSUM) {
-          // checksum_crc64_xor (checksum.rs:105-114): CRC-64/XZ of old_prefix ‖ raw_key[len(new_prefix)..] ‖ value
-          uint32_t kl = sv.klen(e);
-          const uint8_t* ek = sv.kptr(e);
-          t_keys += 1;
-          t_size += (kl - 8) + ro.val_len;
-          int rawlen = raw_key_len(ek, kl - 8);
-          bool okp = rawlen >= 0 && (uint32_t)rawlen >= A.ck_new_prefix_len;
-          for (uint32_t j = 0; okp && j < A.ck_new_prefix_len; ++j) okp = raw_at(ek, j) == A.ck_new_prefix[j];
-          if (rawlen < 0) report_err(A.ctr, A.entry_base + e, DE_BAD_USER_KEY);
-          else if (!okp) { atomicExch(&A.ctr->bad_prefix, 1u); report_err(A.ctr, A.entry_base + e, DE_BAD_RECORD_KEY); }
-          else {
-            const unsigned long long* tab = crc_tab + (lane & 15);  // 16 interleaved copies: lane l only touches bank pair l % 16
-            unsigned long long c = A.ck_init_state;
-            for (uint32_t j = A.ck_new_prefix_len; j < (uint32_t)rawlen; ++j) c = tab[((uint32_t)(c ^ raw_at(ek, j)) & 0xffu) * 16] ^ (c >> 8);
-            const uint8_t* vp = ro.val;
-            uint32_t vn = ro.val_len, j = 0;
-            for (; j + 8 <= vn; j += 8) {  // 8 value bytes per unaligned word load
-              unsigned long long w = ld64(vp + j);
-#pragma unroll
-              for (int b = 0; b < 8; ++b) { c = tab[((uint32_t)(c ^ w) & 0xffu) * 16] ^ (c >> 8); w >>= 8; }
-            }
-            if (j < vn) {
-              unsigned long long w = ld64(vp + j);
-              for (; j < vn; ++j) { c = tab[((uint32_t)(c ^ w) & 0xffu) * 16] ^ (c >> 8); w >>= 8; }
-            }
-            ck_x ^= ~c;
-            ck_kvs += 1;
-            ck_bytes += (unsigned long long)rawlen + ro.val_len + A.ck_old_prefix_len - A.ck_new_prefix_len;
-          }
-        } else if (ro.found) {
-          uint32_t kl = sv.klen(e);
-          t_keys += 1;
-          t_size += (kl - 8) + ro.val_len;
-          row.enc_key = sv.kptr(e);
-          row.enc_key_len = kl - 8;
-          row.commit_ts = ro.commit_ts;
-          int err = row_open(ro.val, ro.val_len, &row.rv);
-          if (!err) err = row_split(P, row, cells);
-          bool keep = false;
-          if (!err) err = eval_conds(P, row, cells, &keep);
-          if (err) report_err(A.ctr, A.entry_base + e, err);
-          else live = keep;
-        }
-      }
+    EntryStats d;
+    d.keys = d.size = d.dflt = d.ck_x = d.ck_kvs = d.ck_bytes = 0; d.newer = 0;
+    int r1 = P1_NONE;
+    if (e < A.c_hi) r1 = entry_phase1<MODE>(P, A, view, walk_hi, e, row, cells, d, crc_tab, lane);
+    live = r1 == P1_LIVE;
+    if (!V::kWholeBlock) {
+      if (__any_sync(0xffffffffu, r1 == P1_REDO) && lane == 0) s_redo[k & 3] = 1;
     }
-    t_live += live;
-
+    unsigned int warp_off = 0, total = 0, lane_off = 0;
     if (MODE == PM_SCAN) {
       // ---- ordered compaction: ballot/popc inside the warp, smem across warps, look-back across tiles ----
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 0] = clock64();
       unsigned int bal = __ballot_sync(0xffffffffu, live);
-      unsigned int lane_off = __popc(bal & ((1u << lane) - 1));
+      lane_off = __popc(bal & ((1u << lane) - 1));
       if (lane == 0) s_warp_cnt[k & 1][wid] = __popc(bal);
       cta256_sync();
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 1] = clock64();
-      unsigned int warp_off = 0, total = 0;
+    } else if (!V::kWholeBlock) {
+      cta256_sync();  // the vote below
+    }
+    if (!V::kWholeBlock) {
+      if (s_redo[k & 3]) return true;
+    }
+    // ---- commit ----
+    ts.keys += d.keys; ts.size += d.size; ts.dflt += d.dflt; ts.newer |= d.newer;
+    if (MODE == PM_CHECKSUM) { ts.ck_x ^= d.ck_x; ts.ck_kvs += d.ck_kvs; ts.ck_bytes += d.ck_bytes; }
+    t_live += live;
+
+    if (MODE == PM_SCAN) {
 #pragma unroll
       for (int w = 0; w < TILE / 32; ++w) {
         unsigned int c = s_warp_cnt[k & 1][w];
@@ -496,22 +506,7 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
       // scan warp (warp 9) turns the tile's row count into its global output base and drains the chunks to HBM as
       // contiguous 8-byte runs, so the look-back latency never stalls the decode.
       const unsigned int pos = warp_off + lane_off;
-      // fast rows: the (at most 8) stored integer columns are decoded by stored position, so every shift is a
-      // compile-time constant
-      unsigned long long vals[8];
       const bool fast = live && row.fast;
-      if (fast) {
-        uint32_t prev = 0;
-#pragma unroll
-        for (int h = 0; h < 8; ++h) {
-          vals[h] = 0;
-          if (h < P.fast_n) {
-            uint32_t end = fast_end(row, h);
-            if (P.fast_out[h] >= 0) vals[h] = fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u);
-            prev = end;
-          }
-        }
-      }
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 2] = clock64();
       for (uint32_t r = 0; r < n_rounds; ++r) {
         const uint32_t g = k * n_rounds + r, q = g % N_OBUF;
@@ -531,14 +526,19 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
             if (v.null) atomicOr(&onull_base[q * ONULL_WORDS + (oc % OBUF_COLS) * (TILE / 32) + (pos >> 5)], 1u << (pos & 31));
           };
           if (fast) {
+            // exact-layout row: the (at most 8) stored integer columns are decoded by stored position, so every shift
+            // is a compile-time constant; the value goes from the staged row bytes to the chunk buffer in one step
+            uint32_t prev = 0;
 #pragma unroll
             for (int h = 0; h < 8; ++h) {
               if (h < P.fast_n) {
+                const uint32_t end = fast_end(row, h);
                 const int oc = P.fast_out[h];
-                if (oc >= 0 && (uint32_t)oc / OBUF_COLS == r) ob[(oc % OBUF_COLS) * TILE] = vals[h];
+                if (oc >= 0 && (uint32_t)oc / OBUF_COLS == r) ob[(oc % OBUF_COLS) * TILE] = fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u);
+                prev = end;
               }
             }
-            for (int j = 0; j < P.n_out_slow; ++j)
+            for (int j = 0; j < P.n_out_slow; ++j)  // handle / Real / repeated columns of such a row
               if ((uint32_t)P.out_slow[j] / OBUF_COLS == r) put(P.out_slow[j]);
           } else {
             const int c_end = (int)(r + 1) * OBUF_COLS < P.n_out ? (int)(r + 1) * OBUF_COLS : P.n_out;
@@ -630,19 +630,47 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
         }
       }
     }
+    return false;
+  };
+
+  for (uint32_t k = 0;; ++k) {
+    const int cur = (int)(k % N_STAGES);
+    long long tc0 = clock64();
+    mbar_wait(&s_full[cur], (k / N_STAGES) & 1);
+    if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) { A.trace[k * 8 + 4] = tc0; A.trace[k * 8 + 5] = clock64(); }
+    const TileMeta m = s_meta[cur];
+    const uint32_t tile = m.tile;
+    if (tile >= n_tiles) {
+      if (MODE == PM_SCAN && tid == 0) {  // tell the scan warp there is no tile k
+        s_tile_of[k % N_CNT] = tile;
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready[k % N_CNT])) : "memory");
+      }
+      break;
+    }
+    if (tid == 0) s_redo[(k + 2) & 3] = 0;  // last read two tiles ago, next written two tiles ahead
+    bool redo = true;
+    if (m.staged) {
+      unsigned char* st = stage_base + (size_t)cur * STAGE_BYTES;
+      SmemView sv;
+      sv.skeys = st + m.keys_adj;
+      sv.svals = st + STAGE_KEY_CAP + m.vals_adj;
+      sv.skoff = reinterpret_cast<const uint32_t*>(st + STAGE_KEY_CAP + STAGE_VAL_CAP) + m.koff_adj;
+      sv.svoff = reinterpret_cast<const uint32_t*>(st + STAGE_KEY_CAP + STAGE_VAL_CAP + STAGE_OFF_CAP) + m.voff_adj;
+      redo = tile_body(sv, m.w_hi < A.e_hi ? m.w_hi : A.e_hi, k, tile);
+    }
+    if (redo) tile_body(A.blk, A.e_hi, k, tile);
     if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 6] = clock64();
     __syncwarp();  // this warp is done with stage `cur`: let the producer refill it
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[cur])) : "memory");
   }
-
   // ---- epilogue: flush CTA-private state ----
   if (MODE == PM_CHECKSUM) {
     for (int off = 16; off > 0; off >>= 1) {
-      ck_x ^= __shfl_xor_sync(0xffffffffu, ck_x, off);
-      ck_kvs += __shfl_xor_sync(0xffffffffu, ck_kvs, off);
-      ck_bytes += __shfl_xor_sync(0xffffffffu, ck_bytes, off);
+      ts.ck_x ^= __shfl_xor_sync(0xffffffffu, ts.ck_x, off);
+      ts.ck_kvs += __shfl_xor_sync(0xffffffffu, ts.ck_kvs, off);
+      ts.ck_bytes += __shfl_xor_sync(0xffffffffu, ts.ck_bytes, off);
     }
-    if (lane == 0 && ck_kvs) { atomicXor(&A.ctr->checksum, ck_x); atomicAdd(&A.ctr->total_kvs, ck_kvs); atomicAdd(&A.ctr->total_bytes, ck_bytes); }
+    if (lane == 0 && ts.ck_kvs) { atomicXor(&A.ctr->checksum, ts.ck_x); atomicAdd(&A.ctr->total_kvs, ts.ck_kvs); atomicAdd(&A.ctr->total_bytes, ts.ck_bytes); }
   }
   if (MODE == PM_TOPN) {
     cta256_sync();
@@ -689,18 +717,18 @@ __global__ void __launch_bounds__(TILE + 64) scan_kernel(const __grid_constant__
   }
   // statistics
   for (int off = 16; off > 0; off >>= 1) {
-    t_keys += __shfl_xor_sync(0xffffffffu, t_keys, off);
-    t_size += __shfl_xor_sync(0xffffffffu, t_size, off);
+    ts.keys += __shfl_xor_sync(0xffffffffu, ts.keys, off);
+    ts.size += __shfl_xor_sync(0xffffffffu, ts.size, off);
     t_live += __shfl_xor_sync(0xffffffffu, t_live, off);
-    t_dflt += __shfl_xor_sync(0xffffffffu, t_dflt, off);
-    t_newer |= __shfl_xor_sync(0xffffffffu, t_newer, off);
+    ts.dflt += __shfl_xor_sync(0xffffffffu, ts.dflt, off);
+    ts.newer |= __shfl_xor_sync(0xffffffffu, ts.newer, off);
   }
   if (lane == 0) {
-    if (t_keys) atomicAdd(&A.ctr->processed_keys, t_keys);
-    if (t_size) atomicAdd(&A.ctr->processed_size, t_size);
+    if (ts.keys) atomicAdd(&A.ctr->processed_keys, ts.keys);
+    if (ts.size) atomicAdd(&A.ctr->processed_size, ts.size);
     if (t_live) atomicAdd(&A.ctr->live_rows, t_live);
-    if (t_dflt) atomicAdd(&A.ctr->default_lookups, t_dflt);
-    if (t_newer) atomicOr(&A.ctr->met_newer, 1u);
+    if (ts.dflt) atomicAdd(&A.ctr->default_lookups, ts.dflt);
+    if (ts.newer) atomicOr(&A.ctr->met_newer, 1u);
   }
 }
 
@@ -810,7 +838,7 @@ __global__ void topn_gather_kernel(const __grid_constant__ DevPlan P, const __gr
   if (i >= *count) return;
   uint32_t e = (uint32_t)(items[i].id - A.entry_base);
   RunOut ro;
-  resolve_run(A.blk, e, A.e_hi, P.read_ts, P.isolation, A.dflt, &ro);
+  resolve_run(A.blk, e, A.e_hi, A.e_hi, P.read_ts, P.isolation, A.dflt, &ro);
   Row row;
   Cells cells;
   int err = ro.err ? ro.err : (ro.found ? DE_NONE : DE_BAD_WRITE);
@@ -939,64 +967,6 @@ cudaError_t launch_agg_result(const DevPlan& plan, unsigned int n_groups, const 
   return cudaGetLastError();
 }
 
-// ---- checksum ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE) checksum_kernel(const __grid_constant__ ChecksumArgs A) {
-  __shared__ unsigned long long s_tab[256];
-  __shared__ unsigned long long s_red[3][TILE / 32];
-  const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  s_tab[tid] = crc64_table_entry(tid);
-  __syncthreads();
-  const uint32_t n = A.e_hi - A.e_lo;
-  const uint32_t n_tiles = (n + TILE - 1) / TILE;
-  unsigned long long x = 0, kvs = 0, bytes = 0;
-  unsigned int newer = 0;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    uint32_t e = A.e_lo + tile * TILE + tid;
-    if (e >= A.e_hi) continue;
-    bool start = (e == A.e_lo) || !same_user_key(A.blk, e - 1, e);
-    if (!start) continue;
-    RunOut ro;
-    resolve_run(A.blk, e, A.e_hi, A.read_ts, A.isolation, A.dflt, &ro);
-    newer |= ro.met_newer;
-    if (ro.err) { report_err(A.ctr, A.entry_base + e, ro.err); continue; }
-    if (!ro.found) continue;
-    const uint8_t* ek = A.blk.keys + A.blk.koff[e];
-    uint32_t ekl = A.blk.koff[e + 1] - A.blk.koff[e] - 8;
-    int rawlen = raw_key_len(ek, ekl);
-    if (rawlen < 0) { report_err(A.ctr, A.entry_base + e, DE_BAD_USER_KEY); continue; }
-    bool ok = (uint32_t)rawlen >= A.new_prefix_len;
-    for (uint32_t j = 0; ok && j < A.new_prefix_len; ++j) ok = raw_at(ek, j) == A.new_prefix[j];
-    if (!ok) { atomicExch(&A.ctr->bad_prefix, 1u); report_err(A.ctr, A.entry_base + e, DE_BAD_RECORD_KEY); continue; }
-    unsigned long long c = A.init_state;
-    for (uint32_t j = A.new_prefix_len; j < (uint32_t)rawlen; ++j) c = s_tab[(uint8_t)(c ^ raw_at(ek, j))] ^ (c >> 8);
-    for (uint32_t j = 0; j < ro.val_len; ++j) c = s_tab[(uint8_t)(c ^ ro.val[j])] ^ (c >> 8);
-    x ^= ~c;
-    kvs += 1;
-    bytes += (unsigned long long)rawlen + ro.val_len + A.old_prefix_len - A.new_prefix_len;
-  }
-  for (int off = 16; off > 0; off >>= 1) {
-    x ^= __shfl_xor_sync(0xffffffffu, x, off);
-    kvs += __shfl_xor_sync(0xffffffffu, kvs, off);
-    bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
-    newer |= __shfl_xor_sync(0xffffffffu, newer, off);
-  }
-  if (lane == 0) { s_red[0][wid] = x; s_red[1][wid] = kvs; s_red[2][wid] = bytes; if (newer) atomicOr(&A.ctr->met_newer, 1u); }
-  __syncthreads();
-  if (tid == 0) {
-    unsigned long long X = 0, K = 0, B = 0;
-    for (int w = 0; w < TILE / 32; ++w) { X ^= s_red[0][w]; K += s_red[1][w]; B += s_red[2][w]; }
-    if (K) { atomicXor(&A.ctr->checksum, X); atomicAdd(&A.ctr->total_kvs, K); atomicAdd(&A.ctr->total_bytes, B); }
-  }
-}
-
-cudaError_t launch_checksum(const ChecksumArgs& a, int grid, cudaStream_t s) {
-  if (a.e_hi <= a.e_lo) return cudaSuccess;
-  uint32_t n_tiles = (a.e_hi - a.e_lo + TILE - 1) / TILE;
-  if (grid <= 0) grid = num_sms() * 4;
-  if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
-  checksum_kernel<<<grid, TILE, 0, s>>>(a);
-  return cudaGetLastError();
-}
 
 // ---- range bounds: lower_bound of each encoded key in each block -------------------------------------------
 __global__ void bounds_kernel(const BlockView* blocks, uint32_t n_blocks, const uint8_t* bounds, const uint32_t* bound_offs, uint32_t n_bounds, uint32_t* out) {

@@ -69,19 +69,6 @@ struct ScanArgs {
   uint32_t topn_cap;                // shared-memory candidate capacity (power of two >= limit + TILE)
 };
 
-struct ChecksumArgs {
-  BlockView blk;
-  DefaultCf dflt;
-  uint32_t e_lo, e_hi;
-  uint64_t entry_base;
-  uint64_t read_ts;
-  int32_t isolation;
-  uint64_t init_state;    // crc register after old_prefix
-  const uint8_t* new_prefix;
-  uint32_t new_prefix_len, old_prefix_len;
-  Counters* ctr;
-};
-
 struct GenArgs {
   b2_gen_spec spec;  // pointers inside are device pointers
   uint8_t* keys; uint32_t* koff; uint8_t* vals; uint32_t* voff;
@@ -109,7 +96,6 @@ cudaError_t launch_topn_copy(const TopItem* items, const unsigned int* count, ui
                              unsigned char* null_out, cudaStream_t s);
 cudaError_t launch_pack_nulls(const unsigned char* nulls, uint32_t n_cols, uint32_t stride, uint32_t n, unsigned long long* bitmaps, uint32_t words_per_col, cudaStream_t s);
 size_t topn_smem_bytes(uint32_t cap);
-cudaError_t launch_checksum(const ChecksumArgs& a, int grid, cudaStream_t s);
 cudaError_t launch_bounds_search(const BlockView* blocks, uint32_t n_blocks, const uint8_t* bounds, const uint32_t* bound_offs, uint32_t n_bounds,
                                  uint32_t* out, cudaStream_t s);
 cudaError_t launch_gen_sizes(const b2_gen_spec& spec, uint32_t* row_entries, uint32_t* row_val_bytes, cudaStream_t s);
