@@ -291,11 +291,10 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
   EntryStats ts;
   ts.keys = ts.size = ts.dflt = ts.ck_x = ts.ck_kvs = ts.ck_bytes = 0; ts.newer = 0;
   unsigned long long t_live = 0;
-  // no-group aggregation: per-thread partial accumulators (registers), reduced at the end
-  unsigned long long t_acc[MODE == PM_AGG ? MAX_ACC_WORDS : 1];
+  // no-group aggregation: one accumulator set per CTA in shared memory, flushed at the end
+  __shared__ unsigned long long s_simple_acc[MODE == PM_AGG ? MAX_ACC_WORDS : 1];
   if (MODE == PM_AGG) {
-#pragma unroll
-    for (int i = 0; i < MAX_ACC_WORDS; ++i) t_acc[i] = 0;
+    for (unsigned int i = tid; i < MAX_ACC_WORDS; i += blockDim.x) s_simple_acc[i] = 0;
   }
 
   // ---- tile pipeline --------------------------------------------------------------------------------------------
@@ -564,33 +563,31 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
       cta256_sync();
       if (s_top_cnt + TILE > A.topn_cap) cta_topn_compact(top_items, A.topn_cap, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
     } else if (MODE == PM_AGG) {
-      if (live) {
-        if (!P.has_group) {
-          // BatchSimpleAggregation: one state set; accumulate privately
-          for (int a = 0; a < P.n_aggs; ++a) {
-            const DevAgg g = P.aggs[a];
-            Value v;
-            int err = eval_expr(P, g.arg, row, cells, &v, nullptr);
-            if (err) { report_err(A.ctr, A.entry_base + e, err); continue; }
-            if (v.null) continue;
-            t_acc[g.acc_off] += 1;
-            if (g.kind == 0) continue;
-            if (g.arg_et == 1) {
-              t_acc[g.acc_off + 1] = f64_bits(bits_f64(t_acc[g.acc_off + 1]) + bits_f64(v.bits));
-            } else {
-              t_acc[g.acc_off + 1] += v.bits & 0xffffffffull;
-              t_acc[g.acc_off + 2] += g.arg_unsigned ? (v.bits >> 32) : (unsigned long long)((long long)v.bits >> 32);
-            }
-          }
-        } else {
-          // BatchFastHashAggregation: group key -> slot (calc_groups_each_row), then per-aggregate update
-          Value gk;
-          int err = eval_expr(P, P.group, row, cells, &gk, nullptr);
-          if (err) report_err(A.ctr, A.entry_base + e, err);
+      // BatchSimpleAggregation / BatchFastHashAggregation.  Rows of one warp that share a group key are combined with
+      // warp reductions first (match.any + redux); the group's leader lane then issues one atomic per accumulator
+      // word, into the CTA's shared-memory table when the key is resident there, else into the HBM table.
+      Value gk;
+      gk.bits = 0; gk.null = false;
+      bool ok = live;
+      if (live && P.has_group) {
+        int err = eval_expr(P, P.group, row, cells, &gk, nullptr);  // calc_groups_each_row
+        if (err) { report_err(A.ctr, A.entry_base + e, err); ok = false; }
+        else if (gk.null) gk.bits = 0;
+        else if (P.group_et == 1 && bits_f64(gk.bits) == 0.0) gk.bits = 0;  // -0.0 and 0.0 are one group
+      }
+      const unsigned int active = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        unsigned int peers = active;
+        if (P.has_group) {
+          const unsigned int nm = __ballot_sync(active, gk.null);
+          peers = __match_any_sync(active, gk.bits) & (gk.null ? nm : ~nm);
+        }
+        const bool leader = (unsigned int)(__ffs(peers) - 1) == lane;
+        const bool solo = (peers & (peers - 1)) == 0;
+        unsigned long long* acc = nullptr;
+        if (leader) {
+          if (!P.has_group) acc = s_simple_acc;
           else {
-            if (P.group_et == 1 && !gk.null && bits_f64(gk.bits) == 0.0) gk.bits = 0;  // -0.0 and 0.0 are one group
-            unsigned long long* acc = nullptr;  // shared-memory accumulators when the key is resident in the CTA table
-            unsigned int gslot = 0xffffffffu;
             if (st.slots && !gk.null) {
               unsigned int mask = st.slots - 1, s = (unsigned int)(mix64(gk.bits) >> 20) & mask;
               for (int probes = 0; probes < 8; ++probes) {
@@ -613,19 +610,45 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
               }
             }
             if (!acc) {
-              gslot = table_find_or_insert(A.tbl, gk.bits, gk.null);
+              unsigned int gslot = table_find_or_insert(A.tbl, gk.bits, gk.null);
               if (gslot == 0xffffffffu) atomicExch(&A.ctr->agg_overflow, 1u);
+              else acc = A.tbl.acc + (size_t)gslot * P.acc_words;
             }
-            if (acc || gslot != 0xffffffffu) {
-              for (int a = 0; a < P.n_aggs; ++a) {
-                const DevAgg g = P.aggs[a];
-                Value v;
-                int err2 = eval_expr(P, g.arg, row, cells, &v, nullptr);
-                if (err2) { report_err(A.ctr, A.entry_base + e, err2); continue; }
-                if (acc) acc_update(acc, g, v);
-                else acc_update(A.tbl.acc + (size_t)gslot * P.acc_words, g, v);
-              }
+          }
+        }
+        for (int a = 0; a < P.n_aggs; ++a) {
+          const DevAgg g = P.aggs[a];
+          Value v;
+          int err2 = eval_expr(P, g.arg, row, cells, &v, nullptr);
+          if (err2) report_err(A.ctr, A.entry_base + e, err2);
+          const bool has = !err2 && !v.null;
+          const unsigned int cnt = solo ? (has ? 1u : 0u) : __reduce_add_sync(peers, has ? 1u : 0u);
+          unsigned long long* w = acc + g.acc_off;  // only dereferenced by a leader that found a slot
+          const bool commit = leader && acc != nullptr && cnt != 0;
+          if (g.kind == 0) {
+            if (commit) atomicAdd(&w[0], (unsigned long long)cnt);
+          } else if (g.arg_et == 1) {
+            double sum = has ? bits_f64(v.bits) : 0.0;
+            if (!solo) {
+              const double mine = sum;
+              sum = 0.0;
+              for (unsigned int mm = peers; mm; mm &= mm - 1) sum += __shfl_sync(peers, mine, __ffs(mm) - 1);  // lane order
             }
+            if (commit) { atomicAdd(&w[0], (unsigned long long)cnt); atomicAdd(reinterpret_cast<double*>(&w[1]), sum); }
+          } else {
+            const uint32_t lo = has ? (uint32_t)v.bits : 0u, hi = has ? (uint32_t)(v.bits >> 32) : 0u;
+            unsigned long long lo_sum, hi_sum;
+            if (solo) {
+              lo_sum = lo;
+              hi_sum = g.arg_unsigned ? (unsigned long long)hi : (unsigned long long)(long long)(int32_t)hi;
+            } else {  // 16-bit pieces: 32 of them cannot overflow a 32-bit redux
+              const unsigned int s0 = __reduce_add_sync(peers, lo & 0xffffu), s1 = __reduce_add_sync(peers, lo >> 16);
+              lo_sum = (unsigned long long)s0 + ((unsigned long long)s1 << 16);
+              const unsigned int t0 = __reduce_add_sync(peers, hi & 0xffffu);
+              if (g.arg_unsigned) hi_sum = (unsigned long long)t0 + ((unsigned long long)__reduce_add_sync(peers, hi >> 16) << 16);
+              else hi_sum = (unsigned long long)((long long)__reduce_add_sync(peers, (int)hi >> 16) * 65536ll + (long long)t0);
+            }
+            if (commit) { atomicAdd(&w[0], (unsigned long long)cnt); atomicAdd(&w[1], lo_sum); atomicAdd(&w[2], hi_sum); }
           }
         }
       }
@@ -681,20 +704,14 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
   }
   if (MODE == PM_AGG) {
     if (!P.has_group) {
-      // warp-shuffle tree, then one atomic per warp into slot 0 of the HBM table
-      for (int w = 0; w < P.acc_words; ++w) {
+      cta256_sync();
+      for (int w = (int)tid; w < P.acc_words; w += TILE) {
         bool is_real = false;
         for (int a = 0; a < P.n_aggs; ++a)
           if (P.aggs[a].kind != 0 && P.aggs[a].arg_et == 1 && P.aggs[a].acc_off + 1 == w) is_real = true;
-        unsigned long long x = t_acc[w];
-        if (is_real) {
-          double d = bits_f64(x);
-          for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-          if (lane == 0 && d != 0.0) atomicAdd(reinterpret_cast<double*>(&A.tbl.acc[w]), d);
-        } else {
-          for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-          if (lane == 0 && x) atomicAdd(&A.tbl.acc[w], x);
-        }
+        unsigned long long x = s_simple_acc[w];
+        if (is_real) { double dd = bits_f64(x); if (dd != 0.0) atomicAdd(reinterpret_cast<double*>(&A.tbl.acc[w]), dd); }
+        else if (x) atomicAdd(&A.tbl.acc[w], x);
       }
     } else if (st.slots) {
       cta256_sync();
