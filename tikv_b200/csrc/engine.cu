@@ -911,7 +911,7 @@ struct b2_exec {
   }
 
   // ---- PM_TOPN: per unit: per-CTA candidate lists -> unit top-N -> payload gather -> merge into the running top-N ----
-  DevBuf tn_lists, tn_counts, tn_pair, tn_pair_cnt, tn_tmp, tn_tmp_cnt, tn_blk_pay, tn_blk_null, tn_run_pay, tn_run_null, tn_tmp_pay, tn_tmp_null, tn_bitmap;
+  DevBuf tn_lvl_a, tn_lvl_a_cnt, tn_lvl_b, tn_lvl_b_cnt, tn_lists, tn_counts, tn_pair, tn_pair_cnt, tn_tmp, tn_tmp_cnt, tn_blk_pay, tn_blk_null, tn_run_pay, tn_run_null, tn_tmp_pay, tn_tmp_null, tn_bitmap;
 
   int run_topn(b2_batch* out) {
     const DevPlan& P = cp.dev;
@@ -929,6 +929,8 @@ struct b2_exec {
       int grid = scan_max_grid(PM_TOPN, std::max(tot0, smem));
       size_t isz = sizeof(TopItem);
       CUDA_TRY(tn_lists.reserve((size_t)grid * limit * isz)); CUDA_TRY(tn_counts.reserve((size_t)grid * 4));
+      CUDA_TRY(tn_lvl_a.reserve((size_t)((grid + 7) / 8) * limit * isz)); CUDA_TRY(tn_lvl_a_cnt.reserve((size_t)((grid + 7) / 8) * 4));
+      CUDA_TRY(tn_lvl_b.reserve((size_t)((grid + 63) / 64) * limit * isz)); CUDA_TRY(tn_lvl_b_cnt.reserve((size_t)((grid + 63) / 64) * 4));
       CUDA_TRY(tn_pair.reserve((size_t)2 * limit * isz)); CUDA_TRY(tn_pair_cnt.reserve(8));
       CUDA_TRY(tn_tmp.reserve((size_t)limit * isz)); CUDA_TRY(tn_tmp_cnt.reserve(4));
       size_t pay_bytes = (size_t)n_out * limit * 8, null_bytes = (size_t)n_out * limit;
@@ -948,6 +950,7 @@ struct b2_exec {
         uint32_t g = (uint32_t)std::min<uint32_t>((uint32_t)grid, n_tiles);
         a.topn.items = (TopItem*)tn_lists.p; a.topn.counts = (unsigned int*)tn_counts.p; a.topn.n_lists = g; a.topn.stride = limit;
         a.topn_cap = cap;
+        a.topn_seed = pair; a.topn_seed_cnt = pair_cnt;
         size_t tot = setup_staging(&a, wblocks[u.block_idx], smem);
         CUDA_TRY(cudaMemsetAsync(tn_counts.p, 0, (size_t)grid * 4, stream));
         kernel_begin();
@@ -955,12 +958,24 @@ struct b2_exec {
         kernel_end();
         // unit top-N (sorted) lands in the second half of `pair`
         TopNLists unit_out; unit_out.items = pair + limit; unit_out.counts = pair_cnt + 1; unit_out.n_lists = 1; unit_out.stride = limit;
-        CUDA_TRY(launch_topn_merge(P, a.topn, unit_out, cap, stream));
+        {  // per-CTA lists -> one list, fan-in 8 per level
+          TopNLists cur = a.topn;
+          int flip = 0;
+          while (cur.n_lists > 8) {
+            TopNLists nxt;
+            nxt.n_lists = (cur.n_lists + 7) / 8; nxt.stride = limit;
+            nxt.items = (TopItem*)(flip ? tn_lvl_b.p : tn_lvl_a.p); nxt.counts = (unsigned int*)(flip ? tn_lvl_b_cnt.p : tn_lvl_a_cnt.p);
+            CUDA_TRY(launch_topn_merge(P, cur, nxt, cap, 8, stream));
+            stats.kernel_launches++;
+            cur = nxt; flip ^= 1;
+          }
+          CUDA_TRY(launch_topn_merge(P, cur, unit_out, cap, cur.n_lists, stream));
+        }
         CUDA_TRY(launch_topn_gather(P, a, pair + limit, pair_cnt + 1, (unsigned long long*)tn_blk_pay.p, (unsigned char*)tn_blk_null.p, limit, stream));
         // running top-N (first half) + unit top-N -> tmp, then back into the first half
         TopNLists both; both.items = pair; both.counts = pair_cnt; both.n_lists = 2; both.stride = limit;
         TopNLists merged; merged.items = (TopItem*)tn_tmp.p; merged.counts = (unsigned int*)tn_tmp_cnt.p; merged.n_lists = 1; merged.stride = limit;
-        CUDA_TRY(launch_topn_merge(P, both, merged, cap, stream));
+        CUDA_TRY(launch_topn_merge(P, both, merged, cap, 2, stream));
         CUDA_TRY(launch_topn_copy((const TopItem*)tn_tmp.p, (const unsigned int*)tn_tmp_cnt.p, n_out, limit, (const unsigned long long*)tn_run_pay.p,
                                   (const unsigned char*)tn_run_null.p, (const unsigned long long*)tn_blk_pay.p, (const unsigned char*)tn_blk_null.p,
                                   (unsigned long long*)tn_tmp_pay.p, (unsigned char*)tn_tmp_null.p, stream));

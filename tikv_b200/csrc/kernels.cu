@@ -81,23 +81,29 @@ __device__ __forceinline__ void acc_update(Acc* acc, const DevAgg& g, const Valu
 __device__ __forceinline__ void cta256_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---- TopN helpers --------------------------------------------------------------------------------------------
-// Sort `cap` candidates in shared memory (bitonic, all threads), keep the best `limit`.
+// Candidate buffer of a CTA: `cap` item slots that never move plus a permutation `idx` (u16) of the slots.  Positions
+// [0, cnt) of `idx` are occupied; a new candidate takes position atomicAdd(cnt) -> slot idx[pos].  Compaction sorts the
+// permutation (bitonic network over positions, every thread owns one compare-exchange per step) and keeps the best
+// `limit` positions: only 2-byte indices are swapped, the 48-byte items are read in place.
+__device__ __forceinline__ unsigned short* topn_idx(TopItem* items, unsigned int cap) { return reinterpret_cast<unsigned short*>(items + cap); }
+
 __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int limit, unsigned int* s_cnt, unsigned int* s_have_thr, TopItem* s_thr,
                                  const DevPlan& P) {
   const unsigned int tid = threadIdx.x, nt = TILE;  // always called by exactly 256 threads
+  unsigned short* idx = topn_idx(items, cap);
   unsigned int cnt = *s_cnt;
-  for (unsigned int i = cnt + tid; i < cap; i += nt) items[i].nulls = 0x80000000u;
+  for (unsigned int i = cnt + tid; i < cap; i += nt) items[idx[i]].nulls = 0x80000000u;  // free slots sort last
   cta256_sync();
   for (unsigned int k = 2; k <= cap; k <<= 1) {
     for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-      for (unsigned int i = tid; i < cap; i += nt) {
-        unsigned int x = i ^ j;
-        if (x > i) {
-          bool up = (i & k) == 0;
-          TopItem a = items[i], b = items[x];
-          bool swap = up ? item_less(b, a, P) : item_less(a, b, P);
-          if (swap) { items[i] = b; items[x] = a; }
-        }
+      for (unsigned int p = tid; p < cap / 2; p += nt) {
+        unsigned int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), x = i | j;
+        bool up = (i & k) == 0;
+        unsigned short ia = idx[i], ib = idx[x];
+        const TopItem& a = items[ia];
+        const TopItem& b = items[ib];
+        bool swap = up ? item_less(b, a, P) : item_less(a, b, P);
+        if (swap) { idx[i] = ib; idx[x] = ia; }
       }
       cta256_sync();
     }
@@ -105,7 +111,7 @@ __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int 
   if (tid == 0) {
     unsigned int keep = cnt < limit ? cnt : limit;
     *s_cnt = keep;
-    if (keep == limit && limit > 0) { *s_thr = items[limit - 1]; *s_have_thr = 1; }
+    if (keep == limit && limit > 0) { *s_thr = items[idx[limit - 1]]; *s_have_thr = 1; }
   }
   cta256_sync();
 }
@@ -275,7 +281,11 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
   __shared__ TopItem s_top_thr;
   TopItem* top_items = reinterpret_cast<TopItem*>(dyn_smem);
   if (MODE == PM_TOPN) {
-    if (tid == 0) { s_top_cnt = 0; s_top_have_thr = 0; }
+    if (tid == 0) {
+      s_top_cnt = 0; s_top_have_thr = 0;
+      if (A.topn_seed && P.limit > 0 && *A.topn_seed_cnt >= (unsigned int)P.limit) { s_top_thr = A.topn_seed[P.limit - 1]; s_top_have_thr = 1; }
+    }
+    for (unsigned int i = tid; i < A.topn_cap; i += blockDim.x) topn_idx(top_items, A.topn_cap)[i] = (unsigned short)i;
     __syncthreads();
   }
 
@@ -557,7 +567,7 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
         if (err) report_err(A.ctr, A.entry_base + e, err);
         else if (!s_top_have_thr || item_less(it, s_top_thr, P)) {
           unsigned int pos = atomicAdd(&s_top_cnt, 1u);
-          top_items[pos] = it;  // pos < topn_cap: the buffer is compacted whenever fewer than TILE slots remain
+          top_items[topn_idx(top_items, A.topn_cap)[pos]] = it;  // pos < topn_cap: the buffer is compacted whenever fewer than TILE slots remain
         }
       }
       cta256_sync();
@@ -699,7 +709,7 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
     cta256_sync();
     cta_topn_compact(top_items, A.topn_cap, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
     unsigned int keep = s_top_cnt;
-    for (unsigned int i = tid; i < keep; i += TILE) A.topn.items[(size_t)blockIdx.x * A.topn.stride + i] = top_items[i];
+    for (unsigned int i = tid; i < keep; i += TILE) A.topn.items[(size_t)blockIdx.x * A.topn.stride + i] = top_items[topn_idx(top_items, A.topn_cap)[i]];
     if (tid == 0) A.topn.counts[blockIdx.x] = keep;
   }
   if (MODE == PM_AGG) {
@@ -806,28 +816,32 @@ cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t
 }
 
 // ---- TopN: merge candidate lists, gather row payloads ------------------------------------------------------------
-size_t topn_smem_bytes(uint32_t cap) { return (size_t)cap * sizeof(TopItem); }
+size_t topn_smem_bytes(uint32_t cap) { return (size_t)cap * sizeof(TopItem) + (size_t)cap * 2; }
 
-// one CTA streams every item of `in` through the same threshold buffer and leaves the best `limit`, sorted, in out list 0
-__global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant__ DevPlan P, TopNLists in, TopNLists out, unsigned int cap) {
+// CTA b streams every item of input lists [b * fan_in, (b + 1) * fan_in) through one threshold buffer and leaves the
+// best `limit`, sorted, in output list b.  The host applies it level by level (fan-in 8) down to a single list.
+__global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant__ DevPlan P, TopNLists in, TopNLists out, unsigned int cap, unsigned int fan_in) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned int s_cnt, s_have_thr;
   __shared__ TopItem s_thr;
   TopItem* items = reinterpret_cast<TopItem*>(dyn_smem);
   const unsigned int tid = threadIdx.x;
   if (tid == 0) { s_cnt = 0; s_have_thr = 0; }
+  for (unsigned int i = tid; i < cap; i += TILE) topn_idx(items, cap)[i] = (unsigned short)i;
   __syncthreads();
-  const unsigned int total = in.n_lists * in.stride;
+  const unsigned int l0 = blockIdx.x * fan_in;
+  const unsigned int l1 = l0 + fan_in < in.n_lists ? l0 + fan_in : in.n_lists;
+  const unsigned int total = (l1 - l0) * in.stride;
   for (unsigned int base = 0; base < total; base += TILE) {
     unsigned int f = base + tid;
     if (f < total) {
-      unsigned int l = f / in.stride, i = f % in.stride;
+      unsigned int l = l0 + f / in.stride, i = f % in.stride;
       if (i < in.counts[l]) {
         TopItem it = in.items[(size_t)l * in.stride + i];
         it.slot = (l << 16) | i;
         if (!s_have_thr || item_less(it, s_thr, P)) {
           unsigned int pos = atomicAdd(&s_cnt, 1u);
-          items[pos] = it;
+          items[topn_idx(items, cap)[pos]] = it;
         }
       }
     }
@@ -837,14 +851,15 @@ __global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant_
   __syncthreads();
   cta_topn_compact(items, cap, (unsigned int)P.limit, &s_cnt, &s_have_thr, &s_thr, P);
   unsigned int keep = s_cnt;
-  for (unsigned int i = tid; i < keep; i += TILE) out.items[i] = items[i];
-  if (tid == 0) out.counts[0] = keep;
+  for (unsigned int i = tid; i < keep; i += TILE) out.items[(size_t)blockIdx.x * out.stride + i] = items[topn_idx(items, cap)[i]];
+  if (tid == 0) out.counts[blockIdx.x] = keep;
 }
 
-cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const TopNLists& out, uint32_t cap, cudaStream_t s) {
+cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const TopNLists& out, uint32_t cap, uint32_t fan_in, cudaStream_t s) {
   size_t smem = topn_smem_bytes(cap);
   if (smem > 48 * 1024) cudaFuncSetAttribute(topn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  topn_merge_kernel<<<1, TILE, smem, s>>>(plan, in, out, cap);
+  unsigned int grid = (in.n_lists + fan_in - 1) / fan_in;
+  topn_merge_kernel<<<grid, TILE, smem, s>>>(plan, in, out, cap, fan_in);
   return cudaGetLastError();
 }
 

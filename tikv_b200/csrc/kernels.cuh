@@ -67,6 +67,8 @@ struct ScanArgs {
   // PM_TOPN
   TopNLists topn;                   // per-CTA result lists (stride = limit)
   uint32_t topn_cap;                // shared-memory candidate capacity (power of two >= limit + TILE)
+  const TopItem* topn_seed;         // running top-N of the units already merged (sorted), or nullptr:
+  const unsigned int* topn_seed_cnt;  //   once it holds `limit` rows its last one is every CTA's initial threshold
 };
 
 struct GenArgs {
@@ -88,7 +90,7 @@ cudaError_t launch_agg_finalize(const DevPlan& plan, const AggTable& t, Counters
 cudaError_t launch_agg_result(const DevPlan& plan, unsigned int n_groups, const unsigned long long* g_keys, const unsigned char* g_null,
                               const unsigned long long* g_acc, unsigned long long** col_data, unsigned long long** col_bitmap, cudaStream_t s);
 // TopN: merge `in` lists into the best `limit` items (sorted) -> out list 0; gather decodes the rows of a list
-cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const TopNLists& out, uint32_t cap, cudaStream_t s);
+cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const TopNLists& out, uint32_t cap, uint32_t fan_in, cudaStream_t s);
 cudaError_t launch_topn_gather(const DevPlan& plan, const ScanArgs& a, const TopItem* items, const unsigned int* count, unsigned long long* pay,
                                unsigned char* pay_null, uint32_t stride, cudaStream_t s);
 cudaError_t launch_topn_copy(const TopItem* items, const unsigned int* count, uint32_t n_out, uint32_t stride, const unsigned long long* pay0,

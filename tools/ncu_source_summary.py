@@ -1,5 +1,5 @@
 import csv,re,sys
-rows=list(csv.reader(open('/tmp/src_cs.csv')))
+rows=list(csv.reader(open(sys.argv[1])))
 cur=None; lines={}
 for r in rows:
     if len(r)>=2 and r[0]=="File Path": cur=r[1]; continue
