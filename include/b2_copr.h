@@ -299,6 +299,22 @@ int32_t b2_exec_schema(b2_exec* h, int32_t* field_tps, uint32_t* field_flags, ui
 int32_t b2_exec_next_batch(b2_exec* h, uint64_t scan_rows, b2_batch* out);
 int32_t b2_exec_collect_stats(b2_exec* h, b2_exec_stats* out);
 int32_t b2_exec_last_error(b2_exec* h, b2_error_info* out);
+/* Response encoding of the batch most recently returned by b2_exec_next_batch / b2_dag_handle on this handle:
+ * encode_result_to_chunk (components/tidb_query_executors/src/runner.rs:1051-1088), i.e. tipb::Chunk.rows_data in
+ * EncodeType::TypeDefault (datum rows, lazy_column_vec.rs:172-187 + vector.rs:362-470) or EncodeType::TypeChunk
+ * (one column block per output column, chunk/column.rs:1052-1072).  Runs on the device from the HBM-resident columns;
+ * only the encoded bytes cross PCIe when `location` is B2_LOC_HOST.  The buffer is valid until the next call on the
+ * handle.  TypeDefault writes every cell in the canonical fixed-width datum form the reference uses for decoded
+ * columns and for all v2 rows (v1 rows' never-evaluated columns keep their stored VAR_INT form in the reference). */
+enum { B2_ENCODE_TYPE_DEFAULT = 0, B2_ENCODE_TYPE_CHUNK = 1 };
+typedef struct b2_encoded_chunk {
+  const uint8_t* rows_data;
+  uint64_t len;
+  uint64_t n_rows;
+  int32_t encode_type;
+  int32_t location;
+} b2_encoded_chunk;
+int32_t b2_exec_encode_batch(b2_exec* h, int32_t encode_type, int32_t location, b2_encoded_chunk* out);
 /* storage_impl.rs:108-123: no newer-ts data and no lock seen */
 int32_t b2_exec_can_be_cached(b2_exec* h);
 void b2_exec_close(b2_exec* h);

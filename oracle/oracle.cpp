@@ -14,6 +14,7 @@
 #include <thread>
 
 #include "orc_exec.h"
+#include "orc_encode.h"
 
 using namespace orc;
 
@@ -28,6 +29,8 @@ struct orc_result {
   int met_newer = NEWER_UNKNOWN;
   uint64_t scanned_rows = 0;
   std::string dec_str;
+  Bytes enc_default;  // Chunk.rows_data of every batch, EncodeType::TypeDefault, concatenated (runner.rs:1062-1071)
+  Bytes enc_chunk;    // the whole result as one EncodeType::TypeChunk chunk (runner.rs:1072-1085)
 };
 
 static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src,
@@ -124,6 +127,11 @@ static int orc_dag_handle_impl(const b2_dag_plan* plan, const b2_key_range* rang
   for (;;) {
     Batch b;
     root->next_batch(batch_size, &b);
+    // encode_result_to_chunk, TypeDefault arm: row by row, output offset by output offset, on the batch as the
+    // executors left it (a column no expression touched is still Raw and goes out as the stored datum bytes)
+    if (keep_rows && !b.cols.empty())
+      for (size_t r : b.logical_rows)
+        for (size_t k = 0; k < offs.size(); ++k) encode_cell_default(res->enc_default, b.cols[offs[k]], r, sch[offs[k]], agg ? &agg->dec_col : nullptr);
     for (size_t k = 0; k < offs.size(); ++k) {
       LazyColumn& c = b.cols.empty() ? res->cols[k] : b.cols[offs[k]];
       if (b.cols.empty()) break;
@@ -152,6 +160,12 @@ static int orc_dag_handle_impl(const b2_dag_plan* plan, const b2_key_range* rang
   res->stats = scan->rs.total;
   res->met_newer = scan->rs.met_newer;
   res->scanned_rows = scan->rs.rows;
+  if (keep_rows)  // TypeChunk arm over the rows produced (chunk boundaries are the server's choice: one chunk here)
+    for (size_t k = 0; k < offs.size(); ++k) {
+      const LazyColumn& c = res->cols[k];
+      encode_column_chunk(res->enc_chunk, res->schema[k].tp, c.nn, c.et == ET_REAL ? nullptr : c.i64.data(), c.et == ET_REAL ? c.f64.data() : nullptr,
+                          c.et == ET_DECIMAL ? res->dec_cols[k].data() : nullptr);
+    }
   return res->err.status;
 }
 
@@ -173,6 +187,11 @@ const char* orc_result_message(orc_result* r) { return r->err.msg.c_str(); }
 void orc_result_stats(orc_result* r, uint64_t* out8) {
   out8[0] = r->stats.write.next; out8[1] = r->stats.write.seek; out8[2] = r->stats.write.over_seek_bound; out8[3] = r->stats.write.processed_keys;
   out8[4] = r->stats.processed_size; out8[5] = r->stats.data.processed_keys; out8[6] = r->stats.lock.processed_keys; out8[7] = (uint64_t)(int64_t)r->met_newer;
+}
+const uint8_t* orc_result_encoded(orc_result* r, int encode_type, uint64_t* len) {
+  const Bytes& b = encode_type == 0 ? r->enc_default : r->enc_chunk;
+  *len = b.size();
+  return b.data();
 }
 void orc_result_free(orc_result* r) { delete r; }
 
@@ -313,6 +332,13 @@ void orc_decimal_from_i64(int64_t v, b2_decimal* out) { Decimal d = dec_from_i64
 void orc_decimal_from_u64(uint64_t v, b2_decimal* out) { Decimal d = dec_from_u64(v); memcpy(out, &d, 40); }
 int orc_decimal_add(const b2_decimal* a, const b2_decimal* b, b2_decimal* out) { Decimal r; int st = dec_add(*(const Decimal*)a, *(const Decimal*)b, &r); memcpy(out, &r, 40); return st; }
 size_t orc_decimal_to_string(const b2_decimal* a, char* out, size_t cap) { std::string s = dec_to_string(*(const Decimal*)a); snprintf(out, cap, "%s", s.c_str()); return s.size(); }
+size_t orc_decimal_write(const b2_decimal* a, int prec, int frac, uint8_t* out) {  // prec < 0: prec_and_frac()
+  Bytes b; uint8_t p = (uint8_t)prec, f = (uint8_t)frac;
+  if (prec < 0) dec_prec_and_frac(*(const Decimal*)a, &p, &f);
+  dec_write(b, *(const Decimal*)a, p, f);
+  memcpy(out, b.data(), b.size());
+  return b.size();
+}
 int orc_decimal_cmp(const b2_decimal* a, const b2_decimal* b) { return dec_cmp(*(const Decimal*)a, *(const Decimal*)b); }
 
 }  // extern "C"

@@ -298,3 +298,103 @@ def table_range(table_id, lo=None, hi=None):
     start = row_key(table_id, lo) if lo is not None else b"t" + enc_i64_cmp(table_id) + b"_r"
     end = row_key(table_id, hi) if hi is not None else b"t" + enc_i64_cmp(table_id) + b"_s"
     return (start, end)
+
+
+# ---- response decoders (independent of both the oracle and the device encoders) ------------------------------------
+def _dec_bin_to_int(buf, pos, prec, frac):
+    """MySQL binary decimal -> (python int scaled by 10**frac, new pos)."""
+    d2b = [0, 1, 1, 2, 2, 3, 3, 4, 4, 4]
+    ints, fr = prec - frac, frac
+    size = (ints // 9) * 4 + d2b[ints % 9] + (fr // 9) * 4 + d2b[fr % 9]
+    raw = bytearray(buf[pos:pos + size])
+    neg = not (raw[0] & 0x80)
+    raw[0] ^= 0x80
+    if neg:
+        raw = bytearray(b ^ 0xFF for b in raw)
+    p, digits = 0, ""
+    for cnt in ([ints % 9] if ints % 9 else []) + [9] * (ints // 9) + [9] * (fr // 9) + ([fr % 9] if fr % 9 else []):
+        nb = d2b[cnt]
+        digits += str(int.from_bytes(raw[p:p + nb], "big")).rjust(cnt, "0")
+        p += nb
+    v = int(digits or "0")
+    return (-v if neg else v), pos + size
+
+
+def decode_datum(buf, pos):
+    """One datum of a TypeDefault row -> (python value, new pos).  Decimals come back as (unscaled int, frac)."""
+    flag = buf[pos]
+    pos += 1
+    if flag == 0:
+        return None, pos
+    if flag in (3, 4):
+        u = int.from_bytes(buf[pos:pos + 8], "big")
+        if flag == 3:
+            u ^= 1 << 63
+            if u >= 1 << 63:
+                u -= 1 << 64
+        return u, pos + 8
+    if flag == 5:
+        u = int.from_bytes(buf[pos:pos + 8], "big")
+        u = u ^ (1 << 63) if u & (1 << 63) else u ^ ((1 << 64) - 1)
+        return struct.unpack("<d", struct.pack("<Q", u))[0], pos + 8
+    if flag == 6:
+        prec, frac = buf[pos], buf[pos + 1]
+        v, pos = _dec_bin_to_int(buf, pos + 2, prec, frac)
+        return (v, frac), pos
+    if flag in (8, 9):
+        u, shift = 0, 0
+        while True:
+            b = buf[pos]
+            pos += 1
+            u |= (b & 0x7F) << shift
+            shift += 7
+            if not b & 0x80:
+                break
+        return ((u >> 1) ^ -(u & 1) if flag == 8 else u), pos
+    raise ValueError(f"datum flag {flag}")
+
+
+def decode_datum_rows(buf, n_cols):
+    rows, pos = [], 0
+    while pos < len(buf):
+        row = []
+        for _ in range(n_cols):
+            v, pos = decode_datum(buf, pos)
+            row.append(v)
+        rows.append(tuple(row))
+    return rows
+
+
+def decode_chunk(buf, elem_sizes):
+    """TypeChunk column blocks -> list of columns of raw little-endian cell bytes (None = NULL)."""
+    cols, pos = [], 0
+    for es in elem_sizes:
+        n, nulls = struct.unpack_from("<II", buf, pos)
+        pos += 8
+        bm = None
+        if nulls:
+            bm = buf[pos:pos + (n + 7) // 8]
+            pos += (n + 7) // 8
+        cells = []
+        for i in range(n):
+            cell = bytes(buf[pos + i * es:pos + (i + 1) * es])
+            cells.append(cell if (bm is None or (bm[i >> 3] >> (i & 7)) & 1) else None)
+        pos += n * es
+        cols.append(cells)
+    assert pos == len(buf), (pos, len(buf))
+    return cols
+
+
+def decimal_struct_value(cell):
+    """40-byte MyDecimal struct (decimal.rs:927-942) -> (unscaled python int, frac digits).  The struct is not canonical
+    (digitsInt may include leading zero words left behind by the order of additions), the value is."""
+    int_cnt, frac_cnt, _res, neg = cell[0], cell[1], cell[2], cell[3]
+    words = struct.unpack_from("<9I", cell, 4)
+    iw, fw = (int_cnt + 8) // 9, (frac_cnt + 8) // 9
+    v = 0
+    for w in words[:iw]:
+        v = v * 10 ** 9 + w
+    for w in words[iw:iw + fw]:
+        v = v * 10 ** 9 + w
+    v //= 10 ** (fw * 9 - frac_cnt)
+    return (-v if neg else v), frac_cnt

@@ -31,6 +31,8 @@ def lib():
         L.orc_result_message.argtypes = [vp]; L.orc_result_message.restype = C.c_char_p
         L.orc_result_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.orc_result_free.argtypes = [vp]
+        L.orc_result_encoded.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]; L.orc_result_encoded.restype = C.POINTER(C.c_uint8)
+        L.orc_decimal_write.argtypes = [C.POINTER(ffi.Decimal), C.c_int, C.c_int, C.c_char_p]; L.orc_decimal_write.restype = C.c_size_t
         L.orc_checksum_handle.argtypes = [C.POINTER(ffi.KeyRange), C.c_uint32, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32,
                                           C.POINTER(ffi.RegionSource), C.POINTER(ffi.ChecksumResponse), C.c_char_p, C.c_size_t]
         L.orc_dag_handle_parallel.argtypes = [C.POINTER(ffi.DagPlan), C.POINTER(ffi.KeyRange), C.c_uint32, C.POINTER(ffi.RegionSource),
@@ -103,6 +105,11 @@ def dag_handle(plan, ranges, region):
     stats = dict(write_next=st[0], write_seek=st[1], over_seek_bound=st[2], processed_keys=st[3], processed_size=st[4],
                  data_processed_keys=st[5], lock_processed_keys=st[6], met_newer=C.c_int64(st[7]).value)
     res = Result(L.orc_result_status(h), L.orc_result_message(h).decode(), L.orc_result_mysql_code(h), cols, kinds, stats)
+    res.encoded = {}
+    for t in (0, 1):  # EncodeType::TypeDefault / TypeChunk
+        ln = C.c_uint64()
+        pp = L.orc_result_encoded(h, t, C.byref(ln))
+        res.encoded[t] = C.string_at(pp, ln.value) if ln.value else b""
     L.orc_result_free(h)
     return res
 

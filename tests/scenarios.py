@@ -52,7 +52,7 @@ def _row_value(rng, fmt, full_range=True):
     return kvfmt.row_v1(d)
 
 
-def dirty_region(seed, n_keys=600, full_range=True, long_values=True):
+def dirty_region(seed, n_keys=600, full_range=True, long_values=True, only_fmt=None):
     """Region with every MVCC shape the forward scanner handles."""
     rng = random.Random(seed)
     r = kvfmt.Region()
@@ -60,6 +60,8 @@ def dirty_region(seed, n_keys=600, full_range=True, long_values=True):
         key = kvfmt.row_key(TABLE, h * 3 - 100)
         shape = rng.random()
         fmt = 2 if rng.random() < 0.6 else 1
+        if only_fmt:
+            fmt = only_fmt
         val = _row_value(rng, fmt, full_range)
         if shape < 0.45:  # single visible put
             r.put(key, val, 10, 20)

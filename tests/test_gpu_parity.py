@@ -323,3 +323,85 @@ def test_topn_large_generated():
     finally:
         for g in gens:
             ffi.lib().b2_gen_destroy(g)
+
+
+# ---- response encoding on the device (runner.rs:1051-1088) -----------------------------------------------------------
+def _one_batch(plan, ranges, region):
+    ex = BatchExecutor(plan, ranges, region, output=ffi.LOC_DEVICE)  # columns stay in HBM: only encoded bytes come back
+    rc, b = ex.next_batch_raw(1 << 30)
+    assert rc == ffi.B2_OK and b.is_drained != ffi.DRAIN_REMAIN
+    return ex
+
+
+def _elem_sizes(ex):
+    return [40 if tp == ffi.TP_NEWDECIMAL else (4 if tp == ffi.TP_FLOAT else 8) for tp, _ in ex.schema()]
+
+
+@pytest.mark.parametrize("name,plan", PLANS, ids=[n for n, _ in PLANS])
+def test_encode_chunk_matches_oracle(name, plan, regions):
+    """EncodeType::TypeChunk of the whole result: byte-identical to the oracle (as a multiset of rows for hash agg)."""
+    region = regions[1].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    exp = orc.dag_handle(plan, sc.WHOLE, region)
+    with _one_batch(plan, sc.WHOLE, region) as ex:
+        got = ex.encode_batch(ffi.ENCODE_TYPE_CHUNK)
+        if not sc.is_agg(name):
+            assert got == exp.encoded[1]
+        else:
+            # group order is unspecified, and a MyDecimal cell is compared by value: its digitsInt keeps whatever
+            # leading zero words the reference's order of additions left behind
+            es = _elem_sizes(ex)
+            norm = lambda cols: sorted(zip(*[[c if c is None or len(c) != 40 else kvfmt.decimal_struct_value(c) for c in col] for col in cols]),
+                                       key=lambda t: tuple((0, 0) if x is None else (1, x) for x in t))
+            a, b = norm(kvfmt.decode_chunk(got, es)), norm(kvfmt.decode_chunk(exp.encoded[1], es))
+            if any(tp in (ffi.TP_DOUBLE, ffi.TP_FLOAT) for tp, _ in ex.schema()):
+                continue_cmp = False  # f64 sums are order dependent; compared with tolerance by test_real_sum
+            else:
+                continue_cmp = True
+            assert len(a) == exp.n_rows
+            if continue_cmp:
+                assert a == b
+
+
+@pytest.mark.parametrize("name,plan", PLANS, ids=[n for n, _ in PLANS])
+def test_encode_default_matches_oracle(name, plan):
+    """EncodeType::TypeDefault, every plan, v2-only and mixed v1/v2 tables: the same rows after datum decode.  (Bytes can
+    differ in exactly one way: a column no expression evaluated is still Raw in the reference and goes out as the stored
+    v1 datum or the plan's default-value datum, e.g. VAR_INT; the device always writes the fixed-width INT/UINT/FLOAT
+    datum the reference itself uses for decoded columns and for every v2 cell.  Same value, any TiDB client decodes both.)"""
+    for only_fmt in (2, None):
+        region = sc.dirty_region(5, n_keys=700, only_fmt=only_fmt).build(read_ts=sc.READ_TS, n_write_blocks=2)
+        exp = orc.dag_handle(plan, sc.WHOLE, region)
+        with _one_batch(plan, sc.WHOLE, region) as ex:
+            got = ex.encode_batch(ffi.ENCODE_TYPE_DEFAULT)
+            n_cols = len(ex.schema())
+        a, b = kvfmt.decode_datum_rows(got, n_cols), kvfmt.decode_datum_rows(exp.encoded[0], n_cols)
+        key = lambda t: tuple((0, 0) if x is None else (1, x) for x in t)
+        norm = lambda rows: sorted(rows, key=key) if sc.is_agg(name) else rows
+        assert len(a) == exp.n_rows
+        if any(isinstance(x, float) for r in b for x in r) and sc.is_agg(name):
+            continue  # f64 sums are order dependent; their values are compared (with tolerance) by test_real_sum
+        assert norm(a) == norm(b), name
+
+
+def test_encode_default_bytes_identical():
+    """Where the reference's bytes are fully determined by the values (v2 rows, no default-filled cells; NULLs, unsigned,
+    Real and the PK handle included) the TypeDefault stream is byte-identical; SUM/COUNT results (Decimal datums) too."""
+    region = sc.dirty_region(9, n_keys=900, only_fmt=2).build(read_ts=sc.READ_TS, n_write_blocks=3)
+    scan = lambda: Plan().table_scan(sc.TABLE, sc.COLUMNS)
+    offs = [sc.C4, sc.C_H, sc.C2, sc.C3, sc.C1, sc.C6]
+    for plan in (scan().build(output_offsets=offs), scan().selection(lt(col(sc.C1), const_int(0))).build(output_offsets=offs),
+                 scan().aggregation([("count", const_int(1)), ("sum", col(sc.C1)), ("avg", col(sc.C3, unsigned=True)), ("sum", col(sc.C2))]).build()):
+        exp = orc.dag_handle(plan, sc.split_ranges(), region)
+        with _one_batch(plan, sc.split_ranges(), region) as ex:
+            assert ex.encode_batch(ffi.ENCODE_TYPE_DEFAULT) == exp.encoded[0] and exp.n_rows > 0
+
+
+def test_encode_empty_and_errors(regions):
+    region = regions[1].build(read_ts=sc.READ_TS)
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(lt(col(sc.C1), const_int(-(1 << 63)))).build()  # no row passes
+    exp = orc.dag_handle(plan, sc.WHOLE, region)
+    with _one_batch(plan, sc.WHOLE, region) as ex:
+        assert ex.encode_batch(ffi.ENCODE_TYPE_DEFAULT) == exp.encoded[0] == b""
+        assert ex.encode_batch(ffi.ENCODE_TYPE_CHUNK) == exp.encoded[1]
+        with pytest.raises(Exception):
+            ex.encode_batch(7)

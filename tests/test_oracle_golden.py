@@ -407,3 +407,29 @@ def test_decimal_value_semantics():
     L.orc_decimal_add(C.byref(a), C.byref(b), C.byref(c))
     n = L.orc_decimal_to_string(C.byref(c), out, 128)
     assert out.value[:n].decode() == "1000000000" and c.int_cnt == 18
+
+
+def test_decimal_binary_encoding_known_answers():
+    """DecimalEncoder::write_decimal (decimal.rs:2025-2132).  The reference's own test (`test_codec`, :3096-3145) only
+    round-trips, so the byte values are pinned on MySQL's documented decimal2bin example: 1234567890.1234 as
+    DECIMAL(14,4) is 81 0D FB 38 D2 04 D2, and its negation is the bitwise complement."""
+    L = orc.lib()
+    d = ffi.Decimal()
+    d.int_cnt, d.frac_cnt, d.result_frac_cnt, d.negative = 10, 4, 4, 0
+    for i, w in enumerate([1, 234567890, 123400000]):
+        d.word_buf[i] = w
+    out = C.create_string_buffer(64)
+    n = L.orc_decimal_write(C.byref(d), 14, 4, out)
+    assert out.raw[:n] == bytes([14, 4, 0x81, 0x0D, 0xFB, 0x38, 0xD2, 0x04, 0xD2])
+    d.negative = 1
+    n = L.orc_decimal_write(C.byref(d), 14, 4, out)
+    assert out.raw[:n] == bytes([14, 4, 0x7E, 0xF2, 0x04, 0xC7, 0x2D, 0xFB, 0x2D])
+    # integers, prec/frac from prec_and_frac() (:1043-1051): what SUM(int) columns put on the wire
+    for v, want in ((0, bytes([1, 0, 0x80])), (5, bytes([1, 0, 0x85])), (-5, bytes([1, 0, 0x7A])), (1234567890, bytes([10, 0, 0x81, 0x0D, 0xFB, 0x38, 0xD2])),
+                    (-(1 << 63), None), ((1 << 63) - 1, None)):
+        L.orc_decimal_from_i64(v, C.byref(d))
+        n = L.orc_decimal_write(C.byref(d), -1, 0, out)
+        if want is not None:
+            assert out.raw[:n] == want, v
+        got, pos = kvfmt._dec_bin_to_int(out.raw, 2, out.raw[0], out.raw[1])
+        assert got == v and pos == n

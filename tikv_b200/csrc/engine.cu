@@ -18,6 +18,7 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include "encode.cuh"
 #include "kernels.cuh"
 #include "plan_compile.h"
 
@@ -754,15 +755,94 @@ struct b2_exec {
         cols[k].null_bitmap = n_rows ? (const uint64_t*)(bm + k * (out_cap / 8)) : nullptr;
       }
     }
+    last_dev.assign(n_out, DevColRef{});
+    last_rows = n_rows;
     for (size_t k = 0; k < n_out; ++k) {
       const OutCol& oc = cp.schema[cp.dev.mode == PM_SCAN ? cp.output_offsets[k] : k];
       cols[k].kind = oc.kind; cols[k].field_tp = oc.field_tp; cols[k].field_flag = oc.field_flag; cols[k].len = n_rows;
+      last_dev[k] = DevColRef{data + k * out_cap * 8, (const unsigned long long*)(bm + k * (out_cap / 8)), oc.kind, oc.field_tp, oc.field_flag};
     }
     out->columns = cols.data(); out->n_columns = (uint32_t)n_out; out->n_rows = n_rows;
     out->is_drained = drained ? B2_DRAIN_DRAINED : B2_DRAIN_REMAIN;
     stats.num_produced_rows += n_rows;
     return failed ? last_err.status : B2_OK;
   }
+  // ---- response encoding of the batch just produced (runner.rs:1051-1088 encode_result_to_chunk) ----
+  struct DevColRef { const void* data; const unsigned long long* bitmap; int kind; int field_tp; uint32_t field_flag; };
+  std::vector<DevColRef> last_dev;  // device-resident columns of the last batch, in output order
+  uint64_t last_rows = 0;
+  DevBuf enc_cols, enc_counts, enc_out, enc_lens, enc_offs, enc_tmp;
+  HostBuf enc_host;
+
+  int encode_batch(int32_t encode_type, int32_t location, b2_encoded_chunk* out) {
+    memset(out, 0, sizeof(*out));
+    out->encode_type = encode_type; out->location = location; out->n_rows = last_rows;
+    const int nc = (int)last_dev.size();
+    const uint64_t n = last_rows;
+    if (encode_type != B2_ENCODE_TYPE_DEFAULT && encode_type != B2_ENCODE_TYPE_CHUNK) { g_last_error = "unknown encode type"; return B2_ERR_INVALID_ARG; }
+    if (nc == 0 || (n == 0 && encode_type == B2_ENCODE_TYPE_DEFAULT)) return B2_OK;
+    std::vector<EncCol> ec((size_t)nc);
+    for (int k = 0; k < nc; ++k) {
+      const DevColRef& d = last_dev[(size_t)k];
+      ec[(size_t)k] = EncCol{d.data, d.bitmap, d.kind, d.field_tp == B2_TP_FLOAT ? 1 : 0, (d.field_flag & B2_FLAG_UNSIGNED) ? 1 : 0, 0u, 0ull};
+    }
+    CUDA_TRY(enc_cols.reserve((size_t)nc * sizeof(EncCol)));
+    CUDA_TRY(enc_counts.reserve((size_t)nc * 4));
+    std::vector<unsigned int> nulls((size_t)nc, 0);
+    if (n) {
+      CUDA_TRY(cudaMemcpyAsync(enc_cols.p, ec.data(), (size_t)nc * sizeof(EncCol), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(launch_enc_null_count((const EncCol*)enc_cols.p, nc, n, (unsigned int*)enc_counts.p, stream));
+      CUDA_TRY(cudaMemcpyAsync(nulls.data(), enc_counts.p, (size_t)nc * 4, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      stats.kernel_launches++;
+    }
+    uint64_t total = 0;
+    if (encode_type == B2_ENCODE_TYPE_CHUNK) {
+      for (int k = 0; k < nc; ++k) {
+        EncCol& c = ec[(size_t)k];
+        c.null_cnt = nulls[(size_t)k]; c.chunk_off = total;
+        uint64_t esz = c.kind == B2_COL_DECIMAL ? 40 : (c.is_f32 ? 4 : 8);
+        total += 8 + (c.null_cnt ? (n + 7) / 8 : 0) + n * esz;
+      }
+      CUDA_TRY(enc_out.reserve(total));
+      CUDA_TRY(cudaMemcpyAsync(enc_cols.p, ec.data(), (size_t)nc * sizeof(EncCol), cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(launch_enc_chunk((const EncCol*)enc_cols.p, nc, n, (unsigned char*)enc_out.p, stream));
+      stats.kernel_launches++;
+    } else {
+      bool fixed = true;
+      for (int k = 0; k < nc; ++k) if (nulls[(size_t)k] || ec[(size_t)k].kind == B2_COL_DECIMAL) fixed = false;
+      const unsigned long long* offs = nullptr;
+      if (fixed) total = n * 9ull * (uint64_t)nc;
+      else {
+        CUDA_TRY(enc_lens.reserve(n * 4)); CUDA_TRY(enc_offs.reserve(n * 8));
+        size_t tb = enc_scan_temp_bytes(n);
+        CUDA_TRY(enc_tmp.reserve(tb));
+        CUDA_TRY(launch_enc_row_len((const EncCol*)enc_cols.p, nc, n, (unsigned int*)enc_lens.p, stream));
+        CUDA_TRY(launch_enc_scan((const unsigned int*)enc_lens.p, (unsigned long long*)enc_offs.p, n, enc_tmp.p, tb, stream));
+        unsigned long long last_off = 0; unsigned int last_len = 0;
+        CUDA_TRY(cudaMemcpyAsync(&last_off, (const unsigned long long*)enc_offs.p + (n - 1), 8, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(&last_len, (const unsigned int*)enc_lens.p + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        total = last_off + last_len;
+        offs = (const unsigned long long*)enc_offs.p;
+        stats.kernel_launches += 2;
+      }
+      CUDA_TRY(enc_out.reserve(total));
+      CUDA_TRY(launch_enc_rows((const EncCol*)enc_cols.p, nc, n, offs, (unsigned int)(9 * nc), (unsigned char*)enc_out.p, stream));
+      stats.kernel_launches++;
+    }
+    out->len = total;
+    if (location == B2_LOC_HOST) {
+      CUDA_TRY(enc_host.reserve(total));
+      CUDA_TRY(cudaMemcpyAsync(enc_host.p, enc_out.p, total, cudaMemcpyDeviceToHost, stream));
+      d2h_bytes += total;
+      out->rows_data = (const uint8_t*)enc_host.p;
+    } else out->rows_data = (const uint8_t*)enc_out.p;
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    stats.d2h_bytes = d2h_bytes;
+    return B2_OK;
+  }
+
   uint64_t d2h_bytes = 0;
 
   // ---- PM_AGG: everything in one go ----
@@ -880,6 +960,8 @@ struct b2_exec {
     // deliver the requested output offsets
     size_t n_out = cp.output_offsets.size();
     cols.assign(n_out, b2_column{});
+    last_dev.assign(n_out, DevColRef{});
+    last_rows = n_groups;
     size_t host_off = 0;
     if (out_loc == B2_LOC_HOST && n_groups) {
       size_t total = 0;
@@ -891,6 +973,7 @@ struct b2_exec {
       const OutCol& oc = cp.schema[k];
       size_t esz = oc.kind == B2_COL_DECIMAL ? 40 : 8;
       cols[i].kind = oc.kind; cols[i].field_tp = oc.field_tp; cols[i].field_flag = oc.field_flag; cols[i].len = n_groups;
+      last_dev[i] = DevColRef{res_cols[k].p, (const unsigned long long*)res_bitmaps[k].p, oc.kind, oc.field_tp, oc.field_flag};
       if (out_loc == B2_LOC_HOST && n_groups) {
         uint8_t* hp = (uint8_t*)h_out.p + host_off;
         CUDA_TRY(cudaMemcpyAsync(hp, res_cols[k].p, (size_t)n_groups * esz, cudaMemcpyDeviceToHost, stream));
@@ -1007,6 +1090,8 @@ struct b2_exec {
     }
     size_t n_sel = cp.output_offsets.size();
     cols.assign(n_sel, b2_column{});
+    last_dev.assign(n_sel, DevColRef{});
+    last_rows = n;
     if (out_loc == B2_LOC_HOST && n) CUDA_TRY(h_out.reserve(n_sel * ((size_t)n * 8 + (size_t)words * 8)));
     for (size_t i = 0; i < n_sel; ++i) {
       uint32_t k = cp.output_offsets[i];
@@ -1015,6 +1100,7 @@ struct b2_exec {
       if (!n) continue;
       const uint8_t* d = (const uint8_t*)tn_run_pay.p + (size_t)k * limit * 8;
       const uint8_t* bm = (const uint8_t*)tn_bitmap.p + (size_t)k * words * 8;
+      last_dev[i] = DevColRef{d, (const unsigned long long*)bm, oc.kind, oc.field_tp, oc.field_flag};
       if (out_loc == B2_LOC_HOST) {
         uint8_t* hp = (uint8_t*)h_out.p + i * ((size_t)n * 8 + (size_t)words * 8);
         CUDA_TRY(cudaMemcpyAsync(hp, d, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
@@ -1106,6 +1192,10 @@ int32_t b2_exec_next_batch(b2_exec* h, uint64_t scan_rows, b2_batch* out) { retu
 int32_t b2_exec_collect_stats(b2_exec* h, b2_exec_stats* out) { *out = h->stats; return B2_OK; }
 int32_t b2_exec_last_error(b2_exec* h, b2_error_info* out) { *out = h->last_err; return B2_OK; }
 int32_t b2_exec_can_be_cached(b2_exec* h) { return (h->check_newer && !h->met_newer_any && !h->saw_lock) ? 1 : 0; }
+int32_t b2_exec_encode_batch(b2_exec* h, int32_t encode_type, int32_t location, b2_encoded_chunk* out) {
+  if (!h || !out) { g_last_error = "null argument"; return B2_ERR_INVALID_ARG; }
+  return h->encode_batch(encode_type, location, out);
+}
 void b2_exec_close(b2_exec* h) { delete h; }
 
 int32_t b2_exec_agg_partials(b2_exec* h, b2_agg_partials* out) {

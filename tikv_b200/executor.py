@@ -105,6 +105,14 @@ class BatchExecutor:
             err = B2Error(e.status, e.message.decode(), e.mysql_code, e.entry_index)
         return BatchResult(cols, kinds, fts, b.is_drained != ffi.DRAIN_REMAIN, err)
 
+    def encode_batch(self, encode_type):
+        """Chunk.rows_data of the batch just returned (runner.rs:1051-1088), encoded on the device, as bytes."""
+        out = ffi.EncodedChunk()
+        rc = self._L.b2_exec_encode_batch(self._h, encode_type, ffi.LOC_HOST, C.byref(out))
+        if rc != ffi.B2_OK:
+            raise B2Error(rc, self._L.b2_last_error_message().decode())
+        return C.string_at(out.rows_data, out.len) if out.len else b""
+
     def last_error(self):
         e = ffi.ErrorInfo()
         self._L.b2_exec_last_error(self._h, C.byref(e))
