@@ -315,6 +315,14 @@ typedef struct b2_encoded_chunk {
   int32_t location;
 } b2_encoded_chunk;
 int32_t b2_exec_encode_batch(b2_exec* h, int32_t encode_type, int32_t location, b2_encoded_chunk* out);
+/* BatchExecutor::take_scanned_range (interface.rs:70-75) -> RangesScanner::take_scanned_range
+ * (tidb_query_common/src/storage/scanner.rs:204-229), forward scans: the raw-key interval [lower, upper) covered since
+ * the previous call.  upper = key of the last row the MVCC scan returned + 0x00, or the end of the last range once the
+ * executor is drained.  The pointers stay valid until the next call on the handle. */
+int32_t b2_exec_take_scanned_range(b2_exec* h, const uint8_t** lower, uint32_t* lower_len, const uint8_t** upper, uint32_t* upper_len);
+/* RangesScanner::collect_scanned_rows_per_range (scanner.rs:196-201): rows returned by the MVCC scan inside each input
+ * range since the previous call.  *n_inout: capacity of `rows` in, number of ranges out. */
+int32_t b2_exec_collect_scanned_rows_per_range(b2_exec* h, uint64_t* rows, uint32_t* n_inout);
 /* storage_impl.rs:108-123: no newer-ts data and no lock seen */
 int32_t b2_exec_can_be_cached(b2_exec* h);
 void b2_exec_close(b2_exec* h);

@@ -398,3 +398,15 @@ def decimal_struct_value(cell):
         v = v * 10 ** 9 + w
     v //= 10 ** (fw * 9 - frac_cnt)
     return (-v if neg else v), frac_cnt
+
+
+def dec_bytes_memcmp(enc):
+    """Inverse of enc_bytes_memcmp (tikv_util/src/codec/bytes.rs:178-228)."""
+    out, pos = b"", 0
+    while True:
+        grp, marker = enc[pos:pos + 8], enc[pos + 8]
+        pad = 0xFF - marker
+        out += grp[:8 - pad]
+        pos += 9
+        if pad:
+            return out

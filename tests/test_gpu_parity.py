@@ -405,3 +405,31 @@ def test_encode_empty_and_errors(regions):
         assert ex.encode_batch(ffi.ENCODE_TYPE_CHUNK) == exp.encoded[1]
         with pytest.raises(Exception):
             ex.encode_batch(7)
+
+
+def test_take_scanned_range_and_rows_per_range(regions):
+    """BatchExecutor::take_scanned_range / collect_scanned_rows_per_range (scanner.rs:196-229) against the oracle's scan:
+    consecutive takes tile the request's key space, each upper bound is the last returned row + 0x00, and the per-range
+    row counts are what the MVCC scan returns range by range."""
+    host = regions[2].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    ranges = sc.split_ranges()
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(lt(col(sc.C1), const_int(0))).build()
+    scans = [orc.mvcc_scan(host, kvfmt.enc_bytes_memcmp(lo), kvfmt.enc_bytes_memcmp(hi))[1] for lo, hi in ranges]
+    all_rows = [kvfmt.dec_bytes_memcmp(k) for rows in scans for (k, _v) in rows]  # raw keys the scanner returns, in request order
+    per_range = [len(rows) for rows in scans]
+    with BatchExecutor(plan, ranges, host) as ex:
+        prev_hi, seen, got_per_range = None, 0, [0] * len(ranges)
+        while True:
+            r = ex.next_batch(150)
+            assert r.error is None
+            lo, hi = ex.take_scanned_range()
+            assert lo == (ranges[0][0] if prev_hi is None else prev_hi)
+            seen = ex.collect_exec_stats().write_processed_keys
+            for i, n in enumerate(ex.collect_scanned_rows_per_range()):
+                got_per_range[i] += n
+            if r.is_drained:
+                assert hi == ranges[-1][1]
+                break
+            assert hi == (all_rows[seen - 1] + b"\x00" if seen and hi != lo else lo)
+            prev_hi = hi
+        assert seen == len(all_rows) and got_per_range == per_range and sum(per_range) > 300

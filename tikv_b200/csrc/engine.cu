@@ -236,6 +236,12 @@ struct b2_exec {
 
   std::vector<SrcBlock> wblocks, dblocks;
   std::vector<std::vector<uint8_t>> range_lo, range_hi;  // encoded bounds per range (hi possibly cut by a lock)
+  std::vector<std::vector<uint8_t>> range_raw_lo, range_raw_hi;  // the caller's raw bounds (take_scanned_range)
+  std::vector<uint8_t> working_begin;                    // RangesScanner::working_range_begin_key (scanner.rs:204-229)
+  uint64_t last_row_taken = 0;                           // Counters::last_row at the previous take
+  uint64_t last_row_seen = 0;
+  DevBuf range_rows;                                     // per range: rows returned by the MVCC scan
+  std::vector<uint64_t> range_rows_taken;                // already handed out by collect_scanned_rows_per_range
   std::vector<int> range_lock_err;                      // 1 = range ends with KeyIsLocked
   std::vector<uint64_t> range_lock_ts;
   std::vector<Unit> units;
@@ -279,7 +285,8 @@ struct b2_exec {
     }
     for (auto& e : kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (DevBuf* b : {&tn_lists, &tn_counts, &tn_pair, &tn_pair_cnt, &tn_tmp, &tn_tmp_cnt, &tn_blk_pay, &tn_blk_null, &tn_run_pay, &tn_run_null, &tn_tmp_pay, &tn_tmp_null, &tn_bitmap}) b->release();
-    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &grp_keys, &grp_null, &grp_acc, &res_ptrs}) b->release();
+    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
+    enc_host.release();
     for (auto& b : res_cols) b.release();
     for (auto& b : res_bitmaps) b.release();
     h_out.release(); h_ctr.release();
@@ -353,6 +360,8 @@ struct b2_exec {
       range_hi.push_back(encode_memcomparable(ranges[i].end, ranges[i].end_len));
       range_lock_err.push_back(0);
       range_lock_ts.push_back(0);
+      range_raw_lo.emplace_back(ranges[i].start, ranges[i].start + ranges[i].start_len);
+      range_raw_hi.emplace_back(ranges[i].end, ranges[i].end + ranges[i].end_len);
     }
     // CF_LOCK (host memory): LatestKvPolicy::handle_lock for every lock inside a range, in key order
     if (src->lock && src->lock->n && isolation != B2_ISO_RC) {
@@ -507,6 +516,9 @@ struct b2_exec {
     memset(&z, 0, sizeof(z));
     z.err = ~0ull;
     CUDA_TRY(cudaMemcpyAsync(ctr_buf.p, &z, sizeof(z), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(range_rows.reserve(std::max<size_t>(1, range_raw_lo.size()) * 8));
+    CUDA_TRY(cudaMemsetAsync(range_rows.p, 0, std::max<size_t>(1, range_raw_lo.size()) * 8, stream));
+    range_rows_taken.assign(range_raw_lo.size(), 0);
     return B2_OK;
   }
   int read_counters(Counters* c) {
@@ -536,6 +548,7 @@ struct b2_exec {
     kev_used = 0;
   }
   void fill_stats(const Counters& c) {
+    last_row_seen = c.last_row;
     stats.write_entries_scanned = entries_scanned;
     stats.write_processed_keys = c.processed_keys;
     stats.processed_size = c.processed_size;
@@ -586,6 +599,7 @@ struct b2_exec {
     a.e_lo = u.e_lo; a.e_hi = u.e_hi;
     a.entry_base = wblocks[u.block_idx].entry_base;
     a.ctr = ctr();
+    a.range_rows = range_rows.p ? (unsigned long long*)range_rows.p + u.range_idx : nullptr;
     return a;
   }
 
@@ -767,6 +781,59 @@ struct b2_exec {
     stats.num_produced_rows += n_rows;
     return failed ? last_err.status : B2_OK;
   }
+
+  // ---- RangesScanner::take_scanned_range (tidb_query_common/src/storage/scanner.rs:204-229), forward scans ----
+  // [lower, upper): lower = where the previous take ended (first take: the first range's start); upper = the last row
+  // the MVCC scan returned so far + 0x00 (update_scanned_range_from_scanned_row :290-300), or the last range's end once
+  // drained.  Raw keys, like b2_key_range.
+  int entry_raw_key(uint64_t global_entry, std::vector<uint8_t>* raw) {
+    for (const SrcBlock& b : wblocks) {
+      if (global_entry < b.entry_base || global_entry >= b.entry_base + b.c.n) continue;
+      uint32_t e = (uint32_t)(global_entry - b.entry_base), off[2];
+      std::vector<uint8_t> enc;
+      if (src_loc == B2_LOC_HOST) { off[0] = b.c.key_offs[e]; off[1] = b.c.key_offs[e + 1]; enc.assign(b.c.keys + off[0], b.c.keys + off[1]); }
+      else {
+        CUDA_TRY(cudaMemcpy(off, b.c.key_offs + e, 8, cudaMemcpyDeviceToHost));
+        enc.resize(off[1] - off[0]);
+        CUDA_TRY(cudaMemcpy(enc.data(), b.c.keys + off[0], enc.size(), cudaMemcpyDeviceToHost));
+      }
+      if (enc.size() < 8) return fail(B2_ERR_CORRUPTED, "CF_WRITE key without timestamp");
+      int rl = raw_key_len(enc.data(), (uint32_t)enc.size() - 8);
+      if (rl < 0) return fail(B2_ERR_CORRUPTED, "bad memcomparable key");
+      raw->clear();
+      for (int j = 0; j < rl; ++j) raw->push_back((uint8_t)raw_at(enc.data(), (uint32_t)j));
+      return B2_OK;
+    }
+    return fail(B2_ERR_INVALID_ARG, "entry index outside every block");
+  }
+  std::vector<uint8_t> taken_lo, taken_hi;
+  int take_scanned_range(const uint8_t** lo, uint32_t* lo_len, const uint8_t** hi, uint32_t* hi_len) {
+    if (working_begin.empty() && !range_raw_lo.empty()) working_begin = range_raw_lo[0];
+    taken_lo = working_begin;
+    if (drained && !range_raw_hi.empty()) taken_hi = range_raw_hi.back();
+    else if (last_row_seen > last_row_taken) {
+      int rc = entry_raw_key(last_row_seen - 1, &taken_hi);
+      if (rc) return rc;
+      taken_hi.push_back(0);
+    } else taken_hi = taken_lo;
+    last_row_taken = last_row_seen;
+    working_begin = taken_hi;
+    *lo = taken_lo.data(); *lo_len = (uint32_t)taken_lo.size(); *hi = taken_hi.data(); *hi_len = (uint32_t)taken_hi.size();
+    return B2_OK;
+  }
+  // RangesScanner::collect_scanned_rows_per_range (scanner.rs:196-201): rows per input range since the last call
+  int collect_scanned_rows_per_range(uint64_t* out, uint32_t* n_inout) {
+    uint32_t n = (uint32_t)range_rows_taken.size();
+    if (out && n && range_rows.p) {
+      std::vector<uint64_t> cur(n);
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      CUDA_TRY(cudaMemcpy(cur.data(), range_rows.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+      for (uint32_t i = 0; i < n && i < *n_inout; ++i) { out[i] = cur[i] - range_rows_taken[i]; range_rows_taken[i] = cur[i]; }
+    }
+    *n_inout = n;
+    return B2_OK;
+  }
+
   // ---- response encoding of the batch just produced (runner.rs:1051-1088 encode_result_to_chunk) ----
   struct DevColRef { const void* data; const unsigned long long* bitmap; int kind; int field_tp; uint32_t field_flag; };
   std::vector<DevColRef> last_dev;  // device-resident columns of the last batch, in output order
@@ -1192,6 +1259,14 @@ int32_t b2_exec_next_batch(b2_exec* h, uint64_t scan_rows, b2_batch* out) { retu
 int32_t b2_exec_collect_stats(b2_exec* h, b2_exec_stats* out) { *out = h->stats; return B2_OK; }
 int32_t b2_exec_last_error(b2_exec* h, b2_error_info* out) { *out = h->last_err; return B2_OK; }
 int32_t b2_exec_can_be_cached(b2_exec* h) { return (h->check_newer && !h->met_newer_any && !h->saw_lock) ? 1 : 0; }
+int32_t b2_exec_take_scanned_range(b2_exec* h, const uint8_t** lower, uint32_t* lower_len, const uint8_t** upper, uint32_t* upper_len) {
+  if (!h || !lower || !lower_len || !upper || !upper_len) { g_last_error = "null argument"; return B2_ERR_INVALID_ARG; }
+  return h->take_scanned_range(lower, lower_len, upper, upper_len);
+}
+int32_t b2_exec_collect_scanned_rows_per_range(b2_exec* h, uint64_t* rows, uint32_t* n_inout) {
+  if (!h || !n_inout) { g_last_error = "null argument"; return B2_ERR_INVALID_ARG; }
+  return h->collect_scanned_rows_per_range(rows, n_inout);
+}
 int32_t b2_exec_encode_batch(b2_exec* h, int32_t encode_type, int32_t location, b2_encoded_chunk* out) {
   if (!h || !out) { g_last_error = "null argument"; return B2_ERR_INVALID_ARG; }
   return h->encode_batch(encode_type, location, out);

@@ -184,6 +184,7 @@ struct SmemView {
 struct EntryStats {  // per-thread partial statistics / checksum state
   unsigned long long keys, size, dflt, ck_x, ck_kvs, ck_bytes;
   unsigned int newer;
+  unsigned int last;  // 1 + largest block entry index a row was returned for
 };
 enum { P1_NONE = 0, P1_LIVE = 1, P1_REDO = 2 };
 
@@ -206,6 +207,7 @@ __device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A,
   const uint8_t* ek = view.kptr(e);
   ts.keys += 1;
   ts.size += (kl - 8) + ro.val_len;
+  ts.last = e + 1;
   if (MODE == PM_CHECKSUM) {
     // checksum_crc64_xor (checksum.rs:105-114): CRC-64/XZ of old_prefix ‖ raw_key[len(new_prefix)..] ‖ value
     int rawlen = raw_key_len(ek, kl - 8);
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
 
   // per-thread statistics, reduced once at the end
   EntryStats ts;
-  ts.keys = ts.size = ts.dflt = ts.ck_x = ts.ck_kvs = ts.ck_bytes = 0; ts.newer = 0;
+  ts.keys = ts.size = ts.dflt = ts.ck_x = ts.ck_kvs = ts.ck_bytes = 0; ts.newer = 0; ts.last = 0;
   unsigned long long t_live = 0;
   // no-group aggregation: one accumulator set per CTA in shared memory, flushed at the end
   __shared__ unsigned long long s_simple_acc[MODE == PM_AGG ? MAX_ACC_WORDS : 1];
@@ -477,7 +479,7 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
     Row row;
     Cells cells;
     EntryStats d;
-    d.keys = d.size = d.dflt = d.ck_x = d.ck_kvs = d.ck_bytes = 0; d.newer = 0;
+    d.keys = d.size = d.dflt = d.ck_x = d.ck_kvs = d.ck_bytes = 0; d.newer = 0; d.last = 0;
     int r1 = P1_NONE;
     if (e < A.c_hi) r1 = entry_phase1<MODE>(P, A, view, walk_hi, e, row, cells, d, crc_tab, lane);
     live = r1 == P1_LIVE;
@@ -501,6 +503,7 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
     }
     // ---- commit ----
     ts.keys += d.keys; ts.size += d.size; ts.dflt += d.dflt; ts.newer |= d.newer;
+    if (d.last > ts.last) ts.last = d.last;
     if (MODE == PM_CHECKSUM) { ts.ck_x ^= d.ck_x; ts.ck_kvs += d.ck_kvs; ts.ck_bytes += d.ck_bytes; }
     t_live += live;
 
@@ -749,9 +752,12 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
     t_live += __shfl_xor_sync(0xffffffffu, t_live, off);
     ts.dflt += __shfl_xor_sync(0xffffffffu, ts.dflt, off);
     ts.newer |= __shfl_xor_sync(0xffffffffu, ts.newer, off);
+    ts.last = max(ts.last, __shfl_xor_sync(0xffffffffu, ts.last, off));
   }
   if (lane == 0) {
     if (ts.keys) atomicAdd(&A.ctr->processed_keys, ts.keys);
+    if (ts.keys && A.range_rows) atomicAdd(A.range_rows, ts.keys);
+    if (ts.last) atomicMax(&A.ctr->last_row, A.entry_base + ts.last);
     if (ts.size) atomicAdd(&A.ctr->processed_size, ts.size);
     if (t_live) atomicAdd(&A.ctr->live_rows, t_live);
     if (ts.dflt) atomicAdd(&A.ctr->default_lookups, ts.dflt);

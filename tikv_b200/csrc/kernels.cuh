@@ -23,6 +23,7 @@ struct Counters {
   unsigned int agg_overflow;           // global group table full
   unsigned int n_groups;               // finalize: number of groups emitted
   unsigned int bad_prefix;             // checksum: key without new_prefix
+  unsigned long long last_row;         // 1 + largest global CF_WRITE entry index the MVCC scan returned a row for (take_scanned_range)
 };
 
 // Open-addressing group table in HBM (fast_hash_aggr_executor.rs:216-229 `Groups`): slot = hash(key) & mask,
@@ -47,6 +48,7 @@ struct ScanArgs {
   uint32_t c_lo, c_hi;  // chunk handled by this launch (runs *starting* in [c_lo, c_hi))
   uint64_t entry_base;  // global index of blk entry 0
   Counters* ctr;
+  unsigned long long* range_rows;   // rows the MVCC scan returned inside this unit's key range (scanned_rows_per_range), or nullptr
   // PM_SCAN
   unsigned long long* tile_status;  // n_tiles + 1 words, zeroed per launch; last word = ticket
   unsigned long long* out_data;     // n_out columns, each `out_cap` u64 cells

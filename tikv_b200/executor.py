@@ -105,6 +105,20 @@ class BatchExecutor:
             err = B2Error(e.status, e.message.decode(), e.mysql_code, e.entry_index)
         return BatchResult(cols, kinds, fts, b.is_drained != ffi.DRAIN_REMAIN, err)
 
+    def take_scanned_range(self):
+        """(lower_inclusive, upper_exclusive) raw keys covered since the previous call (scanner.rs:204-229)."""
+        lo, hi, ln, hn = C.c_void_p(), C.c_void_p(), C.c_uint32(), C.c_uint32()
+        rc = self._L.b2_exec_take_scanned_range(self._h, C.byref(lo), C.byref(ln), C.byref(hi), C.byref(hn))
+        if rc != ffi.B2_OK:
+            raise B2Error(rc, self._L.b2_last_error_message().decode())
+        return C.string_at(lo, ln.value) if ln.value else b"", C.string_at(hi, hn.value) if hn.value else b""
+
+    def collect_scanned_rows_per_range(self):
+        n = C.c_uint32(4096)
+        rows = (C.c_uint64 * 4096)()
+        self._L.b2_exec_collect_scanned_rows_per_range(self._h, rows, C.byref(n))
+        return [rows[i] for i in range(n.value)]
+
     def encode_batch(self, encode_type):
         """Chunk.rows_data of the batch just returned (runner.rs:1051-1088), encoded on the device, as bytes."""
         out = ffi.EncodedChunk()
