@@ -73,6 +73,17 @@ struct DevOrder { DevExpr e; uint8_t desc, et, is_unsigned, _pad; };
 
 enum PlanMode { PM_SCAN = 0, PM_AGG = 1, PM_TOPN = 2, PM_CHECKSUM = 3 };
 
+// A selection condition of the shape `column <cmp> constant` over an integer column of the exact-layout fast path
+struct FastCond {
+  int64_t imm;
+  uint8_t h;         // stored position of the column
+  uint8_t op;        // 0 <  1 <=  2 >  3 >=  4 ==  5 !=   (column on the left; plan_compile flips `const <cmp> column`)
+  uint8_t col_uns;   // compare the column as unsigned (field flag)
+  uint8_t imm_uns;   // the constant is unsigned
+  uint8_t zero_ext;  // decode: zero-extend (v2 UINT class)
+  uint8_t _p[3];
+};
+
 struct DevPlan {
   int32_t mode;
   int32_t n_cols;
@@ -101,6 +112,9 @@ struct DevPlan {
   DevOrder order[MAX_ORDER];
   uint8_t out_cols[MAX_COLS];
   uint8_t out_slow[MAX_COLS];  // indices into out_cols
+  int32_t n_fconds;            // == n_conds when every condition is a FastCond (else 0)
+  int32_t _fcpad;
+  FastCond fconds[MAX_CONDS];
   DevCol cols[MAX_COLS];
   DevNode nodes[MAX_NODES];
 };
@@ -670,6 +684,29 @@ B2_HD bool fast_row_probe(const DevPlan& P, Row& row) {
   if (((ld64(r.v + r.ids_off) ^ P.fast_ids) & (P.fast_n >= 8 ? ~0ull : ((1ull << (8 * P.fast_n)) - 1))) != 0) return false;
   row.o_lo = ld64(r.v + r.offs_off);
   row.o_hi = P.fast_n > 4 ? ld64(r.v + r.offs_off + 8) : 0;
+  if (P.fast_cls == (1u << P.fast_n) - 1u) {
+    // all stored columns are integer-class: the eight widths are checked at once, four 16-bit lanes per register.
+    // width = end - previous end (mod 2^16); it must be 1, 2, 4 or 8: (w & 0xfff0) == 0, w != 0, w & (w - 1) == 0.
+    // (A decreasing offset wraps to a width >= 2^16 - 64 and fails the first test; a row cannot climb past 2^16 in
+    // eight steps of at most 8.)  Lanes beyond fast_n hold row data, not offsets: they are forced to width 1.
+    const uint64_t H = 0x8000800080008000ull, ONE = 0x0001000100010001ull;
+    const uint64_t p_lo = row.o_lo << 16, p_hi = (row.o_hi << 16) | (row.o_lo >> 48);
+    uint64_t d_lo = ((row.o_lo | H) - (p_lo & ~H)) ^ ((row.o_lo ^ ~p_lo) & H);
+    uint64_t d_hi = ((row.o_hi | H) - (p_hi & ~H)) ^ ((row.o_hi ^ ~p_hi) & H);
+    const uint64_t m_lo = P.fast_n >= 4 ? ~0ull : ((1ull << (16 * P.fast_n)) - 1);
+    const uint64_t m_hi = P.fast_n >= 8 ? ~0ull : (P.fast_n <= 4 ? 0ull : ((1ull << (16 * (P.fast_n - 4))) - 1));
+    d_lo = (d_lo & m_lo) | (ONE & ~m_lo);
+    d_hi = (d_hi & m_hi) | (ONE & ~m_hi);
+    const uint64_t big = (d_lo | d_hi) & 0xfff0fff0fff0fff0ull;
+    const uint64_t zero = (((d_lo - ONE) & ~d_lo) | ((d_hi - ONE) & ~d_hi)) & H;  // exact: every lane is < 2^15 once `big` is 0
+    const uint64_t npow2 = (d_lo & (d_lo - ONE)) | (d_hi & (d_hi - ONE));         // no borrows once no lane is 0
+    if (big | zero) return false;
+    if (npow2) return false;
+    const uint32_t last = (uint32_t)(((P.fast_n <= 4 ? row.o_lo : row.o_hi) >> (((P.fast_n - 1) & 3) * 16)) & 0xffffu);
+    if (last > r.vals_len) return false;
+    row.fast = 1;
+    return true;
+  }
   uint32_t prev = 0, bad = 0;
 #pragma unroll
   for (int h = 0; h < 8; ++h) {
@@ -1052,6 +1089,28 @@ B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const 
 // AND of the selection conditions on one row (selection_executor.rs:81-195): sequential, stop at first false/NULL
 B2_HD int eval_conds(const DevPlan& P, const Row& row, const Cells& cells, bool* keep) {
   *keep = true;
+  if (row.fast && P.n_fconds > 0) {
+    // every condition is `integer column <cmp> constant` and the row has the exact layout: no NULLs, no decode errors,
+    // the column is read by stored position (impl_compare.rs:63-149 semantics through cmp_i64)
+    for (int i = 0; i < P.n_fconds; ++i) {
+      const FastCond f = P.fconds[i];
+      const uint32_t h = f.h;
+      const uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
+      const uint32_t start = h == 0 ? 0u : ((uint32_t)((h - 1 < 4 ? row.o_lo : row.o_hi) >> (((h - 1) & 3) * 16)) & 0xffffu);
+      const int c = cmp_i64((int64_t)fast_int_cell(row, start, end, f.zero_ext), f.col_uns, f.imm, f.imm_uns);
+      bool t;
+      switch (f.op) {
+        case 0: t = c < 0; break;
+        case 1: t = c <= 0; break;
+        case 2: t = c > 0; break;
+        case 3: t = c >= 0; break;
+        case 4: t = c == 0; break;
+        default: t = c != 0; break;
+      }
+      if (!t) { *keep = false; return DE_NONE; }
+    }
+    return DE_NONE;
+  }
   for (int i = 0; i < P.n_conds; ++i) {
     Value v;
     const DevExpr ex = P.conds[i];

@@ -292,6 +292,43 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
       else P.out_slow[P.n_out_slow++] = (uint8_t)i;
     }
   }
+  // selection conditions of the shape `integer column <cmp> constant` are evaluated by stored position on fast rows
+  P.n_fconds = 0;
+  if (P.fast_n > 0 && P.n_conds > 0) {
+    bool all = true;
+    for (int i = 0; i < P.n_conds && all; ++i) {
+      const DevExpr ex = P.conds[i];
+      all = false;
+      if (ex.n != 3) break;
+      const DevNode &a = P.nodes[ex.start], &b = P.nodes[ex.start + 1], &f = P.nodes[ex.start + 2];
+      if (f.kind != B2_RPN_FN || f.sig < 100 || f.sig >= 160 || f.sig % 10 != 0) break;
+      auto is_col = [&](const DevNode& n) { return n.kind == B2_RPN_COLUMN_REF && P.cols[n.imm].role == CR_NORMAL && P.cols[n.imm].kind == CK_INT; };
+      auto is_const = [&](const DevNode& n) { return n.kind == B2_RPN_CONST_INT || n.kind == B2_RPN_CONST_UINT; };
+      bool col_first;
+      if (is_col(a) && is_const(b)) col_first = true;
+      else if (is_const(a) && is_col(b)) col_first = false;
+      else break;
+      const DevNode& cn = col_first ? a : b;
+      const DevNode& kn = col_first ? b : a;
+      const DevCol& col = P.cols[cn.imm];
+      FastCond fc;
+      memset(&fc, 0, sizeof(fc));
+      fc.imm = kn.imm; fc.h = col.v2_hint; fc.col_uns = col.is_unsigned; fc.imm_uns = kn.is_unsigned; fc.zero_ext = col.v2_class != V2_INT;
+      int op;  // column on the left
+      switch (f.sig) {
+        case B2_SIG_LT_INT: op = col_first ? 0 : 2; break;
+        case B2_SIG_LE_INT: op = col_first ? 1 : 3; break;
+        case B2_SIG_GT_INT: op = col_first ? 2 : 0; break;
+        case B2_SIG_GE_INT: op = col_first ? 3 : 1; break;
+        case B2_SIG_EQ_INT: op = 4; break;
+        default: op = 5; break;
+      }
+      fc.op = (uint8_t)op;
+      P.fconds[i] = fc;
+      all = true;
+    }
+    if (all) P.n_fconds = P.n_conds;
+  }
   return B2_OK;
 }
 
