@@ -5,6 +5,7 @@ Data shape follows SURVEY.md §8(d)'s "dirty" variant: several versions per key,
 columns with defaults, both row formats in one region.
 """
 import random
+import struct
 
 import kvfmt
 from tikv_b200 import ffi
@@ -173,3 +174,56 @@ def is_agg(name):
 
 def split_ranges():
     return [kvfmt.table_range(TABLE, -1000, 50), kvfmt.table_range(TABLE, 50, 51), kvfmt.table_range(TABLE, 400, 1000), kvfmt.table_range(TABLE, 1200, 5000)]
+
+
+# ---- all-integer table: exercises the exact-layout fast path (SWAR width probe, conditions and outputs by stored position)
+INT_COLUMNS = [ColumnDef(100, pk_handle=True), ColumnDef(7, unsigned=True), ColumnDef(2), ColumnDef(11), ColumnDef(3, unsigned=True),
+               ColumnDef(5, tp=ffi.TP_LONG), ColumnDef(9), ColumnDef(4), ColumnDef(6, unsigned=True)]
+
+
+def int_region(seed, n_keys=500, corrupt=False):
+    """v2 rows holding exactly the 8 stored columns above with every width mix (1/2/4/8 bytes), some rows with a NULL or a
+    missing column (general path), optionally rows with a 3-byte integer or decreasing offsets (errors)."""
+    rng = random.Random(seed)
+    r = kvfmt.Region()
+    mags = [1 << 6, 1 << 14, 1 << 30, 1 << 62]
+    for h in range(n_keys):
+        cols = []
+        for cid, uns in ((7, True), (2, False), (11, False), (3, True), (5, False), (9, False), (4, False), (6, True)):
+            m = rng.choice(mags)
+            v = rng.randrange(0, 2 * m) if uns else rng.randrange(-m, m)
+            if cid == 5:
+                v = rng.randrange(-(1 << 31), 1 << 31) if rng.random() < 0.5 else rng.randrange(-100, 100)
+            cols.append((cid, v, "uint" if uns else "int"))
+        x = rng.random()
+        if x < 0.05:
+            k = rng.randrange(8)
+            cols[k] = (cols[k][0], None, "null")
+        elif x < 0.08:
+            cols.pop(rng.randrange(8))
+        val = bytearray(kvfmt.row_v2(cols))
+        if corrupt and 0.5 < x < 0.52 and len(cols) == 8:
+            # widen the first value to 3 bytes by shifting every offset up by one where possible: rewrite offsets by hand
+            offs_at = 6 + 8
+            ends = list(struct.unpack_from("<8H", val, offs_at))
+            if rng.random() < 0.5 and ends[1] - ends[0] >= 2:
+                ends[0] += 1            # first width + 1 (3, 5 or 9 bytes), second width - 1: not 1/2/4/8 somewhere
+            else:
+                ends[3], ends[4] = ends[4], ends[3]  # decreasing offsets
+            struct.pack_into("<8H", val, offs_at, *ends)
+        r.put(kvfmt.row_key(TABLE, h * 2 + 5), bytes(val), 5, 8)
+    return r
+
+
+def int_plans():
+    from tikv_b200.plan import ne
+    scan = lambda: Plan().table_scan(TABLE, INT_COLUMNS)
+    c = lambda i, **k: col(i, unsigned=INT_COLUMNS[i].flag & ffi.FLAG_UNSIGNED != 0, **k)
+    P = [("all", scan().build()),
+         ("lt_signed", scan().selection(lt(c(2), const_int(0))).build()),
+         ("const_on_left", scan().selection(gt(const_int(1000), c(3))).build(output_offsets=[3, 0, 8, 1, 1, 5])),
+         ("unsigned_vs_negative", scan().selection(gt(c(1), const_int(-5)), le(c(4), const_int(1 << 40))).build()),
+         ("eq_ne", scan().selection(ne(c(5), const_int(7)), ge(c(7), const_int(-(1 << 20)))).build(output_offsets=[7, 6, 5, 4, 3, 2, 1, 0])),
+         ("agg", scan().selection(lt(c(6), const_int(1 << 20))).aggregation([("count", const_int(1)), ("sum", c(1)), ("sum", c(2)), ("avg", c(8))], group_by=[c(5, tp=ffi.TP_LONG)]).build()),
+         ("topn", scan().selection(ge(c(3), const_int(0))).topn([(c(4), True), (c(2), False)], 40).build())]
+    return P

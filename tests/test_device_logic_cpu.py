@@ -143,3 +143,29 @@ def test_topn_device_logic_matches_oracle(name, plan, exact, keys, regions):
     for seed, n_blocks, ranges in ((1, 1, sc.WHOLE), (2, 3, sc.split_ranges())):
         region = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=n_blocks)
         assert_topn(emu.dag_handle(plan, ranges, region), orc.dag_handle(plan, ranges, region), exact, keys, ctx=f"{name}/seed{seed}")
+
+
+@pytest.mark.parametrize("name,plan", sc.int_plans(), ids=[n for n, _ in sc.int_plans()])
+def test_exact_layout_fast_path(name, plan):
+    """All-integer table: SWAR width probe, `column <cmp> const` conditions and outputs by stored position, every width
+    mix, signed/unsigned compares; rows with NULL / missing columns take the general path in the same batch."""
+    region = sc.int_region(3).build(read_ts=sc.READ_TS, n_write_blocks=2)
+    exp = orc.dag_handle(plan, sc.WHOLE, region)
+    got = emu.dag_handle(plan, sc.WHOLE, region)
+    assert exp.status == 0 and exp.n_rows > 0
+    if name == "topn":
+        from compare import assert_topn
+        assert_topn(got, exp, True, None, ctx=name)
+    else:
+        assert_same_rows(got, exp, ordered=name != "agg", ctx=name)
+
+
+def test_exact_layout_fast_path_corrupted_rows():
+    """3/5/9-byte integers and decreasing offsets: the probe must reject the row and the general path must raise the
+    reference's error at the same entry with the rows before it intact."""
+    region = sc.int_region(4, corrupt=True).build(read_ts=sc.READ_TS)
+    plan = sc.int_plans()[1][1]
+    exp = orc.dag_handle(plan, sc.WHOLE, region)
+    got = emu.dag_handle(plan, sc.WHOLE, region)
+    assert exp.status != 0 and got.status == exp.status
+    assert_same_rows(got, exp, ordered=True, ctx="corrupt")
