@@ -100,6 +100,8 @@ struct DevPlan {
   uint32_t fast_cls;     // bit h: stored column h (id order) is integer-class (width must be 1/2/4/8)
   uint32_t fast_uns;     // bit h: stored column h is zero-extended (unsigned)
   int8_t fast_out[8];    // PM_SCAN: output column fed by stored column h (first occurrence), or -1
+  uint8_t fast_round[8]; // PM_SCAN: fast_out[h] / 4 (output chunk round), 0xff when -1
+  uint16_t fast_slot[8]; // PM_SCAN: (fast_out[h] % 4) * 256: cell offset of its column inside the chunk buffer
   int32_t n_out_slow;    // PM_SCAN: outputs of a fast row that still go through cell_value (handle, Real, repeats ...)
   int32_t _fpad2;
   uint64_t fast_ids;   // the expected sorted non-null id bytes of such a row, packed little-endian (fast_n <= 8)
@@ -667,12 +669,9 @@ B2_HD uint32_t fast_end(const Row& row, int h) { return (uint32_t)((h < 4 ? row.
 // integer cell of a fast row: stored column h spans [start, end) of the value area (compat_v1.rs:13-38)
 B2_HD uint64_t fast_int_cell(const Row& row, uint32_t start, uint32_t end, bool zero_extend) {
   uint64_t u = ld64(row.rv.v + row.rv.vals_off + start);
-  uint32_t len = end - start;
-  if (len < 8) {
-    uint32_t sh = 64 - 8 * len;
-    u = zero_extend ? ((u << sh) >> sh) : (uint64_t)(((int64_t)(u << sh)) >> sh);
-  }
-  return u;
+  const uint32_t sh = (64u - 8u * (end - start)) & 63u;  // width 8 -> 0: branch-free, so neighbouring cells overlap
+  u <<= sh;
+  return zero_extend ? (u >> sh) : (uint64_t)((int64_t)u >> sh);
 }
 // Does this v2 row hold exactly the plan's columns (process_v2 would find column k at position v2_hint), all
 // non-null, offsets monotone and inside the value area, integer-class columns 1/2/4/8 bytes wide?  On success the

@@ -125,6 +125,7 @@ __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int 
 // that does not fit is simply read from HBM.
 enum { STAGE_LOOK = 8, STAGE_OFF_CAP = 1104, N_STAGES = 2, OBUF_COLS = 4, N_OBUF = 3, N_CNT = 4 };
 enum { OBUF_BYTES = OBUF_COLS * TILE * 8, ONULL_WORDS = OBUF_COLS * (TILE / 32) };
+static_assert(OBUF_COLS == 4 && TILE == 256, "DevPlan::fast_round / fast_slot (plan_compile.h) assume 4-column chunks of 256 rows");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -406,6 +407,7 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
     // HBM.  The decoding warps never wait for the look-back.
     if (MODE != PM_SCAN) return;
     const unsigned long long F_AGG = 1ull << 62, F_INC = 2ull << 62, VMASK = (1ull << 62) - 1;
+    uint32_t sw_q = 0, sw_phase = 0;
     for (uint32_t k = 0;; ++k) {
       mbar_wait_sleep(&s_cnt_ready[k % N_CNT], (k / N_CNT) & 1);
       const uint32_t tile = s_tile_of[k % N_CNT];
@@ -437,8 +439,9 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
       const unsigned long long base = out_base + excl;
       const unsigned int lim = base + total <= A.out_cap ? (unsigned int)total : (base < A.out_cap ? (unsigned int)(A.out_cap - base) : 0u);
       for (uint32_t r = 0; r < n_rounds; ++r) {
-        const uint32_t g = k * n_rounds + r, q = g % N_OBUF;
-        mbar_wait_sleep(&s_obuf_full[q], (g / N_OBUF) & 1);
+        const uint32_t q = sw_q;
+        mbar_wait_sleep(&s_obuf_full[q], sw_phase);
+        if (++sw_q == N_OBUF) { sw_q = 0; sw_phase ^= 1; }
         const int c0 = (int)r * OBUF_COLS;
         const int nc = P.n_out - c0 < OBUF_COLS ? P.n_out - c0 : OBUF_COLS;
         const unsigned long long* ob = obuf_base + (size_t)q * (OBUF_COLS * TILE);
@@ -472,6 +475,7 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
   // every byte access is an LDS) and on the HBM arrays (tiles that did not fit the stage, or that hold a row the window
   // cannot resolve: a version run longer than the look-ahead, a long value in CF_DEFAULT).  Returns true when the
   // shared-memory attempt must be repeated on the whole block; nothing has been committed in that case.
+  uint32_t ob_q = 0, ob_phase = 0;  // PM_SCAN: next output chunk buffer and how often the ring has wrapped (parity)
   auto tile_body = [&](const auto& view, const uint32_t walk_hi, const uint32_t k, const uint32_t tile) -> bool {
     using V = typename std::remove_cv<typename std::remove_reference<decltype(view)>::type>::type;
     const uint32_t e = A.c_lo + tile * TILE + tid;
@@ -521,8 +525,9 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
       const bool fast = live && row.fast;
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 2] = clock64();
       for (uint32_t r = 0; r < n_rounds; ++r) {
-        const uint32_t g = k * n_rounds + r, q = g % N_OBUF;
-        mbar_wait(&s_obuf_empty[q], ((g / N_OBUF) & 1) ^ 1);  // chunk buffer drained (N_OBUF chunks ago)
+        const uint32_t q = ob_q;  // chunk number (k * n_rounds + r) mod N_OBUF, its use count parity in ob_phase
+        mbar_wait(&s_obuf_empty[q], ob_phase ^ 1);  // chunk buffer drained (N_OBUF chunks ago)
+        if (++ob_q == N_OBUF) { ob_q = 0; ob_phase ^= 1; }
         if (r == 0) {
           if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 3] = clock64();
           // (posted after the wait: at most N_OBUF <= N_CNT - 1 tiles are ever pending at the scan warp)
@@ -545,8 +550,7 @@ __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constan
             for (int h = 0; h < 8; ++h) {
               if (h < P.fast_n) {
                 const uint32_t end = fast_end(row, h);
-                const int oc = P.fast_out[h];
-                if (oc >= 0 && (uint32_t)oc / OBUF_COLS == r) ob[(oc % OBUF_COLS) * TILE] = fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u);
+                if (P.fast_round[h] == r) ob[P.fast_slot[h]] = fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u);
                 prev = end;
               }
             }
