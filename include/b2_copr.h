@@ -24,8 +24,13 @@
 #ifndef B2_COPR_H_
 #define B2_COPR_H_
 
+#ifdef B2_NVRTC /* run-time compilation of the plan-specialised kernel: no host headers */
+typedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t;
+typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t;
+#else
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -216,8 +221,13 @@ typedef struct b2_exec_config {
   int32_t output_location;  /* B2_LOC_HOST: results copied to host memory; B2_LOC_DEVICE: device ptrs */
   int32_t staging_tiles;    /* 0 = default */
   uint64_t cuda_stream;     /* 0 = handle creates its own stream; else a cudaStream_t to run on */
-  uint64_t reserved[4];
+  int32_t jit;              /* plan-specialised kernel (compiled at run time, cached per plan): B2_JIT_AUTO = background
+                             * compile for large requests and switch when ready, B2_JIT_SYNC = wait for it at open,
+                             * B2_JIT_OFF = always the generic kernel.  Environment B2_JIT=auto|sync|off overrides. */
+  int32_t _pad;
+  uint64_t reserved[3];
 } b2_exec_config;
+enum { B2_JIT_AUTO = 0, B2_JIT_SYNC = 1, B2_JIT_OFF = 2 };
 
 /* ---- results ------------------------------------------------------------------------------ */
 enum { B2_COL_I64 = 0, B2_COL_F64 = 1, B2_COL_DECIMAL = 2 };
@@ -267,6 +277,7 @@ typedef struct b2_exec_stats {
   uint64_t kernel_launches;       /* launches of this library's kernels */
   uint64_t h2d_bytes;             /* bytes staged host->device by the engine (host-resident sources) */
   uint64_t d2h_bytes;             /* result bytes copied device->host */
+  uint64_t jit_launches;          /* of kernel_launches: launches of the plan-specialised (run-time compiled) scan kernel */
 } b2_exec_stats;
 
 typedef struct b2_error_info {
@@ -288,6 +299,10 @@ const char* b2_last_error_message(void);
 
 /* runner.rs:111-206 — B2_OK or B2_ERR_UNSUPPORTED (message says why) */
 int32_t b2_check_supported(const b2_dag_plan* plan);
+/* Prepared plan: compile the plan-specialised scan kernel for `device` now (blocking; cached for the process).  Later
+ * requests carrying the same plan start on it.  B2_ERR_UNSUPPORTED: run-time compilation (NVRTC) is not available, the
+ * generic kernels serve the plan. */
+int32_t b2_plan_prepare(const b2_dag_plan* plan, int32_t device);
 
 /* interface.rs:36-97 */
 int32_t b2_exec_open(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges,

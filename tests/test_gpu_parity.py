@@ -453,3 +453,37 @@ def test_exact_layout_fast_path(name, plan):
     assert exp.status != 0 and got.status == exp.status
     if name not in ("agg", "topn"):
         assert_same_rows(got, exp, ordered=True, ctx=name + "/corrupt")
+
+
+def test_plan_specialised_kernels_match_oracle(regions):
+    """The run-time compiled, plan-specialised kernels (jit.cu) against the oracle: scan, selection, simple / hash
+    aggregation and TopN, on the dirty region (every MVCC shape, v1 + v2 rows) and on the all-integer table."""
+    from tikv_b200.executor import BatchExecutor as BE
+    L = ffi.lib()
+    cases = [(n, p, regions[1].build(read_ts=sc.READ_TS, n_write_blocks=2), sc.split_ranges()) for n, p in PLANS if n in
+             ("scan_all", "sel_lt_const", "count_star", "group_by_small", "group_filter_offsets")]
+    ir = sc.int_region(3, n_keys=3000).build(read_ts=sc.READ_TS, n_write_blocks=2)
+    cases += [(n, p, ir, sc.WHOLE) for n, p in sc.int_plans() if n in ("const_on_left", "eq_ne", "agg", "topn")]
+    assert len(cases) >= 7
+    for name, plan, region, ranges in cases:
+        rc = L.b2_plan_prepare(C.byref(plan.c), 0)
+        assert rc == ffi.B2_OK, L.b2_last_error_message()
+        exp = orc.dag_handle(plan, ranges, region)
+        with BE(plan, ranges, region, jit=ffi.JIT_SYNC) as ex:
+            cols, kinds, is_drained = None, None, False
+            parts = []
+            while not is_drained:
+                r = ex.next_batch(700)
+                assert r.error is None
+                parts.append(r)
+                is_drained = r.is_drained
+            st = ex.collect_exec_stats()
+            assert st.jit_launches > 0 and st.jit_launches <= st.kernel_launches
+        got_rows = [row for r in parts for row in r.rows()]
+        if name == "topn":
+            assert got_rows == exp.rows(), name
+        elif sc.is_agg(name) or name == "agg":
+            key = lambda t: tuple((0, 0) if x is None else (1, x) for x in t)
+            assert sorted(got_rows, key=key) == sorted(exp.rows(), key=key), name
+        else:
+            assert got_rows == exp.rows(), name

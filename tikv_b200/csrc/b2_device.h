@@ -10,7 +10,9 @@
 //   components/tidb_query_datatype/src/codec/{datum.rs:1117-1155, datum_codec.rs:401-446}
 //   components/tidb_query_expr/src/{impl_compare.rs:63-240, impl_op.rs:8-127, impl_arithmetic.rs:42-398}
 #pragma once
+#ifndef B2_NVRTC
 #include <stdint.h>
+#endif
 
 #include "../../include/b2_copr.h"
 

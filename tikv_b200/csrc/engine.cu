@@ -19,7 +19,9 @@
 #include <cub/device/device_scan.cuh>
 
 #include "encode.cuh"
+#include "jit.h"
 #include "kernels.cuh"
+#include "plan_literal.h"
 #include "plan_compile.h"
 
 using namespace b2;
@@ -294,6 +296,32 @@ struct b2_exec {
   }
 
   Counters* ctr() { return (Counters*)ctr_buf.p; }
+
+  // ---- plan-specialised kernel (jit.cu): used as soon as its compilation has finished, the generic kernel until then ----
+  enum { JIT_AUTO = 0, JIT_SYNC = 1, JIT_OFF = 2 };
+  int jit_mode = JIT_AUTO;
+  bool jit_started = false;
+  std::shared_future<JitKernel*> jit_fut;
+  void jit_start() {
+    if (jit_started || jit_mode == JIT_OFF || cp.dev.mode == PM_CHECKSUM || !jit_available()) return;
+    jit_fut = jit_get(device, cp.dev);
+    jit_started = true;
+  }
+  const JitKernel* jit_ready() {
+    if (!jit_started) return nullptr;
+    if (jit_fut.wait_for(std::chrono::seconds(0)) != std::future_status::ready) return nullptr;
+    const JitKernel* k = jit_fut.get();
+    return k->ok ? k : nullptr;
+  }
+  // persistent grid = co-resident CTAs of whichever kernel the next launch uses
+  int scan_grid_for(int mode, size_t smem) {
+    if (const JitKernel* k = jit_ready()) return jit_max_blocks_per_sm(k, smem) * scan_num_sms();
+    return scan_max_grid(mode, smem);
+  }
+  cudaError_t scan_launch(const ScanArgs& a, int grid, size_t smem) {
+    if (const JitKernel* k = jit_ready()) { stats.jit_launches++; return jit_launch(k, a, grid, smem, stream); }
+    return launch_scan(cp.dev, a, grid, smem, stream);
+  }
 
   // ---- source setup ----
   int read_offs_end(const b2_cf_block& b, uint64_t* kb, uint64_t* vb) {
@@ -599,6 +627,7 @@ struct b2_exec {
     a.e_lo = u.e_lo; a.e_hi = u.e_hi;
     a.entry_base = wblocks[u.block_idx].entry_base;
     a.ctr = ctr();
+    a.read_ts = cp.dev.read_ts; a.isolation = cp.dev.isolation;
     a.range_rows = range_rows.p ? (unsigned long long*)range_rows.p + u.range_idx : nullptr;
     return a;
   }
@@ -659,9 +688,9 @@ struct b2_exec {
         size_t smem = setup_staging(&a, wblocks[u.block_idx], scan_out_stage_bytes());
         a.out_stage_off = 0;
         if (getenv("B2_TRACE") && !trace_done) { trace_buf.reserve(128 * 8 * 8); cudaMemsetAsync(trace_buf.p, 0, 128 * 8 * 8, stream); a.trace = (unsigned long long*)trace_buf.p; }
-        if (smem != scan_smem) { scan_smem = smem; scan_grid = scan_max_grid(PM_SCAN, smem); }
+        scan_grid = scan_grid_for(PM_SCAN, smem);
         kernel_begin();
-        CUDA_TRY(launch_scan(cp.dev, a, scan_grid, smem, stream));
+        CUDA_TRY(scan_launch(a, scan_grid, smem));
         kernel_end();
         CUDA_TRY(cudaMemcpyAsync(&ctr()->out_base, &ctr()->out_rows, 8, cudaMemcpyDeviceToDevice, stream));
         if (a.trace && !trace_done) {
@@ -959,9 +988,9 @@ struct b2_exec {
         a.tbl.keys = (unsigned long long*)tbl_keys.p; a.tbl.occ = (unsigned int*)tbl_occ.p; a.tbl.acc = (unsigned long long*)tbl_acc.p; a.tbl.cap = tbl_cap;
         a.smem_slots = smem_slots;
         size_t tot = setup_staging(&a, wblocks[u.block_idx], smem);
-        if (tot != grid_smem) { grid_smem = tot; grid = scan_max_grid(PM_AGG, tot); }
+        grid = scan_grid_for(PM_AGG, tot);
         kernel_begin();
-        CUDA_TRY(launch_scan(P, a, grid, tot, stream));
+        CUDA_TRY(scan_launch(a, grid, tot));
         kernel_end();
         release_block(u.block_idx);
         prefetch_after(ui);
@@ -1076,7 +1105,7 @@ struct b2_exec {
       size_t smem = topn_smem_bytes(cap);
       ScanArgs probe; memset(&probe, 0, sizeof(probe));
       size_t tot0 = setup_staging(&probe, wblocks[units[0].block_idx], smem);
-      int grid = scan_max_grid(PM_TOPN, std::max(tot0, smem));
+      int grid = scan_grid_for(PM_TOPN, std::max(tot0, smem));
       size_t isz = sizeof(TopItem);
       CUDA_TRY(tn_lists.reserve((size_t)grid * limit * isz)); CUDA_TRY(tn_counts.reserve((size_t)grid * 4));
       CUDA_TRY(tn_lvl_a.reserve((size_t)((grid + 7) / 8) * limit * isz)); CUDA_TRY(tn_lvl_a_cnt.reserve((size_t)((grid + 7) / 8) * 4));
@@ -1104,7 +1133,7 @@ struct b2_exec {
         size_t tot = setup_staging(&a, wblocks[u.block_idx], smem);
         CUDA_TRY(cudaMemsetAsync(tn_counts.p, 0, (size_t)grid * 4, stream));
         kernel_begin();
-        CUDA_TRY(launch_scan(P, a, (int)g, tot, stream));
+        CUDA_TRY(scan_launch(a, (int)g, tot));
         kernel_end();
         // unit top-N (sorted) lands in the second half of `pair`
         TopNLists unit_out; unit_out.items = pair + limit; unit_out.counts = pair_cnt + 1; unit_out.n_lists = 1; unit_out.stride = limit;
@@ -1223,6 +1252,17 @@ int32_t b2_check_supported(const b2_dag_plan* plan) {
   return rc;
 }
 
+// tooling: the compiled device plan as a C++ aggregate initialiser (plan-specialised kernel builds); returns its length
+extern "C" int64_t b2_plan_literal(const b2_dag_plan* plan, char* buf, uint64_t cap) {
+  CompiledPlan cp;
+  std::string msg;
+  int rc = compile_plan(plan, &cp, &msg);
+  if (rc) { g_last_error = msg; return -rc; }
+  std::string lit = plan_literal(cp.dev);
+  if (buf && cap) { size_t n = std::min<size_t>(lit.size(), (size_t)cap - 1); memcpy(buf, lit.data(), n); buf[n] = 0; }
+  return (int64_t)lit.size();
+}
+
 int32_t b2_exec_open(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src,
                      const b2_exec_config* cfg, b2_exec** out) {
   if (!plan || !src || !out) { g_last_error = "null argument"; return B2_ERR_INVALID_ARG; }
@@ -1242,7 +1282,32 @@ int32_t b2_exec_open(const b2_dag_plan* plan, const b2_key_range* ranges, uint32
   h->cp.dev.isolation = src->isolation_level;
   rc = h->setup_source(src, ranges, n_ranges);
   if (rc) { g_last_error = h->last_err.message; return rc; }
+  // plan-specialised kernel: B2_JIT=off|sync|auto (environment) overrides cfg->jit; `auto` compiles in the background
+  // for requests big enough to matter and switches over when the kernel is ready
+  h->jit_mode = cfg ? cfg->jit : b2_exec::JIT_AUTO;
+  if (const char* ev = getenv("B2_JIT")) h->jit_mode = !strcmp(ev, "off") ? b2_exec::JIT_OFF : (!strcmp(ev, "sync") ? b2_exec::JIT_SYNC : b2_exec::JIT_AUTO);
+  uint64_t total_entries = 0;
+  for (const Unit& u : h->units) total_entries += u.e_hi - u.e_lo;
+  if (h->jit_mode == b2_exec::JIT_SYNC || (h->jit_mode == b2_exec::JIT_AUTO && total_entries >= (1u << 20))) h->jit_start();
+  if (h->jit_mode == b2_exec::JIT_SYNC && h->jit_started) {
+    const JitKernel* k = h->jit_fut.get();
+    if (!k->ok) { g_last_error = "plan-specialised kernel: " + k->error; return B2_ERR_CUDA; }
+  }
   *out = h.release();
+  return B2_OK;
+}
+
+// Prepared plan: compile the plan-specialised kernel for `device` now (blocking), so that later requests with this plan
+// start on it.  B2_ERR_UNSUPPORTED when run-time compilation is not available in this process (the generic kernels work).
+extern "C" int32_t b2_plan_prepare(const b2_dag_plan* plan, int32_t device) {
+  CompiledPlan cp;
+  std::string msg;
+  int rc = compile_plan(plan, &cp, &msg);
+  if (rc) { g_last_error = msg; return rc; }
+  std::string why;
+  if (!jit_available(&why)) { g_last_error = "run-time compilation unavailable: " + why; return B2_ERR_UNSUPPORTED; }
+  const JitKernel* k = jit_get(device, cp.dev).get();
+  if (!k->ok) { g_last_error = "plan-specialised kernel: " + k->error; return B2_ERR_CUDA; }
   return B2_OK;
 }
 

@@ -1,0 +1,182 @@
+// Plan-specialised scan kernels, compiled at run time.
+//
+// The generic scan_kernel<MODE> interprets the device plan (DevPlan in a __grid_constant__ parameter): column tables,
+// RPN nodes, fast-path tables are all run-time data.  A pushed-down DAG repeats for thousands of regions, so the plan
+// is worth compiling once: this file builds a translation unit  "constant DevPlan literal + scan_body<MODE>"  with
+// NVRTC (sm_100a cubin), loads it through the driver API and caches the function per (device, plan).  With the plan a
+// compile-time constant the column loops unroll, dead paths (v1 datums, unused roles, the RPN stack machine, unused
+// modes) disappear and the hot loop shrinks by about a third.
+//
+// libnvrtc / libcuda are dlopen'ed: the library keeps loading (and the generic kernels keep working) where they are
+// absent.  The kernel sources are read from ../csrc relative to this shared object.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <cstdio>
+#include <cstring>
+#include <future>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "jit.h"
+#include "plan_literal.h"
+
+namespace b2 {
+
+namespace {
+
+struct Api {
+  bool ok = false;
+  std::string why;
+  // nvrtc
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  // driver
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+  std::string csrc_dir, cuda_inc;
+};
+
+template <class F>
+bool sym(void* lib, const char* name, F* out) {
+  *out = reinterpret_cast<F>(dlsym(lib, name));
+  return *out != nullptr;
+}
+
+Api& api() {
+  static Api a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* rtc = nullptr;
+    for (const char* n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"})
+      if ((rtc = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    void* drv = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!rtc) { a.why = "libnvrtc not found"; return; }
+    if (!drv) { a.why = "libcuda.so.1 not found"; return; }
+    bool ok = sym(rtc, "nvrtcCreateProgram", &a.CreateProgram) && sym(rtc, "nvrtcCompileProgram", &a.CompileProgram) &&
+              sym(rtc, "nvrtcGetProgramLogSize", &a.GetProgramLogSize) && sym(rtc, "nvrtcGetProgramLog", &a.GetProgramLog) &&
+              sym(rtc, "nvrtcGetCUBINSize", &a.GetCUBINSize) && sym(rtc, "nvrtcGetCUBIN", &a.GetCUBIN) && sym(rtc, "nvrtcDestroyProgram", &a.DestroyProgram) &&
+              sym(drv, "cuModuleLoadData", &a.ModuleLoadData) && sym(drv, "cuModuleGetFunction", &a.ModuleGetFunction) &&
+              sym(drv, "cuFuncSetAttribute", &a.FuncSetAttribute) &&
+              sym(drv, "cuOccupancyMaxActiveBlocksPerMultiprocessor", &a.OccupancyMaxActiveBlocksPerMultiprocessor) && sym(drv, "cuLaunchKernel", &a.LaunchKernel);
+    if (!ok) { a.why = "nvrtc / driver entry point missing"; return; }
+    Dl_info info;
+    if (!dladdr(reinterpret_cast<void*>(static_cast<bool (*)(std::string*)>(&jit_available)), &info) || !info.dli_fname) { a.why = "cannot locate the shared object"; return; }
+    std::string so = info.dli_fname;
+    size_t slash = so.rfind('/');
+    std::string dir = slash == std::string::npos ? "." : so.substr(0, slash);
+    a.csrc_dir = dir + "/../csrc";
+    FILE* f = fopen((a.csrc_dir + "/scan_kernel.cuh").c_str(), "r");
+    if (!f) { a.why = "kernel sources not found next to the library (" + a.csrc_dir + ")"; return; }
+    fclose(f);
+    a.ok = true;
+  });
+  return a;
+}
+
+struct Entry {
+  std::shared_future<JitKernel*> fut;
+};
+std::mutex g_mu;
+// leaked on purpose: a static destructor would block process exit on compilations still in flight
+std::map<std::string, Entry>& g_cache = *new std::map<std::string, Entry>();
+
+JitKernel* compile(int device, int mode, const std::string& literal) {
+  Api& a = api();
+  JitKernel* k = new JitKernel();
+  cudaSetDevice(device);
+  cudaFree(nullptr);  // make sure the primary context exists and is current on this thread
+  std::string src = "#define B2_NVRTC 1\n#include \"scan_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + literal +
+                    ";\n}\nextern \"C\" __global__ void __launch_bounds__(b2::TILE + 64, 2) b2_scan_jit(const __grid_constant__ b2::ScanArgs A) {\n"
+                    "  b2::scan_body<" + std::to_string(mode) + ">(b2::kJitPlan, A);\n}\n";
+  nvrtcProgram prog;
+  if (a.CreateProgram(&prog, src.c_str(), "b2_scan_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { k->error = "nvrtcCreateProgram failed"; return k; }
+  std::string inc = "-I" + a.csrc_dir;
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-DB2_NVRTC=1", "-default-device", inc.c_str(), "-I/usr/local/cuda/include"};
+  nvrtcResult rc = a.CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+  if (rc != NVRTC_SUCCESS) {
+    size_t n = 0;
+    a.GetProgramLogSize(prog, &n);
+    std::string log(n, 0);
+    if (n) a.GetProgramLog(prog, &log[0]);
+    k->error = "nvrtc: " + log.substr(0, 2000);
+    a.DestroyProgram(&prog);
+    return k;
+  }
+  size_t n = 0;
+  a.GetCUBINSize(prog, &n);
+  std::vector<char> cubin(n);
+  a.GetCUBIN(prog, cubin.data());
+  a.DestroyProgram(&prog);
+  CUmodule mod;
+  if (a.ModuleLoadData(&mod, cubin.data()) != CUDA_SUCCESS) { k->error = "cuModuleLoadData failed"; return k; }
+  CUfunction fn;
+  if (a.ModuleGetFunction(&fn, mod, "b2_scan_jit") != CUDA_SUCCESS) { k->error = "kernel symbol missing"; return k; }
+  k->fn = fn;
+  k->ok = true;
+  return k;
+}
+
+}  // namespace
+
+bool jit_available(std::string* why) {
+  Api& a = api();
+  if (!a.ok && why) *why = a.why;
+  return a.ok;
+}
+
+std::shared_future<JitKernel*> jit_get(int device, const DevPlan& plan) {
+  DevPlan p = plan;
+  p.read_ts = 0; p.isolation = 0;  // launch parameters (ScanArgs), not part of the specialisation
+  std::string key = std::to_string(device) + "|" + plan_literal(p);
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_cache.find(key);
+  if (it != g_cache.end()) return it->second.fut;
+  std::string literal = key.substr(key.find('|') + 1);
+  int mode = plan.mode;
+  std::shared_future<JitKernel*> fut = std::async(std::launch::async, [device, mode, literal] { return compile(device, mode, literal); }).share();
+  g_cache[key].fut = fut;
+  return fut;
+}
+
+int jit_max_blocks_per_sm(const JitKernel* k, size_t smem) {
+  int n = 0;
+  if (smem > k->max_dyn_smem) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (smem > k->max_dyn_smem && api().FuncSetAttribute((CUfunction)k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) == CUDA_SUCCESS) k->max_dyn_smem = smem;
+  }
+  if (api().OccupancyMaxActiveBlocksPerMultiprocessor(&n, (CUfunction)k->fn, TILE + 64, smem) != CUDA_SUCCESS || n < 1) n = 1;
+  return n;
+}
+
+cudaError_t jit_launch(const JitKernel* k, const ScanArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if (a.c_hi <= a.c_lo) return cudaSuccess;
+  uint32_t n_tiles = (a.c_hi - a.c_lo + TILE - 1) / TILE;
+  if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
+  void* params[] = {const_cast<ScanArgs*>(&a)};
+  if (smem > k->max_dyn_smem) {  // opt in to large dynamic shared memory (the limit excludes the kernel's static part)
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (smem > k->max_dyn_smem) {
+      if (api().FuncSetAttribute((CUfunction)k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+      k->max_dyn_smem = smem;
+    }
+  }
+  CUresult rc = api().LaunchKernel((CUfunction)k->fn, (unsigned)grid, 1, 1, TILE + 64, 1, 1, (unsigned)smem, (CUstream)s, params, nullptr);
+  if (rc != CUDA_SUCCESS) fprintf(stderr, "b2copr: cuLaunchKernel of the plan-specialised kernel failed: CUresult %d\n", (int)rc);
+  return rc == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;
+}
+
+}  // namespace b2

@@ -10,763 +10,13 @@
 // that key (walks its versions, decodes the row).  CTAs are persistent and pull 256-entry tiles.
 #include <cuda_runtime.h>
 
-#include <type_traits>
-
-#include "kernels.cuh"
+#include "scan_kernel.cuh"
 
 namespace b2 {
 
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void report_err(Counters* c, uint64_t global_entry, int code) {
-  atomicMin(&c->err, (unsigned long long)((global_entry << 8) | (unsigned)code));
-}
-
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
-  return *(const volatile unsigned long long*)p;
-}
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// ---- HBM group table ----------------------------------------------------------------------------------
-// returns slot index, or 0xffffffff when the table is full
-__device__ unsigned int table_find_or_insert(const AggTable& t, uint64_t key, bool is_null) {
-  if (is_null) {
-    if (ld_acquire_u32(&t.occ[t.cap]) != 2) atomicExch(&t.occ[t.cap], 2u);
-    return t.cap;
-  }
-  unsigned int mask = t.cap - 1;
-  unsigned int s = (unsigned int)mix64(key) & mask;
-  for (unsigned int probes = 0; probes < t.cap; ++probes) {
-    unsigned int o = ld_acquire_u32(&t.occ[s]);
-    if (o == 0) {
-      o = atomicCAS(&t.occ[s], 0u, 1u);
-      if (o == 0) {
-        t.keys[s] = key;
-        st_release_u32(&t.occ[s], 2u);
-        return s;
-      }
-    }
-    while (o == 1) o = ld_acquire_u32(&t.occ[s]);
-    if (t.keys[s] == key) return s;
-    s = (s + 1) & mask;
-  }
-  return 0xffffffffu;
-}
-
-// accumulate one aggregate argument into `acc` words (global or shared)
-//   COUNT: [cnt]            SUM/AVG(int): [cnt, sum of low 32 bits, sum of high 32 bits]   SUM/AVG(real): [cnt, f64]
-// The two 32-bit limb sums cannot overflow below 2^32 rows and give the exact i128 sum = hi * 2^32 + lo.
-template <typename Acc>
-__device__ __forceinline__ void acc_update(Acc* acc, const DevAgg& g, const Value& v) {
-  if (v.null) return;
-  atomicAdd(&acc[g.acc_off], 1ull);
-  if (g.kind == 0) return;
-  if (g.arg_et == 1) {
-    atomicAdd(reinterpret_cast<double*>(&acc[g.acc_off + 1]), bits_f64(v.bits));
-  } else {
-    unsigned long long lo = v.bits & 0xffffffffull;
-    unsigned long long hi = g.arg_unsigned ? (v.bits >> 32) : (unsigned long long)((long long)v.bits >> 32);
-    atomicAdd(&acc[g.acc_off + 1], lo);
-    atomicAdd(&acc[g.acc_off + 2], hi);
-  }
-}
-
-// barrier over the 256 row-decoding threads only (the scan kernel runs a 9th, producer-only warp)
-__device__ __forceinline__ void cta256_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// ---- TopN helpers --------------------------------------------------------------------------------------------
-// Candidate buffer of a CTA: `cap` item slots that never move plus a permutation `idx` (u16) of the slots.  Positions
-// [0, cnt) of `idx` are occupied; a new candidate takes position atomicAdd(cnt) -> slot idx[pos].  Compaction sorts the
-// permutation (bitonic network over positions, every thread owns one compare-exchange per step) and keeps the best
-// `limit` positions: only 2-byte indices are swapped, the 48-byte items are read in place.
-__device__ __forceinline__ unsigned short* topn_idx(TopItem* items, unsigned int cap) { return reinterpret_cast<unsigned short*>(items + cap); }
-
-__device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int limit, unsigned int* s_cnt, unsigned int* s_have_thr, TopItem* s_thr,
-                                 const DevPlan& P) {
-  const unsigned int tid = threadIdx.x, nt = TILE;  // always called by exactly 256 threads
-  unsigned short* idx = topn_idx(items, cap);
-  unsigned int cnt = *s_cnt;
-  for (unsigned int i = cnt + tid; i < cap; i += nt) items[idx[i]].nulls = 0x80000000u;  // free slots sort last
-  cta256_sync();
-  for (unsigned int k = 2; k <= cap; k <<= 1) {
-    for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-      for (unsigned int p = tid; p < cap / 2; p += nt) {
-        unsigned int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), x = i | j;
-        bool up = (i & k) == 0;
-        unsigned short ia = idx[i], ib = idx[x];
-        const TopItem& a = items[ia];
-        const TopItem& b = items[ib];
-        bool swap = up ? item_less(b, a, P) : item_less(a, b, P);
-        if (swap) { idx[i] = ib; idx[x] = ia; }
-      }
-      cta256_sync();
-    }
-  }
-  if (tid == 0) {
-    unsigned int keep = cnt < limit ? cnt : limit;
-    *s_cnt = keep;
-    if (keep == limit && limit > 0) { *s_thr = items[idx[limit - 1]]; *s_have_thr = 1; }
-  }
-  cta256_sync();
-}
-
-// ---- TMA bulk staging of a tile's bytes into shared memory --------------------------------------------------------
-// Each 256-entry tile's key bytes, value bytes and offset slices are contiguous in the block's heaps, so one elected
-// thread moves them with four 1-D bulk copies (cp.async.bulk, completion on an mbarrier) while the CTA is still
-// decoding the previous tile.  Threads then parse rows out of shared memory: HBM sees only full-line streaming
-// reads instead of 32 scattered byte addresses per warp instruction.
-// Stage capacities (key / value bytes) are chosen per launch from the block's average entry size (ScanArgs); a tile
-// that does not fit is simply read from HBM.
-enum { STAGE_LOOK = 8, STAGE_OFF_CAP = 1104, N_STAGES = 2, OBUF_COLS = 4, N_OBUF = 3, N_CNT = 4 };
-enum { OBUF_BYTES = OBUF_COLS * TILE * 8, ONULL_WORDS = OBUF_COLS * (TILE / 32) };
-static_assert(OBUF_COLS == 4 && TILE == 256, "DevPlan::fast_round / fast_slot (plan_compile.h) assume 4-column chunks of 256 rows");
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-// same, for the service warps whose waits last a whole tile: let the hardware suspend the thread (time hint in ns)
-// instead of burning issue slots on polls
-__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-struct TileMeta {
-  uint32_t tile;            // tile index, >= n_tiles means "no more work"
-  uint32_t staged;          // 1: entries [w_lo, w_hi) are resident in the stage
-  uint32_t w_lo, w_hi;
-  long long keys_adj, vals_adj;  // stage_ptr + adj + heap_offset = address of that heap byte in shared memory
-  int koff_adj, voff_adj;        // stage_off_ptr[adj + entry] = offset of `entry`
-};
-
-// A tile's window of the block, resident in shared memory (all four pointers are shared-memory addresses, which the
-// compiler can see: every access below compiles to LDS with 32-bit addressing).  Only entries [w_lo, w_hi) exist here.
-struct SmemView {
-  const uint8_t* skeys; const uint32_t* skoff; const uint8_t* svals; const uint32_t* svoff;
-  static constexpr bool kWholeBlock = false;
-  __device__ __forceinline__ const uint8_t* kptr(uint32_t i) const { return skeys + skoff[i]; }
-  __device__ __forceinline__ uint32_t klen(uint32_t i) const { return skoff[i + 1] - skoff[i]; }
-  __device__ __forceinline__ const uint8_t* vptr(uint32_t i) const { return svals + svoff[i]; }
-  __device__ __forceinline__ uint32_t vlen(uint32_t i) const { return svoff[i + 1] - svoff[i]; }
-};
-
-// ---- per-entry front end: MVCC resolve -> row open/split -> predicate (or CRC in PM_CHECKSUM) ----------------------
-struct EntryStats {  // per-thread partial statistics / checksum state
-  unsigned long long keys, size, dflt, ck_x, ck_kvs, ck_bytes;
-  unsigned int newer;
-  unsigned int last;  // 1 + largest block entry index a row was returned for
-};
-enum { P1_NONE = 0, P1_LIVE = 1, P1_REDO = 2 };
-
-// The thread sitting on the first version of a user key resolves that key.  P1_REDO: the shared-memory window was not
-// enough (run longer than the look-ahead, or a long value in CF_DEFAULT) and nothing has been committed: the caller
-// repeats the entry on the whole block.
-template <int MODE, class V>
-__device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A, const V& view, uint32_t walk_hi, uint32_t e, Row& row, Cells& cells,
-                                            EntryStats& ts, const unsigned long long* crc_tab, unsigned int lane) {
-  bool start = (e == A.e_lo) || !same_user_key(view, e - 1, e);
-  if (!start) return P1_NONE;
-  RunOut ro;
-  resolve_run(view, e, A.e_hi, walk_hi, P.read_ts, P.isolation, A.dflt, &ro);
-  if (ro.truncated) return P1_REDO;
-  ts.newer |= ro.met_newer;
-  ts.dflt += ro.dflt_lookup;
-  if (ro.err) { report_err(A.ctr, A.entry_base + e, ro.err); return P1_NONE; }
-  if (!ro.found) return P1_NONE;
-  const uint32_t kl = view.klen(e);
-  const uint8_t* ek = view.kptr(e);
-  ts.keys += 1;
-  ts.size += (kl - 8) + ro.val_len;
-  ts.last = e + 1;
-  if (MODE == PM_CHECKSUM) {
-    // checksum_crc64_xor (checksum.rs:105-114): CRC-64/XZ of old_prefix ‖ raw_key[len(new_prefix)..] ‖ value
-    int rawlen = raw_key_len(ek, kl - 8);
-    bool okp = rawlen >= 0 && (uint32_t)rawlen >= A.ck_new_prefix_len;
-    for (uint32_t j = 0; okp && j < A.ck_new_prefix_len; ++j) okp = raw_at(ek, j) == A.ck_new_prefix[j];
-    if (rawlen < 0) report_err(A.ctr, A.entry_base + e, DE_BAD_USER_KEY);
-    else if (!okp) { atomicExch(&A.ctr->bad_prefix, 1u); report_err(A.ctr, A.entry_base + e, DE_BAD_RECORD_KEY); }
-    else {
-      const unsigned long long* tab = crc_tab + (lane & 15);  // 16 interleaved copies: lane l only touches bank pair l % 16
-      unsigned long long c = A.ck_init_state;
-      for (uint32_t j = A.ck_new_prefix_len; j < (uint32_t)rawlen; ++j) c = tab[((uint32_t)(c ^ raw_at(ek, j)) & 0xffu) * 16] ^ (c >> 8);
-      const uint8_t* vp = ro.val;
-      uint32_t vn = ro.val_len, j = 0;
-      for (; j + 8 <= vn; j += 8) {  // 8 value bytes per unaligned word load
-        unsigned long long w = ld64(vp + j);
-#pragma unroll
-        for (int b = 0; b < 8; ++b) { c = tab[((uint32_t)(c ^ w) & 0xffu) * 16] ^ (c >> 8); w >>= 8; }
-      }
-      if (j < vn) {
-        unsigned long long w = ld64(vp + j);
-        for (; j < vn; ++j) { c = tab[((uint32_t)(c ^ w) & 0xffu) * 16] ^ (c >> 8); w >>= 8; }
-      }
-      ts.ck_x ^= ~c;
-      ts.ck_kvs += 1;
-      ts.ck_bytes += (unsigned long long)rawlen + ro.val_len + A.ck_old_prefix_len - A.ck_new_prefix_len;
-    }
-    return P1_NONE;
-  }
-  row.enc_key = ek;
-  row.enc_key_len = kl - 8;
-  row.commit_ts = ro.commit_ts;
-  int err = row_open(ro.val, ro.val_len, &row.rv);
-  if (!err) err = row_split(P, row, cells);
-  bool keep = false;
-  if (!err) err = eval_conds(P, row, cells, &keep);
-  if (err) { report_err(A.ctr, A.entry_base + e, err); return P1_NONE; }
-  return keep ? P1_LIVE : P1_NONE;
-}
-
-// ---- the fused scan kernel -------------------------------------------------------------------------------
-struct SmemTable {  // per-CTA group table (dynamic shared memory): keys | acc | occ
-  unsigned long long* keys;
-  unsigned long long* acc;
-  unsigned int* occ;
-  unsigned int slots;
-};
-
 template <int MODE>
 __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ unsigned int s_warp_cnt[2][TILE / 32];  // by tile parity: a fast warp may start the next tile while others still read
-  __shared__ unsigned int s_tbl_used;
-
-  const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint32_t n_tiles = (A.c_hi - A.c_lo + TILE - 1) / TILE;
-  const unsigned long long out_base = MODE == PM_SCAN ? A.ctr->out_base : 0ull;  // stable during this launch
-
-  SmemTable st;
-  st.slots = 0;
-  if (MODE == PM_AGG && P.has_group && A.smem_slots) {
-    st.slots = A.smem_slots;
-    st.keys = reinterpret_cast<unsigned long long*>(dyn_smem);
-    st.acc = st.keys + st.slots;
-    st.occ = reinterpret_cast<unsigned int*>(st.acc + (size_t)st.slots * P.acc_words);
-    for (unsigned int i = tid; i < st.slots; i += TILE) st.occ[i] = 0;
-    for (unsigned int i = tid; i < st.slots * P.acc_words; i += TILE) st.acc[i] = 0;
-    if (tid == 0) s_tbl_used = 0;
-    __syncthreads();
-  }
-
-  // PM_TOPN: per-CTA candidate buffer (dynamic shared memory) + current threshold
-  __shared__ unsigned int s_top_cnt, s_top_have_thr;
-  __shared__ TopItem s_top_thr;
-  TopItem* top_items = reinterpret_cast<TopItem*>(dyn_smem);
-  if (MODE == PM_TOPN) {
-    if (tid == 0) {
-      s_top_cnt = 0; s_top_have_thr = 0;
-      if (A.topn_seed && P.limit > 0 && *A.topn_seed_cnt >= (unsigned int)P.limit) { s_top_thr = A.topn_seed[P.limit - 1]; s_top_have_thr = 1; }
-    }
-    for (unsigned int i = tid; i < A.topn_cap; i += blockDim.x) topn_idx(top_items, A.topn_cap)[i] = (unsigned short)i;
-    __syncthreads();
-  }
-
-  // PM_CHECKSUM: bytewise CRC-64/XZ table, replicated 16x (entry i of copy c at [i * 16 + c]) so that the 64-bit
-  // lookups of a half-warp never share a bank pair
-  unsigned long long* crc_tab = reinterpret_cast<unsigned long long*>(dyn_smem);
-  if (MODE == PM_CHECKSUM) {
-    for (unsigned int i = tid; i < 256 * 16; i += blockDim.x) crc_tab[i] = crc64_table_entry(i >> 4);
-    __syncthreads();
-  }
-
-  // per-thread statistics, reduced once at the end
-  EntryStats ts;
-  ts.keys = ts.size = ts.dflt = ts.ck_x = ts.ck_kvs = ts.ck_bytes = 0; ts.newer = 0; ts.last = 0;
-  unsigned long long t_live = 0;
-  // no-group aggregation: one accumulator set per CTA in shared memory, flushed at the end
-  __shared__ unsigned long long s_simple_acc[MODE == PM_AGG ? MAX_ACC_WORDS : 1];
-  if (MODE == PM_AGG) {
-    for (unsigned int i = tid; i < MAX_ACC_WORDS; i += blockDim.x) s_simple_acc[i] = 0;
-  }
-
-  // ---- tile pipeline --------------------------------------------------------------------------------------------
-  // Warp 8 is the producer: it claims tiles, reads the four offsets that bound a tile's bytes and issues the bulk
-  // copies, running up to N_STAGES tiles ahead.  Warps 0-7 decode.  full[s]: producer -> consumers (bytes landed, meta
-  // published); empty[s]: consumers -> producer (stage may be refilled).
-  __shared__ __align__(8) unsigned long long s_full[N_STAGES];
-  __shared__ __align__(8) unsigned long long s_empty[N_STAGES];
-  __shared__ TileMeta s_meta[N_STAGES];
-  // PM_SCAN: consumers -> scan warp.  cnt_ready[k % N_CNT]: tile k's row count (and tile index) posted;
-  // obuf_full / obuf_empty[q]: output chunk buffer q handed to the scan warp / drained to HBM
-  __shared__ __align__(8) unsigned long long s_cnt_ready[N_CNT], s_obuf_full[N_OBUF], s_obuf_empty[N_OBUF];
-  __shared__ unsigned int s_total[N_CNT], s_tile_of[N_CNT];
-  __shared__ unsigned int s_redo[4];  // per tile (mod 4): some thread could not resolve its row inside the shared-memory window
-  unsigned char* stage_base = dyn_smem + A.stage_off;
-  const uint32_t STAGE_KEY_CAP = A.stage_key_cap, STAGE_VAL_CAP = A.stage_val_cap;
-  const uint32_t STAGE_BYTES = STAGE_KEY_CAP + STAGE_VAL_CAP + 2 * STAGE_OFF_CAP;
-  // PM_SCAN output chunk buffers (dynamic shared memory): N_OBUF x [OBUF_COLS][TILE] values, then the NULL masks
-  unsigned long long* obuf_base = reinterpret_cast<unsigned long long*>(dyn_smem + A.out_stage_off);
-  unsigned int* onull_base = reinterpret_cast<unsigned int*>(dyn_smem + A.out_stage_off + N_OBUF * OBUF_BYTES);
-  const uint32_t n_rounds = P.n_out > 0 ? (uint32_t)(P.n_out + OBUF_COLS - 1) / OBUF_COLS : 1u;
-  if (MODE == PM_SCAN)
-    for (unsigned int i = tid; i < N_OBUF * ONULL_WORDS; i += blockDim.x) onull_base[i] = 0;
-  if (tid == 0) {
-    for (int i = 0; i < N_STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], TILE / 32); }
-    for (int i = 0; i < N_CNT; ++i) mbar_init(&s_cnt_ready[i], 1);
-    for (int i = 0; i < 4; ++i) s_redo[i] = 0;
-    for (int i = 0; i < N_OBUF; ++i) { mbar_init(&s_obuf_full[i], TILE / 32); mbar_init(&s_obuf_empty[i], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();  // last CTA-wide barrier: from here on the two roles only meet through the mbarriers
-
-  if (wid == TILE / 32) {
-    if (lane == 0) {
-      // software-pipelined by one tile: the ticket and the four bounding offsets of tile k+1 are fetched while the
-      // producer would otherwise idle on empty[slot]; only the bulk copies themselves wait for the stage
-      uint32_t nx_tile, nx_wlo = 0, nx_whi = 0, nx_k0 = 0, nx_k1 = 0, nx_v0 = 0, nx_v1 = 0;
-      auto claim = [&](uint32_t k) {
-        // PM_SCAN claims tiles in order so that the decoupled look-back only ever waits on running CTAs
-        if (MODE == PM_SCAN) nx_tile = (uint32_t)atomicAdd(&A.tile_status[n_tiles], 1ull);
-        else nx_tile = blockIdx.x + k * gridDim.x;
-        if (nx_tile < n_tiles && A.staging) {
-          uint32_t e0 = A.c_lo + nx_tile * TILE;
-          uint32_t e1 = e0 + TILE < A.c_hi ? e0 + TILE : A.c_hi;
-          nx_wlo = e0 > A.e_lo ? e0 - 1 : e0;
-          nx_whi = e1 + STAGE_LOOK < A.e_hi ? e1 + STAGE_LOOK : A.e_hi;
-          nx_k0 = A.blk.koff[nx_wlo]; nx_k1 = A.blk.koff[nx_whi]; nx_v0 = A.blk.voff[nx_wlo]; nx_v1 = A.blk.voff[nx_whi];
-        }
-      };
-      // (ordered mode claims late instead: a ticket held early would stall every successor's look-back)
-      if (MODE != PM_SCAN) claim(0);
-      for (uint32_t k = 0;; ++k) {
-        const int slot = (int)(k % N_STAGES);
-        TileMeta m;
-        m.staged = 0; m.w_lo = 0; m.w_hi = 0; m.keys_adj = 0; m.vals_adj = 0; m.koff_adj = 0; m.voff_adj = 0;
-        if (MODE == PM_SCAN) { mbar_wait_sleep(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1); claim(k); }
-        m.tile = nx_tile;
-        const uint32_t w_lo = nx_wlo, w_hi = nx_whi, k0 = nx_k0, k1 = nx_k1, v0 = nx_v0, v1 = nx_v1;
-        if (MODE != PM_SCAN) mbar_wait_sleep(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1);
-        uint32_t tx = 0;
-        if (m.tile < n_tiles && A.staging) {
-          unsigned long long ka = (unsigned long long)(A.blk.keys + k0), va = (unsigned long long)(A.blk.vals + v0);
-          unsigned long long oa = (unsigned long long)(A.blk.koff + w_lo), ob = (unsigned long long)(A.blk.voff + w_lo);
-          uint32_t kpad = (uint32_t)(ka & 15), vpad = (uint32_t)(va & 15), opad = (uint32_t)(oa & 15), qpad = (uint32_t)(ob & 15);
-          uint32_t kbytes = (kpad + (k1 - k0) + 15) & ~15u, vbytes = (vpad + (v1 - v0) + 15) & ~15u;
-          uint32_t obytes = (opad + (w_hi - w_lo + 1) * 4 + 15) & ~15u, qbytes = (qpad + (w_hi - w_lo + 1) * 4 + 15) & ~15u;
-          if (kbytes + 16 <= STAGE_KEY_CAP && vbytes + 16 <= STAGE_VAL_CAP && obytes <= STAGE_OFF_CAP && qbytes <= STAGE_OFF_CAP) {
-            m.staged = 1; m.w_lo = w_lo; m.w_hi = w_hi;
-            m.keys_adj = (long long)kpad - (long long)k0; m.vals_adj = (long long)vpad - (long long)v0;
-            m.koff_adj = (int)(opad / 4) - (int)w_lo; m.voff_adj = (int)(qpad / 4) - (int)w_lo;
-            s_meta[slot] = m;
-            unsigned char* st = stage_base + (size_t)slot * STAGE_BYTES;
-            tx = kbytes + vbytes + obytes + qbytes;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // consumers' generic reads of this stage vs. the async writes
-            mbar_expect_tx(&s_full[slot], tx);
-            bulk_g2s(st, (const void*)(ka - kpad), kbytes, &s_full[slot]);
-            bulk_g2s(st + STAGE_KEY_CAP, (const void*)(va - vpad), vbytes, &s_full[slot]);
-            bulk_g2s(st + STAGE_KEY_CAP + STAGE_VAL_CAP, (const void*)(oa - opad), obytes, &s_full[slot]);
-            bulk_g2s(st + STAGE_KEY_CAP + STAGE_VAL_CAP + STAGE_OFF_CAP, (const void*)(ob - qpad), qbytes, &s_full[slot]);
-          }
-        }
-        if (!tx) {
-          s_meta[slot] = m;
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_full[slot])) : "memory");
-        }
-        if (m.tile >= n_tiles) break;
-        if (MODE != PM_SCAN) claim(k + 1);
-      }
-    }
-    return;
-  }
-
-  if (wid == TILE / 32 + 1) {
-    // ---- scan warp (PM_SCAN): turns each tile's row count into its global output base (decoupled look-back, one
-    // warp wide: lane l inspects tile (j - l); the nearest tile that already knows its inclusive prefix ends the walk,
-    // the aggregates in between are summed with shuffles), then drains the tile's output chunks from shared memory to
-    // HBM.  The decoding warps never wait for the look-back.
-    if (MODE != PM_SCAN) return;
-    const unsigned long long F_AGG = 1ull << 62, F_INC = 2ull << 62, VMASK = (1ull << 62) - 1;
-    uint32_t sw_q = 0, sw_phase = 0;
-    for (uint32_t k = 0;; ++k) {
-      mbar_wait_sleep(&s_cnt_ready[k % N_CNT], (k / N_CNT) & 1);
-      const uint32_t tile = s_tile_of[k % N_CNT];
-      if (tile >= n_tiles) break;
-      const unsigned long long total = s_total[k % N_CNT];
-      unsigned long long excl = 0;
-      if (tile == 0) {
-        if (lane == 0) atomicExch(&A.tile_status[0], F_INC | total);
-      } else {
-        if (lane == 0) atomicExch(&A.tile_status[tile], F_AGG | total);
-        long long j = (long long)tile - 1;
-        for (;;) {
-          long long idx = j - (long long)lane;
-          unsigned long long sres = idx >= 0 ? ld_volatile_u64(&A.tile_status[idx]) : F_INC;  // before tile 0: prefix 0
-          unsigned int flag = (unsigned int)(sres >> 62);
-          unsigned int m_inc = __ballot_sync(0xffffffffu, flag == 2), m_zero = __ballot_sync(0xffffffffu, flag == 0);
-          unsigned int upto = m_inc ? (__ffs(m_inc) - 1) : 31;             // lanes 0..upto matter
-          unsigned int need = upto == 31 ? 0xffffffffu : ((2u << upto) - 1);
-          if (m_zero & need) continue;                                       // a needed predecessor has not published yet
-          unsigned long long v = (lane <= upto) ? (sres & VMASK) : 0ull;
-          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-          excl += v;
-          if (m_inc) break;
-          j -= 32;
-        }
-        if (lane == 0) atomicExch(&A.tile_status[tile], F_INC | (excl + total));
-      }
-      if (lane == 0 && total) atomicAdd(&A.ctr->out_rows, total);
-      const unsigned long long base = out_base + excl;
-      const unsigned int lim = base + total <= A.out_cap ? (unsigned int)total : (base < A.out_cap ? (unsigned int)(A.out_cap - base) : 0u);
-      for (uint32_t r = 0; r < n_rounds; ++r) {
-        const uint32_t q = sw_q;
-        mbar_wait_sleep(&s_obuf_full[q], sw_phase);
-        if (++sw_q == N_OBUF) { sw_q = 0; sw_phase ^= 1; }
-        const int c0 = (int)r * OBUF_COLS;
-        const int nc = P.n_out - c0 < OBUF_COLS ? P.n_out - c0 : OBUF_COLS;
-        const unsigned long long* ob = obuf_base + (size_t)q * (OBUF_COLS * TILE);
-        unsigned long long* dst = A.out_data + (size_t)c0 * A.out_cap + base;
-        for (unsigned int i = lane; i < lim; i += 32) {
-#pragma unroll
-          for (int c = 0; c < OBUF_COLS; ++c)
-            if (c < nc) dst[(size_t)c * A.out_cap + i] = ob[c * TILE + i];
-        }
-        // NULL cells are rare: the bitmap is pre-filled with ones and only cleared where needed
-        unsigned int* on = onull_base + q * ONULL_WORDS;
-        unsigned int w = on[lane];  // ONULL_WORDS == 32: word (column c, rows 32 j ..) at [c * 8 + j]
-        if (w) {
-          on[lane] = 0;
-          const int c = (int)(lane / (TILE / 32));
-          while (w) {
-            unsigned int bit = __ffs(w) - 1;
-            w &= w - 1;
-            unsigned long long row_at = base + (lane % (TILE / 32)) * 32 + bit;
-            if (row_at < A.out_cap) atomicAnd(&A.out_bitmap[(size_t)(c0 + c) * (A.out_cap / 64) + (row_at >> 6)], ~(1ull << (row_at & 63)));
-          }
-        }
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_obuf_empty[q])) : "memory");
-      }
-    }
-    return;
-  }
-
-  // One tile, front end to back end, over a view of the block.  Instantiated twice: on the shared-memory window (hot:
-  // every byte access is an LDS) and on the HBM arrays (tiles that did not fit the stage, or that hold a row the window
-  // cannot resolve: a version run longer than the look-ahead, a long value in CF_DEFAULT).  Returns true when the
-  // shared-memory attempt must be repeated on the whole block; nothing has been committed in that case.
-  uint32_t ob_q = 0, ob_phase = 0;  // PM_SCAN: next output chunk buffer and how often the ring has wrapped (parity)
-  auto tile_body = [&](const auto& view, const uint32_t walk_hi, const uint32_t k, const uint32_t tile) -> bool {
-    using V = typename std::remove_cv<typename std::remove_reference<decltype(view)>::type>::type;
-    const uint32_t e = A.c_lo + tile * TILE + tid;
-    bool live = false;
-    Row row;
-    Cells cells;
-    EntryStats d;
-    d.keys = d.size = d.dflt = d.ck_x = d.ck_kvs = d.ck_bytes = 0; d.newer = 0; d.last = 0;
-    int r1 = P1_NONE;
-    if (e < A.c_hi) r1 = entry_phase1<MODE>(P, A, view, walk_hi, e, row, cells, d, crc_tab, lane);
-    live = r1 == P1_LIVE;
-    if (!V::kWholeBlock) {
-      if (__any_sync(0xffffffffu, r1 == P1_REDO) && lane == 0) s_redo[k & 3] = 1;
-    }
-    unsigned int warp_off = 0, total = 0, lane_off = 0;
-    if (MODE == PM_SCAN) {
-      // ---- ordered compaction: ballot/popc inside the warp, smem across warps, look-back across tiles ----
-      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 0] = clock64();
-      unsigned int bal = __ballot_sync(0xffffffffu, live);
-      lane_off = __popc(bal & ((1u << lane) - 1));
-      if (lane == 0) s_warp_cnt[k & 1][wid] = __popc(bal);
-      cta256_sync();
-      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 1] = clock64();
-    } else if (!V::kWholeBlock) {
-      cta256_sync();  // the vote below
-    }
-    if (!V::kWholeBlock) {
-      if (s_redo[k & 3]) return true;
-    }
-    // ---- commit ----
-    ts.keys += d.keys; ts.size += d.size; ts.dflt += d.dflt; ts.newer |= d.newer;
-    if (d.last > ts.last) ts.last = d.last;
-    if (MODE == PM_CHECKSUM) { ts.ck_x ^= d.ck_x; ts.ck_kvs += d.ck_kvs; ts.ck_bytes += d.ck_bytes; }
-    t_live += live;
-
-    if (MODE == PM_SCAN) {
-#pragma unroll
-      for (int w = 0; w < TILE / 32; ++w) {
-        unsigned int c = s_warp_cnt[k & 1][w];
-        if (w < (int)wid) warp_off += c;
-        total += c;
-      }
-      // Selected rows go to shared memory at their tile-local compacted position, OBUF_COLS columns per chunk; the
-      // scan warp (warp 9) turns the tile's row count into its global output base and drains the chunks to HBM as
-      // contiguous 8-byte runs, so the look-back latency never stalls the decode.
-      const unsigned int pos = warp_off + lane_off;
-      const bool fast = live && row.fast;
-      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 2] = clock64();
-      for (uint32_t r = 0; r < n_rounds; ++r) {
-        const uint32_t q = ob_q;  // chunk number (k * n_rounds + r) mod N_OBUF, its use count parity in ob_phase
-        mbar_wait(&s_obuf_empty[q], ob_phase ^ 1);  // chunk buffer drained (N_OBUF chunks ago)
-        if (++ob_q == N_OBUF) { ob_q = 0; ob_phase ^= 1; }
-        if (r == 0) {
-          if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 3] = clock64();
-          // (posted after the wait: at most N_OBUF <= N_CNT - 1 tiles are ever pending at the scan warp)
-          if (tid == 0) { s_total[k % N_CNT] = total; s_tile_of[k % N_CNT] = tile; asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready[k % N_CNT])) : "memory"); }
-        }
-        if (live) {
-          unsigned long long* ob = obuf_base + (size_t)q * (OBUF_COLS * TILE) + pos;
-          auto put = [&](int oc) {  // general cell: any role / kind, may be NULL
-            Value v;
-            int err = cell_value(P, row, cells, P.out_cols[oc], &v);
-            if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; }
-            ob[(oc % OBUF_COLS) * TILE] = v.null ? 0ull : v.bits;
-            if (v.null) atomicOr(&onull_base[q * ONULL_WORDS + (oc % OBUF_COLS) * (TILE / 32) + (pos >> 5)], 1u << (pos & 31));
-          };
-          if (fast) {
-            // exact-layout row: the (at most 8) stored integer columns are decoded by stored position, so every shift
-            // is a compile-time constant; the value goes from the staged row bytes to the chunk buffer in one step
-            uint32_t prev = 0;
-#pragma unroll
-            for (int h = 0; h < 8; ++h) {
-              if (h < P.fast_n) {
-                const uint32_t end = fast_end(row, h);
-                if (P.fast_round[h] == r) ob[P.fast_slot[h]] = fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u);
-                prev = end;
-              }
-            }
-            for (int j = 0; j < P.n_out_slow; ++j)  // handle / Real / repeated columns of such a row
-              if ((uint32_t)P.out_slow[j] / OBUF_COLS == r) put(P.out_slow[j]);
-          } else {
-            const int c_end = (int)(r + 1) * OBUF_COLS < P.n_out ? (int)(r + 1) * OBUF_COLS : P.n_out;
-            for (int oc = (int)r * OBUF_COLS; oc < c_end; ++oc) put(oc);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_obuf_full[q])) : "memory");
-      }
-      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 7] = clock64();
-    } else if (MODE == PM_TOPN) {
-      // BatchTopN: keep the `limit` smallest rows under the order-by key.  A row is a candidate only if it beats
-      // the CTA's current threshold (the limit-th best seen so far); candidates are sorted when the buffer fills.
-      if (live) {
-        TopItem it;
-        int err = make_item(P, row, cells, A.entry_base + e, &it);
-        if (err) report_err(A.ctr, A.entry_base + e, err);
-        else if (!s_top_have_thr || item_less(it, s_top_thr, P)) {
-          unsigned int pos = atomicAdd(&s_top_cnt, 1u);
-          top_items[topn_idx(top_items, A.topn_cap)[pos]] = it;  // pos < topn_cap: the buffer is compacted whenever fewer than TILE slots remain
-        }
-      }
-      cta256_sync();
-      if (s_top_cnt + TILE > A.topn_cap) cta_topn_compact(top_items, A.topn_cap, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
-    } else if (MODE == PM_AGG) {
-      // BatchSimpleAggregation / BatchFastHashAggregation.  Rows of one warp that share a group key are combined with
-      // warp reductions first (match.any + redux); the group's leader lane then issues one atomic per accumulator
-      // word, into the CTA's shared-memory table when the key is resident there, else into the HBM table.
-      Value gk;
-      gk.bits = 0; gk.null = false;
-      bool ok = live;
-      if (live && P.has_group) {
-        int err = eval_expr(P, P.group, row, cells, &gk, nullptr);  // calc_groups_each_row
-        if (err) { report_err(A.ctr, A.entry_base + e, err); ok = false; }
-        else if (gk.null) gk.bits = 0;
-        else if (P.group_et == 1 && bits_f64(gk.bits) == 0.0) gk.bits = 0;  // -0.0 and 0.0 are one group
-      }
-      const unsigned int active = __ballot_sync(0xffffffffu, ok);
-      if (ok) {
-        unsigned int peers = active;
-        if (P.has_group) {
-          const unsigned int nm = __ballot_sync(active, gk.null);
-          peers = __match_any_sync(active, gk.bits) & (gk.null ? nm : ~nm);
-        }
-        const bool leader = (unsigned int)(__ffs(peers) - 1) == lane;
-        const bool solo = (peers & (peers - 1)) == 0;
-        unsigned long long* acc = nullptr;
-        if (leader) {
-          if (!P.has_group) acc = s_simple_acc;
-          else {
-            if (st.slots && !gk.null) {
-              unsigned int mask = st.slots - 1, s = (unsigned int)(mix64(gk.bits) >> 20) & mask;
-              for (int probes = 0; probes < 8; ++probes) {
-                unsigned int o = *(volatile unsigned int*)&st.occ[s];
-                if (o == 0 && *(volatile unsigned int*)&s_tbl_used < (st.slots >> 1) + (st.slots >> 2)) {
-                  o = atomicCAS(&st.occ[s], 0u, 1u);
-                  if (o == 0) {
-                    st.keys[s] = gk.bits;
-                    __threadfence_block();
-                    atomicExch(&st.occ[s], 2u);
-                    atomicAdd(&s_tbl_used, 1u);
-                    acc = st.acc + (size_t)s * P.acc_words;
-                    break;
-                  }
-                }
-                if (o == 0) break;  // table is at its load limit: go to HBM
-                while (o == 1) o = *(volatile unsigned int*)&st.occ[s];
-                if (*(volatile unsigned long long*)&st.keys[s] == gk.bits) { acc = st.acc + (size_t)s * P.acc_words; break; }
-                s = (s + 1) & mask;
-              }
-            }
-            if (!acc) {
-              unsigned int gslot = table_find_or_insert(A.tbl, gk.bits, gk.null);
-              if (gslot == 0xffffffffu) atomicExch(&A.ctr->agg_overflow, 1u);
-              else acc = A.tbl.acc + (size_t)gslot * P.acc_words;
-            }
-          }
-        }
-        for (int a = 0; a < P.n_aggs; ++a) {
-          const DevAgg g = P.aggs[a];
-          Value v;
-          int err2 = eval_expr(P, g.arg, row, cells, &v, nullptr);
-          if (err2) report_err(A.ctr, A.entry_base + e, err2);
-          const bool has = !err2 && !v.null;
-          const unsigned int cnt = solo ? (has ? 1u : 0u) : __reduce_add_sync(peers, has ? 1u : 0u);
-          unsigned long long* w = acc + g.acc_off;  // only dereferenced by a leader that found a slot
-          const bool commit = leader && acc != nullptr && cnt != 0;
-          if (g.kind == 0) {
-            if (commit) atomicAdd(&w[0], (unsigned long long)cnt);
-          } else if (g.arg_et == 1) {
-            double sum = has ? bits_f64(v.bits) : 0.0;
-            if (!solo) {
-              const double mine = sum;
-              sum = 0.0;
-              for (unsigned int mm = peers; mm; mm &= mm - 1) sum += __shfl_sync(peers, mine, __ffs(mm) - 1);  // lane order
-            }
-            if (commit) { atomicAdd(&w[0], (unsigned long long)cnt); atomicAdd(reinterpret_cast<double*>(&w[1]), sum); }
-          } else {
-            const uint32_t lo = has ? (uint32_t)v.bits : 0u, hi = has ? (uint32_t)(v.bits >> 32) : 0u;
-            unsigned long long lo_sum, hi_sum;
-            if (solo) {
-              lo_sum = lo;
-              hi_sum = g.arg_unsigned ? (unsigned long long)hi : (unsigned long long)(long long)(int32_t)hi;
-            } else {  // 16-bit pieces: 32 of them cannot overflow a 32-bit redux
-              const unsigned int s0 = __reduce_add_sync(peers, lo & 0xffffu), s1 = __reduce_add_sync(peers, lo >> 16);
-              lo_sum = (unsigned long long)s0 + ((unsigned long long)s1 << 16);
-              const unsigned int t0 = __reduce_add_sync(peers, hi & 0xffffu);
-              if (g.arg_unsigned) hi_sum = (unsigned long long)t0 + ((unsigned long long)__reduce_add_sync(peers, hi >> 16) << 16);
-              else hi_sum = (unsigned long long)((long long)__reduce_add_sync(peers, (int)hi >> 16) * 65536ll + (long long)t0);
-            }
-            if (commit) { atomicAdd(&w[0], (unsigned long long)cnt); atomicAdd(&w[1], lo_sum); atomicAdd(&w[2], hi_sum); }
-          }
-        }
-      }
-    }
-    return false;
-  };
-
-  for (uint32_t k = 0;; ++k) {
-    const int cur = (int)(k % N_STAGES);
-    long long tc0 = clock64();
-    mbar_wait(&s_full[cur], (k / N_STAGES) & 1);
-    if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) { A.trace[k * 8 + 4] = tc0; A.trace[k * 8 + 5] = clock64(); }
-    const TileMeta m = s_meta[cur];
-    const uint32_t tile = m.tile;
-    if (tile >= n_tiles) {
-      if (MODE == PM_SCAN && tid == 0) {  // tell the scan warp there is no tile k
-        s_tile_of[k % N_CNT] = tile;
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready[k % N_CNT])) : "memory");
-      }
-      break;
-    }
-    if (tid == 0) s_redo[(k + 2) & 3] = 0;  // last read two tiles ago, next written two tiles ahead
-    bool redo = true;
-    if (m.staged) {
-      unsigned char* st = stage_base + (size_t)cur * STAGE_BYTES;
-      SmemView sv;
-      sv.skeys = st + m.keys_adj;
-      sv.svals = st + STAGE_KEY_CAP + m.vals_adj;
-      sv.skoff = reinterpret_cast<const uint32_t*>(st + STAGE_KEY_CAP + STAGE_VAL_CAP) + m.koff_adj;
-      sv.svoff = reinterpret_cast<const uint32_t*>(st + STAGE_KEY_CAP + STAGE_VAL_CAP + STAGE_OFF_CAP) + m.voff_adj;
-      redo = tile_body(sv, m.w_hi < A.e_hi ? m.w_hi : A.e_hi, k, tile);
-    }
-    if (redo) tile_body(A.blk, A.e_hi, k, tile);
-    if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 6] = clock64();
-    __syncwarp();  // this warp is done with stage `cur`: let the producer refill it
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[cur])) : "memory");
-  }
-  // ---- epilogue: flush CTA-private state ----
-  if (MODE == PM_CHECKSUM) {
-    for (int off = 16; off > 0; off >>= 1) {
-      ts.ck_x ^= __shfl_xor_sync(0xffffffffu, ts.ck_x, off);
-      ts.ck_kvs += __shfl_xor_sync(0xffffffffu, ts.ck_kvs, off);
-      ts.ck_bytes += __shfl_xor_sync(0xffffffffu, ts.ck_bytes, off);
-    }
-    if (lane == 0 && ts.ck_kvs) { atomicXor(&A.ctr->checksum, ts.ck_x); atomicAdd(&A.ctr->total_kvs, ts.ck_kvs); atomicAdd(&A.ctr->total_bytes, ts.ck_bytes); }
-  }
-  if (MODE == PM_TOPN) {
-    cta256_sync();
-    cta_topn_compact(top_items, A.topn_cap, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
-    unsigned int keep = s_top_cnt;
-    for (unsigned int i = tid; i < keep; i += TILE) A.topn.items[(size_t)blockIdx.x * A.topn.stride + i] = top_items[topn_idx(top_items, A.topn_cap)[i]];
-    if (tid == 0) A.topn.counts[blockIdx.x] = keep;
-  }
-  if (MODE == PM_AGG) {
-    if (!P.has_group) {
-      cta256_sync();
-      for (int w = (int)tid; w < P.acc_words; w += TILE) {
-        bool is_real = false;
-        for (int a = 0; a < P.n_aggs; ++a)
-          if (P.aggs[a].kind != 0 && P.aggs[a].arg_et == 1 && P.aggs[a].acc_off + 1 == w) is_real = true;
-        unsigned long long x = s_simple_acc[w];
-        if (is_real) { double dd = bits_f64(x); if (dd != 0.0) atomicAdd(reinterpret_cast<double*>(&A.tbl.acc[w]), dd); }
-        else if (x) atomicAdd(&A.tbl.acc[w], x);
-      }
-    } else if (st.slots) {
-      cta256_sync();
-      for (unsigned int s = tid; s < st.slots; s += TILE) {
-        if (st.occ[s] != 2) continue;
-        unsigned int gslot = table_find_or_insert(A.tbl, st.keys[s], false);
-        if (gslot == 0xffffffffu) { atomicExch(&A.ctr->agg_overflow, 1u); continue; }
-        for (int a = 0; a < P.n_aggs; ++a) {
-          const DevAgg g = P.aggs[a];
-          const unsigned long long* src = st.acc + (size_t)s * P.acc_words + g.acc_off;
-          unsigned long long* dst = A.tbl.acc + (size_t)gslot * P.acc_words + g.acc_off;
-          if (src[0] == 0) continue;
-          atomicAdd(&dst[0], src[0]);
-          if (g.kind == 0) continue;
-          if (g.arg_et == 1) atomicAdd(reinterpret_cast<double*>(&dst[1]), bits_f64(src[1]));
-          else { atomicAdd(&dst[1], src[1]); atomicAdd(&dst[2], src[2]); }
-        }
-      }
-    }
-  }
-  // statistics
-  for (int off = 16; off > 0; off >>= 1) {
-    ts.keys += __shfl_xor_sync(0xffffffffu, ts.keys, off);
-    ts.size += __shfl_xor_sync(0xffffffffu, ts.size, off);
-    t_live += __shfl_xor_sync(0xffffffffu, t_live, off);
-    ts.dflt += __shfl_xor_sync(0xffffffffu, ts.dflt, off);
-    ts.newer |= __shfl_xor_sync(0xffffffffu, ts.newer, off);
-    ts.last = max(ts.last, __shfl_xor_sync(0xffffffffu, ts.last, off));
-  }
-  if (lane == 0) {
-    if (ts.keys) atomicAdd(&A.ctr->processed_keys, ts.keys);
-    if (ts.keys && A.range_rows) atomicAdd(A.range_rows, ts.keys);
-    if (ts.last) atomicMax(&A.ctr->last_row, A.entry_base + ts.last);
-    if (ts.size) atomicAdd(&A.ctr->processed_size, ts.size);
-    if (t_live) atomicAdd(&A.ctr->live_rows, t_live);
-    if (ts.dflt) atomicAdd(&A.ctr->default_lookups, ts.dflt);
-    if (ts.newer) atomicOr(&A.ctr->met_newer, 1u);
-  }
+  scan_body<MODE>(P, A);
 }
 
 static int g_num_sms = 0;
@@ -780,6 +30,7 @@ static int num_sms() {
   return g_num_sms;
 }
 
+int scan_num_sms() { return num_sms(); }
 size_t scan_stage_bytes(uint32_t key_cap, uint32_t val_cap) { return (size_t)N_STAGES * (key_cap + val_cap + 2 * STAGE_OFF_CAP); }
 uint32_t scan_stage_entries() { return TILE + STAGE_LOOK + 1; }
 size_t scan_out_stage_bytes() { return (size_t)N_OBUF * OBUF_BYTES + (size_t)N_OBUF * ONULL_WORDS * 4; }

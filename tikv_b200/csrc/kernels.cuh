@@ -1,6 +1,8 @@
 // Kernel-side structures and launch wrappers shared by kernels.cu (device) and engine.cu (host).
 #pragma once
+#ifndef B2_NVRTC
 #include <cuda_runtime.h>
+#endif
 
 #include "b2_device.h"
 
@@ -47,6 +49,9 @@ struct ScanArgs {
   uint32_t e_lo, e_hi;  // entries of the block inside the key range
   uint32_t c_lo, c_hi;  // chunk handled by this launch (runs *starting* in [c_lo, c_hi))
   uint64_t entry_base;  // global index of blk entry 0
+  uint64_t read_ts;     // snapshot timestamp of the request
+  int32_t isolation;    // B2_ISO_* of the request
+  int32_t _pad0;
   Counters* ctr;
   unsigned long long* range_rows;   // rows the MVCC scan returned inside this unit's key range (scanned_rows_per_range), or nullptr
   // PM_SCAN
@@ -80,9 +85,11 @@ struct GenArgs {
   const uint32_t* row_val_off;     // exclusive scan of value bytes per row (n_rows + 1)
 };
 
+#ifndef B2_NVRTC
 // launchers (kernels.cu)
 cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t smem, cudaStream_t s);
 int scan_max_grid(int mode, size_t smem);  // occupancy-based persistent grid size
+int scan_num_sms();
 size_t scan_stage_bytes(uint32_t key_cap, uint32_t val_cap);  // dynamic shared memory needed by the tile stages
 size_t scan_crc_table_bytes();             // PM_CHECKSUM replicated CRC table
 size_t scan_out_stage_bytes();             // PM_SCAN output transpose buffer
@@ -105,5 +112,7 @@ cudaError_t launch_bounds_search(const BlockView* blocks, uint32_t n_blocks, con
 cudaError_t launch_gen_sizes(const b2_gen_spec& spec, uint32_t* row_entries, uint32_t* row_val_bytes, cudaStream_t s);
 cudaError_t launch_gen_write(const GenArgs& a, cudaStream_t s);
 cudaError_t launch_fill_u64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t s);
+
+#endif  // !B2_NVRTC
 
 }  // namespace b2

@@ -73,12 +73,12 @@ def _read_batch(b, location):
 
 
 class BatchExecutor:
-    def __init__(self, plan, ranges, region, output=ffi.LOC_HOST, stream=0):
+    def __init__(self, plan, ranges, region, output=ffi.LOC_HOST, stream=0, jit=ffi.JIT_AUTO):
         self._L = ffi.lib()
         self._plan, self._region = plan, region  # keep ctypes memory alive
         self._kr, self._keep = key_ranges(ranges)
         cfg = ffi.ExecConfig()
-        cfg.output_location, cfg.cuda_stream = output, stream
+        cfg.output_location, cfg.cuda_stream, cfg.jit = output, stream, jit
         self._out_loc = output
         self._h = C.c_void_p()
         rc = self._L.b2_exec_open(C.byref(plan.c), self._kr, len(ranges), C.byref(region.c), C.byref(cfg), C.byref(self._h))

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libb2copr.so")
+LIB_PATH = os.environ.get("B2_LIB") or os.path.join(_HERE, "_build", "libb2copr.so")  # B2_LIB: experimental builds only
 
 # ---- enums -------------------------------------------------------------------------------------
 B2_OK, B2_ERR_STORAGE, B2_ERR_KEY_IS_LOCKED, B2_ERR_WRITE_CONFLICT, B2_ERR_EVALUATE = 0, 1, 2, 3, 4
@@ -93,7 +93,7 @@ class DagPlan(C.Structure):
 
 class ExecConfig(C.Structure):
     _fields_ = [("output_location", C.c_int32), ("staging_tiles", C.c_int32), ("cuda_stream", C.c_uint64),
-                ("reserved", C.c_uint64 * 4)]
+                ("jit", C.c_int32), ("_pad", C.c_int32), ("reserved", C.c_uint64 * 3)]
 
 
 class Decimal(C.Structure):
@@ -116,7 +116,7 @@ class ExecStats(C.Structure):
                 ("write_entries_scanned", C.c_uint64), ("write_processed_keys", C.c_uint64), ("processed_size", C.c_uint64),
                 ("default_lookups", C.c_uint64), ("lock_processed_keys", C.c_uint64), ("met_newer_ts_data", C.c_int32),
                 ("_pad", C.c_int32), ("kernel_time_ns", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("jit_launches", C.c_uint64)]
 
 
 class ErrorInfo(C.Structure):
@@ -149,9 +149,10 @@ class EncodedChunk(C.Structure):
 
 
 ENCODE_TYPE_DEFAULT, ENCODE_TYPE_CHUNK = 0, 1
+JIT_AUTO, JIT_SYNC, JIT_OFF = 0, 1, 2
 
 EXPORTED_SYMBOLS = [
-    "b2_abi_version", "b2_build_info", "b2_last_error_message", "b2_check_supported", "b2_exec_open", "b2_exec_schema",
+    "b2_abi_version", "b2_build_info", "b2_last_error_message", "b2_check_supported", "b2_plan_prepare", "b2_exec_open", "b2_exec_schema",
     "b2_exec_next_batch", "b2_exec_collect_stats", "b2_exec_last_error", "b2_exec_can_be_cached", "b2_exec_encode_batch", "b2_exec_take_scanned_range", "b2_exec_collect_scanned_rows_per_range", "b2_exec_close",
     "b2_exec_agg_partials", "b2_dag_handle", "b2_checksum_handle", "b2_gen_create", "b2_gen_destroy", "b2_copy_to_host", "b2_copy_to_device",
     "b2_device_count", "b2_host_alloc_pinned", "b2_host_free_pinned",
@@ -176,6 +177,8 @@ def lib():
     L.b2_last_error_message.restype = C.c_char_p
     L.b2_check_supported.argtypes = [C.POINTER(DagPlan)]
     L.b2_check_supported.restype = i32
+    L.b2_plan_prepare.argtypes = [C.POINTER(DagPlan), i32]
+    L.b2_plan_prepare.restype = i32
     L.b2_exec_open.argtypes = [C.POINTER(DagPlan), C.POINTER(KeyRange), u32, C.POINTER(RegionSource), C.POINTER(ExecConfig), C.POINTER(vp)]
     L.b2_exec_open.restype = i32
     L.b2_exec_schema.argtypes = [vp, C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)]
