@@ -102,8 +102,6 @@ struct DevPlan {
   uint32_t fast_cls;     // bit h: stored column h (id order) is integer-class (width must be 1/2/4/8)
   uint32_t fast_uns;     // bit h: stored column h is zero-extended (unsigned)
   int8_t fast_out[8];    // PM_SCAN: output column fed by stored column h (first occurrence), or -1
-  uint8_t fast_round[8]; // PM_SCAN: fast_out[h] / 4 (output chunk round), 0xff when -1
-  uint16_t fast_slot[8]; // PM_SCAN: (fast_out[h] % 4) * 256: cell offset of its column inside the chunk buffer
   int32_t n_out_slow;    // PM_SCAN: outputs of a fast row that still go through cell_value (handle, Real, repeats ...)
   int32_t _fpad2;
   uint64_t fast_ids;   // the expected sorted non-null id bytes of such a row, packed little-endian (fast_n <= 8)

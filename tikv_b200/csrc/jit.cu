@@ -105,7 +105,7 @@ JitKernel* compile(int device, int mode, const std::string& literal) {
   nvrtcProgram prog;
   if (a.CreateProgram(&prog, src.c_str(), "b2_scan_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { k->error = "nvrtcCreateProgram failed"; return k; }
   std::string inc = "-I" + a.csrc_dir;
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-DB2_NVRTC=1", "-default-device", inc.c_str(), "-I/usr/local/cuda/include"};
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-DB2_NVRTC=1", "-default-device", inc.c_str(), "-I/usr/local/cuda/include"};
   nvrtcResult rc = a.CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
   if (rc != NVRTC_SUCCESS) {
     size_t n = 0;

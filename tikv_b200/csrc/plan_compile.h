@@ -291,10 +291,6 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
       if (P.fast_n > 0 && col.role == CR_NORMAL && col.kind == CK_INT && P.fast_out[col.v2_hint] < 0) P.fast_out[col.v2_hint] = (int8_t)i;
       else P.out_slow[P.n_out_slow++] = (uint8_t)i;
     }
-    for (int h = 0; h < 8; ++h) {
-      P.fast_round[h] = P.fast_out[h] < 0 ? 0xff : (uint8_t)(P.fast_out[h] / 4);
-      P.fast_slot[h] = P.fast_out[h] < 0 ? 0 : (uint16_t)((P.fast_out[h] % 4) * 256);
-    }
   }
   // selection conditions of the shape `integer column <cmp> constant` are evaluated by stored position on fast rows
   P.n_fconds = 0;

@@ -119,7 +119,11 @@ __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int 
 // that does not fit is simply read from HBM.
 enum { STAGE_LOOK = 8, STAGE_OFF_CAP = 1104, N_STAGES = 2, OBUF_COLS = 4, N_OBUF = 3, N_CNT = 4 };
 enum { OBUF_BYTES = OBUF_COLS * TILE * 8, ONULL_WORDS = OBUF_COLS * (TILE / 32) };
-static_assert(OBUF_COLS == 4 && TILE == 256, "DevPlan::fast_round / fast_slot (plan_compile.h) assume 4-column chunks of 256 rows");
+// A chunk buffer (OBUF_BYTES) is laid out per tile: [4 columns][256 rows] in general, [8 columns][128 rows] when the tile
+// selected at most 128 rows, so that such a tile needs one chunk for 8 output columns instead of two and the ring of
+// N_OBUF buffers gives the scan warp twice the time to finish its look-back before the decode warps need the buffer back.
+static_assert(OBUF_COLS == 4, "chunk layouts are 4 or 8 columns wide (shifts 2 / 3 below)");
+__device__ __forceinline__ uint32_t obuf_cols(unsigned int total) { return total <= TILE / 2 ? 2u * OBUF_COLS : (uint32_t)OBUF_COLS; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -324,7 +328,6 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   // PM_SCAN output chunk buffers (dynamic shared memory): N_OBUF x [OBUF_COLS][TILE] values, then the NULL masks
   unsigned long long* obuf_base = reinterpret_cast<unsigned long long*>(dyn_smem + A.out_stage_off);
   unsigned int* onull_base = reinterpret_cast<unsigned int*>(dyn_smem + A.out_stage_off + N_OBUF * OBUF_BYTES);
-  const uint32_t n_rounds = P.n_out > 0 ? (uint32_t)(P.n_out + OBUF_COLS - 1) / OBUF_COLS : 1u;
   if (MODE == PM_SCAN)
     for (unsigned int i = tid; i < N_OBUF * ONULL_WORDS; i += blockDim.x) onull_base[i] = 0;
   if (tid == 0) {
@@ -410,10 +413,8 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       if (tile >= n_tiles) break;
       const unsigned long long total = s_total[k % N_CNT];
       unsigned long long excl = 0;
-      if (tile == 0) {
-        if (lane == 0) atomicExch(&A.tile_status[0], F_INC | total);
-      } else {
-        if (lane == 0) atomicExch(&A.tile_status[tile], F_AGG | total);
+      // (the tile's own aggregate was published by the decode warps the moment they knew it)
+      if (tile != 0) {
         long long j = (long long)tile - 1;
         for (;;) {
           long long idx = j - (long long)lane;
@@ -434,29 +435,31 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       if (lane == 0 && total) atomicAdd(&A.ctr->out_rows, total);
       const unsigned long long base = out_base + excl;
       const unsigned int lim = base + total <= A.out_cap ? (unsigned int)total : (base < A.out_cap ? (unsigned int)(A.out_cap - base) : 0u);
+      const uint32_t cpc = obuf_cols((unsigned int)total), cshift = cpc == OBUF_COLS ? 2u : 3u, rstride = (OBUF_COLS * TILE) >> cshift;
+      const uint32_t n_rounds = P.n_out > 0 ? ((uint32_t)P.n_out + cpc - 1) >> cshift : 1u;
       for (uint32_t r = 0; r < n_rounds; ++r) {
         const uint32_t q = sw_q;
         mbar_wait_sleep(&s_obuf_full[q], sw_phase);
         if (++sw_q == N_OBUF) { sw_q = 0; sw_phase ^= 1; }
-        const int c0 = (int)r * OBUF_COLS;
-        const int nc = P.n_out - c0 < OBUF_COLS ? P.n_out - c0 : OBUF_COLS;
+        const int c0 = (int)(r * cpc);
+        const int nc = P.n_out - c0 < (int)cpc ? P.n_out - c0 : (int)cpc;
         const unsigned long long* ob = obuf_base + (size_t)q * (OBUF_COLS * TILE);
         unsigned long long* dst = A.out_data + (size_t)c0 * A.out_cap + base;
         for (unsigned int i = lane; i < lim; i += 32) {
 #pragma unroll
-          for (int c = 0; c < OBUF_COLS; ++c)
-            if (c < nc) dst[(size_t)c * A.out_cap + i] = ob[c * TILE + i];
+          for (int c = 0; c < 2 * OBUF_COLS; ++c)
+            if (c < nc) dst[(size_t)c * A.out_cap + i] = ob[c * rstride + i];
         }
         // NULL cells are rare: the bitmap is pre-filled with ones and only cleared where needed
         unsigned int* on = onull_base + q * ONULL_WORDS;
-        unsigned int w = on[lane];  // ONULL_WORDS == 32: word (column c, rows 32 j ..) at [c * 8 + j]
+        unsigned int w = on[lane];  // ONULL_WORDS == 32: word (column c, rows 32 j ..) at [c * (rstride / 32) + j]
         if (w) {
           on[lane] = 0;
-          const int c = (int)(lane / (TILE / 32));
+          const int c = (int)(lane >> (5 - cshift));  // rstride / 32 words per column: 8 (4 columns) or 4 (8 columns)
           while (w) {
             unsigned int bit = __ffs(w) - 1;
             w &= w - 1;
-            unsigned long long row_at = base + (lane % (TILE / 32)) * 32 + bit;
+            unsigned long long row_at = base + (lane & ((rstride >> 5) - 1)) * 32 + bit;
             if (row_at < A.out_cap) atomicAnd(&A.out_bitmap[(size_t)(c0 + c) * (A.out_cap / 64) + (row_at >> 6)], ~(1ull << (row_at & 63)));
           }
         }
@@ -518,10 +521,15 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       // scan warp (warp 9) turns the tile's row count into its global output base and drains the chunks to HBM as
       // contiguous 8-byte runs, so the look-back latency never stalls the decode.
       const unsigned int pos = warp_off + lane_off;
+      // publish the tile's row count for the look-backs of later tiles right away (flag AGGREGATE; tile 0: INCLUSIVE):
+      // the scan warp may be several tiles behind, other CTAs must not wait for it to get here
+      if (tid == 0) atomicExch(&A.tile_status[tile], ((tile == 0 ? 2ull : 1ull) << 62) | total);
       const bool fast = live && row.fast;
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 2] = clock64();
+      const uint32_t cpc = obuf_cols(total), cshift = cpc == OBUF_COLS ? 2u : 3u, rstride = (OBUF_COLS * TILE) >> cshift;  // columns per chunk (4 or 8), row stride
+      const uint32_t n_rounds = P.n_out > 0 ? ((uint32_t)P.n_out + cpc - 1) >> cshift : 1u;
       for (uint32_t r = 0; r < n_rounds; ++r) {
-        const uint32_t q = ob_q;  // chunk number (k * n_rounds + r) mod N_OBUF, its use count parity in ob_phase
+        const uint32_t q = ob_q;  // next buffer of the ring, its use count parity in ob_phase
         mbar_wait(&s_obuf_empty[q], ob_phase ^ 1);  // chunk buffer drained (N_OBUF chunks ago)
         if (++ob_q == N_OBUF) { ob_q = 0; ob_phase ^= 1; }
         if (r == 0) {
@@ -535,8 +543,8 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
             Value v;
             int err = cell_value(P, row, cells, P.out_cols[oc], &v);
             if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; }
-            ob[(oc % OBUF_COLS) * TILE] = v.null ? 0ull : v.bits;
-            if (v.null) atomicOr(&onull_base[q * ONULL_WORDS + (oc % OBUF_COLS) * (TILE / 32) + (pos >> 5)], 1u << (pos & 31));
+            ob[((uint32_t)oc & (cpc - 1)) * rstride] = v.null ? 0ull : v.bits;
+            if (v.null) atomicOr(&onull_base[q * ONULL_WORDS + ((uint32_t)oc & (cpc - 1)) * (rstride / 32) + (pos >> 5)], 1u << (pos & 31));
           };
           if (fast) {
             // exact-layout row: the (at most 8) stored integer columns are decoded by stored position, so every shift
@@ -546,15 +554,16 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
             for (int h = 0; h < 8; ++h) {
               if (h < P.fast_n) {
                 const uint32_t end = fast_end(row, h);
-                if (P.fast_round[h] == r) ob[P.fast_slot[h]] = fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u);
+                const int oc = P.fast_out[h];
+                if (oc >= 0 && ((uint32_t)oc >> cshift) == r) ob[((uint32_t)oc & (cpc - 1)) * rstride] = fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u);
                 prev = end;
               }
             }
             for (int j = 0; j < P.n_out_slow; ++j)  // handle / Real / repeated columns of such a row
-              if ((uint32_t)P.out_slow[j] / OBUF_COLS == r) put(P.out_slow[j]);
+              if (((uint32_t)P.out_slow[j] >> cshift) == r) put(P.out_slow[j]);
           } else {
-            const int c_end = (int)(r + 1) * OBUF_COLS < P.n_out ? (int)(r + 1) * OBUF_COLS : P.n_out;
-            for (int oc = (int)r * OBUF_COLS; oc < c_end; ++oc) put(oc);
+            const int c_end = (int)((r + 1) * cpc) < P.n_out ? (int)((r + 1) * cpc) : P.n_out;
+            for (int oc = (int)(r * cpc); oc < c_end; ++oc) put(oc);
           }
         }
         __syncwarp();
