@@ -34,7 +34,7 @@ int scan_num_sms() { return num_sms(); }
 size_t scan_stage_bytes(uint32_t key_cap, uint32_t val_cap) { return (size_t)N_STAGES * (key_cap + val_cap + 2 * STAGE_OFF_CAP); }
 uint32_t scan_stage_entries() { return TILE + STAGE_LOOK + 1; }
 size_t scan_out_stage_bytes() { return (size_t)N_OBUF * OBUF_BYTES + (size_t)N_OBUF * ONULL_WORDS * 4; }
-size_t scan_crc_table_bytes() { return 256 * 16 * 8; }
+size_t scan_crc_table_bytes() { return 8 * 256 * 8; }
 
 int scan_max_grid(int mode, size_t smem) {
   int per_sm = 0;

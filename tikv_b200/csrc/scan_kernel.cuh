@@ -215,19 +215,29 @@ __device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A,
     if (rawlen < 0) report_err(A.ctr, A.entry_base + e, DE_BAD_USER_KEY);
     else if (!okp) { atomicExch(&A.ctr->bad_prefix, 1u); report_err(A.ctr, A.entry_base + e, DE_BAD_RECORD_KEY); }
     else {
-      const unsigned long long* tab = crc_tab + (lane & 15);  // 16 interleaved copies: lane l only touches bank pair l % 16
+      // slicing-by-8: T[k][i] = CRC of byte i followed by k zero bytes (crc_tab[k * 256 + i]); eight independent lookups
+      // consume eight message bytes, instead of eight dependent ones
+      const unsigned long long* T = crc_tab;
+      auto step1 = [&](unsigned long long c, uint32_t byte) { return T[((uint32_t)c ^ byte) & 0xffu] ^ (c >> 8); };
+      auto step8 = [&](unsigned long long c, unsigned long long w) {
+        c ^= w;
+        const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
+        return T[7 * 256 + (lo & 0xffu)] ^ T[6 * 256 + ((lo >> 8) & 0xffu)] ^ T[5 * 256 + ((lo >> 16) & 0xffu)] ^ T[4 * 256 + (lo >> 24)] ^
+               T[3 * 256 + (hi & 0xffu)] ^ T[2 * 256 + ((hi >> 8) & 0xffu)] ^ T[1 * 256 + ((hi >> 16) & 0xffu)] ^ T[hi >> 24];
+      };
       unsigned long long c = A.ck_init_state;
-      for (uint32_t j = A.ck_new_prefix_len; j < (uint32_t)rawlen; ++j) c = tab[((uint32_t)(c ^ raw_at(ek, j)) & 0xffu) * 16] ^ (c >> 8);
+      // raw key bytes [new_prefix_len, rawlen): raw byte j lives at enc[j + j / 8]; whole 8-byte groups are contiguous
+      uint32_t j = A.ck_new_prefix_len;
+      for (; j < (uint32_t)rawlen && (j & 7u); ++j) c = step1(c, raw_at(ek, j));
+      for (; j + 8 <= (uint32_t)rawlen; j += 8) c = step8(c, ld64(ek + j + (j >> 3)));
+      for (; j < (uint32_t)rawlen; ++j) c = step1(c, raw_at(ek, j));
       const uint8_t* vp = ro.val;
-      uint32_t vn = ro.val_len, j = 0;
-      for (; j + 8 <= vn; j += 8) {  // 8 value bytes per unaligned word load
-        unsigned long long w = ld64(vp + j);
-#pragma unroll
-        for (int b = 0; b < 8; ++b) { c = tab[((uint32_t)(c ^ w) & 0xffu) * 16] ^ (c >> 8); w >>= 8; }
-      }
-      if (j < vn) {
-        unsigned long long w = ld64(vp + j);
-        for (; j < vn; ++j) { c = tab[((uint32_t)(c ^ w) & 0xffu) * 16] ^ (c >> 8); w >>= 8; }
+      const uint32_t vn = ro.val_len;
+      uint32_t i = 0;
+      for (; i + 8 <= vn; i += 8) c = step8(c, ld64(vp + i));
+      if (i < vn) {
+        unsigned long long w = ld64(vp + i);
+        for (; i < vn; ++i) { c = step1(c, (uint32_t)w & 0xffu); w >>= 8; }
       }
       ts.ck_x ^= ~c;
       ts.ck_kvs += 1;
@@ -292,11 +302,16 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     __syncthreads();
   }
 
-  // PM_CHECKSUM: bytewise CRC-64/XZ table, replicated 16x (entry i of copy c at [i * 16 + c]) so that the 64-bit
-  // lookups of a half-warp never share a bank pair
+  // PM_CHECKSUM: CRC-64/XZ slicing-by-8 tables (8 x 256 x u64 = 16 KB)
   unsigned long long* crc_tab = reinterpret_cast<unsigned long long*>(dyn_smem);
   if (MODE == PM_CHECKSUM) {
-    for (unsigned int i = tid; i < 256 * 16; i += blockDim.x) crc_tab[i] = crc64_table_entry(i >> 4);
+    // slicing-by-8 tables of CRC-64/XZ (reflected): T[0] is the byte table, T[k][i] = T[0][T[k-1][i] & 0xff] ^ (T[k-1][i] >> 8)
+    for (unsigned int i = tid; i < 256; i += blockDim.x) crc_tab[i] = crc64_table_entry(i);
+    __syncthreads();
+    for (unsigned int i = tid; i < 256; i += blockDim.x) {
+      unsigned long long t = crc_tab[i];
+      for (int kk = 1; kk < 8; ++kk) { t = crc_tab[(uint32_t)t & 0xffu] ^ (t >> 8); crc_tab[kk * 256 + i] = t; }
+    }
     __syncthreads();
   }
 
