@@ -132,6 +132,7 @@ struct Unit { uint32_t range_idx, block_idx, e_lo, e_hi; };
 struct StageSlot {
   DevBuf keys, koff, vals, voff;
   int block = -1;
+  bool done = false;  // every unit that reads `block` has been launched: the slot may be refilled (after free_ev)
   cudaEvent_t ready = nullptr, free_ev = nullptr;
   bool free_recorded = false;
 };
@@ -515,6 +516,7 @@ struct b2_exec {
     CUDA_TRY(cudaMemcpyAsync(s->voff.p, sb.c.val_offs, ob, cudaMemcpyHostToDevice, copy_stream));
     CUDA_TRY(cudaEventRecord(s->ready, copy_stream));
     s->block = (int)bi;
+    s->done = false;
     stats.default_lookups += 0;
     h2d_bytes += sb.key_bytes + sb.val_bytes + 2 * ob;
     *out = s;
@@ -525,14 +527,25 @@ struct b2_exec {
     for (auto& x : slots)
       if (x.block == (int)bi) { cudaEventRecord(x.free_ev, stream); x.free_recorded = true; }
   }
+  // Called when unit `unit_idx` has been launched completely.  Keeps the H2D stream busy: the next two distinct blocks
+  // are put in flight, the second one into the slot of the block that just finished (its copy waits on free_ev, i.e. on
+  // the kernels that still read the old block, not on the host).
   void prefetch_after(size_t unit_idx) {
     if (src_loc == B2_LOC_DEVICE) return;
-    for (size_t u = unit_idx + 1; u < units.size(); ++u) {
-      if (units[u].block_idx == units[unit_idx].block_idx) continue;
-      bool have = false;
-      for (auto& x : slots) if (x.block == (int)units[u].block_idx) have = true;
-      if (!have) { StageSlot* s; stage_block(units[u].block_idx, &s); }
-      return;
+    const uint32_t cur = units[unit_idx].block_idx;
+    bool cur_needed = unit_idx + 1 < units.size() && units[unit_idx + 1].block_idx == cur;
+    if (!cur_needed)
+      for (auto& x : slots) if (x.block == (int)cur) x.done = true;
+    int ahead = 0;
+    for (size_t u = unit_idx + 1; u < units.size() && ahead < 2; ++u) {
+      const uint32_t b = units[u].block_idx;
+      if (b == cur && cur_needed) continue;
+      StageSlot& sl = slots[b & 1];
+      if (sl.block == (int)b) { if (!sl.done) { ++ahead; } continue; }
+      if (sl.block >= 0 && !sl.done) break;  // that slot still feeds launches to come
+      StageSlot* s;
+      if (stage_block(b, &s)) break;
+      ++ahead;
     }
   }
   uint64_t h2d_bytes = 0;
