@@ -1115,7 +1115,7 @@ struct b2_exec {
     if (limit > 0 && !units.empty()) {  // top_n_executor.rs:304-312: n == 0 drains immediately
       uint32_t cap = 512;
       while (cap < limit + TILE) cap <<= 1;
-      size_t smem = topn_smem_bytes(cap);
+      size_t smem = topn_smem_bytes(cap, P.n_order);
       ScanArgs probe; memset(&probe, 0, sizeof(probe));
       size_t tot0 = setup_staging(&probe, wblocks[units[0].block_idx], smem);
       int grid = scan_grid_for(PM_TOPN, std::max(tot0, smem));

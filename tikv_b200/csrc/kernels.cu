@@ -77,7 +77,7 @@ cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t
 }
 
 // ---- TopN: merge candidate lists, gather row payloads ------------------------------------------------------------
-size_t topn_smem_bytes(uint32_t cap) { return (size_t)cap * sizeof(TopItem) + (size_t)cap * 2; }
+size_t topn_smem_bytes(uint32_t cap, int n_order) { return (((size_t)cap * ((size_t)n_order + 2) * 8 + (size_t)cap * 2) + 15) & ~(size_t)15; }
 
 // CTA b streams every item of input lists [b * fan_in, (b + 1) * fan_in) through one threshold buffer and leaves the
 // best `limit`, sorted, in output list b.  The host applies it level by level (fan-in 8) down to a single list.
@@ -85,10 +85,10 @@ __global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant_
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned int s_cnt, s_have_thr;
   __shared__ TopItem s_thr;
-  TopItem* items = reinterpret_cast<TopItem*>(dyn_smem);
+  const TopBuf tb = topbuf_make(dyn_smem, cap, P);
   const unsigned int tid = threadIdx.x;
   if (tid == 0) { s_cnt = 0; s_have_thr = 0; }
-  for (unsigned int i = tid; i < cap; i += TILE) topn_idx(items, cap)[i] = (unsigned short)i;
+  for (unsigned int i = tid; i < cap; i += TILE) tb.idx[i] = (unsigned short)i;
   __syncthreads();
   const unsigned int l0 = blockIdx.x * fan_in;
   const unsigned int l1 = l0 + fan_in < in.n_lists ? l0 + fan_in : in.n_lists;
@@ -102,22 +102,22 @@ __global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant_
         it.slot = (l << 16) | i;
         if (!s_have_thr || item_less(it, s_thr, P)) {
           unsigned int pos = atomicAdd(&s_cnt, 1u);
-          items[topn_idx(items, cap)[pos]] = it;
+          topbuf_put(tb, tb.idx[pos], it);
         }
       }
     }
     __syncthreads();
-    if (s_cnt + TILE > cap) cta_topn_compact(items, cap, (unsigned int)P.limit, &s_cnt, &s_have_thr, &s_thr, P);
+    if (s_cnt + TILE > cap) cta_topn_compact(tb, (unsigned int)P.limit, &s_cnt, &s_have_thr, &s_thr, P);
   }
   __syncthreads();
-  cta_topn_compact(items, cap, (unsigned int)P.limit, &s_cnt, &s_have_thr, &s_thr, P);
+  cta_topn_compact(tb, (unsigned int)P.limit, &s_cnt, &s_have_thr, &s_thr, P);
   unsigned int keep = s_cnt;
-  for (unsigned int i = tid; i < keep; i += TILE) out.items[(size_t)blockIdx.x * out.stride + i] = items[topn_idx(items, cap)[i]];
+  for (unsigned int i = tid; i < keep; i += TILE) out.items[(size_t)blockIdx.x * out.stride + i] = topbuf_get(tb, tb.idx[i]);
   if (tid == 0) out.counts[blockIdx.x] = keep;
 }
 
 cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const TopNLists& out, uint32_t cap, uint32_t fan_in, cudaStream_t s) {
-  size_t smem = topn_smem_bytes(cap);
+  size_t smem = topn_smem_bytes(cap, plan.n_order);
   if (smem > 48 * 1024) cudaFuncSetAttribute(topn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   unsigned int grid = (in.n_lists + fan_in - 1) / fan_in;
   topn_merge_kernel<<<grid, TILE, smem, s>>>(plan, in, out, cap, fan_in);

@@ -106,7 +106,7 @@ cudaError_t launch_topn_copy(const TopItem* items, const unsigned int* count, ui
                              const unsigned char* null0, const unsigned long long* pay1, const unsigned char* null1, unsigned long long* pay_out,
                              unsigned char* null_out, cudaStream_t s);
 cudaError_t launch_pack_nulls(const unsigned char* nulls, uint32_t n_cols, uint32_t stride, uint32_t n, unsigned long long* bitmaps, uint32_t words_per_col, cudaStream_t s);
-size_t topn_smem_bytes(uint32_t cap);
+size_t topn_smem_bytes(uint32_t cap, int n_order);
 cudaError_t launch_bounds_search(const BlockView* blocks, uint32_t n_blocks, const uint8_t* bounds, const uint32_t* bound_offs, uint32_t n_bounds,
                                  uint32_t* out, cudaStream_t s);
 cudaError_t launch_gen_sizes(const b2_gen_spec& spec, uint32_t* row_entries, uint32_t* row_val_bytes, cudaStream_t s);

@@ -75,18 +75,62 @@ __device__ __forceinline__ void acc_update(Acc* acc, const DevAgg& g, const Valu
 __device__ __forceinline__ void cta256_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---- TopN helpers --------------------------------------------------------------------------------------------
-// Candidate buffer of a CTA: `cap` item slots that never move plus a permutation `idx` (u16) of the slots.  Positions
-// [0, cnt) of `idx` are occupied; a new candidate takes position atomicAdd(cnt) -> slot idx[pos].  Compaction sorts the
-// permutation (bitonic network over positions, every thread owns one compare-exchange per step) and keeps the best
-// `limit` positions: only 2-byte indices are swapped, the 48-byte items are read in place.
-__device__ __forceinline__ unsigned short* topn_idx(TopItem* items, unsigned int cap) { return reinterpret_cast<unsigned short*>(items + cap); }
+// Candidate buffer of a CTA (shared memory): `cap` packed candidates that never move plus a permutation `idx` (u16) of
+// the slots.  A packed candidate is n_order + 2 u64 words: [order-by words][entry id][nulls | slot << 32] (32 bytes for
+// two sort columns instead of the 48-byte TopItem, which keeps two CTAs per SM).  Positions [0, cnt) of `idx` are
+// occupied; a new candidate takes position atomicAdd(cnt) -> slot idx[pos].  Compaction sorts the permutation (bitonic
+// network over positions, every thread owns one compare-exchange per step) and keeps the best `limit` positions: only
+// 2-byte indices are swapped.
+struct TopBuf {
+  unsigned long long* w;  // cap * stride words
+  unsigned short* idx;    // cap
+  unsigned int cap, stride, n;  // n = number of order-by columns
+};
+__device__ __forceinline__ TopBuf topbuf_make(unsigned char* smem, unsigned int cap, const DevPlan& P) {
+  TopBuf t;
+  t.n = (unsigned int)P.n_order; t.stride = t.n + 2; t.cap = cap;
+  t.w = reinterpret_cast<unsigned long long*>(smem);
+  t.idx = reinterpret_cast<unsigned short*>(t.w + (size_t)cap * t.stride);
+  return t;
+}
+__device__ __forceinline__ void topbuf_put(const TopBuf& t, unsigned int slot, const TopItem& it) {
+  unsigned long long* d = t.w + (size_t)slot * t.stride;
+  for (unsigned int k = 0; k < t.n; ++k) d[k] = it.w[k];
+  d[t.n] = it.id;
+  d[t.n + 1] = (unsigned long long)it.nulls | ((unsigned long long)it.slot << 32);
+}
+__device__ __forceinline__ TopItem topbuf_get(const TopBuf& t, unsigned int slot) {
+  const unsigned long long* d = t.w + (size_t)slot * t.stride;
+  TopItem it;
+  for (unsigned int k = 0; k < MAX_ORDER; ++k) it.w[k] = k < t.n ? d[k] : 0ull;
+  it.id = d[t.n];
+  it.nulls = (unsigned int)d[t.n + 1]; it.slot = (unsigned int)(d[t.n + 1] >> 32);
+  return it;
+}
+// item_less on packed candidates (same order as b2_device.h item_less)
+__device__ __forceinline__ bool topbuf_less(const TopBuf& t, unsigned int sa, unsigned int sb, const DevPlan& P) {
+  const unsigned long long* a = t.w + (size_t)sa * t.stride;
+  const unsigned long long* b = t.w + (size_t)sb * t.stride;
+  const unsigned int na_all = (unsigned int)a[t.n + 1], nb_all = (unsigned int)b[t.n + 1];
+  const bool ea = na_all >> 31, eb = nb_all >> 31;
+  if (ea || eb) return !ea && eb;
+  for (unsigned int k = 0; k < t.n; ++k) {
+    unsigned int na = (na_all >> k) & 1, nb = (nb_all >> k) & 1;
+    int c;
+    if (na || nb) c = (int)nb - (int)na;
+    else c = a[k] < b[k] ? -1 : (a[k] > b[k] ? 1 : 0);
+    if (c == 0) continue;
+    if (P.order[k].desc) c = -c;
+    return c < 0;
+  }
+  return a[t.n] < b[t.n];
+}
 
-__device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int limit, unsigned int* s_cnt, unsigned int* s_have_thr, TopItem* s_thr,
-                                 const DevPlan& P) {
-  const unsigned int tid = threadIdx.x, nt = TILE;  // always called by exactly 256 threads
-  unsigned short* idx = topn_idx(items, cap);
+__device__ void cta_topn_compact(const TopBuf& t, unsigned int limit, unsigned int* s_cnt, unsigned int* s_have_thr, TopItem* s_thr, const DevPlan& P) {
+  const unsigned int tid = threadIdx.x, nt = TILE, cap = t.cap;  // always called by exactly 256 threads
+  unsigned short* idx = t.idx;
   unsigned int cnt = *s_cnt;
-  for (unsigned int i = cnt + tid; i < cap; i += nt) items[idx[i]].nulls = 0x80000000u;  // free slots sort last
+  for (unsigned int i = cnt + tid; i < cap; i += nt) t.w[(size_t)idx[i] * t.stride + t.n + 1] = 0x80000000ull;  // free slots sort last
   cta256_sync();
   for (unsigned int k = 2; k <= cap; k <<= 1) {
     for (unsigned int j = k >> 1; j > 0; j >>= 1) {
@@ -94,9 +138,7 @@ __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int 
         unsigned int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), x = i | j;
         bool up = (i & k) == 0;
         unsigned short ia = idx[i], ib = idx[x];
-        const TopItem& a = items[ia];
-        const TopItem& b = items[ib];
-        bool swap = up ? item_less(b, a, P) : item_less(a, b, P);
+        bool swap = up ? topbuf_less(t, ib, ia, P) : topbuf_less(t, ia, ib, P);
         if (swap) { idx[i] = ib; idx[x] = ia; }
       }
       cta256_sync();
@@ -105,7 +147,7 @@ __device__ void cta_topn_compact(TopItem* items, unsigned int cap, unsigned int 
   if (tid == 0) {
     unsigned int keep = cnt < limit ? cnt : limit;
     *s_cnt = keep;
-    if (keep == limit && limit > 0) { *s_thr = items[idx[limit - 1]]; *s_have_thr = 1; }
+    if (keep == limit && limit > 0) { *s_thr = topbuf_get(t, idx[limit - 1]); *s_have_thr = 1; }
   }
   cta256_sync();
 }
@@ -292,13 +334,13 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   // PM_TOPN: per-CTA candidate buffer (dynamic shared memory) + current threshold
   __shared__ unsigned int s_top_cnt, s_top_have_thr;
   __shared__ TopItem s_top_thr;
-  TopItem* top_items = reinterpret_cast<TopItem*>(dyn_smem);
+  const TopBuf tb = topbuf_make(dyn_smem, MODE == PM_TOPN ? A.topn_cap : 0u, P);
   if (MODE == PM_TOPN) {
     if (tid == 0) {
       s_top_cnt = 0; s_top_have_thr = 0;
       if (A.topn_seed && P.limit > 0 && *A.topn_seed_cnt >= (unsigned int)P.limit) { s_top_thr = A.topn_seed[P.limit - 1]; s_top_have_thr = 1; }
     }
-    for (unsigned int i = tid; i < A.topn_cap; i += blockDim.x) topn_idx(top_items, A.topn_cap)[i] = (unsigned short)i;
+    for (unsigned int i = tid; i < A.topn_cap; i += blockDim.x) tb.idx[i] = (unsigned short)i;
     __syncthreads();
   }
 
@@ -594,11 +636,11 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
         if (err) report_err(A.ctr, A.entry_base + e, err);
         else if (!s_top_have_thr || item_less(it, s_top_thr, P)) {
           unsigned int pos = atomicAdd(&s_top_cnt, 1u);
-          top_items[topn_idx(top_items, A.topn_cap)[pos]] = it;  // pos < topn_cap: the buffer is compacted whenever fewer than TILE slots remain
+          topbuf_put(tb, tb.idx[pos], it);  // pos < topn_cap: the buffer is compacted whenever fewer than TILE slots remain
         }
       }
       cta256_sync();
-      if (s_top_cnt + TILE > A.topn_cap) cta_topn_compact(top_items, A.topn_cap, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
+      if (s_top_cnt + TILE > A.topn_cap) cta_topn_compact(tb, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
     } else if (MODE == PM_AGG) {
       // BatchSimpleAggregation / BatchFastHashAggregation.  Rows of one warp that share a group key are combined with
       // warp reductions first (match.any + redux); the group's leader lane then issues one atomic per accumulator
@@ -734,9 +776,9 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   }
   if (MODE == PM_TOPN) {
     cta256_sync();
-    cta_topn_compact(top_items, A.topn_cap, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
+    cta_topn_compact(tb, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
     unsigned int keep = s_top_cnt;
-    for (unsigned int i = tid; i < keep; i += TILE) A.topn.items[(size_t)blockIdx.x * A.topn.stride + i] = top_items[topn_idx(top_items, A.topn_cap)[i]];
+    for (unsigned int i = tid; i < keep; i += TILE) A.topn.items[(size_t)blockIdx.x * A.topn.stride + i] = topbuf_get(tb, tb.idx[i]);
     if (tid == 0) A.topn.counts[blockIdx.x] = keep;
   }
   if (MODE == PM_AGG) {
