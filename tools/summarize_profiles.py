@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 R = sys.argv[1] if len(sys.argv) > 1 else "r1"
 ENTRIES = int(sys.argv[2]) if len(sys.argv) > 2 else 12_500_000  # entries covered by the captured launch (one 12.5M-entry block)
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-for f in (f"bench_{R}.json", f"bench_reference_{R}.json", f"launches_{R}.csv", f"other_configs_{R}.jsonl", f"scan_kernel_{R}.ncu-rep"):
+for f in (f"bench_{R}.json", f"bench_generic_kernel_{R}.json", f"bench_reference_{R}.json", f"launches_{R}.csv", f"other_configs_{R}.jsonl", f"scan_kernel_{R}.ncu-rep"):
     if os.path.exists(os.path.join(G, f)):
         shutil.copy(os.path.join(G, f), os.path.join(P, f))
 rep = os.path.join(P, f"scan_kernel_{R}.ncu-rep")
@@ -26,13 +26,13 @@ keep = ["sm__inst_executed.avg.per_cycle_elapsed", "smsp__issue_active.avg.pct_o
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct"]
 stalls = {n.split("issue_stalled_")[1].split("_per_issue")[0]: float(m[n][0]) for n in h if "average_warps_issue_stalled" in n and n.endswith(".ratio") and m[n][0]}
 rd, wr, dur = num("dram__bytes_read.sum"), num("dram__bytes_write.sum"), num("gpu__time_duration.sum")
-full = {"source": f"profiles/scan_kernel_{R}.ncu-rep (ncu --set full --import-source on --clock-control none -k regex:scan_kernel -s 8 -c 1; bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --chunk 12500000: one launch = one 12.5M-entry block)",
+full = {"source": f"profiles/scan_kernel_{R}.ncu-rep (ncu --set full --import-source on --clock-control none -k 'regex:scan_kernel|b2_scan_jit' -s 8 -c 1; bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --chunk 12500000: one launch = one 12.5M-entry block)",
         "kernel": m["Kernel Name"][0] if "Kernel Name" in m else "scan_kernel<PM_SCAN>", "duration_us_under_ncu": dur * 1e6,
         "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_GBps_under_ncu": (rd + wr) / dur / 1e9,
         "metrics": {k: m[k][0] + (" " + m[k][1] if m[k][1] else "") for k in keep if k in m},
         "stall_cycles_per_issued_instruction": dict(sorted(stalls.items(), key=lambda kv: -kv[1]))}
 json.dump(full, open(os.path.join(P, f"scan_kernel_{R}_ncu_full.json"), "w"), indent=1)
-traffic = {"source": full["source"], "kernel": "b2::scan_kernel<PM_SCAN>", "entries_in_launch": ENTRIES, "dram_bytes_read": rd, "dram_bytes_write": wr,
+traffic = {"source": full["source"], "kernel": full["kernel"], "entries_in_launch": ENTRIES, "dram_bytes_read": rd, "dram_bytes_write": wr,
            "dram_bytes_per_entry": (rd + wr) / ENTRIES,
            "note": "per-launch DRAM traffic of the dominant kernel; bench.py scales it to its own launch size for roofline.traffic"}
 json.dump(traffic, open(os.path.join(P, f"scan_kernel_{R}_traffic.json"), "w"), indent=1)
