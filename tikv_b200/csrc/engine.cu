@@ -978,9 +978,10 @@ struct b2_exec {
     size_t smem = 0;
     uint32_t smem_slots = 0;
     if (P.has_group) {
-      smem_slots = 1024;
-      while (smem_slots > 64 && (size_t)smem_slots * (12 + 8 * P.acc_words) > 36 * 1024) smem_slots >>= 1;
-      smem = (size_t)smem_slots * (12 + 8 * P.acc_words);
+      smem_slots = 2048;  // x 75 % load: 1536 resident groups per CTA
+      if (const char* ev = getenv("B2_SMEM_SLOTS")) smem_slots = (uint32_t)atoi(ev);  // experiments
+      while (smem_slots > 64 && (size_t)smem_slots * (8 + 8 * P.acc_words) > 64 * 1024) smem_slots >>= 1;
+      smem = (size_t)smem_slots * (8 + 8 * P.acc_words);
     }
     Counters c;
     for (;;) {

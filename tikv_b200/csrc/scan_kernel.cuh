@@ -299,12 +299,13 @@ __device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A,
 }
 
 // ---- the fused scan kernel -------------------------------------------------------------------------------
-struct SmemTable {  // per-CTA group table (dynamic shared memory): keys | acc | occ
+struct SmemTable {  // per-CTA group table (dynamic shared memory): keys | acc.  A slot is free while its key is SMEM_EMPTY_KEY
   unsigned long long* keys;
   unsigned long long* acc;
-  unsigned int* occ;
   unsigned int slots;
 };
+// (a group whose key happens to be this value simply lives in the HBM table only)
+#define SMEM_EMPTY_KEY 0xffffffffffffffffull
 
 // The whole kernel as a device function: instantiated by the generic __global__ wrapper (plan in a __grid_constant__
 // parameter) and by the per-plan JIT translation unit (plan as a compile-time constant, jit.cpp).
@@ -312,7 +313,7 @@ template <int MODE>
 __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned int s_warp_cnt[2][TILE / 32];  // by tile parity: a fast warp may start the next tile while others still read
-  __shared__ unsigned int s_tbl_used;
+  __shared__ unsigned int s_tbl_used, s_tbl_miss, s_tbl_off;  // resident groups; rows that fell through to HBM; table given up
 
   const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t n_tiles = (A.c_hi - A.c_lo + TILE - 1) / TILE;
@@ -324,10 +325,9 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     st.slots = A.smem_slots;
     st.keys = reinterpret_cast<unsigned long long*>(dyn_smem);
     st.acc = st.keys + st.slots;
-    st.occ = reinterpret_cast<unsigned int*>(st.acc + (size_t)st.slots * P.acc_words);
-    for (unsigned int i = tid; i < st.slots; i += TILE) st.occ[i] = 0;
+    for (unsigned int i = tid; i < st.slots; i += TILE) st.keys[i] = SMEM_EMPTY_KEY;
     for (unsigned int i = tid; i < st.slots * P.acc_words; i += TILE) st.acc[i] = 0;
-    if (tid == 0) s_tbl_used = 0;
+    if (tid == 0) { s_tbl_used = 0; s_tbl_miss = 0; s_tbl_off = 0; }
     __syncthreads();
   }
 
@@ -667,28 +667,24 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
         if (leader) {
           if (!P.has_group) acc = s_simple_acc;
           else {
-            if (st.slots && !gk.null) {
-              unsigned int mask = st.slots - 1, s = (unsigned int)(mix64(gk.bits) >> 20) & mask;
+            if (st.slots && !s_tbl_off && !gk.null && gk.bits != SMEM_EMPTY_KEY) {
+              // open addressing on the key words themselves: claim a free slot with one 64-bit CAS; accumulators start
+              // at zero and are only ever added to, so there is no "being initialised" state to wait for
+              const unsigned int mask = st.slots - 1, limit = (st.slots >> 1) + (st.slots >> 2);
+              unsigned int s = (unsigned int)(mix64(gk.bits) >> 20) & mask;
               for (int probes = 0; probes < 8; ++probes) {
-                unsigned int o = *(volatile unsigned int*)&st.occ[s];
-                if (o == 0 && *(volatile unsigned int*)&s_tbl_used < (st.slots >> 1) + (st.slots >> 2)) {
-                  o = atomicCAS(&st.occ[s], 0u, 1u);
-                  if (o == 0) {
-                    st.keys[s] = gk.bits;
-                    __threadfence_block();
-                    atomicExch(&st.occ[s], 2u);
-                    atomicAdd(&s_tbl_used, 1u);
-                    acc = st.acc + (size_t)s * P.acc_words;
-                    break;
-                  }
+                unsigned long long kk = *(volatile unsigned long long*)&st.keys[s];
+                if (kk == SMEM_EMPTY_KEY) {
+                  if (*(volatile unsigned int*)&s_tbl_used >= limit) break;  // table is at its load limit: go to HBM
+                  kk = atomicCAS(&st.keys[s], SMEM_EMPTY_KEY, gk.bits);
+                  if (kk == SMEM_EMPTY_KEY) { atomicAdd(&s_tbl_used, 1u); kk = gk.bits; }
                 }
-                if (o == 0) break;  // table is at its load limit: go to HBM
-                while (o == 1) o = *(volatile unsigned int*)&st.occ[s];
-                if (*(volatile unsigned long long*)&st.keys[s] == gk.bits) { acc = st.acc + (size_t)s * P.acc_words; break; }
+                if (kk == gk.bits) { acc = st.acc + (size_t)s * P.acc_words; break; }
                 s = (s + 1) & mask;
               }
             }
             if (!acc) {
+              if (st.slots && !s_tbl_off) atomicAdd(&s_tbl_miss, 1u);
               unsigned int gslot = table_find_or_insert(A.tbl, gk.bits, gk.null);
               if (gslot == 0xffffffffu) atomicExch(&A.ctr->agg_overflow, 1u);
               else acc = A.tbl.acc + (size_t)gslot * P.acc_words;
@@ -750,6 +746,8 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       break;
     }
     if (tid == 0) s_redo[(k + 2) & 3] = 0;  // last read two tiles ago, next written two tiles ahead
+    // high-cardinality GROUP BY: once three quarters of the entries seen went past the CTA table, stop probing it
+    if (MODE == PM_AGG && tid == 0 && k >= 16 && !s_tbl_off && s_tbl_miss * 4u > k * TILE * 3u) s_tbl_off = 1;
     bool redo = true;
     if (m.staged) {
       unsigned char* st = stage_base + (size_t)cur * STAGE_BYTES;
@@ -795,7 +793,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     } else if (st.slots) {
       cta256_sync();
       for (unsigned int s = tid; s < st.slots; s += TILE) {
-        if (st.occ[s] != 2) continue;
+        if (st.keys[s] == SMEM_EMPTY_KEY) continue;
         unsigned int gslot = table_find_or_insert(A.tbl, st.keys[s], false);
         if (gslot == 0xffffffffu) { atomicExch(&A.ctr->agg_overflow, 1u); continue; }
         for (int a = 0; a < P.n_aggs; ++a) {
