@@ -96,6 +96,12 @@ static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges,
       t->n = e.limit;
       t->src = std::move(cur);
       cur = std::move(t);
+    } else if (e.tp == B2_EXEC_LIMIT) {
+      auto lm = std::make_unique<LimitExecutor>();
+      lm->remaining_rows = (size_t)e.limit;
+      lm->is_src_scan_executor = i == 1;  // runner.rs: the child is the scan executor itself
+      lm->src = std::move(cur);
+      cur = std::move(lm);
     } else { *err = Error::make(B2_ERR_UNSUPPORTED, "executor type " + std::to_string(e.tp)); return false; }
   }
   *out = std::move(cur);

@@ -584,6 +584,21 @@ struct SelectionExecutor : Executor {
   }
 };
 
+// ---- limit: limit_executor.rs:11-80 ----
+struct LimitExecutor : Executor {
+  std::unique_ptr<Executor> src;
+  size_t remaining_rows = 0;
+  bool is_src_scan_executor = false;
+  const std::vector<FieldType>& schema() const override { return src->schema(); }
+  ForwardScanner* scanner() override { return src->scanner(); }
+  void next_batch(size_t scan_rows, Batch* out) override {
+    size_t real_scan_rows = is_src_scan_executor ? std::min(scan_rows, remaining_rows) : scan_rows;  // :56-60
+    src->next_batch(real_scan_rows, out);
+    if (out->logical_rows.size() < remaining_rows) remaining_rows -= out->logical_rows.size();
+    else { out->logical_rows.resize(remaining_rows); out->is_drained = true; remaining_rows = 0; }  // :70-77
+  }
+};
+
 // ---- aggregation ----
 struct AggState {
   uint64_t count = 0;

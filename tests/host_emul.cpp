@@ -154,6 +154,13 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
       }
     }
   }
+  if (P.mode == PM_SCAN && cp.scan_limit != ~0ull && R->n_rows >= cp.scan_limit) {
+    // BatchLimitExecutor: the first `limit` rows; a failing row beyond them is never reached (limit_executor.rs:55-80)
+    for (auto& c : R->data) c.resize((size_t)cp.scan_limit);
+    for (auto& c : R->nonnull) c.resize((size_t)cp.scan_limit);
+    R->n_rows = cp.scan_limit;
+    err = ~0ull;
+  }
   if (err != ~0ull) {
     R->dev_err = (int)(err & 0xff); R->err_entry = err >> 8;
     R->status = (R->dev_err >= 20 && R->dev_err < 30) ? B2_ERR_EVALUATE : (R->dev_err <= 5 && R->dev_err != DE_WRITE_CONFLICT ? B2_ERR_STORAGE : (R->dev_err == DE_WRITE_CONFLICT ? B2_ERR_WRITE_CONFLICT : B2_ERR_CORRUPTED));

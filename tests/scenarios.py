@@ -227,3 +227,11 @@ def int_plans():
          ("agg", scan().selection(lt(c(6), const_int(1 << 20))).aggregation([("count", const_int(1)), ("sum", c(1)), ("sum", c(2)), ("avg", c(8))], group_by=[c(5, tp=ffi.TP_LONG)]).build()),
          ("topn", scan().selection(ge(c(3), const_int(0))).topn([(c(4), True), (c(2), False)], 40).build())]
     return P
+
+
+def limit_plans():
+    scan = lambda: Plan().table_scan(TABLE, COLUMNS)
+    return [("limit_scan", scan().limit(37).build()),
+            ("limit_after_selection", scan().selection(lt(col(C1), const_int(0))).limit(100).build(output_offsets=[C_H, C1, C3])),
+            ("limit_zero", scan().limit(0).build()),
+            ("limit_beyond_table", scan().selection(ge(col(C6), const_int(0))).limit(1 << 20).build())]

@@ -169,3 +169,11 @@ def test_exact_layout_fast_path_corrupted_rows():
     got = emu.dag_handle(plan, sc.WHOLE, region)
     assert exp.status != 0 and got.status == exp.status
     assert_same_rows(got, exp, ordered=True, ctx="corrupt")
+
+
+@pytest.mark.parametrize("name,plan", sc.limit_plans(), ids=[n for n, _ in sc.limit_plans()])
+def test_limit(name, plan, regions):
+    region = regions[1].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    exp = orc.dag_handle(plan, sc.split_ranges(), region)
+    got = emu.dag_handle(plan, sc.split_ranges(), region)
+    assert_same_rows(got, exp, ordered=True, ctx=name)

@@ -487,3 +487,13 @@ def test_plan_specialised_kernels_match_oracle(regions):
             assert sorted(got_rows, key=key) == sorted(exp.rows(), key=key), name
         else:
             assert got_rows == exp.rows(), name
+
+
+@pytest.mark.parametrize("name,plan", sc.limit_plans(), ids=[n for n, _ in sc.limit_plans()])
+@pytest.mark.parametrize("batch", [64, 1 << 22])
+def test_limit(name, plan, batch, regions):
+    """BatchLimitExecutor on top of scan / selection (limit_executor.rs): the first n rows in key order, then drained."""
+    region = regions[1].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    exp = orc.dag_handle(plan, sc.split_ranges(), region)
+    got = DagHandler(plan, sc.split_ranges(), region, batch_rows=batch).handle_request()
+    assert_same_rows(got, exp, ordered=True, ctx=name)

@@ -18,6 +18,7 @@ struct CompiledPlan {
   DevPlan dev;
   std::vector<OutCol> schema;            // output schema of the outermost executor
   std::vector<uint32_t> output_offsets;  // indices into `schema` delivered to the caller
+  uint64_t scan_limit = ~0ull;           // BatchLimitExecutor on top of a scan / selection pipeline (limit_executor.rs), ~0 = none
 };
 
 inline int col_kind_of_tp(int tp) {  // def/eval_type.rs:53-95
@@ -260,6 +261,9 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
       }
       if (e.limit > 2048) { *msg = "TopN limit above 2048 is not on the device path yet"; return B2_ERR_UNSUPPORTED; }
       P.n_order = (int)e.n_order_by; P.limit = e.limit;
+    } else if (e.tp == B2_EXEC_LIMIT) {
+      if (P.mode != PM_SCAN || ei + 1 != plan->n_executors) { *msg = "Limit is on the device path only as the last executor of a scan / selection pipeline"; return B2_ERR_UNSUPPORTED; }
+      out->scan_limit = e.limit;
     } else {
       *msg = "executor type " + std::to_string(e.tp) + " is not supported on the device path";
       return B2_ERR_UNSUPPORTED;

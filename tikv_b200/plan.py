@@ -161,6 +161,12 @@ class Plan:
         self._execs.append(e)
         return self
 
+    def limit(self, n):
+        e = ffi.ExecutorDesc()
+        e.tp, e.limit = ffi.EXEC_LIMIT, int(n)
+        self._execs.append(e)
+        return self
+
     def topn(self, order_by, limit):
         """order_by: list of (Expr, desc)."""
         o = (ffi.OrderBy * len(order_by))()
