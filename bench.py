@@ -43,7 +43,7 @@ def table_range():
     return [(pre + b"_r", pre + b"_s")]
 
 
-def gen_blocks(ffi, device, n_rows, n_blocks, first_handle=0):
+def gen_blocks(ffi, device, n_rows, n_blocks, first_handle=0, row_format=2):
     """Generate the table on the device as `n_blocks` CF_WRITE blocks.  Returns (gens, GenBlock list)."""
     L = ffi.lib()
     gens, blks = [], []
@@ -53,7 +53,7 @@ def gen_blocks(ffi, device, n_rows, n_blocks, first_handle=0):
     while left > 0:
         n = min(per, left)
         spec = ffi.GenSpec()
-        spec.table_id, spec.first_handle, spec.n_rows, spec.n_cols, spec.row_format, spec.seed = TABLE_ID, h, n, N_COLS, 2, SEED
+        spec.table_id, spec.first_handle, spec.n_rows, spec.n_cols, spec.row_format, spec.seed = TABLE_ID, h, n, N_COLS, row_format, SEED
         spec.commit_ts, spec.newer_ts = 20, 5000
         g, blk = C.c_void_p(), ffi.GenBlock()
         rc = L.b2_gen_create(device, C.byref(spec), C.byref(g), C.byref(blk))
@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-jit", action="store_true", help="generic kernel only")
+    ap.add_argument("--row-format", type=int, default=2, choices=[1, 2], help="TiDB row format of the synthetic table (BASELINE quotes v2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -253,7 +254,7 @@ def main():
     kernel_kind = "generic (interpreted plan)" if args.no_jit or prep_rc != 0 else "plan-specialised (compiled at run time, cached per plan)"
     if args.no_jit:
         os.environ["B2_JIT"] = "off"
-    gens, blks = gen_blocks(ffi, device, args.rows, args.blocks, first_handle=rank * args.rows)
+    gens, blks = gen_blocks(ffi, device, args.rows, args.blocks, first_handle=rank * args.rows, row_format=args.row_format)
     dev_src = Source(ffi, [b.block for b in blks], ffi.LOC_DEVICE, device)
     n_entries = sum(b.block.n for b in blks)
     in_bytes = sum(b.key_bytes + b.val_bytes + 8 * b.block.n for b in blks)
@@ -342,7 +343,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "C2: BatchTableScan + BatchSelection(col0 < 0) on 1e8 rows x 8 i64 cols, row format v2, 1 version/key (BASELINE.json configs[1])",
+        "config": {"workload": f"C2: BatchTableScan + BatchSelection(col0 < 0) on 1e8 rows x 8 i64 cols, row format v{args.row_format}, 1 version/key (BASELINE.json configs[1])",
                    "rows_per_gpu": args.rows, "cf_write_entries_per_gpu": n_entries, "blocks_per_gpu": args.blocks, "entries_per_batch": args.chunk,
                    "selectivity": rows_out / max(1, args.rows), "parallelism": f"region-sharded x{world}, no data-path collective",
                    "l2": f"inputs {in_bytes / 1e9:.1f} GB per pass >> 126 MB L2 (no flush needed)", "setup_s": round(time.time() - t_setup, 1)},

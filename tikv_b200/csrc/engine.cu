@@ -973,11 +973,12 @@ struct b2_exec {
   // ---- PM_AGG: everything in one go ----
   int alloc_table(unsigned int cap) {
     size_t W = cp.dev.acc_words;
-    CUDA_TRY(tbl_keys.reserve(((size_t)cap + 1) * 8));
-    CUDA_TRY(tbl_occ.reserve(((size_t)cap + 1) * 4));
-    CUDA_TRY(tbl_acc.reserve(((size_t)cap + 1) * 8 * W));
-    CUDA_TRY(cudaMemsetAsync(tbl_occ.p, 0, ((size_t)cap + 1) * 4, stream));
-    CUDA_TRY(cudaMemsetAsync(tbl_acc.p, 0, ((size_t)cap + 1) * 8 * W, stream));
+    CUDA_TRY(tbl_keys.reserve(((size_t)cap + 2) * 8));
+    CUDA_TRY(tbl_occ.reserve(8));
+    CUDA_TRY(tbl_acc.reserve(((size_t)cap + 2) * 8 * W));
+    CUDA_TRY(cudaMemsetAsync(tbl_keys.p, 0xff, ((size_t)cap + 2) * 8, stream));  // AGG_EMPTY_KEY everywhere
+    CUDA_TRY(cudaMemsetAsync(tbl_occ.p, 0, 8, stream));
+    CUDA_TRY(cudaMemsetAsync(tbl_acc.p, 0, ((size_t)cap + 2) * 8 * W, stream));
     tbl_cap = cap;
     return B2_OK;
   }
@@ -1018,7 +1019,7 @@ struct b2_exec {
         if (rc) return rc;
         ScanArgs a = base_args(u, v);
         a.c_lo = u.e_lo; a.c_hi = u.e_hi;
-        a.tbl.keys = (unsigned long long*)tbl_keys.p; a.tbl.occ = (unsigned int*)tbl_occ.p; a.tbl.acc = (unsigned long long*)tbl_acc.p; a.tbl.cap = tbl_cap;
+        a.tbl.keys = (unsigned long long*)tbl_keys.p; a.tbl.special = (unsigned int*)tbl_occ.p; a.tbl.acc = (unsigned long long*)tbl_acc.p; a.tbl.cap = tbl_cap;
         a.smem_slots = smem_slots;
         size_t tot = setup_staging(&a, wblocks[u.block_idx], smem);
         grid = scan_grid_for(PM_AGG, tot);
@@ -1053,8 +1054,8 @@ struct b2_exec {
       ga = (const unsigned long long*)tbl_acc.p;
     } else {
       size_t W = P.acc_words;
-      CUDA_TRY(grp_keys.reserve(((size_t)tbl_cap + 1) * 8)); CUDA_TRY(grp_null.reserve((size_t)tbl_cap + 1)); CUDA_TRY(grp_acc.reserve(((size_t)tbl_cap + 1) * 8 * W));
-      AggTable t; t.keys = (unsigned long long*)tbl_keys.p; t.occ = (unsigned int*)tbl_occ.p; t.acc = (unsigned long long*)tbl_acc.p; t.cap = tbl_cap;
+      CUDA_TRY(grp_keys.reserve(((size_t)tbl_cap + 2) * 8)); CUDA_TRY(grp_null.reserve((size_t)tbl_cap + 2)); CUDA_TRY(grp_acc.reserve(((size_t)tbl_cap + 2) * 8 * W));
+      AggTable t; t.keys = (unsigned long long*)tbl_keys.p; t.special = (unsigned int*)tbl_occ.p; t.acc = (unsigned long long*)tbl_acc.p; t.cap = tbl_cap;
       CUDA_TRY(launch_agg_finalize(P, t, ctr(), (unsigned long long*)grp_keys.p, (unsigned char*)grp_null.p, (unsigned long long*)grp_acc.p, stream));
       int rc = read_counters(&c);
       if (rc) return rc;

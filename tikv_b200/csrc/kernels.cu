@@ -208,17 +208,17 @@ cudaError_t launch_pack_nulls(const unsigned char* nulls, uint32_t n_cols, uint3
 __global__ void agg_finalize_kernel(const __grid_constant__ DevPlan P, AggTable t, Counters* ctr, unsigned long long* out_keys,
                                     unsigned char* out_key_null, unsigned long long* out_acc) {
   unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > t.cap) return;
-  if (t.occ[i] != 2) return;
+  if (i > t.cap + 1) return;
+  if (i < t.cap ? t.keys[i] == AGG_EMPTY_KEY : t.special[i - t.cap] == 0) return;
   unsigned int g = atomicAdd(&ctr->n_groups, 1u);
-  out_keys[g] = i == t.cap ? 0ull : t.keys[i];
+  out_keys[g] = i == t.cap ? 0ull : (i == t.cap + 1 ? AGG_EMPTY_KEY : t.keys[i]);
   out_key_null[g] = i == t.cap;
   for (int w = 0; w < P.acc_words; ++w) out_acc[(size_t)g * P.acc_words + w] = t.acc[(size_t)i * P.acc_words + w];
 }
 
 cudaError_t launch_agg_finalize(const DevPlan& plan, const AggTable& t, Counters* ctr, unsigned long long* out_keys, unsigned char* out_key_null,
                                 unsigned long long* out_acc, cudaStream_t s) {
-  unsigned int n = t.cap + 1;
+  unsigned int n = t.cap + 2;
   agg_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(plan, t, ctr, out_keys, out_key_null, out_acc);
   return cudaGetLastError();
 }

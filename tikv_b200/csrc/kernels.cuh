@@ -28,12 +28,15 @@ struct Counters {
   unsigned long long last_row;         // 1 + largest global CF_WRITE entry index the MVCC scan returned a row for (take_scanned_range)
 };
 
-// Open-addressing group table in HBM (fast_hash_aggr_executor.rs:216-229 `Groups`): slot = hash(key) & mask,
-// linear probing.  Slot `cap` is the NULL-key group; accumulators are u64 words per slot.
+// Open-addressing group table in HBM (fast_hash_aggr_executor.rs:216-229 `Groups`): slot = hash(key) & mask, linear
+// probing on the key words themselves: a free slot holds AGG_EMPTY_KEY and is claimed with one 64-bit CAS (accumulators
+// start at zero and are only added to, so a claimed slot needs no further initialisation).  Slot `cap` is the NULL-key
+// group, slot `cap + 1` the group whose key equals AGG_EMPTY_KEY; `special[0..1]` say whether those two are in use.
+#define AGG_EMPTY_KEY 0xffffffffffffffffull
 struct AggTable {
-  unsigned long long* keys;  // cap + 1
-  unsigned int* occ;         // cap + 1: 0 empty, 1 being claimed, 2 ready
-  unsigned long long* acc;   // (cap + 1) * acc_words
+  unsigned long long* keys;  // cap + 2
+  unsigned int* special;     // 2
+  unsigned long long* acc;   // (cap + 2) * acc_words
   unsigned int cap;          // power of two
 };
 

@@ -30,24 +30,17 @@ __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) 
 // ---- HBM group table ----------------------------------------------------------------------------------
 // returns slot index, or 0xffffffff when the table is full
 __device__ unsigned int table_find_or_insert(const AggTable& t, uint64_t key, bool is_null) {
-  if (is_null) {
-    if (ld_acquire_u32(&t.occ[t.cap]) != 2) atomicExch(&t.occ[t.cap], 2u);
-    return t.cap;
+  if (is_null || key == AGG_EMPTY_KEY) {
+    const unsigned int which = is_null ? 0u : 1u;
+    if (*(volatile unsigned int*)&t.special[which] == 0) atomicExch(&t.special[which], 1u);
+    return t.cap + which;
   }
   unsigned int mask = t.cap - 1;
   unsigned int s = (unsigned int)mix64(key) & mask;
   for (unsigned int probes = 0; probes < t.cap; ++probes) {
-    unsigned int o = ld_acquire_u32(&t.occ[s]);
-    if (o == 0) {
-      o = atomicCAS(&t.occ[s], 0u, 1u);
-      if (o == 0) {
-        t.keys[s] = key;
-        st_release_u32(&t.occ[s], 2u);
-        return s;
-      }
-    }
-    while (o == 1) o = ld_acquire_u32(&t.occ[s]);
-    if (t.keys[s] == key) return s;
+    unsigned long long kk = ld_volatile_u64(&t.keys[s]);  // one L2 round trip per probe
+    if (kk == AGG_EMPTY_KEY) kk = atomicCAS(&t.keys[s], AGG_EMPTY_KEY, (unsigned long long)key);
+    if (kk == AGG_EMPTY_KEY || kk == key) return s;
     s = (s + 1) & mask;
   }
   return 0xffffffffu;
