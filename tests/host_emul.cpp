@@ -278,4 +278,9 @@ int emu_check_supported(const b2_dag_plan* plan, char* msg, size_t cap) {
   return rc;
 }
 
+// codec hooks: the word-wise varint readers of b2_device.h against the oracle's byte-wise restatement
+uint32_t emu_dec_var_u64(const uint8_t* p, uint32_t n, uint64_t* out) { return dec_var_u64(p, n, out); }
+uint32_t emu_first_var_int_len(const uint8_t* p, uint32_t n) { return first_var_int_len(p, n); }
+uint32_t emu_split_datum(const uint8_t* p, uint32_t n) { int err = 0; uint32_t r = split_datum(p, n, &err); return err ? 0 : r; }
+
 }  // extern "C"

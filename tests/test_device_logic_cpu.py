@@ -177,3 +177,29 @@ def test_limit(name, plan, regions):
     exp = orc.dag_handle(plan, sc.split_ranges(), region)
     got = emu.dag_handle(plan, sc.split_ranges(), region)
     assert_same_rows(got, exp, ordered=True, ctx=name)
+
+
+def test_wordwise_varints_match_oracle():
+    """dec_var_u64 / first_var_int_len (one 8-byte load + bit tricks) against the oracle's byte loop: every length 1..10,
+    truncated buffers, over-long encodings (codec number.rs:445-567)."""
+    import ctypes as C
+    import random
+    E, O = emu.lib(), orc.lib()
+    E.emu_dec_var_u64.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint64)]
+    E.emu_first_var_int_len.argtypes = [C.c_char_p, C.c_uint32]
+    E.emu_split_datum.argtypes = [C.c_char_p, C.c_uint32]
+    rng = random.Random(11)
+    cases = []
+    for bits in list(range(0, 65)) * 4:
+        v = rng.getrandbits(bits) if bits else 0
+        cases.append(kvfmt.enc_var_u64(v))
+    cases += [bytes([0x80] * k + [0x01]) for k in range(0, 12)] + [bytes([0xFF] * k) for k in range(1, 13)] + [bytes([0xFF] * 9 + [b]) for b in (0, 1, 2, 0x7F, 0x80, 0xFF)]
+    for enc in cases:
+        for n in range(0, len(enc) + 1):
+            buf = enc[:n] + bytes(rng.getrandbits(8) for _ in range(16))  # garbage after the slice must not matter
+            a, b = C.c_uint64(0), C.c_uint64(0)
+            ra = E.emu_dec_var_u64(buf, n, C.byref(a))
+            rb = O.orc_decode_var_u64(buf, n, C.byref(b))
+            assert ra == rb and (ra == 0 or a.value == b.value), (enc.hex(), n, ra, rb, a.value, b.value)
+            datum = bytes([8]) + buf
+            assert E.emu_split_datum(datum, n + 1) == O.orc_split_datum(datum, n + 1), (enc.hex(), n)

@@ -198,31 +198,43 @@ B2_HD int bytes_cmp(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn
   return an < bn ? -1 : (an > bn ? 1 : 0);
 }
 
-// components/codec/src/number.rs:445-483 try_decode_var_u64. returns bytes consumed, 0 = eof
+B2_HD uint32_t ctz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__ffsll((long long)v) - 1u;
+#else
+  return (uint32_t)__builtin_ctzll(v);
+#endif
+}
+// eight 7-bit groups, one per byte (bit 7 of every byte clear) -> one 56-bit value
+B2_HD uint64_t compress7(uint64_t x) {
+  x = ((x & 0x7f007f007f007f00ull) >> 1) | (x & 0x007f007f007f007full);
+  x = ((x & 0x3fff00003fff0000ull) >> 2) | (x & 0x00003fff00003fffull);
+  x = ((x & 0x0fffffff00000000ull) >> 4) | (x & 0x000000000fffffffull);
+  return x;
+}
+// components/codec/src/number.rs:445-483 try_decode_var_u64. returns bytes consumed, 0 = eof.
+// Word-wise: one unaligned 8-byte load finds the terminating byte (first byte with bit 7 clear) and the payload bits
+// are gathered with three mask-and-shift steps; bytes 9 and 10 of the longest encodings are looked at separately.
+// (With n >= 10 the reference takes the 10th byte unconditionally and keeps only its lowest bit.)
 B2_HD uint32_t dec_var_u64(const uint8_t* p, uint32_t n, uint64_t* out) {
-  uint64_t v = 0;
   if (n == 0) return 0;
-  {  // fast path: 1- and 2-byte varints (column ids, start_ts deltas, small ints) from one word load
-    uint32_t w = ld32(p);
-    if ((w & 0x80u) == 0) { *out = w & 0x7fu; return 1; }
-    if (n >= 2 && (w & 0x8000u) == 0) { *out = (w & 0x7fu) | (((w >> 8) & 0x7fu) << 7); return 2; }
+  const uint64_t w = ld64(p);
+  if ((w & 0x80u) == 0) { *out = w & 0x7fu; return 1; }
+  const uint64_t stop = ~w & 0x8080808080808080ull;
+  if (stop) {
+    const uint32_t len = (ctz64(stop) >> 3) + 1;  // 2..8
+    if (len > n) return 0;
+    const uint64_t x = len == 8 ? w : (w & ((1ull << (8 * len)) - 1));
+    *out = compress7(x & 0x7f7f7f7f7f7f7f7full);
+    return len;
   }
-  if (n >= 10) {
-    for (uint32_t i = 0; i < 9; ++i) {
-      uint64_t b = p[i];
-      v |= (b & 0x7f) << (7 * i);
-      if (b < 0x80) { *out = v; return i + 1; }
-    }
-    v |= ((uint64_t)p[9] & 1) << 63;
-    *out = v;
-    return 10;
-  }
-  uint32_t i = 0, shift = 0;
-  while (i < n && p[i] >= 0x80) { v |= (uint64_t)(p[i] & 0x7f) << shift; shift += 7; ++i; }
-  if (i == n) return 0;
-  v |= (uint64_t)p[i] << shift;
-  *out = v;
-  return i + 1;
+  if (n < 9) return 0;  // every available byte asks for more
+  const uint64_t x = compress7(w & 0x7f7f7f7f7f7f7f7full);
+  const uint64_t b8 = p[8];
+  if (b8 < 0x80) { *out = x | (b8 << 56); return 9; }
+  if (n < 10) return 0;
+  *out = x | ((b8 & 0x7f) << 56) | (((uint64_t)p[9] & 1) << 63);
+  return 10;
 }
 // components/tikv_util/src/codec/number.rs:224-275 (overflow error on a 10th byte > 1)
 B2_HD uint32_t dec_var_u64_tu(const uint8_t* p, uint32_t n, uint64_t* out) {
@@ -249,9 +261,13 @@ B2_HD uint32_t dec_var_i64(const uint8_t* p, uint32_t n, int64_t* out) {
   return c;
 }
 B2_HD uint32_t first_var_int_len(const uint8_t* p, uint32_t n) {  // number.rs:530-567
-  uint32_t lim = n >= 10 ? 9 : n;
-  for (uint32_t i = 0; i < lim; ++i)
-    if (p[i] < 0x80) return i + 1;
+  const uint32_t lim = n >= 10 ? 9 : n;
+  if (lim == 0) return n;
+  const uint64_t stop = ~ld64(p) & 0x8080808080808080ull;
+  if (stop) {
+    const uint32_t len = (ctz64(stop) >> 3) + 1;
+    if (len <= lim) return len;
+  } else if (lim >= 9 && p[8] < 0x80) return 9;
   return n >= 10 ? 10 : n;
 }
 
