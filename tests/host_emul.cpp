@@ -105,7 +105,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
             uint32_t prev = 0;
             for (int h = 0; h < 8 && h < P.fast_n; ++h) {
               uint32_t end = fast_end(row, h);
-              if (P.fast_out[h] >= 0) { R->data[P.fast_out[h]].push_back(fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u)); R->nonnull[P.fast_out[h]].push_back(true); }
+              if (P.fast_out[h] >= 0) { R->data[P.fast_out[h]].push_back(row.fast == 2 ? fast_cell_dyn(row, (uint32_t)h, false, true) : fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u)); R->nonnull[P.fast_out[h]].push_back(true); }
               prev = end;
             }
             for (int j = 0; j < P.n_out_slow; ++j) put(P.out_slow[j]);

@@ -181,7 +181,7 @@ INT_COLUMNS = [ColumnDef(100, pk_handle=True), ColumnDef(7, unsigned=True), Colu
                ColumnDef(5, tp=ffi.TP_LONG), ColumnDef(9), ColumnDef(4), ColumnDef(6, unsigned=True)]
 
 
-def int_region(seed, n_keys=500, corrupt=False):
+def int_region(seed, n_keys=500, corrupt=False, fmt=2):
     """v2 rows holding exactly the 8 stored columns above with every width mix (1/2/4/8 bytes), some rows with a NULL or a
     missing column (general path), optionally rows with a 3-byte integer or decreasing offsets (errors)."""
     rng = random.Random(seed)
@@ -201,6 +201,28 @@ def int_region(seed, n_keys=500, corrupt=False):
             cols[k] = (cols[k][0], None, "null")
         elif x < 0.08:
             cols.pop(rng.randrange(8))
+        if fmt == 1:
+            # v1: `08 id datum` per column; INT / UINT / VAR_INT / VAR_UINT flags mixed, sometimes out of id order, an
+            # unknown extra column, a NIL datum: all but the plain in-order rows take the general datum walk
+            d = []
+            for cid, v, kind in cols:
+                if v is None:
+                    d.append((cid, kvfmt.datum_null()))
+                elif kind == "uint":
+                    d.append((cid, kvfmt.datum_uint(v, comparable=rng.random() < 0.3)))
+                else:
+                    d.append((cid, kvfmt.datum_int(v, comparable=rng.random() < 0.3)))
+            d.sort(key=lambda t: t[0])
+            y = rng.random()
+            if y < 0.04:
+                rng.shuffle(d)
+            elif y < 0.07:
+                d.append((40, kvfmt.datum_int(1)))
+            val = bytearray(kvfmt.row_v1(d))
+            if corrupt and 0.5 < x < 0.52 and len(cols) == 8:
+                val = val[:-1] if val[-1] >= 0x80 or rng.random() < 0.5 else val + b"\x08"  # truncated datum / dangling id marker
+            r.put(kvfmt.row_key(TABLE, h * 2 + 5), bytes(val), 5, 8)
+            continue
         val = bytearray(kvfmt.row_v2(cols))
         if corrupt and 0.5 < x < 0.52 and len(cols) == 8:
             # widen the first value to 3 bytes by shifting every offset up by one where possible: rewrite offsets by hand

@@ -145,11 +145,13 @@ def test_topn_device_logic_matches_oracle(name, plan, exact, keys, regions):
         assert_topn(emu.dag_handle(plan, ranges, region), orc.dag_handle(plan, ranges, region), exact, keys, ctx=f"{name}/seed{seed}")
 
 
+@pytest.mark.parametrize("fmt", [2, 1])
 @pytest.mark.parametrize("name,plan", sc.int_plans(), ids=[n for n, _ in sc.int_plans()])
-def test_exact_layout_fast_path(name, plan):
-    """All-integer table: SWAR width probe, `column <cmp> const` conditions and outputs by stored position, every width
-    mix, signed/unsigned compares; rows with NULL / missing columns take the general path in the same batch."""
-    region = sc.int_region(3).build(read_ts=sc.READ_TS, n_write_blocks=2)
+def test_exact_layout_fast_path(name, plan, fmt):
+    """All-integer table, row formats v2 and v1: layout probes, `column <cmp> const` conditions and outputs by stored
+    position, every width / datum-flag mix, signed/unsigned compares; rows with NULL / missing / extra / reordered
+    columns take the general path in the same batch."""
+    region = sc.int_region(3, fmt=fmt).build(read_ts=sc.READ_TS, n_write_blocks=2)
     exp = orc.dag_handle(plan, sc.WHOLE, region)
     got = emu.dag_handle(plan, sc.WHOLE, region)
     assert exp.status == 0 and exp.n_rows > 0
@@ -160,10 +162,11 @@ def test_exact_layout_fast_path(name, plan):
         assert_same_rows(got, exp, ordered=name != "agg", ctx=name)
 
 
-def test_exact_layout_fast_path_corrupted_rows():
-    """3/5/9-byte integers and decreasing offsets: the probe must reject the row and the general path must raise the
-    reference's error at the same entry with the rows before it intact."""
-    region = sc.int_region(4, corrupt=True).build(read_ts=sc.READ_TS)
+@pytest.mark.parametrize("fmt", [2, 1])
+def test_exact_layout_fast_path_corrupted_rows(fmt):
+    """v2: 3/5/9-byte integers and decreasing offsets; v1: truncated datums and dangling column markers.  The probe must
+    reject the row and the general path must raise the reference's error at the same entry with the rows before it intact."""
+    region = sc.int_region(4, corrupt=True, fmt=fmt).build(read_ts=sc.READ_TS)
     plan = sc.int_plans()[1][1]
     exp = orc.dag_handle(plan, sc.WHOLE, region)
     got = emu.dag_handle(plan, sc.WHOLE, region)

@@ -435,11 +435,12 @@ def test_take_scanned_range_and_rows_per_range(regions):
         assert seen == len(all_rows) and got_per_range == per_range and sum(per_range) > 300
 
 
+@pytest.mark.parametrize("fmt", [2, 1])
 @pytest.mark.parametrize("name,plan", sc.int_plans(), ids=[n for n, _ in sc.int_plans()])
-def test_exact_layout_fast_path(name, plan):
+def test_exact_layout_fast_path(name, plan, fmt):
     """All-integer table through the C ABI: SWAR width probe, conditions and outputs by stored position (every width mix,
     signed/unsigned), rows with NULL / missing columns on the general path of the same tiles."""
-    region = sc.int_region(3, n_keys=3000).build(read_ts=sc.READ_TS, n_write_blocks=2)
+    region = sc.int_region(3, n_keys=3000, fmt=fmt).build(read_ts=sc.READ_TS, n_write_blocks=2)
     exp = orc.dag_handle(plan, sc.WHOLE, region)
     got = DagHandler(plan, sc.WHOLE, DeviceRegion(region)).handle_request()
     if name == "topn":
@@ -447,7 +448,7 @@ def test_exact_layout_fast_path(name, plan):
         assert_topn(got, exp, True, None, ctx=name)
     else:
         assert_same_rows(got, exp, ordered=name != "agg", ctx=name)
-    bad = sc.int_region(4, n_keys=3000, corrupt=True).build(read_ts=sc.READ_TS)
+    bad = sc.int_region(4, n_keys=3000, corrupt=True, fmt=fmt).build(read_ts=sc.READ_TS)
     exp = orc.dag_handle(plan, sc.WHOLE, bad)
     got = DagHandler(plan, sc.WHOLE, bad).handle_request()
     assert exp.status != 0 and got.status == exp.status

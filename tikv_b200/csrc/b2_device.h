@@ -103,7 +103,8 @@ struct DevPlan {
   uint32_t fast_uns;     // bit h: stored column h is zero-extended (unsigned)
   int8_t fast_out[8];    // PM_SCAN: output column fed by stored column h (first occurrence), or -1
   int32_t n_out_slow;    // PM_SCAN: outputs of a fast row that still go through cell_value (handle, Real, repeats ...)
-  int32_t _fpad2;
+  int32_t fast_v1;       // 1: the fast path also covers row-format-v1 rows (all stored columns integer-class, ids <= 63)
+                         //    and the request's data looked like v1 when it was opened (engine samples the first row)
   uint64_t fast_ids;   // the expected sorted non-null id bytes of such a row, packed little-endian (fast_n <= 8)
   uint64_t read_ts;
   uint64_t limit;
@@ -669,7 +670,7 @@ struct Row {
   uint32_t enc_key_len;
   uint64_t commit_ts;
   uint64_t filled;  // bitmask of plan columns present in the row (bit c)
-  uint32_t fast;    // 1: v2 row with exactly the plan's columns, all non-null: cells come from the two offset words below
+  uint32_t fast;    // 1 (v2) / 2 (v1): the row holds exactly the plan's columns, all non-null: cells come from the two offset words below
   uint64_t o_lo, o_hi;  // the row's u16 end-offsets 0..3 / 4..7
 };
 
@@ -682,12 +683,63 @@ B2_HD uint32_t shr_clamp(uint32_t v, uint32_t sh) {  // v >> sh, 0 for sh >= 32
 }
 // end offset of stored column h of a fast row (h is a compile-time constant after unrolling)
 B2_HD uint32_t fast_end(const Row& row, int h) { return (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu; }
+// integer cell of a fast v1 row: the datum of stored column h starts two bytes (VAR_INT flag + one-byte column id)
+// after the end of the previous datum; decode_int_datum (datum_codec.rs:401-421) by flag, lengths validated by the probe
+B2_HD uint64_t fast_int_cell_v1(const Row& row, uint32_t prev_end) {
+  const uint8_t* p = row.rv.v + prev_end + 2;
+  const uint32_t flag = p[0];
+  if (flag == 8) { int64_t v = 0; dec_var_i64(p + 1, 10, &v); return (uint64_t)v; }
+  if (flag == 9) { uint64_t v = 0; dec_var_u64(p + 1, 10, &v); return v; }
+  const uint64_t u = ld_be64(p + 1);
+  return flag == 3 ? u ^ 0x8000000000000000ull : u;
+}
 // integer cell of a fast row: stored column h spans [start, end) of the value area (compat_v1.rs:13-38)
 B2_HD uint64_t fast_int_cell(const Row& row, uint32_t start, uint32_t end, bool zero_extend) {
   uint64_t u = ld64(row.rv.v + row.rv.vals_off + start);
   const uint32_t sh = (64u - 8u * (end - start)) & 63u;  // width 8 -> 0: branch-free, so neighbouring cells overlap
   u <<= sh;
   return zero_extend ? (u >> sh) : (uint64_t)((int64_t)u >> sh);
+}
+// stored column h of a fast row of either format, h known only at run time (conditions, cell_value).  The v1 decoder
+// is kept out of the unrolled per-position loops on purpose: inlined there it tripled the size of the hot loop.
+B2_HD uint64_t fast_cell_dyn(const Row& row, uint32_t h, bool zero_extend, bool v1_enabled) {
+  const uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
+  const uint32_t start = h == 0 ? 0u : ((uint32_t)((h - 1 < 4 ? row.o_lo : row.o_hi) >> (((h - 1) & 3) * 16)) & 0xffffu);
+  return v1_enabled && row.fast == 2 ? fast_int_cell_v1(row, start) : fast_int_cell(row, start, end, zero_extend);
+}
+// Row format v1 twin of fast_row_probe: the row is exactly `08 id datum` for the plan's columns in id order, every datum
+// an INT / UINT / VAR_INT / VAR_UINT that fits the buffer.  The end offsets of the datums go into the same two
+// registers as for v2 rows.  Anything else (NIL, other flags, more or fewer columns, ids >= 64, a truncated varint)
+// takes the general datum walk, which also raises the reference's errors.
+B2_HD bool fast_row_probe_v1(const DevPlan& P, Row& row) {
+  const RowView& r = row.rv;
+  row.fast = 0;
+  if (!P.fast_v1) return false;
+  // straight-line on purpose (no early exits, varint lengths by select): lanes of a warp hold datums of different
+  // lengths, and any branch on them would keep the lanes apart for the rest of the unrolled walk
+  uint32_t pos = 0, bad = 0;
+  uint64_t lo = 0, hi = 0;
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    if (h < P.fast_n) {
+      const uint32_t at = pos < r.n ? pos : 0u;  // keep the loads inside the row even after a mismatch
+      const uint32_t w = ld32(r.v + at);         // 08, zigzag(id), datum flag, first payload byte
+      const uint32_t want = 0x08u | ((uint32_t)((P.fast_ids >> (8 * h)) & 0xffu) << 9);
+      const uint32_t flag = (w >> 16) & 0xffu;
+      const uint64_t pay = ld64(r.v + at + 3);
+      const uint64_t stop = ~pay & 0x8080808080808080ull;
+      const uint32_t vlen = stop ? (ctz64(stop) >> 3) + 1 : ((r.v[at + 11] & 0x80u) ? 10u : 9u);  // varint bytes (number.rs:530-567)
+      const bool is_var = flag == 8 || flag == 9, is_fix = flag == 3 || flag == 4;
+      const uint32_t dl = 1 + (is_var ? vlen : 8u);
+      bad |= ((w & 0xffffu) != want) | (!is_var && !is_fix) | (pos + 2 + dl > r.n);
+      pos += 2 + dl;
+      if (h < 4) lo |= (uint64_t)(pos & 0xffffu) << (16 * h); else hi |= (uint64_t)(pos & 0xffffu) << (16 * (h - 4));
+    }
+  }
+  if (bad || pos != r.n || pos > 0xffffu) return false;
+  row.o_lo = lo; row.o_hi = hi;
+  row.fast = 2;
+  return true;
 }
 // Does this v2 row hold exactly the plan's columns (process_v2 would find column k at position v2_hint), all
 // non-null, offsets monotone and inside the value area, integer-class columns 1/2/4/8 bytes wide?  On success the
@@ -744,7 +796,9 @@ B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
   uint64_t filled = 0;
   row.fast = 0;
   int err = DE_NONE;
-  if (r.fmt == 1) {
+  if (r.fmt == 1 && fast_row_probe_v1(P, row)) {
+    filled = P.fast_filled;
+  } else if (r.fmt == 1) {
     uint32_t pos = 0, n = r.n;
     int decoded = 0;
     while (pos < n && decoded < P.n_cols) {
@@ -816,10 +870,7 @@ B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k
   out->null = false; out->bits = 0;
   const uint64_t S = 0x8000000000000000ull;
   if (row.fast && c.role == CR_NORMAL && c.kind == CK_INT) {  // hot case: integer column of an exact-layout v2 row
-    uint32_t h = c.v2_hint;
-    uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
-    uint32_t start = h == 0 ? 0u : ((uint32_t)((h - 1 < 4 ? row.o_lo : row.o_hi) >> (((h - 1) & 3) * 16)) & 0xffffu);
-    out->bits = fast_int_cell(row, start, end, c.v2_class != V2_INT);
+    out->bits = fast_cell_dyn(row, c.v2_hint, c.v2_class != V2_INT, P.fast_v1 != 0);
     return DE_NONE;
   }
   if (c.role == CR_HANDLE) { out->bits = raw_be64(row.enc_key, 11) ^ S; return DE_NONE; }       // table.rs:214-218
@@ -830,7 +881,7 @@ B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k
   const uint8_t* p = nullptr;
   uint32_t len = 0;
   int kind = CELL_MISSING;
-  if (row.fast) {
+  if (row.fast == 1 || (!P.fast_v1 && row.fast)) {
     uint32_t h = c.v2_hint;
     uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
     uint32_t start = h == 0 ? 0u : ((uint32_t)((h - 1 < 4 ? row.o_lo : row.o_hi) >> (((h - 1) & 3) * 16)) & 0xffffu);
@@ -1109,10 +1160,7 @@ B2_HD int eval_conds(const DevPlan& P, const Row& row, const Cells& cells, bool*
     // the column is read by stored position (impl_compare.rs:63-149 semantics through cmp_i64)
     for (int i = 0; i < P.n_fconds; ++i) {
       const FastCond f = P.fconds[i];
-      const uint32_t h = f.h;
-      const uint32_t end = (uint32_t)((h < 4 ? row.o_lo : row.o_hi) >> ((h & 3) * 16)) & 0xffffu;
-      const uint32_t start = h == 0 ? 0u : ((uint32_t)((h - 1 < 4 ? row.o_lo : row.o_hi) >> (((h - 1) & 3) * 16)) & 0xffffu);
-      const int c = cmp_i64((int64_t)fast_int_cell(row, start, end, f.zero_ext), f.col_uns, f.imm, f.imm_uns);
+      const int c = cmp_i64((int64_t)fast_cell_dyn(row, f.h, f.zero_ext, P.fast_v1 != 0), f.col_uns, f.imm, f.imm_uns);
       bool t;
       switch (f.op) {
         case 0: t = c < 0; break;

@@ -324,6 +324,29 @@ struct b2_exec {
     return launch_scan(cp.dev, a, grid, smem, stream);
   }
 
+  // Row format of the first row a unit will touch (TiDB tables are all-v1 or all-v2 in practice); decides whether the
+  // v1 twin of the exact-layout path is part of the kernel.  A wrong guess only costs speed: every row is checked.
+  bool sample_is_v1() {
+    if (units.empty()) return false;
+    const Unit& u = units[0];
+    const SrcBlock& b = wblocks[u.block_idx];
+    if (u.e_lo >= b.c.n) return false;
+    uint32_t off[2];
+    uint8_t buf[64];
+    memset(buf, 0, sizeof(buf));
+    if (src_loc == B2_LOC_HOST) { off[0] = b.c.val_offs[u.e_lo]; off[1] = b.c.val_offs[u.e_lo + 1]; }
+    else if (cudaMemcpy(off, b.c.val_offs + u.e_lo, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    uint32_t n = std::min<uint32_t>(off[1] - off[0], 48);
+    if (src_loc == B2_LOC_HOST) memcpy(buf, b.c.vals + off[0], n);
+    else if (cudaMemcpy(buf, b.c.vals + off[0], n, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    // write record: type, varint start_ts, then 'v' len row... (write.rs:296-361); anything else: no opinion
+    uint32_t pos = 1;
+    while (pos < n && (buf[pos] & 0x80)) ++pos;
+    ++pos;
+    if (pos + 2 >= n || buf[pos] != 'v') return false;
+    return buf[pos + 2] != 128 && buf[pos + 1] > 1;
+  }
+
   // ---- source setup ----
   int read_offs_end(const b2_cf_block& b, uint64_t* kb, uint64_t* vb) {
     uint32_t k = 0, v = 0;
@@ -1316,6 +1339,8 @@ int32_t b2_exec_open(const b2_dag_plan* plan, const b2_key_range* ranges, uint32
   h->cp.dev.isolation = src->isolation_level;
   rc = h->setup_source(src, ranges, n_ranges);
   if (rc) { g_last_error = h->last_err.message; return rc; }
+  // the exact-layout path for row-format-v1 rows is only compiled in / switched on when the data looks like v1
+  if (h->cp.dev.fast_v1 && !h->sample_is_v1()) h->cp.dev.fast_v1 = 0;
   // plan-specialised kernel: B2_JIT=off|sync|auto (environment) overrides cfg->jit; `auto` compiles in the background
   // for requests big enough to matter and switches over when the kernel is ready
   h->jit_mode = cfg ? cfg->jit : b2_exec::JIT_AUTO;
@@ -1340,7 +1365,12 @@ extern "C" int32_t b2_plan_prepare(const b2_dag_plan* plan, int32_t device) {
   if (rc) { g_last_error = msg; return rc; }
   std::string why;
   if (!jit_available(&why)) { g_last_error = "run-time compilation unavailable: " + why; return B2_ERR_UNSUPPORTED; }
+  // both data-dependent variants: without and (where the plan allows it) with the row-format-v1 exact-layout path
+  std::shared_future<JitKernel*> with_v1;
+  if (cp.dev.fast_v1) with_v1 = jit_get(device, cp.dev);
+  cp.dev.fast_v1 = 0;
   const JitKernel* k = jit_get(device, cp.dev).get();
+  if (k->ok && with_v1.valid()) k = with_v1.get();
   if (!k->ok) { g_last_error = "plan-specialised kernel: " + k->error; return B2_ERR_CUDA; }
   return B2_OK;
 }

@@ -184,7 +184,7 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
       ids.push_back(P.cols[i].col_id);
     }
     std::sort(ids.begin(), ids.end());
-    P.fast_n = 0; P.fast_ids = 0; P.fast_cls = 0; P.fast_uns = 0; P.fast_filled = 0; P.n_out_slow = 0;
+    P.fast_n = 0; P.fast_ids = 0; P.fast_cls = 0; P.fast_uns = 0; P.fast_filled = 0; P.n_out_slow = 0; P.fast_v1 = 0;
     for (int h = 0; h < 8; ++h) P.fast_out[h] = -1;
     if (ok && !ids.empty() && ids.size() <= 8) {
       P.fast_n = (int32_t)ids.size();
@@ -198,6 +198,11 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
         if (col.v2_class == V2_INT || col.v2_class == V2_UINT) P.fast_cls |= 1u << rank;
         if (col.v2_class != V2_INT) P.fast_uns |= 1u << rank;
       }
+      // the v1 twin needs single-byte column ids (zigzag varint of ids <= 63) and integer datums only; a column whose
+      // tp makes decode_int_datum irrelevant (Real ...) keeps v1 rows on the general walk
+      bool v1 = P.fast_cls == (1u << P.fast_n) - 1u && ids.back() <= 63;
+      for (int i = 0; i < P.n_cols; ++i) if (P.cols[i].role == CR_NORMAL && P.cols[i].kind != CK_INT) v1 = false;
+      P.fast_v1 = v1 ? 1 : 0;
     }
   }
   P.mode = PM_SCAN;

@@ -597,16 +597,25 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
             if (v.null) atomicOr(&onull_base[q * ONULL_WORDS + ((uint32_t)oc & (cpc - 1)) * (rstride / 32) + (pos >> 5)], 1u << (pos & 31));
           };
           if (fast) {
-            // exact-layout row: the (at most 8) stored integer columns are decoded by stored position, so every shift
-            // is a compile-time constant; the value goes from the staged row bytes to the chunk buffer in one step
-            uint32_t prev = 0;
+            if (!P.fast_v1 || row.fast == 1) {
+              // exact-layout v2 row: the (at most 8) stored integer columns are decoded by stored position, so every
+              // shift is a compile-time constant; the value goes from the staged row bytes to the chunk buffer in one step
+              uint32_t prev = 0;
 #pragma unroll
-            for (int h = 0; h < 8; ++h) {
-              if (h < P.fast_n) {
-                const uint32_t end = fast_end(row, h);
+              for (int h = 0; h < 8; ++h) {
+                if (h < P.fast_n) {
+                  const uint32_t end = fast_end(row, h);
+                  const int oc = P.fast_out[h];
+                  if (oc >= 0 && ((uint32_t)oc >> cshift) == r) ob[((uint32_t)oc & (cpc - 1)) * rstride] = fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u);
+                  prev = end;
+                }
+              }
+            } else {
+              // exact-layout v1 row: same positions, datums decoded by flag (one rolled loop: the varint reader is big)
+#pragma unroll 1
+              for (int h = 0; h < P.fast_n; ++h) {
                 const int oc = P.fast_out[h];
-                if (oc >= 0 && ((uint32_t)oc >> cshift) == r) ob[((uint32_t)oc & (cpc - 1)) * rstride] = fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u);
-                prev = end;
+                if (oc >= 0 && ((uint32_t)oc >> cshift) == r) ob[((uint32_t)oc & (cpc - 1)) * rstride] = fast_cell_dyn(row, (uint32_t)h, false, true);
               }
             }
             for (int j = 0; j < P.n_out_slow; ++j)  // handle / Real / repeated columns of such a row
