@@ -345,7 +345,8 @@ void b2_exec_close(b2_exec* h);
 /* Partial aggregation state of an Aggregation pipeline, for the multi-GPU / multi-region final merge (what TiDB's
  * final HashAgg does with the per-region partial results; fast_hash_aggr_executor.rs emits partial results only).
  * Valid after the drained batch was produced.  Per group `acc_words` additive u64 words, per aggregate in plan order:
- *   COUNT: [count]   SUM/AVG over Int: [count, sum of low 32 bits, sum of high 32 bits]   SUM/AVG over Real: [count, f64] */
+ *   COUNT: [count]   SUM/AVG over Int: [count, sum of low 32 bits, sum of high 32 bits]   SUM/AVG over Real: [count, f64]
+ *   MAX/MIN: [count, extremum key]: the key merges by unsigned 64-bit maximum (bit w of max_word_mask marks such words) */
 typedef struct b2_agg_partials {
   uint32_t n_groups;
   uint32_t acc_words;
@@ -354,6 +355,7 @@ typedef struct b2_agg_partials {
   const uint64_t* keys;       /* n_groups group keys (bits); unused without GROUP BY */
   const uint8_t* key_null;    /* n_groups flags */
   const uint64_t* acc;        /* n_groups * acc_words */
+  uint64_t max_word_mask;     /* words of a group's state that merge by unsigned maximum instead of addition */
 } b2_agg_partials;
 int32_t b2_exec_agg_partials(b2_exec* h, b2_agg_partials* out);
 

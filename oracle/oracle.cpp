@@ -74,12 +74,13 @@ static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges,
         f.arg_et = last.kind == B2_RPN_CONST_REAL ? ET_REAL : (last.kind == B2_RPN_CONST_INT || last.kind == B2_RPN_CONST_UINT ? ET_INT : eval_type_of(ft.tp));
         f.arg_unsigned = ft.is_unsigned();
         if (f.arg_et != ET_INT && f.arg_et != ET_REAL) { *err = Error::make(B2_ERR_UNSUPPORTED, "aggregate over non Int/Real"); return false; }
-        if (f.kind != B2_AGG_COUNT && f.kind != B2_AGG_SUM && f.kind != B2_AGG_AVG) { *err = Error::make(B2_ERR_UNSUPPORTED, "aggregate kind"); return false; }
+        if (f.kind != B2_AGG_COUNT && f.kind != B2_AGG_SUM && f.kind != B2_AGG_AVG && f.kind != B2_AGG_MAX && f.kind != B2_AGG_MIN) { *err = Error::make(B2_ERR_UNSUPPORTED, "aggregate kind"); return false; }
         a->fns.push_back(f);
         FieldType cnt; cnt.tp = B2_TP_LONGLONG; cnt.flag = B2_FLAG_UNSIGNED;  // impl_count.rs:35-40
         FieldType sum; if (f.arg_et == ET_REAL) { sum.tp = B2_TP_DOUBLE; } else { sum.tp = B2_TP_NEWDECIMAL; }
         if (f.kind == B2_AGG_COUNT || f.kind == B2_AGG_AVG) a->schema_.push_back(cnt);
         if (f.kind == B2_AGG_SUM || f.kind == B2_AGG_AVG) a->schema_.push_back(sum);
+        if (f.kind == B2_AGG_MAX || f.kind == B2_AGG_MIN) a->schema_.push_back(ft);  // the argument's own type, impl_max_min.rs:78-84
       }
       if (e.n_group_by == 1) {
         a->has_group = true; a->group_by = e.group_by[0];

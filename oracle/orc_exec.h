@@ -603,6 +603,7 @@ struct LimitExecutor : Executor {
 struct AggState {
   uint64_t count = 0;
   Decimal dsum = dec_zero(); double fsum = 0; bool has_value = false;
+  int64_t ext_i = 0; double ext_f = 0;  // MAX / MIN extremum (impl_max_min.rs:425-560), valid when has_value
 };
 struct AggFn { int kind; b2_rpn_expr arg; EvalType arg_et; bool arg_unsigned; };
 
@@ -639,6 +640,23 @@ struct AggExecutor : Executor {  // simple (no group by) or fast-hash (one group
         }
         s.has_value = true;
         return true;
+      case B2_AGG_MAX: case B2_AGG_MIN: {
+        // AggFnStateExtremumForInt::update_concrete :517-541 / AggFnStateExtremum :438-452: the first non-NULL value,
+        // then replaced only when the stored extremum compares on the wrong side (E::ORD: Less for MAX, Greater for MIN)
+        if (isnull) return true;
+        const bool is_max = f.kind == B2_AGG_MAX;
+        if (v.et == ET_REAL) {
+          double x = v.real_at(j);
+          if (!s.has_value || (is_max ? s.ext_f < x : s.ext_f > x)) s.ext_f = x;
+        } else {
+          int64_t x = v.int_at(j);
+          bool replace = !s.has_value;
+          if (!replace) replace = f.arg_unsigned ? (is_max ? (uint64_t)s.ext_i < (uint64_t)x : (uint64_t)s.ext_i > (uint64_t)x) : (is_max ? s.ext_i < x : s.ext_i > x);
+          if (replace) s.ext_i = x;
+        }
+        s.has_value = true;
+        return true;
+      }
       default: *err = Error::make(B2_ERR_UNSUPPORTED, "aggregate kind"); return false;
     }
   }
@@ -693,6 +711,15 @@ struct AggExecutor : Executor {  // simple (no group by) or fast-hash (one group
         LazyColumn c; c.decoded = true;
         if (f.arg_et == ET_REAL) { c.et = ET_REAL; for (size_t g = 0; g < ngroups; ++g) { const AggState& s = states[g * fns.size() + fi]; c.f64.push_back(s.has_value ? s.fsum : 0); c.nn.push_back(s.has_value); } }
         else { c.et = ET_DECIMAL; for (size_t g = 0; g < ngroups; ++g) { const AggState& s = states[g * fns.size() + fi]; dec_col.push_back(s.dsum); c.i64.push_back((int64_t)dec_col.size() - 1); c.nn.push_back(s.has_value); } }
+        out->cols.push_back(std::move(c));
+      }
+      if (f.kind == B2_AGG_MAX || f.kind == B2_AGG_MIN) {  // push_result :471-474 / :553-556: Option<T>
+        LazyColumn c; c.decoded = true; c.et = f.arg_et == ET_REAL ? ET_REAL : ET_INT;
+        for (size_t g = 0; g < ngroups; ++g) {
+          const AggState& s = states[g * fns.size() + fi];
+          if (f.arg_et == ET_REAL) { c.f64.push_back(s.has_value ? s.ext_f : 0); c.nn.push_back(s.has_value); }
+          else c.push_int(s.has_value, s.ext_i);
+        }
         out->cols.push_back(std::move(c));
       }
     }

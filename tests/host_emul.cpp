@@ -144,6 +144,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
             if (v.null) continue;
             acc->w[g.acc_off] += 1;
             if (g.kind == 0) continue;
+            if (g.kind >= 3) { uint64_t key = extremum_key(v.bits, g.arg_et, g.arg_unsigned, g.kind == 4); if (key > acc->w[g.acc_off + 1]) acc->w[g.acc_off + 1] = key; continue; }
             if (g.arg_et == 1) acc->w[g.acc_off + 1] = f64_bits(bits_f64(acc->w[g.acc_off + 1]) + bits_f64(v.bits));
             else {
               acc->w[g.acc_off + 1] += v.bits & 0xffffffffull;
@@ -205,6 +206,12 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
           if (ag.arg_et == 1) data[c].push_back(has ? acc[ag.acc_off + 1] : 0);
           else { if (has) limbs_to_decimal(acc[ag.acc_off + 1], acc[ag.acc_off + 2], ag.arg_unsigned, &d); data[c].push_back(0); }
           dec[c].push_back(d); nn[c].push_back(has);
+          ++c;
+        }
+        if (ag.kind == 3 || ag.kind == 4) {
+          bool has = cnt != 0;
+          data[c].push_back(has ? extremum_value(acc[ag.acc_off + 1], ag.arg_et, ag.arg_unsigned, ag.kind == 4) : 0);
+          dec[c].push_back(b2_decimal{}); nn[c].push_back(has);
           ++c;
         }
       }

@@ -257,3 +257,15 @@ def limit_plans():
             ("limit_after_selection", scan().selection(lt(col(C1), const_int(0))).limit(100).build(output_offsets=[C_H, C1, C3])),
             ("limit_zero", scan().limit(0).build()),
             ("limit_beyond_table", scan().selection(ge(col(C6), const_int(0))).limit(1 << 20).build())]
+
+
+def minmax_plans():
+    """MAX / MIN over signed, unsigned and Real arguments (impl_max_min.rs), with and without GROUP BY, NULL inputs, an
+    empty input (no row passes -> no output row for simple agg), groups whose argument is always NULL."""
+    scan = lambda: Plan().table_scan(TABLE, COLUMNS)
+    return [("minmax_simple", scan().aggregation([("max", col(C1)), ("min", col(C1)), ("max", col(C3, unsigned=True)), ("min", col(C3, unsigned=True)),
+                                                   ("max", col(C4, tp=ffi.TP_DOUBLE)), ("min", col(C4, tp=ffi.TP_DOUBLE)), ("min", col(C2)), ("count", const_int(1))]).build()),
+            ("minmax_group", scan().selection(lt(col(C1), const_int(1 << 62))).aggregation([("min", col(C2)), ("max", col(C1)), ("sum", col(C2)), ("max", col(C4, tp=ffi.TP_DOUBLE)),
+                                                                                            ("min", col(C3, unsigned=True))], group_by=[col(C6, tp=ffi.TP_LONG)]).build()),
+            ("minmax_expr", scan().aggregation([("max", plus(col(C6, tp=ffi.TP_LONG), const_int(5))), ("min", col(C_H))], group_by=[col(C2)]).build(output_offsets=[2, 1, 0])),
+            ("minmax_empty", scan().selection(lt(col(C1), const_int(-(1 << 63)))).aggregation([("max", col(C1)), ("min", col(C3, unsigned=True))]).build())]

@@ -206,3 +206,12 @@ def test_wordwise_varints_match_oracle():
             assert ra == rb and (ra == 0 or a.value == b.value), (enc.hex(), n, ra, rb, a.value, b.value)
             datum = bytes([8]) + buf
             assert E.emu_split_datum(datum, n + 1) == O.orc_split_datum(datum, n + 1), (enc.hex(), n)
+
+
+@pytest.mark.parametrize("name,plan", sc.minmax_plans(), ids=[n for n, _ in sc.minmax_plans()])
+def test_min_max(name, plan, regions):
+    region = regions[2].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    exp = orc.dag_handle(plan, sc.WHOLE, region)
+    got = emu.dag_handle(plan, sc.WHOLE, region)
+    assert exp.status == 0
+    assert_same_rows(got, exp, ordered=False, ctx=name)

@@ -107,6 +107,10 @@ def test_merge_single_process_semantics():
     f[:, 1] = torch.tensor([1.5, 2.25], dtype=torch.float64).view(torch.int64)
     k, n, a = bd.merge_agg_partials(torch.tensor([1, 1]), torch.tensor([False, False]), f, real_words=(1,))
     assert a[0, 0] == 2 and a[0, 1:2].view(torch.float64).item() == 3.75
+    # MAX / MIN extremum keys merge by unsigned maximum (word 1), their counts by addition (word 0)
+    m = torch.tensor([[2, 5], [1, -3], [4, 9]], dtype=torch.int64)  # -3 is a huge unsigned key
+    k, n, a = bd.merge_agg_partials(torch.tensor([8, 8, 9]), torch.tensor([False, False, False]), m, max_words=(1,))
+    assert sorted((int(k[i]), int(a[i, 0]), int(a[i, 1])) for i in range(2)) == [(8, 3, -3), (9, 4, 9)]
     # TopN with NULLs: asc puts NULL first, desc puts NULL last
     c, nl = bd.merge_topn([torch.tensor([3, 1, 0, 2])], [torch.tensor([False, False, True, False])], [(0, False, "i64")], 3)
     assert [None if nl[0][i] else int(c[0][i]) for i in range(3)] == [None, 1, 2]

@@ -47,3 +47,37 @@ def test_checksum_partition_merge():
     x = parts[0][0] ^ parts[1][0]
     assert (x, parts[0][1] + parts[1][1], parts[0][2] + parts[1][2]) == orc.checksum(sc.WHOLE, region)[1]
     assert bd.merge_checksum(*parts[0]) == parts[0]
+
+
+def test_min_max_partials_merge_two_shards():
+    """MAX / MIN partial states of two shards: counts add, extremum keys merge by unsigned maximum (max_word_mask)."""
+    import ctypes as C
+    region = sc.dirty_region(8, n_keys=1200).build(read_ts=sc.READ_TS)
+    dev = DeviceRegion(region)
+    plan = (Plan().table_scan(sc.TABLE, sc.COLUMNS)
+            .aggregation([("max", col(sc.C1)), ("min", col(sc.C3, unsigned=True)), ("count", const_int(1))], group_by=[col(sc.C6, tp=ffi.TP_LONG)]).build())
+    parts, mask = [], 0
+    for lo, hi in ((-1000, 1500), (1500, 10000)):
+        with BatchExecutor(plan, [kvfmt.table_range(sc.TABLE, lo, hi)], dev) as ex:
+            r = ex.next_batch(1 << 30)
+            assert r.error is None and r.is_drained
+            parts.append(tuple(t.clone() for t in bd.agg_partials_as_tensors(ex, 0)))
+            p = ffi.AggPartials()
+            assert ffi.lib().b2_exec_agg_partials(ex._h, C.byref(p)) == 0
+            mask = p.max_word_mask
+    assert mask == 0b1010  # words: [cnt, key] [cnt, key] [cnt]
+    keys = torch.cat([p[0] for p in parts]); nul = torch.cat([p[1] for p in parts]); acc = torch.cat([p[2] for p in parts])
+    k, n, a = bd.merge_agg_partials(keys, nul, acc, max_words=[w for w in range(acc.shape[1]) if mask >> w & 1])
+    def dec(key, unsigned, is_min):
+        key &= (1 << 64) - 1
+        if is_min:
+            key ^= (1 << 64) - 1
+        if not unsigned:
+            key ^= 1 << 63
+            return key - (1 << 64) if key >= 1 << 63 else key
+        return key
+    got = sorted(((None if n[i] else int(k[i])), dec(int(a[i, 1]), False, False) if a[i, 0] else None, dec(int(a[i, 3]), True, True) if a[i, 2] else None, int(a[i, 4]))
+                 for i in range(k.shape[0]))
+    exp = orc.dag_handle(plan, sc.WHOLE, region)
+    want = sorted((r[3], r[0], (r[1] & ((1 << 64) - 1)) if r[1] is not None else None, r[2]) for r in exp.rows())
+    assert got == want and len(want) >= 10

@@ -498,3 +498,14 @@ def test_limit(name, plan, batch, regions):
     exp = orc.dag_handle(plan, sc.split_ranges(), region)
     got = DagHandler(plan, sc.split_ranges(), region, batch_rows=batch).handle_request()
     assert_same_rows(got, exp, ordered=True, ctx=name)
+
+
+@pytest.mark.parametrize("name,plan", sc.minmax_plans(), ids=[n for n, _ in sc.minmax_plans()])
+def test_min_max(name, plan, regions):
+    """MAX / MIN (impl_max_min.rs): signed / unsigned / Real arguments, NULL inputs, GROUP BY, empty input."""
+    for seed in (1, 2):
+        region = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=2)
+        exp = orc.dag_handle(plan, sc.split_ranges(), region)
+        got = DagHandler(plan, sc.split_ranges(), DeviceRegion(region)).handle_request()
+        assert exp.status == 0
+        assert_same_rows(got, exp, ordered=False, ctx=f"{name}/seed{seed}")

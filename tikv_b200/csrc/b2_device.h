@@ -70,7 +70,7 @@ struct DevNode {
   int64_t imm;  // const bits (i64 or f64 bits) or column offset
 };
 struct DevExpr { uint16_t start, n; };
-struct DevAgg { DevExpr arg; uint8_t kind /*0 count 1 sum 2 avg*/, arg_et, arg_unsigned, acc_off; };
+struct DevAgg { DevExpr arg; uint8_t kind /*0 count 1 sum 2 avg 3 max 4 min*/, arg_et, arg_unsigned, acc_off; };
 struct DevOrder { DevExpr e; uint8_t desc, et, is_unsigned, _pad; };
 
 enum PlanMode { PM_SCAN = 0, PM_AGG = 1, PM_TOPN = 2, PM_CHECKSUM = 3 };
@@ -1186,6 +1186,23 @@ B2_HD int eval_conds(const DevPlan& P, const Row& row, const Cells& cells, bool*
     if (!t) { *keep = false; return DE_NONE; }
   }
   return DE_NONE;
+}
+
+// MAX / MIN state (impl_max_min.rs:425-560): [count of non-NULL inputs, extremum key].  The key is an order-preserving
+// u64 (signed: sign flip; unsigned: as is; real: IEEE total order), complemented for MIN, so that both are a running
+// unsigned maximum over a zero-initialised word (atomicMax), additive-style mergeable across CTAs and GPUs.
+B2_HD uint64_t extremum_key(uint64_t bits, int arg_et, bool arg_unsigned, bool is_min) {
+  uint64_t k = bits;
+  if (arg_et == 1) {
+    if ((k << 1) == 0) k = 0;  // -0.0 == 0.0
+    k = (k >> 63) ? ~k : (k | 0x8000000000000000ull);
+  } else if (!arg_unsigned) k ^= 0x8000000000000000ull;
+  return is_min ? ~k : k;
+}
+B2_HD uint64_t extremum_value(uint64_t key, int arg_et, bool arg_unsigned, bool is_min) {
+  uint64_t k = is_min ? ~key : key;
+  if (arg_et == 1) return (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return arg_unsigned ? k : (k ^ 0x8000000000000000ull);
 }
 
 // fx-like 64-bit mixer for the group hash table (any good mixer works: group order is unspecified)

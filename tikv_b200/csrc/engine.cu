@@ -1406,6 +1406,9 @@ int32_t b2_exec_agg_partials(b2_exec* h, b2_agg_partials* out) {
   if (h->cp.dev.mode != PM_AGG || !h->drained) { g_last_error = "no aggregation state: not an Aggregation pipeline or not drained yet"; return B2_ERR_INVALID_ARG; }
   out->n_groups = h->part_n; out->acc_words = (uint32_t)h->cp.dev.acc_words; out->location = B2_LOC_DEVICE; out->has_group = h->cp.dev.has_group;
   out->keys = (const uint64_t*)h->part_keys; out->key_null = (const uint8_t*)h->part_null; out->acc = (const uint64_t*)h->part_acc;
+  out->max_word_mask = 0;
+  for (int a = 0; a < h->cp.dev.n_aggs; ++a)
+    if (h->cp.dev.aggs[a].kind >= 3) out->max_word_mask |= 1ull << (h->cp.dev.aggs[a].acc_off + 1);
   return B2_OK;
 }
 

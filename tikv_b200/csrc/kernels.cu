@@ -246,6 +246,12 @@ __global__ void agg_result_kernel(const __grid_constant__ DevPlan P, unsigned in
       if (!has) atomicAnd(&col_bitmap[c][g >> 6], ~(1ull << (g & 63)));
       ++c;
     }
+    if (ag.kind == 3 || ag.kind == 4) {  // MAX / MIN: NULL without a non-NULL input
+      bool has = cnt != 0;
+      col_data[c][g] = has ? extremum_value(acc[ag.acc_off + 1], ag.arg_et, ag.arg_unsigned, ag.kind == 4) : 0ull;
+      if (!has) atomicAnd(&col_bitmap[c][g >> 6], ~(1ull << (g & 63)));
+      ++c;
+    }
   }
   if (P.has_group) {
     col_data[c][g] = g_null[g] ? 0ull : g_keys[g];

@@ -239,14 +239,18 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
           case B2_AGG_COUNT: g.kind = 0; acc += 1; break;
           case B2_AGG_SUM: g.kind = 1; acc += et ? 2 : 3; break;
           case B2_AGG_AVG: g.kind = 2; acc += et ? 2 : 3; break;
+          case B2_AGG_MAX: g.kind = 3; acc += 2; break;
+          case B2_AGG_MIN: g.kind = 4; acc += 2; break;
           default: *msg = "aggregate function " + std::to_string(e.aggrs[k].kind) + " is not on the device path yet"; return B2_ERR_UNSUPPORTED;
         }
-        if (g.kind != 0 && !et && tp == B2_TP_BIT) { *msg = "SUM/AVG over BIT (cast to DOUBLE) is not supported"; return B2_ERR_UNSUPPORTED; }
+        if ((g.kind == 1 || g.kind == 2) && !et && tp == B2_TP_BIT) { *msg = "SUM/AVG over BIT (cast to DOUBLE) is not supported"; return B2_ERR_UNSUPPORTED; }
         if (acc > MAX_ACC_WORDS) { *msg = "aggregate state too large"; return B2_ERR_UNSUPPORTED; }
         OutCol cnt = {B2_COL_I64, B2_TP_LONGLONG, B2_FLAG_UNSIGNED | B2_FLAG_NOT_NULL};  // impl_count.rs:35-40
         OutCol sum = et ? OutCol{B2_COL_F64, B2_TP_DOUBLE, 0} : OutCol{B2_COL_DECIMAL, B2_TP_NEWDECIMAL, 0};
         if (g.kind == 0 || g.kind == 2) schema.push_back(cnt);
         if (g.kind == 1 || g.kind == 2) schema.push_back(sum);
+        if (g.kind == 3 || g.kind == 4)  // one column of the argument's own type (impl_max_min.rs:78-84)
+          schema.push_back(OutCol{et ? B2_COL_F64 : B2_COL_I64, tp, flag & ~(uint32_t)B2_FLAG_NOT_NULL});
       }
       P.n_aggs = (int)e.n_aggrs; P.acc_words = acc;
       if (e.n_group_by == 1) {

@@ -704,6 +704,14 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
           const bool commit = leader && acc != nullptr && cnt != 0;
           if (g.kind == 0) {
             if (commit) atomicAdd(&w[0], (unsigned long long)cnt);
+          } else if (g.kind >= 3) {  // MAX / MIN: running unsigned maximum of the (complemented) order-preserving key
+            unsigned long long key = has ? extremum_key(v.bits, g.arg_et, g.arg_unsigned, g.kind == 4) : 0ull;
+            if (!solo)
+              for (unsigned int mm = peers & (peers - 1); mm; mm &= mm - 1) {  // the leader is the lowest lane
+                unsigned long long other = __shfl_sync(peers, key, __ffs(mm) - 1);
+                key = other > key ? other : key;
+              }
+            if (commit) { atomicAdd(&w[0], (unsigned long long)cnt); atomicMax(&w[1], key); }
           } else if (g.arg_et == 1) {
             double sum = has ? bits_f64(v.bits) : 0.0;
             if (!solo) {
@@ -785,11 +793,15 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     if (!P.has_group) {
       cta256_sync();
       for (int w = (int)tid; w < P.acc_words; w += TILE) {
-        bool is_real = false;
-        for (int a = 0; a < P.n_aggs; ++a)
-          if (P.aggs[a].kind != 0 && P.aggs[a].arg_et == 1 && P.aggs[a].acc_off + 1 == w) is_real = true;
+        bool is_real = false, is_max = false;
+        for (int a = 0; a < P.n_aggs; ++a) {
+          const bool second = P.aggs[a].acc_off + 1 == w;
+          if ((P.aggs[a].kind == 1 || P.aggs[a].kind == 2) && P.aggs[a].arg_et == 1 && second) is_real = true;
+          if (P.aggs[a].kind >= 3 && second) is_max = true;
+        }
         unsigned long long x = s_simple_acc[w];
-        if (is_real) { double dd = bits_f64(x); if (dd != 0.0) atomicAdd(reinterpret_cast<double*>(&A.tbl.acc[w]), dd); }
+        if (is_max) { if (x) atomicMax(&A.tbl.acc[w], x); }
+        else if (is_real) { double dd = bits_f64(x); if (dd != 0.0) atomicAdd(reinterpret_cast<double*>(&A.tbl.acc[w]), dd); }
         else if (x) atomicAdd(&A.tbl.acc[w], x);
       }
     } else if (st.slots) {
@@ -805,7 +817,8 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
           if (src[0] == 0) continue;
           atomicAdd(&dst[0], src[0]);
           if (g.kind == 0) continue;
-          if (g.arg_et == 1) atomicAdd(reinterpret_cast<double*>(&dst[1]), bits_f64(src[1]));
+          if (g.kind >= 3) atomicMax(&dst[1], src[1]);
+          else if (g.arg_et == 1) atomicAdd(reinterpret_cast<double*>(&dst[1]), bits_f64(src[1]));
           else { atomicAdd(&dst[1], src[1]); atomicAdd(&dst[2], src[2]); }
         }
       }

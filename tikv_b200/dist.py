@@ -45,11 +45,12 @@ def _all_gather_var(t):
 
 
 # ---- hash aggregation -------------------------------------------------------------------------------------------
-def merge_agg_partials(keys, key_null, acc, real_words=()):
+def merge_agg_partials(keys, key_null, acc, real_words=(), max_words=()):
     """Final merge of partial aggregation tables.
 
     keys: int64[n] group-key bits, key_null: bool[n], acc: int64[n, W] additive accumulator words (b2_agg_partials).
-    `real_words` lists the word indices that hold f64 sums.  Returns (keys, key_null, acc) with one row per group.
+    `real_words` lists the word indices that hold f64 sums, `max_words` those that merge by unsigned maximum (the MAX /
+    MIN extremum keys, b2_agg_partials.max_word_mask).  Returns (keys, key_null, acc) with one row per group.
     Integer words are summed exactly (two's-complement wraparound is impossible below 2^32 rows per group)."""
     parts = _all_gather_var(torch.cat([keys.view(-1, 1), key_null.to(torch.int64).view(-1, 1), acc], dim=1))
     allp = torch.cat(parts, dim=0)
@@ -60,12 +61,16 @@ def merge_agg_partials(keys, key_null, acc, real_words=()):
     ident = torch.stack([nul, k], dim=1)
     uniq, inv = torch.unique(ident, dim=0, return_inverse=True)
     out = torch.zeros((uniq.shape[0], a.shape[1]), dtype=torch.int64, device=a.device)
-    int_words = [w for w in range(a.shape[1]) if w not in set(real_words)]
+    int_words = [w for w in range(a.shape[1]) if w not in set(real_words) and w not in set(max_words)]
     if int_words:
         out[:, int_words] = torch.zeros((uniq.shape[0], len(int_words)), dtype=torch.int64, device=a.device).index_add_(0, inv, a[:, int_words])
     for w in real_words:
         s = torch.zeros(uniq.shape[0], dtype=torch.float64, device=a.device).index_add_(0, inv, a[:, w].contiguous().view(torch.float64))
         out[:, w] = s.view(torch.int64)
+    for w in max_words:  # unsigned 64-bit maximum = signed maximum after flipping the top bit
+        flipped = a[:, w] ^ (-(1 << 63))
+        m = torch.full((uniq.shape[0],), -(1 << 63), dtype=torch.int64, device=a.device).scatter_reduce_(0, inv, flipped, reduce="amax")
+        out[:, w] = m ^ (-(1 << 63))
     return uniq[:, 1].contiguous(), uniq[:, 0].bool(), out
 
 
