@@ -379,6 +379,10 @@ int32_t b2_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges,
                            const b2_region_source* src, const b2_exec_config* cfg,
                            b2_checksum_response* out, b2_exec_stats* stats);
 
+/* tooling: the compiled device plan of `plan` as a C++ aggregate initialiser (what the run-time compiler is fed);
+ * returns its length, writes at most cap - 1 bytes + NUL into buf, negative status on error */
+int64_t b2_plan_literal(const b2_dag_plan* plan, char* buf, uint64_t cap);
+
 /* ---- synthetic region generator (tooling for tests/bench) -----------------
  * Builds HBM-resident CF_WRITE blocks for a table with an int handle PK and `n_cols` i64
  * columns (ids 1..n_cols), row format v2 (or v1), one Put version per key plus optional

@@ -1022,7 +1022,6 @@ struct b2_exec {
       // serialise on a few addresses; beyond that the HBM table lives in L2 anyway and a big CTA table only costs
       // shared memory (measured, 1e8 rows: 2048 / 1024 / 256 slots -> G=1024: 5.8 / 6.7 / 6.2 ms, G=2^20: 15.9 / 10.0 / 9.9 ms)
       smem_slots = 256;
-      if (const char* ev = getenv("B2_SMEM_SLOTS")) smem_slots = (uint32_t)atoi(ev);  // experiments
       while (smem_slots > 64 && (size_t)smem_slots * (8 + 8 * P.acc_words) > 64 * 1024) smem_slots >>= 1;
       smem = (size_t)smem_slots * (8 + 8 * P.acc_words);
     }

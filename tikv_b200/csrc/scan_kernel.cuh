@@ -46,24 +46,6 @@ __device__ unsigned int table_find_or_insert(const AggTable& t, uint64_t key, bo
   return 0xffffffffu;
 }
 
-// accumulate one aggregate argument into `acc` words (global or shared)
-//   COUNT: [cnt]            SUM/AVG(int): [cnt, sum of low 32 bits, sum of high 32 bits]   SUM/AVG(real): [cnt, f64]
-// The two 32-bit limb sums cannot overflow below 2^32 rows and give the exact i128 sum = hi * 2^32 + lo.
-template <typename Acc>
-__device__ __forceinline__ void acc_update(Acc* acc, const DevAgg& g, const Value& v) {
-  if (v.null) return;
-  atomicAdd(&acc[g.acc_off], 1ull);
-  if (g.kind == 0) return;
-  if (g.arg_et == 1) {
-    atomicAdd(reinterpret_cast<double*>(&acc[g.acc_off + 1]), bits_f64(v.bits));
-  } else {
-    unsigned long long lo = v.bits & 0xffffffffull;
-    unsigned long long hi = g.arg_unsigned ? (v.bits >> 32) : (unsigned long long)((long long)v.bits >> 32);
-    atomicAdd(&acc[g.acc_off + 1], lo);
-    atomicAdd(&acc[g.acc_off + 2], hi);
-  }
-}
-
 // barrier over the 256 row-decoding threads only (the scan kernel runs a 9th, producer-only warp)
 __device__ __forceinline__ void cta256_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
