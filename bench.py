@@ -124,7 +124,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -283,7 +283,8 @@ def main():
         jit_launches += st.jit_launches
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    if args.no_e2e:
+        clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], device=f"cuda:{device}")
     if world > 1:
@@ -325,6 +326,7 @@ def main():
         assert r_e2e == rows_out, "host-buffer path and HBM path disagree on the result size"
         e2e = {"value": args.rows * world / (float(te.item()) / k / 1e3), "unit": "rows/s", "h2d_bytes_per_step": int(st_e.h2d_bytes),
                "d2h_bytes_per_step": int(st_e.d2h_bytes), "ms_per_step": float(te.item()) / k}
+        clocks = sampler.stop()  # sampled across both timed regions (HBM-resident steps and end-to-end steps)
         for p in pinned:
             ffi.lib().b2_host_free_pinned(p)
     for g in gens:
