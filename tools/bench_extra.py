@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def gen(ffi, n_rows, n_blocks, n_cols, lo, rng, nulls=None, seed=0x525C682A2F7CE3DB, table=1000):
+def gen(ffi, n_rows, n_blocks, n_cols, lo, rng, nulls=None, seed=0x525C682A2F7CE3DB, table=1000, dirty=None):
     L = ffi.lib()
     gens, blks = [], []
     per = (n_rows + n_blocks - 1) // n_blocks
@@ -31,6 +31,8 @@ def gen(ffi, n_rows, n_blocks, n_cols, lo, rng, nulls=None, seed=0x525C682A2F7CE
             s.null_per_million = c
             keep.append(c)
         s.commit_ts, s.newer_ts = 20, 5000
+        if dirty:
+            s.extra_versions_per_million, s.delete_per_million, s.lock_rec_per_million = dirty
         g, blk = C.c_void_p(), ffi.GenBlock()
         assert L.b2_gen_create(0, C.byref(s), C.byref(g), C.byref(blk)) == 0, L.b2_last_error_message()
         gens.append(g); blks.append(blk)
@@ -91,6 +93,16 @@ def main():
                 best = dt if best is None or dt < best else best
             print(json.dumps({"workload": "C5 checksum CRC64-XZ", "kvs": res[1], "bytes": res[2], "kvs_per_s": res[1] / best, "ms": best * 1e3,
                               "GBps": (res[2] + 8 * res[1]) / best / 1e9, "frac_of_measured_hbm": (res[2] + 8 * res[1]) / best / 1e9 / peak}))
+        for g in gens:
+            ffi.lib().b2_gen_destroy(g)
+    if not only or "dirty" in only:
+        # C2 on a "dirty" table: 30 % of the keys carry extra (older / newer-than-read_ts) versions, 5 % are
+        # deleted, 5 % have a Lock/Rollback record on top: version runs, skipped records, met_newer_ts_data
+        gens, blks = gen(ffi, args.rows, 8, 8, [0] * 8, [0] * 8, dirty=(300000, 50000, 50000))
+        src = bench.Source(ffi, [b.block for b in blks], ffi.LOC_DEVICE, 0)
+        in_bytes = sum(b.key_bytes + b.val_bytes + 8 * b.block.n for b in blks)
+        n_entries = sum(b.block.n for b in blks)
+        run(f"C2 scan + selection on a dirty table ({n_entries} CF_WRITE entries for {args.rows} keys)", bench.build_plan(), src, in_bytes, args.rows)
         for g in gens:
             ffi.lib().b2_gen_destroy(g)
     if only and "c4" not in only:
