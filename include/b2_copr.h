@@ -150,7 +150,8 @@ enum {
   B2_SIG_UNARY_NOT_INT = 3104, B2_SIG_UNARY_NOT_REAL = 3106,
   B2_SIG_REAL_IS_NULL = 3114, B2_SIG_INT_IS_NULL = 3116,
   B2_SIG_INT_IS_TRUE = 3118, B2_SIG_REAL_IS_TRUE = 3119,
-  B2_SIG_INT_IS_FALSE = 3121, B2_SIG_REAL_IS_FALSE = 3122
+  B2_SIG_INT_IS_FALSE = 3121, B2_SIG_REAL_IS_FALSE = 3122,
+  B2_SIG_IN_INT = 4001, B2_SIG_IN_REAL = 4002 /* variadic: n_args = 1 + list length (impl_compare_in.rs) */
 };
 
 typedef struct b2_rpn_node {

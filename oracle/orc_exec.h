@@ -466,6 +466,29 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
       st.push_back(std::move(v));
     } else if (nd.kind == B2_RPN_FN) {
       int na = nd.n_args;
+      if (nd.sig == B2_SIG_IN_INT || nd.sig == B2_SIG_IN_REAL) {
+        // compare_in_int_type_by_hash :217-258 / compare_in_by_hash :178-215 (varg): args[0] IN (args[1..])
+        if ((int)st.size() < na || na < 1) { *err = Error::make(B2_ERR_INVALID_ARG, "bad rpn arity"); return false; }
+        std::vector<Val> args(st.end() - na, st.end());
+        st.resize(st.size() - na);
+        Val r; r.et = ET_INT; r.is_unsigned = false; r.nn.assign(n, 0); r.i.assign(n, 0);
+        for (size_t j = 0; j < n; ++j) {
+          if (args[0].null_at(j)) continue;
+          bool hit = false, default_null = false;
+          for (int i = 1; i < na; ++i) {
+            if (args[i].null_at(j)) { default_null = true; continue; }
+            if (nd.sig == B2_SIG_IN_REAL) hit |= args[0].real_at(j) == args[i].real_at(j);
+            else {
+              int64_t base_val = args[0].int_at(j), v = args[i].int_at(j);
+              hit |= base_val == v && (base_val >= 0 || args[0].is_unsigned == args[i].is_unsigned);
+            }
+          }
+          if (hit) { r.nn[j] = 1; r.i[j] = 1; }
+          else if (!default_null) { r.nn[j] = 1; r.i[j] = 0; }
+        }
+        st.push_back(std::move(r));
+        continue;
+      }
       if ((int)st.size() < na || na < 1 || na > 2) { *err = Error::make(B2_ERR_INVALID_ARG, "bad rpn arity"); return false; }
       Val b; if (na == 2) { b = std::move(st.back()); st.pop_back(); }
       Val a = std::move(st.back()); st.pop_back();

@@ -10,7 +10,7 @@ import struct
 import kvfmt
 from tikv_b200 import ffi
 from tikv_b200.plan import (ColumnDef, Plan, and_, col, const_int, const_real, const_uint, eq, ge, gt, is_null, le, lt, minus, multiply,
-                            ne, not_, null, nulleq, or_, plus, xor_)
+                            in_, ne, not_, null, nulleq, or_, plus, xor_)
 
 TABLE = 1000
 READ_TS = 1000
@@ -269,3 +269,16 @@ def minmax_plans():
                                                                                             ("min", col(C3, unsigned=True))], group_by=[col(C6, tp=ffi.TP_LONG)]).build()),
             ("minmax_expr", scan().aggregation([("max", plus(col(C6, tp=ffi.TP_LONG), const_int(5))), ("min", col(C_H))], group_by=[col(C2)]).build(output_offsets=[2, 1, 0])),
             ("minmax_empty", scan().selection(lt(col(C1), const_int(-(1 << 63)))).aggregation([("max", col(C1)), ("min", col(C3, unsigned=True))]).build())]
+
+
+def in_plans():
+    """IN lists (impl_compare_in.rs): constants, NULL in the list, NULL base, columns in the list, signed vs unsigned, Real."""
+    scan = lambda: Plan().table_scan(TABLE, COLUMNS)
+    return [("in_consts", scan().selection(in_(col(C6, tp=ffi.TP_LONG), const_int(1), const_int(5), const_int(7), const_int(14))).build()),
+            ("in_with_null", scan().selection(in_(col(C2), const_int(3), null(), const_int(-2))).build(output_offsets=[C_H, C2])),
+            ("in_null_result", scan().selection(is_null(in_(col(C2), const_int(3), null()))).build(output_offsets=[C_H, C2])),
+            ("in_not", scan().selection(not_(in_(col(C2), const_int(3), const_int(4)))).build(output_offsets=[C_H, C2])),
+            ("in_null_base_and_columns", scan().selection(in_(col(C2), col(C6, tp=ffi.TP_LONG), const_int(0))).build(output_offsets=[C_H, C2, C6])),
+            ("in_signedness", scan().selection(in_(col(C3, unsigned=True), const_int(-1), const_uint((1 << 64) - 1), col(C1), const_int(77))).build(output_offsets=[C_H, C3, C1])),
+            ("in_real", scan().selection(in_(col(C4, tp=ffi.TP_DOUBLE), const_real(2.5), const_real(-0.0), const_real(1e300))).build(output_offsets=[C_H, C4])),
+            ("in_as_group_key", scan().aggregation([("count", const_int(1))], group_by=[in_(col(C6, tp=ffi.TP_LONG), const_int(2), const_int(3), null())]).build())]

@@ -215,3 +215,12 @@ def test_min_max(name, plan, regions):
     got = emu.dag_handle(plan, sc.WHOLE, region)
     assert exp.status == 0
     assert_same_rows(got, exp, ordered=False, ctx=name)
+
+
+@pytest.mark.parametrize("name,plan", sc.in_plans(), ids=[n for n, _ in sc.in_plans()])
+def test_in_lists(name, plan, regions):
+    region = regions[1].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    exp = orc.dag_handle(plan, sc.WHOLE, region)
+    got = emu.dag_handle(plan, sc.WHOLE, region)
+    assert exp.status == 0 and exp.n_rows > 0
+    assert_same_rows(got, exp, ordered=not sc.is_agg(name) and "group" not in name, ctx=name)

@@ -509,3 +509,13 @@ def test_min_max(name, plan, regions):
         got = DagHandler(plan, sc.split_ranges(), DeviceRegion(region)).handle_request()
         assert exp.status == 0
         assert_same_rows(got, exp, ordered=False, ctx=f"{name}/seed{seed}")
+
+
+@pytest.mark.parametrize("name,plan", sc.in_plans(), ids=[n for n, _ in sc.in_plans()])
+def test_in_lists(name, plan, regions):
+    """IN (impl_compare_in.rs): NULL semantics, mixed signedness, Real, columns inside the list."""
+    region = regions[2].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    exp = orc.dag_handle(plan, sc.split_ranges(), region)
+    got = DagHandler(plan, sc.split_ranges(), DeviceRegion(region)).handle_request()
+    assert exp.status == 0 and exp.n_rows > 0
+    assert_same_rows(got, exp, ordered="group" not in name, ctx=name)

@@ -27,7 +27,7 @@
 namespace b2 {
 
 // ---- limits of the device plan ----
-enum { MAX_COLS = 64, MAX_NODES = 96, MAX_CONDS = 8, MAX_AGGS = 8, MAX_ORDER = 4, MAX_STACK = 8, MAX_ACC_WORDS = 24 };
+enum { MAX_COLS = 64, MAX_NODES = 96, MAX_CONDS = 8, MAX_AGGS = 8, MAX_ORDER = 4, MAX_STACK = 16, MAX_ACC_WORDS = 24 };
 
 // ---- device error codes (mapped to B2_ERR_* + message in engine.cu) ----
 enum DevErr {
@@ -1054,6 +1054,25 @@ B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const 
     }
     if (nd.kind != B2_RPN_FN) {  // constants
       sv[sp] = nd.imm; sn[sp] = (nd.kind == B2_RPN_CONST_NULL ? 1 : 0) | (nd.is_unsigned ? 2 : 0);
+      ++sp;
+      continue;
+    }
+    if (nd.sig == B2_SIG_IN_INT || nd.sig == B2_SIG_IN_REAL) {
+      // compare_in_int_type_by_hash / compare_in_by_hash (impl_compare_in.rs:178-258): NULL base -> NULL; a list value
+      // equal to the base -> 1 (integers of different signedness only match when the base is non-negative);
+      // otherwise NULL if the list held a NULL, else 0
+      const int base = sp - nd.n_args;
+      const int64_t x = sv[base];
+      const bool xn = sn[base] & 1, xu = sn[base] & 2;
+      bool hit = false, has_null = false;
+      for (int i = 1; i < nd.n_args; ++i) {
+        const int64_t y = sv[base + i];
+        if (sn[base + i] & 1) { has_null = true; continue; }
+        if (nd.sig == B2_SIG_IN_REAL) hit |= bits_f64((uint64_t)x) == bits_f64((uint64_t)y);
+        else hit |= x == y && (x >= 0 || xu == (bool)(sn[base + i] & 2));
+      }
+      sp = base;
+      sv[sp] = hit ? 1 : 0; sn[sp] = (xn || (!hit && has_null)) ? 1 : 0;
       ++sp;
       continue;
     }

@@ -80,6 +80,8 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
           case B2_SIG_LOGICAL_AND: case B2_SIG_LOGICAL_OR: case B2_SIG_LOGICAL_XOR: break;
           case B2_SIG_UNARY_NOT_INT: case B2_SIG_INT_IS_NULL: case B2_SIG_INT_IS_TRUE: case B2_SIG_INT_IS_FALSE: want = 1; break;
           case B2_SIG_UNARY_NOT_REAL: case B2_SIG_REAL_IS_NULL: case B2_SIG_REAL_IS_TRUE: case B2_SIG_REAL_IS_FALSE: want = 1; real_args = true; break;
+          case B2_SIG_IN_INT: want = na; if (na < 1) want = -1; break;
+          case B2_SIG_IN_REAL: want = na; real_args = true; if (na < 1) want = -1; break;
           default: *msg = "ScalarFunction sig " + std::to_string(sig) + " is not supported on the device path"; return false;
         }
         if (na != want || sp < na) { *msg = "bad arity for sig " + std::to_string(sig); return false; }

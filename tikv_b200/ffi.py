@@ -29,7 +29,7 @@ SIG = dict(
     PLUS_REAL=200, PLUS_INT=203, MINUS_REAL=204, MINUS_INT=207, MULTIPLY_REAL=208, MULTIPLY_INT=210,
     MULTIPLY_INT_UNSIGNED=218, LOGICAL_AND=3101, LOGICAL_OR=3102, LOGICAL_XOR=3103,
     UNARY_NOT_INT=3104, UNARY_NOT_REAL=3106, REAL_IS_NULL=3114, INT_IS_NULL=3116,
-    INT_IS_TRUE=3118, REAL_IS_TRUE=3119, INT_IS_FALSE=3121, REAL_IS_FALSE=3122,
+    INT_IS_TRUE=3118, REAL_IS_TRUE=3119, INT_IS_FALSE=3121, REAL_IS_FALSE=3122, IN_INT=4001, IN_REAL=4002,
 )
 
 AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX, AGG_FIRST = 3001, 3002, 3003, 3004, 3005, 3006

@@ -85,6 +85,7 @@ def and_(a, b): return fn("LOGICAL_AND", a, b)
 def or_(a, b): return fn("LOGICAL_OR", a, b)
 def xor_(a, b): return fn("LOGICAL_XOR", a, b)
 def not_(a): return fn("UNARY_NOT_REAL" if a.ekind == "real" else "UNARY_NOT_INT", a)
+def in_(a, *values): return fn("IN_REAL" if a.ekind == "real" else "IN_INT", a, *values)
 def is_null(a): return fn("REAL_IS_NULL" if a.ekind == "real" else "INT_IS_NULL", a)
 
 
