@@ -15,6 +15,7 @@
 #include <nvrtc.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <map>
@@ -138,7 +139,20 @@ bool jit_available(std::string* why) {
   return a.ok;
 }
 
+// Compilations still in flight when the process exits are waited for (this handler is registered after the CUDA runtime's
+// own teardown, so it runs before it): a compile thread must not touch a runtime that is being destroyed.
+static void jit_wait_all_at_exit() {
+  std::vector<std::shared_future<JitKernel*>> pending;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& kv : g_cache) pending.push_back(kv.second.fut);
+  }
+  for (auto& f : pending) f.wait();
+}
+
 std::shared_future<JitKernel*> jit_get(int device, const DevPlan& plan) {
+  static std::once_flag at_exit_once;
+  std::call_once(at_exit_once, [] { std::atexit(jit_wait_all_at_exit); });
   DevPlan p = plan;
   p.read_ts = 0; p.isolation = 0;  // launch parameters (ScanArgs), not part of the specialisation
   std::string key = std::to_string(device) + "|" + plan_literal(p);
