@@ -190,7 +190,8 @@ typedef struct b2_order_by {
 /* tipb::ExecType */
 enum { B2_EXEC_TABLE_SCAN = 0, B2_EXEC_INDEX_SCAN = 1, B2_EXEC_SELECTION = 2,
        B2_EXEC_AGGREGATION = 3 /* hash */, B2_EXEC_TOPN = 4, B2_EXEC_LIMIT = 5,
-       B2_EXEC_STREAM_AGG = 6 };
+       B2_EXEC_STREAM_AGG = 6,
+       B2_EXEC_PROJECTION = 7 /* projection_executor.rs: its expressions travel in `conditions` / `n_conditions` */ };
 
 typedef struct b2_executor_desc {
   int32_t tp; /* B2_EXEC_* */

@@ -97,6 +97,18 @@ static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges,
       t->n = e.limit;
       t->src = std::move(cur);
       cur = std::move(t);
+    } else if (e.tp == B2_EXEC_PROJECTION) {
+      auto pj = std::make_unique<ProjectionExecutor>();
+      const auto& sch = cur->schema();
+      for (uint32_t k = 0; k < e.n_conditions; ++k) {
+        pj->exprs.push_back(e.conditions[k]);
+        const b2_rpn_node& last = e.conditions[k].nodes[e.conditions[k].n_nodes - 1];
+        FieldType ft;
+        if (last.kind == B2_RPN_COLUMN_REF) ft = sch[(size_t)last.i64]; else { ft.tp = last.field_tp; ft.flag = last.field_flag; }
+        pj->schema_.push_back(ft);
+      }
+      pj->src = std::move(cur);
+      cur = std::move(pj);
     } else if (e.tp == B2_EXEC_LIMIT) {
       auto lm = std::make_unique<LimitExecutor>();
       lm->remaining_rows = (size_t)e.limit;

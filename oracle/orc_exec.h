@@ -607,6 +607,39 @@ struct SelectionExecutor : Executor {
   }
 };
 
+// ---- projection: projection_executor.rs:171-240 ----
+struct ProjectionExecutor : Executor {
+  std::unique_ptr<Executor> src;
+  std::vector<b2_rpn_expr> exprs;
+  std::vector<FieldType> schema_;
+  const std::vector<FieldType>& schema() const override { return schema_; }
+  ForwardScanner* scanner() override { return src->scanner(); }
+  void next_batch(size_t scan_rows, Batch* out) override {
+    Batch b;
+    src->next_batch(scan_rows, &b);
+    out->is_drained = b.is_drained; out->err = b.err;
+    out->cols.clear(); out->logical_rows.clear();
+    size_t n = b.logical_rows.size();
+    if (!b.err.ok() || n == 0) { out->cols.assign(exprs.size(), LazyColumn()); for (auto& c : out->cols) c.decoded = true; return; }
+    ExprCtx cx{&src->schema(), &b};
+    for (size_t k = 0; k < exprs.size(); ++k) {
+      Val v; Error e;
+      if (!rpn_eval(exprs[k], cx, &v, &e)) {  // :207-211: the error ends the request, the batch's rows are dropped
+        out->err = e; out->cols.assign(exprs.size(), LazyColumn()); for (auto& c : out->cols) c.decoded = true;
+        return;
+      }
+      LazyColumn c; c.decoded = true; c.et = v.et == ET_REAL ? ET_REAL : ET_INT;
+      for (size_t j = 0; j < n; ++j) {
+        bool nul = v.null_at(j);
+        c.nn.push_back(!nul);
+        if (c.et == ET_REAL) c.f64.push_back(nul ? 0 : v.real_at(j)); else c.i64.push_back(nul ? 0 : v.int_at(j));
+      }
+      out->cols.push_back(std::move(c));
+    }
+    for (size_t j = 0; j < n; ++j) out->logical_rows.push_back(j);
+  }
+};
+
 // ---- limit: limit_executor.rs:11-80 ----
 struct LimitExecutor : Executor {
   std::unique_ptr<Executor> src;

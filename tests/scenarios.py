@@ -282,3 +282,15 @@ def in_plans():
             ("in_signedness", scan().selection(in_(col(C3, unsigned=True), const_int(-1), const_uint((1 << 64) - 1), col(C1), const_int(77))).build(output_offsets=[C_H, C3, C1])),
             ("in_real", scan().selection(in_(col(C4, tp=ffi.TP_DOUBLE), const_real(2.5), const_real(-0.0), const_real(1e300))).build(output_offsets=[C_H, C4])),
             ("in_as_group_key", scan().aggregation([("count", const_int(1))], group_by=[in_(col(C6, tp=ffi.TP_LONG), const_int(2), const_int(3), null())]).build())]
+
+
+def projection_plans():
+    """BatchProjectionExecutor on top of scan / selection: arithmetic, compares, IN, plain column refs, Real results, NULLs;
+    an overflowing expression (error), Projection followed by Limit, a subset of the projected columns."""
+    scan = lambda: Plan().table_scan(TABLE, COLUMNS)
+    c6 = col(C6, tp=ffi.TP_LONG)
+    return [("proj_mixed", scan().projection(plus(c6, const_int(100)), col(C_H), lt(col(C2), const_int(3)), multiply(col(C4, tp=ffi.TP_DOUBLE), const_real(0.5)),
+                                             in_(c6, const_int(1), const_int(2)), col(C3, unsigned=True)).build()),
+            ("proj_after_selection_limit", scan().selection(ge(c6, const_int(3))).projection(minus(col(C_H), c6), col(C2)).limit(55).build()),
+            ("proj_subset", scan().projection(col(C1), plus(c6, c6), is_null(col(C2))).build(output_offsets=[2, 1])),
+            ("proj_overflow", scan().projection(col(C_H), multiply(col(C1), const_int(1 << 40))).build())]

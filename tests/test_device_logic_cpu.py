@@ -224,3 +224,18 @@ def test_in_lists(name, plan, regions):
     got = emu.dag_handle(plan, sc.WHOLE, region)
     assert exp.status == 0 and exp.n_rows > 0
     assert_same_rows(got, exp, ordered=not sc.is_agg(name) and "group" not in name, ctx=name)
+
+
+@pytest.mark.parametrize("name,plan", sc.projection_plans(), ids=[n for n, _ in sc.projection_plans()])
+def test_projection(name, plan, regions):
+    region = sc.dirty_region(1, full_range=name == "proj_overflow").build(read_ts=sc.READ_TS, n_write_blocks=2)
+    exp = orc.dag_handle(plan, sc.WHOLE, region)
+    got = emu.dag_handle(plan, sc.WHOLE, region)
+    if name == "proj_overflow":
+        # an evaluation error ends the request; the reference drops the rows of the batch it happened in (projection_executor.rs
+        # :207-211, batch = 32..1024 rows), the device keeps every row before the failing one: the oracle's rows are a prefix
+        assert exp.status == ffi.B2_ERR_EVALUATE == got.status and exp.mysql_code == 1690
+        assert got.rows()[:len(exp.rows())] == exp.rows()
+        return
+    assert exp.status == 0
+    assert_same_rows(got, exp, ordered=True, ctx=name)

@@ -27,7 +27,7 @@
 namespace b2 {
 
 // ---- limits of the device plan ----
-enum { MAX_COLS = 64, MAX_NODES = 96, MAX_CONDS = 8, MAX_AGGS = 8, MAX_ORDER = 4, MAX_STACK = 16, MAX_ACC_WORDS = 24 };
+enum { MAX_PROJ = 16, MAX_COLS = 64, MAX_NODES = 96, MAX_CONDS = 8, MAX_AGGS = 8, MAX_ORDER = 4, MAX_STACK = 16, MAX_ACC_WORDS = 24 };
 
 // ---- device error codes (mapped to B2_ERR_* + message in engine.cu) ----
 enum DevErr {
@@ -118,6 +118,9 @@ struct DevPlan {
   int32_t n_fconds;            // == n_conds when every condition is a FastCond (else 0)
   int32_t _fcpad;
   FastCond fconds[MAX_CONDS];
+  int32_t n_proj;              // BatchProjectionExecutor on top: out_cols index `proj`, every output is an expression value
+  int32_t _prpad;
+  DevExpr proj[MAX_PROJ];
   DevCol cols[MAX_COLS];
   DevNode nodes[MAX_NODES];
 };
@@ -1222,6 +1225,13 @@ B2_HD uint64_t extremum_value(uint64_t key, int arg_et, bool arg_unsigned, bool 
   uint64_t k = is_min ? ~key : key;
   if (arg_et == 1) return (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
   return arg_unsigned ? k : (k ^ 0x8000000000000000ull);
+}
+
+// one output cell of a PM_SCAN pipeline: a scan column (LazyBatchColumn::ensure_decoded) or, under a Projection
+// (projection_executor.rs:199-222), the value of its `oc`-th selected expression
+B2_HD int output_value(const DevPlan& P, const Row& row, const Cells& cells, int oc, Value* v) {
+  if (P.n_proj) return eval_expr(P, P.proj[P.out_cols[oc]], row, cells, v, nullptr);
+  return cell_value(P, row, cells, P.out_cols[oc], v);
 }
 
 // fx-like 64-bit mixer for the group hash table (any good mixer works: group order is unspecified)

@@ -215,10 +215,11 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
     oc.field_tp = P.cols[i].tp; oc.field_flag = scan.columns[i].flag;
     schema.push_back(oc);
   }
-  bool terminal = false;
+  bool terminal = false, projected = false;
   for (uint32_t ei = 1; ei < plan->n_executors; ++ei) {
     const b2_executor_desc& e = plan->executors[ei];
     if (terminal) { *msg = "executors after Aggregation/TopN are not supported on the device path"; return B2_ERR_UNSUPPORTED; }
+    if (projected && e.tp != B2_EXEC_LIMIT) { *msg = "only Limit may follow a Projection on the device path"; return B2_ERR_UNSUPPORTED; }
     if (e.tp == B2_EXEC_SELECTION) {
       for (uint32_t k = 0; k < e.n_conditions; ++k) {
         if (P.n_conds >= MAX_CONDS) { *msg = "too many selection conditions"; return B2_ERR_UNSUPPORTED; }
@@ -272,6 +273,17 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
       }
       if (e.limit > 2048) { *msg = "TopN limit above 2048 is not on the device path yet"; return B2_ERR_UNSUPPORTED; }
       P.n_order = (int)e.n_order_by; P.limit = e.limit;
+    } else if (e.tp == B2_EXEC_PROJECTION) {
+      if (P.mode != PM_SCAN || P.n_proj) { *msg = "Projection is on the device path only on top of a scan / selection pipeline"; return B2_ERR_UNSUPPORTED; }
+      if (e.n_conditions == 0 || e.n_conditions > MAX_PROJ) { *msg = "Projection with 0 or more than 16 expressions"; return B2_ERR_UNSUPPORTED; }
+      schema.clear();
+      for (uint32_t k = 0; k < e.n_conditions; ++k) {
+        int tp; uint32_t flag; uint8_t et, uns;
+        if (!lower_expr(e.conditions[k], P, &P.proj[k], &et, &uns, &tp, &flag, msg)) return B2_ERR_UNSUPPORTED;
+        schema.push_back(OutCol{et ? B2_COL_F64 : B2_COL_I64, tp, flag});
+      }
+      P.n_proj = (int)e.n_conditions;
+      projected = true;
     } else if (e.tp == B2_EXEC_LIMIT) {
       if (P.mode != PM_SCAN || ei + 1 != plan->n_executors) { *msg = "Limit is on the device path only as the last executor of a scan / selection pipeline"; return B2_ERR_UNSUPPORTED; }
       out->scan_limit = e.limit;
@@ -296,10 +308,13 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
     if (P.mode == PM_TOPN) for (int i = 0; i < P.n_cols; ++i) mat.push_back(i); else mat = out->output_offsets;
     if (mat.size() > MAX_COLS) { *msg = "too many output columns"; return B2_ERR_UNSUPPORTED; }
     for (size_t i = 0; i < mat.size(); ++i) {
-      if (P.cols[mat[i]].kind == CK_OTHER) { *msg = "output column " + std::to_string(mat[i]) + " is not Int/Real: device path cannot materialise it yet"; return B2_ERR_UNSUPPORTED; }
+      if (!P.n_proj && P.cols[mat[i]].kind == CK_OTHER) { *msg = "output column " + std::to_string(mat[i]) + " is not Int/Real: device path cannot materialise it yet"; return B2_ERR_UNSUPPORTED; }
       P.out_cols[i] = (uint8_t)mat[i];
     }
     P.n_out = (int)mat.size();
+    if (P.n_proj) {  // expression outputs: none comes straight from a stored position
+      for (int i = 0; i < P.n_out; ++i) P.out_slow[P.n_out_slow++] = (uint8_t)i;
+    } else
     // fast rows feed integer outputs straight from their stored position; everything else goes through cell_value
     for (int i = 0; i < P.n_out; ++i) {
       const DevCol& col = P.cols[P.out_cols[i]];

@@ -41,6 +41,8 @@ inline std::string plan_literal(const DevPlan& P) {
     const FastCond& f = P.fconds[i];
     o << "{"; i64(f.imm); o << "," << (int)f.h << "," << (int)f.op << "," << (int)f.col_uns << "," << (int)f.imm_uns << "," << (int)f.zero_ext << ",{0,0,0}}" << (i < MAX_CONDS - 1 ? "," : "");
   }
+  o << "}," << P.n_proj << "," << P._prpad << ",{";
+  for (int i = 0; i < MAX_PROJ; ++i) { expr(P.proj[i]); o << (i < MAX_PROJ - 1 ? "," : ""); }
   o << "},{";
   for (int i = 0; i < MAX_COLS; ++i) {
     const DevCol& c = P.cols[i];

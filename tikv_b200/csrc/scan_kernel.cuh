@@ -573,7 +573,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
           unsigned long long* ob = obuf_base + (size_t)q * (OBUF_COLS * TILE) + pos;
           auto put = [&](int oc) {  // general cell: any role / kind, may be NULL
             Value v;
-            int err = cell_value(P, row, cells, P.out_cols[oc], &v);
+            int err = output_value(P, row, cells, oc, &v);
             if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; }
             ob[((uint32_t)oc & (cpc - 1)) * rstride] = v.null ? 0ull : v.bits;
             if (v.null) atomicOr(&onull_base[q * ONULL_WORDS + ((uint32_t)oc & (cpc - 1)) * (rstride / 32) + (pos >> 5)], 1u << (pos & 31));

@@ -33,7 +33,7 @@ SIG = dict(
 )
 
 AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX, AGG_FIRST = 3001, 3002, 3003, 3004, 3005, 3006
-EXEC_TABLE_SCAN, EXEC_INDEX_SCAN, EXEC_SELECTION, EXEC_AGGREGATION, EXEC_TOPN, EXEC_LIMIT, EXEC_STREAM_AGG = range(7)
+EXEC_TABLE_SCAN, EXEC_INDEX_SCAN, EXEC_SELECTION, EXEC_AGGREGATION, EXEC_TOPN, EXEC_LIMIT, EXEC_STREAM_AGG, EXEC_PROJECTION = range(8)
 COL_I64, COL_F64, COL_DECIMAL = 0, 1, 2
 DRAIN_REMAIN, DRAIN_DRAINED, DRAIN_PAGING = 0, 1, 2
 

@@ -148,6 +148,15 @@ class Plan:
         self._execs.append(e)
         return self
 
+    def projection(self, *exprs):
+        """BatchProjectionExecutor: the output columns become the values of `exprs` (carried in `conditions`)."""
+        arr = (ffi.RpnExpr * len(exprs))(*[self._expr(c) for c in exprs])
+        self._keep.append(arr)
+        e = ffi.ExecutorDesc()
+        e.tp, e.conditions, e.n_conditions = ffi.EXEC_PROJECTION, arr, len(exprs)
+        self._execs.append(e)
+        return self
+
     def aggregation(self, aggs, group_by=()):
         """aggs: list of (kind, Expr) with kind in {'count','sum','avg'}."""
         kinds = {"count": ffi.AGG_COUNT, "sum": ffi.AGG_SUM, "avg": ffi.AGG_AVG, "min": ffi.AGG_MIN, "max": ffi.AGG_MAX}
