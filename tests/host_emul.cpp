@@ -97,7 +97,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
           // same split as scan_kernel<PM_SCAN>: fast rows feed integer outputs by stored position, the rest by cell_value
           auto put = [&](int k) {
             Value v;
-            int e2 = output_value(P, row, cells, k, &v);
+            int e2 = output_value(P, row, cells, k, &v);  // (the kernel splits this by instantiation: PM_SCAN / PM_PROJ)
             if (e2) { report(bases[b] + e, e2); v.null = true; v.bits = 0; }
             R->data[k].push_back(v.null ? 0 : v.bits); R->nonnull[k].push_back(!v.null);
           };

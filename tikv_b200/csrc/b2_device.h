@@ -73,7 +73,8 @@ struct DevExpr { uint16_t start, n; };
 struct DevAgg { DevExpr arg; uint8_t kind /*0 count 1 sum 2 avg 3 max 4 min*/, arg_et, arg_unsigned, acc_off; };
 struct DevOrder { DevExpr e; uint8_t desc, et, is_unsigned, _pad; };
 
-enum PlanMode { PM_SCAN = 0, PM_AGG = 1, PM_TOPN = 2, PM_CHECKSUM = 3 };
+enum PlanMode { PM_SCAN = 0, PM_AGG = 1, PM_TOPN = 2, PM_CHECKSUM = 3,
+                PM_PROJ = 4 /* kernel instantiation only: PM_SCAN whose output cells are projection expressions (DevPlan::mode stays PM_SCAN) */ };
 
 // A selection condition of the shape `column <cmp> constant` over an integer column of the exact-layout fast path
 struct FastCond {

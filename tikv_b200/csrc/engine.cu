@@ -724,7 +724,7 @@ struct b2_exec {
         size_t smem = setup_staging(&a, wblocks[u.block_idx], scan_out_stage_bytes());
         a.out_stage_off = 0;
         if (getenv("B2_TRACE") && !trace_done) { trace_buf.reserve(128 * 8 * 8); cudaMemsetAsync(trace_buf.p, 0, 128 * 8 * 8, stream); a.trace = (unsigned long long*)trace_buf.p; }
-        scan_grid = scan_grid_for(PM_SCAN, smem);
+        scan_grid = scan_grid_for(cp.dev.n_proj ? PM_PROJ : PM_SCAN, smem);
         kernel_begin();
         CUDA_TRY(scan_launch(a, scan_grid, smem));
         kernel_end();

@@ -39,7 +39,10 @@ size_t scan_crc_table_bytes() { return 8 * 256 * 8; }
 int scan_max_grid(int mode, size_t smem) {
   int per_sm = 0;
   cudaError_t e;
-  if (mode == PM_SCAN) {
+  if (mode == PM_PROJ) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_PROJ>, TILE + 64, smem);
+  } else if (mode == PM_SCAN) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_SCAN>, TILE + 64, smem);
   } else if (mode == PM_CHECKSUM) {
@@ -60,7 +63,10 @@ cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t
   if (a.c_hi <= a.c_lo) return cudaSuccess;
   uint32_t n_tiles = (a.c_hi - a.c_lo + TILE - 1) / TILE;
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
-  if (plan.mode == PM_SCAN) {
+  if (plan.mode == PM_SCAN && plan.n_proj) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_kernel<PM_PROJ><<<grid, TILE + 64, smem, s>>>(plan, a);
+  } else if (plan.mode == PM_SCAN) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     scan_kernel<PM_SCAN><<<grid, TILE + 64, smem, s>>>(plan, a);
   } else if (plan.mode == PM_CHECKSUM) {

@@ -286,13 +286,16 @@ struct SmemTable {  // per-CTA group table (dynamic shared memory): keys | acc. 
 // parameter) and by the per-plan JIT translation unit (plan as a compile-time constant, jit.cpp).
 template <int MODE>
 __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
+  // PM_PROJ is PM_SCAN with expression-valued output cells: a separate instantiation, so that the expression evaluator
+  // stays out of the plain scan's hot loop (inlined there it cost 3.5x)
+  constexpr bool IS_SCAN = (MODE == PM_SCAN) || (MODE == PM_PROJ);
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned int s_warp_cnt[2][TILE / 32];  // by tile parity: a fast warp may start the next tile while others still read
   __shared__ unsigned int s_tbl_used, s_tbl_miss, s_tbl_off;  // resident groups; rows that fell through to HBM; table given up
 
   const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint32_t n_tiles = (A.c_hi - A.c_lo + TILE - 1) / TILE;
-  const unsigned long long out_base = MODE == PM_SCAN ? A.ctr->out_base : 0ull;  // stable during this launch
+  const unsigned long long out_base = IS_SCAN ? A.ctr->out_base : 0ull;  // stable during this launch
 
   SmemTable st;
   st.slots = 0;
@@ -360,7 +363,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   // PM_SCAN output chunk buffers (dynamic shared memory): N_OBUF x [OBUF_COLS][TILE] values, then the NULL masks
   unsigned long long* obuf_base = reinterpret_cast<unsigned long long*>(dyn_smem + A.out_stage_off);
   unsigned int* onull_base = reinterpret_cast<unsigned int*>(dyn_smem + A.out_stage_off + N_OBUF * OBUF_BYTES);
-  if (MODE == PM_SCAN)
+  if (IS_SCAN)
     for (unsigned int i = tid; i < N_OBUF * ONULL_WORDS; i += blockDim.x) onull_base[i] = 0;
   if (tid == 0) {
     for (int i = 0; i < N_STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], TILE / 32); }
@@ -378,7 +381,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       uint32_t nx_tile, nx_wlo = 0, nx_whi = 0, nx_k0 = 0, nx_k1 = 0, nx_v0 = 0, nx_v1 = 0;
       auto claim = [&](uint32_t k) {
         // PM_SCAN claims tiles in order so that the decoupled look-back only ever waits on running CTAs
-        if (MODE == PM_SCAN) nx_tile = (uint32_t)atomicAdd(&A.tile_status[n_tiles], 1ull);
+        if (IS_SCAN) nx_tile = (uint32_t)atomicAdd(&A.tile_status[n_tiles], 1ull);
         else nx_tile = blockIdx.x + k * gridDim.x;
         if (nx_tile < n_tiles && A.staging) {
           uint32_t e0 = A.c_lo + nx_tile * TILE;
@@ -389,15 +392,15 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
         }
       };
       // (ordered mode claims late instead: a ticket held early would stall every successor's look-back)
-      if (MODE != PM_SCAN) claim(0);
+      if (!IS_SCAN) claim(0);
       for (uint32_t k = 0;; ++k) {
         const int slot = (int)(k % N_STAGES);
         TileMeta m;
         m.staged = 0; m.w_lo = 0; m.w_hi = 0; m.keys_adj = 0; m.vals_adj = 0; m.koff_adj = 0; m.voff_adj = 0;
-        if (MODE == PM_SCAN) { mbar_wait_sleep(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1); claim(k); }
+        if (IS_SCAN) { mbar_wait_sleep(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1); claim(k); }
         m.tile = nx_tile;
         const uint32_t w_lo = nx_wlo, w_hi = nx_whi, k0 = nx_k0, k1 = nx_k1, v0 = nx_v0, v1 = nx_v1;
-        if (MODE != PM_SCAN) mbar_wait_sleep(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1);
+        if (!IS_SCAN) mbar_wait_sleep(&s_empty[slot], ((k / N_STAGES) & 1) ^ 1);
         uint32_t tx = 0;
         if (m.tile < n_tiles && A.staging) {
           unsigned long long ka = (unsigned long long)(A.blk.keys + k0), va = (unsigned long long)(A.blk.vals + v0);
@@ -425,7 +428,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_full[slot])) : "memory");
         }
         if (m.tile >= n_tiles) break;
-        if (MODE != PM_SCAN) claim(k + 1);
+        if (!IS_SCAN) claim(k + 1);
       }
     }
     return;
@@ -436,7 +439,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     // warp wide: lane l inspects tile (j - l); the nearest tile that already knows its inclusive prefix ends the walk,
     // the aggregates in between are summed with shuffles), then drains the tile's output chunks from shared memory to
     // HBM.  The decoding warps never wait for the look-back.
-    if (MODE != PM_SCAN) return;
+    if (!IS_SCAN) return;
     const unsigned long long F_AGG = 1ull << 62, F_INC = 2ull << 62, VMASK = (1ull << 62) - 1;
     uint32_t sw_q = 0, sw_phase = 0;
     for (uint32_t k = 0;; ++k) {
@@ -522,7 +525,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       if (__any_sync(0xffffffffu, r1 == P1_REDO) && lane == 0) s_redo[k & 3] = 1;
     }
     unsigned int warp_off = 0, total = 0, lane_off = 0;
-    if (MODE == PM_SCAN) {
+    if (IS_SCAN) {
       // ---- ordered compaction: ballot/popc inside the warp, smem across warps, look-back across tiles ----
       if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 0] = clock64();
       unsigned int bal = __ballot_sync(0xffffffffu, live);
@@ -542,7 +545,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     if (MODE == PM_CHECKSUM) { ts.ck_x ^= d.ck_x; ts.ck_kvs += d.ck_kvs; ts.ck_bytes += d.ck_bytes; }
     t_live += live;
 
-    if (MODE == PM_SCAN) {
+    if (IS_SCAN) {
 #pragma unroll
       for (int w = 0; w < TILE / 32; ++w) {
         unsigned int c = s_warp_cnt[k & 1][w];
@@ -573,7 +576,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
           unsigned long long* ob = obuf_base + (size_t)q * (OBUF_COLS * TILE) + pos;
           auto put = [&](int oc) {  // general cell: any role / kind, may be NULL
             Value v;
-            int err = output_value(P, row, cells, oc, &v);
+            int err = MODE == PM_PROJ ? eval_expr(P, P.proj[P.out_cols[oc]], row, cells, &v, nullptr) : cell_value(P, row, cells, P.out_cols[oc], &v);
             if (err) { report_err(A.ctr, A.entry_base + e, err); v.null = true; }
             ob[((uint32_t)oc & (cpc - 1)) * rstride] = v.null ? 0ull : v.bits;
             if (v.null) atomicOr(&onull_base[q * ONULL_WORDS + ((uint32_t)oc & (cpc - 1)) * (rstride / 32) + (pos >> 5)], 1u << (pos & 31));
@@ -731,7 +734,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     const TileMeta m = s_meta[cur];
     const uint32_t tile = m.tile;
     if (tile >= n_tiles) {
-      if (MODE == PM_SCAN && tid == 0) {  // tell the scan warp there is no tile k
+      if (IS_SCAN && tid == 0) {  // tell the scan warp there is no tile k
         s_tile_of[k % N_CNT] = tile;
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready[k % N_CNT])) : "memory");
       }
