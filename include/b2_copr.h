@@ -354,10 +354,12 @@ typedef struct b2_agg_partials {
   uint32_t acc_words;
   int32_t location;           /* always B2_LOC_DEVICE */
   int32_t has_group;
-  const uint64_t* keys;       /* n_groups group keys (bits); unused without GROUP BY */
-  const uint8_t* key_null;    /* n_groups flags */
+  const uint64_t* keys;       /* n_groups * key_words group keys (bits, 0 where NULL); unused without GROUP BY */
+  const uint8_t* key_null;    /* n_groups NULL masks: bit q set = the q-th group-by value is NULL */
   const uint64_t* acc;        /* n_groups * acc_words */
   uint64_t max_word_mask;     /* words of a group's state that merge by unsigned maximum instead of addition */
+  uint32_t key_words;         /* group-by expressions (1 for the fast hash executor, 2..4 for BatchSlowHashAggregation) */
+  uint32_t _pad;
 } b2_agg_partials;
 int32_t b2_exec_agg_partials(b2_exec* h, b2_agg_partials* out);
 

@@ -60,7 +60,6 @@ static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges,
       s->src = std::move(cur);
       cur = std::move(s);
     } else if (e.tp == B2_EXEC_AGGREGATION || e.tp == B2_EXEC_STREAM_AGG) {
-      if (e.n_group_by > 1) { *err = Error::make(B2_ERR_UNSUPPORTED, "multi-column GROUP BY (slow hash agg) not restated"); return false; }
       auto a = std::make_unique<AggExecutor>();
       const auto& sch = cur->schema();
       auto ret_type = [&](const b2_rpn_expr& x, FieldType* ft) {
@@ -82,7 +81,14 @@ static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges,
         if (f.kind == B2_AGG_SUM || f.kind == B2_AGG_AVG) a->schema_.push_back(sum);
         if (f.kind == B2_AGG_MAX || f.kind == B2_AGG_MIN) a->schema_.push_back(ft);  // the argument's own type, impl_max_min.rs:78-84
       }
-      if (e.n_group_by == 1) {
+      if (e.n_group_by > 1) {
+        for (uint32_t q = 0; q < e.n_group_by; ++q) {
+          FieldType ft; ret_type(e.group_by[q], &ft);
+          EvalType et = eval_type_of(ft.tp);
+          if (et != ET_INT && et != ET_REAL) { *err = Error::make(B2_ERR_UNSUPPORTED, "group by non Int/Real"); return false; }
+          a->multi_by.push_back(e.group_by[q]); a->multi_ft.push_back(ft); a->schema_.push_back(ft);
+        }
+      } else if (e.n_group_by == 1) {
         a->has_group = true; a->group_by = e.group_by[0];
         ret_type(a->group_by, &a->group_ft);
         a->group_et = eval_type_of(a->group_ft.tp);

@@ -12,6 +12,7 @@
 //   BatchTopNExecutor             top_n_executor.rs:184-273, util/top_n_heap.rs:36-222, scalar.rs:374-411
 //   BatchExecutorsRunner          runner.rs:739-851, 962-1013 (batch growth 32 -> x2 -> 1024)
 #pragma once
+#include <map>
 #include <algorithm>
 #include <cmath>
 #include <memory>
@@ -675,6 +676,12 @@ struct AggExecutor : Executor {  // simple (no group by) or fast-hash (one group
   std::vector<AggState> states;  // group * fns
   bool any_input = false, done = false;
   EvalType group_et = ET_INT;
+  // BatchSlowHashAggregation (slow_hash_aggr_executor.rs:209-420): two or more group-by expressions.  The reference keys
+  // its map on the concatenated encode_sort_key bytes of the values; for Int / Real columns that is the value bits plus
+  // NULL-ness per column (no -0.0 / 0.0 folding: the two encode to different bytes).
+  std::vector<b2_rpn_expr> multi_by; std::vector<FieldType> multi_ft;
+  std::map<std::vector<std::pair<bool, int64_t>>, size_t> multi_groups;
+  std::vector<std::vector<std::pair<bool, int64_t>>> multi_keys;
 
   const std::vector<FieldType>& schema() const override { return schema_; }
   ForwardScanner* scanner() override { return src->scanner(); }
@@ -741,6 +748,21 @@ struct AggExecutor : Executor {  // simple (no group by) or fast-hash (one group
             if (it == groups.end()) { size_t gi = group_keys.size(); groups.emplace(key, gi); group_keys.push_back(key); states.resize(states.size() + fns.size()); row_group[j] = gi; }
             else row_group[j] = it->second;
           }
+        } else if (!multi_by.empty()) {
+          std::vector<Val> gv(multi_by.size());
+          for (size_t q = 0; q < multi_by.size(); ++q) { Error e; if (!rpn_eval(multi_by[q], cx, &gv[q], &e)) { out->err = e; return; } }
+          for (size_t j = 0; j < n; ++j) {
+            std::vector<std::pair<bool, int64_t>> key;
+            for (size_t q = 0; q < multi_by.size(); ++q) {
+              bool isnull = gv[q].null_at(j);
+              int64_t bits = 0;
+              if (!isnull) { if (gv[q].et == ET_REAL) { double d = gv[q].real_at(j); memcpy(&bits, &d, 8); } else bits = gv[q].int_at(j); }
+              key.emplace_back(isnull, bits);
+            }
+            auto it = multi_groups.find(key);
+            if (it == multi_groups.end()) { size_t gi = multi_keys.size(); multi_groups.emplace(key, gi); multi_keys.push_back(key); states.resize(states.size() + fns.size()); row_group[j] = gi; }
+            else row_group[j] = it->second;
+          }
         } else if (states.empty()) states.resize(fns.size());
         for (size_t fi = 0; fi < fns.size(); ++fi) {
           Val v; Error e;
@@ -754,8 +776,8 @@ struct AggExecutor : Executor {  // simple (no group by) or fast-hash (one group
       if (b.is_drained) break;
     }
     // emit: aggregate result columns then the group-by column (fast_hash_aggr_executor.rs:383-413)
-    size_t ngroups = has_group ? group_keys.size() : (any_input ? 1 : 0);  // simple_aggr_executor.rs:141-148
-    if (!has_group && any_input && states.empty()) states.resize(fns.size());
+    size_t ngroups = has_group ? group_keys.size() : (!multi_by.empty() ? multi_keys.size() : (any_input ? 1 : 0));  // simple_aggr_executor.rs:141-148
+    if (!has_group && multi_by.empty() && any_input && states.empty()) states.resize(fns.size());
     for (size_t fi = 0; fi < fns.size(); ++fi) {
       const AggFn& f = fns[fi];
       if (f.kind == B2_AGG_COUNT || f.kind == B2_AGG_AVG) {
@@ -784,6 +806,14 @@ struct AggExecutor : Executor {  // simple (no group by) or fast-hash (one group
       for (auto& k : group_keys) {
         if (group_et == ET_REAL) { double d; memcpy(&d, &k.second, 8); c.f64.push_back(k.first ? 0 : d); c.nn.push_back(!k.first); }
         else c.push_int(!k.first, k.second);
+      }
+      out->cols.push_back(std::move(c));
+    }
+    for (size_t q = 0; q < multi_by.size(); ++q) {  // the group-by columns, in order (slow_hash_aggr_executor.rs:388-420)
+      LazyColumn c; c.decoded = true; c.et = eval_type_of(multi_ft[q].tp) == ET_REAL ? ET_REAL : ET_INT;
+      for (auto& k : multi_keys) {
+        if (c.et == ET_REAL) { double d; memcpy(&d, &k[q].second, 8); c.f64.push_back(k[q].first ? 0 : d); c.nn.push_back(!k[q].first); }
+        else c.push_int(!k[q].first, k[q].second);
       }
       out->cols.push_back(std::move(c));
     }

@@ -58,8 +58,9 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
   R->data.resize(n_out); R->dec.resize(n_out); R->nonnull.resize(n_out); R->kinds.resize(n_out);
   struct TopRow { TopItem it; std::vector<uint64_t> bits; std::vector<uint8_t> nn; };
   std::vector<TopRow> top_rows;
-  std::map<std::pair<int, uint64_t>, GroupAcc> groups;  // (is_null, key bits)
-  std::vector<std::pair<int, uint64_t>> group_order;
+  typedef std::vector<uint64_t> GKey;  // one group-by expression: (is_null, key bits); several: value words then the NULL mask
+  std::map<GKey, GroupAcc> groups;
+  std::vector<GKey> group_order;
   GroupAcc single; memset(&single, 0, sizeof(single));
   uint64_t live_rows = 0;
   uint64_t err = ~0ull;
@@ -126,12 +127,27 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
           top_rows.push_back(std::move(tr));
         } else if (P.mode == PM_AGG) {
           GroupAcc* acc = &single;
-          if (P.has_group) {
+          if (P.n_group > 1) {  // scan_body<PM_AGGM>: composite key, no -0.0 folding
+            GKey key;
+            uint64_t nm = 0;
+            int e2 = 0;
+            for (int q = 0; q < P.n_group && !e2; ++q) {
+              Value v;
+              e2 = eval_expr(P, P.groups[q], row, cells, &v, nullptr);
+              key.push_back(v.null ? 0ull : v.bits);
+              if (v.null) nm |= 1ull << q;
+            }
+            if (e2) { report(bases[b] + e, e2); continue; }
+            key.push_back(nm);
+            auto it = groups.find(key);
+            if (it == groups.end()) { GroupAcc z; memset(&z, 0, sizeof(z)); it = groups.emplace(key, z).first; group_order.push_back(key); }
+            acc = &it->second;
+          } else if (P.has_group) {
             Value gk;
             int e2 = eval_expr(P, P.group, row, cells, &gk, nullptr);
             if (e2) { report(bases[b] + e, e2); continue; }
             if (P.group_et == 1 && !gk.null && bits_f64(gk.bits) == 0.0) gk.bits = 0;
-            auto key = std::make_pair((int)gk.null, gk.null ? 0ull : gk.bits);
+            GKey key = {(uint64_t)gk.null, gk.null ? 0ull : gk.bits};
             auto it = groups.find(key);
             if (it == groups.end()) { GroupAcc z; memset(&z, 0, sizeof(z)); it = groups.emplace(key, z).first; group_order.push_back(key); }
             acc = &it->second;
@@ -186,9 +202,9 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
     for (int k = 0; k < P.n_out; ++k) R->kinds[k] = cp.schema[cp.output_offsets[k]].kind;
   } else if (P.mode == PM_AGG && err == ~0ull) {
     // agg_result_kernel restated: accumulators -> [aggregates..., group key]
-    std::vector<std::pair<std::pair<int, uint64_t>, GroupAcc>> gs;
+    std::vector<std::pair<GKey, GroupAcc>> gs;
     if (P.has_group) for (auto& k : group_order) gs.push_back({k, groups[k]});
-    else if (live_rows > 0) gs.push_back({{0, 0ull}, single});
+    else if (live_rows > 0) gs.push_back({GKey{0, 0ull}, single});
     size_t ncol = cp.schema.size();
     std::vector<std::vector<uint64_t>> data(ncol);
     std::vector<std::vector<b2_decimal>> dec(ncol);
@@ -215,7 +231,12 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
           ++c;
         }
       }
-      if (P.has_group) { data[c].push_back(g.first.first ? 0 : g.first.second); nn[c].push_back(!g.first.first); dec[c].push_back(b2_decimal{}); }
+      if (P.n_group > 1) {
+        for (int q = 0; q < P.n_group; ++q, ++c) {
+          bool isnull = (g.first[P.n_group] >> q) & 1;
+          data[c].push_back(isnull ? 0 : g.first[q]); nn[c].push_back(!isnull); dec[c].push_back(b2_decimal{});
+        }
+      } else if (P.has_group) { data[c].push_back(g.first[0] ? 0 : g.first[1]); nn[c].push_back(!g.first[0]); dec[c].push_back(b2_decimal{}); }
     }
     for (size_t i = 0; i < cp.output_offsets.size(); ++i) {
       uint32_t k = cp.output_offsets[i];

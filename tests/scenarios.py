@@ -271,6 +271,20 @@ def minmax_plans():
             ("minmax_empty", scan().selection(lt(col(C1), const_int(-(1 << 63)))).aggregation([("max", col(C1)), ("min", col(C3, unsigned=True))]).build())]
 
 
+def multi_group_plans():
+    """BatchSlowHashAggregation (slow_hash_aggr_executor.rs): GROUP BY over 2..4 expressions; NULLs in any key position,
+    Real keys (0.0 and -0.0 stay apart here), one group per row, repeated expressions, reordered output offsets."""
+    scan = lambda: Plan().table_scan(TABLE, COLUMNS)
+    c6 = col(C6, tp=ffi.TP_LONG)
+    return [("mg_two_ints", scan().aggregation([("count", const_int(1)), ("sum", col(C1))], group_by=[c6, col(C2)]).build()),
+            ("mg_with_handle", scan().aggregation([("sum", c6), ("count", col(C2))], group_by=[col(C_H), c6]).build()),
+            ("mg_real_negzero", scan().aggregation([("count", const_int(1)), ("max", col(C1))], group_by=[multiply(col(C4, tp=ffi.TP_DOUBLE), const_real(-0.0)), c6]).build()),
+            ("mg_four", scan().aggregation([("avg", col(C1)), ("min", col(C2))], group_by=[c6, col(C2), is_null(col(C5)), col(C3, unsigned=True)]).build()),
+            ("mg_filter_offsets", scan().selection(ge(c6, const_int(4))).aggregation([("sum", col(C2)), ("count", const_int(1))], group_by=[col(C2), c6]).build(output_offsets=[3, 0, 2])),
+            ("mg_same_expr_twice", scan().aggregation([("sum", col(C4, tp=ffi.TP_DOUBLE))], group_by=[c6, c6]).build()),
+            ("mg_no_input", scan().selection(lt(c6, const_int(-5))).aggregation([("count", const_int(1))], group_by=[c6, col(C2)]).build())]
+
+
 def in_plans():
     """IN lists (impl_compare_in.rs): constants, NULL in the list, NULL base, columns in the list, signed vs unsigned, Real."""
     scan = lambda: Plan().table_scan(TABLE, COLUMNS)

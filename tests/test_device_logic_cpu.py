@@ -132,7 +132,9 @@ def test_check_supported_mirrors_runner():
     assert emu.check_supported(Plan().table_scan(5, cols).build())[0] == ffi.B2_ERR_UNSUPPORTED  # varchar output
     assert emu.check_supported(Plan().table_scan(5, cols, desc=True).build(output_offsets=[0]))[0] == ffi.B2_ERR_UNSUPPORTED
     two = Plan().table_scan(5, cols).aggregation([("count", const_int(1))], group_by=[col(0), col(1)]).build()
-    assert emu.check_supported(two)[0] == ffi.B2_ERR_UNSUPPORTED
+    assert emu.check_supported(two)[0] == 0  # BatchSlowHashAggregation: up to 4 Int / Real expressions
+    five = Plan().table_scan(5, cols).aggregation([("count", const_int(1))], group_by=[col(0), col(1), col(0), col(1), col(0)]).build()
+    assert emu.check_supported(five)[0] == ffi.B2_ERR_UNSUPPORTED
     rc, msg = emu.check_supported(Plan().table_scan(5, cols).selection(lt(col(2), const_int(3))).build(output_offsets=[0]))
     assert rc == ffi.B2_ERR_UNSUPPORTED and "Int/Real" in msg
 
@@ -215,6 +217,16 @@ def test_min_max(name, plan, regions):
     got = emu.dag_handle(plan, sc.WHOLE, region)
     assert exp.status == 0
     assert_same_rows(got, exp, ordered=False, ctx=name)
+
+
+@pytest.mark.parametrize("name,plan", sc.multi_group_plans(), ids=[n for n, _ in sc.multi_group_plans()])
+def test_multi_column_group_by(name, plan, regions):
+    for seed in (1, 2):
+        region = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=2)
+        exp = orc.dag_handle(plan, sc.WHOLE, region)
+        got = emu.dag_handle(plan, sc.WHOLE, region)
+        assert exp.status == 0 and (exp.n_rows > 0 or name == "mg_no_input")
+        assert_same_rows(got, exp, ordered=False, ctx=f"{name}/seed{seed}")
 
 
 @pytest.mark.parametrize("name,plan", sc.in_plans(), ids=[n for n, _ in sc.in_plans()])

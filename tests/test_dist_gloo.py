@@ -111,6 +111,11 @@ def test_merge_single_process_semantics():
     m = torch.tensor([[2, 5], [1, -3], [4, 9]], dtype=torch.int64)  # -3 is a huge unsigned key
     k, n, a = bd.merge_agg_partials(torch.tensor([8, 8, 9]), torch.tensor([False, False, False]), m, max_words=(1,))
     assert sorted((int(k[i]), int(a[i, 0]), int(a[i, 1])) for i in range(2)) == [(8, 3, -3), (9, 4, 9)]
+    # composite keys (b2_agg_partials.key_words = 2): [n, 2] key words + NULL mask per group
+    mk = torch.tensor([[1, 2], [1, 2], [1, 0], [1, 0], [0, 0]], dtype=torch.int64)
+    mn = torch.tensor([0, 0, 2, 0, 3], dtype=torch.int64)  # (1,2) (1,2) (1,NULL) (1,0) (NULL,NULL)
+    k, n, a = bd.merge_agg_partials(mk, mn, torch.tensor([[1], [2], [4], [8], [16]], dtype=torch.int64))
+    assert sorted((int(n[i]), [int(x) for x in k[i]], int(a[i, 0])) for i in range(k.shape[0])) == [(0, [1, 0], 8), (0, [1, 2], 3), (2, [1, 0], 4), (3, [0, 0], 16)]
     # TopN with NULLs: asc puts NULL first, desc puts NULL last
     c, nl = bd.merge_topn([torch.tensor([3, 1, 0, 2])], [torch.tensor([False, False, True, False])], [(0, False, "i64")], 3)
     assert [None if nl[0][i] else int(c[0][i]) for i in range(3)] == [None, 1, 2]

@@ -81,3 +81,25 @@ def test_min_max_partials_merge_two_shards():
     exp = orc.dag_handle(plan, sc.WHOLE, region)
     want = sorted((r[3], r[0], (r[1] & ((1 << 64) - 1)) if r[1] is not None else None, r[2]) for r in exp.rows())
     assert got == want and len(want) >= 10
+
+
+def test_multi_column_partials_merge_two_shards():
+    """BatchSlowHashAggregation partial states of two shards (b2_agg_partials.key_words = 2): composite keys + NULL masks
+    merge to the whole-table result."""
+    region = sc.dirty_region(9, n_keys=1200).build(read_ts=sc.READ_TS)
+    dev = DeviceRegion(region)
+    plan = (Plan().table_scan(sc.TABLE, sc.COLUMNS)
+            .aggregation([("count", const_int(1)), ("count", col(sc.C1))], group_by=[col(sc.C6, tp=ffi.TP_LONG), col(sc.C2)]).build())
+    parts = []
+    for lo, hi in ((-1000, 1500), (1500, 10000)):
+        with BatchExecutor(plan, [kvfmt.table_range(sc.TABLE, lo, hi)], dev) as ex:
+            r = ex.next_batch(1 << 30)
+            assert r.error is None and r.is_drained
+            parts.append(tuple(t.clone() for t in bd.agg_partials_as_tensors(ex, 0)))
+    keys = torch.cat([p[0] for p in parts]); nul = torch.cat([p[1] for p in parts]); acc = torch.cat([p[2] for p in parts])
+    assert keys.dim() == 2 and keys.shape[1] == 2
+    k, n, a = bd.merge_agg_partials(keys, nul, acc)
+    nk = lambda t: tuple((0, 0) if x is None else (1, x) for x in t)
+    got = sorted(((int(a[i, 0]), int(a[i, 1]), None if int(n[i]) & 1 else int(k[i, 0]), None if int(n[i]) & 2 else int(k[i, 1])) for i in range(k.shape[0])), key=nk)
+    want = sorted(orc.dag_handle(plan, sc.WHOLE, region).rows(), key=nk)
+    assert got == want and len(want) >= 20

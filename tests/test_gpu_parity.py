@@ -511,6 +511,66 @@ def test_min_max(name, plan, regions):
         assert_same_rows(got, exp, ordered=False, ctx=f"{name}/seed{seed}")
 
 
+@pytest.mark.parametrize("jit", [ffi.JIT_OFF, ffi.JIT_SYNC], ids=["aot", "jit"])
+@pytest.mark.parametrize("name,plan", sc.multi_group_plans(), ids=[n for n, _ in sc.multi_group_plans()])
+def test_multi_column_group_by(name, plan, jit, regions):
+    """BatchSlowHashAggregation (slow_hash_aggr_executor.rs): composite keys of 2..4 Int / Real expressions."""
+    for seed in (1, 2):
+        region = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=2)
+        exp = orc.dag_handle(plan, sc.split_ranges(), region)
+        got = DagHandler(plan, sc.split_ranges(), DeviceRegion(region), jit=jit).handle_request()
+        assert exp.status == 0 and (exp.n_rows > 0 or name == "mg_no_input")
+        # f64 SUM: the addition order differs from the oracle's (atomics), tolerance 1e-12 relative; everything else bit-exact
+        assert_same_rows(got, exp, ordered=False, float_rel_tol=1e-12 if name == "mg_same_expr_twice" else None, ctx=f"{name}/seed{seed}")
+
+
+@pytest.mark.parametrize("bits", [1, 5])
+def test_multi_column_group_by_hash_collisions(bits, regions, monkeypatch):
+    """Composite-key table with the hash tag cut to a few bits (debug knob): every probe meets equal tags with different
+    keys, inside a warp and across CTAs; results must not change."""
+    monkeypatch.setenv("B2_DEBUG_AGG_HASH_BITS", str(bits))
+    for name, plan in sc.multi_group_plans()[:4]:
+        region = regions[1].build(read_ts=sc.READ_TS, n_write_blocks=2)
+        exp = orc.dag_handle(plan, sc.WHOLE, region)
+        got = DagHandler(plan, sc.WHOLE, DeviceRegion(region), jit=ffi.JIT_OFF).handle_request()
+        assert_same_rows(got, exp, ordered=False, ctx=f"{name}/bits{bits}")
+
+
+def test_multi_column_group_by_generated():
+    """Generated table, 200k rows: (a) parity with the oracle for two- and three-column keys incl. a nullable column,
+    (b) at 4M rows the group counts add up and the number of groups is the product of the key cardinalities."""
+    n_cols = 8
+    lo = [0, 0, -(1 << 40), 0, 0, 0, 0, 0]
+    rng = [0, 37, 1 << 41, 0, 5, 0, 3, 0]
+    nulls = [0, 0, 0, 10000, 200000, 0, 0, 0]
+    columns = [ColumnDef(100, pk_handle=True)] + [ColumnDef(i + 1) for i in range(n_cols)]
+    scan = lambda: Plan().table_scan(sc.TABLE, columns)
+    plans = [("g2", scan().aggregation([("count", const_int(1)), ("sum", col(3))], group_by=[col(2), col(7)]).build()),
+             ("g3null", scan().aggregation([("sum", col(1)), ("max", col(3))], group_by=[col(7), col(5), col(2)]).build())]
+    g, blk = _gen_block(200_000, n_cols, 2, 99, lo, rng, nulls, extra=20000, delete=20000, lockrec=20000)
+    try:
+        hb, keep = _block_to_host(blk)
+        host, dev = _source([hb], ffi.LOC_HOST), _source([blk.block], ffi.LOC_DEVICE)
+        for name, plan in plans:
+            e = orc.dag_handle(plan, sc.WHOLE, host)
+            assert e.status == 0 and e.n_rows in (37 * 3, 37 * 3 * 6)
+            assert_same_rows(DagHandler(plan, sc.WHOLE, dev).handle_request(), e, ordered=False, ctx=f"gen/{name}")
+    finally:
+        ffi.lib().b2_gen_destroy(g)
+    n_rows = 4_000_000
+    g, blk = _gen_block(n_rows, n_cols, 2, 5, lo, rng, nulls)
+    try:
+        dev = _source([blk.block], ffi.LOC_DEVICE)
+        r = DagHandler(plans[1][1], sc.WHOLE, dev).handle_request()
+        assert r.n_rows == 37 * 3 * 6
+        cnt = DagHandler(scan().aggregation([("count", const_int(1))], group_by=[col(2), col(7)]).build(), sc.WHOLE, dev).handle_request()
+        assert cnt.n_rows == 37 * 3 and sum(x[0] for x in cnt.rows()) == n_rows
+        one = DagHandler(scan().aggregation([("count", const_int(1))], group_by=[col(0), col(7)]).build(), [kvfmt.table_range(sc.TABLE, 0, 500_000)], dev).handle_request()
+        assert one.n_rows == 500_000 and all(x[0] == 1 for x in one.rows())  # one group per row
+    finally:
+        ffi.lib().b2_gen_destroy(g)
+
+
 @pytest.mark.parametrize("name,plan", sc.in_plans(), ids=[n for n, _ in sc.in_plans()])
 def test_in_lists(name, plan, regions):
     """IN (impl_compare_in.rs): NULL semantics, mixed signedness, Real, columns inside the list."""

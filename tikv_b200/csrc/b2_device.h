@@ -27,7 +27,7 @@
 namespace b2 {
 
 // ---- limits of the device plan ----
-enum { MAX_PROJ = 16, MAX_COLS = 64, MAX_NODES = 96, MAX_CONDS = 8, MAX_AGGS = 8, MAX_ORDER = 4, MAX_STACK = 16, MAX_ACC_WORDS = 24 };
+enum { MAX_GROUP = 4, MAX_PROJ = 16, MAX_COLS = 64, MAX_NODES = 96, MAX_CONDS = 8, MAX_AGGS = 8, MAX_ORDER = 4, MAX_STACK = 16, MAX_ACC_WORDS = 24 };
 
 // ---- device error codes (mapped to B2_ERR_* + message in engine.cu) ----
 enum DevErr {
@@ -74,7 +74,8 @@ struct DevAgg { DevExpr arg; uint8_t kind /*0 count 1 sum 2 avg 3 max 4 min*/, a
 struct DevOrder { DevExpr e; uint8_t desc, et, is_unsigned, _pad; };
 
 enum PlanMode { PM_SCAN = 0, PM_AGG = 1, PM_TOPN = 2, PM_CHECKSUM = 3,
-                PM_PROJ = 4 /* kernel instantiation only: PM_SCAN whose output cells are projection expressions (DevPlan::mode stays PM_SCAN) */ };
+                PM_PROJ = 4 /* kernel instantiation only: PM_SCAN whose output cells are projection expressions (DevPlan::mode stays PM_SCAN) */,
+                PM_AGGM = 5 /* kernel instantiation only: PM_AGG grouped by 2..MAX_GROUP expressions (DevPlan::mode stays PM_AGG) */ };
 
 // A selection condition of the shape `column <cmp> constant` over an integer column of the exact-layout fast path
 struct FastCond {
@@ -122,6 +123,10 @@ struct DevPlan {
   int32_t n_proj;              // BatchProjectionExecutor on top: out_cols index `proj`, every output is an expression value
   int32_t _prpad;
   DevExpr proj[MAX_PROJ];
+  int32_t n_group;             // >= 2: BatchSlowHashAggregation, grouped by `groups` (has_group is 1, `group` unused)
+  int32_t _gpad;
+  DevExpr groups[MAX_GROUP];
+  uint8_t groups_et[MAX_GROUP];  // 0 Int, 1 Real
   DevCol cols[MAX_COLS];
   DevNode nodes[MAX_NODES];
 };

@@ -256,7 +256,7 @@ struct b2_exec {
 
   // device state
   DevBuf ctr_buf, status_buf, out_data, out_bitmap, dflt_views, dflt_store;
-  DevBuf tbl_keys, tbl_occ, tbl_acc, grp_keys, grp_null, grp_acc, res_ptrs;
+  DevBuf tbl_keys, tbl_occ, tbl_acc, tbl_gkeys, tbl_ready, grp_keys, grp_null, grp_acc, res_ptrs;
   std::vector<DevBuf> res_cols, res_bitmaps;
   unsigned int tbl_cap = 0;
   StageSlot slots[2];
@@ -288,7 +288,7 @@ struct b2_exec {
     }
     for (auto& e : kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (DevBuf* b : {&tn_lists, &tn_counts, &tn_pair, &tn_pair_cnt, &tn_tmp, &tn_tmp_cnt, &tn_blk_pay, &tn_blk_null, &tn_run_pay, &tn_run_null, &tn_tmp_pay, &tn_tmp_null, &tn_bitmap}) b->release();
-    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
+    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &tbl_gkeys, &tbl_ready, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
     enc_host.release();
     for (auto& b : res_cols) b.release();
     for (auto& b : res_bitmaps) b.release();
@@ -724,7 +724,7 @@ struct b2_exec {
         size_t smem = setup_staging(&a, wblocks[u.block_idx], scan_out_stage_bytes());
         a.out_stage_off = 0;
         if (getenv("B2_TRACE") && !trace_done) { trace_buf.reserve(128 * 8 * 8); cudaMemsetAsync(trace_buf.p, 0, 128 * 8 * 8, stream); a.trace = (unsigned long long*)trace_buf.p; }
-        scan_grid = scan_grid_for(cp.dev.n_proj ? PM_PROJ : PM_SCAN, smem);
+        scan_grid = scan_grid_for(scan_kernel_mode(cp.dev), smem);
         kernel_begin();
         CUDA_TRY(scan_launch(a, scan_grid, smem));
         kernel_end();
@@ -1002,6 +1002,11 @@ struct b2_exec {
     CUDA_TRY(cudaMemsetAsync(tbl_keys.p, 0xff, ((size_t)cap + 2) * 8, stream));  // AGG_EMPTY_KEY everywhere
     CUDA_TRY(cudaMemsetAsync(tbl_occ.p, 0, 8, stream));
     CUDA_TRY(cudaMemsetAsync(tbl_acc.p, 0, ((size_t)cap + 2) * 8 * W, stream));
+    if (cp.dev.n_group > 1) {  // composite keys: key words per slot + a "key published" flag
+      CUDA_TRY(tbl_gkeys.reserve((size_t)cap * 8 * (cp.dev.n_group + 1)));
+      CUDA_TRY(tbl_ready.reserve((size_t)cap * 4));
+      CUDA_TRY(cudaMemsetAsync(tbl_ready.p, 0, (size_t)cap * 4, stream));
+    }
     tbl_cap = cap;
     return B2_OK;
   }
@@ -1017,7 +1022,8 @@ struct b2_exec {
     }
     size_t smem = 0;
     uint32_t smem_slots = 0;
-    if (P.has_group) {
+    static const unsigned int debug_hash_bits = [] { const char* v = getenv("B2_DEBUG_AGG_HASH_BITS"); return v ? (unsigned int)atoi(v) : 0u; }();
+    if (P.has_group && P.n_group <= 1) {
       // small on purpose (192 resident groups per CTA): it absorbs the low-cardinality case, where global atomics would
       // serialise on a few addresses; beyond that the HBM table lives in L2 anyway and a big CTA table only costs
       // shared memory (measured, 1e8 rows: 2048 / 1024 / 256 slots -> G=1024: 5.8 / 6.7 / 6.2 ms, G=2^20: 15.9 / 10.0 / 9.9 ms)
@@ -1042,9 +1048,10 @@ struct b2_exec {
         ScanArgs a = base_args(u, v);
         a.c_lo = u.e_lo; a.c_hi = u.e_hi;
         a.tbl.keys = (unsigned long long*)tbl_keys.p; a.tbl.special = (unsigned int*)tbl_occ.p; a.tbl.acc = (unsigned long long*)tbl_acc.p; a.tbl.cap = tbl_cap;
+        a.tbl.gkeys = (unsigned long long*)tbl_gkeys.p; a.tbl.ready = (unsigned int*)tbl_ready.p; a.tbl.hash_mask_bits = debug_hash_bits;
         a.smem_slots = smem_slots;
         size_t tot = setup_staging(&a, wblocks[u.block_idx], smem);
-        grid = scan_grid_for(PM_AGG, tot);
+        grid = scan_grid_for(scan_kernel_mode(P), tot);
         kernel_begin();
         CUDA_TRY(scan_launch(a, grid, tot));
         kernel_end();
@@ -1076,8 +1083,9 @@ struct b2_exec {
       ga = (const unsigned long long*)tbl_acc.p;
     } else {
       size_t W = P.acc_words;
-      CUDA_TRY(grp_keys.reserve(((size_t)tbl_cap + 2) * 8)); CUDA_TRY(grp_null.reserve((size_t)tbl_cap + 2)); CUDA_TRY(grp_acc.reserve(((size_t)tbl_cap + 2) * 8 * W));
+      CUDA_TRY(grp_keys.reserve(((size_t)tbl_cap + 2) * 8 * std::max(1, P.n_group))); CUDA_TRY(grp_null.reserve((size_t)tbl_cap + 2)); CUDA_TRY(grp_acc.reserve(((size_t)tbl_cap + 2) * 8 * W));
       AggTable t; t.keys = (unsigned long long*)tbl_keys.p; t.special = (unsigned int*)tbl_occ.p; t.acc = (unsigned long long*)tbl_acc.p; t.cap = tbl_cap;
+      t.gkeys = (unsigned long long*)tbl_gkeys.p; t.ready = (unsigned int*)tbl_ready.p; t.hash_mask_bits = 0;
       CUDA_TRY(launch_agg_finalize(P, t, ctr(), (unsigned long long*)grp_keys.p, (unsigned char*)grp_null.p, (unsigned long long*)grp_acc.p, stream));
       int rc = read_counters(&c);
       if (rc) return rc;
@@ -1406,6 +1414,7 @@ int32_t b2_exec_agg_partials(b2_exec* h, b2_agg_partials* out) {
   out->n_groups = h->part_n; out->acc_words = (uint32_t)h->cp.dev.acc_words; out->location = B2_LOC_DEVICE; out->has_group = h->cp.dev.has_group;
   out->keys = (const uint64_t*)h->part_keys; out->key_null = (const uint8_t*)h->part_null; out->acc = (const uint64_t*)h->part_acc;
   out->max_word_mask = 0;
+  out->key_words = (uint32_t)std::max(1, h->cp.dev.n_group); out->_pad = 0;
   for (int a = 0; a < h->cp.dev.n_aggs; ++a)
     if (h->cp.dev.aggs[a].kind >= 3) out->max_word_mask |= 1ull << (h->cp.dev.aggs[a].acc_off + 1);
   return B2_OK;

@@ -160,7 +160,7 @@ std::shared_future<JitKernel*> jit_get(int device, const DevPlan& plan) {
   auto it = g_cache.find(key);
   if (it != g_cache.end()) return it->second.fut;
   std::string literal = key.substr(key.find('|') + 1);
-  int mode = plan.mode == PM_SCAN && plan.n_proj ? (int)PM_PROJ : plan.mode;
+  int mode = plan.mode == PM_SCAN && plan.n_proj ? (int)PM_PROJ : (plan.mode == PM_AGG && plan.n_group > 1 ? (int)PM_AGGM : plan.mode);
   std::shared_future<JitKernel*> fut = std::async(std::launch::async, [device, mode, literal] { return compile(device, mode, literal); }).share();
   g_cache[key].fut = fut;
   return fut;

@@ -36,24 +36,34 @@ uint32_t scan_stage_entries() { return TILE + STAGE_LOOK + 1; }
 size_t scan_out_stage_bytes() { return (size_t)N_OBUF * OBUF_BYTES + (size_t)N_OBUF * ONULL_WORDS * 4; }
 size_t scan_crc_table_bytes() { return 8 * 256 * 8; }
 
+template <int MODE>
+static cudaError_t scan_occupancy(int* per_sm, size_t smem) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, scan_kernel<MODE>, TILE + 64, smem);
+}
+template <int MODE>
+static void scan_launch_mode(const DevPlan& plan, const ScanArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  scan_kernel<MODE><<<grid, TILE + 64, smem, s>>>(plan, a);
+}
+
+// the kernel instantiation that serves a plan
+int scan_kernel_mode(const DevPlan& plan) {
+  if (plan.mode == PM_SCAN && plan.n_proj) return PM_PROJ;
+  if (plan.mode == PM_AGG && plan.n_group > 1) return PM_AGGM;
+  return plan.mode;
+}
+
 int scan_max_grid(int mode, size_t smem) {
   int per_sm = 0;
   cudaError_t e;
-  if (mode == PM_PROJ) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_PROJ>, TILE + 64, smem);
-  } else if (mode == PM_SCAN) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_SCAN>, TILE + 64, smem);
-  } else if (mode == PM_CHECKSUM) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_CHECKSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_CHECKSUM>, TILE + 64, smem);
-  } else if (mode == PM_TOPN) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_TOPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_TOPN>, TILE + 64, smem);
-  } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<PM_AGG>, TILE + 64, smem);
+  switch (mode) {
+    case PM_PROJ: e = scan_occupancy<PM_PROJ>(&per_sm, smem); break;
+    case PM_SCAN: e = scan_occupancy<PM_SCAN>(&per_sm, smem); break;
+    case PM_CHECKSUM: e = scan_occupancy<PM_CHECKSUM>(&per_sm, smem); break;
+    case PM_TOPN: e = scan_occupancy<PM_TOPN>(&per_sm, smem); break;
+    case PM_AGGM: e = scan_occupancy<PM_AGGM>(&per_sm, smem); break;
+    default: e = scan_occupancy<PM_AGG>(&per_sm, smem); break;
   }
   if (e != cudaSuccess || per_sm < 1) per_sm = 1;
   return per_sm * num_sms();
@@ -63,21 +73,13 @@ cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t
   if (a.c_hi <= a.c_lo) return cudaSuccess;
   uint32_t n_tiles = (a.c_hi - a.c_lo + TILE - 1) / TILE;
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
-  if (plan.mode == PM_SCAN && plan.n_proj) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_PROJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_kernel<PM_PROJ><<<grid, TILE + 64, smem, s>>>(plan, a);
-  } else if (plan.mode == PM_SCAN) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_kernel<PM_SCAN><<<grid, TILE + 64, smem, s>>>(plan, a);
-  } else if (plan.mode == PM_CHECKSUM) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_CHECKSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_kernel<PM_CHECKSUM><<<grid, TILE + 64, smem, s>>>(plan, a);
-  } else if (plan.mode == PM_TOPN) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_TOPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_kernel<PM_TOPN><<<grid, TILE + 64, smem, s>>>(plan, a);
-  } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(scan_kernel<PM_AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_kernel<PM_AGG><<<grid, TILE + 64, smem, s>>>(plan, a);
+  switch (scan_kernel_mode(plan)) {
+    case PM_PROJ: scan_launch_mode<PM_PROJ>(plan, a, grid, smem, s); break;
+    case PM_SCAN: scan_launch_mode<PM_SCAN>(plan, a, grid, smem, s); break;
+    case PM_CHECKSUM: scan_launch_mode<PM_CHECKSUM>(plan, a, grid, smem, s); break;
+    case PM_TOPN: scan_launch_mode<PM_TOPN>(plan, a, grid, smem, s); break;
+    case PM_AGGM: scan_launch_mode<PM_AGGM>(plan, a, grid, smem, s); break;
+    default: scan_launch_mode<PM_AGG>(plan, a, grid, smem, s); break;
   }
   return cudaGetLastError();
 }
@@ -215,6 +217,15 @@ __global__ void agg_finalize_kernel(const __grid_constant__ DevPlan P, AggTable 
                                     unsigned char* out_key_null, unsigned long long* out_acc) {
   unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > t.cap + 1) return;
+  if (P.n_group > 1) {
+    if (i >= t.cap || t.keys[i] == AGG_EMPTY_KEY) return;
+    unsigned int g = atomicAdd(&ctr->n_groups, 1u);
+    const int K = P.n_group;
+    for (int q = 0; q < K; ++q) out_keys[(size_t)g * K + q] = t.gkeys[(size_t)i * (K + 1) + q];
+    out_key_null[g] = (unsigned char)t.gkeys[(size_t)i * (K + 1) + K];
+    for (int w = 0; w < P.acc_words; ++w) out_acc[(size_t)g * P.acc_words + w] = t.acc[(size_t)i * P.acc_words + w];
+    return;
+  }
   if (i < t.cap ? t.keys[i] == AGG_EMPTY_KEY : t.special[i - t.cap] == 0) return;
   unsigned int g = atomicAdd(&ctr->n_groups, 1u);
   out_keys[g] = i == t.cap ? 0ull : (i == t.cap + 1 ? AGG_EMPTY_KEY : t.keys[i]);
@@ -259,7 +270,13 @@ __global__ void agg_result_kernel(const __grid_constant__ DevPlan P, unsigned in
       ++c;
     }
   }
-  if (P.has_group) {
+  if (P.n_group > 1) {
+    for (int q = 0; q < P.n_group; ++q, ++c) {
+      const bool isnull = (g_null[g] >> q) & 1;
+      col_data[c][g] = isnull ? 0ull : g_keys[(size_t)g * P.n_group + q];
+      if (isnull) atomicAnd(&col_bitmap[c][g >> 6], ~(1ull << (g & 63)));
+    }
+  } else if (P.has_group) {
     col_data[c][g] = g_null[g] ? 0ull : g_keys[g];
     if (g_null[g]) atomicAnd(&col_bitmap[c][g >> 6], ~(1ull << (g & 63)));
   }

@@ -38,6 +38,11 @@ struct AggTable {
   unsigned int* special;     // 2
   unsigned long long* acc;   // (cap + 2) * acc_words
   unsigned int cap;          // power of two
+  // grouped by several expressions (PM_AGGM): `keys` holds a 64-bit hash tag of the composite key; the key itself is
+  // gkeys[slot * (n_group + 1) ..] = n_group value words + the NULL mask, valid once ready[slot] != 0
+  unsigned int hash_mask_bits;  // debug (B2_DEBUG_AGG_HASH_BITS): keep only this many hash bits, 0 = all 64
+  unsigned long long* gkeys;
+  unsigned int* ready;
 };
 
 struct TopNLists {
@@ -95,8 +100,10 @@ int scan_max_grid(int mode, size_t smem);  // occupancy-based persistent grid si
 int scan_num_sms();
 size_t scan_stage_bytes(uint32_t key_cap, uint32_t val_cap);  // dynamic shared memory needed by the tile stages
 size_t scan_crc_table_bytes();             // PM_CHECKSUM replicated CRC table
+int scan_kernel_mode(const DevPlan& plan);  // PM_* instantiation that serves `plan`
 size_t scan_out_stage_bytes();             // PM_SCAN output transpose buffer
 uint32_t scan_stage_entries();             // entries a stage must hold (tile + look-behind/ahead)
+// n_group >= 2: out_keys holds n_group words per group, out_key_null the group's NULL mask (bit q = q-th expression)
 cudaError_t launch_agg_finalize(const DevPlan& plan, const AggTable& t, Counters* ctr, unsigned long long* out_keys, unsigned char* out_key_null,
                                 unsigned long long* out_acc, cudaStream_t s);
 cudaError_t launch_agg_result(const DevPlan& plan, unsigned int n_groups, const unsigned long long* g_keys, const unsigned char* g_null,

@@ -227,7 +227,7 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
         P.n_conds++;
       }
     } else if (e.tp == B2_EXEC_AGGREGATION || e.tp == B2_EXEC_STREAM_AGG) {
-      if (e.n_group_by > 1) { *msg = "multi-column GROUP BY (BatchSlowHashAggregation) is not on the device path yet"; return B2_ERR_UNSUPPORTED; }
+      if (e.n_group_by > MAX_GROUP) { *msg = "GROUP BY with more than 4 expressions is not on the device path yet"; return B2_ERR_UNSUPPORTED; }
       if (e.n_aggrs == 0 || e.n_aggrs > MAX_AGGS) { *msg = "0 or too many aggregate functions"; return B2_ERR_UNSUPPORTED; }
       P.mode = PM_AGG; terminal = true;
       schema.clear();
@@ -261,6 +261,14 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
         if (!lower_expr(e.group_by[0], P, &P.group, &et, &uns, &tp, &flag, msg)) return B2_ERR_UNSUPPORTED;
         P.has_group = 1; P.group_et = et; P.group_unsigned = uns;
         schema.push_back(OutCol{et ? B2_COL_F64 : B2_COL_I64, tp, flag});
+      } else if (e.n_group_by > 1) {  // BatchSlowHashAggregation: [aggregates..., group-by columns in order] (slow_hash_aggr_executor.rs:388-420)
+        for (uint32_t q = 0; q < e.n_group_by; ++q) {
+          int tp; uint32_t flag; uint8_t et, uns;
+          if (!lower_expr(e.group_by[q], P, &P.groups[q], &et, &uns, &tp, &flag, msg)) return B2_ERR_UNSUPPORTED;
+          P.groups_et[q] = et;
+          schema.push_back(OutCol{et ? B2_COL_F64 : B2_COL_I64, tp, flag});
+        }
+        P.has_group = 1; P.n_group = (int)e.n_group_by;
       }
     } else if (e.tp == B2_EXEC_TOPN) {
       if (e.n_order_by == 0 || e.n_order_by > MAX_ORDER) { *msg = "TopN with 0 or more than 4 order-by expressions"; return B2_ERR_UNSUPPORTED; }

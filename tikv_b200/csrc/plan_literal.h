@@ -43,6 +43,10 @@ inline std::string plan_literal(const DevPlan& P) {
   }
   o << "}," << P.n_proj << "," << P._prpad << ",{";
   for (int i = 0; i < MAX_PROJ; ++i) { expr(P.proj[i]); o << (i < MAX_PROJ - 1 ? "," : ""); }
+  o << "}," << P.n_group << "," << P._gpad << ",{";
+  for (int i = 0; i < MAX_GROUP; ++i) { expr(P.groups[i]); o << (i < MAX_GROUP - 1 ? "," : ""); }
+  o << "},{";
+  for (int i = 0; i < MAX_GROUP; ++i) o << (int)P.groups_et[i] << (i < MAX_GROUP - 1 ? "," : "");
   o << "},{";
   for (int i = 0; i < MAX_COLS; ++i) {
     const DevCol& c = P.cols[i];

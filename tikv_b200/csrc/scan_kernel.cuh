@@ -46,6 +46,38 @@ __device__ unsigned int table_find_or_insert(const AggTable& t, uint64_t key, bo
   return 0xffffffffu;
 }
 
+// Composite keys (BatchSlowHashAggregation): the table is keyed by a hash tag, claimed with one CAS; the winner then
+// publishes the key words (release on ready[s]); a later arrival with an equal tag waits for them and compares: equal
+// -> same group, different (a 64-bit hash collision) -> keep probing.  `kw` = n_group value words + NULL mask.
+__device__ __forceinline__ unsigned int table_find_or_insert_multi(const AggTable& t, uint64_t tag, const uint64_t (&kw)[MAX_GROUP + 1], int n_words) {
+  const unsigned int mask = t.cap - 1;
+  unsigned int s = (unsigned int)tag & mask;
+  for (unsigned int probes = 0; probes < t.cap; ++probes) {
+    unsigned long long kk = ld_volatile_u64(&t.keys[s]);
+    if (kk == AGG_EMPTY_KEY) {
+      kk = atomicCAS(&t.keys[s], AGG_EMPTY_KEY, (unsigned long long)tag);
+      if (kk == AGG_EMPTY_KEY) {
+#pragma unroll
+        for (int q = 0; q <= MAX_GROUP; ++q)
+          if (q < n_words) t.gkeys[(size_t)s * n_words + q] = kw[q];
+        __threadfence();
+        st_release_u32(&t.ready[s], 1u);
+        return s;
+      }
+    }
+    if (kk == tag) {
+      while (ld_acquire_u32(&t.ready[s]) == 0) {}
+      bool same = true;
+#pragma unroll
+      for (int q = 0; q <= MAX_GROUP; ++q)
+        if (q < n_words) same = same && ld_volatile_u64(&t.gkeys[(size_t)s * n_words + q]) == kw[q];
+      if (same) return s;
+    }
+    s = (s + 1) & mask;
+  }
+  return 0xffffffffu;
+}
+
 // barrier over the 256 row-decoding threads only (the scan kernel runs a 9th, producer-only warp)
 __device__ __forceinline__ void cta256_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -289,6 +321,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   // PM_PROJ is PM_SCAN with expression-valued output cells: a separate instantiation, so that the expression evaluator
   // stays out of the plain scan's hot loop (inlined there it cost 3.5x)
   constexpr bool IS_SCAN = (MODE == PM_SCAN) || (MODE == PM_PROJ);
+  constexpr bool IS_AGG = (MODE == PM_AGG) || (MODE == PM_AGGM);  // PM_AGGM: composite group key, no CTA table
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned int s_warp_cnt[2][TILE / 32];  // by tile parity: a fast warp may start the next tile while others still read
   __shared__ unsigned int s_tbl_used, s_tbl_miss, s_tbl_off;  // resident groups; rows that fell through to HBM; table given up
@@ -628,14 +661,36 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       }
       cta256_sync();
       if (s_top_cnt + TILE > A.topn_cap) cta_topn_compact(tb, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
-    } else if (MODE == PM_AGG) {
-      // BatchSimpleAggregation / BatchFastHashAggregation.  Rows of one warp that share a group key are combined with
+    } else if (IS_AGG) {
+      // BatchSimpleAggregation / BatchFastHashAggregation / BatchSlowHashAggregation (PM_AGGM).  Rows of one warp that share a group key are combined with
       // warp reductions first (match.any + redux); the group's leader lane then issues one atomic per accumulator
       // word, into the CTA's shared-memory table when the key is resident there, else into the HBM table.
       Value gk;
       gk.bits = 0; gk.null = false;
       bool ok = live;
-      if (live && P.has_group) {
+      uint64_t gw[MAX_GROUP + 1];  // PM_AGGM: the composite key (value words, then the NULL mask); gk.bits = its hash tag
+      if (MODE == PM_AGGM) {
+        // slow_hash_aggr_executor.rs:209-239: groups are distinguished by the encoded sort key of every group-by value,
+        // i.e. by value bits and NULL-ness per column (0.0 and -0.0 are different groups here, unlike the fast executor)
+        uint64_t tag = 0x9e3779b97f4a7c15ull, nm = 0;
+#pragma unroll
+        for (int q = 0; q < MAX_GROUP; ++q) {
+          gw[q] = 0;
+          if (q < P.n_group && ok) {
+            Value v;
+            int err = eval_expr(P, P.groups[q], row, cells, &v, nullptr);
+            if (err) { report_err(A.ctr, A.entry_base + e, err); ok = false; }
+            else { gw[q] = v.null ? 0ull : v.bits; nm |= v.null ? (1ull << q) : 0ull; tag = mix64(tag ^ gw[q]); }
+          }
+        }
+#pragma unroll
+        for (int q = MAX_GROUP; q > 0; --q)
+          if (q == P.n_group) { gw[q] = nm; }
+        tag = mix64(tag + nm);
+        if (A.tbl.hash_mask_bits) tag &= (1ull << A.tbl.hash_mask_bits) - 1;
+        if (tag == AGG_EMPTY_KEY) tag = 0;
+        gk.bits = tag;
+      } else if (live && P.has_group) {
         int err = eval_expr(P, P.group, row, cells, &gk, nullptr);  // calc_groups_each_row
         if (err) { report_err(A.ctr, A.entry_base + e, err); ok = false; }
         else if (gk.null) gk.bits = 0;
@@ -644,7 +699,15 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       const unsigned int active = __ballot_sync(0xffffffffu, ok);
       if (ok) {
         unsigned int peers = active;
-        if (P.has_group) {
+        if (MODE == PM_AGGM) {
+          peers = __match_any_sync(active, gk.bits);
+          const int lead = __ffs(peers) - 1;
+          bool same = true;
+#pragma unroll
+          for (int q = 0; q <= MAX_GROUP; ++q)
+            if (q <= P.n_group) same = same && __shfl_sync(peers, gw[q], lead) == gw[q];
+          if (__any_sync(active, !same)) peers = 1u << lane;  // equal tags, different keys inside the warp: no pre-aggregation
+        } else if (P.has_group) {
           const unsigned int nm = __ballot_sync(active, gk.null);
           peers = __match_any_sync(active, gk.bits) & (gk.null ? nm : ~nm);
         }
@@ -652,7 +715,11 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
         const bool solo = (peers & (peers - 1)) == 0;
         unsigned long long* acc = nullptr;
         if (leader) {
-          if (!P.has_group) acc = s_simple_acc;
+          if (MODE == PM_AGGM) {
+            unsigned int gslot = table_find_or_insert_multi(A.tbl, gk.bits, gw, P.n_group + 1);
+            if (gslot == 0xffffffffu) atomicExch(&A.ctr->agg_overflow, 1u);
+            else acc = A.tbl.acc + (size_t)gslot * P.acc_words;
+          } else if (!P.has_group) acc = s_simple_acc;
           else {
             if (st.slots && !s_tbl_off && !gk.null && gk.bits != SMEM_EMPTY_KEY) {
               // open addressing on the key words themselves: claim a free slot with one 64-bit CAS; accumulators start

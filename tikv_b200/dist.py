@@ -49,16 +49,21 @@ def merge_agg_partials(keys, key_null, acc, real_words=(), max_words=()):
     """Final merge of partial aggregation tables.
 
     keys: int64[n] group-key bits, key_null: bool[n], acc: int64[n, W] additive accumulator words (b2_agg_partials).
+    Grouped by K > 1 expressions (b2_agg_partials.key_words): keys is int64[n, K] and key_null the per-group NULL mask
+    (integer, bit q = q-th expression); the result has the same shapes.
     `real_words` lists the word indices that hold f64 sums, `max_words` those that merge by unsigned maximum (the MAX /
     MIN extremum keys, b2_agg_partials.max_word_mask).  Returns (keys, key_null, acc) with one row per group.
     Integer words are summed exactly (two's-complement wraparound is impossible below 2^32 rows per group)."""
-    parts = _all_gather_var(torch.cat([keys.view(-1, 1), key_null.to(torch.int64).view(-1, 1), acc], dim=1))
+    multi = keys.dim() == 2
+    kw = keys.shape[1] if multi else 1
+    parts = _all_gather_var(torch.cat([keys.view(-1, kw), key_null.to(torch.int64).view(-1, 1), acc], dim=1))
     allp = torch.cat(parts, dim=0)
     if allp.shape[0] == 0:
         return keys[:0], key_null[:0], acc[:0]
-    k, nul, a = allp[:, 0], allp[:, 1], allp[:, 2:]
-    k = torch.where(nul.bool(), torch.zeros_like(k), k)
-    ident = torch.stack([nul, k], dim=1)
+    k, nul, a = allp[:, :kw], allp[:, kw], allp[:, kw + 1:]
+    if not multi:
+        k = torch.where(nul.bool().view(-1, 1), torch.zeros_like(k), k)
+    ident = torch.cat([nul.view(-1, 1), k], dim=1)
     uniq, inv = torch.unique(ident, dim=0, return_inverse=True)
     out = torch.zeros((uniq.shape[0], a.shape[1]), dtype=torch.int64, device=a.device)
     int_words = [w for w in range(a.shape[1]) if w not in set(real_words) and w not in set(max_words)]
@@ -71,6 +76,8 @@ def merge_agg_partials(keys, key_null, acc, real_words=(), max_words=()):
         flipped = a[:, w] ^ (-(1 << 63))
         m = torch.full((uniq.shape[0],), -(1 << 63), dtype=torch.int64, device=a.device).scatter_reduce_(0, inv, flipped, reduce="amax")
         out[:, w] = m ^ (-(1 << 63))
+    if multi:
+        return uniq[:, 1:].contiguous(), uniq[:, 0].contiguous(), out
     return uniq[:, 1].contiguous(), uniq[:, 0].bool(), out
 
 
@@ -156,7 +163,10 @@ def agg_partials_as_tensors(executor, device):
         z = torch.zeros(0, dtype=torch.int64, device=dev)
         return z, z.bool(), torch.zeros((0, w), dtype=torch.int64, device=dev)
     acc = torch.as_tensor(_CudaArray(p.acc, (n, w), "<i8"), device=dev).clone()
-    if p.has_group:
+    if p.has_group and p.key_words > 1:
+        keys = torch.as_tensor(_CudaArray(p.keys, (n, p.key_words), "<i8"), device=dev).clone()
+        nul = torch.as_tensor(_CudaArray(p.key_null, (n,), "|u1"), device=dev).to(torch.int64)
+    elif p.has_group:
         keys = torch.as_tensor(_CudaArray(p.keys, (n,), "<i8"), device=dev).clone()
         nul = torch.as_tensor(_CudaArray(p.key_null, (n,), "|u1"), device=dev).bool()
     else:

@@ -168,12 +168,12 @@ class DagResult:
 class DagHandler:
     """RequestHandler for a DAG request: handle_request() runs the executors to drain."""
 
-    def __init__(self, plan, ranges, region, batch_rows=1 << 22):
-        self.plan, self.ranges, self.region, self.batch_rows = plan, ranges, region, batch_rows
+    def __init__(self, plan, ranges, region, batch_rows=1 << 22, jit=None):
+        self.plan, self.ranges, self.region, self.batch_rows, self.jit = plan, ranges, region, batch_rows, jit
 
     def handle_request(self):
         try:
-            ex = BatchExecutor(self.plan, self.ranges, self.region)
+            ex = BatchExecutor(self.plan, self.ranges, self.region) if self.jit is None else BatchExecutor(self.plan, self.ranges, self.region, jit=self.jit)
         except B2Error as e:
             return DagResult(e.status, e.message, 0, [], [], None, False)
         with ex:

@@ -129,7 +129,8 @@ class ChecksumResponse(C.Structure):
 
 class AggPartials(C.Structure):
     _fields_ = [("n_groups", C.c_uint32), ("acc_words", C.c_uint32), ("location", C.c_int32), ("has_group", C.c_int32),
-                ("keys", C.c_void_p), ("key_null", C.c_void_p), ("acc", C.c_void_p), ("max_word_mask", C.c_uint64)]
+                ("keys", C.c_void_p), ("key_null", C.c_void_p), ("acc", C.c_void_p), ("max_word_mask", C.c_uint64),
+                ("key_words", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class GenSpec(C.Structure):

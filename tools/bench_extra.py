@@ -95,6 +95,16 @@ def main():
                               "GBps": (res[2] + 8 * res[1]) / best / 1e9, "frac_of_measured_hbm": (res[2] + 8 * res[1]) / best / 1e9 / peak}))
         for g in gens:
             ffi.lib().b2_gen_destroy(g)
+    # BatchSlowHashAggregation: GROUP BY two i32 keys, SUM(i64); G = G1 * G2 groups
+    for G1, G2 in (((16, 4), (1024, 16), (1024, 1024)) if (not only or "c3m" in only) else ()):
+        gens, blks = gen(ffi, args.rows, 8, 3, [0, 0, -(1 << 40)], [G1, G2, 1 << 41])
+        src = bench.Source(ffi, [b.block for b in blks], ffi.LOC_DEVICE, 0)
+        in_bytes = sum(b.key_bytes + b.val_bytes + 8 * b.block.n for b in blks)
+        cols = [ColumnDef(100, pk_handle=True), ColumnDef(1, tp=ffi.TP_LONG), ColumnDef(2, tp=ffi.TP_LONG), ColumnDef(3)]
+        plan = Plan().table_scan(1000, cols).aggregation([("sum", col(3))], group_by=[col(1, tp=ffi.TP_LONG), col(2, tp=ffi.TP_LONG)]).build()
+        run(f"SlowHashAgg GROUP BY (i32, i32) (G={G1}x{G2}) SUM(i64)", plan, src, in_bytes, args.rows)
+        for g in gens:
+            ffi.lib().b2_gen_destroy(g)
     if not only or "dirty" in only:
         # C2 on a "dirty" table: 30 % of the keys carry extra (older / newer-than-read_ts) versions, 5 % are
         # deleted, 5 % have a Lock/Rollback record on top: version runs, skipped records, met_newer_ts_data
