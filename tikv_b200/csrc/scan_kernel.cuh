@@ -699,17 +699,23 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       const unsigned int active = __ballot_sync(0xffffffffu, ok);
       if (ok) {
         unsigned int peers = active;
+        // A redux / shuffle over `peers` is replayed once per distinct mask in the warp, so pre-aggregating a warp that
+        // holds many groups costs more than it saves: past a few groups every lane commits its own row instead.
         if (MODE == PM_AGGM) {
           peers = __match_any_sync(active, gk.bits);
           const int lead = __ffs(peers) - 1;
-          bool same = true;
+          if (__popc(__ballot_sync(active, lead == (int)lane)) > 8) peers = 1u << lane;
+          else {
+            bool same = true;
 #pragma unroll
-          for (int q = 0; q <= MAX_GROUP; ++q)
-            if (q <= P.n_group) same = same && __shfl_sync(peers, gw[q], lead) == gw[q];
-          if (__any_sync(active, !same)) peers = 1u << lane;  // equal tags, different keys inside the warp: no pre-aggregation
+            for (int q = 0; q <= MAX_GROUP; ++q)
+              if (q <= P.n_group) same = same && __shfl_sync(peers, gw[q], lead) == gw[q];
+            if (__any_sync(active, !same)) peers = 1u << lane;  // equal tags, different keys inside the warp: no pre-aggregation
+          }
         } else if (P.has_group) {
           const unsigned int nm = __ballot_sync(active, gk.null);
           peers = __match_any_sync(active, gk.bits) & (gk.null ? nm : ~nm);
+          if (__popc(__ballot_sync(active, (unsigned int)(__ffs(peers) - 1) == lane)) > 4) peers = 1u << lane;
         }
         const bool leader = (unsigned int)(__ffs(peers) - 1) == lane;
         const bool solo = (peers & (peers - 1)) == 0;

@@ -96,7 +96,7 @@ def main():
         for g in gens:
             ffi.lib().b2_gen_destroy(g)
     # BatchSlowHashAggregation: GROUP BY two i32 keys, SUM(i64); G = G1 * G2 groups
-    for G1, G2 in (((16, 4), (1024, 16), (1024, 1024)) if (not only or "c3m" in only) else ()):
+    for G1, G2 in (((2, 2), (16, 4), (1024, 16), (1024, 1024)) if (not only or "c3m" in only) else ()):
         gens, blks = gen(ffi, args.rows, 8, 3, [0, 0, -(1 << 40)], [G1, G2, 1 << 41])
         src = bench.Source(ffi, [b.block for b in blks], ffi.LOC_DEVICE, 0)
         in_bytes = sum(b.key_bytes + b.val_bytes + 8 * b.block.n for b in blks)
