@@ -151,7 +151,14 @@ enum {
   B2_SIG_REAL_IS_NULL = 3114, B2_SIG_INT_IS_NULL = 3116,
   B2_SIG_INT_IS_TRUE = 3118, B2_SIG_REAL_IS_TRUE = 3119,
   B2_SIG_INT_IS_FALSE = 3121, B2_SIG_REAL_IS_FALSE = 3122,
-  B2_SIG_IN_INT = 4001, B2_SIG_IN_REAL = 4002 /* variadic: n_args = 1 + list length (impl_compare_in.rs) */
+  B2_SIG_IN_INT = 4001, B2_SIG_IN_REAL = 4002, /* variadic: n_args = 1 + list length (impl_compare_in.rs) */
+  /* impl_arithmetic.rs:215-290, 396-455 (signedness variants are picked from the arguments' UNSIGNED flags, like map_int_sig) */
+  B2_SIG_INT_DIVIDE_INT = 213, B2_SIG_MOD_REAL = 215, B2_SIG_MOD_INT = 217,
+  B2_SIG_ABS_INT = 2101, B2_SIG_ABS_UINT = 2102, B2_SIG_ABS_REAL = 2103,           /* impl_math.rs:224-243 */
+  B2_SIG_UNARY_MINUS_INT = 3108, B2_SIG_UNARY_MINUS_REAL = 3109,                    /* impl_op.rs:70-107 */
+  B2_SIG_IF_NULL_INT = 4101, B2_SIG_IF_NULL_REAL = 4102, B2_SIG_IF_INT = 4107, B2_SIG_IF_REAL = 4108, /* impl_control.rs */
+  B2_SIG_COALESCE_INT = 4201, B2_SIG_COALESCE_REAL = 4202,                          /* impl_compare.rs:239-248, variadic */
+  B2_SIG_CASE_WHEN_INT = 4208, B2_SIG_CASE_WHEN_REAL = 4209                         /* impl_control.rs:34-50, variadic: [cond, value]* [else] */
 };
 
 typedef struct b2_rpn_node {

@@ -490,6 +490,32 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
         st.push_back(std::move(r));
         continue;
       }
+      if (nd.sig == B2_SIG_IF_INT || nd.sig == B2_SIG_IF_REAL || nd.sig == B2_SIG_CASE_WHEN_INT || nd.sig == B2_SIG_CASE_WHEN_REAL ||
+          nd.sig == B2_SIG_COALESCE_INT || nd.sig == B2_SIG_COALESCE_REAL) {
+        // if_condition impl_control.rs:88-100, case_when :34-50 (chunks of [cond, value], a trailing single value is the
+        // ELSE), coalesce impl_compare.rs:239-248.  All arguments are already evaluated: only one is picked per row.
+        const bool is_if = nd.sig == B2_SIG_IF_INT || nd.sig == B2_SIG_IF_REAL, is_co = nd.sig == B2_SIG_COALESCE_INT || nd.sig == B2_SIG_COALESCE_REAL;
+        const bool real = nd.sig == B2_SIG_IF_REAL || nd.sig == B2_SIG_CASE_WHEN_REAL || nd.sig == B2_SIG_COALESCE_REAL;
+        if ((int)st.size() < na || na < 1 || (is_if && na != 3)) { *err = Error::make(B2_ERR_INVALID_ARG, "bad rpn arity"); return false; }
+        std::vector<Val> args(st.end() - na, st.end());
+        st.resize(st.size() - na);
+        Val r; r.et = real ? ET_REAL : ET_INT; r.is_unsigned = nd.field_flag & B2_FLAG_UNSIGNED; r.nn.assign(n, 0);
+        if (real) r.f.assign(n, 0); else r.i.assign(n, 0);
+        for (size_t j = 0; j < n; ++j) {
+          int pick = -1;
+          if (is_co) { for (int i = 0; i < na && pick < 0; ++i) if (!args[i].null_at(j)) pick = i; }
+          else if (is_if) pick = (!args[0].null_at(j) && args[0].int_at(j) != 0) ? 1 : 2;
+          else {
+            for (int i = 0; i + 1 < na && pick < 0; i += 2) if (!args[i].null_at(j) && args[i].int_at(j) != 0) pick = i + 1;
+            if (pick < 0 && (na & 1)) pick = na - 1;
+          }
+          if (pick < 0 || args[pick].null_at(j)) continue;
+          r.nn[j] = 1;
+          if (real) r.f[j] = args[pick].real_at(j); else r.i[j] = args[pick].int_at(j);
+        }
+        st.push_back(std::move(r));
+        continue;
+      }
       if ((int)st.size() < na || na < 1 || na > 2) { *err = Error::make(B2_ERR_INVALID_ARG, "bad rpn arity"); return false; }
       Val b; if (na == 2) { b = std::move(st.back()); st.pop_back(); }
       Val a = std::move(st.back()); st.pop_back();
@@ -497,7 +523,8 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
       int sig = nd.sig;
       bool is_cmp_int = sig == B2_SIG_LT_INT || sig == B2_SIG_LE_INT || sig == B2_SIG_GT_INT || sig == B2_SIG_GE_INT || sig == B2_SIG_EQ_INT || sig == B2_SIG_NE_INT || sig == B2_SIG_NULLEQ_INT;
       bool is_cmp_real = sig == B2_SIG_LT_REAL || sig == B2_SIG_LE_REAL || sig == B2_SIG_GT_REAL || sig == B2_SIG_GE_REAL || sig == B2_SIG_EQ_REAL || sig == B2_SIG_NE_REAL || sig == B2_SIG_NULLEQ_REAL;
-      bool is_arith_real = sig == B2_SIG_PLUS_REAL || sig == B2_SIG_MINUS_REAL || sig == B2_SIG_MULTIPLY_REAL;
+      bool is_arith_real = sig == B2_SIG_PLUS_REAL || sig == B2_SIG_MINUS_REAL || sig == B2_SIG_MULTIPLY_REAL || sig == B2_SIG_MOD_REAL ||
+                           sig == B2_SIG_IF_NULL_REAL || sig == B2_SIG_UNARY_MINUS_REAL || sig == B2_SIG_ABS_REAL;
       if (is_arith_real) { r.et = ET_REAL; r.f.assign(n, 0); r.i.clear(); }
       for (size_t j = 0; j < n; ++j) {
         bool an = a.null_at(j), bn = na == 2 ? b.null_at(j) : false;
@@ -572,6 +599,61 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
             bool bad = sig == B2_SIG_MULTIPLY_REAL ? std::isinf(z) : !std::isfinite(z);
             if (bad) { *err = overflow_err("DOUBLE"); return false; }
             r.nn[j] = 1; r.f[j] = z;
+            break;
+          }
+          case B2_SIG_IF_NULL_INT:  // impl_control.rs:7-14
+            if (!an) { r.nn[j] = 1; r.i[j] = a.int_at(j); } else if (!bn) { r.nn[j] = 1; r.i[j] = b.int_at(j); }
+            break;
+          case B2_SIG_IF_NULL_REAL:
+            if (!an) { r.nn[j] = 1; r.f[j] = a.real_at(j); } else if (!bn) { r.nn[j] = 1; r.f[j] = b.real_at(j); }
+            break;
+          case B2_SIG_UNARY_MINUS_INT: {  // impl_op.rs:70-101; lib.rs map_unary_minus_int_func: unsigned argument -> unary_minus_uint
+            if (an) break;
+            int64_t x = a.int_at(j);
+            if (a.is_unsigned ? (uint64_t)x > (uint64_t)INT64_MAX + 1 : x == INT64_MIN) { *err = overflow_err("BIGINT"); return false; }
+            r.nn[j] = 1; r.i[j] = (int64_t)(0 - (uint64_t)x);
+            break;
+          }
+          case B2_SIG_UNARY_MINUS_REAL: if (!an) { r.nn[j] = 1; r.f[j] = -a.real_at(j); } break;  // :103-107
+          case B2_SIG_ABS_INT: {  // impl_math.rs:224-231
+            if (an) break;
+            int64_t x = a.int_at(j);
+            if (x == INT64_MIN) { *err = overflow_err("BIGINT"); return false; }
+            r.nn[j] = 1; r.i[j] = x < 0 ? -x : x;
+            break;
+          }
+          case B2_SIG_ABS_UINT: if (!an) { r.nn[j] = 1; r.i[j] = a.int_at(j); } break;  // :233-237
+          case B2_SIG_ABS_REAL: if (!an) { r.nn[j] = 1; r.f[j] = std::fabs(a.real_at(j)); } break;  // :239-243
+          case B2_SIG_INT_DIVIDE_INT: {  // impl_arithmetic.rs:396-455; helpers codec/overflow.rs:9-58
+            if (an || bn) break;
+            int64_t x = a.int_at(j), y = b.int_at(j);
+            if (y == 0) break;  // Ok(None)
+            bool ovf = false; int64_t z = 0;
+            if (!a.is_unsigned && !b.is_unsigned) { if (x == INT64_MIN && y == -1) ovf = true; else z = x / y; }                       // div_i64
+            else if (!a.is_unsigned && b.is_unsigned) { if (x < 0) ovf = (0 - (uint64_t)x) >= (uint64_t)y; else z = (int64_t)((uint64_t)x / (uint64_t)y); }  // div_i64_with_u64
+            else if (a.is_unsigned && b.is_unsigned) z = (int64_t)((uint64_t)x / (uint64_t)y);
+            else { if (y < 0) ovf = x != 0 && (0 - (uint64_t)y) <= (uint64_t)x; else z = (int64_t)((uint64_t)x / (uint64_t)y); }   // div_u64_with_i64
+            if (ovf) { *err = overflow_err("UNSIGNED BIGINT"); return false; }
+            r.nn[j] = 1; r.i[j] = z;
+            break;
+          }
+          case B2_SIG_MOD_INT: {  // impl_arithmetic.rs:215-278
+            if (an || bn) break;
+            int64_t x = a.int_at(j), y = b.int_at(j);
+            if (y == 0) break;
+            uint64_t ax = x < 0 ? 0 - (uint64_t)x : (uint64_t)x, ay = y < 0 ? 0 - (uint64_t)y : (uint64_t)y;  // overflowing_abs as u64
+            int64_t z;
+            if (!a.is_unsigned && !b.is_unsigned) z = y == -1 ? 0 : x % y;  // (i64::MIN % -1 panics in the reference; 0 is the value)
+            else if (!a.is_unsigned && b.is_unsigned) z = x > 0 ? (int64_t)((uint64_t)x % (uint64_t)y) : (int64_t)(0 - ax % (uint64_t)y);
+            else if (a.is_unsigned && !b.is_unsigned) z = (int64_t)((uint64_t)x % ay);
+            else z = (int64_t)((uint64_t)x % (uint64_t)y);
+            r.nn[j] = 1; r.i[j] = z;
+            break;
+          }
+          case B2_SIG_MOD_REAL: {  // :280-291
+            if (an || bn) break;
+            if (b.real_at(j) == 0.0) break;
+            r.nn[j] = 1; r.f[j] = std::fmod(a.real_at(j), b.real_at(j));
             break;
           }
           default: *err = Error::make(B2_ERR_UNSUPPORTED, "scalar function sig " + std::to_string(sig)); return false;

@@ -9,8 +9,8 @@ import struct
 
 import kvfmt
 from tikv_b200 import ffi
-from tikv_b200.plan import (ColumnDef, Plan, and_, col, const_int, const_real, const_uint, eq, ge, gt, is_null, le, lt, minus, multiply,
-                            in_, ne, not_, null, nulleq, or_, plus, xor_)
+from tikv_b200.plan import (fn, ColumnDef, Plan, and_, col, const_int, const_real, const_uint, eq, ge, gt, is_null, le, lt, minus, multiply,
+                            in_, ne, not_, null, nulleq, or_, plus, xor_, int_divide, mod, neg, abs_, if_null, if_, case_when, coalesce)
 
 TABLE = 1000
 READ_TS = 1000
@@ -285,6 +285,76 @@ def multi_group_plans():
             ("mg_no_input", scan().selection(lt(c6, const_int(-5))).aggregation([("count", const_int(1))], group_by=[c6, col(C2)]).build())]
 
 
+def scalar_plans():
+    """More scalar functions: DIV / MOD in every signedness mix (x / 0 and x % 0 are NULL), MOD over
+    Real, unary minus, ABS, IFNULL, IF, CASE WHEN (with and without ELSE), COALESCE; as projection outputs, selection
+    conditions, aggregate arguments and group keys; and the overflow errors of DIV, unary minus and ABS."""
+    scan = lambda: Plan().table_scan(TABLE, COLUMNS)
+    c1, c2, c3, c4, c5, c6, ch = col(C1), col(C2), col(C3, unsigned=True), col(C4, tp=ffi.TP_DOUBLE), col(C5), col(C6, tp=ffi.TP_LONG), col(C_H)
+    zero, r0 = const_int(0), const_real(0.0)
+    return [("sc_div_signed", scan().projection(ch, int_divide(c1, c2), mod(c1, c2), int_divide(c2, c6), mod(c2, c6), mod(c1, const_int(-1))).build()),
+            ("sc_div_unsigned", scan().projection(ch, int_divide(c3, c3), mod(c3, c3), mod(c3, c2), mod(c2, c3), int_divide(c3, plus(c6, const_int(1))),
+                                                  int_divide(c2, const_uint(1000)), int_divide(const_uint(0), c2), int_divide(c3, abs_(c2))).build()),
+            ("sc_real", scan().projection(ch, mod(c4, const_real(2.5)), mod(c4, multiply(c4, r0)), neg(c4), abs_(c4), if_null(c4, const_real(9.5)),
+                                          coalesce(c4, null(ffi.TP_DOUBLE), const_real(1.0)), if_(c2, c4, neg(c4)),
+                                          case_when(lt(c4, r0), const_real(-1.0), gt(c4, r0), const_real(1.0))).build()),
+            ("sc_unary", scan().projection(ch, neg(c2), abs_(c2), abs_(c3), neg(c6), neg(const_uint(1 << 63))).build()),
+            ("sc_control", scan().projection(ch, if_null(c2, c6), if_(lt(c2, zero), c1, c5), case_when(lt(c2, const_int(-10)), const_int(1), is_null(c2), const_int(2), gt(c6, const_int(8)), c6, c5),
+                                             case_when(lt(c2, zero), c1), coalesce(c2, null(), c5), coalesce(null(), null()), if_(null(), c1, c3), case_when(c5)).build()),
+            ("sc_in_selection_agg", scan().selection(gt(mod(ch, const_int(7)), const_int(2)), ne(if_null(c2, zero), int_divide(c6, const_int(2))))
+                                          .aggregation([("sum", abs_(c2)), ("count", case_when(gt(c6, const_int(5)), c6)), ("max", neg(c6))], group_by=[mod(ch, const_int(5))]).build()),
+            ("sc_err_div_overflow", scan().projection(ch, int_divide(c2, c3)).build()),
+            ("sc_err_div_overflow2", scan().projection(ch, int_divide(c3, c2)).build()),
+            ("sc_err_neg_uint", scan().projection(ch, neg(c3)).build()),
+            ("sc_err_abs_min", scan().projection(ch, abs_(plus(const_int(-(1 << 63)), multiply(c2, zero)))).build()),
+            ("sc_err_neg_min", scan().selection(lt(neg(plus(const_int(-(1 << 63)), c6)), zero)).build())]
+
+
+def scalar_known_answers():
+    """(label, Expr over constants, expected value | None | "error"): the reference's own unit-test vectors for the scalar
+    functions above — impl_arithmetic.rs test_mod_int :735-760, test_mod_int_unsigned :763-805, test_mod_real :808-835,
+    test_int_divide_int :902-948, test_int_divide_int_overflow :951-983; impl_op.rs test_unary_minus_int :425-472;
+    impl_math.rs test_abs_int :854-866; impl_control.rs test_if_null :150-165, test_case_when :168-207, test_if :243-250."""
+    MAX, MIN, UMAX = (1 << 63) - 1, -(1 << 63), (1 << 64) - 1
+
+    def I(v, unsigned=False):
+        if v is None:
+            return null()
+        return const_uint(v & UMAX) if unsigned else const_int(v)
+
+    def R(v):
+        return null(ffi.TP_DOUBLE) if v is None else const_real(v)
+    K = []
+    for a, b, e in [(13, 11, 2), (-13, 11, -2), (13, -11, 2), (-13, -11, -2), (33, 11, 0), (33, -11, 0), (-33, -11, 0), (-11, None, None), (None, -11, None),
+                    (11, 0, None), (-11, 0, None), (MAX, MIN, MAX), (MIN, MAX, -1)]:
+        K.append((f"mod_int({a},{b})", mod(I(a), I(b)), e))
+    K.append(("mod_int(u64max u, i64min)", mod(I(UMAX, True), I(MIN)), MAX))
+    K.append(("mod_int(i64min, u64max u)", mod(I(MIN), I(UMAX, True)), MIN))
+    for a, b, e in [(1.0, None, None), (None, 1.0, None), (1.0, 1.1, 1.0), (-1.0, 1.1, -1.0), (1.0, -1.1, 1.0), (-1.0, -1.1, -1.0), (1.0, 0.0, None)]:
+        K.append((f"mod_real({a},{b})", mod(R(a), R(b)), e))
+    for a, au, b, bu, e in [(13, False, 11, False, 1), (13, False, -11, False, -1), (-13, False, 11, False, -1), (-13, False, -11, False, 1), (33, False, 11, False, 3),
+                            (33, False, -11, False, -3), (-33, False, 11, False, -3), (-33, False, -11, False, 3), (11, False, 0, False, None), (-11, False, 0, False, None),
+                            (-3, False, 5, True, 0), (3, False, -5, False, 0), (MIN + 1, False, -1, False, MAX), (MIN, False, 1, False, MIN), (MAX, False, 1, False, MAX),
+                            (UMAX, True, 1, False, -1),  # u64::MAX as i64
+                            (MIN, False, -1, False, "error"), (-1, False, 1, True, "error"), (-2, False, 1, True, "error"), (1, True, -1, False, "error"), (2, True, -1, False, "error")]:
+        K.append((f"int_divide({a}{'u' if au else ''},{b}{'u' if bu else ''})", int_divide(I(a, au), I(b, bu)), e))
+    for a, e in [(None, None), (MAX + 1, MIN), (12345, -12345), (0, 0), (MAX + 2, "error")]:
+        K.append((f"neg_uint({a})", neg(I(a, True)), e))
+    for a, e in [(None, None), (MAX, -MAX), (-MAX, MAX), (MIN + 1, MAX), (0, 0), (MIN, "error")]:
+        K.append((f"neg_int({a})", neg(I(a)), e))
+    for a, au, e in [(-3, False, 3), (MAX, False, MAX), (UMAX, True, -1), (MIN, False, "error")]:
+        K.append((f"abs({a})", abs_(I(a, au)), e))
+    for a, b, e in [(None, None, None), (None, 1, 1), (2, None, 2), (2, 1, 2)]:
+        K.append((f"if_null({a},{b})", if_null(I(a), I(b)), e))
+    for args, e in [([I(1), R(3.0), I(1), R(5.0)], 3.0), ([I(0), R(3.0), I(1), R(5.0)], 5.0), ([I(None), R(2.0), I(1), R(6.0)], 6.0), ([R(7.0)], 7.0), ([I(0), R(None)], None),
+                    ([I(1), R(None)], None), ([I(1), R(3.5)], 3.5), ([I(2), R(3.5)], 3.5), ([I(0), R(None), I(None), R(None), R(5.5)], 5.5)]:
+        K.append((f"case_when#{len(K)}", case_when(*args) if len(args) > 1 else fn("CASE_WHEN_REAL", args[0], ret_tp=ffi.TP_DOUBLE), e))
+    import math
+    for c, e in [(0, math.pi), (1, math.e), (None, math.pi)]:
+        K.append((f"if({c})", if_(I(c), R(math.e), R(math.pi)), e))
+    return K
+
+
 def in_plans():
     """IN lists (impl_compare_in.rs): constants, NULL in the list, NULL base, columns in the list, signed vs unsigned, Real."""
     scan = lambda: Plan().table_scan(TABLE, COLUMNS)
@@ -308,3 +378,30 @@ def projection_plans():
             ("proj_after_selection_limit", scan().selection(ge(c6, const_int(3))).projection(minus(col(C_H), c6), col(C2)).limit(55).build()),
             ("proj_subset", scan().projection(col(C1), plus(c6, c6), is_null(col(C2))).build(output_offsets=[2, 1])),
             ("proj_overflow", scan().projection(col(C_H), multiply(col(C1), const_int(1 << 40))).build())]
+
+
+def check_scalar_known_answers(run):
+    """Evaluate every scalar_known_answers() expression through `run(plan, ranges, region)` (oracle, emulator or the CUDA
+    path) as a projection over a one-row table and compare with the reference's expected value."""
+    r = kvfmt.Region()
+    r.put(kvfmt.row_key(TABLE, 1), kvfmt.row_v2([(1, 5, "int")]), 1, 2)
+    region = r.build(read_ts=10)
+    cols = [ColumnDef(100, pk_handle=True), ColumnDef(1)]
+    cases = scalar_known_answers()
+    assert len(cases) >= 70
+    scan = lambda: Plan().table_scan(TABLE, cols)
+    ok = [c for c in cases if c[2] != "error"]
+    for label, expr, _ in [c for c in cases if c[2] == "error"]:  # an error ends the request: one plan per case
+        res = run(scan().projection(expr).build(), [kvfmt.table_range(TABLE)], region)
+        assert res.status == ffi.B2_ERR_EVALUATE and getattr(res, "mysql_code", 1690) == 1690, (label, res.status, res.message)
+    for i in range(0, len(ok), 12):  # the others: 12 expressions per projection (one specialised kernel per plan on the GPU)
+        chunk = ok[i:i + 12]
+        res = run(scan().projection(*[c[1] for c in chunk]).build(), [kvfmt.table_range(TABLE)], region)
+        assert res.status == 0, ([c[0] for c in chunk], res.message)
+        got = res.rows()
+        assert len(got) == 1 and len(got[0]) == len(chunk)
+        for (label, _, want), v in zip(chunk, got[0]):
+            if isinstance(want, float):
+                assert v is not None and struct.pack("<d", v) == struct.pack("<d", want), (label, v, want)
+            else:
+                assert v == want, (label, v, want)

@@ -229,6 +229,20 @@ def test_multi_column_group_by(name, plan, regions):
         assert_same_rows(got, exp, ordered=False, ctx=f"{name}/seed{seed}")
 
 
+@pytest.mark.parametrize("name,plan", sc.scalar_plans(), ids=[n for n, _ in sc.scalar_plans()])
+def test_scalar_functions(name, plan, regions):
+    for seed in (1, 2):
+        region = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=2)
+        exp = orc.dag_handle(plan, sc.WHOLE, region)
+        got = emu.dag_handle(plan, sc.WHOLE, region)
+        if "_err_" in name:  # evaluation errors end the request (the oracle's rows are a prefix, see test_projection)
+            assert exp.status == ffi.B2_ERR_EVALUATE == got.status and exp.mysql_code == 1690, (name, exp.status, exp.message)
+            assert got.rows()[:len(exp.rows())] == exp.rows()
+            continue
+        assert exp.status == 0 and exp.n_rows > 0, exp.message
+        assert_same_rows(got, exp, ordered=not sc.is_agg(name) and "agg" not in name, ctx=f"{name}/seed{seed}")
+
+
 @pytest.mark.parametrize("name,plan", sc.in_plans(), ids=[n for n, _ in sc.in_plans()])
 def test_in_lists(name, plan, regions):
     region = regions[1].build(read_ts=sc.READ_TS, n_write_blocks=2)
@@ -251,3 +265,7 @@ def test_projection(name, plan, regions):
         return
     assert exp.status == 0
     assert_same_rows(got, exp, ordered=True, ctx=name)
+
+
+def test_scalar_function_known_answers():
+    sc.check_scalar_known_answers(emu.dag_handle)

@@ -571,6 +571,29 @@ def test_multi_column_group_by_generated():
         ffi.lib().b2_gen_destroy(g)
 
 
+@pytest.mark.parametrize("name,plan", sc.scalar_plans(), ids=[n for n, _ in sc.scalar_plans()])
+def test_scalar_functions(name, plan, regions):
+    """DIV / MOD / unary minus / ABS / IFNULL / IF / CASE WHEN / COALESCE (impl_arithmetic.rs, impl_op.rs, impl_math.rs,
+    impl_control.rs, impl_compare.rs) in projections, selections, aggregate arguments and group keys.  Plans with these
+    functions always run on their plan-specialised kernel, also when the caller asked for JIT_OFF."""
+    jit = ffi.JIT_OFF
+    for seed in (1, 2):
+        region = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=2)
+        exp = orc.dag_handle(plan, sc.split_ranges(), region)
+        got = DagHandler(plan, sc.split_ranges(), DeviceRegion(region), jit=jit).handle_request()
+        if "_err_" in name:
+            assert exp.status == ffi.B2_ERR_EVALUATE == got.status and exp.mysql_code == 1690 == got.mysql_code and got.message == exp.message
+            assert got.rows()[:len(exp.rows())] == exp.rows()
+            continue
+        assert exp.status == 0 and exp.n_rows > 0
+        assert_same_rows(got, exp, ordered="agg" not in name, ctx=f"{name}/seed{seed}")
+
+
+def test_scalar_function_known_answers():
+    """The reference's own unit-test vectors for these functions, through the CUDA path."""
+    sc.check_scalar_known_answers(lambda plan, ranges, region: DagHandler(plan, ranges, DeviceRegion(region)).handle_request())
+
+
 @pytest.mark.parametrize("name,plan", sc.in_plans(), ids=[n for n, _ in sc.in_plans()])
 def test_in_lists(name, plan, regions):
     """IN (impl_compare_in.rs): NULL semantics, mixed signedness, Real, columns inside the list."""

@@ -433,3 +433,10 @@ def test_decimal_binary_encoding_known_answers():
             assert out.raw[:n] == want, v
         got, pos = kvfmt._dec_bin_to_int(out.raw, 2, out.raw[0], out.raw[1])
         assert got == v and pos == n
+
+
+def test_scalar_function_known_answers():
+    """DIV / MOD / unary minus / ABS / IFNULL / IF / CASE WHEN against the reference's own unit-test vectors
+    (scenarios.scalar_known_answers cites them)."""
+    import scenarios as sc
+    sc.check_scalar_known_answers(orc.dag_handle)

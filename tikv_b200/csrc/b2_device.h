@@ -12,6 +12,7 @@
 #pragma once
 #ifndef B2_NVRTC
 #include <stdint.h>
+#include <math.h>
 #endif
 
 #include "../../include/b2_copr.h"
@@ -49,6 +50,7 @@ enum DevErr {
   DE_OVERFLOW_BIGINT = 20,   // 1690 BIGINT value is out of range
   DE_OVERFLOW_UBIGINT = 21,  // 1690 BIGINT UNSIGNED
   DE_OVERFLOW_DOUBLE = 22,   // 1690 DOUBLE
+  DE_OVERFLOW_DIV = 23,      // 1690 "UNSIGNED BIGINT" (codec/overflow.rs:9-58: every integer-division overflow says so)
   DE_UNSUPPORTED_SIG = 30,
   DE_UNSUPPORTED_TYPE = 31,  // row holds a type the device path does not materialise
 };
@@ -989,6 +991,105 @@ B2_HD bool mul_ovf_i64(int64_t a, int64_t b, int64_t* r) {
 B2_HD bool f64_finite(double x) { return (f64_bits(x) & 0x7ff0000000000000ull) != 0x7ff0000000000000ull; }
 B2_HD bool f64_isinf(double x) { return (f64_bits(x) & 0x7fffffffffffffffull) == 0x7ff0000000000000ull; }
 
+// The less common scalar functions.  They are compiled into plan-specialised kernels only (B2_EXT_SIGS=1, set by jit.cu
+// when the plan uses one; the constant plan then keeps just the operators it needs): inside the generic kernels either
+// form cost every aggregation 40 % — inlined through code size, out of line through the registers saved around the call
+// — so a plan with one of these always runs specialised (engine.cu), and the generic evaluator reports them unsupported.
+#ifndef B2_EXT_SIGS
+#if defined(__CUDACC__) || defined(B2_NVRTC)
+#define B2_EXT_SIGS 0
+#else
+#define B2_EXT_SIGS 1  // host emulation of the device logic (tests)
+#endif
+#endif
+B2_HD bool is_ext_sig(int sig) {
+  return sig == B2_SIG_INT_DIVIDE_INT || sig == B2_SIG_MOD_INT || sig == B2_SIG_MOD_REAL || (sig >= B2_SIG_ABS_INT && sig <= B2_SIG_ABS_REAL) ||
+         sig == B2_SIG_UNARY_MINUS_INT || sig == B2_SIG_UNARY_MINUS_REAL || (sig >= B2_SIG_IF_NULL_INT && sig <= B2_SIG_CASE_WHEN_REAL);
+}
+B2_HD int eval_ext_fn(int sig, int na, bool ret_unsigned, int64_t* sv, uint8_t* sn, int* sp_io) {
+  const int64_t I64_MIN = -9223372036854775807ll - 1, I64_MAX = 9223372036854775807ll;
+  const int base = *sp_io - na;
+  int64_t r = 0;
+  bool rn = true;
+  if (sig == B2_SIG_IF_INT || sig == B2_SIG_IF_REAL || sig == B2_SIG_CASE_WHEN_INT || sig == B2_SIG_CASE_WHEN_REAL || sig == B2_SIG_COALESCE_INT ||
+      sig == B2_SIG_COALESCE_REAL) {
+      bool done = false;
+      // if_condition (impl_control.rs:88-100), case_when (:34-50), coalesce (impl_compare.rs:239-248): every argument
+      // has been evaluated already (RPN), the function only picks one of them
+      if (sig == B2_SIG_COALESCE_INT || sig == B2_SIG_COALESCE_REAL) {
+        for (int i = 0; i < na; ++i)
+          if (!done && !(sn[base + i] & 1)) { r = sv[base + i]; rn = false; done = true; }
+      } else if (sig == B2_SIG_IF_INT || sig == B2_SIG_IF_REAL) {
+        const int pick = (!(sn[base] & 1) && sv[base] != 0) ? 1 : 2;
+        r = sv[base + pick]; rn = sn[base + pick] & 1;
+      } else {
+        for (int i = 0; i + 1 < na; i += 2)
+          if (!done && !(sn[base + i] & 1) && sv[base + i] != 0) { r = sv[base + i + 1]; rn = sn[base + i + 1] & 1; done = true; }
+        if (!done && (na & 1)) { r = sv[base + na - 1]; rn = sn[base + na - 1] & 1; }
+      }
+  } else {
+    const int64_t a = sv[base], b = na == 2 ? sv[base + 1] : 0;
+    const bool an = sn[base] & 1, au = sn[base] & 2, bn = na == 2 ? (sn[base + 1] & 1) : false, bu = na == 2 ? (sn[base + 1] & 2) : false;
+    switch (sig) {
+        case B2_SIG_IF_NULL_INT: case B2_SIG_IF_NULL_REAL:  // impl_control.rs:7-14
+          if (!an) { rn = false; r = a; } else if (!bn) { rn = false; r = b; }
+          break;
+        case B2_SIG_UNARY_MINUS_INT:  // impl_op.rs:70-101 (map_unary_minus_int_func picks by the argument's UNSIGNED flag)
+          if (an) break;
+          if (au) { if ((uint64_t)a > 0x8000000000000000ull) return DE_OVERFLOW_BIGINT; }
+          else if (a == I64_MIN) return DE_OVERFLOW_BIGINT;
+          rn = false; r = (int64_t)((uint64_t)0 - (uint64_t)a);
+          break;
+        case B2_SIG_UNARY_MINUS_REAL: if (!an) { rn = false; r = a ^ I64_MIN; } break;  // :103-107
+        case B2_SIG_ABS_INT:  // impl_math.rs:224-231
+          if (an) break;
+          if (a == I64_MIN) return DE_OVERFLOW_BIGINT;
+          rn = false; r = a < 0 ? -a : a;
+          break;
+        case B2_SIG_ABS_UINT: if (!an) { rn = false; r = a; } break;
+        case B2_SIG_ABS_REAL: if (!an) { rn = false; r = a & I64_MAX; } break;
+        case B2_SIG_INT_DIVIDE_INT: {  // impl_arithmetic.rs:396-455 over codec/overflow.rs:9-58; x DIV 0 is NULL
+          if (an || bn || b == 0) break;
+          const uint64_t ua = (uint64_t)a, ub = (uint64_t)b;
+          if (!au && !bu) { if (a == I64_MIN && b == -1) return DE_OVERFLOW_DIV; r = a / b; }
+          else if (!au && bu) { if (a < 0) { if ((uint64_t)0 - ua >= ub) return DE_OVERFLOW_DIV; r = 0; } else r = (int64_t)(ua / ub); }
+          else if (au && bu) r = (int64_t)(ua / ub);
+          else { if (b < 0) { if (ua != 0 && (uint64_t)0 - ub <= ua) return DE_OVERFLOW_DIV; r = 0; } else r = (int64_t)(ua / ub); }
+          rn = false;
+          break;
+        }
+        case B2_SIG_MOD_INT: {  // :215-278; x % 0 is NULL.  (i64::MIN % -1 is 0 here; the reference's `%` panics on it)
+          if (an || bn || b == 0) break;
+          const uint64_t ua = (uint64_t)a, ub = (uint64_t)b;
+          const uint64_t abs_a = a < 0 ? (uint64_t)0 - ua : ua, abs_b = b < 0 ? (uint64_t)0 - ub : ub;
+          if (!au && !bu) r = b == -1 ? 0 : a % b;
+          else if (!au && bu) r = a > 0 ? (int64_t)(ua % ub) : (int64_t)((uint64_t)0 - abs_a % ub);
+          else if (au && !bu) r = (int64_t)(ua % abs_b);
+          else r = (int64_t)(ua % ub);
+          rn = false;
+          break;
+        }
+        case B2_SIG_MOD_REAL: {  // :280-291
+          if (an || bn) break;
+          const double y = bits_f64((uint64_t)b);
+          if (y == 0.0) break;
+          rn = false; r = (int64_t)f64_bits(fmod(bits_f64((uint64_t)a), y));
+          break;
+        }
+        default: return DE_UNSUPPORTED_SIG;
+    }
+  }
+  sv[base] = rn ? 0 : r; sn[base] = (rn ? 1 : 0) | (ret_unsigned ? 2 : 0);
+  *sp_io = base + 1;
+  return DE_NONE;
+}
+
+B2_HD bool plan_uses_ext_sigs(const DevPlan& P) {
+  for (int i = 0; i < P.n_nodes; ++i)
+    if (P.nodes[i].kind == B2_RPN_FN && is_ext_sig(P.nodes[i].sig)) return true;
+  return false;
+}
+
 B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const Cells& cells, Value* result, bool* res_unsigned);
 
 // leaf node (column reference or constant) -> value + flags (bit0 null, bit1 unsigned)
@@ -1084,6 +1185,15 @@ B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const 
       sv[sp] = hit ? 1 : 0; sn[sp] = (xn || (!hit && has_null)) ? 1 : 0;
       ++sp;
       continue;
+    }
+    if (is_ext_sig(nd.sig)) {
+#if B2_EXT_SIGS
+      int e = eval_ext_fn(nd.sig, nd.n_args, nd.is_unsigned, sv, sn, &sp);
+      if (e) return e;
+      continue;
+#else
+      return DE_UNSUPPORTED_SIG;  // never reached: such plans only run on their specialised kernel
+#endif
     }
     int64_t b = 0; uint8_t bf = 0;
     if (nd.n_args == 2) { --sp; b = sv[sp]; bf = sn[sp]; }

@@ -218,6 +218,7 @@ const char* dev_err_message(int code, int* status, int* mysql) {
     case DE_OVERFLOW_BIGINT: *status = B2_ERR_EVALUATE; *mysql = B2_MYSQL_ERR_DATA_OUT_OF_RANGE; return "BIGINT value is out of range";
     case DE_OVERFLOW_UBIGINT: *status = B2_ERR_EVALUATE; *mysql = B2_MYSQL_ERR_DATA_OUT_OF_RANGE; return "BIGINT UNSIGNED value is out of range";
     case DE_OVERFLOW_DOUBLE: *status = B2_ERR_EVALUATE; *mysql = B2_MYSQL_ERR_DATA_OUT_OF_RANGE; return "DOUBLE value is out of range";
+    case DE_OVERFLOW_DIV: *status = B2_ERR_EVALUATE; *mysql = B2_MYSQL_ERR_DATA_OUT_OF_RANGE; return "UNSIGNED BIGINT value is out of range";
     case DE_UNSUPPORTED_SIG: *status = B2_ERR_UNSUPPORTED; return "scalar function not supported on the device";
     case DE_UNSUPPORTED_TYPE: *status = B2_ERR_UNSUPPORTED; return "column type not supported on the device";
     default: *status = B2_ERR_CUDA; return "unknown device error";
@@ -1352,6 +1353,10 @@ int32_t b2_exec_open(const b2_dag_plan* plan, const b2_key_range* ranges, uint32
   // for requests big enough to matter and switches over when the kernel is ready
   h->jit_mode = cfg ? cfg->jit : b2_exec::JIT_AUTO;
   if (const char* ev = getenv("B2_JIT")) h->jit_mode = !strcmp(ev, "off") ? b2_exec::JIT_OFF : (!strcmp(ev, "sync") ? b2_exec::JIT_SYNC : b2_exec::JIT_AUTO);
+  if (plan_uses_ext_sigs(h->cp.dev)) {  // DIV / MOD / IF / CASE ...: only compiled into specialised kernels (b2_device.h)
+    if (!jit_available()) { g_last_error = "this plan's scalar functions need the run-time compiler (libnvrtc), which is not available"; return B2_ERR_UNSUPPORTED; }
+    h->jit_mode = b2_exec::JIT_SYNC;
+  }
   uint64_t total_entries = 0;
   for (const Unit& u : h->units) total_entries += u.e_hi - u.e_lo;
   if (h->jit_mode == b2_exec::JIT_SYNC || (h->jit_mode == b2_exec::JIT_AUTO && total_entries >= (1u << 20))) h->jit_start();

@@ -95,7 +95,7 @@ std::mutex g_mu;
 // leaked on purpose: a static destructor would block process exit on compilations still in flight
 std::map<std::string, Entry>& g_cache = *new std::map<std::string, Entry>();
 
-JitKernel* compile(int device, int mode, const std::string& literal) {
+JitKernel* compile(int device, int mode, bool ext_sigs, const std::string& literal) {
   Api& a = api();
   JitKernel* k = new JitKernel();
   cudaSetDevice(device);
@@ -106,7 +106,8 @@ JitKernel* compile(int device, int mode, const std::string& literal) {
   nvrtcProgram prog;
   if (a.CreateProgram(&prog, src.c_str(), "b2_scan_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { k->error = "nvrtcCreateProgram failed"; return k; }
   std::string inc = "-I" + a.csrc_dir;
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-DB2_NVRTC=1", "-default-device", inc.c_str(), "-I/usr/local/cuda/include"};
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-DB2_NVRTC=1", "-default-device", inc.c_str(), "-I/usr/local/cuda/include",
+                        ext_sigs ? "-DB2_EXT_SIGS=1" : "-DB2_EXT_SIGS=0"};
   nvrtcResult rc = a.CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
   if (rc != NVRTC_SUCCESS) {
     size_t n = 0;
@@ -160,8 +161,9 @@ std::shared_future<JitKernel*> jit_get(int device, const DevPlan& plan) {
   auto it = g_cache.find(key);
   if (it != g_cache.end()) return it->second.fut;
   std::string literal = key.substr(key.find('|') + 1);
+  const bool ext_sigs = plan_uses_ext_sigs(plan);
   int mode = plan.mode == PM_SCAN && plan.n_proj ? (int)PM_PROJ : (plan.mode == PM_AGG && plan.n_group > 1 ? (int)PM_AGGM : plan.mode);
-  std::shared_future<JitKernel*> fut = std::async(std::launch::async, [device, mode, literal] { return compile(device, mode, literal); }).share();
+  std::shared_future<JitKernel*> fut = std::async(std::launch::async, [device, mode, ext_sigs, literal] { return compile(device, mode, ext_sigs, literal); }).share();
   g_cache[key].fut = fut;
   return fut;
 }

@@ -73,6 +73,7 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
         bool cmp = sig >= 100 && sig < 170 && (sig % 10 == 0 || sig % 10 == 1);
         bool real_args = false, real_ret = false;
         int want = 2;
+        bool mixed = false;  // argument types already checked
         if (cmp) real_args = (sig % 10) == 1;
         else switch (sig) {
           case B2_SIG_PLUS_REAL: case B2_SIG_MINUS_REAL: case B2_SIG_MULTIPLY_REAL: real_args = real_ret = true; break;
@@ -82,10 +83,27 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
           case B2_SIG_UNARY_NOT_REAL: case B2_SIG_REAL_IS_NULL: case B2_SIG_REAL_IS_TRUE: case B2_SIG_REAL_IS_FALSE: want = 1; real_args = true; break;
           case B2_SIG_IN_INT: want = na; if (na < 1) want = -1; break;
           case B2_SIG_IN_REAL: want = na; real_args = true; if (na < 1) want = -1; break;
+          case B2_SIG_INT_DIVIDE_INT: case B2_SIG_MOD_INT: case B2_SIG_IF_NULL_INT: break;
+          case B2_SIG_MOD_REAL: case B2_SIG_IF_NULL_REAL: real_args = real_ret = true; break;
+          case B2_SIG_UNARY_MINUS_INT: case B2_SIG_ABS_INT: case B2_SIG_ABS_UINT: want = 1; break;
+          case B2_SIG_UNARY_MINUS_REAL: case B2_SIG_ABS_REAL: want = 1; real_args = real_ret = true; break;
+          case B2_SIG_COALESCE_INT: want = na; if (na < 1) want = -1; break;
+          case B2_SIG_COALESCE_REAL: want = na; real_args = real_ret = true; if (na < 1) want = -1; break;
+          case B2_SIG_IF_INT: case B2_SIG_IF_REAL: case B2_SIG_CASE_WHEN_INT: case B2_SIG_CASE_WHEN_REAL: {
+            // [cond Int, value T]* [else T]  (IF: cond, then, else); case_when_validator impl_control.rs:130-140
+            const bool rr = sig == B2_SIG_IF_REAL || sig == B2_SIG_CASE_WHEN_REAL, is_if = sig == B2_SIG_IF_INT || sig == B2_SIG_IF_REAL;
+            if (na < 1 || (is_if && na != 3) || sp < na) { *msg = "bad arity for sig " + std::to_string(sig); return false; }
+            for (int k = 0; k < na; ++k) {
+              const bool is_cond = is_if ? k == 0 : ((k & 1) == 0 && k + 1 < na);
+              if (st_et[sp - na + k] != ((is_cond || !rr) ? 0 : 1)) { *msg = "argument eval type does not match sig " + std::to_string(sig); return false; }
+            }
+            want = na; real_ret = rr; mixed = true;
+            break;
+          }
           default: *msg = "ScalarFunction sig " + std::to_string(sig) + " is not supported on the device path"; return false;
         }
         if (na != want || sp < na) { *msg = "bad arity for sig " + std::to_string(sig); return false; }
-        for (int k = 0; k < na; ++k)
+        for (int k = 0; k < na && !mixed; ++k)
           if (st_et[sp - 1 - k] != (real_args ? 1 : 0)) { *msg = "argument eval type does not match sig " + std::to_string(sig); return false; }
         sp -= na;
         d.et = real_ret ? 1 : 0;

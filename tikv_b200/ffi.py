@@ -30,6 +30,9 @@ SIG = dict(
     MULTIPLY_INT_UNSIGNED=218, LOGICAL_AND=3101, LOGICAL_OR=3102, LOGICAL_XOR=3103,
     UNARY_NOT_INT=3104, UNARY_NOT_REAL=3106, REAL_IS_NULL=3114, INT_IS_NULL=3116,
     INT_IS_TRUE=3118, REAL_IS_TRUE=3119, INT_IS_FALSE=3121, REAL_IS_FALSE=3122, IN_INT=4001, IN_REAL=4002,
+    INT_DIVIDE_INT=213, MOD_REAL=215, MOD_INT=217, ABS_INT=2101, ABS_UINT=2102, ABS_REAL=2103,
+    UNARY_MINUS_INT=3108, UNARY_MINUS_REAL=3109, IF_NULL_INT=4101, IF_NULL_REAL=4102, IF_INT=4107, IF_REAL=4108,
+    COALESCE_INT=4201, COALESCE_REAL=4202, CASE_WHEN_INT=4208, CASE_WHEN_REAL=4209,
 )
 
 AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX, AGG_FIRST = 3001, 3002, 3003, 3004, 3005, 3006

@@ -101,6 +101,30 @@ def minus(a, b): return _arith("MINUS", a, b)
 def multiply(a, b): return _arith("MULTIPLY", a, b)
 
 
+def _uns(*xs):
+    return any(x.flag & ffi.FLAG_UNSIGNED for x in xs)
+
+
+def _typed(name, first, *args, unsigned=None):
+    real = first.ekind == "real"
+    return fn(f"{name}_REAL" if real else f"{name}_INT", *args, ret_tp=ffi.TP_DOUBLE if real else ffi.TP_LONGLONG,
+              unsigned=(not real and _uns(first)) if unsigned is None else unsigned)
+
+
+def int_divide(a, b): return fn("INT_DIVIDE_INT", a, b, unsigned=_uns(a, b))      # a DIV b
+def mod(a, b): return fn("MOD_REAL", a, b, ret_tp=ffi.TP_DOUBLE) if a.ekind == "real" else fn("MOD_INT", a, b, unsigned=_uns(a))
+def neg(a): return _typed("UNARY_MINUS", a, a, unsigned=False)
+def abs_(a): return fn("ABS_REAL", a, ret_tp=ffi.TP_DOUBLE) if a.ekind == "real" else fn("ABS_UINT" if _uns(a) else "ABS_INT", a, unsigned=_uns(a))
+def if_null(a, b): return _typed("IF_NULL", a, a, b, unsigned=_uns(a, b) if a.ekind != "real" else False)
+def if_(cond, a, b): return _typed("IF", a, cond, a, b, unsigned=_uns(a, b) if a.ekind != "real" else False)
+def coalesce(*xs): return _typed("COALESCE", xs[0], *xs, unsigned=_uns(*xs) if xs[0].ekind != "real" else False)
+
+
+def case_when(*xs):
+    """case_when(cond1, value1, cond2, value2, ..., [else_value])"""
+    return _typed("CASE_WHEN", xs[1] if len(xs) > 1 else xs[0], *xs, unsigned=False)
+
+
 class ColumnDef:
     def __init__(self, col_id, tp=ffi.TP_LONGLONG, unsigned=False, not_null=False, pk_handle=False, default=None):
         self.col_id, self.tp, self.pk_handle, self.default = col_id, tp, pk_handle, default
