@@ -232,7 +232,9 @@ typedef struct b2_exec_config {
   uint64_t cuda_stream;     /* 0 = handle creates its own stream; else a cudaStream_t to run on */
   int32_t jit;              /* plan-specialised kernel (compiled at run time, cached per plan): B2_JIT_AUTO = background
                              * compile for large requests and switch when ready, B2_JIT_SYNC = wait for it at open,
-                             * B2_JIT_OFF = always the generic kernel.  Environment B2_JIT=auto|sync|off overrides. */
+                             * B2_JIT_OFF = always the generic kernel.  Environment B2_JIT=auto|sync|off overrides.
+                             * Plans that use DIV / MOD / unary minus / ABS / IFNULL / IF / CASE WHEN / COALESCE always
+                             * behave as B2_JIT_SYNC: those functions are only compiled into specialised kernels. */
   int32_t _pad;
   uint64_t reserved[3];
 } b2_exec_config;
