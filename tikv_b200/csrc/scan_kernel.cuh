@@ -704,7 +704,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
         if (MODE == PM_AGGM) {
           peers = __match_any_sync(active, gk.bits);
           const int lead = __ffs(peers) - 1;
-          if (__popc(__ballot_sync(active, lead == (int)lane)) > 8) peers = 1u << lane;
+          if (__popc(__ballot_sync(active, lead == (int)lane)) > 28) peers = 1u << lane;  // (nearly) one group per lane
           else {
             bool same = true;
 #pragma unroll
