@@ -2,9 +2,15 @@
 //
 //   scan_kernel<PM_SCAN>  MVCC forward scan -> row decode -> RPN selection -> ordered compaction into columns
 //                         (BatchTableScan + BatchSelection; table_scan_executor.rs, selection_executor.rs)
-//   scan_kernel<PM_AGG>   same front end, then COUNT/SUM/AVG into a per-CTA shared-memory group table that is
+//   scan_kernel<PM_PROJ>  PM_SCAN whose output cells are expression values (BatchProjection; projection_executor.rs)
+//   scan_kernel<PM_AGG>   same front end, then COUNT/SUM/AVG/MAX/MIN into a per-CTA shared-memory group table that is
 //                         flushed into the HBM group table (BatchSimpleAggregation / BatchFastHashAggregation)
-//   gen_*                 synthetic region generator (tooling)
+//   scan_kernel<PM_AGGM>  GROUP BY over 2..4 expressions: composite keys in a hash-tagged HBM table
+//                         (BatchSlowHashAggregation; slow_hash_aggr_executor.rs)
+//   scan_kernel<PM_TOPN>  per-CTA candidate buffers + threshold, merged by topn_merge / gathered by topn_gather (BatchTopN)
+//   scan_kernel<PM_CHECKSUM>  CRC-64/XZ per KV, XOR-folded (checksum.rs)
+//   agg_finalize / agg_result, topn_*, pack_nulls, bounds: result materialisation; gen_*: synthetic region generator (tooling)
+// The same device body (scan_kernel.cuh) is compiled per plan at run time by jit.cu.
 //
 // One thread owns one CF_WRITE entry; only the thread sitting on the first version of a user key does work for
 // that key (walks its versions, decodes the row).  CTAs are persistent and pull 256-entry tiles.
