@@ -377,7 +377,10 @@ def projection_plans():
                                              in_(c6, const_int(1), const_int(2)), col(C3, unsigned=True)).build()),
             ("proj_after_selection_limit", scan().selection(ge(c6, const_int(3))).projection(minus(col(C_H), c6), col(C2)).limit(55).build()),
             ("proj_subset", scan().projection(col(C1), plus(c6, c6), is_null(col(C2))).build(output_offsets=[2, 1])),
-            ("proj_overflow", scan().projection(col(C_H), multiply(col(C1), const_int(1 << 40))).build())]
+            ("proj_overflow", scan().projection(col(C_H), multiply(col(C1), const_int(1 << 40))).build()),
+            # Real multiply feeding an add / subtract: separately rounded steps (a fused multiply-add would differ in the last bit)
+            ("proj_real_chain", scan().projection(col(C_H), plus(multiply(col(C4, tp=ffi.TP_DOUBLE), const_real(1.1)), const_real(0.3)),
+                                                  minus(multiply(col(C4, tp=ffi.TP_DOUBLE), col(C4, tp=ffi.TP_DOUBLE)), multiply(col(C4, tp=ffi.TP_DOUBLE), const_real(1e-3)))).build())]
 
 
 def check_scalar_known_answers(run, error_labels=None):

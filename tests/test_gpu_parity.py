@@ -612,6 +612,8 @@ def test_projection(name, plan):
     region = sc.dirty_region(1, n_keys=900, full_range=name == "proj_overflow").build(read_ts=sc.READ_TS, n_write_blocks=2)
     exp = orc.dag_handle(plan, sc.split_ranges(), region)
     got = DagHandler(plan, sc.split_ranges(), DeviceRegion(region)).handle_request()
+    if name == "proj_real_chain":  # also through the plan-specialised kernel, where the evaluator is unrolled
+        assert_same_rows(DagHandler(plan, sc.split_ranges(), DeviceRegion(region), jit=ffi.JIT_SYNC).handle_request(), exp, ordered=True, ctx=name + "/jit")
     if name == "proj_overflow":
         # an evaluation error ends the request; the reference drops the rows of the batch it happened in (projection_executor.rs
         # :207-211, batch = 32..1024 rows), the device keeps every row before the failing one: the oracle's rows are a prefix

@@ -988,6 +988,29 @@ B2_HD bool mul_ovf_i64(int64_t a, int64_t b, int64_t* r) {
   *r = (int64_t)m;
   return false;
 }
+// IEEE round-to-nearest operations that the compiler may not contract into an FMA: in a plan-specialised kernel the
+// stack machine is unrolled, and `a * b + c` fused would differ from the reference's separately rounded steps
+B2_HD double f64_add(double x, double y) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(x, y);
+#else
+  return x + y;
+#endif
+}
+B2_HD double f64_sub(double x, double y) {
+#if defined(__CUDA_ARCH__)
+  return __dsub_rn(x, y);
+#else
+  return x - y;
+#endif
+}
+B2_HD double f64_mul(double x, double y) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(x, y);
+#else
+  return x * y;
+#endif
+}
 B2_HD bool f64_finite(double x) { return (f64_bits(x) & 0x7ff0000000000000ull) != 0x7ff0000000000000ull; }
 B2_HD bool f64_isinf(double x) { return (f64_bits(x) & 0x7fffffffffffffffull) == 0x7ff0000000000000ull; }
 
@@ -1272,7 +1295,7 @@ B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const 
         case B2_SIG_PLUS_REAL: case B2_SIG_MINUS_REAL: case B2_SIG_MULTIPLY_REAL: {
           if (an || bn) break;
           double x = bits_f64((uint64_t)a), y = bits_f64((uint64_t)b);
-          double z = sig == B2_SIG_PLUS_REAL ? x + y : (sig == B2_SIG_MINUS_REAL ? x - y : x * y);
+          double z = sig == B2_SIG_PLUS_REAL ? f64_add(x, y) : (sig == B2_SIG_MINUS_REAL ? f64_sub(x, y) : f64_mul(x, y));
           bool bad = sig == B2_SIG_MULTIPLY_REAL ? f64_isinf(z) : !f64_finite(z);
           if (bad) return DE_OVERFLOW_DOUBLE;
           rn = false; r = (int64_t)f64_bits(z);
