@@ -56,6 +56,20 @@ def _worker(rank, world, port, q):
     expect = sorted(((r[2], r[0], r[1]) for r in whole.rows()), key=keyf)
     ok_agg = merged == expect and len(expect) > 10
 
+    # composite group keys (BatchSlowHashAggregation partials: [n, 2] key words + NULL masks), MAX merged by unsigned maximum
+    mplan = Plan().table_scan(sc.TABLE, sc.COLUMNS).aggregation([("count", const_int(1)), ("max", col(sc.C6))], group_by=[col(sc.C2), col(sc.C6)]).build()
+    part = orc.dag_handle(mplan, mine, region)
+    rows = part.rows()  # (count, max, c2, c6)
+    mkeys = torch.tensor([[0 if r[2] is None else r[2], 0 if r[3] is None else r[3]] for r in rows], dtype=torch.int64).reshape(-1, 2)
+    mnul = torch.tensor([(1 if r[2] is None else 0) | (2 if r[3] is None else 0) for r in rows], dtype=torch.int64)
+    # MAX state as the device keeps it: [count of non-NULL inputs, order-preserving key = value ^ sign bit]
+    macc = torch.tensor([[r[0], 0 if r[1] is None else 1, 0 if r[1] is None else _i64(r[1] ^ (1 << 63))] for r in rows], dtype=torch.int64).reshape(-1, 3)
+    k2, n2, a2 = bd.merge_agg_partials(mkeys, mnul, macc, max_words=(2,))
+    nk = lambda t: tuple((0, 0) if x is None else (1, x) for x in t)
+    mm = sorted(((int(a2[i, 0]), (_i64(int(a2[i, 2]) ^ (1 << 63)) if int(a2[i, 1]) else None), None if int(n2[i]) & 1 else int(k2[i, 0]), None if int(n2[i]) & 2 else int(k2[i, 1]))
+                 for i in range(k2.shape[0])), key=nk)
+    ok_agg = ok_agg and mm == sorted(orc.dag_handle(mplan, sc.WHOLE, region).rows(), key=nk) and len(mm) > 30
+
     # TopN: ORDER BY c2 DESC, c1 ASC LIMIT 40
     tplan = Plan().table_scan(sc.TABLE, sc.COLUMNS).topn([(col(sc.C2), True), (col(sc.C1), False)], 40).build(output_offsets=[sc.C_H, sc.C1, sc.C2])
     tp = orc.dag_handle(tplan, mine, region)
