@@ -8,6 +8,7 @@
 // bytes (tikv_util/src/codec/bytes.rs:352-), Key+ts (txn_types/src/types.rs:890-914), row v2 byte
 // arrays (row/v2/encoder_for_test.rs:543-609), write-record cases (txn_types/src/write.rs:504-549),
 // table-scan fixture (table_scan_executor.rs:496-512), CRC-64/XZ check value.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
@@ -50,6 +51,10 @@ static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges,
   rs.base_cfg.access_locks.assign(src->access_locks, src->access_locks + src->n_access_locks);
   for (uint32_t i = 0; i < n_ranges; ++i)
     rs.ranges.emplace_back(Bytes(ranges[i].start, ranges[i].start + ranges[i].start_len), Bytes(ranges[i].end, ranges[i].end + ranges[i].end_len));
+  if (plan->executors[0].desc) {  // scan_executor.rs:89-101: ranges in reverse order, each scanned backward
+    rs.desc = true;
+    std::reverse(rs.ranges.begin(), rs.ranges.end());
+  }
   *scan_out = scan.get();
   std::unique_ptr<Executor> cur = std::move(scan);
   for (uint32_t i = 1; i < plan->n_executors; ++i) {
@@ -125,6 +130,32 @@ static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges,
   }
   *out = std::move(cur);
   return true;
+}
+
+struct orc_scan { std::vector<Bytes> keys, vals; Statistics st; Error err; int met_newer; };
+template <class Scanner>
+static orc_scan* mvcc_scan_with(const b2_region_source* src, const uint8_t* lower, size_t lower_len, const uint8_t* upper, size_t upper_len) {
+  orc_scan* r = new orc_scan();
+  CfView w, l, d;
+  w.init(src->write, src->n_write);
+  d.init(src->dflt, src->dflt ? src->n_dflt : 0);
+  l.init(src->lock, src->lock ? 1 : 0);
+  ScannerConfig cfg;
+  cfg.ts = src->read_ts; cfg.isolation_level = src->isolation_level; cfg.check_has_newer_ts_data = src->check_has_newer_ts_data;
+  cfg.bypass_locks.assign(src->bypass_locks, src->bypass_locks + src->n_bypass_locks);
+  cfg.access_locks.assign(src->access_locks, src->access_locks + src->n_access_locks);
+  if (lower) { cfg.has_lower = true; cfg.lower_bound.assign(lower, lower + lower_len); }
+  if (upper) { cfg.has_upper = true; cfg.upper_bound.assign(upper, upper + upper_len); }
+  Scanner fs;
+  fs.init(cfg, &w, &l, &d);
+  for (;;) {
+    ScanOutput so;
+    int rc = fs.read_next(&so, &r->err);
+    if (rc <= 0) break;
+    r->keys.push_back(so.user_key); r->vals.push_back(so.value);
+  }
+  r->st = fs.statistics; r->met_newer = fs.met_newer_ts_data;
+  return r;
 }
 
 extern "C" {
@@ -283,29 +314,12 @@ uint64_t orc_dag_handle_parallel(const b2_dag_plan* plan, const b2_key_range* ra
 
 // Raw MVCC scan over [lower, upper) (encoded user keys; NULL = unbounded) — pins ForwardScanner against the
 // reference's scanner unit tests (forward.rs:1179-1727), including exact next/seek statistics.
-struct orc_scan { std::vector<Bytes> keys, vals; Statistics st; Error err; int met_newer; };
 orc_scan* orc_mvcc_scan(const b2_region_source* src, const uint8_t* lower, size_t lower_len, const uint8_t* upper, size_t upper_len) {
-  orc_scan* r = new orc_scan();
-  CfView w, l, d;
-  w.init(src->write, src->n_write);
-  d.init(src->dflt, src->dflt ? src->n_dflt : 0);
-  l.init(src->lock, src->lock ? 1 : 0);
-  ScannerConfig cfg;
-  cfg.ts = src->read_ts; cfg.isolation_level = src->isolation_level; cfg.check_has_newer_ts_data = src->check_has_newer_ts_data;
-  cfg.bypass_locks.assign(src->bypass_locks, src->bypass_locks + src->n_bypass_locks);
-  cfg.access_locks.assign(src->access_locks, src->access_locks + src->n_access_locks);
-  if (lower) { cfg.has_lower = true; cfg.lower_bound.assign(lower, lower + lower_len); }
-  if (upper) { cfg.has_upper = true; cfg.upper_bound.assign(upper, upper + upper_len); }
-  ForwardScanner fs;
-  fs.init(cfg, &w, &l, &d);
-  for (;;) {
-    ScanOutput so;
-    int rc = fs.read_next(&so, &r->err);
-    if (rc <= 0) break;
-    r->keys.push_back(so.user_key); r->vals.push_back(so.value);
-  }
-  r->st = fs.statistics; r->met_newer = fs.met_newer_ts_data;
-  return r;
+  return mvcc_scan_with<ForwardScanner>(src, lower, lower_len, upper, upper_len);
+}
+// the same over BackwardScanner (backward.rs tests :524-1576): keys come back in descending order
+orc_scan* orc_mvcc_scan_backward(const b2_region_source* src, const uint8_t* lower, size_t lower_len, const uint8_t* upper, size_t upper_len) {
+  return mvcc_scan_with<BackwardScanner>(src, lower, lower_len, upper, upper_len);
 }
 uint64_t orc_scan_rows(orc_scan* r) { return r->keys.size(); }
 const uint8_t* orc_scan_key(orc_scan* r, uint64_t i, size_t* len) { *len = r->keys[i].size(); return r->keys[i].data(); }
@@ -315,6 +329,7 @@ void orc_scan_stats(orc_scan* r, uint64_t* out8) {
   out8[0] = r->st.write.next; out8[1] = r->st.write.seek; out8[2] = r->st.write.over_seek_bound; out8[3] = r->st.write.processed_keys;
   out8[4] = r->st.processed_size; out8[5] = r->st.data.processed_keys; out8[6] = r->st.lock.processed_keys; out8[7] = (uint64_t)(int64_t)r->met_newer;
 }
+void orc_scan_stats_backward(orc_scan* r, uint64_t* out2) { out2[0] = r->st.write.prev; out2[1] = r->st.write.seek_for_prev; }
 void orc_scan_free(orc_scan* r) { delete r; }
 
 // ---- codec hooks for the golden-vector tests ----

@@ -164,18 +164,24 @@ struct RangesScanner {
   ScannerConfig base_cfg;
   const CfView *w = nullptr, *l = nullptr, *d = nullptr;
   ForwardScanner fs;
+  BackwardScanner bs;  // scan_backward_in_range (scanner.rs:25, 145): TableScan.desc
+  bool desc = false;
   Statistics total;
   int met_newer = NEWER_UNKNOWN;
   bool met_lock = false;
   uint64_t rows = 0;
 
   void accumulate() {
-    auto add = [](CfStatistics& a, const CfStatistics& b) { a.processed_keys += b.processed_keys; a.next += b.next; a.seek += b.seek; a.over_seek_bound += b.over_seek_bound; };
-    add(total.write, fs.statistics.write); add(total.lock, fs.statistics.lock); add(total.data, fs.statistics.data);
-    total.processed_size += fs.statistics.processed_size;
-    if (fs.met_newer_ts_data == NEWER_MET) met_newer = NEWER_MET;
-    else if (fs.met_newer_ts_data == NEWER_NOT_MET && met_newer == NEWER_UNKNOWN) met_newer = NEWER_NOT_MET;
-    fs.statistics = Statistics();
+    auto add = [](CfStatistics& a, const CfStatistics& b) {
+      a.processed_keys += b.processed_keys; a.next += b.next; a.prev += b.prev; a.seek += b.seek; a.seek_for_prev += b.seek_for_prev; a.over_seek_bound += b.over_seek_bound;
+    };
+    Statistics& st = desc ? bs.statistics : fs.statistics;
+    const int newer = desc ? bs.met_newer_ts_data : fs.met_newer_ts_data;
+    add(total.write, st.write); add(total.lock, st.lock); add(total.data, st.data);
+    total.processed_size += st.processed_size;
+    if (newer == NEWER_MET) met_newer = NEWER_MET;
+    else if (newer == NEWER_NOT_MET && met_newer == NEWER_UNKNOWN) met_newer = NEWER_NOT_MET;
+    st = Statistics();
   }
   // returns 1 row, 0 drained, -1 error. key out = raw key (storage_impl.rs:82 Key::into_raw)
   int next(Bytes* raw_key, ScanOutput* so, Error* err) {
@@ -186,10 +192,10 @@ struct RangesScanner {
         cfg.has_lower = cfg.has_upper = true;
         cfg.lower_bound = key_from_raw(Slice(ranges[cur].first.data(), ranges[cur].first.size()));
         cfg.upper_bound = key_from_raw(Slice(ranges[cur].second.data(), ranges[cur].second.size()));
-        fs.init(cfg, w, l, d);
+        if (desc) bs.init(cfg, w, l, d); else fs.init(cfg, w, l, d);
         in_range = true;
       }
-      int r = fs.read_next(so, err);
+      int r = desc ? bs.read_next(so, err) : fs.read_next(so, err);
       if (r < 0) { accumulate(); return -1; }
       if (r == 0) { accumulate(); in_range = false; cur++; continue; }
       if (decode_bytes(Slice(so->user_key.data(), so->user_key.size()), raw_key) == (size_t)-1) {

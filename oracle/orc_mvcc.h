@@ -78,6 +78,22 @@ struct Cursor {
   void seek(Slice key, CfStatistics* st) { st->seek++; uint64_t p = cf->lower_bound(key); pos = p < lo ? lo : p; }
   void seek_to_first(CfStatistics* st) { st->seek++; pos = lo; }
   void next(CfStatistics* st) { st->next++; pos++; }
+  // backward movement (storage/kv/cursor.rs reverse_seek :277-336, seek_for_prev :338-383, seek_to_last :496-503, prev :533-545)
+  void prev(CfStatistics* st) { st->prev++; pos--; }  // lo - 1 (or wrap-around below 0) is "not valid"
+  void seek_to_last(CfStatistics* st) { st->seek++; pos = hi - 1; }
+  void seek_for_prev(Slice key, CfStatistics* st) {  // last entry <= key
+    st->seek_for_prev++;
+    uint64_t p = cf->lower_bound(key);
+    if (p < cf->size() && cmp_bytes(cf->key(p), key) == 0) ++p;
+    if (p > hi) p = hi;
+    pos = p - 1;
+  }
+  void reverse_seek(Slice key, CfStatistics* st) {  // last entry < key
+    st->seek_for_prev++;
+    uint64_t p = cf->lower_bound(key);
+    if (p > hi) p = hi;
+    pos = p - 1;
+  }
   Slice key() const { return cf->key(pos); }
   Slice value() const { return cf->value(pos); }
 };
@@ -449,6 +465,200 @@ struct ForwardScanner {
             statistics.processed_size += out->user_key.size() + out->value.size();
             return 1;
           }
+        }
+      }
+    }
+  }
+};
+
+// ---- backward scan: src/storage/mvcc/reader/scanner/backward.rs ----------------------------------------------
+// Same visible version per user key as the forward scanner (the newest Put / Delete with commit_ts <= ts, Lock and
+// Rollback records skipped, gc fence checked on it), keys delivered in descending order.  Test infrastructure for the
+// `desc` table scan; cursor statistics follow the reference's prev / seek pattern.
+static const uint64_t REVERSE_SEEK_BOUND = 16;  // backward.rs:23
+
+struct BackwardScanner {
+  ScannerConfig cfg;
+  const CfView* write_cf = nullptr; const CfView* lock_cf = nullptr; const CfView* default_cf = nullptr;
+  Cursor write, lock;
+  bool has_lock_cursor = false;
+  bool is_started = false;
+  Statistics statistics;
+  int met_newer_ts_data = NEWER_UNKNOWN;
+
+  void init(const ScannerConfig& c, const CfView* w, const CfView* l, const CfView* d) {
+    cfg = c; write_cf = w; lock_cf = l; default_cf = d;
+    Slice lo(cfg.lower_bound.data(), cfg.lower_bound.size()), hi(cfg.upper_bound.data(), cfg.upper_bound.size());
+    write.init(w, lo, cfg.has_lower, hi, cfg.has_upper);
+    has_lock_cursor = l && l->size() > 0 && cfg.isolation_level != B2_ISO_RC;
+    if (has_lock_cursor) lock.init(l, lo, cfg.has_lower, hi, cfg.has_upper);
+    met_newer_ts_data = cfg.check_has_newer_ts_data ? NEWER_NOT_MET : NEWER_UNKNOWN;
+    is_started = false;
+  }
+
+  // scanner/mod.rs near_reverse_load_data_by_write: the value of (user_key, start_ts) in CF_DEFAULT
+  bool load_default(const Bytes& user_key, uint64_t start_ts, Bytes* out, Error* err) {
+    Bytes seek_key = key_append_ts(user_key, start_ts);
+    uint64_t p = default_cf ? default_cf->lower_bound(Slice(seek_key.data(), seek_key.size())) : 0;
+    statistics.data.seek_for_prev++;
+    if (!default_cf || p >= default_cf->size() || cmp_bytes(default_cf->key(p), Slice(seek_key.data(), seek_key.size())) != 0) {
+      *err = Error::make(B2_ERR_STORAGE, "default not found");
+      return false;
+    }
+    statistics.data.processed_keys++;
+    Slice v = default_cf->value(p);
+    out->assign(v.p, v.p + v.n);
+    return true;
+  }
+
+  // backward.rs:460-491
+  void move_write_cursor_to_prev_user_key(const Bytes& current_user_key) {
+    Slice uk(current_user_key.data(), current_user_key.size());
+    for (uint64_t i = 0; i < SEEK_BOUND; ++i) {
+      if (i > 0) write.prev(&statistics.write);
+      if (!write.valid()) return;
+      if (!is_user_key_eq(write.key(), uk)) return;
+    }
+    statistics.write.over_seek_bound++;
+    write.seek_for_prev(uk, &statistics.write);  // the bare user key sorts before every version of it
+  }
+
+  // handle_last_version backward.rs:411-433 + reverse_load_data_by_write :440-458.  1 = value, 0 = none, -1 = error
+  int finish(bool have, const WriteRef& w, const Bytes& short_value, uint64_t commit_ts, const Bytes& user_key, ScanOutput* out, Error* err) {
+    if (!have) return 0;
+    if (!write_check_gc_fence_as_latest_version(w, cfg.ts)) return 0;
+    if (w.write_type == WT_DELETE) return 0;
+    out->has_commit_ts = cfg.load_commit_ts; out->commit_ts = commit_ts;
+    if (cfg.omit_value) { out->value.clear(); return 1; }
+    if (w.has_short_value) { out->value = short_value; return 1; }
+    return load_default(user_key, w.start_ts, &out->value, err) ? 1 : -1;
+  }
+
+  // reverse_get backward.rs:218-405: the write cursor points at the earliest version of user_key
+  int reverse_get(const Bytes& user_key, bool* met_prev_user_key, ScanOutput* out, Error* err) {
+    Slice uk(user_key.data(), user_key.size());
+    bool have = false; WriteRef last; Bytes last_short; uint64_t loaded_commit_ts = 0, last_checked_commit_ts = 0;
+    for (uint64_t i = 0; i < REVERSE_SEEK_BOUND; ++i) {
+      if (i > 0) {
+        write.prev(&statistics.write);
+        if (!write.valid()) return finish(have, last, last_short, loaded_commit_ts, user_key, out, err);
+      }
+      Slice ck = write.key();
+      last_checked_commit_ts = decode_u64_desc(ck.p + ck.n - 8);
+      bool is_done = false;
+      if (!is_user_key_eq(ck, uk)) { *met_prev_user_key = true; is_done = true; }
+      else if (last_checked_commit_ts > cfg.ts) {
+        is_done = true;
+        if (met_newer_ts_data == NEWER_NOT_MET) met_newer_ts_data = NEWER_MET;
+        if (cfg.isolation_level == B2_ISO_RC_CHECK_TS) { *err = Error::make(B2_ERR_WRITE_CONFLICT, "write conflict (RcCheckTs): newer version exists"); return -1; }
+      }
+      if (is_done) return finish(have, last, last_short, loaded_commit_ts, user_key, out, err);
+      WriteRef w; std::string perr;
+      if (!write_parse(write.value(), &w, &perr)) { *err = Error::make(B2_ERR_STORAGE, perr); return -1; }
+      if (w.write_type == WT_PUT || w.write_type == WT_DELETE) {
+        have = true; last = w;
+        last_short.assign(w.short_value.p, w.short_value.p + (w.has_short_value ? w.short_value.n : 0));
+        loaded_commit_ts = last_checked_commit_ts;
+      }
+    }
+    if (last_checked_commit_ts == cfg.ts) {  // :292-307
+      if (met_newer_ts_data == NEWER_NOT_MET) {
+        write.prev(&statistics.write);
+        if (write.valid()) {
+          if (is_user_key_eq(write.key(), uk)) met_newer_ts_data = NEWER_MET; else *met_prev_user_key = true;
+        }
+      }
+      return finish(have, last, last_short, loaded_commit_ts, user_key, out, err);
+    }
+    // many versions: seek to (user_key, ts) and walk forward to the newest Put / Delete below it (:314-404)
+    if (met_newer_ts_data == NEWER_NOT_MET) {
+      Bytes k = key_append_ts(user_key, ~0ull);
+      write.seek(Slice(k.data(), k.size()), &statistics.write);
+      Slice ck = write.key();
+      if (decode_u64_desc(ck.p + ck.n - 8) > cfg.ts) met_newer_ts_data = NEWER_MET;
+    }
+    Bytes k = key_append_ts(user_key, cfg.ts);
+    write.seek(Slice(k.data(), k.size()), &statistics.write);
+    for (;;) {
+      Slice ck = write.key();
+      uint64_t current_ts = decode_u64_desc(ck.p + ck.n - 8);
+      if (current_ts <= last_checked_commit_ts) return finish(have, last, last_short, loaded_commit_ts, user_key, out, err);
+      WriteRef w; std::string perr;
+      if (!write_parse(write.value(), &w, &perr)) { *err = Error::make(B2_ERR_STORAGE, perr); return -1; }
+      if (!write_check_gc_fence_as_latest_version(w, cfg.ts)) return 0;
+      if (w.write_type == WT_PUT) {
+        Bytes sv(w.short_value.p, w.short_value.p + (w.has_short_value ? w.short_value.n : 0));
+        out->has_commit_ts = cfg.load_commit_ts; out->commit_ts = current_ts;
+        if (cfg.omit_value) { out->value.clear(); return 1; }
+        if (w.has_short_value) { out->value = sv; return 1; }
+        return load_default(user_key, w.start_ts, &out->value, err) ? 1 : -1;
+      }
+      if (w.write_type == WT_DELETE) return 0;
+      write.next(&statistics.write);  // Lock / Rollback: next (older) version
+    }
+  }
+
+  // read_next backward.rs:78-216.  1 = row, 0 = drained, -1 = error
+  int read_next(ScanOutput* out, Error* err) {
+    if (!is_started) {
+      if (cfg.has_upper) {
+        Slice ub(cfg.upper_bound.data(), cfg.upper_bound.size());
+        write.reverse_seek(ub, &statistics.write);
+        if (has_lock_cursor) lock.reverse_seek(ub, &statistics.lock);
+      } else {
+        write.seek_to_last(&statistics.write);
+        if (has_lock_cursor) lock.seek_to_last(&statistics.lock);
+      }
+      is_started = true;
+    }
+    for (;;) {
+      bool wv = write.valid(), lv = has_lock_cursor && lock.valid();
+      if (!wv && !lv) return 0;
+      Bytes current_user_key;
+      bool has_write, has_lock;
+      if (!wv) { Slice lk = lock.key(); current_user_key.assign(lk.p, lk.p + lk.n); has_write = false; has_lock = true; }
+      else {
+        Slice wk = write.key();
+        if (wk.n < 8) { *err = Error::make(B2_ERR_STORAGE, "key too short to truncate ts"); return -1; }
+        Slice wuk(wk.p, wk.n - 8);
+        if (!lv) { current_user_key.assign(wuk.p, wuk.p + wuk.n); has_write = true; has_lock = false; }
+        else {
+          Slice lk = lock.key();
+          int c = cmp_bytes(wuk, lk);  // descending: the larger key comes first
+          if (c < 0) { current_user_key.assign(lk.p, lk.p + lk.n); has_write = false; has_lock = true; }
+          else if (c > 0) { current_user_key.assign(wuk.p, wuk.p + wuk.n); has_write = true; has_lock = false; }
+          else { current_user_key.assign(wuk.p, wuk.p + wuk.n); has_write = true; has_lock = true; }
+        }
+      }
+      bool met_prev_user_key = false;
+      if (has_lock) {
+        LockRec lrec; std::string perr;
+        if (!lock_parse(lock.value(), &lrec, &perr)) { *err = Error::make(B2_ERR_STORAGE, perr); return -1; }
+        if (met_newer_ts_data == NEWER_NOT_MET) met_newer_ts_data = NEWER_MET;
+        Slice uk(current_user_key.data(), current_user_key.size());
+        bool conflict = false;
+        if (cfg.isolation_level == B2_ISO_SI) conflict = check_ts_conflict_si(lrec, uk, cfg.ts, cfg.bypass_locks);
+        else if (cfg.isolation_level == B2_ISO_RC_CHECK_TS)
+          conflict = !(lrec.lock_type == 'H' || lrec.lock_type == 'L' || lrec.lock_type == 'S' || ts_set_contains(cfg.bypass_locks, lrec.ts));
+        lock.prev(&statistics.lock);
+        if (conflict) {
+          statistics.lock.processed_keys++;
+          if (cfg.isolation_level == B2_ISO_RC_CHECK_TS) { *err = Error::make(B2_ERR_WRITE_CONFLICT, "write conflict (RcCheckTs): lock"); return -1; }
+          if (!cfg.load_commit_ts && ts_set_contains(cfg.access_locks, lrec.ts)) { *err = Error::make(B2_ERR_UNSUPPORTED, "access_locks read-through is not restated"); return -1; }
+          if (has_write) move_write_cursor_to_prev_user_key(current_user_key);
+          *err = Error::make(B2_ERR_KEY_IS_LOCKED, "key is locked, lock_version=" + std::to_string(lrec.ts));
+          return -1;
+        }
+      }
+      if (has_write) {
+        int r = reverse_get(current_user_key, &met_prev_user_key, out, err);
+        if (r < 0) return -1;
+        if (!met_prev_user_key) move_write_cursor_to_prev_user_key(current_user_key);
+        if (r == 1) {
+          out->user_key = current_user_key;
+          statistics.write.processed_keys++;
+          statistics.processed_size += out->user_key.size() + out->value.size();
+          return 1;
         }
       }
     }

@@ -124,9 +124,12 @@ def checksum(ranges, region, old_prefix=b"", new_prefix=b""):
     return st, (out.checksum, out.total_kvs, out.total_bytes), err.value.decode()
 
 
-def mvcc_scan(region, lower=None, upper=None):
-    """Raw forward scan (encoded user-key bounds).  Returns (status, [(user_key, value)], stats)."""
+def mvcc_scan(region, lower=None, upper=None, desc=False):
+    """Raw forward (or, desc=True, backward) scan (encoded user-key bounds).  Returns (status, [(user_key, value)], stats)."""
     L = lib()
+    L.orc_mvcc_scan_backward.argtypes = [C.POINTER(ffi.RegionSource), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    L.orc_mvcc_scan_backward.restype = C.c_void_p
+    L.orc_scan_stats_backward.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.orc_mvcc_scan.argtypes = [C.POINTER(ffi.RegionSource), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
     L.orc_mvcc_scan.restype = C.c_void_p
     L.orc_scan_rows.argtypes = [C.c_void_p]; L.orc_scan_rows.restype = C.c_uint64
@@ -136,7 +139,7 @@ def mvcc_scan(region, lower=None, upper=None):
     L.orc_scan_status.argtypes = [C.c_void_p]
     L.orc_scan_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.orc_scan_free.argtypes = [C.c_void_p]
-    h = L.orc_mvcc_scan(C.byref(region.c), lower, len(lower) if lower else 0, upper, len(upper) if upper else 0)
+    h = (L.orc_mvcc_scan_backward if desc else L.orc_mvcc_scan)(C.byref(region.c), lower, len(lower) if lower else 0, upper, len(upper) if upper else 0)
     out = []
     ln = C.c_size_t()
     for i in range(L.orc_scan_rows(h)):
@@ -147,6 +150,9 @@ def mvcc_scan(region, lower=None, upper=None):
     L.orc_scan_stats(h, st)
     stats = dict(write_next=st[0], write_seek=st[1], over_seek_bound=st[2], processed_keys=st[3], processed_size=st[4],
                  data_processed_keys=st[5], lock_processed_keys=st[6], met_newer=C.c_int64(st[7]).value)
+    st2 = (C.c_uint64 * 2)()
+    L.orc_scan_stats_backward(h, st2)
+    stats.update(write_prev=st2[0], write_seek_for_prev=st2[1])
     status = L.orc_scan_status(h)
     L.orc_scan_free(h)
     return status, out, stats

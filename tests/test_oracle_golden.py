@@ -440,3 +440,107 @@ def test_scalar_function_known_answers():
     (scenarios.scalar_known_answers cites them)."""
     import scenarios as sc
     sc.check_scalar_known_answers(orc.dag_handle)
+
+
+def test_backward_scanner_basic():
+    """backward.rs test_basic :524-818: REVERSE_SEEK_BOUND = 16, read at ts 17; rows in descending key order and the
+    reference's cursor statistics summed over the five `next()` calls (prev 8+16+17+18+19, seek 4, next 3, one initial
+    seek_for_prev), processed_size 5 x (9-byte encoded key + 1-byte value)."""
+    B = 16
+    r = kvfmt.Region()
+    k = lambda x: bytes([x])
+    for ts in range(1, B // 2 + 1):
+        r.put(k(10), bytes([ts]), ts, ts)
+    for ts in range(1, B + 2):
+        r.put(k(9), bytes([ts]), ts, ts)
+    for ts in range(1, B + 2):
+        if ts < B // 2 + 1:
+            r.put(k(8), bytes([ts]), ts, ts)
+        else:
+            r.rollback(k(8), ts)
+    for ts in range(1, B // 2 + 1):
+        r.put(k(7), bytes([ts]), ts, ts)
+    r.delete(k(7), B // 2 + 1, B // 2 + 1)
+    for ts in range(B // 2 + 2, B + 2):
+        r.rollback(k(7), ts)
+    r.put(k(6), bytes([1]), 1, 1)
+    for ts in range(1, B + 2):
+        r.rollback(k(5), ts)
+    for ts in range(B + 1, B + 3):
+        r.put(k(4), bytes([ts]), ts, ts)
+    st, rows, stats = orc.mvcc_scan(r.build(read_ts=B + 1, check_newer=False), upper=_uk(k(11)), desc=True)
+    assert st == 0
+    assert rows == [(_uk(k(10)), bytes([B // 2])), (_uk(k(9)), bytes([B + 1])), (_uk(k(8)), bytes([B // 2])), (_uk(k(6)), bytes([1])), (_uk(k(4)), bytes([B + 1]))]
+    assert stats["write_prev"] == B // 2 + B + (B + 1) + (B + 2) + (B + 3)
+    assert stats["write_seek"] == 4 and stats["write_next"] == 3 and stats["write_seek_for_prev"] == 1
+    assert stats["processed_size"] == 5 * (9 + 1) and stats["processed_keys"] == 5
+
+
+def test_backward_scan_is_the_reversed_forward_scan():
+    """Both scanners must agree on the visible version of every key (backward.rs:25-31): seeded dirty regions (every MVCC
+    shape, long values, gc fences, many-version keys past both seek bounds), several read timestamps, SI / RC / RcCheckTs,
+    bounded and unbounded ranges."""
+    import scenarios as sc
+    n = 0
+    for seed in range(60):
+        r = sc.dirty_region(500 + seed, n_keys=40)
+        for read_ts, iso in ((sc.READ_TS, ffi.ISO_SI), (15, ffi.ISO_RC), (25, ffi.ISO_SI), (sc.READ_TS + 6, ffi.ISO_RC), (sc.READ_TS, ffi.ISO_RC_CHECK_TS)):
+            region = r.build(read_ts=read_ts, isolation=iso)
+            for lo, hi in ((None, None), (_uk(kvfmt.row_key(sc.TABLE, 10)), _uk(kvfmt.row_key(sc.TABLE, 70)))):
+                fs, frows, fstats = orc.mvcc_scan(region, lo, hi)
+                bs, brows, bstats = orc.mvcc_scan(region, lo, hi, desc=True)
+                assert fs == bs, (seed, read_ts, iso, fs, bs)
+                if fs == 0:
+                    n += 1
+                    assert brows == frows[::-1], (seed, read_ts, iso)
+                    assert bstats["processed_size"] == fstats["processed_size"] and bstats["data_processed_keys"] == fstats["data_processed_keys"]
+                    assert bstats["met_newer"] == fstats["met_newer"], (seed, read_ts, iso)
+    assert n > 400
+
+
+def test_backward_scanner_out_of_bound_cases():
+    """backward.rs test_reverse_get_out_of_bound_1 :821-897, _2 :905-990, test_move_prev_user_key_out_of_bound_1 :998-1075:
+    rows and the summed prev / seek / next / seek_for_prev counters when the cursor runs off the front of the key space."""
+    B, SB = 16, 8
+    # 1: N/2 rollbacks for b (ts 0..), one put for c at 2N, read at 2N: c, then b yields nothing
+    r = kvfmt.Region()
+    for ts in range(B // 2):
+        r.rollback(b"b", ts)
+    r.put(b"c", b"value", 2 * B, 2 * B)
+    st, rows, s = orc.mvcc_scan(r.build(read_ts=2 * B, check_newer=False), desc=True)
+    assert st == 0 and rows == [(_uk(b"c"), b"value")]
+    assert (s["write_seek"], s["write_seek_for_prev"], s["write_next"], s["write_prev"]) == (1, 0, 0, 1 + B // 2)
+    assert s["processed_size"] == len(_uk(b"c")) + 5
+    # 2: b has a put at ts 0 under N/2 rollbacks: it is found as the last version when prev() leaves the key space
+    r = kvfmt.Region()
+    r.put(b"b", b"value_b", 0, 0)
+    for ts in range(1, B // 2 + 1):
+        r.rollback(b"b", ts)
+    r.put(b"c", b"value_c", 2 * B, 2 * B)
+    st, rows, s = orc.mvcc_scan(r.build(read_ts=2 * B, check_newer=False), desc=True)
+    assert st == 0 and rows == [(_uk(b"c"), b"value_c"), (_uk(b"b"), b"value_b")]
+    assert (s["write_seek"], s["write_seek_for_prev"], s["write_next"], s["write_prev"]) == (1, 0, 0, 1 + B // 2 + 1)
+    # 3: move_write_cursor_to_prev_user_key leaves the key space while skipping b's newer versions
+    r = kvfmt.Region()
+    r.put(b"c", b"value", 1, 1)
+    for ts in range(1, SB // 2 + 1):
+        r.put(b"b", bytes([ts]), ts, ts)
+    st, rows, s = orc.mvcc_scan(r.build(read_ts=1, check_newer=False), desc=True)
+    assert st == 0 and rows == [(_uk(b"c"), b"value"), (_uk(b"b"), bytes([1]))]
+    assert (s["write_seek"], s["write_seek_for_prev"], s["write_next"], s["write_prev"]) == (1, 0, 0, 1 + SB // 2)
+
+
+def test_desc_table_scan_is_the_reversed_scan():
+    """TableScan.desc (scan_executor.rs:89-101: ranges reversed, each scanned backward): the rows of the ascending scan in
+    reverse order, through selection too; aggregates do not depend on the direction."""
+    import scenarios as sc
+    from tikv_b200.plan import gt
+    for seed in (1, 2, 3):
+        region = sc.dirty_region(seed).build(read_ts=sc.READ_TS, n_write_blocks=2)
+        for ranges in (sc.WHOLE, sc.split_ranges()):
+            asc = Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(gt(col(sc.C6, tp=ffi.TP_LONG), const_int(3))).build()
+            desc = Plan().table_scan(sc.TABLE, sc.COLUMNS, desc=True).selection(gt(col(sc.C6, tp=ffi.TP_LONG), const_int(3))).build()
+            a, d = orc.dag_handle(asc, ranges, region), orc.dag_handle(desc, ranges, region)
+            assert a.status == 0 == d.status and a.n_rows > 50
+            assert d.rows() == a.rows()[::-1]
+            assert d.stats["processed_keys"] == a.stats["processed_keys"] and d.stats["processed_size"] == a.stats["processed_size"]
