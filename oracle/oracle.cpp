@@ -36,7 +36,10 @@ struct orc_result {
 
 static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src,
                             CfView* w, CfView* l, CfView* d, std::unique_ptr<Executor>* out, TableScanExecutor** scan_out, Error* err) {
-  if (plan->n_executors == 0 || plan->executors[0].tp != B2_EXEC_TABLE_SCAN) { *err = Error::make(B2_ERR_UNSUPPORTED, "first executor must be TableScan"); return false; }
+  if (plan->n_executors == 0 || (plan->executors[0].tp != B2_EXEC_TABLE_SCAN && plan->executors[0].tp != B2_EXEC_INDEX_SCAN)) {
+    *err = Error::make(B2_ERR_UNSUPPORTED, "first executor must be TableScan or IndexScan");
+    return false;
+  }
   auto scan = std::make_unique<TableScanExecutor>();
   scan->init(plan->executors[0]);
   w->init(src->write, src->n_write);

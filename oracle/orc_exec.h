@@ -219,8 +219,64 @@ struct TableScanExecutor : Executor {
   Bytes datum_buf_;
   RangesScanner rs;
   bool ended = false;
+  // BatchIndexScanExecutor (index_scan_executor.rs:47-170), old-format values only (value.len() <= 9, :375-379): the
+  // index columns come from the key's datums, the int handle from the key tail (non-unique index) or from the value
+  // (unique index); the PK handle, if requested, is the last column before the optional physical-table-id column.
+  bool is_index = false;
+  size_t idx_cols_without_handle = 0;
+  bool idx_decode_int_handle = false, idx_physical_table_id = false;
+
+  void init_index(const b2_executor_desc& d) {
+    is_index = true;
+    for (uint32_t i = 0; i < d.n_columns; ++i) { FieldType ft; ft.tp = d.columns[i].tp; ft.flag = d.columns[i].flag; schema_.push_back(ft); }
+    size_t n = d.n_columns;
+    idx_physical_table_id = n > 0 && d.columns[n - 1].col_id == B2_EXTRA_PHYSICAL_TABLE_ID_COL_ID;
+    size_t tail = idx_physical_table_id ? 1 : 0;
+    idx_decode_int_handle = n > tail && d.columns[n - 1 - tail].pk_handle;
+    idx_cols_without_handle = n - tail - (idx_decode_int_handle ? 1 : 0);
+    is_column_filled.assign(n, 0);
+  }
+
+  // process_kv_pair :363-380 -> process_old_collation_kv :514-574
+  bool process_index_kv(Slice key, Slice value, std::vector<LazyColumn>& columns, std::string* err) {
+    if (key.n < 1 || key[0] != 't') { *err = "record or index key expected"; return false; }  // check_index_key table.rs:114-140
+    if (key.n < 11) { *err = "unexpected eof"; return false; }
+    if (key[9] != '_' || key[10] != 'i') { *err = "expected key sep type _i"; return false; }
+    if (key.n < 19) { *err = "unexpected eof"; return false; }
+    if (value.n > 9) { *err = "index value in the new (restored-data) layout is not restated"; return false; }
+    Slice payload = key.sub(19);
+    for (size_t i = 0; i < idx_cols_without_handle; ++i) {  // extract_columns_from_datum_format :493-506
+      if (payload.empty()) { *err = std::to_string(i) + "th column is missing value"; return false; }
+      size_t dl = split_datum(payload, err);
+      if (!dl) return false;
+      columns[i].raw_push(payload.sub(0, dl));
+      payload = payload.sub(dl);
+    }
+    if (idx_decode_int_handle) {
+      int64_t handle;
+      if (payload.empty()) {  // unique index: decode_int_handle_from_value :406-412 (plain big-endian u64)
+        if (value.n < 8) { *err = "Failed to decode handle in value as i64"; return false; }
+        uint64_t u = 0; for (int b = 0; b < 8; ++b) u = (u << 8) | value[b];
+        handle = (int64_t)u;
+      } else {  // non-unique index: decode_int_handle_from_key :451-471
+        uint8_t flag = payload[0];
+        if (flag != INT_FLAG && flag != UINT_FLAG) { *err = "Unexpected handle flag " + std::to_string(flag); return false; }
+        if (payload.n < 9) { *err = flag == INT_FLAG ? "Failed to decode handle in key as i64" : "Failed to decode handle in key as u64"; return false; }
+        uint64_t u = 0; for (int b = 0; b < 8; ++b) u = (u << 8) | payload[1 + b];
+        handle = flag == INT_FLAG ? (int64_t)(u ^ 0x8000000000000000ull) : (int64_t)u;
+      }
+      columns[idx_cols_without_handle].push_int(true, handle);
+    }
+    if (idx_physical_table_id) {  // process_physical_table_id_column: the table id of the key prefix
+      int64_t tid; const char* e = decode_table_id(key, &tid);
+      if (e) { *err = e; return false; }
+      columns[columns.size() - 1].push_int(true, tid);
+    }
+    return true;
+  }
 
   void init(const b2_executor_desc& d) {
+    if (d.tp == B2_EXEC_INDEX_SCAN) { init_index(d); return; }
     for (uint32_t i = 0; i < d.n_columns; ++i) {
       const b2_column_info& ci = d.columns[i];
       FieldType ft; ft.tp = ci.tp; ft.flag = ci.flag;
@@ -236,6 +292,7 @@ struct TableScanExecutor : Executor {
   ForwardScanner* scanner() override { return &rs.fs; }
 
   bool is_decoded_col(size_t i) const {
+    if (is_index) return i >= idx_cols_without_handle;
     for (size_t h : handle_indices) if (h == i) return true;
     auto a = column_id_index.find(B2_EXTRA_PHYSICAL_TABLE_ID_COL_ID);
     if (a != column_id_index.end() && a->second == i) return true;
@@ -408,7 +465,8 @@ struct TableScanExecutor : Executor {
       if (r < 0) { out->err = e; break; }
       if (r == 0) { out->is_drained = true; break; }
       std::string perr;
-      if (!process_kv_pair(Slice(raw_key.data(), raw_key.size()), Slice(so.value.data(), so.value.size()), out->cols, so.has_commit_ts, so.commit_ts, &perr)) {
+      const Slice rk(raw_key.data(), raw_key.size()), rv(so.value.data(), so.value.size());
+      if (!(is_index ? process_index_kv(rk, rv, out->cols, &perr) : process_kv_pair(rk, rv, out->cols, so.has_commit_ts, so.commit_ts, &perr))) {
         // truncate_into_equal_length (lazy_column_vec.rs:210-220)
         size_t m = (size_t)-1;
         for (auto& c : out->cols) m = std::min(m, c.len());

@@ -410,3 +410,9 @@ def dec_bytes_memcmp(enc):
         pos += 9
         if pad:
             return out
+
+
+def index_key(table_id, index_id, payload=b""):
+    """t{table_id}_i{index_id}{payload}: payload = the index columns as memcomparable datums (+ the handle datum for a
+    non-unique index) — table.rs encode_index_seek_key."""
+    return b"t" + enc_i64_cmp(table_id) + b"_i" + enc_i64_cmp(index_id) + payload

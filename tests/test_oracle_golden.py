@@ -544,3 +544,56 @@ def test_desc_table_scan_is_the_reversed_scan():
             assert a.status == 0 == d.status and a.n_rows > 50
             assert d.rows() == a.rows()[::-1]
             assert d.stats["processed_keys"] == a.stats["processed_keys"] and d.stats["processed_size"] == a.stats["processed_size"]
+
+
+def _index_fixture():
+    """index_scan_executor.rs test_basic :1081-1146: TABLE_ID 3, INDEX_ID 42, (i64, f64, handle) entries of a non-unique index."""
+    T, IDX = 3, 42
+    data = [(-5, 0.3, 10), (5, 5.1, 5), (5, 10.5, 2)]
+    r = kvfmt.Region()
+    for a, b, h in data:
+        payload = kvfmt.datum_int(a, comparable=True) + kvfmt.datum_f64(b) + kvfmt.datum_int(h, comparable=True)
+        r.put(kvfmt.index_key(T, IDX, payload), b"0", 1, 2)
+    c0, c1 = ColumnDef(1), ColumnDef(2, tp=ffi.TP_DOUBLE)
+    handle, phys = ColumnDef(3, pk_handle=True), ColumnDef(-3)
+    whole = [(kvfmt.index_key(T, IDX), kvfmt.index_key(T, IDX, b"\xfa"))]  # [Datum::Min, Datum::Max)
+    return T, IDX, r.build(read_ts=10), (c0, c1, handle, phys), whole
+
+
+def test_index_scan_fixture():
+    """index_scan_executor.rs test_basic :1148-1460: index columns only (backward), with the physical table id column,
+    with the int handle taken from the key tail (forward, from a start datum)."""
+    T, IDX, region, (c0, c1, handle, phys), whole = _index_fixture()
+    res = orc.dag_handle(Plan().index_scan(T, [c0, c1], desc=True).build(), whole, region)
+    assert res.status == 0 and res.columns == [[5, 5, -5], [10.5, 5.1, 0.3]]
+    res = orc.dag_handle(Plan().index_scan(T, [c0, c1, phys], desc=True).build(), whole, region)
+    assert res.status == 0 and res.columns == [[5, 5, -5], [10.5, 5.1, 0.3], [T, T, T]]
+    from_five = [(kvfmt.index_key(T, IDX, kvfmt.datum_int(5, comparable=True)), kvfmt.index_key(T, IDX, b"\xfa"))]
+    res = orc.dag_handle(Plan().index_scan(T, [c0, c1, handle]).build(), from_five, region)
+    assert res.status == 0 and res.columns == [[5, 5], [5.1, 10.5], [5, 2]]
+    # a selection on top works like on a table scan
+    res = orc.dag_handle(Plan().index_scan(T, [c0, c1, handle]).selection(lt(col(2), const_int(6))).build(), whole, region)
+    assert res.status == 0 and res.rows() == [(5, 5.1, 5), (5, 10.5, 2)]
+
+
+def test_index_scan_unique_and_errors():
+    """Unique index: the handle is the 8-byte big-endian value (:406-412, :543-552); a key that runs out of datums
+    (":493-500 {}th column is missing value"), a handle datum with the wrong flag (:461-470), a record key (:370)."""
+    T, IDX = 7, 2
+    r = kvfmt.Region()
+    for a, h in ((1, 100), (2, -3), (9, 1 << 40)):
+        r.put(kvfmt.index_key(T, IDX, kvfmt.datum_int(a, comparable=True)), (h & ((1 << 64) - 1)).to_bytes(8, "big"), 1, 2)
+    whole = [(kvfmt.index_key(T, IDX), kvfmt.index_key(T, IDX, b"\xfa"))]
+    cols = [ColumnDef(1), ColumnDef(2, pk_handle=True)]
+    res = orc.dag_handle(Plan().index_scan(T, cols).build(), whole, r.build(read_ts=10))
+    assert res.status == 0 and res.rows() == [(1, 100), (2, -3), (9, 1 << 40)]
+    res = orc.dag_handle(Plan().index_scan(T, [ColumnDef(1), ColumnDef(5), ColumnDef(2, pk_handle=True)]).build(), whole, r.build(read_ts=10))
+    assert res.status == ffi.B2_ERR_CORRUPTED and "1th column is missing value" in res.message
+    bad = kvfmt.Region()
+    bad.put(kvfmt.index_key(T, IDX, kvfmt.datum_int(1, comparable=True) + kvfmt.datum_f64(2.0)), b"0", 1, 2)
+    res = orc.dag_handle(Plan().index_scan(T, cols).build(), whole, bad.build(read_ts=10))
+    assert res.status == ffi.B2_ERR_CORRUPTED and "Unexpected handle flag 5" in res.message
+    rec = kvfmt.Region()
+    rec.put(kvfmt.row_key(T, 1), kvfmt.row_v2([(1, 5, "int")]), 1, 2)
+    res = orc.dag_handle(Plan().index_scan(T, cols).build(), [kvfmt.table_range(T)], rec.build(read_ts=10))
+    assert res.status == ffi.B2_ERR_CORRUPTED and "_i" in res.message

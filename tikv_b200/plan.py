@@ -164,6 +164,14 @@ class Plan:
         self._execs.append(e)
         return self
 
+    def index_scan(self, table_id, columns, desc=False):
+        """BatchIndexScanExecutor: `columns` are the index columns in index order, then optionally the PK handle
+        (pk_handle=True), then optionally the physical table id column (col_id -3).  Oracle only so far: the device path
+        answers B2_ERR_UNSUPPORTED."""
+        self.table_scan(table_id, columns, desc)
+        self._execs[-1].tp = ffi.EXEC_INDEX_SCAN
+        return self
+
     def selection(self, *conds):
         arr = (ffi.RpnExpr * len(conds))(*[self._expr(c) for c in conds])
         self._keep.append(arr)
