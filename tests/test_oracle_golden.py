@@ -597,3 +597,18 @@ def test_index_scan_unique_and_errors():
     rec.put(kvfmt.row_key(T, 1), kvfmt.row_v2([(1, 5, "int")]), 1, 2)
     res = orc.dag_handle(Plan().index_scan(T, cols).build(), [kvfmt.table_range(T)], rec.build(read_ts=10))
     assert res.status == ffi.B2_ERR_CORRUPTED and "_i" in res.message
+
+
+def test_backward_scanner_range():
+    """backward.rs test_range :1289-1417: three versions per key (empty value at ts 1 and 14, [i] at ts 7), read at ts 10,
+    bounded and unbounded ranges, processed_size per scan."""
+    r = kvfmt.Region()
+    for i in range(1, 7):
+        r.put(bytes([i]), b"", 1, 1).put(bytes([i]), bytes([i]), 7, 7).put(bytes([i]), b"", 14, 14)
+    region = r.build(read_ts=10)
+    k = lambda i: _uk(bytes([i]))
+    for lo, hi, want in ((k(3), k(5), [4, 3]), (None, k(3), [2, 1]), (k(5), None, [6, 5]), (None, None, [6, 5, 4, 3, 2, 1])):
+        st, rows, stats = orc.mvcc_scan(region, lo, hi, desc=True)
+        assert st == 0 and rows == [(k(i), bytes([i])) for i in want]
+        assert stats["processed_size"] == sum(len(k(i)) + 1 for i in want)
+        assert stats["met_newer"] == 1  # the ts-14 versions
