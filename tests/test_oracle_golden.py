@@ -612,3 +612,37 @@ def test_backward_scanner_range():
         assert st == 0 and rows == [(k(i), bytes([i])) for i in want]
         assert stats["processed_size"] == sum(len(k(i)) + 1 for i in want)
         assert stats["met_newer"] == 1  # the ts-14 versions
+
+
+def test_index_scan_random_entries():
+    """Seeded random non-unique index over (nullable i64, u64) with the handle in the key: ascending and descending scans
+    return the entries in memcomparable key order, NULLs first, unsigned columns as unsigned; a selection sees the decoded
+    values."""
+    import random
+    rng = random.Random(5)
+    T, IDX = 11, 4
+    r = kvfmt.Region()
+    entries = []
+    for h in range(300):
+        a = None if rng.random() < 0.1 else rng.choice([rng.randrange(-(1 << 63), 1 << 63), rng.randrange(-5, 5)])
+        b = rng.choice([0, 1, (1 << 64) - 1, rng.randrange(0, 1 << 64)])
+        payload = (kvfmt.datum_null() if a is None else kvfmt.datum_int(a, comparable=True)) + kvfmt.datum_uint(b, comparable=True) + kvfmt.datum_int(h, comparable=True)
+        key = kvfmt.index_key(T, IDX, payload)
+        r.put(key, b"0", 3, 4)
+        if rng.random() < 0.2:
+            r.put(key, b"0", 50, 60)      # a newer version than read_ts: the entry is still visible through the old one
+        if rng.random() < 0.1:
+            r.delete(key, 5, 6)           # deleted before read_ts: invisible
+            continue
+        entries.append((key, a, b - (1 << 64) if b >= (1 << 63) else b, h))
+    entries.sort()
+    region = r.build(read_ts=10)
+    cols = [ColumnDef(1), ColumnDef(2, unsigned=True), ColumnDef(3, pk_handle=True)]
+    whole = [(kvfmt.index_key(T, IDX), kvfmt.index_key(T, IDX, b"\xfa"))]
+    want = [(a, b, h) for _, a, b, h in entries]
+    asc = orc.dag_handle(Plan().index_scan(T, cols).build(), whole, region)
+    assert asc.status == 0 and asc.rows() == want and len(want) > 200
+    desc = orc.dag_handle(Plan().index_scan(T, cols, desc=True).build(), whole, region)
+    assert desc.status == 0 and desc.rows() == want[::-1]
+    sel = orc.dag_handle(Plan().index_scan(T, cols).selection(lt(col(0), const_int(0))).build(), whole, region)
+    assert sel.rows() == [t for t in want if t[0] is not None and t[0] < 0]
