@@ -269,3 +269,46 @@ def test_projection(name, plan, regions):
 
 def test_scalar_function_known_answers():
     sc.check_scalar_known_answers(emu.dag_handle)
+
+
+def test_plan_limits_are_reported_not_crashed():
+    """Plans beyond the device path's static limits (plan_compile.h) come back as B2_ERR_UNSUPPORTED / INVALID_ARG with a
+    message — the host then keeps the CPU executors — instead of overrunning a fixed-size table."""
+    from tikv_b200.plan import case_when, fn, if_, plus
+    scan = lambda: Plan().table_scan(sc.TABLE, sc.COLUMNS)
+    c2, c6 = col(sc.C2), col(sc.C6, tp=ffi.TP_LONG)
+    deep = c2
+    for _ in range(40):  # left-deep: few stack slots, many nodes
+        deep = plus(deep, const_int(1))
+    right = const_int(0)
+    for _ in range(20):  # right-deep: the RPN stack grows with every level
+        right = plus(c2, right)
+    cases = {
+        "too many nodes": scan().selection(*[lt(deep, const_int(5)) for _ in range(3)]).build(),
+        "expression too deep": scan().selection(lt(right, const_int(5))).build(),
+        "nine conditions": scan().selection(*[lt(c2, const_int(i)) for i in range(9)]).build(),
+        "nine aggregates": scan().aggregation([("count", c2)] * 9).build(),
+        "five group-by": scan().aggregation([("count", c2)], group_by=[c2, c6, c2, c6, c2]).build(),
+        "five order-by": scan().topn([(c2, False)] * 5, 10).build(),
+        "topn limit": scan().topn([(c2, False)], 5000).build(),
+        "17 projections": scan().projection(*[c2] * 17).build(),
+        "if arity": scan().selection(fn("IF_INT", c2, c6)).build(),
+        "case_when cond type": scan().selection(case_when(col(sc.C4, tp=ffi.TP_DOUBLE), c2)).build(),
+        "cmp arg type": scan().selection(fn("LT_INT", c2, col(sc.C4, tp=ffi.TP_DOUBLE))).build(),
+        "compare arity": scan().selection(fn("LT_INT", c2)).build(),
+        "output offset": scan().build(output_offsets=[99]),
+        "projection then selection": scan().projection(c2).selection(lt(col(0), const_int(1))).build(),
+    }
+    for what, plan in cases.items():
+        rc, msg = emu.check_supported(plan)
+        assert rc in (ffi.B2_ERR_UNSUPPORTED, ffi.B2_ERR_INVALID_ARG) and msg, (what, rc, msg)
+    # and the limits themselves are usable
+    ok = {
+        "eight conditions": scan().selection(*[lt(c2, const_int(i)) for i in range(8)]).build(),
+        "four group-by": scan().aggregation([("count", c2)], group_by=[c2, c6, c2, c6]).build(),
+        "16 projections": scan().projection(*[c2] * 16).build(),
+        "if": scan().selection(if_(c2, c6, c2)).build(),
+    }
+    for what, plan in ok.items():
+        rc, msg = emu.check_supported(plan)
+        assert rc == 0, (what, msg)
