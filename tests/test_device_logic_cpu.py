@@ -274,7 +274,7 @@ def test_scalar_function_known_answers():
 def test_plan_limits_are_reported_not_crashed():
     """Plans beyond the device path's static limits (plan_compile.h) come back as B2_ERR_UNSUPPORTED / INVALID_ARG with a
     message — the host then keeps the CPU executors — instead of overrunning a fixed-size table."""
-    from tikv_b200.plan import case_when, fn, if_, plus
+    from tikv_b200.plan import Expr, case_when, fn, if_, plus
     scan = lambda: Plan().table_scan(sc.TABLE, sc.COLUMNS)
     c2, c6 = col(sc.C2), col(sc.C6, tp=ffi.TP_LONG)
     deep = c2
@@ -296,6 +296,8 @@ def test_plan_limits_are_reported_not_crashed():
         "case_when cond type": scan().selection(case_when(col(sc.C4, tp=ffi.TP_DOUBLE), c2)).build(),
         "cmp arg type": scan().selection(fn("LT_INT", c2, col(sc.C4, tp=ffi.TP_DOUBLE))).build(),
         "compare arity": scan().selection(fn("LT_INT", c2)).build(),
+        "unknown sig": scan().selection(Expr(ffi.RPN_FN, ffi.TP_LONGLONG, sig=999999, args=(c2,))).build(),
+        "varchar NULL constant": scan().selection(lt(c2, Expr(ffi.RPN_CONST_NULL, ffi.TP_VARCHAR))).build(),
         "output offset": scan().build(output_offsets=[99]),
         "projection then selection": scan().projection(c2).selection(lt(col(0), const_int(1))).build(),
     }
