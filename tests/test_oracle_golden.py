@@ -646,3 +646,29 @@ def test_index_scan_random_entries():
     assert desc.status == 0 and desc.rows() == want[::-1]
     sel = orc.dag_handle(Plan().index_scan(T, cols).selection(lt(col(0), const_int(0))).build(), whole, region)
     assert sel.rows() == [t for t in want if t[0] is not None and t[0] < 0]
+
+
+def test_rc_check_ts_fixtures_forward_and_backward():
+    """forward.rs test_rc_read_check_ts :1561-1646 and backward.rs :1489-1575: under RcCheckTs a committed version newer
+    than the read ts or a Put-type lock is a write conflict; Lock-type and pessimistic locks are passed over."""
+    put_lock = lambda k, ts: kvfmt.lock_record(b"P", k, ts, short_value=b"x")
+    r = kvfmt.Region()
+    r.put(b"k0", b"v0", 1, 5).put(b"k1", b"v1", 10, 20).put(b"k2", b"v2", 30, 40).put(b"k2", b"v22", 41, 42).put(b"k3", b"v3", 50, 51)
+    r.put(b"k4", b"val4", 55, 56).add_lock(b"k4", kvfmt.lock_record(b"L", b"k4", 60))
+    r.put(b"k5", b"val5", 57, 58).add_lock(b"k5", kvfmt.lock_record(b"S", b"k5", 65, for_update_ts=65))
+    r.add_lock(b"k6", put_lock(b"k6", 75))
+    st, rows, _ = orc.mvcc_scan(r.build(read_ts=35, isolation=ffi.ISO_RC_CHECK_TS))
+    assert st == ffi.B2_ERR_WRITE_CONFLICT and rows == [(_uk(b"k0"), b"v0"), (_uk(b"k1"), b"v1")]
+    st, rows, _ = orc.mvcc_scan(r.build(read_ts=70, isolation=ffi.ISO_RC_CHECK_TS))
+    assert st == ffi.B2_ERR_WRITE_CONFLICT
+    assert rows == [(_uk(b"k0"), b"v0"), (_uk(b"k1"), b"v1"), (_uk(b"k2"), b"v22"), (_uk(b"k3"), b"v3"), (_uk(b"k4"), b"val4"), (_uk(b"k5"), b"val5")]
+    b = kvfmt.Region()
+    b.add_lock(b"k0", put_lock(b"k0", 60))
+    b.put(b"k1", b"v1", 25, 30).put(b"k2", b"v2", 6, 9).put(b"k2", b"v22", 10, 20).put(b"k3", b"v3", 5, 6)
+    b.put(b"k4", b"val4", 3, 4).add_lock(b"k4", kvfmt.lock_record(b"L", b"k4", 5))
+    b.put(b"k5", b"val5", 1, 2).add_lock(b"k5", kvfmt.lock_record(b"S", b"k5", 3, for_update_ts=3))
+    want = [(_uk(b"k5"), b"val5"), (_uk(b"k4"), b"val4"), (_uk(b"k3"), b"v3"), (_uk(b"k2"), b"v22")]
+    st, rows, _ = orc.mvcc_scan(b.build(read_ts=29, isolation=ffi.ISO_RC_CHECK_TS), desc=True)
+    assert st == ffi.B2_ERR_WRITE_CONFLICT and rows == want            # k1's commit ts 30 > 29
+    st, rows, _ = orc.mvcc_scan(b.build(read_ts=55, isolation=ffi.ISO_RC_CHECK_TS), desc=True)
+    assert st == ffi.B2_ERR_WRITE_CONFLICT and rows == want + [(_uk(b"k1"), b"v1")]  # then k0's Put lock
