@@ -672,3 +672,26 @@ def test_rc_check_ts_fixtures_forward_and_backward():
     assert st == ffi.B2_ERR_WRITE_CONFLICT and rows == want            # k1's commit ts 30 > 29
     st, rows, _ = orc.mvcc_scan(b.build(read_ts=55, isolation=ffi.ISO_RC_CHECK_TS), desc=True)
     assert st == ffi.B2_ERR_WRITE_CONFLICT and rows == want + [(_uk(b"k1"), b"v1")]  # then k0's Put lock
+
+
+def test_gc_fence_fixture_forward_and_backward():
+    """forward.rs prepare_test_data_for_check_gc_fence :1064-1160 (test_latest_kv_check_gc_fence :1537, backward.rs
+    test_backward_scanner_check_gc_fence :1463): versions whose gc fence is at or below the read ts (40) are invisible,
+    a fence of 0 or above the read ts leaves them visible, Lock records above the fenced version are skipped first."""
+    r = kvfmt.Region()
+    f = dict(overlapped_rollback=True)
+    r.put(b"k1", b"v1", 10, 20, gc_fence=50, **f).put(b"k1", b"v1x", 49, 50)
+    r.put(b"k2", b"v2", 11, 20, gc_fence=40, **f)
+    r.put(b"k3", b"v3", 12, 20, gc_fence=30, **f)
+    r.put(b"k4", b"v4", 13, 14, gc_fence=20, **f).put(b"k4", b"v4x", 15, 20, gc_fence=30, **f)
+    r.put(b"k5", b"v5", 13, 14, gc_fence=20, **f).delete(b"k5", 15, 20, gc_fence=30, **f)
+    r.put(b"k6", b"v6", 16, 20, gc_fence=50, **f).lock_rec(b"k6", 25, 26).lock_rec(b"k6", 28, 29).put(b"k6", b"v6x", 49, 50)
+    r.put(b"k7", b"v7", 16, 20, gc_fence=27, **f).lock_rec(b"k7", 25, 26).lock_rec(b"k7", 28, 29)
+    r.put(b"k8", b"v8", 17, 30, gc_fence=0, **f)
+    r.put(b"k9", b"v9", 18, 20, gc_fence=27, **f).lock_rec(b"k9", 25, 26)
+    want = [(_uk(b"k1"), b"v1"), (_uk(b"k6"), b"v6"), (_uk(b"k8"), b"v8")]
+    region = r.build(read_ts=40)
+    st, rows, _ = orc.mvcc_scan(region)
+    assert st == 0 and rows == want
+    st, rows, _ = orc.mvcc_scan(region, desc=True)
+    assert st == 0 and rows == want[::-1]
