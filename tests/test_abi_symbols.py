@@ -74,3 +74,13 @@ def test_open_fails_loudly_without_cuda(lib):
     with pytest.raises(B2Error) as ei:
         BatchExecutor(p, [kvfmt.table_range(5)], r)
     assert ei.value.status == ffi.B2_ERR_CUDA and "no CPU fallback" in ei.value.message
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/b2_copr.h is what cgo / bindgen / a C host would consume: it must compile as C11 with -pedantic."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "b2_copr.h"\nint main(void) { return (int)sizeof(b2_exec_config) == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
