@@ -84,3 +84,38 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_ctypes_mirror_matches_header_layout(tmp_path):
+    """Every struct of include/b2_copr.h against its ctypes mirror in tikv_b200/ffi.py: total size and the offset of every
+    field, taken from a C program compiled against the header (what bindgen would see)."""
+    import subprocess
+    from tikv_b200 import ffi
+    pairs = {"b2_cf_block": ffi.CfBlock, "b2_region_source": ffi.RegionSource, "b2_key_range": ffi.KeyRange, "b2_column_info": ffi.ColumnInfo,
+             "b2_rpn_node": ffi.RpnNode, "b2_rpn_expr": ffi.RpnExpr, "b2_aggr_desc": ffi.AggrDesc, "b2_order_by": ffi.OrderBy,
+             "b2_executor_desc": ffi.ExecutorDesc, "b2_dag_plan": ffi.DagPlan, "b2_exec_config": ffi.ExecConfig, "b2_decimal": ffi.Decimal,
+             "b2_column": ffi.Column, "b2_batch": ffi.Batch, "b2_exec_stats": ffi.ExecStats, "b2_error_info": ffi.ErrorInfo,
+             "b2_checksum_response": ffi.ChecksumResponse, "b2_agg_partials": ffi.AggPartials, "b2_gen_spec": ffi.GenSpec,
+             "b2_gen_block": ffi.GenBlock, "b2_encoded_chunk": ffi.EncodedChunk}
+    header = open(os.path.join(ROOT, "include", "b2_copr.h")).read()
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b2_copr.h"', 'int main(void) {']
+    expect = {}
+    for cname, mirror in pairs.items():
+        m = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, re.S)
+        assert m, cname
+        body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+        names = [re.sub(r"\[.*\]", "", part.strip().split()[-1].lstrip("*")) for d in body.split(";") if d.strip() for part in d.split(",")]
+        assert names == [f[0] for f in mirror._fields_], (cname, names, [f[0] for f in mirror._fields_])
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for n in names:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {n}));')
+        lines.append('  printf("\\n");')
+        expect[cname] = [C.sizeof(mirror)] + [getattr(mirror, n).offset for n in names]
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True)
+    got = {l.split()[0]: [int(x) for x in l.split()[1:]] for l in out.splitlines()}
+    assert got == expect
