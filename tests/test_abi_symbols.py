@@ -119,3 +119,23 @@ def test_ctypes_mirror_matches_header_layout(tmp_path):
     out = subprocess.check_output([str(exe)], text=True)
     got = {l.split()[0]: [int(x) for x in l.split()[1:]] for l in out.splitlines()}
     assert got == expect
+
+
+def test_integration_doc_structs_follow_header():
+    """The #[repr(C)] structs shown in INTEGRATION.md list the header's fields in the header's order (a trailing `_` is
+    allowed where the C name is a Rust type name), and every entry point of the header is bound or named there."""
+    header = open(os.path.join(ROOT, "include", "b2_copr.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    n = 0
+    for m in re.finditer(r"pub struct (b2_\w+) \{(.*?)\}", doc, re.S):
+        name, body = m.group(1), m.group(2)
+        fields = [re.sub(r"^pub\s+", "", f.strip()).split(":")[0].strip().rstrip("_") or "_" for f in re.split(r",(?![^\[]*\])", body) if ":" in f]
+        h = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), header, re.S)
+        assert h, name
+        hb = re.sub(r"/\*.*?\*/", "", h.group(1), flags=re.S)
+        hf = [re.sub(r"\[.*\]", "", part.strip().split()[-1].lstrip("*")) for d in hb.split(";") if d.strip() for part in d.split(",")]
+        assert [f if f.startswith("_") else f for f in fields] == [x.rstrip("_") if not x.startswith("_") else x for x in hf], (name, fields, hf)
+        n += 1
+    assert n >= 12
+    for fn_name in set(re.findall(r"\b(b2_[a-z_]+)\(", header)):
+        assert fn_name in doc, fn_name
