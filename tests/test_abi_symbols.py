@@ -139,3 +139,24 @@ def test_integration_doc_structs_follow_header():
     assert n >= 12
     for fn_name in set(re.findall(r"\b(b2_[a-z_]+)\(", header)):
         assert fn_name in doc, fn_name
+
+
+def test_product_path_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under tikv_b200/ (the shipped package and its CUDA sources) may import,
+    link or mention it, except smoke.py, which is __graft_entry__.smoke()'s checker; libb2copr.so must not depend on it."""
+    import subprocess
+    pat = re.compile(r"\boracle\b|liborc|\bimport orc\b|\borc\.")
+    pkg = os.path.join(ROOT, "tikv_b200")
+    offenders = []
+    for d, _, fs in os.walk(pkg):
+        if "_build" in d or "__pycache__" in d:
+            continue
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")) and f != "smoke.py":
+                text = open(os.path.join(d, f), errors="replace").read()
+                if pat.search(text):
+                    offenders.append(os.path.relpath(os.path.join(d, f), ROOT))
+    assert not offenders, offenders
+    so = os.path.join(pkg, "_build", "libb2copr.so")
+    needed = subprocess.check_output(["readelf", "-d", so], text=True)
+    assert "liborc" not in needed and "libemu" not in needed
