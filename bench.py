@@ -160,6 +160,10 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_name(row_format):
+    return f"C2: BatchTableScan + BatchSelection(col0 < 0) on 1e8 rows x 8 i64 cols, row format v{row_format}, 1 version/key (BASELINE.json configs[1])"
+
+
 def usable_cores():
     """Host threads this process may actually run at once: the affinity mask, capped by the cgroup CPU quota (a
     container can see 128 CPUs and be allowed 32 of them; oversubscribing would understate the CPU arm)."""
@@ -183,14 +187,14 @@ def usable_cores():
     return max(1, n)
 
 
-def cpu_reference_run(ffi, device, sample_rows, threads, steps, warmup):
+def cpu_reference_run(ffi, device, sample_rows, threads, steps, warmup, row_format=2):
     """The CPU arm: oracle (C++ restatement of the reference BatchExecutor pipeline), one region task per thread."""
     import orc
     L = orc.lib()
     plan = build_plan()
     from tikv_b200.plan import key_ranges
     kr, keep = key_ranges(table_range())
-    gens, blks = gen_blocks(ffi, device, sample_rows, 1)
+    gens, blks = gen_blocks(ffi, device, sample_rows, 1, row_format=row_format)
     host_blocks, pinned = blocks_to_pinned_host(ffi, device, blks)
     for g in gens:
         ffi.lib().b2_gen_destroy(g)
@@ -253,13 +257,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_run(ffi, device, args.cpu_sample_rows, cores, args.steps, args.warmup)
+        r = cpu_reference_run(ffi, device, args.cpu_sample_rows, cores, args.steps, args.warmup, args.row_format)
         line = {
             "impl": "reference", "metric": METRIC, "value": r["rows_per_s"], "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic",
-            "config": {"workload": "C2: BatchTableScan + BatchSelection(col0 < 0) on 8 x i64 columns, row format v2 (bounded sample of the 1e8-row table)",
-                       "rows_per_step": r["rows"], "selectivity": 0.5},
+            "config": {"workload": workload_name(args.row_format), "rows_per_step": r["rows"], "selectivity": 0.5,
+                       "sample": f"each step = {cores} region tasks x {args.cpu_sample_rows} rows of that table (a bounded sample of the workload)"},
             "cpu_baseline": {"value": r["rows_per_s"], "unit": "rows/s", "cores": cores, "kind": "port",
                              "sample": f"{cores} region tasks x {args.cpu_sample_rows} rows, one task per thread (restated C++ CPU baseline, not the TiKV Rust binary)"},
             "e2e": {"value": r["rows_per_s"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -357,7 +361,7 @@ def main():
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        r = cpu_reference_run(ffi, device, args.cpu_sample_rows, cores, 1, 1)
+        r = cpu_reference_run(ffi, device, args.cpu_sample_rows, cores, 1, 1, args.row_format)
         cpu = {"value": r["rows_per_s"], "unit": "rows/s", "cores": cores, "kind": "port",
                "sample": f"{cores} region tasks x {args.cpu_sample_rows} rows of the same workload, one task per thread (restated C++ CPU baseline, not the TiKV Rust binary)"}
     if world > 1:
@@ -368,7 +372,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": f"C2: BatchTableScan + BatchSelection(col0 < 0) on 1e8 rows x 8 i64 cols, row format v{args.row_format}, 1 version/key (BASELINE.json configs[1])",
+        "config": {"workload": workload_name(args.row_format),
                    "rows_per_gpu": args.rows, "cf_write_entries_per_gpu": n_entries, "blocks_per_gpu": args.blocks, "entries_per_batch": args.chunk,
                    "selectivity": rows_out / max(1, args.rows), "parallelism": f"region-sharded x{world}, no data-path collective",
                    "l2": f"inputs {in_bytes / 1e9:.1f} GB per pass >> 126 MB L2 (no flush needed)", "setup_s": round(time.time() - t_setup, 1)},

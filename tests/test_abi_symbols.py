@@ -160,3 +160,24 @@ def test_product_path_never_touches_the_oracle():
     so = os.path.join(pkg, "_build", "libb2copr.so")
     needed = subprocess.check_output(["readelf", "-d", so], text=True)
     assert "liborc" not in needed and "libemu" not in needed
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """profiles/bench_r1.json and bench_reference_r1.json (the lines bench.py printed on the B200) carry every key of the
+    bench contract with sane types; the roofline fraction is achieved / peak."""
+    import json
+    ours = json.load(open(os.path.join(ROOT, "profiles", "bench_r1.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "roofline", "e2e", "cpu_baseline", "gpu_launches", "clocks"):
+        assert k in ours, k
+    assert ours["vs_baseline"] is None and ours["higher_is_better"] is True and ours["scaling"] == "weak" and "workload" in ours["config"]
+    rf = ours["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and rf["traffic"]
+    e = ours["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < ours["value"]
+    cb = ours["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] > 0
+    assert ours["gpu_launches"] > 0 and not ours["clocks"]["reasons"] and ours["clocks"]["sm_mhz"] > 0
+    ref = json.load(open(os.path.join(ROOT, "profiles", "bench_reference_r1.json")))
+    assert ref["impl"] == "reference" and ref["metric"] == ours["metric"] and ref["unit"] == ours["unit"] and ref["config"]["workload"].startswith("C2: BatchTableScan + BatchSelection(col0 < 0)")
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 == ref["e2e"]["d2h_bytes_per_step"] and ref["e2e"]["value"] == ref["value"] == ref["cpu_baseline"]["value"]
