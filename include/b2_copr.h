@@ -148,9 +148,9 @@ enum {
   B2_SIG_MULTIPLY_INT_UNSIGNED = 218,
   B2_SIG_LOGICAL_AND = 3101, B2_SIG_LOGICAL_OR = 3102, B2_SIG_LOGICAL_XOR = 3103,
   B2_SIG_UNARY_NOT_INT = 3104, B2_SIG_UNARY_NOT_REAL = 3106,
-  B2_SIG_REAL_IS_NULL = 3114, B2_SIG_INT_IS_NULL = 3116,
-  B2_SIG_INT_IS_TRUE = 3118, B2_SIG_REAL_IS_TRUE = 3119,
-  B2_SIG_INT_IS_FALSE = 3121, B2_SIG_REAL_IS_FALSE = 3122,
+  B2_SIG_REAL_IS_NULL = 3113, B2_SIG_INT_IS_NULL = 3116,
+  B2_SIG_INT_IS_TRUE = 3122, B2_SIG_REAL_IS_TRUE = 3123,
+  B2_SIG_INT_IS_FALSE = 3125, B2_SIG_REAL_IS_FALSE = 3126,
   B2_SIG_IN_INT = 4001, B2_SIG_IN_REAL = 4002, /* variadic: n_args = 1 + list length (impl_compare_in.rs) */
   /* impl_arithmetic.rs:215-290, 396-455 (signedness variants are picked from the arguments' UNSIGNED flags, like map_int_sig) */
   B2_SIG_INT_DIVIDE_INT = 213, B2_SIG_MOD_REAL = 215, B2_SIG_MOD_INT = 217,
@@ -435,6 +435,9 @@ int32_t b2_copy_to_host(int32_t device, void* dst, const void* src_device, uint6
 int32_t b2_copy_to_device(int32_t device, void* dst_device, const void* src, uint64_t bytes);
 int32_t b2_device_count(void);
 void* b2_host_alloc_pinned(uint64_t bytes);
+/* pinned host memory placed on the NUMA node `device` is attached to (falls back to b2_host_alloc_pinned) */
+void* b2_host_alloc_pinned_near(int32_t device, uint64_t bytes);
+int32_t b2_device_numa_node(int32_t device); /* -1 = unknown */
 void b2_host_free_pinned(void* p);
 
 #ifdef __cplusplus

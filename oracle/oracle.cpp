@@ -16,6 +16,7 @@
 
 #include "orc_exec.h"
 #include "orc_encode.h"
+#include "orc_gen.h"
 
 using namespace orc;
 
@@ -314,6 +315,74 @@ uint64_t orc_dag_handle_parallel(const b2_dag_plan* plan, const b2_key_range* ra
   return total;
 }
 
+
+// ---- bench.py's CPU arm: host-generated regions (orc_gen.h), one region task per thread ----------------------------
+// `n_tasks` regions of `rows_per_task` consecutive handles each, starting at spec->first_handle: the same table the device
+// generator of the product builds, so a GPU request over the same handles must return the same result.
+struct orc_bench {
+  std::vector<GenBlock> blocks;
+  std::vector<b2_cf_block> views;
+  std::vector<b2_region_source> srcs;
+};
+orc_bench* orc_bench_create(const b2_gen_spec* spec, uint32_t n_tasks, uint64_t rows_per_task, uint64_t read_ts, uint32_t n_threads) {
+  orc_bench* h = new orc_bench();
+  h->blocks.resize(n_tasks); h->views.resize(n_tasks); h->srcs.resize(n_tasks);
+  std::vector<std::thread> th;
+  std::atomic<uint32_t> next{0};
+  for (uint32_t t = 0; t < std::max(1u, n_threads); ++t)
+    th.emplace_back([&]() {
+      for (;;) {
+        uint32_t i = next.fetch_add(1);
+        if (i >= n_tasks) break;
+        b2_gen_spec s = *spec;
+        s.first_handle = spec->first_handle + (uint64_t)i * rows_per_task;
+        s.n_rows = rows_per_task;
+        gen_block(s, &h->blocks[i]);
+      }
+    });
+  for (auto& x : th) x.join();
+  for (uint32_t i = 0; i < n_tasks; ++i) {
+    h->views[i] = h->blocks[i].view();
+    b2_region_source& r = h->srcs[i];
+    memset(&r, 0, sizeof(r));
+    r.location = B2_LOC_HOST; r.write = &h->views[i]; r.n_write = 1; r.read_ts = read_ts; r.isolation_level = B2_ISO_SI; r.check_has_newer_ts_data = 1;
+  }
+  return h;
+}
+const b2_region_source* orc_bench_source(orc_bench* h, uint32_t task) { return &h->srcs[task]; }
+uint64_t orc_bench_bytes(orc_bench* h) {  // key bytes + value bytes + 8 bytes of offsets per entry
+  uint64_t n = 0;
+  for (auto& b : h->blocks) n += b.koff.back() + b.voff.back() + 8ull * (b.koff.size() - 1);
+  return n;
+}
+uint64_t orc_bench_step(orc_bench* h, const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, uint32_t n_threads, uint64_t* scanned_rows_out,
+                        int* status_out) {
+  return orc_dag_handle_parallel(plan, ranges, n_ranges, h->srcs.data(), (uint32_t)h->srcs.size(), n_threads, scanned_rows_out, status_out);
+}
+int orc_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges, const uint8_t* old_prefix, uint32_t old_len, const uint8_t* new_prefix, uint32_t new_len,
+                        const b2_region_source* src, b2_checksum_response* out, char* msg, size_t msg_cap);
+// checksum.rs:59-98 over every region, one task per thread; XOR / sums of the per-region responses
+int orc_bench_checksum_step(orc_bench* h, const b2_key_range* ranges, uint32_t n_ranges, uint32_t n_threads, b2_checksum_response* out) {
+  std::vector<b2_checksum_response> res(h->srcs.size());
+  std::vector<int> status(h->srcs.size(), 0);
+  std::vector<std::thread> th;
+  std::atomic<uint32_t> next{0};
+  for (uint32_t t = 0; t < std::max(1u, n_threads); ++t)
+    th.emplace_back([&]() {
+      char msg[64];
+      for (;;) {
+        uint32_t i = next.fetch_add(1);
+        if (i >= h->srcs.size()) break;
+        status[i] = orc_checksum_handle(ranges, n_ranges, nullptr, 0, nullptr, 0, &h->srcs[i], &res[i], msg, sizeof(msg));
+      }
+    });
+  for (auto& x : th) x.join();
+  memset(out, 0, sizeof(*out));
+  int st = 0;
+  for (size_t i = 0; i < res.size(); ++i) { out->checksum ^= res[i].checksum; out->total_kvs += res[i].total_kvs; out->total_bytes += res[i].total_bytes; if (status[i]) st = status[i]; }
+  return st;
+}
+void orc_bench_free(orc_bench* h) { delete h; }
 
 // Raw MVCC scan over [lower, upper) (encoded user keys; NULL = unbounded) — pins ForwardScanner against the
 // reference's scanner unit tests (forward.rs:1179-1727), including exact next/seek statistics.

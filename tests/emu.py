@@ -37,6 +37,8 @@ def lib():
         L.emu_stats.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.emu_free.argtypes = [vp]
         L.emu_check_supported.argtypes = [C.POINTER(ffi.DagPlan), C.c_char_p, C.c_size_t]
+        L.emu_set_fast_front.argtypes = [C.c_int]
+        L.emu_fast_hits.restype = C.c_uint64
         _lib = L
     return _lib
 
@@ -99,3 +101,13 @@ def check_supported(plan):
     msg = C.create_string_buffer(256)
     rc = lib().emu_check_supported(C.byref(plan.c), msg, 256)
     return rc, msg.value.decode()
+
+
+def set_fast_front(on):
+    """Switch the clean-entry front end (entry_fast) of the emulation on / off; returns nothing."""
+    lib().emu_set_fast_front(1 if on else 0)
+
+
+def fast_hits():
+    """Entries the clean-entry front end has accepted so far (process-wide counter)."""
+    return lib().emu_fast_hits()

@@ -41,6 +41,35 @@ static BlockView view_of(const b2_cf_block& c) { BlockView v; v.keys = c.keys; v
 
 struct GroupAcc { uint64_t w[MAX_ACC_WORDS]; };
 
+// scan_kernel.cuh entry_fast restated without the warp shuffles: the clean-entry front end built from the same
+// b2_device.h functions.  0 = nothing to do for this entry, 1 = row ready (conditions evaluated into *keep),
+// 3 = not a clean entry: the general functions decide.
+static int entry_fast_host(const DevPlan& P, const BlockView& b, uint32_t e, uint32_t e_lo, uint64_t read_ts, Row& row, Cells& cells, bool* keep,
+                           uint32_t* val_len) {
+  KeyTail t, q;
+  if (!fast_key_tail(b.kptr(e), b.klen(e), &t)) return 3;
+  if (e != e_lo) {
+    if (!fast_key_tail(b.kptr(e - 1), b.klen(e - 1), &q)) return 3;
+    if (key_tail_same(t.a, t.b, q.a, q.b)) return 0;
+  }
+  const uint64_t cts = key_tail_commit_ts(t);
+  if (cts > read_ts) return 3;
+  uint32_t roff, rlen;
+  if (!fast_write_head(b.vptr(e), b.vlen(e), &roff, &rlen)) return 3;
+  row.enc_key = b.kptr(e); row.enc_key_len = 27; row.commit_ts = cts;
+  if (!fast_row_v2(P, b.vptr(e) + roff, rlen, row)) return 3;
+  row.filled = P.fast_filled;
+  if (eval_conds(P, row, cells, keep)) return 3;
+  *val_len = rlen;
+  return 1;
+}
+static bool unit_prefix_ok(const BlockView& b, uint32_t lo, uint32_t hi) {  // kernels.cu unit_prefix_kernel
+  if (hi <= lo || b.klen(lo) < 12 || b.klen(hi - 1) < 12) return false;
+  return record_key_prefix_ok(b.kptr(lo)) && memcmp(b.kptr(lo), b.kptr(hi - 1), 12) == 0;
+}
+static bool g_emu_fast_front = true;
+static uint64_t g_emu_fast_hits = 0;
+
 extern "C" {
 
 emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src) {
@@ -74,7 +103,18 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
     for (uint32_t b = 0; b < src->n_write; ++b) {
       BlockView blk = view_of(src->write[b]);
       uint32_t e_lo = lower_bound_block(src->write[b], lo), e_hi = lower_bound_block(src->write[b], hi);
+      const bool unit_fast = g_emu_fast_front && P.fast_n > 0 && unit_prefix_ok(blk, e_lo, e_hi);
       for (uint32_t e = e_lo; e < e_hi; ++e) {
+        Row row; Cells cells;
+        bool keep = false;
+        int fr = 3;
+        uint32_t fast_val_len = 0;
+        if (unit_fast) fr = entry_fast_host(P, blk, e, e_lo, P.read_ts, row, cells, &keep, &fast_val_len);
+        if (fr == 0) continue;
+        if (fr == 1) {
+          g_emu_fast_hits++;
+          R->processed_keys++; R->processed_size += 27 + fast_val_len;
+        } else {
         bool start = (e == e_lo) || !same_user_key(blk, e - 1, e);
         if (!start) continue;
         RunOut ro;
@@ -84,13 +124,12 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
         if (!ro.found) continue;
         uint32_t ko = blk.koff[e], kl = blk.koff[e + 1] - ko;
         R->processed_keys++; R->processed_size += (kl - 8) + ro.val_len;
-        Row row; Cells cells;
         row.enc_key = blk.keys + ko; row.enc_key_len = kl - 8; row.commit_ts = ro.commit_ts;
         int er = row_open(ro.val, ro.val_len, &row.rv);
         if (!er) er = row_split(P, row, cells);
-        bool keep = false;
         if (!er) er = eval_conds(P, row, cells, &keep);
         if (er) { report(bases[b] + e, er); continue; }
+        }
         if (!keep) continue;
         live_rows++;
         if (err != ~0ull) continue;  // the host discards rows at/after the first failing entry
@@ -284,6 +323,8 @@ emu_result* emu_checksum(const b2_key_range* ranges, uint32_t n_ranges, const ui
   return R;
 }
 
+void emu_set_fast_front(int on) { g_emu_fast_front = on != 0; }
+uint64_t emu_fast_hits(void) { return g_emu_fast_hits; }
 int emu_status(emu_result* r) { return r->status; }
 int emu_dev_err(emu_result* r) { return r->dev_err; }
 uint64_t emu_err_entry(emu_result* r) { return r->err_entry; }

@@ -181,7 +181,7 @@ INT_COLUMNS = [ColumnDef(100, pk_handle=True), ColumnDef(7, unsigned=True), Colu
                ColumnDef(5, tp=ffi.TP_LONG), ColumnDef(9), ColumnDef(4), ColumnDef(6, unsigned=True)]
 
 
-def int_region(seed, n_keys=500, corrupt=False, fmt=2):
+def int_region(seed, n_keys=500, corrupt=False, fmt=2, ts=(5, 8)):
     """v2 rows holding exactly the 8 stored columns above with every width mix (1/2/4/8 bytes), some rows with a NULL or a
     missing column (general path), optionally rows with a 3-byte integer or decreasing offsets (errors)."""
     rng = random.Random(seed)
@@ -221,7 +221,7 @@ def int_region(seed, n_keys=500, corrupt=False, fmt=2):
             val = bytearray(kvfmt.row_v1(d))
             if corrupt and 0.5 < x < 0.52 and len(cols) == 8:
                 val = val[:-1] if val[-1] >= 0x80 or rng.random() < 0.5 else val + b"\x08"  # truncated datum / dangling id marker
-            r.put(kvfmt.row_key(TABLE, h * 2 + 5), bytes(val), 5, 8)
+            r.put(kvfmt.row_key(TABLE, h * 2 + 5), bytes(val), ts[0], ts[1])
             continue
         val = bytearray(kvfmt.row_v2(cols))
         if corrupt and 0.5 < x < 0.52 and len(cols) == 8:
@@ -233,7 +233,7 @@ def int_region(seed, n_keys=500, corrupt=False, fmt=2):
             else:
                 ends[3], ends[4] = ends[4], ends[3]  # decreasing offsets
             struct.pack_into("<8H", val, offs_at, *ends)
-        r.put(kvfmt.row_key(TABLE, h * 2 + 5), bytes(val), 5, 8)
+        r.put(kvfmt.row_key(TABLE, h * 2 + 5), bytes(val), ts[0], ts[1])
     return r
 
 

@@ -755,6 +755,7 @@ B2_HD bool fast_row_probe_v1(const DevPlan& P, Row& row) {
 // Does this v2 row hold exactly the plan's columns (process_v2 would find column k at position v2_hint), all
 // non-null, offsets monotone and inside the value area, integer-class columns 1/2/4/8 bytes wide?  On success the
 // end-offsets stay in two registers: no per-column search, no Cells traffic.
+B2_HD bool fast_offsets_ok(const DevPlan& P, Row& row);
 B2_HD bool fast_row_probe(const DevPlan& P, Row& row) {
   const RowView& r = row.rv;
   row.fast = 0;
@@ -762,6 +763,11 @@ B2_HD bool fast_row_probe(const DevPlan& P, Row& row) {
   if (((ld64(r.v + r.ids_off) ^ P.fast_ids) & (P.fast_n >= 8 ? ~0ull : ((1ull << (8 * P.fast_n)) - 1))) != 0) return false;
   row.o_lo = ld64(r.v + r.offs_off);
   row.o_hi = P.fast_n > 4 ? ld64(r.v + r.offs_off + 8) : 0;
+  return fast_offsets_ok(P, row);
+}
+// the end offsets in row.o_lo / o_hi are monotone, inside the value area, and integer-class columns are 1/2/4/8 bytes wide
+B2_HD bool fast_offsets_ok(const DevPlan& P, Row& row) {
+  const RowView& r = row.rv;
   if (P.fast_cls == (1u << P.fast_n) - 1u) {
     // all stored columns are integer-class: the eight widths are checked at once, four 16-bit lanes per register.
     // width = end - previous end (mod 2^16); it must be 1, 2, 4 or 8: (w & 0xfff0) == 0, w != 0, w & (w - 1) == 0.
@@ -798,6 +804,96 @@ B2_HD bool fast_row_probe(const DevPlan& P, Row& row) {
   if ((bad & 1u) || prev > r.vals_len) return false;
   row.fast = 1;
   return true;
+}
+
+// ---- clean-entry front end -------------------------------------------------------------------------------------
+// The overwhelmingly common CF_WRITE entry of a table scan: an int-handle record key (35 bytes: memcomparable
+// 't' tid "_r" handle, then !commit_ts) that is the first version of its user key, visible at read_ts, holding
+// `P varint(start_ts) v len row` and nothing else, the row being an exact-layout v2 row.  For such an entry the
+// general walk (same_user_key + resolve_run + parse_write + row_open + row_split) collapses into a few word loads
+// with one shared funnel shift each.  Every function below either accepts an entry and yields exactly what the
+// general functions yield for it, or rejects it (then the caller runs the general functions: errors, version walks,
+// CF_DEFAULT lookups, odd keys and rows all live there).
+//
+// N consecutive little-endian 64-bit words from an arbitrary byte address: 2N+1 aligned 32-bit loads, one shift amount.
+// May read up to 3 bytes before and 4 bytes after the 8N requested ones (inside the padded stage / heap).
+template <int N>
+B2_HD void ld64xN(const uint8_t* p, uint64_t (&out)[N]) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t mis = (uint32_t)(unsigned long long)p & 3u;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p - mis);
+  const uint32_t s = mis * 8u;
+  uint32_t x[2 * N + 1];
+#pragma unroll
+  for (int i = 0; i < 2 * N + 1; ++i) x[i] = w[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = ((uint64_t)__funnelshift_r(x[2 * i + 1], x[2 * i + 2], s) << 32) | __funnelshift_r(x[2 * i], x[2 * i + 1], s);
+#else
+  __builtin_memcpy(out, p, 8 * N);
+#endif
+}
+
+// enc[12..36) of a 35-byte CF_WRITE key: a = raw handle bytes 0..4, group marker, handle bytes 5..6;
+// b = handle byte 7, five pad zeros, terminal marker 0xFA, first ts byte; c = ts bytes 1..7 (+ one byte past the key)
+struct KeyTail { uint64_t a, b, c; };
+// true: the key has the shape of an int-handle record key from byte 12 on (bytes 0..11, 't' tid[0..7] FF tid[7] "_r",
+// are validated once per unit of work: every key of a sorted range shares them when its first and last key do)
+B2_HD bool fast_key_tail(const uint8_t* kp, uint32_t klen, KeyTail* t) {
+  if (klen != 35) return false;
+  uint64_t w[3];
+  ld64xN<3>(kp + 12, w);
+  t->a = w[0]; t->b = w[1]; t->c = w[2];
+  return ((w[0] >> 40) & 0xffu) == 0xffu && (w[1] & 0x00ffffffffffff00ull) == 0x00fa000000000000ull;
+}
+B2_HD uint64_t key_tail_commit_ts(const KeyTail& t) { return ~bswap64((t.b >> 56) | (t.c << 8)); }
+// same user key as the entry before?  (both keys validated by fast_key_tail, both inside one unit: bytes 0..11 and 21..26 agree)
+B2_HD bool key_tail_same(uint64_t a, uint64_t b, uint64_t pa, uint64_t pb) { return a == pa && ((b ^ pb) & 0xffu) == 0; }
+// first 12 bytes of the keys of a unit: what check_record_key / decode_int_handle need of them (table.rs:187-226)
+B2_HD bool record_key_prefix_ok(const uint8_t* k) { return k[0] == 't' && k[8] == 0xff && k[10] == '_' && k[11] == 'r'; }
+
+// `P varint(start_ts) v len row`, nothing after the row (parse_write's common record): row = vp + *row_off
+B2_HD bool fast_write_head(const uint8_t* vp, uint32_t vlen, uint32_t* row_off, uint32_t* row_len) {
+  if (vlen < 4) return false;
+  uint64_t w[2];
+  ld64xN<2>(vp, w);
+  // terminal byte of the varint: first of value bytes 1..9 with bit 7 clear (a 10-byte varint is left to the general parser)
+  const uint64_t s0 = ~w[0] & 0x8080808080808000ull;
+  const uint32_t s1 = ~(uint32_t)w[1] & 0x8080u;
+  uint32_t term;
+  if (s0) term = ctz64(s0) >> 3;
+  else if (s1) term = 8u + (ctz64((uint64_t)s1) >> 3);
+  else return false;
+  const uint32_t pos = term + 1;
+  if (pos + 2 > vlen) return false;
+  const uint32_t tag = vp[pos], len = vp[pos + 1];
+  *row_off = pos + 2; *row_len = len;
+  return (w[0] & 0xffu) == 'P' && tag == 'v' && pos + 2 + len == vlen;
+}
+
+// row_open + fast_row_probe fused for a small v2 row without checksum that holds exactly the plan's columns: header,
+// ids and end offsets come out of one run of words (every field sits at a compile-time offset in a specialised kernel)
+B2_HD bool fast_row_v2(const DevPlan& P, const uint8_t* r, uint32_t n, Row& row) {
+  const int K = P.fast_n;
+  row.fast = 0;
+  if (K <= 0 || n < 6u + 3u * (uint32_t)K) return false;
+  uint64_t w[4];
+  if (K <= 2) { uint64_t t[2]; ld64xN<2>(r, t); w[0] = t[0]; w[1] = t[1]; w[2] = w[3] = 0; }
+  else if (K <= 4) { uint64_t t[3]; ld64xN<3>(r, t); w[0] = t[0]; w[1] = t[1]; w[2] = t[2]; w[3] = 0; }
+  else ld64xN<4>(r, w);
+  auto field = [&](int j) -> uint64_t {  // 8 row bytes from byte j
+    const int q = j >> 3, sh = (j & 7) * 8;
+    if (sh == 0) return w[q];
+    return (w[q] >> sh) | (q + 1 < 4 ? (w[q + 1] << (64 - sh)) : 0ull);
+  };
+  // 0x80, flags 0 (small, no checksum), K non-null ids, no null ids
+  if ((w[0] & 0xffffffffffffull) != (0x80ull | ((uint64_t)K << 16))) return false;
+  if (((field(6) ^ P.fast_ids) & (K >= 8 ? ~0ull : ((1ull << (8 * K)) - 1))) != 0) return false;
+  RowView& v = row.rv;
+  v.v = r; v.n = n; v.fmt = 2; v.big = 0; v.nn_cnt = (uint16_t)K; v.null_cnt = 0;
+  v.ids_off = 6; v.null_ids_off = 6u + (uint32_t)K; v.offs_off = 6u + (uint32_t)K; v.vals_off = 6u + 3u * (uint32_t)K; v.vals_len = n - v.vals_off;
+  row.o_lo = field(6 + K);
+  row.o_hi = K > 4 ? field(14 + K) : 0;
+  return fast_offsets_ok(P, row);
 }
 
 // process_kv_pair (table_scan_executor.rs:365-475): everything that can fail regardless of which rows are

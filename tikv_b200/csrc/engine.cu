@@ -7,8 +7,12 @@
 // (src/storage/mvcc/reader/scanner/forward.rs:384-431, txn_types/src/lock.rs:343-416, 520-611),
 // ChecksumContext (src/coprocessor/checksum.rs:26-98).
 #include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -127,7 +131,7 @@ struct SrcBlock {  // caller's block descriptor + sizes
   uint64_t entry_base = 0;
 };
 
-struct Unit { uint32_t range_idx, block_idx, e_lo, e_hi; };
+struct Unit { uint32_t range_idx, block_idx, e_lo, e_hi, fast_ok; };
 
 struct StageSlot {
   DevBuf keys, koff, vals, voff;
@@ -465,7 +469,7 @@ struct b2_exec {
   int compute_units() {
     uint32_t nr = (uint32_t)range_lo.size(), nb = (uint32_t)wblocks.size();
     if (!nr || !nb) return B2_OK;
-    std::vector<uint32_t> res((size_t)nb * nr * 2);
+    std::vector<uint32_t> res((size_t)nb * nr * 2), unit_ok((size_t)nb * nr, 0);
     if (src_loc == B2_LOC_HOST) {
       for (uint32_t b = 0; b < nb; ++b)
         for (uint32_t q = 0; q < nr * 2; ++q) {
@@ -478,6 +482,14 @@ struct b2_exec {
           }
           res[(size_t)b * nr * 2 + q] = lo;
         }
+      for (uint32_t b = 0; b < nb; ++b)
+        for (uint32_t r = 0; r < nr; ++r) {  // (same test as unit_prefix_kernel)
+          const b2_cf_block& B = wblocks[b].c;
+          uint32_t lo = res[(size_t)b * nr * 2 + 2 * r], hi = res[(size_t)b * nr * 2 + 2 * r + 1];
+          if (hi <= lo) continue;
+          const uint8_t *f = B.keys + B.key_offs[lo], *l = B.keys + B.key_offs[hi - 1];
+          unit_ok[(size_t)b * nr + r] = B.key_offs[lo + 1] - B.key_offs[lo] >= 12 && B.key_offs[hi] - B.key_offs[hi - 1] >= 12 && record_key_prefix_ok(f) && memcmp(f, l, 12) == 0;
+        }
     } else {
       std::vector<uint8_t> flat;
       std::vector<uint32_t> offs(1, 0);
@@ -487,24 +499,26 @@ struct b2_exec {
       }
       std::vector<BlockView> views;
       for (auto& w : wblocks) { BlockView v; v.keys = w.c.keys; v.koff = w.c.key_offs; v.vals = w.c.vals; v.voff = w.c.val_offs; v.n = w.c.n; views.push_back(v); }
-      DevBuf d_views, d_flat, d_offs, d_res;
+      DevBuf d_views, d_flat, d_offs, d_res, d_ok;
       cudaError_t e = d_views.reserve(views.size() * sizeof(BlockView));
+      if (e == cudaSuccess) e = d_ok.reserve(unit_ok.size() * 4);
       if (e == cudaSuccess) e = d_flat.reserve(flat.size() + 16);
       if (e == cudaSuccess) e = d_offs.reserve(offs.size() * 4);
       if (e == cudaSuccess) e = d_res.reserve(res.size() * 4);
       if (e == cudaSuccess) e = cudaMemcpyAsync(d_views.p, views.data(), views.size() * sizeof(BlockView), cudaMemcpyHostToDevice, stream);
       if (e == cudaSuccess) e = cudaMemcpyAsync(d_flat.p, flat.data(), flat.size(), cudaMemcpyHostToDevice, stream);
       if (e == cudaSuccess) e = cudaMemcpyAsync(d_offs.p, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, stream);
-      if (e == cudaSuccess) e = launch_bounds_search((const BlockView*)d_views.p, nb, (const uint8_t*)d_flat.p, (const uint32_t*)d_offs.p, nr * 2, (uint32_t*)d_res.p, stream);
+      if (e == cudaSuccess) e = launch_bounds_search((const BlockView*)d_views.p, nb, (const uint8_t*)d_flat.p, (const uint32_t*)d_offs.p, nr * 2, (uint32_t*)d_res.p, (uint32_t*)d_ok.p, stream);
       if (e == cudaSuccess) e = cudaMemcpyAsync(res.data(), d_res.p, res.size() * 4, cudaMemcpyDeviceToHost, stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(unit_ok.data(), d_ok.p, unit_ok.size() * 4, cudaMemcpyDeviceToHost, stream);
       if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-      d_views.release(); d_flat.release(); d_offs.release(); d_res.release();
+      d_views.release(); d_flat.release(); d_offs.release(); d_res.release(); d_ok.release();
       if (e != cudaSuccess) return fail(B2_ERR_CUDA, std::string("range bounds search: ") + cudaGetErrorString(e));
     }
     for (uint32_t r = 0; r < nr; ++r)
       for (uint32_t b = 0; b < nb; ++b) {
         uint32_t lo = res[(size_t)b * nr * 2 + 2 * r], hi = res[(size_t)b * nr * 2 + 2 * r + 1];
-        if (hi > lo) units.push_back(Unit{r, b, lo, hi});
+        if (hi > lo) units.push_back(Unit{r, b, lo, hi, unit_ok[(size_t)b * nr + r]});
       }
     return B2_OK;
   }
@@ -655,6 +669,7 @@ struct b2_exec {
     return total;
   }
   bool use_staging = true;
+  bool use_fast_front = getenv("B2_NO_FAST_FRONT") == nullptr;  // debug switch: general front end only
 
   ScanArgs base_args(const Unit& u, const BlockView& v) {
     ScanArgs a;
@@ -665,6 +680,7 @@ struct b2_exec {
     a.entry_base = wblocks[u.block_idx].entry_base;
     a.ctr = ctr();
     a.read_ts = cp.dev.read_ts; a.isolation = cp.dev.isolation;
+    a.fast_ok = use_fast_front ? u.fast_ok : 0;
     a.range_rows = range_rows.p ? (unsigned long long*)range_rows.p + u.range_idx : nullptr;
     return a;
   }
@@ -1397,7 +1413,11 @@ int32_t b2_exec_schema(b2_exec* h, int32_t* field_tps, uint32_t* field_flags, ui
 
 int32_t b2_exec_next_batch(b2_exec* h, uint64_t scan_rows, b2_batch* out) { return h->next_batch(scan_rows, out); }
 
-int32_t b2_exec_collect_stats(b2_exec* h, b2_exec_stats* out) { *out = h->stats; return B2_OK; }
+int32_t b2_exec_collect_stats(b2_exec* h, b2_exec_stats* out) {
+  h->stats.h2d_bytes = h->h2d_bytes; h->stats.d2h_bytes = h->d2h_bytes;  // (copies made after the last counter read-back included)
+  *out = h->stats;
+  return B2_OK;
+}
 int32_t b2_exec_last_error(b2_exec* h, b2_error_info* out) { *out = h->last_err; return B2_OK; }
 int32_t b2_exec_can_be_cached(b2_exec* h) { return (h->check_newer && !h->met_newer_any && !h->saw_lock) ? 1 : 0; }
 int32_t b2_exec_take_scanned_range(b2_exec* h, const uint8_t** lower, uint32_t* lower_len, const uint8_t** upper, uint32_t* upper_len) {
@@ -1578,6 +1598,59 @@ int32_t b2_copy_to_device(int32_t device, void* dst_device, const void* src, uin
 }
 int32_t b2_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 void* b2_host_alloc_pinned(uint64_t bytes) { void* p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr; return p; }
-void b2_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+// Pinned host memory on the NUMA node the GPU hangs off (staging buffers of host-resident sources: on a two-socket box a
+// buffer on the far socket halves the H2D rate of GPUs 4-7).  The node comes from sysfs (PCI bus id of the device); the
+// pages are bound with mbind(MPOL_BIND) before they are touched, then pinned with cudaHostRegister.  Falls back to
+// cudaMallocHost when any step is unavailable.  Free with b2_host_free_pinned.
+static std::mutex g_near_mu;
+static std::vector<std::pair<void*, size_t>>& near_allocs() { static std::vector<std::pair<void*, size_t>> v; return v; }
+static int gpu_numa_node(int device) {
+  char bus[32];
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return -1;
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+void* b2_host_alloc_pinned_near(int32_t device, uint64_t bytes) {
+  const int node = gpu_numa_node(device);
+  if (node >= 0 && node < 64 && bytes) {
+    const size_t len = ((size_t)bytes + 4095) & ~(size_t)4095;
+    void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p != MAP_FAILED) {
+      unsigned long mask = 1ul << node;
+      long rc = syscall(SYS_mbind, p, len, 2 /* MPOL_BIND */, &mask, 65ul, 0u);
+      if (rc == 0 && cudaSetDevice(device) == cudaSuccess && cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
+        std::lock_guard<std::mutex> g(g_near_mu);
+        near_allocs().push_back({p, len});
+        return p;
+      }
+      cudaGetLastError();
+      munmap(p, len);
+    }
+  }
+  return b2_host_alloc_pinned(bytes);
+}
+int32_t b2_device_numa_node(int32_t device) { return gpu_numa_node(device); }
+void b2_host_free_pinned(void* p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> g(g_near_mu);
+    auto& v = near_allocs();
+    for (size_t i = 0; i < v.size(); ++i)
+      if (v[i].first == p) {
+        cudaHostUnregister(p);
+        munmap(p, v[i].second);
+        v.erase(v.begin() + i);
+        return;
+      }
+  }
+  cudaFreeHost(p);
+}
 
 }  // extern "C"

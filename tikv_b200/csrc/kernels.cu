@@ -312,11 +312,30 @@ __global__ void bounds_kernel(const BlockView* blocks, uint32_t n_blocks, const 
   out[i] = lo;
 }
 
+// per (block, range) unit [lo, hi): do its first and last key share their first 12 bytes, and are those the start of a
+// record key?  Keys are sorted, so every key in between shares them too: the clean-entry front end skips those bytes.
+__global__ void unit_prefix_kernel(const BlockView* blocks, uint32_t n_blocks, uint32_t n_ranges, const uint32_t* bounds, uint32_t* out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_blocks * n_ranges) return;
+  const uint32_t bi = i / n_ranges, r = i % n_ranges;
+  const BlockView b = blocks[bi];
+  const uint32_t lo = bounds[(size_t)bi * n_ranges * 2 + 2 * r], hi = bounds[(size_t)bi * n_ranges * 2 + 2 * r + 1];
+  uint32_t ok = 0;
+  if (hi > lo) {
+    const uint8_t* f = b.keys + b.koff[lo];
+    const uint8_t* l = b.keys + b.koff[hi - 1];
+    ok = b.koff[lo + 1] - b.koff[lo] >= 12 && b.koff[hi] - b.koff[hi - 1] >= 12 && record_key_prefix_ok(f);
+    for (int j = 0; ok && j < 12; ++j) ok = f[j] == l[j];
+  }
+  out[i] = ok;
+}
+
 cudaError_t launch_bounds_search(const BlockView* blocks, uint32_t n_blocks, const uint8_t* bounds, const uint32_t* bound_offs, uint32_t n_bounds,
-                                 uint32_t* out, cudaStream_t s) {
+                                 uint32_t* out, uint32_t* unit_ok, cudaStream_t s) {
   uint32_t n = n_blocks * n_bounds;
   if (!n) return cudaSuccess;
   bounds_kernel<<<(n + 63) / 64, 64, 0, s>>>(blocks, n_blocks, bounds, bound_offs, n_bounds, out);
+  unit_prefix_kernel<<<(n / 2 + 63) / 64, 64, 0, s>>>(blocks, n_blocks, n_bounds / 2, out, unit_ok);
   return cudaGetLastError();
 }
 

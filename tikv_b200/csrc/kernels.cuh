@@ -75,6 +75,9 @@ struct ScanArgs {
   uint32_t stage_off;               // byte offset of the stages inside dynamic shared memory (multiple of 16)
   uint32_t out_stage_off;           // PM_SCAN: byte offset of the output transpose buffer (multiple of 16)
   uint32_t stage_key_cap, stage_val_cap;  // bytes per stage for key / value heaps (multiples of 16)
+  uint32_t fast_ok;                 // 1: every key of [e_lo, e_hi) starts with the same 12 bytes 't' tid "_r" (first and last key of the
+                                    //    sorted unit agree): the clean-entry front end may skip them
+  uint32_t _pad1;
   // PM_CHECKSUM
   uint64_t ck_init_state;           // crc register after old_prefix
   uint32_t ck_new_prefix_len, ck_old_prefix_len;
@@ -117,8 +120,9 @@ cudaError_t launch_topn_copy(const TopItem* items, const unsigned int* count, ui
                              unsigned char* null_out, cudaStream_t s);
 cudaError_t launch_pack_nulls(const unsigned char* nulls, uint32_t n_cols, uint32_t stride, uint32_t n, unsigned long long* bitmaps, uint32_t words_per_col, cudaStream_t s);
 size_t topn_smem_bytes(uint32_t cap, int n_order);
+// out: lower_bound of every bound in every block; unit_ok[block * n_ranges + range]: that unit's keys share a record-key prefix
 cudaError_t launch_bounds_search(const BlockView* blocks, uint32_t n_blocks, const uint8_t* bounds, const uint32_t* bound_offs, uint32_t n_bounds,
-                                 uint32_t* out, cudaStream_t s);
+                                 uint32_t* out, uint32_t* unit_ok, cudaStream_t s);
 cudaError_t launch_gen_sizes(const b2_gen_spec& spec, uint32_t* row_entries, uint32_t* row_val_bytes, cudaStream_t s);
 cudaError_t launch_gen_write(const GenArgs& a, cudaStream_t s);
 cudaError_t launch_fill_u64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t s);

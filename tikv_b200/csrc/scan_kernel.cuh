@@ -234,7 +234,7 @@ struct EntryStats {  // per-thread partial statistics / checksum state
   unsigned int newer;
   unsigned int last;  // 1 + largest block entry index a row was returned for
 };
-enum { P1_NONE = 0, P1_LIVE = 1, P1_REDO = 2 };
+enum { P1_NONE = 0, P1_LIVE = 1, P1_REDO = 2, P1_GENERAL = 3 /* entry_fast only: not a clean entry, run entry_phase1 */ };
 
 // The thread sitting on the first version of a user key resolves that key.  P1_REDO: the shared-memory window was not
 // enough (run longer than the look-ahead, or a long value in CF_DEFAULT) and nothing has been committed: the caller
@@ -302,6 +302,47 @@ __device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A,
   bool keep = false;
   if (!err) err = eval_conds(P, row, cells, &keep);
   if (err) { report_err(A.ctr, A.entry_base + e, err); return P1_NONE; }
+  return keep ? P1_LIVE : P1_NONE;
+}
+
+// Clean-entry front end (b2_device.h: fast_key_tail / fast_write_head / fast_row_v2) for one warp's 32 entries of a
+// staged tile.  Every lane calls it (the predecessor's key words travel by shuffle; lane 0 reads its predecessor
+// itself); `valid` says whether the lane holds an entry of the chunk.  P1_GENERAL from any lane sends the whole warp
+// through entry_phase1 instead: nothing has been counted or reported by then.
+template <int MODE>
+__device__ __forceinline__ int entry_fast(const DevPlan& P, const ScanArgs& A, const SmemView& view, uint32_t e, bool valid, Row& row, Cells& cells,
+                                          EntryStats& ts, unsigned int lane) {
+  const uint32_t ko = view.skoff[e], kl = view.skoff[e + 1] - ko;
+  const uint8_t* kp = view.skeys + ko;
+  KeyTail t;
+  t.a = t.b = t.c = 0;
+  bool ok = fast_key_tail(kp, kl, &t);
+  unsigned long long pa = __shfl_up_sync(0xffffffffu, (unsigned long long)t.a, 1), pb = __shfl_up_sync(0xffffffffu, (unsigned long long)t.b, 1);
+  bool pok = __shfl_up_sync(0xffffffffu, (int)ok, 1) != 0;
+  const bool first = e == A.e_lo;  // the range starts here: a run start whatever lies before it
+  if (lane == 0 && !first) {
+    KeyTail q;
+    q.a = q.b = q.c = 0;
+    pok = fast_key_tail(view.kptr(e - 1), view.klen(e - 1), &q);
+    pa = q.a; pb = q.b;
+  }
+  if (!valid) return P1_NONE;
+  if (!ok || (!first && !pok)) return P1_GENERAL;
+  if (!first && key_tail_same(t.a, t.b, pa, pb)) return P1_NONE;  // an older version of the lane below's key
+  const uint64_t cts = key_tail_commit_ts(t);
+  if (cts > A.read_ts) return P1_GENERAL;  // newer than the snapshot: the general walk steps through the versions
+  const uint32_t vo = view.svoff[e], vl = view.svoff[e + 1] - vo;
+  const uint8_t* vp = view.svals + vo;
+  uint32_t roff, rlen;
+  if (!fast_write_head(vp, vl, &roff, &rlen)) return P1_GENERAL;
+  row.enc_key = kp; row.enc_key_len = 27; row.commit_ts = cts;
+  if (!fast_row_v2(P, vp + roff, rlen, row)) return P1_GENERAL;
+  row.filled = P.fast_filled;
+  bool keep = false;
+  if (eval_conds(P, row, cells, &keep)) return P1_GENERAL;  // evaluation errors are raised by the general path
+  ts.keys += 1;
+  ts.size += 27u + rlen;
+  ts.last = e + 1;
   return keep ? P1_LIVE : P1_NONE;
 }
 
@@ -543,7 +584,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   // cannot resolve: a version run longer than the look-ahead, a long value in CF_DEFAULT).  Returns true when the
   // shared-memory attempt must be repeated on the whole block; nothing has been committed in that case.
   uint32_t ob_q = 0, ob_phase = 0;  // PM_SCAN: next output chunk buffer and how often the ring has wrapped (parity)
-  auto tile_body = [&](const auto& view, const uint32_t walk_hi, const uint32_t k, const uint32_t tile) -> bool {
+  auto tile_body = [&](const auto& view, const uint32_t walk_hi, const uint32_t k, const uint32_t tile) __attribute__((always_inline)) -> bool {
     using V = typename b2_remove_cvref<decltype(view)>::type;
     const uint32_t e = A.c_lo + tile * TILE + tid;
     bool live = false;
@@ -552,7 +593,17 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     EntryStats d;
     d.keys = d.size = d.dflt = d.ck_x = d.ck_kvs = d.ck_bytes = 0; d.newer = 0; d.last = 0;
     int r1 = P1_NONE;
-    if (e < A.c_hi) r1 = entry_phase1<MODE>(P, A, view, walk_hi, e, row, cells, d, crc_tab, lane);
+    bool general = true;
+    if constexpr (!V::kWholeBlock && MODE != PM_CHECKSUM) {
+      // clean entries take the word-wise front end; one odd entry sends its warp through the general one
+      if (A.fast_ok && P.fast_n > 0) {
+        const bool valid = e < A.c_hi;
+        r1 = entry_fast<MODE>(P, A, view, valid ? e : A.c_hi - 1, valid, row, cells, d, lane);
+        general = __any_sync(0xffffffffu, r1 == P1_GENERAL);
+        if (general) { d.keys = d.size = 0; d.last = 0; }
+      }
+    }
+    if (general) r1 = e < A.c_hi ? entry_phase1<MODE>(P, A, view, walk_hi, e, row, cells, d, crc_tab, lane) : (int)P1_NONE;
     live = r1 == P1_LIVE;
     if (!V::kWholeBlock) {
       if (__any_sync(0xffffffffu, r1 == P1_REDO) && lane == 0) s_redo[k & 3] = 1;

@@ -116,6 +116,7 @@ def merge_topn(columns, nulls, order, limit):
     # lexicographic sort = stable sorts from the least significant key to the most significant one
     for ci, desc, kind in reversed(order):
         w, nul = _order_word(allr[:, ci], allr[:, nc + ci].bool(), desc, kind)
+        w = torch.where(nul, torch.zeros_like(w), w)  # a NULL cell may hold any bits: it must not disturb the less significant keys
         w, nul = w[idx], nul[idx]
         # asc: NULLs first, then ascending value; desc: reverse of that
         perm = torch.argsort(w, stable=True, descending=bool(desc))

@@ -195,15 +195,18 @@ class DagHandler:
             return DagResult(status, message, mysql, cols or [], kinds, st, ex.can_be_cached())
 
 
-def checksum(ranges, region, old_prefix=b"", new_prefix=b""):
-    """ChecksumContext::handle_request -> (status, (checksum, total_kvs, total_bytes), message)."""
+def checksum(ranges, region, old_prefix=b"", new_prefix=b"", stream=0, want_stats=False):
+    """ChecksumContext::handle_request -> (status, (checksum, total_kvs, total_bytes[, exec stats]), message)."""
     L = ffi.lib()
     kr, keep = key_ranges(ranges)
     out, st = ffi.ChecksumResponse(), ffi.ExecStats()
-    rc = L.b2_checksum_handle(kr, len(ranges), old_prefix, len(old_prefix), new_prefix, len(new_prefix), C.byref(region.c), None,
+    cfg = ffi.ExecConfig()
+    cfg.cuda_stream = stream
+    rc = L.b2_checksum_handle(kr, len(ranges), old_prefix, len(old_prefix), new_prefix, len(new_prefix), C.byref(region.c), C.byref(cfg) if stream else None,
                               C.byref(out), C.byref(st))
     msg = L.b2_last_error_message().decode() if rc else ""
-    return rc, (out.checksum, out.total_kvs, out.total_bytes), msg
+    res = (out.checksum, out.total_kvs, out.total_bytes) + ((st,) if want_stats else ())
+    return rc, res, msg
 
 
 class DeviceRegion:

@@ -23,17 +23,15 @@ ISO_SI, ISO_RC, ISO_RC_CHECK_TS = 0, 1, 2
 
 RPN_CONST_NULL, RPN_CONST_INT, RPN_CONST_UINT, RPN_CONST_REAL, RPN_COLUMN_REF, RPN_FN = 0, 1, 2, 3, 4, 5
 
-SIG = dict(
-    LT_INT=100, LT_REAL=101, LE_INT=110, LE_REAL=111, GT_INT=120, GT_REAL=121, GE_INT=130, GE_REAL=131,
-    EQ_INT=140, EQ_REAL=141, NE_INT=150, NE_REAL=151, NULLEQ_INT=160, NULLEQ_REAL=161,
-    PLUS_REAL=200, PLUS_INT=203, MINUS_REAL=204, MINUS_INT=207, MULTIPLY_REAL=208, MULTIPLY_INT=210,
-    MULTIPLY_INT_UNSIGNED=218, LOGICAL_AND=3101, LOGICAL_OR=3102, LOGICAL_XOR=3103,
-    UNARY_NOT_INT=3104, UNARY_NOT_REAL=3106, REAL_IS_NULL=3114, INT_IS_NULL=3116,
-    INT_IS_TRUE=3118, REAL_IS_TRUE=3119, INT_IS_FALSE=3121, REAL_IS_FALSE=3122, IN_INT=4001, IN_REAL=4002,
-    INT_DIVIDE_INT=213, MOD_REAL=215, MOD_INT=217, ABS_INT=2101, ABS_UINT=2102, ABS_REAL=2103,
-    UNARY_MINUS_INT=3108, UNARY_MINUS_REAL=3109, IF_NULL_INT=4101, IF_NULL_REAL=4102, IF_INT=4107, IF_REAL=4108,
-    COALESCE_INT=4201, COALESCE_REAL=4202, CASE_WHEN_INT=4208, CASE_WHEN_REAL=4209,
-)
+def _header_enum(prefix):
+    """Enumerators of include/b2_copr.h with this prefix: the header is the single source of the numbers."""
+    import re
+    with open(os.path.join(os.path.dirname(_HERE), "include", "b2_copr.h")) as f:
+        text = f.read()
+    return {m.group(1): int(m.group(2), 0) for m in re.finditer(r"\b" + prefix + r"(\w+)\s*=\s*(0x[0-9a-fA-F]+|\d+)", text)}
+
+
+SIG = _header_enum("B2_SIG_")  # tipb::ScalarFuncSig numbers, never typed twice
 
 AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX, AGG_FIRST = 3001, 3002, 3003, 3004, 3005, 3006
 EXEC_TABLE_SCAN, EXEC_INDEX_SCAN, EXEC_SELECTION, EXEC_AGGREGATION, EXEC_TOPN, EXEC_LIMIT, EXEC_STREAM_AGG, EXEC_PROJECTION = range(8)
@@ -159,7 +157,7 @@ EXPORTED_SYMBOLS = [
     "b2_abi_version", "b2_build_info", "b2_last_error_message", "b2_check_supported", "b2_plan_prepare", "b2_plan_literal", "b2_exec_open", "b2_exec_schema",
     "b2_exec_next_batch", "b2_exec_collect_stats", "b2_exec_last_error", "b2_exec_can_be_cached", "b2_exec_encode_batch", "b2_exec_take_scanned_range", "b2_exec_collect_scanned_rows_per_range", "b2_exec_close",
     "b2_exec_agg_partials", "b2_dag_handle", "b2_checksum_handle", "b2_gen_create", "b2_gen_destroy", "b2_copy_to_host", "b2_copy_to_device",
-    "b2_device_count", "b2_host_alloc_pinned", "b2_host_free_pinned",
+    "b2_device_count", "b2_host_alloc_pinned", "b2_host_alloc_pinned_near", "b2_device_numa_node", "b2_host_free_pinned",
 ]
 
 _lib = None
@@ -220,6 +218,10 @@ def lib():
     L.b2_device_count.restype = i32
     L.b2_host_alloc_pinned.argtypes = [u64]
     L.b2_host_alloc_pinned.restype = vp
+    L.b2_host_alloc_pinned_near.argtypes = [i32, u64]
+    L.b2_host_alloc_pinned_near.restype = vp
+    L.b2_device_numa_node.argtypes = [i32]
+    L.b2_device_numa_node.restype = i32
     L.b2_host_free_pinned.argtypes = [vp]
     L.b2_host_free_pinned.restype = None
     if L.b2_abi_version() != 1:
