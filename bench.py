@@ -252,8 +252,13 @@ def host_mem_available():
 
 
 # ---- CPU arm: the oracle on host-generated regions (nothing of the product library is used here) -----------------------
+class _Src:
+    def __init__(self, c):
+        self.c = c
+
+
 class CpuArm:
-    def __init__(self, table, rows_per_task, tasks, threads):
+    def __init__(self, table, rows_per_task, tasks, threads, first_handle=0):
         import orc
         from tikv_b200 import ffi
         self.L = orc.lib()
@@ -268,7 +273,7 @@ class CpuArm:
         L.orc_bench_bytes.argtypes = [C.c_void_p]
         L.orc_bench_bytes.restype = C.c_uint64
         L.orc_bench_free.argtypes = [C.c_void_p]
-        spec, keep = gen_spec(ffi, table, 0, rows_per_task)
+        spec, keep = gen_spec(ffi, table, first_handle, rows_per_task)
         self.ffi, self.rows_per_task, self.tasks, self.threads = ffi, rows_per_task, tasks, threads
         self.h = L.orc_bench_create(C.byref(spec), tasks, rows_per_task, READ_TS, threads)
 
@@ -365,18 +370,14 @@ def parity_check(ffi, device, name, plan, dev_src, first_handle, sample_rows, st
     import torch
     from tikv_b200.executor import BatchExecutor, _decimal_to_int
     table = "c2" if name == "c5" else name
-    arm = CpuArm(table, sample_rows, 1, 1)
-    # CpuArm generates from handle 0: regenerate at the right handles
-    arm.close()
-    spec, keep = gen_spec(ffi, table, first_handle, sample_rows)
-    arm.h = arm.L.orc_bench_create(C.byref(spec), 1, sample_rows, READ_TS, 1)
+    arm = CpuArm(table, sample_rows, 1, 1, first_handle=first_handle)
     rng = table_range(first_handle, sample_rows)
     t0 = time.perf_counter()
     info = {"rows": sample_rows, "first_handle": first_handle}
     if name == "c5":
         import orc
         from tikv_b200.executor import checksum
-        st, exp, msg = orc.checksum(rng, arm.source())
+        st, exp, msg = orc.checksum(rng, _Src(arm.source()))
         rc, got, msg2 = checksum(rng, dev_src)
         assert st == 0 and rc == 0, (st, rc, msg, msg2)
         assert tuple(exp) == tuple(got), f"checksum parity: oracle {exp} vs CUDA {got}"
@@ -631,7 +632,7 @@ def main():
         host_blocks, pinned = blocks_to_pinned_host(ffi, device, sub_blks)
         host_src = Source(ffi, host_blocks, ffi.LOC_HOST, device)
         plan = plans[head]
-        after = {"c3": after_agg, "c4": after_topn}.get(head)
+        after = after_agg if head == "c3" else None  # (the TopN merge reads device-resident columns: HBM-resident steps only)
         for _ in range(2):
             r_e2e, st_e = run_dag(ffi, plan, table_range(), host_src, ffi.LOC_HOST, args.chunk, stream.cuda_stream, after)
         barrier()

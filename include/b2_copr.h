@@ -314,6 +314,13 @@ int32_t b2_check_supported(const b2_dag_plan* plan);
  * requests carrying the same plan start on it.  B2_ERR_UNSUPPORTED: run-time compilation (NVRTC) is not available, the
  * generic kernels serve the plan. */
 int32_t b2_plan_prepare(const b2_dag_plan* plan, int32_t device);
+/* The same ahead of time and without a GPU: NVRTC compiles the kernel(s) of the plan *shape* into the on-disk cache
+ * (B2_JIT_CACHE_DIR, default <library dir>/jit_cache; keyed by plan shape + kernel sources).  Constants, IN lists, LIMIT,
+ * read_ts and the isolation level are launch parameters, not part of the shape: `col < 5` and `col < 7` share one kernel.
+ * *n_compiled (may be NULL): kernels compiled by this call (0 = all cached already). */
+int32_t b2_plan_precompile(const b2_dag_plan* plan, int32_t* n_compiled);
+/* process-wide counters: NVRTC compilations run so far, kernels loaded from the on-disk cache */
+void b2_jit_counters(uint64_t* nvrtc_compiles, uint64_t* disk_cache_hits);
 
 /* interface.rs:36-97 */
 int32_t b2_exec_open(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges,
@@ -356,7 +363,9 @@ void b2_exec_close(b2_exec* h);
 /* Partial aggregation state of an Aggregation pipeline, for the multi-GPU / multi-region final merge (what TiDB's
  * final HashAgg does with the per-region partial results; fast_hash_aggr_executor.rs emits partial results only).
  * Valid after the drained batch was produced.  Per group `acc_words` additive u64 words, per aggregate in plan order:
- *   COUNT: [count]   SUM/AVG over Int: [count, sum of low 32 bits, sum of high 32 bits]   SUM/AVG over Real: [count, f64]
+ *   COUNT: [count]   SUM/AVG over Int: [count, sum of low 32 bits, sum of high 32 bits]
+ *   SUM/AVG over Real: [count, 66 words]: the exact sum as a 2112-bit fixed-point number (bit 0 = 2^-1074), one signed
+ *   32-bit digit per word, carry-save; partial sums merge by word-wise integer addition and round once at the end
  *   MAX/MIN: [count, extremum key]: the key merges by unsigned 64-bit maximum (bit w of max_word_mask marks such words) */
 typedef struct b2_agg_partials {
   uint32_t n_groups;

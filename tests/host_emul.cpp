@@ -45,7 +45,7 @@ struct GroupAcc { uint64_t w[MAX_ACC_WORDS]; };
 // b2_device.h functions.  0 = nothing to do for this entry, 1 = row ready (conditions evaluated into *keep),
 // 3 = not a clean entry: the general functions decide.
 static int entry_fast_host(const DevPlan& P, const BlockView& b, uint32_t e, uint32_t e_lo, uint64_t read_ts, Row& row, Cells& cells, bool* keep,
-                           uint32_t* val_len) {
+                           uint32_t* val_len) {  // (row.imms is set by the caller)
   KeyTail t, q;
   if (!fast_key_tail(b.kptr(e), b.klen(e), &t)) return 3;
   if (e != e_lo) {
@@ -106,6 +106,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
       const bool unit_fast = g_emu_fast_front && P.fast_n > 0 && unit_prefix_ok(blk, e_lo, e_hi);
       for (uint32_t e = e_lo; e < e_hi; ++e) {
         Row row; Cells cells;
+        row.imms = cp.imms;
         bool keep = false;
         int fr = 3;
         uint32_t fast_val_len = 0;
@@ -200,7 +201,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
             acc->w[g.acc_off] += 1;
             if (g.kind == 0) continue;
             if (g.kind >= 3) { uint64_t key = extremum_key(v.bits, g.arg_et, g.arg_unsigned, g.kind == 4); if (key > acc->w[g.acc_off + 1]) acc->w[g.acc_off + 1] = key; continue; }
-            if (g.arg_et == 1) acc->w[g.acc_off + 1] = f64_bits(bits_f64(acc->w[g.acc_off + 1]) + bits_f64(v.bits));
+            if (g.arg_et == 1) f64_acc_add(v.bits, [&](uint32_t d, int64_t x) { acc->w[g.acc_off + 1 + d] += (uint64_t)x; });
             else {
               acc->w[g.acc_off + 1] += v.bits & 0xffffffffull;
               acc->w[g.acc_off + 2] += g.arg_unsigned ? (v.bits >> 32) : (uint64_t)((int64_t)v.bits >> 32);
@@ -258,7 +259,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
         if (ag.kind == 1 || ag.kind == 2) {
           bool has = cnt != 0;
           b2_decimal d{};
-          if (ag.arg_et == 1) data[c].push_back(has ? acc[ag.acc_off + 1] : 0);
+          if (ag.arg_et == 1) data[c].push_back(has ? f64_acc_round(acc + ag.acc_off + 1) : 0);
           else { if (has) limbs_to_decimal(acc[ag.acc_off + 1], acc[ag.acc_off + 2], ag.arg_unsigned, &d); data[c].push_back(0); }
           dec[c].push_back(d); nn[c].push_back(has);
           ++c;

@@ -150,6 +150,29 @@ def real_sum_plans():
             ("sum_real_group", scan().aggregation([("sum", col(C4, tp=ffi.TP_DOUBLE))], group_by=[col(C6, tp=ffi.TP_LONG)]).build())]
 
 
+def check_exact_real_sums(run, region):
+    """SUM / AVG over Real are exactly rounded on the device path (b2_device.h f64_acc_add / f64_acc_round): the result is
+    the correctly rounded sum of the group's values whatever the order — compare bit for bit with math.fsum over the
+    values the oracle's plain scan returns, and (loosely) with the oracle's own sequential sum."""
+    import math
+    import orc
+    rows = orc.dag_handle(Plan().table_scan(TABLE, COLUMNS).build(output_offsets=[C6, C4]), WHOLE, region).rows()
+    by = {}
+    for g, v in rows:
+        if v is not None:
+            by.setdefault(g, []).append(v)
+    assert by and max(len(v) for v in by.values()) > 10
+    plans = dict(real_sum_plans())
+    got = run(plans["sum_real_group"])
+    assert got.status == 0
+    assert {g: s for s, g in got.rows()} == {g: math.fsum(v) for g, v in by.items()}  # bit-exact: 0 ULP from the true sum's rounding
+    allv = [x for v in by.values() for x in v]
+    got = run(plans["sum_real"])  # [SUM, AVG count, AVG sum]
+    assert got.rows() == [(math.fsum(allv), len(allv), math.fsum(allv))]
+    seq = orc.dag_handle(plans["sum_real"], WHOLE, region).rows()[0][0]
+    assert math.isclose(seq, math.fsum(allv), rel_tol=1e-12)  # the reference's sequential sum is only this close to it
+
+
 def topn_plans():
     """(name, Plan, exact) — exact=False when ties at the cut make the surviving rows ambiguous in the reference too
     (TopNHeap keeps whichever tied rows its binary heap happens to hold): then only the sort keys are compared."""

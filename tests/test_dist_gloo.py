@@ -121,6 +121,18 @@ def test_merge_single_process_semantics():
     f[:, 1] = torch.tensor([1.5, 2.25], dtype=torch.float64).view(torch.int64)
     k, n, a = bd.merge_agg_partials(torch.tensor([1, 1]), torch.tensor([False, False]), f, real_words=(1,))
     assert a[0, 0] == 2 and a[0, 1:2].view(torch.float64).item() == 3.75
+    # exact Real SUM words (66 carry-save digits, b2_device.h f64_acc_add): partial sums merge by integer addition and
+    # round once: 1e308 + 1.0 - 1e308 + 2^-1074 is exactly 1 + 2^-1074 -> 1.0 (a sequential f64 sum would give 0.0 or 5e-324)
+    vals = [1e308, 1.0, -1e308, 5e-324]
+    parts = torch.tensor([[1] + bd.f64_acc_digits(v) for v in vals], dtype=torch.int64)
+    k, n, a = bd.merge_agg_partials(torch.tensor([3, 3, 3, 3]), torch.tensor([False] * 4), parts)
+    assert int(a[0, 0]) == 4 and bd.f64_acc_value(a[0, 1:].tolist()) == 1.0
+    import math
+    import random
+    rng = random.Random(7)
+    xs = [rng.uniform(-1, 1) * 10.0 ** rng.randrange(-300, 300) for _ in range(300)]
+    tot = [sum(d) for d in zip(*[bd.f64_acc_digits(x) for x in xs])]
+    assert bd.f64_acc_value(tot) == math.fsum(xs)
     # MAX / MIN extremum keys merge by unsigned maximum (word 1), their counts by addition (word 0)
     m = torch.tensor([[2, 5], [1, -3], [4, 9]], dtype=torch.int64)  # -3 is a huge unsigned key
     k, n, a = bd.merge_agg_partials(torch.tensor([8, 8, 9]), torch.tensor([False, False, False]), m, max_words=(1,))

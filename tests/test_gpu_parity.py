@@ -85,6 +85,15 @@ def test_real_sum(name, plan, regions):
                      float_rel_tol=1e-12, ctx=name)
 
 
+def test_real_sums_are_exactly_rounded(regions):
+    """north_star: float SUM / AVG within 1 ULP.  The device sum is exact (fixed-point accumulator), so it is the correctly
+    rounded true sum: 0 ULP, on host- and device-resident sources, generic and plan-specialised kernels alike."""
+    host = regions[1].build(read_ts=sc.READ_TS)
+    for region in (host, DeviceRegion(host)):
+        for jit in (ffi.JIT_OFF, ffi.JIT_SYNC):
+            sc.check_exact_real_sums(lambda plan: DagHandler(plan, sc.WHOLE, region, jit=jit).handle_request(), host)
+
+
 def test_isolation_levels_and_read_ts(regions):
     plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).build()
     for ts in (1, 25, 150, sc.READ_TS + 100, (1 << 64) - 1):

@@ -23,3 +23,25 @@ def test_specialised_kernels_compile_with_nvrtc():
         n, status, facts = J.compile_plan(plan, name)
         assert status == "ok", (name, facts)
         assert "registers" in facts
+
+
+def test_literals_are_launch_parameters_and_kernels_are_cached_on_disk():
+    """`col < 0` and `col < 1` (and another TopN LIMIT, another IN list) are one plan shape: the device plan keeps slot
+    numbers, the values travel in ScanArgs::imms.  The second shape-equal plan compiles nothing: its kernel is found in
+    the on-disk cache (b2_plan_precompile needs NVRTC only, no GPU)."""
+    import ctypes as C
+    pytest.importorskip("cuda.bindings.nvrtc")
+    import jit_compile_check as J
+    from tikv_b200 import ffi
+    from tikv_b200.plan import Plan, col, const_int, in_, lt
+    mk = lambda k: Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(lt(col(sc.C2), const_int(k))).build(output_offsets=[sc.C_H])
+    assert J.literal_of(mk(0)) == J.literal_of(mk(1)) == J.literal_of(mk(-(1 << 63)))
+    topn = lambda n: Plan().table_scan(sc.TABLE, sc.COLUMNS).topn([(col(sc.C2), True)], n).build()
+    assert J.literal_of(topn(10)) == J.literal_of(topn(1000))
+    inl = lambda *v: Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(in_(col(sc.C2), *[const_int(x) for x in v])).build()
+    assert J.literal_of(inl(1, 2, 3)) == J.literal_of(inl(7, 8, 9)) != J.literal_of(inl(1, 2))
+    L = ffi.lib()
+    n = C.c_int32(-1)
+    assert L.b2_plan_precompile(C.byref(mk(5).c), C.byref(n)) == 0, L.b2_last_error_message()
+    assert L.b2_plan_precompile(C.byref(mk(6).c), C.byref(n)) == 0
+    assert n.value == 0  # same shape: served by the cache

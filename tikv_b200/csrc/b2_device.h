@@ -28,7 +28,8 @@
 namespace b2 {
 
 // ---- limits of the device plan ----
-enum { MAX_GROUP = 4, MAX_PROJ = 16, MAX_COLS = 64, MAX_NODES = 96, MAX_CONDS = 8, MAX_AGGS = 8, MAX_ORDER = 4, MAX_STACK = 16, MAX_ACC_WORDS = 24 };
+enum { MAX_GROUP = 4, MAX_PROJ = 16, MAX_COLS = 64, MAX_NODES = 96, MAX_CONDS = 8, MAX_AGGS = 8, MAX_ORDER = 4, MAX_STACK = 16, MAX_ACC_WORDS = 144,
+       MAX_IMMS = 48 /* constants of a plan that travel as launch parameters instead of being part of the (compiled) plan */ };
 
 // ---- device error codes (mapped to B2_ERR_* + message in engine.cu) ----
 enum DevErr {
@@ -67,7 +68,8 @@ struct DevCol {
   uint8_t kind, role, is_unsigned, not_null, tp, v2_class, def_state, v2_hint;
 };
 struct DevNode {
-  int32_t sig;
+  int32_t sig;   // FN: tipb ScalarFuncSig.  Constant: 0 = the value is `imm`; s > 0 = the value is launch parameter imms[s - 1]
+                 // (plan_compile.h hoists constants so that `col < 5` and `col < 7` are one plan shape: one compiled kernel)
   uint8_t kind, n_args, et /*0 int 1 real*/, is_unsigned;
   int64_t imm;  // const bits (i64 or f64 bits) or column offset
 };
@@ -87,7 +89,8 @@ struct FastCond {
   uint8_t col_uns;   // compare the column as unsigned (field flag)
   uint8_t imm_uns;   // the constant is unsigned
   uint8_t zero_ext;  // decode: zero-extend (v2 UINT class)
-  uint8_t _p[3];
+  uint8_t imm_slot;  // s > 0: the constant is launch parameter imms[s - 1] (`imm` is 0 then)
+  uint8_t _p[2];
 };
 
 struct DevPlan {
@@ -683,7 +686,9 @@ struct Row {
   uint64_t filled;  // bitmask of plan columns present in the row (bit c)
   uint32_t fast;    // 1 (v2) / 2 (v1): the row holds exactly the plan's columns, all non-null: cells come from the two offset words below
   uint64_t o_lo, o_hi;  // the row's u16 end-offsets 0..3 / 4..7
+  const int64_t* imms;  // the request's hoisted constants (ScanArgs::imms: kernel parameter space on the device)
 };
+B2_HD int64_t node_imm(const Row& row, const DevNode& nd) { return nd.sig > 0 ? row.imms[nd.sig - 1] : nd.imm; }
 
 B2_HD uint32_t shr_clamp(uint32_t v, uint32_t sh) {  // v >> sh, 0 for sh >= 32
 #if defined(__CUDA_ARCH__)
@@ -1220,7 +1225,7 @@ B2_HD int eval_leaf(const DevPlan& P, const DevNode& nd, const Row& row, const C
     *v = (int64_t)x.bits; *f = (x.null ? 1u : 0u) | (P.cols[nd.imm].is_unsigned ? 2u : 0u);
     return DE_NONE;
   }
-  *v = nd.imm; *f = (nd.kind == B2_RPN_CONST_NULL ? 1u : 0u) | (nd.is_unsigned ? 2u : 0u);
+  *v = node_imm(row, nd); *f = (nd.kind == B2_RPN_CONST_NULL ? 1u : 0u) | (nd.is_unsigned ? 2u : 0u);
   return DE_NONE;
 }
 
@@ -1282,7 +1287,7 @@ B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const 
       continue;
     }
     if (nd.kind != B2_RPN_FN) {  // constants
-      sv[sp] = nd.imm; sn[sp] = (nd.kind == B2_RPN_CONST_NULL ? 1 : 0) | (nd.is_unsigned ? 2 : 0);
+      sv[sp] = node_imm(row, nd); sn[sp] = (nd.kind == B2_RPN_CONST_NULL ? 1 : 0) | (nd.is_unsigned ? 2 : 0);
       ++sp;
       continue;
     }
@@ -1417,7 +1422,7 @@ B2_HD int eval_conds(const DevPlan& P, const Row& row, const Cells& cells, bool*
     // the column is read by stored position (impl_compare.rs:63-149 semantics through cmp_i64)
     for (int i = 0; i < P.n_fconds; ++i) {
       const FastCond f = P.fconds[i];
-      const int c = cmp_i64((int64_t)fast_cell_dyn(row, f.h, f.zero_ext, P.fast_v1 != 0), f.col_uns, f.imm, f.imm_uns);
+      const int c = cmp_i64((int64_t)fast_cell_dyn(row, f.h, f.zero_ext, P.fast_v1 != 0), f.col_uns, f.imm_slot ? row.imms[f.imm_slot - 1] : f.imm, f.imm_uns);
       bool t;
       switch (f.op) {
         case 0: t = c < 0; break;
@@ -1443,6 +1448,73 @@ B2_HD int eval_conds(const DevPlan& P, const Row& row, const Cells& cells, bool*
     if (!t) { *keep = false; return DE_NONE; }
   }
   return DE_NONE;
+}
+
+// ---- exact SUM over Real ------------------------------------------------------------------------------------------
+// AggrFnSum<Real> (impl_sum.rs:71-150, summable.rs:25-87) adds f64 values in row order; any parallel order rounds
+// differently.  The device therefore accumulates every value exactly: the sum lives in a 2112-bit fixed-point number
+// (bit 0 = 2^-1074, enough for every finite double) held as F64_ACC_DIGITS 32-bit digits, one per u64 word, carry-save
+// (a word takes 2^31 additions before it could overflow).  Adding a value is at most three integer atomic adds, merging
+// two partial sums (CTAs, launches, GPUs) is word-wise integer addition, and f64_acc_round delivers the correctly rounded
+// (round-to-nearest-even) double of the exact sum: deterministic, independent of order, within 0.5 ULP of the true sum
+// (the reference's own sequential result is within (n-1) ulps-of-partial-sums of it).
+enum { F64_ACC_DIGITS = 66 };
+// x (finite) = sign * m * 2^(s - 1074), m < 2^53, s = max(exponent field, 1) - 1: pieces of m << (s & 31) at digit s >> 5
+template <class AddFn>
+B2_HD void f64_acc_add(uint64_t bits, AddFn add) {
+  uint64_t m = bits & 0xfffffffffffffull;
+  uint32_t e = (uint32_t)(bits >> 52) & 0x7ffu;
+  if (e) m |= 1ull << 52; else e = 1;
+  if (!m) return;
+  const uint32_t s = e - 1, d = s >> 5, o = s & 31u;
+  const uint64_t lo64 = m << o;
+  const uint64_t hi = o ? (m >> (64 - o)) : 0ull;
+  int64_t p0 = (int64_t)(lo64 & 0xffffffffull), p1 = (int64_t)(lo64 >> 32), p2 = (int64_t)hi;
+  if (bits >> 63) { p0 = -p0; p1 = -p1; p2 = -p2; }
+  if (p0) add(d, p0);
+  if (p1) add(d + 1, p1);
+  if (p2) add(d + 2, p2);
+}
+// the correctly rounded value of the accumulator (w: F64_ACC_DIGITS carry-save words)
+template <class W>
+B2_HD uint64_t f64_acc_round(const W* w) {
+  uint32_t dig[F64_ACC_DIGITS + 1];
+  int64_t carry = 0;
+  for (int i = 0; i < F64_ACC_DIGITS; ++i) {
+    const int64_t v = (int64_t)w[i] + carry;  // |w[i]| < 2^63 - 2^32 by construction
+    dig[i] = (uint32_t)v;
+    carry = v >> 32;
+  }
+  dig[F64_ACC_DIGITS] = (uint32_t)carry;
+  const bool neg = carry < 0;
+  if (neg) {  // two's complement magnitude
+    uint64_t c = 1;
+    for (int i = 0; i <= F64_ACC_DIGITS; ++i) { c += (uint32_t)~dig[i]; dig[i] = (uint32_t)c; c >>= 32; }
+  }
+  int top = F64_ACC_DIGITS;
+  while (top >= 0 && dig[top] == 0) --top;
+  if (top < 0) return 0;  // +0.0
+  uint32_t t = dig[top], lz = 0;
+  while (!(t & 0x80000000u)) { t <<= 1; ++lz; }
+  const int p = 32 * top + 31 - (int)lz;  // position of the most significant bit
+  const uint64_t sign = neg ? 0x8000000000000000ull : 0ull;
+  auto digit = [&](int i) -> uint64_t { return i >= 0 && i <= F64_ACC_DIGITS ? dig[i] : 0u; };
+  if (p <= 52) return sign | (digit(0) | (digit(1) << 32));  // subnormal, or exponent field 1: the bits are the value
+  const int q = p - 52, k = q >> 5, r = q & 31;  // mantissa = 53 bits from position q
+  const uint64_t lo = digit(k) | (digit(k + 1) << 32), hi = digit(k + 2);
+  uint64_t m = (r ? ((lo >> r) | (hi << (64 - r))) : lo) & ((1ull << 53) - 1);
+  // round to nearest even on the bits below q
+  const int gq = q - 1;
+  const bool guard = (digit(gq >> 5) >> (gq & 31)) & 1u;
+  bool sticky = (digit(gq >> 5) & ((1ull << (gq & 31)) - 1)) != 0;
+  for (int i = (gq >> 5) - 1; i >= 0 && !sticky; --i) sticky = dig[i] != 0;
+  uint64_t e = (uint64_t)(q + 1);
+  if (guard && (sticky || (m & 1))) {
+    ++m;
+    if (m >> 53) { m >>= 1; ++e; }
+  }
+  if (e >= 2047) return sign | 0x7ff0000000000000ull;  // beyond DBL_MAX
+  return sign | (e << 52) | (m & 0xfffffffffffffull);
 }
 
 // MAX / MIN state (impl_max_min.rs:425-560): [count of non-NULL inputs, extremum key].  The key is an order-preserving

@@ -681,6 +681,8 @@ struct b2_exec {
     a.ctr = ctr();
     a.read_ts = cp.dev.read_ts; a.isolation = cp.dev.isolation;
     a.fast_ok = use_fast_front ? u.fast_ok : 0;
+    memcpy(a.imms, cp.imms, sizeof(a.imms));
+    a.limit = cp.dev.limit;
     a.range_rows = range_rows.p ? (unsigned long long*)range_rows.p + u.range_idx : nullptr;
     return a;
   }
@@ -1044,7 +1046,7 @@ struct b2_exec {
       // small on purpose (192 resident groups per CTA): it absorbs the low-cardinality case, where global atomics would
       // serialise on a few addresses; beyond that the HBM table lives in L2 anyway and a big CTA table only costs
       // shared memory (measured, 1e8 rows: 2048 / 1024 / 256 slots -> G=1024: 5.8 / 6.7 / 6.2 ms, G=2^20: 15.9 / 10.0 / 9.9 ms)
-      smem_slots = 256;
+      smem_slots = P.acc_words > 32 ? 0 : 256;  // (exact Real sums are 67 words per group: those plans use the HBM table only)
       while (smem_slots > 64 && (size_t)smem_slots * (8 + 8 * P.acc_words) > 64 * 1024) smem_slots >>= 1;
       smem = (size_t)smem_slots * (8 + 8 * P.acc_words);
     }
@@ -1401,6 +1403,32 @@ extern "C" int32_t b2_plan_prepare(const b2_dag_plan* plan, int32_t device) {
   if (k->ok && with_v1.valid()) k = with_v1.get();
   if (!k->ok) { g_last_error = "plan-specialised kernel: " + k->error; return B2_ERR_CUDA; }
   return B2_OK;
+}
+
+// Ahead-of-time: compile the plan-specialised kernel(s) of `plan` into the on-disk cache with NVRTC alone — no GPU, no
+// CUDA context (build machines; `__graft_entry__.build()` warms the cache for the bench plans this way).  Returns B2_OK,
+// *n_compiled (may be NULL) = kernels compiled now (0 = everything was cached already).
+extern "C" int32_t b2_plan_precompile(const b2_dag_plan* plan, int32_t* n_compiled) {
+  CompiledPlan cp;
+  std::string msg;
+  int rc = compile_plan(plan, &cp, &msg);
+  if (rc) { g_last_error = msg; return rc; }
+  int done = 0;
+  for (int v1 = (cp.dev.fast_v1 ? 1 : 0); v1 >= 0; --v1) {  // both data-dependent variants, like b2_plan_prepare
+    cp.dev.fast_v1 = v1;
+    std::string err;
+    int r = jit_precompile(cp.dev, &err);
+    if (r < 0) { g_last_error = "plan-specialised kernel: " + err; return B2_ERR_UNSUPPORTED; }
+    done += r == 0;
+  }
+  if (n_compiled) *n_compiled = done;
+  return B2_OK;
+}
+extern "C" void b2_jit_counters(uint64_t* nvrtc_compiles, uint64_t* disk_cache_hits) {
+  unsigned long long a = 0, b = 0;
+  jit_counters(&a, &b);
+  if (nvrtc_compiles) *nvrtc_compiles = a;
+  if (disk_cache_hits) *disk_cache_hits = b;
 }
 
 int32_t b2_exec_schema(b2_exec* h, int32_t* field_tps, uint32_t* field_flags, uint32_t* n_inout) {

@@ -13,6 +13,10 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
 
 #include <cstdio>
 #include <cstdlib>
@@ -49,7 +53,26 @@ struct Api {
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
   std::string csrc_dir, cuda_inc;
+  bool rtc_ok = false;          // NVRTC + kernel sources: enough to compile into the on-disk cache (no GPU needed)
+  std::string cache_dir;        // compiled cubins, keyed by (plan shape, kernel sources, compiler options)
+  unsigned long long src_hash = 0;
 };
+
+unsigned long long fnv1a(const void* p, size_t n, unsigned long long h = 1469598103934665603ull) {
+  const unsigned char* c = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; }
+  return h;
+}
+bool read_file(const std::string& path, std::string* out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  char buf[65536];
+  size_t n;
+  out->clear();
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) out->append(buf, n);
+  fclose(f);
+  return true;
+}
 
 template <class F>
 bool sym(void* lib, const char* name, F* out) {
@@ -66,23 +89,32 @@ Api& api() {
       if ((rtc = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
     void* drv = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
     if (!rtc) { a.why = "libnvrtc not found"; return; }
-    if (!drv) { a.why = "libcuda.so.1 not found"; return; }
     bool ok = sym(rtc, "nvrtcCreateProgram", &a.CreateProgram) && sym(rtc, "nvrtcCompileProgram", &a.CompileProgram) &&
               sym(rtc, "nvrtcGetProgramLogSize", &a.GetProgramLogSize) && sym(rtc, "nvrtcGetProgramLog", &a.GetProgramLog) &&
-              sym(rtc, "nvrtcGetCUBINSize", &a.GetCUBINSize) && sym(rtc, "nvrtcGetCUBIN", &a.GetCUBIN) && sym(rtc, "nvrtcDestroyProgram", &a.DestroyProgram) &&
-              sym(drv, "cuModuleLoadData", &a.ModuleLoadData) && sym(drv, "cuModuleGetFunction", &a.ModuleGetFunction) &&
-              sym(drv, "cuFuncSetAttribute", &a.FuncSetAttribute) &&
-              sym(drv, "cuOccupancyMaxActiveBlocksPerMultiprocessor", &a.OccupancyMaxActiveBlocksPerMultiprocessor) && sym(drv, "cuLaunchKernel", &a.LaunchKernel);
-    if (!ok) { a.why = "nvrtc / driver entry point missing"; return; }
+              sym(rtc, "nvrtcGetCUBINSize", &a.GetCUBINSize) && sym(rtc, "nvrtcGetCUBIN", &a.GetCUBIN) && sym(rtc, "nvrtcDestroyProgram", &a.DestroyProgram);
+    if (!ok) { a.why = "nvrtc entry point missing"; return; }
     Dl_info info;
     if (!dladdr(reinterpret_cast<void*>(static_cast<bool (*)(std::string*)>(&jit_available)), &info) || !info.dli_fname) { a.why = "cannot locate the shared object"; return; }
     std::string so = info.dli_fname;
     size_t slash = so.rfind('/');
     std::string dir = slash == std::string::npos ? "." : so.substr(0, slash);
     a.csrc_dir = dir + "/../csrc";
-    FILE* f = fopen((a.csrc_dir + "/scan_kernel.cuh").c_str(), "r");
-    if (!f) { a.why = "kernel sources not found next to the library (" + a.csrc_dir + ")"; return; }
-    fclose(f);
+    // the sources a specialised kernel is built from: their content is part of the cache key
+    unsigned long long h = 1469598103934665603ull;
+    for (const char* f : {"/scan_kernel.cuh", "/kernels.cuh", "/b2_device.h", "/../../include/b2_copr.h"}) {
+      std::string text;
+      if (!read_file(a.csrc_dir + f, &text)) { a.why = std::string("kernel sources not found next to the library (") + a.csrc_dir + f + ")"; return; }
+      h = fnv1a(text.data(), text.size(), h);
+    }
+    a.src_hash = h;
+    const char* cd = getenv("B2_JIT_CACHE_DIR");
+    a.cache_dir = cd && *cd ? std::string(cd) : dir + "/jit_cache";
+    a.rtc_ok = true;
+    if (!drv) { a.why = "libcuda.so.1 not found"; return; }
+    ok = sym(drv, "cuModuleLoadData", &a.ModuleLoadData) && sym(drv, "cuModuleGetFunction", &a.ModuleGetFunction) &&
+         sym(drv, "cuFuncSetAttribute", &a.FuncSetAttribute) &&
+         sym(drv, "cuOccupancyMaxActiveBlocksPerMultiprocessor", &a.OccupancyMaxActiveBlocksPerMultiprocessor) && sym(drv, "cuLaunchKernel", &a.LaunchKernel);
+    if (!ok) { a.why = "driver entry point missing"; return; }
     a.ok = true;
   });
   return a;
@@ -95,34 +127,83 @@ std::mutex g_mu;
 // leaked on purpose: a static destructor would block process exit on compilations still in flight
 std::map<std::string, Entry>& g_cache = *new std::map<std::string, Entry>();
 
-JitKernel* compile(int device, int mode, bool ext_sigs, const std::string& literal) {
+// ---- on-disk cache of compiled cubins ------------------------------------------------------------------------------
+// One file per (plan shape, kernel instantiation, compiler options, kernel sources): <dir>/<hash>.cubin plus <hash>.key
+// holding the full key (a hash collision or a stale file is detected by comparing it).  Written atomically (rename).
+std::atomic<unsigned long long> g_nvrtc_compiles{0}, g_cache_hits{0};
+std::string cache_key(int mode, bool ext_sigs, const std::string& literal) {
+  return "b2jit1|sm_100a|mode" + std::to_string(mode) + "|ext" + std::to_string((int)ext_sigs) + "|src" + std::to_string(api().src_hash) + "|" + literal;
+}
+std::string cache_path(const std::string& key) {
+  char name[32];
+  snprintf(name, sizeof(name), "%016llx", fnv1a(key.data(), key.size()));
+  return api().cache_dir + "/" + name;
+}
+bool cache_load(const std::string& key, std::vector<char>* cubin) {
+  if (getenv("B2_JIT_NO_DISK_CACHE")) return false;
+  std::string path = cache_path(key), k, c;
+  if (!read_file(path + ".key", &k) || k != key || !read_file(path + ".cubin", &c) || c.empty()) return false;
+  cubin->assign(c.begin(), c.end());
+  return true;
+}
+void cache_store(const std::string& key, const std::vector<char>& cubin) {
+  if (getenv("B2_JIT_NO_DISK_CACHE")) return;
+  mkdir(api().cache_dir.c_str(), 0755);
+  std::string path = cache_path(key), tmp = path + ".tmp" + std::to_string((long)getpid()) + "." + std::to_string((unsigned long long)(uintptr_t)&cubin);
+  for (int pass = 0; pass < 2; ++pass) {
+    const std::string dst = path + (pass ? ".key" : ".cubin");
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;
+    const char* p = pass ? key.data() : cubin.data();
+    size_t n = pass ? key.size() : cubin.size();
+    bool ok = fwrite(p, 1, n, f) == n;
+    ok = fclose(f) == 0 && ok;
+    if (!ok || rename(tmp.c_str(), dst.c_str()) != 0) { remove(tmp.c_str()); return; }
+  }
+}
+
+// NVRTC only (no CUDA context): plan literal -> sm_100a cubin
+bool compile_cubin(int mode, bool ext_sigs, const std::string& literal, std::vector<char>* cubin, std::string* error) {
   Api& a = api();
-  JitKernel* k = new JitKernel();
-  cudaSetDevice(device);
-  cudaFree(nullptr);  // make sure the primary context exists and is current on this thread
   std::string src = "#define B2_NVRTC 1\n#include \"scan_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + literal +
                     ";\n}\nextern \"C\" __global__ void __launch_bounds__(b2::TILE + 64, 2) b2_scan_jit(const __grid_constant__ b2::ScanArgs A) {\n"
                     "  b2::scan_body<" + std::to_string(mode) + ">(b2::kJitPlan, A);\n}\n";
   nvrtcProgram prog;
-  if (a.CreateProgram(&prog, src.c_str(), "b2_scan_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { k->error = "nvrtcCreateProgram failed"; return k; }
+  if (a.CreateProgram(&prog, src.c_str(), "b2_scan_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { *error = "nvrtcCreateProgram failed"; return false; }
   std::string inc = "-I" + a.csrc_dir;
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-DB2_NVRTC=1", "-default-device", inc.c_str(), "-I/usr/local/cuda/include",
                         ext_sigs ? "-DB2_EXT_SIGS=1" : "-DB2_EXT_SIGS=0"};
   nvrtcResult rc = a.CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+  g_nvrtc_compiles++;
   if (rc != NVRTC_SUCCESS) {
     size_t n = 0;
     a.GetProgramLogSize(prog, &n);
     std::string log(n, 0);
     if (n) a.GetProgramLog(prog, &log[0]);
-    k->error = "nvrtc: " + log.substr(0, 2000);
+    *error = "nvrtc: " + log.substr(0, 2000);
     a.DestroyProgram(&prog);
-    return k;
+    return false;
   }
   size_t n = 0;
   a.GetCUBINSize(prog, &n);
-  std::vector<char> cubin(n);
-  a.GetCUBIN(prog, cubin.data());
+  cubin->resize(n);
+  a.GetCUBIN(prog, cubin->data());
   a.DestroyProgram(&prog);
+  return true;
+}
+
+JitKernel* compile(int device, int mode, bool ext_sigs, const std::string& literal) {
+  Api& a = api();
+  JitKernel* k = new JitKernel();
+  cudaSetDevice(device);
+  cudaFree(nullptr);  // make sure the primary context exists and is current on this thread
+  const std::string key = cache_key(mode, ext_sigs, literal);
+  std::vector<char> cubin;
+  if (cache_load(key, &cubin)) g_cache_hits++;
+  else {
+    if (!compile_cubin(mode, ext_sigs, literal, &cubin, &k->error)) return k;
+    cache_store(key, cubin);
+  }
   CUmodule mod;
   if (a.ModuleLoadData(&mod, cubin.data()) != CUDA_SUCCESS) { k->error = "cuModuleLoadData failed"; return k; }
   CUfunction fn;
@@ -155,7 +236,7 @@ std::shared_future<JitKernel*> jit_get(int device, const DevPlan& plan) {
   static std::once_flag at_exit_once;
   std::call_once(at_exit_once, [] { std::atexit(jit_wait_all_at_exit); });
   DevPlan p = plan;
-  p.read_ts = 0; p.isolation = 0;  // launch parameters (ScanArgs), not part of the specialisation
+  p.read_ts = 0; p.isolation = 0; p.limit = 0;  // launch parameters (ScanArgs), not part of the specialisation
   std::string key = std::to_string(device) + "|" + plan_literal(p);
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_cache.find(key);
@@ -167,6 +248,27 @@ std::shared_future<JitKernel*> jit_get(int device, const DevPlan& plan) {
   g_cache[key].fut = fut;
   return fut;
 }
+
+static int jit_mode_of(const DevPlan& plan) { return plan.mode == PM_SCAN && plan.n_proj ? (int)PM_PROJ : (plan.mode == PM_AGG && plan.n_group > 1 ? (int)PM_AGGM : plan.mode); }
+
+// Compile the kernel of `plan` into the on-disk cache without touching a GPU (build machines, ahead-of-time warm-up).
+// 0 = compiled now, 1 = was cached already, negative = failure (message in *error).
+int jit_precompile(const DevPlan& plan, std::string* error) {
+  Api& a = api();
+  if (!a.rtc_ok) { *error = a.why; return -1; }
+  DevPlan p = plan;
+  p.read_ts = 0; p.isolation = 0; p.limit = 0;
+  const std::string literal = plan_literal(p);
+  const bool ext_sigs = plan_uses_ext_sigs(plan);
+  const int mode = jit_mode_of(plan);
+  const std::string key = cache_key(mode, ext_sigs, literal);
+  std::vector<char> cubin;
+  if (cache_load(key, &cubin)) return 1;
+  if (!compile_cubin(mode, ext_sigs, literal, &cubin, error)) return -1;
+  cache_store(key, cubin);
+  return 0;
+}
+void jit_counters(unsigned long long* nvrtc_compiles, unsigned long long* disk_hits) { *nvrtc_compiles = g_nvrtc_compiles.load(); *disk_hits = g_cache_hits.load(); }
 
 int jit_max_blocks_per_sm(const JitKernel* k, size_t smem) {
   int n = 0;

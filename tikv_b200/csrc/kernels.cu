@@ -151,7 +151,7 @@ __global__ void topn_gather_kernel(const __grid_constant__ DevPlan P, const __gr
   int err = ro.err ? ro.err : (ro.found ? DE_NONE : DE_BAD_WRITE);
   if (!err) {
     uint32_t ko = A.blk.koff[e], kl = A.blk.koff[e + 1] - ko;
-    row.enc_key = A.blk.keys + ko; row.enc_key_len = kl - 8; row.commit_ts = ro.commit_ts;
+    row.enc_key = A.blk.keys + ko; row.enc_key_len = kl - 8; row.commit_ts = ro.commit_ts; row.imms = A.imms;
     err = row_open(ro.val, ro.val_len, &row.rv);
     if (!err) err = row_split(P, row, cells);
   }
@@ -259,7 +259,7 @@ __global__ void agg_result_kernel(const __grid_constant__ DevPlan P, unsigned in
     if (ag.kind == 0 || ag.kind == 2) { col_data[c][g] = cnt; ++c; }  // COUNT, or AVG's count column
     if (ag.kind == 1 || ag.kind == 2) {
       bool has = cnt != 0;
-      if (ag.arg_et == 1) col_data[c][g] = has ? acc[ag.acc_off + 1] : 0ull;
+      if (ag.arg_et == 1) col_data[c][g] = has ? f64_acc_round(acc + ag.acc_off + 1) : 0ull;
       else {
         b2_decimal d;
         if (has) limbs_to_decimal(acc[ag.acc_off + 1], acc[ag.acc_off + 2], ag.arg_unsigned, &d);

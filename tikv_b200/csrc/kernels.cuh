@@ -75,6 +75,8 @@ struct ScanArgs {
   uint32_t stage_off;               // byte offset of the stages inside dynamic shared memory (multiple of 16)
   uint32_t out_stage_off;           // PM_SCAN: byte offset of the output transpose buffer (multiple of 16)
   uint32_t stage_key_cap, stage_val_cap;  // bytes per stage for key / value heaps (multiples of 16)
+  int64_t imms[MAX_IMMS];           // the request's constants (DevNode::sig / FastCond::imm_slot index them)
+  uint64_t limit;                   // TopN limit (not part of the compiled plan shape)
   uint32_t fast_ok;                 // 1: every key of [e_lo, e_hi) starts with the same 12 bytes 't' tid "_r" (first and last key of the
                                     //    sorted unit agree): the clean-entry front end may skip them
   uint32_t _pad1;

@@ -19,6 +19,8 @@ struct CompiledPlan {
   std::vector<OutCol> schema;            // output schema of the outermost executor
   std::vector<uint32_t> output_offsets;  // indices into `schema` delivered to the caller
   uint64_t scan_limit = ~0ull;           // BatchLimitExecutor on top of a scan / selection pipeline (limit_executor.rs), ~0 = none
+  int64_t imms[MAX_IMMS] = {};           // hoisted constants, referenced by DevNode::sig / FastCond::imm_slot (ScanArgs::imms at launch)
+  int n_imms = 0;
 };
 
 inline int col_kind_of_tp(int tp) {  // def/eval_type.rs:53-95
@@ -258,8 +260,8 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
         g.acc_off = (uint8_t)acc;
         switch (e.aggrs[k].kind) {
           case B2_AGG_COUNT: g.kind = 0; acc += 1; break;
-          case B2_AGG_SUM: g.kind = 1; acc += et ? 2 : 3; break;
-          case B2_AGG_AVG: g.kind = 2; acc += et ? 2 : 3; break;
+          case B2_AGG_SUM: g.kind = 1; acc += et ? 1 + F64_ACC_DIGITS : 3; break;  // Real: exact fixed-point accumulator (b2_device.h f64_acc_add)
+          case B2_AGG_AVG: g.kind = 2; acc += et ? 1 + F64_ACC_DIGITS : 3; break;
           case B2_AGG_MAX: g.kind = 3; acc += 2; break;
           case B2_AGG_MIN: g.kind = 4; acc += 2; break;
           default: *msg = "aggregate function " + std::to_string(e.aggrs[k].kind) + " is not on the device path yet"; return B2_ERR_UNSUPPORTED;
@@ -369,7 +371,7 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
       const DevCol& col = P.cols[cn.imm];
       FastCond fc;
       memset(&fc, 0, sizeof(fc));
-      fc.imm = kn.imm; fc.h = col.v2_hint; fc.col_uns = col.is_unsigned; fc.imm_uns = kn.is_unsigned; fc.zero_ext = col.v2_class != V2_INT;
+      fc.imm = kn.imm; fc._p[0] = (uint8_t)(col_first ? 1 : 0) /* which node holds the constant: resolved into imm_slot below */; fc.h = col.v2_hint; fc.col_uns = col.is_unsigned; fc.imm_uns = kn.is_unsigned; fc.zero_ext = col.v2_class != V2_INT;
       int op;  // column on the left
       switch (f.sig) {
         case B2_SIG_LT_INT: op = col_first ? 0 : 2; break;
@@ -384,6 +386,23 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
       all = true;
     }
     if (all) P.n_fconds = P.n_conds;
+  }
+  // Constants become launch parameters: the device plan keeps only a slot number, so that requests which differ in their
+  // literals (`col < 5`, `col < 7`, another IN list, another LIMIT) share one plan shape and one specialised kernel.
+  out->n_imms = 0;
+  for (int i = 0; i < P.n_nodes; ++i) {
+    DevNode& nd = P.nodes[i];
+    if ((nd.kind == B2_RPN_CONST_INT || nd.kind == B2_RPN_CONST_UINT || nd.kind == B2_RPN_CONST_REAL) && out->n_imms < MAX_IMMS) {
+      out->imms[out->n_imms] = nd.imm;
+      nd.sig = ++out->n_imms;
+      nd.imm = 0;
+    } else if (nd.kind != B2_RPN_FN) nd.sig = 0;
+  }
+  for (int i = 0; i < P.n_fconds; ++i) {
+    FastCond& fc = P.fconds[i];
+    const DevNode& kn = P.nodes[P.conds[i].start + (fc._p[0] ? 1 : 0)];
+    fc._p[0] = 0;
+    if (kn.sig > 0) { fc.imm_slot = (uint8_t)kn.sig; fc.imm = 0; }
   }
   return B2_OK;
 }

@@ -19,7 +19,7 @@ inline std::string plan_literal(const DevPlan& P) {
   u64(P.fast_filled); o << "," << P.fast_cls << "u," << P.fast_uns << "u,{";
   for (int i = 0; i < 8; ++i) o << (int)P.fast_out[i] << (i < 7 ? "," : "");
   o << "}," << P.n_out_slow << "," << P.fast_v1 << ",";
-  u64(P.fast_ids); o << ","; u64(0 /* read_ts stays a launch parameter */); o << ","; u64(P.limit); o << ",{";
+  u64(P.fast_ids); o << ","; u64(0 /* read_ts stays a launch parameter */); o << ","; u64(0 /* so does the TopN limit (ScanArgs::limit) */); o << ",{";
   for (int i = 0; i < MAX_CONDS; ++i) { expr(P.conds[i]); o << (i < MAX_CONDS - 1 ? "," : ""); }
   o << "},"; expr(P.group);
   o << "," << (int)P.group_et << "," << (int)P.group_unsigned << "," << (int)P._p0 << "," << (int)P._p1 << ",{";
@@ -39,7 +39,7 @@ inline std::string plan_literal(const DevPlan& P) {
   o << "}," << P.n_fconds << "," << P._fcpad << ",{";
   for (int i = 0; i < MAX_CONDS; ++i) {
     const FastCond& f = P.fconds[i];
-    o << "{"; i64(f.imm); o << "," << (int)f.h << "," << (int)f.op << "," << (int)f.col_uns << "," << (int)f.imm_uns << "," << (int)f.zero_ext << ",{0,0,0}}" << (i < MAX_CONDS - 1 ? "," : "");
+    o << "{"; i64(f.imm); o << "," << (int)f.h << "," << (int)f.op << "," << (int)f.col_uns << "," << (int)f.imm_uns << "," << (int)f.zero_ext << "," << (int)f.imm_slot << ",{0,0}}" << (i < MAX_CONDS - 1 ? "," : "");
   }
   o << "}," << P.n_proj << "," << P._prpad << ",{";
   for (int i = 0; i < MAX_PROJ; ++i) { expr(P.proj[i]); o << (i < MAX_PROJ - 1 ? "," : ""); }

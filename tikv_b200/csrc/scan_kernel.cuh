@@ -297,6 +297,7 @@ __device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A,
   row.enc_key = ek;
   row.enc_key_len = kl - 8;
   row.commit_ts = ro.commit_ts;
+  row.imms = A.imms;
   int err = row_open(ro.val, ro.val_len, &row.rv);
   if (!err) err = row_split(P, row, cells);
   bool keep = false;
@@ -335,7 +336,7 @@ __device__ __forceinline__ int entry_fast(const DevPlan& P, const ScanArgs& A, c
   const uint8_t* vp = view.svals + vo;
   uint32_t roff, rlen;
   if (!fast_write_head(vp, vl, &roff, &rlen)) return P1_GENERAL;
-  row.enc_key = kp; row.enc_key_len = 27; row.commit_ts = cts;
+  row.enc_key = kp; row.enc_key_len = 27; row.commit_ts = cts; row.imms = A.imms;
   if (!fast_row_v2(P, vp + roff, rlen, row)) return P1_GENERAL;
   row.filled = P.fast_filled;
   bool keep = false;
@@ -390,7 +391,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   if (MODE == PM_TOPN) {
     if (tid == 0) {
       s_top_cnt = 0; s_top_have_thr = 0;
-      if (A.topn_seed && P.limit > 0 && *A.topn_seed_cnt >= (unsigned int)P.limit) { s_top_thr = A.topn_seed[P.limit - 1]; s_top_have_thr = 1; }
+      if (A.topn_seed && A.limit > 0 && *A.topn_seed_cnt >= (unsigned int)A.limit) { s_top_thr = A.topn_seed[A.limit - 1]; s_top_have_thr = 1; }
     }
     for (unsigned int i = tid; i < A.topn_cap; i += blockDim.x) tb.idx[i] = (unsigned short)i;
     __syncthreads();
@@ -711,7 +712,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
         }
       }
       cta256_sync();
-      if (s_top_cnt + TILE > A.topn_cap) cta_topn_compact(tb, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
+      if (s_top_cnt + TILE > A.topn_cap) cta_topn_compact(tb, (unsigned int)A.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
     } else if (IS_AGG) {
       // BatchSimpleAggregation / BatchFastHashAggregation / BatchSlowHashAggregation (PM_AGGM).  Rows of one warp that share a group key are combined with
       // warp reductions first (match.any + redux); the group's leader lane then issues one atomic per accumulator
@@ -768,6 +769,9 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
           peers = __match_any_sync(active, gk.bits) & (gk.null ? nm : ~nm);
           if (__popc(__ballot_sync(active, (unsigned int)(__ffs(peers) - 1) == lane)) > 4) peers = 1u << lane;
         }
+        bool real_sum = false;  // (folds to a constant in a specialised kernel)
+        for (int a = 0; a < P.n_aggs; ++a) real_sum |= (P.aggs[a].kind == 1 || P.aggs[a].kind == 2) && P.aggs[a].arg_et == 1;
+        if (real_sum) peers = 1u << lane;
         const bool leader = (unsigned int)(__ffs(peers) - 1) == lane;
         const bool solo = (peers & (peers - 1)) == 0;
         unsigned long long* acc = nullptr;
@@ -822,13 +826,12 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
               }
             if (commit) { atomicAdd(&w[0], (unsigned long long)cnt); atomicMax(&w[1], key); }
           } else if (g.arg_et == 1) {
-            double sum = has ? bits_f64(v.bits) : 0.0;
-            if (!solo) {
-              const double mine = sum;
-              sum = 0.0;
-              for (unsigned int mm = peers; mm; mm &= mm - 1) sum += __shfl_sync(peers, mine, __ffs(mm) - 1);  // lane order
+            // exact: every lane adds its own value into the group's fixed-point accumulator (plans with a Real SUM / AVG run
+            // without warp pre-aggregation: `peers` is the lane itself, see above)
+            if (commit) {
+              atomicAdd(&w[0], (unsigned long long)cnt);
+              f64_acc_add(v.bits, [&](uint32_t d, int64_t x) { atomicAdd(&w[1 + d], (unsigned long long)x); });
             }
-            if (commit) { atomicAdd(&w[0], (unsigned long long)cnt); atomicAdd(reinterpret_cast<double*>(&w[1]), sum); }
           } else {
             const uint32_t lo = has ? (uint32_t)v.bits : 0u, hi = has ? (uint32_t)(v.bits >> 32) : 0u;
             unsigned long long lo_sum, hi_sum;
@@ -893,7 +896,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   }
   if (MODE == PM_TOPN) {
     cta256_sync();
-    cta_topn_compact(tb, (unsigned int)P.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
+    cta_topn_compact(tb, (unsigned int)A.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
     unsigned int keep = s_top_cnt;
     for (unsigned int i = tid; i < keep; i += TILE) A.topn.items[(size_t)blockIdx.x * A.topn.stride + i] = topbuf_get(tb, tb.idx[i]);
     if (tid == 0) A.topn.counts[blockIdx.x] = keep;
@@ -902,16 +905,12 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     if (!P.has_group) {
       cta256_sync();
       for (int w = (int)tid; w < P.acc_words; w += TILE) {
-        bool is_real = false, is_max = false;
-        for (int a = 0; a < P.n_aggs; ++a) {
-          const bool second = P.aggs[a].acc_off + 1 == w;
-          if ((P.aggs[a].kind == 1 || P.aggs[a].kind == 2) && P.aggs[a].arg_et == 1 && second) is_real = true;
-          if (P.aggs[a].kind >= 3 && second) is_max = true;
-        }
+        bool is_max = false;
+        for (int a = 0; a < P.n_aggs; ++a)
+          if (P.aggs[a].kind >= 3 && P.aggs[a].acc_off + 1 == w) is_max = true;
         unsigned long long x = s_simple_acc[w];
         if (is_max) { if (x) atomicMax(&A.tbl.acc[w], x); }
-        else if (is_real) { double dd = bits_f64(x); if (dd != 0.0) atomicAdd(reinterpret_cast<double*>(&A.tbl.acc[w]), dd); }
-        else if (x) atomicAdd(&A.tbl.acc[w], x);
+        else if (x) atomicAdd(&A.tbl.acc[w], x);  // counts, integer limbs and the digits of exact Real sums are all additive
       }
     } else if (st.slots) {
       cta256_sync();
@@ -927,7 +926,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
           atomicAdd(&dst[0], src[0]);
           if (g.kind == 0) continue;
           if (g.kind >= 3) atomicMax(&dst[1], src[1]);
-          else if (g.arg_et == 1) atomicAdd(reinterpret_cast<double*>(&dst[1]), bits_f64(src[1]));
+          else if (g.arg_et == 1) { for (int d = 0; d < F64_ACC_DIGITS; ++d) if (src[1 + d]) atomicAdd(&dst[1 + d], src[1 + d]); }
           else { atomicAdd(&dst[1], src[1]); atomicAdd(&dst[2], src[2]); }
         }
       }

@@ -45,14 +45,45 @@ def _all_gather_var(t):
 
 
 # ---- hash aggregation -------------------------------------------------------------------------------------------
+F64_ACC_DIGITS = 66  # b2_device.h: exact Real sums are 66 carry-save 32-bit digits (bit 0 = 2^-1074)
+
+
+def f64_acc_digits(x):
+    """The accumulator words of one finite double (what f64_acc_add adds), as python ints."""
+    import struct
+    bits = struct.unpack("<Q", struct.pack("<d", float(x)))[0]
+    m, e = bits & ((1 << 52) - 1), (bits >> 52) & 0x7FF
+    if e:
+        m |= 1 << 52
+    else:
+        e = 1
+    v = (-m if bits >> 63 else m) << (e - 1)
+    sign = -1 if v < 0 else 1
+    v = abs(v)
+    return [sign * ((v >> (32 * i)) & 0xFFFFFFFF) for i in range(F64_ACC_DIGITS)]
+
+
+def f64_acc_value(words):
+    """Correctly rounded double of an accumulator (f64_acc_round), via exact rational arithmetic."""
+    from fractions import Fraction
+    total = 0
+    for i, w in enumerate(words):
+        w = int(w)
+        if w >= 1 << 63:
+            w -= 1 << 64
+        total += w << (32 * i)
+    return float(Fraction(total, 1 << 1074))
+
+
 def merge_agg_partials(keys, key_null, acc, real_words=(), max_words=()):
     """Final merge of partial aggregation tables.
 
     keys: int64[n] group-key bits, key_null: bool[n], acc: int64[n, W] additive accumulator words (b2_agg_partials).
     Grouped by K > 1 expressions (b2_agg_partials.key_words): keys is int64[n, K] and key_null the per-group NULL mask
     (integer, bit q = q-th expression); the result has the same shapes.
-    `real_words` lists the word indices that hold f64 sums, `max_words` those that merge by unsigned maximum (the MAX /
-    MIN extremum keys, b2_agg_partials.max_word_mask).  Returns (keys, key_null, acc) with one row per group.
+    `max_words` lists the word indices that merge by unsigned maximum (the MAX / MIN extremum keys,
+    b2_agg_partials.max_word_mask); every other word is additive: counts, the 32-bit limb sums of integer SUMs and the
+    digits of exact Real SUMs (`real_words` is only for callers that still carry plain f64 words).  Returns (keys, key_null, acc) with one row per group.
     Integer words are summed exactly (two's-complement wraparound is impossible below 2^32 rows per group)."""
     multi = keys.dim() == 2
     kw = keys.shape[1] if multi else 1

@@ -154,7 +154,7 @@ ENCODE_TYPE_DEFAULT, ENCODE_TYPE_CHUNK = 0, 1
 JIT_AUTO, JIT_SYNC, JIT_OFF = 0, 1, 2
 
 EXPORTED_SYMBOLS = [
-    "b2_abi_version", "b2_build_info", "b2_last_error_message", "b2_check_supported", "b2_plan_prepare", "b2_plan_literal", "b2_exec_open", "b2_exec_schema",
+    "b2_abi_version", "b2_build_info", "b2_last_error_message", "b2_check_supported", "b2_plan_prepare", "b2_plan_precompile", "b2_jit_counters", "b2_plan_literal", "b2_exec_open", "b2_exec_schema",
     "b2_exec_next_batch", "b2_exec_collect_stats", "b2_exec_last_error", "b2_exec_can_be_cached", "b2_exec_encode_batch", "b2_exec_take_scanned_range", "b2_exec_collect_scanned_rows_per_range", "b2_exec_close",
     "b2_exec_agg_partials", "b2_dag_handle", "b2_checksum_handle", "b2_gen_create", "b2_gen_destroy", "b2_copy_to_host", "b2_copy_to_device",
     "b2_device_count", "b2_host_alloc_pinned", "b2_host_alloc_pinned_near", "b2_device_numa_node", "b2_host_free_pinned",
@@ -181,6 +181,10 @@ def lib():
     L.b2_check_supported.restype = i32
     L.b2_plan_prepare.argtypes = [C.POINTER(DagPlan), i32]
     L.b2_plan_prepare.restype = i32
+    L.b2_plan_precompile.argtypes = [C.POINTER(DagPlan), C.POINTER(i32)]
+    L.b2_plan_precompile.restype = i32
+    L.b2_jit_counters.argtypes = [C.POINTER(u64), C.POINTER(u64)]
+    L.b2_jit_counters.restype = None
     L.b2_exec_open.argtypes = [C.POINTER(DagPlan), C.POINTER(KeyRange), u32, C.POINTER(RegionSource), C.POINTER(ExecConfig), C.POINTER(vp)]
     L.b2_exec_open.restype = i32
     L.b2_exec_schema.argtypes = [vp, C.POINTER(i32), C.POINTER(u32), C.POINTER(u32)]

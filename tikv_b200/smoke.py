@@ -5,6 +5,17 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def plans():
+    """The two DAGs smoke() runs (also precompiled by __graft_entry__.build())."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenarios as sc
+    from tikv_b200.plan import Plan, col, const_int, lt
+    scan_filter = Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(lt(col(sc.C1), const_int(0))).build()
+    hash_agg = (Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(lt(col(sc.C1), const_int(1 << 62)))
+                .aggregation([("sum", col(sc.C1)), ("count", const_int(1))], group_by=[col(sc.C6)]).build())
+    return [scan_filter, hash_agg]
+
+
 def run():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import kvfmt
@@ -12,13 +23,10 @@ def run():
     import scenarios as sc
     from compare import assert_same_rows
     from tikv_b200.executor import DagHandler, DeviceRegion, checksum
-    from tikv_b200.plan import Plan, col, const_int, lt
 
     host = sc.dirty_region(3, n_keys=2000).build(read_ts=sc.READ_TS, n_write_blocks=2)
     dev = DeviceRegion(host)
-    scan_filter = Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(lt(col(sc.C1), const_int(0))).build()
-    hash_agg = (Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(lt(col(sc.C1), const_int(1 << 62)))
-                .aggregation([("sum", col(sc.C1)), ("count", const_int(1))], group_by=[col(sc.C6)]).build())
+    scan_filter, hash_agg = plans()
     for name, plan, ordered in (("scan+filter", scan_filter, True), ("scan+filter+hash-agg", hash_agg, False)):
         for region in (host, dev):
             assert_same_rows(DagHandler(plan, sc.WHOLE, region).handle_request(), orc.dag_handle(plan, sc.WHOLE, host), ordered=ordered, ctx=name)

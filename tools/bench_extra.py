@@ -112,7 +112,7 @@ def main():
         src = bench.Source(ffi, [b.block for b in blks], ffi.LOC_DEVICE, 0)
         in_bytes = sum(b.key_bytes + b.val_bytes + 8 * b.block.n for b in blks)
         n_entries = sum(b.block.n for b in blks)
-        run(f"C2 scan + selection on a dirty table ({n_entries} CF_WRITE entries for {args.rows} keys)", bench.build_plan(), src, in_bytes, args.rows)
+        run(f"C2 scan + selection on a dirty table ({n_entries} CF_WRITE entries for {args.rows} keys)", bench.build_plan("c2"), src, in_bytes, args.rows)
         for g in gens:
             ffi.lib().b2_gen_destroy(g)
     if only and "c4" not in only:
