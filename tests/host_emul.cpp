@@ -41,28 +41,44 @@ static BlockView view_of(const b2_cf_block& c) { BlockView v; v.keys = c.keys; v
 
 struct GroupAcc { uint64_t w[MAX_ACC_WORDS]; };
 
-// scan_kernel.cuh entry_fast restated without the warp shuffles: the clean-entry front end built from the same
-// b2_device.h functions.  0 = nothing to do for this entry, 1 = row ready (conditions evaluated into *keep),
-// 3 = not a clean entry: the general functions decide.
-static int entry_fast_host(const DevPlan& P, const BlockView& b, uint32_t e, uint32_t e_lo, uint64_t read_ts, Row& row, Cells& cells, bool* keep,
-                           uint32_t* val_len) {  // (row.imms is set by the caller)
-  KeyTail t, q;
-  if (!fast_key_tail(b.kptr(e), b.klen(e), &t)) return 3;
-  if (e != e_lo) {
-    if (!fast_key_tail(b.kptr(e - 1), b.klen(e - 1), &q)) return 3;
-    if (key_tail_same(t.a, t.b, q.a, q.b)) return 0;
+// fast_kernel.cuh restated for the CPU: the branch-free front end of the lean kernels run over 32 consecutive entries at
+// a time ("lanes" of a warp), with the run-ownership rules of b2_device.h fast_lane_decide.  For every entry it yields
+// FA_COMMIT (the lane holds the visible Put of a plain run: row at val + row_off) and / or FA_PUSH (entry `e - push_back`
+// goes to the general walk).  newer = the entry's commit_ts is above the snapshot.
+struct LaneOut { uint32_t flags, push_back, row_off, row_len; bool newer; KeyTail tail; };
+static void fast_front_warp(const BlockView& b, uint32_t e0, uint32_t e_lo, uint32_t e_hi, uint64_t read_ts, int isolation, LaneOut* out) {
+  bool valid[32], same[32], vis[32], chosen[32], kok[32];
+  uint32_t kind[32];
+  KeyTail t[32];
+  uint32_t start_m = 0, chosen_m = 0, valid_m = 0;
+  for (uint32_t l = 0; l < 32; ++l) {
+    const uint32_t e = e0 + l;
+    valid[l] = e < e_hi;
+    same[l] = vis[l] = chosen[l] = kok[l] = false; kind[l] = 0;
+    out[l] = LaneOut{};
+    if (!valid[l]) continue;
+    valid_m |= 1u << l;
+    const bool k35 = b.klen(e) == 35;
+    kok[l] = k35 && key_tail_load(b.kptr(e), &t[l]);
+    bool pvis = false;
+    if (k35 && e != e_lo && b.klen(e - 1) == 35) {
+      KeyTail q;
+      key_tail_load(b.kptr(e - 1), &q);
+      same[l] = key_tail_same_exact(t[l].a, t[l].b, q.a, q.b);
+      pvis = key_tail_commit_ts(q) <= read_ts;
+    }
+    vis[l] = k35 && key_tail_commit_ts(t[l]) <= read_ts;
+    chosen[l] = vis[l] && (!same[l] || !pvis);
+    if (b.vlen(e) >= 2) kind[l] = fast_write_kind(b.vptr(e), b.vlen(e), &out[l].row_off, &out[l].row_len);
+    if (!same[l]) start_m |= 1u << l;
+    if (chosen[l]) chosen_m |= 1u << l;
+    out[l].newer = k35 && !vis[l];
+    out[l].tail = t[l];
   }
-  const uint64_t cts = key_tail_commit_ts(t);
-  if (cts > read_ts) return 3;
-  uint32_t roff, rlen;
-  if (!fast_write_head(b.vptr(e), b.vlen(e), &roff, &rlen)) return 3;
-  row.enc_key = b.kptr(e); row.enc_key_len = 27; row.commit_ts = cts;
-  if (!fast_row_v2(P, b.vptr(e) + roff, rlen, row)) return 3;
-  row.filled = P.fast_filled;
-  if (eval_conds(P, row, cells, keep)) return 3;
-  *val_len = rlen;
-  return 1;
+  for (uint32_t l = 0; l < 32; ++l)
+    out[l].flags = fast_lane_decide(l, start_m, chosen_m, valid_m, valid[l], same[l], chosen[l], kok[l], kind[l], vis[l], isolation == B2_ISO_RC_CHECK_TS, &out[l].push_back);
 }
+
 static bool unit_prefix_ok(const BlockView& b, uint32_t lo, uint32_t hi) {  // kernels.cu unit_prefix_kernel
   if (hi <= lo || b.klen(lo) < 12 || b.klen(hi - 1) < 12) return false;
   return record_key_prefix_ok(b.kptr(lo)) && memcmp(b.kptr(lo), b.kptr(hi - 1), 12) == 0;
@@ -104,18 +120,48 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
       BlockView blk = view_of(src->write[b]);
       uint32_t e_lo = lower_bound_block(src->write[b], lo), e_hi = lower_bound_block(src->write[b], hi);
       const bool unit_fast = g_emu_fast_front && P.fast_n > 0 && unit_prefix_ok(blk, e_lo, e_hi);
-      for (uint32_t e = e_lo; e < e_hi; ++e) {
+      // pass 1 (lean kernel): per 32-entry warp, commit plain runs, push the others; pass 2 (general kernel, list mode):
+      // the pushed entries.  Without the fast front end every entry is "pushed".
+      std::vector<uint32_t> todo;                       // entries for the general walk, ascending
+      std::vector<std::pair<uint32_t, LaneOut>> fast;   // committed lanes
+      if (unit_fast) {
+        for (uint32_t e0 = e_lo; e0 < e_hi; e0 += 32) {
+          LaneOut lo[32];
+          fast_front_warp(blk, e0, e_lo, e_hi, P.read_ts, P.isolation, lo);
+          for (uint32_t l = 0; l < 32 && e0 + l < e_hi; ++l) {
+            if (lo[l].newer) R->met_newer = 1;
+            if (lo[l].flags & FA_PUSH) todo.push_back(e0 + l - ((lo[l].flags & FA_COMMIT) ? 0 : lo[l].push_back));
+            if ((lo[l].flags & FA_COMMIT) && !(lo[l].flags & FA_PUSH)) fast.push_back({e0 + l, lo[l]});
+          }
+        }
+      } else {
+        for (uint32_t e = e_lo; e < e_hi; ++e) todo.push_back(e);
+      }
+      // merge both streams in entry order (the scan output is ordered)
+      std::sort(todo.begin(), todo.end());
+      size_t fi = 0, ti = 0;
+      while (fi < fast.size() || ti < todo.size()) {
         Row row; Cells cells;
         row.imms = cp.imms;
         bool keep = false;
-        int fr = 3;
-        uint32_t fast_val_len = 0;
-        if (unit_fast) fr = entry_fast_host(P, blk, e, e_lo, P.read_ts, row, cells, &keep, &fast_val_len);
-        if (fr == 0) continue;
-        if (fr == 1) {
+        uint32_t e;
+        bool take_fast = ti >= todo.size() || (fi < fast.size() && fast[fi].first < todo[ti]);
+        if (take_fast) {
+          e = fast[fi].first;
+          const LaneOut& lo = fast[fi].second;
+          ++fi;
+          row.enc_key = blk.kptr(e); row.enc_key_len = 27; row.commit_ts = key_tail_commit_ts(lo.tail);
+          bool ok = fast_row_v2(P, blk.vptr(e) + lo.row_off, lo.row_len, row);
+          if (ok) { row.filled = P.fast_filled; ok = eval_conds(P, row, cells, &keep) == 0; }
+          if (!ok) {  // the row needs the general decoder: the lane pushes its run start instead of committing
+            todo.insert(std::upper_bound(todo.begin() + ti, todo.end(), e - lo.push_back), e - lo.push_back);
+            continue;
+          }
           g_emu_fast_hits++;
-          R->processed_keys++; R->processed_size += 27 + fast_val_len;
+          R->processed_keys++; R->processed_size += 27 + lo.row_len;
         } else {
+          e = todo[ti++];
+          if (ti < todo.size() + 1 && ti >= 2 && todo[ti - 2] == e) { R->status = B2_ERR_INVALID_ARG; R->msg = "emulation: run start pushed twice"; }
         bool start = (e == e_lo) || !same_user_key(blk, e - 1, e);
         if (!start) continue;
         RunOut ro;
@@ -301,7 +347,46 @@ emu_result* emu_checksum(const b2_key_range* ranges, uint32_t n_ranges, const ui
     for (uint32_t b = 0; b < src->n_write; ++b) {
       BlockView blk = view_of(src->write[b]);
       uint32_t e_lo = lower_bound_block(src->write[b], lo), e_hi = lower_bound_block(src->write[b], hi);
-      for (uint32_t e = e_lo; e < e_hi; ++e) {
+      // fast_kernel<PM_CHECKSUM>: clean entries are folded through the linear form of the CRC (b2_device.h): the handle
+      // takes one 8-byte table step from the state after the unit's common key bytes, values are XOR-ed right-aligned
+      const bool unit_fast = g_emu_fast_front && unit_prefix_ok(blk, e_lo, e_hi) && new_len <= 11;
+      uint64_t s11 = st;
+      bool prefix_ok = true;
+      if (unit_fast) {
+        const uint8_t* k0 = blk.kptr(e_lo);
+        for (uint32_t j = 0; j < new_len; ++j) prefix_ok = prefix_ok && raw_at(k0, j) == new_prefix[j];
+        for (uint32_t j = new_len; j < 11; ++j) s11 = crc64_table_entry((uint8_t)(s11 ^ raw_at(k0, j))) ^ (s11 >> 8);
+      }
+      std::vector<unsigned long long> T(8 * 256);
+      for (uint32_t i = 0; i < 256; ++i) T[i] = crc64_table_entry(i);
+      for (uint32_t i = 0; i < 256; ++i) { unsigned long long t = T[i]; for (int kk = 1; kk < 8; ++kk) { t = T[(uint32_t)t & 0xffu] ^ (t >> 8); T[kk * 256 + i] = t; } }
+      uint64_t kacc[256] = {0}, vacc[32] = {0}, fast_cnt = 0;
+      std::vector<uint32_t> todo;
+      if (unit_fast && prefix_ok) {
+        for (uint32_t e0 = e_lo; e0 < e_hi; e0 += 32) {
+          LaneOut lo[32];
+          fast_front_warp(blk, e0, e_lo, e_hi, src->read_ts, src->isolation_level, lo);
+          for (uint32_t l = 0; l < 32 && e0 + l < e_hi; ++l) {
+            const uint32_t e = e0 + l;
+            if (lo[l].flags & FA_PUSH) { todo.push_back(e - ((lo[l].flags & FA_COMMIT) ? 0 : lo[l].push_back)); continue; }
+            if (!(lo[l].flags & FA_COMMIT)) continue;
+            g_emu_fast_hits++;
+            const uint32_t roff = lo[l].row_off, rlen = lo[l].row_len;
+            kacc[rlen] ^= crc_step8(T.data(), s11, key_tail_handle_le(lo[l].tail.a, lo[l].tail.b));
+            const uint8_t* vend = blk.vptr(e) + roff + rlen;
+            for (uint32_t j = 0; 8 * j < rlen; ++j) {  // word j = the 8 value bytes ending 8j bytes before the end
+              uint64_t w = 0;
+              for (uint32_t q = 0; q < 8; ++q) { uint32_t back = 8 * j + (8 - q); if (back <= rlen) w |= (uint64_t)vend[-(int)back] << (8 * q); }
+              vacc[j] ^= w;
+            }
+            ++fast_cnt;
+            R->total_kvs++; R->total_bytes += 19ull + rlen + old_len - new_len;
+          }
+        }
+      } else {
+        for (uint32_t e = e_lo; e < e_hi; ++e) todo.push_back(e);
+      }
+      for (uint32_t e : todo) {
         if (!((e == e_lo) || !same_user_key(blk, e - 1, e))) continue;
         RunOut ro;
         resolve_run(blk, e, e_hi, e_hi, src->read_ts, src->isolation_level, dflt, &ro);
@@ -319,6 +404,12 @@ emu_result* emu_checksum(const b2_key_range* ranges, uint32_t n_ranges, const ui
         for (uint32_t j = 0; j < ro.val_len; ++j) c = crc64_table_entry((uint8_t)(c ^ ro.val[j])) ^ (c >> 8);
         R->checksum ^= ~c; R->total_kvs++; R->total_bytes += (uint64_t)rawlen + ro.val_len + old_len - new_len;
       }
+      // combine the unit's folded state: (odd count ? ~0 : 0) ^ XOR_vlen A^vlen(kacc[vlen]) ^ Lin(vacc)
+      uint64_t fold = (fast_cnt & 1) ? ~0ull : 0ull;
+      for (uint32_t v = 0; v < 256; ++v) if (kacc[v]) fold ^= crc_advance_zeros(T.data(), kacc[v], v);
+      uint64_t lin = 0;
+      for (int j = 31; j >= 0; --j) lin = crc_step8(T.data(), lin, vacc[j]);
+      R->checksum ^= fold ^ lin;
     }
   }
   return R;

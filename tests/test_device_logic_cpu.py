@@ -350,3 +350,51 @@ def test_plan_limits_are_reported_not_crashed():
     for what, plan in ok.items():
         rc, msg = emu.check_supported(plan)
         assert rc == 0, (what, msg)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_run_ownership_of_the_lean_front_end(seed):
+    """Version runs of every length (1..90 entries: inside a warp, across one or several 32-entry warps), made of newer
+    versions, Puts, Deletes, Lock / Rollback records and long values, read at a random snapshot under SI / RC / RcCheckTs:
+    the lean front end (32 lanes at a time, b2_device.h fast_lane_decide) commits the plain runs and pushes every other
+    run start exactly once; the result equals the oracle's and the general walk's."""
+    import random
+    rng = random.Random(1000 + seed)
+    r = kvfmt.Region()
+    mk = lambda: kvfmt.row_v2([(cid, rng.randrange(-(1 << 40), 1 << 40) if not uns else rng.randrange(0, 1 << 40), "uint" if uns else "int")
+                               for cid, uns in ((2, False), (3, True), (4, False), (5, False), (6, True), (7, True), (9, False), (11, False))])
+    for h in range(160):
+        key = kvfmt.row_key(sc.TABLE, h * 2 + 5)
+        n = rng.choice([1, 1, 1, 2, 3, 5, 9, 31, 32, 33, 40, 70, 90]) if rng.random() < 0.5 else 1
+        ts = 1000
+        for _ in range(n):
+            ts -= rng.randrange(2, 9)
+            x = rng.random()
+            if x < 0.62:
+                r.put(key, mk(), ts - 1, ts)
+            elif x < 0.72:
+                r.delete(key, ts - 1, ts)
+            elif x < 0.84:
+                r.lock_rec(key, ts - 1, ts) if rng.random() < 0.5 else r.lock_rec(key, ts - 1, ts, last_change=(ts - rng.randrange(3, 40), rng.randrange(1, 12)))
+            elif x < 0.90:
+                r.rollback(key, ts)
+            else:
+                r.put(key, mk(), ts - 1, ts, force_long=True)
+    plans = dict(sc.int_plans())
+    for iso in (ffi.ISO_SI, ffi.ISO_RC, ffi.ISO_RC_CHECK_TS):
+        for read_ts in (rng.randrange(300, 1000), 1001, 5):
+            region = r.build(read_ts=read_ts, n_write_blocks=rng.choice([1, 2, 3]), isolation=iso)
+            for name in ("all", "agg"):
+                exp = orc.dag_handle(plans[name], sc.WHOLE, region)
+                before = emu.fast_hits()
+                got = emu.dag_handle(plans[name], sc.WHOLE, region)
+                assert got.status == exp.status, (name, iso, read_ts, got.message)
+                assert read_ts != 1001 or exp.status != 0 or emu.fast_hits() - before > 20  # most runs are plain at the newest snapshot
+                assert_same_rows(got, exp, ordered=name != "agg", ctx=f"{name}/iso{iso}/ts{read_ts}")
+                assert got.stats["processed_keys"] == exp.stats["processed_keys"] and got.stats["processed_size"] == exp.stats["processed_size"]
+                assert bool(got.stats["met_newer"]) == (exp.stats["met_newer"] == 1)
+            st, exp_ck, _ = orc.checksum(sc.WHOLE, region)
+            st2, got_ck = emu.checksum(sc.WHOLE, region)
+            assert (st == 0) == (st2 == 0)
+            if st == 0:
+                assert got_ck == exp_ck

@@ -853,6 +853,15 @@ B2_HD bool fast_key_tail(const uint8_t* kp, uint32_t klen, KeyTail* t) {
 B2_HD uint64_t key_tail_commit_ts(const KeyTail& t) { return ~bswap64((t.b >> 56) | (t.c << 8)); }
 // same user key as the entry before?  (both keys validated by fast_key_tail, both inside one unit: bytes 0..11 and 21..26 agree)
 B2_HD bool key_tail_same(uint64_t a, uint64_t b, uint64_t pa, uint64_t pb) { return a == pa && ((b ^ pb) & 0xffu) == 0; }
+// the same for any two 35-byte keys of one unit (no marker validation needed): bytes 12..26 equal
+B2_HD bool key_tail_same_exact(uint64_t a, uint64_t b, uint64_t pa, uint64_t pb) { return a == pa && ((b ^ pb) & 0x00ffffffffffffffull) == 0; }
+// key words of any 35-byte key + whether it is a well-formed int-handle record key from byte 12 on
+B2_HD bool key_tail_load(const uint8_t* kp, KeyTail* t) {
+  uint64_t w[3];
+  ld64xN<3>(kp + 12, w);
+  t->a = w[0]; t->b = w[1]; t->c = w[2];
+  return ((w[0] >> 40) & 0xffu) == 0xffu && (w[1] & 0x00ffffffffffff00ull) == 0x00fa000000000000ull;
+}
 // first 12 bytes of the keys of a unit: what check_record_key / decode_int_handle need of them (table.rs:187-226)
 B2_HD bool record_key_prefix_ok(const uint8_t* k) { return k[0] == 't' && k[8] == 0xff && k[10] == '_' && k[11] == 'r'; }
 
@@ -874,6 +883,104 @@ B2_HD bool fast_write_head(const uint8_t* vp, uint32_t vlen, uint32_t* row_off, 
   *row_off = pos + 2; *row_len = len;
   return (w[0] & 0xffu) == 'P' && tag == 'v' && pos + 2 + len == vlen;
 }
+
+// The same without branches, for the lean kernels (fast_kernel.cuh): bit 0 = `P varint v len row` and nothing after
+// (a visible Put with an inline value), bit 1 = `D varint` and nothing after (a plain Delete).  Anything else is left to
+// the general parser.  *row_off / *row_len are only meaningful with bit 0.
+B2_HD uint32_t fast_write_kind(const uint8_t* vp, uint32_t vlen, uint32_t* row_off, uint32_t* row_len) {
+  uint64_t w[2];
+  ld64xN<2>(vp, w);
+  const uint64_t s0 = ~w[0] & 0x8080808080808000ull;
+  const uint32_t s1 = ~(uint32_t)w[1] & 0x8080u;
+  const uint32_t term = s0 ? (ctz64(s0) >> 3) : (8u + (ctz64((uint64_t)(s1 | 0x800000u)) >> 3));  // 10 when no terminal byte in 1..9
+  const uint32_t pos = term + 1;
+  const bool var_ok = (s0 != 0 || s1 != 0) && vlen >= 2;
+  const uint32_t at = pos + 1 < vlen ? pos : 0;  // keep the two byte loads inside the value
+  const uint32_t tag = vp[at], len = vp[at + 1];
+  const uint32_t type = (uint32_t)w[0] & 0xffu;
+  *row_off = pos + 2; *row_len = len;
+  const bool put = var_ok && type == 'P' && pos + 2 <= vlen && tag == 'v' && pos + 2 + len == vlen;
+  const bool del = var_ok && type == 'D' && pos == vlen;
+  return (put ? 1u : 0u) | (del ? 2u : 0u);
+}
+
+// ---- who owns a version run: the lean kernel or the general walk ------------------------------------------------------
+// The lean kernels (fast_kernel.cuh) look at 32 consecutive entries per warp, one per lane, and decide without walking:
+//   same   the lane's entry has the user key of the entry before it (both 35-byte keys, words equal; never at the range start)
+//   vis    commit_ts <= read_ts.  Versions of a key are sorted newest first, so `vis` is monotone inside a run
+//   chosen vis && (!same || !vis(previous entry)): the first visible version — what forward.rs:310-375 walks to
+//   kind   fast_write_kind of the entry's value: 1 Put with an inline value, 2 plain Delete, 0 anything else
+// A run is *committed* here by its chosen lane when everything about it is plain; otherwise exactly one lane *pushes* the
+// run's first entry onto the list the general kernel works through afterwards (it re-checks that the entry is a run
+// start, so pushing a non-start is harmless; pushing a start twice would double-count: the rules below are exclusive):
+//   (a) a run start whose key is not a well-formed 35-byte record key: pushed by itself; its lanes never commit
+//   (b) the chosen lane holds something that is not a plain Put / Delete, or its row needs the general decoder:
+//       pushed by the chosen lane — if the run starts in this warp (else rule (c) already fired in an earlier warp)
+//   (c) a run start with no chosen lane before the warp ends: the run may go on in the next warp, whose lanes cannot see
+//       this one: pushed by the start lane; lanes of later warps never commit a run that started before their warp
+//   (d) RcCheckTs: a version above the snapshot is a WriteConflict (forward.rs:342-354): pushed by the start lane, and
+//       only a chosen lane that is its run's start commits
+enum { FA_COMMIT = 1, FA_PUSH = 2 };
+B2_HD uint32_t clz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__clz((int)v);
+#else
+  return v ? (uint32_t)__builtin_clz(v) : 32u;
+#endif
+}
+// start_m / chosen_m / valid_m: ballots of (valid && !same), chosen, valid.  Returns FA_* flags; *push_back = how many
+// entries before this lane's entry the pushed run start lies.
+B2_HD uint32_t fast_lane_decide(uint32_t lane, uint32_t start_m, uint32_t chosen_m, uint32_t valid_m, bool valid, bool same, bool chosen, bool kok,
+                                uint32_t kind, bool vis, bool rc_check, uint32_t* push_back) {
+  *push_back = 0;
+  if (!valid) return 0;
+  const uint32_t upto = 0xffffffffu >> (31u - lane);  // lanes 0..lane
+  const uint32_t below = start_m & upto;
+  const bool orphan = below == 0;                     // the run started before this warp
+  const uint32_t sl = orphan ? 0u : 31u - clz32(below);
+  const bool is_start = !same;
+  if (!kok) return is_start ? (uint32_t)FA_PUSH : 0u;  // (a); continuation lanes of such a run share its key: they do nothing
+  uint32_t flags = 0;
+  if (is_start) {
+    const uint32_t above = start_m & ~upto;
+    const uint32_t next = above ? ctz64((uint64_t)above) : 32u;
+    const uint32_t run = (next >= 32u ? ~0u : ((1u << next) - 1u)) & ~(upto >> 1) & valid_m;  // lanes [lane, next)
+    const bool open_end = (run >> (31u - clz32(valid_m))) & 1u;                                 // touches the warp's last valid lane
+    if ((chosen_m & run) == 0 && open_end) flags |= FA_PUSH;                                     // (c)
+    if (rc_check && !vis) flags |= FA_PUSH;                                                      // (d)
+  }
+  if (chosen && !orphan && (!rc_check || is_start)) {
+    *push_back = lane - sl;
+    if (kind == 1u) flags |= FA_COMMIT;      // (the caller turns this into a push when the row needs the general decoder)
+    else if (kind == 0u) flags |= FA_PUSH;   // (b)
+  }
+  return flags;
+}
+
+// ---- CRC-64/XZ as a linear map (checksum.rs:105-114 without a table walk per value byte) ------------------------------
+// One table step is c' = T[(c ^ byte) & 0xff] ^ (c >> 8): linear over GF(2) in (c, byte).  For a message of n bytes from
+// state c0 the final state is A^n(c0) ^ Lin(message), where A is the zero-byte step and Lin(m) = XOR_i A^(n-1-i)(T[m_i])
+// depends only on each byte's distance from the END of the message.  So for the KV message `key part ‖ value`:
+//   ~crc(kv) = ~( A^vlen(state after the key part) ^ Lin(value) )
+// and the XOR over all KVs of a scan is
+//   (odd count ? ~0 : 0)  ^  XOR_vlen A^vlen( XOR of the key states of the KVs with that value length )
+//                         ^  Lin( XOR of all values, right-aligned )
+// i.e. per KV one 8-byte table step for the handle and plain XORs of the value words; the table walks over value bytes
+// happen once per thread at the end of the kernel.  T = slicing-by-8 tables (8 x 256 u64, T[k * 256 + i] = T0 advanced k bytes).
+B2_HD uint64_t crc_step1(const unsigned long long* T, uint64_t c, uint32_t byte) { return T[((uint32_t)c ^ byte) & 0xffu] ^ (c >> 8); }
+B2_HD uint64_t crc_step8(const unsigned long long* T, uint64_t c, uint64_t w) {
+  c ^= w;
+  const uint32_t lo = (uint32_t)c, hi = (uint32_t)(c >> 32);
+  return T[7 * 256 + (lo & 0xffu)] ^ T[6 * 256 + ((lo >> 8) & 0xffu)] ^ T[5 * 256 + ((lo >> 16) & 0xffu)] ^ T[4 * 256 + (lo >> 24)] ^
+         T[3 * 256 + (hi & 0xffu)] ^ T[2 * 256 + ((hi >> 8) & 0xffu)] ^ T[1 * 256 + ((hi >> 16) & 0xffu)] ^ T[hi >> 24];
+}
+B2_HD uint64_t crc_advance_zeros(const unsigned long long* T, uint64_t c, uint32_t n_bytes) {
+  for (; n_bytes >= 8; n_bytes -= 8) c = crc_step8(T, c, 0);
+  for (; n_bytes; --n_bytes) c = crc_step1(T, c, 0);
+  return c;
+}
+// the handle bytes raw[11..19) of an int-handle record key, in message (memory) order, from its key tail words
+B2_HD uint64_t key_tail_handle_le(uint64_t a, uint64_t b) { return (a & 0xffffffffffull) | ((a >> 48) << 40) | ((b & 0xffull) << 56); }
 
 // row_open + fast_row_probe fused for a small v2 row without checksum that holds exactly the plan's columns: header,
 // ids and end offsets come out of one run of words (every field sits at a compile-time offset in a specialised kernel)

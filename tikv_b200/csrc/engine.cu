@@ -112,6 +112,13 @@ struct DevBuf {  // growable device allocation (pooled)
     release();
     return dev_pool().get(n, &p, &cap);
   }
+  // the same for a buffer only ever used on `s`: growing waits for that stream alone, not for the whole device
+  cudaError_t reserve_on(cudaStream_t s, size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaStreamSynchronize(s);
+    release();
+    return dev_pool().get(n, &p, &cap);
+  }
   void release() { if (p) dev_pool().put(p, cap); p = nullptr; cap = 0; }
 };
 struct HostBuf {  // growable pinned host allocation (pooled)
@@ -131,7 +138,7 @@ struct SrcBlock {  // caller's block descriptor + sizes
   uint64_t entry_base = 0;
 };
 
-struct Unit { uint32_t range_idx, block_idx, e_lo, e_hi, fast_ok; };
+struct Unit { uint32_t range_idx, block_idx, e_lo, e_hi, fast_ok; uint32_t prefix[3]; /* the unit's first 12 key bytes when fast_ok */ };
 
 struct StageSlot {
   DevBuf keys, koff, vals, voff;
@@ -293,7 +300,7 @@ struct b2_exec {
     }
     for (auto& e : kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (DevBuf* b : {&tn_lists, &tn_counts, &tn_pair, &tn_pair_cnt, &tn_tmp, &tn_tmp_cnt, &tn_blk_pay, &tn_blk_null, &tn_run_pay, &tn_run_null, &tn_tmp_pay, &tn_tmp_null, &tn_bitmap}) b->release();
-    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &tbl_gkeys, &tbl_ready, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
+    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &tbl_gkeys, &tbl_ready, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &slow_list, &slow_cnt, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
     enc_host.release();
     for (auto& b : res_cols) b.release();
     for (auto& b : res_bitmaps) b.release();
@@ -469,7 +476,7 @@ struct b2_exec {
   int compute_units() {
     uint32_t nr = (uint32_t)range_lo.size(), nb = (uint32_t)wblocks.size();
     if (!nr || !nb) return B2_OK;
-    std::vector<uint32_t> res((size_t)nb * nr * 2), unit_ok((size_t)nb * nr, 0);
+    std::vector<uint32_t> res((size_t)nb * nr * 2), unit_ok((size_t)nb * nr * 4, 0);  // unit_ok: [ok, 12 prefix bytes] per (block, range)
     if (src_loc == B2_LOC_HOST) {
       for (uint32_t b = 0; b < nb; ++b)
         for (uint32_t q = 0; q < nr * 2; ++q) {
@@ -488,7 +495,9 @@ struct b2_exec {
           uint32_t lo = res[(size_t)b * nr * 2 + 2 * r], hi = res[(size_t)b * nr * 2 + 2 * r + 1];
           if (hi <= lo) continue;
           const uint8_t *f = B.keys + B.key_offs[lo], *l = B.keys + B.key_offs[hi - 1];
-          unit_ok[(size_t)b * nr + r] = B.key_offs[lo + 1] - B.key_offs[lo] >= 12 && B.key_offs[hi] - B.key_offs[hi - 1] >= 12 && record_key_prefix_ok(f) && memcmp(f, l, 12) == 0;
+          const bool ok = B.key_offs[lo + 1] - B.key_offs[lo] >= 12 && B.key_offs[hi] - B.key_offs[hi - 1] >= 12 && record_key_prefix_ok(f) && memcmp(f, l, 12) == 0;
+          unit_ok[((size_t)b * nr + r) * 4] = ok;
+          if (ok) memcpy(&unit_ok[((size_t)b * nr + r) * 4 + 1], f, 12);
         }
     } else {
       std::vector<uint8_t> flat;
@@ -518,7 +527,10 @@ struct b2_exec {
     for (uint32_t r = 0; r < nr; ++r)
       for (uint32_t b = 0; b < nb; ++b) {
         uint32_t lo = res[(size_t)b * nr * 2 + 2 * r], hi = res[(size_t)b * nr * 2 + 2 * r + 1];
-        if (hi > lo) units.push_back(Unit{r, b, lo, hi, unit_ok[(size_t)b * nr + r]});
+        if (hi > lo) {
+          const uint32_t* uo = &unit_ok[((size_t)b * nr + r) * 4];
+          units.push_back(Unit{r, b, lo, hi, uo[0], {uo[1], uo[2], uo[3]}});
+        }
       }
     return B2_OK;
   }
@@ -669,6 +681,72 @@ struct b2_exec {
     return total;
   }
   bool use_staging = true;
+  // ---- order-free pipelines: the lean kernel (fast_kernel.cuh) over a unit, then scan_body in list mode over the runs it
+  // handed over (their first entries, appended on the device; the count never visits the host) ----
+  DevBuf slow_list, slow_cnt;
+  bool use_fast_kernel = getenv("B2_NO_FAST_KERNEL") == nullptr;
+  bool fast_kernel_covers() const {
+    if (!use_fast_kernel) return false;
+    if (cp.dev.mode == PM_CHECKSUM) return true;
+    return plan_has_fast_kernel(cp.dev);
+  }
+  // `a`: the unit's arguments (c_lo / c_hi set, mode pointers set).  general_smem_mode / fast_smem_mode: bytes of mode state
+  // in front of the stages; fast_slots: CTA table slots of the lean aggregation kernel.
+  int launch_unit(const ScanArgs& a0, const Unit& u, bool fast, size_t general_smem_mode, size_t fast_smem_mode, uint32_t fast_slots, int* general_grid_out,
+                  int* fast_grid_out) {
+    const int mode = scan_kernel_mode(cp.dev);
+    if (!fast) {
+      ScanArgs a = a0;
+      size_t tot = setup_staging(&a, wblocks[u.block_idx], general_smem_mode);
+      int grid = cp.dev.mode == PM_CHECKSUM ? scan_max_grid(PM_CHECKSUM, tot) : scan_grid_for(mode, tot);
+      if (general_grid_out && *general_grid_out > 0) grid = std::min(grid, *general_grid_out);
+      kernel_begin();
+      CUDA_TRY(cp.dev.mode == PM_CHECKSUM ? launch_scan(cp.dev, a, grid, tot, stream) : scan_launch(a, grid, tot));
+      kernel_end();
+      if (general_grid_out) *general_grid_out = grid;
+      if (fast_grid_out) *fast_grid_out = 0;
+      return B2_OK;
+    }
+    CUDA_TRY(slow_list.reserve_on(stream, (size_t)(u.e_hi - u.e_lo) * 4 + 16));
+    CUDA_TRY(slow_cnt.reserve_on(stream, 16));
+    CUDA_TRY(cudaMemsetAsync(slow_cnt.p, 0, 4, stream));
+    ScanArgs f = a0;
+    f.slow_list = (unsigned int*)slow_list.p; f.slow_count = (unsigned int*)slow_cnt.p;
+    f.smem_slots = fast_slots;
+    size_t ftot = setup_staging(&f, wblocks[u.block_idx], fast_smem_mode);
+    const JitKernel* jk = cp.dev.mode == PM_CHECKSUM ? nullptr : jit_ready();
+    if (jk && !jk->fn_fast) jk = nullptr;
+    int fgrid = jk ? jit_max_blocks_per_sm(jk, ftot, true) * scan_num_sms() : fast_max_grid(cp.dev.mode, ftot);
+    if (fast_grid_out && *fast_grid_out > 0) fgrid = std::min(fgrid, *fast_grid_out);
+    kernel_begin();
+    if (f.staging) {
+      if (jk) { stats.jit_launches++; CUDA_TRY(jit_launch(jk, f, fgrid, ftot, stream, true)); }
+      else CUDA_TRY(launch_fast(cp.dev, f, fgrid, ftot, stream));
+    } else {  // no staging possible (huge entries): everything goes through the general kernel
+      fast = false;
+    }
+    ScanArgs g = a0;
+    size_t gtot = general_smem_mode;
+    int ggrid;
+    if (fast) {
+      g.slow_list = f.slow_list; g.slow_count = f.slow_count; g.list_mode = 1;
+      g.staging = 0; g.stage_off = 0; g.stage_key_cap = g.stage_val_cap = 0;
+      ggrid = cp.dev.mode == PM_CHECKSUM ? scan_max_grid(PM_CHECKSUM, gtot) : scan_grid_for(mode, gtot);
+    } else {
+      gtot = setup_staging(&g, wblocks[u.block_idx], general_smem_mode);
+      ggrid = cp.dev.mode == PM_CHECKSUM ? scan_max_grid(PM_CHECKSUM, gtot) : scan_grid_for(mode, gtot);
+    }
+    if (general_grid_out && *general_grid_out > 0) ggrid = std::min(ggrid, *general_grid_out);
+    if (cp.dev.mode == PM_TOPN && fast) {  // the two kernels leave their per-CTA lists side by side
+      g.topn.items = a0.topn.items + (size_t)fgrid * a0.topn.stride; g.topn.counts = a0.topn.counts + fgrid;
+    }
+    CUDA_TRY(cp.dev.mode == PM_CHECKSUM ? launch_scan(cp.dev, g, ggrid, gtot, stream) : scan_launch(g, ggrid, gtot));
+    kernel_end();
+    stats.kernel_launches += fast ? 1 : 0;
+    if (general_grid_out) *general_grid_out = ggrid;
+    if (fast_grid_out) *fast_grid_out = fast ? fgrid : 0;
+    return B2_OK;
+  }
   bool use_fast_front = getenv("B2_NO_FAST_FRONT") == nullptr;  // debug switch: general front end only
 
   ScanArgs base_args(const Unit& u, const BlockView& v) {
@@ -729,7 +807,7 @@ struct b2_exec {
       }
       if (c_hi > c_lo) {
         uint32_t n_tiles = (c_hi - c_lo + TILE - 1) / TILE;
-        CUDA_TRY(status_buf.reserve(((size_t)n_tiles + 1) * 8));
+        CUDA_TRY(status_buf.reserve_on(stream, ((size_t)n_tiles + 1) * 8));
         CUDA_TRY(cudaMemsetAsync(status_buf.p, 0, ((size_t)n_tiles + 1) * 8, stream));
         BlockView v;
         int rc = acquire_block(u.block_idx, &v);
@@ -1050,6 +1128,14 @@ struct b2_exec {
       while (smem_slots > 64 && (size_t)smem_slots * (8 + 8 * P.acc_words) > 64 * 1024) smem_slots >>= 1;
       smem = (size_t)smem_slots * (8 + 8 * P.acc_words);
     }
+    // the lean kernel's CTA table: as many slots as 64 KB hold (2048 for COUNT + SUM), so that a thousand groups stay resident
+    uint32_t fast_slots = 0;
+    size_t fast_smem = 0;
+    if (P.has_group && P.n_group <= 1) {
+      fast_slots = 4096;
+      while (fast_slots > 64 && (size_t)fast_slots * (8 + 8 * P.acc_words) > 64 * 1024) fast_slots >>= 1;
+      fast_smem = (size_t)fast_slots * (8 + 8 * P.acc_words);
+    }
     Counters c;
     for (;;) {
       int rc = alloc_table(cap);
@@ -1069,11 +1155,11 @@ struct b2_exec {
         a.tbl.keys = (unsigned long long*)tbl_keys.p; a.tbl.special = (unsigned int*)tbl_occ.p; a.tbl.acc = (unsigned long long*)tbl_acc.p; a.tbl.cap = tbl_cap;
         a.tbl.gkeys = (unsigned long long*)tbl_gkeys.p; a.tbl.ready = (unsigned int*)tbl_ready.p; a.tbl.hash_mask_bits = debug_hash_bits;
         a.smem_slots = smem_slots;
-        size_t tot = setup_staging(&a, wblocks[u.block_idx], smem);
-        grid = scan_grid_for(scan_kernel_mode(P), tot);
-        kernel_begin();
-        CUDA_TRY(scan_launch(a, grid, tot));
-        kernel_end();
+        const bool fast = u.fast_ok && fast_kernel_covers();
+        int gg = 0, fg = 0;
+        rc = launch_unit(a, u, fast, smem, fast_smem, fast_slots, &gg, &fg);
+        if (rc) return rc;
+        grid = gg;
         release_block(u.block_idx);
         prefetch_after(ui);
         entries_scanned += u.e_hi - u.e_lo;
@@ -1189,10 +1275,17 @@ struct b2_exec {
       ScanArgs probe; memset(&probe, 0, sizeof(probe));
       size_t tot0 = setup_staging(&probe, wblocks[units[0].block_idx], smem);
       int grid = scan_grid_for(PM_TOPN, std::max(tot0, smem));
+      const bool any_fast = fast_kernel_covers();
+      int fast_grid = 0;
+      if (any_fast) {
+        const JitKernel* jk = jit_ready();
+        fast_grid = jk && jk->fn_fast ? jit_max_blocks_per_sm(jk, std::max(tot0, smem), true) * scan_num_sms() : fast_max_grid(PM_TOPN, std::max(tot0, smem));
+      }
+      const int lists_cap = grid + fast_grid;  // the lean and the general kernel leave their per-CTA lists side by side
       size_t isz = sizeof(TopItem);
-      CUDA_TRY(tn_lists.reserve((size_t)grid * limit * isz)); CUDA_TRY(tn_counts.reserve((size_t)grid * 4));
-      CUDA_TRY(tn_lvl_a.reserve((size_t)((grid + 7) / 8) * limit * isz)); CUDA_TRY(tn_lvl_a_cnt.reserve((size_t)((grid + 7) / 8) * 4));
-      CUDA_TRY(tn_lvl_b.reserve((size_t)((grid + 63) / 64) * limit * isz)); CUDA_TRY(tn_lvl_b_cnt.reserve((size_t)((grid + 63) / 64) * 4));
+      CUDA_TRY(tn_lists.reserve((size_t)lists_cap * limit * isz)); CUDA_TRY(tn_counts.reserve((size_t)lists_cap * 4));
+      CUDA_TRY(tn_lvl_a.reserve((size_t)((lists_cap + 7) / 8) * limit * isz)); CUDA_TRY(tn_lvl_a_cnt.reserve((size_t)((lists_cap + 7) / 8) * 4));
+      CUDA_TRY(tn_lvl_b.reserve((size_t)((lists_cap + 63) / 64) * limit * isz)); CUDA_TRY(tn_lvl_b_cnt.reserve((size_t)((lists_cap + 63) / 64) * 4));
       CUDA_TRY(tn_pair.reserve((size_t)2 * limit * isz)); CUDA_TRY(tn_pair_cnt.reserve(8));
       CUDA_TRY(tn_tmp.reserve((size_t)limit * isz)); CUDA_TRY(tn_tmp_cnt.reserve(4));
       size_t pay_bytes = (size_t)n_out * limit * 8, null_bytes = (size_t)n_out * limit;
@@ -1209,15 +1302,15 @@ struct b2_exec {
         ScanArgs a = base_args(u, v);
         a.c_lo = u.e_lo; a.c_hi = u.e_hi;
         uint32_t n_tiles = (u.e_hi - u.e_lo + TILE - 1) / TILE;
-        uint32_t g = (uint32_t)std::min<uint32_t>((uint32_t)grid, n_tiles);
-        a.topn.items = (TopItem*)tn_lists.p; a.topn.counts = (unsigned int*)tn_counts.p; a.topn.n_lists = g; a.topn.stride = limit;
+        a.topn.items = (TopItem*)tn_lists.p; a.topn.counts = (unsigned int*)tn_counts.p; a.topn.stride = limit;
         a.topn_cap = cap;
         a.topn_seed = pair; a.topn_seed_cnt = pair_cnt;
-        size_t tot = setup_staging(&a, wblocks[u.block_idx], smem);
-        CUDA_TRY(cudaMemsetAsync(tn_counts.p, 0, (size_t)grid * 4, stream));
-        kernel_begin();
-        CUDA_TRY(scan_launch(a, (int)g, tot));
-        kernel_end();
+        CUDA_TRY(cudaMemsetAsync(tn_counts.p, 0, (size_t)lists_cap * 4, stream));
+        const bool fast = any_fast && u.fast_ok;
+        int gg = (int)std::min<uint32_t>((uint32_t)grid, n_tiles), fg = (int)std::min<uint32_t>((uint32_t)std::max(fast_grid, 1), n_tiles);
+        rc = launch_unit(a, u, fast, smem, smem, 0, &gg, &fg);
+        if (rc) return rc;
+        a.topn.n_lists = (uint32_t)(gg + fg);
         // unit top-N (sorted) lands in the second half of `pair`
         TopNLists unit_out; unit_out.items = pair + limit; unit_out.counts = pair_cnt + 1; unit_out.n_lists = 1; unit_out.stride = limit;
         {  // per-CTA lists -> one list, fan-in 8 per level
@@ -1493,6 +1586,7 @@ int32_t b2_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges, const 
   if (cfg && cfg->cuda_stream) h->stream = (cudaStream_t)cfg->cuda_stream;
   else { if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return B2_ERR_CUDA; h->own_stream = true; }
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return B2_ERR_CUDA;
+  memset(&h->cp.dev, 0, sizeof(h->cp.dev));
   h->cp.dev.mode = PM_CHECKSUM;
   int rc = h->setup_source(src, ranges, n_ranges);
   if (rc) { g_last_error = h->last_err.message; return rc; }
@@ -1517,12 +1611,23 @@ int32_t b2_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges, const 
     a.c_lo = u.e_lo; a.c_hi = u.e_hi;
     a.ck_init_state = st; a.ck_new_prefix_len = new_prefix_len; a.ck_old_prefix_len = old_prefix_len;
     memcpy(a.ck_new_prefix, new_prefix, new_prefix_len);
-    size_t smem = h->setup_staging(&a, h->wblocks[u.block_idx], scan_crc_table_bytes());
-    if (smem != ck_smem) { ck_smem = smem; ck_grid = scan_max_grid(PM_CHECKSUM, smem); }
-    h->kernel_begin();
-    cudaError_t ce = launch_scan(h->cp.dev, a, ck_grid, smem, h->stream);
-    h->kernel_end();
-    if (ce != cudaSuccess) { g_last_error = cudaGetErrorString(ce); d_prefix.release(); return B2_ERR_CUDA; }
+    // lean kernel: the unit's keys share their first 11 raw bytes ('t' table-id "_r"); the crc register after old_prefix and
+    // raw[new_prefix_len .. 11) is the same for all of them.  (A new_prefix that reaches into the handle, or that the
+    // unit's keys do not start with, is left to the general kernel, which also raises "Wrong prefix".)
+    bool fast = u.fast_ok && h->fast_kernel_covers() && new_prefix_len <= 11;
+    if (fast) {
+      uint8_t raw[11];
+      const uint8_t* enc = (const uint8_t*)u.prefix;
+      for (int j = 0; j < 8; ++j) raw[j] = enc[j];
+      for (int j = 8; j < 11; ++j) raw[j] = enc[j + 1];
+      uint64_t ks = st;
+      for (uint32_t j = 0; j < new_prefix_len && fast; ++j) fast = raw[j] == new_prefix[j];
+      for (uint32_t j = new_prefix_len; j < 11; ++j) ks = crc64_table_entry((uint8_t)(ks ^ raw[j])) ^ (ks >> 8);
+      a.ck_key_state = ks;
+    }
+    (void)ck_smem; (void)ck_grid;
+    rc = h->launch_unit(a, u, fast, scan_crc_table_bytes(), fast_checksum_bytes(), 0, nullptr, nullptr);
+    if (rc) { d_prefix.release(); return rc; }
     h->release_block(u.block_idx);
     h->prefetch_after(ui);
     h->entries_scanned += u.e_hi - u.e_lo;

@@ -33,6 +33,8 @@
 
 namespace b2 {
 
+enum { FK_THREADS_HOST = TILE + 32 };  // fast_kernel.cuh FK_THREADS (device header, not included here)
+
 namespace {
 
 struct Api {
@@ -101,7 +103,7 @@ Api& api() {
     a.csrc_dir = dir + "/../csrc";
     // the sources a specialised kernel is built from: their content is part of the cache key
     unsigned long long h = 1469598103934665603ull;
-    for (const char* f : {"/scan_kernel.cuh", "/kernels.cuh", "/b2_device.h", "/../../include/b2_copr.h"}) {
+    for (const char* f : {"/scan_kernel.cuh", "/fast_kernel.cuh", "/kernels.cuh", "/b2_device.h", "/../../include/b2_copr.h"}) {
       std::string text;
       if (!read_file(a.csrc_dir + f, &text)) { a.why = std::string("kernel sources not found next to the library (") + a.csrc_dir + f + ")"; return; }
       h = fnv1a(text.data(), text.size(), h);
@@ -131,8 +133,8 @@ std::map<std::string, Entry>& g_cache = *new std::map<std::string, Entry>();
 // One file per (plan shape, kernel instantiation, compiler options, kernel sources): <dir>/<hash>.cubin plus <hash>.key
 // holding the full key (a hash collision or a stale file is detected by comparing it).  Written atomically (rename).
 std::atomic<unsigned long long> g_nvrtc_compiles{0}, g_cache_hits{0};
-std::string cache_key(int mode, bool ext_sigs, const std::string& literal) {
-  return "b2jit1|sm_100a|mode" + std::to_string(mode) + "|ext" + std::to_string((int)ext_sigs) + "|src" + std::to_string(api().src_hash) + "|" + literal;
+std::string cache_key(int mode, bool ext_sigs, bool fast, const std::string& literal) {
+  return "b2jit2|sm_100a|mode" + std::to_string(mode) + "|ext" + std::to_string((int)ext_sigs) + "|fast" + std::to_string((int)fast) + "|src" + std::to_string(api().src_hash) + "|" + literal;
 }
 std::string cache_path(const std::string& key) {
   char name[32];
@@ -163,11 +165,14 @@ void cache_store(const std::string& key, const std::vector<char>& cubin) {
 }
 
 // NVRTC only (no CUDA context): plan literal -> sm_100a cubin
-bool compile_cubin(int mode, bool ext_sigs, const std::string& literal, std::vector<char>* cubin, std::string* error) {
+bool compile_cubin(int mode, bool ext_sigs, bool fast, const std::string& literal, std::vector<char>* cubin, std::string* error) {
   Api& a = api();
-  std::string src = "#define B2_NVRTC 1\n#include \"scan_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + literal +
+  std::string src = "#define B2_NVRTC 1\n#include \"fast_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + literal +
                     ";\n}\nextern \"C\" __global__ void __launch_bounds__(b2::TILE + 64, 2) b2_scan_jit(const __grid_constant__ b2::ScanArgs A) {\n"
                     "  b2::scan_body<" + std::to_string(mode) + ">(b2::kJitPlan, A);\n}\n";
+  if (fast)
+    src += "extern \"C\" __global__ void __launch_bounds__(b2::FK_THREADS, 2) b2_fast_jit(const __grid_constant__ b2::ScanArgs A) {\n"
+           "  b2::fast_body<" + std::to_string(mode) + ">(b2::kJitPlan, A);\n}\n";
   nvrtcProgram prog;
   if (a.CreateProgram(&prog, src.c_str(), "b2_scan_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { *error = "nvrtcCreateProgram failed"; return false; }
   std::string inc = "-I" + a.csrc_dir;
@@ -192,16 +197,16 @@ bool compile_cubin(int mode, bool ext_sigs, const std::string& literal, std::vec
   return true;
 }
 
-JitKernel* compile(int device, int mode, bool ext_sigs, const std::string& literal) {
+JitKernel* compile(int device, int mode, bool ext_sigs, bool fast, const std::string& literal) {
   Api& a = api();
   JitKernel* k = new JitKernel();
   cudaSetDevice(device);
   cudaFree(nullptr);  // make sure the primary context exists and is current on this thread
-  const std::string key = cache_key(mode, ext_sigs, literal);
+  const std::string key = cache_key(mode, ext_sigs, fast, literal);
   std::vector<char> cubin;
   if (cache_load(key, &cubin)) g_cache_hits++;
   else {
-    if (!compile_cubin(mode, ext_sigs, literal, &cubin, &k->error)) return k;
+    if (!compile_cubin(mode, ext_sigs, fast, literal, &cubin, &k->error)) return k;
     cache_store(key, cubin);
   }
   CUmodule mod;
@@ -209,6 +214,11 @@ JitKernel* compile(int device, int mode, bool ext_sigs, const std::string& liter
   CUfunction fn;
   if (a.ModuleGetFunction(&fn, mod, "b2_scan_jit") != CUDA_SUCCESS) { k->error = "kernel symbol missing"; return k; }
   k->fn = fn;
+  if (fast) {
+    CUfunction ff;
+    if (a.ModuleGetFunction(&ff, mod, "b2_fast_jit") != CUDA_SUCCESS) { k->error = "lean kernel symbol missing"; return k; }
+    k->fn_fast = ff;
+  }
   k->ok = true;
   return k;
 }
@@ -244,9 +254,19 @@ std::shared_future<JitKernel*> jit_get(int device, const DevPlan& plan) {
   std::string literal = key.substr(key.find('|') + 1);
   const bool ext_sigs = plan_uses_ext_sigs(plan);
   int mode = plan.mode == PM_SCAN && plan.n_proj ? (int)PM_PROJ : (plan.mode == PM_AGG && plan.n_group > 1 ? (int)PM_AGGM : plan.mode);
-  std::shared_future<JitKernel*> fut = std::async(std::launch::async, [device, mode, ext_sigs, literal] { return compile(device, mode, ext_sigs, literal); }).share();
+  const bool fast = plan_has_fast_kernel(plan);
+  std::shared_future<JitKernel*> fut = std::async(std::launch::async, [device, mode, ext_sigs, fast, literal] { return compile(device, mode, ext_sigs, fast, literal); }).share();
   g_cache[key].fut = fut;
   return fut;
+}
+
+bool plan_has_fast_kernel(const DevPlan& plan) {
+  if (plan.fast_n <= 0) return false;
+  if (plan.mode == PM_TOPN) return true;
+  if (plan.mode != PM_AGG || plan.n_group > 1) return false;
+  for (int a = 0; a < plan.n_aggs; ++a)
+    if ((plan.aggs[a].kind == 1 || plan.aggs[a].kind == 2) && plan.aggs[a].arg_et == 1) return false;  // exact Real sums: 67 words per group
+  return true;
 }
 
 static int jit_mode_of(const DevPlan& plan) { return plan.mode == PM_SCAN && plan.n_proj ? (int)PM_PROJ : (plan.mode == PM_AGG && plan.n_group > 1 ? (int)PM_AGGM : plan.mode); }
@@ -261,38 +281,43 @@ int jit_precompile(const DevPlan& plan, std::string* error) {
   const std::string literal = plan_literal(p);
   const bool ext_sigs = plan_uses_ext_sigs(plan);
   const int mode = jit_mode_of(plan);
-  const std::string key = cache_key(mode, ext_sigs, literal);
+  const bool fast = plan_has_fast_kernel(plan);
+  const std::string key = cache_key(mode, ext_sigs, fast, literal);
   std::vector<char> cubin;
   if (cache_load(key, &cubin)) return 1;
-  if (!compile_cubin(mode, ext_sigs, literal, &cubin, error)) return -1;
+  if (!compile_cubin(mode, ext_sigs, fast, literal, &cubin, error)) return -1;
   cache_store(key, cubin);
   return 0;
 }
 void jit_counters(unsigned long long* nvrtc_compiles, unsigned long long* disk_hits) { *nvrtc_compiles = g_nvrtc_compiles.load(); *disk_hits = g_cache_hits.load(); }
 
-int jit_max_blocks_per_sm(const JitKernel* k, size_t smem) {
+int jit_max_blocks_per_sm(const JitKernel* k, size_t smem, bool fast) {
   int n = 0;
-  if (smem > k->max_dyn_smem) {
+  CUfunction fn = (CUfunction)(fast ? k->fn_fast : k->fn);
+  size_t& lim = fast ? k->max_dyn_smem_fast : k->max_dyn_smem;
+  if (smem > lim) {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (smem > k->max_dyn_smem && api().FuncSetAttribute((CUfunction)k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) == CUDA_SUCCESS) k->max_dyn_smem = smem;
+    if (smem > lim && api().FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) == CUDA_SUCCESS) lim = smem;
   }
-  if (api().OccupancyMaxActiveBlocksPerMultiprocessor(&n, (CUfunction)k->fn, TILE + 64, smem) != CUDA_SUCCESS || n < 1) n = 1;
+  if (api().OccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, fast ? (int)FK_THREADS_HOST : TILE + 64, smem) != CUDA_SUCCESS || n < 1) n = 1;
   return n;
 }
 
-cudaError_t jit_launch(const JitKernel* k, const ScanArgs& a, int grid, size_t smem, cudaStream_t s) {
+cudaError_t jit_launch(const JitKernel* k, const ScanArgs& a, int grid, size_t smem, cudaStream_t s, bool fast) {
   if (a.c_hi <= a.c_lo) return cudaSuccess;
   uint32_t n_tiles = (a.c_hi - a.c_lo + TILE - 1) / TILE;
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
   void* params[] = {const_cast<ScanArgs*>(&a)};
-  if (smem > k->max_dyn_smem) {  // opt in to large dynamic shared memory (the limit excludes the kernel's static part)
+  CUfunction fn = (CUfunction)(fast ? k->fn_fast : k->fn);
+  size_t& lim = fast ? k->max_dyn_smem_fast : k->max_dyn_smem;
+  if (smem > lim) {  // opt in to large dynamic shared memory (the limit excludes the kernel's static part)
     std::lock_guard<std::mutex> lk(g_mu);
-    if (smem > k->max_dyn_smem) {
-      if (api().FuncSetAttribute((CUfunction)k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return cudaErrorInvalidValue;
-      k->max_dyn_smem = smem;
+    if (smem > lim) {
+      if (api().FuncSetAttribute(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) return cudaErrorInvalidValue;
+      lim = smem;
     }
   }
-  CUresult rc = api().LaunchKernel((CUfunction)k->fn, (unsigned)grid, 1, 1, TILE + 64, 1, 1, (unsigned)smem, (CUstream)s, params, nullptr);
+  CUresult rc = api().LaunchKernel(fn, (unsigned)grid, 1, 1, fast ? (unsigned)FK_THREADS_HOST : TILE + 64, 1, 1, (unsigned)smem, (CUstream)s, params, nullptr);
   if (rc != CUDA_SUCCESS) fprintf(stderr, "b2copr: cuLaunchKernel of the plan-specialised kernel failed: CUresult %d\n", (int)rc);
   return rc == CUDA_SUCCESS ? cudaSuccess : cudaErrorLaunchFailure;
 }

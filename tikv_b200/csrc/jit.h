@@ -11,8 +11,10 @@ namespace b2 {
 
 struct JitKernel {
   bool ok = false;
-  void* fn = nullptr;  // CUfunction
+  void* fn = nullptr;  // CUfunction: scan_body specialised for the plan
   mutable size_t max_dyn_smem = 48 * 1024;  // dynamic shared memory the function has been opted in to
+  void* fn_fast = nullptr;  // CUfunction: fast_body (fast_kernel.cuh) for the order-free pipelines it covers, else null
+  mutable size_t max_dyn_smem_fast = 48 * 1024;
   std::string error;
 };
 
@@ -24,7 +26,9 @@ std::shared_future<JitKernel*> jit_get(int device, const DevPlan& plan);
 int jit_precompile(const DevPlan& plan, std::string* error);
 // process-wide: NVRTC compilations run, kernels served from the on-disk cache
 void jit_counters(unsigned long long* nvrtc_compiles, unsigned long long* disk_hits);
-int jit_max_blocks_per_sm(const JitKernel* k, size_t smem);
-cudaError_t jit_launch(const JitKernel* k, const ScanArgs& a, int grid, size_t smem, cudaStream_t s);
+int jit_max_blocks_per_sm(const JitKernel* k, size_t smem, bool fast = false);
+cudaError_t jit_launch(const JitKernel* k, const ScanArgs& a, int grid, size_t smem, cudaStream_t s, bool fast = false);
+// does fast_body cover this plan?  (aggregation by at most one expression without Real sums, TopN)
+bool plan_has_fast_kernel(const DevPlan& plan);
 
 }  // namespace b2

@@ -16,9 +16,14 @@
 // that key (walks its versions, decodes the row).  CTAs are persistent and pull 256-entry tiles.
 #include <cuda_runtime.h>
 
-#include "scan_kernel.cuh"
+#include "fast_kernel.cuh"
 
 namespace b2 {
+
+template <int MODE>
+__global__ void __launch_bounds__(FK_THREADS, 2) fast_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A) {
+  fast_body<MODE>(P, A);
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(TILE + 64, 2) scan_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A) {
@@ -86,6 +91,36 @@ cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t
     case PM_TOPN: scan_launch_mode<PM_TOPN>(plan, a, grid, smem, s); break;
     case PM_AGGM: scan_launch_mode<PM_AGGM>(plan, a, grid, smem, s); break;
     default: scan_launch_mode<PM_AGG>(plan, a, grid, smem, s); break;
+  }
+  return cudaGetLastError();
+}
+
+size_t fast_stage_bytes(uint32_t key_cap, uint32_t val_cap) { return (size_t)FK_STAGES * (key_cap + val_cap + 2 * STAGE_OFF_CAP); }
+size_t fast_checksum_bytes() { return 8 * 256 * 8 + 256 * 8; }
+template <int MODE>
+static cudaError_t fast_occupancy(int* per_sm, size_t smem) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(fast_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fast_kernel<MODE>, FK_THREADS, smem);
+}
+int fast_max_grid(int mode, size_t smem) {
+  int per_sm = 0;
+  cudaError_t e = mode == PM_TOPN ? fast_occupancy<PM_TOPN>(&per_sm, smem) : (mode == PM_CHECKSUM ? fast_occupancy<PM_CHECKSUM>(&per_sm, smem) : fast_occupancy<PM_AGG>(&per_sm, smem));
+  if (e != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * num_sms();
+}
+template <int MODE>
+static void fast_launch_mode(const DevPlan& plan, const ScanArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if (smem > 48 * 1024) cudaFuncSetAttribute(fast_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  fast_kernel<MODE><<<grid, FK_THREADS, smem, s>>>(plan, a);
+}
+cudaError_t launch_fast(const DevPlan& plan, const ScanArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if (a.c_hi <= a.c_lo) return cudaSuccess;
+  uint32_t n_tiles = (a.c_hi - a.c_lo + TILE - 1) / TILE;
+  if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
+  switch (plan.mode) {
+    case PM_TOPN: fast_launch_mode<PM_TOPN>(plan, a, grid, smem, s); break;
+    case PM_CHECKSUM: fast_launch_mode<PM_CHECKSUM>(plan, a, grid, smem, s); break;
+    default: fast_launch_mode<PM_AGG>(plan, a, grid, smem, s); break;
   }
   return cudaGetLastError();
 }
@@ -314,6 +349,7 @@ __global__ void bounds_kernel(const BlockView* blocks, uint32_t n_blocks, const 
 
 // per (block, range) unit [lo, hi): do its first and last key share their first 12 bytes, and are those the start of a
 // record key?  Keys are sorted, so every key in between shares them too: the clean-entry front end skips those bytes.
+// out: 4 words per unit: ok flag, then the unit's first 12 key bytes (3 words, little-endian)
 __global__ void unit_prefix_kernel(const BlockView* blocks, uint32_t n_blocks, uint32_t n_ranges, const uint32_t* bounds, uint32_t* out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_blocks * n_ranges) return;
@@ -326,8 +362,9 @@ __global__ void unit_prefix_kernel(const BlockView* blocks, uint32_t n_blocks, u
     const uint8_t* l = b.keys + b.koff[hi - 1];
     ok = b.koff[lo + 1] - b.koff[lo] >= 12 && b.koff[hi] - b.koff[hi - 1] >= 12 && record_key_prefix_ok(f);
     for (int j = 0; ok && j < 12; ++j) ok = f[j] == l[j];
+    for (int w = 0; w < 3; ++w) out[4 * i + 1 + w] = ok ? ((uint32_t)f[4 * w] | ((uint32_t)f[4 * w + 1] << 8) | ((uint32_t)f[4 * w + 2] << 16) | ((uint32_t)f[4 * w + 3] << 24)) : 0u;
   }
-  out[i] = ok;
+  out[4 * i] = ok;
 }
 
 cudaError_t launch_bounds_search(const BlockView* blocks, uint32_t n_blocks, const uint8_t* bounds, const uint32_t* bound_offs, uint32_t n_bounds,

@@ -77,6 +77,12 @@ struct ScanArgs {
   uint32_t stage_key_cap, stage_val_cap;  // bytes per stage for key / value heaps (multiples of 16)
   int64_t imms[MAX_IMMS];           // the request's constants (DevNode::sig / FastCond::imm_slot index them)
   uint64_t limit;                   // TopN limit (not part of the compiled plan shape)
+  // hand-over between the lean kernel (fast_kernel.cuh) and the general one: first entries of the runs the lean kernel left alone
+  unsigned int* slow_list;          // capacity >= c_hi - c_lo
+  unsigned int* slow_count;
+  uint32_t list_mode;               // scan_body: 1 = process the entries of slow_list (count read on the device) instead of [c_lo, c_hi)
+  uint32_t _pad2;
+  uint64_t ck_key_state;            // lean checksum: crc register after old_prefix and the unit's common raw key bytes [new_prefix_len, 11)
   uint32_t fast_ok;                 // 1: every key of [e_lo, e_hi) starts with the same 12 bytes 't' tid "_r" (first and last key of the
                                     //    sorted unit agree): the clean-entry front end may skip them
   uint32_t _pad1;
@@ -101,6 +107,11 @@ struct GenArgs {
 #ifndef B2_NVRTC
 // launchers (kernels.cu)
 cudaError_t launch_scan(const DevPlan& plan, const ScanArgs& a, int grid, size_t smem, cudaStream_t s);
+// the lean kernels (fast_kernel.cuh): PM_AGG (at most one group-by expression, no Real sums), PM_TOPN, PM_CHECKSUM
+cudaError_t launch_fast(const DevPlan& plan, const ScanArgs& a, int grid, size_t smem, cudaStream_t s);
+int fast_max_grid(int mode, size_t smem);
+size_t fast_stage_bytes(uint32_t key_cap, uint32_t val_cap);
+size_t fast_checksum_bytes();             // PM_CHECKSUM tables + per-length key states
 int scan_max_grid(int mode, size_t smem);  // occupancy-based persistent grid size
 int scan_num_sms();
 size_t scan_stage_bytes(uint32_t key_cap, uint32_t val_cap);  // dynamic shared memory needed by the tile stages

@@ -369,7 +369,9 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   __shared__ unsigned int s_tbl_used, s_tbl_miss, s_tbl_off;  // resident groups; rows that fell through to HBM; table given up
 
   const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint32_t n_tiles = (A.c_hi - A.c_lo + TILE - 1) / TILE;
+  // list mode (order-free pipelines): the entries the lean kernel handed over, 256 per tile, read from the HBM arrays
+  const uint32_t n_list = !IS_SCAN && A.list_mode ? *(volatile unsigned int*)A.slow_count : 0u;
+  const uint32_t n_tiles = !IS_SCAN && A.list_mode ? (n_list + TILE - 1) / TILE : (A.c_hi - A.c_lo + TILE - 1) / TILE;
   const unsigned long long out_base = IS_SCAN ? A.ctr->out_base : 0ull;  // stable during this launch
 
   SmemTable st;
@@ -587,7 +589,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   uint32_t ob_q = 0, ob_phase = 0;  // PM_SCAN: next output chunk buffer and how often the ring has wrapped (parity)
   auto tile_body = [&](const auto& view, const uint32_t walk_hi, const uint32_t k, const uint32_t tile) __attribute__((always_inline)) -> bool {
     using V = typename b2_remove_cvref<decltype(view)>::type;
-    const uint32_t e = A.c_lo + tile * TILE + tid;
+    const uint32_t e = !IS_SCAN && A.list_mode ? (tile * TILE + tid < n_list ? A.slow_list[tile * TILE + tid] : A.c_hi) : A.c_lo + tile * TILE + tid;
     bool live = false;
     Row row;
     Cells cells;

@@ -40,9 +40,12 @@ def compile_cubin(plan):
     mode = J.mode_of(lit)
     if not os.environ.get("B2_KEEP_V1"):  # the engine clears fast_v1 when the data is row format v2 (it samples the first row)
         lit, n = re.subn(r"(u,\{-?\d+(?:,-?\d+){7}\},\d+),1,", r"\1,0,", lit, count=1)
-    src = ("#define B2_NVRTC 1\n#include \"scan_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + lit + ";\n}\n"
+    src = ("#define B2_NVRTC 1\n#include \"fast_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + lit + ";\n}\n"
            "extern \"C\" __global__ void __launch_bounds__(b2::TILE + 64, 2) b2_scan_jit(const __grid_constant__ b2::ScanArgs A) {\n"
            "  b2::scan_body<" + str(mode) + ">(b2::kJitPlan, A);\n}\n")
+    if mode in (1, 2) and os.environ.get("B2_FAST", "1") == "1":
+        src += ("extern \"C\" __global__ void __launch_bounds__(b2::FK_THREADS, " + os.environ.get("B2_FAST_MINB", "2") + ") b2_fast_jit(const __grid_constant__ b2::ScanArgs A) {\n"
+                "  b2::fast_body<" + str(mode) + ">(b2::kJitPlan, A);\n}\n")
     err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"b2_scan_jit.cu", 0, [], [])
     opts = [b"--gpu-architecture=sm_100a", b"--std=c++17", b"-lineinfo", b"-DB2_NVRTC=1", b"-default-device",
             ("-I" + os.path.join(ROOT, "tikv_b200", "csrc")).encode(), b"-I/usr/local/cuda/include", b"--ptxas-options=-v", b"-DB2_EXT_SIGS=0"] + [o.encode() for o in os.environ.get("B2_JIT_EXTRA", "").split()]
@@ -70,7 +73,21 @@ def main():
     per_line = collections.Counter()
     ops = collections.Counter()
     total = 0
+    want_fn = os.environ.get("FN", "b2_fast_jit" if "b2_fast_jit" in dis else "b2_scan_jit")
+    fn = None
+    per_fn = collections.Counter()
     for l in dis.splitlines():
+        mf = re.match(r"\s*\.text\.(\w+):", l) or re.match(r"^(b2_\w+):", l.strip())
+        if mf:
+            fn = mf.group(1)
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", l)
+        if m:
+            per_fn[fn] += 1
+        if fn != want_fn:
+            mm = re.search(r'//## File "([^"]+)", line (\d+)', l)
+            if mm:
+                cur = (os.path.basename(mm.group(1)), int(mm.group(2)))
+            continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', l)
         if m:
             cur = (os.path.basename(m.group(1)), int(m.group(2)))
@@ -80,6 +97,7 @@ def main():
             total += 1
             per_line[cur] += 1
             ops[m.group(2).split(".")[0]] += 1
+    print("per kernel:", dict(per_fn), "| buckets below are for", want_fn)
     print("SASS instructions:", total)
     print("ops:", ", ".join(f"{k} {v}" for k, v in ops.most_common(14)))
     # per function of b2_device.h / 20-line bucket of scan_kernel.cuh
@@ -100,7 +118,7 @@ def main():
         return name
     agg = collections.Counter()
     for (f, ln), c in ((k, v) for k, v in per_line.items() if k):
-        agg[("dev:" + func_of(ln)) if f == "b2_device.h" else f"{f}:{ln // 10 * 10}"] += c
+        agg[("dev:" + func_of(ln)) if f == "b2_device.h" else f"{f}:{ln // 20 * 20}"] += c
     for k, v in agg.most_common(int(os.environ.get("TOPK", "40"))):
         print(f"  {k:40s} {v}")
 
