@@ -433,3 +433,89 @@ def check_scalar_known_answers(run, error_labels=None):
                 assert v is not None and struct.pack("<d", v) == struct.pack("<d", want), (label, v, want)
             else:
                 assert v == want, (label, v, want)
+
+
+# ---- the reference's own executor fixtures (MockExecutor batches restated as table rows) ------------------------------
+def reference_executor_fixtures():
+    """[(name, region, plan, expected rows, ordered, compared columns)] for
+      * BatchFastHashAggregationExecutor / BatchSlowHashAggregationExecutor test_it_works_integration
+        (fast_hash_aggr_executor.rs:509-634 over util/aggr_executor.rs:434-520 make_src_executor_1),
+      * BatchTopNExecutor test_integration_1/2/3 (top_n_executor.rs:463-757) and test_top_unsigned (:1022-1212).
+    The MockExecutor's logical rows become table rows (handle = logical position), so that the whole path — MVCC scan,
+    row decode, expression evaluation, the executor — must reproduce the reference's expected output."""
+    from tikv_b200.plan import plus
+    TP_D = ffi.TP_DOUBLE
+    out = []
+
+    def table(col_defs, rows, fmt=2):
+        r = kvfmt.Region()
+        for h, vals in enumerate(rows):
+            cells = []
+            for (cid, kind), v in zip(col_defs, vals):
+                cells.append((cid, v, kind if v is not None else "null"))
+            if fmt == 2:
+                val = kvfmt.row_v2(cells)
+            else:
+                d = []
+                for cid, v, kind in cells:
+                    d.append((cid, kvfmt.datum_null() if v is None else (kvfmt.datum_f64(v) if kind == "f64" else (kvfmt.datum_uint(v) if kind == "uint" else kvfmt.datum_int(v)))))
+                val = kvfmt.row_v1(d)
+            r.put(kvfmt.row_key(TABLE, h + 1), val, 5, 8)
+        return r.build(read_ts=READ_TS)
+
+    # --- hash aggregation: COUNT(1), COUNT(col_1 + 5.0), AVG(col_0) GROUP BY col_0 + col_1
+    rows = [(None, 1.0, 1), (7.0, 2.0, None), (None, None, None), (None, 4.5, None), (1.5, 4.5, 5)]
+    cols = [ColumnDef(1, tp=TP_D), ColumnDef(2, tp=TP_D), ColumnDef(4)]
+    c0, c1 = col(0, tp=TP_D), col(1, tp=TP_D)
+    for fmt in (2, 1):
+        region = table([(1, "f64"), (2, "f64"), (4, "int")], rows, fmt)
+        for n_groups, label in ((1, "fast"), (2, "slow")):
+            gb = [plus(c0, c1)] * n_groups if n_groups == 1 else [plus(c0, c1), c0]  # the slow executor, keyed on two expressions
+            plan = Plan().table_scan(TABLE, cols).aggregation([("count", const_int(1)), ("count", plus(c1, const_real(5.0))), ("avg", c0)], group_by=gb).build()
+            if n_groups == 1:
+                exp = [(1, 1, 1, 7.0, 9.0), (1, 1, 1, 1.5, 6.0), (3, 2, 0, None, None)]
+            else:  # (col_0 + col_1, col_0): the NULL group stays whole — col_0 is NULL in all three of its rows
+                exp = [(1, 1, 1, 7.0, 9.0, 7.0), (1, 1, 1, 1.5, 6.0, 1.5), (3, 2, 0, None, None, None)]
+            out.append((f"hash_agg_{label}_v{fmt}", region, plan, exp, False, None))
+
+    # --- TopN: Col0 (Int) Col1 (Int) Col2 (Real)
+    rows = [(None, -1, -1.0), (None, None, 2.0), (None, 1, 4.0), (-1, None, None), (-10, 10, 3.0), (-10, None, -5.0), (-10, -10, 0.0)]
+    cols = [ColumnDef(1), ColumnDef(2), ColumnDef(3, tp=TP_D)]
+    region = table([(1, "int"), (2, "int"), (3, "f64")], rows)
+    scan = lambda: Plan().table_scan(TABLE, cols)
+    out.append(("topn_integration_1", region, scan().topn([(col(2, tp=TP_D), False)], 100).build(),
+                [(-1, None, None), (-10, None, -5.0), (None, -1, -1.0), (-10, -10, 0.0), (None, None, 2.0), (-10, 10, 3.0), (None, 1, 4.0)], True, None))
+    out.append(("topn_integration_2", region, scan().topn([(col(0), True), (col(1), False)], 7).build(),
+                [(-1, None, None), (-10, None, -5.0), (-10, -10, 0.0), (-10, 10, 3.0), (None, None, 2.0), (None, -1, -1.0), (None, 1, 4.0)], True, None))
+    out.append(("topn_integration_3", region, scan().topn([(is_null(col(0)), False), (col(0), False), (plus(col(1), const_int(1)), True)], 5).build(),
+                [(-10, 10, 3.0), (-10, -10, 0.0), (-10, None, -5.0), (-1, None, None), (None, 1, 4.0)], True, None))
+
+    # --- TopN over unsigned columns: Col0 (u64) Col1 (i64) Col2 (u32)
+    U = (1 << 64)
+    rows = [(U - 1, -3, 4294967295), (None, None, None), (U - 3, -1, 4294967295), (2000, 2000, 2000), ((1 << 63) - 1, (1 << 63) - 1, 2147483647),
+            (300, 300, 300), (1 << 63, -(1 << 63), 2147483648)]
+    cols = [ColumnDef(1, unsigned=True), ColumnDef(2), ColumnDef(3, tp=ffi.TP_LONG, unsigned=True)]
+    region = table([(1, "uint"), (2, "int"), (3, "uint")], rows)
+    s64 = lambda v: None if v is None else (v - U if v >= (1 << 63) else v)  # columns come back as i64 bits
+    cases = [(0, False, [None, 300, 2000, (1 << 63) - 1, 1 << 63]), (0, True, [U - 1, U - 3, 1 << 63, (1 << 63) - 1, 2000]),
+             (1, False, [None, -(1 << 63), -3, -1, 300]), (1, True, [(1 << 63) - 1, 2000, 300, -1, -3]),
+             (2, False, [None, 300, 2000, 2147483647, 2147483648]), (2, True, [4294967295, 4294967295, 2147483648, 2147483647, 2000])]
+    for ci, desc, exp in cases:
+        c = col(ci, unsigned=ci != 1, tp=ffi.TP_LONG if ci == 2 else ffi.TP_LONGLONG)
+        plan = Plan().table_scan(TABLE, cols).topn([(c, desc)], 5).build()
+        out.append((f"topn_unsigned_col{ci}_{'desc' if desc else 'asc'}", region, plan, [(s64(v),) for v in exp], True, [ci]))
+    return out
+
+
+def check_reference_fixture(fx, run):
+    """run(plan, region) -> result with .status / .rows(); compares with the reference's expected rows."""
+    name, region, plan, exp, ordered, cols = fx
+    got = run(plan, region)
+    assert got.status == 0, (name, getattr(got, "message", ""))
+    rows = got.rows()
+    if cols is not None:
+        rows = [tuple(r[c] for c in cols) for r in rows]
+    if not ordered:
+        key = lambda r: tuple((0, 0) if v is None else (1, v) for v in r)
+        rows, exp = sorted(rows, key=key), sorted(exp, key=key)
+    assert rows == exp, f"{name}: {rows} != reference {exp}"

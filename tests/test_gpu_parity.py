@@ -631,3 +631,15 @@ def test_projection(name, plan):
         return
     assert exp.status == 0
     assert_same_rows(got, exp, ordered=True, ctx=name)
+
+
+_FIXTURES = sc.reference_executor_fixtures()
+
+
+@pytest.mark.parametrize("fx", _FIXTURES, ids=[f[0] for f in _FIXTURES])
+def test_reference_executor_fixtures(fx):
+    """The reference's own aggregation / TopN test expectations (fast_hash_aggr_executor.rs:509-634, top_n_executor.rs:
+    528-757, 1105-1212) through the CUDA path: generic and plan-specialised kernels, host- and device-resident sources."""
+    for jit in (ffi.JIT_OFF, ffi.JIT_SYNC):
+        sc.check_reference_fixture(fx, lambda plan, region: DagHandler(plan, sc.WHOLE, region, jit=jit).handle_request())
+    sc.check_reference_fixture(fx, lambda plan, region: DagHandler(plan, sc.WHOLE, DeviceRegion(region)).handle_request())

@@ -695,3 +695,23 @@ def test_gc_fence_fixture_forward_and_backward():
     assert st == 0 and rows == want
     st, rows, _ = orc.mvcc_scan(region, desc=True)
     assert st == 0 and rows == want[::-1]
+
+
+# ---- the reference's executor tests: aggregation and TopN ------------------------------------------------
+import scenarios as sc  # noqa: E402
+
+_FIXTURES = sc.reference_executor_fixtures()
+
+
+@pytest.mark.parametrize("fx", _FIXTURES, ids=[f[0] for f in _FIXTURES])
+def test_reference_executor_fixtures_pin_the_oracle(fx):
+    """fast_hash_aggr_executor.rs:509-634 (also run through the slow executor there), top_n_executor.rs:528-757 and
+    :1105-1212: the oracle's aggregation and TopN executors must produce what the reference's tests assert."""
+    sc.check_reference_fixture(fx, lambda plan, region: orc.dag_handle(plan, sc.WHOLE, region))
+
+
+@pytest.mark.parametrize("fx", _FIXTURES, ids=[f[0] for f in _FIXTURES])
+def test_reference_executor_fixtures_device_logic(fx):
+    """the same through the device row logic driven on the CPU (tests/host_emul.cpp)"""
+    import emu
+    sc.check_reference_fixture(fx, lambda plan, region: emu.dag_handle(plan, sc.WHOLE, region))
