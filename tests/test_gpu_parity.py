@@ -644,3 +644,83 @@ def test_reference_executor_fixtures(fx):
     for jit in jits:
         sc.check_reference_fixture(fx, lambda plan, region: DagHandler(plan, sc.WHOLE, region, jit=jit).handle_request())
     sc.check_reference_fixture(fx, lambda plan, region: DagHandler(plan, sc.WHOLE, DeviceRegion(region)).handle_request())
+
+
+# ---- backward scan (TableScan.desc; scan_executor.rs:89-101, backward.rs:78-225) ------------------------------------------
+def test_desc_table_scan_matches_oracle(regions):
+    """the device path of `desc` scans (reversed chunks, rows reversed on the device) against the oracle's
+    BackwardScanner pipeline: plain scan, selection, projection-free subsets, Limit, small batches, every isolation level,
+    host- and device-resident sources, multi-range requests."""
+    from tikv_b200.plan import gt
+    scan = lambda: Plan().table_scan(sc.TABLE, sc.COLUMNS, desc=True)
+    plans = [("all", scan().build()), ("sel", scan().selection(gt(col(sc.C6, tp=ffi.TP_LONG), const_int(3))).build(output_offsets=[sc.C_H, sc.C1, sc.C6])),
+             ("limit", scan().selection(lt(col(sc.C1), const_int(0))).limit(41).build()), ("limit_plain", scan().limit(7).build())]
+    for seed in (1, 2):
+        host = regions[seed].build(read_ts=sc.READ_TS, n_write_blocks=3)
+        for region in (host, DeviceRegion(host)):
+            for ranges in (sc.WHOLE, sc.split_ranges()):
+                for name, plan in plans:
+                    exp = orc.dag_handle(plan, ranges, host)
+                    for batch in (1 << 22, 97):
+                        got = DagHandler(plan, ranges, region, batch_rows=batch).handle_request()
+                        assert_same_rows(got, exp, ordered=True, ctx=f"desc/{name}/seed{seed}/batch{batch}")
+                    if name == "all":
+                        assert got.stats.write_processed_keys == exp.stats["processed_keys"] and got.stats.processed_size == exp.stats["processed_size"]
+    for ts, iso in ((25, ffi.ISO_RC), (sc.READ_TS, ffi.ISO_RC_CHECK_TS)):
+        region = regions[2].build(read_ts=ts, isolation=iso)
+        exp, got = orc.dag_handle(plans[0][1], sc.WHOLE, region), DagHandler(plans[0][1], sc.WHOLE, region, batch_rows=200).handle_request()
+        assert got.status == exp.status and got.rows() == exp.rows()
+
+
+def test_desc_aggregation_topn_errors_and_locks(regions):
+    """Direction-independent pipelines under `desc` (aggregates; TopN, whose ties go to the row scanned first = the larger
+    key), the first error of a backward scan (the failing row with the largest key; the rows above it are still returned)
+    and a conflicting lock (rows above the lock first, then KeyIsLocked)."""
+    host = regions[1].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    scan = lambda: Plan().table_scan(sc.TABLE, sc.COLUMNS, desc=True)
+    agg = scan().aggregation([("sum", col(sc.C1)), ("count", const_int(1))], group_by=[col(sc.C6, tp=ffi.TP_LONG)]).build()
+    assert_same_rows(DagHandler(agg, sc.WHOLE, host).handle_request(), orc.dag_handle(agg, sc.WHOLE, host), ordered=False, ctx="desc agg")
+    topn = scan().topn([(col(sc.C6), True)], 60).build()  # heavy ties on C6: only the scan order decides which rows stay
+    exp, got = orc.dag_handle(topn, sc.WHOLE, host), DagHandler(topn, sc.WHOLE, host).handle_request()
+    assert got.status == 0 == exp.status and [r[sc.C6] for r in got.rows()] == [r[sc.C6] for r in exp.rows()]
+    # two corrupted rows: a backward scan reports the one with the larger key and returns the rows above it
+    T = sc.TABLE
+    r = kvfmt.Region()
+    for h in range(500):
+        r.put(kvfmt.row_key(T, h), kvfmt.row_v2([(1, h, "int"), (2, h % 5, "int"), (3, 7, "uint"), (4, 1.0, "f64"), (6, 1, "int")]), 10, 20)
+    r.raw_write(kvfmt.row_key(T, 100), 50, b"Xjunk").raw_write(kvfmt.row_key(T, 400), 50, b"Xjunk")
+    bad = r.build(read_ts=100)
+    plan = scan().build()
+    exp, got = orc.dag_handle(plan, sc.WHOLE, bad), DagHandler(plan, sc.WHOLE, bad, batch_rows=64).handle_request()
+    assert exp.status == ffi.B2_ERR_STORAGE == got.status and got.rows() == exp.rows() and len(got.rows()) == 99
+    # a Put lock in the middle: the rows with larger keys come out, then the request fails
+    lk = kvfmt.Region()
+    lk.write = [w for w in r.write if b"Xjunk" not in w[1]]
+    lk.add_lock(kvfmt.row_key(T, 250), kvfmt.lock_record(b"P", kvfmt.row_key(T, 250), 60))
+    locked = lk.build(read_ts=100)
+    exp, got = orc.dag_handle(plan, sc.WHOLE, locked), DagHandler(plan, sc.WHOLE, locked, batch_rows=64).handle_request()
+    assert exp.status == ffi.B2_ERR_KEY_IS_LOCKED == got.status and got.rows() == exp.rows() and len(got.rows()) == 249
+
+
+def test_desc_take_scanned_range(regions):
+    """scanner.rs:204-229 with scan_backward_in_range: consecutive takes tile the key space from the top: each lower bound
+    is the key of the last (smallest) row returned, the next take's upper bound; the last take reaches the first range's start."""
+    host = regions[2].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    ranges = sc.split_ranges()
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS, desc=True).build()
+    scans = [orc.mvcc_scan(host, kvfmt.enc_bytes_memcmp(lo), kvfmt.enc_bytes_memcmp(hi))[1] for lo, hi in ranges]
+    all_rows = [kvfmt.dec_bytes_memcmp(k) for rows in scans for (k, _v) in rows][::-1]  # raw keys in the order a backward scan returns them
+    with BatchExecutor(plan, ranges, host) as ex:
+        prev_lo, seen = None, 0
+        while True:
+            r = ex.next_batch(150)
+            assert r.error is None
+            lo, hi = ex.take_scanned_range()
+            assert hi == (ranges[-1][1] if prev_lo is None else prev_lo)
+            seen = ex.collect_exec_stats().write_processed_keys
+            if r.is_drained:
+                assert lo == ranges[0][0]
+                break
+            assert lo == (all_rows[seen - 1] if seen and lo != hi else hi)
+            prev_lo = lo
+        assert seen == len(all_rows) > 300

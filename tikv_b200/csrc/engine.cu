@@ -260,6 +260,7 @@ struct b2_exec {
   std::vector<int> range_lock_err;                      // 1 = range ends with KeyIsLocked
   std::vector<uint64_t> range_lock_ts;
   std::vector<Unit> units;
+  uint32_t first_live_range = 0;                         // backward scans: ranges below a conflicting lock's range are never reached
   size_t cur_unit = 0;
   uint32_t cur_entry = 0;
   bool started = false, drained = false, failed = false;
@@ -300,7 +301,7 @@ struct b2_exec {
     }
     for (auto& e : kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (DevBuf* b : {&tn_lists, &tn_counts, &tn_pair, &tn_pair_cnt, &tn_tmp, &tn_tmp_cnt, &tn_blk_pay, &tn_blk_null, &tn_run_pay, &tn_run_null, &tn_tmp_pay, &tn_tmp_null, &tn_bitmap}) b->release();
-    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &tbl_gkeys, &tbl_ready, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &slow_list, &slow_cnt, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
+    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &tbl_gkeys, &tbl_ready, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &slow_list, &slow_cnt, &rev_data, &rev_bitmap, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
     enc_host.release();
     for (auto& b : res_cols) b.release();
     for (auto& b : res_bitmaps) b.release();
@@ -430,12 +431,21 @@ struct b2_exec {
     // CF_LOCK (host memory): LatestKvPolicy::handle_lock for every lock inside a range, in key order
     if (src->lock && src->lock->n && isolation != B2_ISO_RC) {
       const b2_cf_block& L = *src->lock;
-      for (uint32_t r = 0; r < n_ranges; ++r) {
-        for (uint32_t i = 0; i < L.n; ++i) {
+      // forward: ranges and locks in ascending order, the first conflict ends the scan; backward (TableScan.desc):
+      // both in descending order, rows above the largest conflicting lock are produced first
+      for (uint32_t rr = 0; rr < n_ranges; ++rr) {
+        const uint32_t r = cp.desc ? n_ranges - 1 - rr : rr;
+        for (uint32_t ii = 0; ii < L.n; ++ii) {
+          const uint32_t i = cp.desc ? L.n - 1 - ii : ii;
           const uint8_t* k = L.keys + L.key_offs[i];
           size_t kn = L.key_offs[i + 1] - L.key_offs[i];
+          if (cp.desc) {
+            if (cmp_bytes_host(k, kn, range_hi[r].data(), range_hi[r].size()) >= 0) continue;
+            if (cmp_bytes_host(k, kn, range_lo[r].data(), range_lo[r].size()) < 0) break;
+          } else {
           if (cmp_bytes_host(k, kn, range_lo[r].data(), range_lo[r].size()) < 0) continue;
           if (cmp_bytes_host(k, kn, range_hi[r].data(), range_hi[r].size()) >= 0) break;
+          }
           saw_lock = true;
           HostLock lk;
           if (!parse_lock(L.vals + L.val_offs[i], L.val_offs[i + 1] - L.val_offs[i], &lk)) return fail(B2_ERR_STORAGE, "bad format lock");
@@ -459,14 +469,19 @@ struct b2_exec {
           if (!conflict) continue;
           for (uint32_t a = 0; a < src->n_access_locks; ++a)
             if (src->access_locks[a] == lk.ts) return fail(B2_ERR_UNSUPPORTED, "access_locks read-through is not supported on the device path");
-          // rows before this key are produced, then the request fails (forward.rs:401-428)
-          range_hi[r].assign(k, k + kn);
+          // rows before this key are produced, then the request fails (forward.rs:401-428; backward.rs:176-225: rows after it)
+          if (cp.desc) { range_lo[r].assign(k, k + kn); range_lo[r].insert(range_lo[r].end(), 9, (uint8_t)0xff); }  // past every version of that key
+          else range_hi[r].assign(k, k + kn);
           range_lock_err[r] = isolation == B2_ISO_SI ? B2_ERR_KEY_IS_LOCKED : B2_ERR_WRITE_CONFLICT;
           range_lock_ts[r] = lk.ts;
           lock_keys_seen++;
           break;
         }
-        if (range_lock_err[r]) { range_lo.resize(r + 1); range_hi.resize(r + 1); range_lock_err.resize(r + 1); range_lock_ts.resize(r + 1); break; }
+        if (range_lock_err[r]) {
+          if (cp.desc) first_live_range = r;  // ranges below it are never reached
+          else { range_lo.resize(r + 1); range_hi.resize(r + 1); range_lock_err.resize(r + 1); range_lock_ts.resize(r + 1); }
+          break;
+        }
       }
     }
     return compute_units();
@@ -524,7 +539,7 @@ struct b2_exec {
       d_views.release(); d_flat.release(); d_offs.release(); d_res.release(); d_ok.release();
       if (e != cudaSuccess) return fail(B2_ERR_CUDA, std::string("range bounds search: ") + cudaGetErrorString(e));
     }
-    for (uint32_t r = 0; r < nr; ++r)
+    for (uint32_t r = first_live_range; r < nr; ++r)
       for (uint32_t b = 0; b < nb; ++b) {
         uint32_t lo = res[(size_t)b * nr * 2 + 2 * r], hi = res[(size_t)b * nr * 2 + 2 * r + 1];
         if (hi > lo) {
@@ -605,7 +620,7 @@ struct b2_exec {
     CUDA_TRY(h_ctr.reserve(sizeof(Counters)));
     Counters z;
     memset(&z, 0, sizeof(z));
-    z.err = ~0ull;
+    z.err = ~0ull; z.first_row = ~0ull;
     CUDA_TRY(cudaMemcpyAsync(ctr_buf.p, &z, sizeof(z), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(range_rows.reserve(std::max<size_t>(1, range_raw_lo.size()) * 8));
     CUDA_TRY(cudaMemsetAsync(range_rows.p, 0, std::max<size_t>(1, range_raw_lo.size()) * 8, stream));
@@ -653,9 +668,10 @@ struct b2_exec {
 
   int device_error(const Counters& c) {
     if (c.err == ~0ull) return B2_OK;
+    const unsigned long long e = cp.desc ? c.err_max : c.err;  // the failing row a scan in this direction meets first
     int status, mysql;
-    const char* m = dev_err_message((int)(c.err & 0xff), &status, &mysql);
-    return fail(status, m, mysql, c.err >> 8);
+    const char* m = dev_err_message((int)(e & 0xff), &status, &mysql);
+    return fail(status, m, mysql, e >> 8);
   }
 
   // shared-memory staging: capacities from the block's average entry size (+30 %), stages placed after `mode_bytes`
@@ -759,6 +775,7 @@ struct b2_exec {
     a.ctr = ctr();
     a.read_ts = cp.dev.read_ts; a.isolation = cp.dev.isolation;
     a.fast_ok = use_fast_front ? u.fast_ok : 0;
+    a.desc = cp.desc ? 1u : 0u;
     memcpy(a.imms, cp.imms, sizeof(a.imms));
     a.limit = cp.dev.limit;
     a.range_rows = range_rows.p ? (unsigned long long*)range_rows.p + u.range_idx : nullptr;
@@ -790,7 +807,7 @@ struct b2_exec {
     CUDA_TRY(cudaMemsetAsync(out_bitmap.p, 0xff, out_cap / 8 * n_out, stream));
     Counters z;
     memset(&z, 0, sizeof(z));
-    z.err = ~0ull;
+    z.err = ~0ull; z.first_row = ~0ull;
     // keep request-level statistics, reset the per-batch row counters
     CUDA_TRY(cudaMemsetAsync(&ctr()->out_rows, 0, 8, stream));
     CUDA_TRY(cudaMemsetAsync(&ctr()->out_base, 0, 8, stream));
@@ -879,7 +896,7 @@ struct b2_exec {
       if (c.err != ~0ull) {
         // rows before the failing row stay valid (interface.rs:229-235): redo this batch up to it, then report
         cur_unit = save_unit; cur_entry = save_entry; entries_scanned = save_scanned;
-        Counters z; memset(&z, 0, sizeof(z)); z.err = ~0ull;
+        Counters z; memset(&z, 0, sizeof(z)); z.err = ~0ull; z.first_row = ~0ull;
         CUDA_TRY(cudaMemcpyAsync(ctr_buf.p, &z, sizeof(z), cudaMemcpyHostToDevice, stream));
         Counters c2;
         rc = run_scan_pass(budget, c.err >> 8, &hit_lock, &lock_r, &c2);
@@ -906,6 +923,137 @@ struct b2_exec {
     }
     return publish_scan_columns(produced, out);
   }
+  // ---- backward scan (TableScan.desc; scan_executor.rs:89-101, backward.rs:78-225) ----
+  // The rows of a backward scan are the rows of the forward scan in reverse order (the MVCC rule per key is the same), so
+  // a batch is one chunk of at most `scan_rows` entries taken from the *end* of what is left — units last to first, inside
+  // a unit from its upper end down — run through the forward kernel and reversed on the device.  A chunk only emits runs
+  // that *start* inside it, and its walks may go past its upper end, so a version run is never split.
+  bool desc_started = false;
+  size_t d_unit = 0;       // unit being consumed (counts down)
+  uint32_t d_hi = 0;       // exclusive upper entry of what is left of it
+  DevBuf rev_data, rev_bitmap;
+  uint64_t rev_cap = 0;
+  int run_desc_chunk(const Unit& u, uint32_t c_lo, uint32_t c_hi, Counters* c) {
+    const size_t n_out = cp.dev.n_out;
+    const uint64_t cap = std::max<uint64_t>(64, ((uint64_t)(c_hi - c_lo) + 63) & ~63ull);
+    if (cap > out_cap) {
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      CUDA_TRY(out_data.reserve(cap * 8 * n_out)); CUDA_TRY(out_bitmap.reserve(cap / 8 * n_out));
+      out_cap = cap;
+    }
+    CUDA_TRY(cudaMemsetAsync(out_bitmap.p, 0xff, out_cap / 8 * n_out, stream));
+    Counters z;
+    memset(&z, 0, sizeof(z));
+    z.err = ~0ull; z.first_row = ~0ull;
+    // per-chunk counters; request-level statistics are carried on the host (desc_stats)
+    CUDA_TRY(cudaMemcpyAsync(ctr_buf.p, &z, sizeof(z), cudaMemcpyHostToDevice, stream));
+    const uint32_t n_tiles = (c_hi - c_lo + TILE - 1) / TILE;
+    CUDA_TRY(status_buf.reserve_on(stream, ((size_t)n_tiles + 1) * 8));
+    CUDA_TRY(cudaMemsetAsync(status_buf.p, 0, ((size_t)n_tiles + 1) * 8, stream));
+    BlockView v;
+    int rc = acquire_block(u.block_idx, &v);
+    if (rc) return rc;
+    ScanArgs a = base_args(u, v);
+    a.c_lo = c_lo; a.c_hi = c_hi;
+    a.tile_status = (unsigned long long*)status_buf.p;
+    a.out_data = (unsigned long long*)out_data.p; a.out_bitmap = (unsigned long long*)out_bitmap.p;
+    a.out_cap = out_cap;
+    size_t smem = setup_staging(&a, wblocks[u.block_idx], scan_out_stage_bytes());
+    a.out_stage_off = 0;
+    scan_grid = scan_grid_for(scan_kernel_mode(cp.dev), smem);
+    kernel_begin();
+    CUDA_TRY(scan_launch(a, scan_grid, smem));
+    kernel_end();
+    release_block(u.block_idx);
+    stats.num_iterations++;
+    return read_counters(c);
+  }
+  Counters desc_stats{};  // request-level sums of the per-chunk counters
+  void desc_accumulate(const Counters& c) {
+    desc_stats.processed_keys += c.processed_keys; desc_stats.processed_size += c.processed_size; desc_stats.default_lookups += c.default_lookups;
+    desc_stats.met_newer |= c.met_newer; desc_stats.live_rows += c.live_rows;
+    first_row_seen = std::min<uint64_t>(first_row_seen, c.first_row);
+  }
+  int next_scan_batch_desc(uint64_t scan_rows, b2_batch* out) {
+    cols.clear();
+    uint64_t budget = std::max<uint64_t>(1, std::min<uint64_t>(scan_rows, 1ull << 31));
+    uint64_t produced = 0;
+    const bool limited = cp.scan_limit != ~0ull;
+    if (limited && limit_remaining == ~0ull) limit_remaining = cp.scan_limit;
+    if (limited && limit_remaining == 0) drained = true;
+    if (limited && cp.dev.n_conds == 0) budget = std::min<uint64_t>(budget, std::max<uint64_t>(4096, limit_remaining * 2));
+    if (!desc_started) { desc_started = true; d_unit = units.size(); d_hi = 0; }
+    while (!drained && !failed && produced == 0) {
+      if (d_hi == 0) {  // next unit down
+        if (d_unit == 0) { drained = true; break; }
+        --d_unit;
+        d_hi = units[d_unit].e_hi;
+      }
+      const Unit& u = units[d_unit];
+      const uint32_t c_hi = d_hi;
+      const uint32_t c_lo = (uint64_t)c_hi - u.e_lo > budget ? (uint32_t)(c_hi - budget) : u.e_lo;
+      Counters c;
+      int rc = run_desc_chunk(u, c_lo, c_hi, &c);
+      if (rc) return rc;
+      entries_scanned += c_hi - c_lo;
+      if (c.err != ~0ull) {
+        // a backward scan meets the failing row with the largest key first: the rows above it stay valid (interface.rs:229-235)
+        const uint64_t base = wblocks[u.block_idx].entry_base;
+        const uint32_t after = (uint32_t)((c.err_max >> 8) - base) + 1;
+        Counters c2;
+        memset(&c2, 0, sizeof(c2));
+        c2.err = ~0ull;
+        if (after < c_hi) { rc = run_desc_chunk(u, after, c_hi, &c2); if (rc) return rc; }
+        produced = c2.err == ~0ull ? c2.out_rows : 0;
+        chunk_total = produced;
+        desc_accumulate(c2);
+        if (!(limited && produced >= limit_remaining)) device_error(c);
+        drained = true;
+        break;
+      }
+      desc_accumulate(c);
+      produced = c.out_rows;
+      chunk_total = produced;
+      d_hi = c_lo > u.e_lo ? c_lo : 0;
+      if (d_hi == 0) {  // the unit is finished; was it the lowest one of a range that ends in a conflicting lock?
+        const bool range_done = d_unit == 0 || units[d_unit - 1].range_idx != u.range_idx;
+        if (range_done && u.range_idx < range_lock_err.size() && range_lock_err[u.range_idx]) {
+          if (!(limited && produced >= limit_remaining)) lock_failure(u.range_idx);
+          drained = true;
+          break;
+        }
+      }
+    }
+    if (limited) {
+      if (produced < limit_remaining) limit_remaining -= produced;
+      else { produced = limit_remaining; limit_remaining = 0; drained = true; }
+    }
+    if (!failed && !drained && d_hi == 0 && d_unit == 0) drained = true;
+    if (!failed && drained && !(limited && limit_remaining == 0)) check_trailing_lock();
+    // statistics of the request so far
+    Counters tot = desc_stats;
+    tot.last_row = 0;
+    fill_stats(tot);
+    // reverse the chunk's rows (the kernel wrote them in ascending key order)
+    const size_t n_out = cp.dev.n_out;
+    if (produced) {
+      const uint64_t cap = std::max<uint64_t>(64, (produced + 63) & ~63ull);
+      if (cap > rev_cap) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(rev_data.reserve(cap * 8 * n_out)); CUDA_TRY(rev_bitmap.reserve(cap / 8 * n_out));
+        rev_cap = cap;
+      }
+      CUDA_TRY(cudaMemsetAsync(rev_bitmap.p, 0xff, rev_cap / 8 * n_out, stream));
+      // (a Limit may have cut the chunk: the first `produced` rows of the reversed order are the last ones the kernel wrote)
+      CUDA_TRY(launch_reverse_rows((const unsigned long long*)out_data.p, (const unsigned long long*)out_bitmap.p, out_cap, (unsigned long long*)rev_data.p,
+                                   (unsigned long long*)rev_bitmap.p, rev_cap, chunk_total, produced, (uint32_t)n_out, stream));
+      stats.kernel_launches++;
+    }
+    return publish_scan_columns(produced, out, &rev_data, &rev_bitmap, rev_cap);
+  }
+  uint64_t chunk_total = 0;         // rows the last chunk's kernel wrote
+  uint64_t first_row_seen = ~0ull;  // smallest global entry index a row was returned for so far
+
   uint64_t limit_remaining = ~0ull;
   int scan_grid = 0;
   DevBuf trace_buf;
@@ -922,11 +1070,12 @@ struct b2_exec {
       if (range_lock_err[r]) { lock_failure((uint32_t)r); return; }
   }
 
-  int publish_scan_columns(uint64_t n_rows, b2_batch* out) {
+  int publish_scan_columns(uint64_t n_rows, b2_batch* out, const DevBuf* src_data = nullptr, const DevBuf* src_bitmap = nullptr, uint64_t src_cap = 0) {
     size_t n_out = cp.dev.n_out;
     cols.resize(n_out);
-    const uint8_t* data = (const uint8_t*)out_data.p;
-    const uint8_t* bm = (const uint8_t*)out_bitmap.p;
+    const uint8_t* data = (const uint8_t*)(src_data ? src_data->p : out_data.p);
+    const uint8_t* bm = (const uint8_t*)(src_bitmap ? src_bitmap->p : out_bitmap.p);
+    const uint64_t out_cap = src_data ? src_cap : this->out_cap;
     if (out_loc == B2_LOC_HOST && n_rows) {
       size_t per_col = n_rows * 8, per_bm = ((n_rows + 63) / 64) * 8;
       CUDA_TRY(h_out.reserve((per_col + per_bm) * n_out));
@@ -985,7 +1134,23 @@ struct b2_exec {
     return fail(B2_ERR_INVALID_ARG, "entry index outside every block");
   }
   std::vector<uint8_t> taken_lo, taken_hi;
+  uint64_t first_row_taken = ~0ull;
   int take_scanned_range(const uint8_t** lo, uint32_t* lo_len, const uint8_t** hi, uint32_t* hi_len) {
+    if (cp.desc) {
+      // scanner.rs:204-229, scan_backward_in_range: [key of the last (smallest) row returned, where the previous take
+      // ended); first take: up to the last range's end; once drained: down to the first range's start
+      if (working_begin.empty() && !range_raw_hi.empty()) working_begin = range_raw_hi.back();
+      taken_hi = working_begin;
+      if (drained && !range_raw_lo.empty()) taken_lo = range_raw_lo[0];
+      else if (first_row_seen != ~0ull && first_row_seen < first_row_taken) {
+        int rc = entry_raw_key(first_row_seen, &taken_lo);
+        if (rc) return rc;
+      } else taken_lo = taken_hi;
+      first_row_taken = first_row_seen;
+      working_begin = taken_lo;
+      *lo = taken_lo.data(); *lo_len = (uint32_t)taken_lo.size(); *hi = taken_hi.data(); *hi_len = (uint32_t)taken_hi.size();
+      return B2_OK;
+    }
     if (working_begin.empty() && !range_raw_lo.empty()) working_begin = range_raw_lo[0];
     taken_lo = working_begin;
     if (drained && !range_raw_hi.empty()) taken_hi = range_raw_hi.back();
@@ -1400,7 +1565,7 @@ struct b2_exec {
     cudaEventCreate(&t0); cudaEventCreate(&t1);
     cudaEventRecord(t0, stream);
     int rc;
-    if (cp.dev.mode == PM_SCAN) rc = next_scan_batch(scan_rows, out);
+    if (cp.dev.mode == PM_SCAN) rc = cp.desc ? next_scan_batch_desc(scan_rows, out) : next_scan_batch(scan_rows, out);
     else if (cp.dev.mode == PM_AGG) rc = run_agg(out);
     else rc = run_topn(out);
     cudaEventRecord(t1, stream);

@@ -221,7 +221,7 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
             for (int a = 0; a < MAX_AGGS; ++a)
               if (a < P.n_aggs && ok) ok = eval_expr(P, P.aggs[a].arg, row, cells, &av[a], nullptr) == 0;
           } else {
-            ok = make_item(P, row, cells, A.entry_base + e, &item) == 0;
+            ok = make_item(P, row, cells, A.desc ? ~(A.entry_base + e) : A.entry_base + e, &item) == 0;
           }
         }
         if (!ok) { push = true; commit = false; }  // the general decoder / evaluator owns this run (and raises its error)

@@ -178,7 +178,8 @@ __global__ void topn_gather_kernel(const __grid_constant__ DevPlan P, const __gr
                                    unsigned long long* pay, unsigned char* pay_null, unsigned int stride) {
   unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *count) return;
-  uint32_t e = (uint32_t)(items[i].id - A.entry_base);
+  const unsigned long long gid = A.desc ? ~items[i].id : items[i].id;
+  uint32_t e = (uint32_t)(gid - A.entry_base);
   RunOut ro;
   resolve_run(A.blk, e, A.e_hi, A.e_hi, P.read_ts, P.isolation, A.dflt, &ro);
   Row row;
@@ -194,12 +195,12 @@ __global__ void topn_gather_kernel(const __grid_constant__ DevPlan P, const __gr
     Value v; v.null = true; v.bits = 0;
     if (!err) {
       int e2 = cell_value(P, row, cells, P.out_cols[k], &v);
-      if (e2) { report_err(A.ctr, items[i].id, e2); v.null = true; v.bits = 0; }
+      if (e2) { report_err(A.ctr, gid, e2); v.null = true; v.bits = 0; }
     }
     pay[(size_t)k * stride + i] = v.null ? 0ull : v.bits;
     pay_null[(size_t)k * stride + i] = v.null ? 1 : 0;
   }
-  if (err) report_err(A.ctr, items[i].id, err);
+  if (err) report_err(A.ctr, gid, err);
 }
 
 cudaError_t launch_topn_gather(const DevPlan& plan, const ScanArgs& a, const TopItem* items, const unsigned int* count, unsigned long long* pay,
@@ -373,6 +374,24 @@ cudaError_t launch_bounds_search(const BlockView* blocks, uint32_t n_blocks, con
   if (!n) return cudaSuccess;
   bounds_kernel<<<(n + 63) / 64, 64, 0, s>>>(blocks, n_blocks, bounds, bound_offs, n_bounds, out);
   unit_prefix_kernel<<<(n / 2 + 63) / 64, 64, 0, s>>>(blocks, n_blocks, n_bounds / 2, out, unit_ok);
+  return cudaGetLastError();
+}
+
+__global__ void reverse_rows_kernel(const unsigned long long* in, const unsigned long long* bm_in, uint64_t in_cap, unsigned long long* out, unsigned long long* bm_out,
+                                    uint64_t out_cap, uint64_t n_rows, uint64_t n_take, uint32_t n_cols) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_take) return;
+  const uint64_t j = n_rows - 1 - i;
+  for (uint32_t c = 0; c < n_cols; ++c) {
+    out[(size_t)c * out_cap + i] = in[(size_t)c * in_cap + j];
+    const bool nonnull = (bm_in[(size_t)c * (in_cap / 64) + (j >> 6)] >> (j & 63)) & 1ull;
+    if (!nonnull) atomicAnd(&bm_out[(size_t)c * (out_cap / 64) + (i >> 6)], ~(1ull << (i & 63)));  // NULLs are rare: the bitmap starts as all ones
+  }
+}
+cudaError_t launch_reverse_rows(const unsigned long long* in, const unsigned long long* bm_in, uint64_t in_cap, unsigned long long* out, unsigned long long* bm_out,
+                                uint64_t out_cap, uint64_t n_rows, uint64_t n_take, uint32_t n_cols, cudaStream_t s) {
+  if (!n_take || !n_cols) return cudaSuccess;
+  reverse_rows_kernel<<<(unsigned)((n_take + 255) / 256), 256, 0, s>>>(in, bm_in, in_cap, out, bm_out, out_cap, n_rows, n_take, n_cols);
   return cudaGetLastError();
 }
 

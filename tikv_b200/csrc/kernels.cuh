@@ -26,6 +26,8 @@ struct Counters {
   unsigned int n_groups;               // finalize: number of groups emitted
   unsigned int bad_prefix;             // checksum: key without new_prefix
   unsigned long long last_row;         // 1 + largest global CF_WRITE entry index the MVCC scan returned a row for (take_scanned_range)
+  unsigned long long err_max;          // max over failing rows of (global_entry << 8 | DevErr): the first error of a backward scan; 0 = none
+  unsigned long long first_row;        // smallest global CF_WRITE entry index a row was returned for (take_scanned_range, backward); ~0 = none
 };
 
 // Open-addressing group table in HBM (fast_hash_aggr_executor.rs:216-229 `Groups`): slot = hash(key) & mask, linear
@@ -83,6 +85,8 @@ struct ScanArgs {
   uint32_t list_mode;               // scan_body: 1 = process the entries of slow_list (count read on the device) instead of [c_lo, c_hi)
   uint32_t _pad2;
   uint64_t ck_key_state;            // lean checksum: crc register after old_prefix and the unit's common raw key bytes [new_prefix_len, 11)
+  uint32_t desc;                    // backward scan (TableScan.desc): TopN ties go to the larger key (item ids are complemented)
+  uint32_t _pad3;
   uint32_t fast_ok;                 // 1: every key of [e_lo, e_hi) starts with the same 12 bytes 't' tid "_r" (first and last key of the
                                     //    sorted unit agree): the clean-entry front end may skip them
   uint32_t _pad1;
@@ -139,6 +143,9 @@ cudaError_t launch_bounds_search(const BlockView* blocks, uint32_t n_blocks, con
 cudaError_t launch_gen_sizes(const b2_gen_spec& spec, uint32_t* row_entries, uint32_t* row_val_bytes, cudaStream_t s);
 cudaError_t launch_gen_write(const GenArgs& a, cudaStream_t s);
 cudaError_t launch_fill_u64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t s);
+// backward scans: out row i = in row (n_rows - 1 - i) for i < n_take, every column and its non-NULL bitmap; out bitmaps pre-filled with ones
+cudaError_t launch_reverse_rows(const unsigned long long* in, const unsigned long long* bm_in, uint64_t in_cap, unsigned long long* out, unsigned long long* bm_out,
+                                uint64_t out_cap, uint64_t n_rows, uint64_t n_take, uint32_t n_cols, cudaStream_t s);
 
 #endif  // !B2_NVRTC
 

@@ -21,6 +21,7 @@ struct CompiledPlan {
   uint64_t scan_limit = ~0ull;           // BatchLimitExecutor on top of a scan / selection pipeline (limit_executor.rs), ~0 = none
   int64_t imms[MAX_IMMS] = {};           // hoisted constants, referenced by DevNode::sig / FastCond::imm_slot (ScanArgs::imms at launch)
   int n_imms = 0;
+  bool desc = false;                     // TableScan.desc
 };
 
 inline int col_kind_of_tp(int tp) {  // def/eval_type.rs:53-95
@@ -164,7 +165,7 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
   if (!plan || plan->n_executors == 0 || !plan->executors) { *msg = "empty plan"; return B2_ERR_INVALID_ARG; }
   const b2_executor_desc& scan = plan->executors[0];
   if (scan.tp != B2_EXEC_TABLE_SCAN) { *msg = "first executor must be TableScan (index scans are not on the device path yet)"; return B2_ERR_UNSUPPORTED; }
-  if (scan.desc) { *msg = "backward scan is not supported on the device path"; return B2_ERR_UNSUPPORTED; }
+  out->desc = scan.desc != 0;  // scan_executor.rs:89-101: ranges in reverse order, each scanned backward (engine.cu: reversed chunks)
   if (scan.n_columns == 0 || scan.n_columns > MAX_COLS) { *msg = "TableScan with 0 or more than 64 columns"; return B2_ERR_UNSUPPORTED; }
   P.n_cols = (int)scan.n_columns;
   for (int i = 0; i < P.n_cols; ++i) {

@@ -3,6 +3,18 @@
 #pragma once
 #include "kernels.cuh"
 
+// per-tile clock stamps of CTA 0 (debug builds only: -DB2_TRACE_BUILD; in the product build they cost ~30 instructions per
+// 32 rows for nothing)
+#ifdef B2_TRACE_BUILD
+#define B2_TRACE_STAMP(i) do { if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + (i)] = clock64(); } while (0)
+#define B2_TRACE_T0() long long tc0 = clock64()
+#define B2_TRACE_WAIT() do { if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) { A.trace[k * 8 + 4] = tc0; A.trace[k * 8 + 5] = clock64(); } } while (0)
+#else
+#define B2_TRACE_STAMP(i) do { } while (0)
+#define B2_TRACE_T0() do { } while (0)
+#define B2_TRACE_WAIT() do { } while (0)
+#endif
+
 namespace b2 {
 
 template <class T> struct b2_remove_cvref { typedef T type; };
@@ -13,6 +25,7 @@ template <class T> struct b2_remove_cvref<const T> { typedef T type; };
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void report_err(Counters* c, uint64_t global_entry, int code) {
   atomicMin(&c->err, (unsigned long long)((global_entry << 8) | (unsigned)code));
+  atomicMax(&c->err_max, (unsigned long long)((global_entry << 8) | (unsigned)code));
 }
 
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
@@ -416,6 +429,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   EntryStats ts;
   ts.keys = ts.size = ts.dflt = ts.ck_x = ts.ck_kvs = ts.ck_bytes = 0; ts.newer = 0; ts.last = 0;
   unsigned long long t_live = 0;
+  unsigned int t_first = 0xffffffffu;  // smallest block entry index a row was returned for
   // no-group aggregation: one accumulator set per CTA in shared memory, flushed at the end
   __shared__ unsigned long long s_simple_acc[MODE == PM_AGG ? MAX_ACC_WORDS : 1];
   if (MODE == PM_AGG) {
@@ -614,12 +628,12 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     unsigned int warp_off = 0, total = 0, lane_off = 0;
     if (IS_SCAN) {
       // ---- ordered compaction: ballot/popc inside the warp, smem across warps, look-back across tiles ----
-      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 0] = clock64();
+      B2_TRACE_STAMP(0);
       unsigned int bal = __ballot_sync(0xffffffffu, live);
       lane_off = __popc(bal & ((1u << lane) - 1));
       if (lane == 0) s_warp_cnt[k & 1][wid] = __popc(bal);
       cta256_sync();
-      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 1] = clock64();
+      B2_TRACE_STAMP(1);
     } else if (!V::kWholeBlock) {
       cta256_sync();  // the vote below
     }
@@ -629,6 +643,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     // ---- commit ----
     ts.keys += d.keys; ts.size += d.size; ts.dflt += d.dflt; ts.newer |= d.newer;
     if (d.last > ts.last) ts.last = d.last;
+    if (d.last && d.last - 1 < t_first) t_first = d.last - 1;
     if (MODE == PM_CHECKSUM) { ts.ck_x ^= d.ck_x; ts.ck_kvs += d.ck_kvs; ts.ck_bytes += d.ck_bytes; }
     t_live += live;
 
@@ -647,7 +662,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       // the scan warp may be several tiles behind, other CTAs must not wait for it to get here
       if (tid == 0) atomicExch(&A.tile_status[tile], ((tile == 0 ? 2ull : 1ull) << 62) | total);
       const bool fast = live && row.fast;
-      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 2] = clock64();
+      B2_TRACE_STAMP(2);
       const uint32_t cpc = obuf_cols(total), cshift = cpc == OBUF_COLS ? 2u : 3u, rstride = (OBUF_COLS * TILE) >> cshift;  // columns per chunk (4 or 8), row stride
       const uint32_t n_rounds = P.n_out > 0 ? ((uint32_t)P.n_out + cpc - 1) >> cshift : 1u;
       for (uint32_t r = 0; r < n_rounds; ++r) {
@@ -655,7 +670,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
         mbar_wait(&s_obuf_empty[q], ob_phase ^ 1);  // chunk buffer drained (N_OBUF chunks ago)
         if (++ob_q == N_OBUF) { ob_q = 0; ob_phase ^= 1; }
         if (r == 0) {
-          if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 3] = clock64();
+          B2_TRACE_STAMP(3);
           // (posted after the wait: at most N_OBUF <= N_CNT - 1 tiles are ever pending at the scan warp)
           if (tid == 0) { s_total[k % N_CNT] = total; s_tile_of[k % N_CNT] = tile; asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_cnt_ready[k % N_CNT])) : "memory"); }
         }
@@ -669,7 +684,18 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
             if (v.null) atomicOr(&onull_base[q * ONULL_WORDS + ((uint32_t)oc & (cpc - 1)) * (rstride / 32) + (pos >> 5)], 1u << (pos & 31));
           };
           if (fast) {
-            if (!P.fast_v1 || row.fast == 1) {
+            if ((!P.fast_v1 || row.fast == 1) && fast_all8(P, row)) {
+              // every stored column is 8 bytes wide: the cells this chunk needs come out of one run of aligned words
+              uint32_t need = 0;
+#pragma unroll
+              for (int h = 0; h < 8; ++h)
+                if (h < P.fast_n && P.fast_out[h] >= 0 && ((uint32_t)P.fast_out[h] >> cshift) == r) need |= 1u << h;
+              uint64_t cv[8];
+              fast_cells8(row, need, cv);
+#pragma unroll
+              for (int h = 0; h < 8; ++h)
+                if ((need >> h) & 1u) ob[((uint32_t)P.fast_out[h] & (cpc - 1)) * rstride] = cv[h];
+            } else if (!P.fast_v1 || row.fast == 1) {
               // exact-layout v2 row: the (at most 8) stored integer columns are decoded by stored position, so every
               // shift is a compile-time constant; the value goes from the staged row bytes to the chunk buffer in one step
               uint32_t prev = 0;
@@ -700,13 +726,13 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_obuf_full[q])) : "memory");
       }
-      if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 7] = clock64();
+      B2_TRACE_STAMP(7);
     } else if (MODE == PM_TOPN) {
       // BatchTopN: keep the `limit` smallest rows under the order-by key.  A row is a candidate only if it beats
       // the CTA's current threshold (the limit-th best seen so far); candidates are sorted when the buffer fills.
       if (live) {
         TopItem it;
-        int err = make_item(P, row, cells, A.entry_base + e, &it);
+        int err = make_item(P, row, cells, A.desc ? ~(A.entry_base + e) : A.entry_base + e, &it);  // (ties go to the row scanned first)
         if (err) report_err(A.ctr, A.entry_base + e, err);
         else if (!s_top_have_thr || item_less(it, s_top_thr, P)) {
           unsigned int pos = atomicAdd(&s_top_cnt, 1u);
@@ -857,9 +883,9 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
 
   for (uint32_t k = 0;; ++k) {
     const int cur = (int)(k % N_STAGES);
-    long long tc0 = clock64();
+    B2_TRACE_T0();
     mbar_wait(&s_full[cur], (k / N_STAGES) & 1);
-    if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) { A.trace[k * 8 + 4] = tc0; A.trace[k * 8 + 5] = clock64(); }
+    B2_TRACE_WAIT();
     const TileMeta m = s_meta[cur];
     const uint32_t tile = m.tile;
     if (tile >= n_tiles) {
@@ -883,7 +909,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       redo = tile_body(sv, m.w_hi < A.e_hi ? m.w_hi : A.e_hi, k, tile);
     }
     if (redo) tile_body(A.blk, A.e_hi, k, tile);
-    if (A.trace && blockIdx.x == 0 && tid == 0 && k < 128) A.trace[k * 8 + 6] = clock64();
+    B2_TRACE_STAMP(6);
     __syncwarp();  // this warp is done with stage `cur`: let the producer refill it
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_empty[cur])) : "memory");
   }
@@ -942,11 +968,13 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     ts.dflt += __shfl_xor_sync(0xffffffffu, ts.dflt, off);
     ts.newer |= __shfl_xor_sync(0xffffffffu, ts.newer, off);
     ts.last = max(ts.last, __shfl_xor_sync(0xffffffffu, ts.last, off));
+    t_first = min(t_first, __shfl_xor_sync(0xffffffffu, t_first, off));
   }
   if (lane == 0) {
     if (ts.keys) atomicAdd(&A.ctr->processed_keys, ts.keys);
     if (ts.keys && A.range_rows) atomicAdd(A.range_rows, ts.keys);
     if (ts.last) atomicMax(&A.ctr->last_row, A.entry_base + ts.last);
+    if (ts.last) atomicMin(&A.ctr->first_row, A.entry_base + t_first);
     if (ts.size) atomicAdd(&A.ctr->processed_size, ts.size);
     if (t_live) atomicAdd(&A.ctr->live_rows, t_live);
     if (ts.dflt) atomicAdd(&A.ctr->default_lookups, ts.dflt);
