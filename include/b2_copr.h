@@ -36,7 +36,7 @@ typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; t
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 1
+#define B2_ABI_VERSION 2
 
 /* ---- status codes (tidb_query_common::error::Error classes, dag/mod.rs:231-244) ---- */
 enum {
@@ -49,7 +49,8 @@ enum {
   B2_ERR_DEADLINE = 6,
   B2_ERR_UNSUPPORTED = 7,    /* plan not supported on the device path: host falls back */
   B2_ERR_CUDA = 8,
-  B2_ERR_INVALID_ARG = 9
+  B2_ERR_INVALID_ARG = 9,
+  B2_PENDING = 100           /* b2_exec_poll: the batch started by b2_exec_next_batch_async is not ready yet */
 };
 
 /* MySQL error codes preserved across the boundary */
@@ -154,6 +155,7 @@ enum {
   B2_SIG_IN_INT = 4001, B2_SIG_IN_REAL = 4002, /* variadic: n_args = 1 + list length (impl_compare_in.rs) */
   /* impl_arithmetic.rs:215-290, 396-455 (signedness variants are picked from the arguments' UNSIGNED flags, like map_int_sig) */
   B2_SIG_INT_DIVIDE_INT = 213, B2_SIG_MOD_REAL = 215, B2_SIG_MOD_INT = 217,
+  B2_SIG_DIVIDE_REAL = 211, /* impl_arithmetic.rs:515-533: x / 0 is NULL + warning 1365 "Division by 0" (expr/ctx.rs:267-286) */
   B2_SIG_ABS_INT = 2101, B2_SIG_ABS_UINT = 2102, B2_SIG_ABS_REAL = 2103,           /* impl_math.rs:224-243 */
   B2_SIG_UNARY_MINUS_INT = 3108, B2_SIG_UNARY_MINUS_REAL = 3109,                    /* impl_op.rs:70-107 */
   B2_SIG_IF_NULL_INT = 4101, B2_SIG_IF_NULL_REAL = 4102, B2_SIG_IF_INT = 4107, B2_SIG_IF_REAL = 4108, /* impl_control.rs */
@@ -236,7 +238,12 @@ typedef struct b2_exec_config {
                              * Plans that use DIV / MOD / unary minus / ABS / IFNULL / IF / CASE WHEN / COALESCE always
                              * behave as B2_JIT_SYNC: those functions are only compiled into specialised kernels. */
   int32_t _pad;
-  uint64_t reserved[3];
+  uint64_t deadline_ns;     /* CLOCK_MONOTONIC nanoseconds; once passed, calls answer B2_ERR_DEADLINE before (and between) launches:
+                             * Deadline::check at the top of every batch, runner.rs:974; tikv_util deadline.rs.  0 = none */
+  uint64_t paging_size;     /* b2_dag_handle only: a paging request (runner.rs:790-806) stops after the batch in which this many rows
+                             * have been produced and answers B2_DRAIN_PAGING; b2_exec_take_scanned_range then gives the range to
+                             * resume from.  0 = not a paging request */
+  uint64_t reserved[1];
 } b2_exec_config;
 enum { B2_JIT_AUTO = 0, B2_JIT_SYNC = 1, B2_JIT_OFF = 2 };
 
@@ -331,6 +338,20 @@ int32_t b2_exec_schema(b2_exec* h, int32_t* field_tps, uint32_t* field_flags, ui
  * (interface.rs:229-235) and b2_exec_last_error gives details. */
 int32_t b2_exec_next_batch(b2_exec* h, uint64_t scan_rows, b2_batch* out);
 int32_t b2_exec_collect_stats(b2_exec* h, b2_exec_stats* out);
+/* next_batch without blocking the caller (the reference's `async fn next_batch` on a yatp thread, interface.rs:53): _async
+ * starts the batch on the handle's worker and returns at once; b2_exec_poll answers B2_PENDING until it has finished, then
+ * the batch's own status with *out filled (exactly what b2_exec_next_batch would have returned).  One batch in flight per
+ * handle; no other call on the handle in between except poll. */
+int32_t b2_exec_next_batch_async(b2_exec* h, uint64_t scan_rows);
+int32_t b2_exec_poll(b2_exec* h, b2_batch* out);
+/* EvalWarnings of the request so far (BatchExecuteResult::warnings, interface.rs:205-236; expr/ctx.rs:180-215): *count_out =
+ * warning_cnt (every warning raised), of which at most min(cap, 64) are written (max_warning_cnt). */
+typedef struct b2_warning {
+  int32_t mysql_code;
+  int32_t _pad;
+  char message[120];
+} b2_warning;
+int32_t b2_exec_warnings(b2_exec* h, b2_warning* out, uint32_t cap, uint64_t* count_out);
 int32_t b2_exec_last_error(b2_exec* h, b2_error_info* out);
 /* Response encoding of the batch most recently returned by b2_exec_next_batch / b2_dag_handle on this handle:
  * encode_result_to_chunk (components/tidb_query_executors/src/runner.rs:1051-1088), i.e. tipb::Chunk.rows_data in
@@ -400,6 +421,16 @@ int32_t b2_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges,
                            const uint8_t* new_prefix, uint32_t new_prefix_len,
                            const b2_region_source* src, const b2_exec_config* cfg,
                            b2_checksum_response* out, b2_exec_stats* stats);
+
+/* ---- HBM-resident block cache ---------------------------------------------------------------------------------------
+ * TiKV serves repeated reads of a region from its block cache; here the cached copy lives in device memory, so a warm
+ * request runs at HBM speed instead of PCIe speed.  b2_region_pin copies the CF blocks of `host_src` (B2_LOC_HOST) to the
+ * device once, keyed by (device, region_id, data_version), and fills *dev_src with a B2_LOC_DEVICE source over the cached
+ * copy (same read_ts / isolation fields; valid until the matching b2_region_unpin).  Pinning the same key again returns
+ * the existing copy.  B2_ERR_UNSUPPORTED when the cache budget (B2_BLOCK_CACHE_BYTES, default 64 GiB per device) is full. */
+int32_t b2_region_pin(int32_t device, uint64_t region_id, uint64_t data_version, const b2_region_source* host_src, b2_region_source* dev_src);
+int32_t b2_region_unpin(int32_t device, uint64_t region_id, uint64_t data_version);
+void b2_region_cache_stats(int32_t device, uint64_t* bytes_cached, uint64_t* hits, uint64_t* misses);
 
 /* tooling: the compiled device plan of `plan` as a C++ aggregate initialiser (what the run-time compiler is fed);
  * returns its length, writes at most cap - 1 bytes + NUL into buf, negative status on error */

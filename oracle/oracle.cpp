@@ -33,6 +33,7 @@ struct orc_result {
   std::string dec_str;
   Bytes enc_default;  // Chunk.rows_data of every batch, EncodeType::TypeDefault, concatenated (runner.rs:1062-1071)
   Bytes enc_chunk;    // the whole result as one EncodeType::TypeChunk chunk (runner.rs:1072-1085)
+  uint64_t warning_cnt = 0;  // SelectResponse.warning_count (runner.rs:845)
 };
 
 static bool build_executors(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src,
@@ -171,6 +172,8 @@ extern "C" {
 static int orc_dag_handle_impl(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t n_ranges, const b2_region_source* src, orc_result** out, int keep_rows) {
   orc_result* res = new orc_result();
   *out = res;
+  warning_count() = 0;
+  struct KeepWarnings { orc_result* r; ~KeepWarnings() { r->warning_cnt = warning_count(); } } keep_warnings{res};
   CfView w, l, d;
   std::unique_ptr<Executor> root;
   TableScanExecutor* scan = nullptr;
@@ -253,6 +256,7 @@ const uint8_t* orc_result_encoded(orc_result* r, int encode_type, uint64_t* len)
   *len = b.size();
   return b.data();
 }
+uint64_t orc_result_warning_count(orc_result* r) { return r->warning_cnt; }
 void orc_result_free(orc_result* r) { delete r; }
 
 // ChecksumContext::handle_request (src/coprocessor/checksum.rs:59-98)

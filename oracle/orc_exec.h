@@ -505,6 +505,8 @@ inline int cmp_int(int64_t a, bool au, int64_t b, bool bu) {  // impl_compare.rs
 }
 
 struct ExprCtx { const std::vector<FieldType>* schema; Batch* batch; };
+// EvalContext::warnings (expr/ctx.rs:180-215) of the request running on this thread: only "Division by 0" can occur here
+inline uint64_t& warning_count() { static thread_local uint64_t n = 0; return n; }
 
 inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err) {
   size_t n = cx.batch->logical_rows.size();
@@ -587,7 +589,7 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
       int sig = nd.sig;
       bool is_cmp_int = sig == B2_SIG_LT_INT || sig == B2_SIG_LE_INT || sig == B2_SIG_GT_INT || sig == B2_SIG_GE_INT || sig == B2_SIG_EQ_INT || sig == B2_SIG_NE_INT || sig == B2_SIG_NULLEQ_INT;
       bool is_cmp_real = sig == B2_SIG_LT_REAL || sig == B2_SIG_LE_REAL || sig == B2_SIG_GT_REAL || sig == B2_SIG_GE_REAL || sig == B2_SIG_EQ_REAL || sig == B2_SIG_NE_REAL || sig == B2_SIG_NULLEQ_REAL;
-      bool is_arith_real = sig == B2_SIG_PLUS_REAL || sig == B2_SIG_MINUS_REAL || sig == B2_SIG_MULTIPLY_REAL || sig == B2_SIG_MOD_REAL ||
+      bool is_arith_real = sig == B2_SIG_PLUS_REAL || sig == B2_SIG_MINUS_REAL || sig == B2_SIG_MULTIPLY_REAL || sig == B2_SIG_MOD_REAL || sig == B2_SIG_DIVIDE_REAL ||
                            sig == B2_SIG_IF_NULL_REAL || sig == B2_SIG_UNARY_MINUS_REAL || sig == B2_SIG_ABS_REAL;
       if (is_arith_real) { r.et = ET_REAL; r.f.assign(n, 0); r.i.clear(); }
       for (size_t j = 0; j < n; ++j) {
@@ -712,6 +714,14 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
             else if (a.is_unsigned && !b.is_unsigned) z = (int64_t)((uint64_t)x % ay);
             else z = (int64_t)((uint64_t)x % (uint64_t)y);
             r.nn[j] = 1; r.i[j] = z;
+            break;
+          }
+          case B2_SIG_DIVIDE_REAL: {  // impl_arithmetic.rs:515-533
+            if (an || bn) break;
+            if (b.real_at(j) == 0.0) { warning_count() += 1; break; }  // ctx.handle_division_by_zero(): a warning, the result is NULL
+            double z = a.real_at(j) / b.real_at(j);
+            if (std::isinf(z)) { *err = overflow_err("DOUBLE"); return false; }
+            r.nn[j] = 1; r.f[j] = z;
             break;
           }
           case B2_SIG_MOD_REAL: {  // :280-291

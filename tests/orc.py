@@ -105,6 +105,9 @@ def dag_handle(plan, ranges, region):
     stats = dict(write_next=st[0], write_seek=st[1], over_seek_bound=st[2], processed_keys=st[3], processed_size=st[4],
                  data_processed_keys=st[5], lock_processed_keys=st[6], met_newer=C.c_int64(st[7]).value)
     res = Result(L.orc_result_status(h), L.orc_result_message(h).decode(), L.orc_result_mysql_code(h), cols, kinds, stats)
+    L.orc_result_warning_count.argtypes = [C.c_void_p]
+    L.orc_result_warning_count.restype = C.c_uint64
+    res.warning_count = L.orc_result_warning_count(h)  # SelectResponse.warning_count ("Division by 0", expr/ctx.rs:267-286)
     res.encoded = {}
     for t in (0, 1):  # EncodeType::TypeDefault / TypeChunk
         ln = C.c_uint64()

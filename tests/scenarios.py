@@ -9,7 +9,7 @@ import struct
 
 import kvfmt
 from tikv_b200 import ffi
-from tikv_b200.plan import (fn, ColumnDef, Plan, and_, col, const_int, const_real, const_uint, eq, ge, gt, is_null, le, lt, minus, multiply,
+from tikv_b200.plan import (divide, fn, ColumnDef, Plan, and_, col, const_int, const_real, const_uint, eq, ge, gt, is_null, le, lt, minus, multiply,
                             in_, ne, not_, null, nulleq, or_, plus, xor_, int_divide, mod, neg, abs_, if_null, if_, case_when, coalesce)
 
 TABLE = 1000
@@ -321,6 +321,7 @@ def scalar_plans():
             ("sc_real", scan().projection(ch, mod(c4, const_real(2.5)), mod(c4, multiply(c4, r0)), neg(c4), abs_(c4), if_null(c4, const_real(9.5)),
                                           coalesce(c4, null(ffi.TP_DOUBLE), const_real(1.0)), if_(c2, c4, neg(c4)),
                                           case_when(lt(c4, r0), const_real(-1.0), gt(c4, r0), const_real(1.0))).build()),
+            ("sc_divide_real", scan().projection(ch, divide(c4, const_real(0.5)), divide(c4, multiply(c4, r0)), divide(const_real(1.0), c4)).build()),
             ("sc_unary", scan().projection(ch, neg(c2), abs_(c2), abs_(c3), neg(c6), neg(const_uint(1 << 63))).build()),
             ("sc_control", scan().projection(ch, if_null(c2, c6), if_(lt(c2, zero), c1, c5), case_when(lt(c2, const_int(-10)), const_int(1), is_null(c2), const_int(2), gt(c6, const_int(8)), c6, c5),
                                              case_when(lt(c2, zero), c1), coalesce(c2, null(), c5), coalesce(null(), null()), if_(null(), c1, c3), case_when(c5)).build()),

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_abi_version_and_structs(lib):
     from tikv_b200 import ffi
-    assert lib.b2_abi_version() == 1
+    assert lib.b2_abi_version() == 2
     assert b"sm_100a" in lib.b2_build_info()
     # struct sizes the Rust/cgo side would mirror
     assert C.sizeof(ffi.Decimal) == 40 and C.sizeof(ffi.CfBlock) == 40 and C.sizeof(ffi.RpnNode) == 40

@@ -724,3 +724,134 @@ def test_desc_take_scanned_range(regions):
             assert lo == (all_rows[seen - 1] if seen and lo != hi else hi)
             prev_lo = lo
         assert seen == len(all_rows) > 300
+
+
+# ---- ABI v2: deadline, async batches, warnings, paging, HBM block cache -----------------------------------------------
+def test_deadline_exceeded(regions):
+    """runner.rs:974 `self.deadline.check()?`: a request whose deadline has passed answers B2_ERR_DEADLINE (before any launch)."""
+    import time
+    host = regions[1].build(read_ts=sc.READ_TS)
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).build()
+    with BatchExecutor(plan, sc.WHOLE, host, deadline_ns=time.monotonic_ns() - 1) as ex:
+        r = ex.next_batch(1 << 20)
+        assert r.error is not None and r.error.status == ffi.B2_ERR_DEADLINE and r.n_rows == 0 and r.is_drained
+    with BatchExecutor(plan, sc.WHOLE, host, deadline_ns=time.monotonic_ns() + 60 * 10 ** 9) as ex:
+        assert ex.next_batch(1 << 20).error is None
+
+
+def test_async_next_batch_equals_sync(regions):
+    """b2_exec_next_batch_async + b2_exec_poll (the reference's `async fn next_batch`): same batches as the blocking call."""
+    import time
+    host = regions[2].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(lt(col(sc.C1), const_int(0))).build()
+    exp = DagHandler(plan, sc.WHOLE, host, batch_rows=300).handle_request()
+    rows = []
+    with BatchExecutor(plan, sc.WHOLE, host) as ex:
+        while True:
+            ex.next_batch_async(300)
+            polls = 0
+            while True:
+                r = ex.poll()
+                if r is not None:
+                    break
+                polls += 1
+                time.sleep(0.0005)
+            assert r.error is None
+            rows += r.rows()
+            if r.is_drained:
+                break
+    assert rows == exp.rows() and len(rows) > 100
+
+
+def test_division_by_zero_warnings(regions):
+    """DivideReal (impl_arithmetic.rs:515-533): x / 0 is NULL and raises warning 1365 "Division by 0" per evaluated row
+    (expr/ctx.rs:267-286); the count equals the oracle's SelectResponse.warning_count, at most 64 details are kept."""
+    from tikv_b200.plan import divide, multiply as mul, const_real
+    host = regions[1].build(read_ts=sc.READ_TS)
+    c4 = col(sc.C4, tp=ffi.TP_DOUBLE)
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).projection(col(sc.C_H), divide(c4, mul(c4, const_real(0.0))), divide(const_real(1.0), c4)).build()
+    exp = orc.dag_handle(plan, sc.WHOLE, host)
+    assert exp.status == 0 and exp.warning_count > 100
+    for region in (host, DeviceRegion(host)):
+        with BatchExecutor(plan, sc.WHOLE, region) as ex:
+            rows, per_batch = [], 0
+            while True:
+                rc, b = ex.next_batch_raw(257)
+                assert rc == 0
+                per_batch += b.n_warnings
+                r = ex._L  # noqa: F841
+                from tikv_b200.executor import _read_batch
+                cols, _, _ = _read_batch(b, ffi.LOC_HOST)
+                rows += list(zip(*cols)) if cols else []
+                if b.is_drained != ffi.DRAIN_REMAIN:
+                    break
+            total, details = ex.warnings()
+        assert rows == exp.rows()
+        assert total == exp.warning_count == per_batch and len(details) == 64 and details[0] == (1365, "Division by 0")
+
+
+def test_region_block_cache(regions):
+    """b2_region_pin: the CF blocks of a host-resident region are copied to HBM once (keyed by region id + data version);
+    requests over the returned device source see the same data; a second pin is a cache hit; unpin releases the copy."""
+    host = regions[1].build(read_ts=sc.READ_TS, n_write_blocks=3)
+    L = ffi.lib()
+    dev_src = ffi.RegionSource()
+    h0, m0, b0 = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    L.b2_region_cache_stats(0, C.byref(b0), C.byref(h0), C.byref(m0))
+    assert L.b2_region_pin(0, 4242, 7, C.byref(host.c), C.byref(dev_src)) == 0, L.b2_last_error_message()
+    again = ffi.RegionSource()
+    assert L.b2_region_pin(0, 4242, 7, C.byref(host.c), C.byref(again)) == 0
+    b1, h1, m1 = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    L.b2_region_cache_stats(0, C.byref(b1), C.byref(h1), C.byref(m1))
+    assert m1.value == m0.value + 1 and h1.value == h0.value + 1 and b1.value > b0.value
+    assert dev_src.location == ffi.LOC_DEVICE and dev_src.n_write == 3 and again.write[0].keys == dev_src.write[0].keys
+
+    class Pinned:  # a region object as the executors expect it
+        c = dev_src
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).aggregation([("sum", col(sc.C1)), ("count", const_int(1))], group_by=[col(sc.C6, tp=ffi.TP_LONG)]).build()
+    assert_same_rows(DagHandler(plan, sc.WHOLE, Pinned).handle_request(), orc.dag_handle(plan, sc.WHOLE, host), ordered=False, ctx="pinned agg")
+    scan = Plan().table_scan(sc.TABLE, sc.COLUMNS).build()
+    assert_same_rows(DagHandler(scan, sc.split_ranges(), Pinned).handle_request(), orc.dag_handle(scan, sc.split_ranges(), host), ctx="pinned scan")
+    assert L.b2_region_unpin(0, 4242, 7) == 0 and L.b2_region_unpin(0, 4242, 7) == 0
+    assert L.b2_region_unpin(0, 4242, 7) == ffi.B2_ERR_INVALID_ARG
+    L.b2_region_cache_stats(0, C.byref(b1), C.byref(h1), C.byref(m1))
+    assert b1.value == b0.value
+
+
+def test_paging_request(regions):
+    """b2_dag_handle with paging_size (runner.rs:790-806): a page of rows in key order, B2_DRAIN_PAGING, and the scanned
+    range to resume from; resuming at its upper bound until drained yields the whole result exactly once."""
+    from tikv_b200.executor import _read_batch
+    from tikv_b200.plan import key_ranges
+    host = regions[2].build(read_ts=sc.READ_TS, n_write_blocks=2)
+    plan = Plan().table_scan(sc.TABLE, sc.COLUMNS).selection(lt(col(sc.C1), const_int(0))).build()
+    exp = orc.dag_handle(plan, sc.WHOLE, host).rows()
+    L = ffi.lib()
+    rows, start, pages = [], sc.WHOLE[0][0], 0
+    while True:
+        kr, keep = key_ranges([(start, sc.WHOLE[0][1])])
+        cfg = ffi.ExecConfig()
+        cfg.output_location, cfg.paging_size = ffi.LOC_HOST, 100
+        b, h = ffi.Batch(), C.c_void_p()
+        rc = L.b2_dag_handle(C.byref(plan.c), kr, 1, C.byref(host.c), C.byref(cfg), C.byref(b), C.byref(h))
+        assert rc == 0, L.b2_last_error_message()
+        cols, _, _ = _read_batch(b, ffi.LOC_HOST)
+        rows += list(zip(*cols)) if cols else []
+        pages += 1
+        lo, hi, ln, hn = C.c_void_p(), C.c_void_p(), C.c_uint32(), C.c_uint32()
+        assert L.b2_exec_take_scanned_range(h, C.byref(lo), C.byref(ln), C.byref(hi), C.byref(hn)) == 0
+        upper = C.string_at(hi, hn.value)
+        drained = b.is_drained
+        L.b2_exec_close(h)
+        if drained != ffi.DRAIN_PAGING:
+            assert drained == ffi.DRAIN_DRAINED
+            break
+        assert upper > start
+        start = upper
+    assert rows == exp and pages > 2
+    agg = Plan().table_scan(sc.TABLE, sc.COLUMNS).aggregation([("count", const_int(1))]).build()
+    kr, keep = key_ranges(sc.WHOLE)
+    cfg = ffi.ExecConfig()
+    cfg.paging_size = 10
+    b, h = ffi.Batch(), C.c_void_p()
+    assert L.b2_dag_handle(C.byref(agg.c), kr, 1, C.byref(host.c), C.byref(cfg), C.byref(b), C.byref(h)) == ffi.B2_ERR_UNSUPPORTED

@@ -110,6 +110,8 @@ struct DevPlan {
   uint32_t fast_uns;     // bit h: stored column h is zero-extended (unsigned)
   int8_t fast_out[8];    // PM_SCAN: output column fed by stored column h (first occurrence), or -1
   int32_t n_out_slow;    // PM_SCAN: outputs of a fast row that still go through cell_value (handle, Real, repeats ...)
+  uint32_t fast_need;    // bit h: stored column h (id order) is read by some expression of the plan (conditions, group keys,
+                         //   aggregate arguments, sort keys): the lean kernels decode those once per row
   int32_t fast_v1;       // 1: the fast path also covers row-format-v1 rows (all stored columns integer-class, ids <= 63)
                          //    and the request's data looked like v1 when it was opened (engine samples the first row)
   uint64_t fast_ids;   // the expected sorted non-null id bytes of such a row, packed little-endian (fast_n <= 8)
@@ -213,9 +215,17 @@ B2_HD int bytes_cmp(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t bn
   return an < bn ? -1 : (an > bn ? 1 : 0);
 }
 
+B2_HD uint32_t ctz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__ffs((int)v) - 1u;  // BREV + FLO
+#else
+  return (uint32_t)__builtin_ctz(v);
+#endif
+}
 B2_HD uint32_t ctz64(uint64_t v) {
 #if defined(__CUDA_ARCH__)
-  return (uint32_t)__ffsll((long long)v) - 1u;
+  const uint32_t lo = (uint32_t)v;  // (the 64-bit __ffsll costs three times the 32-bit one)
+  return lo ? ctz32(lo) : 32u + ctz32((uint32_t)(v >> 32));
 #else
   return (uint32_t)__builtin_ctzll(v);
 #endif
@@ -687,6 +697,10 @@ struct Row {
   uint32_t fast;    // 1 (v2) / 2 (v1): the row holds exactly the plan's columns, all non-null: cells come from the two offset words below
   uint64_t o_lo, o_hi;  // the row's u16 end-offsets 0..3 / 4..7
   const int64_t* imms;  // the request's hoisted constants (ScanArgs::imms: kernel parameter space on the device)
+  uint64_t cv[8];       // lean kernels, plan-specialised builds: the integer cells of the stored columns the plan's expressions
+  uint32_t cv_mask = 0; //   read (DevPlan::fast_need), decoded once per row; bit h set = cv[h] is valid
+  mutable uint32_t warn = 0;  // EvalWarnings raised while evaluating expressions on this row ("Division by 0", expr/ctx.rs:267-286);
+                              // counted into the request only when the row's tile is committed
 };
 B2_HD int64_t node_imm(const Row& row, const DevNode& nd) { return nd.sig > 0 ? row.imms[nd.sig - 1] : nd.imm; }
 
@@ -744,6 +758,20 @@ B2_HD void fast_cells8(const Row& row, uint32_t need, uint64_t (&out)[8]) {
     if ((need >> h) & 1u) __builtin_memcpy(&out[h], p + 8 * h, 8);
   }
 #endif
+}
+
+// decode the stored integer columns in `need` (bit h) of a fast v2 row into row.cv (compile-time positions when unrolled)
+B2_HD void fast_fill_cells(const DevPlan& P, Row& row, uint32_t need) {
+  uint32_t prev = 0;
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    if (h < P.fast_n) {
+      const uint32_t end = fast_end(row, h);
+      if ((need >> h) & 1u) row.cv[h] = fast_int_cell(row, prev, end, (P.fast_uns >> h) & 1u);
+      prev = end;
+    }
+  }
+  row.cv_mask = need;
 }
 
 // stored column h of a fast row of either format, h known only at run time (conditions, cell_value).  The v1 decoder
@@ -881,6 +909,16 @@ B2_HD bool fast_key_tail(const uint8_t* kp, uint32_t klen, KeyTail* t) {
   return ((w[0] >> 40) & 0xffu) == 0xffu && (w[1] & 0x00ffffffffffff00ull) == 0x00fa000000000000ull;
 }
 B2_HD uint64_t key_tail_commit_ts(const KeyTail& t) { return ~bswap64((t.b >> 56) | (t.c << 8)); }
+// commit_ts <= read_ts without assembling the timestamp: the key holds !commit_ts big-endian, so compare it with !read_ts
+B2_HD bool key_tail_visible(const KeyTail& t, uint64_t not_read_ts) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t bh = (uint32_t)(t.b >> 32), cl = (uint32_t)t.c, ch = (uint32_t)(t.c >> 32);
+  const uint32_t hi = __byte_perm(bh, cl, 0x3456), lo = __byte_perm(cl, ch, 0x3456);  // bytes (b7 c0 c1 c2) and (c3 c4 c5 c6), most significant first
+  return (((uint64_t)hi << 32) | lo) >= not_read_ts;
+#else
+  return bswap64((t.b >> 56) | (t.c << 8)) >= not_read_ts;
+#endif
+}
 // same user key as the entry before?  (both keys validated by fast_key_tail, both inside one unit: bytes 0..11 and 21..26 agree)
 B2_HD bool key_tail_same(uint64_t a, uint64_t b, uint64_t pa, uint64_t pb) { return a == pa && ((b ^ pb) & 0xffu) == 0; }
 // the same for any two 35-byte keys of one unit (no marker validation needed): bytes 12..26 equal
@@ -922,7 +960,7 @@ B2_HD uint32_t fast_write_kind(const uint8_t* vp, uint32_t vlen, uint32_t* row_o
   ld64xN<2>(vp, w);
   const uint64_t s0 = ~w[0] & 0x8080808080808000ull;
   const uint32_t s1 = ~(uint32_t)w[1] & 0x8080u;
-  const uint32_t term = s0 ? (ctz64(s0) >> 3) : (8u + (ctz64((uint64_t)(s1 | 0x800000u)) >> 3));  // 10 when no terminal byte in 1..9
+  const uint32_t term = s0 ? (ctz64(s0) >> 3) : (8u + (ctz32(s1 | 0x800000u) >> 3));  // 10 when no terminal byte in 1..9
   const uint32_t pos = term + 1;
   const bool var_ok = (s0 != 0 || s1 != 0) && vlen >= 2;
   const uint32_t at = pos + 1 < vlen ? pos : 0;  // keep the two byte loads inside the value
@@ -964,6 +1002,8 @@ B2_HD uint32_t fast_lane_decide(uint32_t lane, uint32_t start_m, uint32_t chosen
                                 uint32_t kind, bool vis, bool rc_check, uint32_t* push_back) {
   *push_back = 0;
   if (!valid) return 0;
+  if (start_m == valid_m && chosen_m == valid_m && !rc_check)  // the warp holds 32 single-version, visible keys: nothing to look up
+    return !kok || kind == 0u ? (uint32_t)FA_PUSH : (kind == 1u ? (uint32_t)FA_COMMIT : 0u);
   const uint32_t upto = 0xffffffffu >> (31u - lane);  // lanes 0..lane
   const uint32_t below = start_m & upto;
   const bool orphan = below == 0;                     // the run started before this warp
@@ -973,7 +1013,7 @@ B2_HD uint32_t fast_lane_decide(uint32_t lane, uint32_t start_m, uint32_t chosen
   uint32_t flags = 0;
   if (is_start) {
     const uint32_t above = start_m & ~upto;
-    const uint32_t next = above ? ctz64((uint64_t)above) : 32u;
+    const uint32_t next = above ? ctz32(above) : 32u;
     const uint32_t run = (next >= 32u ? ~0u : ((1u << next) - 1u)) & ~(upto >> 1) & valid_m;  // lanes [lane, next)
     const bool open_end = (run >> (31u - clz32(valid_m))) & 1u;                                 // touches the warp's last valid lane
     if ((chosen_m & run) == 0 && open_end) flags |= FA_PUSH;                                     // (c)
@@ -1119,6 +1159,7 @@ B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k
   out->null = false; out->bits = 0;
   const uint64_t S = 0x8000000000000000ull;
   if (row.fast && c.role == CR_NORMAL && c.kind == CK_INT) {  // hot case: integer column of an exact-layout v2 row
+    if ((row.cv_mask >> c.v2_hint) & 1u) { out->bits = row.cv[c.v2_hint]; return DE_NONE; }
     out->bits = fast_cell_dyn(row, c.v2_hint, c.v2_class != V2_INT, P.fast_v1 != 0);
     return DE_NONE;
   }
@@ -1249,6 +1290,13 @@ B2_HD double f64_mul(double x, double y) {
   return x * y;
 #endif
 }
+B2_HD double f64_div(double x, double y) {
+#if defined(__CUDA_ARCH__)
+  return __ddiv_rn(x, y);
+#else
+  return x / y;
+#endif
+}
 B2_HD bool f64_finite(double x) { return (f64_bits(x) & 0x7ff0000000000000ull) != 0x7ff0000000000000ull; }
 B2_HD bool f64_isinf(double x) { return (f64_bits(x) & 0x7fffffffffffffffull) == 0x7ff0000000000000ull; }
 
@@ -1264,10 +1312,10 @@ B2_HD bool f64_isinf(double x) { return (f64_bits(x) & 0x7fffffffffffffffull) ==
 #endif
 #endif
 B2_HD bool is_ext_sig(int sig) {
-  return sig == B2_SIG_INT_DIVIDE_INT || sig == B2_SIG_MOD_INT || sig == B2_SIG_MOD_REAL || (sig >= B2_SIG_ABS_INT && sig <= B2_SIG_ABS_REAL) ||
+  return sig == B2_SIG_INT_DIVIDE_INT || sig == B2_SIG_MOD_INT || sig == B2_SIG_MOD_REAL || sig == B2_SIG_DIVIDE_REAL || (sig >= B2_SIG_ABS_INT && sig <= B2_SIG_ABS_REAL) ||
          sig == B2_SIG_UNARY_MINUS_INT || sig == B2_SIG_UNARY_MINUS_REAL || (sig >= B2_SIG_IF_NULL_INT && sig <= B2_SIG_CASE_WHEN_REAL);
 }
-B2_HD int eval_ext_fn(int sig, int na, bool ret_unsigned, int64_t* sv, uint8_t* sn, int* sp_io) {
+B2_HD int eval_ext_fn(int sig, int na, bool ret_unsigned, int64_t* sv, uint8_t* sn, int* sp_io, uint32_t* warn) {
   const int64_t I64_MIN = -9223372036854775807ll - 1, I64_MAX = 9223372036854775807ll;
   const int base = *sp_io - na;
   int64_t r = 0;
@@ -1328,6 +1376,15 @@ B2_HD int eval_ext_fn(int sig, int na, bool ret_unsigned, int64_t* sv, uint8_t* 
           else if (au && !bu) r = (int64_t)(ua % abs_b);
           else r = (int64_t)(ua % ub);
           rn = false;
+          break;
+        }
+        case B2_SIG_DIVIDE_REAL: {  // :515-533: x / 0 is NULL with warning 1365 (handle_division_by_zero); an infinite quotient overflows
+          if (an || bn) break;
+          const double y = bits_f64((uint64_t)b);
+          if (y == 0.0) { *warn += 1; break; }
+          const double z = f64_div(bits_f64((uint64_t)a), y);
+          if (f64_isinf(z)) return DE_OVERFLOW_DOUBLE;
+          rn = false; r = (int64_t)f64_bits(z);
           break;
         }
         case B2_SIG_MOD_REAL: {  // :280-291
@@ -1449,7 +1506,7 @@ B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const 
     }
     if (is_ext_sig(nd.sig)) {
 #if B2_EXT_SIGS
-      int e = eval_ext_fn(nd.sig, nd.n_args, nd.is_unsigned, sv, sn, &sp);
+      int e = eval_ext_fn(nd.sig, nd.n_args, nd.is_unsigned, sv, sn, &sp, &row.warn);
       if (e) return e;
       continue;
 #else
@@ -1559,7 +1616,7 @@ B2_HD int eval_conds(const DevPlan& P, const Row& row, const Cells& cells, bool*
     // the column is read by stored position (impl_compare.rs:63-149 semantics through cmp_i64)
     for (int i = 0; i < P.n_fconds; ++i) {
       const FastCond f = P.fconds[i];
-      const int c = cmp_i64((int64_t)fast_cell_dyn(row, f.h, f.zero_ext, P.fast_v1 != 0), f.col_uns, f.imm_slot ? row.imms[f.imm_slot - 1] : f.imm, f.imm_uns);
+      const int c = cmp_i64((int64_t)(((row.cv_mask >> f.h) & 1u) ? row.cv[f.h] : fast_cell_dyn(row, f.h, f.zero_ext, P.fast_v1 != 0)), f.col_uns, f.imm_slot ? row.imms[f.imm_slot - 1] : f.imm, f.imm_uns);
       bool t;
       switch (f.op) {
         case 0: t = c < 0; break;

@@ -13,6 +13,9 @@
 
 #include <algorithm>
 #include <cctype>
+#include <ctime>
+#include <future>
+#include <map>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -281,6 +284,23 @@ struct b2_exec {
   b2_error_info last_err{};
   b2_exec_stats stats{};
   uint64_t entries_scanned = 0;
+
+  // ---- deadline (runner.rs:974 `self.deadline.check()?` at the top of every batch; here also between unit launches) ----
+  uint64_t deadline_ns = 0;
+  static uint64_t now_ns() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec; }
+  bool deadline_exceeded() {
+    if (!deadline_ns || now_ns() < deadline_ns) return false;
+    fail(B2_ERR_DEADLINE, "deadline is exceeded");
+    drained = true;
+    return true;
+  }
+  // ---- evaluation warnings (BatchExecuteResult::warnings; only "Division by 0" can be raised by the supported functions) ----
+  uint64_t warnings_total = 0, warnings_reported = 0;
+  // ---- b2_exec_next_batch_async ----
+  std::future<int> async_fut;
+  b2_batch async_batch{};
+  bool async_running = false;
+  uint64_t paging_size = 0;
 
   int fail(int status, const std::string& msg, int mysql = 0, uint64_t entry = ~0ull) {
     last_err.status = status; last_err.mysql_code = mysql; last_err.entry_index = entry;
@@ -663,6 +683,7 @@ struct b2_exec {
     stats.met_newer_ts_data = check_newer ? ((c.met_newer || saw_lock) ? 1 : 0) : -1;
     stats.h2d_bytes = h2d_bytes; stats.d2h_bytes = d2h_bytes;
     met_newer_any = c.met_newer || saw_lock;
+    warnings_total = cp.desc && cp.dev.mode == PM_SCAN ? desc_warnings : c.warn_div0;
   }
   bool met_newer_any = false;
 
@@ -814,6 +835,7 @@ struct b2_exec {
     *hit_lock_range = false;
     while (budget && cur_unit < units.size()) {
       const Unit& u = units[cur_unit];
+      if (deadline_exceeded()) break;
       if (cur_entry < u.e_lo) cur_entry = u.e_lo;
       uint64_t base = wblocks[u.block_idx].entry_base;
       uint32_t c_lo = cur_entry, c_hi = (uint32_t)std::min<uint64_t>(u.e_hi, (uint64_t)c_lo + budget);
@@ -969,9 +991,10 @@ struct b2_exec {
     return read_counters(c);
   }
   Counters desc_stats{};  // request-level sums of the per-chunk counters
+  uint64_t desc_warnings = 0;
   void desc_accumulate(const Counters& c) {
     desc_stats.processed_keys += c.processed_keys; desc_stats.processed_size += c.processed_size; desc_stats.default_lookups += c.default_lookups;
-    desc_stats.met_newer |= c.met_newer; desc_stats.live_rows += c.live_rows;
+    desc_stats.met_newer |= c.met_newer; desc_stats.live_rows += c.live_rows; desc_warnings += c.warn_div0;
     first_row_seen = std::min<uint64_t>(first_row_seen, c.first_row);
   }
   int next_scan_batch_desc(uint64_t scan_rows, b2_batch* out) {
@@ -1297,9 +1320,12 @@ struct b2_exec {
     uint32_t fast_slots = 0;
     size_t fast_smem = 0;
     if (P.has_group && P.n_group <= 1) {
-      fast_slots = 4096;
-      while (fast_slots > 64 && (size_t)fast_slots * (8 + 8 * P.acc_words) > 64 * 1024) fast_slots >>= 1;
-      fast_smem = (size_t)fast_slots * (8 + 8 * P.acc_words);
+      // direct-addressed: accumulators of the group keys 0 .. slots-1 (+ 4 bytes of occupancy each); 1024 slots of COUNT + SUM
+      // are 28 KB, which still lets three CTAs share an SM
+      static const uint32_t want = [] { const char* v = getenv("B2_AGG_DIRECT_SLOTS"); return v ? (uint32_t)atoi(v) : 1024u; }();
+      fast_slots = want;
+      while (fast_slots > 64 && (size_t)fast_slots * (4 + 8 * P.acc_words) > 28 * 1024 * (want / 1024 ? want / 1024 : 1)) fast_slots >>= 1;
+      fast_smem = ((size_t)fast_slots * (4 + 8 * P.acc_words) + 15) & ~(size_t)15;
     }
     Counters c;
     for (;;) {
@@ -1312,6 +1338,7 @@ struct b2_exec {
       entries_scanned = 0;
       for (size_t ui = 0; ui < units.size(); ++ui) {
         const Unit& u = units[ui];
+        if (deadline_exceeded()) { cudaStreamSynchronize(stream); return publish_agg(0, nullptr, nullptr, nullptr, out); }
         BlockView v;
         rc = acquire_block(u.block_idx, &v);
         if (rc) return rc;
@@ -1461,6 +1488,7 @@ struct b2_exec {
       unsigned int* pair_cnt = (unsigned int*)tn_pair_cnt.p;
       for (size_t ui = 0; ui < units.size(); ++ui) {
         const Unit& u = units[ui];
+        if (deadline_exceeded()) break;
         BlockView v;
         rc = acquire_block(u.block_idx, &v);
         if (rc) return rc;
@@ -1517,7 +1545,8 @@ struct b2_exec {
     rc = read_counters(&c);
     if (rc) return rc;
     fill_stats(c);
-    if (c.err != ~0ull) { device_error(c); n = 0; }
+    if (failed) n = 0;  // (deadline)
+    else if (c.err != ~0ull) { device_error(c); n = 0; }
     else { check_trailing_lock(); if (failed) n = 0; }
     // publish: payload columns of the running list, NULL flags packed into BitVec words
     uint32_t words = (std::max<uint32_t>(limit, 1) + 63) / 64;
@@ -1557,6 +1586,7 @@ struct b2_exec {
     memset(out, 0, sizeof(*out));
     cudaSetDevice(device);
     if (failed || drained) { out->is_drained = B2_DRAIN_DRAINED; return failed ? last_err.status : B2_OK; }
+    if (deadline_exceeded()) { out->is_drained = B2_DRAIN_DRAINED; return last_err.status; }
     if (!started) {
       started = true;
       if (cp.dev.mode == PM_SCAN) { int rc = init_device_state(); if (rc) return rc; }
@@ -1574,6 +1604,8 @@ struct b2_exec {
     cudaEventElapsedTime(&ms, t0, t1);
     stats.time_processed_ns += (uint64_t)(ms * 1e6);
     cudaEventDestroy(t0); cudaEventDestroy(t1);
+    out->n_warnings = (uint32_t)std::min<uint64_t>(warnings_total - warnings_reported, 0xffffffffull);
+    warnings_reported = warnings_total;
     return rc;
   }
 };
@@ -1619,6 +1651,14 @@ int32_t b2_exec_open(const b2_dag_plan* plan, const b2_key_range* ranges, uint32
   e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { g_last_error = cudaGetErrorString(e); return B2_ERR_CUDA; }
   h->out_loc = cfg ? cfg->output_location : B2_LOC_DEVICE;
+  h->deadline_ns = cfg ? cfg->deadline_ns : 0;
+  h->paging_size = cfg ? cfg->paging_size : 0;
+  if (h->paging_size && h->cp.dev.mode != PM_SCAN) {
+    // Aggregation / TopN under paging depend on the reference's 1024-row batch boundaries (aggr_executor.rs:226-236,
+    // top_n_executor.rs:304-318): the CPU executors keep those requests
+    g_last_error = "paging is on the device path for scan / selection / projection pipelines only";
+    return B2_ERR_UNSUPPORTED;
+  }
   h->cp.dev.read_ts = src->read_ts;
   h->cp.dev.isolation = src->isolation_level;
   rc = h->setup_source(src, ranges, n_ranges);
@@ -1718,7 +1758,10 @@ int32_t b2_exec_encode_batch(b2_exec* h, int32_t encode_type, int32_t location, 
   if (!h || !out) { g_last_error = "null argument"; return B2_ERR_INVALID_ARG; }
   return h->encode_batch(encode_type, location, out);
 }
-void b2_exec_close(b2_exec* h) { delete h; }
+void b2_exec_close(b2_exec* h) {
+  if (h && h->async_running) h->async_fut.wait();  // a batch still in flight
+  delete h;
+}
 
 int32_t b2_exec_agg_partials(b2_exec* h, b2_agg_partials* out) {
   if (h->cp.dev.mode != PM_AGG || !h->drained) { g_last_error = "no aggregation state: not an Aggregation pipeline or not drained yet"; return B2_ERR_INVALID_ARG; }
@@ -1737,8 +1780,146 @@ int32_t b2_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint3
   int rc = b2_exec_open(plan, ranges, n_ranges, src, cfg, &h);
   if (rc) return rc;
   *out_handle = h;
+  if (h->paging_size) {
+    // runner.rs:790-806: a paging request stops after the batch in which `paging_size` rows have been produced and
+    // hands back the scanned range.  One bounded batch here (rows come in key order, so any prefix is a valid page): the
+    // batch covers enough entries for the page on an unselective plan; a selective one simply returns a shorter page.
+    const uint64_t budget = std::min<uint64_t>(std::max<uint64_t>(h->paging_size * 2, 4096), 1ull << 24);
+    rc = h->next_batch(budget, out);
+    if (rc == B2_OK && out->is_drained == B2_DRAIN_REMAIN) out->is_drained = B2_DRAIN_PAGING;
+    return rc;
+  }
   // run to drain in one batch: aggregations always do; scans process every unit in one go when the source is one chunk
   return h->next_batch(~0ull, out);
+}
+
+// ---- async next_batch: the batch runs on a worker thread of the handle, the caller polls ----
+int32_t b2_exec_next_batch_async(b2_exec* h, uint64_t scan_rows) {
+  if (!h) { g_last_error = "null argument"; return B2_ERR_INVALID_ARG; }
+  if (h->async_running) { g_last_error = "a batch is already in flight on this handle"; return B2_ERR_INVALID_ARG; }
+  h->async_running = true;
+  h->async_fut = std::async(std::launch::async, [h, scan_rows] { return h->next_batch(scan_rows, &h->async_batch); });
+  return B2_OK;
+}
+int32_t b2_exec_poll(b2_exec* h, b2_batch* out) {
+  if (!h || !out) { g_last_error = "null argument"; return B2_ERR_INVALID_ARG; }
+  if (!h->async_running) { g_last_error = "no batch in flight"; return B2_ERR_INVALID_ARG; }
+  if (h->async_fut.wait_for(std::chrono::seconds(0)) != std::future_status::ready) return B2_PENDING;
+  const int rc = h->async_fut.get();
+  h->async_running = false;
+  *out = h->async_batch;
+  if (rc) g_last_error = h->last_err.message;
+  return rc;
+}
+
+int32_t b2_exec_warnings(b2_exec* h, b2_warning* out, uint32_t cap, uint64_t* count_out) {
+  if (!h || !count_out) { g_last_error = "null argument"; return B2_ERR_INVALID_ARG; }
+  *count_out = h->warnings_total;
+  const uint64_t n = std::min<uint64_t>(std::min<uint64_t>(h->warnings_total, cap), 64);  // DEFAULT_MAX_WARNING_CNT, expr/ctx.rs:62
+  for (uint64_t i = 0; out && i < n; ++i) {
+    out[i].mysql_code = B2_MYSQL_ERR_DIVISION_BY_ZERO; out[i]._pad = 0;
+    snprintf(out[i].message, sizeof(out[i].message), "Division by 0");
+  }
+  return B2_OK;
+}
+
+// ---- HBM-resident block cache ----
+namespace {
+struct PinnedRegion {
+  std::vector<DevBuf> bufs;
+  std::vector<b2_cf_block> write, dflt;
+  b2_cf_block lock{};
+  std::vector<std::vector<uint8_t>> lock_host;  // CF_LOCK stays in host memory (the ABI reads it on the host)
+  std::vector<uint32_t> lock_ko, lock_vo;
+  bool has_lock = false;
+  uint64_t bytes = 0;
+  int refs = 0;
+};
+struct CacheKey { int device; uint64_t region, version; bool operator<(const CacheKey& o) const { return device != o.device ? device < o.device : (region != o.region ? region < o.region : version < o.version); } };
+std::mutex g_cache_mu;
+std::map<CacheKey, std::unique_ptr<PinnedRegion>>& region_cache() { static auto* m = new std::map<CacheKey, std::unique_ptr<PinnedRegion>>(); return *m; }
+uint64_t g_cache_bytes[64] = {0}, g_cache_hits[64] = {0}, g_cache_misses[64] = {0};
+uint64_t cache_budget() { const char* v = getenv("B2_BLOCK_CACHE_BYTES"); return v ? strtoull(v, nullptr, 10) : (64ull << 30); }
+}  // namespace
+
+int32_t b2_region_pin(int32_t device, uint64_t region_id, uint64_t data_version, const b2_region_source* src, b2_region_source* out) {
+  if (!src || !out || src->location != B2_LOC_HOST || device < 0 || device >= 64) { g_last_error = "b2_region_pin: a host-resident source and a device ordinal below 64 are required"; return B2_ERR_INVALID_ARG; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_last_error = "cudaSetDevice failed"; return B2_ERR_CUDA; }
+  std::lock_guard<std::mutex> g(g_cache_mu);
+  const CacheKey key{device, region_id, data_version};
+  auto it = region_cache().find(key);
+  if (it == region_cache().end()) {
+    g_cache_misses[device]++;
+    std::unique_ptr<PinnedRegion> pr(new PinnedRegion());
+    uint64_t need = 0;
+    auto sizes = [&](const b2_cf_block& b, uint64_t* kb, uint64_t* vb) { *kb = b.n ? b.key_offs[b.n] : 0; *vb = b.n ? b.val_offs[b.n] : 0; };
+    for (uint32_t i = 0; i < src->n_write; ++i) { uint64_t kb, vb; sizes(src->write[i], &kb, &vb); need += kb + vb + 8ull * (src->write[i].n + 1) + 128; }
+    for (uint32_t i = 0; src->dflt && i < src->n_dflt; ++i) { uint64_t kb, vb; sizes(src->dflt[i], &kb, &vb); need += kb + vb + 8ull * (src->dflt[i].n + 1) + 128; }
+    if (g_cache_bytes[device] + need > cache_budget()) { g_last_error = "block cache budget exceeded (B2_BLOCK_CACHE_BYTES)"; return B2_ERR_UNSUPPORTED; }
+    cudaStream_t st;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { g_last_error = "cudaStreamCreate failed"; return B2_ERR_CUDA; }
+    bool ok = true;
+    auto up = [&](const void* p, size_t bytes) -> const void* {
+      pr->bufs.emplace_back();
+      DevBuf& d = pr->bufs.back();
+      if (d.reserve(((bytes + 31) & ~(size_t)15) + 16) != cudaSuccess) { ok = false; return nullptr; }
+      if (bytes && cudaMemcpyAsync(d.p, p, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
+      return d.p;
+    };
+    auto copy_blocks = [&](const b2_cf_block* bs, uint32_t n, std::vector<b2_cf_block>* dst) {
+      for (uint32_t i = 0; i < n && ok; ++i) {
+        uint64_t kb, vb; sizes(bs[i], &kb, &vb);
+        b2_cf_block d{};
+        d.keys = (const uint8_t*)up(bs[i].keys, kb); d.key_offs = (const uint32_t*)up(bs[i].key_offs, 4ull * (bs[i].n + 1));
+        d.vals = (const uint8_t*)up(bs[i].vals, vb); d.val_offs = (const uint32_t*)up(bs[i].val_offs, 4ull * (bs[i].n + 1));
+        d.n = bs[i].n;
+        dst->push_back(d);
+      }
+    };
+    copy_blocks(src->write, src->n_write, &pr->write);
+    if (src->dflt) copy_blocks(src->dflt, src->n_dflt, &pr->dflt);
+    if (ok && cudaStreamSynchronize(st) != cudaSuccess) ok = false;
+    cudaStreamDestroy(st);
+    if (!ok) { for (auto& b : pr->bufs) b.release(); g_last_error = "block cache: device allocation or copy failed"; return B2_ERR_CUDA; }
+    if (src->lock && src->lock->n) {  // keep a private host copy of CF_LOCK
+      const b2_cf_block& L = *src->lock;
+      pr->lock_host.resize(2);
+      pr->lock_host[0].assign(L.keys, L.keys + L.key_offs[L.n]); pr->lock_host[1].assign(L.vals, L.vals + L.val_offs[L.n]);
+      pr->lock_ko.assign(L.key_offs, L.key_offs + L.n + 1); pr->lock_vo.assign(L.val_offs, L.val_offs + L.n + 1);
+      pr->lock.keys = pr->lock_host[0].data(); pr->lock.key_offs = pr->lock_ko.data(); pr->lock.vals = pr->lock_host[1].data(); pr->lock.val_offs = pr->lock_vo.data(); pr->lock.n = L.n;
+      pr->has_lock = true;
+    }
+    pr->bytes = need;
+    g_cache_bytes[device] += need;
+    it = region_cache().emplace(key, std::move(pr)).first;
+  } else g_cache_hits[device]++;
+  PinnedRegion& pr = *it->second;
+  pr.refs++;
+  *out = *src;
+  out->location = B2_LOC_DEVICE; out->device = device;
+  out->write = pr.write.data(); out->n_write = (uint32_t)pr.write.size();
+  out->dflt = pr.dflt.empty() ? nullptr : pr.dflt.data(); out->n_dflt = (uint32_t)pr.dflt.size();
+  out->lock = pr.has_lock ? &pr.lock : nullptr;
+  return B2_OK;
+}
+int32_t b2_region_unpin(int32_t device, uint64_t region_id, uint64_t data_version) {
+  std::lock_guard<std::mutex> g(g_cache_mu);
+  auto it = region_cache().find(CacheKey{device, region_id, data_version});
+  if (it == region_cache().end()) { g_last_error = "b2_region_unpin: not pinned"; return B2_ERR_INVALID_ARG; }
+  if (--it->second->refs > 0) return B2_OK;
+  cudaSetDevice(device);
+  cudaDeviceSynchronize();  // requests still reading the cached blocks
+  for (auto& b : it->second->bufs) b.release();
+  g_cache_bytes[device] -= it->second->bytes;
+  region_cache().erase(it);
+  return B2_OK;
+}
+void b2_region_cache_stats(int32_t device, uint64_t* bytes_cached, uint64_t* hits, uint64_t* misses) {
+  std::lock_guard<std::mutex> g(g_cache_mu);
+  const int d = device >= 0 && device < 64 ? device : 0;
+  if (bytes_cached) *bytes_cached = g_cache_bytes[d];
+  if (hits) *hits = g_cache_hits[d];
+  if (misses) *misses = g_cache_misses[d];
 }
 
 int32_t b2_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges, const uint8_t* old_prefix, uint32_t old_prefix_len,

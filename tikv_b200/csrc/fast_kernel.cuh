@@ -40,13 +40,18 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
   __shared__ TopItem s_top_thr;
 
   // ---- mode state in dynamic shared memory (before the stages) ----
+  // PM_AGG with GROUP BY: the CTA table is addressed by the group key itself — slot k holds the accumulators of key k for
+  // 0 <= k < slots (status codes, type ids, small dictionaries: the low-cardinality GROUP BY worth keeping on chip); no
+  // hashing, no probing, no key compare.  occ[k] says whether key k was seen.  Every other key (and NULL) goes to the HBM
+  // table.  Flushed into the HBM table once, at the end.
   SmemTable st;
   st.slots = 0; st.keys = nullptr; st.acc = nullptr;
+  unsigned int* occ = nullptr;
   if (MODE == PM_AGG && P.has_group && A.smem_slots) {
     st.slots = A.smem_slots;
-    st.keys = reinterpret_cast<unsigned long long*>(dyn_smem);
-    st.acc = st.keys + st.slots;
-    for (unsigned int i = tid; i < st.slots; i += FK_THREADS) st.keys[i] = SMEM_EMPTY_KEY;
+    st.acc = reinterpret_cast<unsigned long long*>(dyn_smem);
+    occ = reinterpret_cast<unsigned int*>(st.acc + (size_t)st.slots * P.acc_words);
+    for (unsigned int i = tid; i < st.slots; i += FK_THREADS) occ[i] = 0;
     for (unsigned int i = tid; i < st.slots * P.acc_words; i += FK_THREADS) st.acc[i] = 0;
   }
   const TopBuf tb = topbuf_make(dyn_smem, MODE == PM_TOPN ? A.topn_cap : 0u, P);
@@ -123,7 +128,8 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
 
   // ---- decoding warps ----
   unsigned long long n_keys = 0, n_size = 0, n_live = 0;
-  unsigned int n_newer = 0, n_last = 0;
+  unsigned int n_keys32 = 0, n_size32 = 0;  // per-lane counts (folded into the 64-bit ones before they could wrap)
+  unsigned int n_newer = 0, n_last = 0, n_warn = 0;
   // PM_AGG without GROUP BY: accumulators in registers
   unsigned long long r_cnt[MAX_AGGS], r_lo[MAX_AGGS], r_hi[MAX_AGGS];
 #pragma unroll
@@ -167,8 +173,8 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
       KeyTail t;
       const bool k35 = kl == 35;
       const bool kok = key_tail_load(kp, &t) && k35;
-      const uint64_t cts = key_tail_commit_ts(t);
-      const bool vis = k35 && cts <= A.read_ts;
+      const uint64_t cts = key_tail_commit_ts(t);  // (only kept when the plan reads the commit-ts column)
+      const bool vis = k35 && key_tail_visible(t, ~A.read_ts);
       // the entry before: its key words travel up one lane; lane 0 reads them itself
       unsigned int pa_lo = __shfl_up_sync(0xffffffffu, (unsigned int)t.a, 1), pa_hi = __shfl_up_sync(0xffffffffu, (unsigned int)(t.a >> 32), 1);
       unsigned int pb_lo = __shfl_up_sync(0xffffffffu, (unsigned int)t.b, 1);
@@ -179,7 +185,7 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
         const bool q35 = sv.klen(e - 1) == 35;
         key_tail_load(sv.kptr(e - 1), &q);
         pa_lo = (unsigned int)q.a; pa_hi = (unsigned int)(q.a >> 32); pb_lo = (unsigned int)q.b;
-        px = ((unsigned int)(q.b >> 32) & 0xffffffu) | (q35 ? 1u << 24 : 0u) | ((q35 && key_tail_commit_ts(q) <= A.read_ts) ? 1u << 25 : 0u);
+        px = ((unsigned int)(q.b >> 32) & 0xffffffu) | (q35 ? 1u << 24 : 0u) | ((q35 && key_tail_visible(q, ~A.read_ts)) ? 1u << 25 : 0u);
       }
       const bool same = valid && !first && k35 && ((px >> 24) & 1u) && (unsigned int)t.a == pa_lo && (unsigned int)(t.a >> 32) == pa_hi &&
                         (unsigned int)t.b == pb_lo && (((unsigned int)(t.b >> 32) ^ px) & 0xffffffu) == 0;
@@ -208,6 +214,9 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
         bool keep = false;
         if (ok) {
           row.filled = P.fast_filled;
+#ifdef B2_JIT_PLAN
+          fast_fill_cells(P, row, P.fast_need);  // every stored column an expression reads, once (compile-time positions)
+#endif
           ok = eval_conds(P, row, cells, &keep) == 0;
         }
         if (ok && keep) {
@@ -226,8 +235,9 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
         }
         if (!ok) { push = true; commit = false; }  // the general decoder / evaluator owns this run (and raises its error)
         live = commit && keep;
+        if (commit) n_warn += row.warn;
       }
-      if (commit) { n_keys += 1; n_size += 27u + rlen; n_last = e + 1; }
+      if (commit) { n_keys32 += 1; n_size32 += 27u + rlen; n_last = e + 1; }
     }
 
     // ---- hand-over list: one atomic per warp ----
@@ -239,6 +249,7 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
       if (push) A.slow_list[base + __popc(pm & ((1u << lane) - 1u))] = push_e;
     }
     n_live += live ? 1u : 0u;
+    if ((k & 0xfffu) == 0xfffu) { n_keys += n_keys32; n_size += n_size32; n_keys32 = 0; n_size32 = 0; }  // (a lane adds < 2^20 per 4096 tiles)
 
     // ---- commit ----
     if (MODE == PM_AGG) {
@@ -262,34 +273,24 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
         }
       } else {
         const unsigned int active = __ballot_sync(0xffffffffu, live);
+        // warp pre-aggregation only pays while the CTA has met a handful of groups (few, hot accumulators): uniform switch
+        const bool preagg = st.slots && *(volatile unsigned int*)&s_tbl_used <= 8u;
         if (live) {
+          const bool direct = st.slots && !gk.null && gk.bits < (unsigned long long)st.slots;
           unsigned int peers = 1u << lane;
-          // warp pre-aggregation only pays while the CTA has met a handful of groups (few hot accumulators)
-          if (st.slots && *(volatile unsigned int*)&s_tbl_used <= 8u) {
+          if (preagg) {
             const unsigned int nm = __ballot_sync(active, gk.null);
             peers = __match_any_sync(active, gk.bits) & (gk.null ? nm : ~nm);
           }
-          const bool leader = (unsigned int)(__ffs(peers) - 1) == lane;
-          const bool solo = (peers & (peers - 1)) == 0;
+          const bool leader = !preagg || (unsigned int)(__ffs(peers) - 1) == lane;
+          const bool solo = !preagg || (peers & (peers - 1)) == 0;
           unsigned long long* acc = nullptr;
           if (leader) {
-            if (st.slots && !s_tbl_off && !gk.null && gk.bits != SMEM_EMPTY_KEY) {
-              const unsigned int mask = st.slots - 1, limit = (st.slots >> 1) + (st.slots >> 2);
-              unsigned int s = (hash32(gk.bits) >> 8) & mask;
-#pragma unroll 1
-              for (int probes = 0; probes < 6; ++probes) {
-                unsigned long long kk = *(volatile unsigned long long*)&st.keys[s];
-                if (kk == SMEM_EMPTY_KEY) {
-                  if (*(volatile unsigned int*)&s_tbl_used >= limit) break;
-                  kk = atomicCAS(&st.keys[s], SMEM_EMPTY_KEY, gk.bits);
-                  if (kk == SMEM_EMPTY_KEY) { atomicAdd(&s_tbl_used, 1u); kk = gk.bits; }
-                }
-                if (kk == gk.bits) { acc = st.acc + (size_t)s * P.acc_words; break; }
-                s = (s + 1) & mask;
-              }
-            }
-            if (!acc) {
-              if (st.slots && !s_tbl_off) atomicAdd(&s_tbl_miss, 1u);
+            if (direct) {
+              const unsigned int slot = (unsigned int)gk.bits;
+              if (*(volatile unsigned int*)&occ[slot] == 0 && atomicExch(&occ[slot], 1u) == 0) atomicAdd(&s_tbl_used, 1u);
+              acc = st.acc + (size_t)slot * P.acc_words;
+            } else {
               const unsigned int gslot = table_find_or_insert(A.tbl, gk.bits, gk.null);
               if (gslot == 0xffffffffu) atomicExch(&A.ctr->agg_overflow, 1u);
               else acc = A.tbl.acc + (size_t)gslot * P.acc_words;
@@ -331,8 +332,6 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
             }
           }
         }
-        // high-cardinality GROUP BY: once three quarters of the rows went past the CTA table, stop probing it
-        if (tid == 0 && k >= 16 && st.slots && !s_tbl_off && s_tbl_miss * 4u > k * TILE * 3u) s_tbl_off = 1;
       }
     } else if (MODE == PM_TOPN) {
       if (live && (!s_top_have_thr || item_less(item, s_top_thr, P))) {
@@ -428,8 +427,8 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
     } else if (st.slots) {
       cta256_sync();
       for (unsigned int s = tid; s < st.slots; s += TILE) {
-        if (st.keys[s] == SMEM_EMPTY_KEY) continue;
-        const unsigned int gslot = table_find_or_insert(A.tbl, st.keys[s], false);
+        if (occ[s] == 0) continue;
+        const unsigned int gslot = table_find_or_insert(A.tbl, (unsigned long long)s, false);
         if (gslot == 0xffffffffu) { atomicExch(&A.ctr->agg_overflow, 1u); continue; }
         for (int a = 0; a < P.n_aggs; ++a) {
           const DevAgg g = P.aggs[a];
@@ -445,12 +444,14 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
     }
   }
   // statistics
+  n_keys += n_keys32; n_size += n_size32;
   for (int off = 16; off > 0; off >>= 1) {
     n_keys += __shfl_xor_sync(0xffffffffu, n_keys, off);
     n_size += __shfl_xor_sync(0xffffffffu, n_size, off);
     n_live += __shfl_xor_sync(0xffffffffu, n_live, off);
     n_newer |= __shfl_xor_sync(0xffffffffu, n_newer, off);
     n_last = max(n_last, __shfl_xor_sync(0xffffffffu, n_last, off));
+    n_warn += __shfl_xor_sync(0xffffffffu, n_warn, off);
   }
   if (lane == 0) {
     if (n_keys) atomicAdd(&A.ctr->processed_keys, n_keys);
@@ -459,6 +460,7 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
     if (n_size) atomicAdd(&A.ctr->processed_size, n_size);
     if (n_live) atomicAdd(&A.ctr->live_rows, n_live);
     if (n_newer) atomicOr(&A.ctr->met_newer, 1u);
+    if (n_warn) atomicAdd(&A.ctr->warn_div0, (unsigned long long)n_warn);
   }
 }
 

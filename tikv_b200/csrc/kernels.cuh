@@ -27,6 +27,7 @@ struct Counters {
   unsigned int bad_prefix;             // checksum: key without new_prefix
   unsigned long long last_row;         // 1 + largest global CF_WRITE entry index the MVCC scan returned a row for (take_scanned_range)
   unsigned long long err_max;          // max over failing rows of (global_entry << 8 | DevErr): the first error of a backward scan; 0 = none
+  unsigned long long warn_div0;        // "Division by 0" warnings (1365) raised on committed rows
   unsigned long long first_row;        // smallest global CF_WRITE entry index a row was returned for (take_scanned_range, backward); ~0 = none
 };
 

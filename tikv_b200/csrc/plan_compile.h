@@ -87,7 +87,7 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
           case B2_SIG_IN_INT: want = na; if (na < 1) want = -1; break;
           case B2_SIG_IN_REAL: want = na; real_args = true; if (na < 1) want = -1; break;
           case B2_SIG_INT_DIVIDE_INT: case B2_SIG_MOD_INT: case B2_SIG_IF_NULL_INT: break;
-          case B2_SIG_MOD_REAL: case B2_SIG_IF_NULL_REAL: real_args = real_ret = true; break;
+          case B2_SIG_MOD_REAL: case B2_SIG_IF_NULL_REAL: case B2_SIG_DIVIDE_REAL: real_args = real_ret = true; break;
           case B2_SIG_UNARY_MINUS_INT: case B2_SIG_ABS_INT: case B2_SIG_ABS_UINT: want = 1; break;
           case B2_SIG_UNARY_MINUS_REAL: case B2_SIG_ABS_REAL: want = 1; real_args = real_ret = true; break;
           case B2_SIG_COALESCE_INT: want = na; if (na < 1) want = -1; break;
@@ -388,6 +388,14 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
     }
     if (all) P.n_fconds = P.n_conds;
   }
+  // stored columns read by expressions: decoded once per row by the lean kernels (Row::cv)
+  P.fast_need = 0;
+  if (P.fast_n > 0)
+    for (int i = 0; i < P.n_nodes; ++i)
+      if (P.nodes[i].kind == B2_RPN_COLUMN_REF) {
+        const DevCol& c = P.cols[P.nodes[i].imm];
+        if (c.role == CR_NORMAL && c.kind == CK_INT) P.fast_need |= 1u << c.v2_hint;
+      }
   // Constants become launch parameters: the device plan keeps only a slot number, so that requests which differ in their
   // literals (`col < 5`, `col < 7`, another IN list, another LIMIT) share one plan shape and one specialised kernel.
   out->n_imms = 0;

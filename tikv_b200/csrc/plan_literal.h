@@ -18,7 +18,7 @@ inline std::string plan_literal(const DevPlan& P) {
     << P.n_order << "," << P.n_out << "," << P.isolation << "," << P.need_value << "," << P.has_handle_cols << "," << P.fast_n << "," << P._fpad << ",";
   u64(P.fast_filled); o << "," << P.fast_cls << "u," << P.fast_uns << "u,{";
   for (int i = 0; i < 8; ++i) o << (int)P.fast_out[i] << (i < 7 ? "," : "");
-  o << "}," << P.n_out_slow << "," << P.fast_v1 << ",";
+  o << "}," << P.n_out_slow << "," << P.fast_need << "u," << P.fast_v1 << ",";
   u64(P.fast_ids); o << ","; u64(0 /* read_ts stays a launch parameter */); o << ","; u64(0 /* so does the TopN limit (ScanArgs::limit) */); o << ",{";
   for (int i = 0; i < MAX_CONDS; ++i) { expr(P.conds[i]); o << (i < MAX_CONDS - 1 ? "," : ""); }
   o << "},"; expr(P.group);

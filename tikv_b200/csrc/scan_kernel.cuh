@@ -246,6 +246,7 @@ struct EntryStats {  // per-thread partial statistics / checksum state
   unsigned long long keys, size, dflt, ck_x, ck_kvs, ck_bytes;
   unsigned int newer;
   unsigned int last;  // 1 + largest block entry index a row was returned for
+  unsigned int warn;  // evaluation warnings (Division by 0)
 };
 enum { P1_NONE = 0, P1_LIVE = 1, P1_REDO = 2, P1_GENERAL = 3 /* entry_fast only: not a clean entry, run entry_phase1 */ };
 
@@ -316,6 +317,7 @@ __device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A,
   bool keep = false;
   if (!err) err = eval_conds(P, row, cells, &keep);
   if (err) { report_err(A.ctr, A.entry_base + e, err); return P1_NONE; }
+  ts.warn += row.warn; row.warn = 0;
   return keep ? P1_LIVE : P1_NONE;
 }
 
@@ -357,6 +359,7 @@ __device__ __forceinline__ int entry_fast(const DevPlan& P, const ScanArgs& A, c
   ts.keys += 1;
   ts.size += 27u + rlen;
   ts.last = e + 1;
+  ts.warn += row.warn; row.warn = 0;
   return keep ? P1_LIVE : P1_NONE;
 }
 
@@ -427,7 +430,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
 
   // per-thread statistics, reduced once at the end
   EntryStats ts;
-  ts.keys = ts.size = ts.dflt = ts.ck_x = ts.ck_kvs = ts.ck_bytes = 0; ts.newer = 0; ts.last = 0;
+  ts.keys = ts.size = ts.dflt = ts.ck_x = ts.ck_kvs = ts.ck_bytes = 0; ts.newer = 0; ts.last = 0; ts.warn = 0;
   unsigned long long t_live = 0;
   unsigned int t_first = 0xffffffffu;  // smallest block entry index a row was returned for
   // no-group aggregation: one accumulator set per CTA in shared memory, flushed at the end
@@ -608,7 +611,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     Row row;
     Cells cells;
     EntryStats d;
-    d.keys = d.size = d.dflt = d.ck_x = d.ck_kvs = d.ck_bytes = 0; d.newer = 0; d.last = 0;
+    d.keys = d.size = d.dflt = d.ck_x = d.ck_kvs = d.ck_bytes = 0; d.newer = 0; d.last = 0; d.warn = 0;
     int r1 = P1_NONE;
     bool general = true;
     if constexpr (!V::kWholeBlock && MODE != PM_CHECKSUM) {
@@ -617,7 +620,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
         const bool valid = e < A.c_hi;
         r1 = entry_fast<MODE>(P, A, view, valid ? e : A.c_hi - 1, valid, row, cells, d, lane);
         general = __any_sync(0xffffffffu, r1 == P1_GENERAL);
-        if (general) { d.keys = d.size = 0; d.last = 0; }
+        if (general) { d.keys = d.size = 0; d.last = 0; d.warn = 0; }
       }
     }
     if (general) r1 = e < A.c_hi ? entry_phase1<MODE>(P, A, view, walk_hi, e, row, cells, d, crc_tab, lane) : (int)P1_NONE;
@@ -641,7 +644,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       if (s_redo[k & 3]) return true;
     }
     // ---- commit ----
-    ts.keys += d.keys; ts.size += d.size; ts.dflt += d.dflt; ts.newer |= d.newer;
+    ts.keys += d.keys; ts.size += d.size; ts.dflt += d.dflt; ts.newer |= d.newer; ts.warn += d.warn;
     if (d.last > ts.last) ts.last = d.last;
     if (d.last && d.last - 1 < t_first) t_first = d.last - 1;
     if (MODE == PM_CHECKSUM) { ts.ck_x ^= d.ck_x; ts.ck_kvs += d.ck_kvs; ts.ck_bytes += d.ck_bytes; }
@@ -878,6 +881,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
         }
       }
     }
+    if (live) ts.warn += row.warn;  // warnings of the expressions evaluated after the commit point (outputs, group keys, arguments, sort keys)
     return false;
   };
 
@@ -968,6 +972,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     ts.dflt += __shfl_xor_sync(0xffffffffu, ts.dflt, off);
     ts.newer |= __shfl_xor_sync(0xffffffffu, ts.newer, off);
     ts.last = max(ts.last, __shfl_xor_sync(0xffffffffu, ts.last, off));
+    ts.warn += __shfl_xor_sync(0xffffffffu, ts.warn, off);
     t_first = min(t_first, __shfl_xor_sync(0xffffffffu, t_first, off));
   }
   if (lane == 0) {
@@ -979,6 +984,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     if (t_live) atomicAdd(&A.ctr->live_rows, t_live);
     if (ts.dflt) atomicAdd(&A.ctr->default_lookups, ts.dflt);
     if (ts.newer) atomicOr(&A.ctr->met_newer, 1u);
+    if (ts.warn) atomicAdd(&A.ctr->warn_div0, (unsigned long long)ts.warn);
   }
 }
 

@@ -73,12 +73,12 @@ def _read_batch(b, location):
 
 
 class BatchExecutor:
-    def __init__(self, plan, ranges, region, output=ffi.LOC_HOST, stream=0, jit=ffi.JIT_AUTO):
+    def __init__(self, plan, ranges, region, output=ffi.LOC_HOST, stream=0, jit=ffi.JIT_AUTO, deadline_ns=0):
         self._L = ffi.lib()
         self._plan, self._region = plan, region  # keep ctypes memory alive
         self._kr, self._keep = key_ranges(ranges)
         cfg = ffi.ExecConfig()
-        cfg.output_location, cfg.cuda_stream, cfg.jit = output, stream, jit
+        cfg.output_location, cfg.cuda_stream, cfg.jit, cfg.deadline_ns = output, stream, jit, deadline_ns
         self._out_loc = output
         self._h = C.c_void_p()
         rc = self._L.b2_exec_open(C.byref(plan.c), self._kr, len(ranges), C.byref(region.c), C.byref(cfg), C.byref(self._h))
@@ -104,6 +104,34 @@ class BatchExecutor:
             e = self.last_error()
             err = B2Error(e.status, e.message.decode(), e.mysql_code, e.entry_index)
         return BatchResult(cols, kinds, fts, b.is_drained != ffi.DRAIN_REMAIN, err)
+
+    def next_batch_async(self, scan_rows):
+        """Start a batch without blocking (interface.rs:53 `async fn next_batch`); poll() collects it."""
+        rc = self._L.b2_exec_next_batch_async(self._h, scan_rows)
+        if rc != ffi.B2_OK:
+            raise B2Error(rc, self._L.b2_last_error_message().decode())
+
+    def poll(self):
+        """None while the batch is in flight, else the BatchResult b2_exec_next_batch would have returned."""
+        b = ffi.Batch()
+        rc = self._L.b2_exec_poll(self._h, C.byref(b))
+        if rc == ffi.B2_PENDING:
+            return None
+        cols, kinds, fts = _read_batch(b, self._out_loc)
+        err = None
+        if rc != ffi.B2_OK:
+            e = self.last_error()
+            err = B2Error(e.status, e.message.decode(), e.mysql_code, e.entry_index)
+        r = BatchResult(cols, kinds, fts, b.is_drained != ffi.DRAIN_REMAIN, err)
+        r.n_warnings = b.n_warnings
+        return r
+
+    def warnings(self):
+        """(warning_cnt, [(mysql_code, message)]) of the request so far (EvalWarnings, expr/ctx.rs:180-215)."""
+        out = (ffi.Warning * 64)()
+        n = C.c_uint64()
+        self._L.b2_exec_warnings(self._h, out, 64, C.byref(n))
+        return n.value, [(out[i].mysql_code, out[i].message.decode()) for i in range(min(n.value, 64))]
 
     def take_scanned_range(self):
         """(lower_inclusive, upper_exclusive) raw keys covered since the previous call (scanner.rs:204-229)."""

@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("B2_LIB") or os.path.join(_HERE, "_build", "libb2copr.
 # ---- enums -------------------------------------------------------------------------------------
 B2_OK, B2_ERR_STORAGE, B2_ERR_KEY_IS_LOCKED, B2_ERR_WRITE_CONFLICT, B2_ERR_EVALUATE = 0, 1, 2, 3, 4
 B2_ERR_CORRUPTED, B2_ERR_DEADLINE, B2_ERR_UNSUPPORTED, B2_ERR_CUDA, B2_ERR_INVALID_ARG = 5, 6, 7, 8, 9
+B2_PENDING = 100
 
 TP_TINY, TP_SHORT, TP_LONG, TP_FLOAT, TP_DOUBLE, TP_NULL, TP_TIMESTAMP, TP_LONGLONG, TP_INT24 = 1, 2, 3, 4, 5, 6, 7, 8, 9
 TP_DATE, TP_DURATION, TP_DATETIME, TP_YEAR, TP_VARCHAR, TP_BIT = 10, 11, 12, 13, 15, 16
@@ -94,7 +95,7 @@ class DagPlan(C.Structure):
 
 class ExecConfig(C.Structure):
     _fields_ = [("output_location", C.c_int32), ("staging_tiles", C.c_int32), ("cuda_stream", C.c_uint64),
-                ("jit", C.c_int32), ("_pad", C.c_int32), ("reserved", C.c_uint64 * 3)]
+                ("jit", C.c_int32), ("_pad", C.c_int32), ("deadline_ns", C.c_uint64), ("paging_size", C.c_uint64), ("reserved", C.c_uint64 * 1)]
 
 
 class Decimal(C.Structure):
@@ -134,6 +135,10 @@ class AggPartials(C.Structure):
                 ("key_words", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+class Warning(C.Structure):
+    _fields_ = [("mysql_code", C.c_int32), ("_pad", C.c_int32), ("message", C.c_char * 120)]
+
+
 class GenSpec(C.Structure):
     _fields_ = [("table_id", C.c_int64), ("first_handle", C.c_uint64), ("n_rows", C.c_uint64), ("n_cols", C.c_uint32),
                 ("row_format", C.c_int32), ("seed", C.c_uint64), ("col_lo", C.POINTER(C.c_int64)),
@@ -155,7 +160,7 @@ JIT_AUTO, JIT_SYNC, JIT_OFF = 0, 1, 2
 
 EXPORTED_SYMBOLS = [
     "b2_abi_version", "b2_build_info", "b2_last_error_message", "b2_check_supported", "b2_plan_prepare", "b2_plan_precompile", "b2_jit_counters", "b2_plan_literal", "b2_exec_open", "b2_exec_schema",
-    "b2_exec_next_batch", "b2_exec_collect_stats", "b2_exec_last_error", "b2_exec_can_be_cached", "b2_exec_encode_batch", "b2_exec_take_scanned_range", "b2_exec_collect_scanned_rows_per_range", "b2_exec_close",
+    "b2_exec_next_batch", "b2_exec_next_batch_async", "b2_exec_poll", "b2_exec_warnings", "b2_region_pin", "b2_region_unpin", "b2_region_cache_stats", "b2_exec_collect_stats", "b2_exec_last_error", "b2_exec_can_be_cached", "b2_exec_encode_batch", "b2_exec_take_scanned_range", "b2_exec_collect_scanned_rows_per_range", "b2_exec_close",
     "b2_exec_agg_partials", "b2_dag_handle", "b2_checksum_handle", "b2_gen_create", "b2_gen_destroy", "b2_copy_to_host", "b2_copy_to_device",
     "b2_device_count", "b2_host_alloc_pinned", "b2_host_alloc_pinned_near", "b2_device_numa_node", "b2_host_free_pinned",
 ]
@@ -191,6 +196,18 @@ def lib():
     L.b2_exec_schema.restype = i32
     L.b2_exec_next_batch.argtypes = [vp, u64, C.POINTER(Batch)]
     L.b2_exec_next_batch.restype = i32
+    L.b2_exec_next_batch_async.argtypes = [vp, u64]
+    L.b2_exec_next_batch_async.restype = i32
+    L.b2_exec_poll.argtypes = [vp, C.POINTER(Batch)]
+    L.b2_exec_poll.restype = i32
+    L.b2_exec_warnings.argtypes = [vp, C.POINTER(Warning), u32, C.POINTER(u64)]
+    L.b2_exec_warnings.restype = i32
+    L.b2_region_pin.argtypes = [i32, u64, u64, C.POINTER(RegionSource), C.POINTER(RegionSource)]
+    L.b2_region_pin.restype = i32
+    L.b2_region_unpin.argtypes = [i32, u64, u64]
+    L.b2_region_unpin.restype = i32
+    L.b2_region_cache_stats.argtypes = [i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.b2_region_cache_stats.restype = None
     L.b2_exec_collect_stats.argtypes = [vp, C.POINTER(ExecStats)]
     L.b2_exec_collect_stats.restype = i32
     L.b2_exec_last_error.argtypes = [vp, C.POINTER(ErrorInfo)]
@@ -228,7 +245,7 @@ def lib():
     L.b2_device_numa_node.restype = i32
     L.b2_host_free_pinned.argtypes = [vp]
     L.b2_host_free_pinned.restype = None
-    if L.b2_abi_version() != 1:
+    if L.b2_abi_version() != 2:
         raise RuntimeError("libb2copr ABI version mismatch")
     _lib = L
     return L

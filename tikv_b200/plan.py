@@ -111,6 +111,7 @@ def _typed(name, first, *args, unsigned=None):
               unsigned=(not real and _uns(first)) if unsigned is None else unsigned)
 
 
+def divide(a, b): return fn("DIVIDE_REAL", a, b, ret_tp=ffi.TP_DOUBLE)                 # a / b over Real: x / 0 is NULL + warning 1365
 def int_divide(a, b): return fn("INT_DIVIDE_INT", a, b, unsigned=_uns(a, b))      # a DIV b
 def mod(a, b): return fn("MOD_REAL", a, b, ret_tp=ffi.TP_DOUBLE) if a.ekind == "real" else fn("MOD_INT", a, b, unsigned=_uns(a))
 def neg(a): return _typed("UNARY_MINUS", a, a, unsigned=False)

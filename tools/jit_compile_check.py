@@ -41,7 +41,7 @@ def compile_plan(plan, name):
             mode = 4
         if e.tp in (ffi.EXEC_AGGREGATION, ffi.EXEC_STREAM_AGG) and e.n_group_by > 1:
             mode = 5
-    src = ("#define B2_NVRTC 1\n#include \"scan_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + lit + ";\n}\n"
+    src = ("#define B2_NVRTC 1\n#define B2_JIT_PLAN 1\n#include \"scan_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + lit + ";\n}\n"
            "extern \"C\" __global__ void __launch_bounds__(b2::TILE + 64, 2) b2_scan_jit(const __grid_constant__ b2::ScanArgs A) {\n"
            "  b2::scan_body<" + str(mode) + ">(b2::kJitPlan, A);\n}\n")
     err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"b2_scan_jit.cu", 0, [], [])
