@@ -142,6 +142,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
       size_t fi = 0, ti = 0;
       while (fi < fast.size() || ti < todo.size()) {
         Row row; Cells cells;
+        uint8_t idx_buf[IDX_RAW_MAX];
         row.imms = cp.imms;
         bool keep = false;
         uint32_t e;
@@ -172,8 +173,9 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
         uint32_t ko = blk.koff[e], kl = blk.koff[e + 1] - ko;
         R->processed_keys++; R->processed_size += (kl - 8) + ro.val_len;
         row.enc_key = blk.keys + ko; row.enc_key_len = kl - 8; row.commit_ts = ro.commit_ts;
-        int er = row_open(ro.val, ro.val_len, &row.rv);
-        if (!er) er = row_split(P, row, cells);
+        int er;
+        if (P.idx_cols > 0) er = index_row_split(P, row, cells, ro.val, ro.val_len, idx_buf);
+        else { er = row_open(ro.val, ro.val_len, &row.rv); if (!er) er = row_split(P, row, cells); }
         if (!er) er = eval_conds(P, row, cells, &keep);
         if (er) { report(bases[b] + e, er); continue; }
         }
@@ -266,7 +268,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
   }
   if (err != ~0ull) {
     R->dev_err = (int)(err & 0xff); R->err_entry = err >> 8;
-    R->status = (R->dev_err >= 20 && R->dev_err < 30) ? B2_ERR_EVALUATE : (R->dev_err <= 5 && R->dev_err != DE_WRITE_CONFLICT ? B2_ERR_STORAGE : (R->dev_err == DE_WRITE_CONFLICT ? B2_ERR_WRITE_CONFLICT : B2_ERR_CORRUPTED));
+    R->status = R->dev_err == DE_IDX_NEW_LAYOUT ? B2_ERR_UNSUPPORTED : (R->dev_err >= 20 && R->dev_err < 30) ? B2_ERR_EVALUATE : (R->dev_err <= 5 && R->dev_err != DE_WRITE_CONFLICT ? B2_ERR_STORAGE : (R->dev_err == DE_WRITE_CONFLICT ? B2_ERR_WRITE_CONFLICT : B2_ERR_CORRUPTED));
     if (P.mode == PM_SCAN) {
       // keep only rows before the failing entry: they were pushed in order, rows after it were skipped above
     }

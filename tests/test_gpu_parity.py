@@ -855,3 +855,49 @@ def test_paging_request(regions):
     cfg.paging_size = 10
     b, h = ffi.Batch(), C.c_void_p()
     assert L.b2_dag_handle(C.byref(agg.c), kr, 1, C.byref(host.c), C.byref(cfg), C.byref(b), C.byref(h)) == ffi.B2_ERR_UNSUPPORTED
+
+
+def test_index_scan_matches_oracle():
+    """BatchIndexScan on the device (index_row_split: key datums -> columns, handle from the key tail or the
+    value), forward and backward, with selection / aggregation / TopN on top, against the oracle (itself pinned on
+    index_scan_executor.rs test_basic, tests/test_oracle_golden.py)."""
+    import random
+    rng = random.Random(5)
+    T, IDX = 11, 4
+    r = kvfmt.Region()
+    for h in range(2000):
+        a = None if rng.random() < 0.1 else rng.choice([rng.randrange(-(1 << 63), 1 << 63), rng.randrange(-5, 5)])
+        b = rng.choice([0, 1, (1 << 64) - 1, rng.randrange(0, 1 << 64)])
+        payload = (kvfmt.datum_null() if a is None else kvfmt.datum_int(a, comparable=True)) + kvfmt.datum_uint(b, comparable=True) + kvfmt.datum_int(h, comparable=True)
+        key = kvfmt.index_key(T, IDX, payload)
+        r.put(key, b"0", 3, 4)
+        if rng.random() < 0.2:
+            r.put(key, b"0", 50, 60)
+        if rng.random() < 0.1:
+            r.delete(key, 5, 6)
+    host = r.build(read_ts=10, n_write_blocks=2)
+    cols = [ColumnDef(1), ColumnDef(2, unsigned=True), ColumnDef(3, pk_handle=True), ColumnDef(-3)]
+    whole = [(kvfmt.index_key(T, IDX), kvfmt.index_key(T, IDX, b"\xfa"))]
+    scan = lambda desc=False: Plan().index_scan(T, cols, desc=desc)
+    plans = [("asc", scan().build(), True), ("desc", scan(True).build(), True), ("sel", scan().selection(lt(col(0), const_int(3))).build(output_offsets=[2, 0]), True),
+             ("agg", scan().aggregation([("count", const_int(1)), ("sum", col(0))], group_by=[col(1, unsigned=True)]).build(), False),
+             ("topn", scan().topn([(col(0), True), (col(2), False)], 25).build(), True)]
+    for region in (host, DeviceRegion(host)):
+        for name, plan, ordered in plans:
+            exp = orc.dag_handle(plan, whole, host)
+            got = DagHandler(plan, whole, region, batch_rows=300).handle_request()
+            assert exp.status == 0 and exp.n_rows > 5
+            assert_same_rows(got, exp, ordered=ordered, ctx=f"index {name}")
+    # unique index (handle in the value) and the error shapes
+    T2, IDX2 = 7, 2
+    u = kvfmt.Region()
+    for a, h in ((1, 100), (2, -3), (9, 1 << 40)):
+        u.put(kvfmt.index_key(T2, IDX2, kvfmt.datum_int(a, comparable=True)), (h & ((1 << 64) - 1)).to_bytes(8, "big"), 1, 2)
+    w2 = [(kvfmt.index_key(T2, IDX2), kvfmt.index_key(T2, IDX2, b"\xfa"))]
+    c2 = [ColumnDef(1), ColumnDef(2, pk_handle=True)]
+    assert DagHandler(Plan().index_scan(T2, c2).build(), w2, u.build(read_ts=10)).handle_request().rows() == [(1, 100), (2, -3), (9, 1 << 40)]
+    missing = DagHandler(Plan().index_scan(T2, [ColumnDef(1), ColumnDef(5), ColumnDef(2, pk_handle=True)]).build(), w2, u.build(read_ts=10)).handle_request()
+    assert missing.status == ffi.B2_ERR_CORRUPTED
+    rec = kvfmt.Region()
+    rec.put(kvfmt.row_key(T2, 1), kvfmt.row_v2([(1, 5, "int")]), 1, 2)
+    assert DagHandler(Plan().index_scan(T2, c2).build(), [kvfmt.table_range(T2)], rec.build(read_ts=10)).handle_request().status == ffi.B2_ERR_CORRUPTED

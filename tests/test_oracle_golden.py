@@ -715,3 +715,52 @@ def test_reference_executor_fixtures_device_logic(fx):
     """the same through the device row logic driven on the CPU (tests/host_emul.cpp)"""
     import emu
     sc.check_reference_fixture(fx, lambda plan, region: emu.dag_handle(plan, sc.WHOLE, region))
+
+
+def test_index_scan_device_logic():
+    """The device row logic for BatchIndexScan (b2_device.h index_row_split: the columns are the key's datums, the handle
+    comes from the key tail or the value) driven on the CPU against the oracle: the reference fixture, a unique index,
+    the three error shapes, a seeded random non-unique index with NULLs / unsigned columns / versions / deletes."""
+    import emu
+    import random
+    T, IDX, region, (c0, c1, handle, phys), whole = _index_fixture()
+    for cols, ranges in (([c0, c1], whole), ([c0, c1, phys], whole), ([c0, c1, handle], whole), ([c0, c1, handle, phys], whole)):
+        plan = Plan().index_scan(T, cols).build()
+        exp, got = orc.dag_handle(plan, ranges, region), emu.dag_handle(plan, ranges, region)
+        assert got.status == 0 == exp.status and got.rows() == exp.rows() and got.n_rows == 3
+    sel = Plan().index_scan(T, [c0, c1, handle]).selection(lt(col(2), const_int(6))).build()
+    assert emu.dag_handle(sel, whole, region).rows() == [(5, 5.1, 5), (5, 10.5, 2)]
+    T, IDX = 7, 2
+    r = kvfmt.Region()
+    for a, h in ((1, 100), (2, -3), (9, 1 << 40)):
+        r.put(kvfmt.index_key(T, IDX, kvfmt.datum_int(a, comparable=True)), (h & ((1 << 64) - 1)).to_bytes(8, "big"), 1, 2)
+    whole = [(kvfmt.index_key(T, IDX), kvfmt.index_key(T, IDX, b"\xfa"))]
+    cols = [ColumnDef(1), ColumnDef(2, pk_handle=True)]
+    assert emu.dag_handle(Plan().index_scan(T, cols).build(), whole, r.build(read_ts=10)).rows() == [(1, 100), (2, -3), (9, 1 << 40)]
+    assert emu.dag_handle(Plan().index_scan(T, [ColumnDef(1), ColumnDef(5), ColumnDef(2, pk_handle=True)]).build(), whole, r.build(read_ts=10)).status == ffi.B2_ERR_CORRUPTED
+    bad = kvfmt.Region()
+    bad.put(kvfmt.index_key(T, IDX, kvfmt.datum_int(1, comparable=True) + kvfmt.datum_f64(2.0)), b"0", 1, 2)
+    assert emu.dag_handle(Plan().index_scan(T, cols).build(), whole, bad.build(read_ts=10)).status == ffi.B2_ERR_CORRUPTED
+    rec = kvfmt.Region()
+    rec.put(kvfmt.row_key(T, 1), kvfmt.row_v2([(1, 5, "int")]), 1, 2)
+    assert emu.dag_handle(Plan().index_scan(T, cols).build(), [kvfmt.table_range(T)], rec.build(read_ts=10)).status == ffi.B2_ERR_CORRUPTED
+    rng = random.Random(5)
+    T, IDX = 11, 4
+    r = kvfmt.Region()
+    for h in range(300):
+        a = None if rng.random() < 0.1 else rng.choice([rng.randrange(-(1 << 63), 1 << 63), rng.randrange(-5, 5)])
+        b = rng.choice([0, 1, (1 << 64) - 1, rng.randrange(0, 1 << 64)])
+        payload = (kvfmt.datum_null() if a is None else kvfmt.datum_int(a, comparable=True)) + kvfmt.datum_uint(b, comparable=True) + kvfmt.datum_int(h, comparable=True)
+        key = kvfmt.index_key(T, IDX, payload)
+        r.put(key, b"0", 3, 4)
+        if rng.random() < 0.2:
+            r.put(key, b"0", 50, 60)
+        if rng.random() < 0.1:
+            r.delete(key, 5, 6)
+    region = r.build(read_ts=10, n_write_blocks=2)
+    cols = [ColumnDef(1), ColumnDef(2, unsigned=True), ColumnDef(3, pk_handle=True)]
+    whole = [(kvfmt.index_key(T, IDX), kvfmt.index_key(T, IDX, b"\xfa"))]
+    for plan in (Plan().index_scan(T, cols).build(), Plan().index_scan(T, cols).selection(lt(col(0), const_int(3))).build(),
+                 Plan().index_scan(T, cols).aggregation([("count", const_int(1)), ("sum", col(0))], group_by=[col(1, unsigned=True)]).build()):
+        exp, got = orc.dag_handle(plan, whole, region), emu.dag_handle(plan, whole, region)
+        assert got.status == 0 == exp.status and sorted(got.rows(), key=repr) == sorted(exp.rows(), key=repr) and exp.n_rows > 5

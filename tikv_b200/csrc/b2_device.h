@@ -54,11 +54,16 @@ enum DevErr {
   DE_OVERFLOW_DIV = 23,      // 1690 "UNSIGNED BIGINT" (codec/overflow.rs:9-58: every integer-division overflow says so)
   DE_UNSUPPORTED_SIG = 30,
   DE_UNSUPPORTED_TYPE = 31,  // row holds a type the device path does not materialise
+  DE_IDX_BAD_KEY = 40,       // check_index_key (table.rs:114-140): not 't' tid "_i" idx ...
+  DE_IDX_MISSING_COL = 41,   // "{i}th column is missing value" (index_scan_executor.rs:493-506)
+  DE_IDX_BAD_HANDLE = 42,    // handle flag / length (index_scan_executor.rs:406-412, 451-471)
+  DE_IDX_NEW_LAYOUT = 43,    // index value in the new (restored-data) layout: left to the CPU executor
 };
 
 // ---- plan as seen by the kernels ----
 enum ColKind { CK_INT = 0, CK_REAL = 1, CK_OTHER = 2 };
-enum ColRole { CR_NORMAL = 0, CR_HANDLE = 1, CR_TABLE_ID = 2, CR_COMMIT_TS = 3, CR_SHADOWED = 4 /* duplicate col id: never filled */ };
+enum ColRole { CR_NORMAL = 0, CR_HANDLE = 1, CR_TABLE_ID = 2, CR_COMMIT_TS = 3, CR_SHADOWED = 4 /* duplicate col id: never filled */,
+               CR_IDX_HANDLE = 5 /* BatchIndexScan: the int handle, from the key tail (non-unique index) or the value (unique) */ };
 enum V2Class { V2_INT = 0, V2_UINT = 1, V2_COPY = 2, V2_BYTES = 3, V2_NIL = 4, V2_UNSUPPORTED = 5 };  // write_v2_as_datum arms
 enum DefState { DS_NONE = 0, DS_VALUE = 1, DS_NULL = 2, DS_ERROR = 3 };
 
@@ -104,7 +109,8 @@ struct DevPlan {
   int32_t need_value;  // 0 when no column is read from the row value (key-only)
   int32_t has_handle_cols;
   int32_t fast_n;      // > 0: rows holding exactly these `fast_n` non-null column ids (and no NULL ids) take the register fast path
-  int32_t _fpad;
+  int32_t idx_cols;    // BatchIndexScan (index_scan_executor.rs): > 0 = the first `idx_cols` columns are index columns decoded from the
+                       //   key's datums, then optionally the int handle (role CR_IDX_HANDLE) and the physical table id column; 0 = table scan
   uint64_t fast_filled;  // `filled` mask of such a row (every row-stored plan column)
   uint32_t fast_cls;     // bit h: stored column h (id order) is integer-class (width must be 1/2/4/8)
   uint32_t fast_uns;     // bit h: stored column h is zero-extended (unsigned)
@@ -696,6 +702,7 @@ struct Row {
   uint64_t filled;  // bitmask of plan columns present in the row (bit c)
   uint32_t fast;    // 1 (v2) / 2 (v1): the row holds exactly the plan's columns, all non-null: cells come from the two offset words below
   uint64_t o_lo, o_hi;  // the row's u16 end-offsets 0..3 / 4..7
+  uint64_t idx_handle;  // BatchIndexScan: the row's int handle (bits)
   const int64_t* imms;  // the request's hoisted constants (ScanArgs::imms: kernel parameter space on the device)
   uint64_t cv[8];       // lean kernels, plan-specialised builds: the integer cells of the stored columns the plan's expressions
   uint32_t cv_mask = 0; //   read (DevPlan::fast_need), decoded once per row; bit h set = cv[h] is valid
@@ -1151,6 +1158,54 @@ B2_HD int row_split(const DevPlan& P, Row& row, Cells& cells) {
   return DE_NONE;
 }
 
+// BatchIndexScanExecutor::process_kv_pair -> process_old_collation_kv (index_scan_executor.rs:363-380, 514-574): the index
+// columns are the datums of the key after 't' tid "_i" idx (19 raw bytes), the int handle follows them in the key (non-unique
+// index) or is the value (unique index, 8 bytes big-endian).  The raw key bytes [19, rawlen) are copied into `buf` (the
+// memcomparable group markers removed), `cells` point at the datums there, and the row then decodes like a v1 row.
+enum { IDX_RAW_MAX = 112 };
+B2_HD int index_row_split(const DevPlan& P, Row& row, Cells& cells, const uint8_t* val, uint32_t val_len, uint8_t* buf) {
+  const uint8_t* ek = row.enc_key;
+  const int rawlen = raw_key_len(ek, row.enc_key_len);
+  if (rawlen < 0) return DE_BAD_USER_KEY;
+  if (rawlen < 1 || raw_at(ek, 0) != 't') return DE_IDX_BAD_KEY;
+  if (rawlen < 11) return DE_ROW_EOF;
+  if (raw_at(ek, 9) != '_' || raw_at(ek, 10) != 'i') return DE_IDX_BAD_KEY;
+  if (rawlen < 19) return DE_ROW_EOF;
+  if (val_len > 9) return DE_IDX_NEW_LAYOUT;
+  const uint32_t n = (uint32_t)rawlen - 19u;
+  if (n > IDX_RAW_MAX) return DE_UNSUPPORTED_TYPE;
+  for (uint32_t j = 0; j < n; ++j) buf[j] = (uint8_t)raw_at(ek, 19u + j);
+  row.rv.v = buf; row.rv.n = n; row.rv.fmt = 1;
+  row.fast = 0;
+  uint32_t pos = 0;
+  uint64_t filled = 0;
+  int err = DE_NONE;
+  for (int i = 0; i < P.idx_cols; ++i) {  // extract_columns_from_datum_format :493-506
+    if (pos >= n) return DE_IDX_MISSING_COL;
+    const uint32_t dl = split_datum(buf + pos, n - pos, &err);
+    if (!dl) return err;
+    cells.off[i] = pos; cells.len_kind[i] = (dl << 2) | CELL_V1;
+    filled |= 1ull << i;
+    pos += dl;
+  }
+  for (int k = P.idx_cols; k < P.n_cols; ++k) {
+    filled |= 1ull << k;
+    if (P.cols[k].role != CR_IDX_HANDLE) continue;
+    if (pos >= n) {  // unique index: decode_int_handle_from_value :406-412
+      if (val_len < 8) return DE_IDX_BAD_HANDLE;
+      row.idx_handle = ld_be64(val);
+    } else {         // decode_int_handle_from_key :451-471
+      const uint32_t flag = buf[pos];
+      if ((flag != 3 && flag != 4) || n - pos < 9) return DE_IDX_BAD_HANDLE;
+      uint64_t u = 0;
+      for (int b = 0; b < 8; ++b) u = (u << 8) | buf[pos + 1 + b];
+      row.idx_handle = flag == 3 ? (u ^ 0x8000000000000000ull) : u;
+    }
+  }
+  row.filled = filled;
+  return DE_NONE;
+}
+
 struct Value { uint64_t bits; bool null; };
 
 // Decode plan column `k` of the row (LazyBatchColumn::ensure_decoded for one cell, lazy_column.rs:165-221).
@@ -1164,6 +1219,7 @@ B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k
     return DE_NONE;
   }
   if (c.role == CR_HANDLE) { out->bits = raw_be64(row.enc_key, 11) ^ S; return DE_NONE; }       // table.rs:214-218
+  if (c.role == CR_IDX_HANDLE) { out->bits = row.idx_handle; return DE_NONE; }
   if (c.role == CR_TABLE_ID) { out->bits = raw_be64(row.enc_key, 1) ^ S; return DE_NONE; }
   if (c.role == CR_COMMIT_TS) { out->bits = row.commit_ts; return DE_NONE; }
   if (c.kind == CK_OTHER) return DE_UNSUPPORTED_TYPE;
@@ -1808,6 +1864,24 @@ B2_HD bool item_less(const TopItem& a, const TopItem& b, const DevPlan& P) {
   return a.id < b.id;
 }
 
+// order-preserving word of one non-NULL order-by value (sign flip / IEEE total order, -0.0 == 0.0)
+B2_HD unsigned long long order_key_word(const DevOrder& o, unsigned long long w) {
+  if (o.et == 1) {
+    if (bits_f64(w) == 0.0) w = 0;
+    return (w >> 63) ? ~w : (w | 0x8000000000000000ull);
+  }
+  return o.is_unsigned ? w : (w ^ 0x8000000000000000ull);
+}
+// Can a row whose FIRST sort key is `v0` still beat `thr`?  (false = it certainly cannot: skip the rest of its keys)
+B2_HD bool first_key_may_beat(const DevPlan& P, const Value& v0, const TopItem& thr) {
+  const unsigned int tn = thr.nulls & 1u, rn = v0.null ? 1u : 0u;
+  int c;
+  if (rn || tn) c = (int)tn - (int)rn;  // NULL sorts first
+  else { const unsigned long long w = order_key_word(P.order[0], v0.bits); c = w < thr.w[0] ? -1 : (w > thr.w[0] ? 1 : 0); }
+  if (P.order[0].desc) c = -c;
+  return c <= 0;
+}
+
 B2_HD int make_item(const DevPlan& P, const Row& row, const Cells& cells, uint64_t id, TopItem* it) {
   it->nulls = 0; it->id = id; it->slot = 0;
   for (int k = 0; k < MAX_ORDER; ++k) it->w[k] = 0;
@@ -1816,12 +1890,7 @@ B2_HD int make_item(const DevPlan& P, const Row& row, const Cells& cells, uint64
     int e = eval_expr(P, P.order[k].e, row, cells, &v, nullptr);
     if (e) return e;
     if (v.null) { it->nulls |= 1u << k; continue; }
-    unsigned long long w = v.bits;
-    if (P.order[k].et == 1) {
-      if (bits_f64(w) == 0.0) w = 0;  // -0.0 == 0.0
-      w = (w >> 63) ? ~w : (w | 0x8000000000000000ull);
-    } else if (!P.order[k].is_unsigned) w ^= 0x8000000000000000ull;
-    it->w[k] = w;
+    it->w[k] = order_key_word(P.order[k], v.bits);
   }
   return DE_NONE;
 }

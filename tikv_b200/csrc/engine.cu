@@ -233,6 +233,10 @@ const char* dev_err_message(int code, int* status, int* mysql) {
     case DE_OVERFLOW_UBIGINT: *status = B2_ERR_EVALUATE; *mysql = B2_MYSQL_ERR_DATA_OUT_OF_RANGE; return "BIGINT UNSIGNED value is out of range";
     case DE_OVERFLOW_DOUBLE: *status = B2_ERR_EVALUATE; *mysql = B2_MYSQL_ERR_DATA_OUT_OF_RANGE; return "DOUBLE value is out of range";
     case DE_OVERFLOW_DIV: *status = B2_ERR_EVALUATE; *mysql = B2_MYSQL_ERR_DATA_OUT_OF_RANGE; return "UNSIGNED BIGINT value is out of range";
+    case DE_IDX_BAD_KEY: *status = B2_ERR_CORRUPTED; return "record or index key expected";
+    case DE_IDX_MISSING_COL: *status = B2_ERR_CORRUPTED; return "index column is missing value";
+    case DE_IDX_BAD_HANDLE: *status = B2_ERR_CORRUPTED; return "Failed to decode handle of the index entry";
+    case DE_IDX_NEW_LAYOUT: *status = B2_ERR_UNSUPPORTED; return "index value in the new (restored-data) layout is not on the device path";
     case DE_UNSUPPORTED_SIG: *status = B2_ERR_UNSUPPORTED; return "scalar function not supported on the device";
     case DE_UNSUPPORTED_TYPE: *status = B2_ERR_UNSUPPORTED; return "column type not supported on the device";
     default: *status = B2_ERR_CUDA; return "unknown device error";

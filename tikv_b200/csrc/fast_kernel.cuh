@@ -36,7 +36,7 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
   __shared__ __align__(8) unsigned long long s_full[FK_STAGES], s_empty[FK_STAGES];
   __shared__ TileMeta s_meta[FK_STAGES];
   __shared__ unsigned int s_tbl_used, s_tbl_miss, s_tbl_off;
-  __shared__ unsigned int s_top_cnt, s_top_have_thr;
+  __shared__ unsigned int s_top_cnt, s_top_have_thr, s_top_next_sync;
   __shared__ TopItem s_top_thr;
 
   // ---- mode state in dynamic shared memory (before the stages) ----
@@ -68,7 +68,7 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
     }
   }
   if (tid == 0) {
-    s_tbl_used = 0; s_tbl_miss = 0; s_tbl_off = 0; s_top_cnt = 0; s_top_have_thr = 0;
+    s_tbl_used = 0; s_tbl_miss = 0; s_tbl_off = 0; s_top_cnt = 0; s_top_have_thr = 0; s_top_next_sync = 0;
     if (MODE == PM_TOPN && A.topn_seed && A.limit > 0 && *A.topn_seed_cnt >= (unsigned int)A.limit) { s_top_thr = A.topn_seed[A.limit - 1]; s_top_have_thr = 1; }
     for (int i = 0; i < FK_STAGES; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], TILE / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -148,7 +148,7 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
     const uint32_t e_raw = A.c_lo + tile * TILE + tid;
     const bool valid = e_raw < A.c_hi;
     const uint32_t e = valid ? e_raw : A.c_hi - 1;
-    bool push = false, live = false;
+    bool push = false, live = false, cand = false;
     uint32_t push_e = e_raw;
     // per-mode values computed before the hand-over decision (an evaluation error turns the commit into a push)
     Value gk; gk.bits = 0; gk.null = false;
@@ -230,7 +230,12 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
             for (int a = 0; a < MAX_AGGS; ++a)
               if (a < P.n_aggs && ok) ok = eval_expr(P, P.aggs[a].arg, row, cells, &av[a], nullptr) == 0;
           } else {
-            ok = make_item(P, row, cells, A.desc ? ~(A.entry_base + e) : A.entry_base + e, &item) == 0;
+            // most rows lose against the CTA's threshold on their first sort key alone (the threshold only changes inside a
+            // CTA-wide compaction, so reading it here is race-free)
+            Value v0;
+            ok = eval_expr(P, P.order[0].e, row, cells, &v0, nullptr) == 0;
+            cand = ok && (!s_top_have_thr || first_key_may_beat(P, v0, s_top_thr));
+            if (cand) ok = make_item(P, row, cells, A.desc ? ~(A.entry_base + e) : A.entry_base + e, &item) == 0;
           }
         }
         if (!ok) { push = true; commit = false; }  // the general decoder / evaluator owns this run (and raises its error)
@@ -334,12 +339,18 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
         }
       }
     } else if (MODE == PM_TOPN) {
-      if (live && (!s_top_have_thr || item_less(item, s_top_thr, P))) {
+      if (live && cand && (!s_top_have_thr || item_less(item, s_top_thr, P))) {
         const unsigned int pos = atomicAdd(&s_top_cnt, 1u);
-        topbuf_put(tb, tb.idx[pos], item);  // pos < topn_cap: compacted below whenever fewer than TILE slots remain
+        topbuf_put(tb, tb.idx[pos], item);  // pos < topn_cap: see the rendezvous schedule below
       }
-      cta256_sync();
-      if (s_top_cnt + TILE > A.topn_cap) cta_topn_compact(tb, (unsigned int)A.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
+      // CTA rendezvous only as often as the buffer could fill up: at most TILE candidates arrive per tile, so after a
+      // rendezvous that left `cnt` of them the next one is due (cap - cnt) / TILE tiles later
+      if (k == s_top_next_sync) {
+        cta256_sync();
+        if (s_top_cnt + 2 * TILE > A.topn_cap) cta_topn_compact(tb, (unsigned int)A.limit, &s_top_cnt, &s_top_have_thr, &s_top_thr, P);
+        if (tid == 0) { const unsigned int room = (A.topn_cap - s_top_cnt) / TILE; s_top_next_sync = k + (room > 1 ? room - 1 : 1); }
+        cta256_sync();
+      }
     } else {  // PM_CHECKSUM
       const unsigned int cm = __ballot_sync(0xffffffffu, live);
       if (cm) {

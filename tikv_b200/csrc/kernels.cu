@@ -184,12 +184,16 @@ __global__ void topn_gather_kernel(const __grid_constant__ DevPlan P, const __gr
   resolve_run(A.blk, e, A.e_hi, A.e_hi, P.read_ts, P.isolation, A.dflt, &ro);
   Row row;
   Cells cells;
+  uint8_t idx_buf[IDX_RAW_MAX];
   int err = ro.err ? ro.err : (ro.found ? DE_NONE : DE_BAD_WRITE);
   if (!err) {
     uint32_t ko = A.blk.koff[e], kl = A.blk.koff[e + 1] - ko;
     row.enc_key = A.blk.keys + ko; row.enc_key_len = kl - 8; row.commit_ts = ro.commit_ts; row.imms = A.imms;
-    err = row_open(ro.val, ro.val_len, &row.rv);
-    if (!err) err = row_split(P, row, cells);
+    if (P.idx_cols > 0) err = index_row_split(P, row, cells, ro.val, ro.val_len, idx_buf);
+    else {
+      err = row_open(ro.val, ro.val_len, &row.rv);
+      if (!err) err = row_split(P, row, cells);
+    }
   }
   for (int k = 0; k < P.n_out; ++k) {
     Value v; v.null = true; v.bits = 0;

@@ -164,7 +164,8 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
   memset(&P, 0, sizeof(P));
   if (!plan || plan->n_executors == 0 || !plan->executors) { *msg = "empty plan"; return B2_ERR_INVALID_ARG; }
   const b2_executor_desc& scan = plan->executors[0];
-  if (scan.tp != B2_EXEC_TABLE_SCAN) { *msg = "first executor must be TableScan (index scans are not on the device path yet)"; return B2_ERR_UNSUPPORTED; }
+  if (scan.tp != B2_EXEC_TABLE_SCAN && scan.tp != B2_EXEC_INDEX_SCAN) { *msg = "first executor must be TableScan or IndexScan"; return B2_ERR_UNSUPPORTED; }
+  const bool is_index = scan.tp == B2_EXEC_INDEX_SCAN;
   out->desc = scan.desc != 0;  // scan_executor.rs:89-101: ranges in reverse order, each scanned backward (engine.cu: reversed chunks)
   if (scan.n_columns == 0 || scan.n_columns > MAX_COLS) { *msg = "TableScan with 0 or more than 64 columns"; return B2_ERR_UNSUPPORTED; }
   P.n_cols = (int)scan.n_columns;
@@ -177,12 +178,27 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
     c.kind = (uint8_t)col_kind_of_tp(ci.tp);
     c.v2_class = (uint8_t)v2_class_of(ci.tp, c.is_unsigned);
     c.role = CR_NORMAL;
-    if (ci.pk_handle) { c.role = CR_HANDLE; c.kind = CK_INT; P.has_handle_cols = 1; }
+    if (ci.pk_handle && is_index) { c.role = CR_IDX_HANDLE; c.kind = CK_INT; }
+    else if (ci.pk_handle) { c.role = CR_HANDLE; c.kind = CK_INT; P.has_handle_cols = 1; }
     else if (ci.col_id == B2_EXTRA_PHYSICAL_TABLE_ID_COL_ID) { c.role = CR_TABLE_ID; c.kind = CK_INT; }
     else if (ci.col_id == B2_EXTRA_COMMIT_TS_COL_ID) { c.role = CR_COMMIT_TS; c.kind = CK_INT; }
     lower_default(ci, c);
   }
+  if (is_index) {
+    // index_scan_executor.rs:47-170: [index columns in index order][int handle (pk_handle)]?[physical table id (col id -3)]?
+    int n = P.n_cols;
+    const bool has_tid = n > 0 && P.cols[n - 1].role == CR_TABLE_ID;
+    const int tail = has_tid ? 1 : 0;
+    const bool has_handle = n > tail && P.cols[n - 1 - tail].role == CR_IDX_HANDLE;
+    P.idx_cols = n - tail - (has_handle ? 1 : 0);
+    if (P.idx_cols <= 0) { *msg = "IndexScan without index columns"; return B2_ERR_UNSUPPORTED; }
+    for (int i = 0; i < P.idx_cols; ++i) {
+      if (P.cols[i].role != CR_NORMAL) { *msg = "IndexScan: the handle / physical table id columns must come last"; return B2_ERR_UNSUPPORTED; }
+      if (P.cols[i].kind == CK_OTHER) { *msg = "IndexScan over a column that is not Int/Real is not on the device path yet"; return B2_ERR_UNSUPPORTED; }
+    }
+  }
   // duplicate column ids: only the last one is ever filled (table_scan_executor.rs:90-94)
+  if (!is_index)
   for (int i = 0; i < P.n_cols; ++i) {
     if (P.cols[i].role == CR_HANDLE) continue;
     for (int j = i + 1; j < P.n_cols; ++j)
@@ -207,6 +223,7 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
       ids.push_back(P.cols[i].col_id);
     }
     std::sort(ids.begin(), ids.end());
+    if (is_index) ok = false;  // index rows carry no row value
     P.fast_n = 0; P.fast_ids = 0; P.fast_cls = 0; P.fast_uns = 0; P.fast_filled = 0; P.n_out_slow = 0; P.fast_v1 = 0;
     for (int h = 0; h < 8; ++h) P.fast_out[h] = -1;
     if (ok && !ids.empty() && ids.size() <= 8) {

@@ -15,7 +15,7 @@ inline std::string plan_literal(const DevPlan& P) {
   auto expr = [&](const DevExpr& e) { o << "{" << e.start << "," << e.n << "}"; };
   o << "{";
   o << P.mode << "," << P.n_cols << "," << P.n_nodes << "," << P.n_conds << "," << P.n_aggs << "," << P.has_group << "," << P.acc_words << ","
-    << P.n_order << "," << P.n_out << "," << P.isolation << "," << P.need_value << "," << P.has_handle_cols << "," << P.fast_n << "," << P._fpad << ",";
+    << P.n_order << "," << P.n_out << "," << P.isolation << "," << P.need_value << "," << P.has_handle_cols << "," << P.fast_n << "," << P.idx_cols << ",";
   u64(P.fast_filled); o << "," << P.fast_cls << "u," << P.fast_uns << "u,{";
   for (int i = 0; i < 8; ++i) o << (int)P.fast_out[i] << (i < 7 ? "," : "");
   o << "}," << P.n_out_slow << "," << P.fast_need << "u," << P.fast_v1 << ",";

@@ -255,7 +255,7 @@ enum { P1_NONE = 0, P1_LIVE = 1, P1_REDO = 2, P1_GENERAL = 3 /* entry_fast only:
 // repeats the entry on the whole block.
 template <int MODE, class V>
 __device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A, const V& view, uint32_t walk_hi, uint32_t e, Row& row, Cells& cells,
-                                            EntryStats& ts, const unsigned long long* crc_tab, unsigned int lane) {
+                                            EntryStats& ts, const unsigned long long* crc_tab, unsigned int lane, uint8_t* idx_buf) {
   bool start = (e == A.e_lo) || !same_user_key(view, e - 1, e);
   if (!start) return P1_NONE;
   RunOut ro;
@@ -312,8 +312,12 @@ __device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A,
   row.enc_key_len = kl - 8;
   row.commit_ts = ro.commit_ts;
   row.imms = A.imms;
-  int err = row_open(ro.val, ro.val_len, &row.rv);
-  if (!err) err = row_split(P, row, cells);
+  int err;
+  if (P.idx_cols > 0) err = index_row_split(P, row, cells, ro.val, ro.val_len, idx_buf);  // BatchIndexScan: the columns are the key's datums
+  else {
+    err = row_open(ro.val, ro.val_len, &row.rv);
+    if (!err) err = row_split(P, row, cells);
+  }
   bool keep = false;
   if (!err) err = eval_conds(P, row, cells, &keep);
   if (err) { report_err(A.ctr, A.entry_base + e, err); return P1_NONE; }
@@ -610,6 +614,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     bool live = false;
     Row row;
     Cells cells;
+    uint8_t idx_buf[IDX_RAW_MAX];  // BatchIndexScan: the row's raw key bytes after the index id (unused, and optimised away, otherwise)
     EntryStats d;
     d.keys = d.size = d.dflt = d.ck_x = d.ck_kvs = d.ck_bytes = 0; d.newer = 0; d.last = 0; d.warn = 0;
     int r1 = P1_NONE;
@@ -623,7 +628,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
         if (general) { d.keys = d.size = 0; d.last = 0; d.warn = 0; }
       }
     }
-    if (general) r1 = e < A.c_hi ? entry_phase1<MODE>(P, A, view, walk_hi, e, row, cells, d, crc_tab, lane) : (int)P1_NONE;
+    if (general) r1 = e < A.c_hi ? entry_phase1<MODE>(P, A, view, walk_hi, e, row, cells, d, crc_tab, lane, idx_buf) : (int)P1_NONE;
     live = r1 == P1_LIVE;
     if (!V::kWholeBlock) {
       if (__any_sync(0xffffffffu, r1 == P1_REDO) && lane == 0) s_redo[k & 3] = 1;
