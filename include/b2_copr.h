@@ -77,8 +77,10 @@ enum {
  * One block = n KV entries in ascending key order (RocksDB iteration order, data prefix
  * 'z' already stripped as RegionSnapshot does).  Entry i: key  = keys[key_offs[i]..key_offs[i+1])
  *                                                        value= vals[val_offs[i]..val_offs[i+1])
- * Heaps must be 16-byte aligned and readable up to the next multiple of 16 bytes past
- * offs[n] (the loader moves whole 16-byte lines).  All versions of one user key live in the
+ * Heaps must be 16-byte aligned and readable for at least 16 bytes past offs[n] (the loader
+ * moves whole 16-byte lines and the parsers read 8-byte words that may start on the last
+ * bytes of the last entry; host-resident blocks are padded by the engine when it stages them,
+ * B2_LOC_DEVICE callers pad their own buffers).  All versions of one user key live in the
  * same block.  `location` says where the pointers live.                                    */
 enum { B2_LOC_HOST = 0, B2_LOC_DEVICE = 1 };
 

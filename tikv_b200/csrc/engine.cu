@@ -325,7 +325,7 @@ struct b2_exec {
     }
     for (auto& e : kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (DevBuf* b : {&tn_lists, &tn_counts, &tn_pair, &tn_pair_cnt, &tn_tmp, &tn_tmp_cnt, &tn_blk_pay, &tn_blk_null, &tn_run_pay, &tn_run_null, &tn_tmp_pay, &tn_tmp_null, &tn_bitmap}) b->release();
-    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &tbl_gkeys, &tbl_ready, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &slow_list, &slow_cnt, &rev_data, &rev_bitmap, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
+    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &tbl_gkeys, &tbl_ready, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &range_rows_prev, &slow_list, &slow_cnt, &rev_data, &rev_bitmap, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
     enc_host.release();
     for (auto& b : res_cols) b.release();
     for (auto& b : res_bitmaps) b.release();
@@ -913,6 +913,10 @@ struct b2_exec {
     while (!drained && !failed && produced == 0) {
       if (cur_unit >= units.size()) { drained = true; break; }
       size_t save_unit = cur_unit; uint32_t save_entry = cur_entry; uint64_t save_scanned = entries_scanned;
+      // the per-range row counts as they were before this batch (restored if the batch has to be redone)
+      const size_t rr_bytes = std::max<size_t>(1, range_raw_lo.size()) * 8;
+      CUDA_TRY(range_rows_prev.reserve_on(stream, rr_bytes));
+      CUDA_TRY(cudaMemcpyAsync(range_rows_prev.p, range_rows.p, rr_bytes, cudaMemcpyDeviceToDevice, stream));
       bool hit_lock = false; uint32_t lock_r = 0;
       Counters c;
       int rc = run_scan_pass(budget, ~0ull, &hit_lock, &lock_r, &c);
@@ -920,19 +924,25 @@ struct b2_exec {
       fill_stats(c);
       produced = c.out_rows;
       if (c.err != ~0ull) {
-        // rows before the failing row stay valid (interface.rs:229-235): redo this batch up to it, then report
+        // rows before the failing row stay valid (interface.rs:229-235): redo this batch up to it, then report.  The redo
+        // starts from the request-level counters of the batches before this one, so nothing is counted twice and the
+        // statistics describe exactly the rows that were returned (the reference's partial-result semantics).
         cur_unit = save_unit; cur_entry = save_entry; entries_scanned = save_scanned;
-        Counters z; memset(&z, 0, sizeof(z)); z.err = ~0ull; z.first_row = ~0ull;
+        Counters z = good_ctr;
+        z.err = ~0ull; z.first_row = ~0ull; z.err_max = 0; z.out_rows = 0; z.out_base = 0;
         CUDA_TRY(cudaMemcpyAsync(ctr_buf.p, &z, sizeof(z), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(range_rows.p, range_rows_prev.p, rr_bytes, cudaMemcpyDeviceToDevice, stream));
         Counters c2;
         rc = run_scan_pass(budget, c.err >> 8, &hit_lock, &lock_r, &c2);
         if (rc) return rc;
+        fill_stats(c2);
         produced = c2.err == ~0ull ? c2.out_rows : 0;
         // (the reference never reaches a failing row that lies beyond the rows a Limit still wants)
         if (!(limited && produced >= limit_remaining)) device_error(c);
         drained = true;
         break;
       }
+      good_ctr = c;
       if (hit_lock) {
         if (!(limited && produced >= limit_remaining)) lock_failure(lock_r);
         drained = true;
@@ -1081,6 +1091,8 @@ struct b2_exec {
   uint64_t chunk_total = 0;         // rows the last chunk's kernel wrote
   uint64_t first_row_seen = ~0ull;  // smallest global entry index a row was returned for so far
 
+  Counters good_ctr{};       // device counters after the last batch that completed without an error
+  DevBuf range_rows_prev;
   uint64_t limit_remaining = ~0ull;
   int scan_grid = 0;
   DevBuf trace_buf;
