@@ -20,3 +20,14 @@ def _built():
     if not os.path.exists(so):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
     yield
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _warm_kernel_cache(request, _built):
+    """On a GPU box, before the first GPU test: compile the plan-specialised kernels the parity tests use that are not
+    in the on-disk cache yet, on all host cores at once (tests/jit_warm.py).  One after the other inside the tests they
+    cost 5-100 s of NVRTC time each; results do not depend on this step."""
+    if os.path.exists("/dev/nvidia0") and "not gpu" not in (request.config.getoption("-m") or "") and not os.environ.get("B2_NO_JIT_WARM"):
+        import jit_warm
+        jit_warm.warm()
+    yield

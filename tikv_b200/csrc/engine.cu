@@ -1502,15 +1502,23 @@ struct b2_exec {
       CUDA_TRY(cudaMemsetAsync(tn_pair_cnt.p, 0, 8, stream));
       TopItem* pair = (TopItem*)tn_pair.p;
       unsigned int* pair_cnt = (unsigned int*)tn_pair_cnt.p;
+      // The running top-N seeds every later launch with its N-th item, and a CTA drops rows that cannot beat it after one
+      // comparison.  The very first rows have no such bound, so the request starts with short chunks that grow 8x each:
+      // after c rows the bound passes about limit / c of what follows, i.e. every chunk hands ~8 x limit candidates to
+      // the merge below instead of one full list per CTA.
+      uint64_t seeded_rows = 0;
       for (size_t ui = 0; ui < units.size(); ++ui) {
-        const Unit& u = units[ui];
+       const Unit& u = units[ui];
+       BlockView v;
+       rc = acquire_block(u.block_idx, &v);
+       if (rc) return rc;
+       for (uint32_t c_lo = u.e_lo; c_lo < u.e_hi;) {
         if (deadline_exceeded()) break;
-        BlockView v;
-        rc = acquire_block(u.block_idx, &v);
-        if (rc) return rc;
+        const uint64_t want = std::max<uint64_t>(16 * TILE, 7 * seeded_rows);
+        const uint32_t c_hi = (uint64_t)(u.e_hi - c_lo) <= want + want / 2 ? u.e_hi : c_lo + (uint32_t)want;
         ScanArgs a = base_args(u, v);
-        a.c_lo = u.e_lo; a.c_hi = u.e_hi;
-        uint32_t n_tiles = (u.e_hi - u.e_lo + TILE - 1) / TILE;
+        a.c_lo = c_lo; a.c_hi = c_hi;
+        uint32_t n_tiles = (c_hi - c_lo + TILE - 1) / TILE;
         a.topn.items = (TopItem*)tn_lists.p; a.topn.counts = (unsigned int*)tn_counts.p; a.topn.stride = limit;
         a.topn_cap = cap;
         a.topn_seed = pair; a.topn_seed_cnt = pair_cnt;
@@ -1547,11 +1555,14 @@ struct b2_exec {
         CUDA_TRY(cudaMemcpyAsync(pair_cnt, tn_tmp_cnt.p, 4, cudaMemcpyDeviceToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(tn_run_pay.p, tn_tmp_pay.p, pay_bytes, cudaMemcpyDeviceToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(tn_run_null.p, tn_tmp_null.p, null_bytes, cudaMemcpyDeviceToDevice, stream));
-        release_block(u.block_idx);
-        prefetch_after(ui);
-        entries_scanned += u.e_hi - u.e_lo;
+        entries_scanned += c_hi - c_lo;
+        seeded_rows += c_hi - c_lo;
         stats.num_iterations++;
         stats.kernel_launches += 4;
+        c_lo = c_hi;
+       }
+       release_block(u.block_idx);
+       prefetch_after(ui);
       }
       CUDA_TRY(cudaMemcpyAsync(h_ctr.p, pair_cnt, 4, cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1800,7 +1811,7 @@ int32_t b2_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint3
     // runner.rs:790-806: a paging request stops after the batch in which `paging_size` rows have been produced and
     // hands back the scanned range.  One bounded batch here (rows come in key order, so any prefix is a valid page): the
     // batch covers enough entries for the page on an unselective plan; a selective one simply returns a shorter page.
-    const uint64_t budget = std::min<uint64_t>(std::max<uint64_t>(h->paging_size * 2, 4096), 1ull << 24);
+    const uint64_t budget = std::min<uint64_t>(std::max<uint64_t>(h->paging_size * 2, 64), 1ull << 24);
     rc = h->next_batch(budget, out);
     if (rc == B2_OK && out->is_drained == B2_DRAIN_REMAIN) out->is_drained = B2_DRAIN_PAGING;
     return rc;

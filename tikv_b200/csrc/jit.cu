@@ -177,7 +177,7 @@ bool compile_cubin(int mode, bool ext_sigs, bool fast, const std::string& litera
   if (a.CreateProgram(&prog, src.c_str(), "b2_scan_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { *error = "nvrtcCreateProgram failed"; return false; }
   std::string inc = "-I" + a.csrc_dir;
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-DB2_NVRTC=1", "-default-device", inc.c_str(), "-I/usr/local/cuda/include",
-                        ext_sigs ? "-DB2_EXT_SIGS=1" : "-DB2_EXT_SIGS=0"};
+                        ext_sigs ? "-DB2_EXT_SIGS=1" : "-DB2_EXT_SIGS=0", "--split-compile=0"};
   nvrtcResult rc = a.CompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
   g_nvrtc_compiles++;
   if (rc != NVRTC_SUCCESS) {

@@ -141,18 +141,27 @@ __global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant_
   __syncthreads();
   const unsigned int l0 = blockIdx.x * fan_in;
   const unsigned int l1 = l0 + fan_in < in.n_lists ? l0 + fan_in : in.n_lists;
-  const unsigned int total = (l1 - l0) * in.stride;
+  // walk the occupied part of the input lists only: ends[q] = items in lists l0..l0+q
+  unsigned int ends[16];
+  unsigned int total = 0;
+#pragma unroll
+  for (unsigned int q = 0; q < 16; ++q) {
+    if (l0 + q < l1) total += in.counts[l0 + q] < in.stride ? in.counts[l0 + q] : in.stride;
+    ends[q] = total;
+  }
   for (unsigned int base = 0; base < total; base += TILE) {
     unsigned int f = base + tid;
     if (f < total) {
-      unsigned int l = l0 + f / in.stride, i = f % in.stride;
-      if (i < in.counts[l]) {
-        TopItem it = in.items[(size_t)l * in.stride + i];
-        it.slot = (l << 16) | i;
-        if (!s_have_thr || item_less(it, s_thr, P)) {
-          unsigned int pos = atomicAdd(&s_cnt, 1u);
-          topbuf_put(tb, tb.idx[pos], it);
-        }
+      unsigned int q = 0, first = 0;
+#pragma unroll
+      for (unsigned int z = 0; z < 15; ++z)
+        if (f >= ends[z]) { q = z + 1; first = ends[z]; }
+      const unsigned int l = l0 + q, i = f - first;
+      TopItem it = in.items[(size_t)l * in.stride + i];
+      it.slot = (l << 16) | i;
+      if (!s_have_thr || item_less(it, s_thr, P)) {
+        unsigned int pos = atomicAdd(&s_cnt, 1u);
+        topbuf_put(tb, tb.idx[pos], it);
       }
     }
     __syncthreads();

@@ -147,9 +147,11 @@ __device__ __forceinline__ bool topbuf_less(const TopBuf& t, unsigned int sa, un
 }
 
 __device__ void cta_topn_compact(const TopBuf& t, unsigned int limit, unsigned int* s_cnt, unsigned int* s_have_thr, TopItem* s_thr, const DevPlan& P) {
-  const unsigned int tid = threadIdx.x, nt = TILE, cap = t.cap;  // always called by exactly 256 threads
+  const unsigned int tid = threadIdx.x, nt = TILE;  // always called by exactly 256 threads
   unsigned short* idx = t.idx;
   unsigned int cnt = *s_cnt;
+  unsigned int cap = 2;  // the sorting network covers the occupied prefix only (a nearly empty buffer costs next to nothing)
+  while (cap < cnt) cap <<= 1;
   for (unsigned int i = cnt + tid; i < cap; i += nt) t.w[(size_t)idx[i] * t.stride + t.n + 1] = 0x80000000ull;  // free slots sort last
   cta256_sync();
   for (unsigned int k = 2; k <= cap; k <<= 1) {
