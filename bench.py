@@ -439,7 +439,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU of the headline table")
     ap.add_argument("--blocks", type=int, default=16, help="CF_WRITE blocks (regions) per GPU of the headline table")
     ap.add_argument("--sub-rows", type=int, default=100_000_000, help="rows per GPU of the sub-record tables (C2/C5, C4)")
-    ap.add_argument("--chunk", type=int, default=1 << 27, help="CF_WRITE entries per next_batch (scan pipelines)")
+    ap.add_argument("--chunk", type=int, default=1 << 24, help="CF_WRITE entries per next_batch (scan pipelines)")
     ap.add_argument("--cpu-sample-rows", type=int, default=2_000_000, help="rows per region task of the CPU arm")
     ap.add_argument("--e2e-rows", type=int, default=0, help="rows of the end-to-end (host buffer) request; 0 = as many of --rows as host memory allows")
     ap.add_argument("--parity-rows", type=int, default=1_000_000)

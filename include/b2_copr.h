@@ -36,7 +36,7 @@ typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; t
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 2
+#define B2_ABI_VERSION 3
 
 /* ---- status codes (tidb_query_common::error::Error classes, dag/mod.rs:231-244) ---- */
 enum {
@@ -128,6 +128,8 @@ typedef struct b2_column_info {
   int32_t pk_handle;         /* int handle stored in the key */
   uint32_t default_len;
   const uint8_t* default_val;/* datum-encoded default, NULL/0 = none */
+  int32_t decimal;           /* tipb ColumnInfo.decimal: the fsp of DATE / DATETIME / TIMESTAMP columns */
+  int32_t _pad;
 } b2_column_info;
 
 /* RPN node kinds (tidb_query_expr/src/types/expr.rs:11-30) */
@@ -250,7 +252,11 @@ typedef struct b2_exec_config {
 enum { B2_JIT_AUTO = 0, B2_JIT_SYNC = 1, B2_JIT_OFF = 2 };
 
 /* ---- results ------------------------------------------------------------------------------ */
-enum { B2_COL_I64 = 0, B2_COL_F64 = 1, B2_COL_DECIMAL = 2 };
+enum { B2_COL_I64 = 0, B2_COL_F64 = 1, B2_COL_DECIMAL = 2,
+       B2_COL_BYTES = 3,    /* VARCHAR / BLOB ...: `offsets` + byte heap (ChunkedVecBytes, chunked_vec_bytes.rs:9-15)      */
+       B2_COL_TIME = 4,     /* DATE / DATETIME / TIMESTAMP: u64 CoreTime bit field (mysql/time/mod.rs:167-196)           */
+       B2_COL_DURATION = 5, /* i64 nanoseconds (mysql/duration.rs)                                                      */
+       B2_COL_JSON = 6 };   /* binary JSON [type code][value] per cell, `offsets` + byte heap (chunked_vec_json.rs)      */
 
 /* #[repr(C)] Decimal, codec/mysql/decimal.rs:927-942 (raw 40 bytes as write_decimal_to_chunk dumps) */
 typedef struct b2_decimal {
@@ -265,8 +271,10 @@ typedef struct b2_column {
   uint32_t field_flag;
   uint32_t _pad;
   uint64_t len;
-  const void* data;           /* len elements of i64 / f64 / b2_decimal; NULL cells hold 0 */
+  const void* data;           /* len elements of i64 / f64 / u64 / b2_decimal (NULL cells hold 0); BYTES / JSON: the byte heap */
   const uint64_t* null_bitmap;/* bit i (word i>>6, bit i&63) = 1 => non-null (bit_vec.rs:25-38) */
+  const int64_t* offsets;     /* BYTES / JSON only: len + 1 offsets into `data`, cell i = data[offsets[i] .. offsets[i+1])
+                                 (the layout of a var-length chunk column, chunk/column.rs:1052-1072); NULL otherwise */
 } b2_column;
 
 enum { B2_DRAIN_REMAIN = 0, B2_DRAIN_DRAINED = 1, B2_DRAIN_PAGING = 2 };

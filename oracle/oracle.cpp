@@ -16,6 +16,7 @@
 
 #include "orc_exec.h"
 #include "orc_encode.h"
+#include "orc_chunk.h"
 #include "orc_gen.h"
 
 using namespace orc;
@@ -26,6 +27,7 @@ struct orc_result {
   std::vector<LazyColumn> cols;       // decoded; ET_DECIMAL cols index into decimals
   std::vector<Decimal> decimals;
   std::vector<std::vector<Decimal>> dec_cols;  // per column decimal cells
+  std::vector<RawChunkCol> raw_cols;           // per column: cells of a column that stayed Raw (bytes, time, duration, decimal, json)
   std::vector<FieldType> schema;
   Statistics stats;
   int met_newer = NEWER_UNKNOWN;
@@ -184,6 +186,7 @@ static int orc_dag_handle_impl(const b2_dag_plan* plan, const b2_key_range* rang
   else for (uint32_t i = 0; i < sch.size(); ++i) offs.push_back(i);
   res->cols.assign(offs.size(), LazyColumn());
   res->dec_cols.assign(offs.size(), std::vector<Decimal>());
+  res->raw_cols.assign(offs.size(), RawChunkCol());
   for (size_t k = 0; k < offs.size(); ++k) { res->schema.push_back(sch[offs[k]]); res->cols[k].decoded = true; res->cols[k].et = eval_type_of(sch[offs[k]].tp); }
   size_t batch_size = BATCH_INITIAL_SIZE;
   AggExecutor* agg = dynamic_cast<AggExecutor*>(root.get());
@@ -199,6 +202,15 @@ static int orc_dag_handle_impl(const b2_dag_plan* plan, const b2_key_range* rang
       LazyColumn& c = b.cols.empty() ? res->cols[k] : b.cols[offs[k]];
       if (b.cols.empty()) break;
       std::string perr;
+      // a column the executors left Raw whose type they never decode goes straight to its chunk cells (Column::from_raw_datums)
+      if (!c.decoded && raw_kind_of(sch[offs[k]].tp) != RK_NONE) {
+        RawChunkCol& rc = res->raw_cols[k];
+        rc.kind = raw_kind_of(sch[offs[k]].tp);
+        bool ok = true;
+        for (size_t r : b.logical_rows) if (!append_raw_datum(rc, c.raw_get(r), sch[offs[k]], &perr)) { ok = false; break; }
+        if (!ok) { if (b.err.ok()) b.err = Error::make(B2_ERR_CORRUPTED, perr); b.logical_rows.clear(); break; }
+        continue;
+      }
       if (!ensure_decoded(c, sch[offs[k]], b.logical_rows, &perr)) { if (b.err.ok()) b.err = Error::make(B2_ERR_CORRUPTED, perr); b.logical_rows.clear(); break; }
     }
     if (!b.cols.empty())
@@ -206,6 +218,7 @@ static int orc_dag_handle_impl(const b2_dag_plan* plan, const b2_key_range* rang
         for (size_t k = 0; k < offs.size(); ++k) {
           const LazyColumn& c = b.cols[offs[k]];
           LazyColumn& o = res->cols[k];
+          if (res->raw_cols[k].kind != RK_NONE) continue;
           o.nn.push_back(c.nn[r]);
           if (c.et == ET_REAL) o.f64.push_back(c.f64[r]);
           else if (c.et == ET_DECIMAL) { res->dec_cols[k].push_back(agg->dec_col[(size_t)c.i64[r]]); o.i64.push_back(0); }
@@ -214,7 +227,7 @@ static int orc_dag_handle_impl(const b2_dag_plan* plan, const b2_key_range* rang
         res->n_rows++;
       }
     if (!keep_rows)
-      for (size_t k = 0; k < offs.size(); ++k) { res->cols[k].nn.clear(); res->cols[k].i64.clear(); res->cols[k].f64.clear(); res->dec_cols[k].clear(); }
+      for (size_t k = 0; k < offs.size(); ++k) { res->cols[k].nn.clear(); res->cols[k].i64.clear(); res->cols[k].f64.clear(); res->dec_cols[k].clear(); res->raw_cols[k].clear(); }
     if (!b.err.ok()) { res->err = b.err; break; }
     if (b.is_drained) break;
     if (batch_size < BATCH_MAX_SIZE) { batch_size *= BATCH_GROW_FACTOR; if (batch_size > BATCH_MAX_SIZE) batch_size = BATCH_MAX_SIZE; }  // runner.rs:1098-1105
@@ -226,6 +239,7 @@ static int orc_dag_handle_impl(const b2_dag_plan* plan, const b2_key_range* rang
   if (keep_rows)  // TypeChunk arm over the rows produced (chunk boundaries are the server's choice: one chunk here)
     for (size_t k = 0; k < offs.size(); ++k) {
       const LazyColumn& c = res->cols[k];
+      if (res->raw_cols[k].kind != RK_NONE) { encode_raw_chunk(res->enc_chunk, res->raw_cols[k]); continue; }
       encode_column_chunk(res->enc_chunk, res->schema[k].tp, c.nn, c.et == ET_REAL ? nullptr : c.i64.data(), c.et == ET_REAL ? c.f64.data() : nullptr,
                           c.et == ET_DECIMAL ? res->dec_cols[k].data() : nullptr);
     }
@@ -238,10 +252,27 @@ int orc_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, uint32_t
 
 uint64_t orc_result_rows(orc_result* r) { return r->n_rows; }
 uint32_t orc_result_cols(orc_result* r) { return (uint32_t)r->cols.size(); }
-int orc_result_col_kind(orc_result* r, uint32_t c) { return r->cols[c].et == ET_REAL ? B2_COL_F64 : (r->cols[c].et == ET_DECIMAL ? B2_COL_DECIMAL : B2_COL_I64); }
+int orc_result_col_kind(orc_result* r, uint32_t c) {
+  switch (r->raw_cols[c].kind) {
+    case RK_BYTES: return B2_COL_BYTES;
+    case RK_TIME: return B2_COL_TIME;
+    case RK_DURATION: return B2_COL_DURATION;
+    case RK_DECIMAL: return B2_COL_DECIMAL;
+    case RK_JSON: return B2_COL_JSON;
+    default: break;
+  }
+  return r->cols[c].et == ET_REAL ? B2_COL_F64 : (r->cols[c].et == ET_DECIMAL ? B2_COL_DECIMAL : B2_COL_I64);
+}
+// cells of a column that stayed Raw: fixed cells (8 / 40 bytes) or byte heap + (rows + 1) offsets
+const uint8_t* orc_result_col_raw(orc_result* r, uint32_t c, uint64_t* data_len, const int64_t** offsets) {
+  const RawChunkCol& rc = r->raw_cols[c];
+  if (rc.kind == RK_NONE) { *data_len = 0; *offsets = nullptr; return nullptr; }
+  *data_len = rc.data.size(); *offsets = rc.var() ? rc.offsets.data() : nullptr;
+  return rc.data.data();
+}
 const int64_t* orc_result_col_i64(orc_result* r, uint32_t c) { return r->cols[c].i64.data(); }
 const double* orc_result_col_f64(orc_result* r, uint32_t c) { return r->cols[c].f64.data(); }
-const uint8_t* orc_result_col_nonnull(orc_result* r, uint32_t c) { return r->cols[c].nn.data(); }
+const uint8_t* orc_result_col_nonnull(orc_result* r, uint32_t c) { return r->raw_cols[c].kind != RK_NONE ? r->raw_cols[c].nn.data() : r->cols[c].nn.data(); }
 const b2_decimal* orc_result_col_decimal(orc_result* r, uint32_t c) { return (const b2_decimal*)r->dec_cols[c].data(); }
 const char* orc_result_decimal_str(orc_result* r, uint32_t c, uint64_t row) { r->dec_str = dec_to_string(r->dec_cols[c][row]); return r->dec_str.c_str(); }
 int orc_result_status(orc_result* r) { return r->err.status; }

@@ -28,7 +28,7 @@ const size_t BATCH_MAX_SIZE = 1024;    // logical_rows.rs:5
 const size_t BATCH_GROW_FACTOR = 2;    // runner.rs:51
 
 enum EvalType { ET_INT, ET_REAL, ET_DECIMAL, ET_OTHER };
-struct FieldType { int tp = 0; uint32_t flag = 0; bool is_unsigned() const { return flag & B2_FLAG_UNSIGNED; } };
+struct FieldType { int tp = 0; uint32_t flag = 0; int decimal = 0; bool is_unsigned() const { return flag & B2_FLAG_UNSIGNED; } };
 
 inline EvalType eval_type_of(int tp) {  // def/eval_type.rs:53-95
   switch (tp) {
@@ -228,7 +228,7 @@ struct TableScanExecutor : Executor {
 
   void init_index(const b2_executor_desc& d) {
     is_index = true;
-    for (uint32_t i = 0; i < d.n_columns; ++i) { FieldType ft; ft.tp = d.columns[i].tp; ft.flag = d.columns[i].flag; schema_.push_back(ft); }
+    for (uint32_t i = 0; i < d.n_columns; ++i) { FieldType ft; ft.tp = d.columns[i].tp; ft.flag = d.columns[i].flag; ft.decimal = d.columns[i].decimal; schema_.push_back(ft); }
     size_t n = d.n_columns;
     idx_physical_table_id = n > 0 && d.columns[n - 1].col_id == B2_EXTRA_PHYSICAL_TABLE_ID_COL_ID;
     size_t tail = idx_physical_table_id ? 1 : 0;
@@ -279,7 +279,7 @@ struct TableScanExecutor : Executor {
     if (d.tp == B2_EXEC_INDEX_SCAN) { init_index(d); return; }
     for (uint32_t i = 0; i < d.n_columns; ++i) {
       const b2_column_info& ci = d.columns[i];
-      FieldType ft; ft.tp = ci.tp; ft.flag = ci.flag;
+      FieldType ft; ft.tp = ci.tp; ft.flag = ci.flag; ft.decimal = ci.decimal;
       schema_.push_back(ft);
       default_val.push_back(ci.default_val ? Bytes(ci.default_val, ci.default_val + ci.default_len) : Bytes());
       if (ci.pk_handle) handle_indices.push_back(i);

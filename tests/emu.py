@@ -38,6 +38,7 @@ def lib():
         L.emu_free.argtypes = [vp]
         L.emu_check_supported.argtypes = [C.POINTER(ffi.DagPlan), C.c_char_p, C.c_size_t]
         L.emu_set_fast_front.argtypes = [C.c_int]
+        L.emu_parse_decimal.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p]
         L.emu_fast_hits.restype = C.c_uint64
         _lib = L
     return _lib
@@ -62,6 +63,11 @@ def _stats(L, h):
     return dict(processed_keys=st[0], processed_size=st[1], met_newer=st[2], default_lookups=st[3], checksum=st[4], total_kvs=st[5], total_bytes=st[6])
 
 
+def plan_scan_only(plan):
+    """No aggregation in the plan: a DECIMAL output column is a stored column (cell references), not a SUM result."""
+    return all(plan.c.executors[i].tp not in (ffi.EXEC_AGGREGATION, ffi.EXEC_STREAM_AGG) for i in range(plan.c.n_executors))
+
+
 def dag_handle(plan, ranges, region):
     import struct
     L = lib()
@@ -73,7 +79,24 @@ def dag_handle(plan, ranges, region):
         kind = L.emu_col_kind(h, c)
         nn = L.emu_col_nonnull(h, c)
         d = L.emu_col_data(h, c)
-        if kind == ffi.COL_F64:
+        if kind in (ffi.COL_BYTES, ffi.COL_JSON) or (kind == ffi.COL_DECIMAL and plan_scan_only(plan)):
+            # the kernels leave cell references (address << 16 | length); the raw_* kernels of the device path resolve them
+            from tikv_b200.executor import _decimal_value
+            vals = []
+            for i in range(n):
+                if not nn[i]:
+                    vals.append(None)
+                    continue
+                cell = C.string_at(d[i] >> 16, d[i] & 0xffff)
+                if kind == ffi.COL_DECIMAL:
+                    out = (C.c_uint8 * 40)()
+                    assert L.emu_parse_decimal(cell, len(cell), out) == 1, cell
+                    vals.append(_decimal_value(bytes(out)))
+                else:
+                    vals.append(cell)
+        elif kind == ffi.COL_TIME:
+            vals = [d[i] if nn[i] else None for i in range(n)]
+        elif kind == ffi.COL_F64:
             vals = [struct.unpack("<d", struct.pack("<Q", d[i]))[0] if nn[i] else None for i in range(n)]
         elif kind == ffi.COL_DECIMAL:
             raw = L.emu_col_dec(h, c)

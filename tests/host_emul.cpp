@@ -153,6 +153,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
           ++fi;
           row.enc_key = blk.kptr(e); row.enc_key_len = 27; row.commit_ts = key_tail_commit_ts(lo.tail);
           bool ok = fast_row_v2(P, blk.vptr(e) + lo.row_off, lo.row_len, row);
+          row.gv = blk.vptr(e) + lo.row_off;
           if (ok) { row.filled = P.fast_filled; ok = eval_conds(P, row, cells, &keep) == 0; }
           if (!ok) {  // the row needs the general decoder: the lane pushes its run start instead of committing
             todo.insert(std::upper_bound(todo.begin() + ti, todo.end(), e - lo.push_back), e - lo.push_back);
@@ -175,7 +176,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
         row.enc_key = blk.keys + ko; row.enc_key_len = kl - 8; row.commit_ts = ro.commit_ts;
         int er;
         if (P.idx_cols > 0) er = index_row_split(P, row, cells, ro.val, ro.val_len, idx_buf);
-        else { er = row_open(ro.val, ro.val_len, &row.rv); if (!er) er = row_split(P, row, cells); }
+        else { er = row_open(ro.val, ro.val_len, &row.rv); row.gv = ro.val; if (!er) er = row_split(P, row, cells); }
         if (!er) er = eval_conds(P, row, cells, &keep);
         if (er) { report(bases[b] + e, er); continue; }
         }
@@ -433,6 +434,7 @@ void emu_stats(emu_result* r, uint64_t* out7) {
   out7[0] = r->processed_keys; out7[1] = r->processed_size; out7[2] = r->met_newer; out7[3] = r->dflt;
   out7[4] = r->checksum; out7[5] = r->total_kvs; out7[6] = r->total_bytes;
 }
+int emu_parse_decimal(const uint8_t* p, uint32_t n, b2_decimal* out) { return raw_decimal_parse(p, n, out) ? 1 : 0; }
 void emu_free(emu_result* r) { delete r; }
 int emu_check_supported(const b2_dag_plan* plan, char* msg, size_t cap) {
   CompiledPlan cp; std::string m;

@@ -131,6 +131,75 @@ def datum_bytes(b):
     return bytes([COMPACT_BYTES]) + enc_var_i64(len(b)) + b
 
 
+# ---- non Int/Real cells (codec/mysql/{decimal,time,duration,json}) ----
+_DIG2BYTES = [0, 1, 1, 2, 2, 3, 3, 4, 4, 4]
+
+
+def decimal_bin(value, prec, frac):
+    """decimal.rs write_decimal (:2025-2132) for a value that fits (prec, frac): [prec, frac, MySQL binary decimal].
+    `value` is a decimal.Decimal / int / str."""
+    import decimal
+    ctx = decimal.Context(prec=200)
+    d = ctx.create_decimal(value)
+    neg = d < 0
+    q = d.copy_abs().quantize(decimal.Decimal(1).scaleb(-frac, ctx), context=ctx) if frac else d.copy_abs().to_integral_value(context=ctx)
+    digits = f"{q:f}"
+    ip, _, fp = digits.partition(".")
+    ip = ip.lstrip("0")
+    int_cnt = prec - frac
+    assert len(ip) <= int_cnt and len(fp) == frac, (value, prec, frac)
+    ip = ip.rjust(int_cnt, "0")
+    out = bytearray()
+    lead = int_cnt % 9
+    if lead:
+        out += int(ip[:lead]).to_bytes(_DIG2BYTES[lead], "big")
+    for i in range(lead, int_cnt, 9):
+        out += int(ip[i:i + 9]).to_bytes(4, "big")
+    full = frac // 9 * 9
+    for i in range(0, full, 9):
+        out += int(fp[i:i + 9]).to_bytes(4, "big")
+    if frac % 9:
+        out += int(fp[full:]).to_bytes(_DIG2BYTES[frac % 9], "big")
+    if neg and any(out):
+        out = bytearray(b ^ 0xFF for b in out)
+    out[0] ^= 0x80
+    return bytes([prec, frac]) + bytes(out)
+
+
+def time_packed(year, month, day, hour=0, minute=0, second=0, micro=0):
+    """Time::to_packed_u64 (mysql/time/mod.rs:2045-2074)."""
+    ymd = ((year * 13 + month) << 5) | day
+    hms = (hour << 12) | (minute << 6) | second
+    return (((ymd << 17) | hms) << 24) | micro
+
+
+def time_bits(year, month, day, hour=0, minute=0, second=0, micro=0, fsp=0, date=False):
+    """The CoreTime bit field of a chunk cell (mysql/time/mod.rs:167-196), written independently of the decoders."""
+    return (year << 50) | (month << 46) | (day << 41) | (hour << 36) | (minute << 30) | (second << 24) | (micro << 4) | (0b1110 if date else fsp << 1)
+
+
+def json_string(sv):
+    """binary JSON string: type code 0x0c, varint length, bytes (mysql/json/binary.rs)."""
+    b = sv.encode()
+    return bytes([0x0C]) + enc_var_u64(len(b)) + b
+
+
+def json_i64(v):
+    return bytes([0x09]) + struct.pack("<q", v)
+
+
+def datum_decimal(value, prec, frac):
+    return bytes([6]) + decimal_bin(value, prec, frac)
+
+
+def datum_time(packed, comparable=False):
+    return datum_uint(packed, comparable)
+
+
+def datum_duration(nanos, fixed=False):
+    return bytes([7]) + enc_i64_cmp(nanos) if fixed else bytes([VAR_INT]) + enc_var_i64(nanos)
+
+
 def row_v1(cols):
     """cols: list of (col_id, datum_bytes)."""
     out = bytearray()
@@ -167,6 +236,12 @@ def row_v2(cols, checksum=None):
             vals.append(enc_f64_cmp(v))
         elif k == "bytes":
             vals.append(bytes(v))
+        elif k == "time":      # packed u64, compact unsigned (compat_v1.rs:83-90)
+            vals.append(_v2_int(v, True))
+        elif k == "duration":  # nanoseconds, compact signed (:94-100)
+            vals.append(_v2_int(v, False))
+        elif k == "decimal":   # (value, prec, frac) -> [prec, frac, bin] (:101-105)
+            vals.append(decimal_bin(*v))
         else:
             raise ValueError(k)
     total = sum(len(x) for x in vals)

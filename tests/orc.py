@@ -25,6 +25,7 @@ def lib():
         L.orc_result_col_i64.argtypes = [vp, C.c_uint32]; L.orc_result_col_i64.restype = C.POINTER(C.c_int64)
         L.orc_result_col_f64.argtypes = [vp, C.c_uint32]; L.orc_result_col_f64.restype = C.POINTER(C.c_double)
         L.orc_result_col_nonnull.argtypes = [vp, C.c_uint32]; L.orc_result_col_nonnull.restype = C.POINTER(C.c_uint8)
+        L.orc_result_col_raw.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.POINTER(C.c_int64))]; L.orc_result_col_raw.restype = C.c_void_p
         L.orc_result_decimal_str.argtypes = [vp, C.c_uint32, C.c_uint64]; L.orc_result_decimal_str.restype = C.c_char_p
         L.orc_result_status.argtypes = [vp]
         L.orc_result_mysql_code.argtypes = [vp]
@@ -90,6 +91,14 @@ def dag_handle(plan, ranges, region):
     for c in range(L.orc_result_cols(h)):
         kind = L.orc_result_col_kind(h, c)
         nn = L.orc_result_col_nonnull(h, c)
+        raw_len, offs = C.c_uint64(), C.POINTER(C.c_int64)()
+        raw = L.orc_result_col_raw(h, c, C.byref(raw_len), C.byref(offs))
+        if raw:  # a column that stayed Raw up to the response: chunk cells (bytes / json / time bits / duration / decimal struct)
+            from tikv_b200.executor import raw_cell_values
+            o = [offs[i] for i in range(n + 1)] if offs else None
+            cols.append(raw_cell_values(kind, C.string_at(raw, raw_len.value), o, [bool(nn[i]) for i in range(n)]))
+            kinds.append(kind)
+            continue
         if kind == ffi.COL_F64:
             p = L.orc_result_col_f64(h, c)
             vals = [p[i] if nn[i] else None for i in range(n)]

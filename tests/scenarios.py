@@ -520,3 +520,120 @@ def check_reference_fixture(fx, run):
         key = lambda r: tuple((0, 0) if v is None else (1, v) for v in r)
         rows, exp = sorted(rows, key=key), sorted(exp, key=key)
     assert rows == exp, f"{name}: {rows} != reference {exp}"
+
+
+# ---- tables with bytes / time / duration / decimal / json columns (they stay Raw in the reference until the response) ------
+MIXED_COLUMNS = [
+    ColumnDef(100, pk_handle=True),
+    ColumnDef(1),                                   # BIGINT
+    ColumnDef(2, tp=ffi.TP_VARCHAR),
+    ColumnDef(3, tp=ffi.TP_DATETIME, decimal=3),
+    ColumnDef(4, tp=ffi.TP_DATE),
+    ColumnDef(5, tp=ffi.TP_NEWDECIMAL),
+    ColumnDef(6, tp=ffi.TP_DURATION, decimal=2),
+    ColumnDef(7, tp=ffi.TP_JSON),
+    ColumnDef(8, tp=ffi.TP_DOUBLE),
+    ColumnDef(9, tp=ffi.TP_BLOB),
+]
+M_H, M_INT, M_STR, M_DT, M_DATE, M_DEC, M_DUR, M_JSON, M_F64, M_BLOB = range(10)
+
+
+def mixed_region(seed, n_keys=700, json_in_v1=False):
+    """Rows of MIXED_COLUMNS in row formats v2 and v1 (v1 rows carry no JSON cell: the device does not size binary JSON
+    datums), with NULLs, empty and long strings, zero dates, negative / fractional decimals, several versions per key and a
+    few long values in CF_DEFAULT."""
+    rng = random.Random(seed)
+    r = kvfmt.Region()
+
+    def cells(fmt):
+        out = {}
+        out[1] = None if rng.random() < 0.1 else rng.randrange(-1000, 1000)
+        out[2] = None if rng.random() < 0.1 else bytes(rng.randrange(32, 127) for _ in range(rng.choice([0, 1, 3, 8, 9, 40, 300])))
+        out[3] = None if rng.random() < 0.1 else (0 if rng.random() < 0.1 else kvfmt.time_packed(rng.randrange(1000, 9999), rng.randrange(1, 13), rng.randrange(1, 29), rng.randrange(24), rng.randrange(60), rng.randrange(60), rng.randrange(1000) * 1000))
+        out[4] = None if rng.random() < 0.1 else (0 if rng.random() < 0.1 else kvfmt.time_packed(rng.randrange(1, 9999), rng.randrange(1, 13), rng.randrange(1, 29)))
+        if rng.random() < 0.1:
+            out[5] = None
+        else:
+            prec, frac = rng.choice([(1, 0), (9, 0), (10, 2), (14, 4), (18, 9), (30, 10), (65, 30), (5, 5)])
+            digs = "".join(rng.choice("0123456789") for _ in range(prec)) if rng.random() < 0.9 else "0" * prec
+            txt = (digs[:prec - frac] or "0") + ("." + digs[prec - frac:] if frac else "")
+            out[5] = (("-" if rng.random() < 0.5 else "") + txt, prec, frac)
+        out[6] = None if rng.random() < 0.1 else rng.choice([0, 1, -1, 10 ** 9, -3 * 10 ** 12, rng.randrange(-10 ** 15, 10 ** 15)])
+        out[7] = None if rng.random() < 0.2 else rng.choice([kvfmt.json_string("x" * rng.randrange(0, 50)), kvfmt.json_i64(rng.randrange(-5, 5)), bytes([0x04, 0x01])])
+        out[8] = None if rng.random() < 0.1 else rng.uniform(-5, 5)
+        out[9] = None if rng.random() < 0.3 else bytes(rng.randrange(256) for _ in range(rng.choice([0, 5, 17, 700])))
+        if fmt == 2:
+            kinds = {1: "int", 2: "bytes", 3: "time", 4: "time", 5: "decimal", 6: "duration", 7: "bytes", 8: "f64", 9: "bytes"}
+            return kvfmt.row_v2([(cid, v, kinds[cid]) for cid, v in out.items()])
+        d = []
+        for cid, v in out.items():
+            if cid == 7 and not json_in_v1:
+                continue
+            if v is None:
+                if rng.random() < 0.5:
+                    d.append((cid, kvfmt.datum_null()))
+                continue  # (a missing cell of a nullable column is NULL as well)
+            enc = {1: lambda: kvfmt.datum_int(v), 2: lambda: kvfmt.datum_bytes(v), 3: lambda: kvfmt.datum_time(v), 4: lambda: kvfmt.datum_time(v, comparable=rng.random() < 0.3),
+                   5: lambda: kvfmt.datum_decimal(*v), 6: lambda: kvfmt.datum_duration(v, fixed=rng.random() < 0.5), 7: lambda: bytes([10]) + v,
+                   8: lambda: kvfmt.datum_f64(v), 9: lambda: kvfmt.datum_bytes(v)}[cid]()
+            d.append((cid, enc))
+        rng.shuffle(d)
+        return kvfmt.row_v1(d)
+
+    for h in range(n_keys):
+        key = kvfmt.row_key(TABLE, h * 2 - 50)
+        fmt = 2 if rng.random() < 0.6 else 1
+        shape = rng.random()
+        if shape < 0.7:
+            r.put(key, cells(fmt), 10, 20)
+        elif shape < 0.85:
+            r.put(key, cells(fmt), 5, 8)
+            r.put(key, cells(fmt), 10, 20)
+            r.put(key, cells(fmt), READ_TS + 5, READ_TS + 9)
+        elif shape < 0.92:
+            r.put(key, cells(fmt), 10, 20)
+            r.delete(key, 30, 40)
+        else:
+            r.put(key, cells(fmt), 10, 20, force_long=True)
+    return r
+
+
+def mixed_plans():
+    scan = lambda: Plan().table_scan(TABLE, MIXED_COLUMNS)
+    return [("mixed_all", scan().build()),
+            ("mixed_sel", scan().selection(lt(col(M_INT), const_int(0))).build(output_offsets=[M_STR, M_H, M_DEC, M_DT, M_JSON])),
+            ("mixed_sel_real_limit", scan().selection(gt(col(M_F64, tp=ffi.TP_DOUBLE), const_real(0.0))).limit(120).build(output_offsets=[M_BLOB, M_DATE, M_DUR, M_INT])),
+            ("mixed_only_fixed", scan().build(output_offsets=[M_DT, M_DATE, M_DUR, M_H])),
+            ("mixed_only_strings", scan().build(output_offsets=[M_STR, M_BLOB, M_JSON]))]
+
+
+# The reference's own 12-column row (row/v2/encoder_for_test.rs:560-588 `test_encode`): the expected bytes of that test
+# are the stored row value here; the values are the ones the test encodes.
+REF_MIXED_ROW = bytes([
+    128, 0, 11, 0, 1, 0, 1, 3, 6, 7, 8, 9, 12, 13, 14, 15, 16, 33, 2, 0, 3, 0, 11, 0, 14, 0, 16, 0, 24, 0, 25, 0, 33, 0, 36, 0, 65, 0, 69, 0, 232, 3, 3, 64, 3, 51, 51, 51, 51,
+    51, 50, 97, 98, 99, 255, 127, 191, 252, 204, 204, 204, 204, 204, 205, 2, 0, 0, 0, 135, 51, 230, 158, 25, 1, 0, 129, 1, 1, 0, 0, 0, 28, 0, 0, 0, 19, 0, 0, 0, 3, 0, 12, 22, 0,
+    0, 0, 107, 101, 121, 5, 118, 97, 108, 117, 101, 0, 202, 154, 59])
+REF_MIXED_COLUMNS = [ColumnDef(1), ColumnDef(12), ColumnDef(33), ColumnDef(3, unsigned=True), ColumnDef(8), ColumnDef(7, tp=ffi.TP_VARCHAR), ColumnDef(9, tp=ffi.TP_DOUBLE),
+                     ColumnDef(6, tp=ffi.TP_DOUBLE), ColumnDef(13, tp=ffi.TP_DATETIME), ColumnDef(14, tp=ffi.TP_NEWDECIMAL), ColumnDef(15, tp=ffi.TP_JSON),
+                     ColumnDef(16, tp=ffi.TP_DURATION), ColumnDef(100, pk_handle=True)]
+REF_MIXED_JSON = bytes([1, 1, 0, 0, 0, 28, 0, 0, 0, 19, 0, 0, 0, 3, 0, 12, 22, 0, 0, 0, 107, 101, 121, 5, 118, 97, 108, 117, 101])  # {"key":"value"}
+REF_MIXED_VALUES = (1000, 2, None, 3, 32767, b"abc", 1.8, -1.8, kvfmt.time_bits(2018, 1, 19, 3, 14, 7), 1, REF_MIXED_JSON, 10 ** 9, 7)
+
+
+def ref_mixed_region():
+    r = kvfmt.Region()
+    r.put(kvfmt.row_key(TABLE, 7), REF_MIXED_ROW, 10, 20)
+    return r
+
+
+def check_mixed(run, seed=1, n_keys=700):
+    """Every mixed_plans() result of `run(plan, ranges, region)` equals the oracle's, cell for cell."""
+    import orc
+    region = mixed_region(seed, n_keys).build(read_ts=READ_TS, n_write_blocks=2)
+    for name, plan in mixed_plans():
+        exp = orc.dag_handle(plan, WHOLE, region)
+        got = run(plan, WHOLE, region)
+        assert exp.status == 0 and exp.n_rows > 50, (name, exp.status, exp.message)
+        assert got.status == 0, (name, got.status, got.message)
+        assert got.kinds == exp.kinds, (name, got.kinds, exp.kinds)
+        assert got.rows() == exp.rows(), name

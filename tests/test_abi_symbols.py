@@ -34,11 +34,11 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_abi_version_and_structs(lib):
     from tikv_b200 import ffi
-    assert lib.b2_abi_version() == 2
+    assert lib.b2_abi_version() == 3
     assert b"sm_100a" in lib.b2_build_info()
     # struct sizes the Rust/cgo side would mirror
     assert C.sizeof(ffi.Decimal) == 40 and C.sizeof(ffi.CfBlock) == 40 and C.sizeof(ffi.RpnNode) == 40
-    assert C.sizeof(ffi.Column) == 40 and C.sizeof(ffi.ChecksumResponse) == 24
+    assert C.sizeof(ffi.Column) == 48 and C.sizeof(ffi.ColumnInfo) == 40 and C.sizeof(ffi.ChecksumResponse) == 24
 
 
 def test_sass_is_sm100a(lib):
@@ -55,7 +55,8 @@ def test_check_supported_without_gpu(lib):
     cols = [ColumnDef(1, pk_handle=True), ColumnDef(2), ColumnDef(3, tp=ffi.TP_VARCHAR)]
     ok = Plan().table_scan(5, cols).selection(lt(col(1), const_int(3))).build(output_offsets=[0, 1])
     assert lib.b2_check_supported(C.byref(ok.c)) == ffi.B2_OK
-    bad = Plan().table_scan(5, cols).build()
+    assert lib.b2_check_supported(C.byref(Plan().table_scan(5, cols).build().c)) == ffi.B2_OK  # VARCHAR output: materialised since ABI 3
+    bad = Plan().table_scan(5, cols).selection(lt(col(2), const_int(3))).build()
     assert lib.b2_check_supported(C.byref(bad.c)) == ffi.B2_ERR_UNSUPPORTED
     assert b"Int/Real" in lib.b2_last_error_message()
 

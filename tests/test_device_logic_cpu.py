@@ -134,7 +134,8 @@ def test_check_supported_mirrors_runner():
     cols = [ColumnDef(1, pk_handle=True), ColumnDef(2), ColumnDef(3, tp=ffi.TP_VARCHAR)]
     ok = Plan().table_scan(5, cols).selection(lt(col(1), const_int(3))).build(output_offsets=[0, 1])
     assert emu.check_supported(ok)[0] == 0
-    assert emu.check_supported(Plan().table_scan(5, cols).build())[0] == ffi.B2_ERR_UNSUPPORTED  # varchar output
+    assert emu.check_supported(Plan().table_scan(5, cols).build())[0] == ffi.B2_OK  # varchar output: materialised since ABI 3
+    assert emu.check_supported(Plan().table_scan(5, cols + [ColumnDef(4, tp=ffi.TP_ENUM)]).build())[0] == ffi.B2_ERR_UNSUPPORTED  # enum output
     assert emu.check_supported(Plan().table_scan(5, cols, desc=True).build(output_offsets=[0]))[0] == ffi.B2_OK  # backward scans are on the device path
     two = Plan().table_scan(5, cols).aggregation([("count", const_int(1))], group_by=[col(0), col(1)]).build()
     assert emu.check_supported(two)[0] == 0  # BatchSlowHashAggregation: up to 4 Int / Real expressions

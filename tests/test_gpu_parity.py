@@ -901,3 +901,36 @@ def test_index_scan_matches_oracle():
     rec = kvfmt.Region()
     rec.put(kvfmt.row_key(T2, 1), kvfmt.row_v2([(1, 5, "int")]), 1, 2)
     assert DagHandler(Plan().index_scan(T2, c2).build(), [kvfmt.table_range(T2)], rec.build(read_ts=10)).handle_request().status == ffi.B2_ERR_CORRUPTED
+
+
+# ---- bytes / time / duration / decimal / json output columns ---------------------------------------------
+def test_reference_mixed_row_on_the_device():
+    """The reference's own 12-column v2 row (encoder_for_test.rs:560-588) through the CUDA path: the values that test
+    encoded, and a TypeChunk block byte-identical to the oracle's."""
+    host = sc.ref_mixed_region().build(read_ts=sc.READ_TS)
+    plan = Plan().table_scan(sc.TABLE, sc.REF_MIXED_COLUMNS).build()
+    for region in (host, DeviceRegion(host)):
+        got = DagHandler(plan, sc.WHOLE, region).handle_request()
+        assert got.status == 0, got.message
+        assert got.rows() == [sc.REF_MIXED_VALUES]
+    with BatchExecutor(plan, sc.WHOLE, host) as ex:
+        r = ex.next_batch(1 << 20)
+        assert r.error is None and r.n_rows == 1
+        assert ex.encode_batch(ffi.ENCODE_TYPE_CHUNK) == orc.dag_handle(plan, sc.WHOLE, host).encoded[1]
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_mixed_tables_match_oracle(seed):
+    """Scans of a table with VARCHAR / BLOB / DATETIME / DATE / DECIMAL / DURATION / JSON columns (rows in both formats,
+    NULLs, empty and 700-byte strings, values in CF_DEFAULT): every cell equals the oracle's, host- and device-resident
+    sources, small batches and one big one; the TypeChunk encoding of the whole result is byte-identical."""
+    sc.check_mixed(lambda plan, ranges, region: DagHandler(plan, ranges, region).handle_request(), seed=seed)
+    sc.check_mixed(lambda plan, ranges, region: DagHandler(plan, ranges, DeviceRegion(region), batch_rows=97).handle_request(), seed=seed)
+    host = sc.mixed_region(seed).build(read_ts=sc.READ_TS, n_write_blocks=2)
+    for name, plan in sc.mixed_plans():
+        if "limit" in name:
+            continue
+        with BatchExecutor(plan, sc.WHOLE, DeviceRegion(host)) as ex:
+            r = ex.next_batch(1 << 22)
+            assert r.error is None and r.is_drained
+            assert ex.encode_batch(ffi.ENCODE_TYPE_CHUNK) == orc.dag_handle(plan, sc.WHOLE, host).encoded[1], name

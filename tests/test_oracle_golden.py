@@ -5,6 +5,7 @@ import struct
 
 import pytest
 
+import emu
 import kvfmt
 import orc
 from tikv_b200 import ffi
@@ -764,3 +765,62 @@ def test_index_scan_device_logic():
                  Plan().index_scan(T, cols).aggregation([("count", const_int(1)), ("sum", col(0))], group_by=[col(1, unsigned=True)]).build()):
         exp, got = orc.dag_handle(plan, whole, region), emu.dag_handle(plan, whole, region)
         assert got.status == 0 == exp.status and sorted(got.rows(), key=repr) == sorted(exp.rows(), key=repr) and exp.n_rows > 5
+
+
+# ---- bytes / time / duration / decimal / json columns ---------------------------------------------------------------------
+def test_reference_mixed_row_decodes_to_the_encoded_values():
+    """The expected bytes of the reference's own `test_encode` (row/v2/encoder_for_test.rs:560-588: Int, unsigned, NULL,
+    bytes, f64, DATETIME, DECIMAL, JSON, DURATION in one v2 row) scanned back: the oracle, and the emulated device logic,
+    return the values that test encoded — the DATETIME as the CoreTime bit field of 2018-01-19 03:14:07 written out by hand
+    here, the decimal as 1, the JSON document and the duration (1 s = 1e9 ns) byte for byte."""
+    region = sc.ref_mixed_region().build(read_ts=sc.READ_TS)
+    plan = Plan().table_scan(sc.TABLE, sc.REF_MIXED_COLUMNS).build()
+    for run in (orc.dag_handle, emu.dag_handle):
+        res = run(plan, sc.WHOLE, region)
+        assert res.status == 0, res.message
+        assert res.rows() == [sc.REF_MIXED_VALUES], run.__module__
+    assert res.kinds == [ffi.COL_I64] * 5 + [ffi.COL_BYTES, ffi.COL_F64, ffi.COL_F64, ffi.COL_TIME, ffi.COL_DECIMAL, ffi.COL_JSON, ffi.COL_DURATION, ffi.COL_I64]
+
+
+def test_decimal_cells_known_answers():
+    """MySQL's documented binary decimal example (1234567890.1234 as DECIMAL(14,4) is 81 0D FB 38 D2 04 D2, its negation
+    the byte-wise complement) and edge shapes, through the oracle's read_decimal and the device's raw_decimal_parse."""
+    import decimal
+    assert kvfmt.decimal_bin("1234567890.1234", 14, 4).hex() == "0e04810dfb38d204d2"
+    assert kvfmt.decimal_bin("-1234567890.1234", 14, 4).hex() == "0e047ef204c72dfb2d"
+    cases = [("1234567890.1234", 14, 4), ("-1234567890.1234", 14, 4), ("0", 1, 0), ("-0.5", 2, 1), ("0.000000001", 18, 9), ("99999.99999", 10, 5),
+             ("-123456789012345678901234567890.123456789012345678901234567890", 65, 30), ("0.00", 5, 2), ("1", 65, 0), ("-0.99999", 5, 5)]
+    cols = [ColumnDef(100, pk_handle=True), ColumnDef(1, tp=ffi.TP_NEWDECIMAL)]
+    r = kvfmt.Region()
+    for i, (v, p, f) in enumerate(cases):
+        r.put(kvfmt.row_key(sc.TABLE, i), kvfmt.row_v2([(1, (v, p, f), "decimal")]) if i % 2 else kvfmt.row_v1([(1, kvfmt.datum_decimal(v, p, f))]), 10, 20)
+    region = r.build(read_ts=sc.READ_TS)
+    plan = Plan().table_scan(sc.TABLE, cols).build(output_offsets=[1])
+    big = decimal.Context(prec=200)
+    for run in (orc.dag_handle, emu.dag_handle):
+        got = [x[0] for x in run(plan, sc.WHOLE, region).rows()]
+        assert [big.create_decimal(g) for g in got] == [big.create_decimal(v) for v, p, f in cases], run.__module__
+
+
+def test_mixed_tables_device_logic_matches_oracle():
+    """Tables with bytes / DATETIME / DATE / DECIMAL / DURATION / JSON columns, rows in both formats, NULLs, long values:
+    the emulated device logic (cell references resolved on the host) against the oracle's from_raw_datums restatement."""
+    for seed in (1, 2):
+        sc.check_mixed(emu.dag_handle, seed=seed, n_keys=500)
+
+
+def test_mixed_table_unsupported_shapes_are_refused():
+    """What the device path does not materialise is refused when the plan is checked (the caller keeps its CPU executor):
+    TIMESTAMP (session time zone), TopN over bytes columns, backward scans with bytes columns, expressions over them."""
+    L = ffi.lib()
+    scan = lambda cols=sc.MIXED_COLUMNS, **kw: Plan().table_scan(sc.TABLE, cols, **kw)
+    bad = [scan().topn([(col(sc.M_INT), False)], 5).build(),
+           scan(desc=True).build(),
+           scan().selection(lt(col(sc.M_DUR), const_int(0))).build(),
+           scan([ColumnDef(100, pk_handle=True), ColumnDef(1, tp=ffi.TP_TIMESTAMP)]).build()]
+    for p in bad:
+        assert L.b2_check_supported(C.byref(p.c)) == ffi.B2_ERR_UNSUPPORTED
+    ok = [scan().build(), scan(desc=True).build(output_offsets=[sc.M_DT, sc.M_DUR, sc.M_INT]),
+          scan().aggregation([("sum", col(sc.M_INT))], group_by=[col(sc.M_INT)]).build()]
+    for p in ok:
+        assert L.b2_check_supported(C.byref(p.c)) == ffi.B2_OK, L.b2_last_error_message()

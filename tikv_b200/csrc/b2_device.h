@@ -54,6 +54,7 @@ enum DevErr {
   DE_OVERFLOW_DIV = 23,      // 1690 "UNSIGNED BIGINT" (codec/overflow.rs:9-58: every integer-division overflow says so)
   DE_UNSUPPORTED_SIG = 30,
   DE_UNSUPPORTED_TYPE = 31,  // row holds a type the device path does not materialise
+  DE_RAW_TOO_LONG = 32,      // bytes / json / decimal cell of 64 KiB or more (cell references carry 16 length bits)
   DE_IDX_BAD_KEY = 40,       // check_index_key (table.rs:114-140): not 't' tid "_i" idx ...
   DE_IDX_MISSING_COL = 41,   // "{i}th column is missing value" (index_scan_executor.rs:493-506)
   DE_IDX_BAD_HANDLE = 42,    // handle flag / length (index_scan_executor.rs:406-412, 451-471)
@@ -61,7 +62,12 @@ enum DevErr {
 };
 
 // ---- plan as seen by the kernels ----
-enum ColKind { CK_INT = 0, CK_REAL = 1, CK_OTHER = 2 };
+enum ColKind { CK_INT = 0, CK_REAL = 1, CK_OTHER = 2,
+               // never evaluated, only materialised (they stay LazyBatchColumn::Raw in the reference until the response is encoded):
+               CK_TIME = 3,   // DATE / DATETIME -> u64 CoreTime bits (Time::from_packed_u64, mysql/time/mod.rs:2002-2043)
+               CK_DUR = 4,    // DURATION -> i64 nanoseconds
+               CK_BYTES = 5, CK_JSON = 6, CK_DEC = 7 };  // cell reference (address << 16 | length) resolved after the scan kernel
+B2_HD bool ck_is_ref(int k) { return k >= CK_BYTES; }
 enum ColRole { CR_NORMAL = 0, CR_HANDLE = 1, CR_TABLE_ID = 2, CR_COMMIT_TS = 3, CR_SHADOWED = 4 /* duplicate col id: never filled */,
                CR_IDX_HANDLE = 5 /* BatchIndexScan: the int handle, from the key tail (non-unique index) or the value (unique) */ };
 enum V2Class { V2_INT = 0, V2_UINT = 1, V2_COPY = 2, V2_BYTES = 3, V2_NIL = 4, V2_UNSUPPORTED = 5 };  // write_v2_as_datum arms
@@ -71,6 +77,7 @@ struct DevCol {
   int64_t col_id;
   int64_t default_bits;
   uint8_t kind, role, is_unsigned, not_null, tp, v2_class, def_state, v2_hint;
+  uint8_t fsp, _p[7];  // CK_TIME: fractional-second digits of the column (tipb ColumnInfo.decimal, -1 -> 0)
 };
 struct DevNode {
   int32_t sig;   // FN: tipb ScalarFuncSig.  Constant: 0 = the value is `imm`; s > 0 = the value is launch parameter imms[s - 1]
@@ -131,7 +138,7 @@ struct DevPlan {
   uint8_t out_cols[MAX_COLS];
   uint8_t out_slow[MAX_COLS];  // indices into out_cols
   int32_t n_fconds;            // == n_conds when every condition is a FastCond (else 0)
-  int32_t _fcpad;
+  int32_t n_raw;               // PM_SCAN: output columns that are cell references (bytes / json / decimal), resolved by the raw_* kernels
   FastCond fconds[MAX_CONDS];
   int32_t n_proj;              // BatchProjectionExecutor on top: out_cols index `proj`, every output is an expression value
   int32_t _prpad;
@@ -158,6 +165,7 @@ struct BlockView {
   B2_HD uint32_t klen(uint32_t i) const { return koff[i + 1] - koff[i]; }
   B2_HD const uint8_t* vptr(uint32_t i) const { return vals + voff[i]; }
   B2_HD uint32_t vlen(uint32_t i) const { return voff[i + 1] - voff[i]; }
+  B2_HD const uint8_t* gval(const uint8_t* p) const { return p; }  // a value byte's address in HBM (the view is the HBM heap itself)
 };
 
 // ---- byte access -------------------------------------------------------------------------------
@@ -706,6 +714,8 @@ struct Row {
   const int64_t* imms;  // the request's hoisted constants (ScanArgs::imms: kernel parameter space on the device)
   uint64_t cv[8];       // lean kernels, plan-specialised builds: the integer cells of the stored columns the plan's expressions
   uint32_t cv_mask = 0; //   read (DevPlan::fast_need), decoded once per row; bit h set = cv[h] is valid
+  const uint8_t* gv = nullptr;  // address of rv.v[0] in the block's HBM heap (rv.v may be a shared-memory copy): what the cell
+                                //   references of bytes / json / decimal columns are made of (set only when the plan has such columns)
   mutable uint32_t warn = 0;  // EvalWarnings raised while evaluating expressions on this row ("Division by 0", expr/ctx.rs:267-286);
                               // counted into the request only when the row's tile is committed
 };
@@ -1208,6 +1218,120 @@ B2_HD int index_row_split(const DevPlan& P, Row& row, Cells& cells, const uint8_
 
 struct Value { uint64_t bits; bool null; };
 
+// Time::from_packed_u64 (mysql/time/mod.rs:2002-2043) for DATE / DATETIME: packed = ((y * 13 + m) << 5 | d) << 17 | h << 12 | mi << 6 | s,
+// then << 24 | micro; the result is the CoreTime bit field (:167-196): year 63..50, month 49..46, day 45..41, hour 40..36,
+// minute 35..30, second 29..24, micro 23..4, fsp_tt 3..0 (Date = 0b1110, DateTime = fsp << 1).  Zero stays all-zero fields.
+B2_HD uint64_t time_bits_from_packed(uint64_t value, bool is_date, uint32_t fsp) {
+  const uint64_t fsp_tt = is_date ? 0xeull : ((uint64_t)fsp << 1);
+  if (value == 0) return fsp_tt;
+  const uint64_t ymdhms = value >> 24, ymd = ymdhms >> 17, ym = ymd >> 5, hms = ymdhms & 0x1ffffu;
+  const uint64_t day = ymd & 31, month = ym % 13, year = ym / 13, second = hms & 63, minute = (hms >> 6) & 63, hour = hms >> 12, micro = value & 0xffffffu;
+  return ((year & 0x3fff) << 50) | ((month & 15) << 46) | ((day & 31) << 41) | ((hour & 31) << 36) | ((minute & 63) << 30) | ((second & 63) << 24) |
+         ((micro & 0xfffff) << 4) | fsp_tt;
+}
+// DecimalDecoder::read_decimal (mysql/decimal.rs:2204-2289): (precision, frac, binary decimal) -> the 40-byte struct of a chunk cell
+B2_HD bool raw_decimal_parse(const unsigned char* p, unsigned int n, b2_decimal* out) {
+  if (n < 3) return false;
+  const unsigned int prec = p[0], frac = p[1];
+  if (prec < frac) return false;
+  p += 2; n -= 2;
+  const unsigned char d2b[10] = {0, 1, 1, 2, 2, 3, 3, 4, 4, 4};
+  const unsigned int pow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
+  const unsigned int int_cnt = prec - frac, iw = int_cnt / 9, lead = int_cnt - iw * 9, fw = frac / 9, trail = frac - fw * 9;
+  if (iw + (lead > 0) + fw + (trail > 0) > 9) return false;
+  const unsigned int mask = (p[0] & 0x80) ? 0u : 0xffffffffu;
+  b2_decimal d;
+  d.int_cnt = (unsigned char)int_cnt; d.frac_cnt = (unsigned char)frac; d.result_frac_cnt = (unsigned char)frac; d.negative = mask != 0;
+  for (int i = 0; i < 9; ++i) d.word_buf[i] = 0;
+  bool first = true, ok = true;
+  auto word = [&](unsigned int size) -> unsigned int {  // read_word :2159-2200: big-endian, sign-extended, first byte's top bit flipped
+    if (n < size) { ok = false; return 0u; }
+    unsigned int b0 = p[0];
+    if (first) { b0 ^= 0x80u; first = false; }
+    int r = (int)(signed char)b0;
+    for (unsigned int i = 1; i < size; ++i) r = (int)(((unsigned int)r << 8) | p[i]);
+    p += size; n -= size;
+    return (unsigned int)r;
+  };
+  unsigned int w = 0;
+  if (lead) {
+    d.word_buf[w] = word(d2b[lead]) ^ mask;
+    if (!ok || d.word_buf[w] >= pow10[lead + 1]) return false;
+    if (d.word_buf[w] != 0) ++w; else d.int_cnt -= (unsigned char)lead;
+  }
+  for (unsigned int i = 0; i < iw; ++i) {
+    d.word_buf[w] = word(4) ^ mask;
+    if (!ok || d.word_buf[w] > 999999999u) return false;
+    if (w > 0 || d.word_buf[w] != 0) ++w; else d.int_cnt -= 9;
+  }
+  for (unsigned int i = 0; i < fw; ++i) {
+    d.word_buf[w] = word(4) ^ mask;
+    if (!ok || d.word_buf[w] > 999999999u) return false;
+    ++w;
+  }
+  if (trail) {
+    const unsigned long long x = (unsigned long long)(word(d2b[trail]) ^ mask) * pow10[9 - trail];
+    if (!ok || x > 999999999ull) return false;
+    d.word_buf[w] = (unsigned int)x;
+  }
+  if (d.int_cnt == 0 && d.frac_cnt == 0) { d.int_cnt = 1; d.negative = 0; for (int i = 0; i < 9; ++i) d.word_buf[i] = 0; }  // Decimal::zero()
+  d.result_frac_cnt = (unsigned char)frac;
+  *out = d;
+  return true;
+}
+B2_HD uint64_t raw_ref_make(const uint8_t* gaddr, uint32_t len) { return ((uint64_t)(unsigned long long)gaddr << 16) | len; }
+B2_HD const uint8_t* raw_ref_addr(uint64_t r) { return (const uint8_t*)(unsigned long long)(r >> 16); }
+B2_HD uint32_t raw_ref_len(uint64_t r) { return (uint32_t)(r & 0xffffu); }
+
+// One cell of a column the executors never decode (Column::from_raw_datums, chunk/column.rs:72-151, per-type appenders
+// :697-913; v2 cells as write_v2_as_datum would have converted them, compat_v1.rs:54-129).  DATE / DATETIME and DURATION
+// become their 8-byte chunk cell here; bytes / json / decimal become a reference to the cell's payload in HBM, which the
+// kernels in kernels.cu (raw_*) turn into the column's heap / 40-byte structs once the launch's rows are in place.
+B2_HD int cell_value_raw(const DevCol& c, const Row& row, const uint8_t* p, uint32_t len, int kind, Value* out) {
+  const uint64_t S = 0x8000000000000000ull;
+  const uint8_t* q = p;
+  uint32_t qn = len;
+  uint32_t flag = 0xffu;  // v2: no datum flag
+  if (kind != CELL_V2) {
+    flag = p[0]; q = p + 1; qn = len - 1;
+    if (flag == 0) { out->null = true; return DE_NONE; }
+  }
+  if (c.kind == CK_TIME) {
+    uint64_t u;
+    if (kind == CELL_V2) { if (len != 1 && len != 2 && len != 4 && len != 8) return DE_ROW_V2_BAD_INT; u = ld_le(p, (int)len); }
+    else if (flag == 4) { if (qn < 8) return DE_DATUM_DECODE; u = ld_be64(q); }
+    else if (flag == 9) { if (!dec_var_u64(q, qn, &u)) return DE_DATUM_DECODE; }
+    else return DE_DATUM_DECODE;
+    out->bits = time_bits_from_packed(u, c.tp == B2_TP_DATE, c.fsp);
+    return DE_NONE;
+  }
+  if (c.kind == CK_DUR) {
+    if (kind == CELL_V2) {
+      if (len != 1 && len != 2 && len != 4 && len != 8) return DE_ROW_V2_BAD_INT;
+      uint64_t u = ld_le(p, (int)len);
+      if (len < 8) { const uint32_t sh = 64 - 8 * len; u = (uint64_t)(((int64_t)(u << sh)) >> sh); }
+      out->bits = u;
+    } else if (flag == 7) { if (qn < 8) return DE_DATUM_DECODE; out->bits = ld_be64(q) ^ S; }
+    else if (flag == 8) { int64_t v; if (!dec_var_i64(q, qn, &v)) return DE_DATUM_DECODE; out->bits = (uint64_t)v; }
+    else return DE_DATUM_DECODE;
+    return DE_NONE;
+  }
+  if (kind != CELL_V2) {
+    if (c.kind == CK_BYTES) {
+      if (flag == 1) return DE_UNSUPPORTED_TYPE;  // memcomparable bytes (index keys): the cell is not a slice of the stored bytes
+      if (flag != 2) return DE_DATUM_DECODE;
+      int64_t vn;
+      const uint32_t used = dec_var_i64(q, qn, &vn);
+      if (!used || vn < 0 || (uint64_t)vn > qn - used) return DE_DATUM_DECODE;
+      q += used; qn = (uint32_t)vn;
+    } else if (c.kind == CK_DEC) { if (flag != 6) return DE_DATUM_DECODE; }
+    else return DE_DATUM_DECODE;  // CK_JSON: a v1 JSON datum never gets here (split_datum does not size binary JSON on the device)
+  }
+  if (qn > 0xffffu) return DE_RAW_TOO_LONG;
+  out->bits = raw_ref_make(row.gv + (q - row.rv.v), qn);
+  return DE_NONE;
+}
+
 // Decode plan column `k` of the row (LazyBatchColumn::ensure_decoded for one cell, lazy_column.rs:165-221).
 B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k, Value* out) {
   const DevCol& c = P.cols[k];
@@ -1242,6 +1366,7 @@ B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k
     out->null = true;  // DS_NULL, or nullable without default
     return DE_NONE;
   }
+  if (c.kind >= CK_TIME) return cell_value_raw(c, row, p, len, kind, out);
   if (kind == CELL_V2) {
     if (c.kind == CK_INT) {
       // compat_v1.rs:13-38: sign- or zero-extend by width, then INT/UINT datum -> i64 bits

@@ -59,7 +59,12 @@ __global__ void __launch_bounds__(256) enc_chunk_kernel(const EncCol* cols, unsi
     }
   }
   unsigned char* data = base + 8 + bm_bytes;
-  if (c.kind == B2_COL_DECIMAL) {
+  if (c.kind == B2_COL_BYTES || c.kind == B2_COL_JSON) {  // var-length column: (n + 1) i64 offsets, then the cells back to back
+    for (unsigned long long i = gtid; i <= n_rows; i += gsz) put_bytes_le(data + i * 8, (unsigned long long)c.offsets[i], 8);
+    unsigned char* heap = data + (n_rows + 1) * 8;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(c.data);
+    for (unsigned long long i = gtid; i < c.heap_len; i += gsz) heap[i] = src[i];
+  } else if (c.kind == B2_COL_DECIMAL) {
     const unsigned int* src = reinterpret_cast<const unsigned int*>(c.data);
     for (unsigned long long i = gtid; i < n_rows * 10; i += gsz) {  // 40-byte structs as 10 words; NULL cells are zero
       unsigned long long r = i / 10;

@@ -15,6 +15,8 @@ struct EncCol {
   int is_unsigned;                   // UINT_FLAG instead of INT_FLAG in TypeDefault
   unsigned int null_cnt;             // TypeChunk header
   unsigned long long chunk_off;      // byte offset of this column's block in the TypeChunk output
+  const long long* offsets;          // B2_COL_BYTES / B2_COL_JSON: n_rows + 1 offsets into `data` (the byte heap)
+  unsigned long long heap_len;       //   bytes of the heap in use (= offsets[n_rows])
 };
 
 cudaError_t launch_enc_null_count(const EncCol* cols, int n_cols, unsigned long long n_rows, unsigned int* counts, cudaStream_t s);

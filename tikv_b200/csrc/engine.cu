@@ -329,7 +329,9 @@ struct b2_exec {
     enc_host.release();
     for (auto& b : res_cols) b.release();
     for (auto& b : res_bitmaps) b.release();
-    h_out.release(); h_ctr.release();
+    h_out.release(); h_ctr.release(); h_raw.release(); h_raw_out.release();
+    raw_state.release(); raw_sums.release();
+    for (RawOut& r : raw_outs) { r.offs.release(); r.heap.release(); }
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 
@@ -830,6 +832,23 @@ struct b2_exec {
       out_cap = cap;
     }
     CUDA_TRY(cudaMemsetAsync(out_bitmap.p, 0xff, out_cap / 8 * n_out, stream));
+    if (cp.dev.n_raw) {
+      // every byte a cell reference of this pass can point at: the value heaps of the blocks it touches (+ CF_DEFAULT)
+      uint64_t vb = 0;
+      {
+        size_t u = cur_unit; uint64_t l = budget; int last_blk = -1;
+        while (l && u < units.size()) {
+          if ((int)units[u].block_idx != last_blk) { vb += wblocks[units[u].block_idx].val_bytes; last_blk = (int)units[u].block_idx; }
+          uint32_t lo = std::max(u == cur_unit ? cur_entry : 0u, units[u].e_lo);
+          uint64_t take = std::min<uint64_t>(l, units[u].e_hi - lo);
+          l -= take; ++u;
+        }
+        for (const SrcBlock& d : dblocks) vb += d.val_bytes;
+      }
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      int rrc = raw_prepare(out_cap, vb);
+      if (rrc) return rrc;
+    }
     Counters z;
     memset(&z, 0, sizeof(z));
     z.err = ~0ull; z.first_row = ~0ull;
@@ -868,6 +887,7 @@ struct b2_exec {
         kernel_begin();
         CUDA_TRY(scan_launch(a, scan_grid, smem));
         kernel_end();
+        if (cp.dev.n_raw) { int rrc = raw_materialise(a, c_hi - c_lo); if (rrc) return rrc; }
         CUDA_TRY(cudaMemcpyAsync(&ctr()->out_base, &ctr()->out_rows, 8, cudaMemcpyDeviceToDevice, stream));
         if (a.trace && !trace_done) {
           trace_done = true;
@@ -957,6 +977,7 @@ struct b2_exec {
       drained = true;
       if (!(limited && limit_remaining == 0)) check_trailing_lock();
     }
+    if (cp.dev.n_raw && produced && !raw_outs.empty() && raw_collect() != B2_OK) produced = 0;
     return publish_scan_columns(produced, out);
   }
   // ---- backward scan (TableScan.desc; scan_executor.rs:89-101, backward.rs:78-225) ----
@@ -1091,6 +1112,64 @@ struct b2_exec {
   uint64_t chunk_total = 0;         // rows the last chunk's kernel wrote
   uint64_t first_row_seen = ~0ull;  // smallest global entry index a row was returned for so far
 
+  // bytes / json / decimal output columns (kernels.cu raw_*): per column an offsets array + byte heap (or decimal structs),
+  // a device-resident heap cursor, one error word
+  struct RawOut { int out_idx; int kind; DevBuf offs, heap; uint64_t heap_cap = 0; uint64_t used = 0; };
+  std::vector<RawOut> raw_outs;
+  DevBuf raw_state, raw_sums;   // raw_state: [n_raw] heap cursors, then the error word
+  HostBuf h_raw, h_raw_out;
+  uint64_t raw_cap_rows = 0;
+  int raw_prepare(uint64_t cap_rows, uint64_t value_bytes) {
+    if (raw_outs.empty())
+      for (int k = 0; k < cp.dev.n_out; ++k) {
+        const int ck = cp.dev.cols[cp.dev.out_cols[k]].kind;
+        if (!cp.dev.n_proj && ck_is_ref(ck)) { raw_outs.emplace_back(); raw_outs.back().out_idx = k; raw_outs.back().kind = ck; }
+      }
+    const size_t n = raw_outs.size();
+    for (RawOut& r : raw_outs) {
+      if (r.kind == CK_DEC) { CUDA_TRY(r.heap.reserve(cap_rows * 40)); r.heap_cap = cap_rows * 40; }
+      else { CUDA_TRY(r.offs.reserve((cap_rows + 1) * 8)); CUDA_TRY(r.heap.reserve(std::max<uint64_t>(value_bytes, 16))); r.heap_cap = value_bytes; }
+    }
+    CUDA_TRY(raw_state.reserve_on(stream, (n + 1) * 8));
+    CUDA_TRY(cudaMemsetAsync(raw_state.p, 0, (n + 1) * 8, stream));
+    CUDA_TRY(raw_sums.reserve(std::max<size_t>(1, n) * ((cap_rows + 1023) / 1024 + 1) * 8));
+    raw_cap_rows = cap_rows;
+    return B2_OK;
+  }
+  // after a scan launch: resolve the cell references of the rows it appended ([out_base, out_rows) on the device)
+  int raw_materialise(const ScanArgs& a, uint64_t max_rows) {
+    RawArgs R;
+    memset(&R, 0, sizeof(R));
+    for (size_t i = 0; i < raw_outs.size(); ++i) {
+      RawOut& r = raw_outs[i];
+      R.col[i].cells = a.out_data + (size_t)r.out_idx * a.out_cap;
+      R.col[i].offsets = (long long*)r.offs.p; R.col[i].heap = (unsigned char*)r.heap.p;
+      R.col[i].heap_used = (unsigned long long*)raw_state.p + i; R.col[i].heap_cap = r.heap_cap;
+      if (r.kind == CK_DEC) R.dec_idx[R.n_dec++] = (unsigned char)i; else R.var_idx[R.n_var++] = (unsigned char)i;
+    }
+    R.row_lo = &ctr()->out_base; R.row_hi = &ctr()->out_rows;
+    R.sums = (unsigned long long*)raw_sums.p; R.sums_stride = (raw_cap_rows + 1023) / 1024 + 1;
+    R.err = (unsigned int*)((unsigned long long*)raw_state.p + raw_outs.size());
+    CUDA_TRY(launch_raw_materialise(R, max_rows, stream));
+    stats.kernel_launches += (R.n_var ? 3 : 0) + (R.n_dec ? 1 : 0);
+    return B2_OK;
+  }
+  // after the pass's counters are on the host: heap sizes and the error word
+  int raw_collect() {
+    const size_t n = raw_outs.size();
+    CUDA_TRY(h_raw.reserve((n + 1) * 8));
+    CUDA_TRY(cudaMemcpyAsync(h_raw.p, raw_state.p, (n + 1) * 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    const uint64_t* h = (const uint64_t*)h_raw.p;
+    for (size_t i = 0; i < n; ++i) raw_outs[i].used = h[i];
+    if ((uint32_t)h[n]) {
+      failed = true;
+      last_err.status = B2_ERR_CORRUPTED; last_err.mysql_code = 0; last_err.entry_index = ~0ull;
+      snprintf(last_err.message, sizeof(last_err.message), "%s", (uint32_t)h[n] == 1 ? "decimal cell does not decode (decimal.rs read_decimal)" : "bytes column heap overflow");
+      return last_err.status;
+    }
+    return B2_OK;
+  }
   Counters good_ctr{};       // device counters after the last batch that completed without an error
   DevBuf range_rows_prev;
   uint64_t limit_remaining = ~0ull;
@@ -1140,7 +1219,44 @@ struct b2_exec {
     for (size_t k = 0; k < n_out; ++k) {
       const OutCol& oc = cp.schema[cp.dev.mode == PM_SCAN ? cp.output_offsets[k] : k];
       cols[k].kind = oc.kind; cols[k].field_tp = oc.field_tp; cols[k].field_flag = oc.field_flag; cols[k].len = n_rows;
+      cols[k].offsets = nullptr;
       last_dev[k] = DevColRef{data + k * out_cap * 8, (const unsigned long long*)(bm + k * (out_cap / 8)), oc.kind, oc.field_tp, oc.field_flag};
+    }
+    // bytes / json / decimal columns: the 8-byte cells above are references; the column itself is the heap the raw_* kernels filled
+    if (cp.dev.n_raw && n_rows) {
+      size_t need = 0;
+      for (RawOut& r : raw_outs) {
+        if (r.kind != CK_DEC) r.used = 0;  // (rows beyond n_rows were materialised too: the heap in use ends at offsets[n_rows])
+        need += r.kind == CK_DEC ? n_rows * 40 : (n_rows + 1) * 8;
+      }
+      std::vector<long long> ends(raw_outs.size(), 0);
+      for (size_t i = 0; i < raw_outs.size(); ++i)
+        if (raw_outs[i].kind != CK_DEC) CUDA_TRY(cudaMemcpyAsync(&ends[i], (const long long*)raw_outs[i].offs.p + n_rows, 8, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      for (size_t i = 0; i < raw_outs.size(); ++i) if (raw_outs[i].kind != CK_DEC) { raw_outs[i].used = (uint64_t)ends[i]; need += (raw_outs[i].used + 15) & ~15ull; }
+      uint8_t* hp = nullptr;
+      if (out_loc == B2_LOC_HOST) { CUDA_TRY(h_raw_out.reserve(need + 64)); hp = (uint8_t*)h_raw_out.p; }
+      for (RawOut& r : raw_outs) {
+        const size_t k = (size_t)r.out_idx;
+        DevColRef& d = last_dev[k];
+        d.raw = true; d.data = r.heap.p;
+        if (r.kind != CK_DEC) { d.offsets = (const long long*)r.offs.p; d.heap_len = r.used; }
+        if (out_loc == B2_LOC_HOST) {
+          if (r.kind == CK_DEC) {
+            CUDA_TRY(cudaMemcpyAsync(hp, r.heap.p, n_rows * 40, cudaMemcpyDeviceToHost, stream));
+            cols[k].data = hp; hp += (n_rows * 40 + 15) & ~15ull; d2h_bytes += n_rows * 40;
+          } else {
+            CUDA_TRY(cudaMemcpyAsync(hp, r.offs.p, (n_rows + 1) * 8, cudaMemcpyDeviceToHost, stream));
+            cols[k].offsets = (const int64_t*)hp; hp += (n_rows + 1) * 8;
+            if (r.used) CUDA_TRY(cudaMemcpyAsync(hp, r.heap.p, r.used, cudaMemcpyDeviceToHost, stream));
+            cols[k].data = hp; hp += (r.used + 15) & ~15ull; d2h_bytes += (n_rows + 1) * 8 + r.used;
+          }
+        } else {
+          cols[k].data = r.heap.p;
+          cols[k].offsets = r.kind == CK_DEC ? nullptr : (const int64_t*)r.offs.p;
+        }
+      }
+      if (out_loc == B2_LOC_HOST) CUDA_TRY(cudaStreamSynchronize(stream));
     }
     out->columns = cols.data(); out->n_columns = (uint32_t)n_out; out->n_rows = n_rows;
     out->is_drained = drained ? B2_DRAIN_DRAINED : B2_DRAIN_REMAIN;
@@ -1217,7 +1333,7 @@ struct b2_exec {
   }
 
   // ---- response encoding of the batch just produced (runner.rs:1051-1088 encode_result_to_chunk) ----
-  struct DevColRef { const void* data; const unsigned long long* bitmap; int kind; int field_tp; uint32_t field_flag; };
+  struct DevColRef { const void* data; const unsigned long long* bitmap; int kind; int field_tp; uint32_t field_flag; const long long* offsets = nullptr; uint64_t heap_len = 0; bool raw = false; };
   std::vector<DevColRef> last_dev;  // device-resident columns of the last batch, in output order
   uint64_t last_rows = 0;
   DevBuf enc_cols, enc_counts, enc_out, enc_lens, enc_offs, enc_tmp;
@@ -1233,7 +1349,12 @@ struct b2_exec {
     std::vector<EncCol> ec((size_t)nc);
     for (int k = 0; k < nc; ++k) {
       const DevColRef& d = last_dev[(size_t)k];
-      ec[(size_t)k] = EncCol{d.data, d.bitmap, d.kind, d.field_tp == B2_TP_FLOAT ? 1 : 0, (d.field_flag & B2_FLAG_UNSIGNED) ? 1 : 0, 0u, 0ull};
+      ec[(size_t)k] = EncCol{d.data, d.bitmap, d.kind, d.field_tp == B2_TP_FLOAT ? 1 : 0, (d.field_flag & B2_FLAG_UNSIGNED) ? 1 : 0, 0u, 0ull, d.offsets, d.heap_len};
+      if (encode_type == B2_ENCODE_TYPE_DEFAULT && (d.raw || d.kind == B2_COL_TIME || d.kind == B2_COL_DURATION)) {
+        // the reference copies the stored datum of such a column (lazy_column.rs:242-257); the decoded cell does not determine it
+        g_last_error = "TypeDefault encoding of bytes / json / decimal / time / duration scan columns is not on the device path (use TypeChunk)";
+        return B2_ERR_UNSUPPORTED;
+      }
     }
     CUDA_TRY(enc_cols.reserve((size_t)nc * sizeof(EncCol)));
     CUDA_TRY(enc_counts.reserve((size_t)nc * 4));
@@ -1251,7 +1372,8 @@ struct b2_exec {
         EncCol& c = ec[(size_t)k];
         c.null_cnt = nulls[(size_t)k]; c.chunk_off = total;
         uint64_t esz = c.kind == B2_COL_DECIMAL ? 40 : (c.is_f32 ? 4 : 8);
-        total += 8 + (c.null_cnt ? (n + 7) / 8 : 0) + n * esz;
+        if (c.kind == B2_COL_BYTES || c.kind == B2_COL_JSON) total += 8 + (c.null_cnt ? (n + 7) / 8 : 0) + (n + 1) * 8 + c.heap_len;
+        else total += 8 + (c.null_cnt ? (n + 7) / 8 : 0) + n * esz;
       }
       CUDA_TRY(enc_out.reserve(total));
       CUDA_TRY(cudaMemcpyAsync(enc_cols.p, ec.data(), (size_t)nc * sizeof(EncCol), cudaMemcpyHostToDevice, stream));

@@ -167,6 +167,7 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
       sv.svals = stg + STAGE_KEY_CAP + s_meta[cur].vals_adj;
       sv.skoff = reinterpret_cast<const uint32_t*>(stg + STAGE_KEY_CAP + STAGE_VAL_CAP) + s_meta[cur].koff_adj;
       sv.svoff = reinterpret_cast<const uint32_t*>(stg + STAGE_KEY_CAP + STAGE_VAL_CAP + STAGE_OFF_CAP) + s_meta[cur].voff_adj;
+      sv.gvals = A.blk.vals;
       const uint32_t ko = sv.skoff[e], kl = sv.skoff[e + 1] - ko, vo = sv.svoff[e], vl = sv.svoff[e + 1] - vo;
       const uint8_t* kp = sv.skeys + ko;
       const uint8_t* vp = sv.svals + vo;

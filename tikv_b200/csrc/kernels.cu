@@ -408,6 +408,127 @@ cudaError_t launch_reverse_rows(const unsigned long long* in, const unsigned lon
   return cudaGetLastError();
 }
 
+// ---- bytes / json / decimal output columns -----------------------------------------------------------------------
+// The scan kernel leaves one cell reference per row (b2_device.h raw_ref_make: HBM address << 16 | length; NULL rows hold
+// 0).  The rows a launch appended are [*row_lo, *row_hi) — device-resident counters, so these kernels chain on the stream
+// without a host round trip.  Var-length columns: per-1024-row byte sums -> one CTA scans the sums (and moves the column's
+// heap cursor) -> every 1024-row block writes its offsets (the chunk column's own i64 offsets, chunk/column.rs:1052-1072)
+// and copies its cells into the heap.  Decimal columns: one thread parses one cell's (precision, frac, binary) payload
+// into the 40-byte struct a chunk column stores (DecimalDecoder::read_decimal, mysql/decimal.rs:2204-2289).
+enum { RAW_BLOCK = 1024 };
+__global__ void __launch_bounds__(256) raw_block_sums_kernel(RawArgs R) {
+  const RawCol& c = R.col[R.var_idx[blockIdx.y]];
+  const unsigned long long lo = *R.row_lo, hi = *R.row_hi;
+  const unsigned long long r0 = lo + (unsigned long long)blockIdx.x * RAW_BLOCK;
+  if (r0 >= hi) return;
+  unsigned int sum = 0;
+  for (unsigned int i = threadIdx.x; i < RAW_BLOCK; i += 256)
+    if (r0 + i < hi) sum += raw_ref_len(c.cells[r0 + i]);
+  __shared__ unsigned int s_w[8];
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    R.sums[(size_t)blockIdx.y * R.sums_stride + blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(1024) raw_scan_sums_kernel(RawArgs R) {
+  const int v = blockIdx.x;
+  const RawCol& c = R.col[R.var_idx[v]];
+  const unsigned long long lo = *R.row_lo, hi = *R.row_hi;
+  const unsigned long long nblk = hi > lo ? (hi - lo + RAW_BLOCK - 1) / RAW_BLOCK : 0;
+  unsigned long long* sums = R.sums + (size_t)v * R.sums_stride;
+  __shared__ unsigned long long s_w[32];
+  __shared__ unsigned long long s_carry;
+  if (threadIdx.x == 0) s_carry = *c.heap_used;
+  __syncthreads();
+  for (unsigned long long base = 0; base < nblk; base += 1024) {
+    const unsigned long long i = base + threadIdx.x;
+    const unsigned long long x = i < nblk ? sums[i] : 0ull;
+    unsigned long long incl = x;
+    for (int off = 1; off < 32; off <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, off); if ((threadIdx.x & 31) >= off) incl += y; }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned long long before = s_carry;
+    for (unsigned int w = 0; w < (threadIdx.x >> 5); ++w) before += s_w[w];
+    if (i < nblk) sums[i] = before + incl - x;  // the block's first heap offset
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = before + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (lo == 0) c.offsets[0] = 0;
+    *c.heap_used = s_carry;
+    if (s_carry > c.heap_cap) atomicExch(R.err, 2u);  // (cannot happen: the heap is sized for every value byte the pass can touch)
+  }
+}
+__global__ void __launch_bounds__(256) raw_copy_kernel(RawArgs R) {
+  const int v = blockIdx.y;
+  const RawCol& c = R.col[R.var_idx[v]];
+  const unsigned long long lo = *R.row_lo, hi = *R.row_hi;
+  const unsigned long long r0 = lo + (unsigned long long)blockIdx.x * RAW_BLOCK;
+  if (r0 >= hi || *R.err == 2u) return;
+  __shared__ unsigned long long s_ref[RAW_BLOCK];
+  __shared__ unsigned long long s_off[RAW_BLOCK];
+  __shared__ unsigned int s_w[8];
+  const unsigned int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // thread t owns rows 4t .. 4t+3 of the block
+  unsigned long long ref[4];
+  unsigned int len[4], mine = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned long long r = r0 + 4 * tid + j;
+    ref[j] = r < hi ? c.cells[r] : 0ull;
+    len[j] = raw_ref_len(ref[j]);
+    mine += len[j];
+  }
+  unsigned int incl = mine;
+  for (int off = 1; off < 32; off <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= (unsigned)off) incl += y; }
+  if (lane == 31) s_w[wid] = incl;
+  __syncthreads();
+  unsigned long long at = R.sums[(size_t)v * R.sums_stride + blockIdx.x] + incl - mine;
+  for (unsigned int w = 0; w < wid; ++w) at += s_w[w];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned long long r = r0 + 4 * tid + j;
+    s_ref[4 * tid + j] = ref[j]; s_off[4 * tid + j] = at;
+    at += len[j];
+    if (r < hi) c.offsets[r + 1] = (long long)at;
+  }
+  __syncthreads();
+  const unsigned int n = (unsigned int)(hi - r0 < RAW_BLOCK ? hi - r0 : RAW_BLOCK);
+  for (unsigned int i = wid; i < n; i += 8) {  // one warp per cell, lanes stride over its bytes
+    const unsigned char* src = raw_ref_addr(s_ref[i]);
+    const unsigned int l = raw_ref_len(s_ref[i]);
+    unsigned char* dst = c.heap + s_off[i];
+    for (unsigned int b = lane; b < l; b += 32) dst[b] = src[b];
+  }
+}
+__global__ void raw_decimal_kernel(RawArgs R) {
+  const RawCol& c = R.col[R.dec_idx[blockIdx.y]];
+  const unsigned long long lo = *R.row_lo, hi = *R.row_hi;
+  const unsigned long long r = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= hi) return;
+  const unsigned long long ref = c.cells[r];
+  b2_decimal d;
+  memset(&d, 0, sizeof(d));
+  if (ref != 0 && !raw_decimal_parse(raw_ref_addr(ref), raw_ref_len(ref), &d)) { atomicCAS(R.err, 0u, 1u); memset(&d, 0, sizeof(d)); }
+  reinterpret_cast<b2_decimal*>(c.heap)[r] = d;
+}
+cudaError_t launch_raw_materialise(const RawArgs& R, uint64_t max_rows, cudaStream_t s) {
+  if (!max_rows) return cudaSuccess;
+  const unsigned int nblk = (unsigned int)((max_rows + RAW_BLOCK - 1) / RAW_BLOCK);
+  if (R.n_var) {
+    raw_block_sums_kernel<<<dim3(nblk, R.n_var), 256, 0, s>>>(R);
+    raw_scan_sums_kernel<<<R.n_var, 1024, 0, s>>>(R);
+    raw_copy_kernel<<<dim3(nblk, R.n_var), 256, 0, s>>>(R);
+  }
+  if (R.n_dec) raw_decimal_kernel<<<dim3((unsigned int)((max_rows + 255) / 256), R.n_dec), 256, 0, s>>>(R);
+  return cudaGetLastError();
+}
+
 __global__ void fill_u64_kernel(unsigned long long* p, unsigned long long v, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;

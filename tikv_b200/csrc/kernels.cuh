@@ -145,6 +145,24 @@ cudaError_t launch_gen_sizes(const b2_gen_spec& spec, uint32_t* row_entries, uin
 cudaError_t launch_gen_write(const GenArgs& a, cudaStream_t s);
 cudaError_t launch_fill_u64(unsigned long long* p, unsigned long long v, size_t n, cudaStream_t s);
 // backward scans: out row i = in row (n_rows - 1 - i) for i < n_take, every column and its non-NULL bitmap; out bitmaps pre-filled with ones
+// bytes / json / decimal output columns of the rows one scan launch appended (kernels.cu raw_*)
+enum { MAX_RAW = 16 };
+struct RawCol {
+  unsigned long long* cells;      // the column's cell references (ScanArgs::out_data + column * out_cap)
+  long long* offsets;             // var-length: out_cap + 1 offsets
+  unsigned char* heap;            // var-length: byte heap; decimal: out_cap b2_decimal structs
+  unsigned long long* heap_used;  // var-length: the heap cursor (device-resident, carried from launch to launch)
+  unsigned long long heap_cap;
+};
+struct RawArgs {
+  RawCol col[MAX_RAW];
+  unsigned char var_idx[MAX_RAW], dec_idx[MAX_RAW];  // indices into col
+  unsigned int n_var, n_dec;
+  const unsigned long long* row_lo; const unsigned long long* row_hi;  // the launch's rows (device counters)
+  unsigned long long* sums; unsigned long long sums_stride;            // scratch: n_var x ceil(max_rows / 1024)
+  unsigned int* err;              // 1 = a decimal cell does not decode, 2 = heap overflow
+};
+cudaError_t launch_raw_materialise(const RawArgs& R, uint64_t max_rows, cudaStream_t s);
 cudaError_t launch_reverse_rows(const unsigned long long* in, const unsigned long long* bm_in, uint64_t in_cap, unsigned long long* out, unsigned long long* bm_out,
                                 uint64_t out_cap, uint64_t n_rows, uint64_t n_take, uint32_t n_cols, cudaStream_t s);
 

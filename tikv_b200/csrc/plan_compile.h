@@ -31,6 +31,28 @@ inline int col_kind_of_tp(int tp) {  // def/eval_type.rs:53-95
     default: return CK_OTHER;
   }
 }
+// kinds of a scan column: the two above are evaluated by expressions; the rest can only be carried to the output
+inline int scan_col_kind(int tp, int decimal) {
+  switch (tp) {
+    case B2_TP_DATE: case B2_TP_DATETIME: return decimal >= -1 && decimal <= 6 ? CK_TIME : CK_OTHER;  // (TIMESTAMP converts through the session time zone: CPU)
+    case B2_TP_DURATION: return CK_DUR;
+    case B2_TP_VARCHAR: case B2_TP_VARSTRING: case B2_TP_STRING: case B2_TP_BLOB: case 0xf9: case 0xfa: case 0xfb: case 0xff: return CK_BYTES;
+    case B2_TP_JSON: return CK_JSON;
+    case B2_TP_NEWDECIMAL: return CK_DEC;
+    default: return col_kind_of_tp(tp);
+  }
+}
+inline int out_kind_of(int ck) {
+  switch (ck) {
+    case CK_REAL: return B2_COL_F64;
+    case CK_TIME: return B2_COL_TIME;
+    case CK_DUR: return B2_COL_DURATION;
+    case CK_BYTES: return B2_COL_BYTES;
+    case CK_JSON: return B2_COL_JSON;
+    case CK_DEC: return B2_COL_DECIMAL;
+    default: return B2_COL_I64;
+  }
+}
 inline int v2_class_of(int tp, bool is_unsigned) {  // compat_v1.rs:55-129 write_v2_as_datum
   switch (tp) {
     case B2_TP_TINY: case B2_TP_SHORT: case B2_TP_INT24: case B2_TP_LONG: case B2_TP_LONGLONG: return is_unsigned ? V2_UINT : V2_INT;
@@ -67,7 +89,7 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
       case B2_RPN_COLUMN_REF: {
         if (s.i64 < 0 || s.i64 >= P.n_cols) { *msg = "column offset out of range"; return false; }
         const DevCol& c = P.cols[s.i64];
-        if (c.kind == CK_OTHER) { *msg = "expression over a column that is not Int/Real"; return false; }
+        if (c.kind > CK_REAL) { *msg = "expression over a column that is not Int/Real"; return false; }
         d.et = c.kind; d.is_unsigned = c.is_unsigned;
         break;
       }
@@ -175,7 +197,8 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
     c.col_id = ci.col_id; c.tp = (uint8_t)ci.tp;
     c.is_unsigned = (ci.flag & B2_FLAG_UNSIGNED) ? 1 : 0;
     c.not_null = (ci.flag & B2_FLAG_NOT_NULL) ? 1 : 0;
-    c.kind = (uint8_t)col_kind_of_tp(ci.tp);
+    c.kind = (uint8_t)scan_col_kind(ci.tp, ci.decimal);
+    c.fsp = (uint8_t)(ci.decimal > 0 && ci.decimal <= 6 ? ci.decimal : 0);
     c.v2_class = (uint8_t)v2_class_of(ci.tp, c.is_unsigned);
     c.role = CR_NORMAL;
     if (ci.pk_handle && is_index) { c.role = CR_IDX_HANDLE; c.kind = CK_INT; }
@@ -194,7 +217,7 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
     if (P.idx_cols <= 0) { *msg = "IndexScan without index columns"; return B2_ERR_UNSUPPORTED; }
     for (int i = 0; i < P.idx_cols; ++i) {
       if (P.cols[i].role != CR_NORMAL) { *msg = "IndexScan: the handle / physical table id columns must come last"; return B2_ERR_UNSUPPORTED; }
-      if (P.cols[i].kind == CK_OTHER) { *msg = "IndexScan over a column that is not Int/Real is not on the device path yet"; return B2_ERR_UNSUPPORTED; }
+      if (P.cols[i].kind > CK_REAL) { *msg = "IndexScan over a column that is not Int/Real is not on the device path yet"; return B2_ERR_UNSUPPORTED; }
     }
   }
   // duplicate column ids: only the last one is ever filled (table_scan_executor.rs:90-94)
@@ -249,7 +272,7 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
   std::vector<OutCol> schema;
   for (int i = 0; i < P.n_cols; ++i) {
     OutCol oc;
-    oc.kind = P.cols[i].kind == CK_REAL ? B2_COL_F64 : B2_COL_I64;
+    oc.kind = out_kind_of(P.cols[i].kind);
     oc.field_tp = P.cols[i].tp; oc.field_flag = scan.columns[i].flag;
     schema.push_back(oc);
   }
@@ -354,7 +377,17 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
     if (P.mode == PM_TOPN) for (int i = 0; i < P.n_cols; ++i) mat.push_back(i); else mat = out->output_offsets;
     if (mat.size() > MAX_COLS) { *msg = "too many output columns"; return B2_ERR_UNSUPPORTED; }
     for (size_t i = 0; i < mat.size(); ++i) {
-      if (!P.n_proj && P.cols[mat[i]].kind == CK_OTHER) { *msg = "output column " + std::to_string(mat[i]) + " is not Int/Real: device path cannot materialise it yet"; return B2_ERR_UNSUPPORTED; }
+      const DevCol& mc = P.cols[mat[i]];
+      if (!P.n_proj && mc.kind == CK_OTHER) { *msg = "output column " + std::to_string(mat[i]) + " has a type the device path cannot materialise (TIMESTAMP, ENUM, SET, BIT > 64 ...)"; return B2_ERR_UNSUPPORTED; }
+      if (!P.n_proj && mc.kind >= CK_TIME) {
+        const b2_column_info& ci = scan.columns[mat[i]];
+        if (ci.default_val && ci.default_len && ci.default_val[0] != 0) { *msg = "default value of a non Int/Real output column is not materialised on the device path"; return B2_ERR_UNSUPPORTED; }
+        if (ck_is_ref(mc.kind)) {
+          if (P.mode == PM_TOPN) { *msg = "TopN over a table with bytes / json / decimal columns is not on the device path yet"; return B2_ERR_UNSUPPORTED; }
+          if (out->desc) { *msg = "backward scan with bytes / json / decimal output columns is not on the device path yet"; return B2_ERR_UNSUPPORTED; }
+          P.n_raw++;
+        }
+      }
       P.out_cols[i] = (uint8_t)mat[i];
     }
     P.n_out = (int)mat.size();

@@ -36,7 +36,7 @@ inline std::string plan_literal(const DevPlan& P) {
   for (int i = 0; i < MAX_COLS; ++i) o << (int)P.out_cols[i] << (i < MAX_COLS - 1 ? "," : "");
   o << "},{";
   for (int i = 0; i < MAX_COLS; ++i) o << (int)P.out_slow[i] << (i < MAX_COLS - 1 ? "," : "");
-  o << "}," << P.n_fconds << "," << P._fcpad << ",{";
+  o << "}," << P.n_fconds << "," << P.n_raw << ",{";
   for (int i = 0; i < MAX_CONDS; ++i) {
     const FastCond& f = P.fconds[i];
     o << "{"; i64(f.imm); o << "," << (int)f.h << "," << (int)f.op << "," << (int)f.col_uns << "," << (int)f.imm_uns << "," << (int)f.zero_ext << "," << (int)f.imm_slot << ",{0,0}}" << (i < MAX_CONDS - 1 ? "," : "");
@@ -52,7 +52,7 @@ inline std::string plan_literal(const DevPlan& P) {
     const DevCol& c = P.cols[i];
     o << "{"; i64(c.col_id); o << ","; i64(c.default_bits);
     o << "," << (int)c.kind << "," << (int)c.role << "," << (int)c.is_unsigned << "," << (int)c.not_null << "," << (int)c.tp << "," << (int)c.v2_class << "," << (int)c.def_state << ","
-      << (int)c.v2_hint << "}" << (i < MAX_COLS - 1 ? "," : "");
+      << (int)c.v2_hint << "," << (int)c.fsp << ",{0,0,0,0,0,0,0}}" << (i < MAX_COLS - 1 ? "," : "");
   }
   o << "},{";
   for (int i = 0; i < MAX_NODES; ++i) {

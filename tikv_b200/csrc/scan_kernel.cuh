@@ -236,7 +236,9 @@ struct TileMeta {
 // compiler can see: every access below compiles to LDS with 32-bit addressing).  Only entries [w_lo, w_hi) exist here.
 struct SmemView {
   const uint8_t* skeys; const uint32_t* skoff; const uint8_t* svals; const uint32_t* svoff;
+  const uint8_t* gvals;  // the block's value heap in HBM: svals + o and gvals + o hold the same byte
   static constexpr bool kWholeBlock = false;
+  __device__ __forceinline__ const uint8_t* gval(const uint8_t* p) const { return gvals + (p - svals); }
   __device__ __forceinline__ const uint8_t* kptr(uint32_t i) const { return skeys + skoff[i]; }
   __device__ __forceinline__ uint32_t klen(uint32_t i) const { return skoff[i + 1] - skoff[i]; }
   __device__ __forceinline__ const uint8_t* vptr(uint32_t i) const { return svals + svoff[i]; }
@@ -318,6 +320,7 @@ __device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A,
   if (P.idx_cols > 0) err = index_row_split(P, row, cells, ro.val, ro.val_len, idx_buf);  // BatchIndexScan: the columns are the key's datums
   else {
     err = row_open(ro.val, ro.val_len, &row.rv);
+    if (P.n_raw) row.gv = ro.dflt_lookup ? ro.val : view.gval(ro.val);  // (a CF_DEFAULT value is always read in place)
     if (!err) err = row_split(P, row, cells);
   }
   bool keep = false;
@@ -360,6 +363,7 @@ __device__ __forceinline__ int entry_fast(const DevPlan& P, const ScanArgs& A, c
   row.enc_key = kp; row.enc_key_len = 27; row.commit_ts = cts; row.imms = A.imms;
   if (!fast_row_v2(P, vp + roff, rlen, row)) return P1_GENERAL;
   row.filled = P.fast_filled;
+  if (P.n_raw) row.gv = view.gval(vp + roff);
   bool keep = false;
   if (eval_conds(P, row, cells, &keep)) return P1_GENERAL;  // evaluation errors are raised by the general path
   ts.keys += 1;
@@ -917,6 +921,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
       sv.svals = st + STAGE_KEY_CAP + m.vals_adj;
       sv.skoff = reinterpret_cast<const uint32_t*>(st + STAGE_KEY_CAP + STAGE_VAL_CAP) + m.koff_adj;
       sv.svoff = reinterpret_cast<const uint32_t*>(st + STAGE_KEY_CAP + STAGE_VAL_CAP + STAGE_OFF_CAP) + m.voff_adj;
+      sv.gvals = A.blk.vals;
       redo = tile_body(sv, m.w_hi < A.e_hi ? m.w_hi : A.e_hi, k, tile);
     }
     if (redo) tile_body(A.blk, A.e_hi, k, tile);

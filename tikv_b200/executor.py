@@ -31,6 +31,33 @@ def _decimal_to_int(raw40):
     return -v if neg else v
 
 
+def _decimal_value(raw40):
+    """b2_decimal -> python int (no fraction digits) or decimal.Decimal."""
+    import decimal
+    int_cnt, frac_cnt, neg = raw40[0], raw40[1], raw40[3]
+    if frac_cnt == 0:
+        return _decimal_to_int(raw40)
+    words = np.frombuffer(raw40[4:40], dtype="<u4")
+    iw, fw = (int_cnt + 8) // 9, (frac_cnt + 8) // 9
+    v = 0
+    for w in words[:iw + fw]:
+        v = v * 10 ** 9 + int(w)
+    v //= 10 ** (fw * 9 - frac_cnt)
+    return decimal.Decimal(-v if neg else v).scaleb(-frac_cnt, decimal.Context(prec=200))
+
+
+def raw_cell_values(kind, data, offsets, non_null):
+    """Cells of a BYTES / JSON (heap + offsets) or TIME / DURATION / DECIMAL (fixed cells) column as python values:
+    bytes, the u64 CoreTime bit field, i64 nanoseconds, int / decimal.Decimal; None = NULL."""
+    n = len(non_null)
+    if kind in (ffi.COL_BYTES, ffi.COL_JSON):
+        return [bytes(data[offsets[i]:offsets[i + 1]]) if non_null[i] else None for i in range(n)]
+    if kind == ffi.COL_DECIMAL:
+        return [_decimal_value(bytes(data[40 * i:40 * i + 40])) if non_null[i] else None for i in range(n)]
+    a = np.frombuffer(data, dtype="<u8" if kind == ffi.COL_TIME else "<i8", count=n)
+    return [int(a[i]) if non_null[i] else None for i in range(n)]
+
+
 class BatchResult:
     """BatchExecuteResult with compacted, decoded columns (logical_rows is the identity)."""
 
@@ -59,7 +86,13 @@ def _read_batch(b, location):
         words = (n + 63) // 64
         bm = np.ctypeslib.as_array(C.cast(c.null_bitmap, C.POINTER(C.c_uint64)), shape=(words,))
         nn = ((bm[np.arange(n) >> 6] >> (np.arange(n) & 63).astype(np.uint64)) & np.uint64(1)).astype(bool)
-        if c.kind == ffi.COL_I64:
+        if c.kind in (ffi.COL_BYTES, ffi.COL_JSON):
+            offs = np.ctypeslib.as_array(C.cast(c.offsets, C.POINTER(C.c_int64)), shape=(n + 1,))
+            heap = C.string_at(c.data, int(offs[n])) if offs[n] else b""
+            vals = raw_cell_values(c.kind, heap, [int(x) for x in offs], list(nn))
+        elif c.kind in (ffi.COL_TIME, ffi.COL_DURATION):
+            vals = raw_cell_values(c.kind, C.string_at(c.data, 8 * n), None, list(nn))
+        elif c.kind == ffi.COL_I64:
             a = np.ctypeslib.as_array(C.cast(c.data, C.POINTER(C.c_int64)), shape=(n,))
             vals = [int(a[j]) if nn[j] else None for j in range(n)]
         elif c.kind == ffi.COL_F64:
@@ -67,7 +100,7 @@ def _read_batch(b, location):
             vals = [float(a[j]) if nn[j] else None for j in range(n)]
         else:
             raw = np.ctypeslib.as_array(C.cast(c.data, C.POINTER(C.c_uint8)), shape=(n * 40,)).tobytes()
-            vals = [_decimal_to_int(raw[40 * j:40 * j + 40]) if nn[j] else None for j in range(n)]
+            vals = [_decimal_value(raw[40 * j:40 * j + 40]) if nn[j] else None for j in range(n)]
         cols.append(vals)
     return cols, kinds, fts
 

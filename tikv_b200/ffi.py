@@ -36,7 +36,7 @@ SIG = _header_enum("B2_SIG_")  # tipb::ScalarFuncSig numbers, never typed twice
 
 AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX, AGG_FIRST = 3001, 3002, 3003, 3004, 3005, 3006
 EXEC_TABLE_SCAN, EXEC_INDEX_SCAN, EXEC_SELECTION, EXEC_AGGREGATION, EXEC_TOPN, EXEC_LIMIT, EXEC_STREAM_AGG, EXEC_PROJECTION = range(8)
-COL_I64, COL_F64, COL_DECIMAL = 0, 1, 2
+COL_I64, COL_F64, COL_DECIMAL, COL_BYTES, COL_TIME, COL_DURATION, COL_JSON = 0, 1, 2, 3, 4, 5, 6
 DRAIN_REMAIN, DRAIN_DRAINED, DRAIN_PAGING = 0, 1, 2
 
 
@@ -60,7 +60,7 @@ class KeyRange(C.Structure):
 
 class ColumnInfo(C.Structure):
     _fields_ = [("col_id", C.c_int64), ("tp", C.c_int32), ("flag", C.c_uint32), ("pk_handle", C.c_int32),
-                ("default_len", C.c_uint32), ("default_val", C.c_char_p)]
+                ("default_len", C.c_uint32), ("default_val", C.c_char_p), ("decimal", C.c_int32), ("_pad", C.c_int32)]
 
 
 class RpnNode(C.Structure):
@@ -105,7 +105,7 @@ class Decimal(C.Structure):
 
 class Column(C.Structure):
     _fields_ = [("kind", C.c_int32), ("field_tp", C.c_int32), ("field_flag", C.c_uint32), ("_pad", C.c_uint32),
-                ("len", C.c_uint64), ("data", C.c_void_p), ("null_bitmap", C.c_void_p)]
+                ("len", C.c_uint64), ("data", C.c_void_p), ("null_bitmap", C.c_void_p), ("offsets", C.c_void_p)]
 
 
 class Batch(C.Structure):
@@ -245,7 +245,7 @@ def lib():
     L.b2_device_numa_node.restype = i32
     L.b2_host_free_pinned.argtypes = [vp]
     L.b2_host_free_pinned.restype = None
-    if L.b2_abi_version() != 2:
+    if L.b2_abi_version() != 3:
         raise RuntimeError("libb2copr ABI version mismatch")
     _lib = L
     return L

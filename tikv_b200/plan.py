@@ -127,8 +127,8 @@ def case_when(*xs):
 
 
 class ColumnDef:
-    def __init__(self, col_id, tp=ffi.TP_LONGLONG, unsigned=False, not_null=False, pk_handle=False, default=None):
-        self.col_id, self.tp, self.pk_handle, self.default = col_id, tp, pk_handle, default
+    def __init__(self, col_id, tp=ffi.TP_LONGLONG, unsigned=False, not_null=False, pk_handle=False, default=None, decimal=0):
+        self.col_id, self.tp, self.pk_handle, self.default, self.decimal = col_id, tp, pk_handle, default, decimal
         self.flag = (ffi.FLAG_UNSIGNED if unsigned else 0) | (ffi.FLAG_NOT_NULL if not_null else 0)
 
 
@@ -154,6 +154,7 @@ class Plan:
         arr = (ffi.ColumnInfo * len(columns))()
         for i, cd in enumerate(columns):
             arr[i].col_id, arr[i].tp, arr[i].flag, arr[i].pk_handle = cd.col_id, cd.tp, cd.flag, int(cd.pk_handle)
+            arr[i].decimal = cd.decimal
             if cd.default is not None:
                 buf = C.create_string_buffer(bytes(cd.default), len(cd.default))
                 self._keep.append(buf)
