@@ -324,7 +324,7 @@ struct b2_exec {
       if (s.free_ev) cudaEventDestroy(s.free_ev);
     }
     for (auto& e : kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    for (DevBuf* b : {&tn_lists, &tn_counts, &tn_pair, &tn_pair_cnt, &tn_tmp, &tn_tmp_cnt, &tn_blk_pay, &tn_blk_null, &tn_run_pay, &tn_run_null, &tn_tmp_pay, &tn_tmp_null, &tn_bitmap}) b->release();
+    for (DevBuf* b : {&tn_work, &tn_lists, &tn_counts, &tn_pair, &tn_pair_cnt, &tn_tmp, &tn_tmp_cnt, &tn_blk_pay, &tn_blk_null, &tn_run_pay, &tn_run_null, &tn_tmp_pay, &tn_tmp_null, &tn_bitmap}) b->release();
     for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &tbl_gkeys, &tbl_ready, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &range_rows_prev, &slow_list, &slow_cnt, &rev_data, &rev_bitmap, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
     enc_host.release();
     for (auto& b : res_cols) b.release();
@@ -1589,7 +1589,7 @@ struct b2_exec {
   }
 
   // ---- PM_TOPN: per unit: per-CTA candidate lists -> unit top-N -> payload gather -> merge into the running top-N ----
-  DevBuf tn_lvl_a, tn_lvl_a_cnt, tn_lvl_b, tn_lvl_b_cnt, tn_lists, tn_counts, tn_pair, tn_pair_cnt, tn_tmp, tn_tmp_cnt, tn_blk_pay, tn_blk_null, tn_run_pay, tn_run_null, tn_tmp_pay, tn_tmp_null, tn_bitmap;
+  DevBuf tn_work, tn_lvl_a, tn_lvl_a_cnt, tn_lvl_b, tn_lvl_b_cnt, tn_lists, tn_counts, tn_pair, tn_pair_cnt, tn_tmp, tn_tmp_cnt, tn_blk_pay, tn_blk_null, tn_run_pay, tn_run_null, tn_tmp_pay, tn_tmp_null, tn_bitmap;
 
   int run_topn(b2_batch* out) {
     const DevPlan& P = cp.dev;
@@ -1607,9 +1607,12 @@ struct b2_exec {
       int grid = scan_grid_for(PM_TOPN, std::max(tot0, smem));
       const bool any_fast = fast_kernel_covers();
       int fast_grid = 0;
-      if (any_fast) {
+      if (any_fast) {  // the lean kernel keeps its candidate buffers in HBM (ScanArgs::topn_work): shared memory holds the stages only
         const JitKernel* jk = jit_ready();
-        fast_grid = jk && jk->fn_fast ? jit_max_blocks_per_sm(jk, std::max(tot0, smem), true) * scan_num_sms() : fast_max_grid(PM_TOPN, std::max(tot0, smem));
+        ScanArgs fprobe; memset(&fprobe, 0, sizeof(fprobe));
+        const size_t ftot0 = setup_staging(&fprobe, wblocks[units[0].block_idx], 0);
+        fast_grid = jk && jk->fn_fast ? jit_max_blocks_per_sm(jk, ftot0, true) * scan_num_sms() : fast_max_grid(PM_TOPN, ftot0);
+        CUDA_TRY(tn_work.reserve((size_t)fast_grid * smem));
       }
       const int lists_cap = grid + fast_grid;  // the lean and the general kernel leave their per-CTA lists side by side
       size_t isz = sizeof(TopItem);
@@ -1644,10 +1647,11 @@ struct b2_exec {
         a.topn.items = (TopItem*)tn_lists.p; a.topn.counts = (unsigned int*)tn_counts.p; a.topn.stride = limit;
         a.topn_cap = cap;
         a.topn_seed = pair; a.topn_seed_cnt = pair_cnt;
+        a.topn_work = (unsigned char*)tn_work.p; a.topn_work_stride = smem;
         CUDA_TRY(cudaMemsetAsync(tn_counts.p, 0, (size_t)lists_cap * 4, stream));
         const bool fast = any_fast && u.fast_ok;
         int gg = (int)std::min<uint32_t>((uint32_t)grid, n_tiles), fg = (int)std::min<uint32_t>((uint32_t)std::max(fast_grid, 1), n_tiles);
-        rc = launch_unit(a, u, fast, smem, smem, 0, &gg, &fg);
+        rc = launch_unit(a, u, fast, smem, 0, 0, &gg, &fg);
         if (rc) return rc;
         a.topn.n_lists = (uint32_t)(gg + fg);
         // unit top-N (sorted) lands in the second half of `pair`
@@ -1669,7 +1673,8 @@ struct b2_exec {
         // running top-N (first half) + unit top-N -> tmp, then back into the first half
         TopNLists both; both.items = pair; both.counts = pair_cnt; both.n_lists = 2; both.stride = limit;
         TopNLists merged; merged.items = (TopItem*)tn_tmp.p; merged.counts = (unsigned int*)tn_tmp_cnt.p; merged.n_lists = 1; merged.stride = limit;
-        CUDA_TRY(launch_topn_merge(P, both, merged, cap, 2, stream));
+        (void)both; (void)merged;
+        CUDA_TRY(launch_topn_merge2(P, pair, pair_cnt, pair + limit, pair_cnt + 1, (TopItem*)tn_tmp.p, (unsigned int*)tn_tmp_cnt.p, limit, stream));
         CUDA_TRY(launch_topn_copy((const TopItem*)tn_tmp.p, (const unsigned int*)tn_tmp_cnt.p, n_out, limit, (const unsigned long long*)tn_run_pay.p,
                                   (const unsigned char*)tn_run_null.p, (const unsigned long long*)tn_blk_pay.p, (const unsigned char*)tn_blk_null.p,
                                   (unsigned long long*)tn_tmp_pay.p, (unsigned char*)tn_tmp_null.p, stream));

@@ -54,7 +54,7 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
     for (unsigned int i = tid; i < st.slots; i += FK_THREADS) occ[i] = 0;
     for (unsigned int i = tid; i < st.slots * P.acc_words; i += FK_THREADS) st.acc[i] = 0;
   }
-  const TopBuf tb = topbuf_make(dyn_smem, MODE == PM_TOPN ? A.topn_cap : 0u, P);
+  const TopBuf tb = topbuf_make(MODE == PM_TOPN && A.topn_work ? A.topn_work + (size_t)blockIdx.x * A.topn_work_stride : dyn_smem, MODE == PM_TOPN ? A.topn_cap : 0u, P);
   if (MODE == PM_TOPN)
     for (unsigned int i = tid; i < A.topn_cap; i += FK_THREADS) tb.idx[i] = (unsigned short)i;
   unsigned long long* crc_tab = reinterpret_cast<unsigned long long*>(dyn_smem);  // PM_CHECKSUM: slicing-by-8 tables, then kacc[256]

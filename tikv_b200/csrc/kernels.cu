@@ -182,6 +182,34 @@ cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const To
   return cudaGetLastError();
 }
 
+// Two sorted lists (the running top-N, then one unit's) -> the best `limit` of both, sorted: every item finds its rank by
+// a binary search in the other list (ids make the order total, so ranks are distinct).  slot = (source list << 16 | index),
+// what topn_copy_kernel uses to pick the payload.
+__global__ void __launch_bounds__(256) topn_merge2_kernel(const __grid_constant__ DevPlan P, const TopItem* a, const unsigned int* a_cnt, const TopItem* b,
+                                                          const unsigned int* b_cnt, TopItem* out, unsigned int* out_cnt, unsigned int limit) {
+  const unsigned int na = *a_cnt < limit ? *a_cnt : limit, nb = *b_cnt < limit ? *b_cnt : limit;
+  for (unsigned int t = threadIdx.x; t < na + nb; t += blockDim.x) {
+    const bool from_a = t < na;
+    const unsigned int i = from_a ? t : t - na;
+    TopItem it = from_a ? a[i] : b[i];
+    const TopItem* o = from_a ? b : a;
+    unsigned int lo = 0, hi = from_a ? nb : na;
+    while (lo < hi) {  // items of the other list that come before `it`
+      const unsigned int mid = (lo + hi) >> 1;
+      if (item_less(o[mid], it, P)) lo = mid + 1; else hi = mid;
+    }
+    const unsigned int rank = i + lo;
+    it.slot = ((from_a ? 0u : 1u) << 16) | i;
+    if (rank < limit) out[rank] = it;
+  }
+  if (threadIdx.x == 0) *out_cnt = na + nb < limit ? na + nb : limit;
+}
+cudaError_t launch_topn_merge2(const DevPlan& plan, const TopItem* a, const unsigned int* a_cnt, const TopItem* b, const unsigned int* b_cnt, TopItem* out,
+                               unsigned int* out_cnt, uint32_t limit, cudaStream_t s) {
+  topn_merge2_kernel<<<1, 256, 0, s>>>(plan, a, a_cnt, b, b_cnt, out, out_cnt, limit);
+  return cudaGetLastError();
+}
+
 // decode every scan column of the selected rows (take_all_append_to, top_n_heap.rs:56-133); one thread per row
 __global__ void topn_gather_kernel(const __grid_constant__ DevPlan P, const __grid_constant__ ScanArgs A, const TopItem* items, const unsigned int* count,
                                    unsigned long long* pay, unsigned char* pay_null, unsigned int stride) {

@@ -100,6 +100,8 @@ struct ScanArgs {
   uint32_t topn_cap;                // shared-memory candidate capacity (power of two >= limit + TILE)
   const TopItem* topn_seed;         // running top-N of the units already merged (sorted), or nullptr:
   const unsigned int* topn_seed_cnt;  //   once it holds `limit` rows its last one is every CTA's initial threshold
+  unsigned char* topn_work;           // lean TopN kernel: the CTAs' candidate buffers live in HBM / L2 (topn_work + blockIdx.x * stride): a
+  unsigned long long topn_work_stride;//   seeded CTA touches its buffer for a handful of rows per launch, and shared memory buys a third CTA per SM
 };
 
 struct GenArgs {
@@ -136,6 +138,8 @@ cudaError_t launch_topn_gather(const DevPlan& plan, const ScanArgs& a, const Top
 cudaError_t launch_topn_copy(const TopItem* items, const unsigned int* count, uint32_t n_out, uint32_t stride, const unsigned long long* pay0,
                              const unsigned char* null0, const unsigned long long* pay1, const unsigned char* null1, unsigned long long* pay_out,
                              unsigned char* null_out, cudaStream_t s);
+cudaError_t launch_topn_merge2(const DevPlan& plan, const TopItem* a, const unsigned int* a_cnt, const TopItem* b, const unsigned int* b_cnt, TopItem* out,
+                               unsigned int* out_cnt, uint32_t limit, cudaStream_t s);
 cudaError_t launch_pack_nulls(const unsigned char* nulls, uint32_t n_cols, uint32_t stride, uint32_t n, unsigned long long* bitmaps, uint32_t words_per_col, cudaStream_t s);
 size_t topn_smem_bytes(uint32_t cap, int n_order);
 // out: lower_bound of every bound in every block; unit_ok[block * n_ranges + range]: that unit's keys share a record-key prefix
