@@ -28,6 +28,20 @@ def _warm_kernel_cache(request, _built):
     in the on-disk cache yet, on all host cores at once (tests/jit_warm.py).  One after the other inside the tests they
     cost 5-100 s of NVRTC time each; results do not depend on this step."""
     if os.path.exists("/dev/nvidia0") and "not gpu" not in (request.config.getoption("-m") or "") and not os.environ.get("B2_NO_JIT_WARM"):
+        import time
         import jit_warm
-        jit_warm.warm()
+        t0 = time.time()
+        done, errs = jit_warm.warm()
+        yield
+        try:  # how many kernels the tests still had to compile themselves (tuning aid, never a failure)
+            import ctypes as C
+            from tikv_b200 import ffi
+            a, b = C.c_uint64(), C.c_uint64()
+            ffi.lib().b2_jit_counters(C.byref(a), C.byref(b))
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "jit_warm.log"), "w") as f:
+                f.write(f"warm-up: {done} kernels compiled in {time.time() - t0:.0f} s, errors: {errs[:2]}\nduring the tests: {a.value} NVRTC compilations, {b.value} disk-cache hits\n")
+        except Exception:
+            pass
+        return
     yield

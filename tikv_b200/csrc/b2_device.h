@@ -24,6 +24,14 @@
 #define B2_HD inline
 #define B2_HD_NOINLINE inline
 #endif
+// Decoders that only the general (dirty-data / v1 / odd-row) paths call: out of line in plan-specialised builds, where the
+// interpreter around them folds away and they would otherwise be inlined dozens of times into the kernel (B2_COLD_OUTLINE,
+// set by jit.cu).  The clean-entry paths have their own branch-free decoders.
+#if defined(B2_COLD_OUTLINE) && !defined(B2_NO_COLD_OUTLINE) && defined(__CUDACC__)
+#define B2_COLD __device__ __noinline__
+#else
+#define B2_COLD B2_HD
+#endif
 
 namespace b2 {
 
@@ -255,7 +263,7 @@ B2_HD uint64_t compress7(uint64_t x) {
 // Word-wise: one unaligned 8-byte load finds the terminating byte (first byte with bit 7 clear) and the payload bits
 // are gathered with three mask-and-shift steps; bytes 9 and 10 of the longest encodings are looked at separately.
 // (With n >= 10 the reference takes the 10th byte unconditionally and keeps only its lowest bit.)
-B2_HD uint32_t dec_var_u64(const uint8_t* p, uint32_t n, uint64_t* out) {
+B2_COLD uint32_t dec_var_u64(const uint8_t* p, uint32_t n, uint64_t* out) {
   if (n == 0) return 0;
   const uint64_t w = ld64(p);
   if ((w & 0x80u) == 0) { *out = w & 0x7fu; return 1; }
@@ -290,7 +298,7 @@ B2_HD uint32_t dec_var_u64_tu(const uint8_t* p, uint32_t n, uint64_t* out) {
   }
   return 0;
 }
-B2_HD uint32_t dec_var_i64(const uint8_t* p, uint32_t n, int64_t* out) {
+B2_COLD uint32_t dec_var_i64(const uint8_t* p, uint32_t n, int64_t* out) {
   uint64_t uv;
   uint32_t c = dec_var_u64(p, n, &uv);
   if (!c) return 0;
@@ -588,7 +596,7 @@ struct Cells {  // per-column cell location for v1 rows (filled by row_split)
 };
 
 // split_datum (datum.rs:1117-1155, desc = false): length of the first datum or 0 + err
-B2_HD uint32_t split_datum(const uint8_t* p, uint32_t n, int* err) {
+B2_COLD uint32_t split_datum(const uint8_t* p, uint32_t n, int* err) {
   if (n == 0) { *err = DE_ROW_BAD_DATUM; return 0; }
   uint32_t pos;
   const uint8_t* r = p + 1;
@@ -712,7 +720,8 @@ struct Row {
   uint64_t o_lo, o_hi;  // the row's u16 end-offsets 0..3 / 4..7
   uint64_t idx_handle;  // BatchIndexScan: the row's int handle (bits)
   const int64_t* imms;  // the request's hoisted constants (ScanArgs::imms: kernel parameter space on the device)
-  uint64_t cv[8];       // lean kernels, plan-specialised builds: the integer cells of the stored columns the plan's expressions
+  uint64_t* cv = nullptr;  // lean kernels, plan-specialised builds: the integer cells of the stored columns the plan's expressions
+                        //   (a caller-owned array of 8 words: kept out of the row so that indexing it never forces the row into local memory)
   uint32_t cv_mask = 0; //   read (DevPlan::fast_need), decoded once per row; bit h set = cv[h] is valid
   const uint8_t* gv = nullptr;  // address of rv.v[0] in the block's HBM heap (rv.v may be a shared-memory copy): what the cell
                                 //   references of bytes / json / decimal columns are made of (set only when the plan has such columns)
@@ -1287,7 +1296,9 @@ B2_HD uint32_t raw_ref_len(uint64_t r) { return (uint32_t)(r & 0xffffu); }
 // :697-913; v2 cells as write_v2_as_datum would have converted them, compat_v1.rs:54-129).  DATE / DATETIME and DURATION
 // become their 8-byte chunk cell here; bytes / json / decimal become a reference to the cell's payload in HBM, which the
 // kernels in kernels.cu (raw_*) turn into the column's heap / 40-byte structs once the launch's rows are in place.
-B2_HD int cell_value_raw(const DevCol& c, const Row& row, const uint8_t* p, uint32_t len, int kind, Value* out) {
+// (`heap` = the HBM address of p's first byte: the caller maps p, which may point into a shared-memory copy of the row, through Row::gv;
+//  the row itself is not passed: an out-of-line function taking the row by reference would pin it in local memory for every caller)
+B2_COLD int cell_value_raw(const DevCol& c, const uint8_t* heap, const uint8_t* p, uint32_t len, int kind, Value* out) {
   const uint64_t S = 0x8000000000000000ull;
   const uint8_t* q = p;
   uint32_t qn = len;
@@ -1328,7 +1339,7 @@ B2_HD int cell_value_raw(const DevCol& c, const Row& row, const uint8_t* p, uint
     else return DE_DATUM_DECODE;  // CK_JSON: a v1 JSON datum never gets here (split_datum does not size binary JSON on the device)
   }
   if (qn > 0xffffu) return DE_RAW_TOO_LONG;
-  out->bits = raw_ref_make(row.gv + (q - row.rv.v), qn);
+  out->bits = raw_ref_make(heap + (q - p), qn);
   return DE_NONE;
 }
 
@@ -1366,7 +1377,7 @@ B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k
     out->null = true;  // DS_NULL, or nullable without default
     return DE_NONE;
   }
-  if (c.kind >= CK_TIME) return cell_value_raw(c, row, p, len, kind, out);
+  if (c.kind >= CK_TIME) return cell_value_raw(c, row.gv + (p - r.v), p, len, kind, out);
   if (kind == CELL_V2) {
     if (c.kind == CK_INT) {
       // compat_v1.rs:13-38: sign- or zero-extend by width, then INT/UINT datum -> i64 bits

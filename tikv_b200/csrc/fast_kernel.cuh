@@ -210,6 +210,8 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
       } else if (commit) {
         Row row;
         Cells cells;
+        uint64_t cell_cache[8];
+        row.cv = cell_cache;
         row.enc_key = kp; row.enc_key_len = 27; row.commit_ts = cts; row.imms = A.imms;
         bool ok = fast_row_v2(P, rowp, rlen, row);
         bool keep = false;

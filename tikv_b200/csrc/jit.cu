@@ -134,7 +134,8 @@ std::map<std::string, Entry>& g_cache = *new std::map<std::string, Entry>();
 // holding the full key (a hash collision or a stale file is detected by comparing it).  Written atomically (rename).
 std::atomic<unsigned long long> g_nvrtc_compiles{0}, g_cache_hits{0};
 std::string cache_key(int mode, bool ext_sigs, bool fast, const std::string& literal) {
-  return "b2jit3|sm_100a|mode" + std::to_string(mode) + "|ext" + std::to_string((int)ext_sigs) + "|fast" + std::to_string((int)fast) + "|src" + std::to_string(api().src_hash) + "|" + literal;
+  const char* defs = getenv("B2_JIT_DEFS");  // experiment switches change the source text
+  return "b2jit4|sm_100a|mode" + std::to_string(mode) + "|ext" + std::to_string((int)ext_sigs) + "|fast" + std::to_string((int)fast) + "|src" + std::to_string(api().src_hash) + "|" + (defs ? defs : "") + "|" + literal;
 }
 std::string cache_path(const std::string& key) {
   char name[32];
@@ -167,7 +168,9 @@ void cache_store(const std::string& key, const std::vector<char>& cubin) {
 // NVRTC only (no CUDA context): plan literal -> sm_100a cubin
 bool compile_cubin(int mode, bool ext_sigs, bool fast, const std::string& literal, std::vector<char>* cubin, std::string* error) {
   Api& a = api();
-  std::string src = "#define B2_NVRTC 1\n#define B2_JIT_PLAN 1\n#include \"fast_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + literal +
+  std::string defs;  // experiment switches: B2_JIT_DEFS="-DX -DY" (part of the cache key through the source text)
+  if (const char* ev = getenv("B2_JIT_DEFS")) { std::string e(ev); size_t i = 0; while ((i = e.find("-D", i)) != std::string::npos) { size_t j = e.find(' ', i); std::string d = e.substr(i + 2, j == std::string::npos ? j : j - i - 2); defs += "#define " + d + " 1\n"; i = j == std::string::npos ? e.size() : j; } }
+  std::string src = defs + "#define B2_COLD_OUTLINE 1\n#define B2_NVRTC 1\n#define B2_JIT_PLAN 1\n#include \"fast_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + literal +
                     ";\n}\nextern \"C\" __global__ void __launch_bounds__(b2::TILE + 64, 2) b2_scan_jit(const __grid_constant__ b2::ScanArgs A) {\n"
                     "  b2::scan_body<" + std::to_string(mode) + ">(b2::kJitPlan, A);\n}\n";
   if (fast)

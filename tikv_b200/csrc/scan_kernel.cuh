@@ -156,12 +156,29 @@ __device__ void cta_topn_compact(const TopBuf& t, unsigned int limit, unsigned i
   cta256_sync();
   for (unsigned int k = 2; k <= cap; k <<= 1) {
     for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-      for (unsigned int p = tid; p < cap / 2; p += nt) {
-        unsigned int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), x = i | j;
-        bool up = (i & k) == 0;
-        unsigned short ia = idx[i], ib = idx[x];
-        bool swap = up ? topbuf_less(t, ib, ia, P) : topbuf_less(t, ia, ib, P);
-        if (swap) { idx[i] = ib; idx[x] = ia; }
+      // a thread's compare-exchanges of one step touch disjoint pairs: issue the loads of four of them before the first
+      // store (written as one loop the compiler has to assume the index stores alias the next pair's loads)
+      for (unsigned int base = 0; base < cap / 2; base += 4 * nt) {
+        unsigned int pi[4], px[4];
+        unsigned short va[4], vb[4];
+        bool sw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned int p = base + tid + (unsigned int)u * nt;
+          const unsigned int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+          pi[u] = i; px[u] = i | j;
+          const bool on = p < cap / 2;
+          va[u] = on ? idx[pi[u]] : (unsigned short)0; vb[u] = on ? idx[px[u]] : (unsigned short)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool on = base + tid + (unsigned int)u * nt < cap / 2;
+          const bool up = (pi[u] & k) == 0;
+          sw[u] = on && (up ? topbuf_less(t, vb[u], va[u], P) : topbuf_less(t, va[u], vb[u], P));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (sw[u]) { idx[pi[u]] = vb[u]; idx[px[u]] = va[u]; }
       }
       cta256_sync();
     }
@@ -399,6 +416,10 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   const uint32_t n_list = !IS_SCAN && A.list_mode ? *(volatile unsigned int*)A.slow_count : 0u;
   const uint32_t n_tiles = !IS_SCAN && A.list_mode ? (n_list + TILE - 1) / TILE : (A.c_hi - A.c_lo + TILE - 1) / TILE;
   const unsigned long long out_base = IS_SCAN ? A.ctr->out_base : 0ull;  // stable during this launch
+  if (!IS_SCAN && A.list_mode && n_list == 0) {  // the lean kernel handed nothing over (the usual case on clean data)
+    if (MODE == PM_TOPN && tid == 0) A.topn.counts[blockIdx.x] = 0;
+    return;
+  }
 
   SmemTable st;
   st.slots = 0;
