@@ -24,9 +24,9 @@
 #define B2_HD inline
 #define B2_HD_NOINLINE inline
 #endif
-// Decoders that only the general (dirty-data / v1 / odd-row) paths call: out of line in plan-specialised builds, where the
-// interpreter around them folds away and they would otherwise be inlined dozens of times into the kernel (B2_COLD_OUTLINE,
-// set by jit.cu).  The clean-entry paths have their own branch-free decoders.
+// Decoders that only the general (dirty-data / v1 / odd-row) paths call: out of line when jit.cu sets B2_COLD_OUTLINE (plans
+// with the rarer scalar functions, whose unrolled evaluators make NVRTC slow), inlined everywhere else: the scan kernel's
+// register allocation is sensitive to it (measured both ways).  The clean-entry paths have their own branch-free decoders.
 #if defined(B2_COLD_OUTLINE) && !defined(B2_NO_COLD_OUTLINE) && defined(__CUDACC__)
 #define B2_COLD __device__ __noinline__
 #else
@@ -1354,7 +1354,9 @@ B2_HD int cell_value(const DevPlan& P, const Row& row, const Cells& cells, int k
     return DE_NONE;
   }
   if (c.role == CR_HANDLE) { out->bits = raw_be64(row.enc_key, 11) ^ S; return DE_NONE; }       // table.rs:214-218
+#ifndef B2_NO_IDX
   if (c.role == CR_IDX_HANDLE) { out->bits = row.idx_handle; return DE_NONE; }
+#endif
   if (c.role == CR_TABLE_ID) { out->bits = raw_be64(row.enc_key, 1) ^ S; return DE_NONE; }
   if (c.role == CR_COMMIT_TS) { out->bits = row.commit_ts; return DE_NONE; }
   if (c.kind == CK_OTHER) return DE_UNSUPPORTED_TYPE;

@@ -1656,14 +1656,14 @@ struct b2_exec {
         a.topn.n_lists = (uint32_t)(gg + fg);
         // unit top-N (sorted) lands in the second half of `pair`
         TopNLists unit_out; unit_out.items = pair + limit; unit_out.counts = pair_cnt + 1; unit_out.n_lists = 1; unit_out.stride = limit;
-        {  // per-CTA lists -> one list, fan-in 8 per level
+        {  // per-CTA lists -> one list, fan-in 16 per level (after the first chunks the lists are nearly empty: fewer launches matter more than narrow merges)
           TopNLists cur = a.topn;
           int flip = 0;
-          while (cur.n_lists > 8) {
+          while (cur.n_lists > 16) {
             TopNLists nxt;
-            nxt.n_lists = (cur.n_lists + 7) / 8; nxt.stride = limit;
+            nxt.n_lists = (cur.n_lists + 15) / 16; nxt.stride = limit;
             nxt.items = (TopItem*)(flip ? tn_lvl_b.p : tn_lvl_a.p); nxt.counts = (unsigned int*)(flip ? tn_lvl_b_cnt.p : tn_lvl_a_cnt.p);
-            CUDA_TRY(launch_topn_merge(P, cur, nxt, cap, 8, stream));
+            CUDA_TRY(launch_topn_merge(P, cur, nxt, cap, 16, stream));
             stats.kernel_launches++;
             cur = nxt; flip ^= 1;
           }

@@ -334,8 +334,11 @@ __device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A,
   row.commit_ts = ro.commit_ts;
   row.imms = A.imms;
   int err;
+#ifndef B2_NO_IDX
   if (P.idx_cols > 0) err = index_row_split(P, row, cells, ro.val, ro.val_len, idx_buf);  // BatchIndexScan: the columns are the key's datums
-  else {
+  else
+#endif
+  {
     err = row_open(ro.val, ro.val_len, &row.rv);
     if (P.n_raw) row.gv = ro.dflt_lookup ? ro.val : view.gval(ro.val);  // (a CF_DEFAULT value is always read in place)
     if (!err) err = row_split(P, row, cells);
@@ -641,7 +644,11 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
     bool live = false;
     Row row;
     Cells cells;
+#ifndef B2_NO_IDX
     uint8_t idx_buf[IDX_RAW_MAX];  // BatchIndexScan: the row's raw key bytes after the index id (unused, and optimised away, otherwise)
+#else
+    uint8_t* idx_buf = nullptr;    // (a kernel specialised for a table scan carries none of the index-row decoder)
+#endif
     EntryStats d;
     d.keys = d.size = d.dflt = d.ck_x = d.ck_kvs = d.ck_bytes = 0; d.newer = 0; d.last = 0; d.warn = 0;
     int r1 = P1_NONE;

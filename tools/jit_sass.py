@@ -40,7 +40,7 @@ def compile_cubin(plan):
     mode = J.mode_of(lit)
     if not os.environ.get("B2_KEEP_V1"):  # the engine clears fast_v1 when the data is row format v2 (it samples the first row)
         lit, n = re.subn(r"(u,\{-?\d+(?:,-?\d+){7}\},\d+,\d+u),1,", r"\1,0,", lit, count=1)
-    src = (os.environ.get("B2_SRC_DEFS", "#define B2_COLD_OUTLINE 1\n") + "#define B2_NVRTC 1\n#define B2_JIT_PLAN 1\n#include \"fast_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + lit + ";\n}\n"
+    src = (os.environ.get("B2_SRC_DEFS", "#define B2_NO_IDX 1\n") + "#define B2_NVRTC 1\n#define B2_JIT_PLAN 1\n#include \"fast_kernel.cuh\"\nnamespace b2 { __constant__ const DevPlan kJitPlan =\n" + lit + ";\n}\n"
            "extern \"C\" __global__ void __launch_bounds__(b2::TILE + 64, 2) b2_scan_jit(const __grid_constant__ b2::ScanArgs A) {\n"
            "  b2::scan_body<" + str(mode) + ">(b2::kJitPlan, A);\n}\n")
     if mode in (1, 2) and os.environ.get("B2_FAST", "1") == "1":
