@@ -130,7 +130,8 @@ size_t topn_smem_bytes(uint32_t cap, int n_order) { return (((size_t)cap * ((siz
 
 // CTA b streams every item of input lists [b * fan_in, (b + 1) * fan_in) through one threshold buffer and leaves the
 // best `limit`, sorted, in output list b.  The host applies it level by level (fan-in 8) down to a single list.
-__global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant__ DevPlan P, TopNLists in, TopNLists out, unsigned int cap, unsigned int fan_in) {
+__global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant__ DevPlan P, TopNLists in, TopNLists out, unsigned int cap, unsigned int fan_in,
+                                                         unsigned int rm_bytes /* dynamic shared memory available to the rank merge */) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned int s_cnt, s_have_thr;
   __shared__ TopItem s_thr;
@@ -148,6 +149,66 @@ __global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant_
   for (unsigned int q = 0; q < 16; ++q) {
     if (l0 + q < l1) total += in.counts[l0 + q] < in.stride ? in.counts[l0 + q] : in.stride;
     ends[q] = total;
+  }
+  // Rank merge: the input lists are sorted and the order is total (ids), so when all their items fit in shared memory
+  // every item finds its output position as own index + the number of smaller items in each other list (binary searches
+  // in shared memory): no sorting network, cost proportional to the items present.
+  const unsigned int rstride = (unsigned int)P.n_order + 2;
+  if ((size_t)total * rstride * 8 <= (size_t)rm_bytes) {
+    unsigned long long* rw = reinterpret_cast<unsigned long long*>(dyn_smem);
+    for (unsigned int f = tid; f < total; f += TILE) {
+      unsigned int q = 0, first = 0;
+#pragma unroll
+      for (unsigned int z = 0; z < 15; ++z)
+        if (f >= ends[z]) { q = z + 1; first = ends[z]; }
+      const TopItem it = in.items[(size_t)(l0 + q) * in.stride + (f - first)];
+      unsigned long long* d = rw + (size_t)f * rstride;
+      for (int k = 0; k < P.n_order; ++k) d[k] = it.w[k];
+      d[P.n_order] = it.id;
+      d[P.n_order + 1] = (unsigned long long)it.nulls | ((unsigned long long)(((l0 + q) << 16) | (f - first)) << 32);
+    }
+    __syncthreads();
+    auto less = [&](const unsigned long long* a, const unsigned long long* b) -> bool {  // item_less on packed words
+      const unsigned int na_all = (unsigned int)a[rstride - 1], nb_all = (unsigned int)b[rstride - 1];
+      for (int k = 0; k < P.n_order; ++k) {
+        const unsigned int na = (na_all >> k) & 1, nb = (nb_all >> k) & 1;
+        int c;
+        if (na || nb) c = (int)nb - (int)na;
+        else c = a[k] < b[k] ? -1 : (a[k] > b[k] ? 1 : 0);
+        if (c == 0) continue;
+        if (P.order[k].desc) c = -c;
+        return c < 0;
+      }
+      return a[P.n_order] < b[P.n_order];
+    };
+    for (unsigned int f = tid; f < total; f += TILE) {
+      unsigned int q = 0, first = 0;
+#pragma unroll
+      for (unsigned int z = 0; z < 15; ++z)
+        if (f >= ends[z]) { q = z + 1; first = ends[z]; }
+      const unsigned long long* me = rw + (size_t)f * rstride;
+      unsigned int rank = f - first;
+      unsigned int lo_z = 0;
+#pragma unroll 1
+      for (unsigned int z = 0; z < 16; ++z) {
+        const unsigned int hi_z = ends[z];
+        if (z != q && hi_z > lo_z) {
+          unsigned int lo = lo_z, hi = hi_z;
+          while (lo < hi) { const unsigned int mid = (lo + hi) >> 1; if (less(rw + (size_t)mid * rstride, me)) lo = mid + 1; else hi = mid; }
+          rank += lo - lo_z;
+        }
+        lo_z = hi_z;
+      }
+      if (rank < (unsigned int)P.limit) {
+        TopItem it;
+        for (int k = 0; k < MAX_ORDER; ++k) it.w[k] = k < P.n_order ? me[k] : 0ull;
+        it.id = me[P.n_order];
+        it.nulls = (unsigned int)me[P.n_order + 1]; it.slot = (unsigned int)(me[P.n_order + 1] >> 32);
+        out.items[(size_t)blockIdx.x * out.stride + rank] = it;
+      }
+    }
+    if (tid == 0) out.counts[blockIdx.x] = total < (unsigned int)P.limit ? total : (unsigned int)P.limit;
+    return;
   }
   for (unsigned int base = 0; base < total; base += TILE) {
     unsigned int f = base + tid;
@@ -175,10 +236,11 @@ __global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant_
 }
 
 cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const TopNLists& out, uint32_t cap, uint32_t fan_in, cudaStream_t s) {
-  size_t smem = topn_smem_bytes(cap, plan.n_order);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(topn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = std::max<size_t>(topn_smem_bytes(cap, plan.n_order), 200 * 1024);  // room for the rank merge: 6400 items of two sort keys
+  static size_t attr_bytes = 0;  // (one process drives one device)
+  if (smem > attr_bytes) { cudaFuncSetAttribute(topn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_bytes = smem; }
   unsigned int grid = (in.n_lists + fan_in - 1) / fan_in;
-  topn_merge_kernel<<<grid, TILE, smem, s>>>(plan, in, out, cap, fan_in);
+  topn_merge_kernel<<<grid, TILE, smem, s>>>(plan, in, out, cap, fan_in, (unsigned int)smem);
   return cudaGetLastError();
 }
 

@@ -7,7 +7,7 @@ R=${1:-r2}
 mkdir -p gpurun_out
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_$R.json 2> gpurun_out/bench_reference_$R.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_$R.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_$R.csv \
   python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-parity > gpurun_out/launches_$R.log 2>&1
 SMALL="--rows 100000000 --blocks 8 --steps 1 --warmup 3 --no-e2e --no-cpu --no-sub --no-parity"   # one launch = one 12.5M-entry block
 ncu --set full --import-source on --clock-control none -k 'regex:fast_kernel|b2_fast_jit' -s 30 -c 1 -f -o gpurun_out/agg_kernel_$R python bench.py $SMALL > gpurun_out/ncu_agg_$R.log 2>&1
