@@ -162,6 +162,70 @@ def run_dag(ffi, plan, ranges, src, out_loc, chunk, stream=0, after=None):
     return rows, st
 
 
+def sst_e2e(ffi, device, blks, plan, after, args, stream, barrier, max_over_ranks, e2e_rows, world):
+    """End to end from RocksDB data blocks in pinned host memory.  Setup (untimed): the generated regions are encoded on the
+    device (b2_sst_encode, ~32 KiB blocks, restart interval 16, 'z' + internal-key footer + trailer: the stored form of a
+    TiKV write-CF block, src/config/mod.rs:966) and copied to the host.  Timed, per step: b2_sst_decode of every region
+    (H2D of the compressed bytes + expansion on the device) and the request over the decoded blocks, result to the host."""
+    import numpy as np
+    import torch
+    from tikv_b200.executor import SstDecoder
+    L = ffi.lib()
+    enc_host, keep, flat_bytes, enc_bytes = [], [], 0, 0
+    for b in blks:
+        per = max(16, 32768 // max(8, int((b.key_bytes + b.val_bytes) / max(1, b.block.n)) - 9))
+        h, enc = C.c_void_p(), ffi.SstEncoded()
+        if L.b2_sst_encode(device, C.byref(b.block), per, 16, 1, ord("z"), 8, 5, C.byref(h), C.byref(enc)) != 0:
+            raise RuntimeError("b2_sst_encode: " + L.b2_last_error_message().decode())
+        p = L.b2_host_alloc_pinned_near(device, enc.data_len + 64)
+        if not p:
+            raise RuntimeError("pinned host allocation failed")
+        keep.append(p)
+        offs = np.zeros(enc.n_blocks + 1, dtype=np.uint64)
+        if L.b2_copy_to_host(device, p, enc.data, enc.data_len) != 0 or L.b2_copy_to_host(device, offs.ctypes.data, enc.block_offs, 8 * len(offs)) != 0:
+            raise RuntimeError("D2H copy failed")
+        L.b2_sst_free(h)
+        enc_host.append((p, offs))
+        flat_bytes += b.key_bytes + b.val_bytes + 8 * b.block.n
+        enc_bytes += enc.data_len
+    decs = [SstDecoder(device) for _ in blks]
+    try:
+        def step():
+            arr, h2d, dms = [], 0, 0.0
+            for d, (p, offs) in zip(decs, enc_host):
+                blk, st = d.decode(p, offs)
+                arr.append(blk)
+                h2d += st.h2d_bytes
+                dms += st.decode_ms
+            src = Source(ffi, arr, ffi.LOC_DEVICE, device)
+            rows, st = run_dag(ffi, plan, table_range(), src, ffi.LOC_HOST, args.chunk, stream.cuda_stream, after)
+            return rows, st, h2d, dms
+        for _ in range(2):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        k = max(1, min(args.steps, 3))
+        dms_acc = 0.0
+        for _ in range(k):
+            rows, st, h2d, dms = step()
+            dms_acc += dms
+        e1.record(stream)
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / k
+    finally:
+        for d in decs:
+            d.close()
+        for p in keep:
+            L.b2_host_free_pinned(p)
+    return {"value": e2e_rows * world / (ms / 1e3), "unit": "rows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(st.d2h_bytes), "ms_per_step": ms,
+            "rows_per_gpu": int(e2e_rows), "rows_out": int(rows), "decode_ms_per_step": dms_acc / k,
+            "source": "RocksDB data blocks (uncompressed, prefix-compressed keys, 'z' prefix + internal-key footer + trailer) in pinned host memory, "
+                      "expanded on the device by b2_sst_decode",
+            "compressed_to_flat_bytes": enc_bytes / max(1, flat_bytes),
+            "note": "cold: every data block crosses PCIe inside the timed region"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -444,6 +508,7 @@ def main():
     ap.add_argument("--e2e-rows", type=int, default=0, help="rows of the end-to-end (host buffer) request; 0 = as many of --rows as host memory allows")
     ap.add_argument("--parity-rows", type=int, default=1_000_000)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sst", action="store_true", help="end to end from flat CF blocks only (skip the RocksDB data-block source)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the C2 / C4 / C5 sub-records")
     ap.add_argument("--no-parity", action="store_true")
@@ -629,10 +694,19 @@ def main():
         e2e_blocks = min(e2e_blocks, max(1, -(-want * len(blks) // args.rows)))
         sub_blks = blks[:e2e_blocks]
         e2e_rows = sum(b.n_user_keys for b in sub_blks)
-        host_blocks, pinned = blocks_to_pinned_host(ffi, device, sub_blks)
-        host_src = Source(ffi, host_blocks, ffi.LOC_HOST, device)
         plan = plans[head]
         after = after_agg if head == "c3" else None  # (the TopN merge reads device-resident columns: HBM-resident steps only)
+        # (a) the regions as TiKV's block cache holds them: RocksDB data blocks (uncompressed, prefix-compressed keys, 'z' data
+        # prefix, internal-key footer, block trailer) in pinned host memory; every step expands them on the device
+        # (b2_sst_decode) and runs the request over the decoded blocks.  Fewer bytes cross PCIe than with flat blocks.
+        e2e_sst = None
+        if not args.no_sst:
+            try:
+                e2e_sst = sst_e2e(ffi, device, sub_blks, plan, after, args, stream, barrier, max_over_ranks, e2e_rows, world)
+            except Exception as ex:  # the flat-block request below still measures the end-to-end path
+                e2e_sst = {"error": str(ex)[:300]}
+        host_blocks, pinned = blocks_to_pinned_host(ffi, device, sub_blks)
+        host_src = Source(ffi, host_blocks, ffi.LOC_HOST, device)
         for _ in range(2):
             r_e2e, st_e = run_dag(ffi, plan, table_range(), host_src, ffi.LOC_HOST, args.chunk, stream.cuda_stream, after)
         barrier()
@@ -644,9 +718,18 @@ def main():
         e1.record(stream)
         barrier()
         ms_e = max_over_ranks(e0.elapsed_time(e1)) / k
+        part = "" if e2e_rows == args.rows else f"; {e2e_blocks} of {len(blks)} regions of the table (pinned host memory budget), same plan"
         e2e = {"value": e2e_rows * world / (ms_e / 1e3), "unit": "rows/s", "h2d_bytes_per_step": int(st_e.h2d_bytes), "d2h_bytes_per_step": int(st_e.d2h_bytes),
-               "ms_per_step": ms_e, "rows_per_gpu": int(e2e_rows),
-               "note": "cold: every block crosses PCIe inside the timed region" + ("" if e2e_rows == args.rows else f"; {e2e_blocks} of {len(blks)} regions of the table (pinned host memory budget), same plan")}
+               "ms_per_step": ms_e, "rows_per_gpu": int(e2e_rows), "source": "flat CF blocks (b2_cf_block) in pinned host memory",
+               "note": "cold: every block crosses PCIe inside the timed region" + part}
+        if e2e_sst and "value" in e2e_sst:
+            assert e2e_sst.pop("rows_out") == r_e2e
+            flat = e2e
+            e2e = e2e_sst
+            e2e["note"] += part
+            e2e["flat"] = flat
+        elif e2e_sst:
+            e2e["sst_error"] = e2e_sst["error"]
         # warm: the same host-resident regions pinned in the HBM block cache (b2_region_pin, keyed by region id + data version):
         # a repeated request reads HBM, only the result crosses PCIe
         for g in gens:

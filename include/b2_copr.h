@@ -16,6 +16,9 @@
  *   b2_region_source    <- trait Storage (bulk instead of row-at-a-time pull)
  *                          components/tidb_query_common/src/storage/mod.rs:32-71
  *   b2_dag_plan         <- tipb::DagRequest as consumed by build_executors, runner.rs:252-603
+ *   b2_sst_decode       <- the RocksDB data-block iterator under RegionSnapshot / Cursor
+ *                          (components/engine_rocks, external librocksdb: BlockBasedTable data blocks;
+ *                          block size / format version set in src/config/mod.rs:966, :704)
  *
  * Plain C types only: pointers, sizes, PODs.  No C++/torch types cross this line.
  * Handles are single-threaded (externally synchronised), like `BatchExecutor: Send`.
@@ -36,7 +39,7 @@ typedef int int32_t; typedef unsigned int uint32_t; typedef long long int64_t; t
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 3
+#define B2_ABI_VERSION 4
 
 /* ---- status codes (tidb_query_common::error::Error classes, dag/mod.rs:231-244) ---- */
 enum {
@@ -437,10 +440,64 @@ int32_t b2_checksum_handle(const b2_key_range* ranges, uint32_t n_ranges,
  * request runs at HBM speed instead of PCIe speed.  b2_region_pin copies the CF blocks of `host_src` (B2_LOC_HOST) to the
  * device once, keyed by (device, region_id, data_version), and fills *dev_src with a B2_LOC_DEVICE source over the cached
  * copy (same read_ts / isolation fields; valid until the matching b2_region_unpin).  Pinning the same key again returns
- * the existing copy.  B2_ERR_UNSUPPORTED when the cache budget (B2_BLOCK_CACHE_BYTES, default 64 GiB per device) is full. */
+ * the existing copy.  B2_ERR_UNSUPPORTED when the cache budget (B2_BLOCK_CACHE_BYTES, default 3/4 of the device memory) is full. */
 int32_t b2_region_pin(int32_t device, uint64_t region_id, uint64_t data_version, const b2_region_source* host_src, b2_region_source* dev_src);
 int32_t b2_region_unpin(int32_t device, uint64_t region_id, uint64_t data_version);
 void b2_region_cache_stats(int32_t device, uint64_t* bytes_cached, uint64_t* hits, uint64_t* misses);
+
+/* ---- RocksDB data blocks as the data source (the on-disk block reader) -----------------------------
+ * TiKV's block cache holds *uncompressed* BlockBasedTable data blocks whose keys are prefix-compressed between restart
+ * points (RocksDB is an external dependency of the reference; block size and format version come from
+ * src/config/mod.rs:966 and :704).  b2_sst_decode takes a run of such blocks, in key order, and expands them on the
+ * device into the flat b2_cf_block layout the scan kernels read: the bytes that cross PCIe are the compressed ones.
+ *
+ *   data block  := entry* restart[u32 LE x num_restarts] num_restarts[u32 LE]   (+ 5-byte trailer: type, checksum)
+ *   entry       := varint32 shared | varint32 non_shared | varint32 value_len | key[shared..] | value
+ *   key         := key_prefix_len bytes (TiKV: 'z', components/keys/src/lib.rs:28) | CF key | key_suffix_len bytes
+ *                  (RocksDB internal-key footer: fixed64 LE of seq << 8 | type)
+ *
+ * Supported: binary-search data blocks (no hash index: top bit of num_restarts clear), value type kTypeValue (1) in every
+ * footer -- i.e. files that hold one RocksDB version of each key (bottommost level, ingested SSTs).  Anything else
+ * answers B2_ERR_UNSUPPORTED and the host keeps its merging iterator.  Compressed blocks (LZ4 / ZSTD / Snappy) must be
+ * uncompressed by the caller (the block cache already did).  Checksums of the trailer are not verified.              */
+typedef struct b2_sst_blocks {
+  const uint8_t* data;        /* the blocks, back to back or with gaps; host or device memory (see `location`) */
+  const uint64_t* block_offs; /* host memory, n_blocks + 1 ascending offsets into data: block b = [block_offs[b], block_offs[b+1])
+                                 (the BlockHandle list an index block yields) */
+  uint32_t n_blocks;
+  uint32_t trailer_len;       /* bytes at the end of every slice that are not block contents: 5 with the block trailer, else 0 */
+  uint32_t key_prefix_len;    /* dropped from the front of every key (1 for TiKV data keys) */
+  uint32_t key_suffix_len;    /* dropped from the end of every key: 8 = internal-key footer (checked), 0 = user keys only */
+} b2_sst_blocks;
+
+typedef struct b2_sst_stats {
+  uint64_t n_entries, key_bytes, val_bytes; /* of the decoded block */
+  uint64_t n_restart_intervals;
+  uint64_t h2d_bytes;                       /* compressed bytes + offsets copied host -> device by this call */
+  float decode_ms;                          /* device time of the expansion kernels (CUDA events) */
+  uint32_t _pad;
+} b2_sst_stats;
+
+typedef struct b2_sst b2_sst; /* owner of the decoded device block */
+/* Decode `in` on `device`.  *h == NULL creates a handle, otherwise the handle's buffers are reused (they only grow).
+ * On success *out holds B2_LOC_DEVICE pointers owned by the handle (valid until the next decode on it or b2_sst_free),
+ * padded as b2_cf_block requires.  Blocking.  The decoded heaps must stay below 4 GiB each (u32 offsets). */
+int32_t b2_sst_decode(int32_t device, int32_t location, const b2_sst_blocks* in, b2_sst** h, b2_cf_block* out, b2_sst_stats* stats);
+void b2_sst_free(b2_sst* h);
+/* tooling (tests / bench): the inverse.  Encodes a device-resident flat block as data blocks of `entries_per_block`
+ * entries with a restart point every `restart_interval` entries, key_prefix / internal-key footer (seq 0, kTypeValue)
+ * added as asked, 5-byte trailer (type 0, checksum field zero) when trailer_len == 5.  The encoded bytes and the
+ * n_blocks + 1 offsets stay on the device, owned by the handle; copy them out with b2_copy_to_host. */
+typedef struct b2_sst_encoded {
+  const uint8_t* data;        /* device */
+  const uint64_t* block_offs; /* device, n_blocks + 1 */
+  uint64_t data_len;
+  uint32_t n_blocks;
+  uint32_t _pad;
+} b2_sst_encoded;
+int32_t b2_sst_encode(int32_t device, const b2_cf_block* flat_device_block, uint32_t entries_per_block, uint32_t restart_interval,
+                      uint32_t key_prefix_len, uint8_t key_prefix_byte, uint32_t key_suffix_len, uint32_t trailer_len,
+                      b2_sst** h, b2_sst_encoded* out);
 
 /* tooling: the compiled device plan of `plan` as a C++ aggregate initialiser (what the run-time compiler is fed);
  * returns its length, writes at most cap - 1 bytes + NUL into buf, negative status on error */

@@ -18,6 +18,7 @@
 #include "orc_encode.h"
 #include "orc_chunk.h"
 #include "orc_gen.h"
+#include "orc_sst.h"
 
 using namespace orc;
 
@@ -487,5 +488,35 @@ size_t orc_decimal_write(const b2_decimal* a, int prec, int frac, uint8_t* out) 
   return b.size();
 }
 int orc_decimal_cmp(const b2_decimal* a, const b2_decimal* b) { return dec_cmp(*(const Decimal*)a, *(const Decimal*)b); }
+
+// ---- RocksDB data blocks (orc_sst.h): builder and iterator for the block-reader tests ----
+struct orc_sst_buf { std::string data, keys, vals; std::vector<uint64_t> offs; std::vector<uint32_t> koff, voff; };
+void* orc_sst_build(const b2_cf_block* flat, uint32_t restart_interval, uint32_t block_size, uint32_t entries_per_block, uint32_t key_prefix_len, uint8_t key_prefix_byte,
+                    uint32_t key_suffix_len, uint32_t trailer_len) {
+  SstOptions o;
+  o.restart_interval = restart_interval; o.block_size = block_size; o.entries_per_block = entries_per_block; o.key_prefix_len = key_prefix_len; o.key_prefix_byte = key_prefix_byte;
+  o.key_suffix_len = key_suffix_len; o.trailer_len = trailer_len;
+  auto* r = new orc_sst_buf();
+  sst_build(flat->keys, flat->key_offs, flat->vals, flat->val_offs, flat->n, o, &r->data, &r->offs);
+  return r;
+}
+// 0 ok, 1 corrupted, 2 unsupported; *out holds the flat block (orc_sst_flat)
+int orc_sst_decode(const uint8_t* data, const uint64_t* block_offs, uint32_t n_blocks, uint32_t trailer_len, uint32_t key_prefix_len, uint32_t key_suffix_len, void** out) {
+  auto* r = new orc_sst_buf();
+  int rc = sst_decode(data, block_offs, n_blocks, trailer_len, key_prefix_len, key_suffix_len, &r->keys, &r->koff, &r->vals, &r->voff);
+  *out = r;
+  return rc;
+}
+const uint8_t* orc_sst_data(void* h, uint64_t* len, const uint64_t** offs, uint32_t* n_blocks) {
+  auto* r = (orc_sst_buf*)h;
+  *len = r->data.size(); *offs = r->offs.data(); *n_blocks = (uint32_t)r->offs.size() - 1;
+  return (const uint8_t*)r->data.data();
+}
+void orc_sst_flat(void* h, b2_cf_block* out) {
+  auto* r = (orc_sst_buf*)h;
+  out->keys = (const uint8_t*)r->keys.data(); out->key_offs = r->koff.data(); out->vals = (const uint8_t*)r->vals.data(); out->val_offs = r->voff.data();
+  out->n = (uint32_t)r->koff.size() - 1;
+}
+void orc_sst_free(void* h) { delete (orc_sst_buf*)h; }
 
 }  // extern "C"

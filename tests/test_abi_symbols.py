@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_abi_version_and_structs(lib):
     from tikv_b200 import ffi
-    assert lib.b2_abi_version() == 3
+    assert lib.b2_abi_version() == 4
     assert b"sm_100a" in lib.b2_build_info()
     # struct sizes the Rust/cgo side would mirror
     assert C.sizeof(ffi.Decimal) == 40 and C.sizeof(ffi.CfBlock) == 40 and C.sizeof(ffi.RpnNode) == 40
@@ -97,7 +97,8 @@ def test_ctypes_mirror_matches_header_layout(tmp_path):
              "b2_executor_desc": ffi.ExecutorDesc, "b2_dag_plan": ffi.DagPlan, "b2_exec_config": ffi.ExecConfig, "b2_decimal": ffi.Decimal,
              "b2_column": ffi.Column, "b2_batch": ffi.Batch, "b2_exec_stats": ffi.ExecStats, "b2_error_info": ffi.ErrorInfo,
              "b2_checksum_response": ffi.ChecksumResponse, "b2_agg_partials": ffi.AggPartials, "b2_gen_spec": ffi.GenSpec,
-             "b2_gen_block": ffi.GenBlock, "b2_encoded_chunk": ffi.EncodedChunk}
+             "b2_gen_block": ffi.GenBlock, "b2_encoded_chunk": ffi.EncodedChunk, "b2_sst_blocks": ffi.SstBlocks, "b2_sst_stats": ffi.SstStats,
+             "b2_sst_encoded": ffi.SstEncoded}
     header = open(os.path.join(ROOT, "include", "b2_copr.h")).read()
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b2_copr.h"', 'int main(void) {']
     expect = {}

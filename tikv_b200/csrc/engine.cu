@@ -34,6 +34,7 @@
 using namespace b2;
 
 static thread_local std::string g_last_error;
+namespace b2 { void set_last_error(const std::string& m) { g_last_error = m; } }  // for the other translation units (sst.cu)
 
 #define CUDA_TRY(expr)                                                                                   \
   do {                                                                                                   \
@@ -1993,7 +1994,12 @@ struct CacheKey { int device; uint64_t region, version; bool operator<(const Cac
 std::mutex g_cache_mu;
 std::map<CacheKey, std::unique_ptr<PinnedRegion>>& region_cache() { static auto* m = new std::map<CacheKey, std::unique_ptr<PinnedRegion>>(); return *m; }
 uint64_t g_cache_bytes[64] = {0}, g_cache_hits[64] = {0}, g_cache_misses[64] = {0};
-uint64_t cache_budget() { const char* v = getenv("B2_BLOCK_CACHE_BYTES"); return v ? strtoull(v, nullptr, 10) : (64ull << 30); }
+uint64_t cache_budget() {  // B2_BLOCK_CACHE_BYTES, else three quarters of the current device's memory
+  if (const char* v = getenv("B2_BLOCK_CACHE_BYTES")) return strtoull(v, nullptr, 10);
+  size_t fr = 0, tot = 0;
+  if (cudaMemGetInfo(&fr, &tot) != cudaSuccess || !tot) return 64ull << 30;
+  return (uint64_t)tot / 4 * 3;
+}
 }  // namespace
 
 int32_t b2_region_pin(int32_t device, uint64_t region_id, uint64_t data_version, const b2_region_source* src, b2_region_source* out) {

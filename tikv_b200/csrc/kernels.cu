@@ -235,7 +235,72 @@ __global__ void __launch_bounds__(TILE) topn_merge_kernel(const __grid_constant_
   if (tid == 0) out.counts[blockIdx.x] = keep;
 }
 
+// The same merge without a shared-memory budget: the input lists are sorted and the order is total (ids), so an item's
+// output position is its own index + the number of items that come before it in each sibling list.  Every item is
+// independent: blockIdx.y splits a group's items over as many CTAs as the occupied part needs, and a thread runs its
+// (up to 15) binary searches in lockstep so that their L2 round trips overlap.  Only the first `limit - i` items of a
+// sibling can keep item i inside the output, which bounds every search.  Cost follows the items present.
+__global__ void __launch_bounds__(256) topn_rank_merge_kernel(const __grid_constant__ DevPlan P, TopNLists in, TopNLists out, unsigned int fan_in) {
+  const unsigned int limit = (unsigned int)P.limit;
+  const unsigned int l0 = blockIdx.x * fan_in;
+  const unsigned int l1 = l0 + fan_in < in.n_lists ? l0 + fan_in : in.n_lists;
+  const unsigned int clip = in.stride < limit ? in.stride : limit;
+  unsigned int ends[16];
+  unsigned int total = 0;
+#pragma unroll
+  for (unsigned int q = 0; q < 16; ++q) {
+    if (l0 + q < l1) { const unsigned int c = in.counts[l0 + q]; total += c < clip ? c : clip; }
+    ends[q] = total;
+  }
+  if (blockIdx.y == 0 && threadIdx.x == 0) out.counts[blockIdx.x] = total < limit ? total : limit;
+  for (unsigned int f = blockIdx.y * blockDim.x + threadIdx.x; f < total; f += gridDim.y * blockDim.x) {
+    unsigned int q = 0, first = 0;
+#pragma unroll
+    for (unsigned int z = 0; z < 15; ++z)
+      if (f >= ends[z]) { q = z + 1; first = ends[z]; }
+    const unsigned int i = f - first;
+    TopItem me = in.items[(size_t)(l0 + q) * in.stride + i];
+    const unsigned int room = limit - i;  // i < clip <= limit
+    unsigned int lo[16], hi[16];
+#pragma unroll
+    for (unsigned int z = 0; z < 16; ++z) {
+      const unsigned int cnt = ends[z] - (z ? ends[z - 1] : 0u);
+      lo[z] = 0;
+      hi[z] = z == q ? 0u : (cnt < room ? cnt : room);
+    }
+    bool more = true;
+    while (more) {
+      more = false;
+#pragma unroll
+      for (unsigned int z = 0; z < 16; ++z)
+        if (lo[z] < hi[z]) {
+          const unsigned int mid = (lo[z] + hi[z]) >> 1;
+          if (item_less(in.items[(size_t)(l0 + z) * in.stride + mid], me, P)) lo[z] = mid + 1; else hi[z] = mid;
+          more = true;
+        }
+    }
+    unsigned int rank = i;
+#pragma unroll
+    for (unsigned int z = 0; z < 16; ++z) rank += lo[z];
+    if (rank < limit) {
+      me.slot = ((l0 + q) << 16) | i;
+      out.items[(size_t)blockIdx.x * out.stride + rank] = me;
+    }
+  }
+}
+
 cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const TopNLists& out, uint32_t cap, uint32_t fan_in, cudaStream_t s) {
+  static const bool staged = getenv("B2_TOPN_MERGE_STAGED") != nullptr;  // the shared-memory merge of earlier builds (A/B runs)
+  if (!staged && fan_in <= 16) {
+    const unsigned int groups = (in.n_lists + fan_in - 1) / fan_in;
+    const unsigned int lists = fan_in < in.n_lists ? fan_in : in.n_lists;
+    const unsigned int clip = in.stride < (unsigned int)plan.limit ? in.stride : (unsigned int)plan.limit;
+    unsigned int y = (lists * clip + 255) / 256;
+    if (y < 1) y = 1;
+    if (y > 64) y = 64;
+    topn_rank_merge_kernel<<<dim3(groups, y), 256, 0, s>>>(plan, in, out, fan_in);
+    return cudaGetLastError();
+  }
   size_t smem = std::max<size_t>(topn_smem_bytes(cap, plan.n_order), 200 * 1024);  // room for the rank merge: 6400 items of two sort keys
   static size_t attr_bytes = 0;  // (one process drives one device)
   if (smem > attr_bytes) { cudaFuncSetAttribute(topn_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_bytes = smem; }

@@ -303,3 +303,65 @@ class DeviceRegion:
             s.dflt, s.n_dflt = self._d, 1
         torch.cuda.synchronize(dev)
         self.c = s
+
+
+class SstDecoder:
+    """b2_sst_decode: a run of RocksDB data blocks (uncompressed, prefix-compressed keys) -> a device-resident flat CF
+    block owned by this object.  `data` is a host buffer (bytes / numpy uint8 / address) or a device address."""
+
+    def __init__(self, device=0):
+        self.device, self.h = device, C.c_void_p()
+        self._keep = None
+
+    def decode(self, data, block_offs, trailer_len=5, key_prefix_len=1, key_suffix_len=8, location=ffi.LOC_HOST):
+        L = ffi.lib()
+        offs = np.ascontiguousarray(np.asarray(block_offs, dtype=np.uint64))
+        if isinstance(data, (bytes, bytearray)):
+            data = np.frombuffer(bytes(data), dtype=np.uint8)
+        ptr = data.ctypes.data if isinstance(data, np.ndarray) else int(data)
+        self._keep = (data, offs)
+        d = ffi.SstBlocks()
+        d.data, d.block_offs, d.n_blocks = ptr, offs.ctypes.data, len(offs) - 1
+        d.trailer_len, d.key_prefix_len, d.key_suffix_len = trailer_len, key_prefix_len, key_suffix_len
+        blk, st = ffi.CfBlock(), ffi.SstStats()
+        rc = L.b2_sst_decode(self.device, location, C.byref(d), C.byref(self.h), C.byref(blk), C.byref(st))
+        if rc != 0:
+            raise B2Error(rc, L.b2_last_error_message().decode())
+        return blk, st
+
+    def close(self):
+        if self.h:
+            ffi.lib().b2_sst_free(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class SstRegion:
+    """A region source whose CF_WRITE blocks arrive as RocksDB data blocks: each (data, block_offs) run is expanded on
+    the device (b2_sst_decode) and the request reads the decoded blocks from HBM.  The other fields follow `like`."""
+
+    def __init__(self, like, runs, device=0, **fmt):
+        self._dec = [SstDecoder(device) for _ in runs]
+        self.stats = []
+        arr = (ffi.CfBlock * len(runs))()
+        for i, (data, offs) in enumerate(runs):
+            arr[i], st = self._dec[i].decode(data, offs, **fmt)
+            self.stats.append(st)
+        s = ffi.RegionSource()
+        C.memmove(C.byref(s), C.byref(like.c), C.sizeof(s))
+        s.location, s.device = ffi.LOC_DEVICE, device
+        s.write, s.n_write = arr, len(runs)
+        self._w, self._like = arr, like
+        if like.c.n_dflt:  # CF_DEFAULT of the model region must live where `location` says
+            self._dflt = DeviceRegion(like, device)
+            s.dflt, s.n_dflt = self._dflt.c.dflt, self._dflt.c.n_dflt
+        self.c = s
+
+    def close(self):
+        for d in self._dec:
+            d.close()

@@ -151,6 +151,20 @@ class GenBlock(C.Structure):
     _fields_ = [("block", CfBlock), ("key_bytes", C.c_uint64), ("val_bytes", C.c_uint64), ("n_user_keys", C.c_uint64)]
 
 
+class SstBlocks(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("block_offs", C.c_void_p), ("n_blocks", C.c_uint32), ("trailer_len", C.c_uint32),
+                ("key_prefix_len", C.c_uint32), ("key_suffix_len", C.c_uint32)]
+
+
+class SstStats(C.Structure):
+    _fields_ = [("n_entries", C.c_uint64), ("key_bytes", C.c_uint64), ("val_bytes", C.c_uint64), ("n_restart_intervals", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("decode_ms", C.c_float), ("_pad", C.c_uint32)]
+
+
+class SstEncoded(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("block_offs", C.c_void_p), ("data_len", C.c_uint64), ("n_blocks", C.c_uint32), ("_pad", C.c_uint32)]
+
+
 class EncodedChunk(C.Structure):
     _fields_ = [("rows_data", C.c_void_p), ("len", C.c_uint64), ("n_rows", C.c_uint64), ("encode_type", C.c_int32), ("location", C.c_int32)]
 
@@ -162,6 +176,7 @@ EXPORTED_SYMBOLS = [
     "b2_abi_version", "b2_build_info", "b2_last_error_message", "b2_check_supported", "b2_plan_prepare", "b2_plan_precompile", "b2_jit_counters", "b2_plan_literal", "b2_exec_open", "b2_exec_schema",
     "b2_exec_next_batch", "b2_exec_next_batch_async", "b2_exec_poll", "b2_exec_warnings", "b2_region_pin", "b2_region_unpin", "b2_region_cache_stats", "b2_exec_collect_stats", "b2_exec_last_error", "b2_exec_can_be_cached", "b2_exec_encode_batch", "b2_exec_take_scanned_range", "b2_exec_collect_scanned_rows_per_range", "b2_exec_close",
     "b2_exec_agg_partials", "b2_dag_handle", "b2_checksum_handle", "b2_gen_create", "b2_gen_destroy", "b2_copy_to_host", "b2_copy_to_device",
+    "b2_sst_decode", "b2_sst_free", "b2_sst_encode",
     "b2_device_count", "b2_host_alloc_pinned", "b2_host_alloc_pinned_near", "b2_device_numa_node", "b2_host_free_pinned",
 ]
 
@@ -232,6 +247,12 @@ def lib():
     L.b2_gen_create.restype = i32
     L.b2_gen_destroy.argtypes = [vp]
     L.b2_gen_destroy.restype = None
+    L.b2_sst_decode.argtypes = [i32, i32, C.POINTER(SstBlocks), C.POINTER(vp), C.POINTER(CfBlock), C.POINTER(SstStats)]
+    L.b2_sst_decode.restype = i32
+    L.b2_sst_free.argtypes = [vp]
+    L.b2_sst_free.restype = None
+    L.b2_sst_encode.argtypes = [i32, C.POINTER(CfBlock), u32, u32, u32, C.c_uint8, u32, u32, C.POINTER(vp), C.POINTER(SstEncoded)]
+    L.b2_sst_encode.restype = i32
     L.b2_copy_to_host.argtypes = [i32, vp, vp, u64]
     L.b2_copy_to_host.restype = i32
     L.b2_copy_to_device.argtypes = [i32, vp, vp, u64]
@@ -245,7 +266,7 @@ def lib():
     L.b2_device_numa_node.restype = i32
     L.b2_host_free_pinned.argtypes = [vp]
     L.b2_host_free_pinned.restype = None
-    if L.b2_abi_version() != 3:
+    if L.b2_abi_version() != 4:
         raise RuntimeError("libb2copr ABI version mismatch")
     _lib = L
     return L
