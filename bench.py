@@ -189,14 +189,16 @@ def sst_e2e(ffi, device, blks, plan, after, args, stream, barrier, max_over_rank
         flat_bytes += b.key_bytes + b.val_bytes + 8 * b.block.n
         enc_bytes += enc.data_len
     decs = [SstDecoder(device) for _ in blks]
+    pool = None
     try:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=2)  # two regions in flight: one expands while the other's bytes cross PCIe
+
         def step():
-            arr, h2d, dms = [], 0, 0.0
-            for d, (p, offs) in zip(decs, enc_host):
-                blk, st = d.decode(p, offs)
-                arr.append(blk)
-                h2d += st.h2d_bytes
-                dms += st.decode_ms
+            res = list(pool.map(lambda a: a[0].decode(a[1][0], a[1][1]), zip(decs, enc_host)))
+            arr = [blk for blk, _ in res]
+            h2d = sum(st.h2d_bytes for _, st in res)
+            dms = sum(st.decode_ms for _, st in res)
             src = Source(ffi, arr, ffi.LOC_DEVICE, device)
             rows, st = run_dag(ffi, plan, table_range(), src, ffi.LOC_HOST, args.chunk, stream.cuda_stream, after)
             return rows, st, h2d, dms
@@ -214,6 +216,8 @@ def sst_e2e(ffi, device, blks, plan, after, args, stream, barrier, max_over_rank
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1)) / k
     finally:
+        if pool:
+            pool.shutdown()
         for d in decs:
             d.close()
         for p in keep:

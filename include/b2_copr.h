@@ -137,7 +137,9 @@ typedef struct b2_column_info {
 
 /* RPN node kinds (tidb_query_expr/src/types/expr.rs:11-30) */
 enum { B2_RPN_CONST_NULL = 0, B2_RPN_CONST_INT = 1, B2_RPN_CONST_UINT = 2, B2_RPN_CONST_REAL = 3,
-       B2_RPN_COLUMN_REF = 4, B2_RPN_FN = 5 };
+       B2_RPN_COLUMN_REF = 4, B2_RPN_FN = 5,
+       B2_RPN_CONST_TIME = 6,      /* i64 = Time::to_packed_u64 (the payload of tipb ExprType::MysqlTime); field_tp DATE / DATETIME */
+       B2_RPN_CONST_DURATION = 7   /* i64 = nanoseconds (tipb ExprType::MysqlDuration) */ };
 
 /* Scalar function signatures.  Names follow tipb::ScalarFuncSig; numeric values follow
  * tipb expression.proto as pinned by Cargo.lock (pingcap/tipb @ 1374320b, not vendored in
@@ -167,7 +169,20 @@ enum {
   B2_SIG_UNARY_MINUS_INT = 3108, B2_SIG_UNARY_MINUS_REAL = 3109,                    /* impl_op.rs:70-107 */
   B2_SIG_IF_NULL_INT = 4101, B2_SIG_IF_NULL_REAL = 4102, B2_SIG_IF_INT = 4107, B2_SIG_IF_REAL = 4108, /* impl_control.rs */
   B2_SIG_COALESCE_INT = 4201, B2_SIG_COALESCE_REAL = 4202,                          /* impl_compare.rs:239-248, variadic */
-  B2_SIG_CASE_WHEN_INT = 4208, B2_SIG_CASE_WHEN_REAL = 4209                         /* impl_control.rs:34-50, variadic: [cond, value]* [else] */
+  B2_SIG_CASE_WHEN_INT = 4208, B2_SIG_CASE_WHEN_REAL = 4209,                        /* impl_control.rs:34-50, variadic: [cond, value]* [else] */
+  /* comparisons over DATE / DATETIME and DURATION values (impl_compare.rs:63-240 with `Ord for Time`,
+   * mysql/time/mod.rs:2814-2840: the fsp / time-type bits do not take part; `Ord for Duration`: nanoseconds) */
+  B2_SIG_LT_TIME = 104, B2_SIG_LT_DURATION = 105, B2_SIG_LE_TIME = 114, B2_SIG_LE_DURATION = 115,
+  B2_SIG_GT_TIME = 124, B2_SIG_GT_DURATION = 125, B2_SIG_GE_TIME = 134, B2_SIG_GE_DURATION = 135,
+  B2_SIG_EQ_TIME = 144, B2_SIG_EQ_DURATION = 145, B2_SIG_NE_TIME = 154, B2_SIG_NE_DURATION = 155,
+  B2_SIG_NULLEQ_TIME = 164, B2_SIG_NULLEQ_DURATION = 165,
+  B2_SIG_TIME_IS_NULL = 3115, B2_SIG_DURATION_IS_NULL = 3117,
+  B2_SIG_IN_TIME = 4005, B2_SIG_IN_DURATION = 4006,
+  /* impl_op.rs:144-175 */
+  B2_SIG_BIT_AND = 3118, B2_SIG_BIT_OR = 3119, B2_SIG_BIT_XOR = 3120, B2_SIG_BIT_NEG = 3121,
+  /* impl_cast.rs:281-305 (Int -> Int keeps the bits), :466-501 (Int -> Real by the signedness of either side),
+   * :505-507 (Real -> Real); UNION's in_union metadata is not carried by this ABI (treated as false) */
+  B2_SIG_CAST_INT_AS_INT = 0, B2_SIG_CAST_INT_AS_REAL = 1, B2_SIG_CAST_REAL_AS_REAL = 11
 };
 
 typedef struct b2_rpn_node {

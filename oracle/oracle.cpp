@@ -213,6 +213,11 @@ static int orc_dag_handle_impl(const b2_dag_plan* plan, const b2_key_range* rang
         continue;
       }
       if (!ensure_decoded(c, sch[offs[k]], b.logical_rows, &perr)) { if (b.err.ok()) b.err = Error::make(B2_ERR_CORRUPTED, perr); b.logical_rows.clear(); break; }
+      if (c.et == ET_TIME || c.et == ET_DURATION) {  // a DateTime / Duration column an expression decoded: the same 8-byte chunk cells (column.rs:446-496)
+        RawChunkCol& rc = res->raw_cols[k];
+        rc.kind = c.et == ET_TIME ? RK_TIME : RK_DURATION;
+        for (size_t r : b.logical_rows) { rc.nn.push_back(c.nn[r]); put_le64(rc.data, c.nn[r] ? (uint64_t)c.i64[r] : 0); }
+      }
     }
     if (!b.cols.empty())
       for (size_t r : b.logical_rows) {

@@ -95,21 +95,6 @@ inline bool dec_read(Slice s, Decimal* out, std::string* err) {  // decimal.rs:2
   return true;
 }
 
-// Time::from_packed_u64 for DATE / DATETIME (TIMESTAMP converts through the session time zone: not restated).
-inline bool time_from_packed(uint64_t value, int tp, int decimal, uint64_t* bits, std::string* err) {
-  if (tp == B2_TP_TIMESTAMP) { *err = "oracle does not restate TIMESTAMP time-zone conversion"; return false; }
-  if (decimal != -1 && (decimal < 0 || decimal > 6)) { *err = "Invalid fsp"; return false; }
-  const uint64_t fsp = decimal == -1 ? 0 : (uint64_t)decimal;
-  const bool date = tp == B2_TP_DATE;
-  const uint64_t fsp_tt = date ? 0xeull : (fsp << 1);  // set_tt, then set_fsp (ignored for Date)
-  if (value == 0) { *bits = fsp_tt; return true; }     // Time::new(zero): every field 0 (Date also clears fsp)
-  const uint64_t ymdhms = value >> 24, ymd = ymdhms >> 17, ym = ymd >> 5, hms = ymdhms & ((1u << 17) - 1);
-  const uint64_t day = ymd & 31, month = ym % 13, year = ym / 13, second = hms & 63, minute = (hms >> 6) & 63, hour = hms >> 12, micro = value & ((1u << 24) - 1);
-  *bits = ((year & 0x3fff) << 50) | ((month & 15) << 46) | ((day & 31) << 41) | ((hour & 31) << 36) | ((minute & 63) << 30) | ((second & 63) << 24) |
-          ((micro & 0xfffff) << 4) | fsp_tt;
-  return true;
-}
-
 inline void put_le64(Bytes& o, uint64_t v) { for (int k = 0; k < 8; ++k) o.push_back((uint8_t)(v >> (8 * k))); }
 
 // one cell of Column::from_raw_datums

@@ -99,7 +99,12 @@ inline void write_datum_decimal(Bytes& o, const Decimal& d) {
 inline void encode_cell_default(Bytes& o, const LazyColumn& c, size_t r, const FieldType& ft, const std::vector<Decimal>* dec_cells) {
   if (!c.decoded) { Slice s = c.raw_get(r); o.insert(o.end(), s.p, s.p + s.n); return; }
   if (!c.nn[r]) { write_datum_null(o); return; }
-  if (c.et == ET_REAL) write_datum_f64(o, c.f64[r]);
+  if (c.et == ET_TIME) {  // a decoded DateTime goes out as its packed u64 (Time::to_packed_u64, datum.rs write_datum)
+    const uint64_t b = (uint64_t)c.i64[r];
+    const uint64_t year = (b >> 50) & 0x3fff, month = (b >> 46) & 15, day = (b >> 41) & 31, hour = (b >> 36) & 31, minute = (b >> 30) & 63, second = (b >> 24) & 63, micro = (b >> 4) & 0xfffff;
+    write_datum_u64(o, (((((year * 13 + month) << 5) | day) << 17) | (hour << 12) | (minute << 6) | second) << 24 | micro);
+  } else if (c.et == ET_DURATION) { o.push_back(DURATION_FLAG); uint64_t u = (uint64_t)c.i64[r] ^ 0x8000000000000000ull; for (int k = 7; k >= 0; --k) o.push_back((uint8_t)(u >> (8 * k))); }
+  else if (c.et == ET_REAL) write_datum_f64(o, c.f64[r]);
   else if (c.et == ET_DECIMAL) write_datum_decimal(o, (*dec_cells)[(size_t)c.i64[r]]);
   else if (ft.is_unsigned()) write_datum_u64(o, (uint64_t)c.i64[r]);
   else write_datum_i64(o, c.i64[r]);

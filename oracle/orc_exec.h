@@ -27,7 +27,7 @@ const size_t BATCH_INITIAL_SIZE = 32;  // runner.rs:39
 const size_t BATCH_MAX_SIZE = 1024;    // logical_rows.rs:5
 const size_t BATCH_GROW_FACTOR = 2;    // runner.rs:51
 
-enum EvalType { ET_INT, ET_REAL, ET_DECIMAL, ET_OTHER };
+enum EvalType { ET_INT, ET_REAL, ET_DECIMAL, ET_OTHER, ET_TIME /* DATE / DATETIME: CoreTime bits */, ET_DURATION /* nanoseconds */ };
 struct FieldType { int tp = 0; uint32_t flag = 0; int decimal = 0; bool is_unsigned() const { return flag & B2_FLAG_UNSIGNED; } };
 
 inline EvalType eval_type_of(int tp) {  // def/eval_type.rs:53-95
@@ -123,17 +123,67 @@ struct LazyColumn {
   void push_int(bool non_null, int64_t v) { i64.push_back(non_null ? v : 0); nn.push_back(non_null); }
 };
 
+// Time::from_packed_u64 for DATE / DATETIME (TIMESTAMP converts through the session time zone: not restated).
+inline bool time_from_packed(uint64_t value, int tp, int decimal, uint64_t* bits, std::string* err) {
+  if (tp == B2_TP_TIMESTAMP) { *err = "oracle does not restate TIMESTAMP time-zone conversion"; return false; }
+  if (decimal != -1 && (decimal < 0 || decimal > 6)) { *err = "Invalid fsp"; return false; }
+  const uint64_t fsp = decimal == -1 ? 0 : (uint64_t)decimal;
+  const bool date = tp == B2_TP_DATE;
+  const uint64_t fsp_tt = date ? 0xeull : (fsp << 1);  // set_tt, then set_fsp (ignored for Date)
+  if (value == 0) { *bits = fsp_tt; return true; }     // Time::new(zero): every field 0 (Date also clears fsp)
+  const uint64_t ymdhms = value >> 24, ymd = ymdhms >> 17, ym = ymd >> 5, hms = ymdhms & ((1u << 17) - 1);
+  const uint64_t day = ymd & 31, month = ym % 13, year = ym / 13, second = hms & 63, minute = (hms >> 6) & 63, hour = hms >> 12, micro = value & ((1u << 24) - 1);
+  *bits = ((year & 0x3fff) << 50) | ((month & 15) << 46) | ((day & 31) << 41) | ((hour & 31) << 36) | ((minute & 63) << 30) | ((second & 63) << 24) |
+          ((micro & 0xfffff) << 4) | fsp_tt;
+  return true;
+}
+
+
+// DateTime / Duration cells of an expression operand (decode_date_time_datum / decode_duration_datum, datum_codec.rs)
+inline bool decode_time_datum(Slice d, const FieldType& ft, bool* is_null, int64_t* out, std::string* err) {
+  *is_null = false; *out = 0;
+  if (d.empty()) { *err = "Failed to decode datum flag"; return false; }
+  Slice p = d.sub(1);
+  uint64_t v;
+  switch (d[0]) {
+    case NIL_FLAG: *is_null = true; return true;
+    case UINT_FLAG: if (p.n < 8) { *err = "unexpected eof"; return false; } v = get_u64_be(p.p); break;
+    case VAR_UINT_FLAG: if (!decode_var_u64(p, &v)) { *err = "unexpected eof"; return false; } break;
+    default: *err = "Unsupported datum flag " + std::to_string(d[0]) + " for DateTime vector."; return false;
+  }
+  uint64_t bits;
+  if (!time_from_packed(v, ft.tp, ft.decimal, &bits, err)) return false;
+  *out = (int64_t)bits;
+  return true;
+}
+inline bool decode_duration_datum(Slice d, bool* is_null, int64_t* out, std::string* err) {
+  *is_null = false; *out = 0;
+  if (d.empty()) { *err = "Failed to decode datum flag"; return false; }
+  Slice p = d.sub(1);
+  switch (d[0]) {
+    case NIL_FLAG: *is_null = true; return true;
+    case DURATION_FLAG: if (p.n < 8) { *err = "unexpected eof"; return false; } *out = decode_i64(p.p); return true;
+    case VAR_INT_FLAG: if (!decode_var_i64(p, out)) { *err = "unexpected eof"; return false; } return true;
+    default: *err = "Unsupported datum flag " + std::to_string(d[0]) + " for Duration vector"; return false;
+  }
+}
+inline bool et_int_like(EvalType et) { return et == ET_INT || et == ET_TIME || et == ET_DURATION; }
+
 // lazy_column.rs:165-221 ensure_decoded: decode only logical rows, others become NULL
 inline bool ensure_decoded(LazyColumn& c, const FieldType& ft, const std::vector<size_t>& logical_rows, std::string* err) {
   if (c.decoded) return true;
   EvalType et = eval_type_of(ft.tp);
-  if (et != ET_INT && et != ET_REAL) { *err = "oracle decodes Int/Real columns only"; return false; }
+  if (ft.tp == B2_TP_DATE || ft.tp == B2_TP_DATETIME) et = ET_TIME;
+  if (ft.tp == B2_TP_DURATION) et = ET_DURATION;
+  if (!et_int_like(et) && et != ET_REAL) { *err = "oracle decodes Int / Real / DateTime / Duration operands only"; return false; }
   size_t n = c.raw_offsets.size();
   std::vector<int64_t> iv; std::vector<double> fv; std::vector<uint8_t> nn(n, 0);
-  if (et == ET_INT) iv.assign(n, 0); else fv.assign(n, 0);
+  if (et_int_like(et)) iv.assign(n, 0); else fv.assign(n, 0);
   for (size_t r : logical_rows) {
     bool is_null;
     if (et == ET_INT) { int64_t v; if (!decode_int_datum(c.raw_get(r), &is_null, &v, err)) return false; iv[r] = v; }
+    else if (et == ET_TIME) { int64_t v; if (!decode_time_datum(c.raw_get(r), ft, &is_null, &v, err)) return false; iv[r] = v; }
+    else if (et == ET_DURATION) { int64_t v; if (!decode_duration_datum(c.raw_get(r), &is_null, &v, err)) return false; iv[r] = v; }
     else { double v; if (!decode_real_datum(c.raw_get(r), ft.tp, &is_null, &v, err)) return false; fv[r] = v; }
     nn[r] = !is_null;
   }
@@ -513,10 +563,20 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
   std::vector<Val> st;
   for (uint32_t k = 0; k < e.n_nodes; ++k) {
     const b2_rpn_node& nd = e.nodes[k];
-    if (nd.kind == B2_RPN_CONST_NULL || nd.kind == B2_RPN_CONST_INT || nd.kind == B2_RPN_CONST_UINT || nd.kind == B2_RPN_CONST_REAL) {
+    if (nd.kind == B2_RPN_CONST_TIME || nd.kind == B2_RPN_CONST_DURATION) {  // ExprType::MysqlTime / MysqlDuration constants
+      Val v; v.scalar = true; v.s_null = false;
+      if (nd.kind == B2_RPN_CONST_TIME) {
+        uint64_t bits; std::string perr;
+        if (!time_from_packed((uint64_t)nd.i64, nd.field_tp, 0, &bits, &perr)) { *err = Error::make(B2_ERR_UNSUPPORTED, perr); return false; }
+        v.et = ET_TIME; v.s_i = (int64_t)bits;
+      } else { v.et = ET_DURATION; v.s_i = nd.i64; }
+      st.push_back(std::move(v));
+    } else if (nd.kind == B2_RPN_CONST_NULL || nd.kind == B2_RPN_CONST_INT || nd.kind == B2_RPN_CONST_UINT || nd.kind == B2_RPN_CONST_REAL) {
       Val v; v.scalar = true;
       v.et = nd.kind == B2_RPN_CONST_REAL ? ET_REAL : (nd.kind == B2_RPN_CONST_NULL ? eval_type_of(nd.field_tp) : ET_INT);
-      if (v.et != ET_REAL) v.et = ET_INT;
+      if (nd.kind == B2_RPN_CONST_NULL && (nd.field_tp == B2_TP_DATE || nd.field_tp == B2_TP_DATETIME)) v.et = ET_TIME;
+      else if (nd.kind == B2_RPN_CONST_NULL && nd.field_tp == B2_TP_DURATION) v.et = ET_DURATION;
+      else if (v.et != ET_REAL) v.et = ET_INT;
       v.is_unsigned = (nd.field_flag & B2_FLAG_UNSIGNED) || nd.kind == B2_RPN_CONST_UINT;
       v.s_null = nd.kind == B2_RPN_CONST_NULL; v.s_i = nd.i64; v.s_f = nd.f64;
       st.push_back(std::move(v));
@@ -528,11 +588,50 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
       const LazyColumn& c = cx.batch->cols[ci];
       Val v; v.et = c.et; v.is_unsigned = (*cx.schema)[ci].is_unsigned();
       v.nn.resize(n);
-      if (c.et == ET_INT) v.i.resize(n); else v.f.resize(n);
-      for (size_t j = 0; j < n; ++j) { size_t r = cx.batch->logical_rows[j]; v.nn[j] = c.nn[r]; if (c.et == ET_INT) v.i[j] = c.i64[r]; else v.f[j] = c.f64[r]; }
+      if (et_int_like(c.et)) v.i.resize(n); else v.f.resize(n);
+      for (size_t j = 0; j < n; ++j) { size_t r = cx.batch->logical_rows[j]; v.nn[j] = c.nn[r]; if (et_int_like(c.et)) v.i[j] = c.i64[r]; else v.f[j] = c.f64[r]; }
       st.push_back(std::move(v));
     } else if (nd.kind == B2_RPN_FN) {
       int na = nd.n_args;
+      {  // DateTime / Duration comparisons, IN, IS NULL (impl_compare.rs:63-240 over `Ord for Time`, mysql/time/mod.rs:2814-2840:
+         // set_fsp_tt(0) on both sides, then the u64 bit fields compare; `Ord for Duration`: the nanoseconds compare)
+        const int sig = nd.sig;
+        const bool tcmp = sig >= 100 && sig < 170 && (sig % 10 == 4 || sig % 10 == 5);
+        const bool tin = sig == B2_SIG_IN_TIME || sig == B2_SIG_IN_DURATION, tnull = sig == B2_SIG_TIME_IS_NULL || sig == B2_SIG_DURATION_IS_NULL;
+        if (tcmp || tin || tnull) {
+          const EvalType need = (tcmp ? sig % 10 == 4 : (sig == B2_SIG_IN_TIME || sig == B2_SIG_TIME_IS_NULL)) ? ET_TIME : ET_DURATION;
+          if ((int)st.size() < na || na < 1 || (tcmp && na != 2) || (tnull && na != 1)) { *err = Error::make(B2_ERR_INVALID_ARG, "bad rpn arity"); return false; }
+          std::vector<Val> args(st.end() - na, st.end());
+          st.resize(st.size() - na);
+          for (auto& a : args) if (a.et != need) { *err = Error::make(B2_ERR_INVALID_ARG, "argument eval type does not match the function"); return false; }
+          auto key = [&](const Val& v, size_t j) -> int64_t { return need == ET_TIME ? (int64_t)((uint64_t)v.int_at(j) & ~15ull) : v.int_at(j); };
+          auto cmp = [&](int64_t x, int64_t y) -> int { return need == ET_TIME ? ((uint64_t)x < (uint64_t)y ? -1 : (uint64_t)x > (uint64_t)y) : (x < y ? -1 : x > y); };
+          Val r; r.et = ET_INT; r.is_unsigned = false; r.nn.assign(n, 0); r.i.assign(n, 0);
+          for (size_t j = 0; j < n; ++j) {
+            if (tnull) { r.nn[j] = 1; r.i[j] = args[0].null_at(j); continue; }
+            if (tin) {
+              if (args[0].null_at(j)) continue;
+              bool hit = false, default_null = false;
+              for (int i = 1; i < na; ++i) { if (args[i].null_at(j)) { default_null = true; continue; } hit |= key(args[0], j) == key(args[i], j); }
+              if (hit) { r.nn[j] = 1; r.i[j] = 1; } else if (!default_null) { r.nn[j] = 1; r.i[j] = 0; }
+              continue;
+            }
+            const bool an = args[0].null_at(j), bn = args[1].null_at(j), nulleq = sig / 10 * 10 == B2_SIG_NULLEQ_INT;
+            if (an && bn) { if (nulleq) { r.nn[j] = 1; r.i[j] = 1; } continue; }
+            if (an || bn) { if (nulleq) { r.nn[j] = 1; r.i[j] = 0; } continue; }
+            const int c = cmp(key(args[0], j), key(args[1], j));
+            bool res;
+            switch (sig / 10 * 10) {
+              case B2_SIG_LT_INT: res = c < 0; break; case B2_SIG_LE_INT: res = c <= 0; break;
+              case B2_SIG_GT_INT: res = c > 0; break; case B2_SIG_GE_INT: res = c >= 0; break;
+              case B2_SIG_NE_INT: res = c != 0; break; default: res = c == 0; break;
+            }
+            r.nn[j] = 1; r.i[j] = res;
+          }
+          st.push_back(std::move(r));
+          continue;
+        }
+      }
       if (nd.sig == B2_SIG_IN_INT || nd.sig == B2_SIG_IN_REAL) {
         // compare_in_int_type_by_hash :217-258 / compare_in_by_hash :178-215 (varg): args[0] IN (args[1..])
         if ((int)st.size() < na || na < 1) { *err = Error::make(B2_ERR_INVALID_ARG, "bad rpn arity"); return false; }
@@ -590,7 +689,8 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
       bool is_cmp_int = sig == B2_SIG_LT_INT || sig == B2_SIG_LE_INT || sig == B2_SIG_GT_INT || sig == B2_SIG_GE_INT || sig == B2_SIG_EQ_INT || sig == B2_SIG_NE_INT || sig == B2_SIG_NULLEQ_INT;
       bool is_cmp_real = sig == B2_SIG_LT_REAL || sig == B2_SIG_LE_REAL || sig == B2_SIG_GT_REAL || sig == B2_SIG_GE_REAL || sig == B2_SIG_EQ_REAL || sig == B2_SIG_NE_REAL || sig == B2_SIG_NULLEQ_REAL;
       bool is_arith_real = sig == B2_SIG_PLUS_REAL || sig == B2_SIG_MINUS_REAL || sig == B2_SIG_MULTIPLY_REAL || sig == B2_SIG_MOD_REAL || sig == B2_SIG_DIVIDE_REAL ||
-                           sig == B2_SIG_IF_NULL_REAL || sig == B2_SIG_UNARY_MINUS_REAL || sig == B2_SIG_ABS_REAL;
+                           sig == B2_SIG_IF_NULL_REAL || sig == B2_SIG_UNARY_MINUS_REAL || sig == B2_SIG_ABS_REAL || sig == B2_SIG_CAST_INT_AS_REAL ||
+                           sig == B2_SIG_CAST_REAL_AS_REAL;
       if (is_arith_real) { r.et = ET_REAL; r.f.assign(n, 0); r.i.clear(); }
       for (size_t j = 0; j < n; ++j) {
         bool an = a.null_at(j), bn = na == 2 ? b.null_at(j) : false;
@@ -689,6 +789,17 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
             break;
           }
           case B2_SIG_ABS_UINT: if (!an) { r.nn[j] = 1; r.i[j] = a.int_at(j); } break;  // :233-237
+          case B2_SIG_BIT_AND: if (!an && !bn) { r.nn[j] = 1; r.i[j] = a.int_at(j) & b.int_at(j); } break;  // impl_op.rs:144-175
+          case B2_SIG_BIT_OR: if (!an && !bn) { r.nn[j] = 1; r.i[j] = a.int_at(j) | b.int_at(j); } break;
+          case B2_SIG_BIT_XOR: if (!an && !bn) { r.nn[j] = 1; r.i[j] = a.int_at(j) ^ b.int_at(j); } break;
+          case B2_SIG_BIT_NEG: if (!an) { r.nn[j] = 1; r.i[j] = ~a.int_at(j); } break;
+          // impl_cast.rs:281-305 (cast_signed_int_as_unsigned_int / cast_int_as_int_others: the bits stay; in_union is false),
+          // :466-501 (signed -> signed real: `as f64`; any unsigned side: `as u64 as f64`), :505-507
+          case B2_SIG_CAST_INT_AS_INT: if (!an) { r.nn[j] = 1; r.i[j] = a.int_at(j); } break;
+          case B2_SIG_CAST_INT_AS_REAL:
+            if (!an) { r.nn[j] = 1; r.f[j] = (a.is_unsigned || (nd.field_flag & B2_FLAG_UNSIGNED)) ? (double)(uint64_t)a.int_at(j) : (double)a.int_at(j); }
+            break;
+          case B2_SIG_CAST_REAL_AS_REAL: if (!an) { r.nn[j] = 1; r.f[j] = a.real_at(j); } break;
           case B2_SIG_ABS_REAL: if (!an) { r.nn[j] = 1; r.f[j] = std::fabs(a.real_at(j)); } break;  // :239-243
           case B2_SIG_INT_DIVIDE_INT: {  // impl_arithmetic.rs:396-455; helpers codec/overflow.rs:9-58
             if (an || bn) break;

@@ -105,6 +105,7 @@ inline bool sst_get_var32(const uint8_t*& p, const uint8_t* lim, uint32_t* v) {
 inline int sst_decode(const uint8_t* data, const uint64_t* block_offs, uint32_t n_blocks, uint32_t trailer_len, uint32_t key_prefix_len, uint32_t key_suffix_len,
                       std::string* keys, std::vector<uint32_t>* koff, std::string* vals, std::vector<uint32_t>* voff) {
   keys->clear(); vals->clear(); koff->assign(1, 0); voff->assign(1, 0);
+  bool unsupported = false;
   for (uint32_t b = 0; b < n_blocks; ++b) {
     if (block_offs[b + 1] < block_offs[b] + trailer_len + 4) return 1;
     const uint8_t* base = data + block_offs[b];
@@ -114,24 +115,41 @@ inline int sst_decode(const uint8_t* data, const uint64_t* block_offs, uint32_t 
     if (nr >> 31) return 2;
     if (nr == 0 || (uint64_t)nr * 4 + 4 > len) return 1;
     const uint8_t *p = base, *lim = base + len - 4 - 4 * nr;
+    // The restart array is what Seek lands on (Block::Iter::Seek -> SeekToRestartPoint + DecodeEntry, which reports a
+    // corrupted block when a restart entry has shared != 0), and what the device decoder cuts its work at: every restart
+    // offset must be the start of an entry with shared == 0, the first one 0, in ascending order.
+    std::vector<uint32_t> rs(nr);
+    memcpy(rs.data(), lim, 4ull * nr);
+    if (rs[0] != 0) return 1;
+    for (uint32_t j = 1; j < nr; ++j)
+      if (rs[j] < rs[j - 1] || rs[j] > (uint32_t)(lim - base)) return 1;
+    uint32_t next_restart = 0;
     std::string key;
     while (p < lim) {
       uint32_t sh, ns, vl;
+      const uint32_t at = (uint32_t)(p - base);
+      while (next_restart < nr && rs[next_restart] < at) return 1;  // a restart offset inside an entry
       if (!sst_get_var32(p, lim, &sh) || !sst_get_var32(p, lim, &ns) || !sst_get_var32(p, lim, &vl)) return 1;
+      if (next_restart < nr && rs[next_restart] == at) {
+        if (sh != 0) return 1;
+        while (next_restart < nr && rs[next_restart] == at) ++next_restart;
+      }
       if (sh > key.size() || (uint64_t)(lim - p) < (uint64_t)ns + vl) return 1;
       key.resize(sh);
       key.append((const char*)p, ns);
       p += ns;
       if (key.size() < (size_t)key_prefix_len + key_suffix_len) return 1;
-      if (key_suffix_len == 8 && (uint8_t)key[key.size() - 8] != 1) return 2;
+      if (key_suffix_len == 8 && (uint8_t)key[key.size() - 8] != 1) unsupported = true;  // reported after the structure of every block was checked
       keys->append(key, key_prefix_len, key.size() - key_prefix_len - key_suffix_len);
       vals->append((const char*)p, vl);
       p += vl;
       koff->push_back((uint32_t)keys->size());
       voff->push_back((uint32_t)vals->size());
     }
+    for (; next_restart < nr; ++next_restart)
+      if (rs[next_restart] != (uint32_t)(lim - base)) return 1;  // (a restart offset at the very end: an empty last interval)
   }
-  return 0;
+  return unsupported ? 2 : 0;
 }
 
 }  // namespace orc

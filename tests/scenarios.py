@@ -10,7 +10,8 @@ import struct
 import kvfmt
 from tikv_b200 import ffi
 from tikv_b200.plan import (divide, fn, ColumnDef, Plan, and_, col, const_int, const_real, const_uint, eq, ge, gt, is_null, le, lt, minus, multiply,
-                            in_, ne, not_, null, nulleq, or_, plus, xor_, int_divide, mod, neg, abs_, if_null, if_, case_when, coalesce)
+                            in_, ne, not_, null, nulleq, or_, plus, xor_, int_divide, mod, neg, abs_, if_null, if_, case_when, coalesce, const_time, const_duration,
+                            bit_and, bit_or, bit_xor, bit_neg, cast_int_as_int, cast_int_as_real, cast_real_as_real)
 
 TABLE = 1000
 READ_TS = 1000
@@ -308,6 +309,10 @@ def multi_group_plans():
             ("mg_no_input", scan().selection(lt(c6, const_int(-5))).aggregation([("count", const_int(1))], group_by=[c6, col(C2)]).build())]
 
 
+def one_():
+    return const_int(1)
+
+
 def scalar_plans():
     """More scalar functions: DIV / MOD in every signedness mix (x / 0 and x % 0 are NULL), MOD over
     Real, unary minus, ABS, IFNULL, IF, CASE WHEN (with and without ELSE), COALESCE; as projection outputs, selection
@@ -327,6 +332,10 @@ def scalar_plans():
                                              case_when(lt(c2, zero), c1), coalesce(c2, null(), c5), coalesce(null(), null()), if_(null(), c1, c3), case_when(c5)).build()),
             ("sc_in_selection_agg", scan().selection(gt(mod(ch, const_int(7)), const_int(2)), ne(if_null(c2, zero), int_divide(c6, const_int(2))))
                                           .aggregation([("sum", abs_(c2)), ("count", case_when(gt(c6, const_int(5)), c6)), ("max", neg(c6))], group_by=[mod(ch, const_int(5))]).build()),
+            ("sc_bits_casts", scan().projection(ch, bit_and(c1, c3), bit_or(c2, c6), bit_xor(c1, c2), bit_neg(c2), cast_int_as_int(c2, unsigned=True), cast_int_as_real(c2),
+                                                cast_int_as_real(c3), cast_int_as_real(c2, unsigned=True), cast_real_as_real(c4)).build()),
+            ("sc_bits_sel_agg", scan().selection(ne(bit_and(ch, const_int(3)), zero), lt(cast_int_as_real(c6), const_real(7.5)))
+                                      .aggregation([("sum", bit_and(c1, const_int(0xffff))), ("count", one_())], group_by=[bit_and(ch, const_int(7))]).build()),
             ("sc_err_div_overflow", scan().projection(ch, int_divide(c2, c3)).build()),
             ("sc_err_div_overflow2", scan().projection(ch, int_divide(c3, c2)).build()),
             ("sc_err_neg_uint", scan().projection(ch, neg(c3)).build()),
@@ -376,6 +385,31 @@ def scalar_known_answers():
     import math
     for c, e in [(0, math.pi), (1, math.e), (None, math.pi)]:
         K.append((f"if({c})", if_(I(c), R(math.e), R(math.pi)), e))
+    # impl_op.rs test_bit_and :589-605, test_bit_or :608-624, test_bit_xor :627-643, test_bit_neg :646-660
+    for a, b, e in [(123, 321, 65), (-123, 321, 257), (None, 1, None), (1, None, None), (None, None, None)]:
+        K.append((f"bit_and({a},{b})", bit_and(I(a), I(b)), e))
+    for a, b, e in [(123, 321, 379), (-123, 321, -59), (None, 1, None), (1, None, None), (None, None, None)]:
+        K.append((f"bit_or({a},{b})", bit_or(I(a), I(b)), e))
+    for a, b, e in [(123, 321, 314), (-123, 321, -316), (None, 1, None), (1, None, None), (None, None, None)]:
+        K.append((f"bit_xor({a},{b})", bit_xor(I(a), I(b)), e))
+    for a, e in [(123, -124), (-123, 122), (0, -1), (None, None)]:
+        K.append((f"bit_neg({a})", bit_neg(I(a)), e))
+    # impl_cast.rs test_int_as_int_others :1878-1890, test_signed_int_as_unsigned_int :1893-1916 (in_union false),
+    # test_signed_int_as_signed_real :3250-3266, test_signed_int_as_unsigned_real :3269-3297 (in_union false),
+    # test_unsigned_int_as_signed_or_unsigned_real :3300-3315, test_real_as_signed_real :3318-3338
+    for a in (MAX, MIN, -1, None):
+        K.append((f"cast_int_as_int({a})", cast_int_as_int(I(a)), a))
+    for a in (-10, 10, MIN, MAX):
+        K.append((f"cast_int_as_uint({a})", cast_int_as_int(I(a), unsigned=True), a))  # the same bits, read as u64 by the caller
+    for a in (MIN, 0, MAX, None):
+        K.append((f"cast_int_as_real({a})", cast_int_as_real(I(a)), None if a is None else float(a)))
+    for a in (MAX, 0):
+        K.append((f"cast_int_as_ureal({a})", cast_int_as_real(I(a), unsigned=True), float(a)))
+    K.append(("cast_int_as_ureal(-1)", cast_int_as_real(I(-1), unsigned=True), float(UMAX)))  # `as u64 as f64`
+    for a in (0, UMAX, MAX):
+        K.append((f"cast_uint_as_real({a})", cast_int_as_real(I(a, True)), float(a)))
+    for a in (float.fromhex("-0x1.fffffep+127"), float.fromhex("0x1.fffffep+127"), -1.7976931348623157e308, 0.0, 1.7976931348623157e308, float(MIN), float(MAX), float(UMAX), None):
+        K.append((f"cast_real_as_real({a})", cast_real_as_real(R(a)), a))
     return K
 
 
@@ -604,6 +638,14 @@ def mixed_plans():
             ("mixed_sel", scan().selection(lt(col(M_INT), const_int(0))).build(output_offsets=[M_STR, M_H, M_DEC, M_DT, M_JSON])),
             ("mixed_sel_real_limit", scan().selection(gt(col(M_F64, tp=ffi.TP_DOUBLE), const_real(0.0))).limit(120).build(output_offsets=[M_BLOB, M_DATE, M_DUR, M_INT])),
             ("mixed_only_fixed", scan().build(output_offsets=[M_DT, M_DATE, M_DUR, M_H])),
+            # DATE / DATETIME / DURATION predicates (impl_compare.rs over `Ord for Time` / `Ord for Duration`)
+            ("mixed_sel_datetime", scan().selection(lt(col(M_DT, tp=ffi.TP_DATETIME), const_time(kvfmt.time_packed(5000, 6, 15, 12, 30, 0, 0)))).build(output_offsets=[M_H, M_DT, M_STR])),
+            ("mixed_sel_date_in_null", scan().selection(or_(is_null(col(M_DATE, tp=ffi.TP_DATE)),
+                                                            in_(col(M_DATE, tp=ffi.TP_DATE), const_time(0, ffi.TP_DATE), null(ffi.TP_DATE), const_time(kvfmt.time_packed(2000, 1, 1), ffi.TP_DATE)))).build(output_offsets=[M_H, M_DATE])),
+            ("mixed_sel_datetime_vs_date", scan().selection(ge(col(M_DT, tp=ffi.TP_DATETIME), col(M_DATE, tp=ffi.TP_DATE))).build(output_offsets=[M_H, M_DT, M_DATE])),
+            ("mixed_sel_duration", scan().selection(ge(col(M_DUR, tp=ffi.TP_DURATION), const_duration(0)), ne(col(M_DUR, tp=ffi.TP_DURATION), const_duration(10 ** 9))).build(output_offsets=[M_H, M_DUR, M_BLOB])),
+            ("mixed_count_nulleq_duration", scan().selection(nulleq(col(M_DUR, tp=ffi.TP_DURATION), const_duration(1))).aggregation([("count", const_int(1))]).build()),
+            ("mixed_count_zero_dates", scan().selection(eq(col(M_DT, tp=ffi.TP_DATETIME), const_time(0))).aggregation([("count", const_int(1)), ("count", col(M_INT))]).build()),
             ("mixed_only_strings", scan().build(output_offsets=[M_STR, M_BLOB, M_JSON]))]
 
 
@@ -633,7 +675,9 @@ def check_mixed(run, seed=1, n_keys=700):
     for name, plan in mixed_plans():
         exp = orc.dag_handle(plan, WHOLE, region)
         got = run(plan, WHOLE, region)
-        assert exp.status == 0 and exp.n_rows > 50, (name, exp.status, exp.message)
+        assert exp.status == 0 and exp.n_rows > (0 if "count" in name else 50), (name, exp.status, exp.message)
+        if "count" in name:
+            assert exp.rows()[0][0] > 5, (name, exp.rows())
         assert got.status == 0, (name, got.status, got.message)
         assert got.kinds == exp.kinds, (name, got.kinds, exp.kinds)
         assert got.rows() == exp.rows(), name

@@ -58,7 +58,12 @@ def test_check_supported_without_gpu(lib):
     assert lib.b2_check_supported(C.byref(Plan().table_scan(5, cols).build().c)) == ffi.B2_OK  # VARCHAR output: materialised since ABI 3
     bad = Plan().table_scan(5, cols).selection(lt(col(2), const_int(3))).build()
     assert lib.b2_check_supported(C.byref(bad.c)) == ffi.B2_ERR_UNSUPPORTED
-    assert b"Int/Real" in lib.b2_last_error_message()
+    assert b"not Int / Real" in lib.b2_last_error_message()
+    # DATETIME / DURATION columns take part in comparisons (ABI 4); a time-valued expression is still the CPU's
+    from tikv_b200.plan import const_time
+    tcols = [ColumnDef(1, pk_handle=True), ColumnDef(2, tp=ffi.TP_DATETIME)]
+    assert lib.b2_check_supported(C.byref(Plan().table_scan(5, tcols).selection(lt(col(1, tp=ffi.TP_DATETIME), const_time(1 << 40))).build().c)) == ffi.B2_OK
+    assert lib.b2_check_supported(C.byref(Plan().table_scan(5, tcols).selection(col(1, tp=ffi.TP_DATETIME)).build().c)) == ffi.B2_ERR_UNSUPPORTED
 
 
 def test_open_fails_loudly_without_cuda(lib):

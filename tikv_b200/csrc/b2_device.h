@@ -1506,6 +1506,7 @@ B2_HD bool f64_isinf(double x) { return (f64_bits(x) & 0x7fffffffffffffffull) ==
 #endif
 #endif
 B2_HD bool is_ext_sig(int sig) {
+  if ((sig >= B2_SIG_BIT_AND && sig <= B2_SIG_BIT_NEG) || sig == B2_SIG_CAST_INT_AS_INT || sig == B2_SIG_CAST_INT_AS_REAL || sig == B2_SIG_CAST_REAL_AS_REAL) return true;
   return sig == B2_SIG_INT_DIVIDE_INT || sig == B2_SIG_MOD_INT || sig == B2_SIG_MOD_REAL || sig == B2_SIG_DIVIDE_REAL || (sig >= B2_SIG_ABS_INT && sig <= B2_SIG_ABS_REAL) ||
          sig == B2_SIG_UNARY_MINUS_INT || sig == B2_SIG_UNARY_MINUS_REAL || (sig >= B2_SIG_IF_NULL_INT && sig <= B2_SIG_CASE_WHEN_REAL);
 }
@@ -1534,6 +1535,14 @@ B2_HD int eval_ext_fn(int sig, int na, bool ret_unsigned, int64_t* sv, uint8_t* 
     const int64_t a = sv[base], b = na == 2 ? sv[base + 1] : 0;
     const bool an = sn[base] & 1, au = sn[base] & 2, bn = na == 2 ? (sn[base + 1] & 1) : false, bu = na == 2 ? (sn[base + 1] & 2) : false;
     switch (sig) {
+        case B2_SIG_BIT_AND: if (!an && !bn) { rn = false; r = a & b; } break;  // impl_op.rs:144-175
+        case B2_SIG_BIT_OR: if (!an && !bn) { rn = false; r = a | b; } break;
+        case B2_SIG_BIT_XOR: if (!an && !bn) { rn = false; r = a ^ b; } break;
+        case B2_SIG_BIT_NEG: if (!an) { rn = false; r = ~a; } break;
+        case B2_SIG_CAST_INT_AS_INT: case B2_SIG_CAST_REAL_AS_REAL: if (!an) { rn = false; r = a; } break;  // impl_cast.rs:281-305, 505-507 (in_union false)
+        case B2_SIG_CAST_INT_AS_REAL:  // impl_cast.rs:466-501: `as f64` of the signed value only when both sides are signed
+          if (!an) { rn = false; r = (int64_t)f64_bits((au || ret_unsigned) ? (double)(uint64_t)a : (double)a); }
+          break;
         case B2_SIG_IF_NULL_INT: case B2_SIG_IF_NULL_REAL:  // impl_control.rs:7-14
           if (!an) { rn = false; r = a; } else if (!bn) { rn = false; r = b; }
           break;
@@ -1611,6 +1620,7 @@ B2_HD int eval_leaf(const DevPlan& P, const DevNode& nd, const Row& row, const C
     int e = cell_value(P, row, cells, (int)nd.imm, &x);
     if (e) return e;
     *v = (int64_t)x.bits; *f = (x.null ? 1u : 0u) | (P.cols[nd.imm].is_unsigned ? 2u : 0u);
+    if (P.cols[nd.imm].kind == CK_TIME) { *v &= ~15ll; *f |= 2u; }  // `Ord for Time`: the fsp / time-type bits do not take part; the rest orders as u64
     return DE_NONE;
   }
   *v = node_imm(row, nd); *f = (nd.kind == B2_RPN_CONST_NULL ? 1u : 0u) | (nd.is_unsigned ? 2u : 0u);
@@ -1671,6 +1681,7 @@ B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const 
       int e = cell_value(P, row, cells, (int)nd.imm, &v);
       if (e) return e;
       sv[sp] = (int64_t)v.bits; sn[sp] = (v.null ? 1 : 0) | (P.cols[nd.imm].is_unsigned ? 2 : 0);
+      if (P.cols[nd.imm].kind == CK_TIME) { sv[sp] &= ~15ll; sn[sp] |= 2; }
       ++sp;
       continue;
     }

@@ -1621,13 +1621,19 @@ struct b2_exec {
       CUDA_TRY(tn_lvl_a.reserve((size_t)((lists_cap + 7) / 8) * limit * isz)); CUDA_TRY(tn_lvl_a_cnt.reserve((size_t)((lists_cap + 7) / 8) * 4));
       CUDA_TRY(tn_lvl_b.reserve((size_t)((lists_cap + 63) / 64) * limit * isz)); CUDA_TRY(tn_lvl_b_cnt.reserve((size_t)((lists_cap + 63) / 64) * 4));
       CUDA_TRY(tn_pair.reserve((size_t)2 * limit * isz)); CUDA_TRY(tn_pair_cnt.reserve(8));
-      CUDA_TRY(tn_tmp.reserve((size_t)limit * isz)); CUDA_TRY(tn_tmp_cnt.reserve(4));
+      CUDA_TRY(tn_tmp.reserve((size_t)limit * isz)); CUDA_TRY(tn_tmp_cnt.reserve(8));
       size_t pay_bytes = (size_t)n_out * limit * 8, null_bytes = (size_t)n_out * limit;
       for (DevBuf* b : {&tn_blk_pay, &tn_run_pay, &tn_tmp_pay}) CUDA_TRY(b->reserve(pay_bytes));
       for (DevBuf* b : {&tn_blk_null, &tn_run_null, &tn_tmp_null}) CUDA_TRY(b->reserve(null_bytes));
       CUDA_TRY(cudaMemsetAsync(tn_pair_cnt.p, 0, 8, stream));
-      TopItem* pair = (TopItem*)tn_pair.p;
-      unsigned int* pair_cnt = (unsigned int*)tn_pair_cnt.p;
+      CUDA_TRY(cudaMemsetAsync(tn_tmp_cnt.p, 0, 4, stream));
+      // the running top-N and the buffer the next merge writes swap roles after every chunk (no copies back):
+      // run_* = the running list, its count, payload columns, NULL flags; nxt_* = where merge2 / copy put the new one
+      TopItem *run_items = (TopItem*)tn_pair.p, *nxt_items = (TopItem*)tn_tmp.p;
+      unsigned int *run_cnt = (unsigned int*)tn_pair_cnt.p, *nxt_cnt = (unsigned int*)tn_tmp_cnt.p;
+      DevBuf *run_pay = &tn_run_pay, *nxt_pay = &tn_tmp_pay, *run_null = &tn_run_null, *nxt_null = &tn_tmp_null;
+      TopItem* const unit_items = (TopItem*)tn_pair.p + limit;  // the chunk's own top-N (second half of tn_pair)
+      unsigned int* const unit_cnt = (unsigned int*)tn_pair_cnt.p + 1;
       // The running top-N seeds every later launch with its N-th item, and a CTA drops rows that cannot beat it after one
       // comparison.  The very first rows have no such bound, so the request starts with short chunks that grow 8x each:
       // after c rows the bound passes about limit / c of what follows, i.e. every chunk hands ~8 x limit candidates to
@@ -1647,7 +1653,7 @@ struct b2_exec {
         uint32_t n_tiles = (c_hi - c_lo + TILE - 1) / TILE;
         a.topn.items = (TopItem*)tn_lists.p; a.topn.counts = (unsigned int*)tn_counts.p; a.topn.stride = limit;
         a.topn_cap = cap;
-        a.topn_seed = pair; a.topn_seed_cnt = pair_cnt;
+        a.topn_seed = run_items; a.topn_seed_cnt = run_cnt;
         a.topn_work = (unsigned char*)tn_work.p; a.topn_work_stride = smem;
         CUDA_TRY(cudaMemsetAsync(tn_counts.p, 0, (size_t)lists_cap * 4, stream));
         const bool fast = any_fast && u.fast_ok;
@@ -1656,7 +1662,7 @@ struct b2_exec {
         if (rc) return rc;
         a.topn.n_lists = (uint32_t)(gg + fg);
         // unit top-N (sorted) lands in the second half of `pair`
-        TopNLists unit_out; unit_out.items = pair + limit; unit_out.counts = pair_cnt + 1; unit_out.n_lists = 1; unit_out.stride = limit;
+        TopNLists unit_out; unit_out.items = unit_items; unit_out.counts = unit_cnt; unit_out.n_lists = 1; unit_out.stride = limit;
         {  // per-CTA lists -> one list, fan-in 16 per level (after the first chunks the lists are nearly empty: fewer launches matter more than narrow merges)
           TopNLists cur = a.topn;
           int flip = 0;
@@ -1670,19 +1676,12 @@ struct b2_exec {
           }
           CUDA_TRY(launch_topn_merge(P, cur, unit_out, cap, cur.n_lists, stream));
         }
-        CUDA_TRY(launch_topn_gather(P, a, pair + limit, pair_cnt + 1, (unsigned long long*)tn_blk_pay.p, (unsigned char*)tn_blk_null.p, limit, stream));
-        // running top-N (first half) + unit top-N -> tmp, then back into the first half
-        TopNLists both; both.items = pair; both.counts = pair_cnt; both.n_lists = 2; both.stride = limit;
-        TopNLists merged; merged.items = (TopItem*)tn_tmp.p; merged.counts = (unsigned int*)tn_tmp_cnt.p; merged.n_lists = 1; merged.stride = limit;
-        (void)both; (void)merged;
-        CUDA_TRY(launch_topn_merge2(P, pair, pair_cnt, pair + limit, pair_cnt + 1, (TopItem*)tn_tmp.p, (unsigned int*)tn_tmp_cnt.p, limit, stream));
-        CUDA_TRY(launch_topn_copy((const TopItem*)tn_tmp.p, (const unsigned int*)tn_tmp_cnt.p, n_out, limit, (const unsigned long long*)tn_run_pay.p,
-                                  (const unsigned char*)tn_run_null.p, (const unsigned long long*)tn_blk_pay.p, (const unsigned char*)tn_blk_null.p,
-                                  (unsigned long long*)tn_tmp_pay.p, (unsigned char*)tn_tmp_null.p, stream));
-        CUDA_TRY(cudaMemcpyAsync(pair, tn_tmp.p, (size_t)limit * isz, cudaMemcpyDeviceToDevice, stream));
-        CUDA_TRY(cudaMemcpyAsync(pair_cnt, tn_tmp_cnt.p, 4, cudaMemcpyDeviceToDevice, stream));
-        CUDA_TRY(cudaMemcpyAsync(tn_run_pay.p, tn_tmp_pay.p, pay_bytes, cudaMemcpyDeviceToDevice, stream));
-        CUDA_TRY(cudaMemcpyAsync(tn_run_null.p, tn_tmp_null.p, null_bytes, cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(launch_topn_gather(P, a, unit_items, unit_cnt, (unsigned long long*)tn_blk_pay.p, (unsigned char*)tn_blk_null.p, limit, stream));
+        // running top-N + the chunk's top-N -> the other buffer set, which becomes the running one
+        CUDA_TRY(launch_topn_merge2(P, run_items, run_cnt, unit_items, unit_cnt, nxt_items, nxt_cnt, limit, stream));
+        CUDA_TRY(launch_topn_copy(nxt_items, nxt_cnt, n_out, limit, (const unsigned long long*)run_pay->p, (const unsigned char*)run_null->p,
+                                  (const unsigned long long*)tn_blk_pay.p, (const unsigned char*)tn_blk_null.p, (unsigned long long*)nxt_pay->p, (unsigned char*)nxt_null->p, stream));
+        std::swap(run_items, nxt_items); std::swap(run_cnt, nxt_cnt); std::swap(run_pay, nxt_pay); std::swap(run_null, nxt_null);
         entries_scanned += c_hi - c_lo;
         seeded_rows += c_hi - c_lo;
         stats.num_iterations++;
@@ -1692,7 +1691,8 @@ struct b2_exec {
        release_block(u.block_idx);
        prefetch_after(ui);
       }
-      CUDA_TRY(cudaMemcpyAsync(h_ctr.p, pair_cnt, 4, cudaMemcpyDeviceToHost, stream));
+      if (run_pay != &tn_run_pay) { std::swap(tn_run_pay, tn_tmp_pay); std::swap(tn_run_null, tn_tmp_null); }  // the result is read from tn_run_* below
+      CUDA_TRY(cudaMemcpyAsync(h_ctr.p, run_cnt, 4, cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaStreamSynchronize(stream));
       n = *(uint32_t*)h_ctr.p;
     }

@@ -297,7 +297,7 @@ cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const To
     const unsigned int clip = in.stride < (unsigned int)plan.limit ? in.stride : (unsigned int)plan.limit;
     unsigned int y = (lists * clip + 255) / 256;
     if (y < 1) y = 1;
-    if (y > 64) y = 64;
+    if (y > 16) y = 16;  // (a full group then takes four rounds per thread; the usual, nearly empty lists cost the launch of fewer CTAs)
     topn_rank_merge_kernel<<<dim3(groups, y), 256, 0, s>>>(plan, in, out, fan_in);
     return cudaGetLastError();
   }
@@ -315,7 +315,7 @@ cudaError_t launch_topn_merge(const DevPlan& plan, const TopNLists& in, const To
 __global__ void __launch_bounds__(256) topn_merge2_kernel(const __grid_constant__ DevPlan P, const TopItem* a, const unsigned int* a_cnt, const TopItem* b,
                                                           const unsigned int* b_cnt, TopItem* out, unsigned int* out_cnt, unsigned int limit) {
   const unsigned int na = *a_cnt < limit ? *a_cnt : limit, nb = *b_cnt < limit ? *b_cnt : limit;
-  for (unsigned int t = threadIdx.x; t < na + nb; t += blockDim.x) {
+  for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < na + nb; t += gridDim.x * blockDim.x) {
     const bool from_a = t < na;
     const unsigned int i = from_a ? t : t - na;
     TopItem it = from_a ? a[i] : b[i];
@@ -329,11 +329,12 @@ __global__ void __launch_bounds__(256) topn_merge2_kernel(const __grid_constant_
     it.slot = ((from_a ? 0u : 1u) << 16) | i;
     if (rank < limit) out[rank] = it;
   }
-  if (threadIdx.x == 0) *out_cnt = na + nb < limit ? na + nb : limit;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out_cnt = na + nb < limit ? na + nb : limit;
 }
 cudaError_t launch_topn_merge2(const DevPlan& plan, const TopItem* a, const unsigned int* a_cnt, const TopItem* b, const unsigned int* b_cnt, TopItem* out,
                                unsigned int* out_cnt, uint32_t limit, cudaStream_t s) {
-  topn_merge2_kernel<<<1, 256, 0, s>>>(plan, a, a_cnt, b, b_cnt, out, out_cnt, limit);
+  const unsigned int grid = (2 * limit + 255) / 256 < 1 ? 1 : ((2 * limit + 255) / 256 > 16 ? 16 : (2 * limit + 255) / 256);  // one item per thread: the binary searches are L2 round trips
+  topn_merge2_kernel<<<grid, 256, 0, s>>>(plan, a, a_cnt, b, b_cnt, out, out_cnt, limit);
   return cudaGetLastError();
 }
 

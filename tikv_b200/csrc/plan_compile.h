@@ -82,14 +82,28 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
       case B2_RPN_CONST_REAL: d.et = 1; d.imm = (int64_t)f64_bits(s.f64); break;
       case B2_RPN_CONST_NULL: {
         int k = col_kind_of_tp(s.field_tp);
+        if (s.field_tp == B2_TP_DATE || s.field_tp == B2_TP_DATETIME) { d.et = 2; d.is_unsigned = 1; d.imm = 0; break; }
+        if (s.field_tp == B2_TP_DURATION) { d.et = 3; d.imm = 0; break; }
         if (k == CK_OTHER) { *msg = "NULL constant of a non Int/Real type"; return false; }
         d.et = (uint8_t)k; d.imm = 0;
         break;
       }
+      // DATE / DATETIME and DURATION values take part in comparisons only (eval types 2 and 3 below): a time is its CoreTime
+      // bit field without the fsp / type nibble, ordered as u64 (`Ord for Time`), a duration its signed nanoseconds, so
+      // their comparison functions lower to the integer ones
+      case B2_RPN_CONST_TIME: {
+        if (s.field_tp != B2_TP_DATE && s.field_tp != B2_TP_DATETIME) { *msg = "time constant of a type other than DATE / DATETIME (TIMESTAMP needs the session time zone)"; return false; }
+        d.kind = B2_RPN_CONST_UINT; d.et = 2; d.is_unsigned = 1;
+        d.imm = (int64_t)(time_bits_from_packed((uint64_t)s.i64, s.field_tp == B2_TP_DATE, 0) & ~15ull);
+        break;
+      }
+      case B2_RPN_CONST_DURATION: d.kind = B2_RPN_CONST_INT; d.et = 3; d.is_unsigned = 0; break;
       case B2_RPN_COLUMN_REF: {
         if (s.i64 < 0 || s.i64 >= P.n_cols) { *msg = "column offset out of range"; return false; }
         const DevCol& c = P.cols[s.i64];
-        if (c.kind > CK_REAL) { *msg = "expression over a column that is not Int/Real"; return false; }
+        if (c.kind == CK_TIME) { d.et = 2; d.is_unsigned = 1; break; }
+        if (c.kind == CK_DUR) { d.et = 3; d.is_unsigned = 0; break; }
+        if (c.kind > CK_REAL) { *msg = "expression over a column that is not Int / Real / DATE / DATETIME / DURATION"; return false; }
         d.et = c.kind; d.is_unsigned = c.is_unsigned;
         break;
       }
@@ -99,8 +113,27 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
         bool real_args = false, real_ret = false;
         int want = 2;
         bool mixed = false;  // argument types already checked
+        {  // time / duration: comparisons, IN, IS NULL -> their integer twins over the lowered operands
+          const bool tcmp = sig >= 100 && sig < 170 && (sig % 10 == 4 || sig % 10 == 5);
+          const bool tin = sig == B2_SIG_IN_TIME || sig == B2_SIG_IN_DURATION, tnull = sig == B2_SIG_TIME_IS_NULL || sig == B2_SIG_DURATION_IS_NULL;
+          if (tcmp || tin || tnull) {
+            const uint8_t need = (tcmp ? sig % 10 == 4 : (sig == B2_SIG_IN_TIME || sig == B2_SIG_TIME_IS_NULL)) ? 2 : 3;
+            const int w = tcmp ? 2 : (tnull ? 1 : na);
+            if (na != w || na < 1 || sp < na) { *msg = "bad arity for sig " + std::to_string(sig); return false; }
+            for (int k = 0; k < na; ++k)
+              if (st_et[sp - 1 - k] != need) { *msg = "argument eval type does not match sig " + std::to_string(sig); return false; }
+            d.sig = tcmp ? sig / 10 * 10 : (tin ? B2_SIG_IN_INT : B2_SIG_INT_IS_NULL);
+            sp -= na;
+            d.et = 0;
+            break;
+          }
+        }
         if (cmp) real_args = (sig % 10) == 1;
         else switch (sig) {
+          case B2_SIG_BIT_AND: case B2_SIG_BIT_OR: case B2_SIG_BIT_XOR: break;
+          case B2_SIG_BIT_NEG: case B2_SIG_CAST_INT_AS_INT: want = 1; break;
+          case B2_SIG_CAST_INT_AS_REAL: want = 1; real_ret = true; break;
+          case B2_SIG_CAST_REAL_AS_REAL: want = 1; real_args = real_ret = true; break;
           case B2_SIG_PLUS_REAL: case B2_SIG_MINUS_REAL: case B2_SIG_MULTIPLY_REAL: real_args = real_ret = true; break;
           case B2_SIG_PLUS_INT: case B2_SIG_MINUS_INT: case B2_SIG_MULTIPLY_INT: case B2_SIG_MULTIPLY_INT_UNSIGNED:
           case B2_SIG_LOGICAL_AND: case B2_SIG_LOGICAL_OR: case B2_SIG_LOGICAL_XOR: break;
@@ -141,6 +174,7 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
     P.nodes[P.n_nodes++] = d;
   }
   if (sp != 1) { *msg = "expression does not reduce to one value"; return false; }
+  if (st_et[0] >= 2) { *msg = "DATE / DATETIME / DURATION valued expression: only comparisons over them are on the device path"; return false; }
   const b2_rpn_node& last = x.nodes[x.n_nodes - 1];
   const DevNode& dl = P.nodes[P.n_nodes - 1];
   if (ret_et) *ret_et = dl.et;

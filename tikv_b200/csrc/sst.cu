@@ -11,11 +11,11 @@
 //   sst_restarts  one thread per data block: reads the footer, validates it           -> restart points per block
 //   sst_count     one thread per restart interval: entries, key bytes, value bytes   -> prefix sums give every
 //                 interval its place in the flat block
-//   sst_expand    one thread per restart interval: rebuilds every key from its predecessor *in the output heap*
-//                 (the shared bytes were written by the same thread one entry earlier), strips the data prefix and the
-//                 internal-key footer (whose value type must be kTypeValue), copies the value, writes both offsets
-// The walk is byte-granular and divergent by nature; it runs at a few hundred GB/s, an order of magnitude above the PCIe
-// link the compressed bytes arrive over, which is the point: fewer bytes cross the link (52 instead of 69 per C3 entry).
+//   sst_expand    one warp per restart interval: the current key lives in the warp's registers (byte j in lane j % 32),
+//                 every entry overwrites the bytes past `shared` and streams the key, minus the data prefix and the
+//                 internal-key footer (whose value type must be kTypeValue), and the value out as consecutive bytes
+// The expansion runs an order of magnitude above the PCIe link the compressed bytes arrive over, which is the point:
+// fewer bytes cross the link (53 instead of 69 per C3 entry).
 #include <cub/cub.cuh>
 #include <cuda_runtime.h>
 
@@ -128,42 +128,95 @@ __global__ void sst_count_kernel(SstView S, const unsigned int* ibase, unsigned 
 
 struct FlatOut { uint8_t* keys; unsigned int* koff; uint8_t* vals; unsigned int* voff; };
 
-__global__ void sst_expand_kernel(SstView S, const unsigned int* ibase, unsigned int n_iv, const unsigned int* base_n, const unsigned long long* base_k,
-                                  const unsigned long long* base_v, FlatOut O, unsigned int* err) {
-  const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per restart interval.  The current full key lives in the warp's registers, byte j in lane j % 32, slot j / 32
+// (four slots: keys up to 128 bytes), so "keep the first `shared` bytes, take the rest from the entry" is a predicated
+// byte load per slot with consecutive lanes on consecutive addresses, and the key leaves as consecutive byte stores: the
+// heaps are written in full sectors.  Headers are parsed by every lane alike (same addresses: one transaction).  A key
+// longer than 128 bytes sends the rest of its interval down the sequential path on lane 0, which rebuilds keys from
+// the previous key in the output heap.
+__global__ void __launch_bounds__(256) sst_expand_kernel(SstView S, const unsigned int* ibase, unsigned int n_iv, const unsigned int* base_n,
+                                                         const unsigned long long* base_k, const unsigned long long* base_v, FlatOut O, unsigned int* err) {
+  const unsigned int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t > n_iv) return;
-  if (t == n_iv) { O.koff[base_n[t]] = (unsigned int)base_k[t]; O.voff[base_n[t]] = (unsigned int)base_v[t]; return; }
+  if (t == n_iv) { if (lane == 0) { O.koff[base_n[t]] = (unsigned int)base_k[t]; O.voff[base_n[t]] = (unsigned int)base_v[t]; } return; }
   Interval iv;
   if (!interval_of(S, ibase, t, &iv, err)) return;
   unsigned int e = base_n[t];
   const unsigned int e_end = base_n[t + 1];
   unsigned int ko = (unsigned int)base_k[t], vo = (unsigned int)base_v[t];
   const uint8_t* p = iv.p;
-  unsigned int pfl = 0, pko = 0;
-  unsigned long long psuf = 0;
   const unsigned int PL = S.pl, SL = S.sl;
+  unsigned int kb0 = 0, kb1 = 0, kb2 = 0, kb3 = 0;  // bytes lane, 32 + lane, 64 + lane, 96 + lane of the current full key
+  unsigned int pfl = 0, pko = 0;
 #pragma unroll 1
   while (e < e_end) {  // (validated by sst_count_kernel)
     unsigned int sh, ns, vl;
     p += get_var32(p, iv.end, &sh);
     p += get_var32(p, iv.end, &ns);
     p += get_var32(p, iv.end, &vl);
+    const unsigned int fl = sh + ns;
+    if (fl > 128) break;
+    const unsigned int body_end = fl - SL;
+    if (lane == 0) { O.koff[e] = ko; O.voff[e] = vo; }
+#define SST_SLOT(kb, base)                                                          \
+    if ((base) < fl) {                                                                \
+      const unsigned int j = (base) + lane;                                           \
+      if (j >= sh && j < fl) kb = p[j - sh];                                          \
+      if (j >= PL && j < body_end) O.keys[ko + (j - PL)] = (uint8_t)kb;               \
+      if (SL == 8 && j == body_end && kb != 1) raise(err, SST_UNSUPPORTED);           \
+    }
+    SST_SLOT(kb0, 0u) SST_SLOT(kb1, 32u) SST_SLOT(kb2, 64u) SST_SLOT(kb3, 96u)
+#undef SST_SLOT
+    p += ns;
+#pragma unroll 1
+    for (unsigned int i = lane; i < vl; i += 32) O.vals[vo + i] = p[i];
+    p += vl;
+    pko = ko; pfl = fl;
+    ko += body_end - PL; vo += vl;
+    ++e;
+  }
+  if (e >= e_end) return;
+  // ---- sequential path (lane 0): the interval holds a key longer than 128 bytes ----
+  // footer of the previous key (it is not in the output heap): gather its SL bytes from the lanes
+  unsigned long long psuf = 0;
+  if (SL == 8 && pfl) {
+    for (unsigned int q = 0; q < 8; ++q) {
+      const unsigned int j = pfl - 8 + q, slot = j >> 5;
+      const unsigned int v = slot == 0 ? kb0 : (slot == 1 ? kb1 : (slot == 2 ? kb2 : kb3));
+      psuf |= (unsigned long long)(__shfl_sync(0xffffffffu, v, j & 31) & 0xff) << (8 * q);
+    }
+  }
+  __syncwarp();
+  if (lane != 0) return;
+  // (p was advanced past the three varints of entry e: walk again from its start)
+  const uint8_t* q = iv.p;
+  {  // re-find entry e's start: entries before it were consumed in order
+    unsigned int skip = e - base_n[t];
+    while (skip--) { unsigned int a, b, c; q += get_var32(q, iv.end, &a); q += get_var32(q, iv.end, &b); q += get_var32(q, iv.end, &c); q += b + c; }
+  }
+  const volatile uint8_t* okeys = O.keys;  // bytes other lanes stored: read them back from memory, not from a stale L1 line
+#pragma unroll 1
+  while (e < e_end) {
+    unsigned int sh, ns, vl;
+    q += get_var32(q, iv.end, &sh);
+    q += get_var32(q, iv.end, &ns);
+    q += get_var32(q, iv.end, &vl);
     const unsigned int fl = sh + ns, body_end = fl - SL, pbody_end = pfl - SL;
     unsigned long long suf = 0;
     O.koff[e] = ko; O.voff[e] = vo;
 #pragma unroll 1
     for (unsigned int j = PL; j < fl; ++j) {
       uint8_t c;
-      if (j < sh) c = j < pbody_end ? O.keys[pko + (j - PL)] : (uint8_t)(psuf >> (8 * (j - pbody_end)));
-      else c = p[j - sh];
+      if (j < sh) c = j < pbody_end ? okeys[pko + (j - PL)] : (uint8_t)(psuf >> (8 * (j - pbody_end)));
+      else c = q[j - sh];
       if (j < body_end) O.keys[ko + (j - PL)] = c;
       else suf |= (unsigned long long)c << (8 * (j - body_end));
     }
     if (SL == 8 && (suf & 0xff) != 1) raise(err, SST_UNSUPPORTED);  // kTypeDeletion / Merge / ...: the host's merging iterator must resolve them
-    p += ns;
+    q += ns;
 #pragma unroll 1
-    for (unsigned int i = 0; i < vl; ++i) O.vals[vo + i] = p[i];
-    p += vl;
+    for (unsigned int i = 0; i < vl; ++i) O.vals[vo + i] = q[i];
+    q += vl;
     pko = ko; pfl = fl; psuf = suf;
     ko += body_end - PL; vo += vl;
     ++e;
@@ -254,10 +307,11 @@ struct b2_sst {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   RawBuf keys, koff, vals, voff;  // decoded block (b2_sst_decode)
   RawBuf enc, enc_offs;           // encoded blocks (b2_sst_encode)
+  RawBuf boffs, nres, cnt_n, cnt_k, cnt_v, tmp, err;  // offsets, restart / entry counts and their prefix sums
   void destroy() {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    for (RawBuf* b : {&enc, &enc_offs, &keys, &koff, &vals, &voff}) b->free();
+    for (RawBuf* b : {&enc, &enc_offs, &keys, &koff, &vals, &voff, &boffs, &nres, &cnt_n, &cnt_k, &cnt_v, &tmp, &err}) b->free();
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -265,13 +319,21 @@ struct b2_sst {
 };
 
 namespace {
-// Staging and counting buffers are shared by every handle of a device (a decode call is blocking and holds the lock): the
-// handles of a request's 16 regions own their decoded blocks only, not 16 copies of the compressed bytes.
-struct SstScratch {
+// The compressed bytes of a host-resident run are staged in one of two per-device buffers (shared by every handle: the 16
+// regions of a request do not keep 16 copies of their compressed form).  Two, so that two requests (threads) overlap:
+// while one expands its run, the other's bytes cross PCIe.
+struct Staging {
   std::mutex mu;
-  RawBuf enc, boffs, nres, cnt_n, cnt_k, cnt_v, tmp, err;
+  RawBuf buf;
 };
-SstScratch& scratch(int device) { static SstScratch s[64]; return s[device & 63]; }
+Staging* staging_acquire(int device) {
+  static Staging st[64][2];
+  Staging* a = st[device & 63];
+  if (a[0].mu.try_lock()) return &a[0];
+  if (a[1].mu.try_lock()) return &a[1];
+  a[0].mu.lock();
+  return &a[0];
+}
 int sst_fail(int st, const std::string& m) { b2::set_last_error(m); return st; }
 #define SST_TRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return sst_fail(B2_ERR_CUDA, std::string("b2_sst: ") + #x + ": " + cudaGetErrorString(_e)); } while (0)
 
@@ -292,14 +354,14 @@ int sst_handle(int32_t device, b2_sst** h) {
 }
 
 template <typename T>
-int scan_inplace(b2_sst* s, SstScratch& w, T* a, size_t n) {
+int scan_inplace(b2_sst* s, b2_sst& w, T* a, size_t n) {
   size_t tb = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tb, a, a, (int)n, s->stream);
   SST_TRY(w.tmp.reserve(tb + 16));
   SST_TRY(cub::DeviceScan::ExclusiveSum(w.tmp.p, tb, a, a, (int)n, s->stream));
   return B2_OK;
 }
-int check_err(b2_sst* s, SstScratch& w, const char* what) {
+int check_err(b2_sst* s, b2_sst& w, const char* what) {
   unsigned int code = 0;
   SST_TRY(cudaMemcpyAsync(&code, w.err.p, 4, cudaMemcpyDeviceToHost, s->stream));
   SST_TRY(cudaStreamSynchronize(s->stream));
@@ -319,8 +381,7 @@ int32_t b2_sst_decode(int32_t device, int32_t location, const b2_sst_blocks* in,
   int rc = sst_handle(device, hp);
   if (rc) return rc;
   b2_sst* s = *hp;
-  SstScratch& w = scratch(device);
-  std::lock_guard<std::mutex> lock(w.mu);
+  b2_sst& w = *s;
   const uint32_t nb = in->n_blocks;
   for (uint32_t b = 0; b < nb; ++b)
     if (in->block_offs[b + 1] < in->block_offs[b]) return sst_fail(B2_ERR_INVALID_ARG, "b2_sst_decode: block_offs must ascend");
@@ -335,11 +396,16 @@ int32_t b2_sst_decode(int32_t device, int32_t location, const b2_sst_blocks* in,
   h2d += rel.size() * 8;
   SstView S;
   S.boffs = (const unsigned long long*)w.boffs.p; S.n_blocks = nb; S.trailer = in->trailer_len; S.pl = in->key_prefix_len; S.sl = in->key_suffix_len;
+  struct StagingHold {  // released on every return path
+    Staging* st = nullptr;
+    ~StagingHold() { if (st) st->mu.unlock(); }
+  } hold;
   if (location == B2_LOC_HOST) {
-    SST_TRY(w.enc.reserve((size_t)(hi - lo) + 16));
-    if (hi > lo) SST_TRY(cudaMemcpyAsync(w.enc.p, in->data + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s->stream));
+    hold.st = staging_acquire(device);
+    SST_TRY(hold.st->buf.reserve((size_t)(hi - lo) + 16));
+    if (hi > lo) SST_TRY(cudaMemcpyAsync(hold.st->buf.p, in->data + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, s->stream));
     h2d += hi - lo;
-    S.data = (const uint8_t*)w.enc.p;
+    S.data = (const uint8_t*)hold.st->buf.p;
   } else S.data = in->data + lo;
   SST_TRY(cudaEventRecord(s->ev0, s->stream));
   uint32_t n_iv = 0, n_ent = 0;
@@ -368,7 +434,7 @@ int32_t b2_sst_decode(int32_t device, int32_t location, const b2_sst_blocks* in,
   FlatOut O;
   O.keys = (uint8_t*)s->keys.p; O.koff = (unsigned int*)s->koff.p; O.vals = (uint8_t*)s->vals.p; O.voff = (unsigned int*)s->voff.p;
   if (nb) {
-    sst_expand_kernel<<<(n_iv + 1 + 127) / 128, 128, 0, s->stream>>>(S, (const unsigned int*)w.nres.p, n_iv, (const unsigned int*)w.cnt_n.p,
+    sst_expand_kernel<<<(unsigned int)(((size_t)n_iv + 1 + 7) / 8), 256, 0, s->stream>>>(S, (const unsigned int*)w.nres.p, n_iv, (const unsigned int*)w.cnt_n.p,
                                                                     (const unsigned long long*)w.cnt_k.p, (const unsigned long long*)w.cnt_v.p, O, (unsigned int*)w.err.p);
     SST_TRY(cudaGetLastError());
   } else {
@@ -401,8 +467,7 @@ int32_t b2_sst_encode(int32_t device, const b2_cf_block* flat, uint32_t entries_
   int rc = sst_handle(device, hp);
   if (rc) return rc;
   b2_sst* s = *hp;
-  SstScratch& w = scratch(device);
-  std::lock_guard<std::mutex> lock(w.mu);
+  b2_sst& w = *s;
   const uint32_t n = flat->n, nb = (n + entries_per_block - 1) / entries_per_block;
   FlatIn F; F.keys = flat->keys; F.koff = flat->key_offs; F.vals = flat->vals; F.voff = flat->val_offs; F.n = n;
   EncOpt o; o.per_block = entries_per_block; o.restart = restart_interval; o.pl = key_prefix_len; o.sl = key_suffix_len; o.trailer = trailer_len; o.prefix_byte = key_prefix_byte;

@@ -20,6 +20,10 @@ def eval_kind(tp):
         return "real"
     if tp == ffi.TP_NEWDECIMAL:
         return "decimal"
+    if tp in (ffi.TP_DATE, ffi.TP_DATETIME):
+        return "time"
+    if tp == ffi.TP_DURATION:
+        return "duration"
     return "other"
 
 
@@ -61,6 +65,15 @@ def const_real(v):
     return Expr(ffi.RPN_CONST_REAL, ffi.TP_DOUBLE, 0, f64=float(v))
 
 
+def const_time(packed, tp=ffi.TP_DATETIME):
+    """DATE / DATETIME constant; `packed` = Time::to_packed_u64, what TiDB sends in ExprType::MysqlTime."""
+    return Expr(ffi.RPN_CONST_TIME, tp, 0, i64=int(packed))
+
+
+def const_duration(nanos):
+    return Expr(ffi.RPN_CONST_DURATION, ffi.TP_DURATION, 0, i64=int(nanos))
+
+
 def null(tp=ffi.TP_LONGLONG):
     return Expr(ffi.RPN_CONST_NULL, tp, 0)
 
@@ -69,9 +82,11 @@ def fn(sig_name, *args, ret_tp=ffi.TP_LONGLONG, unsigned=False):
     return Expr(ffi.RPN_FN, ret_tp, ffi.FLAG_UNSIGNED if unsigned else 0, sig=ffi.SIG[sig_name], args=args)
 
 
+_SUFFIX = {"real": "REAL", "time": "TIME", "duration": "DURATION"}
+
+
 def _cmp(name, a, b):
-    k = "REAL" if a.ekind == "real" else "INT"
-    return fn(f"{name}_{k}", a, b)
+    return fn(f"{name}_{_SUFFIX.get(a.ekind, 'INT')}", a, b)
 
 
 def lt(a, b): return _cmp("LT", a, b)
@@ -85,8 +100,15 @@ def and_(a, b): return fn("LOGICAL_AND", a, b)
 def or_(a, b): return fn("LOGICAL_OR", a, b)
 def xor_(a, b): return fn("LOGICAL_XOR", a, b)
 def not_(a): return fn("UNARY_NOT_REAL" if a.ekind == "real" else "UNARY_NOT_INT", a)
-def in_(a, *values): return fn("IN_REAL" if a.ekind == "real" else "IN_INT", a, *values)
-def is_null(a): return fn("REAL_IS_NULL" if a.ekind == "real" else "INT_IS_NULL", a)
+def in_(a, *values): return fn(f"IN_{_SUFFIX.get(a.ekind, 'INT')}", a, *values)
+def is_null(a): return fn(f"{_SUFFIX.get(a.ekind, 'INT')}_IS_NULL", a)
+def bit_and(a, b): return fn("BIT_AND", a, b, unsigned=True)   # MySQL bit operators return BIGINT UNSIGNED
+def bit_or(a, b): return fn("BIT_OR", a, b, unsigned=True)
+def bit_xor(a, b): return fn("BIT_XOR", a, b, unsigned=True)
+def bit_neg(a): return fn("BIT_NEG", a, unsigned=True)
+def cast_int_as_int(a, unsigned=False): return fn("CAST_INT_AS_INT", a, unsigned=unsigned)
+def cast_int_as_real(a, unsigned=False): return fn("CAST_INT_AS_REAL", a, ret_tp=ffi.TP_DOUBLE, unsigned=unsigned)
+def cast_real_as_real(a): return fn("CAST_REAL_AS_REAL", a, ret_tp=ffi.TP_DOUBLE)
 
 
 def _arith(name, a, b):
