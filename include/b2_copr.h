@@ -176,7 +176,7 @@ enum {
   B2_SIG_GT_TIME = 124, B2_SIG_GT_DURATION = 125, B2_SIG_GE_TIME = 134, B2_SIG_GE_DURATION = 135,
   B2_SIG_EQ_TIME = 144, B2_SIG_EQ_DURATION = 145, B2_SIG_NE_TIME = 154, B2_SIG_NE_DURATION = 155,
   B2_SIG_NULLEQ_TIME = 164, B2_SIG_NULLEQ_DURATION = 165,
-  B2_SIG_TIME_IS_NULL = 3115, B2_SIG_DURATION_IS_NULL = 3117,
+  B2_SIG_TIME_IS_NULL = 3115, B2_SIG_DURATION_IS_NULL = 3112,
   B2_SIG_IN_TIME = 4005, B2_SIG_IN_DURATION = 4006,
   /* impl_op.rs:144-175 */
   B2_SIG_BIT_AND = 3118, B2_SIG_BIT_OR = 3119, B2_SIG_BIT_XOR = 3120, B2_SIG_BIT_NEG = 3121,

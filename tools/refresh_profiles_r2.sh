@@ -14,5 +14,7 @@ ncu --set full --import-source on --clock-control none -k 'regex:fast_kernel|b2_
 ncu --set full --import-source on --clock-control none -k 'regex:scan_kernel|b2_scan_jit' -s 30 -c 1 -f -o gpurun_out/scan_kernel_$R python bench.py --only c2 --chunk 12500000 $SMALL > gpurun_out/ncu_scan_$R.log 2>&1
 ncu --set full --import-source on --clock-control none -k 'regex:fast_kernel|b2_fast_jit' -s 40 -c 1 -f -o gpurun_out/topn_kernel_$R python bench.py --only c4 $SMALL > gpurun_out/ncu_topn_$R.log 2>&1
 ncu --set full --import-source on --clock-control none -k 'regex:fast_kernel|b2_fast_jit' -s 30 -c 1 -f -o gpurun_out/checksum_kernel_$R python bench.py --only c5 $SMALL > gpurun_out/ncu_checksum_$R.log 2>&1
+python tools/sst_probe.py 20000000 > gpurun_out/sst_probe_$R.log 2>&1
+ncu --set full --import-source on --clock-control none -k 'regex:sst_expand' -s 2 -c 1 -f -o gpurun_out/sst_expand_$R python tools/sst_probe.py 20000000 > gpurun_out/ncu_sst_$R.log 2>&1
 tail -c 600 gpurun_out/bench_$R.json; tail -c 300 gpurun_out/bench_reference_$R.json
 ls -la gpurun_out/*$R*

@@ -11,8 +11,10 @@ G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 KERNELS = {"agg_kernel": "C3 lean kernel (fast_body<PM_AGG>, plan-specialised): scan + selection + hash aggregation",
            "scan_kernel": "C2 scan kernel (scan_body<PM_SCAN>, plan-specialised): scan + selection + ordered compaction",
            "topn_kernel": "C4 lean kernel (fast_body<PM_TOPN>, plan-specialised)",
-           "checksum_kernel": "C5 lean kernel (fast_body<PM_CHECKSUM>)"}
-for f in [f"bench_{R}.json", f"bench_reference_{R}.json", f"launches_{R}.csv"] + [f"{k}_{R}.ncu-rep" for k in KERNELS]:
+           "checksum_kernel": "C5 lean kernel (fast_body<PM_CHECKSUM>)",
+           "sst_expand": "block reader, expansion pass (sst_expand_kernel, one warp per restart interval): 2e7 C3 entries of RocksDB data blocks -> flat block"}
+ENTRIES_OF = {"sst_expand": 20_000_000}
+for f in [f"bench_{R}.json", f"bench_reference_{R}.json", f"launches_{R}.csv", f"sst_probe_{R}.log"] + [f"{k}_{R}.ncu-rep" for k in KERNELS]:
     if os.path.exists(os.path.join(G, f)):
         shutil.copy(os.path.join(G, f), os.path.join(P, f))
 keep = ["sm__inst_executed.avg.per_cycle_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -25,6 +27,7 @@ for k, what in KERNELS.items():
         continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
+    ENTRIES = ENTRIES_OF.get(k, int(sys.argv[2]) if len(sys.argv) > 2 else 12_500_000)
     h, u, v = rows[0], rows[1], rows[2]
     m = {n: (v[i], u[i]) for i, n in enumerate(h)}
 
@@ -33,7 +36,7 @@ for k, what in KERNELS.items():
         return float(x.replace(",", "")) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1}.get(unit, 1)
     stalls = {n.split("issue_stalled_")[1].split("_per_issue")[0]: float(m[n][0]) for n in h if "average_warps_issue_stalled" in n and n.endswith(".ratio") and m[n][0]}
     rd, wr, dur = num("dram__bytes_read.sum"), num("dram__bytes_write.sum"), num("gpu__time_duration.sum")
-    src = f"profiles/{k}_{R}.ncu-rep (tools/refresh_profiles_r2.sh: ncu --set full --import-source on --clock-control none, one launch = one {ENTRIES}-entry block of the 1e8-row table)"
+    src = f"profiles/{k}_{R}.ncu-rep (tools/refresh_profiles_r2.sh: ncu --set full --import-source on --clock-control none, one launch = {ENTRIES} entries)"
     inst = float(m["smsp__inst_executed.sum"][0].replace(",", ""))
     full = {"source": src, "what": what, "kernel": m["Kernel Name"][0] if "Kernel Name" in m else k, "duration_us_under_ncu": dur * 1e6,
             "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_GBps_under_ncu": (rd + wr) / dur / 1e9,
