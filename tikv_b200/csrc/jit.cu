@@ -135,7 +135,7 @@ std::map<std::string, Entry>& g_cache = *new std::map<std::string, Entry>();
 std::atomic<unsigned long long> g_nvrtc_compiles{0}, g_cache_hits{0};
 std::string cache_key(int mode, bool ext_sigs, int fast /* bit 0: lean kernel too, bit 1: table scan (no index-row decoder) */, const std::string& literal) {
   const char* defs = getenv("B2_JIT_DEFS");  // experiment switches change the source text
-  return "b2jit4|sm_100a|mode" + std::to_string(mode) + "|ext" + std::to_string((int)ext_sigs) + "|fast" + std::to_string((int)fast) + "|src" + std::to_string(api().src_hash) + "|" + (defs ? defs : "") + "|" + literal;
+  return "b2jit5|sm_100a|mode" + std::to_string(mode) + "|ext" + std::to_string((int)ext_sigs) + "|fast" + std::to_string((int)fast) + "|src" + std::to_string(api().src_hash) + "|" + (defs ? defs : "") + "|" + literal;
 }
 std::string cache_path(const std::string& key) {
   char name[32];
@@ -178,7 +178,7 @@ bool compile_cubin(int mode, bool ext_sigs, int fast, const std::string& literal
                     ";\n}\nextern \"C\" __global__ void __launch_bounds__(b2::TILE + 64, 2) b2_scan_jit(const __grid_constant__ b2::ScanArgs A) {\n"
                     "  b2::scan_body<" + std::to_string(mode) + ">(b2::kJitPlan, A);\n}\n";
   if (fast & 1)
-    src += "extern \"C\" __global__ void __launch_bounds__(b2::FK_THREADS, 2) b2_fast_jit(const __grid_constant__ b2::ScanArgs A) {\n"
+    src += "extern \"C\" __global__ void __launch_bounds__(b2::FK_THREADS, 3) b2_fast_jit(const __grid_constant__ b2::ScanArgs A) {\n"
            "  b2::fast_body<" + std::to_string(mode) + ">(b2::kJitPlan, A);\n}\n";
   nvrtcProgram prog;
   if (a.CreateProgram(&prog, src.c_str(), "b2_scan_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) { *error = "nvrtcCreateProgram failed"; return false; }

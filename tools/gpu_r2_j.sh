@@ -1,0 +1,16 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r2l.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_r2l.log; tail -4 gpurun_out/pytest_r2l.log
+R=r2l
+timeout 900 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --no-parity > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err
+tail -c 1000 gpurun_out/bench_$R.err
+python - <<'P'
+import json
+d=json.load(open('gpurun_out/bench_r2l.json'))
+print('value',d['value'],'ms',d['ms_per_step'],'frac',d['roofline']['frac'], 'kernel ms', d['roofline']['kernel_ms_per_step'], 'merge', d.get('merge_ms'))
+for s in d.get('sub',[]): print(s['workload'][:20], s['value'], s['ms_per_step'], s['roofline']['frac'], s['roofline']['kernel_ms_per_step'], s.get('merge_ms'))
+P
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 330 -c 120 --csv --log-file gpurun_out/launches_c4_$R.csv \
+    python bench.py --only c4 --rows 100000000 --blocks 8 --steps 2 --warmup 3 --no-e2e --no-cpu --no-sub --no-parity > gpurun_out/ncu_l4_$R.log 2>&1
+grep -c . gpurun_out/launches_c4_$R.csv
