@@ -139,7 +139,9 @@ typedef struct b2_column_info {
 enum { B2_RPN_CONST_NULL = 0, B2_RPN_CONST_INT = 1, B2_RPN_CONST_UINT = 2, B2_RPN_CONST_REAL = 3,
        B2_RPN_COLUMN_REF = 4, B2_RPN_FN = 5,
        B2_RPN_CONST_TIME = 6,      /* i64 = Time::to_packed_u64 (the payload of tipb ExprType::MysqlTime); field_tp DATE / DATETIME */
-       B2_RPN_CONST_DURATION = 7   /* i64 = nanoseconds (tipb ExprType::MysqlDuration) */ };
+       B2_RPN_CONST_DURATION = 7,  /* i64 = nanoseconds (tipb ExprType::MysqlDuration) */
+       B2_RPN_CONST_BYTES = 8      /* tipb ExprType::Bytes / String: i64 = address of the bytes (host memory, borrowed for the
+                                      handle's lifetime like the plan itself), n_args = their length (< 65536) */ };
 
 /* Scalar function signatures.  Names follow tipb::ScalarFuncSig; numeric values follow
  * tipb expression.proto as pinned by Cargo.lock (pingcap/tipb @ 1374320b, not vendored in
@@ -182,7 +184,12 @@ enum {
   B2_SIG_BIT_AND = 3118, B2_SIG_BIT_OR = 3119, B2_SIG_BIT_XOR = 3120, B2_SIG_BIT_NEG = 3121,
   /* impl_cast.rs:281-305 (Int -> Int keeps the bits), :466-501 (Int -> Real by the signedness of either side),
    * :505-507 (Real -> Real); UNION's in_union metadata is not carried by this ABI (treated as false) */
-  B2_SIG_CAST_INT_AS_INT = 0, B2_SIG_CAST_INT_AS_REAL = 1, B2_SIG_CAST_REAL_AS_REAL = 11
+  B2_SIG_CAST_INT_AS_INT = 0, B2_SIG_CAST_INT_AS_REAL = 1, B2_SIG_CAST_REAL_AS_REAL = 11,
+  /* impl_like.rs:7-74: LIKE(target bytes, pattern bytes, escape int) over a bytes column / constant.  The collator is the
+   * node's own collation, the charset the target's when target and pattern agree, else the node's (lib.rs:99-135
+   * map_like_sig).  On the device path: the binary collation and the *_bin collations of utf8 / utf8mb4 (their
+   * force-no-pad comparison of one character is byte equality); `_` then steps one byte or one UTF-8 character. */
+  B2_SIG_LIKE = 4310
 };
 
 typedef struct b2_rpn_node {
@@ -191,7 +198,8 @@ typedef struct b2_rpn_node {
   int32_t n_args;     /* FN arity */
   int32_t field_tp;   /* return field type B2_TP_* */
   uint32_t field_flag;/* return field flags (UNSIGNED matters for compare dispatch, lib.rs:223-259) */
-  int32_t _pad;
+  int32_t collation;  /* tipb FieldType.collate of the node's type as TiDB sends it (Collation::from_i32, field_type.rs:130-146:
+                         63 / -63 binary, -46 / -83 / -65 utf8mb4_bin, >= 0 otherwise: utf8mb4_bin without padding ...); only LIKE reads it */
   int64_t i64;        /* CONST_INT/UINT payload, or COLUMN_REF offset into the child schema */
   double f64;         /* CONST_REAL payload */
 } b2_rpn_node;

@@ -27,7 +27,7 @@ const size_t BATCH_INITIAL_SIZE = 32;  // runner.rs:39
 const size_t BATCH_MAX_SIZE = 1024;    // logical_rows.rs:5
 const size_t BATCH_GROW_FACTOR = 2;    // runner.rs:51
 
-enum EvalType { ET_INT, ET_REAL, ET_DECIMAL, ET_OTHER, ET_TIME /* DATE / DATETIME: CoreTime bits */, ET_DURATION /* nanoseconds */ };
+enum EvalType { ET_INT, ET_REAL, ET_DECIMAL, ET_OTHER, ET_TIME /* DATE / DATETIME: CoreTime bits */, ET_DURATION /* nanoseconds */, ET_BYTES };
 struct FieldType { int tp = 0; uint32_t flag = 0; int decimal = 0; bool is_unsigned() const { return flag & B2_FLAG_UNSIGNED; } };
 
 inline EvalType eval_type_of(int tp) {  // def/eval_type.rs:53-95
@@ -539,6 +539,8 @@ struct Val {  // one stack node restricted to the batch's logical rows (index j 
   bool is_unsigned = false;
   bool s_null = true; int64_t s_i = 0; double s_f = 0;
   std::vector<int64_t> i; std::vector<double> f; std::vector<uint8_t> nn;
+  std::vector<Bytes> b; Bytes s_b;  // ET_BYTES
+  const Bytes& bytes_at(size_t j) const { return scalar ? s_b : b[j]; }
   bool null_at(size_t j) const { return scalar ? s_null : !nn[j]; }
   int64_t int_at(size_t j) const { return scalar ? s_i : i[j]; }
   double real_at(size_t j) const { return scalar ? s_f : f[j]; }
@@ -555,6 +557,93 @@ inline int cmp_int(int64_t a, bool au, int64_t b, bool bu) {  // impl_compare.rs
 }
 
 struct ExprCtx { const std::vector<FieldType>* schema; Batch* batch; };
+
+inline bool tp_is_bytes(int tp) {  // EvalType::Bytes (def/eval_type.rs:53-95)
+  switch (tp) { case B2_TP_VARCHAR: case B2_TP_VARSTRING: case B2_TP_STRING: case B2_TP_BLOB: case 0xf9: case 0xfa: case 0xfb: case 0xff: return true; default: return false; }
+}
+// decode_bytes_datum (datum_codec.rs): NIL, compact bytes, memcomparable bytes
+inline bool decode_bytes_datum(Slice d, bool* is_null, Bytes* out, std::string* err) {
+  *is_null = false; out->clear();
+  if (d.empty()) { *err = "Failed to decode datum flag"; return false; }
+  Slice p = d.sub(1);
+  switch (d[0]) {
+    case NIL_FLAG: *is_null = true; return true;
+    case COMPACT_BYTES_FLAG: {
+      int64_t vn; size_t n = decode_var_i64(p, &vn);
+      if (!n || vn < 0 || p.n - n < (size_t)vn) { *err = "unexpected eof"; return false; }
+      out->assign(p.p + n, p.p + n + vn);
+      return true;
+    }
+    case BYTES_FLAG: if (decode_bytes(p, out) == (size_t)-1) { *err = "unexpected eof"; return false; } return true;
+    default: *err = "Unsupported datum flag " + std::to_string(d[0]) + " for Bytes vector"; return false;
+  }
+}
+
+// ---- LIKE (impl_like.rs:7-74) ----
+// Charset::decode_one: binary = one byte (charset.rs:17-24); utf8mb4 = core::str::next_code_point (charset.rs:43-54: the
+// lead byte decides the length, nothing is validated)
+inline size_t like_decode_one(const uint8_t* s, size_t n, bool utf8, uint32_t* code) {
+  if (n == 0) return 0;
+  uint32_t x = s[0];
+  if (!utf8 || x < 128) { *code = x; return 1; }
+  uint32_t y = n > 1 ? (s[1] & 0x3f) : 0, ch = ((x & 0x1f) << 6) | y;
+  size_t len = 2;
+  if (x >= 0xe0) {
+    uint32_t yz = (y << 6) | (n > 2 ? (s[2] & 0x3f) : 0);
+    ch = ((x & 0x1f) << 12) | yz; len = 3;
+    if (x >= 0xf0) { ch = ((x & 7) << 18) | (yz << 6) | (n > 3 ? (s[3] & 0x3f) : 0); len = 4; }
+  }
+  *code = ch;
+  return std::min(len, n);
+}
+// like::<C, CS> for a collator C whose sort_compare(.., force_no_pad = true) of two single characters is byte equality
+// (CollatorBinary, CollatorUtf8Mb4Bin, CollatorUtf8Mb4BinNoPadding)
+inline bool like_eval(const Bytes& target, const Bytes& pattern, int64_t escape_i, bool utf8) {
+  const uint32_t escape = (uint32_t)escape_i;
+  size_t px = 0, tx = 0, next_px = 0, next_tx = 0;
+  while (px < pattern.size() || tx < target.size()) {
+    uint32_t code = 0, tc = 0;
+    size_t poff = like_decode_one(pattern.data() + px, pattern.size() - px, utf8, &code);
+    if (poff) {
+      if (code == '_') {
+        size_t toff = like_decode_one(target.data() + tx, target.size() - tx, utf8, &tc);
+        if (toff) { px += poff; tx += toff; continue; }
+      } else if (code == '%') {
+        px += poff; next_px = px;
+        if (next_px >= pattern.size()) return true;
+        next_tx = tx;
+        continue;
+      } else {
+        bool brk = false;
+        if (code == escape && px + poff < pattern.size()) {
+          px += poff;
+          uint32_t c2;
+          poff = like_decode_one(pattern.data() + px, pattern.size() - px, utf8, &c2);
+          if (!poff) brk = true;
+        }
+        if (brk) break;
+        size_t toff = like_decode_one(target.data() + tx, target.size() - tx, utf8, &tc);
+        if (toff && toff == poff && memcmp(target.data() + tx, pattern.data() + px, toff) == 0) { tx += toff; px += poff; continue; }
+      }
+    }
+    if (0 < next_px && next_tx < target.size()) {
+      size_t toff = like_decode_one(target.data() + next_tx, target.size() - next_tx, utf8, &tc);
+      next_tx += toff ? toff : 1;
+      px = next_px; tx = next_tx;
+      continue;
+    }
+    return false;
+  }
+  return true;
+}
+// Collation::from_i32 (field_type.rs:130-146) restricted to what like_eval covers: charset 0 binary, 1 utf8mb4; false = other
+inline bool like_collation(int n, int* charset) {
+  switch (n) {
+    case -63: case 63: case 47: *charset = 0; return true;
+    case -46: case -83: case -65: case -309: *charset = 1; return true;
+    default: if (n >= 0) { *charset = 1; return true; } return false;
+  }
+}
 // EvalContext::warnings (expr/ctx.rs:180-215) of the request running on this thread: only "Division by 0" can occur here
 inline uint64_t& warning_count() { static thread_local uint64_t n = 0; return n; }
 
@@ -563,7 +652,12 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
   std::vector<Val> st;
   for (uint32_t k = 0; k < e.n_nodes; ++k) {
     const b2_rpn_node& nd = e.nodes[k];
-    if (nd.kind == B2_RPN_CONST_TIME || nd.kind == B2_RPN_CONST_DURATION) {  // ExprType::MysqlTime / MysqlDuration constants
+    if (nd.kind == B2_RPN_CONST_BYTES) {
+      Val v; v.scalar = true; v.s_null = false; v.et = ET_BYTES;
+      const uint8_t* src = (const uint8_t*)(uintptr_t)nd.i64;
+      if (nd.n_args > 0) v.s_b.assign(src, src + nd.n_args);
+      st.push_back(std::move(v));
+    } else if (nd.kind == B2_RPN_CONST_TIME || nd.kind == B2_RPN_CONST_DURATION) {  // ExprType::MysqlTime / MysqlDuration constants
       Val v; v.scalar = true; v.s_null = false;
       if (nd.kind == B2_RPN_CONST_TIME) {
         uint64_t bits; std::string perr;
@@ -574,7 +668,8 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
     } else if (nd.kind == B2_RPN_CONST_NULL || nd.kind == B2_RPN_CONST_INT || nd.kind == B2_RPN_CONST_UINT || nd.kind == B2_RPN_CONST_REAL) {
       Val v; v.scalar = true;
       v.et = nd.kind == B2_RPN_CONST_REAL ? ET_REAL : (nd.kind == B2_RPN_CONST_NULL ? eval_type_of(nd.field_tp) : ET_INT);
-      if (nd.kind == B2_RPN_CONST_NULL && (nd.field_tp == B2_TP_DATE || nd.field_tp == B2_TP_DATETIME)) v.et = ET_TIME;
+      if (nd.kind == B2_RPN_CONST_NULL && tp_is_bytes(nd.field_tp)) v.et = ET_BYTES;
+      else if (nd.kind == B2_RPN_CONST_NULL && (nd.field_tp == B2_TP_DATE || nd.field_tp == B2_TP_DATETIME)) v.et = ET_TIME;
       else if (nd.kind == B2_RPN_CONST_NULL && nd.field_tp == B2_TP_DURATION) v.et = ET_DURATION;
       else if (v.et != ET_REAL) v.et = ET_INT;
       v.is_unsigned = (nd.field_flag & B2_FLAG_UNSIGNED) || nd.kind == B2_RPN_CONST_UINT;
@@ -584,6 +679,19 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
       size_t ci = (size_t)nd.i64;
       if (ci >= cx.batch->cols.size()) { *err = Error::make(B2_ERR_INVALID_ARG, "column offset out of range"); return false; }
       std::string perr;
+      if (tp_is_bytes((*cx.schema)[ci].tp) && !cx.batch->cols[ci].decoded) {
+        // Bytes operand.  (The reference decodes the whole column here, lazy_column.rs:165-221; the cells it then sends are the
+        // same bytes, so this restatement reads the operands from the raw datums and leaves the column Raw.)
+        const LazyColumn& c = cx.batch->cols[ci];
+        Val v; v.et = ET_BYTES; v.nn.resize(n); v.b.resize(n);
+        for (size_t j = 0; j < n; ++j) {
+          bool is_null;
+          if (!decode_bytes_datum(c.raw_get(cx.batch->logical_rows[j]), &is_null, &v.b[j], &perr)) { *err = Error::make(B2_ERR_CORRUPTED, perr); return false; }
+          v.nn[j] = !is_null;
+        }
+        st.push_back(std::move(v));
+        continue;
+      }
       if (!ensure_decoded(cx.batch->cols[ci], (*cx.schema)[ci], cx.batch->logical_rows, &perr)) { *err = Error::make(B2_ERR_CORRUPTED, perr); return false; }
       const LazyColumn& c = cx.batch->cols[ci];
       Val v; v.et = c.et; v.is_unsigned = (*cx.schema)[ci].is_unsigned();
@@ -593,6 +701,28 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
       st.push_back(std::move(v));
     } else if (nd.kind == B2_RPN_FN) {
       int na = nd.n_args;
+      if (nd.sig == B2_SIG_LIKE) {  // like::<C, CS>(target, pattern, escape), lib.rs:99-135 map_like_sig picks C and CS
+        if ((int)st.size() < 3 || na != 3) { *err = Error::make(B2_ERR_INVALID_ARG, "bad rpn arity"); return false; }
+        std::vector<Val> args(st.end() - 3, st.end());
+        st.resize(st.size() - 3);
+        if (args[0].et != ET_BYTES || args[1].et != ET_BYTES || args[2].et != ET_INT) { *err = Error::make(B2_ERR_INVALID_ARG, "argument eval type does not match the function"); return false; }
+        // the operands' own collations: the last nodes of the target and pattern subtrees
+        int kk = (int)k - 1;
+        auto skip = [&](int& q) { int want = 1; while (want > 0 && q >= 0) { const b2_rpn_node& z = e.nodes[q]; want += (z.kind == B2_RPN_FN ? z.n_args : 0) - 1; --q; } };
+        skip(kk); const int pat = kk; skip(kk); const int tgt = kk;
+        int cs_r, cs_t, cs_p;
+        if (tgt < 0 || !like_collation(nd.collation, &cs_r) || !like_collation(e.nodes[tgt].collation, &cs_t) || !like_collation(e.nodes[pat].collation, &cs_p)) {
+          *err = Error::make(B2_ERR_UNSUPPORTED, "oracle restates LIKE for the binary and *_bin collations only"); return false;
+        }
+        const bool utf8 = (cs_t == cs_p ? cs_t : cs_r) == 1;
+        Val r; r.et = ET_INT; r.is_unsigned = false; r.nn.assign(n, 0); r.i.assign(n, 0);
+        for (size_t j = 0; j < n; ++j) {
+          if (args[0].null_at(j) || args[1].null_at(j) || args[2].null_at(j)) continue;
+          r.nn[j] = 1; r.i[j] = like_eval(args[0].bytes_at(j), args[1].bytes_at(j), args[2].int_at(j), utf8);
+        }
+        st.push_back(std::move(r));
+        continue;
+      }
       {  // DateTime / Duration comparisons, IN, IS NULL (impl_compare.rs:63-240 over `Ord for Time`, mysql/time/mod.rs:2814-2840:
          // set_fsp_tt(0) on both sides, then the u64 bit fields compare; `Ord for Duration`: the nanoseconds compare)
         const int sig = nd.sig;

@@ -93,6 +93,7 @@ emu_result* emu_dag_handle(const b2_dag_plan* plan, const b2_key_range* ranges, 
   CompiledPlan cp;
   R->status = compile_plan(plan, &cp, &R->msg);
   if (R->status) return R;
+  patch_pool_imms(cp, cp.pool.data());  // bytes constants: cell references into the host copy of the pool
   DevPlan& P = cp.dev;
   P.read_ts = src->read_ts; P.isolation = src->isolation_level;
   std::vector<BlockView> dviews;

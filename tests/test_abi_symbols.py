@@ -58,7 +58,7 @@ def test_check_supported_without_gpu(lib):
     assert lib.b2_check_supported(C.byref(Plan().table_scan(5, cols).build().c)) == ffi.B2_OK  # VARCHAR output: materialised since ABI 3
     bad = Plan().table_scan(5, cols).selection(lt(col(2), const_int(3))).build()
     assert lib.b2_check_supported(C.byref(bad.c)) == ffi.B2_ERR_UNSUPPORTED
-    assert b"not Int / Real" in lib.b2_last_error_message()
+    assert b"eval type does not match" in lib.b2_last_error_message()  # (a VARCHAR operand is a LIKE operand only)
     # DATETIME / DURATION columns take part in comparisons (ABI 4); a time-valued expression is still the CPU's
     from tikv_b200.plan import const_time
     tcols = [ColumnDef(1, pk_handle=True), ColumnDef(2, tp=ffi.TP_DATETIME)]
@@ -207,10 +207,10 @@ def test_scalar_function_numbers_follow_tipb():
             "DurationIsNull": 3112, "RealIsNull": 3113, "TimeIsNull": 3115, "IntIsNull": 3116, "BitAndSig": 3118, "BitOrSig": 3119, "BitXorSig": 3120, "BitNegSig": 3121,
             "IntIsTrue": 3122, "RealIsTrue": 3123, "IntIsFalse": 3125, "RealIsFalse": 3126,
             "InInt": 4001, "InReal": 4002, "InTime": 4005, "InDuration": 4006,
-            "IfNullInt": 4101, "IfNullReal": 4102, "IfInt": 4107, "IfReal": 4108, "CoalesceInt": 4201, "CoalesceReal": 4202, "CaseWhenInt": 4208, "CaseWhenReal": 4209}
+            "IfNullInt": 4101, "IfNullReal": 4102, "IfInt": 4107, "IfReal": 4108, "CoalesceInt": 4201, "CoalesceReal": 4202, "CaseWhenInt": 4208, "CaseWhenReal": 4209, "LikeSig": 4310}
 
     def b2_name(n):
-        n = {"BitAndSig": "BitAnd", "BitOrSig": "BitOr", "BitXorSig": "BitXor", "BitNegSig": "BitNeg", "AbsUInt": "AbsUint"}.get(n, n)
+        n = {"BitAndSig": "BitAnd", "BitOrSig": "BitOr", "BitXorSig": "BitXor", "BitNegSig": "BitNeg", "AbsUInt": "AbsUint", "LikeSig": "Like"}.get(n, n)
         for a, b in (("LT", "Lt"), ("LE", "Le"), ("GT", "Gt"), ("GE", "Ge"), ("EQ", "Eq"), ("NE", "Ne")):
             if n.startswith(a) and n[2:3].isupper():
                 n = b + n[2:]

@@ -142,7 +142,7 @@ def test_check_supported_mirrors_runner():
     five = Plan().table_scan(5, cols).aggregation([("count", const_int(1))], group_by=[col(0), col(1), col(0), col(1), col(0)]).build()
     assert emu.check_supported(five)[0] == ffi.B2_ERR_UNSUPPORTED
     rc, msg = emu.check_supported(Plan().table_scan(5, cols).selection(lt(col(2), const_int(3))).build(output_offsets=[0]))
-    assert rc == ffi.B2_ERR_UNSUPPORTED and "not Int / Real" in msg
+    assert rc == ffi.B2_ERR_UNSUPPORTED and "eval type does not match" in msg
 
 
 @pytest.mark.parametrize("name,plan,exact,keys", sc.topn_plans(), ids=[t[0] for t in sc.topn_plans()])
@@ -306,6 +306,17 @@ def test_projection(name, plan, regions):
 
 def test_scalar_function_known_answers():
     sc.check_scalar_known_answers(emu.dag_handle)
+
+
+def test_like_known_answers():
+    """impl_like.rs test_like / test_like_wide_character through the device logic (like_match, plan lowering, the bytes
+    constants' pool); _ci collations are reported unsupported."""
+    sc.check_like_known_answers(emu.dag_handle)
+    from tikv_b200.plan import ColumnDef, Plan, const_bytes, like
+    cols = [ColumnDef(100, pk_handle=True), ColumnDef(1)]
+    ci = Plan().table_scan(sc.TABLE, cols).projection(like(const_bytes("ßssß".encode(), -45), const_bytes("_sSß".encode(), -45), collation=-45)).build()
+    rc, msg = emu.check_supported(ci)
+    assert rc == ffi.B2_ERR_UNSUPPORTED and "collation" in msg
 
 
 def test_plan_limits_are_reported_not_crashed():

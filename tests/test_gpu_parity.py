@@ -605,6 +605,11 @@ def test_scalar_function_known_answers():
                                   error_labels=("int_divide(-9223372036854775808,-1)", "neg_uint(9223372036854775809)", "abs(-9223372036854775808)"))
 
 
+def test_like_known_answers():
+    """impl_like.rs test_like / test_like_wide_character through the CUDA path (plan-specialised kernels, patterns in HBM)."""
+    sc.check_like_known_answers(lambda plan, ranges, region: DagHandler(plan, ranges, DeviceRegion(region)).handle_request())
+
+
 @pytest.mark.parametrize("name,plan", sc.in_plans(), ids=[n for n, _ in sc.in_plans()])
 def test_in_lists(name, plan, regions):
     """IN (impl_compare_in.rs): NULL semantics, mixed signedness, Real, columns inside the list."""

@@ -443,6 +443,13 @@ def test_scalar_function_known_answers():
     sc.check_scalar_known_answers(orc.dag_handle)
 
 
+def test_like_known_answers():
+    """LIKE (impl_like.rs) against the reference's own vectors, test_like and test_like_wide_character, for the binary and
+    utf8mb4_bin collations, including the charset choice of map_like_sig when target and pattern disagree."""
+    import scenarios as sc
+    sc.check_like_known_answers(orc.dag_handle)
+
+
 def test_backward_scanner_basic():
     """backward.rs test_basic :524-818: REVERSE_SEEK_BOUND = 16, read at ts 17; rows in descending key order and the
     reference's cursor statistics summed over the five `next()` calls (prev 8+16+17+18+19, seek 4, next 3, one initial

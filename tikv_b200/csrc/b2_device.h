@@ -1505,7 +1505,73 @@ B2_HD bool f64_isinf(double x) { return (f64_bits(x) & 0x7fffffffffffffffull) ==
 #define B2_EXT_SIGS 1  // host emulation of the device logic (tests)
 #endif
 #endif
+// ---- LIKE (impl_like.rs:7-74) ----
+// One character of `s` (n bytes left): its code and, as the return value, its length; 0 at the end.  Binary charset: one byte
+// (charset.rs:17-24).  utf8mb4: core::str::next_code_point as CharsetUtf8mb4::decode_one runs it (charset.rs:43-54) -- the
+// lead byte gives the length, nothing is validated; a sequence cut off by the end of the string uses what is there.
+B2_HD uint32_t like_next(const uint8_t* s, uint32_t n, bool utf8, uint32_t* code) {
+  if (n == 0) return 0;
+  const uint32_t x = s[0];
+  if (!utf8 || x < 128) { *code = x; return 1; }
+  const uint32_t y = n > 1 ? (s[1] & 0x3fu) : 0;
+  uint32_t ch = ((x & 0x1fu) << 6) | y, len = 2;
+  if (x >= 0xe0) {
+    const uint32_t yz = (y << 6) | (n > 2 ? (s[2] & 0x3fu) : 0);
+    ch = ((x & 0x1fu) << 12) | yz; len = 3;
+    if (x >= 0xf0) { ch = ((x & 7u) << 18) | (yz << 6) | (n > 3 ? (s[3] & 0x3fu) : 0); len = 4; }
+  }
+  *code = ch;
+  return len < n ? len : n;
+}
+// like::<C, CS> for the collators whose force-no-pad comparison of one character is byte equality (binary, *_bin)
+B2_HD bool like_match(const uint8_t* t, uint32_t tn, const uint8_t* p, uint32_t pn, uint32_t escape, bool utf8) {
+  uint32_t px = 0, tx = 0, next_px = 0, next_tx = 0;
+  while (px < pn || tx < tn) {
+    uint32_t code = 0, poff = like_next(p + px, pn - px, utf8, &code);
+    if (poff) {
+      uint32_t tc;
+      if (code == '_') {
+        const uint32_t toff = like_next(t + tx, tn - tx, utf8, &tc);
+        if (toff) { px += poff; tx += toff; continue; }
+      } else if (code == '%') {
+        px += poff;
+        next_px = px;
+        if (next_px >= pn) return true;  // the last '%' matches whatever is left
+        next_tx = tx;
+        continue;
+      } else {
+        bool stop = false;
+        if (code == escape && px + poff < pn) {
+          px += poff;
+          uint32_t c2;
+          poff = like_next(p + px, pn - px, utf8, &c2);
+          if (!poff) stop = true;
+        }
+        if (stop) break;
+        const uint32_t toff = like_next(t + tx, tn - tx, utf8, &tc);
+        if (toff && toff == poff) {
+          bool same = true;
+          for (uint32_t i = 0; i < toff; ++i) same = same && t[tx + i] == p[px + i];
+          if (same) { tx += toff; px += poff; continue; }
+        }
+      }
+    }
+    // mismatch: back to the position after the last '%', one target character further
+    if (0 < next_px && next_tx < tn) {
+      uint32_t tc;
+      const uint32_t toff = like_next(t + next_tx, tn - next_tx, utf8, &tc);
+      next_tx += toff ? toff : 1;
+      px = next_px;
+      tx = next_tx;
+      continue;
+    }
+    return false;
+  }
+  return true;
+}
+
 B2_HD bool is_ext_sig(int sig) {
+  if (sig == B2_SIG_LIKE) return true;
   if ((sig >= B2_SIG_BIT_AND && sig <= B2_SIG_BIT_NEG) || sig == B2_SIG_CAST_INT_AS_INT || sig == B2_SIG_CAST_INT_AS_REAL || sig == B2_SIG_CAST_REAL_AS_REAL) return true;
   return sig == B2_SIG_INT_DIVIDE_INT || sig == B2_SIG_MOD_INT || sig == B2_SIG_MOD_REAL || sig == B2_SIG_DIVIDE_REAL || (sig >= B2_SIG_ABS_INT && sig <= B2_SIG_ABS_REAL) ||
          sig == B2_SIG_UNARY_MINUS_INT || sig == B2_SIG_UNARY_MINUS_REAL || (sig >= B2_SIG_IF_NULL_INT && sig <= B2_SIG_CASE_WHEN_REAL);
@@ -1709,6 +1775,17 @@ B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const 
       ++sp;
       continue;
     }
+#if B2_EXT_SIGS
+    if (nd.sig == B2_SIG_LIKE) {  // (target, pattern: cell references into HBM; escape: int) -> int; NULL if any argument is
+      const int base = sp - 3;
+      const bool nul = (sn[base] | sn[base + 1] | sn[base + 2]) & 1;
+      const uint64_t tr = (uint64_t)sv[base], pr = (uint64_t)sv[base + 1];
+      sv[base] = nul ? 0 : (int64_t)like_match(raw_ref_addr(tr), raw_ref_len(tr), raw_ref_addr(pr), raw_ref_len(pr), (uint32_t)sv[base + 2], nd.imm != 0);
+      sn[base] = nul ? 1 : 0;
+      sp = base + 1;
+      continue;
+    }
+#endif
     if (is_ext_sig(nd.sig)) {
 #if B2_EXT_SIGS
       int e = eval_ext_fn(nd.sig, nd.n_args, nd.is_unsigned, sv, sn, &sp, &row.warn);

@@ -326,7 +326,7 @@ struct b2_exec {
     }
     for (auto& e : kev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     for (DevBuf* b : {&tn_work, &tn_lists, &tn_counts, &tn_pair, &tn_pair_cnt, &tn_tmp, &tn_tmp_cnt, &tn_blk_pay, &tn_blk_null, &tn_run_pay, &tn_run_null, &tn_tmp_pay, &tn_tmp_null, &tn_bitmap}) b->release();
-    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &tbl_gkeys, &tbl_ready, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &range_rows_prev, &slow_list, &slow_cnt, &rev_data, &rev_bitmap, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
+    for (DevBuf* b : {&ctr_buf, &status_buf, &out_data, &out_bitmap, &dflt_views, &dflt_store, &tbl_keys, &tbl_occ, &tbl_acc, &tbl_gkeys, &tbl_ready, &grp_keys, &grp_null, &grp_acc, &res_ptrs, &range_rows, &range_rows_prev, &slow_list, &slow_cnt, &const_pool, &rev_data, &rev_bitmap, &enc_cols, &enc_counts, &enc_out, &enc_lens, &enc_offs, &enc_tmp, &tn_lvl_a, &tn_lvl_a_cnt, &tn_lvl_b, &tn_lvl_b_cnt}) b->release();
     enc_host.release();
     for (auto& b : res_cols) b.release();
     for (auto& b : res_bitmaps) b.release();
@@ -728,6 +728,7 @@ struct b2_exec {
   // ---- order-free pipelines: the lean kernel (fast_kernel.cuh) over a unit, then scan_body in list mode over the runs it
   // handed over (their first entries, appended on the device; the count never visits the host) ----
   DevBuf slow_list, slow_cnt;
+  DevBuf const_pool;  // bytes constants of the plan (CompiledPlan::pool)
   bool use_fast_kernel = getenv("B2_NO_FAST_KERNEL") == nullptr;
   bool fast_kernel_covers() const {
     if (!use_fast_kernel) return false;
@@ -1816,6 +1817,13 @@ int32_t b2_exec_open(const b2_dag_plan* plan, const b2_key_range* ranges, uint32
   }
   h->cp.dev.read_ts = src->read_ts;
   h->cp.dev.isolation = src->isolation_level;
+  if (!h->cp.pool.empty()) {  // bytes constants (LIKE patterns): to HBM, their launch parameters become cell references into it
+    e = h->const_pool.reserve(h->cp.pool.size() + 16);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->const_pool.p, h->cp.pool.data(), h->cp.pool.size(), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { g_last_error = std::string("bytes constants: ") + cudaGetErrorString(e); return B2_ERR_CUDA; }
+    patch_pool_imms(h->cp, (const uint8_t*)h->const_pool.p);
+  }
   rc = h->setup_source(src, ranges, n_ranges);
   if (rc) { g_last_error = h->last_err.message; return rc; }
   // the exact-layout path for row-format-v1 rows is only compiled in / switched on when the data looks like v1

@@ -22,7 +22,16 @@ struct CompiledPlan {
   int64_t imms[MAX_IMMS] = {};           // hoisted constants, referenced by DevNode::sig / FastCond::imm_slot (ScanArgs::imms at launch)
   int n_imms = 0;
   bool desc = false;                     // TableScan.desc
+  // bytes constants (LIKE patterns): the bytes live in `pool`, uploaded with the request; their constants are launch
+  // parameters holding a cell reference (address << 16 | length) that patch_pool_imms fills once the pool has an address
+  std::vector<uint8_t> pool;
+  struct PoolImm { int slot; uint32_t off, len; };
+  std::vector<PoolImm> pool_imms;
 };
+// bytes constants seen by lower_expr while a plan is being compiled: (node index in DevPlan::nodes, offset, length)
+struct PoolRef { int node; uint32_t off, len; };
+inline std::vector<uint8_t>& lowering_pool() { static thread_local std::vector<uint8_t> p; return p; }
+inline std::vector<PoolRef>& lowering_pool_refs() { static thread_local std::vector<PoolRef> r; return r; }
 
 inline int col_kind_of_tp(int tp) {  // def/eval_type.rs:53-95
   switch (tp) {
@@ -84,6 +93,7 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
         int k = col_kind_of_tp(s.field_tp);
         if (s.field_tp == B2_TP_DATE || s.field_tp == B2_TP_DATETIME) { d.et = 2; d.is_unsigned = 1; d.imm = 0; break; }
         if (s.field_tp == B2_TP_DURATION) { d.et = 3; d.imm = 0; break; }
+        if (scan_col_kind(s.field_tp, 0) == CK_BYTES) { d.et = 4; d.imm = 0; break; }
         if (k == CK_OTHER) { *msg = "NULL constant of a non Int/Real type"; return false; }
         d.et = (uint8_t)k; d.imm = 0;
         break;
@@ -98,12 +108,23 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
         break;
       }
       case B2_RPN_CONST_DURATION: d.kind = B2_RPN_CONST_INT; d.et = 3; d.is_unsigned = 0; break;
+      case B2_RPN_CONST_BYTES: {  // eval type 4: a cell reference; only LIKE takes them
+        if (s.n_args < 0 || s.n_args > 0xffff || (s.n_args && !s.i64)) { *msg = "bytes constant longer than 65535 bytes (or null pointer)"; return false; }
+        std::vector<uint8_t>& pool = lowering_pool();
+        lowering_pool_refs().push_back(PoolRef{P.n_nodes, (uint32_t)pool.size(), (uint32_t)s.n_args});
+        const uint8_t* src = (const uint8_t*)(uintptr_t)s.i64;
+        pool.insert(pool.end(), src, src + s.n_args);
+        pool.resize((pool.size() + 15) & ~(size_t)15, 0);
+        d.kind = B2_RPN_CONST_UINT; d.et = 4; d.is_unsigned = 1; d.n_args = 0; d.imm = 0;
+        break;
+      }
       case B2_RPN_COLUMN_REF: {
         if (s.i64 < 0 || s.i64 >= P.n_cols) { *msg = "column offset out of range"; return false; }
         const DevCol& c = P.cols[s.i64];
         if (c.kind == CK_TIME) { d.et = 2; d.is_unsigned = 1; break; }
         if (c.kind == CK_DUR) { d.et = 3; d.is_unsigned = 0; break; }
-        if (c.kind > CK_REAL) { *msg = "expression over a column that is not Int / Real / DATE / DATETIME / DURATION"; return false; }
+        if (c.kind == CK_BYTES) { d.et = 4; d.is_unsigned = 1; break; }
+        if (c.kind > CK_REAL) { *msg = "expression over a column that is not Int / Real / DATE / DATETIME / DURATION / bytes"; return false; }
         d.et = c.kind; d.is_unsigned = c.is_unsigned;
         break;
       }
@@ -127,6 +148,35 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
             d.et = 0;
             break;
           }
+        }
+        if (sig == B2_SIG_LIKE) {  // (bytes, bytes, int) -> int; charset and collator as map_like_sig picks them (lib.rs:99-135)
+          if (na != 3 || sp < 3) { *msg = "bad arity for sig " + std::to_string(sig); return false; }
+          if (st_et[sp - 3] != 4 || st_et[sp - 2] != 4 || st_et[sp - 1] != 0) { *msg = "argument eval type does not match sig " + std::to_string(sig); return false; }
+          // collation -> (byte-equality collator?, charset): field_type.rs:130-146
+          auto coll = [](int n, bool* bin_eq, int* cs) {  // cs: 0 binary, 1 utf8mb4
+            switch (n) {
+              case -63: case 63: case 47: *bin_eq = true; *cs = 0; return true;                 // Binary
+              case -46: case -83: case -65: case -309: *bin_eq = true; *cs = 1; return true;   // Utf8Mb4Bin, Utf8Mb40900Bin
+              default: if (n >= 0) { *bin_eq = true; *cs = 1; return true; }                    // Utf8Mb4BinNoPadding
+                       return false;                                                          // _ci collations, latin1, gbk: CPU
+            }
+          };
+          // the children's collations: the nodes that produced the two byte operands (their last nodes in post-order)
+          int tgt = -1, pat = -1;
+          {  // walk back over the operand subtrees: escape (1 value), pattern, target
+            int need = 1, k = (int)i - 1;
+            auto skip = [&](int& k2) { int want = 1; while (want > 0 && k2 >= 0) { const b2_rpn_node& q = x.nodes[k2]; want += (q.kind == B2_RPN_FN ? q.n_args : 0) - 1; --k2; } };
+            (void)need;
+            skip(k); pat = k; skip(k); tgt = k;
+          }
+          bool be_r, be_t, be_p; int cs_r, cs_t, cs_p;
+          if (tgt < 0 || pat < 0 || !coll(s.collation, &be_r, &cs_r) || !coll(x.nodes[tgt].collation, &be_t, &cs_t) || !coll(x.nodes[pat].collation, &be_p, &cs_p)) {
+            *msg = "LIKE under a collation that is not binary / *_bin is not on the device path"; return false;
+          }
+          d.imm = cs_t == cs_p ? cs_t : cs_r;
+          sp -= 3;
+          d.et = 0;
+          break;
         }
         if (cmp) real_args = (sig % 10) == 1;
         else switch (sig) {
@@ -218,6 +268,8 @@ inline void lower_default(const b2_column_info& ci, DevCol& c) {
 inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string* msg) {
   DevPlan& P = out->dev;
   memset(&P, 0, sizeof(P));
+  lowering_pool().clear(); lowering_pool_refs().clear();
+  out->pool.clear(); out->pool_imms.clear();
   if (!plan || plan->n_executors == 0 || !plan->executors) { *msg = "empty plan"; return B2_ERR_INVALID_ARG; }
   const b2_executor_desc& scan = plan->executors[0];
   if (scan.tp != B2_EXEC_TABLE_SCAN && scan.tp != B2_EXEC_INDEX_SCAN) { *msg = "first executor must be TableScan or IndexScan"; return B2_ERR_UNSUPPORTED; }
@@ -483,8 +535,20 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
   // Constants become launch parameters: the device plan keeps only a slot number, so that requests which differ in their
   // literals (`col < 5`, `col < 7`, another IN list, another LIMIT) share one plan shape and one specialised kernel.
   out->n_imms = 0;
+  out->pool.swap(lowering_pool());
+  lowering_pool().clear();
+  for (const PoolRef& r : lowering_pool_refs()) {  // bytes constants first: they must get a slot (their value is an address)
+    if (out->n_imms >= MAX_IMMS) { lowering_pool_refs().clear(); *msg = "too many constants for the bytes constants to become launch parameters"; return B2_ERR_UNSUPPORTED; }
+    out->pool_imms.push_back(CompiledPlan::PoolImm{out->n_imms, r.off, r.len});
+    out->imms[out->n_imms] = 0;
+    P.nodes[r.node].sig = ++out->n_imms;
+    P.nodes[r.node].imm = 0;
+    P.nodes[r.node].n_args = 1;  // (marks the node as placed)
+  }
+  lowering_pool_refs().clear();
   for (int i = 0; i < P.n_nodes; ++i) {
     DevNode& nd = P.nodes[i];
+    if (nd.kind == B2_RPN_CONST_UINT && nd.et == 4 && nd.n_args == 1) { nd.n_args = 0; continue; }
     if ((nd.kind == B2_RPN_CONST_INT || nd.kind == B2_RPN_CONST_UINT || nd.kind == B2_RPN_CONST_REAL) && out->n_imms < MAX_IMMS) {
       out->imms[out->n_imms] = nd.imm;
       nd.sig = ++out->n_imms;
@@ -498,6 +562,12 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
     if (kn.sig > 0) { fc.imm_slot = (uint8_t)kn.sig; fc.imm = 0; }
   }
   return B2_OK;
+}
+
+// the bytes constants' launch parameters, once the pool sits at `base` (device memory for the kernels, host memory for the
+// host build of the device logic)
+inline void patch_pool_imms(CompiledPlan& cp, const uint8_t* base) {
+  for (const CompiledPlan::PoolImm& r : cp.pool_imms) cp.imms[r.slot] = (int64_t)raw_ref_make(base + r.off, r.len);
 }
 
 // memcomparable encoding of a raw key (tikv_util/src/codec/bytes.rs:25-55), for range bounds

@@ -24,22 +24,33 @@ def eval_kind(tp):
         return "time"
     if tp == ffi.TP_DURATION:
         return "duration"
+    if tp in (ffi.TP_VARCHAR, ffi.TP_VARSTRING, ffi.TP_STRING, ffi.TP_BLOB, 0xf9, 0xfa, 0xfb, 0xff):
+        return "bytes"
     return "other"
 
 
 class Expr:
     """Expression tree node; `.tp/.flag` is the node's return FieldType."""
 
-    def __init__(self, kind, tp, flag=0, sig=0, args=(), i64=0, f64=0.0):
+    def __init__(self, kind, tp, flag=0, sig=0, args=(), i64=0, f64=0.0, collation=0, data=None):
         self.kind, self.tp, self.flag, self.sig, self.args, self.i64, self.f64 = kind, tp, flag, sig, tuple(args), i64, f64
+        self.collation, self.data = collation, data
 
-    def rpn(self, out=None):
+    def rpn(self, out=None, keep=None):
+        """Post-order nodes; `keep` collects the buffers bytes constants point into (the Plan owns them)."""
         out = [] if out is None else out
         for a in self.args:
-            a.rpn(out)
+            a.rpn(out, keep)
         n = ffi.RpnNode()
         n.kind, n.sig, n.n_args, n.field_tp, n.field_flag = self.kind, self.sig, len(self.args), self.tp, self.flag
-        n.i64, n.f64 = self.i64, self.f64
+        n.i64, n.f64, n.collation = self.i64, self.f64, self.collation
+        if self.kind == ffi.RPN_CONST_BYTES:
+            buf = C.create_string_buffer(bytes(self.data), max(1, len(self.data)))
+            if keep is not None:
+                keep.append(buf)
+            else:
+                self._buf = buf
+            n.i64, n.n_args = C.addressof(buf), len(self.data)
         out.append(n)
         return out
 
@@ -48,8 +59,23 @@ class Expr:
         return eval_kind(self.tp)
 
 
-def col(offset, tp=ffi.TP_LONGLONG, unsigned=False):
-    return Expr(ffi.RPN_COLUMN_REF, tp, ffi.FLAG_UNSIGNED if unsigned else 0, i64=offset)
+COLLATION_BINARY, COLLATION_UTF8MB4_BIN = 63, -46  # tipb FieldType.collate as TiDB sends it (field_type.rs:130-146)
+
+
+def col(offset, tp=ffi.TP_LONGLONG, unsigned=False, collation=0):
+    return Expr(ffi.RPN_COLUMN_REF, tp, ffi.FLAG_UNSIGNED if unsigned else 0, i64=offset, collation=collation)
+
+
+def const_bytes(b, collation=COLLATION_BINARY, tp=ffi.TP_VARCHAR):
+    """Bytes / String constant (tipb ExprType::Bytes / String)."""
+    return Expr(ffi.RPN_CONST_BYTES, tp, 0, collation=collation, data=bytes(b))
+
+
+def like(target, pattern, escape=92, collation=COLLATION_BINARY):
+    """target LIKE pattern ESCAPE chr(escape) (impl_like.rs); `collation` is the LikeSig node's own."""
+    e = fn("LIKE", target, pattern, const_int(escape))
+    e.collation = collation
+    return e
 
 
 def const_int(v):
@@ -164,7 +190,7 @@ class Plan:
         self.columns = []
 
     def _expr(self, e):
-        nodes = e.rpn()
+        nodes = e.rpn(keep=self._keep)
         arr = (ffi.RpnNode * len(nodes))(*nodes)
         self._keep.append(arr)
         x = ffi.RpnExpr()
