@@ -140,6 +140,8 @@ enum { B2_RPN_CONST_NULL = 0, B2_RPN_CONST_INT = 1, B2_RPN_CONST_UINT = 2, B2_RP
        B2_RPN_COLUMN_REF = 4, B2_RPN_FN = 5,
        B2_RPN_CONST_TIME = 6,      /* i64 = Time::to_packed_u64 (the payload of tipb ExprType::MysqlTime); field_tp DATE / DATETIME */
        B2_RPN_CONST_DURATION = 7,  /* i64 = nanoseconds (tipb ExprType::MysqlDuration) */
+       B2_RPN_CONST_DECIMAL = 9,   /* tipb ExprType::MysqlDecimal: i64 = address of its payload (precision byte, fraction byte,
+                                      binary decimal: what a stored DECIMAL cell holds), n_args = the payload's length */
        B2_RPN_CONST_BYTES = 8      /* tipb ExprType::Bytes / String: i64 = address of the bytes (host memory, borrowed for the
                                       handle's lifetime like the plan itself), n_args = their length (< 65536) */ };
 
@@ -180,6 +182,9 @@ enum {
   B2_SIG_NULLEQ_TIME = 164, B2_SIG_NULLEQ_DURATION = 165,
   B2_SIG_TIME_IS_NULL = 3115, B2_SIG_DURATION_IS_NULL = 3112,
   B2_SIG_IN_TIME = 4005, B2_SIG_IN_DURATION = 4006,
+  /* comparisons over DECIMAL values (`Ord for Decimal`, decimal.rs:2323-2338: by value, the signs first) */
+  B2_SIG_LT_DECIMAL = 102, B2_SIG_LE_DECIMAL = 112, B2_SIG_GT_DECIMAL = 122, B2_SIG_GE_DECIMAL = 132, B2_SIG_EQ_DECIMAL = 142,
+  B2_SIG_NE_DECIMAL = 152, B2_SIG_NULLEQ_DECIMAL = 162, B2_SIG_DECIMAL_IS_NULL = 3111, B2_SIG_IN_DECIMAL = 4003,
   /* impl_op.rs:144-175 */
   B2_SIG_BIT_AND = 3118, B2_SIG_BIT_OR = 3119, B2_SIG_BIT_XOR = 3120, B2_SIG_BIT_NEG = 3121,
   /* impl_cast.rs:281-305 (Int -> Int keeps the bits), :466-501 (Int -> Real by the signedness of either side),

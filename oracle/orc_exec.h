@@ -27,7 +27,7 @@ const size_t BATCH_INITIAL_SIZE = 32;  // runner.rs:39
 const size_t BATCH_MAX_SIZE = 1024;    // logical_rows.rs:5
 const size_t BATCH_GROW_FACTOR = 2;    // runner.rs:51
 
-enum EvalType { ET_INT, ET_REAL, ET_DECIMAL, ET_OTHER, ET_TIME /* DATE / DATETIME: CoreTime bits */, ET_DURATION /* nanoseconds */, ET_BYTES };
+enum EvalType { ET_INT, ET_REAL, ET_DECIMAL, ET_OTHER, ET_TIME /* DATE / DATETIME: CoreTime bits */, ET_DURATION /* nanoseconds */, ET_BYTES, ET_DEC /* Decimal operand of a comparison */ };
 struct FieldType { int tp = 0; uint32_t flag = 0; int decimal = 0; bool is_unsigned() const { return flag & B2_FLAG_UNSIGNED; } };
 
 inline EvalType eval_type_of(int tp) {  // def/eval_type.rs:53-95
@@ -541,6 +541,8 @@ struct Val {  // one stack node restricted to the batch's logical rows (index j 
   std::vector<int64_t> i; std::vector<double> f; std::vector<uint8_t> nn;
   std::vector<Bytes> b; Bytes s_b;  // ET_BYTES
   const Bytes& bytes_at(size_t j) const { return scalar ? s_b : b[j]; }
+  std::vector<Decimal> d; Decimal s_d;  // ET_DEC
+  const Decimal& dec_at(size_t j) const { return scalar ? s_d : d[j]; }
   bool null_at(size_t j) const { return scalar ? s_null : !nn[j]; }
   int64_t int_at(size_t j) const { return scalar ? s_i : i[j]; }
   double real_at(size_t j) const { return scalar ? s_f : f[j]; }
@@ -557,6 +559,15 @@ inline int cmp_int(int64_t a, bool au, int64_t b, bool bu) {  // impl_compare.rs
 }
 
 struct ExprCtx { const std::vector<FieldType>* schema; Batch* batch; };
+
+inline bool dec_read(Slice s, Decimal* out, std::string* err);  // orc_chunk.h (decimal.rs:2204-2289)
+inline bool decode_decimal_datum(Slice d, bool* is_null, Decimal* out, std::string* err) {  // decode_decimal_datum, datum_codec.rs
+  *is_null = false;
+  if (d.empty()) { *err = "Failed to decode datum flag"; return false; }
+  if (d[0] == NIL_FLAG) { *is_null = true; *out = dec_zero(); return true; }
+  if (d[0] != DECIMAL_FLAG) { *err = "Unsupported datum flag " + std::to_string(d[0]) + " for Decimal vector"; return false; }
+  return dec_read(d.sub(1), out, err);
+}
 
 inline bool tp_is_bytes(int tp) {  // EvalType::Bytes (def/eval_type.rs:53-95)
   switch (tp) { case B2_TP_VARCHAR: case B2_TP_VARSTRING: case B2_TP_STRING: case B2_TP_BLOB: case 0xf9: case 0xfa: case 0xfb: case 0xff: return true; default: return false; }
@@ -652,7 +663,12 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
   std::vector<Val> st;
   for (uint32_t k = 0; k < e.n_nodes; ++k) {
     const b2_rpn_node& nd = e.nodes[k];
-    if (nd.kind == B2_RPN_CONST_BYTES) {
+    if (nd.kind == B2_RPN_CONST_DECIMAL) {  // ExprType::MysqlDecimal: prec, frac, binary decimal
+      Val v; v.scalar = true; v.s_null = false; v.et = ET_DEC;
+      std::string perr;
+      if (!dec_read(Slice((const uint8_t*)(uintptr_t)nd.i64, (size_t)nd.n_args), &v.s_d, &perr)) { *err = Error::make(B2_ERR_INVALID_ARG, perr); return false; }
+      st.push_back(std::move(v));
+    } else if (nd.kind == B2_RPN_CONST_BYTES) {
       Val v; v.scalar = true; v.s_null = false; v.et = ET_BYTES;
       const uint8_t* src = (const uint8_t*)(uintptr_t)nd.i64;
       if (nd.n_args > 0) v.s_b.assign(src, src + nd.n_args);
@@ -669,6 +685,7 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
       Val v; v.scalar = true;
       v.et = nd.kind == B2_RPN_CONST_REAL ? ET_REAL : (nd.kind == B2_RPN_CONST_NULL ? eval_type_of(nd.field_tp) : ET_INT);
       if (nd.kind == B2_RPN_CONST_NULL && tp_is_bytes(nd.field_tp)) v.et = ET_BYTES;
+      else if (nd.kind == B2_RPN_CONST_NULL && nd.field_tp == B2_TP_NEWDECIMAL) { v.et = ET_DEC; v.s_d = dec_zero(); }
       else if (nd.kind == B2_RPN_CONST_NULL && (nd.field_tp == B2_TP_DATE || nd.field_tp == B2_TP_DATETIME)) v.et = ET_TIME;
       else if (nd.kind == B2_RPN_CONST_NULL && nd.field_tp == B2_TP_DURATION) v.et = ET_DURATION;
       else if (v.et != ET_REAL) v.et = ET_INT;
@@ -679,6 +696,17 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
       size_t ci = (size_t)nd.i64;
       if (ci >= cx.batch->cols.size()) { *err = Error::make(B2_ERR_INVALID_ARG, "column offset out of range"); return false; }
       std::string perr;
+      if ((*cx.schema)[ci].tp == B2_TP_NEWDECIMAL && !cx.batch->cols[ci].decoded) {  // Decimal operand (the column stays Raw, as for bytes below)
+        const LazyColumn& c = cx.batch->cols[ci];
+        Val v; v.et = ET_DEC; v.nn.resize(n); v.d.resize(n);
+        for (size_t j = 0; j < n; ++j) {
+          bool is_null;
+          if (!decode_decimal_datum(c.raw_get(cx.batch->logical_rows[j]), &is_null, &v.d[j], &perr)) { *err = Error::make(B2_ERR_CORRUPTED, perr); return false; }
+          v.nn[j] = !is_null;
+        }
+        st.push_back(std::move(v));
+        continue;
+      }
       if (tp_is_bytes((*cx.schema)[ci].tp) && !cx.batch->cols[ci].decoded) {
         // Bytes operand.  (The reference decodes the whole column here, lazy_column.rs:165-221; the cells it then sends are the
         // same bytes, so this restatement reads the operands from the raw datums and leaves the column Raw.)
@@ -722,6 +750,40 @@ inline bool rpn_eval(const b2_rpn_expr& e, ExprCtx& cx, Val* result, Error* err)
         }
         st.push_back(std::move(r));
         continue;
+      }
+      {  // Decimal comparisons, IN, IS NULL (impl_compare.rs:63-240 over `Ord for Decimal`, decimal.rs:2323-2338)
+        const int sig = nd.sig;
+        const bool dcmp = sig >= 100 && sig < 170 && sig % 10 == 2, din = sig == B2_SIG_IN_DECIMAL, dnull = sig == B2_SIG_DECIMAL_IS_NULL;
+        if (dcmp || din || dnull) {
+          if ((int)st.size() < na || na < 1 || (dcmp && na != 2) || (dnull && na != 1)) { *err = Error::make(B2_ERR_INVALID_ARG, "bad rpn arity"); return false; }
+          std::vector<Val> args(st.end() - na, st.end());
+          st.resize(st.size() - na);
+          for (auto& a : args) if (a.et != ET_DEC) { *err = Error::make(B2_ERR_INVALID_ARG, "argument eval type does not match the function"); return false; }
+          Val r; r.et = ET_INT; r.is_unsigned = false; r.nn.assign(n, 0); r.i.assign(n, 0);
+          for (size_t j = 0; j < n; ++j) {
+            if (dnull) { r.nn[j] = 1; r.i[j] = args[0].null_at(j); continue; }
+            if (din) {
+              if (args[0].null_at(j)) continue;
+              bool hit = false, default_null = false;
+              for (int i = 1; i < na; ++i) { if (args[i].null_at(j)) { default_null = true; continue; } hit |= dec_cmp(args[0].dec_at(j), args[i].dec_at(j)) == 0; }
+              if (hit) { r.nn[j] = 1; r.i[j] = 1; } else if (!default_null) { r.nn[j] = 1; r.i[j] = 0; }
+              continue;
+            }
+            const bool an = args[0].null_at(j), bn = args[1].null_at(j), nulleq = sig / 10 * 10 == B2_SIG_NULLEQ_INT;
+            if (an && bn) { if (nulleq) { r.nn[j] = 1; r.i[j] = 1; } continue; }
+            if (an || bn) { if (nulleq) { r.nn[j] = 1; r.i[j] = 0; } continue; }
+            const int c = dec_cmp(args[0].dec_at(j), args[1].dec_at(j));
+            bool res;
+            switch (sig / 10 * 10) {
+              case B2_SIG_LT_INT: res = c < 0; break; case B2_SIG_LE_INT: res = c <= 0; break;
+              case B2_SIG_GT_INT: res = c > 0; break; case B2_SIG_GE_INT: res = c >= 0; break;
+              case B2_SIG_NE_INT: res = c != 0; break; default: res = c == 0; break;
+            }
+            r.nn[j] = 1; r.i[j] = res;
+          }
+          st.push_back(std::move(r));
+          continue;
+        }
       }
       {  // DateTime / Duration comparisons, IN, IS NULL (impl_compare.rs:63-240 over `Ord for Time`, mysql/time/mod.rs:2814-2840:
          // set_fsp_tt(0) on both sides, then the u64 bit fields compare; `Ord for Duration`: the nanoseconds compare)

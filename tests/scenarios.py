@@ -11,7 +11,7 @@ import kvfmt
 from tikv_b200 import ffi
 from tikv_b200.plan import (divide, fn, ColumnDef, Plan, and_, col, const_int, const_real, const_uint, eq, ge, gt, is_null, le, lt, minus, multiply,
                             in_, ne, not_, null, nulleq, or_, plus, xor_, int_divide, mod, neg, abs_, if_null, if_, case_when, coalesce, const_time, const_duration,
-                            bit_and, bit_or, bit_xor, bit_neg, cast_int_as_int, cast_int_as_real, cast_real_as_real, const_bytes, like)
+                            bit_and, bit_or, bit_xor, bit_neg, cast_int_as_int, cast_int_as_real, cast_real_as_real, const_bytes, like, const_decimal)
 
 TABLE = 1000
 READ_TS = 1000
@@ -689,6 +689,15 @@ def mixed_plans():
                                                                  like(col(M_STR, tp=ffi.TP_VARCHAR, collation=-46), const_bytes(b"_%z", -46), collation=-46))).build(output_offsets=[M_H, M_STR, M_INT])),
             ("mixed_sel_like_blob_escape", scan().selection(not_(like(col(M_BLOB, tp=ffi.TP_BLOB, collation=63), const_bytes(b"%!%%"), escape=ord("!")))).build(output_offsets=[M_H, M_BLOB])),
             ("mixed_count_like_prefix", scan().selection(like(col(M_STR, tp=ffi.TP_VARCHAR, collation=63), const_bytes(b"a%"))).aggregation([("count", const_int(1))]).build()),
+            # DECIMAL comparisons (impl_compare.rs over `Ord for Decimal`): column vs constant in several (precision, fraction)
+            # shapes, IN with a NULL, IS NULL, column vs itself
+            ("mixed_sel_decimal_lt", scan().selection(lt(col(M_DEC, tp=ffi.TP_NEWDECIMAL), const_decimal(kvfmt.decimal_bin("0.5", 3, 2)))).build(output_offsets=[M_H, M_DEC])),
+            ("mixed_sel_decimal_ge_big", scan().selection(ge(col(M_DEC, tp=ffi.TP_NEWDECIMAL), const_decimal(kvfmt.decimal_bin("1000000000.000000001", 30, 9)))).build(output_offsets=[M_H, M_DEC, M_STR])),
+            ("mixed_sel_decimal_in_null", scan().selection(or_(is_null(col(M_DEC, tp=ffi.TP_NEWDECIMAL)),
+                                                               in_(col(M_DEC, tp=ffi.TP_NEWDECIMAL), const_decimal(kvfmt.decimal_bin("0", 1, 0)), null(ffi.TP_NEWDECIMAL),
+                                                                   const_decimal(kvfmt.decimal_bin("-0.00000", 5, 5))))).build(output_offsets=[M_H, M_DEC])),
+            ("mixed_count_decimal_eq_self", scan().selection(eq(col(M_DEC, tp=ffi.TP_NEWDECIMAL), col(M_DEC, tp=ffi.TP_NEWDECIMAL)), ne(col(M_DEC, tp=ffi.TP_NEWDECIMAL), const_decimal(kvfmt.decimal_bin("7", 1, 0))))
+                                                  .aggregation([("count", const_int(1))]).build()),
             ("mixed_count_nulleq_duration", scan().selection(nulleq(col(M_DUR, tp=ffi.TP_DURATION), const_duration(1))).aggregation([("count", const_int(1))]).build()),
             ("mixed_count_zero_dates", scan().selection(eq(col(M_DT, tp=ffi.TP_DATETIME), const_time(0))).aggregation([("count", const_int(1)), ("count", col(M_INT))]).build()),
             ("mixed_only_strings", scan().build(output_offsets=[M_STR, M_BLOB, M_JSON]))]

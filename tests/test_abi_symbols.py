@@ -196,7 +196,8 @@ def test_scalar_function_numbers_follow_tipb():
     header must agree with them (five values had drifted)."""
     from tikv_b200 import ffi
     tipb = {"CastIntAsInt": 0, "CastIntAsReal": 1, "CastRealAsReal": 11,
-            "LTInt": 100, "LTReal": 101, "LTTime": 104, "LTDuration": 105, "LEInt": 110, "LEReal": 111, "LETime": 114, "LEDuration": 115,
+            "LTInt": 100, "LTReal": 101, "LTDecimal": 102, "LEDecimal": 112, "GTDecimal": 122, "GEDecimal": 132, "EQDecimal": 142, "NEDecimal": 152, "NullEQDecimal": 162,
+            "DecimalIsNull": 3111, "InDecimal": 4003, "LTTime": 104, "LTDuration": 105, "LEInt": 110, "LEReal": 111, "LETime": 114, "LEDuration": 115,
             "GTInt": 120, "GTReal": 121, "GTTime": 124, "GTDuration": 125, "GEInt": 130, "GEReal": 131, "GETime": 134, "GEDuration": 135,
             "EQInt": 140, "EQReal": 141, "EQTime": 144, "EQDuration": 145, "NEInt": 150, "NEReal": 151, "NETime": 154, "NEDuration": 155,
             "NullEQInt": 160, "NullEQReal": 161, "NullEQTime": 164, "NullEQDuration": 165,

@@ -149,7 +149,8 @@ struct DevPlan {
   int32_t n_raw;               // PM_SCAN: output columns that are cell references (bytes / json / decimal), resolved by the raw_* kernels
   FastCond fconds[MAX_CONDS];
   int32_t n_proj;              // BatchProjectionExecutor on top: out_cols index `proj`, every output is an expression value
-  int32_t _prpad;
+  int32_t expr_refs;           // 1: some expression reads a cell reference (bytes / DECIMAL leaf: LIKE, Decimal comparisons): rows carry the HBM
+                               //    address of their value (Row::gv) in every mode, and the lean kernels (which do not) stay out
   DevExpr proj[MAX_PROJ];
   int32_t n_group;             // >= 2: BatchSlowHashAggregation, grouped by `groups` (has_group is 1, `group` unused)
   int32_t _gpad;
@@ -1505,6 +1506,34 @@ B2_HD bool f64_isinf(double x) { return (f64_bits(x) & 0x7fffffffffffffffull) ==
 #define B2_EXT_SIGS 1  // host emulation of the device logic (tests)
 #endif
 #endif
+// ---- Decimal comparison (`Ord for Decimal`, decimal.rs:2323-2338 over calc_sub_carry :265-342) ----
+// -1 / 0 / 1 for a < b / a == b / a > b.  Operands are parsed cells (raw_decimal_parse): the signs decide when they differ;
+// otherwise the magnitudes compare by the number of integer words left after the leading zero words, then word by word
+// through the fraction words (trailing zero words do not count).
+B2_HD int dec_cmp_dev(const b2_decimal& a, const b2_decimal& b) {
+  if (a.negative != b.negative) return a.negative ? -1 : 1;
+  int l_int = (a.int_cnt + 8) / 9, l_frac = (a.frac_cnt + 8) / 9, r_int = (b.int_cnt + 8) / 9, r_frac = (b.frac_cnt + 8) / 9;
+  const int l_stop = l_int, r_stop = r_int;
+  int l_idx = 0, r_idx = 0;
+  while (l_idx < l_stop && a.word_buf[l_idx] == 0) ++l_idx;
+  while (r_idx < r_stop && b.word_buf[r_idx] == 0) ++r_idx;
+  l_int = l_stop - l_idx; r_int = r_stop - r_idx;
+  int carry;  // -1 equal, 0 |a| > |b|, 1 |a| < |b|
+  if (r_int > l_int) carry = 1;
+  else if (r_int < l_int) carry = 0;
+  else {
+    int l_end = l_stop + l_frac - 1, r_end = r_stop + r_frac - 1;
+    while (l_idx <= l_end && a.word_buf[l_end] == 0) --l_end;
+    while (r_idx <= r_end && b.word_buf[r_end] == 0) --r_end;
+    while (l_idx <= l_end && r_idx <= r_end && a.word_buf[l_idx] == b.word_buf[r_idx]) { ++l_idx; ++r_idx; }
+    if (l_idx <= l_end) carry = (r_idx <= r_end && b.word_buf[r_idx] > a.word_buf[l_idx]) ? 1 : 0;
+    else if (r_idx <= r_end) carry = 1;
+    else carry = -1;
+  }
+  if (carry < 0) return 0;
+  return ((carry > 0) == (a.negative != 0)) ? 1 : -1;
+}
+
 // ---- LIKE (impl_like.rs:7-74) ----
 // One character of `s` (n bytes left): its code and, as the return value, its length; 0 at the end.  Binary charset: one byte
 // (charset.rs:17-24).  utf8mb4: core::str::next_code_point as CharsetUtf8mb4::decode_one runs it (charset.rs:43-54) -- the
@@ -1570,8 +1599,9 @@ B2_HD bool like_match(const uint8_t* t, uint32_t tn, const uint8_t* p, uint32_t 
   return true;
 }
 
+B2_HD bool is_dec_sig(int sig) { return (sig >= 100 && sig < 170 && sig % 10 == 2) || sig == B2_SIG_IN_DECIMAL || sig == B2_SIG_DECIMAL_IS_NULL; }
 B2_HD bool is_ext_sig(int sig) {
-  if (sig == B2_SIG_LIKE) return true;
+  if (sig == B2_SIG_LIKE || is_dec_sig(sig)) return true;
   if ((sig >= B2_SIG_BIT_AND && sig <= B2_SIG_BIT_NEG) || sig == B2_SIG_CAST_INT_AS_INT || sig == B2_SIG_CAST_INT_AS_REAL || sig == B2_SIG_CAST_REAL_AS_REAL) return true;
   return sig == B2_SIG_INT_DIVIDE_INT || sig == B2_SIG_MOD_INT || sig == B2_SIG_MOD_REAL || sig == B2_SIG_DIVIDE_REAL || (sig >= B2_SIG_ABS_INT && sig <= B2_SIG_ABS_REAL) ||
          sig == B2_SIG_UNARY_MINUS_INT || sig == B2_SIG_UNARY_MINUS_REAL || (sig >= B2_SIG_IF_NULL_INT && sig <= B2_SIG_CASE_WHEN_REAL);
@@ -1709,7 +1739,7 @@ B2_HD int eval_expr(const DevPlan& P, DevExpr ex, const Row& row, const Cells& c
     const DevNode& n1 = P.nodes[ex.start + 1];
     const DevNode& n2 = P.nodes[ex.start + 2];
     int sig = n2.sig;
-    if (n0.kind != B2_RPN_FN && n1.kind != B2_RPN_FN && n2.kind == B2_RPN_FN && sig >= 100 && sig < 160) {
+    if (n0.kind != B2_RPN_FN && n1.kind != B2_RPN_FN && n2.kind == B2_RPN_FN && sig >= 100 && sig < 160 && sig % 10 <= 1) {  // (Int / Real compares: the others carry cell references)
       int64_t a, b; uint32_t af, bf;
       int e = eval_leaf(P, n0, row, cells, &a, &af);
       if (e) return e;
@@ -1776,6 +1806,46 @@ B2_HD int eval_expr_general(const DevPlan& P, DevExpr ex, const Row& row, const 
       continue;
     }
 #if B2_EXT_SIGS
+    if (is_dec_sig(nd.sig)) {  // operands: cell references to (precision, fraction, binary decimal) payloads, columns and constants alike
+      const int na = nd.n_args, base = sp - na;
+      int64_t r = 0; bool rn = true;
+      if (nd.sig == B2_SIG_DECIMAL_IS_NULL) { rn = false; r = sn[base] & 1; }
+      else {
+        b2_decimal x;
+        const bool xn = sn[base] & 1;
+        if (!xn && !raw_decimal_parse(raw_ref_addr((uint64_t)sv[base]), raw_ref_len((uint64_t)sv[base]), &x)) return DE_DATUM_DECODE;
+        if (nd.sig == B2_SIG_IN_DECIMAL) {
+          bool hit = false, has_null = false;
+          for (int i = 1; i < na; ++i) {
+            if (sn[base + i] & 1) { has_null = true; continue; }
+            b2_decimal y;
+            if (!raw_decimal_parse(raw_ref_addr((uint64_t)sv[base + i]), raw_ref_len((uint64_t)sv[base + i]), &y)) return DE_DATUM_DECODE;
+            if (!xn) hit |= dec_cmp_dev(x, y) == 0;
+          }
+          rn = xn || (!hit && has_null); r = hit;
+        } else {
+          const bool yn = sn[base + 1] & 1, nulleq = nd.sig == B2_SIG_NULLEQ_DECIMAL;
+          b2_decimal y;
+          if (!yn && !raw_decimal_parse(raw_ref_addr((uint64_t)sv[base + 1]), raw_ref_len((uint64_t)sv[base + 1]), &y)) return DE_DATUM_DECODE;
+          if (xn || yn) { if (nulleq) { rn = false; r = xn && yn; } }
+          else {
+            const int c = dec_cmp_dev(x, y);
+            rn = false;
+            switch (nd.sig) {
+              case B2_SIG_LT_DECIMAL: r = c < 0; break;
+              case B2_SIG_LE_DECIMAL: r = c <= 0; break;
+              case B2_SIG_GT_DECIMAL: r = c > 0; break;
+              case B2_SIG_GE_DECIMAL: r = c >= 0; break;
+              case B2_SIG_NE_DECIMAL: r = c != 0; break;
+              default: r = c == 0; break;  // EQ, NULLEQ
+            }
+          }
+        }
+      }
+      sv[base] = rn ? 0 : r; sn[base] = rn ? 1 : 0;
+      sp = base + 1;
+      continue;
+    }
     if (nd.sig == B2_SIG_LIKE) {  // (target, pattern: cell references into HBM; escape: int) -> int; NULL if any argument is
       const int base = sp - 3;
       const bool nul = (sn[base] | sn[base + 1] | sn[base + 2]) & 1;

@@ -604,6 +604,13 @@ struct b2_exec {
     }
     CUDA_TRY(cudaMemcpyAsync(s->keys.p, sb.c.keys, sb.key_bytes, cudaMemcpyHostToDevice, copy_stream));
     CUDA_TRY(cudaMemcpyAsync(s->vals.p, sb.c.vals, sb.val_bytes, cudaMemcpyHostToDevice, copy_stream));
+    // the readable bytes past the heaps (word-wide loads of the last entries land there) are zero, as the padding contract of
+    // device-resident blocks has them: nothing may depend on what an earlier request left in a recycled buffer
+    static const bool pad_zero = getenv("B2_NO_STAGE_PAD") == nullptr;
+    if (pad_zero) {
+      CUDA_TRY(cudaMemsetAsync((uint8_t*)s->keys.p + sb.key_bytes, 0, kb - sb.key_bytes, copy_stream));
+      CUDA_TRY(cudaMemsetAsync((uint8_t*)s->vals.p + sb.val_bytes, 0, vb - sb.val_bytes, copy_stream));
+    }
     CUDA_TRY(cudaMemcpyAsync(s->koff.p, sb.c.key_offs, ob, cudaMemcpyHostToDevice, copy_stream));
     CUDA_TRY(cudaMemcpyAsync(s->voff.p, sb.c.val_offs, ob, cudaMemcpyHostToDevice, copy_stream));
     CUDA_TRY(cudaEventRecord(s->ready, copy_stream));

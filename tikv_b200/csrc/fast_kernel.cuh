@@ -78,6 +78,13 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
   unsigned char* stage_base = dyn_smem + A.stage_off;
   const uint32_t STAGE_KEY_CAP = A.stage_key_cap, STAGE_VAL_CAP = A.stage_val_cap;
   const uint32_t STAGE_BYTES = STAGE_KEY_CAP + STAGE_VAL_CAP + 2 * STAGE_OFF_CAP;
+#ifdef B2_ZERO_STAGES
+  {  // (experiment: what the previous kernel left in the stages must not matter)
+    uint4* z = reinterpret_cast<uint4*>(stage_base);
+    for (unsigned int i = tid; i < FK_STAGES * STAGE_BYTES / 16; i += FK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+  }
+#endif
 
   // ---- producer warp: bulk copies of each tile's key / value bytes and offset slices, FK_STAGES tiles ahead ----
   if (wid == TILE / 32) {

@@ -268,7 +268,7 @@ std::shared_future<JitKernel*> jit_get(int device, const DevPlan& plan) {
 }
 
 bool plan_has_fast_kernel(const DevPlan& plan) {
-  if (plan.fast_n <= 0) return false;
+  if (plan.fast_n <= 0 || plan.expr_refs) return false;  // (the lean kernels do not track a row's HBM address: LIKE / Decimal operands need it)
   if (plan.mode == PM_TOPN) return true;
   if (plan.mode != PM_AGG || plan.n_group > 1) return false;
   for (int a = 0; a < plan.n_aggs; ++a)

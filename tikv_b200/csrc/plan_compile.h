@@ -94,6 +94,7 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
         if (s.field_tp == B2_TP_DATE || s.field_tp == B2_TP_DATETIME) { d.et = 2; d.is_unsigned = 1; d.imm = 0; break; }
         if (s.field_tp == B2_TP_DURATION) { d.et = 3; d.imm = 0; break; }
         if (scan_col_kind(s.field_tp, 0) == CK_BYTES) { d.et = 4; d.imm = 0; break; }
+        if (s.field_tp == B2_TP_NEWDECIMAL) { d.et = 5; d.imm = 0; break; }
         if (k == CK_OTHER) { *msg = "NULL constant of a non Int/Real type"; return false; }
         d.et = (uint8_t)k; d.imm = 0;
         break;
@@ -108,6 +109,7 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
         break;
       }
       case B2_RPN_CONST_DURATION: d.kind = B2_RPN_CONST_INT; d.et = 3; d.is_unsigned = 0; break;
+      case B2_RPN_CONST_DECIMAL:  // eval type 5: a cell reference to (precision, fraction, binary decimal); comparisons take them
       case B2_RPN_CONST_BYTES: {  // eval type 4: a cell reference; only LIKE takes them
         if (s.n_args < 0 || s.n_args > 0xffff || (s.n_args && !s.i64)) { *msg = "bytes constant longer than 65535 bytes (or null pointer)"; return false; }
         std::vector<uint8_t>& pool = lowering_pool();
@@ -115,7 +117,11 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
         const uint8_t* src = (const uint8_t*)(uintptr_t)s.i64;
         pool.insert(pool.end(), src, src + s.n_args);
         pool.resize((pool.size() + 15) & ~(size_t)15, 0);
-        d.kind = B2_RPN_CONST_UINT; d.et = 4; d.is_unsigned = 1; d.n_args = 0; d.imm = 0;
+        if (s.kind == B2_RPN_CONST_DECIMAL) {
+          b2_decimal chk;
+          if (!raw_decimal_parse(src, (unsigned int)s.n_args, &chk)) { *msg = "decimal constant is not a valid (precision, fraction, binary decimal) payload"; return false; }
+        }
+        d.kind = B2_RPN_CONST_UINT; d.et = s.kind == B2_RPN_CONST_DECIMAL ? 5 : 4; d.is_unsigned = 1; d.n_args = 0; d.imm = 0;
         break;
       }
       case B2_RPN_COLUMN_REF: {
@@ -124,7 +130,8 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
         if (c.kind == CK_TIME) { d.et = 2; d.is_unsigned = 1; break; }
         if (c.kind == CK_DUR) { d.et = 3; d.is_unsigned = 0; break; }
         if (c.kind == CK_BYTES) { d.et = 4; d.is_unsigned = 1; break; }
-        if (c.kind > CK_REAL) { *msg = "expression over a column that is not Int / Real / DATE / DATETIME / DURATION / bytes"; return false; }
+        if (c.kind == CK_DEC) { d.et = 5; d.is_unsigned = 1; break; }
+        if (c.kind > CK_REAL) { *msg = "expression over a column that is not Int / Real / DATE / DATETIME / DURATION / bytes / DECIMAL"; return false; }
         d.et = c.kind; d.is_unsigned = c.is_unsigned;
         break;
       }
@@ -148,6 +155,16 @@ inline bool lower_expr(const b2_rpn_expr& x, DevPlan& P, DevExpr* out, uint8_t* 
             d.et = 0;
             break;
           }
+        }
+        if (is_dec_sig(sig)) {  // comparisons, IN, IS NULL over DECIMAL cells and constants -> int
+          const bool dcmp = sig >= 100 && sig < 170;
+          const int w = dcmp ? 2 : (sig == B2_SIG_DECIMAL_IS_NULL ? 1 : na);
+          if (na != w || na < 1 || sp < na) { *msg = "bad arity for sig " + std::to_string(sig); return false; }
+          for (int k = 0; k < na; ++k)
+            if (st_et[sp - 1 - k] != 5) { *msg = "argument eval type does not match sig " + std::to_string(sig); return false; }
+          sp -= na;
+          d.et = 0;
+          break;
         }
         if (sig == B2_SIG_LIKE) {  // (bytes, bytes, int) -> int; charset and collator as map_like_sig picks them (lib.rs:99-135)
           if (na != 3 || sp < 3) { *msg = "bad arity for sig " + std::to_string(sig); return false; }
@@ -532,6 +549,8 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
         const DevCol& c = P.cols[P.nodes[i].imm];
         if (c.role == CR_NORMAL && c.kind == CK_INT) P.fast_need |= 1u << c.v2_hint;
       }
+  for (int i = 0; i < P.n_nodes; ++i)
+    if (P.nodes[i].kind == B2_RPN_COLUMN_REF && P.cols[P.nodes[i].imm].kind >= CK_BYTES) P.expr_refs = 1;
   // Constants become launch parameters: the device plan keeps only a slot number, so that requests which differ in their
   // literals (`col < 5`, `col < 7`, another IN list, another LIMIT) share one plan shape and one specialised kernel.
   out->n_imms = 0;
@@ -548,7 +567,7 @@ inline int compile_plan(const b2_dag_plan* plan, CompiledPlan* out, std::string*
   lowering_pool_refs().clear();
   for (int i = 0; i < P.n_nodes; ++i) {
     DevNode& nd = P.nodes[i];
-    if (nd.kind == B2_RPN_CONST_UINT && nd.et == 4 && nd.n_args == 1) { nd.n_args = 0; continue; }
+    if (nd.kind == B2_RPN_CONST_UINT && (nd.et == 4 || nd.et == 5) && nd.n_args == 1) { nd.n_args = 0; continue; }
     if ((nd.kind == B2_RPN_CONST_INT || nd.kind == B2_RPN_CONST_UINT || nd.kind == B2_RPN_CONST_REAL) && out->n_imms < MAX_IMMS) {
       out->imms[out->n_imms] = nd.imm;
       nd.sig = ++out->n_imms;

@@ -41,7 +41,7 @@ inline std::string plan_literal(const DevPlan& P) {
     const FastCond& f = P.fconds[i];
     o << "{"; i64(f.imm); o << "," << (int)f.h << "," << (int)f.op << "," << (int)f.col_uns << "," << (int)f.imm_uns << "," << (int)f.zero_ext << "," << (int)f.imm_slot << ",{0,0}}" << (i < MAX_CONDS - 1 ? "," : "");
   }
-  o << "}," << P.n_proj << "," << P._prpad << ",{";
+  o << "}," << P.n_proj << "," << P.expr_refs << ",{";
   for (int i = 0; i < MAX_PROJ; ++i) { expr(P.proj[i]); o << (i < MAX_PROJ - 1 ? "," : ""); }
   o << "}," << P.n_group << "," << P._gpad << ",{";
   for (int i = 0; i < MAX_GROUP; ++i) { expr(P.groups[i]); o << (i < MAX_GROUP - 1 ? "," : ""); }

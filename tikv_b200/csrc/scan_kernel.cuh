@@ -340,7 +340,7 @@ __device__ __forceinline__ int entry_phase1(const DevPlan& P, const ScanArgs& A,
 #endif
   {
     err = row_open(ro.val, ro.val_len, &row.rv);
-    if (P.n_raw) row.gv = ro.dflt_lookup ? ro.val : view.gval(ro.val);  // (a CF_DEFAULT value is always read in place)
+    if (P.n_raw || P.expr_refs) row.gv = ro.dflt_lookup ? ro.val : view.gval(ro.val);  // (a CF_DEFAULT value is always read in place)
     if (!err) err = row_split(P, row, cells);
   }
   bool keep = false;
@@ -383,7 +383,7 @@ __device__ __forceinline__ int entry_fast(const DevPlan& P, const ScanArgs& A, c
   row.enc_key = kp; row.enc_key_len = 27; row.commit_ts = cts; row.imms = A.imms;
   if (!fast_row_v2(P, vp + roff, rlen, row)) return P1_GENERAL;
   row.filled = P.fast_filled;
-  if (P.n_raw) row.gv = view.gval(vp + roff);
+  if (P.n_raw || P.expr_refs) row.gv = view.gval(vp + roff);
   bool keep = false;
   if (eval_conds(P, row, cells, &keep)) return P1_GENERAL;  // evaluation errors are raised by the general path
   ts.keys += 1;

@@ -22,7 +22,7 @@ EXTRA_PHYSICAL_TABLE_ID_COL_ID, EXTRA_COMMIT_TS_COL_ID = -3, -5
 LOC_HOST, LOC_DEVICE = 0, 1
 ISO_SI, ISO_RC, ISO_RC_CHECK_TS = 0, 1, 2
 
-RPN_CONST_NULL, RPN_CONST_INT, RPN_CONST_UINT, RPN_CONST_REAL, RPN_COLUMN_REF, RPN_FN, RPN_CONST_TIME, RPN_CONST_DURATION, RPN_CONST_BYTES = 0, 1, 2, 3, 4, 5, 6, 7, 8
+RPN_CONST_NULL, RPN_CONST_INT, RPN_CONST_UINT, RPN_CONST_REAL, RPN_COLUMN_REF, RPN_FN, RPN_CONST_TIME, RPN_CONST_DURATION, RPN_CONST_BYTES, RPN_CONST_DECIMAL = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 def _header_enum(prefix):
     """Enumerators of include/b2_copr.h with this prefix: the header is the single source of the numbers."""

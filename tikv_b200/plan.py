@@ -44,7 +44,7 @@ class Expr:
         n = ffi.RpnNode()
         n.kind, n.sig, n.n_args, n.field_tp, n.field_flag = self.kind, self.sig, len(self.args), self.tp, self.flag
         n.i64, n.f64, n.collation = self.i64, self.f64, self.collation
-        if self.kind == ffi.RPN_CONST_BYTES:
+        if self.kind in (ffi.RPN_CONST_BYTES, ffi.RPN_CONST_DECIMAL):
             buf = C.create_string_buffer(bytes(self.data), max(1, len(self.data)))
             if keep is not None:
                 keep.append(buf)
@@ -69,6 +69,11 @@ def col(offset, tp=ffi.TP_LONGLONG, unsigned=False, collation=0):
 def const_bytes(b, collation=COLLATION_BINARY, tp=ffi.TP_VARCHAR):
     """Bytes / String constant (tipb ExprType::Bytes / String)."""
     return Expr(ffi.RPN_CONST_BYTES, tp, 0, collation=collation, data=bytes(b))
+
+
+def const_decimal(payload):
+    """DECIMAL constant (tipb ExprType::MysqlDecimal); `payload` = precision byte, fraction byte, MySQL binary decimal."""
+    return Expr(ffi.RPN_CONST_DECIMAL, ffi.TP_NEWDECIMAL, 0, data=bytes(payload))
 
 
 def like(target, pattern, escape=92, collation=COLLATION_BINARY):
@@ -108,7 +113,7 @@ def fn(sig_name, *args, ret_tp=ffi.TP_LONGLONG, unsigned=False):
     return Expr(ffi.RPN_FN, ret_tp, ffi.FLAG_UNSIGNED if unsigned else 0, sig=ffi.SIG[sig_name], args=args)
 
 
-_SUFFIX = {"real": "REAL", "time": "TIME", "duration": "DURATION"}
+_SUFFIX = {"real": "REAL", "time": "TIME", "duration": "DURATION", "decimal": "DECIMAL"}
 
 
 def _cmp(name, a, b):

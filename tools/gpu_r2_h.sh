@@ -1,7 +1,7 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-R=r2h
+R=r2n
 timeout 1500 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/pytest_$R.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$R.log
 tail -25 gpurun_out/pytest_$R.log
 cat gpurun_out/jit_warm.log
@@ -10,7 +10,7 @@ timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$R.json 2> 
 tail -c 1000 gpurun_out/bench_$R.err
 python - <<'P'
 import json
-d=json.load(open('gpurun_out/bench_r2h.json'))
+d=json.load(open('gpurun_out/bench_r2n.json'))
 e=d['e2e']
 print({k:v for k,v in e.items() if k not in('flat','warm','source','note')})
 print('flat',e.get('flat',{}).get('ms_per_step'),'warm',e.get('warm',{}).get('ms_per_step'))
