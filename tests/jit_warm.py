@@ -29,7 +29,7 @@ def test_plans():
     plans += [p for n, p in sc.plans() if n in ("scan_all", "sel_lt_const", "count_star", "group_by_small", "group_filter_offsets")]
     plans += [p for n, p in sc.int_plans() if n in ("const_on_left", "eq_ne", "agg", "topn")]
     sc.check_like_known_answers(rec)
-    plans += [p for n, p in sc.mixed_plans() if "like" in n]
+    plans += [p for n, p in sc.mixed_plans() if "like" in n or "decimal" in n]
     sc.check_scalar_known_answers(rec, error_labels=("int_divide(-9223372036854775808,-1)", "neg_uint(9223372036854775809)", "abs(-9223372036854775808)"))
     for fx in sc.reference_executor_fixtures():
         if fx[0] in ("hash_agg_fast_v2", "topn_integration_3", "topn_unsigned_col0_desc"):
