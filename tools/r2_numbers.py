@@ -2,6 +2,7 @@
 """Markdown summary of a bench line (profiles/bench_r2.json by default) for DESIGN.md / README.md."""
 import json, sys
 f = sys.argv[1] if len(sys.argv) > 1 else "profiles/bench_r2.json"
+f_path = f
 d = json.loads(open(f).read().strip().splitlines()[-1])
 ref = None
 try:
@@ -10,9 +11,23 @@ except Exception:
     pass
 
 
+import os
+KFILE = {"C3": "agg_kernel", "C2": "scan_kernel", "C4": "topn_kernel", "C5": "checksum_kernel"}
+
+
+def traffic_ratio(name, rf, rows):
+    """DRAM bytes per entry of the kernel's ncu capture / algorithmic bytes per entry of the bench workload."""
+    f = os.path.join(os.path.dirname(f_path), KFILE.get(name, "") + "_r2_traffic.json")
+    if not os.path.exists(f):
+        return None
+    return json.load(open(f))["dram_bytes_per_entry"] / (rf["algorithmic_bytes_per_step"] / rows)
+
+
 def row(r, rows):
     rf = r["roofline"]
-    t = rf.get("traffic")
+    name = r.get('config', {}).get('workload', r.get('workload', '')).split(':')[0]
+    tr = traffic_ratio(name, rf, rows)
+    t = tr * rf["algorithmic_bytes_per_step"] if tr else None
     return (f"| {r.get('config', {}).get('workload', r.get('workload', '')).split(':')[0]} | {rows:.0e} | {r['ms_per_step']:.2f} | {rows * d['n_gpus'] / (r['ms_per_step'] / 1e3):.3g} | "
             f"{rf['kernel_ms_per_step']:.2f} | {rf['achieved']:.0f} | **{rf['frac']:.3f}** | {(t / rf['algorithmic_bytes_per_step']):.2f}× |" if t else
             f"| {r.get('config', {}).get('workload', r.get('workload', '')).split(':')[0]} | {rows:.0e} | {r['ms_per_step']:.2f} | {rows * d['n_gpus'] / (r['ms_per_step'] / 1e3):.3g} | "
