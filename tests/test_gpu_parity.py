@@ -605,6 +605,24 @@ def test_scalar_function_known_answers():
                                   error_labels=("int_divide(-9223372036854775808,-1)", "neg_uint(9223372036854775809)", "abs(-9223372036854775808)"))
 
 
+def test_units_of_a_single_entry():
+    """A CF_WRITE block (and so a unit) holding one entry: every lane past the end of its only tile is clamped onto that
+    entry.  The lean kernels once looked one entry back from it (index -1 into the staged offsets): an illegal address about
+    one run in three (round 2: dirty_region(3, 2000 keys) splits into 3034 + 3034 + 1 entries)."""
+    r = kvfmt.Region()
+    for h in range(601):
+        r.put(kvfmt.row_key(sc.TABLE, h), kvfmt.row_v2([(1, h * 7 - 300, "int"), (2, h % 5, "int"), (3, h, "uint"), (4, 0.5 * h, "f64"), (6, h % 9, "int")]), 10, 20)
+    host = r.build(read_ts=sc.READ_TS, n_write_blocks=2)
+    assert [b.n for b in host.wblocks] == [300, 300, 1]
+    plans = [(n, p) for n, p in PLANS if n in ("count_star", "group_by_small", "agg_after_filter", "sel_lt_const")] + [(t[0], t[1]) for t in sc.topn_plans()[:2]]
+    for region in (DeviceRegion(host), host, DeviceRegion(sc.dirty_region(3, n_keys=2000).build(read_ts=sc.READ_TS, n_write_blocks=2))):
+        ref = region._host if isinstance(region, DeviceRegion) else region
+        for _ in range(3):
+            for name, plan in plans:
+                assert_same_rows(DagHandler(plan, sc.WHOLE, region).handle_request(), orc.dag_handle(plan, sc.WHOLE, ref), ordered=not sc.is_agg(name), ctx=name)
+            assert checksum(sc.WHOLE, region)[:2] == orc.checksum(sc.WHOLE, ref)[:2]
+
+
 def test_like_known_answers():
     """impl_like.rs test_like / test_like_wide_character through the CUDA path (plan-specialised kernels, patterns in HBM)."""
     sc.check_like_known_answers(lambda plan, ranges, region: DagHandler(plan, ranges, DeviceRegion(region)).handle_request())

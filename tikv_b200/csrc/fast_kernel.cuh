@@ -78,13 +78,6 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
   unsigned char* stage_base = dyn_smem + A.stage_off;
   const uint32_t STAGE_KEY_CAP = A.stage_key_cap, STAGE_VAL_CAP = A.stage_val_cap;
   const uint32_t STAGE_BYTES = STAGE_KEY_CAP + STAGE_VAL_CAP + 2 * STAGE_OFF_CAP;
-#ifdef B2_ZERO_STAGES
-  {  // (experiment: what the previous kernel left in the stages must not matter)
-    uint4* z = reinterpret_cast<uint4*>(stage_base);
-    for (unsigned int i = tid; i < FK_STAGES * STAGE_BYTES / 16; i += FK_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
-  }
-#endif
 
   // ---- producer warp: bulk copies of each tile's key / value bytes and offset slices, FK_STAGES tiles ahead ----
   if (wid == TILE / 32) {
@@ -187,7 +180,9 @@ __device__ __forceinline__ void fast_body(const DevPlan& P, const ScanArgs& A) {
       unsigned int pa_lo = __shfl_up_sync(0xffffffffu, (unsigned int)t.a, 1), pa_hi = __shfl_up_sync(0xffffffffu, (unsigned int)(t.a >> 32), 1);
       unsigned int pb_lo = __shfl_up_sync(0xffffffffu, (unsigned int)t.b, 1);
       unsigned int px = __shfl_up_sync(0xffffffffu, ((unsigned int)(t.b >> 32) & 0xffffffu) | (k35 ? 1u << 24 : 0u) | (vis ? 1u << 25 : 0u), 1);
-      const bool first = e_raw == A.e_lo;
+      // (on the clamped index: in a unit of one entry the lanes past the end hold that entry too, and looking one entry back
+      //  from it would index the offsets with -1)
+      const bool first = e == A.e_lo;
       if (lane == 0 && !first) {
         KeyTail q;
         const bool q35 = sv.klen(e - 1) == 35;

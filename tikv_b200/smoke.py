@@ -25,9 +25,7 @@ def run():
     import sstfmt
     from tikv_b200.executor import DagHandler, DeviceRegion, SstRegion, checksum
 
-    # (seed 1: the region shape the GPU parity tests run.  Seed 3 with 2000 keys in two blocks trips an open issue in the lean
-    #  aggregation kernel about one run in three -- DESIGN.md "Known issue", tools/smoke_debug.py reproduces it)
-    host = sc.dirty_region(1, n_keys=2000).build(read_ts=sc.READ_TS, n_write_blocks=2)
+    host = sc.dirty_region(3, n_keys=2000).build(read_ts=sc.READ_TS, n_write_blocks=2)  # (three blocks: 3034 + 3034 + 1 entries)
     dev = DeviceRegion(host)
     scan_filter, hash_agg = plans()
     for name, plan, ordered in (("scan+filter", scan_filter, True), ("scan+filter+hash-agg", hash_agg, False)):
