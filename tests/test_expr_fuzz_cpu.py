@@ -1,0 +1,108 @@
+"""`-m "not gpu"`: LIKE and DECIMAL comparisons of the oracle and of the device logic (compiled for the host) against two
+independent references: Python's `re` (a LIKE pattern without escapes is a regular expression: `%` -> `.*`, `_` -> one
+byte / one character) and Python's `decimal` arithmetic.  Seeded random strings, patterns and decimals in every
+(precision, fraction) shape the mixed-table scenarios use."""
+import decimal
+import random
+import re
+
+import pytest
+
+import emu
+import kvfmt
+import orc
+from tikv_b200 import ffi
+from tikv_b200.plan import ColumnDef, Plan, col, const_bytes, const_decimal, const_int, eq, ge, gt, in_, le, like, lt, ne, nulleq
+
+TABLE = 77
+COLS = [ColumnDef(100, pk_handle=True), ColumnDef(1, tp=ffi.TP_VARCHAR), ColumnDef(2, tp=ffi.TP_NEWDECIMAL)]
+SHAPES = [(1, 0), (9, 0), (10, 2), (14, 4), (18, 9), (30, 10), (65, 30), (5, 5), (20, 0), (12, 11)]
+
+
+def rand_decimal(rng):
+    prec, frac = rng.choice(SHAPES)
+    digs = "".join(rng.choice("0123456789") for _ in range(prec)) if rng.random() < 0.85 else ("0" * prec if rng.random() < 0.5 else "0" * (prec - 1) + "1")
+    if rng.random() < 0.3:  # small magnitudes collide across shapes: equality cases
+        digs = "0" * (prec - 1) + rng.choice("0125")
+    txt = (digs[:prec - frac] or "0") + ("." + digs[prec - frac:] if frac else "")
+    return ("-" if rng.random() < 0.5 else "") + txt, prec, frac
+
+
+def build(rng, n, alphabet):
+    r = kvfmt.Region()
+    rows = []
+    for h in range(n):
+        s = None if rng.random() < 0.1 else "".join(rng.choice(alphabet) for _ in range(rng.choice([0, 1, 2, 3, 5, 8, 13])))
+        d = None if rng.random() < 0.1 else rand_decimal(rng)
+        cells = [(1, None if s is None else s.encode(), "bytes"), (2, d, "decimal")]
+        r.put(kvfmt.row_key(TABLE, h), kvfmt.row_v2(cells), 10, 20)
+        rows.append((h, s, d))
+    return r.build(read_ts=100), rows
+
+
+def like_regex(pattern, binary):
+    out = []
+    for ch in (pattern.encode() if binary else pattern):
+        c = bytes([ch]) if binary else ch
+        if c in (b"%", "%"):
+            out.append(b".*" if binary else ".*")
+        elif c in (b"_", "_"):
+            out.append(b"." if binary else ".")
+        else:
+            out.append(re.escape(c))
+    return re.compile((b"" if binary else "").join(out), re.S)
+
+
+@pytest.mark.parametrize("run", [orc.dag_handle, emu.dag_handle], ids=["oracle", "device-logic"])
+def test_like_against_regular_expressions(run):
+    rng = random.Random(20260922)
+    for collation, alphabet in ((63, "ab%_c"), (-46, "abé测🐶c"), (63, "abé测c")):
+        region, rows = build(rng, 300, alphabet)
+        binary = collation == 63
+        pats = ["%", "_", "", "a%", "%a", "%a%", "_b%", "a_c", "%_%_%", "ab", "%é%", "测_", "__", "%b_", "a%b%c", "___%"]
+        pats += ["".join(rng.choice("ab%_c" if binary and "é" not in alphabet else "abé%_测") for _ in range(rng.randrange(1, 6))) for _ in range(14)]
+        for i in range(0, len(pats), 10):
+            chunk = pats[i:i + 10]
+            exprs = [like(col(1, tp=ffi.TP_VARCHAR, collation=collation), const_bytes(p.encode(), collation), escape=0, collation=collation) for p in chunk]  # (escape 0: no character is one)
+            plan = Plan().table_scan(TABLE, COLS).projection(col(0), *exprs).build()
+            res = run(plan, [kvfmt.table_range(TABLE)], region)
+            assert res.status == 0, res.message
+            got = {r[0]: r[1:] for r in res.rows()}
+            for h, s, _ in rows:
+                for p, g in zip(chunk, got[h]):
+                    if s is None:
+                        assert g is None
+                        continue
+                    want = like_regex(p, binary).fullmatch(s.encode() if binary else s) is not None
+                    assert g == int(want), (collation, s, p, g, want)
+
+
+@pytest.mark.parametrize("run", [orc.dag_handle, emu.dag_handle], ids=["oracle", "device-logic"])
+def test_decimal_comparisons_against_python_decimal(run):
+    rng = random.Random(7)
+    ctx = decimal.Context(prec=200)
+    region, rows = build(rng, 400, "ab")
+    dc = col(2, tp=ffi.TP_NEWDECIMAL)
+    for _ in range(12):
+        cv = rand_decimal(rng)
+        k = const_decimal(kvfmt.decimal_bin(*cv))
+        other = rand_decimal(rng)
+        exprs = [f(dc, k) for f in (lt, le, gt, ge, eq, ne, nulleq)] + [in_(dc, k, const_decimal(kvfmt.decimal_bin(*other)))]
+        plan = Plan().table_scan(TABLE, COLS).projection(col(0), *exprs).build()
+        res = run(plan, [kvfmt.table_range(TABLE)], region)
+        assert res.status == 0, res.message
+        got = {r[0]: r[1:] for r in res.rows()}
+        c, o = ctx.create_decimal(cv[0]), ctx.create_decimal(other[0])
+        for h, _, d in rows:
+            g = got[h]
+            if d is None:
+                assert g[:6] == (None,) * 6 and g[6] == 0 and g[7] is None
+                continue
+            x = ctx.create_decimal(d[0])
+            want = (x < c, x <= c, x > c, x >= c, x == c, x != c, x == c, x == c or x == o)
+            assert g == tuple(int(w) for w in want), (d, cv, other, g, want)
+    # a selection + count over the same column: the rows the predicate keeps
+    cv = ("0.5", 3, 2)
+    plan = Plan().table_scan(TABLE, COLS).selection(ge(dc, const_decimal(kvfmt.decimal_bin(*cv)))).aggregation([("count", const_int(1))]).build()
+    res = run(plan, [kvfmt.table_range(TABLE)], region)
+    assert res.rows() == [(sum(1 for _, _, d in rows if d is not None and ctx.create_decimal(d[0]) >= decimal.Decimal("0.5")),)]
