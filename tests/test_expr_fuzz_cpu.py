@@ -106,3 +106,44 @@ def test_decimal_comparisons_against_python_decimal(run):
     plan = Plan().table_scan(TABLE, COLS).selection(ge(dc, const_decimal(kvfmt.decimal_bin(*cv)))).aggregation([("count", const_int(1))]).build()
     res = run(plan, [kvfmt.table_range(TABLE)], region)
     assert res.rows() == [(sum(1 for _, _, d in rows if d is not None and ctx.create_decimal(d[0]) >= decimal.Decimal("0.5")),)]
+
+
+@pytest.mark.parametrize("run", [orc.dag_handle, emu.dag_handle], ids=["oracle", "device-logic"])
+def test_time_and_duration_comparisons_against_python_tuples(run):
+    """DATETIME(fsp 3) / DATE columns against constants of the other type and fsp, DURATION against nanosecond constants:
+    `Ord for Time` is the order of (year, month, day, hour, minute, second, microsecond) — the fsp / type nibble must not
+    take part — and `Ord for Duration` the order of the signed nanoseconds."""
+    from tikv_b200.plan import const_duration, const_time
+    rng = random.Random(99)
+    cols = [ColumnDef(100, pk_handle=True), ColumnDef(1, tp=ffi.TP_DATETIME, decimal=3), ColumnDef(2, tp=ffi.TP_DATE), ColumnDef(3, tp=ffi.TP_DURATION)]
+
+    def rand_time(date):
+        if rng.random() < 0.08:
+            return (0, 0, 0, 0, 0, 0, 0)
+        t = (rng.choice([1, 999, 2024, 2024, 2025, 9999]), rng.randrange(1, 13), rng.randrange(1, 29))
+        return t + ((0, 0, 0, 0) if date else (rng.randrange(24), rng.randrange(60), rng.randrange(60), rng.randrange(1000) * 1000))
+    r = kvfmt.Region()
+    rows = []
+    for h in range(300):
+        dt, d = (None if rng.random() < 0.1 else rand_time(False)), (None if rng.random() < 0.1 else rand_time(True))
+        du = None if rng.random() < 0.1 else rng.choice([0, 1, -1, 10 ** 9, -3 * 10 ** 12, rng.randrange(-10 ** 15, 10 ** 15)])
+        r.put(kvfmt.row_key(TABLE, h), kvfmt.row_v2([(1, None if dt is None else kvfmt.time_packed(*dt), "time"), (2, None if d is None else kvfmt.time_packed(*d), "time"), (3, du, "duration")]), 10, 20)
+        rows.append((h, dt, d, du))
+    region = r.build(read_ts=100)
+    c_dt, c_d, c_du = col(1, tp=ffi.TP_DATETIME), col(2, tp=ffi.TP_DATE), col(3, tp=ffi.TP_DURATION)
+    for _ in range(8):
+        kt, kd, kn = rand_time(False), rand_time(True), rng.choice([0, 1, -1, 10 ** 9, rng.randrange(-10 ** 15, 10 ** 15)])
+        exprs = [lt(c_dt, const_time(kvfmt.time_packed(*kt))), ge(c_dt, const_time(kvfmt.time_packed(*kd), ffi.TP_DATE)), eq(c_d, const_time(kvfmt.time_packed(*kd), ffi.TP_DATE)),
+                 le(c_d, const_time(kvfmt.time_packed(*kt))), gt(c_dt, c_d), nulleq(c_d, c_dt), lt(c_du, const_duration(kn)), ne(c_du, const_duration(kn)),
+                 in_(c_d, const_time(kvfmt.time_packed(*kd), ffi.TP_DATE), const_time(0, ffi.TP_DATE))]
+        res = run(Plan().table_scan(TABLE, cols).projection(col(0), *exprs).build(), [kvfmt.table_range(TABLE)], region)
+        assert res.status == 0, res.message
+        got = {x[0]: x[1:] for x in res.rows()}
+
+        def n(v):  # NULL-propagating comparison result
+            return None if v is None else int(v)
+        for h, dt, d, du in rows:
+            want = (n(None if dt is None else dt < kt), n(None if dt is None else dt >= kd), n(None if d is None else d == kd), n(None if d is None else d <= kt),
+                    n(None if dt is None or d is None else dt > d), int((d is None and dt is None) or (d is not None and dt is not None and d == dt)),
+                    n(None if du is None else du < kn), n(None if du is None else du != kn), n(None if d is None else d in (kd, (0,) * 7)))
+            assert got[h] == want, (h, dt, d, du, kt, kd, kn, got[h], want)

@@ -80,3 +80,42 @@ def test_empty_input_and_rejected_blocks():
         bad[rng.randrange(len(bad) - 5)] ^= 1 << rng.randrange(8)
         rc, kvs = sstfmt.decode(bytes(bad), [0, len(bad)])
         assert rc in (0, 1, 2)
+
+
+def py_decode_block(block, trailer_len=5, key_prefix_len=1, key_suffix_len=8):
+    """A third reading of the layout, in plain Python (no restart array needed for a forward walk)."""
+    def var32(p):
+        v = s = 0
+        while True:
+            b = block[p]; p += 1
+            v |= (b & 0x7F) << s; s += 7
+            if not b & 0x80:
+                return v, p
+    end = len(block) - trailer_len
+    nr = struct.unpack_from("<I", block, end - 4)[0]
+    lim = end - 4 - 4 * nr
+    restarts = struct.unpack_from("<%dI" % nr, block, lim)
+    p, key, out, starts = 0, b"", [], []
+    while p < lim:
+        starts.append(p)
+        sh, p = var32(p); ns, p = var32(p); vl, p = var32(p)
+        key = key[:sh] + block[p:p + ns]; p += ns
+        assert key[len(key) - key_suffix_len:] == (b"\x01" + b"\0" * 7)[:key_suffix_len] or not key_suffix_len
+        out.append((key[key_prefix_len:len(key) - key_suffix_len], block[p:p + vl])); p += vl
+    assert p == lim and all(r in starts for r in restarts) and restarts[0] == 0
+    return out
+
+
+def test_builder_output_read_by_an_independent_python_walker():
+    host = sc.dirty_region(11, n_keys=500).build(read_ts=sc.READ_TS)
+    for opts in (dict(), dict(restart_interval=4, block_size=1500), dict(block_size=0, entries_per_block=50)):
+        blk = host.wblocks[0]
+        data, offs = sstfmt.build(blk, **opts)
+        kvs = []
+        for a, b in zip(offs, offs[1:]):
+            kvs += py_decode_block(data[a:b])
+        assert kvs == blk.kvs
+        ri = opts.get("restart_interval", 16)
+        for a, b in zip(offs, offs[1:]):  # a restart point every `restart_interval` entries
+            nr = struct.unpack_from("<I", data, b - 5 - 4)[0]
+            assert nr == -(-len(py_decode_block(data[a:b])) // ri)
