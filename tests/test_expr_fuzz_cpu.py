@@ -147,3 +147,32 @@ def test_time_and_duration_comparisons_against_python_tuples(run):
                     n(None if dt is None or d is None else dt > d), int((d is None and dt is None) or (d is not None and dt is not None and d == dt)),
                     n(None if du is None else du < kn), n(None if du is None else du != kn), n(None if d is None else d in (kd, (0,) * 7)))
             assert got[h] == want, (h, dt, d, du, kt, kd, kn, got[h], want)
+
+
+@pytest.mark.parametrize("run", [orc.dag_handle, emu.dag_handle], ids=["oracle", "device-logic"])
+def test_reference_comparison_truth_table(run):
+    """impl_compare.rs generate_numeric_compare_cases (63 rows over {NULL, 3.5, -2.1} x {Gt, Ge, Lt, Le, Eq, Ne, NullEq}), the
+    table behind the reference's test_compare_real / test_compare_duration (values mapped through
+    Duration::from_millis(v * 1000)) / test_compare_decimal (f64 -> Decimal): tests/golden/compare_cases.json, extracted
+    from the reference by tests/golden/gen_compare_cases.py."""
+    import json
+    import os
+    from tikv_b200.plan import const_duration, const_real, null
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "compare_cases.json")))["cases"]
+    assert len(cases) == 63
+    ops = {"Gt": gt, "Ge": ge, "Lt": lt, "Le": le, "Eq": eq, "Ne": ne, "NullEq": nulleq}
+    kinds = {
+        "real": lambda v: null(ffi.TP_DOUBLE) if v is None else const_real(v),
+        "duration": lambda v: null(ffi.TP_DURATION) if v is None else const_duration(int(v * 1000.0) * 1_000_000),
+        "decimal": lambda v: null(ffi.TP_NEWDECIMAL) if v is None else const_decimal(kvfmt.decimal_bin(repr(v), 2, 1)),
+    }
+    r = kvfmt.Region()
+    r.put(kvfmt.row_key(TABLE, 1), kvfmt.row_v2([(1, b"x", "bytes")]), 10, 20)
+    region = r.build(read_ts=100)
+    for kind, mk in kinds.items():
+        for i in range(0, len(cases), 9):
+            chunk = cases[i:i + 9]
+            exprs = [ops[c["op"]](mk(c["a"]), mk(c["b"])) for c in chunk]
+            res = run(Plan().table_scan(TABLE, COLS).projection(*exprs).build(), [kvfmt.table_range(TABLE)], region)
+            assert res.status == 0, (kind, res.message)
+            assert list(res.rows()[0]) == [c["expect"] for c in chunk], (kind, chunk, res.rows()[0])
