@@ -347,7 +347,8 @@ def scalar_known_answers():
     """(label, Expr over constants, expected value | None | "error"): the reference's own unit-test vectors for the scalar
     functions above — impl_arithmetic.rs test_mod_int :735-760, test_mod_int_unsigned :763-805, test_mod_real :808-835,
     test_int_divide_int :902-948, test_int_divide_int_overflow :951-983; impl_op.rs test_unary_minus_int :425-472;
-    impl_math.rs test_abs_int :854-866; impl_control.rs test_if_null :150-165, test_case_when :168-207, test_if :243-250."""
+    impl_math.rs test_abs_int :854-866; impl_control.rs test_if_null :150-165, test_case_when :168-207, test_if :243-250;
+    test_plus_int / test_plus_real / test_minus_int / test_minus_real; the bit operators and casts (cited where they are added)."""
     MAX, MIN, UMAX = (1 << 63) - 1, -(1 << 63), (1 << 64) - 1
 
     def I(v, unsigned=False):
@@ -408,6 +409,17 @@ def scalar_known_answers():
     K.append(("cast_int_as_ureal(-1)", cast_int_as_real(I(-1), unsigned=True), float(UMAX)))  # `as u64 as f64`
     for a in (0, UMAX, MAX):
         K.append((f"cast_uint_as_real({a})", cast_int_as_real(I(a, True)), float(a)))
+    # impl_arithmetic.rs test_plus_int :551-588, test_plus_real :591-617, test_minus_int :636-678, test_minus_real :681-713
+    FMAX = 1.7976931348623157e308
+    for a, au, b, bu, e in [(None, False, 1, False, None), (1, False, None, False, None), (17, False, 25, False, 42), (MIN, False, MAX + 1, True, 0)]:
+        K.append((f"plus_int({a}{'u' if au else ''},{b}{'u' if bu else ''})", plus(I(a, au), I(b, bu)), e))
+    for a, au, b, bu, e in [(None, False, 1, False, None), (1, False, None, False, None), (12, False, 1, False, 11), (0, True, MIN, False, MIN),  # (i64::MAX as u64 + 1) as i64
+                            (MIN, False, MAX, False, "error"), (MAX, False, MIN, False, "error"), (-1, False, 2, True, "error"), (1, True, 2, False, "error")]:
+        K.append((f"minus_int({a}{'u' if au else ''},{b}{'u' if bu else ''})", minus(I(a, au), I(b, bu)), e))
+    for a, b, e in [(1.01001, -0.01, 1.00001), (1e308, 1e308, "error"), (FMAX - 1.0, 2.0, FMAX)]:
+        K.append((f"plus_real({a},{b})", plus(R(a), R(b)), e))
+    for a, b, e in [(1.01001, -0.01, 1.02001), (-FMAX, FMAX, "error"), (-FMAX, 1.0, -FMAX)]:
+        K.append((f"minus_real({a},{b})", minus(R(a), R(b)), e))
     for a in (float.fromhex("-0x1.fffffep+127"), float.fromhex("0x1.fffffep+127"), -1.7976931348623157e308, 0.0, 1.7976931348623157e308, float(MIN), float(MAX), float(UMAX), None):
         K.append((f"cast_real_as_real({a})", cast_real_as_real(R(a)), a))
     return K
