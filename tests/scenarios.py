@@ -422,6 +422,21 @@ def scalar_known_answers():
         K.append((f"minus_real({a},{b})", minus(R(a), R(b)), e))
     for a in (float.fromhex("-0x1.fffffep+127"), float.fromhex("0x1.fffffep+127"), -1.7976931348623157e308, 0.0, 1.7976931348623157e308, float(MIN), float(MAX), float(UMAX), None):
         K.append((f"cast_real_as_real({a})", cast_real_as_real(R(a)), a))
+    # impl_op.rs test_logical_and / _or / _xor, test_unary_not_int / _real, test_is_null (Int, Real, Decimal, Time, Duration arms)
+    for a, b, e in [(1, 1, 1), (1, 0, 0), (0, 0, 0), (2, -1, 1), (0, None, 0), (None, 1, None)]:
+        K.append((f"and({a},{b})", and_(I(a), I(b)), e))
+    for a, b, e in [(1, 1, 1), (1, 0, 1), (0, 0, 0), (2, -1, 1), (1, None, 1), (None, 0, None)]:
+        K.append((f"or({a},{b})", or_(I(a), I(b)), e))
+    for a, b, e in [(1, 1, 0), (1, 0, 1), (0, 0, 0), (2, -1, 0), (-1, 0, 1), (0, None, None), (None, 1, None)]:
+        K.append((f"xor({a},{b})", xor_(I(a), I(b)), e))
+    for a, e in [(None, None), (0, 1), (1, 0), (2, 0), (-1, 0)]:
+        K.append((f"not_int({a})", not_(I(a)), e))
+    for a, e in [(None, None), (0.0, 1), (1.0, 0), (0.3, 0)]:
+        K.append((f"not_real({a})", not_(R(a)), e))
+    K += [("is_null(int NULL)", is_null(I(None)), 1), ("is_null(int 0)", is_null(I(0)), 0), ("is_null(real NULL)", is_null(R(None)), 1), ("is_null(real 0)", is_null(R(0.0)), 0),
+          ("is_null(decimal NULL)", is_null(null(ffi.TP_NEWDECIMAL)), 1), ("is_null(decimal 1)", is_null(const_decimal(kvfmt.decimal_bin("1", 1, 0))), 0),
+          ("is_null(time NULL)", is_null(null(ffi.TP_DATETIME)), 1), ("is_null(time zero)", is_null(const_time(0)), 0),
+          ("is_null(duration NULL)", is_null(null(ffi.TP_DURATION)), 1), ("is_null(duration 1ns)", is_null(const_duration(1)), 0)]
     return K
 
 
@@ -500,7 +515,7 @@ def check_scalar_known_answers(run, error_labels=None):
     region = r.build(read_ts=10)
     cols = [ColumnDef(100, pk_handle=True), ColumnDef(1)]
     cases = scalar_known_answers()
-    assert len(cases) >= 70
+    assert len(cases) >= 170
     scan = lambda: Plan().table_scan(TABLE, cols)
     ok = [c for c in cases if c[2] != "error"]
     for label, expr, _ in [c for c in cases if c[2] == "error"]:  # an error ends the request: one plan per case
